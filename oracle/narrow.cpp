@@ -1,0 +1,960 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see na.hpp header).
+// Narrow phase restated from the reference:
+//   pipeline/narrow_phase/contact_generator/default_contact_dispatcher.rs:27-97 (dispatch priority)
+//   .../ball_ball_manifold_generator.rs:28-67 + query/contact/contact_ball_ball.rs:8-38
+//   .../plane_ball_manifold_generator.rs:30-83
+//   .../plane_convex_polyhedron_manifold_generator.rs:29-81
+//   .../ball_convex_polyhedron_manifold_generator.rs:28-122 + query/point/point_aabb.rs:9-135,
+//        query/point/point_support_map.rs:15-53,90-117
+//   .../convex_polyhedron_convex_polyhedron_manifold_generator.rs:83-167
+//   shape/cuboid.rs:185-405, shape/convex.rs:388-540, shape/convex_polygonal_feature3.rs:217-401,
+//   utils/point_in_poly2d.rs:5-26, query/ray/ray_plane.rs:9-23,
+//   query/closest_points/closest_points_segment_segment.rs:62-141,
+//   query/contact/contact_manifold.rs:165-236 (distance-based tracking, 0.02),
+//   pipeline/narrow_phase/narrow_phase.rs:56-104,168-197, pipeline/object/query_type.rs:39-51.
+#include <chrono>
+#include <cstring>
+#include <vector>
+#include "gjk_epa.hpp"
+#include "oracle.h"
+#include "scene.hpp"
+
+namespace orc {
+
+struct AABB {
+    V3 mins, maxs;
+};
+AABB fat_aabb(const Objects& o, uint32_t i, real margin);
+void broad_phase_dbvt(uint32_t n, const AABB* fat, const uint32_t* groups, std::vector<uint32_t>& pairs_out);
+
+// ---------------------------------------------------------------------------------------------
+// ConvexPolygonalFeature (convex_polygonal_feature3.rs:39-54)
+// ---------------------------------------------------------------------------------------------
+struct Feature {
+    std::vector<V3> vertices;
+    std::vector<V3> edge_normals;
+    bool has_normal = false;
+    V3 normal = {0, 0, 0};
+    uint32_t feature_id = FID_UNKNOWN;
+    std::vector<uint32_t> vertices_id, edges_id;
+    void clear() {
+        vertices.clear();
+        edge_normals.clear();
+        vertices_id.clear();
+        edges_id.clear();
+        has_normal = false;
+        feature_id = FID_UNKNOWN;
+    }
+    void push(V3 p, uint32_t id) {
+        vertices.push_back(p);
+        vertices_id.push_back(id);
+    }
+    void transform_by(const Iso& m) {
+        for (auto& p : vertices) p = iso_mul_point(m, p);
+        for (auto& n : edge_normals) n = iso_mul_vec(m, n);
+        if (has_normal) normal = iso_mul_vec(m, normal);
+    }
+    void recompute_edge_normals() {  // :157-170
+        edge_normals.clear();
+        for (size_t i1 = 0; i1 < vertices.size(); ++i1) {
+            size_t i2 = (i1 + 1) % vertices.size();
+            V3 dpt = vertices[i2] - vertices[i1];
+            V3 sn = cross(dpt, normal), nn;
+            if (try_normalize(sn, EPS, &nn))
+                edge_normals.push_back(nn);
+            else
+                edge_normals.push_back(v3(0, 0, 0));
+        }
+    }
+    size_t nedges() const {
+        size_t l = vertices.size();
+        return l == 1 ? 0 : (l == 2 ? 1 : l);
+    }
+    bool edge(uint32_t edge_id, V3* a, V3* b) const {  // :134-143
+        for (size_t i1 = 0; i1 < vertices.size(); ++i1) {
+            if (i1 < edges_id.size() && edges_id[i1] == edge_id) {
+                size_t i2 = (i1 + 1) % vertices.size();
+                *a = vertices[i1];
+                *b = vertices[i2];
+                return true;
+            }
+        }
+        return false;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Cuboid (cuboid.rs)
+// ---------------------------------------------------------------------------------------------
+static void cuboid_face(V3 he, uint32_t i, Feature& out) {  // cuboid.rs:185-277 (dim3)
+    out.clear();
+    uint32_t i1;
+    real sign;
+    if (i < 3) {
+        i1 = i;
+        sign = 1;
+    } else {
+        i1 = i - 3;
+        sign = -1;
+    }
+    uint32_t i2 = (i1 + 1) % 3, i3 = (i1 + 2) % 3;
+    uint32_t edge_i2, edge_i3;
+    if (sign > 0) {
+        edge_i2 = i2;
+        edge_i3 = i3;
+    } else {
+        edge_i2 = i3;
+        edge_i3 = i2;
+    }
+    uint32_t mask_i2 = ~(1u << edge_i2), mask_i3 = ~(1u << edge_i3);
+    V3 vertex = he;
+    vertex[i1] *= sign;
+    uint32_t sbit = sign < 0 ? 1 : 0, msbit = sign < 0 ? 0 : 1;
+    uint32_t vertex_id = sbit << i1;
+    out.push(vertex, fid(F_VERTEX, vertex_id));
+    out.edges_id.push_back(fid(F_EDGE, edge_i2 | ((vertex_id & mask_i2) << 2)));
+
+    vertex[i2] = -sign * he[i2];
+    vertex[i3] = sign * he[i3];
+    vertex_id |= (msbit << i2) | (sbit << i3);
+    out.push(vertex, fid(F_VERTEX, vertex_id));
+    out.edges_id.push_back(fid(F_EDGE, edge_i3 | ((vertex_id & mask_i3) << 2)));
+
+    vertex[i2] = -he[i2];
+    vertex[i3] = -he[i3];
+    vertex_id |= (1u << i2) | (1u << i3);
+    out.push(vertex, fid(F_VERTEX, vertex_id));
+    out.edges_id.push_back(fid(F_EDGE, edge_i2 | ((vertex_id & mask_i2) << 2)));
+
+    vertex[i2] = sign * he[i2];
+    vertex[i3] = -sign * he[i3];
+    vertex_id = (sbit << i1) | (sbit << i2) | (msbit << i3);
+    out.push(vertex, fid(F_VERTEX, vertex_id));
+    out.edges_id.push_back(fid(F_EDGE, edge_i3 | ((vertex_id & mask_i3) << 2)));
+
+    V3 normal = v3(0, 0, 0);
+    normal[i1] = sign;
+    out.normal = normal;
+    out.has_normal = true;
+    out.feature_id = sign > 0 ? fid(F_FACE, i1) : fid(F_FACE, i1 + 3);
+    out.recompute_edge_normals();
+}
+
+static void cuboid_support_face_toward(V3 he, const Iso& m, V3 dir, Feature& out) {  // cuboid.rs:279-307
+    out.clear();
+    V3 ld = iso_inv_vec(m, dir);
+    uint32_t iamax = 0;
+    real amax = std::fabs(ld[0]);
+    for (uint32_t i = 1; i < 3; ++i) {
+        real c = std::fabs(ld[i]);
+        if (c > amax) {
+            amax = c;
+            iamax = i;
+        }
+    }
+    if (ld[iamax] > 0)
+        cuboid_face(he, iamax, out);
+    else
+        cuboid_face(he, iamax + 3, out);
+    out.transform_by(m);
+}
+
+static void cuboid_support_feature_toward(V3 he, const Iso& m, V3 dir, real angle, Feature& out) {  // cuboid.rs:309-405
+    V3 ld = iso_inv_vec(m, dir);
+    real cang = std::cos(angle);
+    V3 sp = he;
+    out.clear();
+    real sang = std::sin(angle);
+    uint32_t sp_id = 0;
+    for (uint32_t i1 = 0; i1 < 3; ++i1) {
+        real sign = signum(ld[i1]);
+        if (sign * ld[i1] >= cang) {
+            if (sign > 0)
+                cuboid_face(he, i1, out);
+            else
+                cuboid_face(he, i1 + 3, out);
+            out.transform_by(m);
+            return;
+        } else if (sign < 0) {
+            sp[i1] *= sign;
+            sp_id |= 1u << i1;
+        }
+    }
+    for (uint32_t i = 0; i < 3; ++i) {
+        real sign = signum(ld[i]);
+        if (sign * ld[i] <= sang) {
+            sp[i] = -he[i];
+            V3 p1 = sp;
+            sp[i] = he[i];
+            V3 p2 = sp;
+            uint32_t p2_id = sp_id & ~(1u << i);
+            out.push(iso_mul_point(m, p1), fid(F_VERTEX, sp_id | (1u << i)));
+            out.push(iso_mul_point(m, p2), fid(F_VERTEX, p2_id));
+            uint32_t edge_id = fid(F_EDGE, i | (p2_id << 2));
+            out.edges_id.push_back(edge_id);
+            out.feature_id = edge_id;
+            return;
+        }
+    }
+    out.push(iso_mul_point(m, sp), fid(F_VERTEX, sp_id));
+    out.feature_id = fid(F_VERTEX, sp_id);
+}
+
+static V3 cuboid_feature_normal(uint32_t f) {  // cuboid.rs:502-563 (dim3)
+    uint32_t id = fid_id(f);
+    V3 dir = v3(0, 0, 0);
+    switch (fid_kind(f)) {
+        case F_FACE:
+            if (id < 3)
+                dir[id] = 1;
+            else
+                dir[id - 3] = -1;
+            return dir;
+        case F_EDGE: {
+            uint32_t edge = id & 3u, face1 = (edge + 1) % 3, face2 = (edge + 2) % 3, signs = id >> 2;
+            dir[face1] = (signs & (1u << face1)) ? -1 : 1;
+            dir[face2] = (signs & (1u << face2)) ? -1 : 1;
+            return normalize(dir);
+        }
+        default:
+            for (uint32_t i = 0; i < 3; ++i) dir[i] = (id & (1u << i)) ? -1 : 1;
+            return normalize(dir);
+    }
+}
+
+// AABB::project_point_with_feature for a cuboid (point_aabb.rs:9-135, point_cuboid.rs:17-27)
+static void cuboid_project_point_with_feature(V3 he, const Iso& m, V3 pt, bool* inside_out, V3* proj_out, uint32_t* feature) {
+    V3 mins = v3(0, 0, 0) + (-he), maxs = v3(0, 0, 0) + he;
+    V3 ls_pt = iso_inv_point(m, pt);
+    V3 mins_pt = mins - ls_pt, pt_maxs = ls_pt - maxs;
+    V3 zero = v3(0, 0, 0);
+    V3 shift = sup(mins_pt, zero) - sup(pt_maxs, zero);
+    bool inside = shift.x == 0 && shift.y == 0 && shift.z == 0;
+    V3 ls_proj;
+    if (!inside) {
+        ls_proj = ls_pt + shift;
+    } else {
+        real best = -FMAX;
+        bool is_mins = false;
+        int best_id = 0;
+        for (int i = 0; i < 3; ++i) {
+            real mins_pt_i = mins_pt[i], pt_maxs_i = pt_maxs[i];
+            if (mins_pt_i < pt_maxs_i) {
+                if (pt_maxs[i] > best) {
+                    best_id = i;
+                    is_mins = false;
+                    best = pt_maxs_i;
+                }
+            } else if (mins_pt_i > best) {
+                best_id = i;
+                is_mins = true;
+                best = mins_pt_i;
+            }
+        }
+        shift = v3(0, 0, 0);
+        if (is_mins)
+            shift[best_id] = best;
+        else
+            shift[best_id] = -best;
+        ls_proj = ls_pt + shift;
+    }
+    *inside_out = inside;
+    *proj_out = iso_mul_point(m, ls_proj);
+    int nzero_shifts = 0, last_zero_shift = 0, last_not_zero_shift = 0;
+    for (int i = 0; i < 3; ++i) {
+        if (shift[i] == 0) {
+            nzero_shifts++;
+            last_zero_shift = i;
+        } else
+            last_not_zero_shift = i;
+    }
+    V3 center = (mins + maxs) * real(0.5);
+    if (nzero_shifts == 3) {
+        for (int i = 0; i < 3; ++i) {
+            if (ls_proj[i] > maxs[i] - EPS) {
+                *feature = fid(F_FACE, i);
+                return;
+            }
+            if (ls_proj[i] <= mins[i] + EPS) {
+                *feature = fid(F_FACE, i + 3);
+                return;
+            }
+        }
+        *feature = FID_UNKNOWN;
+    } else if (nzero_shifts == 2) {
+        if (ls_proj[last_not_zero_shift] < center[last_not_zero_shift])
+            *feature = fid(F_FACE, last_not_zero_shift + 3);
+        else
+            *feature = fid(F_FACE, last_not_zero_shift);
+    } else {
+        uint32_t id = 0;
+        for (int i = 0; i < 3; ++i)
+            if (ls_proj[i] < center[i]) id |= 1u << i;
+        if (nzero_shifts == 0)
+            *feature = fid(F_VERTEX, id);
+        else
+            *feature = fid(F_EDGE, (id << 2) | (uint32_t)last_zero_shift);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ConvexHull (convex.rs)
+// ---------------------------------------------------------------------------------------------
+static void hull_face(const Hull& H, uint32_t id, Feature& out) {  // convex.rs:443-461
+    out.clear();
+    uint32_t first = H.face_first[id], last = first + H.face_num[id];
+    for (uint32_t i = first; i < last; ++i) {
+        uint32_t vid = H.vaf[i], eid = H.eaf[i];
+        out.push(H.pt(vid), fid(F_VERTEX, vid));
+        out.edges_id.push_back(fid(F_EDGE, eid));
+    }
+    out.normal = H.fnormal(id);
+    out.has_normal = true;
+    out.feature_id = fid(F_FACE, id);
+    out.recompute_edge_normals();
+}
+static void hull_support_face_toward(const Hull& H, const Iso& m, V3 dir, Feature& out) {  // convex.rs:487-509
+    V3 ls_dir = iso_inv_vec(m, dir);
+    uint32_t best = 0;
+    real max_dot = dot(H.fnormal(0), ls_dir);
+    for (uint32_t i = 1; i < H.nf; ++i) {
+        real d = dot(H.fnormal(i), ls_dir);
+        if (d > max_dot) {
+            max_dot = d;
+            best = i;
+        }
+    }
+    hull_face(H, best, out);
+    out.transform_by(m);
+}
+static uint32_t hull_support_feature_id_toward_eps(const Hull& H, V3 local_dir, real eps) {  // convex.rs:388-415
+    real seps = std::sin(eps), ceps = std::cos(eps);
+    uint32_t sp = 0;
+    real best_dot = dot(H.pt(0), local_dir);
+    for (uint32_t i = 1; i < H.nv; ++i) {
+        real d = dot(H.pt(i), local_dir);
+        if (d > best_dot) {
+            best_dot = d;
+            sp = i;
+        }
+    }
+    uint32_t first = H.vert_first_adj[sp], num = H.vert_num_adj[sp];
+    for (uint32_t i = 0; i < num; ++i) {
+        uint32_t face_id = H.fav[first + i];
+        if (dot(H.fnormal(face_id), local_dir) >= ceps) return fid(F_FACE, face_id);
+    }
+    for (uint32_t i = 0; i < num; ++i) {
+        uint32_t edge_id = H.eav[first + i];
+        if (std::fabs(dot(H.edir(edge_id), local_dir)) <= seps) return fid(F_EDGE, edge_id);
+    }
+    return fid(F_VERTEX, sp);
+}
+static void hull_support_feature_toward(const Hull& H, const Iso& m, V3 dir, real angle, Feature& out) {  // convex.rs:511-540
+    out.clear();
+    V3 local_dir = iso_inv_vec(m, dir);
+    uint32_t f = hull_support_feature_id_toward_eps(H, local_dir, angle);
+    switch (fid_kind(f)) {
+        case F_VERTEX:
+            out.push(H.pt(fid_id(f)), f);
+            out.feature_id = f;
+            break;
+        case F_EDGE: {
+            uint32_t e = fid_id(f), v1 = H.edge_vertices[2 * e], v2 = H.edge_vertices[2 * e + 1];
+            out.push(H.pt(v1), fid(F_VERTEX, v1));
+            out.push(H.pt(v2), fid(F_VERTEX, v2));
+            out.feature_id = f;
+            out.edges_id.push_back(f);
+            break;
+        }
+        default:
+            hull_face(H, fid_id(f), out);
+            break;
+    }
+    out.transform_by(m);
+}
+static V3 hull_feature_normal(const Hull& H, uint32_t f) {  // convex.rs:463-485
+    uint32_t id = fid_id(f);
+    switch (fid_kind(f)) {
+        case F_FACE:
+            return H.fnormal(id);
+        case F_EDGE:
+            return normalize(H.fnormal(H.edge_faces[2 * id]) + H.fnormal(H.edge_faces[2 * id + 1]));
+        default: {
+            uint32_t first = H.vert_first_adj[id], last = first + H.vert_num_adj[id];
+            V3 n = v3(0, 0, 0);
+            for (uint32_t i = first; i < last; ++i) n = n + H.fnormal(H.fav[i]);
+            return normalize(n);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shapes
+// ---------------------------------------------------------------------------------------------
+struct Shape {
+    uint32_t type;
+    real radius;
+    V3 he;      // cuboid half extents / plane normal
+    Hull hull;
+};
+static Shape get_shape(const Objects& o, uint32_t i) {
+    Shape s;
+    s.type = o.shape_type[i];
+    s.radius = o.shape_param[4 * i];
+    s.he = o.p3(i);
+    if (s.type == HULL) s.hull = hull_view(o.hulls, o.hull_id(i));
+    return s;
+}
+static Support as_support(const Shape& s) {
+    Support g;
+    g.he = s.he;
+    g.radius = s.radius;
+    if (s.type == CUBOID)
+        g.kind = Support::S_CUBOID;
+    else if (s.type == HULL) {
+        g.kind = Support::S_HULL;
+        g.hull = s.hull;
+    } else
+        g.kind = Support::S_BALL;
+    return g;
+}
+static bool is_convex_polyhedron(const Shape& s) { return s.type == CUBOID || s.type == HULL; }
+static void support_face_toward(const Shape& s, const Iso& m, V3 dir, Feature& out) {
+    if (s.type == CUBOID)
+        cuboid_support_face_toward(s.he, m, dir, out);
+    else
+        hull_support_face_toward(s.hull, m, dir, out);
+}
+static void support_feature_toward(const Shape& s, const Iso& m, V3 dir, real angle, Feature& out) {
+    if (s.type == CUBOID)
+        cuboid_support_feature_toward(s.he, m, dir, angle, out);
+    else
+        hull_support_feature_toward(s.hull, m, dir, angle, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ContactManifold (contact_manifold.rs), fresh manifold, DistanceBased(0.02)
+// ---------------------------------------------------------------------------------------------
+struct Tracked {
+    Contact c;
+    uint32_t f1, f2;
+};
+struct Manifold {
+    std::vector<Tracked> contacts;
+    std::vector<std::pair<V3, size_t>> cache;
+    size_t deepest = 0;
+    void push(const Contact& c, uint32_t f1, uint32_t f2, V3 tracking_pt) {  // :165-236
+        const real threshold = real(0.02);
+        size_t closest = cache.size();
+        real closest_dist = threshold * threshold;
+        for (size_t i = 0; i < cache.size(); ++i) {
+            real d = norm_squared(tracking_pt - cache[i].first);
+            if (d < closest_dist) {
+                closest_dist = d;
+                closest = i;
+            }
+        }
+        bool is_deepest = contacts.empty() || c.depth > contacts[deepest].c.depth;
+        if (closest == cache.size()) {
+            contacts.push_back({c, f1, f2});
+            cache.push_back({tracking_pt, contacts.size() - 1});
+            if (is_deepest) deepest = contacts.size() - 1;
+        } else {
+            size_t ci = cache[closest].second;
+            if (is_deepest) deepest = ci;
+            if (c.depth <= contacts[ci].c.depth) return;
+            contacts[ci] = {c, f1, f2};
+            cache[closest].first = tracking_pt;
+        }
+    }
+};
+
+static Contact contact_new_wo_depth(V3 w1, V3 w2, V3 n) { return {w1, w2, n, -dot(n, w2 - w1)}; }
+
+// ---------------------------------------------------------------------------------------------
+// Generators
+// ---------------------------------------------------------------------------------------------
+static const uint32_t FACE0 = (F_FACE << 30);
+
+static void gen_ball_ball(const Iso& ma, real r1, const Iso& mb, real r2, real prediction, Manifold& mf) {
+    V3 c1 = ma.t, c2 = mb.t;
+    V3 delta = c2 - c1;
+    real d2 = norm_squared(delta);
+    real sum_radius = r1 + r2;
+    real sre = sum_radius + prediction;
+    if (d2 < sre * sre) {
+        V3 normal = d2 != 0 ? normalize(delta) : v3(1, 0, 0);
+        Contact c = {c1 + normal * r1, c2 + normal * (-r2), normal, sum_radius - std::sqrt(d2)};
+        mf.push(c, FACE0, FACE0, v3(0, 0, 0));
+    }
+}
+
+// plane_ball_manifold_generator.rs:30-83.  (m1, plane) (m2, ball)
+static void gen_plane_ball(const Iso& m1, V3 plane_n, const Iso& m2, real radius, real prediction, bool flip, Manifold& mf) {
+    V3 n = iso_mul_vec(m1, plane_n);
+    V3 pc = m1.t, bc = m2.t;
+    real dist = dot(bc - pc, n);
+    real depth = -dist + radius;
+    if (depth > -prediction) {
+        V3 world1 = bc + n * (-dist);
+        V3 world2 = bc + n * (-radius);
+        if (!flip)
+            mf.push({world1, world2, n, depth}, FACE0, FACE0, v3(0, 0, 0));
+        else
+            mf.push({world2, world1, -n, depth}, FACE0, FACE0, v3(0, 0, 0));
+    }
+}
+
+// plane_convex_polyhedron_manifold_generator.rs:29-81
+static void gen_plane_convex(const Iso& m1, V3 plane_n, const Iso& m2, const Shape& cp, real prediction, bool flip, Manifold& mf) {
+    V3 n = iso_mul_vec(m1, plane_n);
+    V3 pc = m1.t;
+    Feature feat;
+    support_face_toward(cp, m2, -n, feat);
+    for (size_t i = 0; i < feat.vertices.size(); ++i) {
+        V3 world2 = feat.vertices[i];
+        V3 dpt = world2 - pc;
+        real dist = dot(dpt, n);
+        if (dist <= prediction) {
+            V3 world1 = world2 + (-n * dist);
+            V3 local2 = iso_inv_point(m2, world2);
+            uint32_t f2 = feat.vertices_id[i];
+            if (!flip)
+                mf.push({world1, world2, n, -dist}, FACE0, f2, local2);
+            else
+                mf.push({world2, world1, -n, -dist}, f2, FACE0, local2);
+        }
+    }
+}
+
+// point_support_map.rs:15-53 (solid = false) for a hull
+static void hull_project_point(const Hull& H, const Iso& m_in, V3 point, bool* inside, V3* proj, GJKStats* st) {
+    Iso id = iso_identity();
+    Iso m = m_in;
+    m.t = (-point) + m_in.t;  // Translation::from(-point.coords) * m
+    Support shape;
+    shape.kind = Support::S_HULL;
+    shape.hull = H;
+    Support origin;
+    origin.kind = Support::S_ORIGIN;
+    V3 dir;
+    if (!unit_try_new(-m.t, EPS, &dir)) dir = v3(1, 0, 0);
+    VoronoiSimplex simplex;
+    simplex.reset(cso_from_shapes(m, shape, id, origin, dir));
+    GJKResult r = gjk_closest_points(m, shape, id, origin, FMAX, simplex, st);  // gjk::project_origin
+    if (r.kind == GJK_CLOSEST_POINTS) {
+        *inside = false;
+        *proj = r.p1 + point;
+        return;
+    }
+    // GJK_INTERSECTION (anything else is unreachable!() in the reference)
+    EPA epa;
+    if (st) st->epa_calls++;
+    V3 p1, p2, n;
+    *inside = true;
+    if (epa.closest_points(m, shape, id, origin, simplex, &p1, &p2, &n, st))
+        *proj = p1 + point;
+    else {
+        if (st) st->epa_fail++;
+        *proj = point;
+    }
+}
+// point_support_map.rs:97-116
+static void hull_project_point_with_feature(const Hull& H, const Iso& m, V3 point, bool* inside, V3* proj, uint32_t* feature, GJKStats* st) {
+    hull_project_point(H, m, point, inside, proj, st);
+    V3 dpt = point - *proj;
+    V3 local_dir = *inside ? iso_inv_vec(m, -dpt) : iso_inv_vec(m, dpt);
+    V3 u;
+    if (unit_try_new(local_dir, EPS, &u))
+        *feature = hull_support_feature_id_toward_eps(H, u, real(3.14159265358979323846 / 180.0));
+    else
+        *feature = FID_UNKNOWN;
+}
+
+// ball_convex_polyhedron_manifold_generator.rs:28-122.  (m1, ball) (m2, convex polyhedron)
+static void gen_ball_convex(const Iso& m1, real radius, const Iso& m2, const Shape& cp, real prediction, bool flip, Manifold& mf,
+                            GJKStats* st) {
+    V3 ball_center = m1.t;
+    bool inside;
+    V3 world2;
+    uint32_t f2;
+    if (cp.type == CUBOID)
+        cuboid_project_point_with_feature(cp.he, m2, ball_center, &inside, &world2, &f2);
+    else
+        hull_project_point_with_feature(cp.hull, m2, ball_center, &inside, &world2, &f2, st);
+    V3 dpt = world2 - ball_center;
+    real depth;
+    V3 normal, dir;
+    real dist;
+    if (unit_try_new_and_get(dpt, EPS, &dir, &dist)) {
+        if (inside) {
+            depth = dist + radius;
+            normal = -dir;
+        } else {
+            depth = -dist + radius;
+            normal = dir;
+        }
+    } else {
+        if (f2 == FID_UNKNOWN) return;
+        depth = radius;
+        normal = -(cp.type == CUBOID ? cuboid_feature_normal(f2) : hull_feature_normal(cp.hull, f2));
+    }
+    if (depth >= -prediction) {
+        V3 world1 = ball_center + normal * radius;
+        // geometry of f2: an Edge feature needs cp.edge(f2) (cannot fail); nothing else can reject the contact
+        if (!flip)
+            mf.push({world1, world2, normal, depth}, FACE0, f2, v3(0, 0, 0));
+        else
+            mf.push({world2, world1, -normal, depth}, f2, FACE0, v3(0, 0, 0));
+    }
+}
+
+// utils/point_in_poly2d.rs:5-26
+static bool point_in_poly2d(V2 pt, const std::vector<V2>& poly) {
+    if (poly.empty()) return false;
+    real sign = 0;
+    for (size_t i1 = 0; i1 < poly.size(); ++i1) {
+        size_t i2 = (i1 + 1) % poly.size();
+        V2 seg_dir = sub2(poly[i2], poly[i1]);
+        V2 dpt = sub2(pt, poly[i1]);
+        real perp = perp2(dpt, seg_dir);
+        if (sign == 0)
+            sign = perp;
+        else if (sign * perp < 0)
+            return false;
+    }
+    return true;
+}
+// ray_plane.rs:9-23
+static bool line_toi_with_plane(V3 plane_center, V3 plane_normal, V3 line_origin, V3 line_dir, real* toi) {
+    V3 dpos = plane_center - line_origin;
+    real denom = dot(plane_normal, line_dir);
+    if (relative_eq(denom, real(0))) return false;
+    *toi = dot(plane_normal, dpos) / denom;
+    return true;
+}
+// closest_points_segment_segment.rs:62-141 for D = 2.  Returns true iff both locations are OnEdge.
+static bool seg_seg_2d(V2 a1, V2 b1, V2 a2, V2 b2, real* s_out, real* t_out) {
+    const real eps = EPS, _0 = 0, _1 = 1;
+    V2 d1 = sub2(b1, a1), d2 = sub2(b2, a2), r = sub2(a1, a2);
+    real a = dot2(d1, d1), e = dot2(d2, d2), f = dot2(d2, r);
+    real s, t;
+    if (a <= eps && e <= eps) {
+        s = _0;
+        t = _0;
+    } else if (a <= eps) {
+        s = _0;
+        t = clampf(f / e, _0, _1);
+    } else {
+        real c = dot2(d1, r);
+        if (e <= eps) {
+            t = _0;
+            s = clampf(-c / a, _0, _1);
+        } else {
+            real b = dot2(d1, d2);
+            real ae = a * e, bb = b * b, denom = ae - bb;
+            bool parallel = denom <= eps || ulps_eq(ae, bb);
+            if (!parallel)
+                s = clampf((b * f - c * e) / denom, _0, _1);
+            else
+                s = _0;
+            t = (b * s + f) / e;
+            if (t < _0) {
+                t = _0;
+                s = clampf(-c / a, _0, _1);
+            } else if (t > _1) {
+                t = _1;
+                s = clampf((b - c) / a, _0, _1);
+            }
+        }
+    }
+    *s_out = s;
+    *t_out = t;
+    return s != _0 && s != _1 && t != _0 && t != _1;
+}
+
+struct NewContact {
+    Contact c;
+    uint32_t f1, f2;
+};
+
+// convex_polygonal_feature3.rs:217-338
+static void clip(const Feature& self, const Feature& other, V3 normal, real prediction, std::vector<NewContact>& out) {
+    if (self.vertices.size() <= 2 && other.vertices.size() <= 2) return;
+    V3 basis[2];
+    orthonormal_basis(normal, &basis[0], &basis[1]);
+    V3 ref_pt = self.vertices[0];
+    std::vector<V2> poly1, poly2;
+    for (auto& pt : self.vertices) {
+        V3 dpt = pt - ref_pt;
+        poly1.push_back({dot(basis[0], dpt), dot(basis[1], dpt)});
+    }
+    for (auto& pt : other.vertices) {
+        V3 dpt = pt - ref_pt;
+        poly2.push_back({dot(basis[0], dpt), dot(basis[1], dpt)});
+    }
+    if (poly2.size() > 2) {
+        for (size_t i = 0; i < poly1.size(); ++i) {
+            V2 pt = poly1[i];
+            if (point_in_poly2d(pt, poly2)) {
+                V3 origin = ref_pt + basis[0] * pt.x + basis[1] * pt.y;
+                real toi2;
+                if (line_toi_with_plane(other.vertices[0], other.normal, origin, normal, &toi2)) {
+                    V3 world2 = origin + normal * toi2;
+                    V3 world1 = self.vertices[i];
+                    Contact c = contact_new_wo_depth(world1, world2, normal);
+                    if (-c.depth <= prediction) out.push_back({c, self.vertices_id[i], other.feature_id});
+                }
+            }
+        }
+    }
+    if (poly1.size() > 2) {
+        for (size_t i = 0; i < poly2.size(); ++i) {
+            V2 pt = poly2[i];
+            if (point_in_poly2d(pt, poly1)) {
+                V3 origin = ref_pt + basis[0] * pt.x + basis[1] * pt.y;
+                real toi1;
+                if (line_toi_with_plane(self.vertices[0], self.normal, origin, normal, &toi1)) {
+                    V3 world1 = origin + normal * toi1;
+                    V3 world2 = other.vertices[i];
+                    Contact c = contact_new_wo_depth(world1, world2, normal);
+                    if (-c.depth <= prediction) out.push_back({c, self.feature_id, other.vertices_id[i]});
+                }
+            }
+        }
+    }
+    size_t nedges1 = self.nedges(), nedges2 = other.nedges();
+    for (size_t i1 = 0; i1 < nedges1; ++i1) {
+        size_t j1 = (i1 + 1) % poly1.size();
+        for (size_t i2 = 0; i2 < nedges2; ++i2) {
+            size_t j2 = (i2 + 1) % poly2.size();
+            real s, t;
+            if (seg_seg_2d(poly1[i1], poly1[j1], poly2[i2], poly2[j2], &s, &t)) {
+                // Segment::point_at(OnEdge([1 - s, s])) = a * bcoords[0] + b.coords * bcoords[1]
+                V3 world1 = self.vertices[i1] * (real(1) - s) + self.vertices[j1] * s;
+                V3 world2 = other.vertices[i2] * (real(1) - t) + other.vertices[j2] * t;
+                Contact c = contact_new_wo_depth(world1, world2, normal);
+                if (-c.depth <= prediction) out.push_back({c, self.edges_id[i1], other.edges_id[i2]});
+            }
+        }
+    }
+}
+
+// convex_polygonal_feature3.rs:341-401: returns false when the reference drops the contact
+static bool feature_ok_for_manifold(const Feature& ft, uint32_t f) {
+    switch (fid_kind(f)) {
+        case F_FACE:
+        case F_VERTEX:
+            return true;
+        case F_EDGE: {
+            V3 a, b, d;
+            if (!ft.edge(f, &a, &b)) return false;  // .expect("Invalid edge id.") would panic
+            return unit_try_new(b - a, EPS, &d);
+        }
+        default:
+            return false;
+    }
+}
+
+// convex_polyhedron_convex_polyhedron_manifold_generator.rs:83-167 (fresh generator: last_gjk_dir = None)
+static void gen_convex_convex(const Iso& ma, const Shape& a, const Iso& mb, const Shape& b, real pred_linear, real ang1, real ang2,
+                              Manifold& mf, GJKStats* st) {
+    Support ga = as_support(a), gb = as_support(b);
+    VoronoiSimplex simplex;
+    GJKResult r = contact_support_map_support_map_with_params(ma, ga, mb, gb, pred_linear, simplex, nullptr, st);
+    std::vector<NewContact> new_contacts;
+    Feature m1, m2;
+    if (r.kind == GJK_CLOSEST_POINTS) {
+        Contact contact = contact_new_wo_depth(r.p1, r.p2, r.dir);
+        if (contact.depth > 0) {
+            support_face_toward(a, ma, contact.normal, m1);
+            support_face_toward(b, mb, -contact.normal, m2);
+            clip(m1, m2, contact.normal, pred_linear, new_contacts);
+        } else {
+            support_feature_toward(a, ma, contact.normal, ang1, m1);
+            support_feature_toward(b, mb, -contact.normal, ang2, m2);
+            clip(m1, m2, contact.normal, pred_linear, new_contacts);
+        }
+        if (new_contacts.empty()) new_contacts.push_back({contact, m1.feature_id, m2.feature_id});
+    }
+    for (auto& nc : new_contacts) {
+        if (!feature_ok_for_manifold(m1, nc.f1)) continue;
+        if (!feature_ok_for_manifold(m2, nc.f2)) continue;
+        V3 local1 = iso_inv_point(ma, nc.c.world1);
+        mf.push(nc.c, nc.f1, nc.f2, local1);
+    }
+}
+
+// default_contact_dispatcher.rs:27-97
+enum Algo : uint8_t { A_NONE = 0, A_BALL_BALL, A_PLANE_BALL, A_PLANE_CONVEX, A_BALL_CONVEX, A_CONVEX_CONVEX };
+
+static uint8_t generate_contacts(const Objects& o, uint32_t i1, uint32_t i2, Manifold& mf, GJKStats* st) {
+    Shape a = get_shape(o, i1), b = get_shape(o, i2);
+    Iso ma = o.iso(i1), mb = o.iso(i2);
+    // query_type.rs:39-51
+    real linear = o.query_limit[i1] + o.query_limit[i2];
+    real ang1 = o.ang_pred[i1], ang2 = o.ang_pred[i2];
+    bool a_ball = a.type == BALL, b_ball = b.type == BALL, a_plane = a.type == PLANE, b_plane = b.type == PLANE;
+    bool a_sm = a.type != PLANE, b_sm = b.type != PLANE;  // is_support_map
+    if (a_ball && b_ball) {
+        gen_ball_ball(ma, a.radius, mb, b.radius, linear, mf);
+        return A_BALL_BALL;
+    } else if (a_plane && b_ball) {
+        gen_plane_ball(ma, a.he, mb, b.radius, linear, false, mf);
+        return A_PLANE_BALL;
+    } else if (a_ball && b_plane) {
+        gen_plane_ball(mb, b.he, ma, a.radius, linear, true, mf);
+        return A_PLANE_BALL;
+    } else if (a_plane && b_sm) {
+        gen_plane_convex(ma, a.he, mb, b, linear, false, mf);
+        return A_PLANE_CONVEX;
+    } else if (b_plane && a_sm) {
+        gen_plane_convex(mb, b.he, ma, a, linear, true, mf);
+        return A_PLANE_CONVEX;
+    } else if (a_ball && is_convex_polyhedron(b)) {
+        gen_ball_convex(ma, a.radius, mb, b, linear, false, mf, st);
+        return A_BALL_CONVEX;
+    } else if (b_ball && is_convex_polyhedron(a)) {
+        gen_ball_convex(mb, b.radius, ma, a, linear, true, mf, st);
+        return A_BALL_CONVEX;
+    } else if (is_convex_polyhedron(a) && is_convex_polyhedron(b)) {
+        gen_convex_convex(ma, a, mb, b, linear, ang1, ang2, mf, st);
+        return A_CONVEX_CONVEX;
+    }
+    return A_NONE;  // e.g. plane x plane: pair kept by the broad phase, no interaction edge
+}
+
+}  // namespace orc
+
+using namespace orc;
+
+static Objects make_objects(const orc_objects* o) {
+    Objects r;
+    r.n = o->n;
+    r.pos = o->pos;
+    r.rot = o->rot;
+    r.shape_type = o->shape_type;
+    r.shape_param = o->shape_param;
+    r.groups = o->groups;
+    r.query_limit = o->query_limit;
+    r.ang_pred = o->ang_pred;
+    r.hulls = reinterpret_cast<const HullLibrary*>(o->hulls);
+    return r;
+}
+
+static void write_contact(orc_contact* d, const Tracked& t) {
+    for (int k = 0; k < 3; ++k) {
+        d->world1[k] = t.c.world1[k];
+        d->world2[k] = t.c.world2[k];
+        d->normal[k] = t.c.normal[k];
+    }
+    d->depth = t.c.depth;
+    d->f1 = t.f1;
+    d->f2 = t.f2;
+}
+
+extern "C" {
+
+uint64_t orc_narrow_phase(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, orc_contact* out, uint64_t cap,
+                          uint32_t* manifold_off, uint8_t* algo_out, uint32_t* stats) {
+    Objects o = make_objects(objs);
+    uint64_t nc = 0;
+    GJKStats st;
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        Manifold mf;
+        uint8_t algo = generate_contacts(o, pairs[2 * p], pairs[2 * p + 1], mf, &st);
+        if (algo_out) algo_out[p] = algo;
+        if (manifold_off) manifold_off[p] = (uint32_t)nc;
+        for (auto& t : mf.contacts) {
+            if (nc < cap && out) write_contact(&out[nc], t);
+            nc++;
+        }
+    }
+    if (manifold_off) manifold_off[n_pairs] = (uint32_t)nc;
+    if (stats) {
+        stats[0] = st.gjk_iters, stats[1] = st.epa_iters, stats[2] = st.epa_max_verts, stats[3] = st.epa_max_faces;
+        stats[4] = st.epa_max_heap, stats[5] = st.epa_calls, stats[6] = st.epa_fail;
+    }
+    return nc;
+}
+
+void orc_world_update_timed(const orc_objects* objs, real margin, double* times, uint64_t* counts) {
+    using clk = std::chrono::steady_clock;
+    Objects o = make_objects(objs);
+    auto t0 = clk::now();
+    std::vector<AABB> fat(o.n);
+    for (uint32_t i = 0; i < o.n; ++i) fat[i] = fat_aabb(o, i, margin);
+    auto t1 = clk::now();
+    std::vector<uint32_t> pairs;
+    broad_phase_dbvt(o.n, fat.data(), o.groups, pairs);
+    auto t2 = clk::now();
+    uint64_t nc = 0, np = pairs.size() / 2, n_with = 0;
+    for (uint64_t p = 0; p < np; ++p) {
+        Manifold mf;
+        generate_contacts(o, pairs[2 * p], pairs[2 * p + 1], mf, nullptr);
+        nc += mf.contacts.size();
+        n_with += !mf.contacts.empty();
+    }
+    auto t3 = clk::now();
+    times[0] = std::chrono::duration<double>(t1 - t0).count();
+    times[1] = std::chrono::duration<double>(t2 - t1).count();
+    times[2] = std::chrono::duration<double>(t3 - t2).count();
+    counts[0] = np;
+    counts[1] = nc;
+    counts[2] = n_with;
+}
+
+// query::contact (contact_shape_shape.rs:10-48) between objects 0 and 1.
+int orc_query_contact(const orc_objects* objs, real prediction, orc_contact* out) {
+    Objects o = make_objects(objs);
+    Shape a = get_shape(o, 0), b = get_shape(o, 1);
+    Iso m1 = o.iso(0), m2 = o.iso(1);
+    Manifold mf;
+    bool have = false;
+    Contact c;
+    if (a.type == BALL && b.type == BALL) {
+        gen_ball_ball(m1, a.radius, m2, b.radius, prediction, mf);
+    } else if (a.type == PLANE && b.type != PLANE) {
+        // contact_plane_support_map.rs:7-27
+        V3 n = iso_mul_vec(m1, a.he);
+        Support g = as_support(b);
+        V3 deepest = g.support_point(m2, -n);
+        real distance = dot(n, m1.t - deepest);
+        if (distance > -prediction) {
+            c = {deepest + n * distance, deepest, n, distance};
+            have = true;
+        }
+    } else if (b.type == PLANE && a.type != PLANE) {
+        V3 n = iso_mul_vec(m2, b.he);
+        Support g = as_support(a);
+        V3 deepest = g.support_point(m1, -n);
+        real distance = dot(n, m2.t - deepest);
+        if (distance > -prediction) {
+            c = {deepest, deepest + n * distance, -n, distance};
+            have = true;
+        }
+    } else if (a.type == BALL && is_convex_polyhedron(b)) {
+        gen_ball_convex(m1, a.radius, m2, b, prediction, false, mf, nullptr);
+    } else if (b.type == BALL && is_convex_polyhedron(a)) {
+        gen_ball_convex(m2, b.radius, m1, a, prediction, true, mf, nullptr);
+    } else if (a.type != PLANE && b.type != PLANE) {
+        Support ga = as_support(a), gb = as_support(b);
+        VoronoiSimplex simplex;
+        GJKResult r = contact_support_map_support_map_with_params(m1, ga, m2, gb, prediction, simplex, nullptr, nullptr);
+        if (r.kind == GJK_CLOSEST_POINTS) {
+            c = contact_new_wo_depth(r.p1, r.p2, r.dir);
+            have = true;
+        }
+    }
+    if (!have && !mf.contacts.empty()) {
+        c = mf.contacts[0].c;
+        have = true;
+    }
+    if (have) {
+        Tracked t = {c, FID_UNKNOWN, FID_UNKNOWN};
+        write_contact(out, t);
+    }
+    return have ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY.
+ * CPU restatement of the ncollide3d hot path (one CollisionWorld::update step + TriMesh ray casting)
+ * used to check the CUDA path and as bench.py's cpu_baseline.  The product never links this.
+ * The Rust reference cannot be built in this image (no rustc/cargo; nalgebra not vendored), so this
+ * is a restatement ("port"), pinned against the reference's own known-answer tests (tests/test_oracle_kat.py).
+ */
+#ifndef ORC_ORACLE_H
+#define ORC_ORACLE_H
+#include <stdint.h>
+#ifndef ORC_REAL
+#define ORC_REAL float
+#endif
+typedef ORC_REAL real; /* f32 on the path; f64 build only for the reference's f64 KATs */
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_hull_library {
+    uint32_t n_hulls;
+    const uint32_t *vert_off, *face_off, *edge_off, *fadj_off, *vadj_off;
+    const real* points;
+    const uint32_t *vert_first_adj, *vert_num_adj;
+    const uint32_t *face_first, *face_num;
+    const real* face_normal;
+    const uint32_t *vertices_adj_to_face, *edges_adj_to_face;
+    const uint32_t *edge_vertices, *edge_faces;
+    const real* edge_dir;
+    const uint32_t *faces_adj_to_vertex, *edges_adj_to_vertex;
+} orc_hull_library;
+
+typedef struct orc_objects {
+    uint32_t n;
+    const real* pos;         /* 3 per object */
+    const real* rot;         /* 4 per object, (i,j,k,w) */
+    const uint32_t* shape_type; /* 0 ball, 1 cuboid, 2 convex hull, 3 plane */
+    const real* shape_param; /* 4 per object: r | half extents | hull id bits | plane normal */
+    const uint32_t* groups;   /* 3 per object or NULL */
+    const real* query_limit;
+    const real* ang_pred;
+    const orc_hull_library* hulls;
+} orc_objects;
+
+typedef struct orc_contact {
+    real world1[3], world2[3], normal[3], depth;
+    uint32_t f1, f2;
+} orc_contact;
+
+void orc_compute_aabbs(const orc_objects* objs, real margin, int fat, real* out_minmax);
+uint64_t orc_broad_phase(uint32_t n, const real* aabb_minmax, const uint32_t* groups, int mode, uint32_t* out_pairs,
+                         uint64_t cap);
+
+/* Narrow phase for the given (object1, object2) pairs, object1 being the first argument of
+ * generate_contacts.  manifold_off has n_pairs+1 entries.  algo_out (optional) gets the dispatched
+ * algorithm per pair.  Returns the number of contacts (may exceed cap). */
+uint64_t orc_narrow_phase(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, orc_contact* out, uint64_t cap,
+                          uint32_t* manifold_off, uint8_t* algo_out, uint32_t* stats);
+
+/* One reference-faithful fresh-world CollisionWorld::update (DBVT broad phase + narrow phase); returns
+ * seconds spent in [aabb, broad, narrow] through times[3]; n_pairs / n_contacts through counts[2]. */
+void orc_world_update_timed(const orc_objects* objs, real margin, double* times, uint64_t* counts);
+
+/* One-shot query::contact(m1, g1, m2, g2, prediction) (query/contact/contact_shape_shape.rs:10-48) for
+ * objects 0 and 1 of objs; returns 1 and fills out when a contact exists. */
+int orc_query_contact(const orc_objects* objs, real prediction, orc_contact* out);
+
+/* Convex hull tables: see hull.cpp. */
+
+/* TriMesh ray casting. */
+typedef struct orc_trimesh orc_trimesh;
+orc_trimesh* orc_trimesh_create(uint32_t n_verts, const real* xyz, uint32_t n_tris, const uint32_t* idx);
+void orc_trimesh_destroy(orc_trimesh*);
+/* mode 0: reference-faithful BVT best-first search; mode 1: brute force, global min toi over accepted hits,
+ * ties -> smallest face index.  pose = t(3) q(4) or NULL for identity.  toi < 0 => miss. face = i or i+T (back face). */
+void orc_trimesh_ray_cast(const orc_trimesh*, const real* pose, uint64_t n_rays, const real* origins, const real* dirs,
+                          real max_toi, int mode, real* toi, uint32_t* face, real* normal);
+void orc_aabb_toi_with_ray(const real* minmax, const real* origin, const real* dir, real max_toi, int solid, real* toi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

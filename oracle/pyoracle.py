@@ -1,0 +1,195 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  ctypes binding of oracle/_build/liboracle_f{32,64}.so.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs only.
+The product package (ncollide_b200/) must never import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build(force=False):
+    """Compile the oracle (g++, seconds).  Building the checker is not using it."""
+    out = os.path.join(_HERE, "_build", "liboracle_f32.so")
+    if force or not os.path.exists(out) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(out)
+        for f in os.listdir(_HERE)
+        if f.endswith((".cpp", ".hpp", ".h"))
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return out
+
+
+class _HullLib(C.Structure):
+    _fields_ = [("n_hulls", C.c_uint32)] + [
+        (n, C.c_void_p)
+        for n in (
+            "vert_off face_off edge_off fadj_off vadj_off points vert_first_adj vert_num_adj face_first face_num "
+            "face_normal vertices_adj_to_face edges_adj_to_face edge_vertices edge_faces edge_dir "
+            "faces_adj_to_vertex edges_adj_to_vertex"
+        ).split()
+    ]
+
+
+class _Objects(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint32),
+        ("pos", C.c_void_p),
+        ("rot", C.c_void_p),
+        ("shape_type", C.c_void_p),
+        ("shape_param", C.c_void_p),
+        ("groups", C.c_void_p),
+        ("query_limit", C.c_void_p),
+        ("ang_pred", C.c_void_p),
+        ("hulls", C.c_void_p),
+    ]
+
+
+FLOAT_HULL_FIELDS = {"points", "face_normal", "edge_dir"}
+
+
+class Oracle:
+    def __init__(self, dtype=np.float32):
+        build()
+        self.dtype = np.dtype(dtype)
+        name = "liboracle_f32.so" if self.dtype == np.float32 else "liboracle_f64.so"
+        self.lib = C.CDLL(os.path.join(_HERE, "_build", name))
+        self.creal = C.c_float if self.dtype == np.float32 else C.c_double
+        L = self.lib
+        L.orc_broad_phase.restype = C.c_uint64
+        L.orc_narrow_phase.restype = C.c_uint64
+        L.orc_trimesh_create.restype = C.c_void_p
+        L.orc_query_contact.restype = C.c_int
+        self.contact_dtype = np.dtype(
+            [("world1", self.dtype, 3), ("world2", self.dtype, 3), ("normal", self.dtype, 3), ("depth", self.dtype), ("f1", np.uint32), ("f2", np.uint32)],
+            align=True,
+        )
+
+    # -- marshalling ---------------------------------------------------------------------------
+    def _objects(self, scene):
+        keep = []
+
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data
+
+        hl = _HullLib()
+        lib = scene.hulls
+        hl.n_hulls = lib.n_hulls
+        for f in lib.FIELDS:
+            setattr(hl, f, arr(getattr(lib, f), self.dtype if f in FLOAT_HULL_FIELDS else np.uint32))
+        keep.append(hl)
+        o = _Objects()
+        o.n = scene.n
+        o.pos = arr(scene.pos, self.dtype)
+        o.rot = arr(scene.rot, self.dtype)
+        o.shape_type = arr(scene.shape_type, np.uint32)
+        o.shape_param = arr(scene.shape_param, self.dtype)
+        o.groups = arr(scene.groups, np.uint32) if scene.groups is not None else None
+        o.query_limit = arr(scene.query_limit, self.dtype)
+        o.ang_pred = arr(scene.ang_pred, self.dtype)
+        o.hulls = C.addressof(hl)
+        return o, keep
+
+    # -- API -----------------------------------------------------------------------------------
+    def compute_aabbs(self, scene, fat=True):
+        o, keep = self._objects(scene)
+        out = np.zeros((scene.n, 6), dtype=self.dtype)
+        self.lib.orc_compute_aabbs(C.byref(o), self.creal(scene.margin), C.c_int(1 if fat else 0), C.c_void_p(out.ctypes.data))
+        return out
+
+    def broad_phase(self, aabbs, groups=None, mode=1):
+        """Returns [P,2] u32 pairs (larger handle, smaller handle). mode: 0 DBVT-faithful, 1 sweep, 2 brute force."""
+        aabbs = np.ascontiguousarray(aabbs, dtype=self.dtype)
+        n = len(aabbs)
+        g = np.ascontiguousarray(groups, dtype=np.uint32) if groups is not None else None
+        gp = C.c_void_p(g.ctypes.data) if g is not None else None
+        cap = max(16 * n, 1024)
+        while True:
+            out = np.zeros((cap, 2), dtype=np.uint32)
+            np_ = self.lib.orc_broad_phase(C.c_uint32(n), C.c_void_p(aabbs.ctypes.data), gp, C.c_int(mode), C.c_void_p(out.ctypes.data), C.c_uint64(cap))
+            if np_ <= cap:
+                return out[:np_].copy()
+            cap = int(np_)
+
+    def narrow_phase(self, scene, pairs):
+        """pairs: [P,2] (object1, object2).  Returns (contacts structured array, manifold_off[P+1], algo[P], stats[8])."""
+        o, keep = self._objects(scene)
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        P = len(pairs)
+        cap = max(4 * P, 64)
+        off = np.zeros(P + 1, dtype=np.uint32)
+        algo = np.zeros(P, dtype=np.uint8)
+        stats = np.zeros(8, dtype=np.uint32)
+        while True:
+            out = np.zeros(cap, dtype=self.contact_dtype)
+            nc = self.lib.orc_narrow_phase(
+                C.byref(o), C.c_uint64(P), C.c_void_p(pairs.ctypes.data), C.c_void_p(out.ctypes.data), C.c_uint64(cap),
+                C.c_void_p(off.ctypes.data), C.c_void_p(algo.ctypes.data), C.c_void_p(stats.ctypes.data),
+            )
+            if nc <= cap:
+                return out[:nc].copy(), off, algo, stats
+            cap = int(nc)
+
+    def world_update_timed(self, scene):
+        o, keep = self._objects(scene)
+        times = (C.c_double * 3)()
+        counts = (C.c_uint64 * 3)()
+        self.lib.orc_world_update_timed(C.byref(o), self.creal(scene.margin), times, counts)
+        return list(times), list(counts)
+
+    def query_contact(self, scene, prediction):
+        o, keep = self._objects(scene)
+        out = np.zeros(1, dtype=self.contact_dtype)
+        r = self.lib.orc_query_contact(C.byref(o), self.creal(prediction), C.c_void_p(out.ctypes.data))
+        return out[0] if r else None
+
+    def trimesh(self, verts, tris):
+        return OracleTriMesh(self, verts, tris)
+
+    def aabb_toi_with_ray(self, minmax, origin, direction, max_toi, solid):
+        mm = np.ascontiguousarray(minmax, dtype=self.dtype)
+        o = np.ascontiguousarray(origin, dtype=self.dtype)
+        d = np.ascontiguousarray(direction, dtype=self.dtype)
+        t = self.creal(0)
+        self.lib.orc_aabb_toi_with_ray(C.c_void_p(mm.ctypes.data), C.c_void_p(o.ctypes.data), C.c_void_p(d.ctypes.data), self.creal(max_toi), C.c_int(int(solid)), C.byref(t))
+        return None if t.value < 0 else t.value
+
+
+class OracleTriMesh:
+    def __init__(self, oracle, verts, tris):
+        self.o = oracle
+        v = np.ascontiguousarray(verts, dtype=oracle.dtype)
+        t = np.ascontiguousarray(tris, dtype=np.uint32)
+        self.ntris = len(t)
+        self.h = C.c_void_p(oracle.lib.orc_trimesh_create(C.c_uint32(len(v)), C.c_void_p(v.ctypes.data), C.c_uint32(len(t)), C.c_void_p(t.ctypes.data)))
+
+    def ray_cast(self, origins, dirs, max_toi=None, pose=None, mode=0):
+        dt = self.o.dtype
+        o = np.ascontiguousarray(origins, dtype=dt)
+        d = np.ascontiguousarray(dirs, dtype=dt)
+        n = len(o)
+        toi = np.zeros(n, dtype=dt)
+        face = np.zeros(n, dtype=np.uint32)
+        normal = np.zeros((n, 3), dtype=dt)
+        if max_toi is None:
+            max_toi = np.finfo(dt).max
+        p = np.ascontiguousarray(pose, dtype=dt) if pose is not None else None
+        self.o.lib.orc_trimesh_ray_cast(
+            self.h, C.c_void_p(p.ctypes.data) if p is not None else None, C.c_uint64(n), C.c_void_p(o.ctypes.data), C.c_void_p(d.ctypes.data),
+            self.o.creal(max_toi), C.c_int(mode), C.c_void_p(toi.ctypes.data), C.c_void_p(face.ctypes.data), C.c_void_p(normal.ctypes.data),
+        )
+        return toi, face, normal
+
+    def __del__(self):
+        try:
+            self.o.lib.orc_trimesh_destroy(self.h)
+        except Exception:
+            pass
