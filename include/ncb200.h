@@ -1,0 +1,186 @@
+/* ncb200 — C ABI of the B200-native collision hot path (one CollisionWorld::update step + TriMesh ray casting).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ / torch types, no unwinding.
+ * Every entry point names the reference (dimforge/ncollide, paths relative to the reference root) item it
+ * replaces.  The reference itself has no FFI; INTEGRATION.md shows the Rust `extern "C"` block and the
+ * BroadPhase / ContactManifoldGenerator / RayCast shims a maintainer would add on top of this header.
+ *
+ * Conventions
+ *   - f32 everywhere on the path; ids are u32 on the wire (usize in the reference).
+ *   - Return value: 0 = ok, < 0 = error (ncb_last_error gives the text), > 0 = an output capacity was too
+ *     small: outputs were truncated, the n_* out-parameters hold the NEEDED counts; call again with larger buffers.
+ *   - One context per GPU (one process per GPU); a context is not re-entrant (calls on it are serialised by the
+ *     caller, as `&mut self` is in the reference).
+ *   - There is no CPU fallback: every compute entry point fails with NCB_ERR_CUDA when no device is usable.
+ */
+#ifndef NCB200_H
+#define NCB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NCB_OK 0
+#define NCB_ERR_CUDA (-1)
+#define NCB_ERR_ARG (-2)
+#define NCB_ERR_STATE (-3)
+#define NCB_ERR_UNSUPPORTED (-4)
+
+/* shape_type values (shape/ball.rs, shape/cuboid.rs, shape/convex.rs, shape/plane.rs) */
+#define NCB_SHAPE_BALL 0u
+#define NCB_SHAPE_CUBOID 1u
+#define NCB_SHAPE_CONVEX_HULL 2u
+#define NCB_SHAPE_PLANE 3u
+
+/* FeatureId (shape/feature_id.rs): kind in bits 31..30 (0 vertex, 1 edge, 2 face, 3 unknown), id in bits 29..0. */
+#define NCB_FEATURE_VERTEX 0u
+#define NCB_FEATURE_EDGE 1u
+#define NCB_FEATURE_FACE 2u
+#define NCB_FEATURE_UNKNOWN 3u
+
+/* Contact algorithm chosen per pair (DefaultContactDispatcher::get_contact_algorithm,
+ * pipeline/narrow_phase/contact_generator/default_contact_dispatcher.rs:27-97). */
+#define NCB_ALGO_NONE 0u
+#define NCB_ALGO_BALL_BALL 1u
+#define NCB_ALGO_PLANE_BALL 2u
+#define NCB_ALGO_PLANE_CONVEX 3u
+#define NCB_ALGO_BALL_CONVEX 4u
+#define NCB_ALGO_CONVEX_CONVEX 5u
+
+typedef struct ncb_ctx ncb_ctx;
+typedef struct ncb_mesh ncb_mesh;
+
+/* Tables of ConvexHull::try_new (shape/convex.rs:109-335) for a library of hulls, concatenated; ids are LOCAL to
+ * each hull; *_off arrays have n_hulls + 1 entries.  Limits: <= 64 vertices per hull, <= 16 vertices per face. */
+typedef struct ncb_hull_library {
+    uint32_t n_hulls;
+    const uint32_t* vert_off; /* -> points, vert_first_adj, vert_num_adj */
+    const uint32_t* face_off; /* -> face_first, face_num, face_normal */
+    const uint32_t* edge_off; /* -> edge_vertices, edge_faces, edge_dir */
+    const uint32_t* fadj_off; /* -> vertices_adj_to_face, edges_adj_to_face */
+    const uint32_t* vadj_off; /* -> faces_adj_to_vertex, edges_adj_to_vertex */
+    const float* points;      /* xyz */
+    const uint32_t* vert_first_adj;
+    const uint32_t* vert_num_adj;
+    const uint32_t* face_first;
+    const uint32_t* face_num;
+    const float* face_normal; /* xyz */
+    const uint32_t* vertices_adj_to_face;
+    const uint32_t* edges_adj_to_face;
+    const uint32_t* edge_vertices; /* 2 per edge */
+    const uint32_t* edge_faces;    /* 2 per edge */
+    const float* edge_dir;         /* xyz */
+    const uint32_t* faces_adj_to_vertex;
+    const uint32_t* edges_adj_to_vertex;
+} ncb_hull_library;
+
+/* SoA collision objects = what CollisionObject holds on the path (pipeline/object/collision_object.rs:62-113):
+ * position (Isometry3: translation + unit quaternion i,j,k,w), shape, CollisionGroups, GeometricQueryType::Contacts. */
+typedef struct ncb_objects {
+    uint32_t n;
+    const float* pos;           /* 3 per object */
+    const float* rot;           /* 4 per object */
+    const uint32_t* shape_type; /* NCB_SHAPE_* */
+    const float* shape_param;   /* 4 per object: radius | half extents | (float)hull id | plane normal */
+    const uint32_t* groups;     /* 3 per object: membership, whitelist, blacklist; NULL = CollisionGroups::new() */
+    const float* query_limit;   /* Contacts(linear, _) */
+    const float* ang_pred;      /* Contacts(_, angular) */
+} ncb_objects;
+
+/* query::Contact (query/contact/contact.rs:15-27) + the two feature ids of its ContactKinematic + owning pair. */
+typedef struct ncb_contact {
+    float world1[3];
+    float world2[3];
+    float normal[3];
+    float depth;
+    uint32_t f1, f2;
+    uint32_t pair; /* index into the pair array of the same call */
+} ncb_contact;
+
+typedef struct ncb_update_counts {
+    uint32_t n_pairs;          /* broad-phase pairs (DBVTBroadPhase::num_interferences) */
+    uint32_t n_contacts;       /* contacts over all manifolds */
+    uint32_t n_contact_pairs;  /* pairs whose manifold is not empty */
+    uint32_t n_algo[6];        /* pairs per NCB_ALGO_* */
+    uint32_t epa_overflow;     /* pairs whose EPA exceeded the fixed device capacity (result = "no contact"; 0 expected) */
+    uint32_t ref_panics;       /* pairs on which the reference itself would have panicked (assert / unwrap) */
+} ncb_update_counts;
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+int ncb_create(int device, ncb_ctx** out);
+void ncb_destroy(ncb_ctx* ctx);
+const char* ncb_last_error(const ncb_ctx* ctx); /* NULL ctx: error of the last failed ncb_create on this thread */
+/* Use the caller's CUDA stream (cudaStream_t as void*) instead of the context's own; NULL restores it. */
+int ncb_set_stream(ncb_ctx* ctx, void* cuda_stream);
+void* ncb_get_stream(ncb_ctx* ctx);
+int ncb_synchronize(ncb_ctx* ctx);
+
+/* ---- shapes and objects -------------------------------------------------------------------------------------- */
+/* ConvexHull tables (host pointers), copied to the device once. */
+int ncb_set_hulls(ncb_ctx* ctx, const ncb_hull_library* lib);
+/* CollisionWorld::add for a whole world (pipeline/world.rs:66-96): host SoA -> device. */
+int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* objs);
+/* CollisionObject::set_position for all objects (pipeline/object/collision_object.rs:186-190). */
+int ncb_set_positions(ncb_ctx* ctx, uint32_t n, const float* pos, const float* rot);
+
+/* ---- stage entry points (each mirrors one reference routine, host buffers in/out) ---------------------------- */
+/* CollisionObjectRef::compute_aabb (collision_object.rs:89-93); fat != 0 additionally applies
+ * DBVTBroadPhase's loosened(margin) (dbvt_broad_phase.rs:341).  out: 6 floats per object (mins, maxs). */
+int ncb_compute_aabbs(ncb_ctx* ctx, float margin, int fat, float* out_minmax);
+/* BroadPhase::update on a fresh proxy set (pipeline/broad_phase/broad_phase.rs:65, dbvt_broad_phase.rs:174-259):
+ * proxies 0..n-1 with the given (already loosened) AABBs; out pairs = (larger handle, smaller handle), i.e. the
+ * argument order of interference_started.  groups may be NULL. */
+int ncb_broad_phase(ncb_ctx* ctx, uint32_t n, const float* aabb_minmax, const uint32_t* groups, uint32_t* out_pairs,
+                    uint32_t cap_pairs, uint32_t* n_pairs);
+/* ContactManifoldGenerator::generate_contacts for a batch of pairs over the objects set by ncb_set_objects
+ * (contact_generator/contact_manifold_generator.rs:10-36); pairs[2p] is the first shape.  manifold_start/count
+ * (optional, n_pairs entries) locate each pair's contacts inside out_contacts. */
+int ncb_generate_contacts(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* pairs, ncb_contact* out_contacts,
+                          uint32_t cap_contacts, uint32_t* n_contacts, uint32_t* manifold_start, uint8_t* manifold_count,
+                          uint8_t* algo);
+
+/* ---- fused hot path ------------------------------------------------------------------------------------------ */
+/* One fresh-world CollisionWorld::update (pipeline/world.rs:104-119 -> glue/update.rs:117-135) over the objects
+ * currently on the device; results stay on the device.  q_begin/q_end restrict the broad-phase QUERY leaves to a
+ * slice of the Morton order (multi-GPU sharding, pass 0 / UINT32_MAX for everything). */
+int ncb_world_update_device(ncb_ctx* ctx, float margin, uint32_t q_begin, uint32_t q_end, ncb_update_counts* counts);
+/* Copy the results of the last update to host buffers (any pointer may be NULL). */
+int ncb_world_fetch(ncb_ctx* ctx, uint32_t* pairs, uint32_t cap_pairs, uint8_t* pair_algo, uint32_t* manifold_start,
+                    uint8_t* manifold_count, ncb_contact* contacts, uint32_t cap_contacts);
+/* Host-buffer convenience = ncb_set_objects + ncb_world_update_device + ncb_world_fetch (the end-to-end call). */
+int ncb_world_update(ncb_ctx* ctx, const ncb_objects* objs, float margin, uint32_t* pairs, uint32_t cap_pairs,
+                     uint8_t* pair_algo, uint32_t* manifold_start, uint8_t* manifold_count, ncb_contact* contacts,
+                     uint32_t cap_contacts, ncb_update_counts* counts);
+
+/* Device pointers of internal buffers, for multi-GPU plumbing (NCCL all-gather of AABBs) and zero-copy consumers.
+ * which: 0 aabb_lo (float4 per object: mins, w unused) 1 aabb_hi, 2 pairs (uint2), 3 contacts (ncb_contact),
+ * 4 pos (3 floats), 5 rot (4 floats). */
+void* ncb_device_ptr(ncb_ctx* ctx, int which);
+/* Split update for multi-GPU: stage 0 = AABBs of objects [obj_begin, obj_end) only; stage 1 = everything after the
+ * AABBs (LBVH + pair search for query slice + narrow phase). */
+int ncb_world_update_stage(ncb_ctx* ctx, int stage, float margin, uint32_t begin, uint32_t end, ncb_update_counts* counts);
+
+/* Per-stage device times of the last ncb_world_update_device, measured with CUDA events on the context's stream
+ * when enabled.  names/ms are arrays of at least 16 entries; returns the number of stages filled. */
+int ncb_profile_enable(ncb_ctx* ctx, int on);
+int ncb_profile_get(ncb_ctx* ctx, const char** names, float* ms, uint32_t* launches);
+
+/* ---- RayCast for TriMesh ------------------------------------------------------------------------------------- */
+/* TriMesh::new (shape/trimesh.rs:100-197): uploads the mesh and builds the device BVH. */
+int ncb_trimesh_create(ncb_ctx* ctx, uint32_t n_verts, const float* xyz, uint32_t n_tris, const uint32_t* idx, ncb_mesh** out);
+void ncb_trimesh_destroy(ncb_mesh* mesh);
+/* RayCast::toi_and_normal_with_ray for a batch (query/ray/ray_trimesh.rs:22-50): pose_tq = translation(3) +
+ * quaternion ijkw(4) or NULL (identity); origins/dirs 3 floats per ray; toi < 0 = None; face = i, or i + n_tris
+ * for a back-face hit (ray_trimesh.rs:41-45); normal (optional) in world space. */
+int ncb_trimesh_ray_cast(ncb_mesh* mesh, const float* pose_tq, uint32_t n_rays, const float* origins, const float* dirs,
+                         float max_toi, float* toi, uint32_t* face, float* normal);
+/* Same with device-resident rays / results (pointers are device pointers); asynchronous on the context's stream. */
+int ncb_trimesh_ray_cast_device(ncb_mesh* mesh, const float* pose_tq_host, uint32_t n_rays, const float* d_origins,
+                                const float* d_dirs, float max_toi, float* d_toi, uint32_t* d_face, float* d_normal);
+
+const char* ncb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NCB200_H */

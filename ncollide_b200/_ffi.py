@@ -1,0 +1,128 @@
+"""ctypes binding of libncb200.so (include/ncb200.h).  No fallback: if the CUDA library is missing or no GPU is
+usable, calls fail loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libncb200.so")
+
+EXPORTED_SYMBOLS = [
+    "ncb_version", "ncb_create", "ncb_destroy", "ncb_last_error", "ncb_set_stream", "ncb_get_stream", "ncb_synchronize",
+    "ncb_set_hulls", "ncb_set_objects", "ncb_set_positions", "ncb_compute_aabbs", "ncb_broad_phase", "ncb_generate_contacts",
+    "ncb_world_update_device", "ncb_world_fetch", "ncb_world_update", "ncb_device_ptr", "ncb_world_update_stage",
+    "ncb_profile_enable", "ncb_profile_get", "ncb_trimesh_create", "ncb_trimesh_destroy", "ncb_trimesh_ray_cast",
+    "ncb_trimesh_ray_cast_device",
+]
+
+HULL_FIELDS = (
+    "vert_off face_off edge_off fadj_off vadj_off points vert_first_adj vert_num_adj face_first face_num face_normal "
+    "vertices_adj_to_face edges_adj_to_face edge_vertices edge_faces edge_dir faces_adj_to_vertex edges_adj_to_vertex"
+).split()
+_FLOAT_HULL_FIELDS = {"points", "face_normal", "edge_dir"}
+
+
+class HullLibraryC(C.Structure):
+    _fields_ = [("n_hulls", C.c_uint32)] + [(n, C.c_void_p) for n in HULL_FIELDS]
+
+
+class ObjectsC(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint32),
+        ("pos", C.c_void_p),
+        ("rot", C.c_void_p),
+        ("shape_type", C.c_void_p),
+        ("shape_param", C.c_void_p),
+        ("groups", C.c_void_p),
+        ("query_limit", C.c_void_p),
+        ("ang_pred", C.c_void_p),
+    ]
+
+
+class UpdateCountsC(C.Structure):
+    _fields_ = [
+        ("n_pairs", C.c_uint32),
+        ("n_contacts", C.c_uint32),
+        ("n_contact_pairs", C.c_uint32),
+        ("n_algo", C.c_uint32 * 6),
+        ("epa_overflow", C.c_uint32),
+        ("ref_panics", C.c_uint32),
+    ]
+
+
+CONTACT_DTYPE = np.dtype(
+    [("world1", np.float32, 3), ("world2", np.float32, 3), ("normal", np.float32, 3), ("depth", np.float32),
+     ("f1", np.uint32), ("f2", np.uint32), ("pair", np.uint32)]
+)
+assert CONTACT_DTYPE.itemsize == 52
+
+_lib = None
+
+
+class NcbError(RuntimeError):
+    pass
+
+
+def load_library():
+    """Loads libncb200.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NcbError(
+            f"{LIB_PATH} is missing: build it with `python -m ncollide_b200.build` (nvcc, sm_100a). "
+            "ncollide_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    lib.ncb_version.restype = C.c_char_p
+    lib.ncb_last_error.restype = C.c_char_p
+    lib.ncb_last_error.argtypes = [C.c_void_p]
+    lib.ncb_get_stream.restype = C.c_void_p
+    lib.ncb_device_ptr.restype = C.c_void_p
+    lib.ncb_device_ptr.argtypes = [C.c_void_p, C.c_int]
+    lib.ncb_destroy.argtypes = [C.c_void_p]
+    lib.ncb_trimesh_destroy.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def as_f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+def as_u32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    return a if shape is None else a.reshape(shape)
+
+
+def pack_hull_library(lib):
+    """lib: shapes.HullLibrary -> (HullLibraryC, keepalive list)"""
+    keep = []
+    h = HullLibraryC()
+    h.n_hulls = lib.n_hulls
+    for f in HULL_FIELDS:
+        a = np.ascontiguousarray(getattr(lib, f), dtype=np.float32 if f in _FLOAT_HULL_FIELDS else np.uint32)
+        keep.append(a)
+        setattr(h, f, a.ctypes.data)
+    return h, keep
+
+
+def pack_objects(scene):
+    keep = [
+        as_f32(scene.pos), as_f32(scene.rot), as_u32(scene.shape_type), as_f32(scene.shape_param),
+        as_u32(scene.groups) if scene.groups is not None else None, as_f32(scene.query_limit), as_f32(scene.ang_pred),
+    ]
+    o = ObjectsC()
+    o.n = len(keep[0])
+    o.pos, o.rot, o.shape_type, o.shape_param = (k.ctypes.data for k in keep[:4])
+    o.groups = keep[4].ctypes.data if keep[4] is not None else None
+    o.query_limit, o.ang_pred = keep[5].ctypes.data, keep[6].ctypes.data
+    return o, keep

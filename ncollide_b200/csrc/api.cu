@@ -1,0 +1,559 @@
+// C ABI of libncb200.so (see include/ncb200.h): context, uploads, the fused world update and its stage entry points.
+// No torch types, no CPU fallback: every compute entry point needs a CUDA device and fails loudly otherwise.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include "ncb_internal.h"
+
+using namespace ncb;
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            char b__[512];                                                                               \
+            snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            ctx->err = b__;                                                                              \
+            return NCB_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+#define REQUIRE(cond, code, msg) \
+    do {                         \
+        if (!(cond)) {           \
+            ctx->err = (msg);    \
+            return (code);       \
+        }                        \
+    } while (0)
+
+// ---- stage timers ------------------------------------------------------------------------------------------
+static void timer_begin(ncb_ctx* c) {
+    StageTimer& t = c->timer;
+    t.n = 0;
+    if (!t.enabled) return;
+    if (!t.created) {
+        for (int i = 0; i <= StageTimer::MAX; ++i) cudaEventCreate(&t.ev[i]);
+        t.created = true;
+    }
+    cudaEventRecord(t.ev[0], c->stream);
+}
+static void timer_mark(ncb_ctx* c, const char* name, uint32_t launches) {
+    StageTimer& t = c->timer;
+    if (!t.enabled || t.n >= StageTimer::MAX) return;
+    t.names[t.n] = name;
+    t.launches[t.n] = launches;
+    t.n++;
+    cudaEventRecord(t.ev[t.n], c->stream);
+}
+
+static DevObjects dev_objects(ncb_ctx* c) {
+    DevObjects o;
+    o.n = c->n;
+    o.pos = c->pos.p;
+    o.rot = c->rot.p;
+    o.type = c->type.p;
+    o.param = c->param.p;
+    o.groups = c->has_groups ? c->groups.p : nullptr;
+    o.qlimit = c->qlimit.p;
+    o.ang = c->ang.p;
+    o.ang_cs = c->ang_cs.p;
+    return o;
+}
+
+static int reserve_broad(ncb_ctx* ctx, uint32_t n) {
+    CK(ctx->aabb_lo.reserve(n));
+    CK(ctx->aabb_hi.reserve(n));
+    CK(ctx->keys_a.reserve(n));
+    CK(ctx->keys_b.reserve(n));
+    CK(ctx->idx_a.reserve(n));
+    CK(ctx->idx_b.reserve(n));
+    CK(ctx->leaf_lo.reserve(n));
+    CK(ctx->leaf_hi.reserve(n));
+    CK(ctx->nodes.reserve(4 * (size_t)n));
+    CK(ctx->parent.reserve(2 * (size_t)n));
+    CK(ctx->flags.reserve(n));
+    CK(ctx->cub_tmp.reserve(lbvh_temp_bytes(n) + 256));
+    CK(ctx->counters.reserve(1));
+    return NCB_OK;
+}
+static int reserve_pairs(ncb_ctx* ctx, size_t cap) {
+    CK(ctx->pairs_raw.reserve(cap));
+    CK(ctx->pairs.reserve(cap));
+    CK(ctx->keys_raw.reserve(cap));
+    CK(ctx->pair_algo.reserve(cap));
+    CK(ctx->manifold_start.reserve(cap));
+    CK(ctx->manifold_count.reserve(cap));
+    return NCB_OK;
+}
+
+static int reset_counters(ncb_ctx* ctx) {
+    DevCounters z;
+    memset(&z, 0, sizeof z);
+    for (int k = 0; k < 3; ++k) {
+        z.bounds[k] = 0x7f7fffff;          // ordered-int of +FLT_MAX
+        z.bounds[3 + k] = (int)0x80800000;  // ordered-int of -FLT_MAX  (0xff7fffff ^ 0x7fffffff)
+    }
+    *ctx->h_counters = z;
+    CK(cudaMemcpyAsync(ctx->counters.p, ctx->h_counters, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
+    return NCB_OK;
+}
+
+extern "C" {
+
+const char* ncb_version(void) { return "ncb200 0.1 (sm_100a)"; }
+
+int ncb_create(int device, ncb_ctx** out) {
+    if (!out) return NCB_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (ncb200 has no CPU fallback)";
+        return NCB_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        g_create_err = "device index out of range";
+        return NCB_ERR_ARG;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e);
+        return NCB_ERR_CUDA;
+    }
+    ncb_ctx* c = new ncb_ctx;
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_counters, sizeof(DevCounters));
+    if (e != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e);
+        delete c;
+        return NCB_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return NCB_OK;
+}
+
+static void free_hulls(ncb_ctx* c) {
+    for (void* p : c->hull_allocs) cudaFree(p);
+    c->hull_allocs.clear();
+    memset(&c->hulls, 0, sizeof c->hulls);
+}
+
+void ncb_destroy(ncb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_hulls(c);
+    c->ang_cs.release();
+    c->pos.release(), c->qlimit.release(), c->ang.release(), c->rot.release(), c->param.release(), c->type.release(), c->groups.release();
+    c->aabb_lo.release(), c->aabb_hi.release(), c->keys_a.release(), c->keys_b.release(), c->idx_a.release(), c->idx_b.release();
+    c->cub_tmp.release(), c->leaf_lo.release(), c->leaf_hi.release(), c->nodes.release(), c->parent.release(), c->flags.release();
+    c->pairs_raw.release(), c->pairs.release(), c->keys_raw.release(), c->pair_algo.release(), c->counters.release();
+    c->contacts.release(), c->manifold_start.release(), c->manifold_count.release(), c->pair_index.release();
+    if (c->timer.created)
+        for (int i = 0; i <= StageTimer::MAX; ++i) cudaEventDestroy(c->timer.ev[i]);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* ncb_last_error(const ncb_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int ncb_set_stream(ncb_ctx* ctx, void* s) {
+    if (!ctx) return NCB_ERR_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return NCB_OK;
+}
+void* ncb_get_stream(ncb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int ncb_synchronize(ncb_ctx* ctx) {
+    if (!ctx) return NCB_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NCB_OK;
+}
+
+int ncb_profile_enable(ncb_ctx* ctx, int on) {
+    if (!ctx) return NCB_ERR_ARG;
+    ctx->timer.enabled = on != 0;
+    return NCB_OK;
+}
+int ncb_profile_get(ncb_ctx* ctx, const char** names, float* ms, uint32_t* launches) {
+    if (!ctx) return NCB_ERR_ARG;
+    StageTimer& t = ctx->timer;
+    if (!t.enabled || t.n == 0) return 0;
+    cudaEventSynchronize(t.ev[t.n]);
+    for (int i = 0; i < t.n; ++i) {
+        float v = 0;
+        cudaEventElapsedTime(&v, t.ev[i], t.ev[i + 1]);
+        if (names) names[i] = t.names[i];
+        if (ms) ms[i] = v;
+        if (launches) launches[i] = t.launches[i];
+    }
+    return t.n;
+}
+
+}  // extern "C"
+
+// ---- uploads -----------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t upload(ncb_ctx* c, const T* host, size_t count, const T** dev_out) {
+    T* d = nullptr;
+    size_t bytes = (count ? count : 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)&d, bytes);
+    if (e != cudaSuccess) return e;
+    c->hull_allocs.push_back(d);
+    if (count) e = cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+    *dev_out = d;
+    return e;
+}
+
+extern "C" {
+
+int ncb_set_hulls(ncb_ctx* ctx, const ncb_hull_library* L) {
+    if (!ctx || !L) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_hulls(ctx);
+    uint32_t nh = L->n_hulls;
+    if (nh == 0) return NCB_OK;
+    uint32_t nv = L->vert_off[nh], nf = L->face_off[nh], ne = L->edge_off[nh], nfa = L->fadj_off[nh], nva = L->vadj_off[nh];
+    for (uint32_t h = 0; h < nh; ++h) {
+        REQUIRE(L->vert_off[h + 1] - L->vert_off[h] >= 1 && L->vert_off[h + 1] - L->vert_off[h] <= 64, NCB_ERR_UNSUPPORTED,
+                "convex hulls must have 1..64 vertices");
+        REQUIRE(L->face_off[h + 1] > L->face_off[h], NCB_ERR_UNSUPPORTED, "convex hull without faces");
+    }
+    for (uint32_t f = 0; f < nf; ++f) REQUIRE(L->face_num[f] <= 16, NCB_ERR_UNSUPPORTED, "convex hull faces must have <= 16 vertices");
+    DevHulls& H = ctx->hulls;
+    H.n_hulls = nh;
+    CK(upload(ctx, L->vert_off, nh + 1, &H.vert_off));
+    CK(upload(ctx, L->face_off, nh + 1, &H.face_off));
+    CK(upload(ctx, L->edge_off, nh + 1, &H.edge_off));
+    CK(upload(ctx, L->fadj_off, nh + 1, &H.fadj_off));
+    CK(upload(ctx, L->vadj_off, nh + 1, &H.vadj_off));
+    CK(upload(ctx, L->points, 3 * (size_t)nv, &H.points));
+    CK(upload(ctx, L->vert_first_adj, nv, &H.vert_first_adj));
+    CK(upload(ctx, L->vert_num_adj, nv, &H.vert_num_adj));
+    CK(upload(ctx, L->face_first, nf, &H.face_first));
+    CK(upload(ctx, L->face_num, nf, &H.face_num));
+    CK(upload(ctx, L->face_normal, 3 * (size_t)nf, &H.face_normal));
+    CK(upload(ctx, L->vertices_adj_to_face, nfa, &H.vaf));
+    CK(upload(ctx, L->edges_adj_to_face, nfa, &H.eaf));
+    CK(upload(ctx, L->edge_vertices, 2 * (size_t)ne, &H.edge_vertices));
+    CK(upload(ctx, L->edge_faces, 2 * (size_t)ne, &H.edge_faces));
+    CK(upload(ctx, L->edge_dir, 3 * (size_t)ne, &H.edge_dir));
+    CK(upload(ctx, L->faces_adj_to_vertex, nva, &H.fav));
+    CK(upload(ctx, L->edges_adj_to_vertex, nva, &H.eav));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NCB_OK;
+}
+
+int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* o) {
+    if (!ctx || !o) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t n = o->n;
+    REQUIRE(n == 0 || (o->pos && o->rot && o->shape_type && o->shape_param && o->query_limit && o->ang_pred), NCB_ERR_ARG,
+            "ncb_set_objects: null array");
+    cudaStream_t s = ctx->stream;
+    CK(ctx->pos.reserve(3 * (size_t)n));
+    CK(ctx->rot.reserve(n));
+    CK(ctx->type.reserve(n));
+    CK(ctx->param.reserve(n));
+    CK(ctx->qlimit.reserve(n));
+    CK(ctx->ang.reserve(n));
+    CK(ctx->ang_cs.reserve(n));
+    // cos/sin of the angular prediction: the reference evaluates them with libm (f32::cos / f32::sin in
+    // Cuboid::support_feature_toward, cuboid.rs:317,331 and ConvexHull::support_feature_id_toward_eps, convex.rs:389);
+    // CUDA's cosf/sinf are not the same function, so they are evaluated here, once per distinct value.
+    ctx->h_ang_cs.resize(n);
+    {
+        float last = 0.f;
+        float2 cs = make_float2(1.f, 0.f);
+        for (uint32_t i = 0; i < n; ++i) {
+            float a = o->ang_pred[i];
+            if (a != last) {
+                last = a;
+                cs = make_float2(cosf(a), sinf(a));
+            }
+            ctx->h_ang_cs[i] = cs;
+        }
+    }
+    if (n) {
+        CK(cudaMemcpyAsync(ctx->ang_cs.p, ctx->h_ang_cs.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->pos.p, o->pos, 12 * (size_t)n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->rot.p, o->rot, 16 * (size_t)n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->type.p, o->shape_type, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->param.p, o->shape_param, 16 * (size_t)n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->qlimit.p, o->query_limit, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->ang.p, o->ang_pred, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+    }
+    ctx->has_groups = o->groups != nullptr;
+    if (o->groups && n) {
+        CK(ctx->groups.reserve(3 * (size_t)n));
+        CK(cudaMemcpyAsync(ctx->groups.p, o->groups, 12 * (size_t)n, cudaMemcpyHostToDevice, s));
+    }
+    ctx->n = n;
+    CK(reserve_broad(ctx, n) == NCB_OK ? cudaSuccess : cudaErrorMemoryAllocation);
+    return NCB_OK;
+}
+
+int ncb_set_positions(ncb_ctx* ctx, uint32_t n, const float* pos, const float* rot) {
+    if (!ctx) return NCB_ERR_ARG;
+    REQUIRE(n == ctx->n, NCB_ERR_ARG, "ncb_set_positions: n differs from the object count");
+    CK(cudaSetDevice(ctx->device));
+    if (n) {
+        CK(cudaMemcpyAsync(ctx->pos.p, pos, 12 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->rot.p, rot, 16 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return NCB_OK;
+}
+
+// ---- stage entry points ------------------------------------------------------------------------------------
+__global__ void k_unpack_aabb(const float4* lo, const float4* hi, uint32_t n, float* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = lo[i], b = hi[i];
+    float* d = out + 6 * (size_t)i;
+    d[0] = a.x, d[1] = a.y, d[2] = a.z, d[3] = b.x, d[4] = b.y, d[5] = b.z;
+}
+__global__ void k_pack_aabb(const float* in, uint32_t n, float4* lo, float4* hi) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* s = in + 6 * (size_t)i;
+    lo[i] = make_float4(s[0], s[1], s[2], 0.f);
+    hi[i] = make_float4(s[3], s[4], s[5], __uint_as_float(0u));
+}
+
+int ncb_compute_aabbs(ncb_ctx* ctx, float margin, int mode, float* out_minmax) {
+    if (!ctx || !out_minmax) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t n = ctx->n;
+    if (n == 0) return NCB_OK;
+    CK(launch_aabbs(ctx, dev_objects(ctx), margin, mode, 0, n));
+    float* tmp = reinterpret_cast<float*>(ctx->nodes.p);  // 16 n floats available
+    k_unpack_aabb<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->aabb_lo.p, ctx->aabb_hi.p, n, tmp);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_minmax, tmp, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return NCB_OK;
+}
+
+static int read_counters(ncb_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->last_counters = *ctx->h_counters;
+    return NCB_OK;
+}
+
+int ncb_broad_phase(ncb_ctx* ctx, uint32_t n, const float* aabb_minmax, const uint32_t* groups, uint32_t* out_pairs, uint32_t cap_pairs,
+                    uint32_t* n_pairs) {
+    if (!ctx || !n_pairs || (n && !aabb_minmax)) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    *n_pairs = 0;
+    if (n == 0) return NCB_OK;
+    int r = reserve_broad(ctx, n);
+    if (r) return r;
+    cudaStream_t s = ctx->stream;
+    float* tmp = reinterpret_cast<float*>(ctx->nodes.p);
+    CK(cudaMemcpyAsync(tmp, aabb_minmax, 24 * (size_t)n, cudaMemcpyHostToDevice, s));
+    k_pack_aabb<<<(n + 255) / 256, 256, 0, s>>>(tmp, n, ctx->aabb_lo.p, ctx->aabb_hi.p);
+    CK(cudaGetLastError());
+    const uint32_t* dgroups = nullptr;
+    if (groups) {
+        CK(ctx->pair_index.reserve(3 * (size_t)n));
+        CK(cudaMemcpyAsync(ctx->pair_index.p, groups, 12 * (size_t)n, cudaMemcpyHostToDevice, s));
+        dgroups = ctx->pair_index.p;
+    }
+    size_t cap = cap_pairs ? cap_pairs : 1;
+    r = reserve_pairs(ctx, cap);
+    if (r) return r;
+    r = reset_counters(ctx);
+    if (r) return r;
+    CK(launch_lbvh_build(ctx, n, nullptr));
+    CK(launch_pair_search(ctx, n, dgroups, 0, n, (uint32_t)cap));
+    r = read_counters(ctx);
+    if (r) return r;
+    uint32_t found = ctx->last_counters.n_pairs;
+    *n_pairs = found;
+    uint32_t w = found < cap_pairs ? found : cap_pairs;
+    if (out_pairs && w) {
+        CK(cudaMemcpyAsync(out_pairs, ctx->pairs_raw.p, 8 * (size_t)w, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return found > cap_pairs ? 1 : NCB_OK;
+}
+
+static void fill_counts(ncb_ctx* ctx, ncb_update_counts* counts) {
+    if (!counts) return;
+    const DevCounters& c = ctx->last_counters;
+    memset(counts, 0, sizeof *counts);
+    counts->n_pairs = c.n_pairs;
+    counts->n_contacts = c.n_contacts;
+    counts->n_contact_pairs = c.n_contact_pairs;
+    counts->epa_overflow = c.epa_overflow;
+    counts->ref_panics = c.ref_panics;
+    counts->n_algo[NCB_ALGO_BALL_BALL] = c.key_hist[K_BALL_BALL];
+    counts->n_algo[NCB_ALGO_PLANE_BALL] = c.key_hist[K_PLANE_BALL];
+    counts->n_algo[NCB_ALGO_PLANE_CONVEX] = c.key_hist[K_PLANE_CUBOID] + c.key_hist[K_PLANE_HULL];
+    counts->n_algo[NCB_ALGO_BALL_CONVEX] = c.key_hist[K_BALL_CUBOID] + c.key_hist[K_BALL_HULL];
+    counts->n_algo[NCB_ALGO_CONVEX_CONVEX] = c.key_hist[K_CUBOID_CUBOID] + c.key_hist[K_CUBOID_HULL] + c.key_hist[K_HULL_HULL];
+    counts->n_algo[NCB_ALGO_NONE] = c.key_hist[K_NONE];
+}
+
+int ncb_generate_contacts(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* pairs, ncb_contact* out_contacts, uint32_t cap_contacts,
+                          uint32_t* n_contacts, uint32_t* manifold_start, uint8_t* manifold_count, uint8_t* algo) {
+    if (!ctx || !n_contacts || (n_pairs && !pairs)) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    *n_contacts = 0;
+    if (n_pairs == 0) return NCB_OK;
+    REQUIRE(ctx->n > 0, NCB_ERR_STATE, "ncb_generate_contacts: call ncb_set_objects first");
+    cudaStream_t s = ctx->stream;
+    int r = reserve_pairs(ctx, n_pairs);
+    if (r) return r;
+    CK(ctx->pair_index.reserve(n_pairs));
+    CK(ctx->counters.reserve(1));
+    size_t capc = cap_contacts ? cap_contacts : 1;
+    CK(ctx->contacts.reserve(capc));
+    r = reset_counters(ctx);
+    if (r) return r;
+    CK(cudaMemcpyAsync(ctx->pairs_raw.p, pairs, 8 * (size_t)n_pairs, cudaMemcpyHostToDevice, s));
+    CK(launch_classify_pairs(ctx, ctx->pairs_raw.p, n_pairs));
+    CK(launch_pair_sort(ctx, n_pairs, ctx->pair_index.p));
+    CK(launch_narrow_phase(ctx, dev_objects(ctx), ctx->pairs.p, ctx->pair_index.p, n_pairs, (uint32_t)capc));
+    r = read_counters(ctx);
+    if (r) return r;
+    uint32_t nc = ctx->last_counters.n_contacts;
+    *n_contacts = nc;
+    uint32_t w = nc < cap_contacts ? nc : cap_contacts;
+    if (out_contacts && w) CK(cudaMemcpyAsync(out_contacts, ctx->contacts.p, sizeof(ncb_contact) * (size_t)w, cudaMemcpyDeviceToHost, s));
+    if (manifold_start) CK(cudaMemcpyAsync(manifold_start, ctx->manifold_start.p, 4 * (size_t)n_pairs, cudaMemcpyDeviceToHost, s));
+    if (manifold_count) CK(cudaMemcpyAsync(manifold_count, ctx->manifold_count.p, (size_t)n_pairs, cudaMemcpyDeviceToHost, s));
+    if (algo) {
+        // algo per ORIGINAL pair: scatter back on the host from the sorted order
+        std::vector<uint8_t> sorted_algo(n_pairs);
+        std::vector<uint32_t> index(n_pairs);
+        CK(cudaMemcpyAsync(sorted_algo.data(), ctx->pair_algo.p, n_pairs, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(index.data(), ctx->pair_index.p, 4 * (size_t)n_pairs, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (uint32_t p = 0; p < n_pairs; ++p) algo[index[p]] = sorted_algo[p];
+    }
+    CK(cudaStreamSynchronize(s));
+    return nc > cap_contacts ? 1 : NCB_OK;
+}
+
+// ---- fused hot path ----------------------------------------------------------------------------------------
+static int update_after_aabbs(ncb_ctx* ctx, uint32_t q_begin, uint32_t q_end) {
+    uint32_t n = ctx->n;
+    // capacities: grow-on-overflow, remembered across calls
+    size_t cap_pairs = ctx->cap_pairs_hint ? ctx->cap_pairs_hint : (size_t)6 * n + 1024;
+    size_t cap_contacts = ctx->cap_contacts_hint ? ctx->cap_contacts_hint : (size_t)6 * n + 1024;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        int r = reserve_pairs(ctx, cap_pairs);
+        if (r) return r;
+        CK(ctx->contacts.reserve(cap_contacts));
+        r = reset_counters(ctx);
+        if (r) return r;
+        timer_begin(ctx);
+        CK(launch_lbvh_build(ctx, n, ctx->type.p));
+        timer_mark(ctx, "lbvh_build", 7);
+        CK(launch_pair_search(ctx, n, ctx->has_groups ? ctx->groups.p : nullptr, q_begin, q_end, (uint32_t)cap_pairs));
+        timer_mark(ctx, "pair_search", 2);
+        CK(launch_pair_sort(ctx, (uint32_t)cap_pairs, nullptr));
+        timer_mark(ctx, "pair_sort", 3);
+        CK(launch_narrow_phase(ctx, dev_objects(ctx), ctx->pairs.p, nullptr, (uint32_t)cap_pairs, (uint32_t)cap_contacts));
+        timer_mark(ctx, "narrow_phase", 10);
+        r = read_counters(ctx);
+        if (r) return r;
+        const DevCounters& c = ctx->last_counters;
+        bool over = false;
+        if (c.n_pairs > cap_pairs) {
+            cap_pairs = (size_t)c.n_pairs + c.n_pairs / 8 + 1024;
+            over = true;
+        }
+        if (c.n_contacts > cap_contacts) {
+            cap_contacts = (size_t)c.n_contacts + c.n_contacts / 8 + 1024;
+            over = true;
+        }
+        ctx->cap_pairs_hint = (uint32_t)cap_pairs;
+        ctx->cap_contacts_hint = (uint32_t)cap_contacts;
+        if (!over) {
+            ctx->last_n_pairs = c.n_pairs;
+            ctx->last_n_contacts = c.n_contacts;
+            return NCB_OK;
+        }
+    }
+    ctx->err = "pair/contact buffers still too small after 3 attempts";
+    return NCB_ERR_STATE;
+}
+
+int ncb_world_update_stage(ncb_ctx* ctx, int stage, float margin, uint32_t begin, uint32_t end, ncb_update_counts* counts) {
+    if (!ctx) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t n = ctx->n;
+    if (stage == 0) {
+        if (end > n) end = n;
+        CK(launch_aabbs(ctx, dev_objects(ctx), margin, 2, begin, end));
+        return NCB_OK;
+    }
+    if (n == 0) {
+        memset(&ctx->last_counters, 0, sizeof ctx->last_counters);
+        ctx->last_n_pairs = ctx->last_n_contacts = 0;
+        fill_counts(ctx, counts);
+        return NCB_OK;
+    }
+    int r = update_after_aabbs(ctx, begin, end);
+    if (r) return r;
+    fill_counts(ctx, counts);
+    return NCB_OK;
+}
+
+int ncb_world_update_device(ncb_ctx* ctx, float margin, uint32_t q_begin, uint32_t q_end, ncb_update_counts* counts) {
+    if (!ctx) return NCB_ERR_ARG;
+    int r = ncb_world_update_stage(ctx, 0, margin, 0, ctx->n, nullptr);
+    if (r) return r;
+    return ncb_world_update_stage(ctx, 1, margin, q_begin, q_end, counts);
+}
+
+int ncb_world_fetch(ncb_ctx* ctx, uint32_t* pairs, uint32_t cap_pairs, uint8_t* pair_algo, uint32_t* manifold_start,
+                    uint8_t* manifold_count, ncb_contact* contacts, uint32_t cap_contacts) {
+    if (!ctx) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    uint32_t np = ctx->last_n_pairs, nc = ctx->last_n_contacts;
+    uint32_t wp = np < cap_pairs ? np : cap_pairs, wc = nc < cap_contacts ? nc : cap_contacts;
+    if (pairs && wp) CK(cudaMemcpyAsync(pairs, ctx->pairs.p, 8 * (size_t)wp, cudaMemcpyDeviceToHost, s));
+    if (pair_algo && wp) CK(cudaMemcpyAsync(pair_algo, ctx->pair_algo.p, wp, cudaMemcpyDeviceToHost, s));
+    if (manifold_start && wp) CK(cudaMemcpyAsync(manifold_start, ctx->manifold_start.p, 4 * (size_t)wp, cudaMemcpyDeviceToHost, s));
+    if (manifold_count && wp) CK(cudaMemcpyAsync(manifold_count, ctx->manifold_count.p, wp, cudaMemcpyDeviceToHost, s));
+    if (contacts && wc) CK(cudaMemcpyAsync(contacts, ctx->contacts.p, sizeof(ncb_contact) * (size_t)wc, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ((pairs && np > cap_pairs) || (contacts && nc > cap_contacts)) ? 1 : NCB_OK;
+}
+
+int ncb_world_update(ncb_ctx* ctx, const ncb_objects* objs, float margin, uint32_t* pairs, uint32_t cap_pairs, uint8_t* pair_algo,
+                     uint32_t* manifold_start, uint8_t* manifold_count, ncb_contact* contacts, uint32_t cap_contacts,
+                     ncb_update_counts* counts) {
+    int r = ncb_set_objects(ctx, objs);
+    if (r) return r;
+    r = ncb_world_update_device(ctx, margin, 0, 0xffffffffu, counts);
+    if (r) return r;
+    return ncb_world_fetch(ctx, pairs, cap_pairs, pair_algo, manifold_start, manifold_count, contacts, cap_contacts);
+}
+
+void* ncb_device_ptr(ncb_ctx* ctx, int which) {
+    if (!ctx) return nullptr;
+    switch (which) {
+        case 0: return ctx->aabb_lo.p;
+        case 1: return ctx->aabb_hi.p;
+        case 2: return ctx->pairs.p;
+        case 3: return ctx->contacts.p;
+        case 4: return ctx->pos.p;
+        case 5: return ctx->rot.p;
+        default: return nullptr;
+    }
+}
+
+}  // extern "C"

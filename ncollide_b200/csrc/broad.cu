@@ -1,0 +1,463 @@
+// Broad phase on the device: per-object AABBs, LBVH (Morton codes -> radix sort -> Karras build -> bottom-up refit),
+// overlap pair search with warp-aggregated emission, and a counting sort of the pairs by shape-type key.
+//
+// Replaces (reference, file:line):
+//   k_aabb          pipeline/object/collision_object.rs:89-93, bounding_volume/aabb_{ball,cuboid,convex,plane}.rs,
+//                   bounding_volume/aabb_utils.rs:59-79, bounding_volume/aabb.rs:180-199, dbvt_broad_phase.rs:341
+//   LBVH            partitioning/dbvt.rs:158-255 (the incremental tree is replaced, not ported)
+//   k_pair_search   pipeline/broad_phase/dbvt_broad_phase.rs:218-253, partitioning/bvh.rs:24-45,
+//                   query/visitors/bounding_volume_interferences_collector.rs:41-51,
+//                   pipeline/object/collision_groups.rs:353-359
+//   pair keys       pipeline/narrow_phase/contact_generator/default_contact_dispatcher.rs:27-97
+// The fresh-world pair set is tree independent: {(i, j) : j < i, fat_i ∩ fat_j != ∅, allowed(i, j)}.
+#include <cooperative_groups.h>
+#include <cub/cub.cuh>
+#include "ncb_internal.h"
+#include "vec.cuh"
+
+namespace ncb {
+
+#define LEAF_BIT 0x80000000u
+static const float OUTLIER_ABS = 1.0e30f;  // planes have +-f32::MAX/2 boxes (aabb_plane.rs:16-20): kept out of the tree
+
+__device__ __forceinline__ int f2o(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float o2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// ------------------------------------------------------------------------------------------------------------
+// K1: AABBs.  One thread per object; 128-bit loads of the quaternion / shape record, float4 SoA stores.
+// mode 0: bounding_volume::aabb(shape, pos); 1: + loosen(query_limit) (compute_aabb); 2: + loosened(margin).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_aabb(DevObjects o, DevHulls H, float margin, int mode, uint32_t begin, uint32_t end,
+                                              float4* __restrict__ lo, float4* __restrict__ hi) {
+    uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    uint32_t type = o.type[i];
+    float4 q4 = __ldg(&o.rot[i]);
+    float4 p4 = __ldg(&o.param[i]);
+    V3 t = v3(o.pos[3 * i], o.pos[3 * i + 1], o.pos[3 * i + 2]);
+    Quat q = Quat{q4.x, q4.y, q4.z, q4.w};
+    V3 mins, maxs;
+    if (type == NCB_SHAPE_BALL) {
+        float r = p4.x;
+        mins = t + v3(-r, -r, -r);
+        maxs = t + v3(r, r, r);
+    } else if (type == NCB_SHAPE_CUBOID) {
+        V3 he = absolute_transform_vector(q, v3(p4.x, p4.y, p4.z));
+        mins = t - he;
+        maxs = t + he;
+    } else if (type == NCB_SHAPE_CONVEX_HULL) {
+        uint32_t h = (uint32_t)p4.x;
+        uint32_t v0 = H.vert_off[h], v1 = H.vert_off[h + 1];
+        Iso m = Iso{t, q};
+        const float* P = H.points + 3 * (size_t)v0;
+        V3 w0 = iso_mul_point(m, v3(__ldg(P), __ldg(P + 1), __ldg(P + 2)));
+        mins = w0;
+        maxs = w0;
+        for (uint32_t k = 1; k < v1 - v0; ++k) {
+            V3 w = iso_mul_point(m, v3(__ldg(P + 3 * k), __ldg(P + 3 * k + 1), __ldg(P + 3 * k + 2)));
+            mins = vmin(mins, w);
+            maxs = vmax(maxs, w);
+        }
+    } else {
+        float mx = NCB_FMAX * 0.5f;
+        mins = v3(-mx, -mx, -mx);
+        maxs = v3(mx, mx, mx);
+    }
+    if (mode >= 1) {
+        float ql = o.qlimit[i];
+        mins = mins + v3(-ql, -ql, -ql);
+        maxs = maxs + v3(ql, ql, ql);
+    }
+    if (mode >= 2) {
+        mins = mins + v3(-margin, -margin, -margin);
+        maxs = maxs + v3(margin, margin, margin);
+    }
+    lo[i] = make_float4(mins.x, mins.y, mins.z, 0.0f);
+    hi[i] = make_float4(maxs.x, maxs.y, maxs.z, __uint_as_float(type));
+}
+
+cudaError_t launch_aabbs(ncb_ctx* c, const DevObjects& o, float margin, int mode, uint32_t begin, uint32_t end) {
+    if (end <= begin) return cudaSuccess;
+    uint32_t n = end - begin;
+    k_aabb<<<(n + 255) / 256, 256, 0, c->stream>>>(o, c->hulls, margin, mode, begin, end, c->aabb_lo.p, c->aabb_hi.p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2: scene bounds of the AABB centres (outliers excluded) + Morton codes.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_outlier(float4 lo, float4 hi) {
+    float m = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(lo.y)), fabsf(lo.z)), fmaxf(fmaxf(fabsf(hi.x), fabsf(hi.y)), fabsf(hi.z)));
+    return !(m < OUTLIER_ABS);  // also true for NaN
+}
+
+__global__ void __launch_bounds__(256) k_bounds(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n,
+                                                DevCounters* cnt) {
+    float mn[3] = {NCB_FMAX, NCB_FMAX, NCB_FMAX}, mx[3] = {-NCB_FMAX, -NCB_FMAX, -NCB_FMAX};
+    uint32_t nout = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 a = __ldg(&lo[i]), b = __ldg(&hi[i]);
+        if (is_outlier(a, b)) {
+            nout++;
+            continue;
+        }
+        float cx = (a.x + b.x) * 0.5f, cy = (a.y + b.y) * 0.5f, cz = (a.z + b.z) * 0.5f;
+        mn[0] = fminf(mn[0], cx), mn[1] = fminf(mn[1], cy), mn[2] = fminf(mn[2], cz);
+        mx[0] = fmaxf(mx[0], cx), mx[1] = fmaxf(mx[1], cy), mx[2] = fmaxf(mx[2], cz);
+    }
+    for (int off = 16; off; off >>= 1) {
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], off));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], off));
+        }
+        nout += __shfl_xor_sync(0xffffffffu, nout, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(&cnt->bounds[k], f2o(mn[k]));
+            atomicMax(&cnt->bounds[3 + k], f2o(mx[k]));
+        }
+        if (nout) atomicAdd(&cnt->n_outliers, nout);
+    }
+}
+
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n,
+                                                const DevCounters* __restrict__ cnt, uint32_t* __restrict__ keys,
+                                                uint32_t* __restrict__ idx) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = __ldg(&lo[i]), b = __ldg(&hi[i]);
+    uint32_t key;
+    if (is_outlier(a, b)) {
+        key = 0x40000000u;  // after every 30-bit code
+    } else {
+        float bx = o2f(cnt->bounds[0]), by = o2f(cnt->bounds[1]), bz = o2f(cnt->bounds[2]);
+        float ex = o2f(cnt->bounds[3]) - bx, ey = o2f(cnt->bounds[4]) - by, ez = o2f(cnt->bounds[5]) - bz;
+        float e = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-20f));
+        float s = 1023.0f / e;
+        float cx = ((a.x + b.x) * 0.5f - bx) * s, cy = ((a.y + b.y) * 0.5f - by) * s, cz = ((a.z + b.z) * 0.5f - bz) * s;
+        uint32_t ux = (uint32_t)fminf(fmaxf(cx, 0.0f), 1023.0f);
+        uint32_t uy = (uint32_t)fminf(fmaxf(cy, 0.0f), 1023.0f);
+        uint32_t uz = (uint32_t)fminf(fmaxf(cz, 0.0f), 1023.0f);
+        key = (expand_bits10(ux) << 2) | (expand_bits10(uy) << 1) | expand_bits10(uz);
+    }
+    keys[i] = key;
+    idx[i] = i;
+}
+
+// Gather the boxes into Morton order; lo.w <- handle, hi.w keeps the shape type.
+__global__ void __launch_bounds__(256) k_gather_leaves(const float4* __restrict__ lo, const float4* __restrict__ hi,
+                                                       const uint32_t* __restrict__ idx, uint32_t n, float4* __restrict__ llo,
+                                                       float4* __restrict__ lhi) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h = __ldg(&idx[i]);
+    float4 a = __ldg(&lo[h]), b = __ldg(&hi[h]);
+    a.w = __uint_as_float(h);
+    llo[i] = a;
+    lhi[i] = b;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K4: Karras (2012) radix tree over the sorted codes (ties broken by position) + bottom-up refit.
+// Node layout (4 x float4 per internal node, one 64 B record):
+//   [0] left  box mins, w = left child  (LEAF_BIT | leaf position, or internal index)
+//   [1] left  box maxs, w = right child
+//   [2] right box mins, w = split  (last sorted position covered by the left child)
+//   [3] right box maxs, w = last   (last sorted position covered by the node)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int delta_fn(const uint32_t* __restrict__ keys, int m, int i, int j) {
+    if (j < 0 || j >= m) return -1;
+    uint32_t a = __ldg(&keys[i]), b = __ldg(&keys[j]);
+    if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clz(a ^ b);
+}
+
+__global__ void __launch_bounds__(256) k_karras(const uint32_t* __restrict__ keys, uint32_t n, const DevCounters* __restrict__ cnt,
+                                                float4* __restrict__ nodes, uint32_t* __restrict__ parent) {
+    int m = (int)(n - cnt->n_outliers);
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m - 1) return;
+    int d = (delta_fn(keys, m, i, i + 1) - delta_fn(keys, m, i, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta_fn(keys, m, i, i - d);
+    int lmax = 2;
+    while (delta_fn(keys, m, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta_fn(keys, m, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta_fn(keys, m, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta_fn(keys, m, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int first = min(i, j), last = max(i, j);
+    uint32_t left = (first == gamma) ? (LEAF_BIT | (uint32_t)gamma) : (uint32_t)gamma;
+    uint32_t right = (last == gamma + 1) ? (LEAF_BIT | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
+    // only the .w lanes are written here; the boxes come from k_refit
+    reinterpret_cast<uint32_t*>(&nodes[4 * (size_t)i + 0])[3] = left;
+    reinterpret_cast<uint32_t*>(&nodes[4 * (size_t)i + 1])[3] = right;
+    reinterpret_cast<uint32_t*>(&nodes[4 * (size_t)i + 2])[3] = (uint32_t)gamma;
+    reinterpret_cast<uint32_t*>(&nodes[4 * (size_t)i + 3])[3] = (uint32_t)last;
+    // parent links: bit 31 = "I am the right child"
+    if (left & LEAF_BIT)
+        parent[n + gamma] = (uint32_t)i;
+    else
+        parent[gamma] = (uint32_t)i;
+    if (right & LEAF_BIT)
+        parent[n + gamma + 1] = (uint32_t)i | LEAF_BIT;
+    else
+        parent[gamma + 1] = (uint32_t)i | LEAF_BIT;
+    if (i == 0) parent[0] = 0xffffffffu;
+}
+
+__global__ void __launch_bounds__(256) k_refit(const float4* __restrict__ llo, const float4* __restrict__ lhi, uint32_t n,
+                                               const DevCounters* __restrict__ cnt, float4* nodes, const uint32_t* __restrict__ parent,
+                                               uint32_t* flags) {
+    uint32_t m = n - cnt->n_outliers;
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m || m < 2) return;
+    float4 a = __ldg(&llo[j]), b = __ldg(&lhi[j]);
+    float3 mn = make_float3(a.x, a.y, a.z), mx = make_float3(b.x, b.y, b.z);
+    uint32_t p = parent[n + j];
+    for (;;) {
+        uint32_t node = p & ~LEAF_BIT;
+        bool right = (p & LEAF_BIT) != 0;
+        float* rec = reinterpret_cast<float*>(&nodes[4 * (size_t)node + (right ? 2 : 0)]);
+        // xyz only: the .w lanes hold topology
+        __stcg(rec + 0, mn.x), __stcg(rec + 1, mn.y), __stcg(rec + 2, mn.z);
+        __stcg(rec + 4, mx.x), __stcg(rec + 5, mx.y), __stcg(rec + 6, mx.z);
+        __threadfence();
+        if (atomicAdd(&flags[node], 1u) == 0) return;  // the sibling subtree is not finished: its thread continues
+        const float* other = reinterpret_cast<const float*>(&nodes[4 * (size_t)node + (right ? 0 : 2)]);
+        mn.x = fminf(mn.x, __ldcg(other + 0)), mn.y = fminf(mn.y, __ldcg(other + 1)), mn.z = fminf(mn.z, __ldcg(other + 2));
+        mx.x = fmaxf(mx.x, __ldcg(other + 4)), mx.y = fmaxf(mx.y, __ldcg(other + 5)), mx.z = fmaxf(mx.z, __ldcg(other + 6));
+        if (node == 0) return;
+        p = parent[node];
+    }
+}
+
+size_t lbvh_temp_bytes(uint32_t n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)n, 0, 31);
+    return bytes;
+}
+
+// Builds the LBVH over c->aabb_lo/hi[0..n).  Needs c->counters zeroed (bounds initialised) by the caller.
+cudaError_t launch_lbvh_build(ncb_ctx* c, uint32_t n, const uint32_t*) {
+    cudaStream_t s = c->stream;
+    if (n == 0) return cudaSuccess;
+    int gs = c->sm_count * 8;
+    uint32_t nb = (n + 255) / 256;
+    k_bounds<<<min((uint32_t)gs, nb), 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, n, c->counters.p);
+    k_morton<<<nb, 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, n, c->counters.p, c->keys_a.p, c->idx_a.p);
+    size_t bytes = c->cub_tmp.cap;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, c->keys_a.p, c->keys_b.p, c->idx_a.p, c->idx_b.p, (int)n, 0, 31, s);
+    if (e != cudaSuccess) return e;
+    k_gather_leaves<<<nb, 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, c->idx_b.p, n, c->leaf_lo.p, c->leaf_hi.p);
+    e = cudaMemsetAsync(c->flags.p, 0, (size_t)n * sizeof(uint32_t), s);
+    if (e != cudaSuccess) return e;
+    k_karras<<<nb, 256, 0, s>>>(c->keys_b.p, n, c->counters.p, c->nodes.p, c->parent.p);
+    k_refit<<<nb, 256, 0, s>>>(c->leaf_lo.p, c->leaf_hi.p, n, c->counters.p, c->nodes.p, c->parent.p, c->flags.p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K5: pair search.  One thread per query leaf, in Morton order (neighbouring lanes traverse neighbouring boxes).
+// A query at sorted position i reports only leaves at positions j > i, so each unordered pair is emitted once;
+// it is oriented (larger handle, smaller handle) = the argument order of interference_started.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __constant__ uint8_t c_key_table[16] = {
+    // [t1 * 4 + t2], t = ball, cuboid, hull, plane
+    K_BALL_BALL,   K_BALL_CUBOID,   K_BALL_HULL,   K_PLANE_BALL,    //
+    K_BALL_CUBOID, K_CUBOID_CUBOID, K_CUBOID_HULL, K_PLANE_CUBOID,  //
+    K_BALL_HULL,   K_CUBOID_HULL,   K_HULL_HULL,   K_PLANE_HULL,    //
+    K_PLANE_BALL,  K_PLANE_CUBOID,  K_PLANE_HULL,  K_NONE};
+
+// NCB_ALGO_* per key
+__device__ __constant__ uint8_t c_algo_of_key[16] = {NCB_ALGO_BALL_BALL,     NCB_ALGO_PLANE_BALL,  NCB_ALGO_PLANE_CONVEX,  NCB_ALGO_PLANE_CONVEX,
+                                                     NCB_ALGO_BALL_CONVEX,   NCB_ALGO_BALL_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_CONVEX_CONVEX,
+                                                     NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_NONE,        0, 0, 0, 0, 0, 0};
+
+__device__ __forceinline__ bool groups_allow(const uint32_t* __restrict__ g, uint32_t a, uint32_t b) {
+    if (!g) return true;
+    uint32_t m1 = __ldg(&g[3 * a]), w1 = __ldg(&g[3 * a + 1]), b1 = __ldg(&g[3 * a + 2]);
+    uint32_t m2 = __ldg(&g[3 * b]), w2 = __ldg(&g[3 * b + 1]), b2 = __ldg(&g[3 * b + 2]);
+    return (m1 & b2) == 0 && (m2 & b1) == 0 && (m1 & w2) != 0 && (m2 & w1) != 0;
+}
+
+// Warp-aggregated append: one atomicAdd per converged group of emitting lanes.
+__device__ __forceinline__ void emit_pair(uint32_t ha, uint32_t ta, uint32_t hb, uint32_t tb, uint2* __restrict__ pairs,
+                                          uint8_t* __restrict__ keys, uint32_t cap, DevCounters* cnt) {
+    cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
+    uint32_t base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(&cnt->n_pairs, (uint32_t)g.size());
+    base = g.shfl(base, 0);
+    uint32_t slot = base + g.thread_rank();
+    if (slot < cap) {
+        uint32_t h1, h2, t1, t2;
+        if (ha > hb) {
+            h1 = ha, t1 = ta, h2 = hb, t2 = tb;
+        } else {
+            h1 = hb, t1 = tb, h2 = ha, t2 = ta;
+        }
+        pairs[slot] = make_uint2(h1, h2);
+        keys[slot] = c_key_table[(t1 & 3) * 4 + (t2 & 3)];
+    }
+}
+
+__device__ __forceinline__ bool boxes_intersect(float4 alo, float4 ahi, float4 blo, float4 bhi) {
+    // AABB::intersects (aabb.rs:156-158): inclusive; false on NaN
+    return alo.x <= bhi.x && alo.y <= bhi.y && alo.z <= bhi.z && ahi.x >= blo.x && ahi.y >= blo.y && ahi.z >= blo.z;
+}
+
+__global__ void __launch_bounds__(128) k_pair_search(const float4* __restrict__ llo, const float4* __restrict__ lhi,
+                                                     const float4* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ groups,
+                                                     uint32_t q_begin, uint32_t q_end, uint2* __restrict__ pairs,
+                                                     uint8_t* __restrict__ keys, uint32_t cap, DevCounters* cnt) {
+    uint32_t m = n - cnt->n_outliers;
+    uint32_t i = q_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m || i >= q_end || m < 2) return;
+    float4 qlo = __ldg(&llo[i]), qhi = __ldg(&lhi[i]);
+    uint32_t hq = __float_as_uint(qlo.w), tq = __float_as_uint(qhi.w);
+    uint32_t stack[64];
+    int sp = 0;
+    uint32_t node = 0;
+    for (;;) {
+        const float4* rec = nodes + 4 * (size_t)node;
+        float4 Llo = __ldg(rec + 0), Lhi = __ldg(rec + 1), Rlo = __ldg(rec + 2), Rhi = __ldg(rec + 3);
+        uint32_t left = __float_as_uint(Llo.w), right = __float_as_uint(Lhi.w);
+        uint32_t split = __float_as_uint(Rlo.w), last = __float_as_uint(Rhi.w);
+        bool goL = split > i && boxes_intersect(qlo, qhi, Llo, Lhi);
+        bool goR = last > i && boxes_intersect(qlo, qhi, Rlo, Rhi);
+        if (goL && (left & LEAF_BIT)) {
+            uint32_t j = left & ~LEAF_BIT;
+            uint32_t hj = __float_as_uint(__ldg(&llo[j].w)), tj = __float_as_uint(__ldg(&lhi[j].w));
+            if (groups_allow(groups, hq, hj)) emit_pair(hq, tq, hj, tj, pairs, keys, cap, cnt);
+            goL = false;
+        }
+        if (goR && (right & LEAF_BIT)) {
+            uint32_t j = right & ~LEAF_BIT;
+            uint32_t hj = __float_as_uint(__ldg(&llo[j].w)), tj = __float_as_uint(__ldg(&lhi[j].w));
+            if (groups_allow(groups, hq, hj)) emit_pair(hq, tq, hj, tj, pairs, keys, cap, cnt);
+            goR = false;
+        }
+        if (goL) {
+            if (goR && sp < 64) stack[sp++] = right;
+            node = left;
+        } else if (goR) {
+            node = right;
+        } else {
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+}
+
+// Outliers (planes, boxes beyond 1e30) sit after the tree leaves in the sorted arrays and are tested against
+// everything: their boxes overlap (almost) every object, so a tree would not prune anything.
+__global__ void __launch_bounds__(256) k_pair_outliers(const float4* __restrict__ llo, const float4* __restrict__ lhi, uint32_t n,
+                                                       const uint32_t* __restrict__ groups, uint32_t q_begin, uint32_t q_end,
+                                                       uint2* __restrict__ pairs, uint8_t* __restrict__ keys, uint32_t cap,
+                                                       DevCounters* cnt) {
+    uint32_t nout = cnt->n_outliers;
+    if (nout == 0) return;
+    uint32_t m = n - nout;
+    uint32_t i = q_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || i >= q_end) return;
+    float4 alo = __ldg(&llo[i]), ahi = __ldg(&lhi[i]);
+    uint32_t ha = __float_as_uint(alo.w), ta = __float_as_uint(ahi.w);
+    for (uint32_t o = max(m, i + 1); o < n; ++o) {
+        float4 blo = __ldg(&llo[o]), bhi = __ldg(&lhi[o]);
+        if (boxes_intersect(alo, ahi, blo, bhi)) {
+            uint32_t hb = __float_as_uint(blo.w), tb = __float_as_uint(bhi.w);
+            if (groups_allow(groups, ha, hb)) emit_pair(ha, ta, hb, tb, pairs, keys, cap, cnt);
+        }
+    }
+}
+
+cudaError_t launch_pair_search(ncb_ctx* c, uint32_t n, const uint32_t* groups, uint32_t q_begin, uint32_t q_end, uint32_t cap_pairs) {
+    if (n == 0) return cudaSuccess;
+    cudaStream_t s = c->stream;
+    q_end = min(q_end, n);
+    if (q_end <= q_begin) return cudaSuccess;
+    uint32_t nq = q_end - q_begin;
+    k_pair_search<<<(nq + 127) / 128, 128, 0, s>>>(c->leaf_lo.p, c->leaf_hi.p, c->nodes.p, n, groups, q_begin, q_end, c->pairs_raw.p,
+                                                   c->keys_raw.p, cap_pairs, c->counters.p);
+    k_pair_outliers<<<(nq + 255) / 256, 256, 0, s>>>(c->leaf_lo.p, c->leaf_hi.p, n, groups, q_begin, q_end, c->pairs_raw.p,
+                                                     c->keys_raw.p, cap_pairs, c->counters.p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K6: counting sort of the pairs by type key (histogram -> scan -> scatter), all sized on the device:
+// persistent grid-stride kernels read n_pairs from the counters, so the host never synchronises mid-update.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_key_hist(const uint8_t* __restrict__ keys, uint32_t cap, DevCounters* cnt) {
+    __shared__ uint32_t h[16];
+    if (threadIdx.x < 16) h[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t np = min(cnt->n_pairs, cap);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) atomicAdd(&h[keys[p] & 15], 1u);
+    __syncthreads();
+    if (threadIdx.x < 16 && h[threadIdx.x]) atomicAdd(&cnt->key_hist[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void k_key_scan(DevCounters* cnt) {
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int k = 0; k < 16; ++k) {
+            cnt->key_start[k] = acc;
+            cnt->key_cursor[k] = acc;
+            acc += cnt->key_hist[k];
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_key_scatter(const uint2* __restrict__ pin, const uint8_t* __restrict__ kin, uint32_t cap,
+                                                     uint2* __restrict__ pout, uint8_t* __restrict__ algo_out, uint32_t* __restrict__ index_out,
+                                                     DevCounters* cnt) {
+    uint32_t np = min(cnt->n_pairs, cap);
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < np; base += stride) {
+        uint32_t p = base + threadIdx.x;
+        bool valid = p < np;
+        uint32_t key = valid ? (kin[p] & 15) : 31;
+        unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (valid) {
+            int lane = threadIdx.x & 31;
+            int leader = __ffs(peers) - 1;
+            uint32_t b = 0;
+            if (lane == leader) b = atomicAdd(&cnt->key_cursor[key], (uint32_t)__popc(peers));
+            b = __shfl_sync(peers, b, leader);
+            uint32_t dst = b + __popc(peers & ((1u << lane) - 1));
+            pout[dst] = pin[p];
+            algo_out[dst] = c_algo_of_key[key];
+            if (index_out) index_out[dst] = p;
+        }
+    }
+}
+
+cudaError_t launch_pair_sort(ncb_ctx* c, uint32_t cap_pairs, uint32_t* index_out) {
+    cudaStream_t s = c->stream;
+    int gs = c->sm_count * 4;
+    k_key_hist<<<gs, 256, 0, s>>>(c->keys_raw.p, cap_pairs, c->counters.p);
+    k_key_scan<<<1, 32, 0, s>>>(c->counters.p);
+    k_key_scatter<<<gs, 256, 0, s>>>(c->pairs_raw.p, c->keys_raw.p, cap_pairs, c->pairs.p, c->pair_algo.p, index_out,
+                                       c->counters.p);
+    return cudaGetLastError();
+}
+
+}  // namespace ncb

@@ -1,0 +1,758 @@
+// Device GJK / EPA for one pair per thread, fixed capacity, no recursion, no heap allocation.
+//
+// Replaces (reference, file:line): query/algorithms/gjk.rs:76-177,367-388; voronoi_simplex3.rs:49-280;
+// cso_point.rs:70-85; query/point/point_segment.rs:52-91, point_triangle.rs:61-309, point_tetrahedron.rs:35-353;
+// query/algorithms/epa3.rs:219-454 (std BinaryHeap + Vec + recursive silhouette flood -> fixed arrays + explicit
+// stack); query/contact/contact_support_map_support_map.rs:38-79; shape/support_map.rs:26-29; shape/cuboid.rs:137-145;
+// utils/point_cloud_support_point.rs:6-24.
+//
+// Contact parity needs the SAME iteration path as the reference (SURVEY.md §7 hard part 3b): same start direction,
+// same support tie-breaks, same simplex permutations, same exit tests, no FMA contraction.
+#pragma once
+#include "ncb_internal.h"
+#include "vec.cuh"
+
+namespace ncb {
+
+#define EPA_MAX_VERTS 48
+#define EPA_MAX_FACES 192
+#define EPA_MAX_HEAP 160
+#define EPA_MAX_STACK 160
+
+struct HullView {
+    uint32_t nv, nf;
+    const float* pts;
+    const float* fnormal;
+    const uint32_t *face_first, *face_num, *vaf, *eaf;
+    const uint32_t *vfirst, *vnum, *fav, *eav;
+    const uint32_t *edge_vertices, *edge_faces;
+    const float* edge_dir;
+    NCB_HD V3 pt(uint32_t i) const { return v3(__ldg(pts + 3 * i), __ldg(pts + 3 * i + 1), __ldg(pts + 3 * i + 2)); }
+    NCB_HD V3 fn(uint32_t i) const { return v3(__ldg(fnormal + 3 * i), __ldg(fnormal + 3 * i + 1), __ldg(fnormal + 3 * i + 2)); }
+    NCB_HD V3 edir(uint32_t i) const { return v3(__ldg(edge_dir + 3 * i), __ldg(edge_dir + 3 * i + 1), __ldg(edge_dir + 3 * i + 2)); }
+};
+
+NCB_HD HullView hull_view(const DevHulls& L, uint32_t h) {
+    HullView H;
+    uint32_t v0 = __ldg(L.vert_off + h), f0 = __ldg(L.face_off + h), e0 = __ldg(L.edge_off + h);
+    uint32_t fa0 = __ldg(L.fadj_off + h), va0 = __ldg(L.vadj_off + h);
+    H.nv = __ldg(L.vert_off + h + 1) - v0;
+    H.nf = __ldg(L.face_off + h + 1) - f0;
+    H.pts = L.points + 3 * (size_t)v0;
+    H.fnormal = L.face_normal + 3 * (size_t)f0;
+    H.face_first = L.face_first + f0;
+    H.face_num = L.face_num + f0;
+    H.vaf = L.vaf + fa0;
+    H.eaf = L.eaf + fa0;
+    H.vfirst = L.vert_first_adj + v0;
+    H.vnum = L.vert_num_adj + v0;
+    H.fav = L.fav + va0;
+    H.eav = L.eav + va0;
+    H.edge_vertices = L.edge_vertices + 2 * (size_t)e0;
+    H.edge_faces = L.edge_faces + 2 * (size_t)e0;
+    H.edge_dir = L.edge_dir + 3 * (size_t)e0;
+    return H;
+}
+
+// A support-mapped operand.  kind: 0 cuboid, 1 hull, 2 constant origin.
+struct Support {
+    int kind;
+    V3 he;
+    HullView hull;
+};
+
+NCB_HD V3 local_support_point(const Support& g, V3 dir) {
+    if (g.kind == 0) return v3(copysignf(g.he.x, dir.x), copysignf(g.he.y, dir.y), copysignf(g.he.z, dir.z));
+    uint32_t best = 0;
+    float best_dot = dot(g.hull.pt(0), dir);
+    for (uint32_t i = 1; i < g.hull.nv; ++i) {
+        float d = dot(g.hull.pt(i), dir);
+        if (d > best_dot) {
+            best_dot = d;
+            best = i;
+        }
+    }
+    return g.hull.pt(best);
+}
+NCB_HD V3 support_point(const Support& g, const Iso& m, V3 dir) {
+    if (g.kind == 2) return v3(0.f, 0.f, 0.f);
+    V3 ld = iso_inv_vec(m, dir);
+    return iso_mul_point(m, local_support_point(g, ld));
+}
+
+struct CSOPoint {
+    V3 point, orig1, orig2;
+};
+NCB_HD CSOPoint cso_from_shapes(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, V3 dir) {
+    CSOPoint c;
+    c.orig1 = support_point(g1, m1, dir);
+    c.orig2 = support_point(g2, m2, -dir);
+    c.point = c.orig1 - c.orig2;
+    return c;
+}
+
+// ---- Voronoi-region projections of the ORIGIN's generalisation `p` (identity isometry) ---------------------
+enum { LOC_VERTEX = 0, LOC_EDGE = 1, LOC_FACE = 2, LOC_SOLID = 3 };
+struct Loc {
+    int kind, id;
+    float b0, b1, b2;
+};
+NCB_HD Loc mkloc(int kind, int id, float b0 = 0.f, float b1 = 0.f, float b2 = 0.f) { return Loc{kind, id, b0, b1, b2}; }
+
+NCB_HD V3 proj_segment(V3 a, V3 b, V3 p, Loc& loc) {
+    V3 ab = b - a, ap = p - a;
+    float ab_ap = dot(ab, ap), sqnab = norm_squared(ab);
+    if (ab_ap <= 0.f) {
+        loc = mkloc(LOC_VERTEX, 0);
+        return a;
+    }
+    if (ab_ap >= sqnab) {
+        loc = mkloc(LOC_VERTEX, 1);
+        return b;
+    }
+    float u = ab_ap / sqnab;
+    loc = mkloc(LOC_EDGE, 0, 1.f - u, u);
+    return a + ab * u;
+}
+
+// solid = true variant only (the one the simplex and EPA use)
+__device__ __noinline__ V3 proj_triangle(V3 a, V3 b, V3 c, V3 p, Loc& loc) {
+    V3 ab = b - a, ac = c - a, ap = p - a;
+    float ab_ap = dot(ab, ap), ac_ap = dot(ac, ap);
+    if (ab_ap <= 0.f && ac_ap <= 0.f) {
+        loc = mkloc(LOC_VERTEX, 0);
+        return a;
+    }
+    V3 bp = p - b;
+    float ab_bp = dot(ab, bp), ac_bp = dot(ac, bp);
+    if (ab_bp >= 0.f && ac_bp <= ab_bp) {
+        loc = mkloc(LOC_VERTEX, 1);
+        return b;
+    }
+    V3 cp = p - c;
+    float ab_cp = dot(ab, cp), ac_cp = dot(ac, cp);
+    if (ac_cp >= 0.f && ab_cp <= ac_cp) {
+        loc = mkloc(LOC_VERTEX, 2);
+        return c;
+    }
+    V3 bc = c - b;
+    V3 n = cross(ab, ac);
+    float vc = dot(n, cross(ab, ap));
+    if (vc < 0.f && ab_ap >= 0.f && ab_bp <= 0.f) {
+        float v = ab_ap / norm_squared(ab);
+        loc = mkloc(LOC_EDGE, 0, 1.f - v, v);
+        return a + ab * v;
+    }
+    float vb = -dot(n, cross(ac, cp));
+    if (vb < 0.f && ac_ap >= 0.f && ac_cp <= 0.f) {
+        float w = ac_ap / norm_squared(ac);
+        loc = mkloc(LOC_EDGE, 2, 1.f - w, w);
+        return a + ac * w;
+    }
+    float va = dot(n, cross(bc, bp));
+    if (va < 0.f && ac_bp - ab_bp >= 0.f && ab_cp - ac_cp >= 0.f) {
+        float w = dot(bc, bp) / norm_squared(bc);
+        loc = mkloc(LOC_EDGE, 1, 1.f - w, w);
+        return b + bc * w;
+    }
+    int clockwise = dot(n, ap) >= 0.f ? 0 : 1;
+    if (va + vb + vc != 0.f) {
+        float denom = 1.f / (va + vb + vc);
+        float v = vb * denom, w = vc * denom;
+        loc = mkloc(LOC_FACE, clockwise, 1.f - v - w, v, w);
+        return a + ab * v + ac * w;
+    }
+    loc = mkloc(LOC_SOLID, 0);
+    return p;
+}
+
+NCB_HD bool tetra_edge(int i, V3 a, V3 nabc, V3 nabd, V3 ap, V3 ab, float ap_ab, float bp_ab, float& dabc, float& dabd, V3& proj,
+                       Loc& loc) {
+    float ab_ab = ap_ab - bp_ab;
+    V3 ap_x_ab = cross(ap, ab);
+    dabc = dot(ap_x_ab, nabc);
+    dabd = dot(ap_x_ab, nabd);
+    if (ab_ab != 0.f && dabc >= 0.f && dabd >= 0.f && ap_ab >= 0.f && ap_ab <= ab_ab) {
+        float u = ap_ab / ab_ab;
+        loc = mkloc(LOC_EDGE, i, 1.f - u, u);
+        proj = a + ab * u;
+        return true;
+    }
+    return false;
+}
+NCB_HD bool tetra_face(int i, V3 a, V3 b, V3 c, V3 ap, V3 bp, V3 cp, V3 ab, V3 ac, V3 ad, float dabc, float dbca, float dacb, V3& proj,
+                       Loc& loc) {
+    if (dabc < 0.f && dbca < 0.f && dacb < 0.f) {
+        V3 n = cross(ab, ac);
+        if (dot(n, ad) * dot(n, ap) < 0.f) {
+            V3 normal;
+            if (!try_normalize(n, NCB_EPS, normal)) return false;
+            float vc = dot(normal, cross(ap, bp));
+            float va = dot(normal, cross(bp, cp));
+            float vb = dot(normal, cross(cp, ap));
+            float denom = va + vb + vc;
+            float inv_denom = 1.f / denom;
+            float b0 = va * inv_denom, b1 = vb * inv_denom, b2 = vc * inv_denom;
+            loc = mkloc(LOC_FACE, i, b0, b1, b2);
+            proj = a * b0 + b * b1 + c * b2;
+            return true;
+        }
+    }
+    return false;
+}
+__device__ __noinline__ V3 proj_tetrahedron(V3 a, V3 b, V3 c, V3 d, V3 p, Loc& loc) {
+    V3 ab = b - a, ac = c - a, ad = d - a, ap = p - a;
+    float ap_ab = dot(ap, ab), ap_ac = dot(ap, ac), ap_ad = dot(ap, ad);
+    if (ap_ab <= 0.f && ap_ac <= 0.f && ap_ad <= 0.f) {
+        loc = mkloc(LOC_VERTEX, 0);
+        return a;
+    }
+    V3 bc = c - b, bd = d - b, bp = p - b;
+    float bp_bc = dot(bp, bc), bp_bd = dot(bp, bd), bp_ab = dot(bp, ab);
+    if (bp_bc <= 0.f && bp_bd <= 0.f && bp_ab >= 0.f) {
+        loc = mkloc(LOC_VERTEX, 1);
+        return b;
+    }
+    V3 cd = d - c, cp = p - c;
+    float cp_ac = dot(cp, ac), cp_bc = dot(cp, bc), cp_cd = dot(cp, cd);
+    if (cp_cd <= 0.f && cp_bc >= 0.f && cp_ac >= 0.f) {
+        loc = mkloc(LOC_VERTEX, 2);
+        return c;
+    }
+    V3 dp = p - d;
+    float dp_cd = dot(dp, cd), dp_bd = dot(dp, bd), dp_ad = dot(dp, ad);
+    if (dp_ad >= 0.f && dp_bd >= 0.f && dp_cd >= 0.f) {
+        loc = mkloc(LOC_VERTEX, 3);
+        return d;
+    }
+    V3 proj;
+    V3 nabc = cross(ab, ac), nabd = cross(ab, ad);
+    float dabc, dabd;
+    if (tetra_edge(0, a, nabc, nabd, ap, ab, ap_ab, bp_ab, dabc, dabd, proj, loc)) return proj;
+    V3 nacd = cross(ac, ad);
+    float dacd, dacb;
+    if (tetra_edge(1, a, nacd, -nabc, ap, ac, ap_ac, cp_ac, dacd, dacb, proj, loc)) return proj;
+    float dadb, dadc;
+    if (tetra_edge(2, a, -nabd, -nacd, ap, ad, ap_ad, dp_ad, dadb, dadc, proj, loc)) return proj;
+    V3 nbcd = cross(bc, bd);
+    float dbca, dbcd;
+    if (tetra_edge(3, b, nabc, nbcd, bp, bc, bp_bc, cp_bc, dbca, dbcd, proj, loc)) return proj;
+    float dbdc, dbda;
+    if (tetra_edge(4, b, -nbcd, nabd, bp, bd, bp_bd, dp_bd, dbdc, dbda, proj, loc)) return proj;
+    float dcda, dcdb;
+    if (tetra_edge(5, c, nacd, nbcd, cp, cd, cp_cd, dp_cd, dcda, dcdb, proj, loc)) return proj;
+    if (tetra_face(0, a, b, c, ap, bp, cp, ab, ac, ad, dabc, dbca, dacb, proj, loc)) return proj;
+    if (tetra_face(1, a, b, d, ap, bp, dp, ab, ad, ac, dadb, dabd, dbda, proj, loc)) return proj;
+    if (tetra_face(2, a, c, d, ap, cp, dp, ac, ad, ab, dacd, dcda, dadc, proj, loc)) return proj;
+    if (tetra_face(3, b, c, d, bp, cp, dp, bc, bd, -ab, dbcd, dcdb, dbdc, proj, loc)) return proj;
+    loc = mkloc(LOC_SOLID, 0);
+    return p;
+}
+
+// ---- VoronoiSimplex -----------------------------------------------------------------------------------------
+struct Simplex {
+    CSOPoint v[4];
+    float proj[3], prev_proj[3];
+    int prev_vertices[4];
+    int dim, prev_dim;
+};
+
+NCB_HD void simplex_init(Simplex& s, const CSOPoint& p) {
+    // VoronoiSimplex::new() + reset(p)
+    CSOPoint o;
+    o.point = o.orig1 = o.orig2 = v3(0.f, 0.f, 0.f);
+    s.v[1] = s.v[2] = s.v[3] = o;
+    s.v[0] = p;
+    for (int i = 0; i < 3; ++i) s.proj[i] = s.prev_proj[i] = 0.f;
+    for (int i = 0; i < 4; ++i) s.prev_vertices[i] = i;
+    s.dim = 0;
+    s.prev_dim = 0;
+}
+NCB_HD void simplex_swap(Simplex& s, int a, int b) {
+    CSOPoint t = s.v[a];
+    s.v[a] = s.v[b];
+    s.v[b] = t;
+    int u = s.prev_vertices[a];
+    s.prev_vertices[a] = s.prev_vertices[b];
+    s.prev_vertices[b] = u;
+}
+NCB_HD bool simplex_add_point(Simplex& s, const CSOPoint& pt) {
+    const float eps_tol = NCB_EPS * 10.0f;
+    s.prev_dim = s.dim;
+    for (int i = 0; i < 3; ++i) s.prev_proj[i] = s.proj[i];
+    for (int i = 0; i < 4; ++i) s.prev_vertices[i] = i;
+    if (s.dim == 0) {
+        if (norm_squared(s.v[0].point - pt.point) < eps_tol) return false;
+    } else if (s.dim == 1) {
+        V3 ab = s.v[1].point - s.v[0].point, ac = pt.point - s.v[0].point;
+        if (norm_squared(cross(ab, ac)) < eps_tol) return false;
+    } else {
+        V3 ab = s.v[1].point - s.v[0].point, ac = s.v[2].point - s.v[0].point, ap = pt.point - s.v[0].point;
+        V3 n = normalize(cross(ab, ac));
+        if (fabsf(dot(n, ap)) < eps_tol) return false;
+    }
+    s.dim += 1;
+    s.v[s.dim] = pt;
+    return true;
+}
+__device__ __noinline__ V3 simplex_project_origin_and_reduce(Simplex& s) {
+    const V3 O = v3(0.f, 0.f, 0.f);
+    Loc loc;
+    if (s.dim == 0) {
+        s.proj[0] = 1.f;
+        return s.v[0].point;
+    }
+    if (s.dim == 1) {
+        V3 p = proj_segment(s.v[0].point, s.v[1].point, O, loc);
+        if (loc.kind == LOC_VERTEX) {
+            if (loc.id == 1) simplex_swap(s, 0, 1);
+            s.proj[0] = 1.f;
+            s.dim = 0;
+        } else {
+            s.proj[0] = loc.b0;
+            s.proj[1] = loc.b1;
+        }
+        return p;
+    }
+    if (s.dim == 2) {
+        V3 p = proj_triangle(s.v[0].point, s.v[1].point, s.v[2].point, O, loc);
+        if (loc.kind == LOC_VERTEX) {
+            simplex_swap(s, 0, loc.id);
+            s.proj[0] = 1.f;
+            s.dim = 0;
+        } else if (loc.kind == LOC_EDGE) {
+            if (loc.id == 0) {
+                s.proj[0] = loc.b0, s.proj[1] = loc.b1;
+            } else if (loc.id == 1) {
+                simplex_swap(s, 0, 2);
+                s.proj[0] = loc.b1, s.proj[1] = loc.b0;
+            } else {
+                simplex_swap(s, 1, 2);
+                s.proj[0] = loc.b0, s.proj[1] = loc.b1;
+            }
+            s.dim = 1;
+        } else if (loc.kind == LOC_FACE) {
+            s.proj[0] = loc.b0, s.proj[1] = loc.b1, s.proj[2] = loc.b2;
+        }
+        return p;
+    }
+    V3 p = proj_tetrahedron(s.v[0].point, s.v[1].point, s.v[2].point, s.v[3].point, O, loc);
+    if (loc.kind == LOC_VERTEX) {
+        simplex_swap(s, 0, loc.id);
+        s.proj[0] = 1.f;
+        s.dim = 0;
+    } else if (loc.kind == LOC_EDGE) {
+        switch (loc.id) {
+            case 0: break;
+            case 1: simplex_swap(s, 1, 2); break;
+            case 2: simplex_swap(s, 1, 3); break;
+            case 3: simplex_swap(s, 0, 2); break;
+            case 4: simplex_swap(s, 0, 3); break;
+            default:
+                simplex_swap(s, 0, 2);
+                simplex_swap(s, 1, 3);
+                break;
+        }
+        if (loc.id == 3 || loc.id == 4) {
+            s.proj[0] = loc.b1, s.proj[1] = loc.b0;
+        } else {
+            s.proj[0] = loc.b0, s.proj[1] = loc.b1;
+        }
+        s.dim = 1;
+    } else if (loc.kind == LOC_FACE) {
+        if (loc.id == 0) {
+            s.proj[0] = loc.b0, s.proj[1] = loc.b1, s.proj[2] = loc.b2;
+        } else if (loc.id == 1) {
+            s.v[2] = s.v[3];
+            s.proj[0] = loc.b0, s.proj[1] = loc.b1, s.proj[2] = loc.b2;
+        } else if (loc.id == 2) {
+            s.v[1] = s.v[3];
+            s.proj[0] = loc.b0, s.proj[1] = loc.b2, s.proj[2] = loc.b1;
+        } else {
+            s.v[0] = s.v[3];
+            s.proj[0] = loc.b2, s.proj[1] = loc.b0, s.proj[2] = loc.b1;
+        }
+        s.dim = 2;
+    }
+    return p;
+}
+
+// gjk.rs:367-388
+NCB_HD void gjk_result(const Simplex& s, bool prev, V3& p1, V3& p2) {
+    V3 r0 = v3(0.f, 0.f, 0.f), r1 = v3(0.f, 0.f, 0.f);
+    if (prev) {
+        for (int i = 0; i < s.prev_dim + 1; ++i) {
+            float coord = s.prev_proj[i];
+            const CSOPoint& pt = s.v[s.prev_vertices[i]];
+            r0 = r0 + pt.orig1 * coord;
+            r1 = r1 + pt.orig2 * coord;
+        }
+    } else {
+        for (int i = 0; i < s.dim + 1; ++i) {
+            float coord = s.proj[i];
+            r0 = r0 + s.v[i].orig1 * coord;
+            r1 = r1 + s.v[i].orig2 * coord;
+        }
+    }
+    p1 = r0;
+    p2 = r1;
+}
+
+enum { GJK_INTERSECTION = 0, GJK_CLOSEST_POINTS = 1, GJK_NO_INTERSECTION = 3 };
+
+// gjk::closest_points with exact_dist = true
+__device__ __noinline__ int gjk_closest_points(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, float max_dist,
+                                               Simplex& s, V3& p1, V3& p2, V3& out_dir) {
+    const float eps_tol = NCB_EPS * 10.0f;
+    const float eps_rel = sqrtf(eps_tol);
+    V3 proj = simplex_project_origin_and_reduce(s);
+    V3 old_dir;
+    {
+        V3 pd;
+        if (!unit_try_new(proj, 0.f, pd)) return GJK_INTERSECTION;
+        old_dir = -pd;
+    }
+    float max_bound = NCB_FMAX;
+    V3 dir;
+    int niter = 0;
+    for (;;) {
+        float old_max_bound = max_bound;
+        float dist;
+        if (!unit_try_new_and_get(-proj, eps_tol, dir, dist)) return GJK_INTERSECTION;
+        max_bound = dist;
+        if (max_bound >= old_max_bound) {
+            gjk_result(s, true, p1, p2);
+            out_dir = old_dir;
+            return GJK_CLOSEST_POINTS;
+        }
+        CSOPoint cso = cso_from_shapes(m1, g1, m2, g2, dir);
+        float min_bound = -dot(dir, cso.point);
+        if (min_bound > max_dist) {
+            out_dir = dir;
+            return GJK_NO_INTERSECTION;
+        } else if (max_bound - min_bound <= eps_rel * max_bound) {
+            gjk_result(s, false, p1, p2);
+            out_dir = dir;
+            return GJK_CLOSEST_POINTS;
+        }
+        if (!simplex_add_point(s, cso)) {
+            gjk_result(s, false, p1, p2);
+            out_dir = dir;
+            return GJK_CLOSEST_POINTS;
+        }
+        old_dir = dir;
+        proj = simplex_project_origin_and_reduce(s);
+        if (s.dim == 3) {
+            if (min_bound >= eps_tol) {
+                gjk_result(s, true, p1, p2);
+                out_dir = old_dir;
+                return GJK_CLOSEST_POINTS;
+            }
+            return GJK_INTERSECTION;
+        }
+        niter += 1;
+        if (niter == 10000) {
+            out_dir = v3(1.f, 0.f, 0.f);
+            return GJK_NO_INTERSECTION;
+        }
+    }
+}
+
+// ---- EPA ----------------------------------------------------------------------------------------------------
+struct EpaFace {
+    uint16_t pts[3], adj[3];
+    float nx, ny, nz;
+    float bc[3];
+    uint32_t deleted;
+};
+struct EpaHeapItem {
+    uint32_t id;
+    float neg_dist;
+};
+struct EpaState {
+    CSOPoint verts[EPA_MAX_VERTS];
+    EpaFace faces[EPA_MAX_FACES];
+    EpaHeapItem heap[EPA_MAX_HEAP];
+    uint16_t sil_face[EPA_MAX_STACK];
+    uint8_t sil_opp[EPA_MAX_STACK];
+    uint16_t stk_face[EPA_MAX_STACK];
+    uint8_t stk_opp[EPA_MAX_STACK];
+    int nverts, nfaces, nheap, nsil;
+    bool overflow, panicked;
+};
+
+// Rust std BinaryHeap<FaceId>: `<=` comes from partial_cmp on neg_dist.
+NCB_HD void heap_sift_up(EpaState& e, int start, int pos) {
+    EpaHeapItem elt = e.heap[pos];
+    while (pos > start) {
+        int parent = (pos - 1) / 2;
+        if (elt.neg_dist <= e.heap[parent].neg_dist) break;
+        e.heap[pos] = e.heap[parent];
+        pos = parent;
+    }
+    e.heap[pos] = elt;
+}
+NCB_HD void heap_push(EpaState& e, uint32_t id, float nd) {
+    if (e.nheap >= EPA_MAX_HEAP) {
+        e.overflow = true;
+        return;
+    }
+    e.heap[e.nheap].id = id;
+    e.heap[e.nheap].neg_dist = nd;
+    e.nheap++;
+    heap_sift_up(e, 0, e.nheap - 1);
+}
+NCB_HD bool heap_pop(EpaState& e, EpaHeapItem& out) {
+    if (e.nheap == 0) return false;
+    EpaHeapItem item = e.heap[--e.nheap];
+    if (e.nheap > 0) {
+        EpaHeapItem t = e.heap[0];
+        e.heap[0] = item;
+        item = t;
+        int end = e.nheap, pos = 0, child = 1;
+        EpaHeapItem elt = e.heap[0];
+        while (end >= 2 && child <= end - 2) {
+            if (e.heap[child].neg_dist <= e.heap[child + 1].neg_dist) child += 1;
+            e.heap[pos] = e.heap[child];
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        if (child == end - 1) {
+            e.heap[pos] = e.heap[child];
+            pos = child;
+        }
+        e.heap[pos] = elt;
+        heap_sift_up(e, 0, pos);
+    }
+    out = item;
+    return true;
+}
+
+NCB_HD V3 face_normal(const EpaFace& f) { return v3(f.nx, f.ny, f.nz); }
+
+// Face::new (epa3.rs:93-114); returns false on capacity overflow.
+__device__ __noinline__ bool epa_face_new(EpaState& e, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t a0, uint32_t a1, uint32_t a2,
+                                          bool& proj_inside) {
+    if (e.nfaces >= EPA_MAX_FACES) {
+        e.overflow = true;
+        return false;
+    }
+    V3 A = e.verts[p0].point, B = e.verts[p1].point, C = e.verts[p2].point;
+    Loc loc;
+    proj_triangle(A, B, C, v3(0.f, 0.f, 0.f), loc);
+    EpaFace& f = e.faces[e.nfaces++];
+    f.pts[0] = (uint16_t)p0, f.pts[1] = (uint16_t)p1, f.pts[2] = (uint16_t)p2;
+    f.adj[0] = (uint16_t)a0, f.adj[1] = (uint16_t)a1, f.adj[2] = (uint16_t)a2;
+    V3 n;
+    if (!unit_try_new(cross(B - A, C - A), NCB_EPS, n)) n = v3(0.f, 0.f, 0.f);  // utils::ccw_face_normal
+    f.nx = n.x, f.ny = n.y, f.nz = n.z;
+    f.deleted = 0;
+    if (loc.kind == LOC_FACE) {
+        f.bc[0] = loc.b0, f.bc[1] = loc.b1, f.bc[2] = loc.b2;
+        proj_inside = true;
+    } else {
+        f.bc[0] = f.bc[1] = f.bc[2] = 0.f;
+        proj_inside = false;
+    }
+    return true;
+}
+NCB_HD void epa_face_closest_points(const EpaState& e, const EpaFace& f, V3& p1, V3& p2) {
+    p1 = e.verts[f.pts[0]].orig1 * f.bc[0] + e.verts[f.pts[1]].orig1 * f.bc[1] + e.verts[f.pts[2]].orig1 * f.bc[2];
+    p2 = e.verts[f.pts[0]].orig2 * f.bc[0] + e.verts[f.pts[1]].orig2 * f.bc[1] + e.verts[f.pts[2]].orig2 * f.bc[2];
+}
+NCB_HD uint32_t epa_next_ccw(EpaState& e, const EpaFace& f, uint32_t id) {
+    if (f.pts[0] == id) return 1;
+    if (f.pts[1] == id) return 2;
+    if (f.pts[2] != id) e.panicked = true;  // assert_eq! in the reference
+    return 0;
+}
+NCB_HD bool epa_can_be_seen_by(const EpaState& e, const EpaFace& f, uint32_t point, uint32_t opp) {
+    V3 p0 = e.verts[f.pts[opp]].point;
+    V3 pt = e.verts[point].point;
+    if (dot(pt - p0, face_normal(f)) >= -(NCB_EPS * 10.0f)) return true;
+    V3 p1 = e.verts[f.pts[(opp + 1) % 3]].point, p2 = e.verts[f.pts[(opp + 2) % 3]].point;
+    // utils::is_affinely_dependent_triangle(p1, p2, pt)
+    V3 p1p2 = p2 - p1, p1p3 = pt - p1;
+    float eps_tol = NCB_EPS * 100.0f;
+    return relative_eq(norm_squared(cross(p1p2, p1p3)), 0.f, eps_tol * eps_tol);
+}
+// compute_silhouette (epa3.rs:432-454): the recursion becomes a LIFO of (face, opp) visits in the same order.
+__device__ __noinline__ void epa_compute_silhouette(EpaState& e, uint32_t point, uint32_t id0, uint32_t opp0) {
+    int sp = 0;
+    e.stk_face[sp] = (uint16_t)id0, e.stk_opp[sp] = (uint8_t)opp0, sp++;
+    while (sp > 0) {
+        sp--;
+        uint32_t id = e.stk_face[sp], opp = e.stk_opp[sp];
+        EpaFace& f = e.faces[id];
+        if (f.deleted) continue;
+        if (!epa_can_be_seen_by(e, f, point, opp)) {
+            if (e.nsil >= EPA_MAX_STACK) {
+                e.overflow = true;
+                return;
+            }
+            e.sil_face[e.nsil] = (uint16_t)id, e.sil_opp[e.nsil] = (uint8_t)opp, e.nsil++;
+        } else {
+            f.deleted = 1;
+            uint32_t adj_pt_id1 = (opp + 2) % 3, adj_pt_id2 = opp;
+            uint32_t adj1 = f.adj[adj_pt_id1], adj2 = f.adj[adj_pt_id2];
+            uint32_t o1 = epa_next_ccw(e, e.faces[adj1], f.pts[adj_pt_id1]);
+            uint32_t o2 = epa_next_ccw(e, e.faces[adj2], f.pts[adj_pt_id2]);
+            if (e.panicked) return;
+            if (sp + 2 > EPA_MAX_STACK) {
+                e.overflow = true;
+                return;
+            }
+            // visit adj1 first, then adj2
+            e.stk_face[sp] = (uint16_t)adj2, e.stk_opp[sp] = (uint8_t)o2, sp++;
+            e.stk_face[sp] = (uint16_t)adj1, e.stk_opp[sp] = (uint8_t)o1, sp++;
+        }
+    }
+}
+
+// EPA::closest_points (epa3.rs:219-430).  false = None (also on capacity overflow, flagged in e.overflow).
+__device__ __noinline__ bool epa_closest_points(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2,
+                                                const Simplex& s, V3& out1, V3& out2, V3& out_n) {
+    const float eps_tol = NCB_EPS * 100.0f;
+    const float gjk_eps_tol = NCB_EPS * 10.0f;
+    e.nverts = e.nfaces = e.nheap = e.nsil = 0;
+    e.overflow = false;
+    e.panicked = false;
+    for (int i = 0; i < s.dim + 1; ++i) e.verts[e.nverts++] = s.v[i];
+#define NCB_EPA_PUSH(ID, ND)                 \
+    {                                        \
+        float nd__ = (ND);                   \
+        if (nd__ > gjk_eps_tol) return false; \
+        heap_push(e, (ID), nd__);            \
+    }
+    if (s.dim == 0) {
+        out1 = v3(0.f, 0.f, 0.f);
+        out2 = v3(0.f, 0.f, 0.f);
+        out_n = v3(0.f, 1.f, 0.f);
+        return true;
+    } else if (s.dim == 3) {
+        V3 dp1 = e.verts[1].point - e.verts[0].point;
+        V3 dp2 = e.verts[2].point - e.verts[0].point;
+        V3 dp3 = e.verts[3].point - e.verts[0].point;
+        if (dot(cross(dp1, dp2), dp3) > 0.f) {
+            CSOPoint t = e.verts[1];
+            e.verts[1] = e.verts[2];
+            e.verts[2] = t;
+        }
+        bool in1, in2, in3, in4;
+        epa_face_new(e, 0, 1, 2, 3, 1, 2, in1);
+        epa_face_new(e, 1, 3, 2, 3, 2, 0, in2);
+        epa_face_new(e, 0, 2, 3, 0, 1, 3, in3);
+        epa_face_new(e, 0, 3, 1, 2, 1, 0, in4);
+        if (in1) NCB_EPA_PUSH(0, -dot(face_normal(e.faces[0]), e.verts[0].point));
+        if (in2) NCB_EPA_PUSH(1, -dot(face_normal(e.faces[1]), e.verts[1].point));
+        if (in3) NCB_EPA_PUSH(2, -dot(face_normal(e.faces[2]), e.verts[2].point));
+        if (in4) NCB_EPA_PUSH(3, -dot(face_normal(e.faces[3]), e.verts[3].point));
+    } else {
+        if (s.dim == 1) {
+            V3 dpt = e.verts[1].point - e.verts[0].point;
+            V3 first, second;
+            orthonormal_basis(dpt, first, second);
+            e.verts[e.nverts++] = cso_from_shapes(m1, g1, m2, g2, first);
+        }
+        bool in;
+        epa_face_new(e, 0, 1, 2, 1, 1, 1, in);
+        epa_face_new(e, 0, 2, 1, 0, 0, 0, in);
+        NCB_EPA_PUSH(0, 0.f);
+        NCB_EPA_PUSH(1, 0.f);
+    }
+    int niter = 0;
+    float max_dist = NCB_FMAX;
+    if (e.nheap == 0) {  // heap.peek().unwrap() panics in the reference
+        e.panicked = true;
+        return false;
+    }
+    EpaHeapItem best_face_id = e.heap[0];
+    EpaHeapItem face_id;
+    while (heap_pop(e, face_id)) {
+        EpaFace face = e.faces[face_id.id];
+        if (face.deleted) continue;
+        V3 fnorm = face_normal(face);
+        if (e.nverts >= EPA_MAX_VERTS) {
+            e.overflow = true;
+            return false;
+        }
+        CSOPoint cso = cso_from_shapes(m1, g1, m2, g2, fnorm);
+        uint32_t support_point_id = (uint32_t)e.nverts;
+        e.verts[e.nverts++] = cso;
+        float candidate_max_dist = dot(cso.point, fnorm);
+        if (candidate_max_dist < max_dist) {
+            best_face_id = face_id;
+            max_dist = candidate_max_dist;
+        }
+        float curr_dist = -face_id.neg_dist;
+        if (max_dist - curr_dist < eps_tol) {
+            const EpaFace& bf = e.faces[best_face_id.id];
+            epa_face_closest_points(e, bf, out1, out2);
+            out_n = face_normal(bf);
+            return true;
+        }
+        e.faces[face_id.id].deleted = 1;
+        uint32_t o1 = epa_next_ccw(e, e.faces[face.adj[0]], face.pts[0]);
+        uint32_t o2 = epa_next_ccw(e, e.faces[face.adj[1]], face.pts[1]);
+        uint32_t o3 = epa_next_ccw(e, e.faces[face.adj[2]], face.pts[2]);
+        if (e.panicked) return false;
+        epa_compute_silhouette(e, support_point_id, face.adj[0], o1);
+        epa_compute_silhouette(e, support_point_id, face.adj[1], o2);
+        epa_compute_silhouette(e, support_point_id, face.adj[2], o3);
+        if (e.panicked || e.overflow) return false;
+        uint32_t first_new_face_id = (uint32_t)e.nfaces;
+        if (e.nsil == 0) return false;
+        for (int k = 0; k < e.nsil; ++k) {
+            uint32_t efid = e.sil_face[k], eopp = e.sil_opp[k];
+            if (!e.faces[efid].deleted) {
+                uint32_t new_face_id = (uint32_t)e.nfaces;
+                uint32_t pt_id1 = e.faces[efid].pts[(eopp + 2) % 3];
+                uint32_t pt_id2 = e.faces[efid].pts[(eopp + 1) % 3];
+                bool inside;
+                if (!epa_face_new(e, pt_id1, pt_id2, support_point_id, efid, new_face_id + 1, new_face_id - 1, inside)) return false;
+                e.faces[efid].adj[(eopp + 1) % 3] = (uint16_t)new_face_id;
+                if (inside) {
+                    V3 pt = e.verts[e.faces[new_face_id].pts[0]].point;
+                    float dist = dot(face_normal(e.faces[new_face_id]), pt);
+                    if (dist < curr_dist) {
+                        epa_face_closest_points(e, face, out1, out2);
+                        out_n = fnorm;
+                        return true;
+                    }
+                    NCB_EPA_PUSH(new_face_id, -dist);
+                    if (e.overflow) return false;
+                }
+            }
+        }
+        if (first_new_face_id == (uint32_t)e.nfaces) return false;
+        e.faces[first_new_face_id].adj[2] = (uint16_t)(e.nfaces - 1);
+        e.faces[e.nfaces - 1].adj[1] = (uint16_t)first_new_face_id;
+        e.nsil = 0;
+        niter += 1;
+        if (niter > 10000) return false;
+    }
+#undef NCB_EPA_PUSH
+    const EpaFace& bf = e.faces[best_face_id.id];
+    epa_face_closest_points(e, bf, out1, out2);
+    out_n = face_normal(bf);
+    return true;
+}
+
+// contact_support_map_support_map_with_params (init_dir = None: fresh generator).
+// Returns GJK_CLOSEST_POINTS / GJK_NO_INTERSECTION.
+__device__ __noinline__ int contact_sm_sm(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2,
+                                          float prediction, V3& p1, V3& p2, V3& dir_out, uint32_t* epa_overflow, uint32_t* ref_panics) {
+    V3 dir;
+    if (!unit_try_new(m2.t - m1.t, NCB_EPS, dir)) dir = v3(1.f, 0.f, 0.f);
+    Simplex s;
+    simplex_init(s, cso_from_shapes(m1, g1, m2, g2, dir));
+    int r = gjk_closest_points(m1, g1, m2, g2, prediction, s, p1, p2, dir_out);
+    if (r != GJK_INTERSECTION) return r;
+    if (epa_closest_points(e, m1, g1, m2, g2, s, p1, p2, dir_out)) return GJK_CLOSEST_POINTS;
+    if (e.overflow) atomicAdd(epa_overflow, 1u);
+    if (e.panicked) atomicAdd(ref_panics, 1u);
+    dir_out = v3(1.f, 0.f, 0.f);
+    return GJK_NO_INTERSECTION;
+}
+
+}  // namespace ncb

@@ -1,0 +1,898 @@
+// Narrow phase on the device: one pair per thread, one persistent grid-stride kernel per shape-type key segment
+// (pairs were counting-sorted by key in broad.cu, so a warp runs a single algorithm).
+//
+// Replaces (reference, file:line):
+//   NarrowPhase::update / update_contact      pipeline/narrow_phase/narrow_phase.rs:56-104,168-197
+//   DefaultContactDispatcher                  contact_generator/default_contact_dispatcher.rs:27-97
+//   BallBallManifoldGenerator                 contact_generator/ball_ball_manifold_generator.rs:28-67, query/contact/contact_ball_ball.rs:8-38
+//   PlaneBallManifoldGenerator                contact_generator/plane_ball_manifold_generator.rs:30-83
+//   PlaneConvexPolyhedronManifoldGenerator    contact_generator/plane_convex_polyhedron_manifold_generator.rs:29-81
+//   BallConvexPolyhedronManifoldGenerator     contact_generator/ball_convex_polyhedron_manifold_generator.rs:28-122,
+//                                             query/point/point_aabb.rs:9-135, query/point/point_support_map.rs:15-53,90-117
+//   ConvexPolyhedronConvexPolyhedronManifoldGenerator  contact_generator/convex_polyhedron_convex_polyhedron_manifold_generator.rs:83-167
+//   Cuboid / ConvexHull features              shape/cuboid.rs:185-405,502-563, shape/convex.rs:388-540
+//   ConvexPolygonalFeature::clip / add_contact_to_manifold   shape/convex_polygonal_feature3.rs:217-401
+//   ContactManifold::push (DistanceBased 0.02) query/contact/contact_manifold.rs:165-236
+#include <cooperative_groups.h>
+#include <cmath>
+#include "gjk.cuh"
+#include "ncb_internal.h"
+#include "vec.cuh"
+
+namespace ncb {
+
+#define FEAT_MAX 16   // vertices per polygonal feature
+#define MANIFOLD_MAX 32
+
+#define FID(kind, id) ((((uint32_t)(kind)) << 30) | ((uint32_t)(id)&0x3fffffffu))
+#define FID_KIND(f) ((f) >> 30)
+#define FID_ID(f) ((f)&0x3fffffffu)
+#define FID_UNKNOWN 0xc0000000u
+#define FACE0 0x80000000u
+
+struct Shape {
+    uint32_t type;
+    float radius;
+    V3 he;  // cuboid half extents / plane normal
+    HullView hull;
+};
+
+NCB_HD Shape load_shape(const DevObjects& o, const DevHulls& H, uint32_t i, uint32_t type) {
+    Shape s;
+    float4 p = __ldg(&o.param[i]);
+    s.type = type;
+    s.radius = p.x;
+    s.he = v3(p.x, p.y, p.z);
+    if (type == NCB_SHAPE_CONVEX_HULL) s.hull = hull_view(H, (uint32_t)p.x);
+    return s;
+}
+NCB_HD Iso load_iso(const DevObjects& o, uint32_t i) {
+    float4 q = __ldg(&o.rot[i]);
+    Iso m;
+    m.t = v3(__ldg(o.pos + 3 * i), __ldg(o.pos + 3 * i + 1), __ldg(o.pos + 3 * i + 2));
+    m.q = Quat{q.x, q.y, q.z, q.w};
+    return m;
+}
+NCB_HD Support as_support(const Shape& s) {
+    Support g;
+    g.kind = s.type == NCB_SHAPE_CUBOID ? 0 : 1;
+    g.he = s.he;
+    g.hull = s.hull;
+    return g;
+}
+
+// ---- ConvexPolygonalFeature (vertices, ids, optional normal); edge normals are never read on this path -------
+struct Feature {
+    V3 v[FEAT_MAX];
+    uint32_t vid[FEAT_MAX], eid[FEAT_MAX];
+    int nv, ne;
+    bool has_normal;
+    V3 normal;
+    uint32_t feature_id;
+};
+NCB_HD void feat_clear(Feature& f) {
+    f.nv = 0;
+    f.ne = 0;
+    f.has_normal = false;
+    f.feature_id = FID_UNKNOWN;
+}
+NCB_HD void feat_push(Feature& f, V3 p, uint32_t id) {
+    if (f.nv < FEAT_MAX) {
+        f.v[f.nv] = p;
+        f.vid[f.nv] = id;
+        f.nv++;
+    }
+}
+NCB_HD void feat_push_edge(Feature& f, uint32_t id) {
+    if (f.ne < FEAT_MAX) f.eid[f.ne++] = id;
+}
+NCB_HD void feat_transform(Feature& f, const Iso& m) {
+    for (int i = 0; i < f.nv; ++i) f.v[i] = iso_mul_point(m, f.v[i]);
+    if (f.has_normal) f.normal = iso_mul_vec(m, f.normal);
+}
+NCB_HD int feat_nedges(const Feature& f) { return f.nv == 1 ? 0 : (f.nv == 2 ? 1 : f.nv); }
+
+// Cuboid::face (cuboid.rs:185-277, dim3)
+__device__ __noinline__ void cuboid_face(V3 he, uint32_t i, Feature& out) {
+    feat_clear(out);
+    uint32_t i1;
+    float sign;
+    if (i < 3) {
+        i1 = i;
+        sign = 1.f;
+    } else {
+        i1 = i - 3;
+        sign = -1.f;
+    }
+    uint32_t i2 = (i1 + 1) % 3, i3 = (i1 + 2) % 3;
+    uint32_t edge_i2 = sign > 0.f ? i2 : i3, edge_i3 = sign > 0.f ? i3 : i2;
+    uint32_t mask_i2 = ~(1u << edge_i2), mask_i3 = ~(1u << edge_i3);
+    V3 vertex = he;
+    vset(vertex, i1, vget(vertex, i1) * sign);
+    uint32_t sbit = sign < 0.f ? 1 : 0, msbit = sign < 0.f ? 0 : 1;
+    uint32_t vertex_id = sbit << i1;
+    feat_push(out, vertex, FID(NCB_FEATURE_VERTEX, vertex_id));
+    feat_push_edge(out, FID(NCB_FEATURE_EDGE, edge_i2 | ((vertex_id & mask_i2) << 2)));
+    vset(vertex, i2, -sign * vget(he, i2));
+    vset(vertex, i3, sign * vget(he, i3));
+    vertex_id |= (msbit << i2) | (sbit << i3);
+    feat_push(out, vertex, FID(NCB_FEATURE_VERTEX, vertex_id));
+    feat_push_edge(out, FID(NCB_FEATURE_EDGE, edge_i3 | ((vertex_id & mask_i3) << 2)));
+    vset(vertex, i2, -vget(he, i2));
+    vset(vertex, i3, -vget(he, i3));
+    vertex_id |= (1u << i2) | (1u << i3);
+    feat_push(out, vertex, FID(NCB_FEATURE_VERTEX, vertex_id));
+    feat_push_edge(out, FID(NCB_FEATURE_EDGE, edge_i2 | ((vertex_id & mask_i2) << 2)));
+    vset(vertex, i2, sign * vget(he, i2));
+    vset(vertex, i3, -sign * vget(he, i3));
+    vertex_id = (sbit << i1) | (sbit << i2) | (msbit << i3);
+    feat_push(out, vertex, FID(NCB_FEATURE_VERTEX, vertex_id));
+    feat_push_edge(out, FID(NCB_FEATURE_EDGE, edge_i3 | ((vertex_id & mask_i3) << 2)));
+    V3 normal = v3(0.f, 0.f, 0.f);
+    vset(normal, i1, sign);
+    out.normal = normal;
+    out.has_normal = true;
+    out.feature_id = sign > 0.f ? FID(NCB_FEATURE_FACE, i1) : FID(NCB_FEATURE_FACE, i1 + 3);
+}
+// Cuboid::support_face_toward (cuboid.rs:279-307)
+NCB_HD void cuboid_support_face_toward(V3 he, const Iso& m, V3 dir, Feature& out) {
+    V3 ld = iso_inv_vec(m, dir);
+    uint32_t iamax = 0;
+    float amax = fabsf(ld.x);
+    if (fabsf(ld.y) > amax) {
+        amax = fabsf(ld.y);
+        iamax = 1;
+    }
+    if (fabsf(ld.z) > amax) {
+        amax = fabsf(ld.z);
+        iamax = 2;
+    }
+    cuboid_face(he, vget(ld, iamax) > 0.f ? iamax : iamax + 3, out);
+    feat_transform(out, m);
+}
+// Cuboid::support_feature_toward (cuboid.rs:309-405, dim3)
+__device__ __noinline__ void cuboid_support_feature_toward(V3 he, const Iso& m, V3 dir, float2 ang_cs, Feature& out) {
+    V3 ld = iso_inv_vec(m, dir);
+    float cang = ang_cs.x, sang = ang_cs.y;
+    V3 sp = he;
+    feat_clear(out);
+    uint32_t sp_id = 0;
+    for (uint32_t i1 = 0; i1 < 3; ++i1) {
+        float c = vget(ld, i1);
+        float sign = signumf(c);
+        if (sign * c >= cang) {
+            cuboid_face(he, sign > 0.f ? i1 : i1 + 3, out);
+            feat_transform(out, m);
+            return;
+        } else if (sign < 0.f) {
+            vset(sp, i1, vget(sp, i1) * sign);
+            sp_id |= 1u << i1;
+        }
+    }
+    for (uint32_t i = 0; i < 3; ++i) {
+        float c = vget(ld, i);
+        float sign = signumf(c);
+        if (sign * c <= sang) {
+            vset(sp, i, -vget(he, i));
+            V3 p1 = sp;
+            vset(sp, i, vget(he, i));
+            V3 p2 = sp;
+            uint32_t p2_id = sp_id & ~(1u << i);
+            feat_push(out, iso_mul_point(m, p1), FID(NCB_FEATURE_VERTEX, sp_id | (1u << i)));
+            feat_push(out, iso_mul_point(m, p2), FID(NCB_FEATURE_VERTEX, p2_id));
+            uint32_t edge_id = FID(NCB_FEATURE_EDGE, i | (p2_id << 2));
+            feat_push_edge(out, edge_id);
+            out.feature_id = edge_id;
+            return;
+        }
+    }
+    feat_push(out, iso_mul_point(m, sp), FID(NCB_FEATURE_VERTEX, sp_id));
+    out.feature_id = FID(NCB_FEATURE_VERTEX, sp_id);
+}
+// Cuboid::feature_normal (cuboid.rs:502-563)
+NCB_HD V3 cuboid_feature_normal(uint32_t f) {
+    uint32_t id = FID_ID(f);
+    V3 dir = v3(0.f, 0.f, 0.f);
+    uint32_t kind = FID_KIND(f);
+    if (kind == NCB_FEATURE_FACE) {
+        if (id < 3)
+            vset(dir, id, 1.f);
+        else
+            vset(dir, id - 3, -1.f);
+        return dir;
+    }
+    if (kind == NCB_FEATURE_EDGE) {
+        uint32_t edge = id & 3u, face1 = (edge + 1) % 3, face2 = (edge + 2) % 3, signs = id >> 2;
+        vset(dir, face1, (signs & (1u << face1)) ? -1.f : 1.f);
+        vset(dir, face2, (signs & (1u << face2)) ? -1.f : 1.f);
+        return normalize(dir);
+    }
+    for (uint32_t i = 0; i < 3; ++i) vset(dir, i, (id & (1u << i)) ? -1.f : 1.f);
+    return normalize(dir);
+}
+
+// ConvexHull::face (convex.rs:443-461)
+NCB_HD void hull_face(const HullView& H, uint32_t id, Feature& out) {
+    feat_clear(out);
+    uint32_t first = __ldg(H.face_first + id), last = first + __ldg(H.face_num + id);
+    for (uint32_t i = first; i < last; ++i) {
+        uint32_t vid = __ldg(H.vaf + i), eid = __ldg(H.eaf + i);
+        feat_push(out, H.pt(vid), FID(NCB_FEATURE_VERTEX, vid));
+        feat_push_edge(out, FID(NCB_FEATURE_EDGE, eid));
+    }
+    out.normal = H.fn(id);
+    out.has_normal = true;
+    out.feature_id = FID(NCB_FEATURE_FACE, id);
+}
+// ConvexHull::support_face_toward (convex.rs:487-509)
+__device__ __noinline__ void hull_support_face_toward(const HullView& H, const Iso& m, V3 dir, Feature& out) {
+    V3 ls_dir = iso_inv_vec(m, dir);
+    uint32_t best = 0;
+    float max_dot = dot(H.fn(0), ls_dir);
+    for (uint32_t i = 1; i < H.nf; ++i) {
+        float d = dot(H.fn(i), ls_dir);
+        if (d > max_dot) {
+            max_dot = d;
+            best = i;
+        }
+    }
+    hull_face(H, best, out);
+    feat_transform(out, m);
+}
+// ConvexHull::support_feature_id_toward_eps (convex.rs:388-415)
+__device__ __noinline__ uint32_t hull_support_feature_id_toward_eps(const HullView& H, V3 local_dir, float2 eps_cs) {
+    float seps = eps_cs.y, ceps = eps_cs.x;
+    uint32_t sp = 0;
+    float best_dot = dot(H.pt(0), local_dir);
+    for (uint32_t i = 1; i < H.nv; ++i) {
+        float d = dot(H.pt(i), local_dir);
+        if (d > best_dot) {
+            best_dot = d;
+            sp = i;
+        }
+    }
+    uint32_t first = __ldg(H.vfirst + sp), num = __ldg(H.vnum + sp);
+    for (uint32_t i = 0; i < num; ++i) {
+        uint32_t face_id = __ldg(H.fav + first + i);
+        if (dot(H.fn(face_id), local_dir) >= ceps) return FID(NCB_FEATURE_FACE, face_id);
+    }
+    for (uint32_t i = 0; i < num; ++i) {
+        uint32_t edge_id = __ldg(H.eav + first + i);
+        if (fabsf(dot(H.edir(edge_id), local_dir)) <= seps) return FID(NCB_FEATURE_EDGE, edge_id);
+    }
+    return FID(NCB_FEATURE_VERTEX, sp);
+}
+// ConvexHull::support_feature_toward (convex.rs:511-540)
+NCB_HD void hull_support_feature_toward(const HullView& H, const Iso& m, V3 dir, float2 angle, Feature& out) {
+    feat_clear(out);
+    V3 local_dir = iso_inv_vec(m, dir);
+    uint32_t f = hull_support_feature_id_toward_eps(H, local_dir, angle);
+    uint32_t kind = FID_KIND(f);
+    if (kind == NCB_FEATURE_VERTEX) {
+        feat_push(out, H.pt(FID_ID(f)), f);
+        out.feature_id = f;
+    } else if (kind == NCB_FEATURE_EDGE) {
+        uint32_t e = FID_ID(f), v1 = __ldg(H.edge_vertices + 2 * e), v2 = __ldg(H.edge_vertices + 2 * e + 1);
+        feat_push(out, H.pt(v1), FID(NCB_FEATURE_VERTEX, v1));
+        feat_push(out, H.pt(v2), FID(NCB_FEATURE_VERTEX, v2));
+        out.feature_id = f;
+        feat_push_edge(out, f);
+    } else {
+        hull_face(H, FID_ID(f), out);
+    }
+    feat_transform(out, m);
+}
+// ConvexHull::feature_normal (convex.rs:463-485)
+NCB_HD V3 hull_feature_normal(const HullView& H, uint32_t f) {
+    uint32_t id = FID_ID(f), kind = FID_KIND(f);
+    if (kind == NCB_FEATURE_FACE) return H.fn(id);
+    if (kind == NCB_FEATURE_EDGE) return normalize(H.fn(__ldg(H.edge_faces + 2 * id)) + H.fn(__ldg(H.edge_faces + 2 * id + 1)));
+    uint32_t first = __ldg(H.vfirst + id), last = first + __ldg(H.vnum + id);
+    V3 n = v3(0.f, 0.f, 0.f);
+    for (uint32_t i = first; i < last; ++i) n = n + H.fn(__ldg(H.fav + i));
+    return normalize(n);
+}
+
+NCB_HD void support_face_toward(const Shape& s, const Iso& m, V3 dir, Feature& out) {
+    if (s.type == NCB_SHAPE_CUBOID)
+        cuboid_support_face_toward(s.he, m, dir, out);
+    else
+        hull_support_face_toward(s.hull, m, dir, out);
+}
+NCB_HD void support_feature_toward(const Shape& s, const Iso& m, V3 dir, float2 angle, Feature& out) {
+    if (s.type == NCB_SHAPE_CUBOID)
+        cuboid_support_feature_toward(s.he, m, dir, angle, out);
+    else
+        hull_support_feature_toward(s.hull, m, dir, angle, out);
+}
+
+// ---- ContactManifold (fresh manifold, DistanceBased(0.02)) --------------------------------------------------
+struct ManifoldContact {
+    V3 w1, w2, n;
+    float depth;
+    uint32_t f1, f2;
+};
+struct Manifold {
+    ManifoldContact c[MANIFOLD_MAX];
+    V3 track[MANIFOLD_MAX];
+    int n;
+    int deepest;
+};
+NCB_HD void manifold_push(Manifold& mf, V3 w1, V3 w2, V3 n, float depth, uint32_t f1, uint32_t f2, V3 tracking_pt) {
+    const float threshold = 0.02f;
+    int closest = mf.n;
+    float closest_dist = threshold * threshold;
+    for (int i = 0; i < mf.n; ++i) {
+        float d = norm_squared(tracking_pt - mf.track[i]);
+        if (d < closest_dist) {
+            closest_dist = d;
+            closest = i;
+        }
+    }
+    if (closest == mf.n) {
+        if (mf.n < MANIFOLD_MAX) {
+            ManifoldContact& c = mf.c[mf.n];
+            c.w1 = w1, c.w2 = w2, c.n = n, c.depth = depth, c.f1 = f1, c.f2 = f2;
+            mf.track[mf.n] = tracking_pt;
+            mf.n++;
+        }
+    } else {
+        ManifoldContact& c = mf.c[closest];
+        if (depth <= c.depth) return;
+        c.w1 = w1, c.w2 = w2, c.n = n, c.depth = depth, c.f1 = f1, c.f2 = f2;
+        mf.track[closest] = tracking_pt;
+    }
+}
+
+// ---- generators -----------------------------------------------------------------------------------------------
+NCB_HD void gen_ball_ball(const Iso& ma, float r1, const Iso& mb, float r2, float prediction, Manifold& mf) {
+    V3 c1 = ma.t, c2 = mb.t;
+    V3 delta = c2 - c1;
+    float d2 = norm_squared(delta);
+    float sum_radius = r1 + r2;
+    float sre = sum_radius + prediction;
+    if (d2 < sre * sre) {
+        V3 normal = d2 != 0.f ? normalize(delta) : v3(1.f, 0.f, 0.f);
+        manifold_push(mf, c1 + normal * r1, c2 + normal * (-r2), normal, sum_radius - sqrtf(d2), FACE0, FACE0, v3(0.f, 0.f, 0.f));
+    }
+}
+NCB_HD void gen_plane_ball(const Iso& m1, V3 plane_n, const Iso& m2, float radius, float prediction, bool flip, Manifold& mf) {
+    V3 n = iso_mul_vec(m1, plane_n);
+    V3 pc = m1.t, bc = m2.t;
+    float dist = dot(bc - pc, n);
+    float depth = -dist + radius;
+    if (depth > -prediction) {
+        V3 world1 = bc + n * (-dist);
+        V3 world2 = bc + n * (-radius);
+        if (!flip)
+            manifold_push(mf, world1, world2, n, depth, FACE0, FACE0, v3(0.f, 0.f, 0.f));
+        else
+            manifold_push(mf, world2, world1, -n, depth, FACE0, FACE0, v3(0.f, 0.f, 0.f));
+    }
+}
+__device__ __noinline__ void gen_plane_convex(const Iso& m1, V3 plane_n, const Iso& m2, const Shape& cp, float prediction, bool flip,
+                                              Manifold& mf, Feature& feat) {
+    V3 n = iso_mul_vec(m1, plane_n);
+    V3 pc = m1.t;
+    support_face_toward(cp, m2, -n, feat);
+    for (int i = 0; i < feat.nv; ++i) {
+        V3 world2 = feat.v[i];
+        float dist = dot(world2 - pc, n);
+        if (dist <= prediction) {
+            V3 world1 = world2 + (-n * dist);
+            V3 local2 = iso_inv_point(m2, world2);
+            uint32_t f2 = feat.vid[i];
+            if (!flip)
+                manifold_push(mf, world1, world2, n, -dist, FACE0, f2, local2);
+            else
+                manifold_push(mf, world2, world1, -n, -dist, f2, FACE0, local2);
+        }
+    }
+}
+
+// AABB::project_point_with_feature through Cuboid (point_cuboid.rs:17-27, point_aabb.rs:9-135)
+__device__ __noinline__ void cuboid_project_point_with_feature(V3 he, const Iso& m, V3 pt, bool& inside_out, V3& proj_out,
+                                                               uint32_t& feature) {
+    V3 mins = v3(0.f, 0.f, 0.f) + (-he), maxs = v3(0.f, 0.f, 0.f) + he;
+    V3 ls_pt = iso_inv_point(m, pt);
+    V3 mins_pt = mins - ls_pt, pt_maxs = ls_pt - maxs;
+    V3 zero = v3(0.f, 0.f, 0.f);
+    V3 shift = vmax(mins_pt, zero) - vmax(pt_maxs, zero);
+    bool inside = shift.x == 0.f && shift.y == 0.f && shift.z == 0.f;
+    V3 ls_proj;
+    if (!inside) {
+        ls_proj = ls_pt + shift;
+    } else {
+        float best = -NCB_FMAX;
+        bool is_mins = false;
+        int best_id = 0;
+        for (int i = 0; i < 3; ++i) {
+            float a = vget(mins_pt, i), b = vget(pt_maxs, i);
+            if (a < b) {
+                if (b > best) {
+                    best_id = i;
+                    is_mins = false;
+                    best = b;
+                }
+            } else if (a > best) {
+                best_id = i;
+                is_mins = true;
+                best = a;
+            }
+        }
+        shift = v3(0.f, 0.f, 0.f);
+        vset(shift, best_id, is_mins ? best : -best);
+        ls_proj = ls_pt + shift;
+    }
+    inside_out = inside;
+    proj_out = iso_mul_point(m, ls_proj);
+    int nzero = 0, last_zero = 0, last_not_zero = 0;
+    for (int i = 0; i < 3; ++i) {
+        if (vget(shift, i) == 0.f) {
+            nzero++;
+            last_zero = i;
+        } else
+            last_not_zero = i;
+    }
+    V3 center = (mins + maxs) * 0.5f;
+    if (nzero == 3) {
+        for (int i = 0; i < 3; ++i) {
+            if (vget(ls_proj, i) > vget(maxs, i) - NCB_EPS) {
+                feature = FID(NCB_FEATURE_FACE, i);
+                return;
+            }
+            if (vget(ls_proj, i) <= vget(mins, i) + NCB_EPS) {
+                feature = FID(NCB_FEATURE_FACE, i + 3);
+                return;
+            }
+        }
+        feature = FID_UNKNOWN;
+    } else if (nzero == 2) {
+        feature = vget(ls_proj, last_not_zero) < vget(center, last_not_zero) ? FID(NCB_FEATURE_FACE, last_not_zero + 3)
+                                                                               : FID(NCB_FEATURE_FACE, last_not_zero);
+    } else {
+        uint32_t id = 0;
+        for (int i = 0; i < 3; ++i)
+            if (vget(ls_proj, i) < vget(center, i)) id |= 1u << i;
+        feature = nzero == 0 ? FID(NCB_FEATURE_VERTEX, id) : FID(NCB_FEATURE_EDGE, (id << 2) | (uint32_t)last_zero);
+    }
+}
+
+// ConvexHull::project_point_with_feature (point_support_map.rs:15-53 with solid = false, :97-116)
+__device__ __noinline__ void hull_project_point_with_feature(EpaState& e, const HullView& H, const Iso& m_in, V3 point, bool& inside,
+                                                             V3& proj, uint32_t& feature, float2 one_degree_cs, uint32_t* epa_overflow,
+                                                             uint32_t* ref_panics) {
+    Iso id;
+    id.t = v3(0.f, 0.f, 0.f);
+    id.q = Quat{0.f, 0.f, 0.f, 1.f};
+    Iso m = m_in;
+    m.t = (-point) + m_in.t;
+    Support shape;
+    shape.kind = 1;
+    shape.hull = H;
+    Support origin;
+    origin.kind = 2;
+    V3 dir;
+    if (!unit_try_new(-m.t, NCB_EPS, dir)) dir = v3(1.f, 0.f, 0.f);
+    Simplex s;
+    simplex_init(s, cso_from_shapes(m, shape, id, origin, dir));
+    V3 p1, p2, d;
+    int r = gjk_closest_points(m, shape, id, origin, NCB_FMAX, s, p1, p2, d);
+    if (r == GJK_CLOSEST_POINTS) {
+        inside = false;
+        proj = p1 + point;
+    } else {
+        inside = true;
+        if (epa_closest_points(e, m, shape, id, origin, s, p1, p2, d))
+            proj = p1 + point;
+        else {
+            if (e.overflow) atomicAdd(epa_overflow, 1u);
+            if (e.panicked) atomicAdd(ref_panics, 1u);
+            proj = point;
+        }
+    }
+    V3 dpt = point - proj;
+    V3 local_dir = inside ? iso_inv_vec(m_in, -dpt) : iso_inv_vec(m_in, dpt);
+    V3 u;
+    if (unit_try_new(local_dir, NCB_EPS, u))
+        feature = hull_support_feature_id_toward_eps(H, u, one_degree_cs);
+    else
+        feature = FID_UNKNOWN;
+}
+
+// (m1, ball) (m2, convex polyhedron)
+NCB_HD void gen_ball_convex_finish(V3 ball_center, float radius, const Shape& cp, bool inside, V3 world2, uint32_t f2, float prediction,
+                                   bool flip, Manifold& mf) {
+    V3 dpt = world2 - ball_center;
+    float depth, dist;
+    V3 normal, dir;
+    if (unit_try_new_and_get(dpt, NCB_EPS, dir, dist)) {
+        if (inside) {
+            depth = dist + radius;
+            normal = -dir;
+        } else {
+            depth = -dist + radius;
+            normal = dir;
+        }
+    } else {
+        if (f2 == FID_UNKNOWN) return;
+        depth = radius;
+        normal = -(cp.type == NCB_SHAPE_CUBOID ? cuboid_feature_normal(f2) : hull_feature_normal(cp.hull, f2));
+    }
+    if (depth >= -prediction) {
+        V3 world1 = ball_center + normal * radius;
+        if (!flip)
+            manifold_push(mf, world1, world2, normal, depth, FACE0, f2, v3(0.f, 0.f, 0.f));
+        else
+            manifold_push(mf, world2, world1, -normal, depth, f2, FACE0, v3(0.f, 0.f, 0.f));
+    }
+}
+
+// ---- polygon clipping -----------------------------------------------------------------------------------------
+NCB_HD bool point_in_poly2d(V2 pt, const V2* poly, int n) {
+    if (n == 0) return false;
+    float sign = 0.f;
+    for (int i1 = 0; i1 < n; ++i1) {
+        int i2 = (i1 + 1) % n;
+        V2 seg_dir = V2{poly[i2].x - poly[i1].x, poly[i2].y - poly[i1].y};
+        V2 dpt = V2{pt.x - poly[i1].x, pt.y - poly[i1].y};
+        float perp = dpt.x * seg_dir.y - dpt.y * seg_dir.x;
+        if (sign == 0.f)
+            sign = perp;
+        else if (sign * perp < 0.f)
+            return false;
+    }
+    return true;
+}
+NCB_HD bool line_toi_with_plane(V3 plane_center, V3 plane_normal, V3 line_origin, V3 line_dir, float& toi) {
+    V3 dpos = plane_center - line_origin;
+    float denom = dot(plane_normal, line_dir);
+    if (relative_eq(denom, 0.f)) return false;
+    toi = dot(plane_normal, dpos) / denom;
+    return true;
+}
+NCB_HD float dot2(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+// closest_points_segment_segment_with_locations_nD, D = 2; true iff both locations are OnEdge
+NCB_HD bool seg_seg_2d(V2 a1, V2 b1, V2 a2, V2 b2, float& s_out, float& t_out) {
+    const float eps = NCB_EPS;
+    V2 d1 = V2{b1.x - a1.x, b1.y - a1.y}, d2 = V2{b2.x - a2.x, b2.y - a2.y}, r = V2{a1.x - a2.x, a1.y - a2.y};
+    float a = dot2(d1, d1), e = dot2(d2, d2), f = dot2(d2, r);
+    float s, t;
+    if (a <= eps && e <= eps) {
+        s = 0.f;
+        t = 0.f;
+    } else if (a <= eps) {
+        s = 0.f;
+        t = clampf(f / e, 0.f, 1.f);
+    } else {
+        float c = dot2(d1, r);
+        if (e <= eps) {
+            t = 0.f;
+            s = clampf(-c / a, 0.f, 1.f);
+        } else {
+            float b = dot2(d1, d2);
+            float ae = a * e, bb = b * b, denom = ae - bb;
+            bool parallel = denom <= eps || ulps_eq(ae, bb);
+            s = !parallel ? clampf((b * f - c * e) / denom, 0.f, 1.f) : 0.f;
+            t = (b * s + f) / e;
+            if (t < 0.f) {
+                t = 0.f;
+                s = clampf(-c / a, 0.f, 1.f);
+            } else if (t > 1.f) {
+                t = 1.f;
+                s = clampf((b - c) / a, 0.f, 1.f);
+            }
+        }
+    }
+    s_out = s;
+    t_out = t;
+    return s != 0.f && s != 1.f && t != 0.f && t != 1.f;
+}
+
+// add_contact_to_manifold's early returns (convex_polygonal_feature3.rs:355-393)
+NCB_HD bool feature_ok_for_manifold(const Feature& ft, uint32_t f) {
+    uint32_t kind = FID_KIND(f);
+    if (kind == NCB_FEATURE_FACE || kind == NCB_FEATURE_VERTEX) return true;
+    if (kind == NCB_FEATURE_EDGE) {
+        for (int i1 = 0; i1 < ft.nv; ++i1) {
+            if (i1 < ft.ne && ft.eid[i1] == f) {
+                int i2 = (i1 + 1) % ft.nv;
+                V3 d;
+                return unit_try_new(ft.v[i2] - ft.v[i1], NCB_EPS, d);
+            }
+        }
+        return false;
+    }
+    return false;
+}
+
+struct ClipCtx {
+    const Iso* ma;
+    Manifold* mf;
+    const Feature *m1, *m2;
+    int n_new;
+};
+NCB_HD void clip_emit(ClipCtx& cc, V3 w1, V3 w2, V3 normal, float prediction, uint32_t f1, uint32_t f2) {
+    float depth = -dot(normal, w2 - w1);  // Contact::new_wo_depth
+    if (-depth <= prediction) {
+        cc.n_new++;
+        if (!feature_ok_for_manifold(*cc.m1, f1)) return;
+        if (!feature_ok_for_manifold(*cc.m2, f2)) return;
+        V3 local1 = iso_inv_point(*cc.ma, w1);
+        manifold_push(*cc.mf, w1, w2, normal, depth, f1, f2, local1);
+    }
+}
+
+// ConvexPolygonalFeature::clip (convex_polygonal_feature3.rs:217-338); candidates go straight into the manifold
+// in the reference's order (the reference buffers them in a Vec and pushes them afterwards: same result).
+__device__ __noinline__ void clip(const Feature& self, const Feature& other, V3 normal, float prediction, ClipCtx& cc) {
+    if (self.nv <= 2 && other.nv <= 2) return;
+    V3 b0, b1;
+    orthonormal_basis(normal, b0, b1);
+    V3 ref_pt = self.v[0];
+    V2 poly1[FEAT_MAX], poly2[FEAT_MAX];
+    for (int i = 0; i < self.nv; ++i) {
+        V3 dpt = self.v[i] - ref_pt;
+        poly1[i] = V2{dot(b0, dpt), dot(b1, dpt)};
+    }
+    for (int i = 0; i < other.nv; ++i) {
+        V3 dpt = other.v[i] - ref_pt;
+        poly2[i] = V2{dot(b0, dpt), dot(b1, dpt)};
+    }
+    if (other.nv > 2) {
+        for (int i = 0; i < self.nv; ++i) {
+            V2 pt = poly1[i];
+            if (point_in_poly2d(pt, poly2, other.nv)) {
+                V3 origin = ref_pt + b0 * pt.x + b1 * pt.y;
+                float toi2;
+                if (line_toi_with_plane(other.v[0], other.normal, origin, normal, toi2)) {
+                    V3 world2 = origin + normal * toi2;
+                    clip_emit(cc, self.v[i], world2, normal, prediction, self.vid[i], other.feature_id);
+                }
+            }
+        }
+    }
+    if (self.nv > 2) {
+        for (int i = 0; i < other.nv; ++i) {
+            V2 pt = poly2[i];
+            if (point_in_poly2d(pt, poly1, self.nv)) {
+                V3 origin = ref_pt + b0 * pt.x + b1 * pt.y;
+                float toi1;
+                if (line_toi_with_plane(self.v[0], self.normal, origin, normal, toi1)) {
+                    V3 world1 = origin + normal * toi1;
+                    clip_emit(cc, world1, other.v[i], normal, prediction, self.feature_id, other.vid[i]);
+                }
+            }
+        }
+    }
+    int nedges1 = feat_nedges(self), nedges2 = feat_nedges(other);
+    for (int i1 = 0; i1 < nedges1; ++i1) {
+        int j1 = (i1 + 1) % self.nv;
+        for (int i2 = 0; i2 < nedges2; ++i2) {
+            int j2 = (i2 + 1) % other.nv;
+            float s, t;
+            if (seg_seg_2d(poly1[i1], poly1[j1], poly2[i2], poly2[j2], s, t)) {
+                V3 world1 = self.v[i1] * (1.f - s) + self.v[j1] * s;
+                V3 world2 = other.v[i2] * (1.f - t) + other.v[j2] * t;
+                clip_emit(cc, world1, world2, normal, prediction, self.eid[i1], other.eid[i2]);
+            }
+        }
+    }
+}
+
+__device__ __noinline__ void gen_convex_convex(EpaState& e, const Iso& ma, const Shape& a, const Iso& mb, const Shape& b, float linear,
+                                               float2 ang1, float2 ang2, Manifold& mf, Feature& m1, Feature& m2, uint32_t* epa_overflow,
+                                               uint32_t* ref_panics) {
+    Support ga = as_support(a), gb = as_support(b);
+    V3 p1, p2, dir;
+    int r = contact_sm_sm(e, ma, ga, mb, gb, linear, p1, p2, dir, epa_overflow, ref_panics);
+    if (r != GJK_CLOSEST_POINTS) return;
+    float depth = -dot(dir, p2 - p1);
+    if (depth > 0.f) {
+        support_face_toward(a, ma, dir, m1);
+        support_face_toward(b, mb, -dir, m2);
+    } else {
+        support_feature_toward(a, ma, dir, ang1, m1);
+        support_feature_toward(b, mb, -dir, ang2, m2);
+    }
+    ClipCtx cc;
+    cc.ma = &ma;
+    cc.mf = &mf;
+    cc.m1 = &m1;
+    cc.m2 = &m2;
+    cc.n_new = 0;
+    clip(m1, m2, dir, linear, cc);
+    if (cc.n_new == 0) {
+        if (feature_ok_for_manifold(m1, m1.feature_id) && feature_ok_for_manifold(m2, m2.feature_id))
+            manifold_push(mf, p1, p2, dir, depth, m1.feature_id, m2.feature_id, iso_inv_point(ma, p1));
+    }
+}
+
+// ---- result write-out: warp-aggregated allocation of contact slots --------------------------------------------
+NCB_HD void write_manifold(const Manifold& mf, bool valid, uint32_t pair_slot, uint32_t out_index, ncb_contact* __restrict__ contacts,
+                           uint32_t cap_contacts, uint32_t* __restrict__ manifold_start, uint8_t* __restrict__ manifold_count,
+                           DevCounters* cnt) {
+    // all 32 lanes call this (valid = false for idle lanes)
+    uint32_t n = valid ? (uint32_t)mf.n : 0u;
+    uint32_t incl = n;
+    int lane = threadIdx.x & 31;
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t nz = __popc(__ballot_sync(0xffffffffu, n != 0));
+    uint32_t base = 0;
+    if (lane == 31 && total) {
+        base = atomicAdd(&cnt->n_contacts, total);
+        atomicAdd(&cnt->n_contact_pairs, nz);
+    }
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (!valid) return;
+    uint32_t start = base + incl - n;
+    manifold_start[out_index] = start;
+    manifold_count[out_index] = (uint8_t)n;
+    for (uint32_t k = 0; k < n; ++k) {
+        uint32_t dst = start + k;
+        if (dst >= cap_contacts) break;
+        const ManifoldContact& c = mf.c[k];
+        ncb_contact o;
+        o.world1[0] = c.w1.x, o.world1[1] = c.w1.y, o.world1[2] = c.w1.z;
+        o.world2[0] = c.w2.x, o.world2[1] = c.w2.y, o.world2[2] = c.w2.z;
+        o.normal[0] = c.n.x, o.normal[1] = c.n.y, o.normal[2] = c.n.z;
+        o.depth = c.depth;
+        o.f1 = c.f1, o.f2 = c.f2;
+        o.pair = out_index;
+        contacts[dst] = o;
+    }
+}
+
+struct NarrowArgs {
+    DevObjects o;
+    DevHulls H;
+    const uint2* pairs;
+    const uint32_t* pair_index;  // optional: original index of each sorted pair
+    ncb_contact* contacts;
+    uint32_t cap_contacts;
+    uint32_t* manifold_start;
+    uint8_t* manifold_count;
+    DevCounters* cnt;
+    uint32_t cap_pairs;
+    float2 one_degree_cs;  // cos / sin of (pi / 180) as f32, from the host libm (convex.rs:543)
+};
+
+// One persistent kernel per key; the segment bounds are read from the device counters.
+template <int KEY>
+__global__ void __launch_bounds__(128) k_narrow(NarrowArgs A) {
+    uint32_t seg_begin = A.cnt->key_start[KEY];
+    uint32_t seg_end = seg_begin + A.cnt->key_hist[KEY];
+    uint32_t stride = gridDim.x * blockDim.x;
+    // local-memory working set, only instantiated for the keys that need it
+    Manifold mf;
+    for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
+        uint32_t p = base + threadIdx.x;
+        bool valid = p < seg_end;
+        mf.n = 0;
+        mf.deepest = 0;
+        if (valid) {
+            uint2 pr = __ldg(&A.pairs[p]);
+            uint32_t i1 = pr.x, i2 = pr.y;
+            uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
+            Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
+            float linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
+            if (KEY == K_BALL_BALL) {
+                gen_ball_ball(ma, __ldg(&A.o.param[i1]).x, mb, __ldg(&A.o.param[i2]).x, linear, mf);
+            } else if (KEY == K_PLANE_BALL) {
+                Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+                if (t1 == NCB_SHAPE_PLANE)
+                    gen_plane_ball(ma, a.he, mb, b.radius, linear, false, mf);
+                else
+                    gen_plane_ball(mb, b.he, ma, a.radius, linear, true, mf);
+            } else if (KEY == K_PLANE_CUBOID || KEY == K_PLANE_HULL) {
+                Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+                Feature feat;
+                if (t1 == NCB_SHAPE_PLANE)
+                    gen_plane_convex(ma, a.he, mb, b, linear, false, mf, feat);
+                else
+                    gen_plane_convex(mb, b.he, ma, a, linear, true, mf, feat);
+            } else if (KEY == K_BALL_CUBOID) {
+                Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+                bool flip = t1 != NCB_SHAPE_BALL;
+                const Shape& ball = flip ? b : a;
+                const Shape& cp = flip ? a : b;
+                const Iso& mball = flip ? mb : ma;
+                const Iso& mcp = flip ? ma : mb;
+                bool inside;
+                V3 world2;
+                uint32_t f2;
+                cuboid_project_point_with_feature(cp.he, mcp, mball.t, inside, world2, f2);
+                gen_ball_convex_finish(mball.t, ball.radius, cp, inside, world2, f2, linear, flip, mf);
+            } else if (KEY == K_BALL_HULL) {
+                Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+                bool flip = t1 != NCB_SHAPE_BALL;
+                const Shape& ball = flip ? b : a;
+                const Shape& cp = flip ? a : b;
+                const Iso& mball = flip ? mb : ma;
+                const Iso& mcp = flip ? ma : mb;
+                bool inside;
+                V3 world2;
+                uint32_t f2;
+                EpaState e;
+                hull_project_point_with_feature(e, cp.hull, mcp, mball.t, inside, world2, f2, A.one_degree_cs, &A.cnt->epa_overflow,
+                                                &A.cnt->ref_panics);
+                gen_ball_convex_finish(mball.t, ball.radius, cp, inside, world2, f2, linear, flip, mf);
+            } else if (KEY == K_CUBOID_CUBOID || KEY == K_CUBOID_HULL || KEY == K_HULL_HULL) {
+                Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+                float2 ang1 = __ldg(&A.o.ang_cs[i1]), ang2 = __ldg(&A.o.ang_cs[i2]);
+                EpaState e;
+                Feature f1, f2;
+                gen_convex_convex(e, ma, a, mb, b, linear, ang1, ang2, mf, f1, f2, &A.cnt->epa_overflow, &A.cnt->ref_panics);
+            }
+        }
+        uint32_t out_index = valid ? (A.pair_index ? __ldg(&A.pair_index[p]) : p) : 0;
+        write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+    }
+}
+
+// K_NONE pairs (plane x plane) and pairs beyond a key segment get an empty manifold.
+__global__ void __launch_bounds__(256) k_narrow_none(NarrowArgs A) {
+    uint32_t seg_begin = A.cnt->key_start[K_NONE];
+    uint32_t seg_end = seg_begin + A.cnt->key_hist[K_NONE];
+    for (uint32_t p = seg_begin + blockIdx.x * blockDim.x + threadIdx.x; p < seg_end; p += gridDim.x * blockDim.x) {
+        uint32_t out_index = A.pair_index ? A.pair_index[p] : p;
+        A.manifold_start[out_index] = 0;
+        A.manifold_count[out_index] = 0;
+    }
+}
+
+cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, uint32_t cap_pairs,
+                                uint32_t cap_contacts) {
+    NarrowArgs A;
+    A.o = o;
+    A.H = c->hulls;
+    A.pairs = pairs;
+    A.pair_index = pair_index;
+    A.contacts = c->contacts.p;
+    A.cap_contacts = cap_contacts;
+    A.manifold_start = c->manifold_start.p;
+    A.manifold_count = c->manifold_count.p;
+    A.cnt = c->counters.p;
+    A.cap_pairs = cap_pairs;
+    {
+        float one_degree = (float)(3.14159265358979323846 / 180.0);
+        A.one_degree_cs = make_float2(cosf(one_degree), sinf(one_degree));
+    }
+    cudaStream_t s = c->stream;
+    int sm = c->sm_count;
+    k_narrow<K_BALL_BALL><<<sm * 8, 128, 0, s>>>(A);
+    k_narrow<K_PLANE_BALL><<<sm * 4, 128, 0, s>>>(A);
+    k_narrow<K_PLANE_CUBOID><<<sm * 4, 128, 0, s>>>(A);
+    k_narrow<K_PLANE_HULL><<<sm * 4, 128, 0, s>>>(A);
+    k_narrow<K_BALL_CUBOID><<<sm * 8, 128, 0, s>>>(A);
+    k_narrow<K_BALL_HULL><<<sm * 4, 128, 0, s>>>(A);
+    k_narrow<K_CUBOID_CUBOID><<<sm * 4, 128, 0, s>>>(A);
+    k_narrow<K_CUBOID_HULL><<<sm * 4, 128, 0, s>>>(A);
+    k_narrow<K_HULL_HULL><<<sm * 4, 128, 0, s>>>(A);
+    k_narrow_none<<<sm, 256, 0, s>>>(A);
+    return cudaGetLastError();
+}
+
+// Classify caller-provided pairs (ncb_generate_contacts): key per pair from the two shape types.
+__device__ __constant__ uint8_t c_key_table2[16] = {K_BALL_BALL,   K_BALL_CUBOID,   K_BALL_HULL,   K_PLANE_BALL,   K_BALL_CUBOID, K_CUBOID_CUBOID,
+                                                    K_CUBOID_HULL, K_PLANE_CUBOID,  K_BALL_HULL,   K_CUBOID_HULL,  K_HULL_HULL,   K_PLANE_HULL,
+                                                    K_PLANE_BALL,  K_PLANE_CUBOID,  K_PLANE_HULL,  K_NONE};
+__global__ void __launch_bounds__(256) k_classify_pairs(const uint2* __restrict__ pairs, uint32_t n, const uint32_t* __restrict__ type,
+                                                        uint8_t* __restrict__ keys, DevCounters* cnt) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) cnt->n_pairs = n;
+    if (p >= n) return;
+    uint2 pr = pairs[p];
+    keys[p] = c_key_table2[(type[pr.x] & 3) * 4 + (type[pr.y] & 3)];
+}
+cudaError_t launch_classify_pairs(ncb_ctx* c, const uint2* pairs, uint32_t n) {
+    if (n == 0) return cudaSuccess;
+    k_classify_pairs<<<(n + 255) / 256, 256, 0, c->stream>>>(pairs, n, c->type.p, c->keys_raw.p, c->counters.p);
+    return cudaGetLastError();
+}
+
+}  // namespace ncb

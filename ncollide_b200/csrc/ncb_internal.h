@@ -1,0 +1,153 @@
+// Internal declarations shared by the translation units of libncb200.so (context, device buffers, launchers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/ncb200.h"
+
+namespace ncb {
+
+// Pair type keys (pair_search classifies; the narrow phase runs one persistent kernel per key segment).
+enum PairKey : uint32_t {
+    K_BALL_BALL = 0,
+    K_PLANE_BALL = 1,
+    K_PLANE_CUBOID = 2,
+    K_PLANE_HULL = 3,
+    K_BALL_CUBOID = 4,
+    K_BALL_HULL = 5,
+    K_CUBOID_CUBOID = 6,
+    K_CUBOID_HULL = 7,
+    K_HULL_HULL = 8,
+    K_NONE = 9,
+    K_COUNT = 10
+};
+
+struct DevHulls {
+    uint32_t n_hulls;
+    const uint32_t *vert_off, *face_off, *edge_off, *fadj_off, *vadj_off;
+    const float* points;
+    const uint32_t *vert_first_adj, *vert_num_adj;
+    const uint32_t *face_first, *face_num;
+    const float* face_normal;
+    const uint32_t *vaf, *eaf;
+    const uint32_t *edge_vertices, *edge_faces;
+    const float* edge_dir;
+    const uint32_t *fav, *eav;
+};
+
+struct DevObjects {
+    uint32_t n;
+    const float* pos;        // 3 per object
+    const float4* rot;       // i j k w
+    const uint32_t* type;
+    const float4* param;
+    const uint32_t* groups;  // 3 per object or nullptr
+    const float* qlimit;
+    const float* ang;
+    const float2* ang_cs;    // (cos, sin) of ang, evaluated on the host with libm like the reference does
+};
+
+// Counters living in one device allocation (zeroed per update with one memset).
+struct DevCounters {
+    uint32_t n_pairs;          // emitted by pair search (may exceed capacity)
+    uint32_t n_contacts;       // allocated by the narrow phase (may exceed capacity)
+    uint32_t n_contact_pairs;
+    uint32_t epa_overflow;
+    uint32_t ref_panics;
+    uint32_t n_outliers;       // objects kept out of the LBVH (planes / non-finite boxes)
+    uint32_t key_hist[16];     // pairs per PairKey
+    uint32_t key_start[16];    // exclusive scan of key_hist
+    uint32_t key_cursor[16];   // scatter cursors
+    int bounds[6];             // ordered-int encoded min xyz / max xyz of AABB centres
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct StageTimer {
+    static const int MAX = 24;
+    bool enabled = false;
+    int n = 0;
+    const char* names[MAX];
+    uint32_t launches[MAX];
+    cudaEvent_t ev[MAX + 1];
+    bool created = false;
+};
+
+}  // namespace ncb
+
+struct ncb_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    int sm_count = 148;
+
+    // objects
+    uint32_t n = 0, n_planes = 0;
+    bool has_groups = false;
+    ncb::DevBuf<float> pos, qlimit, ang;
+    ncb::DevBuf<float4> rot, param;
+    ncb::DevBuf<float2> ang_cs;
+    ncb::DevBuf<uint32_t> type, groups;
+    std::vector<float2> h_ang_cs;
+    // hulls
+    ncb::DevHulls hulls = {};
+    std::vector<void*> hull_allocs;
+
+    // broad phase
+    ncb::DevBuf<float4> aabb_lo, aabb_hi;        // handle order
+    ncb::DevBuf<uint32_t> keys_a, keys_b, idx_a, idx_b;
+    ncb::DevBuf<uint8_t> cub_tmp;
+    ncb::DevBuf<float4> leaf_lo, leaf_hi;        // Morton order; lo.w = handle bits, hi.w = shape type bits
+    ncb::DevBuf<float4> nodes;                   // 4 float4 per internal node
+    ncb::DevBuf<uint32_t> parent;                // [0,n) internal parents, [n,2n) leaf parents
+    ncb::DevBuf<uint32_t> flags;
+    ncb::DevBuf<uint2> pairs_raw, pairs;         // emission order / sorted by key
+    ncb::DevBuf<uint8_t> keys_raw, pair_algo;
+    ncb::DevBuf<ncb::DevCounters> counters;
+    // narrow phase
+    ncb::DevBuf<ncb_contact> contacts;
+    ncb::DevBuf<uint32_t> manifold_start;
+    ncb::DevBuf<uint8_t> manifold_count;
+    ncb::DevBuf<uint32_t> pair_index;
+
+    ncb::DevCounters last_counters = {};
+    uint32_t last_n_pairs = 0, last_n_contacts = 0;
+    uint32_t cap_pairs_hint = 0, cap_contacts_hint = 0;
+
+    ncb::StageTimer timer;
+    ncb::DevCounters* h_counters = nullptr;  // pinned
+};
+
+namespace ncb {
+
+// broad.cu
+cudaError_t launch_aabbs(ncb_ctx* c, const DevObjects& o, float margin, int fat, uint32_t begin, uint32_t end);
+cudaError_t launch_lbvh_build(ncb_ctx* c, uint32_t n, const uint32_t* type_or_null);
+cudaError_t launch_pair_search(ncb_ctx* c, uint32_t n, const uint32_t* groups, uint32_t q_begin, uint32_t q_end, uint32_t cap_pairs);
+cudaError_t launch_pair_sort(ncb_ctx* c, uint32_t cap_pairs, uint32_t* index_out);
+size_t lbvh_temp_bytes(uint32_t n);
+// narrow.cu
+cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, uint32_t cap_pairs,
+                                uint32_t cap_contacts);
+cudaError_t launch_classify_pairs(ncb_ctx* c, const uint2* pairs, uint32_t n);
+}  // namespace ncb

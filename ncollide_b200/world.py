@@ -1,0 +1,389 @@
+"""Host-side mirror of the reference's pipeline interface for the hot path, over the C ABI (include/ncb200.h).
+
+  * ``CollisionWorld``   pipeline/world.rs:28-119   (``new(margin)``, ``add``, ``update``, ``contact_pairs``)
+  * ``BroadPhase``       pipeline/broad_phase/broad_phase.rs:41-86 (``create_proxy``, ``deferred_set_bounding_volume``,
+                         ``update(handler)`` with is_interference_allowed / interference_started)
+  * ``NarrowPhase``      contact_generator/contact_manifold_generator.rs:10-36 (batched ``generate_contacts``)
+  * ``TriMesh``          shape/trimesh.rs:100-197 + query/ray/ray_trimesh.rs:22-50 (batched ``toi_and_normal_with_ray``)
+
+Same names, argument meaning and error behaviour as the reference where a Python batch API allows it; misuse that
+panics in the reference raises here.  Everything computes on the GPU through libncb200.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import CONTACT_DTYPE, NcbError, as_f32, as_u32, ptr
+from .scenes import DEFAULT_GROUPS, WorldScene
+from .shapes import HullLibrary
+
+ALGO_NAMES = ["none", "ball_ball", "plane_ball", "plane_convex", "ball_convex", "convex_convex"]
+
+
+@dataclass
+class UpdateResult:
+    pairs: np.ndarray  # [P,2] u32 (object1 = larger handle, object2)
+    pair_algo: np.ndarray  # [P] u8 NCB_ALGO_*
+    manifold_start: np.ndarray  # [P] u32
+    manifold_count: np.ndarray  # [P] u8
+    contacts: np.ndarray  # [C] CONTACT_DTYPE
+    counts: dict
+
+    def contacts_of(self, p):
+        s = int(self.manifold_start[p])
+        return self.contacts[s : s + int(self.manifold_count[p])]
+
+
+class Context:
+    """One per GPU (ncb_create)."""
+
+    def __init__(self, device=0):
+        self.lib = _ffi.load_library()
+        h = C.c_void_p()
+        r = self.lib.ncb_create(C.c_int(device), C.byref(h))
+        if r != 0:
+            raise NcbError(f"ncb_create failed ({r}): {self.lib.ncb_last_error(None).decode()}")
+        self.h = h
+        self._keep = []
+
+    def check(self, r, what):
+        if r < 0:
+            raise NcbError(f"{what} failed ({r}): {self.lib.ncb_last_error(self.h).decode()}")
+        return r
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ncb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- uploads -----------------------------------------------------------------------------------
+    def set_hulls(self, lib: HullLibrary):
+        hc, keep = _ffi.pack_hull_library(lib)
+        self.check(self.lib.ncb_set_hulls(self.h, C.byref(hc)), "ncb_set_hulls")
+
+    def set_objects(self, scene: WorldScene):
+        oc, keep = _ffi.pack_objects(scene)
+        self.check(self.lib.ncb_set_objects(self.h, C.byref(oc)), "ncb_set_objects")
+        self.n = oc.n
+
+    def set_scene(self, scene: WorldScene):
+        self.set_hulls(scene.hulls)
+        self.set_objects(scene)
+
+    def set_positions(self, pos, rot):
+        pos, rot = as_f32(pos), as_f32(rot)
+        self.check(self.lib.ncb_set_positions(self.h, C.c_uint32(len(pos)), ptr(pos), ptr(rot)), "ncb_set_positions")
+
+    def synchronize(self):
+        self.check(self.lib.ncb_synchronize(self.h), "ncb_synchronize")
+
+    # -- stage entry points ---------------------------------------------------------------------------
+    def compute_aabbs(self, margin, mode=2):
+        """mode 0: shape AABB, 1: + query_limit (compute_aabb), 2: + margin (what the broad phase stores)."""
+        out = np.zeros((self.n, 6), dtype=np.float32)
+        self.check(self.lib.ncb_compute_aabbs(self.h, C.c_float(margin), C.c_int(mode), ptr(out)), "ncb_compute_aabbs")
+        return out
+
+    def broad_phase(self, aabbs, groups=None):
+        aabbs = as_f32(aabbs).reshape(-1, 6)
+        n = len(aabbs)
+        g = as_u32(groups) if groups is not None else None
+        cap = max(8 * n, 1024)
+        while True:
+            out = np.zeros((cap, 2), dtype=np.uint32)
+            npairs = C.c_uint32()
+            r = self.check(
+                self.lib.ncb_broad_phase(self.h, C.c_uint32(n), ptr(aabbs), ptr(g), ptr(out), C.c_uint32(cap), C.byref(npairs)),
+                "ncb_broad_phase",
+            )
+            if r == 0:
+                return out[: npairs.value].copy()
+            cap = int(npairs.value) + 16
+
+    def generate_contacts(self, pairs):
+        pairs = as_u32(pairs).reshape(-1, 2)
+        P = len(pairs)
+        cap = max(4 * P, 64)
+        start = np.zeros(P, dtype=np.uint32)
+        count = np.zeros(P, dtype=np.uint8)
+        algo = np.zeros(P, dtype=np.uint8)
+        while True:
+            out = np.zeros(cap, dtype=CONTACT_DTYPE)
+            nc = C.c_uint32()
+            r = self.check(
+                self.lib.ncb_generate_contacts(self.h, C.c_uint32(P), ptr(pairs), ptr(out), C.c_uint32(cap), C.byref(nc), ptr(start), ptr(count), ptr(algo)),
+                "ncb_generate_contacts",
+            )
+            if r == 0:
+                return UpdateResult(pairs, algo, start, count, out[: nc.value].copy(), {"n_contacts": nc.value})
+            cap = int(nc.value) + 16
+
+    # -- fused update -----------------------------------------------------------------------------------
+    @staticmethod
+    def _counts(c):
+        return {
+            "n_pairs": c.n_pairs,
+            "n_contacts": c.n_contacts,
+            "n_contact_pairs": c.n_contact_pairs,
+            "n_algo": {ALGO_NAMES[i]: c.n_algo[i] for i in range(6)},
+            "epa_overflow": c.epa_overflow,
+            "ref_panics": c.ref_panics,
+        }
+
+    def world_update_device(self, margin, q_begin=0, q_end=0xFFFFFFFF):
+        c = _ffi.UpdateCountsC()
+        self.check(
+            self.lib.ncb_world_update_device(self.h, C.c_float(margin), C.c_uint32(q_begin), C.c_uint32(q_end), C.byref(c)),
+            "ncb_world_update_device",
+        )
+        return self._counts(c)
+
+    def world_fetch(self, counts):
+        P, Cn = counts["n_pairs"], counts["n_contacts"]
+        pairs = np.zeros((P, 2), dtype=np.uint32)
+        algo = np.zeros(P, dtype=np.uint8)
+        start = np.zeros(P, dtype=np.uint32)
+        count = np.zeros(P, dtype=np.uint8)
+        contacts = np.zeros(Cn, dtype=CONTACT_DTYPE)
+        self.check(
+            self.lib.ncb_world_fetch(self.h, ptr(pairs), C.c_uint32(P), ptr(algo), ptr(start), ptr(count), ptr(contacts), C.c_uint32(Cn)),
+            "ncb_world_fetch",
+        )
+        return UpdateResult(pairs, algo, start, count, contacts, counts)
+
+    def world_update(self, scene: WorldScene, bufs=None):
+        """The end-to-end host-buffer call (ncb_world_update): uploads the objects, runs the step, copies results back."""
+        oc, keep = _ffi.pack_objects(scene)
+        n = oc.n
+        if bufs is None:
+            bufs = self.alloc_result_buffers(max(8 * n, 1024), max(8 * n, 1024))
+        while True:
+            c = _ffi.UpdateCountsC()
+            r = self.check(
+                self.lib.ncb_world_update(
+                    self.h, C.byref(oc), C.c_float(scene.margin), ptr(bufs["pairs"]), C.c_uint32(len(bufs["pairs"])), ptr(bufs["algo"]),
+                    ptr(bufs["start"]), ptr(bufs["count"]), ptr(bufs["contacts"]), C.c_uint32(len(bufs["contacts"])), C.byref(c),
+                ),
+                "ncb_world_update",
+            )
+            if r == 0:
+                P, Cn = c.n_pairs, c.n_contacts
+                return UpdateResult(bufs["pairs"][:P], bufs["algo"][:P], bufs["start"][:P], bufs["count"][:P], bufs["contacts"][:Cn], self._counts(c))
+            bufs = self.alloc_result_buffers(c.n_pairs + 16, c.n_contacts + 16)
+
+    @staticmethod
+    def alloc_result_buffers(cap_pairs, cap_contacts):
+        return {
+            "pairs": np.zeros((cap_pairs, 2), dtype=np.uint32),
+            "algo": np.zeros(cap_pairs, dtype=np.uint8),
+            "start": np.zeros(cap_pairs, dtype=np.uint32),
+            "count": np.zeros(cap_pairs, dtype=np.uint8),
+            "contacts": np.zeros(cap_contacts, dtype=CONTACT_DTYPE),
+        }
+
+    def profile_enable(self, on=True):
+        self.lib.ncb_profile_enable(self.h, C.c_int(1 if on else 0))
+
+    def profile_get(self):
+        names = (C.c_char_p * 32)()
+        ms = (C.c_float * 32)()
+        launches = (C.c_uint32 * 32)()
+        n = self.lib.ncb_profile_get(self.h, names, ms, launches)
+        return [(names[i].decode(), float(ms[i]), int(launches[i])) for i in range(max(n, 0))]
+
+    def trimesh(self, verts, tris):
+        return TriMesh(self, verts, tris)
+
+
+class GeometricQueryType:
+    """pipeline/object/query_type.rs:13-19 — only Contacts(linear, angular) is on the path."""
+
+    @staticmethod
+    def Contacts(linear, angular):
+        return ("contacts", float(linear), float(angular))
+
+
+class CollisionWorld:
+    """pipeline/world.rs: ``CollisionWorld::new(margin)``, ``add``, ``update``, ``contact_pairs``.
+
+    Objects are appended to host SoA arrays by ``add`` (handle = insertion index, as the slab gives on a fresh
+    world); ``update`` runs one fresh-world step on the device and returns / stores the result.
+    """
+
+    def __init__(self, margin, device=0, ctx=None):
+        self.margin = float(margin)
+        self.ctx = ctx or Context(device)
+        self._pos, self._rot, self._type, self._param, self._groups, self._ql, self._ang = [], [], [], [], [], [], []
+        self._hulls = []
+        self._hull_ids = {}
+        self.result = None
+        self._dirty = True
+
+    def add(self, position, shape, groups=None, query_type=None, data=None):
+        """position = (translation xyz, quaternion ijkw); returns the object handle."""
+        if query_type is None or query_type[0] != "contacts":
+            raise ValueError("only GeometricQueryType::Contacts is supported on the accelerated path")
+        t, q = position
+        self._pos.append(np.asarray(t, dtype=np.float32))
+        self._rot.append(np.asarray(q, dtype=np.float32))
+        self._type.append(shape.type_id)
+        if shape.type_id == 2:
+            key = id(shape)
+            if key not in self._hull_ids:
+                self._hull_ids[key] = len(self._hulls)
+                self._hulls.append(shape)
+            self._param.append(np.array([self._hull_ids[key], 0, 0, 0], dtype=np.float32))
+        else:
+            self._param.append(shape.param())
+        self._groups.append(np.asarray(groups if groups is not None else DEFAULT_GROUPS, dtype=np.uint32))
+        self._ql.append(query_type[1])
+        self._ang.append(query_type[2])
+        self._dirty = True
+        return len(self._pos) - 1
+
+    def scene(self):
+        n = len(self._pos)
+        return WorldScene(
+            pos=np.array(self._pos, dtype=np.float32).reshape(n, 3),
+            rot=np.array(self._rot, dtype=np.float32).reshape(n, 4),
+            shape_type=np.array(self._type, dtype=np.uint32),
+            shape_param=np.array(self._param, dtype=np.float32).reshape(n, 4),
+            groups=np.array(self._groups, dtype=np.uint32).reshape(n, 3),
+            query_limit=np.array(self._ql, dtype=np.float32),
+            ang_pred=np.array(self._ang, dtype=np.float32),
+            hulls=HullLibrary(self._hulls),
+            margin=self.margin,
+        )
+
+    def update(self):
+        s = self.scene()
+        if self._dirty:
+            self.ctx.set_hulls(s.hulls)
+            self._dirty = False
+        self.result = self.ctx.world_update(s)
+        return self.result
+
+    def contact_pairs(self, effective_only=True):
+        """Iterator of (handle1, handle2, algorithm, contacts) — world.rs:452-470."""
+        r = self.result
+        if r is None:
+            return
+        for p in range(len(r.pairs)):
+            if r.pair_algo[p] == 0:
+                continue
+            c = r.contacts_of(p)
+            if effective_only and len(c) == 0:
+                continue
+            yield int(r.pairs[p, 0]), int(r.pairs[p, 1]), ALGO_NAMES[r.pair_algo[p]], c
+
+
+class BroadPhaseInterferenceHandler:
+    """pipeline/broad_phase/broad_phase.rs:28-38"""
+
+    def is_interference_allowed(self, a, b):
+        return True
+
+    def interference_started(self, a, b):
+        pass
+
+    def interference_stopped(self, a, b):
+        pass
+
+
+class BroadPhase:
+    """Mirror of the ``BroadPhase`` trait for a fresh proxy set: ``create_proxy`` queues (bv, data),
+    ``deferred_set_bounding_volume`` loosens by the margin like DBVTBroadPhase (dbvt_broad_phase.rs:325-347),
+    ``update(handler)`` runs the device pair search and replays is_interference_allowed / interference_started
+    in the reference's argument order (later proxy first)."""
+
+    def __init__(self, margin, ctx=None, device=0):
+        self.margin = np.float32(margin)
+        self.ctx = ctx or Context(device)
+        self._bv, self._data = [], []
+        self.pairs = set()
+
+    def create_proxy(self, bv, data):
+        self._bv.append(np.asarray(bv, dtype=np.float32).reshape(6))
+        self._data.append(data)
+        return len(self._bv) - 1
+
+    def proxy(self, handle):
+        if handle < 0 or handle >= len(self._bv):
+            return None
+        return self._bv[handle], self._data[handle]
+
+    def deferred_set_bounding_volume(self, handle, bv):
+        if handle < 0 or handle >= len(self._bv):
+            raise RuntimeError("Attempting to set the bounding volume of an object that does not exist.")
+        b = np.asarray(bv, dtype=np.float32).reshape(6).copy()
+        b[:3] = b[:3] + (-self.margin)
+        b[3:] = b[3:] + self.margin
+        self._bv[handle] = b
+
+    def num_interferences(self):
+        return len(self.pairs)
+
+    def update(self, handler):
+        if not self._bv:
+            return
+        cand = self.ctx.broad_phase(np.stack(self._bv))
+        for a, b in cand[np.lexsort((cand[:, 1], cand[:, 0]))]:
+            a, b = int(a), int(b)
+            if handler.is_interference_allowed(self._data[a], self._data[b]):
+                key = (min(a, b), max(a, b))
+                if key not in self.pairs:
+                    self.pairs.add(key)
+                    handler.interference_started(self._data[a], self._data[b])
+
+
+class TriMesh:
+    """``TriMesh::new(points, indices, None)`` + batched ``RayCast::toi_and_normal_with_ray``."""
+
+    def __init__(self, ctx: Context, verts, tris):
+        self.ctx = ctx
+        self.verts = as_f32(verts).reshape(-1, 3)
+        self.tris = as_u32(tris).reshape(-1, 3)
+        h = C.c_void_p()
+        ctx.check(
+            ctx.lib.ncb_trimesh_create(ctx.h, C.c_uint32(len(self.verts)), ptr(self.verts), C.c_uint32(len(self.tris)), ptr(self.tris), C.byref(h)),
+            "ncb_trimesh_create",
+        )
+        self.h = h
+        self.n_tris = len(self.tris)
+
+    def toi_and_normal_with_ray(self, pose, origins, dirs, max_toi=None, want_normals=True):
+        """pose: None or 7 floats (t xyz, q ijkw).  Returns (toi [-1 = None], face [i or i+T], normals)."""
+        o, d = as_f32(origins).reshape(-1, 3), as_f32(dirs).reshape(-1, 3)
+        n = len(o)
+        toi = np.zeros(n, dtype=np.float32)
+        face = np.zeros(n, dtype=np.uint32)
+        normal = np.zeros((n, 3), dtype=np.float32) if want_normals else None
+        p = as_f32(pose) if pose is not None else None
+        if max_toi is None:
+            max_toi = np.finfo(np.float32).max
+        self.ctx.check(
+            self.ctx.lib.ncb_trimesh_ray_cast(self.h, ptr(p), C.c_uint32(n), ptr(o), ptr(d), C.c_float(max_toi), ptr(toi), ptr(face), ptr(normal)),
+            "ncb_trimesh_ray_cast",
+        )
+        return toi, face, normal
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.ncb_trimesh_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -254,10 +254,13 @@ static Objects make_objects(const orc_objects* o) {
 
 extern "C" {
 
-void orc_compute_aabbs(const orc_objects* objs, real margin, int fat, real* out_minmax) {
+// mode 0: bounding_volume::aabb(shape, pos); 1: compute_aabb (+ query_limit); 2: fat (+ margin)
+void orc_compute_aabbs(const orc_objects* objs, real margin, int mode, real* out_minmax) {
     Objects o = make_objects(objs);
     for (uint32_t i = 0; i < o.n; ++i) {
-        AABB a = fat ? fat_aabb(o, i, margin) : shape_aabb(o, i);
+        AABB a = shape_aabb(o, i);
+        if (mode >= 1) aabb_loosen(a, o.query_limit[i]);
+        if (mode >= 2) aabb_loosen(a, margin);
         real* d = out_minmax + 6 * (size_t)i;
         d[0] = a.mins.x, d[1] = a.mins.y, d[2] = a.mins.z, d[3] = a.maxs.x, d[4] = a.maxs.y, d[5] = a.maxs.z;
     }

@@ -45,7 +45,7 @@ typedef struct orc_contact {
     uint32_t f1, f2;
 } orc_contact;
 
-void orc_compute_aabbs(const orc_objects* objs, real margin, int fat, real* out_minmax);
+void orc_compute_aabbs(const orc_objects* objs, real margin, int mode, real* out_minmax);
 uint64_t orc_broad_phase(uint32_t n, const real* aabb_minmax, const uint32_t* groups, int mode, uint32_t* out_pairs,
                          uint64_t cap);
 

@@ -99,10 +99,13 @@ class Oracle:
         return o, keep
 
     # -- API -----------------------------------------------------------------------------------
-    def compute_aabbs(self, scene, fat=True):
+    def compute_aabbs(self, scene, fat=True, mode=None):
+        """mode 0: shape AABB, 1: + query_limit, 2: + margin (fat=True -> 2, fat=False -> 0)."""
         o, keep = self._objects(scene)
         out = np.zeros((scene.n, 6), dtype=self.dtype)
-        self.lib.orc_compute_aabbs(C.byref(o), self.creal(scene.margin), C.c_int(1 if fat else 0), C.c_void_p(out.ctypes.data))
+        if mode is None:
+            mode = 2 if fat else 0
+        self.lib.orc_compute_aabbs(C.byref(o), self.creal(scene.margin), C.c_int(mode), C.c_void_p(out.ctypes.data))
         return out
 
     def broad_phase(self, aabbs, groups=None, mode=1):

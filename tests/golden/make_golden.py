@@ -1,0 +1,79 @@
+"""Generates the golden fixtures in this directory from the CPU oracle.
+
+The reference is Rust and cannot be built or imported in this image (no rustc/cargo, nalgebra not vendored), so these
+vectors are NOT outputs of the reference binary: they are outputs of the oracle (oracle/), which is itself pinned on
+the reference's own known-answer tests (tests/test_oracle_kat.py).  They guard the oracle and the device against drift.
+
+    python -m tests.golden.make_golden
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from ncollide_b200.scenes import WorldScene, config_scene, make_ray_scene, make_world_scene  # noqa: E402
+from ncollide_b200.shapes import ConvexHull, HullLibrary  # noqa: E402
+
+HULL_FIELDS = HullLibrary.FIELDS
+
+
+def scene_to_dict(s):
+    d = {k: getattr(s, k) for k in ("pos", "rot", "shape_type", "shape_param", "groups", "query_limit", "ang_pred")}
+    d["margin"] = np.float32(s.margin)
+    d["hull_n"] = np.uint32(s.hulls.n_hulls)
+    for f in HULL_FIELDS:
+        d["hull_" + f] = getattr(s.hulls, f)
+    return d
+
+
+class _Lib:
+    FIELDS = HULL_FIELDS
+
+
+def scene_from_npz(z):
+    lib = _Lib()
+    lib.n_hulls = int(z["hull_n"])
+    for f in HULL_FIELDS:
+        setattr(lib, f, z["hull_" + f])
+    lib.max_verts = 0
+    return WorldScene(
+        pos=z["pos"], rot=z["rot"], shape_type=z["shape_type"], shape_param=z["shape_param"], groups=z["groups"],
+        query_limit=z["query_limit"], ang_pred=z["ang_pred"], hulls=lib, margin=float(z["margin"]),
+    )
+
+
+def main():
+    from oracle.pyoracle import Oracle
+
+    o = Oracle()
+    scenes = {
+        "world_cfg1_balls_300": config_scene(1, 300),
+        "world_cfg2_mixed_plane_400": config_scene(2, 400),
+        "world_cfg3_mixed_hulls_500": make_world_scene(500, 1003, (1, 1, 1), side=5.5, n_hulls=12, angular=0.02),
+    }
+    for name, s in scenes.items():
+        d = scene_to_dict(s)
+        fat = o.compute_aabbs(s)
+        pairs = o.broad_phase(fat, s.groups, 0)
+        c, off, algo, _ = o.narrow_phase(s, pairs)
+        d.update(fat_aabbs=fat, pairs=pairs, manifold_off=off, algo=algo)
+        for n in ("world1", "world2", "normal", "depth", "f1", "f2"):
+            d["c_" + n] = c[n]
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+        print(name, s.n, "objects", len(pairs), "pairs", len(c), "contacts")
+    for kind in ("terrain", "soup"):
+        rs = make_ray_scene(kind, 2000, 600, seed=1004)
+        om = o.trimesh(rs.verts, rs.tris)
+        toi, face, normal = om.ray_cast(rs.origins, rs.dirs, mode=0)
+        np.savez_compressed(os.path.join(HERE, f"rays_{kind}_2000.npz"), verts=rs.verts, tris=rs.tris, origins=rs.origins, dirs=rs.dirs,
+                            toi=toi, face=face, normal=normal)
+        print(kind, (toi >= 0).sum(), "hits")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,331 @@
+"""GPU parity tests: the CUDA path (through the C ABI, include/ncb200.h) against the CPU oracle on identical seeded
+inputs.  Bit-exact for AABBs, pair sets, feature ids, manifold sizes and ray-hit faces; contacts / TOI within the
+north-star tolerance (1e-4 relative / 1e-5 absolute).  Run with `pytest -m gpu` on a B200."""
+import numpy as np
+import pytest
+
+from ncollide_b200.scenes import DEFAULT_GROUPS, config_scene, make_ray_scene, make_world_scene
+from ncollide_b200.shapes import BALL, CUBOID, HULL, PLANE, ConvexHull, HullLibrary
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-4, 1e-5  # BASELINE.json north_star tolerance for contact points / normals / depths / TOI
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from ncollide_b200.world import Context
+
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def canon(pairs):
+    p = np.sort(np.asarray(pairs, dtype=np.uint32).reshape(-1, 2), axis=1)
+    return p[np.lexsort((p[:, 1], p[:, 0]))]
+
+
+def close(a, b):
+    return np.allclose(a, b, rtol=RTOL, atol=ATOL)
+
+
+SCENES = [
+    lambda: config_scene(1),
+    lambda: config_scene(2, 4000),
+    lambda: config_scene(3, 6000),
+    lambda: make_world_scene(3000, 77, (1, 1, 1), side=9.0, angular=0.05, n_hulls=64, name="dense_angular"),
+    lambda: make_world_scene(2000, 78, (0, 1, 1), side=7.0, n_hulls=32, linear=0.05, margin=0.01, name="dense_convex"),
+]
+
+
+@pytest.mark.parametrize("mk", SCENES)
+def test_aabbs_bit_exact(ctx, oracle, mk):
+    s = mk()
+    ctx.set_scene(s)
+    for mode in (0, 1, 2):
+        got = ctx.compute_aabbs(s.margin, mode)
+        want = oracle.compute_aabbs(s, mode=mode)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"{s.name} mode {mode}"
+
+
+@pytest.mark.parametrize("mk", SCENES)
+def test_broad_phase_pair_set_bit_exact(ctx, oracle, mk):
+    s = mk()
+    fat = oracle.compute_aabbs(s)
+    got = ctx.broad_phase(fat, s.groups)
+    want = oracle.broad_phase(fat, s.groups, mode=1)
+    assert np.all(got[:, 0] > got[:, 1]), "pairs must be (larger handle, smaller handle)"
+    assert np.array_equal(canon(got), canon(want)), s.name
+    assert len(np.unique(canon(got), axis=0)) == len(got), "duplicate pairs"
+    want_dbvt = oracle.broad_phase(fat, s.groups, mode=0)
+    assert np.array_equal(canon(got), canon(want_dbvt))
+
+
+def compare_manifolds(res, s, oracle, label):
+    """res: UpdateResult for pairs res.pairs; oracle narrow phase is run on the same pairs in the same order."""
+    oc, ooff, oalgo, ostats = oracle.narrow_phase(s, res.pairs)
+    assert np.array_equal(res.pair_algo, oalgo), f"{label}: dispatched algorithm differs"
+    ocount = np.diff(ooff)
+    bad = np.nonzero(res.manifold_count != ocount)[0]
+    assert len(bad) == 0, f"{label}: manifold sizes differ on {len(bad)} pairs, first {bad[:5]} algo {oalgo[bad[:5]]}"
+    # gather the device contacts in oracle order
+    idx = np.concatenate([np.arange(st, st + c) for st, c in zip(res.manifold_start, res.manifold_count)]) if len(oc) else np.zeros(0, int)
+    dc = res.contacts[idx.astype(np.int64)]
+    assert len(dc) == len(oc)
+    if len(oc) == 0:
+        return
+    assert np.array_equal(dc["f1"], oc["f1"]) and np.array_equal(dc["f2"], oc["f2"]), f"{label}: feature ids differ"
+    pair_of = np.repeat(np.arange(len(res.pairs)), res.manifold_count)
+    assert np.array_equal(dc["pair"], pair_of), f"{label}: contact.pair back-references differ"
+    for name in ("world1", "world2", "normal", "depth"):
+        ok = np.isclose(dc[name], oc[name], rtol=RTOL, atol=ATOL)
+        if not ok.all():
+            w = np.nonzero(~ok.reshape(len(oc), -1).all(axis=1))[0]
+            raise AssertionError(f"{label}: {name} differs on {len(w)} contacts, e.g. pair {pair_of[w[0]]} algo {oalgo[pair_of[w[0]]]}: {dc[name][w[0]]} vs {oc[name][w[0]]}")
+    exact = sum(np.array_equal(dc[n].view(np.uint32), oc[n].view(np.uint32)) for n in ("world1", "world2", "normal", "depth"))
+    return exact == 4
+
+
+@pytest.mark.parametrize("mk", SCENES)
+def test_generate_contacts_parity(ctx, oracle, mk):
+    s = mk()
+    ctx.set_scene(s)
+    fat = oracle.compute_aabbs(s)
+    pairs = oracle.broad_phase(fat, s.groups, mode=0)  # reference callback order and orientation
+    res = ctx.generate_contacts(pairs)
+    compare_manifolds(res, s, oracle, s.name)
+
+
+@pytest.mark.parametrize("mk", SCENES)
+def test_world_update_parity(ctx, oracle, mk):
+    s = mk()
+    ctx.set_hulls(s.hulls)
+    res = ctx.world_update(s)
+    assert res.counts["epa_overflow"] == 0
+    fat = oracle.compute_aabbs(s)
+    want = oracle.broad_phase(fat, s.groups, mode=1)
+    assert np.array_equal(canon(res.pairs), canon(want)), "pair set"
+    assert np.all(res.pairs[:, 0] > res.pairs[:, 1])
+    compare_manifolds(res, s, oracle, s.name)
+    assert res.counts["n_contact_pairs"] == int((res.manifold_count > 0).sum())
+    assert sum(res.counts["n_algo"].values()) == len(res.pairs)
+
+
+def test_world_update_is_deterministic_as_a_set(ctx):
+    s = config_scene(3, 5000)
+    ctx.set_hulls(s.hulls)
+    a = ctx.world_update(s)
+    b = ctx.world_update(s)
+    assert np.array_equal(canon(a.pairs), canon(b.pairs))
+
+    def key(r):
+        out = {}
+        for i, p in enumerate(map(tuple, r.pairs.tolist())):
+            c = r.contacts_of(i)
+            out[p] = b"".join(np.ascontiguousarray(c[n]).tobytes() for n in ("world1", "world2", "normal", "depth", "f1", "f2"))
+        return out
+
+    assert key(a) == key(b)
+
+
+def mini_scene(objs, linear=0.02, angular=0.0, margin=0.02, hulls=None, groups=None):
+    from ncollide_b200.scenes import WorldScene
+
+    n = len(objs)
+    return WorldScene(
+        pos=np.array([o[2] for o in objs], dtype=np.float32).reshape(n, 3),
+        rot=np.array([o[3] if len(o) > 3 else (0, 0, 0, 1) for o in objs], dtype=np.float32).reshape(n, 4),
+        shape_type=np.array([o[0] for o in objs], dtype=np.uint32),
+        shape_param=np.array([list(o[1]) + [0] * (4 - len(o[1])) for o in objs], dtype=np.float32).reshape(n, 4),
+        groups=np.asarray(groups, dtype=np.uint32) if groups is not None else np.tile(np.array(DEFAULT_GROUPS, dtype=np.uint32), (n, 1)),
+        query_limit=np.full(n, linear, dtype=np.float32),
+        ang_pred=np.full(n, angular, dtype=np.float32),
+        hulls=hulls or HullLibrary([]),
+        margin=margin,
+    )
+
+
+def test_edge_cases_empty_single_and_coincident(ctx, oracle):
+    empty = mini_scene([])
+    ctx.set_hulls(empty.hulls)
+    r = ctx.world_update(empty)
+    assert len(r.pairs) == 0 and len(r.contacts) == 0
+    one = mini_scene([(BALL, [0.5], (0, 0, 0))])
+    r = ctx.world_update(one)
+    assert len(r.pairs) == 0
+    # many coincident objects: identical Morton codes, every pair overlaps (ties broken by position in the LBVH)
+    k = 40
+    same = mini_scene([(BALL, [0.5], (1, 2, 3))] * k)
+    r = ctx.world_update(same)
+    assert len(r.pairs) == k * (k - 1) // 2
+    compare_manifolds(r, same, oracle, "coincident")
+    # the reference's dbvt_broad_phase3d example: 4 balls -> 6 pairs; without two of them -> 1
+    ex = mini_scene([(BALL, [0.5], p) for p in [(0, 0, 0), (0, 0.5, 0), (0.5, 0, 0), (0.5, 0.5, 0)]], linear=0.0, margin=0.2)
+    tight = oracle.compute_aabbs(ex, fat=False)
+    assert len(ctx.broad_phase(tight)) == 6
+    assert len(ctx.broad_phase(tight[2:])) == 1
+
+
+def test_planes_and_groups(ctx, oracle):
+    rng = np.random.default_rng(5)
+    objs = [(PLANE, [0, 1, 0], (0, 0, 0)), (PLANE, [1, 0, 0], (0, 0, 0))]
+    for i in range(300):
+        p = tuple(rng.uniform(-0.5, 3, size=3))
+        if i % 2:
+            objs.append((BALL, [0.4], p))
+        else:
+            q = rng.standard_normal(4)
+            objs.append((CUBOID, list(rng.uniform(0.2, 0.5, 3)), p, tuple(q / np.linalg.norm(q))))
+    n = len(objs)
+    groups = np.tile(np.array(DEFAULT_GROUPS, dtype=np.uint32), (n, 1))
+    # objects 10..60 are members of group 3 only and blacklist group 5; 60..120 are members of group 5
+    groups[10:60] = (1 << 3, 0x3FFFFFFF, 1 << 5)
+    groups[60:120] = (1 << 5, 0x3FFFFFFF, 0)
+    s = mini_scene(objs, groups=groups)
+    ctx.set_hulls(s.hulls)
+    r = ctx.world_update(s)
+    fat = oracle.compute_aabbs(s)
+    want = oracle.broad_phase(fat, s.groups, mode=2)
+    assert np.array_equal(canon(r.pairs), canon(want))
+    assert (1, 0) in set(map(tuple, r.pairs.tolist())), "plane x plane stays a broad-phase pair"
+    compare_manifolds(r, s, oracle, "planes+groups")
+
+
+def test_reference_kats_on_device(ctx, oracle):
+    # tests/geometry/contact.rs:8-26 (issue #182): just-touching cuboids must give finite results
+    s = mini_scene([(CUBOID, [0.5, 0.5, 0.1], (0, 0, 0)), (CUBOID, [0.5, 0.5, 0.1], (0, 1, 0))], linear=0.0, margin=0.02)
+    ctx.set_hulls(s.hulls)
+    r = ctx.world_update(s)
+    assert len(r.pairs) == 1
+    for name in ("world1", "world2", "normal", "depth"):
+        assert np.all(np.isfinite(r.contacts[name]))
+    compare_manifolds(r, s, oracle, "issue182")
+    # tests/geometry/epa3.rs:7-22 first case (f32): depth 0.5 along -x
+    s = mini_scene([(CUBOID, [2, 1, 1], (0, 0, 0)), (CUBOID, [2, 1, 1], (3.5, 0, 0))], linear=10.0, margin=0.0)
+    r = ctx.world_update(s)
+    assert len(r.pairs) == 1 and r.manifold_count[0] >= 1
+    c = r.contacts_of(0)
+    assert np.max(c["depth"]) == np.float32(0.5) and tuple(c["normal"][0]) == (-1.0, 0.0, 0.0)
+    compare_manifolds(r, s, oracle, "epa3")
+    # examples/contact_query3d.rs:8-35 through the world (ball r=1 vs unit cuboid)
+    for p, sign in (((1, 1, 1), 1), ((2, 2, 2), -1), ((3, 3, 3), 0)):
+        s = mini_scene([(CUBOID, [1, 1, 1], (0, 0, 0)), (BALL, [1.0], p)], linear=0.5, margin=2.0)
+        r = ctx.world_update(s)
+        compare_manifolds(r, s, oracle, "contact_query3d")
+        if sign == 0:
+            assert len(r.contacts) == 0
+        else:
+            assert np.sign(r.contacts["depth"][0]) == sign
+
+
+def test_hull_library_kats(ctx, oracle):
+    cube = ConvexHull.try_from_points(np.array([[x, y, z] for x in (-0.5, 0.5) for y in (-0.5, 0.5) for z in (-0.5, 0.5)], dtype=np.float32))
+    octa = ConvexHull.try_new([(0, 0, 1), (0, 0, -1), (0, 1, 0), (0, -1, 0), (1, 0, 0), (-1, 0, 0)],
+                              [0, 4, 2, 0, 3, 4, 5, 0, 2, 5, 3, 0, 1, 5, 2, 1, 3, 5, 4, 1, 2, 4, 3, 1])
+    lib = HullLibrary([cube, octa])
+    rng = np.random.default_rng(9)
+    objs = []
+    for i in range(400):
+        q = rng.standard_normal(4)
+        q = tuple(q / np.linalg.norm(q)) if i % 3 else (0, 0, 0, 1)
+        objs.append((HULL, [i % 2], tuple(rng.uniform(0, 4, 3)), q))
+    objs.append((PLANE, [0, 0, 1], (0, 0, 0.2)))
+    s = mini_scene(objs, hulls=lib, angular=0.02)
+    ctx.set_hulls(lib)
+    r = ctx.world_update(s)
+    assert r.counts["epa_overflow"] == 0
+    compare_manifolds(r, s, oracle, "hull kats")
+
+
+# ---- ray casting -----------------------------------------------------------------------------------------------
+def ulp_diff(a, b):
+    ia = np.asarray(a, dtype=np.float32).view(np.int32).astype(np.int64)
+    ib = np.asarray(b, dtype=np.float32).view(np.int32).astype(np.int64)
+    return np.abs(ia - ib)
+
+
+def check_rays(ctx, oracle, rs, brute, pose=None):
+    mesh = ctx.trimesh(rs.verts, rs.tris)
+    om = oracle.trimesh(rs.verts, rs.tris)
+    toi, face, normal = mesh.toi_and_normal_with_ray(pose, rs.origins, rs.dirs)
+    T = len(rs.tris)
+    # reference-faithful BVT best-first answer
+    rtoi, rface, rnormal = om.ray_cast(rs.origins, rs.dirs, pose=pose, mode=0)
+    refs = [("bvt", rtoi, rface, rnormal)]
+    if brute:
+        btoi, bface, bnormal = om.ray_cast(rs.origins, rs.dirs, pose=pose, mode=1)
+        # device semantics == brute-force definition, bit for bit
+        assert np.array_equal(face, bface), f"{rs.name}: {(face != bface).sum()} faces differ from the brute-force definition"
+        assert np.array_equal(toi.view(np.uint32), btoi.view(np.uint32))
+        hit = btoi >= 0
+        assert close(normal[hit], bnormal[hit])
+        refs.append(("brute", btoi, bface, bnormal))
+    # against the reference-faithful traversal: identical outside the tie class
+    diff = np.nonzero(face != rface)[0]
+    for i in diff:
+        assert toi[i] >= 0 and rtoi[i] >= 0, f"{rs.name}: ray {i} hit/miss disagreement"
+        assert ulp_diff(toi[i], rtoi[i]) <= 4, f"{rs.name}: ray {i} face {face[i]} vs {rface[i]} toi {toi[i]} vs {rtoi[i]}"
+    same = face == rface
+    assert close(toi[same], rtoi[same])
+    hit = same & (rtoi >= 0)
+    assert close(normal[hit], rnormal[hit])
+    assert (face[toi >= 0] % T < T).all()
+    mesh.close()
+    return len(diff), int((toi >= 0).sum())
+
+
+@pytest.mark.parametrize("kind", ["terrain", "soup"])
+def test_ray_cast_small_vs_brute_force(ctx, oracle, kind):
+    rs = make_ray_scene(kind, 5000, 3000, seed=11)
+    nties, nhits = check_rays(ctx, oracle, rs, brute=True)
+    assert nhits > 100
+
+
+@pytest.mark.parametrize("kind", ["terrain", "soup"])
+def test_ray_cast_medium_vs_bvt(ctx, oracle, kind):
+    rs = make_ray_scene(kind, 200_000, 100_000, seed=12)
+    nties, nhits = check_rays(ctx, oracle, rs, brute=False)
+    assert nhits > 1000
+    assert nties <= 10
+
+
+def test_ray_cast_with_pose_and_max_toi(ctx, oracle):
+    rs = make_ray_scene("terrain", 20_000, 5000, seed=13, random_pose=True)
+    # move the rays into world space so that they still hit the posed mesh
+    t, q = rs.pose[:3].astype(np.float64), rs.pose[3:].astype(np.float64)
+
+    def rot(v):
+        qv = q[:3]
+        tt = 2 * np.cross(qv, v)
+        return v + q[3] * tt + np.cross(qv, tt)
+
+    rs.origins = (rot(rs.origins.astype(np.float64)) + t).astype(np.float32)
+    rs.dirs = rot(rs.dirs.astype(np.float64)).astype(np.float32)
+    check_rays(ctx, oracle, rs, brute=True, pose=rs.pose)
+    mesh = ctx.trimesh(rs.verts, rs.tris)
+    om = oracle.trimesh(rs.verts, rs.tris)
+    toi, face, _ = mesh.toi_and_normal_with_ray(rs.pose, rs.origins, rs.dirs, max_toi=4.0)
+    btoi, bface, _ = om.ray_cast(rs.origins, rs.dirs, max_toi=4.0, pose=rs.pose, mode=1)
+    assert np.array_equal(face, bface) and np.array_equal(toi.view(np.uint32), btoi.view(np.uint32))
+    assert (toi[toi >= 0] <= 4.0).all() and (toi < 0).any()
+
+
+def test_ray_cast_edge_cases(ctx, oracle):
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=np.float32)
+    one = ctx.trimesh(v, np.array([[0, 1, 2]], dtype=np.uint32))
+    toi, face, n = one.toi_and_normal_with_ray(None, [[0.2, 0.2, 1]], [[0, 0, -1]])
+    assert toi[0] == 1.0 and face[0] == 0 and tuple(n[0]) == (0, 0, 1)
+    toi, face, n = one.toi_and_normal_with_ray(None, [[0.2, 0.2, -1]], [[0, 0, 1]])
+    assert toi[0] == 1.0 and face[0] == 1 and tuple(n[0]) == (0, 0, -1)  # back face -> i + n_tris
+    toi, face, n = one.toi_and_normal_with_ray(None, [[2, 2, 1]], [[0, 0, -1]])
+    assert toi[0] < 0
+    toi, face, n = one.toi_and_normal_with_ray(None, np.zeros((0, 3)), np.zeros((0, 3)))
+    assert len(toi) == 0
+    # duplicated triangles: ties go to the smallest face index
+    two = ctx.trimesh(v, np.array([[0, 1, 2], [0, 1, 2], [0, 1, 3]], dtype=np.uint32))
+    toi, face, n = two.toi_and_normal_with_ray(None, [[0.2, 0.2, 1]], [[0, 0, -1]])
+    assert face[0] == 0
+    om = oracle.trimesh(v, np.array([[0, 1, 2], [0, 1, 2], [0, 1, 3]], dtype=np.uint32))
+    bt, bf, bn = om.ray_cast(np.array([[0.2, 0.2, 1]], dtype=np.float32), np.array([[0, 0, -1]], dtype=np.float32), mode=1)
+    assert bf[0] == face[0]
