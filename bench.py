@@ -1,0 +1,486 @@
+#!/usr/bin/env python
+"""bench.py — one fresh-world CollisionWorld::update per step on synthetic scenes (BASELINE.json configs[2]:
+1M mixed balls / cuboids / convex hulls), plus batched TriMesh ray casting as a secondary figure.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n-objects M] [--no-rays] [--no-cpu]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL): weak scaling — the world has N x 1M objects; every rank
+computes the AABBs of its own 1M-object block, the AABBs are all-gathered (NCCL over NVLink), the LBVH is
+replicated, and each rank runs the pair search for its slice of the Morton order and the narrow phase of its own
+pairs.  `value` = (total objects / 1M) / step time = 1M-shape world updates per second over the whole job.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, "port": the Rust reference cannot be built
+here — no rustc/cargo, nalgebra not vendored) on the host cores; it is single-threaded like the reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "world updates/sec at 1M shapes (contact pairs/sec and Mrays/s vs TriMesh reported alongside)"
+UNIT = "updates/s (1M-shape worlds)"
+N_PER_GPU = 1_000_000
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc = None
+        self.lines = []
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def run_reference(args):
+    """CPU arm: reference-faithful DBVT broad phase + narrow phase of the oracle, single thread (the reference is
+    single-threaded: no thread / rayon / atomic use anywhere in its src/)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from ncollide_b200.scenes import config_scene
+    from oracle.pyoracle import Oracle
+
+    orc = Oracle()
+    total_steps = args.steps + args.warmup
+    # ~10 s per 1M-object step on one core: bound the sample so the whole run stays within a few minutes
+    n = args.n_objects or N_PER_GPU
+    budget_s = 200.0
+    est = 10.0 * n / 1e6
+    if est * total_steps > budget_s:
+        n = max(20_000, int(n * budget_s / (est * total_steps)))
+    scene = config_scene(3, n)
+    times = []
+    counts = None
+    for i in range(total_steps):
+        t, counts = orc.world_update_timed(scene)
+        if i >= args.warmup:
+            times.append(sum(t))
+    ms = 1e3 * sum(times) / len(times)
+    value = (n / 1e6) / (ms / 1e3)
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg3 mixed balls/cuboids/hulls fresh-world update, {n} objects (sample of the 1M-object workload, same density)",
+                   "n_objects": n, "pairs": counts[0], "contacts": counts[1]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{n} of 1000000 objects per step, same density; C++ restatement of the reference (DBVT + per-pair generators), not the Rust binary"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "contact_pairs_per_sec": counts[2] / (ms / 1e3),
+        "host_cores_available": os.cpu_count(),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+class _CudaArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 3}
+
+
+def run_native(args):
+    import torch
+
+    from ncollide_b200.scenes import config_scene, make_ray_scene
+    from ncollide_b200.world import Context
+    from ncollide_b200 import _ffi
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = Context(local_rank)
+    stream = torch.cuda.Stream(dev)  # a real (non-default) stream, shared by torch, NCCL ordering and the library
+    torch.cuda.set_stream(stream)
+    ctx.lib.ncb_set_stream(ctx.h, C.c_void_p(stream.cuda_stream))
+
+    n_per = args.n_objects or N_PER_GPU
+    n_total = n_per * world
+    scene = config_scene(3, n_total)
+    ctx.set_hulls(scene.hulls)
+
+    # pinned host staging for the end-to-end arm
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+
+    keep = []
+    pin_scene = type(scene)(**{**scene.__dict__})
+    for f in ("pos", "rot", "shape_type", "shape_param", "groups", "query_limit", "ang_pred"):
+        t, a = pinned(getattr(scene, f))
+        keep.append(t)
+        setattr(pin_scene, f, a)
+    ctx.set_objects(pin_scene)
+    ctx.synchronize()
+
+    my_begin, my_end = rank * n_per, (rank + 1) * n_per
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    lib, h = ctx.lib, ctx.h
+    counts_c = _ffi.UpdateCountsC()
+
+    def step_device():
+        """One update with device-resident inputs."""
+        if world == 1:
+            r = lib.ncb_world_update_device(h, C.c_float(scene.margin), C.c_uint32(0), C.c_uint32(0xFFFFFFFF), C.byref(counts_c))
+            ctx.check(r, "ncb_world_update_device")
+        else:
+            ctx.check(lib.ncb_world_update_stage(h, 0, C.c_float(scene.margin), C.c_uint32(my_begin), C.c_uint32(my_end), None), "stage0")
+            for which in (0, 1):
+                full = torch.as_tensor(_CudaArray(lib.ncb_device_ptr(h, which), (n_total, 4), "<f4"), device=dev)
+                shard = full[my_begin:my_end].clone()
+                dist.all_gather_into_tensor(full, shard)
+            # query slice = this rank's share of the Morton order
+            ctx.check(lib.ncb_world_update_stage(h, 1, C.c_float(scene.margin), C.c_uint32(my_begin), C.c_uint32(my_end), C.byref(counts_c)), "stage1")
+        return ctx._counts(counts_c)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed_steps(fn, steps, warmup, with_flush=True):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            if with_flush:
+                flush.fill_(1)  # L2 flush (256 MiB > 126 MB L2) between timed iterations, outside the timed events
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            out = fn()
+            e1.record(stream)
+            evs.append((e0, e1))
+        barrier()
+        ms = [a.elapsed_time(b) for a, b in evs]
+        return ms, out
+
+    # ---- timed region: device-resident inputs -------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_list, counts = timed_steps(step_device, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_mean = sum(ms_list) / len(ms_list)
+    if dist is not None:
+        t = torch.tensor([ms_mean], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+        agg = torch.tensor([counts["n_pairs"], counts["n_contacts"], counts["n_contact_pairs"]], device=dev, dtype=torch.int64)
+        dist.all_reduce(agg)
+        tot_pairs, tot_contacts, tot_contact_pairs = (int(x) for x in agg.tolist())
+    else:
+        ms_step = ms_mean
+        tot_pairs, tot_contacts, tot_contact_pairs = counts["n_pairs"], counts["n_contacts"], counts["n_contact_pairs"]
+    value = (n_total / 1e6) / (ms_step / 1e3)
+
+    # ---- per-stage times (CUDA events on the launching stream) for the roofline ----------------------------
+    ctx.profile_enable(True)
+    stage_acc = {}
+    launches_total = 0
+    reps = 3
+    for _ in range(reps):
+        flush.fill_(1)
+        step_device()
+        prof = ctx.profile_get()
+        launches_total = sum(p[2] for p in prof)
+        for name, ms, _l in prof:
+            stage_acc[name] = stage_acc.get(name, 0.0) + ms / reps
+    ctx.profile_enable(False)
+
+    peak, peak_kind = measured_peaks()
+    stages = []
+    for name, ms in stage_acc.items():
+        stages.append({"stage": name, "ms": round(ms, 4)})
+    dom_name = max(stage_acc, key=stage_acc.get) if stage_acc else None
+    total_bytes = world_total_bytes(n_total // world if world > 1 else n_total, counts, scene)
+    roofline = None
+    if dom_name:
+        dom_ms = stage_acc[dom_name]
+        dom_bytes = stage_bytes(dom_name, n_total // world if world > 1 else n_total, counts, scene)
+        ach = dom_bytes / (dom_ms / 1e3) / 1e9
+        roofline = {
+            "bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "peak_kind": f"{peak_kind} copy bandwidth", "kernel_ms": dom_ms, "algorithmic_bytes": dom_bytes,
+            "share_of_step": dom_ms / max(sum(stage_acc.values()), 1e-9),
+            "whole_step": {"algorithmic_bytes": total_bytes, "achieved": total_bytes / (ms_step / 1e3) / 1e9,
+                           "frac": total_bytes / (ms_step / 1e3) / 1e9 / peak},
+        }
+
+    # ---- end to end: host buffers through ncb_world_update (N = 1) / staged calls (N > 1) -------------------
+    bufs = ctx.alloc_result_buffers(int(counts["n_pairs"] * 1.1) + 1024, int(counts["n_contacts"] * 1.1) + 1024)
+    pin_out = {}
+    for k, a in bufs.items():
+        t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
+        keep.append(t)
+        pin_out[k] = t.numpy().view(a.dtype).reshape(a.shape)
+    oc, okeep = _ffi.pack_objects(pin_scene)
+
+    def step_e2e():
+        if world == 1:
+            r = lib.ncb_world_update(
+                h, C.byref(oc), C.c_float(scene.margin), _ffi.ptr(pin_out["pairs"]), C.c_uint32(len(pin_out["pairs"])), _ffi.ptr(pin_out["algo"]),
+                _ffi.ptr(pin_out["start"]), _ffi.ptr(pin_out["count"]), _ffi.ptr(pin_out["contacts"]), C.c_uint32(len(pin_out["contacts"])),
+                C.byref(counts_c))
+            ctx.check(r, "ncb_world_update")
+        else:
+            # every rank uploads the poses of its own block, steps, and reads its own results back
+            lib.ncb_set_positions(h, C.c_uint32(n_total), _ffi.ptr(pin_scene.pos), _ffi.ptr(pin_scene.rot))
+            step_device()
+            ctx.check(lib.ncb_world_fetch(h, _ffi.ptr(pin_out["pairs"]), C.c_uint32(len(pin_out["pairs"])), _ffi.ptr(pin_out["algo"]),
+                                          _ffi.ptr(pin_out["start"]), _ffi.ptr(pin_out["count"]), _ffi.ptr(pin_out["contacts"]),
+                                          C.c_uint32(len(pin_out["contacts"]))), "fetch")
+        return ctx._counts(counts_c)
+
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = (n_total / 1e6) / (e2e_ms / 1e3)
+    n_up = n_total
+    h2d = n_up * (12 + 16 + 4 + 16 + 12 + 4 + 4 + 8) if world == 1 else n_total * 28
+    d2h = counts["n_pairs"] * (8 + 1 + 4 + 1) + counts["n_contacts"] * 52 + 256
+
+    # ---- secondary figure: batched TriMesh ray casting (configs[3]) ---------------------------------------
+    rays = None
+    if not args.no_rays:
+        n_tris, n_rays = (1_000_000, 1_000_000) if not args.n_objects else (max(1000, args.n_objects), max(1000, args.n_objects))
+        rs = make_ray_scene("terrain", n_tris, n_rays * world, seed=1004)
+        mesh = ctx.trimesh(rs.verts, rs.tris)
+        lo, hi = rank * n_rays, (rank + 1) * n_rays
+        d_o = torch.from_numpy(rs.origins[lo:hi]).to(dev)
+        d_d = torch.from_numpy(rs.dirs[lo:hi]).to(dev)
+        d_toi = torch.empty(n_rays, dtype=torch.float32, device=dev)
+        d_face = torch.empty(n_rays, dtype=torch.int32, device=dev)
+        d_n = torch.empty((n_rays, 3), dtype=torch.float32, device=dev)
+        fmax = float(np.finfo(np.float32).max)
+
+        def ray_step():
+            ctx.check(lib.ncb_trimesh_ray_cast_device(mesh.h, None, C.c_uint32(n_rays), C.c_void_p(d_o.data_ptr()), C.c_void_p(d_d.data_ptr()),
+                                                      C.c_float(fmax), C.c_void_p(d_toi.data_ptr()), C.c_void_p(d_face.data_ptr()),
+                                                      C.c_void_p(d_n.data_ptr())), "ray_cast_device")
+
+        rms, _ = timed_steps(ray_step, max(args.steps, 5), 3)
+        rms_mean = sum(rms) / len(rms)
+        if dist is not None:
+            t = torch.tensor([rms_mean], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rms_mean = float(t.item())
+        T, V = len(rs.tris), len(rs.verts)
+        ray_bytes = n_rays * (24 + 8 + 12) + V * 12 + T * 12 + (2 * T - 1) * 32
+        # end to end with host buffers
+        toi_h = np.zeros(n_rays, np.float32)
+        t0 = time.perf_counter()
+        mesh.toi_and_normal_with_ray(None, rs.origins[lo:hi], rs.dirs[lo:hi])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            mesh.toi_and_normal_with_ray(None, rs.origins[lo:hi], rs.dirs[lo:hi])
+        barrier()
+        ray_e2e_ms = (time.perf_counter() - t0) * 1e3 / 3
+        rays = {
+            "metric": "Mrays/s vs TriMesh", "value": n_rays * world / (rms_mean / 1e3) / 1e6, "unit": "Mrays/s", "ms_per_batch": rms_mean,
+            "workload": f"{n_rays} rays per GPU vs {T}-triangle terrain TriMesh (first hit + TOI + normal)",
+            "hit_fraction": float((d_toi >= 0).float().mean().item()),
+            "roofline": {"bound": "hbm", "achieved": ray_bytes / (rms_mean / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": ray_bytes / (rms_mean / 1e3) / 1e9 / peak, "algorithmic_bytes": ray_bytes, "traffic": None},
+            "e2e": {"value": n_rays * world / (ray_e2e_ms / 1e3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * 20},
+        }
+        mesh.close()
+
+    # ---- CPU baseline beside it (rank 0, N = 1): the oracle port on a bounded sample -----------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle.pyoracle import Oracle
+
+        orc = Oracle()
+        n_cpu = min(n_total, 1_000_000)
+        cs = scene if n_cpu == n_total else config_scene(3, n_cpu)
+        t, c = orc.world_update_timed(cs)
+        cpu_ms = sum(t) * 1e3
+        cpu = {"value": (n_cpu / 1e6) / (cpu_ms / 1e3), "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"one full {n_cpu}-object cfg3 step (aabb {t[0]:.2f}s + DBVT broad phase {t[1]:.2f}s + narrow phase {t[2]:.2f}s); "
+                         "C++ restatement of the reference, single thread like the reference, not the Rust binary",
+               "host_cores_available": os.cpu_count(), "pairs": c[0], "contacts": c[1]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"configs[2]: {n_per} mixed balls/cuboids/convex hulls (<=32 verts) per GPU, fresh-world update "
+                            "(AABBs -> LBVH -> pair search -> contact manifolds)",
+                "n_objects_total": n_total, "pairs": tot_pairs, "contacts": tot_contacts, "contact_pairs": tot_contact_pairs,
+                "parallelism": "single GPU" if world == 1 else f"{world} ranks: AABB block per rank + NCCL all-gather, replicated LBVH, query slices",
+                "l2": "256 MiB flush between timed iterations; working set > L2",
+                "seed": 1003,
+            },
+            "contact_pairs_per_sec": tot_contact_pairs / (ms_step / 1e3),
+            "broad_phase_pairs_per_sec": tot_pairs / (ms_step / 1e3),
+            "stages_ms": stages,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches_total * args.steps),
+            "gpu_launches_per_step": int(launches_total),
+            "clocks": clocks,
+            "counts": {k: v for k, v in counts.items() if k != "n_algo"} | {"n_algo": counts["n_algo"]},
+            "rays": rays,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def stage_bytes(name, n, counts, scene):
+    P, Cn = counts["n_pairs"], counts["n_contacts"]
+    H = int((scene.shape_type == 2).sum()) * n / max(scene.n, 1)
+    vbar = float(np.diff(scene.hulls.vert_off).mean()) if scene.hulls.n_hulls else 0.0
+    na = counts["n_algo"]
+    types = scene.shape_type
+    fb, fc, fh = [(types == t).mean() for t in (0, 1, 2)]
+    # pairs per key from the dispatched algorithm counts and the type mix
+    bc_total = max(na["ball_convex"], 1)
+    cc_total = max(na["convex_convex"], 1)
+    w_bcub, w_bh = fc / max(fc + fh, 1e-9), fh / max(fc + fh, 1e-9)
+    w_cc, w_ch, w_hh = fc * fc, 2 * fc * fh, fh * fh
+    wsum = max(w_cc + w_ch + w_hh, 1e-9)
+    key_pairs = {
+        "narrow_ball_ball": na["ball_ball"], "narrow_plane": na["plane_ball"] + na["plane_convex"],
+        "narrow_ball_cuboid": na["ball_convex"] * w_bcub, "narrow_ball_hull": na["ball_convex"] * w_bh,
+        "narrow_cuboid_cuboid": na["convex_convex"] * w_cc / wsum, "narrow_cuboid_hull": na["convex_convex"] * w_ch / wsum,
+        "narrow_hull_hull": na["convex_convex"] * w_hh / wsum,
+    }
+    hull_ops = {"narrow_ball_ball": 0, "narrow_plane": 0, "narrow_ball_cuboid": 0, "narrow_ball_hull": 1, "narrow_cuboid_cuboid": 0,
+                "narrow_cuboid_hull": 1, "narrow_hull_hull": 2}
+    if name == "aabb":
+        return n * (28 + 16 + 24) + H * 12 * vbar
+    if name == "morton_sort":
+        return n * (24 + 8)
+    if name == "lbvh_build":
+        return n * (24 + 64)
+    if name == "pair_search":
+        return n * (24 + 12) + P * 8
+    if name == "pair_sort":
+        return P * 9 * 2
+    if name in key_pairs:
+        kp = key_pairs[name]
+        share = kp / max(P, 1)
+        return kp * (2 * 44 + 4) + kp * hull_ops[name] * 12 * vbar + Cn * share * 48
+    return 0.0
+
+
+def world_total_bytes(n, counts, scene):
+    names = ["aabb", "pair_search", "narrow_ball_ball", "narrow_plane", "narrow_ball_cuboid", "narrow_ball_hull", "narrow_cuboid_cuboid",
+             "narrow_cuboid_hull", "narrow_hull_hull"]
+    return float(sum(stage_bytes(k, n, counts, scene) for k in names))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native")
+    ap.add_argument("--n-objects", type=int, default=0, help="objects per GPU (default 1,000,000)")
+    ap.add_argument("--no-rays", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_native(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

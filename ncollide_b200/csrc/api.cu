@@ -28,26 +28,6 @@ static thread_local std::string g_create_err;
         }                        \
     } while (0)
 
-// ---- stage timers ------------------------------------------------------------------------------------------
-static void timer_begin(ncb_ctx* c) {
-    StageTimer& t = c->timer;
-    t.n = 0;
-    if (!t.enabled) return;
-    if (!t.created) {
-        for (int i = 0; i <= StageTimer::MAX; ++i) cudaEventCreate(&t.ev[i]);
-        t.created = true;
-    }
-    cudaEventRecord(t.ev[0], c->stream);
-}
-static void timer_mark(ncb_ctx* c, const char* name, uint32_t launches) {
-    StageTimer& t = c->timer;
-    if (!t.enabled || t.n >= StageTimer::MAX) return;
-    t.names[t.n] = name;
-    t.launches[t.n] = launches;
-    t.n++;
-    cudaEventRecord(t.ev[t.n], c->stream);
-}
-
 static DevObjects dev_objects(ncb_ctx* c) {
     DevObjects o;
     o.n = c->n;
@@ -456,15 +436,13 @@ static int update_after_aabbs(ncb_ctx* ctx, uint32_t q_begin, uint32_t q_end) {
         CK(ctx->contacts.reserve(cap_contacts));
         r = reset_counters(ctx);
         if (r) return r;
-        timer_begin(ctx);
+        if (!ctx->timer_external || attempt > 0) timer_begin(ctx);
         CK(launch_lbvh_build(ctx, n, ctx->type.p));
-        timer_mark(ctx, "lbvh_build", 7);
         CK(launch_pair_search(ctx, n, ctx->has_groups ? ctx->groups.p : nullptr, q_begin, q_end, (uint32_t)cap_pairs));
         timer_mark(ctx, "pair_search", 2);
         CK(launch_pair_sort(ctx, (uint32_t)cap_pairs, nullptr));
         timer_mark(ctx, "pair_sort", 3);
         CK(launch_narrow_phase(ctx, dev_objects(ctx), ctx->pairs.p, nullptr, (uint32_t)cap_pairs, (uint32_t)cap_contacts));
-        timer_mark(ctx, "narrow_phase", 10);
         r = read_counters(ctx);
         if (r) return r;
         const DevCounters& c = ctx->last_counters;
@@ -495,7 +473,10 @@ int ncb_world_update_stage(ncb_ctx* ctx, int stage, float margin, uint32_t begin
     uint32_t n = ctx->n;
     if (stage == 0) {
         if (end > n) end = n;
+        timer_begin(ctx);
+        ctx->timer_external = true;
         CK(launch_aabbs(ctx, dev_objects(ctx), margin, 2, begin, end));
+        timer_mark(ctx, "aabb", 1);
         return NCB_OK;
     }
     if (n == 0) {
@@ -505,6 +486,7 @@ int ncb_world_update_stage(ncb_ctx* ctx, int stage, float margin, uint32_t begin
         return NCB_OK;
     }
     int r = update_after_aabbs(ctx, begin, end);
+    ctx->timer_external = false;
     if (r) return r;
     fill_counts(ctx, counts);
     return NCB_OK;

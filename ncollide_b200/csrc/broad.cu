@@ -268,11 +268,13 @@ cudaError_t launch_lbvh_build(ncb_ctx* c, uint32_t n, const uint32_t*) {
     size_t bytes = c->cub_tmp.cap;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, c->keys_a.p, c->keys_b.p, c->idx_a.p, c->idx_b.p, (int)n, 0, 31, s);
     if (e != cudaSuccess) return e;
+    timer_mark(c, "morton_sort", 6);
     k_gather_leaves<<<nb, 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, c->idx_b.p, n, c->leaf_lo.p, c->leaf_hi.p);
     e = cudaMemsetAsync(c->flags.p, 0, (size_t)n * sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
     k_karras<<<nb, 256, 0, s>>>(c->keys_b.p, n, c->counters.p, c->nodes.p, c->parent.p);
     k_refit<<<nb, 256, 0, s>>>(c->leaf_lo.p, c->leaf_hi.p, n, c->counters.p, c->nodes.p, c->parent.p, c->flags.p);
+    timer_mark(c, "lbvh_build", 4);
     return cudaGetLastError();
 }
 

@@ -865,15 +865,22 @@ cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pa
     cudaStream_t s = c->stream;
     int sm = c->sm_count;
     k_narrow<K_BALL_BALL><<<sm * 8, 128, 0, s>>>(A);
+    timer_mark(c, "narrow_ball_ball", 1);
     k_narrow<K_PLANE_BALL><<<sm * 4, 128, 0, s>>>(A);
     k_narrow<K_PLANE_CUBOID><<<sm * 4, 128, 0, s>>>(A);
     k_narrow<K_PLANE_HULL><<<sm * 4, 128, 0, s>>>(A);
-    k_narrow<K_BALL_CUBOID><<<sm * 8, 128, 0, s>>>(A);
-    k_narrow<K_BALL_HULL><<<sm * 4, 128, 0, s>>>(A);
-    k_narrow<K_CUBOID_CUBOID><<<sm * 4, 128, 0, s>>>(A);
-    k_narrow<K_CUBOID_HULL><<<sm * 4, 128, 0, s>>>(A);
-    k_narrow<K_HULL_HULL><<<sm * 4, 128, 0, s>>>(A);
     k_narrow_none<<<sm, 256, 0, s>>>(A);
+    timer_mark(c, "narrow_plane", 4);
+    k_narrow<K_BALL_CUBOID><<<sm * 8, 128, 0, s>>>(A);
+    timer_mark(c, "narrow_ball_cuboid", 1);
+    k_narrow<K_BALL_HULL><<<sm * 4, 128, 0, s>>>(A);
+    timer_mark(c, "narrow_ball_hull", 1);
+    k_narrow<K_CUBOID_CUBOID><<<sm * 4, 128, 0, s>>>(A);
+    timer_mark(c, "narrow_cuboid_cuboid", 1);
+    k_narrow<K_CUBOID_HULL><<<sm * 4, 128, 0, s>>>(A);
+    timer_mark(c, "narrow_cuboid_hull", 1);
+    k_narrow<K_HULL_HULL><<<sm * 4, 128, 0, s>>>(A);
+    timer_mark(c, "narrow_hull_hull", 1);
     return cudaGetLastError();
 }
 

@@ -135,10 +135,31 @@ struct ncb_ctx {
     uint32_t cap_pairs_hint = 0, cap_contacts_hint = 0;
 
     ncb::StageTimer timer;
+    bool timer_external = false;  // stage 0 (AABBs) already started the timer of this update
     ncb::DevCounters* h_counters = nullptr;  // pinned
 };
 
 namespace ncb {
+
+// ---- stage timers (CUDA events on the context's stream, only when ncb_profile_enable(ctx, 1)) ----------------
+inline void timer_begin(ncb_ctx* c) {
+    StageTimer& t = c->timer;
+    t.n = 0;
+    if (!t.enabled) return;
+    if (!t.created) {
+        for (int i = 0; i <= StageTimer::MAX; ++i) cudaEventCreate(&t.ev[i]);
+        t.created = true;
+    }
+    cudaEventRecord(t.ev[0], c->stream);
+}
+inline void timer_mark(ncb_ctx* c, const char* name, uint32_t launches) {
+    StageTimer& t = c->timer;
+    if (!t.enabled || t.n >= StageTimer::MAX) return;
+    t.names[t.n] = name;
+    t.launches[t.n] = launches;
+    t.n++;
+    cudaEventRecord(t.ev[t.n], c->stream);
+}
 
 // broad.cu
 cudaError_t launch_aabbs(ncb_ctx* c, const DevObjects& o, float margin, int fat, uint32_t begin, uint32_t end);
