@@ -443,6 +443,17 @@ def stage_bytes(name, n, counts, scene):
     }
     hull_ops = {"narrow_ball_ball": 0, "narrow_plane": 0, "narrow_ball_cuboid": 0, "narrow_ball_hull": 1, "narrow_cuboid_cuboid": 0,
                 "narrow_cuboid_hull": 1, "narrow_hull_hull": 2}
+    cc = na["convex_convex"]
+    cc_hull_ops = (key_pairs["narrow_cuboid_hull"] + 2 * key_pairs["narrow_hull_hull"]) / max(cc, 1)  # hull operands per cc pair
+    cc_contacts = Cn * cc / max(P, 1)
+    if name == "cc_gjk":      # read the pair + both operands (+ hull vertices), decide
+        return cc * (2 * 44 + 4) + cc * cc_hull_ops * 12 * vbar
+    if name == "cc_epa":      # re-read operands of the penetrating subset, hand the witness points on
+        ne = counts.get("n_epa_pairs", 0)
+        return ne * (2 * 44 + 40) + ne * cc_hull_ops * 12 * vbar
+    if name == "cc_manifold":  # operands of the pairs that reach clipping + the contacts written
+        nm = counts.get("n_manifold_jobs", 0)
+        return nm * (2 * 44 + 40) + cc_contacts * 48 + cc * 5
     if name == "aabb":
         return n * (28 + 16 + 24) + H * 12 * vbar
     if name == "morton_sort":
@@ -461,6 +472,7 @@ def stage_bytes(name, n, counts, scene):
 
 
 def world_total_bytes(n, counts, scene):
+    # compulsory bytes of the whole step: object records in, AABBs, pairs, operands per pair, contacts out
     names = ["aabb", "pair_search", "narrow_ball_ball", "narrow_plane", "narrow_ball_cuboid", "narrow_ball_hull", "narrow_cuboid_cuboid",
              "narrow_cuboid_hull", "narrow_hull_hull"]
     return float(sum(stage_bytes(k, n, counts, scene) for k in names))

@@ -104,6 +104,8 @@ typedef struct ncb_update_counts {
     uint32_t n_algo[6];        /* pairs per NCB_ALGO_* */
     uint32_t epa_overflow;     /* pairs whose EPA exceeded the fixed device capacity (result = "no contact"; 0 expected) */
     uint32_t ref_panics;       /* pairs on which the reference itself would have panicked (assert / unwrap) */
+    uint32_t n_epa_pairs;      /* convex-convex pairs that needed EPA (GJK found the origin inside the CSO) */
+    uint32_t n_manifold_jobs;  /* convex-convex pairs that reached feature clipping */
 } ncb_update_counts;
 
 /* ---- context ------------------------------------------------------------------------------------------------ */
@@ -124,9 +126,11 @@ int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* objs);
 int ncb_set_positions(ncb_ctx* ctx, uint32_t n, const float* pos, const float* rot);
 
 /* ---- stage entry points (each mirrors one reference routine, host buffers in/out) ---------------------------- */
-/* CollisionObjectRef::compute_aabb (collision_object.rs:89-93); fat != 0 additionally applies
- * DBVTBroadPhase's loosened(margin) (dbvt_broad_phase.rs:341).  out: 6 floats per object (mins, maxs). */
-int ncb_compute_aabbs(ncb_ctx* ctx, float margin, int fat, float* out_minmax);
+/* mode 0: bounding_volume::aabb(shape, position) (shape/shape.rs aabb, bounding_volume/aabb_*.rs);
+ * mode 1: CollisionObjectRef::compute_aabb = mode 0 loosened by query_limit (collision_object.rs:89-93);
+ * mode 2: additionally DBVTBroadPhase's loosened(margin) (dbvt_broad_phase.rs:341) = the box the broad phase stores.
+ * out: 6 floats per object (mins, maxs). */
+int ncb_compute_aabbs(ncb_ctx* ctx, float margin, int mode, float* out_minmax);
 /* BroadPhase::update on a fresh proxy set (pipeline/broad_phase/broad_phase.rs:65, dbvt_broad_phase.rs:174-259):
  * proxies 0..n-1 with the given (already loosened) AABBs; out pairs = (larger handle, smaller handle), i.e. the
  * argument order of interference_started.  groups may be NULL. */

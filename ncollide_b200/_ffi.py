@@ -50,6 +50,8 @@ class UpdateCountsC(C.Structure):
         ("n_algo", C.c_uint32 * 6),
         ("epa_overflow", C.c_uint32),
         ("ref_panics", C.c_uint32),
+        ("n_epa_pairs", C.c_uint32),
+        ("n_manifold_jobs", C.c_uint32),
     ]
 
 

@@ -65,6 +65,8 @@ static int reserve_pairs(ncb_ctx* ctx, size_t cap) {
     CK(ctx->pair_algo.reserve(cap));
     CK(ctx->manifold_start.reserve(cap));
     CK(ctx->manifold_count.reserve(cap));
+    CK(ctx->epa_queue.reserve(26 * cap));
+    CK(ctx->cp_queue.reserve(10 * cap));
     return NCB_OK;
 }
 
@@ -135,6 +137,7 @@ void ncb_destroy(ncb_ctx* c) {
     c->cub_tmp.release(), c->leaf_lo.release(), c->leaf_hi.release(), c->nodes.release(), c->parent.release(), c->flags.release();
     c->pairs_raw.release(), c->pairs.release(), c->keys_raw.release(), c->pair_algo.release(), c->counters.release();
     c->contacts.release(), c->manifold_start.release(), c->manifold_count.release(), c->pair_index.release();
+    c->epa_queue.release(), c->cp_queue.release();
     if (c->timer.created)
         for (int i = 0; i <= StageTimer::MAX; ++i) cudaEventDestroy(c->timer.ev[i]);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -381,6 +384,10 @@ static void fill_counts(ncb_ctx* ctx, ncb_update_counts* counts) {
     counts->n_algo[NCB_ALGO_BALL_CONVEX] = c.key_hist[K_BALL_CUBOID] + c.key_hist[K_BALL_HULL];
     counts->n_algo[NCB_ALGO_CONVEX_CONVEX] = c.key_hist[K_CUBOID_CUBOID] + c.key_hist[K_CUBOID_HULL] + c.key_hist[K_HULL_HULL];
     counts->n_algo[NCB_ALGO_NONE] = c.key_hist[K_NONE];
+    for (int k = K_CUBOID_CUBOID; k <= K_HULL_HULL; ++k) {
+        counts->n_epa_pairs += c.epa_cursor[k] - c.key_start[k];
+        counts->n_manifold_jobs += c.cp_cursor[k] - c.key_start[k];
+    }
 }
 
 int ncb_generate_contacts(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* pairs, ncb_contact* out_contacts, uint32_t cap_contacts,

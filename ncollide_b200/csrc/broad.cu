@@ -424,6 +424,8 @@ __global__ void k_key_scan(DevCounters* cnt) {
         for (int k = 0; k < 16; ++k) {
             cnt->key_start[k] = acc;
             cnt->key_cursor[k] = acc;
+            cnt->epa_cursor[k] = acc;
+            cnt->cp_cursor[k] = acc;
             acc += cnt->key_hist[k];
         }
     }

@@ -611,25 +611,25 @@ __device__ __noinline__ void epa_compute_silhouette(EpaState& e, uint32_t point,
 
 // EPA::closest_points (epa3.rs:219-430).  false = None (also on capacity overflow, flagged in e.overflow).
 __device__ __noinline__ bool epa_closest_points(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2,
-                                                const Simplex& s, V3& out1, V3& out2, V3& out_n) {
+                                                int sdim, const CSOPoint* sv, V3& out1, V3& out2, V3& out_n) {
     const float eps_tol = NCB_EPS * 100.0f;
     const float gjk_eps_tol = NCB_EPS * 10.0f;
     e.nverts = e.nfaces = e.nheap = e.nsil = 0;
     e.overflow = false;
     e.panicked = false;
-    for (int i = 0; i < s.dim + 1; ++i) e.verts[e.nverts++] = s.v[i];
+    for (int i = 0; i < sdim + 1; ++i) e.verts[e.nverts++] = sv[i];
 #define NCB_EPA_PUSH(ID, ND)                 \
     {                                        \
         float nd__ = (ND);                   \
         if (nd__ > gjk_eps_tol) return false; \
         heap_push(e, (ID), nd__);            \
     }
-    if (s.dim == 0) {
+    if (sdim == 0) {
         out1 = v3(0.f, 0.f, 0.f);
         out2 = v3(0.f, 0.f, 0.f);
         out_n = v3(0.f, 1.f, 0.f);
         return true;
-    } else if (s.dim == 3) {
+    } else if (sdim == 3) {
         V3 dp1 = e.verts[1].point - e.verts[0].point;
         V3 dp2 = e.verts[2].point - e.verts[0].point;
         V3 dp3 = e.verts[3].point - e.verts[0].point;
@@ -648,7 +648,7 @@ __device__ __noinline__ bool epa_closest_points(EpaState& e, const Iso& m1, cons
         if (in3) NCB_EPA_PUSH(2, -dot(face_normal(e.faces[2]), e.verts[2].point));
         if (in4) NCB_EPA_PUSH(3, -dot(face_normal(e.faces[3]), e.verts[3].point));
     } else {
-        if (s.dim == 1) {
+        if (sdim == 1) {
             V3 dpt = e.verts[1].point - e.verts[0].point;
             V3 first, second;
             orthonormal_basis(dpt, first, second);
@@ -748,7 +748,7 @@ __device__ __noinline__ int contact_sm_sm(EpaState& e, const Iso& m1, const Supp
     simplex_init(s, cso_from_shapes(m1, g1, m2, g2, dir));
     int r = gjk_closest_points(m1, g1, m2, g2, prediction, s, p1, p2, dir_out);
     if (r != GJK_INTERSECTION) return r;
-    if (epa_closest_points(e, m1, g1, m2, g2, s, p1, p2, dir_out)) return GJK_CLOSEST_POINTS;
+    if (epa_closest_points(e, m1, g1, m2, g2, s.dim, s.v, p1, p2, dir_out)) return GJK_CLOSEST_POINTS;
     if (e.overflow) atomicAdd(epa_overflow, 1u);
     if (e.panicked) atomicAdd(ref_panics, 1u);
     dir_out = v3(1.f, 0.f, 0.f);

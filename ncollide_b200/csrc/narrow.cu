@@ -483,7 +483,7 @@ __device__ __noinline__ void hull_project_point_with_feature(EpaState& e, const 
         proj = p1 + point;
     } else {
         inside = true;
-        if (epa_closest_points(e, m, shape, id, origin, s, p1, p2, d))
+        if (epa_closest_points(e, m, shape, id, origin, s.dim, s.v, p1, p2, d))
             proj = p1 + point;
         else {
             if (e.overflow) atomicAdd(epa_overflow, 1u);
@@ -680,13 +680,10 @@ __device__ __noinline__ void clip(const Feature& self, const Feature& other, V3 
     }
 }
 
-__device__ __noinline__ void gen_convex_convex(EpaState& e, const Iso& ma, const Shape& a, const Iso& mb, const Shape& b, float linear,
-                                               float2 ang1, float2 ang2, Manifold& mf, Feature& m1, Feature& m2, uint32_t* epa_overflow,
-                                               uint32_t* ref_panics) {
-    Support ga = as_support(a), gb = as_support(b);
-    V3 p1, p2, dir;
-    int r = contact_sm_sm(e, ma, ga, mb, gb, linear, p1, p2, dir, epa_overflow, ref_panics);
-    if (r != GJK_CLOSEST_POINTS) return;
+// ConvexPolyhedronConvexPolyhedronManifoldGenerator::generate_contacts after the GJK/EPA result is known
+// (convex_polyhedron_convex_polyhedron_manifold_generator.rs:112-161).
+__device__ __noinline__ void convex_convex_manifold(const Iso& ma, const Shape& a, const Iso& mb, const Shape& b, float linear, float2 ang1,
+                                                    float2 ang2, V3 p1, V3 p2, V3 dir, Manifold& mf, Feature& m1, Feature& m2) {
     float depth = -dot(dir, p2 - p1);
     if (depth > 0.f) {
         support_face_toward(a, ma, dir, m1);
@@ -759,7 +756,158 @@ struct NarrowArgs {
     DevCounters* cnt;
     uint32_t cap_pairs;
     float2 one_degree_cs;  // cos / sin of (pi / 180) as f32, from the host libm (convex.rs:543)
+    uint32_t* epa_queue;   // EPA_REC_WORDS per record
+    uint32_t* cp_queue;    // CP_REC_WORDS per record
 };
+
+// ---- convex x convex in three compacted phases -------------------------------------------------------------------
+// One thread per pair through GJK + EPA + clipping makes a warp wait for its slowest lane (penetrating pairs cost
+// 10-100x a separated pair: measured 4.8 of 32 lanes active).  Instead:
+//   k_cc_gjk      all pairs of the key segment: GJK only; separated pairs finish here, penetrating pairs append their
+//                 simplex to the EPA queue, pairs with closest points append a record to the manifold queue;
+//   k_cc_epa      EPA over the compacted EPA queue, appends to the manifold queue;
+//   k_cc_manifold support features + clipping + manifold over the compacted manifold queue.
+// Queues live at [key_start[key], cursor[key]) of two arrays sized like the pair array; cursors are device counters.
+#define EPA_REC_WORDS 26
+#define CP_REC_WORDS 10
+
+NCB_HD uint32_t queue_append(uint32_t* cursor, bool want) {
+    // warp-aggregated slot allocation; all 32 lanes call it
+    unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return 0;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(m & ((1u << lane) - 1));
+}
+NCB_HD void cp_store(uint32_t* q, uint32_t slot, uint32_t p, V3 p1, V3 p2, V3 dir) {
+    float* r = reinterpret_cast<float*>(q + (size_t)slot * CP_REC_WORDS);
+    q[(size_t)slot * CP_REC_WORDS] = p;
+    r[1] = p1.x, r[2] = p1.y, r[3] = p1.z, r[4] = p2.x, r[5] = p2.y, r[6] = p2.z, r[7] = dir.x, r[8] = dir.y, r[9] = dir.z;
+}
+
+template <int KEY>
+__global__ void __launch_bounds__(128) k_cc_gjk(NarrowArgs A) {
+    uint32_t seg_begin = A.cnt->key_start[KEY];
+    uint32_t seg_end = seg_begin + A.cnt->key_hist[KEY];
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
+        uint32_t p = base + threadIdx.x;
+        bool valid = p < seg_end;
+        int r = GJK_NO_INTERSECTION;
+        V3 p1, p2, dir;
+        Simplex s;
+        if (valid) {
+            uint2 pr = __ldg(&A.pairs[p]);
+            uint32_t i1 = pr.x, i2 = pr.y;
+            uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
+            Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
+            float linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
+            Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+            Support ga = as_support(a), gb = as_support(b);
+            // contact_support_map_support_map_with_params, init_dir = None (fresh generator)
+            V3 d0;
+            if (!unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
+            simplex_init(s, cso_from_shapes(ma, ga, mb, gb, d0));
+            r = gjk_closest_points(ma, ga, mb, gb, linear, s, p1, p2, dir);
+            if (r == GJK_NO_INTERSECTION) {
+                uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
+                A.manifold_start[out_index] = 0;
+                A.manifold_count[out_index] = 0;
+            }
+        }
+        uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], valid && r == GJK_CLOSEST_POINTS);
+        if (valid && r == GJK_CLOSEST_POINTS) cp_store(A.cp_queue, slot, p, p1, p2, dir);
+        slot = queue_append(&A.cnt->epa_cursor[KEY], valid && r == GJK_INTERSECTION);
+        if (valid && r == GJK_INTERSECTION) {
+            uint32_t* q = A.epa_queue + (size_t)slot * EPA_REC_WORDS;
+            float* f = reinterpret_cast<float*>(q);
+            q[0] = p;
+            q[1] = (uint32_t)s.dim;
+            for (int i = 0; i < 4; ++i) {
+                f[2 + 6 * i + 0] = s.v[i].orig1.x, f[2 + 6 * i + 1] = s.v[i].orig1.y, f[2 + 6 * i + 2] = s.v[i].orig1.z;
+                f[2 + 6 * i + 3] = s.v[i].orig2.x, f[2 + 6 * i + 4] = s.v[i].orig2.y, f[2 + 6 * i + 5] = s.v[i].orig2.z;
+            }
+        }
+    }
+}
+
+template <int KEY>
+__global__ void __launch_bounds__(64) k_cc_epa(NarrowArgs A) {
+    uint32_t seg_begin = A.cnt->key_start[KEY];
+    uint32_t seg_end = A.cnt->epa_cursor[KEY];
+    uint32_t stride = gridDim.x * blockDim.x;
+    EpaState e;
+    for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
+        uint32_t w = base + threadIdx.x;
+        bool valid = w < seg_end;
+        bool ok = false;
+        uint32_t p = 0;
+        V3 p1, p2, n;
+        if (valid) {
+            const uint32_t* q = A.epa_queue + (size_t)w * EPA_REC_WORDS;
+            const float* f = reinterpret_cast<const float*>(q);
+            p = q[0];
+            int sdim = (int)q[1];
+            CSOPoint sv[4];
+            for (int i = 0; i < 4; ++i) {
+                sv[i].orig1 = v3(f[2 + 6 * i + 0], f[2 + 6 * i + 1], f[2 + 6 * i + 2]);
+                sv[i].orig2 = v3(f[2 + 6 * i + 3], f[2 + 6 * i + 4], f[2 + 6 * i + 5]);
+                sv[i].point = sv[i].orig1 - sv[i].orig2;  // bit-identical to the value GJK computed (CSOPoint::new)
+            }
+            uint2 pr = __ldg(&A.pairs[p]);
+            uint32_t i1 = pr.x, i2 = pr.y;
+            uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
+            Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
+            Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+            Support ga = as_support(a), gb = as_support(b);
+            ok = epa_closest_points(e, ma, ga, mb, gb, sdim, sv, p1, p2, n);
+            if (!ok) {
+                if (e.overflow) atomicAdd(&A.cnt->epa_overflow, 1u);
+                if (e.panicked) atomicAdd(&A.cnt->ref_panics, 1u);
+                uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
+                A.manifold_start[out_index] = 0;
+                A.manifold_count[out_index] = 0;
+            }
+        }
+        uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], valid && ok);
+        if (valid && ok) cp_store(A.cp_queue, slot, p, p1, p2, n);
+    }
+}
+
+template <int KEY>
+__global__ void __launch_bounds__(128) k_cc_manifold(NarrowArgs A) {
+    uint32_t seg_begin = A.cnt->key_start[KEY];
+    uint32_t seg_end = A.cnt->cp_cursor[KEY];
+    uint32_t stride = gridDim.x * blockDim.x;
+    Manifold mf;
+    for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
+        uint32_t w = base + threadIdx.x;
+        bool valid = w < seg_end;
+        mf.n = 0;
+        mf.deepest = 0;
+        uint32_t p = 0;
+        if (valid) {
+            const uint32_t* q = A.cp_queue + (size_t)w * CP_REC_WORDS;
+            const float* f = reinterpret_cast<const float*>(q);
+            p = q[0];
+            V3 p1 = v3(f[1], f[2], f[3]), p2 = v3(f[4], f[5], f[6]), dir = v3(f[7], f[8], f[9]);
+            uint2 pr = __ldg(&A.pairs[p]);
+            uint32_t i1 = pr.x, i2 = pr.y;
+            uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
+            Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
+            float linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
+            Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+            float2 ang1 = __ldg(&A.o.ang_cs[i1]), ang2 = __ldg(&A.o.ang_cs[i2]);
+            Feature f1, f2;
+            convex_convex_manifold(ma, a, mb, b, linear, ang1, ang2, p1, p2, dir, mf, f1, f2);
+        }
+        uint32_t out_index = valid ? (A.pair_index ? __ldg(&A.pair_index[p]) : p) : 0;
+        write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+    }
+}
 
 // One persistent kernel per key; the segment bounds are read from the device counters.
 template <int KEY>
@@ -821,12 +969,6 @@ __global__ void __launch_bounds__(128) k_narrow(NarrowArgs A) {
                 hull_project_point_with_feature(e, cp.hull, mcp, mball.t, inside, world2, f2, A.one_degree_cs, &A.cnt->epa_overflow,
                                                 &A.cnt->ref_panics);
                 gen_ball_convex_finish(mball.t, ball.radius, cp, inside, world2, f2, linear, flip, mf);
-            } else if (KEY == K_CUBOID_CUBOID || KEY == K_CUBOID_HULL || KEY == K_HULL_HULL) {
-                Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
-                float2 ang1 = __ldg(&A.o.ang_cs[i1]), ang2 = __ldg(&A.o.ang_cs[i2]);
-                EpaState e;
-                Feature f1, f2;
-                gen_convex_convex(e, ma, a, mb, b, linear, ang1, ang2, mf, f1, f2, &A.cnt->epa_overflow, &A.cnt->ref_panics);
             }
         }
         uint32_t out_index = valid ? (A.pair_index ? __ldg(&A.pair_index[p]) : p) : 0;
@@ -858,6 +1000,8 @@ cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pa
     A.manifold_count = c->manifold_count.p;
     A.cnt = c->counters.p;
     A.cap_pairs = cap_pairs;
+    A.epa_queue = c->epa_queue.p;
+    A.cp_queue = c->cp_queue.p;
     {
         float one_degree = (float)(3.14159265358979323846 / 180.0);
         A.one_degree_cs = make_float2(cosf(one_degree), sinf(one_degree));
@@ -875,12 +1019,18 @@ cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pa
     timer_mark(c, "narrow_ball_cuboid", 1);
     k_narrow<K_BALL_HULL><<<sm * 4, 128, 0, s>>>(A);
     timer_mark(c, "narrow_ball_hull", 1);
-    k_narrow<K_CUBOID_CUBOID><<<sm * 4, 128, 0, s>>>(A);
-    timer_mark(c, "narrow_cuboid_cuboid", 1);
-    k_narrow<K_CUBOID_HULL><<<sm * 4, 128, 0, s>>>(A);
-    timer_mark(c, "narrow_cuboid_hull", 1);
-    k_narrow<K_HULL_HULL><<<sm * 4, 128, 0, s>>>(A);
-    timer_mark(c, "narrow_hull_hull", 1);
+    k_cc_gjk<K_CUBOID_CUBOID><<<sm * 8, 128, 0, s>>>(A);
+    k_cc_gjk<K_CUBOID_HULL><<<sm * 8, 128, 0, s>>>(A);
+    k_cc_gjk<K_HULL_HULL><<<sm * 8, 128, 0, s>>>(A);
+    timer_mark(c, "cc_gjk", 3);
+    k_cc_epa<K_CUBOID_CUBOID><<<sm * 8, 64, 0, s>>>(A);
+    k_cc_epa<K_CUBOID_HULL><<<sm * 8, 64, 0, s>>>(A);
+    k_cc_epa<K_HULL_HULL><<<sm * 8, 64, 0, s>>>(A);
+    timer_mark(c, "cc_epa", 3);
+    k_cc_manifold<K_CUBOID_CUBOID><<<sm * 8, 128, 0, s>>>(A);
+    k_cc_manifold<K_CUBOID_HULL><<<sm * 8, 128, 0, s>>>(A);
+    k_cc_manifold<K_HULL_HULL><<<sm * 8, 128, 0, s>>>(A);
+    timer_mark(c, "cc_manifold", 3);
     return cudaGetLastError();
 }
 

@@ -59,6 +59,8 @@ struct DevCounters {
     uint32_t key_hist[16];     // pairs per PairKey
     uint32_t key_start[16];    // exclusive scan of key_hist
     uint32_t key_cursor[16];   // scatter cursors
+    uint32_t epa_cursor[16];   // per key: end of the EPA work queue (starts at key_start[key])
+    uint32_t cp_cursor[16];    // per key: end of the closest-points (manifold) work queue
     int bounds[6];             // ordered-int encoded min xyz / max xyz of AABB centres
 };
 
@@ -129,6 +131,8 @@ struct ncb_ctx {
     ncb::DevBuf<uint32_t> manifold_start;
     ncb::DevBuf<uint8_t> manifold_count;
     ncb::DevBuf<uint32_t> pair_index;
+    ncb::DevBuf<uint32_t> epa_queue;             // 26 words per record
+    ncb::DevBuf<uint32_t> cp_queue;              // 10 words per record
 
     ncb::DevCounters last_counters = {};
     uint32_t last_n_pairs = 0, last_n_contacts = 0;

@@ -138,6 +138,8 @@ class Context:
             "n_algo": {ALGO_NAMES[i]: c.n_algo[i] for i in range(6)},
             "epa_overflow": c.epa_overflow,
             "ref_panics": c.ref_panics,
+            "n_epa_pairs": c.n_epa_pairs,
+            "n_manifold_jobs": c.n_manifold_jobs,
         }
 
     def world_update_device(self, margin, q_begin=0, q_end=0xFFFFFFFF):
