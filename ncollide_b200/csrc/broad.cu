@@ -426,6 +426,7 @@ __global__ void k_key_scan(DevCounters* cnt) {
             cnt->key_cursor[k] = acc;
             cnt->epa_cursor[k] = acc;
             cnt->cp_cursor[k] = acc;
+            cnt->epa_fetch[k] = acc;
             acc += cnt->key_hist[k];
         }
     }

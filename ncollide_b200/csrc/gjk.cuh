@@ -17,7 +17,7 @@ namespace ncb {
 #define EPA_MAX_VERTS 48
 #define EPA_MAX_FACES 192
 #define EPA_MAX_HEAP 160
-#define EPA_MAX_STACK 160
+#define EPA_MAX_STACK 128
 
 struct HullView {
     uint32_t nv, nf;
@@ -459,118 +459,145 @@ __device__ __noinline__ int gjk_closest_points(const Iso& m1, const Support& g1,
 }
 
 // ---- EPA ----------------------------------------------------------------------------------------------------
-struct EpaFace {
-    uint16_t pts[3], adj[3];
-    float nx, ny, nz;
-    float bc[3];
-    uint32_t deleted;
-};
+// Per-thread polytope in local memory, split hot / cold so that the expansion loop touches as few bytes as possible:
+//   hot : vertex CSO points, packed face topology (3 vertex ids + deleted flag | 3 neighbour ids), face normals, heap
+//   cold: the original support points (orig1 / orig2) of each vertex, read once for the result
+// Barycentric coordinates of a face are NOT stored: they are recomputed (same inputs, same arithmetic, same bits) for
+// the one face the result is read from.
 struct EpaHeapItem {
     uint32_t id;
     float neg_dist;
 };
 struct EpaState {
-    CSOPoint verts[EPA_MAX_VERTS];
-    EpaFace faces[EPA_MAX_FACES];
-    EpaHeapItem heap[EPA_MAX_HEAP];
-    uint16_t sil_face[EPA_MAX_STACK];
-    uint8_t sil_opp[EPA_MAX_STACK];
-    uint16_t stk_face[EPA_MAX_STACK];
-    uint8_t stk_opp[EPA_MAX_STACK];
-    int nverts, nfaces, nheap, nsil;
+    V3 vpoint[EPA_MAX_VERTS];
+    uint32_t ftopo[EPA_MAX_FACES][2];  // [0] = pts0 | pts1 << 8 | pts2 << 16 | deleted << 24 ; [1] = adj0 | adj1 << 8 | adj2 << 16
+    V3 fnormal[EPA_MAX_FACES];
+    float hdist[EPA_MAX_HEAP];
+    uint8_t hid[EPA_MAX_HEAP];
+    uint8_t sil_face[EPA_MAX_STACK], sil_opp[EPA_MAX_STACK];
+    uint8_t stk_face[EPA_MAX_STACK], stk_opp[EPA_MAX_STACK];
+    V3 vorig1[EPA_MAX_VERTS], vorig2[EPA_MAX_VERTS];
+    int nverts, nfaces, nheap, nsil, niter;
+    float max_dist;
+    EpaHeapItem best_face_id;
     bool overflow, panicked;
 };
+static_assert(EPA_MAX_FACES <= 255 && EPA_MAX_VERTS <= 255, "ids are packed in 8 bits");
+
+NCB_HD uint32_t f_pt(const EpaState& e, uint32_t f, uint32_t k) { return (e.ftopo[f][0] >> (8 * k)) & 0xffu; }
+NCB_HD uint32_t f_adj(const EpaState& e, uint32_t f, uint32_t k) { return (e.ftopo[f][1] >> (8 * k)) & 0xffu; }
+NCB_HD bool f_deleted(const EpaState& e, uint32_t f) { return (e.ftopo[f][0] >> 24) != 0; }
+NCB_HD void f_set_deleted(EpaState& e, uint32_t f) { e.ftopo[f][0] |= 0x01000000u; }
+NCB_HD void f_set_adj(EpaState& e, uint32_t f, uint32_t k, uint32_t v) {
+    e.ftopo[f][1] = (e.ftopo[f][1] & ~(0xffu << (8 * k))) | (v << (8 * k));
+}
+NCB_HD void epa_push_vertex(EpaState& e, const CSOPoint& c) {
+    e.vpoint[e.nverts] = c.point;
+    e.vorig1[e.nverts] = c.orig1;
+    e.vorig2[e.nverts] = c.orig2;
+    e.nverts++;
+}
 
 // Rust std BinaryHeap<FaceId>: `<=` comes from partial_cmp on neg_dist.
 NCB_HD void heap_sift_up(EpaState& e, int start, int pos) {
-    EpaHeapItem elt = e.heap[pos];
+    float ed = e.hdist[pos];
+    uint8_t ei = e.hid[pos];
     while (pos > start) {
         int parent = (pos - 1) / 2;
-        if (elt.neg_dist <= e.heap[parent].neg_dist) break;
-        e.heap[pos] = e.heap[parent];
+        if (ed <= e.hdist[parent]) break;
+        e.hdist[pos] = e.hdist[parent];
+        e.hid[pos] = e.hid[parent];
         pos = parent;
     }
-    e.heap[pos] = elt;
+    e.hdist[pos] = ed;
+    e.hid[pos] = ei;
 }
 NCB_HD void heap_push(EpaState& e, uint32_t id, float nd) {
     if (e.nheap >= EPA_MAX_HEAP) {
         e.overflow = true;
         return;
     }
-    e.heap[e.nheap].id = id;
-    e.heap[e.nheap].neg_dist = nd;
+    e.hid[e.nheap] = (uint8_t)id;
+    e.hdist[e.nheap] = nd;
     e.nheap++;
     heap_sift_up(e, 0, e.nheap - 1);
 }
 NCB_HD bool heap_pop(EpaState& e, EpaHeapItem& out) {
     if (e.nheap == 0) return false;
-    EpaHeapItem item = e.heap[--e.nheap];
+    --e.nheap;
+    float item_d = e.hdist[e.nheap];
+    uint8_t item_i = e.hid[e.nheap];
     if (e.nheap > 0) {
-        EpaHeapItem t = e.heap[0];
-        e.heap[0] = item;
-        item = t;
+        float td = e.hdist[0];
+        uint8_t ti = e.hid[0];
+        // swap(item, data[0]); sift_down_to_bottom(0)
         int end = e.nheap, pos = 0, child = 1;
-        EpaHeapItem elt = e.heap[0];
+        float ed = item_d;
+        uint8_t ei = item_i;
+        item_d = td;
+        item_i = ti;
         while (end >= 2 && child <= end - 2) {
-            if (e.heap[child].neg_dist <= e.heap[child + 1].neg_dist) child += 1;
-            e.heap[pos] = e.heap[child];
+            if (e.hdist[child] <= e.hdist[child + 1]) child += 1;
+            e.hdist[pos] = e.hdist[child];
+            e.hid[pos] = e.hid[child];
             pos = child;
             child = 2 * pos + 1;
         }
         if (child == end - 1) {
-            e.heap[pos] = e.heap[child];
+            e.hdist[pos] = e.hdist[child];
+            e.hid[pos] = e.hid[child];
             pos = child;
         }
-        e.heap[pos] = elt;
+        e.hdist[pos] = ed;
+        e.hid[pos] = ei;
         heap_sift_up(e, 0, pos);
     }
-    out = item;
+    out.id = item_i;
+    out.neg_dist = item_d;
     return true;
 }
 
-NCB_HD V3 face_normal(const EpaFace& f) { return v3(f.nx, f.ny, f.nz); }
-
-// Face::new (epa3.rs:93-114); returns false on capacity overflow.
+// Face::new (epa3.rs:93-114): normal + "projection of the origin lies inside the face".  false on overflow.
 __device__ __noinline__ bool epa_face_new(EpaState& e, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t a0, uint32_t a1, uint32_t a2,
                                           bool& proj_inside) {
     if (e.nfaces >= EPA_MAX_FACES) {
         e.overflow = true;
         return false;
     }
-    V3 A = e.verts[p0].point, B = e.verts[p1].point, C = e.verts[p2].point;
+    V3 A = e.vpoint[p0], B = e.vpoint[p1], C = e.vpoint[p2];
     Loc loc;
     proj_triangle(A, B, C, v3(0.f, 0.f, 0.f), loc);
-    EpaFace& f = e.faces[e.nfaces++];
-    f.pts[0] = (uint16_t)p0, f.pts[1] = (uint16_t)p1, f.pts[2] = (uint16_t)p2;
-    f.adj[0] = (uint16_t)a0, f.adj[1] = (uint16_t)a1, f.adj[2] = (uint16_t)a2;
+    int f = e.nfaces++;
+    e.ftopo[f][0] = p0 | (p1 << 8) | (p2 << 16);
+    e.ftopo[f][1] = a0 | (a1 << 8) | (a2 << 16);
     V3 n;
     if (!unit_try_new(cross(B - A, C - A), NCB_EPS, n)) n = v3(0.f, 0.f, 0.f);  // utils::ccw_face_normal
-    f.nx = n.x, f.ny = n.y, f.nz = n.z;
-    f.deleted = 0;
-    if (loc.kind == LOC_FACE) {
-        f.bc[0] = loc.b0, f.bc[1] = loc.b1, f.bc[2] = loc.b2;
-        proj_inside = true;
-    } else {
-        f.bc[0] = f.bc[1] = f.bc[2] = 0.f;
-        proj_inside = false;
-    }
+    e.fnormal[f] = n;
+    proj_inside = loc.kind == LOC_FACE;
     return true;
 }
-NCB_HD void epa_face_closest_points(const EpaState& e, const EpaFace& f, V3& p1, V3& p2) {
-    p1 = e.verts[f.pts[0]].orig1 * f.bc[0] + e.verts[f.pts[1]].orig1 * f.bc[1] + e.verts[f.pts[2]].orig1 * f.bc[2];
-    p2 = e.verts[f.pts[0]].orig2 * f.bc[0] + e.verts[f.pts[1]].orig2 * f.bc[1] + e.verts[f.pts[2]].orig2 * f.bc[2];
+// Face::closest_points (epa3.rs:116-126) with the barycentric coordinates recomputed as Face::new computed them.
+__device__ __noinline__ void epa_face_closest_points(const EpaState& e, uint32_t f, V3& p1, V3& p2) {
+    uint32_t i0 = f_pt(e, f, 0), i1 = f_pt(e, f, 1), i2 = f_pt(e, f, 2);
+    Loc loc;
+    proj_triangle(e.vpoint[i0], e.vpoint[i1], e.vpoint[i2], v3(0.f, 0.f, 0.f), loc);
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    if (loc.kind == LOC_FACE) b0 = loc.b0, b1 = loc.b1, b2 = loc.b2;
+    p1 = e.vorig1[i0] * b0 + e.vorig1[i1] * b1 + e.vorig1[i2] * b2;
+    p2 = e.vorig2[i0] * b0 + e.vorig2[i1] * b1 + e.vorig2[i2] * b2;
 }
-NCB_HD uint32_t epa_next_ccw(EpaState& e, const EpaFace& f, uint32_t id) {
-    if (f.pts[0] == id) return 1;
-    if (f.pts[1] == id) return 2;
-    if (f.pts[2] != id) e.panicked = true;  // assert_eq! in the reference
+NCB_HD uint32_t epa_next_ccw(EpaState& e, uint32_t f, uint32_t id) {
+    uint32_t t = e.ftopo[f][0];
+    if ((t & 0xffu) == id) return 1;
+    if (((t >> 8) & 0xffu) == id) return 2;
+    if (((t >> 16) & 0xffu) != id) e.panicked = true;  // assert_eq! in the reference
     return 0;
 }
-NCB_HD bool epa_can_be_seen_by(const EpaState& e, const EpaFace& f, uint32_t point, uint32_t opp) {
-    V3 p0 = e.verts[f.pts[opp]].point;
-    V3 pt = e.verts[point].point;
-    if (dot(pt - p0, face_normal(f)) >= -(NCB_EPS * 10.0f)) return true;
-    V3 p1 = e.verts[f.pts[(opp + 1) % 3]].point, p2 = e.verts[f.pts[(opp + 2) % 3]].point;
+NCB_HD bool epa_can_be_seen_by(const EpaState& e, uint32_t f, uint32_t point, uint32_t opp) {
+    V3 p0 = e.vpoint[f_pt(e, f, opp)];
+    V3 pt = e.vpoint[point];
+    if (dot(pt - p0, e.fnormal[f]) >= -(NCB_EPS * 10.0f)) return true;
+    V3 p1 = e.vpoint[f_pt(e, f, (opp + 1) % 3)], p2 = e.vpoint[f_pt(e, f, (opp + 2) % 3)];
     // utils::is_affinely_dependent_triangle(p1, p2, pt)
     V3 p1p2 = p2 - p1, p1p3 = pt - p1;
     float eps_tol = NCB_EPS * 100.0f;
@@ -579,80 +606,83 @@ NCB_HD bool epa_can_be_seen_by(const EpaState& e, const EpaFace& f, uint32_t poi
 // compute_silhouette (epa3.rs:432-454): the recursion becomes a LIFO of (face, opp) visits in the same order.
 __device__ __noinline__ void epa_compute_silhouette(EpaState& e, uint32_t point, uint32_t id0, uint32_t opp0) {
     int sp = 0;
-    e.stk_face[sp] = (uint16_t)id0, e.stk_opp[sp] = (uint8_t)opp0, sp++;
+    e.stk_face[sp] = (uint8_t)id0, e.stk_opp[sp] = (uint8_t)opp0, sp++;
     while (sp > 0) {
         sp--;
         uint32_t id = e.stk_face[sp], opp = e.stk_opp[sp];
-        EpaFace& f = e.faces[id];
-        if (f.deleted) continue;
-        if (!epa_can_be_seen_by(e, f, point, opp)) {
+        if (f_deleted(e, id)) continue;
+        if (!epa_can_be_seen_by(e, id, point, opp)) {
             if (e.nsil >= EPA_MAX_STACK) {
                 e.overflow = true;
                 return;
             }
-            e.sil_face[e.nsil] = (uint16_t)id, e.sil_opp[e.nsil] = (uint8_t)opp, e.nsil++;
+            e.sil_face[e.nsil] = (uint8_t)id, e.sil_opp[e.nsil] = (uint8_t)opp, e.nsil++;
         } else {
-            f.deleted = 1;
+            f_set_deleted(e, id);
             uint32_t adj_pt_id1 = (opp + 2) % 3, adj_pt_id2 = opp;
-            uint32_t adj1 = f.adj[adj_pt_id1], adj2 = f.adj[adj_pt_id2];
-            uint32_t o1 = epa_next_ccw(e, e.faces[adj1], f.pts[adj_pt_id1]);
-            uint32_t o2 = epa_next_ccw(e, e.faces[adj2], f.pts[adj_pt_id2]);
+            uint32_t adj1 = f_adj(e, id, adj_pt_id1), adj2 = f_adj(e, id, adj_pt_id2);
+            uint32_t o1 = epa_next_ccw(e, adj1, f_pt(e, id, adj_pt_id1));
+            uint32_t o2 = epa_next_ccw(e, adj2, f_pt(e, id, adj_pt_id2));
             if (e.panicked) return;
             if (sp + 2 > EPA_MAX_STACK) {
                 e.overflow = true;
                 return;
             }
             // visit adj1 first, then adj2
-            e.stk_face[sp] = (uint16_t)adj2, e.stk_opp[sp] = (uint8_t)o2, sp++;
-            e.stk_face[sp] = (uint16_t)adj1, e.stk_opp[sp] = (uint8_t)o1, sp++;
+            e.stk_face[sp] = (uint8_t)adj2, e.stk_opp[sp] = (uint8_t)o2, sp++;
+            e.stk_face[sp] = (uint8_t)adj1, e.stk_opp[sp] = (uint8_t)o1, sp++;
         }
     }
 }
 
-// EPA::closest_points (epa3.rs:219-430).  false = None (also on capacity overflow, flagged in e.overflow).
-__device__ __noinline__ bool epa_closest_points(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2,
-                                                int sdim, const CSOPoint* sv, V3& out1, V3& out2, V3& out_n) {
-    const float eps_tol = NCB_EPS * 100.0f;
-    const float gjk_eps_tol = NCB_EPS * 10.0f;
+enum { EPA_CONTINUE = 0, EPA_DONE_OK = 1, EPA_DONE_FAIL = 2 };
+
+#define NCB_EPA_PUSH(ID, ND)                              \
+    {                                                     \
+        float nd__ = (ND);                                \
+        if (nd__ > NCB_EPS * 10.0f) return EPA_DONE_FAIL; \
+        heap_push(e, (ID), nd__);                         \
+    }
+
+// EPA::closest_points, part 1 (epa3.rs:219-328): initial polytope from the GJK simplex.
+__device__ __noinline__ int epa_init(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, int sdim,
+                                     const CSOPoint* sv, V3& out1, V3& out2, V3& out_n) {
     e.nverts = e.nfaces = e.nheap = e.nsil = 0;
+    e.niter = 0;
     e.overflow = false;
     e.panicked = false;
-    for (int i = 0; i < sdim + 1; ++i) e.verts[e.nverts++] = sv[i];
-#define NCB_EPA_PUSH(ID, ND)                 \
-    {                                        \
-        float nd__ = (ND);                   \
-        if (nd__ > gjk_eps_tol) return false; \
-        heap_push(e, (ID), nd__);            \
-    }
+    for (int i = 0; i < sdim + 1; ++i) epa_push_vertex(e, sv[i]);
     if (sdim == 0) {
         out1 = v3(0.f, 0.f, 0.f);
         out2 = v3(0.f, 0.f, 0.f);
         out_n = v3(0.f, 1.f, 0.f);
-        return true;
+        return EPA_DONE_OK;
     } else if (sdim == 3) {
-        V3 dp1 = e.verts[1].point - e.verts[0].point;
-        V3 dp2 = e.verts[2].point - e.verts[0].point;
-        V3 dp3 = e.verts[3].point - e.verts[0].point;
+        V3 dp1 = e.vpoint[1] - e.vpoint[0];
+        V3 dp2 = e.vpoint[2] - e.vpoint[0];
+        V3 dp3 = e.vpoint[3] - e.vpoint[0];
         if (dot(cross(dp1, dp2), dp3) > 0.f) {
-            CSOPoint t = e.verts[1];
-            e.verts[1] = e.verts[2];
-            e.verts[2] = t;
+            V3 t = e.vpoint[1];
+            e.vpoint[1] = e.vpoint[2];
+            e.vpoint[2] = t;
+            t = e.vorig1[1], e.vorig1[1] = e.vorig1[2], e.vorig1[2] = t;
+            t = e.vorig2[1], e.vorig2[1] = e.vorig2[2], e.vorig2[2] = t;
         }
         bool in1, in2, in3, in4;
         epa_face_new(e, 0, 1, 2, 3, 1, 2, in1);
         epa_face_new(e, 1, 3, 2, 3, 2, 0, in2);
         epa_face_new(e, 0, 2, 3, 0, 1, 3, in3);
         epa_face_new(e, 0, 3, 1, 2, 1, 0, in4);
-        if (in1) NCB_EPA_PUSH(0, -dot(face_normal(e.faces[0]), e.verts[0].point));
-        if (in2) NCB_EPA_PUSH(1, -dot(face_normal(e.faces[1]), e.verts[1].point));
-        if (in3) NCB_EPA_PUSH(2, -dot(face_normal(e.faces[2]), e.verts[2].point));
-        if (in4) NCB_EPA_PUSH(3, -dot(face_normal(e.faces[3]), e.verts[3].point));
+        if (in1) NCB_EPA_PUSH(0, -dot(e.fnormal[0], e.vpoint[0]));
+        if (in2) NCB_EPA_PUSH(1, -dot(e.fnormal[1], e.vpoint[1]));
+        if (in3) NCB_EPA_PUSH(2, -dot(e.fnormal[2], e.vpoint[2]));
+        if (in4) NCB_EPA_PUSH(3, -dot(e.fnormal[3], e.vpoint[3]));
     } else {
         if (sdim == 1) {
-            V3 dpt = e.verts[1].point - e.verts[0].point;
+            V3 dpt = e.vpoint[1] - e.vpoint[0];
             V3 first, second;
             orthonormal_basis(dpt, first, second);
-            e.verts[e.nverts++] = cso_from_shapes(m1, g1, m2, g2, first);
+            epa_push_vertex(e, cso_from_shapes(m1, g1, m2, g2, first));
         }
         bool in;
         epa_face_new(e, 0, 1, 2, 1, 1, 1, in);
@@ -660,82 +690,103 @@ __device__ __noinline__ bool epa_closest_points(EpaState& e, const Iso& m1, cons
         NCB_EPA_PUSH(0, 0.f);
         NCB_EPA_PUSH(1, 0.f);
     }
-    int niter = 0;
-    float max_dist = NCB_FMAX;
+    e.max_dist = NCB_FMAX;
     if (e.nheap == 0) {  // heap.peek().unwrap() panics in the reference
         e.panicked = true;
-        return false;
+        return EPA_DONE_FAIL;
     }
-    EpaHeapItem best_face_id = e.heap[0];
+    e.best_face_id.id = e.hid[0];
+    e.best_face_id.neg_dist = e.hdist[0];
+    return EPA_CONTINUE;
+}
+
+// EPA::closest_points, part 2: ONE turn of `while let Some(face_id) = self.heap.pop()` (epa3.rs:330-425).
+__device__ __noinline__ int epa_step(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, V3& out1, V3& out2,
+                                     V3& out_n) {
+    const float eps_tol = NCB_EPS * 100.0f;
     EpaHeapItem face_id;
-    while (heap_pop(e, face_id)) {
-        EpaFace face = e.faces[face_id.id];
-        if (face.deleted) continue;
-        V3 fnorm = face_normal(face);
-        if (e.nverts >= EPA_MAX_VERTS) {
-            e.overflow = true;
-            return false;
-        }
-        CSOPoint cso = cso_from_shapes(m1, g1, m2, g2, fnorm);
-        uint32_t support_point_id = (uint32_t)e.nverts;
-        e.verts[e.nverts++] = cso;
-        float candidate_max_dist = dot(cso.point, fnorm);
-        if (candidate_max_dist < max_dist) {
-            best_face_id = face_id;
-            max_dist = candidate_max_dist;
-        }
-        float curr_dist = -face_id.neg_dist;
-        if (max_dist - curr_dist < eps_tol) {
-            const EpaFace& bf = e.faces[best_face_id.id];
-            epa_face_closest_points(e, bf, out1, out2);
-            out_n = face_normal(bf);
-            return true;
-        }
-        e.faces[face_id.id].deleted = 1;
-        uint32_t o1 = epa_next_ccw(e, e.faces[face.adj[0]], face.pts[0]);
-        uint32_t o2 = epa_next_ccw(e, e.faces[face.adj[1]], face.pts[1]);
-        uint32_t o3 = epa_next_ccw(e, e.faces[face.adj[2]], face.pts[2]);
-        if (e.panicked) return false;
-        epa_compute_silhouette(e, support_point_id, face.adj[0], o1);
-        epa_compute_silhouette(e, support_point_id, face.adj[1], o2);
-        epa_compute_silhouette(e, support_point_id, face.adj[2], o3);
-        if (e.panicked || e.overflow) return false;
-        uint32_t first_new_face_id = (uint32_t)e.nfaces;
-        if (e.nsil == 0) return false;
-        for (int k = 0; k < e.nsil; ++k) {
-            uint32_t efid = e.sil_face[k], eopp = e.sil_opp[k];
-            if (!e.faces[efid].deleted) {
-                uint32_t new_face_id = (uint32_t)e.nfaces;
-                uint32_t pt_id1 = e.faces[efid].pts[(eopp + 2) % 3];
-                uint32_t pt_id2 = e.faces[efid].pts[(eopp + 1) % 3];
-                bool inside;
-                if (!epa_face_new(e, pt_id1, pt_id2, support_point_id, efid, new_face_id + 1, new_face_id - 1, inside)) return false;
-                e.faces[efid].adj[(eopp + 1) % 3] = (uint16_t)new_face_id;
-                if (inside) {
-                    V3 pt = e.verts[e.faces[new_face_id].pts[0]].point;
-                    float dist = dot(face_normal(e.faces[new_face_id]), pt);
-                    if (dist < curr_dist) {
-                        epa_face_closest_points(e, face, out1, out2);
-                        out_n = fnorm;
-                        return true;
-                    }
-                    NCB_EPA_PUSH(new_face_id, -dist);
-                    if (e.overflow) return false;
+    if (!heap_pop(e, face_id)) {  // heap exhausted: the best face so far (epa3.rs:427-429)
+        epa_face_closest_points(e, e.best_face_id.id, out1, out2);
+        out_n = e.fnormal[e.best_face_id.id];
+        return EPA_DONE_OK;
+    }
+    uint32_t fid = face_id.id;
+    if (f_deleted(e, fid)) return EPA_CONTINUE;
+    // snapshot of the popped face (the reference clones it before the polytope is edited)
+    uint32_t fp0 = f_pt(e, fid, 0), fp1 = f_pt(e, fid, 1), fp2 = f_pt(e, fid, 2);
+    uint32_t fa0 = f_adj(e, fid, 0), fa1 = f_adj(e, fid, 1), fa2 = f_adj(e, fid, 2);
+    V3 fnorm = e.fnormal[fid];
+    if (e.nverts >= EPA_MAX_VERTS) {
+        e.overflow = true;
+        return EPA_DONE_FAIL;
+    }
+    CSOPoint cso = cso_from_shapes(m1, g1, m2, g2, fnorm);
+    uint32_t support_point_id = (uint32_t)e.nverts;
+    epa_push_vertex(e, cso);
+    float candidate_max_dist = dot(cso.point, fnorm);
+    if (candidate_max_dist < e.max_dist) {
+        e.best_face_id = face_id;
+        e.max_dist = candidate_max_dist;
+    }
+    float curr_dist = -face_id.neg_dist;
+    if (e.max_dist - curr_dist < eps_tol) {
+        epa_face_closest_points(e, e.best_face_id.id, out1, out2);
+        out_n = e.fnormal[e.best_face_id.id];
+        return EPA_DONE_OK;
+    }
+    f_set_deleted(e, fid);
+    uint32_t o1 = epa_next_ccw(e, fa0, fp0);
+    uint32_t o2 = epa_next_ccw(e, fa1, fp1);
+    uint32_t o3 = epa_next_ccw(e, fa2, fp2);
+    if (e.panicked) return EPA_DONE_FAIL;
+    epa_compute_silhouette(e, support_point_id, fa0, o1);
+    epa_compute_silhouette(e, support_point_id, fa1, o2);
+    epa_compute_silhouette(e, support_point_id, fa2, o3);
+    if (e.panicked || e.overflow) return EPA_DONE_FAIL;
+    uint32_t first_new_face_id = (uint32_t)e.nfaces;
+    if (e.nsil == 0) return EPA_DONE_FAIL;
+    for (int k = 0; k < e.nsil; ++k) {
+        uint32_t efid = e.sil_face[k], eopp = e.sil_opp[k];
+        if (!f_deleted(e, efid)) {
+            uint32_t new_face_id = (uint32_t)e.nfaces;
+            uint32_t pt_id1 = f_pt(e, efid, (eopp + 2) % 3);
+            uint32_t pt_id2 = f_pt(e, efid, (eopp + 1) % 3);
+            bool inside;
+            // adj = [edge.face_id, new_face_id + 1, new_face_id - 1] (the last two are patched below for the ends)
+            if (!epa_face_new(e, pt_id1, pt_id2, support_point_id, efid, (new_face_id + 1) & 0xffu, (new_face_id - 1) & 0xffu, inside))
+                return EPA_DONE_FAIL;
+            f_set_adj(e, efid, (eopp + 1) % 3, new_face_id);
+            if (inside) {
+                V3 pt = e.vpoint[f_pt(e, new_face_id, 0)];
+                float dist = dot(e.fnormal[new_face_id], pt);
+                if (dist < curr_dist) {
+                    // the popped face as it was when cloned (epa3.rs:393-398)
+                    // its topology words are unchanged except the deleted flag, which closest_points does not read
+                    epa_face_closest_points(e, fid, out1, out2);
+                    out_n = fnorm;
+                    return EPA_DONE_OK;
                 }
+                NCB_EPA_PUSH(new_face_id, -dist);
+                if (e.overflow) return EPA_DONE_FAIL;
             }
         }
-        if (first_new_face_id == (uint32_t)e.nfaces) return false;
-        e.faces[first_new_face_id].adj[2] = (uint16_t)(e.nfaces - 1);
-        e.faces[e.nfaces - 1].adj[1] = (uint16_t)first_new_face_id;
-        e.nsil = 0;
-        niter += 1;
-        if (niter > 10000) return false;
     }
+    if (first_new_face_id == (uint32_t)e.nfaces) return EPA_DONE_FAIL;
+    f_set_adj(e, first_new_face_id, 2, (uint32_t)(e.nfaces - 1));
+    f_set_adj(e, (uint32_t)(e.nfaces - 1), 1, first_new_face_id);
+    e.nsil = 0;
+    e.niter += 1;
+    if (e.niter > 10000) return EPA_DONE_FAIL;
+    return EPA_CONTINUE;
+}
 #undef NCB_EPA_PUSH
-    const EpaFace& bf = e.faces[best_face_id.id];
-    epa_face_closest_points(e, bf, out1, out2);
-    out_n = face_normal(bf);
-    return true;
+
+// EPA::closest_points (epa3.rs:219-430).  false = None (also on capacity overflow, flagged in e.overflow).
+__device__ __noinline__ bool epa_closest_points(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2,
+                                                int sdim, const CSOPoint* sv, V3& out1, V3& out2, V3& out_n) {
+    int st = epa_init(e, m1, g1, m2, g2, sdim, sv, out1, out2, out_n);
+    while (st == EPA_CONTINUE) st = epa_step(e, m1, g1, m2, g2, out1, out2, out_n);
+    return st == EPA_DONE_OK;
 }
 
 // contact_support_map_support_map_with_params (init_dir = None: fresh generator).

@@ -15,6 +15,7 @@
 //   ContactManifold::push (DistanceBased 0.02) query/contact/contact_manifold.rs:165-236
 #include <cooperative_groups.h>
 #include <cmath>
+#include <cstdlib>
 #include "gjk.cuh"
 #include "ncb_internal.h"
 #include "vec.cuh"
@@ -834,46 +835,71 @@ __global__ void __launch_bounds__(128) k_cc_gjk(NarrowArgs A) {
     }
 }
 
+// EPA over the compacted queue.  Lanes are independent workers: an idle lane fetches the next queue entry and builds
+// its initial polytope; a busy lane executes ONE expansion step per turn of the outer loop.  All busy lanes therefore
+// run the same code (one step) regardless of how many steps their pair needs; refills are batched (>= REFILL_MIN idle
+// lanes) so that the initialisation path is not paid on every turn.
+#define EPA_REFILL_MIN 8
 template <int KEY>
 __global__ void __launch_bounds__(64) k_cc_epa(NarrowArgs A) {
-    uint32_t seg_begin = A.cnt->key_start[KEY];
-    uint32_t seg_end = A.cnt->epa_cursor[KEY];
-    uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t seg_end = A.cnt->epa_cursor[KEY];
+    uint32_t* fetch = &A.cnt->epa_fetch[KEY];
+    const int lane = threadIdx.x & 31;
     EpaState e;
-    for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
-        uint32_t w = base + threadIdx.x;
-        bool valid = w < seg_end;
-        bool ok = false;
-        uint32_t p = 0;
-        V3 p1, p2, n;
-        if (valid) {
-            const uint32_t* q = A.epa_queue + (size_t)w * EPA_REC_WORDS;
-            const float* f = reinterpret_cast<const float*>(q);
-            p = q[0];
-            int sdim = (int)q[1];
-            CSOPoint sv[4];
-            for (int i = 0; i < 4; ++i) {
-                sv[i].orig1 = v3(f[2 + 6 * i + 0], f[2 + 6 * i + 1], f[2 + 6 * i + 2]);
-                sv[i].orig2 = v3(f[2 + 6 * i + 3], f[2 + 6 * i + 4], f[2 + 6 * i + 5]);
-                sv[i].point = sv[i].orig1 - sv[i].orig2;  // bit-identical to the value GJK computed (CSOPoint::new)
+    bool active = false, exhausted = false;
+    uint32_t p = 0;
+    Iso ma, mb;
+    Support ga, gb;
+    V3 p1, p2, n;
+    for (;;) {
+        int status = EPA_CONTINUE;
+        unsigned idle = __ballot_sync(0xffffffffu, !active);
+        bool refill = !exhausted && (idle == 0xffffffffu || __popc(idle) >= EPA_REFILL_MIN);
+        if (refill) {  // warp-uniform
+            uint32_t base = 0;
+            int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + __popc(idle) >= seg_end) exhausted = true;  // nothing left after this batch
+            if (!active) {
+                uint32_t w = base + __popc(idle & ((1u << lane) - 1));
+                if (w < seg_end) {
+                    const uint32_t* q = A.epa_queue + (size_t)w * EPA_REC_WORDS;
+                    const float* f = reinterpret_cast<const float*>(q);
+                    p = q[0];
+                    int sdim = (int)q[1];
+                    CSOPoint sv[4];
+                    for (int i = 0; i < 4; ++i) {
+                        sv[i].orig1 = v3(f[2 + 6 * i + 0], f[2 + 6 * i + 1], f[2 + 6 * i + 2]);
+                        sv[i].orig2 = v3(f[2 + 6 * i + 3], f[2 + 6 * i + 4], f[2 + 6 * i + 5]);
+                        sv[i].point = sv[i].orig1 - sv[i].orig2;  // bit-identical to the value GJK computed (CSOPoint::new)
+                    }
+                    uint2 pr = __ldg(&A.pairs[p]);
+                    uint32_t i1 = pr.x, i2 = pr.y;
+                    uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
+                    ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
+                    Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+                    ga = as_support(a), gb = as_support(b);
+                    active = true;
+                    status = epa_init(e, ma, ga, mb, gb, sdim, sv, p1, p2, n);
+                }
             }
-            uint2 pr = __ldg(&A.pairs[p]);
-            uint32_t i1 = pr.x, i2 = pr.y;
-            uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
-            Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
-            Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
-            Support ga = as_support(a), gb = as_support(b);
-            ok = epa_closest_points(e, ma, ga, mb, gb, sdim, sv, p1, p2, n);
-            if (!ok) {
-                if (e.overflow) atomicAdd(&A.cnt->epa_overflow, 1u);
-                if (e.panicked) atomicAdd(&A.cnt->ref_panics, 1u);
-                uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
-                A.manifold_start[out_index] = 0;
-                A.manifold_count[out_index] = 0;
-            }
+        } else if (active) {
+            status = epa_step(e, ma, ga, mb, gb, p1, p2, n);
         }
-        uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], valid && ok);
-        if (valid && ok) cp_store(A.cp_queue, slot, p, p1, p2, n);
+        bool ok = active && status == EPA_DONE_OK;
+        bool fail = active && status == EPA_DONE_FAIL;
+        uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], ok);
+        if (ok) cp_store(A.cp_queue, slot, p, p1, p2, n);
+        if (fail) {
+            if (e.overflow) atomicAdd(&A.cnt->epa_overflow, 1u);
+            if (e.panicked) atomicAdd(&A.cnt->ref_panics, 1u);
+            uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
+            A.manifold_start[out_index] = 0;
+            A.manifold_count[out_index] = 0;
+        }
+        if (ok || fail) active = false;
+        if (exhausted && __all_sync(0xffffffffu, !active)) break;
     }
 }
 
@@ -1008,6 +1034,10 @@ cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pa
     }
     cudaStream_t s = c->stream;
     int sm = c->sm_count;
+    // tuning knobs (CTAs per SM of the persistent kernels); defaults chosen from ncu runs, see profiles/
+    static int gjk_bpsm = getenv("NCB_GJK_BPSM") ? atoi(getenv("NCB_GJK_BPSM")) : 8;
+    static int epa_bpsm = getenv("NCB_EPA_BPSM") ? atoi(getenv("NCB_EPA_BPSM")) : 8;
+    static int man_bpsm = getenv("NCB_MAN_BPSM") ? atoi(getenv("NCB_MAN_BPSM")) : 8;
     k_narrow<K_BALL_BALL><<<sm * 8, 128, 0, s>>>(A);
     timer_mark(c, "narrow_ball_ball", 1);
     k_narrow<K_PLANE_BALL><<<sm * 4, 128, 0, s>>>(A);
@@ -1019,17 +1049,17 @@ cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pa
     timer_mark(c, "narrow_ball_cuboid", 1);
     k_narrow<K_BALL_HULL><<<sm * 4, 128, 0, s>>>(A);
     timer_mark(c, "narrow_ball_hull", 1);
-    k_cc_gjk<K_CUBOID_CUBOID><<<sm * 8, 128, 0, s>>>(A);
-    k_cc_gjk<K_CUBOID_HULL><<<sm * 8, 128, 0, s>>>(A);
-    k_cc_gjk<K_HULL_HULL><<<sm * 8, 128, 0, s>>>(A);
+    k_cc_gjk<K_CUBOID_CUBOID><<<sm * gjk_bpsm, 128, 0, s>>>(A);
+    k_cc_gjk<K_CUBOID_HULL><<<sm * gjk_bpsm, 128, 0, s>>>(A);
+    k_cc_gjk<K_HULL_HULL><<<sm * gjk_bpsm, 128, 0, s>>>(A);
     timer_mark(c, "cc_gjk", 3);
-    k_cc_epa<K_CUBOID_CUBOID><<<sm * 8, 64, 0, s>>>(A);
-    k_cc_epa<K_CUBOID_HULL><<<sm * 8, 64, 0, s>>>(A);
-    k_cc_epa<K_HULL_HULL><<<sm * 8, 64, 0, s>>>(A);
+    k_cc_epa<K_CUBOID_CUBOID><<<sm * epa_bpsm, 64, 0, s>>>(A);
+    k_cc_epa<K_CUBOID_HULL><<<sm * epa_bpsm, 64, 0, s>>>(A);
+    k_cc_epa<K_HULL_HULL><<<sm * epa_bpsm, 64, 0, s>>>(A);
     timer_mark(c, "cc_epa", 3);
-    k_cc_manifold<K_CUBOID_CUBOID><<<sm * 8, 128, 0, s>>>(A);
-    k_cc_manifold<K_CUBOID_HULL><<<sm * 8, 128, 0, s>>>(A);
-    k_cc_manifold<K_HULL_HULL><<<sm * 8, 128, 0, s>>>(A);
+    k_cc_manifold<K_CUBOID_CUBOID><<<sm * man_bpsm, 128, 0, s>>>(A);
+    k_cc_manifold<K_CUBOID_HULL><<<sm * man_bpsm, 128, 0, s>>>(A);
+    k_cc_manifold<K_HULL_HULL><<<sm * man_bpsm, 128, 0, s>>>(A);
     timer_mark(c, "cc_manifold", 3);
     return cudaGetLastError();
 }
