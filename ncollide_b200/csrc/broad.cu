@@ -427,6 +427,7 @@ __global__ void k_key_scan(DevCounters* cnt) {
             cnt->epa_cursor[k] = acc;
             cnt->cp_cursor[k] = acc;
             cnt->epa_fetch[k] = acc;
+            cnt->gjk_fetch[k] = acc;
             acc += cnt->key_hist[k];
         }
     }

@@ -398,64 +398,84 @@ NCB_HD void gjk_result(const Simplex& s, bool prev, V3& p1, V3& p2) {
     p2 = r1;
 }
 
-enum { GJK_INTERSECTION = 0, GJK_CLOSEST_POINTS = 1, GJK_NO_INTERSECTION = 3 };
+enum { GJK_INTERSECTION = 0, GJK_CLOSEST_POINTS = 1, GJK_NO_INTERSECTION = 3, GJK_CONTINUE = 4 };
 
-// gjk::closest_points with exact_dist = true
-__device__ __noinline__ int gjk_closest_points(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, float max_dist,
-                                               Simplex& s, V3& p1, V3& p2, V3& out_dir) {
+// gjk::closest_points (gjk.rs:76-177, exact_dist = true) split into its prologue and ONE turn of its loop, so that a
+// warp of independent lanes can each advance their own pair by one iteration per turn.
+struct GjkState {
+    Simplex s;
+    V3 proj, old_dir;
+    float max_bound;
+    int niter;
+};
+
+__device__ __noinline__ int gjk_begin(GjkState& g) {
+    g.proj = simplex_project_origin_and_reduce(g.s);
+    V3 pd;
+    if (!unit_try_new(g.proj, 0.f, pd)) return GJK_INTERSECTION;
+    g.old_dir = -pd;
+    g.max_bound = NCB_FMAX;
+    g.niter = 0;
+    return GJK_CONTINUE;
+}
+
+__device__ __noinline__ int gjk_iter(GjkState& g, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, float max_dist, V3& p1,
+                                     V3& p2, V3& out_dir) {
     const float eps_tol = NCB_EPS * 10.0f;
     const float eps_rel = sqrtf(eps_tol);
-    V3 proj = simplex_project_origin_and_reduce(s);
-    V3 old_dir;
-    {
-        V3 pd;
-        if (!unit_try_new(proj, 0.f, pd)) return GJK_INTERSECTION;
-        old_dir = -pd;
-    }
-    float max_bound = NCB_FMAX;
+    Simplex& s = g.s;
+    float old_max_bound = g.max_bound;
     V3 dir;
-    int niter = 0;
-    for (;;) {
-        float old_max_bound = max_bound;
-        float dist;
-        if (!unit_try_new_and_get(-proj, eps_tol, dir, dist)) return GJK_INTERSECTION;
-        max_bound = dist;
-        if (max_bound >= old_max_bound) {
-            gjk_result(s, true, p1, p2);
-            out_dir = old_dir;
-            return GJK_CLOSEST_POINTS;
-        }
-        CSOPoint cso = cso_from_shapes(m1, g1, m2, g2, dir);
-        float min_bound = -dot(dir, cso.point);
-        if (min_bound > max_dist) {
-            out_dir = dir;
-            return GJK_NO_INTERSECTION;
-        } else if (max_bound - min_bound <= eps_rel * max_bound) {
-            gjk_result(s, false, p1, p2);
-            out_dir = dir;
-            return GJK_CLOSEST_POINTS;
-        }
-        if (!simplex_add_point(s, cso)) {
-            gjk_result(s, false, p1, p2);
-            out_dir = dir;
-            return GJK_CLOSEST_POINTS;
-        }
-        old_dir = dir;
-        proj = simplex_project_origin_and_reduce(s);
-        if (s.dim == 3) {
-            if (min_bound >= eps_tol) {
-                gjk_result(s, true, p1, p2);
-                out_dir = old_dir;
-                return GJK_CLOSEST_POINTS;
-            }
-            return GJK_INTERSECTION;
-        }
-        niter += 1;
-        if (niter == 10000) {
-            out_dir = v3(1.f, 0.f, 0.f);
-            return GJK_NO_INTERSECTION;
-        }
+    float dist;
+    if (!unit_try_new_and_get(-g.proj, eps_tol, dir, dist)) return GJK_INTERSECTION;
+    g.max_bound = dist;
+    if (g.max_bound >= old_max_bound) {
+        gjk_result(s, true, p1, p2);
+        out_dir = g.old_dir;
+        return GJK_CLOSEST_POINTS;
     }
+    CSOPoint cso = cso_from_shapes(m1, g1, m2, g2, dir);
+    float min_bound = -dot(dir, cso.point);
+    if (min_bound > max_dist) {
+        out_dir = dir;
+        return GJK_NO_INTERSECTION;
+    } else if (g.max_bound - min_bound <= eps_rel * g.max_bound) {
+        gjk_result(s, false, p1, p2);
+        out_dir = dir;
+        return GJK_CLOSEST_POINTS;
+    }
+    if (!simplex_add_point(s, cso)) {
+        gjk_result(s, false, p1, p2);
+        out_dir = dir;
+        return GJK_CLOSEST_POINTS;
+    }
+    g.old_dir = dir;
+    g.proj = simplex_project_origin_and_reduce(s);
+    if (s.dim == 3) {
+        if (min_bound >= eps_tol) {
+            gjk_result(s, true, p1, p2);
+            out_dir = g.old_dir;
+            return GJK_CLOSEST_POINTS;
+        }
+        return GJK_INTERSECTION;
+    }
+    g.niter += 1;
+    if (g.niter == 10000) {
+        out_dir = v3(1.f, 0.f, 0.f);
+        return GJK_NO_INTERSECTION;
+    }
+    return GJK_CONTINUE;
+}
+
+// gjk::closest_points with exact_dist = true (whole loop; used where the caller is not a lane-level state machine)
+__device__ __noinline__ int gjk_closest_points(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, float max_dist,
+                                               Simplex& s, V3& p1, V3& p2, V3& out_dir) {
+    GjkState g;
+    g.s = s;
+    int st = gjk_begin(g);
+    while (st == GJK_CONTINUE) st = gjk_iter(g, m1, g1, m2, g2, max_dist, p1, p2, out_dir);
+    s = g.s;
+    return st;
 }
 
 // ---- EPA ----------------------------------------------------------------------------------------------------
@@ -604,8 +624,11 @@ NCB_HD bool epa_can_be_seen_by(const EpaState& e, uint32_t f, uint32_t point, ui
     return relative_eq(norm_squared(cross(p1p2, p1p3)), 0.f, eps_tol * eps_tol);
 }
 // compute_silhouette (epa3.rs:432-454): the recursion becomes a LIFO of (face, opp) visits in the same order.
-__device__ __noinline__ void epa_compute_silhouette(EpaState& e, uint32_t point, uint32_t id0, uint32_t opp0) {
+__device__ __noinline__ void epa_compute_silhouette3(EpaState& e, uint32_t point, uint32_t id0, uint32_t opp0, uint32_t id1, uint32_t opp1,
+                                                     uint32_t id2, uint32_t opp2) {
     int sp = 0;
+    e.stk_face[sp] = (uint8_t)id2, e.stk_opp[sp] = (uint8_t)opp2, sp++;
+    e.stk_face[sp] = (uint8_t)id1, e.stk_opp[sp] = (uint8_t)opp1, sp++;
     e.stk_face[sp] = (uint8_t)id0, e.stk_opp[sp] = (uint8_t)opp0, sp++;
     while (sp > 0) {
         sp--;
@@ -705,13 +728,15 @@ __device__ __noinline__ int epa_step(EpaState& e, const Iso& m1, const Support& 
                                      V3& out_n) {
     const float eps_tol = NCB_EPS * 100.0f;
     EpaHeapItem face_id;
-    if (!heap_pop(e, face_id)) {  // heap exhausted: the best face so far (epa3.rs:427-429)
-        epa_face_closest_points(e, e.best_face_id.id, out1, out2);
-        out_n = e.fnormal[e.best_face_id.id];
-        return EPA_DONE_OK;
-    }
+    // `if face.deleted { continue; }` (epa3.rs:334-336): stale heap entries are skipped inside the same turn
+    do {
+        if (!heap_pop(e, face_id)) {  // heap exhausted: the best face so far (epa3.rs:427-429)
+            epa_face_closest_points(e, e.best_face_id.id, out1, out2);
+            out_n = e.fnormal[e.best_face_id.id];
+            return EPA_DONE_OK;
+        }
+    } while (f_deleted(e, face_id.id));
     uint32_t fid = face_id.id;
-    if (f_deleted(e, fid)) return EPA_CONTINUE;
     // snapshot of the popped face (the reference clones it before the polytope is edited)
     uint32_t fp0 = f_pt(e, fid, 0), fp1 = f_pt(e, fid, 1), fp2 = f_pt(e, fid, 2);
     uint32_t fa0 = f_adj(e, fid, 0), fa1 = f_adj(e, fid, 1), fa2 = f_adj(e, fid, 2);
@@ -739,9 +764,9 @@ __device__ __noinline__ int epa_step(EpaState& e, const Iso& m1, const Support& 
     uint32_t o2 = epa_next_ccw(e, fa1, fp1);
     uint32_t o3 = epa_next_ccw(e, fa2, fp2);
     if (e.panicked) return EPA_DONE_FAIL;
-    epa_compute_silhouette(e, support_point_id, fa0, o1);
-    epa_compute_silhouette(e, support_point_id, fa1, o2);
-    epa_compute_silhouette(e, support_point_id, fa2, o3);
+    // compute_silhouette x3 (epa3.rs:364-366) as ONE LIFO walk: the three roots are stacked in reverse order, so the
+    // flood from adj[0] completes before adj[1] is looked at, exactly like the three sequential recursive calls
+    epa_compute_silhouette3(e, support_point_id, fa0, o1, fa1, o2, fa2, o3);
     if (e.panicked || e.overflow) return EPA_DONE_FAIL;
     uint32_t first_new_face_id = (uint32_t)e.nfaces;
     if (e.nsil == 0) return EPA_DONE_FAIL;

@@ -789,42 +789,68 @@ NCB_HD void cp_store(uint32_t* q, uint32_t slot, uint32_t p, V3 p1, V3 p2, V3 di
     r[1] = p1.x, r[2] = p1.y, r[3] = p1.z, r[4] = p2.x, r[5] = p2.y, r[6] = p2.z, r[7] = dir.x, r[8] = dir.y, r[9] = dir.z;
 }
 
+// GJK over a key segment; same lane-level scheme as k_cc_epa below: idle lanes fetch the next pair (batched refills),
+// busy lanes advance their own pair by ONE GJK iteration per turn.
+#define GJK_REFILL_MIN 8
 template <int KEY>
 __global__ void __launch_bounds__(128) k_cc_gjk(NarrowArgs A) {
-    uint32_t seg_begin = A.cnt->key_start[KEY];
-    uint32_t seg_end = seg_begin + A.cnt->key_hist[KEY];
-    uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
-        uint32_t p = base + threadIdx.x;
-        bool valid = p < seg_end;
-        int r = GJK_NO_INTERSECTION;
-        V3 p1, p2, dir;
-        Simplex s;
-        if (valid) {
-            uint2 pr = __ldg(&A.pairs[p]);
-            uint32_t i1 = pr.x, i2 = pr.y;
-            uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
-            Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
-            float linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
-            Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
-            Support ga = as_support(a), gb = as_support(b);
-            // contact_support_map_support_map_with_params, init_dir = None (fresh generator)
-            V3 d0;
-            if (!unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
-            simplex_init(s, cso_from_shapes(ma, ga, mb, gb, d0));
-            r = gjk_closest_points(ma, ga, mb, gb, linear, s, p1, p2, dir);
-            if (r == GJK_NO_INTERSECTION) {
-                uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
-                A.manifold_start[out_index] = 0;
-                A.manifold_count[out_index] = 0;
+    const uint32_t seg_end = A.cnt->key_start[KEY] + A.cnt->key_hist[KEY];
+    uint32_t* fetch = &A.cnt->gjk_fetch[KEY];
+    const int lane = threadIdx.x & 31;
+    GjkState g;
+    bool active = false, exhausted = false;
+    uint32_t p = 0;
+    Iso ma, mb;
+    Support ga, gb;
+    float linear = 0.f;
+    V3 p1, p2, dir;
+    for (;;) {
+        int status = GJK_CONTINUE;
+        unsigned idle = __ballot_sync(0xffffffffu, !active);
+        bool refill = !exhausted && (idle == 0xffffffffu || __popc(idle) >= GJK_REFILL_MIN);
+        if (refill) {  // warp-uniform
+            uint32_t base = 0;
+            int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + __popc(idle) >= seg_end) exhausted = true;
+            if (!active) {
+                uint32_t w = base + __popc(idle & ((1u << lane) - 1));
+                if (w < seg_end) {
+                    p = w;
+                    uint2 pr = __ldg(&A.pairs[p]);
+                    uint32_t i1 = pr.x, i2 = pr.y;
+                    uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
+                    ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
+                    linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
+                    Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+                    ga = as_support(a), gb = as_support(b);
+                    // contact_support_map_support_map_with_params, init_dir = None (fresh generator)
+                    V3 d0;
+                    if (!unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
+                    simplex_init(g.s, cso_from_shapes(ma, ga, mb, gb, d0));
+                    active = true;
+                    status = gjk_begin(g);
+                }
             }
+        } else if (active) {
+            status = gjk_iter(g, ma, ga, mb, gb, linear, p1, p2, dir);
         }
-        uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], valid && r == GJK_CLOSEST_POINTS);
-        if (valid && r == GJK_CLOSEST_POINTS) cp_store(A.cp_queue, slot, p, p1, p2, dir);
-        slot = queue_append(&A.cnt->epa_cursor[KEY], valid && r == GJK_INTERSECTION);
-        if (valid && r == GJK_INTERSECTION) {
+        bool done = active && status != GJK_CONTINUE;
+        if (done && status == GJK_NO_INTERSECTION) {
+            uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
+            A.manifold_start[out_index] = 0;
+            A.manifold_count[out_index] = 0;
+        }
+        bool want_cp = done && status == GJK_CLOSEST_POINTS;
+        uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], want_cp);
+        if (want_cp) cp_store(A.cp_queue, slot, p, p1, p2, dir);
+        bool want_epa = done && status == GJK_INTERSECTION;
+        slot = queue_append(&A.cnt->epa_cursor[KEY], want_epa);
+        if (want_epa) {
             uint32_t* q = A.epa_queue + (size_t)slot * EPA_REC_WORDS;
             float* f = reinterpret_cast<float*>(q);
+            const Simplex& s = g.s;
             q[0] = p;
             q[1] = (uint32_t)s.dim;
             for (int i = 0; i < 4; ++i) {
@@ -832,6 +858,8 @@ __global__ void __launch_bounds__(128) k_cc_gjk(NarrowArgs A) {
                 f[2 + 6 * i + 3] = s.v[i].orig2.x, f[2 + 6 * i + 4] = s.v[i].orig2.y, f[2 + 6 * i + 5] = s.v[i].orig2.z;
             }
         }
+        if (done) active = false;
+        if (exhausted && __all_sync(0xffffffffu, !active)) break;
     }
 }
 

@@ -62,6 +62,7 @@ struct DevCounters {
     uint32_t epa_cursor[16];   // per key: end of the EPA work queue (starts at key_start[key])
     uint32_t cp_cursor[16];    // per key: end of the closest-points (manifold) work queue
     uint32_t epa_fetch[16];    // per key: next EPA queue entry to hand to an idle lane (dynamic fetch)
+    uint32_t gjk_fetch[16];    // per key: next pair of the key segment to hand to an idle lane
     int bounds[6];             // ordered-int encoded min xyz / max xyz of AABB centres
 };
 
