@@ -2,6 +2,7 @@
 // No torch types, no CPU fallback: every compute entry point needs a CUDA device and fails loudly otherwise.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "ncb_internal.h"
 
@@ -110,6 +111,11 @@ int ncb_create(int device, ncb_ctx** out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_counters, sizeof(DevCounters));
+    if (e == cudaSuccess && !getenv("NCB_NO_SIDE_STREAM")) {
+        e = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         g_create_err = cudaGetErrorString(e);
         delete c;
@@ -141,6 +147,9 @@ void ncb_destroy(ncb_ctx* c) {
     if (c->timer.created)
         for (int i = 0; i <= StageTimer::MAX; ++i) cudaEventDestroy(c->timer.ev[i]);
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -384,10 +393,8 @@ static void fill_counts(ncb_ctx* ctx, ncb_update_counts* counts) {
     counts->n_algo[NCB_ALGO_BALL_CONVEX] = c.key_hist[K_BALL_CUBOID] + c.key_hist[K_BALL_HULL];
     counts->n_algo[NCB_ALGO_CONVEX_CONVEX] = c.key_hist[K_CUBOID_CUBOID] + c.key_hist[K_CUBOID_HULL] + c.key_hist[K_HULL_HULL];
     counts->n_algo[NCB_ALGO_NONE] = c.key_hist[K_NONE];
-    for (int k = K_CUBOID_CUBOID; k <= K_HULL_HULL; ++k) {
-        counts->n_epa_pairs += c.epa_cursor[k] - c.key_start[k];
-        counts->n_manifold_jobs += c.cp_cursor[k] - c.key_start[k];
-    }
+    counts->n_epa_pairs = c.epa_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID];
+    counts->n_manifold_jobs = c.cp_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID];
 }
 
 int ncb_generate_contacts(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* pairs, ncb_contact* out_contacts, uint32_t cap_contacts,

@@ -398,84 +398,64 @@ NCB_HD void gjk_result(const Simplex& s, bool prev, V3& p1, V3& p2) {
     p2 = r1;
 }
 
-enum { GJK_INTERSECTION = 0, GJK_CLOSEST_POINTS = 1, GJK_NO_INTERSECTION = 3, GJK_CONTINUE = 4 };
+enum { GJK_INTERSECTION = 0, GJK_CLOSEST_POINTS = 1, GJK_NO_INTERSECTION = 3 };
 
-// gjk::closest_points (gjk.rs:76-177, exact_dist = true) split into its prologue and ONE turn of its loop, so that a
-// warp of independent lanes can each advance their own pair by one iteration per turn.
-struct GjkState {
-    Simplex s;
-    V3 proj, old_dir;
-    float max_bound;
-    int niter;
-};
-
-__device__ __noinline__ int gjk_begin(GjkState& g) {
-    g.proj = simplex_project_origin_and_reduce(g.s);
-    V3 pd;
-    if (!unit_try_new(g.proj, 0.f, pd)) return GJK_INTERSECTION;
-    g.old_dir = -pd;
-    g.max_bound = NCB_FMAX;
-    g.niter = 0;
-    return GJK_CONTINUE;
-}
-
-__device__ __noinline__ int gjk_iter(GjkState& g, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, float max_dist, V3& p1,
-                                     V3& p2, V3& out_dir) {
-    const float eps_tol = NCB_EPS * 10.0f;
-    const float eps_rel = sqrtf(eps_tol);
-    Simplex& s = g.s;
-    float old_max_bound = g.max_bound;
-    V3 dir;
-    float dist;
-    if (!unit_try_new_and_get(-g.proj, eps_tol, dir, dist)) return GJK_INTERSECTION;
-    g.max_bound = dist;
-    if (g.max_bound >= old_max_bound) {
-        gjk_result(s, true, p1, p2);
-        out_dir = g.old_dir;
-        return GJK_CLOSEST_POINTS;
-    }
-    CSOPoint cso = cso_from_shapes(m1, g1, m2, g2, dir);
-    float min_bound = -dot(dir, cso.point);
-    if (min_bound > max_dist) {
-        out_dir = dir;
-        return GJK_NO_INTERSECTION;
-    } else if (g.max_bound - min_bound <= eps_rel * g.max_bound) {
-        gjk_result(s, false, p1, p2);
-        out_dir = dir;
-        return GJK_CLOSEST_POINTS;
-    }
-    if (!simplex_add_point(s, cso)) {
-        gjk_result(s, false, p1, p2);
-        out_dir = dir;
-        return GJK_CLOSEST_POINTS;
-    }
-    g.old_dir = dir;
-    g.proj = simplex_project_origin_and_reduce(s);
-    if (s.dim == 3) {
-        if (min_bound >= eps_tol) {
-            gjk_result(s, true, p1, p2);
-            out_dir = g.old_dir;
-            return GJK_CLOSEST_POINTS;
-        }
-        return GJK_INTERSECTION;
-    }
-    g.niter += 1;
-    if (g.niter == 10000) {
-        out_dir = v3(1.f, 0.f, 0.f);
-        return GJK_NO_INTERSECTION;
-    }
-    return GJK_CONTINUE;
-}
-
-// gjk::closest_points with exact_dist = true (whole loop; used where the caller is not a lane-level state machine)
+// gjk::closest_points with exact_dist = true
 __device__ __noinline__ int gjk_closest_points(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, float max_dist,
                                                Simplex& s, V3& p1, V3& p2, V3& out_dir) {
-    GjkState g;
-    g.s = s;
-    int st = gjk_begin(g);
-    while (st == GJK_CONTINUE) st = gjk_iter(g, m1, g1, m2, g2, max_dist, p1, p2, out_dir);
-    s = g.s;
-    return st;
+    const float eps_tol = NCB_EPS * 10.0f;
+    const float eps_rel = sqrtf(eps_tol);
+    V3 proj = simplex_project_origin_and_reduce(s);
+    V3 old_dir;
+    {
+        V3 pd;
+        if (!unit_try_new(proj, 0.f, pd)) return GJK_INTERSECTION;
+        old_dir = -pd;
+    }
+    float max_bound = NCB_FMAX;
+    V3 dir;
+    int niter = 0;
+    for (;;) {
+        float old_max_bound = max_bound;
+        float dist;
+        if (!unit_try_new_and_get(-proj, eps_tol, dir, dist)) return GJK_INTERSECTION;
+        max_bound = dist;
+        if (max_bound >= old_max_bound) {
+            gjk_result(s, true, p1, p2);
+            out_dir = old_dir;
+            return GJK_CLOSEST_POINTS;
+        }
+        CSOPoint cso = cso_from_shapes(m1, g1, m2, g2, dir);
+        float min_bound = -dot(dir, cso.point);
+        if (min_bound > max_dist) {
+            out_dir = dir;
+            return GJK_NO_INTERSECTION;
+        } else if (max_bound - min_bound <= eps_rel * max_bound) {
+            gjk_result(s, false, p1, p2);
+            out_dir = dir;
+            return GJK_CLOSEST_POINTS;
+        }
+        if (!simplex_add_point(s, cso)) {
+            gjk_result(s, false, p1, p2);
+            out_dir = dir;
+            return GJK_CLOSEST_POINTS;
+        }
+        old_dir = dir;
+        proj = simplex_project_origin_and_reduce(s);
+        if (s.dim == 3) {
+            if (min_bound >= eps_tol) {
+                gjk_result(s, true, p1, p2);
+                out_dir = old_dir;
+                return GJK_CLOSEST_POINTS;
+            }
+            return GJK_INTERSECTION;
+        }
+        niter += 1;
+        if (niter == 10000) {
+            out_dir = v3(1.f, 0.f, 0.f);
+            return GJK_NO_INTERSECTION;
+        }
+    }
 }
 
 // ---- EPA ----------------------------------------------------------------------------------------------------

@@ -789,68 +789,45 @@ NCB_HD void cp_store(uint32_t* q, uint32_t slot, uint32_t p, V3 p1, V3 p2, V3 di
     r[1] = p1.x, r[2] = p1.y, r[3] = p1.z, r[4] = p2.x, r[5] = p2.y, r[6] = p2.z, r[7] = dir.x, r[8] = dir.y, r[9] = dir.z;
 }
 
-// GJK over a key segment; same lane-level scheme as k_cc_epa below: idle lanes fetch the next pair (batched refills),
-// busy lanes advance their own pair by ONE GJK iteration per turn.
-#define GJK_REFILL_MIN 8
-template <int KEY>
+// The three convex-convex keys are adjacent in the key order, so their pairs form ONE contiguous range of the sorted
+// pair array and share one EPA queue and one manifold queue (cursor slot CCQ): a single launch per phase, one tail.
+#define CCQ K_CUBOID_CUBOID
 __global__ void __launch_bounds__(128) k_cc_gjk(NarrowArgs A) {
-    const uint32_t seg_end = A.cnt->key_start[KEY] + A.cnt->key_hist[KEY];
-    uint32_t* fetch = &A.cnt->gjk_fetch[KEY];
-    const int lane = threadIdx.x & 31;
-    GjkState g;
-    bool active = false, exhausted = false;
-    uint32_t p = 0;
-    Iso ma, mb;
-    Support ga, gb;
-    float linear = 0.f;
-    V3 p1, p2, dir;
-    for (;;) {
-        int status = GJK_CONTINUE;
-        unsigned idle = __ballot_sync(0xffffffffu, !active);
-        bool refill = !exhausted && (idle == 0xffffffffu || __popc(idle) >= GJK_REFILL_MIN);
-        if (refill) {  // warp-uniform
-            uint32_t base = 0;
-            int leader = __ffs(idle) - 1;
-            if (lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (base + __popc(idle) >= seg_end) exhausted = true;
-            if (!active) {
-                uint32_t w = base + __popc(idle & ((1u << lane) - 1));
-                if (w < seg_end) {
-                    p = w;
-                    uint2 pr = __ldg(&A.pairs[p]);
-                    uint32_t i1 = pr.x, i2 = pr.y;
-                    uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
-                    ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
-                    linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
-                    Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
-                    ga = as_support(a), gb = as_support(b);
-                    // contact_support_map_support_map_with_params, init_dir = None (fresh generator)
-                    V3 d0;
-                    if (!unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
-                    simplex_init(g.s, cso_from_shapes(ma, ga, mb, gb, d0));
-                    active = true;
-                    status = gjk_begin(g);
-                }
+    const int KEY = CCQ;
+    uint32_t seg_begin = A.cnt->key_start[K_CUBOID_CUBOID];
+    uint32_t seg_end = A.cnt->key_start[K_HULL_HULL] + A.cnt->key_hist[K_HULL_HULL];
+    uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
+        uint32_t p = base + threadIdx.x;
+        bool valid = p < seg_end;
+        int r = GJK_NO_INTERSECTION;
+        V3 p1, p2, dir;
+        Simplex s;
+        if (valid) {
+            uint2 pr = __ldg(&A.pairs[p]);
+            uint32_t i1 = pr.x, i2 = pr.y;
+            uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
+            Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
+            float linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
+            Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+            Support ga = as_support(a), gb = as_support(b);
+            // contact_support_map_support_map_with_params, init_dir = None (fresh generator)
+            V3 d0;
+            if (!unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
+            simplex_init(s, cso_from_shapes(ma, ga, mb, gb, d0));
+            r = gjk_closest_points(ma, ga, mb, gb, linear, s, p1, p2, dir);
+            if (r == GJK_NO_INTERSECTION) {
+                uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
+                A.manifold_start[out_index] = 0;
+                A.manifold_count[out_index] = 0;
             }
-        } else if (active) {
-            status = gjk_iter(g, ma, ga, mb, gb, linear, p1, p2, dir);
         }
-        bool done = active && status != GJK_CONTINUE;
-        if (done && status == GJK_NO_INTERSECTION) {
-            uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
-            A.manifold_start[out_index] = 0;
-            A.manifold_count[out_index] = 0;
-        }
-        bool want_cp = done && status == GJK_CLOSEST_POINTS;
-        uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], want_cp);
-        if (want_cp) cp_store(A.cp_queue, slot, p, p1, p2, dir);
-        bool want_epa = done && status == GJK_INTERSECTION;
-        slot = queue_append(&A.cnt->epa_cursor[KEY], want_epa);
-        if (want_epa) {
+        uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], valid && r == GJK_CLOSEST_POINTS);
+        if (valid && r == GJK_CLOSEST_POINTS) cp_store(A.cp_queue, slot, p, p1, p2, dir);
+        slot = queue_append(&A.cnt->epa_cursor[KEY], valid && r == GJK_INTERSECTION);
+        if (valid && r == GJK_INTERSECTION) {
             uint32_t* q = A.epa_queue + (size_t)slot * EPA_REC_WORDS;
             float* f = reinterpret_cast<float*>(q);
-            const Simplex& s = g.s;
             q[0] = p;
             q[1] = (uint32_t)s.dim;
             for (int i = 0; i < 4; ++i) {
@@ -858,8 +835,6 @@ __global__ void __launch_bounds__(128) k_cc_gjk(NarrowArgs A) {
                 f[2 + 6 * i + 3] = s.v[i].orig2.x, f[2 + 6 * i + 4] = s.v[i].orig2.y, f[2 + 6 * i + 5] = s.v[i].orig2.z;
             }
         }
-        if (done) active = false;
-        if (exhausted && __all_sync(0xffffffffu, !active)) break;
     }
 }
 
@@ -868,8 +843,8 @@ __global__ void __launch_bounds__(128) k_cc_gjk(NarrowArgs A) {
 // run the same code (one step) regardless of how many steps their pair needs; refills are batched (>= REFILL_MIN idle
 // lanes) so that the initialisation path is not paid on every turn.
 #define EPA_REFILL_MIN 8
-template <int KEY>
 __global__ void __launch_bounds__(64) k_cc_epa(NarrowArgs A) {
+    const int KEY = CCQ;
     const uint32_t seg_end = A.cnt->epa_cursor[KEY];
     uint32_t* fetch = &A.cnt->epa_fetch[KEY];
     const int lane = threadIdx.x & 31;
@@ -931,8 +906,8 @@ __global__ void __launch_bounds__(64) k_cc_epa(NarrowArgs A) {
     }
 }
 
-template <int KEY>
 __global__ void __launch_bounds__(128) k_cc_manifold(NarrowArgs A) {
+    const int KEY = CCQ;
     uint32_t seg_begin = A.cnt->key_start[KEY];
     uint32_t seg_end = A.cnt->cp_cursor[KEY];
     uint32_t stride = gridDim.x * blockDim.x;
@@ -1066,29 +1041,29 @@ cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pa
     static int gjk_bpsm = getenv("NCB_GJK_BPSM") ? atoi(getenv("NCB_GJK_BPSM")) : 8;
     static int epa_bpsm = getenv("NCB_EPA_BPSM") ? atoi(getenv("NCB_EPA_BPSM")) : 8;
     static int man_bpsm = getenv("NCB_MAN_BPSM") ? atoi(getenv("NCB_MAN_BPSM")) : 8;
-    k_narrow<K_BALL_BALL><<<sm * 8, 128, 0, s>>>(A);
-    timer_mark(c, "narrow_ball_ball", 1);
-    k_narrow<K_PLANE_BALL><<<sm * 4, 128, 0, s>>>(A);
-    k_narrow<K_PLANE_CUBOID><<<sm * 4, 128, 0, s>>>(A);
-    k_narrow<K_PLANE_HULL><<<sm * 4, 128, 0, s>>>(A);
-    k_narrow_none<<<sm, 256, 0, s>>>(A);
-    timer_mark(c, "narrow_plane", 4);
-    k_narrow<K_BALL_CUBOID><<<sm * 8, 128, 0, s>>>(A);
-    timer_mark(c, "narrow_ball_cuboid", 1);
-    k_narrow<K_BALL_HULL><<<sm * 4, 128, 0, s>>>(A);
-    timer_mark(c, "narrow_ball_hull", 1);
-    k_cc_gjk<K_CUBOID_CUBOID><<<sm * gjk_bpsm, 128, 0, s>>>(A);
-    k_cc_gjk<K_CUBOID_HULL><<<sm * gjk_bpsm, 128, 0, s>>>(A);
-    k_cc_gjk<K_HULL_HULL><<<sm * gjk_bpsm, 128, 0, s>>>(A);
-    timer_mark(c, "cc_gjk", 3);
-    k_cc_epa<K_CUBOID_CUBOID><<<sm * epa_bpsm, 64, 0, s>>>(A);
-    k_cc_epa<K_CUBOID_HULL><<<sm * epa_bpsm, 64, 0, s>>>(A);
-    k_cc_epa<K_HULL_HULL><<<sm * epa_bpsm, 64, 0, s>>>(A);
-    timer_mark(c, "cc_epa", 3);
-    k_cc_manifold<K_CUBOID_CUBOID><<<sm * man_bpsm, 128, 0, s>>>(A);
-    k_cc_manifold<K_CUBOID_HULL><<<sm * man_bpsm, 128, 0, s>>>(A);
-    k_cc_manifold<K_HULL_HULL><<<sm * man_bpsm, 128, 0, s>>>(A);
-    timer_mark(c, "cc_manifold", 3);
+    // Two independent chains: the convex-convex phases on the context's stream, everything else on a side stream
+    // (each persistent kernel alone leaves most issue slots idle; together they overlap).
+    cudaStream_t s2 = c->side_stream ? c->side_stream : s;
+    if (c->side_stream) {
+        cudaEventRecord(c->ev_fork, s);
+        cudaStreamWaitEvent(s2, c->ev_fork, 0);
+    }
+    k_narrow<K_BALL_HULL><<<sm * 4, 128, 0, s2>>>(A);
+    k_narrow<K_BALL_CUBOID><<<sm * 8, 128, 0, s2>>>(A);
+    k_narrow<K_BALL_BALL><<<sm * 8, 128, 0, s2>>>(A);
+    k_narrow<K_PLANE_BALL><<<sm * 2, 128, 0, s2>>>(A);
+    k_narrow<K_PLANE_CUBOID><<<sm * 2, 128, 0, s2>>>(A);
+    k_narrow<K_PLANE_HULL><<<sm * 2, 128, 0, s2>>>(A);
+    k_narrow_none<<<sm, 256, 0, s2>>>(A);
+    if (c->side_stream) cudaEventRecord(c->ev_join, s2);
+    k_cc_gjk<<<sm * gjk_bpsm, 128, 0, s>>>(A);
+    timer_mark(c, "cc_gjk", 1);
+    k_cc_epa<<<sm * epa_bpsm, 64, 0, s>>>(A);
+    timer_mark(c, "cc_epa", 1);
+    k_cc_manifold<<<sm * man_bpsm, 128, 0, s>>>(A);
+    timer_mark(c, "cc_manifold", 1);
+    if (c->side_stream) cudaStreamWaitEvent(s, c->ev_join, 0);
+    timer_mark(c, "narrow_other_join", 7);
     return cudaGetLastError();
 }
 

@@ -102,6 +102,8 @@ struct StageTimer {
 struct ncb_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t side_stream = nullptr;  // second chain of the narrow phase (fork / join with events)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     int sm_count = 148;
 
