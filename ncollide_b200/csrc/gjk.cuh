@@ -83,10 +83,22 @@ NCB_HD V3 support_point(const Support& g, const Iso& m, V3 dir) {
 struct CSOPoint {
     V3 point, orig1, orig2;
 };
+// CSOPoint::from_shapes (cso_point.rs:70-85).  The two support evaluations are independent, so they are issued in a
+// canonical order (the O(1) operand first, the vertex-scanning hull second) whatever the pair's orientation is: lanes
+// of a warp holding (cuboid, hull) and (hull, cuboid) pairs then run the same code at the same time.  Values are
+// unchanged: each operand still sees its own isometry and direction.
 NCB_HD CSOPoint cso_from_shapes(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, V3 dir) {
     CSOPoint c;
-    c.orig1 = support_point(g1, m1, dir);
-    c.orig2 = support_point(g2, m2, -dir);
+    bool swap = g1.kind == 1 && g2.kind != 1;
+    const Support& ga = swap ? g2 : g1;
+    const Support& gb = swap ? g1 : g2;
+    const Iso& ia = swap ? m2 : m1;
+    const Iso& ib = swap ? m1 : m2;
+    V3 da = swap ? -dir : dir;
+    V3 sa = support_point(ga, ia, da);
+    V3 sb = support_point(gb, ib, -da);
+    c.orig1 = swap ? sb : sa;
+    c.orig2 = swap ? sa : sb;
     c.point = c.orig1 - c.orig2;
     return c;
 }
@@ -476,6 +488,7 @@ struct EpaState {
     uint8_t hid[EPA_MAX_HEAP];
     uint8_t sil_face[EPA_MAX_STACK], sil_opp[EPA_MAX_STACK];
     uint8_t stk_face[EPA_MAX_STACK], stk_opp[EPA_MAX_STACK];
+    float hpend[EPA_MAX_STACK];  // -dist of the faces created in this turn, pushed on the heap after the loop
     V3 vorig1[EPA_MAX_VERTS], vorig2[EPA_MAX_VERTS];
     int nverts, nfaces, nheap, nsil, niter;
     float max_dist;
@@ -750,6 +763,7 @@ __device__ __noinline__ int epa_step(EpaState& e, const Iso& m1, const Support& 
     if (e.panicked || e.overflow) return EPA_DONE_FAIL;
     uint32_t first_new_face_id = (uint32_t)e.nfaces;
     if (e.nsil == 0) return EPA_DONE_FAIL;
+    int npend = 0;
     for (int k = 0; k < e.nsil; ++k) {
         uint32_t efid = e.sil_face[k], eopp = e.sil_opp[k];
         if (!f_deleted(e, efid)) {
@@ -771,11 +785,17 @@ __device__ __noinline__ int epa_step(EpaState& e, const Iso& m1, const Support& 
                     out_n = fnorm;
                     return EPA_DONE_OK;
                 }
-                NCB_EPA_PUSH(new_face_id, -dist);
-                if (e.overflow) return EPA_DONE_FAIL;
+                // FaceId::new(new_face_id, -dist)? then heap.push: the validity test stays here, in order; the sift
+                // itself is deferred to one converged loop below (pushes commute with nothing else in this loop)
+                if (-dist > NCB_EPS * 10.0f) return EPA_DONE_FAIL;
+                e.stk_face[npend] = (uint8_t)new_face_id;  // the DFS stack is free at this point: reuse it
+                e.hpend[npend] = -dist;
+                npend++;
             }
         }
     }
+    for (int k = 0; k < npend; ++k) heap_push(e, e.stk_face[k], e.hpend[k]);
+    if (e.overflow) return EPA_DONE_FAIL;
     if (first_new_face_id == (uint32_t)e.nfaces) return EPA_DONE_FAIL;
     f_set_adj(e, first_new_face_id, 2, (uint32_t)(e.nfaces - 1));
     f_set_adj(e, (uint32_t)(e.nfaces - 1), 1, first_new_face_id);

@@ -607,20 +607,41 @@ NCB_HD bool feature_ok_for_manifold(const Feature& ft, uint32_t f) {
     return false;
 }
 
+// Candidates found by clip() are buffered and handed to the manifold afterwards, like the reference's `new_contacts`
+// Vec (convex_polyhedron_convex_polyhedron_manifold_generator.rs:147-161).  Besides mirroring the reference, this keeps
+// the (rare, lane-dependent) manifold work out of clip's nested loops so that lanes stay converged in both parts.
+#define CLIP_CAND_MAX 24
+struct ClipCand {
+    V3 w1, w2;
+    uint32_t f1, f2;
+};
 struct ClipCtx {
     const Iso* ma;
     Manifold* mf;
     const Feature *m1, *m2;
-    int n_new;
+    V3 normal;
+    int n_new;   // candidates within the prediction distance so far (buffered + already flushed)
+    int n_buf;
+    ClipCand buf[CLIP_CAND_MAX];
 };
+NCB_HD void clip_flush(ClipCtx& cc) {
+    for (int k = 0; k < cc.n_buf; ++k) {
+        const ClipCand& c = cc.buf[k];
+        if (!feature_ok_for_manifold(*cc.m1, c.f1)) continue;
+        if (!feature_ok_for_manifold(*cc.m2, c.f2)) continue;
+        float depth = -dot(cc.normal, c.w2 - c.w1);  // Contact::new_wo_depth
+        V3 local1 = iso_inv_point(*cc.ma, c.w1);
+        manifold_push(*cc.mf, c.w1, c.w2, cc.normal, depth, c.f1, c.f2, local1);
+    }
+    cc.n_buf = 0;
+}
 NCB_HD void clip_emit(ClipCtx& cc, V3 w1, V3 w2, V3 normal, float prediction, uint32_t f1, uint32_t f2) {
     float depth = -dot(normal, w2 - w1);  // Contact::new_wo_depth
     if (-depth <= prediction) {
         cc.n_new++;
-        if (!feature_ok_for_manifold(*cc.m1, f1)) return;
-        if (!feature_ok_for_manifold(*cc.m2, f2)) return;
-        V3 local1 = iso_inv_point(*cc.ma, w1);
-        manifold_push(*cc.mf, w1, w2, normal, depth, f1, f2, local1);
+        if (cc.n_buf == CLIP_CAND_MAX) clip_flush(cc);  // order-preserving spill, practically never taken
+        ClipCand& c = cc.buf[cc.n_buf++];
+        c.w1 = w1, c.w2 = w2, c.f1 = f1, c.f2 = f2;
     }
 }
 
@@ -686,12 +707,25 @@ __device__ __noinline__ void clip(const Feature& self, const Feature& other, V3 
 __device__ __noinline__ void convex_convex_manifold(const Iso& ma, const Shape& a, const Iso& mb, const Shape& b, float linear, float2 ang1,
                                                     float2 ang2, V3 p1, V3 p2, V3 dir, Manifold& mf, Feature& m1, Feature& m2) {
     float depth = -dot(dir, p2 - p1);
-    if (depth > 0.f) {
-        support_face_toward(a, ma, dir, m1);
-        support_face_toward(b, mb, -dir, m2);
-    } else {
-        support_feature_toward(a, ma, dir, ang1, m1);
-        support_feature_toward(b, mb, -dir, ang2, m2);
+    {
+        // the two feature extractions are independent: issue the cuboid one first and the hull one second whatever the
+        // pair's orientation is, so that mixed (cuboid, hull) / (hull, cuboid) lanes stay converged
+        bool swap = a.type == NCB_SHAPE_CONVEX_HULL && b.type != NCB_SHAPE_CONVEX_HULL;
+        const Shape& sa = swap ? b : a;
+        const Shape& sb = swap ? a : b;
+        const Iso& ia = swap ? mb : ma;
+        const Iso& ib = swap ? ma : mb;
+        V3 da = swap ? -dir : dir;
+        float2 anga = swap ? ang2 : ang1, angb = swap ? ang1 : ang2;
+        Feature& fa = swap ? m2 : m1;
+        Feature& fb = swap ? m1 : m2;
+        if (depth > 0.f) {
+            support_face_toward(sa, ia, da, fa);
+            support_face_toward(sb, ib, -da, fb);
+        } else {
+            support_feature_toward(sa, ia, da, anga, fa);
+            support_feature_toward(sb, ib, -da, angb, fb);
+        }
     }
     ClipCtx cc;
     cc.ma = &ma;
@@ -699,7 +733,10 @@ __device__ __noinline__ void convex_convex_manifold(const Iso& ma, const Shape& 
     cc.m1 = &m1;
     cc.m2 = &m2;
     cc.n_new = 0;
+    cc.n_buf = 0;
+    cc.normal = dir;
     clip(m1, m2, dir, linear, cc);
+    clip_flush(cc);
     if (cc.n_new == 0) {
         if (feature_ok_for_manifold(m1, m1.feature_id) && feature_ok_for_manifold(m2, m2.feature_id))
             manifold_push(mf, p1, p2, dir, depth, m1.feature_id, m2.feature_id, iso_inv_point(ma, p1));
