@@ -172,6 +172,8 @@ def run_native(args):
     ctx.lib.ncb_set_stream(ctx.h, C.c_void_p(stream.cuda_stream))
 
     n_per = args.n_objects or N_PER_GPU
+    if args.rays_only:
+        n_per = 2000
     n_total = n_per * world
     scene = config_scene(3, n_total)
     ctx.set_hulls(scene.hulls)
@@ -190,7 +192,10 @@ def run_native(args):
     ctx.set_objects(pin_scene)
     ctx.synchronize()
 
-    my_begin, my_end = rank * n_per, (rank + 1) * n_per
+    from ncollide_b200.parallel import ShardedWorld
+
+    sharded = ShardedWorld(ctx, scene, world, rank, dev)
+    my_begin, my_end = sharded.obj_begin, sharded.obj_end
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     lib, h = ctx.lib, ctx.h
     counts_c = _ffi.UpdateCountsC()
@@ -201,13 +206,7 @@ def run_native(args):
             r = lib.ncb_world_update_device(h, C.c_float(scene.margin), C.c_uint32(0), C.c_uint32(0xFFFFFFFF), C.byref(counts_c))
             ctx.check(r, "ncb_world_update_device")
         else:
-            ctx.check(lib.ncb_world_update_stage(h, 0, C.c_float(scene.margin), C.c_uint32(my_begin), C.c_uint32(my_end), None), "stage0")
-            for which in (0, 1):
-                full = torch.as_tensor(_CudaArray(lib.ncb_device_ptr(h, which), (n_total, 4), "<f4"), device=dev)
-                shard = full[my_begin:my_end].clone()
-                dist.all_gather_into_tensor(full, shard)
-            # query slice = this rank's share of the Morton order
-            ctx.check(lib.ncb_world_update_stage(h, 1, C.c_float(scene.margin), C.c_uint32(my_begin), C.c_uint32(my_end), C.byref(counts_c)), "stage1")
+            return sharded.step(counts_c)
         return ctx._counts(counts_c)
 
     def barrier():
@@ -331,7 +330,7 @@ def run_native(args):
     # ---- secondary figure: batched TriMesh ray casting (configs[3]) ---------------------------------------
     rays = None
     if not args.no_rays:
-        n_tris, n_rays = (1_000_000, 1_000_000) if not args.n_objects else (max(1000, args.n_objects), max(1000, args.n_objects))
+        n_tris, n_rays = (1_000_000, 1_000_000) if (not args.n_objects or args.rays_only) else (max(1000, args.n_objects), max(1000, args.n_objects))
         rs = make_ray_scene("terrain", n_tris, n_rays * world, seed=1004)
         mesh = ctx.trimesh(rs.verts, rs.tris)
         lo, hi = rank * n_rays, (rank + 1) * n_rays
@@ -374,6 +373,11 @@ def run_native(args):
             "e2e": {"value": n_rays * world / (ray_e2e_ms / 1e3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * 20},
         }
         mesh.close()
+        if args.rays_only:
+            if rank == 0:
+                print(json.dumps(rays))
+            ctx.close()
+            return 0
 
     # ---- CPU baseline beside it (rank 0, N = 1): the oracle port on a bounded sample -----------------------
     cpu = None
@@ -487,6 +491,7 @@ def main():
     ap.add_argument("--n-objects", type=int, default=0, help="objects per GPU (default 1,000,000)")
     ap.add_argument("--no-rays", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--rays-only", action="store_true", help="debug: only the ray-casting sub-benchmark, prints its dict")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
