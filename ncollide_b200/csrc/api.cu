@@ -40,6 +40,7 @@ static DevObjects dev_objects(ncb_ctx* c) {
     o.qlimit = c->qlimit.p;
     o.ang = c->ang.p;
     o.ang_cs = c->ang_cs.p;
+    o.ang_stride = c->ang_stride;
     return o;
 }
 
@@ -260,8 +261,13 @@ int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* o) {
     // cos/sin of the angular prediction: the reference evaluates them with libm (f32::cos / f32::sin in
     // Cuboid::support_feature_toward, cuboid.rs:317,331 and ConvexHull::support_feature_id_toward_eps, convex.rs:389);
     // CUDA's cosf/sinf are not the same function, so they are evaluated here, once per distinct value.
-    ctx->h_ang_cs.resize(n);
-    {
+    bool uniform_ang = true;
+    for (uint32_t i = 1; i < n && uniform_ang; ++i) uniform_ang = o->ang_pred[i] == o->ang_pred[0];
+    ctx->ang_stride = uniform_ang ? 0u : 1u;
+    ctx->h_ang_cs.resize(uniform_ang ? (n ? 1 : 0) : n);
+    if (uniform_ang) {
+        if (n) ctx->h_ang_cs[0] = make_float2(cosf(o->ang_pred[0]), sinf(o->ang_pred[0]));
+    } else {
         float last = 0.f;
         float2 cs = make_float2(1.f, 0.f);
         for (uint32_t i = 0; i < n; ++i) {
@@ -274,7 +280,7 @@ int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* o) {
         }
     }
     if (n) {
-        CK(cudaMemcpyAsync(ctx->ang_cs.p, ctx->h_ang_cs.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->ang_cs.p, ctx->h_ang_cs.data(), 8 * ctx->h_ang_cs.size(), cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->pos.p, o->pos, 12 * (size_t)n, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->rot.p, o->rot, 16 * (size_t)n, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->type.p, o->shape_type, 4 * (size_t)n, cudaMemcpyHostToDevice, s));

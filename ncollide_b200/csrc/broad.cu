@@ -327,45 +327,102 @@ __device__ __forceinline__ bool boxes_intersect(float4 alo, float4 ahi, float4 b
     return alo.x <= bhi.x && alo.y <= bhi.y && alo.z <= bhi.z && ahi.x >= blo.x && ahi.y >= blo.y && ahi.z >= blo.z;
 }
 
+// Candidate leaves are buffered per thread during the walk and emitted after it: the walk itself then contains no
+// atomics, no group / handle gathers and no stores, and the emission runs converged (one atomicAdd per warp for all
+// the pairs its 32 queries found).  A query with more than PAIR_BUF candidates spills through emit_pair() in-loop.
+#define PAIR_BUF 12
 __global__ void __launch_bounds__(128) k_pair_search(const float4* __restrict__ llo, const float4* __restrict__ lhi,
                                                      const float4* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ groups,
                                                      uint32_t q_begin, uint32_t q_end, uint2* __restrict__ pairs,
                                                      uint8_t* __restrict__ keys, uint32_t cap, DevCounters* cnt) {
     uint32_t m = n - cnt->n_outliers;
     uint32_t i = q_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m || i >= q_end || m < 2) return;
-    float4 qlo = __ldg(&llo[i]), qhi = __ldg(&lhi[i]);
-    uint32_t hq = __float_as_uint(qlo.w), tq = __float_as_uint(qhi.w);
-    uint32_t stack[64];
-    int sp = 0;
-    uint32_t node = 0;
-    for (;;) {
-        const float4* rec = nodes + 4 * (size_t)node;
-        float4 Llo = __ldg(rec + 0), Lhi = __ldg(rec + 1), Rlo = __ldg(rec + 2), Rhi = __ldg(rec + 3);
-        uint32_t left = __float_as_uint(Llo.w), right = __float_as_uint(Lhi.w);
-        uint32_t split = __float_as_uint(Rlo.w), last = __float_as_uint(Rhi.w);
-        bool goL = split > i && boxes_intersect(qlo, qhi, Llo, Lhi);
-        bool goR = last > i && boxes_intersect(qlo, qhi, Rlo, Rhi);
-        if (goL && (left & LEAF_BIT)) {
-            uint32_t j = left & ~LEAF_BIT;
-            uint32_t hj = __float_as_uint(__ldg(&llo[j].w)), tj = __float_as_uint(__ldg(&lhi[j].w));
-            if (groups_allow(groups, hq, hj)) emit_pair(hq, tq, hj, tj, pairs, keys, cap, cnt);
-            goL = false;
+    bool valid = i < m && i < q_end && m >= 2;
+    uint32_t buf[PAIR_BUF];
+    int nb = 0;
+    uint32_t hq = 0, tq = 0;
+    if (valid) {
+        float4 qlo = __ldg(&llo[i]), qhi = __ldg(&lhi[i]);
+        hq = __float_as_uint(qlo.w), tq = __float_as_uint(qhi.w);
+        uint32_t stack[64];
+        int sp = 0;
+        uint32_t node = 0;
+        for (;;) {
+            const float4* rec = nodes + 4 * (size_t)node;
+            float4 Llo = __ldg(rec + 0), Lhi = __ldg(rec + 1), Rlo = __ldg(rec + 2), Rhi = __ldg(rec + 3);
+            uint32_t left = __float_as_uint(Llo.w), right = __float_as_uint(Lhi.w);
+            uint32_t split = __float_as_uint(Rlo.w), last = __float_as_uint(Rhi.w);
+            bool goL = split > i && boxes_intersect(qlo, qhi, Llo, Lhi);
+            bool goR = last > i && boxes_intersect(qlo, qhi, Rlo, Rhi);
+            if (goL && (left & LEAF_BIT)) {
+                uint32_t j = left & ~LEAF_BIT;
+                if (nb < PAIR_BUF)
+                    buf[nb++] = j;
+                else {
+                    uint32_t hj = __float_as_uint(__ldg(&llo[j].w)), tj = __float_as_uint(__ldg(&lhi[j].w));
+                    if (groups_allow(groups, hq, hj)) emit_pair(hq, tq, hj, tj, pairs, keys, cap, cnt);
+                }
+                goL = false;
+            }
+            if (goR && (right & LEAF_BIT)) {
+                uint32_t j = right & ~LEAF_BIT;
+                if (nb < PAIR_BUF)
+                    buf[nb++] = j;
+                else {
+                    uint32_t hj = __float_as_uint(__ldg(&llo[j].w)), tj = __float_as_uint(__ldg(&lhi[j].w));
+                    if (groups_allow(groups, hq, hj)) emit_pair(hq, tq, hj, tj, pairs, keys, cap, cnt);
+                }
+                goR = false;
+            }
+            if (goL) {
+                if (goR && sp < 64) stack[sp++] = right;
+                node = left;
+            } else if (goR) {
+                node = right;
+            } else {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
         }
-        if (goR && (right & LEAF_BIT)) {
-            uint32_t j = right & ~LEAF_BIT;
+    }
+    // ---- converged emission: resolve handles / types / groups, compact, one allocation per warp ----
+    uint32_t hjs[PAIR_BUF];
+    uint8_t tjs[PAIR_BUF];
+    int na = 0;
+#pragma unroll
+    for (int k = 0; k < PAIR_BUF; ++k) {
+        if (k < nb) {
+            uint32_t j = buf[k];
             uint32_t hj = __float_as_uint(__ldg(&llo[j].w)), tj = __float_as_uint(__ldg(&lhi[j].w));
-            if (groups_allow(groups, hq, hj)) emit_pair(hq, tq, hj, tj, pairs, keys, cap, cnt);
-            goR = false;
+            if (groups_allow(groups, hq, hj)) {
+                hjs[na] = hj;
+                tjs[na] = (uint8_t)tj;
+                na++;
+            }
         }
-        if (goL) {
-            if (goR && sp < 64) stack[sp++] = right;
-            node = left;
-        } else if (goR) {
-            node = right;
-        } else {
-            if (sp == 0) break;
-            node = stack[--sp];
+    }
+    int lane = threadIdx.x & 31;
+    uint32_t incl = (uint32_t)na;
+    for (int off = 1; off < 32; off <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(&cnt->n_pairs, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    uint32_t slot = base + incl - (uint32_t)na;
+    for (int k = 0; k < na; ++k, ++slot) {
+        if (slot < cap) {
+            uint32_t hb = hjs[k], tb = tjs[k];
+            uint32_t h1, h2, t1, t2;
+            if (hq > hb) {
+                h1 = hq, t1 = tq, h2 = hb, t2 = tb;
+            } else {
+                h1 = hb, t1 = tb, h2 = hq, t2 = tq;
+            }
+            pairs[slot] = make_uint2(h1, h2);
+            keys[slot] = c_key_table[(t1 & 3) * 4 + (t2 & 3)];
         }
     }
 }

@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(128) k_cc_manifold(NarrowArgs A) {
             Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
             float linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
             Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
-            float2 ang1 = __ldg(&A.o.ang_cs[i1]), ang2 = __ldg(&A.o.ang_cs[i2]);
+            float2 ang1 = __ldg(&A.o.ang_cs[i1 * A.o.ang_stride]), ang2 = __ldg(&A.o.ang_cs[i2 * A.o.ang_stride]);
             Feature f1, f2;
             convex_convex_manifold(ma, a, mb, b, linear, ang1, ang2, p1, p2, dir, mf, f1, f2);
         }

@@ -46,6 +46,7 @@ struct DevObjects {
     const float* qlimit;
     const float* ang;
     const float2* ang_cs;    // (cos, sin) of ang, evaluated on the host with libm like the reference does
+    uint32_t ang_stride;     // 1: one entry per object; 0: every object has the same angular prediction (entry 0)
 };
 
 // Counters living in one device allocation (zeroed per update with one memset).
@@ -115,6 +116,7 @@ struct ncb_ctx {
     ncb::DevBuf<float2> ang_cs;
     ncb::DevBuf<uint32_t> type, groups;
     std::vector<float2> h_ang_cs;
+    uint32_t ang_stride = 1;
     // hulls
     ncb::DevHulls hulls = {};
     std::vector<void*> hull_allocs;

@@ -329,3 +329,72 @@ def test_ray_cast_edge_cases(ctx, oracle):
     om = oracle.trimesh(v, np.array([[0, 1, 2], [0, 1, 2], [0, 1, 3]], dtype=np.uint32))
     bt, bf, bn = om.ray_cast(np.array([[0.2, 0.2, 1]], dtype=np.float32), np.array([[0, 0, -1]], dtype=np.float32), mode=1)
     assert bf[0] == face[0]
+
+
+def test_query_slices_partition_the_pair_set(ctx, oracle):
+    """Multi-GPU sharding rule on one device: every Morton-order query slice emits its own pairs, the union is the
+    full pair set, no pair is emitted twice, and per-pair manifolds do not depend on the slicing."""
+    import ctypes as C
+
+    from ncollide_b200 import _ffi
+
+    s = config_scene(3, 7001)
+    ctx.set_scene(s)
+    full = ctx.world_fetch(ctx.world_update_device(s.margin))
+    n = s.n
+    cuts = [0, 1500, 1501, 4000, n]
+    got_pairs = []
+    per_pair = {}
+    for b, e in zip(cuts, cuts[1:]):
+        c = _ffi.UpdateCountsC()
+        ctx.check(ctx.lib.ncb_world_update_stage(ctx.h, 0, C.c_float(s.margin), C.c_uint32(0), C.c_uint32(n), None), "stage 0")
+        ctx.check(ctx.lib.ncb_world_update_stage(ctx.h, 1, C.c_float(s.margin), C.c_uint32(b), C.c_uint32(e), C.byref(c)), "stage 1")
+        r = ctx.world_fetch(ctx._counts(c))
+        got_pairs.append(r.pairs.copy())
+        for i, p in enumerate(map(tuple, r.pairs.tolist())):
+            per_pair[p] = r.contacts_of(i)[["world1", "world2", "normal", "depth", "f1", "f2"]].copy()
+    allp = np.concatenate(got_pairs)
+    assert len(allp) == len(full.pairs), "a pair was emitted by two slices or by none"
+    assert np.array_equal(canon(allp), canon(full.pairs))
+    for i, p in enumerate(map(tuple, full.pairs.tolist())):
+        a = full.contacts_of(i)[["world1", "world2", "normal", "depth", "f1", "f2"]]
+        b = per_pair[p]
+        assert len(a) == len(b)
+        for name in ("world1", "world2", "normal", "depth", "f1", "f2"):
+            assert np.array_equal(a[name], b[name])
+
+
+def test_golden_fixtures_on_device(ctx):
+    """tests/golden/*.npz (oracle outputs, see make_golden.py) reproduced by the device."""
+    import glob
+    import os
+
+    from tests.golden.make_golden import scene_from_npz
+
+    root = os.path.dirname(os.path.abspath(__file__))
+    for f in sorted(glob.glob(os.path.join(root, "golden", "world_*.npz"))):
+        z = np.load(f)
+        s = scene_from_npz(z)
+        ctx.set_hulls(s.hulls)
+        r = ctx.world_update(s)
+        assert np.array_equal(canon(r.pairs), canon(z["pairs"])), f
+        order = {tuple(p): i for i, p in enumerate(map(tuple, z["pairs"].tolist()))}
+        off = z["manifold_off"]
+        for i, p in enumerate(map(tuple, r.pairs.tolist())):
+            j = order[p]
+            c = r.contacts_of(i)
+            sl = slice(off[j], off[j + 1])
+            assert len(c) == off[j + 1] - off[j], (f, p)
+            assert np.array_equal(c["f1"], z["c_f1"][sl]) and np.array_equal(c["f2"], z["c_f2"][sl])
+            for name in ("world1", "world2", "normal", "depth"):
+                assert np.allclose(c[name], z["c_" + name][sl], rtol=RTOL, atol=ATOL), (f, p, name)
+    for f in sorted(glob.glob(os.path.join(root, "golden", "rays_*.npz"))):
+        z = np.load(f)
+        mesh = ctx.trimesh(z["verts"], z["tris"])
+        toi, face, normal = mesh.toi_and_normal_with_ray(None, z["origins"], z["dirs"])
+        diff = np.nonzero(face != z["face"])[0]
+        for i in diff:
+            assert ulp_diff(toi[i], z["toi"][i]) <= 4
+        same = face == z["face"]
+        assert np.array_equal(toi[same], z["toi"][same])
+        mesh.close()
