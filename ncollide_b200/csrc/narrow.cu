@@ -796,6 +796,7 @@ struct NarrowArgs {
     float2 one_degree_cs;  // cos / sin of (pi / 180) as f32, from the host libm (convex.rs:543)
     uint32_t* epa_queue;   // EPA_REC_WORDS per record
     uint32_t* cp_queue;    // CP_REC_WORDS per record
+    int epa_refill_min;    // idle lanes needed before a warp refills (batched initialisation)
 };
 
 // ---- convex x convex in three compacted phases -------------------------------------------------------------------
@@ -879,8 +880,11 @@ __global__ void __launch_bounds__(128) k_cc_gjk(NarrowArgs A) {
 // its initial polytope; a busy lane executes ONE expansion step per turn of the outer loop.  All busy lanes therefore
 // run the same code (one step) regardless of how many steps their pair needs; refills are batched (>= REFILL_MIN idle
 // lanes) so that the initialisation path is not paid on every turn.
-#define EPA_REFILL_MIN 8
-__global__ void __launch_bounds__(64) k_cc_epa(NarrowArgs A) {
+#define EPA_REFILL_MIN 32
+#ifndef NCB_EPA_MINBLOCKS
+#define NCB_EPA_MINBLOCKS 12
+#endif
+__global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) {
     const int KEY = CCQ;
     const uint32_t seg_end = A.cnt->epa_cursor[KEY];
     uint32_t* fetch = &A.cnt->epa_fetch[KEY];
@@ -894,7 +898,7 @@ __global__ void __launch_bounds__(64) k_cc_epa(NarrowArgs A) {
     for (;;) {
         int status = EPA_CONTINUE;
         unsigned idle = __ballot_sync(0xffffffffu, !active);
-        bool refill = !exhausted && (idle == 0xffffffffu || __popc(idle) >= EPA_REFILL_MIN);
+        bool refill = !exhausted && (idle == 0xffffffffu || __popc(idle) >= A.epa_refill_min);
         if (refill) {  // warp-uniform
             uint32_t base = 0;
             int leader = __ffs(idle) - 1;
@@ -1066,6 +1070,8 @@ cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pa
     A.manifold_count = c->manifold_count.p;
     A.cnt = c->counters.p;
     A.cap_pairs = cap_pairs;
+    static int refill_min = getenv("NCB_EPA_REFILL") ? atoi(getenv("NCB_EPA_REFILL")) : EPA_REFILL_MIN;
+    A.epa_refill_min = refill_min;
     A.epa_queue = c->epa_queue.p;
     A.cp_queue = c->cp_queue.p;
     {
@@ -1076,7 +1082,7 @@ cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pa
     int sm = c->sm_count;
     // tuning knobs (CTAs per SM of the persistent kernels); defaults chosen from ncu runs, see profiles/
     static int gjk_bpsm = getenv("NCB_GJK_BPSM") ? atoi(getenv("NCB_GJK_BPSM")) : 8;
-    static int epa_bpsm = getenv("NCB_EPA_BPSM") ? atoi(getenv("NCB_EPA_BPSM")) : 8;
+    static int epa_bpsm = getenv("NCB_EPA_BPSM") ? atoi(getenv("NCB_EPA_BPSM")) : 12;
     static int man_bpsm = getenv("NCB_MAN_BPSM") ? atoi(getenv("NCB_MAN_BPSM")) : 8;
     // Two independent chains: the convex-convex phases on the context's stream, everything else on a side stream
     // (each persistent kernel alone leaves most issue slots idle; together they overlap).
