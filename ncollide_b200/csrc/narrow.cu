@@ -459,46 +459,45 @@ __device__ __noinline__ void cuboid_project_point_with_feature(V3 he, const Iso&
     }
 }
 
-// ConvexHull::project_point_with_feature (point_support_map.rs:15-53 with solid = false, :97-116)
-__device__ __noinline__ void hull_project_point_with_feature(EpaState& e, const HullView& H, const Iso& m_in, V3 point, bool& inside,
-                                                             V3& proj, uint32_t& feature, float2 one_degree_cs, uint32_t* epa_overflow,
-                                                             uint32_t* ref_panics) {
+// ConvexHull::project_point_with_feature (point_support_map.rs:15-53 with solid = false, :97-116), in two parts so that
+// the rare "point inside the hull" case (EPA) can be deferred to its own compacted kernel.
+struct HullProjSetup {
+    Iso m;  // Translation::from(-point) * m
+    Support shape, origin;
+};
+NCB_HD HullProjSetup hull_proj_setup(const HullView& H, const Iso& m_in, V3 point) {
+    HullProjSetup u;
+    u.m = m_in;
+    u.m.t = (-point) + m_in.t;
+    u.shape.kind = 1;
+    u.shape.hull = H;
+    u.origin.kind = 2;
+    return u;
+}
+NCB_HD Iso iso_id() {
     Iso id;
     id.t = v3(0.f, 0.f, 0.f);
     id.q = Quat{0.f, 0.f, 0.f, 1.f};
-    Iso m = m_in;
-    m.t = (-point) + m_in.t;
-    Support shape;
-    shape.kind = 1;
-    shape.hull = H;
-    Support origin;
-    origin.kind = 2;
+    return id;
+}
+// gjk::project_origin: GJK_CLOSEST_POINTS (outside, proj set) or GJK_INTERSECTION (inside: simplex s feeds EPA)
+__device__ __noinline__ int hull_project_gjk(const HullProjSetup& u, V3 point, Simplex& s, V3& proj) {
+    Iso id = iso_id();
     V3 dir;
-    if (!unit_try_new(-m.t, NCB_EPS, dir)) dir = v3(1.f, 0.f, 0.f);
-    Simplex s;
-    simplex_init(s, cso_from_shapes(m, shape, id, origin, dir));
+    if (!unit_try_new(-u.m.t, NCB_EPS, dir)) dir = v3(1.f, 0.f, 0.f);
+    simplex_init(s, cso_from_shapes(u.m, u.shape, id, u.origin, dir));
     V3 p1, p2, d;
-    int r = gjk_closest_points(m, shape, id, origin, NCB_FMAX, s, p1, p2, d);
-    if (r == GJK_CLOSEST_POINTS) {
-        inside = false;
-        proj = p1 + point;
-    } else {
-        inside = true;
-        if (epa_closest_points(e, m, shape, id, origin, s.dim, s.v, p1, p2, d))
-            proj = p1 + point;
-        else {
-            if (e.overflow) atomicAdd(epa_overflow, 1u);
-            if (e.panicked) atomicAdd(ref_panics, 1u);
-            proj = point;
-        }
-    }
+    int r = gjk_closest_points(u.m, u.shape, id, u.origin, NCB_FMAX, s, p1, p2, d);
+    if (r == GJK_CLOSEST_POINTS) proj = p1 + point;
+    return r == GJK_CLOSEST_POINTS ? GJK_CLOSEST_POINTS : GJK_INTERSECTION;
+}
+// the feature of the projection (point_support_map.rs:104-116)
+NCB_HD uint32_t hull_project_feature(const HullView& H, const Iso& m_in, V3 point, bool inside, V3 proj, float2 one_degree_cs) {
     V3 dpt = point - proj;
     V3 local_dir = inside ? iso_inv_vec(m_in, -dpt) : iso_inv_vec(m_in, dpt);
     V3 u;
-    if (unit_try_new(local_dir, NCB_EPS, u))
-        feature = hull_support_feature_id_toward_eps(H, u, one_degree_cs);
-    else
-        feature = FID_UNKNOWN;
+    if (unit_try_new(local_dir, NCB_EPS, u)) return hull_support_feature_id_toward_eps(H, u, one_degree_cs);
+    return FID_UNKNOWN;
 }
 
 // (m1, ball) (m2, convex polyhedron)
@@ -990,6 +989,8 @@ __global__ void __launch_bounds__(128) k_narrow(NarrowArgs A) {
     for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
         uint32_t p = base + threadIdx.x;
         bool valid = p < seg_end;
+        bool deferred = false;
+        Simplex bh_simplex;
         mf.n = 0;
         mf.deepest = 0;
         if (valid) {
@@ -1032,14 +1033,81 @@ __global__ void __launch_bounds__(128) k_narrow(NarrowArgs A) {
                 const Shape& cp = flip ? a : b;
                 const Iso& mball = flip ? mb : ma;
                 const Iso& mcp = flip ? ma : mb;
-                bool inside;
+                HullProjSetup u = hull_proj_setup(cp.hull, mcp, mball.t);
                 V3 world2;
-                uint32_t f2;
-                EpaState e;
-                hull_project_point_with_feature(e, cp.hull, mcp, mball.t, inside, world2, f2, A.one_degree_cs, &A.cnt->epa_overflow,
-                                                &A.cnt->ref_panics);
-                gen_ball_convex_finish(mball.t, ball.radius, cp, inside, world2, f2, linear, flip, mf);
+                if (hull_project_gjk(u, mball.t, bh_simplex, world2) == GJK_CLOSEST_POINTS) {
+                    uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, false, world2, A.one_degree_cs);
+                    gen_ball_convex_finish(mball.t, ball.radius, cp, false, world2, f2, linear, flip, mf);
+                } else {
+                    deferred = true;  // ball centre inside the hull: EPA, in k_bh_epa
+                }
             }
+        }
+        if (KEY == K_BALL_HULL) {
+            uint32_t slot = queue_append(&A.cnt->epa_cursor[K_BALL_HULL], deferred);
+            if (deferred) {
+                uint32_t* q = A.epa_queue + (size_t)slot * EPA_REC_WORDS;
+                float* f = reinterpret_cast<float*>(q);
+                q[0] = p;
+                q[1] = (uint32_t)bh_simplex.dim;
+                for (int i = 0; i < 4; ++i) {
+                    f[2 + 6 * i + 0] = bh_simplex.v[i].orig1.x, f[2 + 6 * i + 1] = bh_simplex.v[i].orig1.y, f[2 + 6 * i + 2] = bh_simplex.v[i].orig1.z;
+                    f[2 + 6 * i + 3] = bh_simplex.v[i].orig2.x, f[2 + 6 * i + 4] = bh_simplex.v[i].orig2.y, f[2 + 6 * i + 5] = bh_simplex.v[i].orig2.z;
+                }
+            }
+        }
+        uint32_t out_index = valid ? (A.pair_index ? __ldg(&A.pair_index[p]) : p) : 0;
+        write_manifold(mf, valid && !deferred, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+    }
+}
+
+// Ball x hull pairs whose ball centre is inside the hull: EPA::project_origin + the rest of the generator.
+__global__ void __launch_bounds__(64) k_bh_epa(NarrowArgs A) {
+    uint32_t seg_begin = A.cnt->key_start[K_BALL_HULL];
+    uint32_t seg_end = A.cnt->epa_cursor[K_BALL_HULL];
+    uint32_t stride = gridDim.x * blockDim.x;
+    EpaState e;
+    Manifold mf;
+    for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
+        uint32_t w = base + threadIdx.x;
+        bool valid = w < seg_end;
+        mf.n = 0;
+        mf.deepest = 0;
+        uint32_t p = 0;
+        if (valid) {
+            const uint32_t* q = A.epa_queue + (size_t)w * EPA_REC_WORDS;
+            const float* f = reinterpret_cast<const float*>(q);
+            p = q[0];
+            int sdim = (int)q[1];
+            CSOPoint sv[4];
+            for (int i = 0; i < 4; ++i) {
+                sv[i].orig1 = v3(f[2 + 6 * i + 0], f[2 + 6 * i + 1], f[2 + 6 * i + 2]);
+                sv[i].orig2 = v3(f[2 + 6 * i + 3], f[2 + 6 * i + 4], f[2 + 6 * i + 5]);
+                sv[i].point = sv[i].orig1 - sv[i].orig2;
+            }
+            uint2 pr = __ldg(&A.pairs[p]);
+            uint32_t i1 = pr.x, i2 = pr.y;
+            uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
+            Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
+            float linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
+            Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+            bool flip = t1 != NCB_SHAPE_BALL;
+            const Shape& ball = flip ? b : a;
+            const Shape& cp = flip ? a : b;
+            const Iso& mball = flip ? mb : ma;
+            const Iso& mcp = flip ? ma : mb;
+            HullProjSetup u = hull_proj_setup(cp.hull, mcp, mball.t);
+            Iso id = iso_id();
+            V3 p1, p2, d, world2;
+            if (epa_closest_points(e, u.m, u.shape, id, u.origin, sdim, sv, p1, p2, d))
+                world2 = p1 + mball.t;
+            else {
+                if (e.overflow) atomicAdd(&A.cnt->epa_overflow, 1u);
+                if (e.panicked) atomicAdd(&A.cnt->ref_panics, 1u);
+                world2 = mball.t;
+            }
+            uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, true, world2, A.one_degree_cs);
+            gen_ball_convex_finish(mball.t, ball.radius, cp, true, world2, f2, linear, flip, mf);
         }
         uint32_t out_index = valid ? (A.pair_index ? __ldg(&A.pair_index[p]) : p) : 0;
         write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
@@ -1091,7 +1159,8 @@ cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pa
         cudaEventRecord(c->ev_fork, s);
         cudaStreamWaitEvent(s2, c->ev_fork, 0);
     }
-    k_narrow<K_BALL_HULL><<<sm * 4, 128, 0, s2>>>(A);
+    k_narrow<K_BALL_HULL><<<sm * 8, 128, 0, s2>>>(A);
+    k_bh_epa<<<sm * 4, 64, 0, s2>>>(A);
     k_narrow<K_BALL_CUBOID><<<sm * 8, 128, 0, s2>>>(A);
     k_narrow<K_BALL_BALL><<<sm * 8, 128, 0, s2>>>(A);
     k_narrow<K_PLANE_BALL><<<sm * 2, 128, 0, s2>>>(A);
