@@ -34,6 +34,15 @@ UNIT = "updates/s (1M-shape worlds)"
 N_PER_GPU = 1_000_000
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -276,7 +285,8 @@ def run_native(args):
         dom_bytes = stage_bytes(dom_name, n_total // world if world > 1 else n_total, counts, scene)
         ach = dom_bytes / (dom_ms / 1e3) / 1e9
         roofline = {
-            "bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": measured_traffic(dom_name) if (n_per == N_PER_GPU) else None,
             "peak_kind": f"{peak_kind} copy bandwidth", "kernel_ms": dom_ms, "algorithmic_bytes": dom_bytes,
             "share_of_step": dom_ms / max(sum(stage_acc.values()), 1e-9),
             "whole_step": {"algorithmic_bytes": total_bytes, "achieved": total_bytes / (ms_step / 1e3) / 1e9,
@@ -369,7 +379,8 @@ def run_native(args):
             "workload": f"{n_rays} rays per GPU vs {T}-triangle terrain TriMesh (first hit + TOI + normal)",
             "hit_fraction": float((d_toi >= 0).float().mean().item()),
             "roofline": {"bound": "hbm", "achieved": ray_bytes / (rms_mean / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": ray_bytes / (rms_mean / 1e3) / 1e9 / peak, "algorithmic_bytes": ray_bytes, "traffic": None},
+                         "frac": ray_bytes / (rms_mean / 1e3) / 1e9 / peak, "algorithmic_bytes": ray_bytes,
+                         "traffic": measured_traffic("k_ray_cast") if n_rays == 1_000_000 else None},
             "e2e": {"value": n_rays * world / (ray_e2e_ms / 1e3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * 20},
         }
         mesh.close()

@@ -829,7 +829,10 @@ NCB_HD void cp_store(uint32_t* q, uint32_t slot, uint32_t p, V3 p1, V3 p2, V3 di
 // The three convex-convex keys are adjacent in the key order, so their pairs form ONE contiguous range of the sorted
 // pair array and share one EPA queue and one manifold queue (cursor slot CCQ): a single launch per phase, one tail.
 #define CCQ K_CUBOID_CUBOID
-__global__ void __launch_bounds__(128) k_cc_gjk(NarrowArgs A) {
+#ifndef NCB_GJK_MINBLOCKS
+#define NCB_GJK_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(128, NCB_GJK_MINBLOCKS) k_cc_gjk(NarrowArgs A) {
     const int KEY = CCQ;
     uint32_t seg_begin = A.cnt->key_start[K_CUBOID_CUBOID];
     uint32_t seg_end = A.cnt->key_start[K_HULL_HULL] + A.cnt->key_hist[K_HULL_HULL];
@@ -881,7 +884,7 @@ __global__ void __launch_bounds__(128) k_cc_gjk(NarrowArgs A) {
 // lanes) so that the initialisation path is not paid on every turn.
 #define EPA_REFILL_MIN 32
 #ifndef NCB_EPA_MINBLOCKS
-#define NCB_EPA_MINBLOCKS 12
+#define NCB_EPA_MINBLOCKS 16
 #endif
 __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) {
     const int KEY = CCQ;
@@ -946,7 +949,10 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) 
     }
 }
 
-__global__ void __launch_bounds__(128) k_cc_manifold(NarrowArgs A) {
+#ifndef NCB_MAN_MINBLOCKS
+#define NCB_MAN_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(128, NCB_MAN_MINBLOCKS) k_cc_manifold(NarrowArgs A) {
     const int KEY = CCQ;
     uint32_t seg_begin = A.cnt->key_start[KEY];
     uint32_t seg_end = A.cnt->cp_cursor[KEY];
@@ -1149,9 +1155,9 @@ cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pa
     cudaStream_t s = c->stream;
     int sm = c->sm_count;
     // tuning knobs (CTAs per SM of the persistent kernels); defaults chosen from ncu runs, see profiles/
-    static int gjk_bpsm = getenv("NCB_GJK_BPSM") ? atoi(getenv("NCB_GJK_BPSM")) : 8;
-    static int epa_bpsm = getenv("NCB_EPA_BPSM") ? atoi(getenv("NCB_EPA_BPSM")) : 12;
-    static int man_bpsm = getenv("NCB_MAN_BPSM") ? atoi(getenv("NCB_MAN_BPSM")) : 8;
+    static int gjk_bpsm = getenv("NCB_GJK_BPSM") ? atoi(getenv("NCB_GJK_BPSM")) : 6;
+    static int epa_bpsm = getenv("NCB_EPA_BPSM") ? atoi(getenv("NCB_EPA_BPSM")) : 16;
+    static int man_bpsm = getenv("NCB_MAN_BPSM") ? atoi(getenv("NCB_MAN_BPSM")) : 6;
     // Two independent chains: the convex-convex phases on the context's stream, everything else on a side stream
     // (each persistent kernel alone leaves most issue slots idle; together they overlap).
     cudaStream_t s2 = c->side_stream ? c->side_stream : s;
