@@ -311,7 +311,7 @@ def run_native(args):
             ctx.check(r, "ncb_world_update")
         else:
             # every rank uploads the poses of its own block, steps, and reads its own results back
-            lib.ncb_set_positions(h, C.c_uint32(n_total), _ffi.ptr(pin_scene.pos), _ffi.ptr(pin_scene.rot))
+            sharded.upload_own_poses(pin_scene.pos, pin_scene.rot)
             step_device()
             ctx.check(lib.ncb_world_fetch(h, _ffi.ptr(pin_out["pairs"]), C.c_uint32(len(pin_out["pairs"])), _ffi.ptr(pin_out["algo"]),
                                           _ffi.ptr(pin_out["start"]), _ffi.ptr(pin_out["count"]), _ffi.ptr(pin_out["contacts"]),
@@ -334,7 +334,7 @@ def run_native(args):
         e2e_ms = float(t.item())
     e2e_value = (n_total / 1e6) / (e2e_ms / 1e3)
     n_up = n_total
-    h2d = n_up * (12 + 16 + 4 + 16 + 12 + 4 + 4 + 8) if world == 1 else n_total * 28
+    h2d = n_up * (12 + 16 + 4 + 16 + 12 + 4 + 4) + 8 if world == 1 else n_per * 28
     d2h = counts["n_pairs"] * (8 + 1 + 4 + 1) + counts["n_contacts"] * 52 + 256
 
     # ---- secondary figure: batched TriMesh ray casting (configs[3]) ---------------------------------------

@@ -124,6 +124,9 @@ int ncb_set_hulls(ncb_ctx* ctx, const ncb_hull_library* lib);
 int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* objs);
 /* CollisionObject::set_position for all objects (pipeline/object/collision_object.rs:186-190). */
 int ncb_set_positions(ncb_ctx* ctx, uint32_t n, const float* pos, const float* rot);
+/* Same for the objects [begin, begin + count) only (multi-GPU: every rank uploads its own block; the blocks are then
+ * all-gathered on the device buffers returned by ncb_device_ptr(ctx, 4 / 5)). pos / rot point at the block. */
+int ncb_set_positions_range(ncb_ctx* ctx, uint32_t begin, uint32_t count, const float* pos, const float* rot);
 
 /* ---- stage entry points (each mirrors one reference routine, host buffers in/out) ---------------------------- */
 /* mode 0: bounding_volume::aabb(shape, position) (shape/shape.rs aabb, bounding_volume/aabb_*.rs);

@@ -309,6 +309,17 @@ int ncb_set_positions(ncb_ctx* ctx, uint32_t n, const float* pos, const float* r
     return NCB_OK;
 }
 
+int ncb_set_positions_range(ncb_ctx* ctx, uint32_t begin, uint32_t count, const float* pos, const float* rot) {
+    if (!ctx) return NCB_ERR_ARG;
+    REQUIRE((uint64_t)begin + count <= ctx->n, NCB_ERR_ARG, "ncb_set_positions_range: range exceeds the object count");
+    CK(cudaSetDevice(ctx->device));
+    if (count) {
+        CK(cudaMemcpyAsync(ctx->pos.p + 3 * (size_t)begin, pos, 12 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->rot.p + begin, rot, 16 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return NCB_OK;
+}
+
 // ---- stage entry points ------------------------------------------------------------------------------------
 __global__ void k_unpack_aabb(const float4* lo, const float4* hi, uint32_t n, float* out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

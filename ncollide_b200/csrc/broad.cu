@@ -115,7 +115,21 @@ __global__ void __launch_bounds__(256) k_bounds(const float4* __restrict__ lo, c
         }
         nout += __shfl_xor_sync(0xffffffffu, nout, off);
     }
-    if ((threadIdx.x & 31) == 0) {
+    // block-level combine in shared memory, then 7 global atomics per CTA (not per warp)
+    __shared__ float s_mn[8][3], s_mx[8][3];
+    __shared__ uint32_t s_out[8];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        for (int k = 0; k < 3; ++k) s_mn[warp][k] = mn[k], s_mx[warp][k] = mx[k];
+        s_out[warp] = nout;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nw = blockDim.x >> 5;
+        for (int w = 1; w < nw; ++w) {
+            for (int k = 0; k < 3; ++k) mn[k] = fminf(mn[k], s_mn[w][k]), mx[k] = fmaxf(mx[k], s_mx[w][k]);
+            nout += s_out[w];
+        }
         for (int k = 0; k < 3; ++k) {
             atomicMin(&cnt->bounds[k], f2o(mn[k]));
             atomicMax(&cnt->bounds[3 + k], f2o(mx[k]));
@@ -261,7 +275,7 @@ size_t lbvh_temp_bytes(uint32_t n) {
 cudaError_t launch_lbvh_build(ncb_ctx* c, uint32_t n, const uint32_t*) {
     cudaStream_t s = c->stream;
     if (n == 0) return cudaSuccess;
-    int gs = c->sm_count * 8;
+    int gs = c->sm_count * 4;
     uint32_t nb = (n + 255) / 256;
     k_bounds<<<min((uint32_t)gs, nb), 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, n, c->counters.p);
     k_morton<<<nb, 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, n, c->counters.p, c->keys_a.p, c->idx_a.p);

@@ -57,6 +57,26 @@ class ShardedWorld:
         lib, h = self.ctx.lib, self.ctx.h
         return [torch.as_tensor(_CudaArray(lib.ncb_device_ptr(h, w), (self.n, 4), "<f4"), device=self.device) for w in (0, 1)]
 
+    def pose_tensors(self):
+        import torch
+
+        lib, h = self.ctx.lib, self.ctx.h
+        return [
+            torch.as_tensor(_CudaArray(lib.ncb_device_ptr(h, 4), (self.n, 3), "<f4"), device=self.device),
+            torch.as_tensor(_CudaArray(lib.ncb_device_ptr(h, 5), (self.n, 4), "<f4"), device=self.device),
+        ]
+
+    def upload_own_poses(self, pos, rot):
+        """End-to-end input path: this rank uploads the poses of ITS block from host memory, then the blocks are
+        all-gathered so that every rank holds every pose (narrow-phase operands are read from the replicated arrays)."""
+        b, e = self.obj_begin, self.obj_end
+        from ._ffi import ptr
+
+        self.ctx.check(self.ctx.lib.ncb_set_positions_range(self.ctx.h, C.c_uint32(b), C.c_uint32(e - b), ptr(pos[b:e]), ptr(rot[b:e])), "set_positions_range")
+        if self.world > 1:
+            for t in self.pose_tensors():
+                all_gather_rows(t, b, e, self.world)
+
     def step(self, counts_c):
         lib, h, m = self.ctx.lib, self.ctx.h, C.c_float(self.scene.margin)
         self.ctx.check(lib.ncb_world_update_stage(h, 0, m, C.c_uint32(self.obj_begin), C.c_uint32(self.obj_end), None), "stage 0")
