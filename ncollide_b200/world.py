@@ -167,6 +167,7 @@ class Context:
         """The end-to-end host-buffer call (ncb_world_update): uploads the objects, runs the step, copies results back."""
         oc, keep = _ffi.pack_objects(scene)
         n = oc.n
+        self.n = n
         if bufs is None:
             bufs = self.alloc_result_buffers(max(8 * n, 1024), max(8 * n, 1024))
         while True:

@@ -398,3 +398,35 @@ def test_golden_fixtures_on_device(ctx):
         same = face == z["face"]
         assert np.array_equal(toi[same], z["toi"][same])
         mesh.close()
+
+
+def test_full_size_1M_world_update_parity(ctx, oracle):
+    """BASELINE.json configs[2] at its full size: 1,000,000 mixed balls / cuboids / hulls.  The canonical pair set must be
+    bit-exact against the reference-faithful DBVT broad phase of the oracle, and every manifold within tolerance."""
+    s = config_scene(3)
+    assert s.n == 1_000_000
+    ctx.set_hulls(s.hulls)
+    res = ctx.world_update(s)
+    assert res.counts["epa_overflow"] == 0 and res.counts["ref_panics"] == 0
+    fat = oracle.compute_aabbs(s)
+    got = ctx.compute_aabbs(s.margin, 2)
+    assert np.array_equal(got.view(np.uint32), fat.view(np.uint32)), "fat AABBs differ at 1M"
+    want = oracle.broad_phase(fat, s.groups, mode=0)
+    assert len(want) == len(res.pairs)
+    assert np.array_equal(canon(res.pairs), canon(want)), "pair set differs at 1M"
+    compare_manifolds(res, s, oracle, "cfg3 1M")
+    # size-independent properties
+    c = res.contacts
+    assert np.allclose(np.linalg.norm(c["normal"], axis=1), 1, atol=1e-5)
+    d = -np.einsum("ij,ij->i", c["normal"], c["world2"] - c["world1"])
+    assert np.allclose(d, c["depth"], atol=3e-5)
+    assert int(res.manifold_count.sum()) == len(c)
+
+
+def test_full_size_1M_ray_cast_parity(ctx, oracle):
+    """BASELINE.json configs[3] at full size: 1M rays vs a 1M-triangle terrain TriMesh, against the reference-faithful BVT
+    best-first search of the oracle (face ids identical outside the tie class, TOI within tolerance)."""
+    rs = make_ray_scene("terrain", 1_000_000, 1_000_000, seed=1004)
+    nties, nhits = check_rays(ctx, oracle, rs, brute=False)
+    assert nhits > 500_000
+    assert nties <= 50
