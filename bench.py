@@ -443,10 +443,8 @@ def stage_bytes(name, n, counts, scene):
     vbar = float(np.diff(scene.hulls.vert_off).mean()) if scene.hulls.n_hulls else 0.0
     na = counts["n_algo"]
     types = scene.shape_type
-    fb, fc, fh = [(types == t).mean() for t in (0, 1, 2)]
-    # pairs per key from the dispatched algorithm counts and the type mix
-    bc_total = max(na["ball_convex"], 1)
-    cc_total = max(na["convex_convex"], 1)
+    fc, fh = [(types == t).mean() for t in (1, 2)]
+    # pairs per key estimated from the dispatched algorithm counts and the cuboid / hull mix of the scene
     w_bcub, w_bh = fc / max(fc + fh, 1e-9), fh / max(fc + fh, 1e-9)
     w_cc, w_ch, w_hh = fc * fc, 2 * fc * fh, fh * fh
     wsum = max(w_cc + w_ch + w_hh, 1e-9)
