@@ -185,6 +185,36 @@ int ncb_trimesh_ray_cast(ncb_mesh* mesh, const float* pose_tq, uint32_t n_rays, 
 int ncb_trimesh_ray_cast_device(ncb_mesh* mesh, const float* pose_tq_host, uint32_t n_rays, const float* d_origins,
                                 const float* d_dirs, float max_toi, float* d_toi, uint32_t* d_face, float* d_normal);
 
+/* ---- Persistent broad phase: the BroadPhase trait surface over several updates -------------- */
+/* Replaces DBVTBroadPhase (pipeline/broad_phase/dbvt_broad_phase.rs) behind pipeline/broad_phase/broad_phase.rs:68-99.
+ * Handles are slab keys handed out LIFO like the reference's (`slab` crate).  Boxes are 6 floats (mins, maxs).
+ * After each ncb_bp_update the interference set equals the reference's: { (i, j) : stored boxes intersect (inclusive),
+ * groups allow }, where a stored box changes only when a new box is not contained in it (then: new.loosened(margin)).
+ * The collision groups of a handle must not change while it is alive (the reference's world re-creates the proxy). */
+typedef struct ncb_bp ncb_bp;
+/* DBVTBroadPhase::new(margin) (dbvt_broad_phase.rs:75-88) */
+int ncb_bp_create(ncb_ctx* ctx, float margin, ncb_bp** out);
+void ncb_bp_destroy(ncb_bp* bp);
+/* BroadPhase::create_proxy (:275-280) for n boxes, in order; out_handles[n]. */
+int ncb_bp_create_proxies(ncb_bp* bp, uint32_t n, const float* aabb_minmax, uint32_t* out_handles);
+/* BroadPhase::deferred_set_bounding_volume (:325-347) for n (handle, box) entries, in order.  NCB_ERR_ARG when a
+ * handle does not exist (the reference panics). */
+int ncb_bp_set_bounding_volumes(ncb_bp* bp, uint32_t n, const uint32_t* handles, const float* aabb_minmax);
+/* BroadPhase::remove (:282-323).  The dropped interferences are readable as the "stopped" list of ncb_bp_events. */
+int ncb_bp_remove(ncb_bp* bp, uint32_t n, const uint32_t* handles, uint32_t* n_removed);
+/* BroadPhase::update (:174-259).  groups = 3 words per handle slot (membership, whitelist, blacklist) or NULL. */
+int ncb_bp_update(ncb_bp* bp, const uint32_t* groups, uint32_t n_group_slots, uint32_t* n_started, uint32_t* n_stopped);
+/* Events of the last ncb_bp_update / ncb_bp_remove, sorted: started[2 * n_started] = the arguments of
+ * BroadPhaseInterferenceHandler::interference_started (re-inserted proxy first; when both moved, the one updated
+ * later first), stopped[2 * n_stopped] = those of interference_stopped (smaller handle first). */
+int ncb_bp_events(ncb_bp* bp, uint32_t* started, uint32_t* stopped);
+/* BroadPhase::num_interferences (:349-351) */
+int ncb_bp_num_interferences(ncb_bp* bp, uint32_t* n);
+/* The current interference set, sorted, (smaller, larger) handle per pair; cap in pairs; returns 1 when truncated. */
+int ncb_bp_pairs(ncb_bp* bp, uint32_t* pairs, uint32_t cap, uint32_t* n);
+/* BroadPhase::proxy (:262-273): returns 1 and the stored (loosened) box when the proxy is attached, else 0. */
+int ncb_bp_proxy(ncb_bp* bp, uint32_t handle, float* minmax);
+
 const char* ncb_version(void);
 
 #ifdef __cplusplus

@@ -16,6 +16,8 @@ EXPORTED_SYMBOLS = [
     "ncb_world_update_device", "ncb_world_fetch", "ncb_world_update", "ncb_device_ptr", "ncb_world_update_stage",
     "ncb_profile_enable", "ncb_profile_get", "ncb_trimesh_create", "ncb_trimesh_destroy", "ncb_trimesh_ray_cast",
     "ncb_trimesh_ray_cast_device",
+    "ncb_bp_create", "ncb_bp_destroy", "ncb_bp_create_proxies", "ncb_bp_set_bounding_volumes", "ncb_bp_remove", "ncb_bp_update",
+    "ncb_bp_events", "ncb_bp_num_interferences", "ncb_bp_pairs", "ncb_bp_proxy",
 ]
 
 HULL_FIELDS = (
@@ -87,6 +89,8 @@ def load_library():
     lib.ncb_device_ptr.argtypes = [C.c_void_p, C.c_int]
     lib.ncb_destroy.argtypes = [C.c_void_p]
     lib.ncb_trimesh_destroy.argtypes = [C.c_void_p]
+    lib.ncb_bp_destroy.argtypes = [C.c_void_p]
+    lib.ncb_bp_destroy.restype = None
     _lib = lib
     return lib
 

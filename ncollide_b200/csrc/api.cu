@@ -468,7 +468,7 @@ static int update_after_aabbs(ncb_ctx* ctx, uint32_t q_begin, uint32_t q_end) {
         r = reset_counters(ctx);
         if (r) return r;
         if (!ctx->timer_external || attempt > 0) timer_begin(ctx);
-        CK(launch_lbvh_build(ctx, n, ctx->type.p));
+        CK(launch_lbvh_build(ctx, n, nullptr));
         CK(launch_pair_search(ctx, n, ctx->has_groups ? ctx->groups.p : nullptr, q_begin, q_end, (uint32_t)cap_pairs));
         timer_mark(ctx, "pair_search", 2);
         CK(launch_pair_sort(ctx, (uint32_t)cap_pairs, nullptr));

@@ -1,0 +1,580 @@
+// Persistent (multi-step) broad phase behind the reference's BroadPhase trait surface:
+// create_proxy / remove / deferred_set_bounding_volume / update with interference_started / interference_stopped.
+//
+// Replaces (reference, file:line): pipeline/broad_phase/dbvt_broad_phase.rs:101-147 (purge), :174-259 (update),
+// :262-347 (proxy, create_proxy, remove, deferred_set_bounding_volume); slab handle reuse (LIFO) as the `slab` crate.
+//
+// Semantics used: after every update() the reference's pair set equals {(i, j): stored boxes intersect, pair allowed}
+//   - a proxy's stored box only changes when the new box is NOT contained in it (then it becomes new.loosened(margin));
+//   - re-inserted leaves query both trees, every other pair is re-validated by the purge (`updated` is never reset in
+//     the reference, dbvt_broad_phase.rs:39,206), DBVT internal boxes are supersets, so nothing is missed or kept wrongly.
+// So an update is: apply pending boxes -> LBVH over the attached proxies -> all pairs -> sorted 64-bit keys ->
+// started = new \ old, stopped = old \ new.  interference_started(a, b) gets the re-inserted leaf first (the later
+// one in update order when both moved); interference_stopped gets SortedPair order (smaller handle first).
+#include <cub/cub.cuh>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "ncb_internal.h"
+
+using namespace ncb;
+
+#define SEQ_NONE 0xffffffffu
+enum : uint32_t { ST_DETACHED = 0, ST_ATTACHED = 1, ST_REMOVING = 2, ST_VACANT = 3 };
+
+struct ncb_bp {
+    ncb_ctx* owner = nullptr;
+    ncb_ctx* work = nullptr;  // private LBVH / pair buffers
+    float margin = 0.f;
+    // host slab (LIFO reuse like the `slab` crate)
+    std::vector<int64_t> next_free;  // -2 occupied, else next vacant
+    std::vector<uint8_t> attached;   // host mirror: 0 detached (pending), 1 attached
+    size_t next = 0, len = 0;
+    uint32_t n_attached = 0;
+    uint32_t seq = 0;  // pending entries issued since the last update
+    // device state, indexed by handle slot
+    DevBuf<float4> box_lo, box_hi, pend_lo, pend_hi;
+    DevBuf<uint32_t> pend_seq, upd_seq, win, d_attached;
+    size_t slots_cap = 0;
+    // staging
+    DevBuf<float> stage_f;
+    DevBuf<uint32_t> stage_u, alive, groups_dev;
+    DevBuf<unsigned long long> keys_old, keys_new, keys_tmp;
+    DevBuf<uint8_t> cub_tmp;
+    DevBuf<unsigned long long> ev_a, ev_b, ev_sorted;  // started / stopped events as (first << 32 | second)
+    DevBuf<uint32_t> ev_u32, counters;
+    uint32_t n_old = 0;
+    uint32_t n_started = 0, n_stopped = 0;  // events of the last update() / remove()
+    std::string err;
+};
+
+namespace {
+
+__global__ void k_bp_fill(uint32_t* p, uint32_t v, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// create_proxy: pending box = bv as given (no margin), dbvt_broad_phase.rs:275-280
+__global__ void k_bp_stage_create(const uint32_t* __restrict__ handles, const float* __restrict__ mm, uint32_t n, uint32_t seq0, float4* pend_lo,
+                                  float4* pend_hi, uint32_t* pend_seq, uint32_t* d_attached) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h = handles[i];
+    const float* s = mm + 6 * (size_t)i;
+    pend_lo[h] = make_float4(s[0], s[1], s[2], 0.f);
+    pend_hi[h] = make_float4(s[3], s[4], s[5], 0.f);
+    // a recycled slot may still carry a queued entry of its previous owner (the reference's queue is keyed by handle):
+    // the new leaf then takes that earlier place in the update order
+    pend_seq[h] = min(pend_seq[h], seq0 + i);
+    d_attached[h] = ST_DETACHED;
+}
+// deferred_set_bounding_volume (:325-347), pass 1: which entries push, who wins per handle, first sequence number
+__global__ void k_bp_stage_set1(const uint32_t* __restrict__ handles, const float* __restrict__ mm, uint32_t n, uint32_t seq0,
+                                const float4* __restrict__ box_lo, const float4* __restrict__ box_hi, const uint32_t* __restrict__ d_attached,
+                                uint32_t* win, uint32_t* pend_seq) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h = handles[i];
+    const float* s = mm + 6 * (size_t)i;
+    bool needs = true;
+    if (d_attached[h] == ST_ATTACHED) {
+        float4 lo = box_lo[h], hi = box_hi[h];
+        bool contains = lo.x <= s[0] && lo.y <= s[1] && lo.z <= s[2] && hi.x >= s[3] && hi.y >= s[4] && hi.z >= s[5];  // aabb.rs:161
+        needs = !contains;
+    }
+    if (needs) {
+        atomicMax(&win[h], i + 1);
+        atomicMin(&pend_seq[h], seq0 + i);
+    }
+}
+// pass 2: the last pushing entry of each handle writes bv.loosened(margin)
+__global__ void k_bp_stage_set2(const uint32_t* __restrict__ handles, const float* __restrict__ mm, uint32_t n, float margin,
+                                const uint32_t* __restrict__ win, float4* pend_lo, float4* pend_hi) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h = handles[i];
+    if (win[h] != i + 1) return;
+    const float* s = mm + 6 * (size_t)i;
+    pend_lo[h] = make_float4(s[0] + (-margin), s[1] + (-margin), s[2] + (-margin), 0.f);
+    pend_hi[h] = make_float4(s[3] + margin, s[4] + margin, s[5] + margin, 0.f);
+}
+__global__ void k_bp_clear_win(const uint32_t* __restrict__ handles, uint32_t n, uint32_t* win) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) win[handles[i]] = 0;
+}
+// update, step 1: apply pending boxes
+__global__ void k_bp_apply(uint32_t slots, float4* box_lo, float4* box_hi, const float4* __restrict__ pend_lo, const float4* __restrict__ pend_hi,
+                           uint32_t* pend_seq, uint32_t* upd_seq, uint32_t* d_attached) {
+    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= slots) return;
+    uint32_t s = pend_seq[h];
+    pend_seq[h] = SEQ_NONE;
+    if (d_attached[h] == ST_VACANT) s = SEQ_NONE;  // queued entries of removed proxies are dropped (:180-182)
+    upd_seq[h] = s;
+    if (s != SEQ_NONE) {
+        box_lo[h] = pend_lo[h];
+        box_hi[h] = pend_hi[h];
+        d_attached[h] = ST_ATTACHED;
+    }
+}
+__global__ void k_bp_gather(const uint32_t* __restrict__ alive, uint32_t m, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
+                            float4* lo, float4* hi) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    uint32_t h = alive[k];
+    lo[k] = box_lo[h];
+    hi[k] = box_hi[h];
+}
+__global__ void k_bp_keys(const uint2* __restrict__ pairs, uint32_t np, unsigned long long* keys) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    uint2 pr = pairs[p];
+    uint32_t lo = min(pr.x, pr.y), hi = max(pr.x, pr.y);
+    keys[p] = ((unsigned long long)lo << 32) | hi;
+}
+__device__ bool bp_contains_key(const unsigned long long* __restrict__ keys, uint32_t n, unsigned long long k) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        unsigned long long v = keys[mid];
+        if (v < k)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo < n && keys[lo] == k;
+}
+// out = a \ b (both sorted); mode 1 orients the pair like interference_started
+__global__ void k_bp_diff(const unsigned long long* __restrict__ a, uint32_t na, const unsigned long long* __restrict__ b, uint32_t nb, int mode,
+                          const uint32_t* __restrict__ upd_seq, unsigned long long* out, uint32_t* counter) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= na) return;
+    unsigned long long k = a[i];
+    if (bp_contains_key(b, nb, k)) return;
+    uint32_t slot = atomicAdd(counter, 1u);
+    uint32_t lo = (uint32_t)(k >> 32), hi = (uint32_t)k;
+    uint32_t first = lo, second = hi;
+    if (mode == 1) {
+        uint32_t sl = upd_seq[lo], sh = upd_seq[hi];
+        // the re-inserted leaf comes first; when both were re-inserted, the later one met the earlier one in the tree
+        bool hi_first = (sh != SEQ_NONE) && (sl == SEQ_NONE || sh > sl);
+        if (hi_first) first = hi, second = lo;
+    }
+    out[slot] = ((unsigned long long)first << 32) | second;
+}
+__global__ void k_bp_unpack(const unsigned long long* __restrict__ ev, uint32_t n, uint32_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long k = ev[i];
+    out[2 * i] = (uint32_t)(k >> 32);
+    out[2 * i + 1] = (uint32_t)k;
+}
+// remove(): drop the keys that involve a removed handle
+__global__ void k_bp_mark_removed(unsigned long long* keys, uint32_t n, const uint32_t* __restrict__ d_attached, unsigned long long* out,
+                                  uint32_t* counter) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long k = keys[i];
+    uint32_t lo = (uint32_t)(k >> 32), hi = (uint32_t)k;
+    if (d_attached[lo] == ST_REMOVING || d_attached[hi] == ST_REMOVING) {
+        out[atomicAdd(counter, 1u)] = k;
+        keys[i] = ~0ull;
+    }
+}
+__global__ void k_bp_set_flags(const uint32_t* __restrict__ handles, uint32_t n, uint32_t v, uint32_t* d_attached) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    d_attached[handles[i]] = v;
+}
+
+}  // namespace
+
+#define CKB(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            char b__[512];                                                                                \
+            snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            bp->err = b__;                                                                                \
+            bp->owner->err = b__;                                                                         \
+            return NCB_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+static int bp_grow(ncb_bp* bp, size_t slots) {
+    if (slots <= bp->slots_cap) return NCB_OK;
+    size_t want = slots + slots / 2 + 1024;
+    cudaStream_t s = bp->owner->stream;
+    auto grow4 = [&](DevBuf<float4>& b) -> cudaError_t {
+        DevBuf<float4> nb;
+        cudaError_t e = nb.reserve(want);
+        if (e != cudaSuccess) return e;
+        if (b.p && bp->slots_cap) e = cudaMemcpyAsync(nb.p, b.p, bp->slots_cap * sizeof(float4), cudaMemcpyDeviceToDevice, s);
+        cudaStreamSynchronize(s);
+        b.release();
+        b = nb;
+        return e;
+    };
+    auto growu = [&](DevBuf<uint32_t>& b, uint32_t fill) -> cudaError_t {
+        DevBuf<uint32_t> nb;
+        cudaError_t e = nb.reserve(want);
+        if (e != cudaSuccess) return e;
+        k_bp_fill<<<(unsigned)((nb.cap + 255) / 256), 256, 0, s>>>(nb.p, fill, nb.cap);
+        if (b.p && bp->slots_cap) e = cudaMemcpyAsync(nb.p, b.p, bp->slots_cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
+        cudaStreamSynchronize(s);
+        b.release();
+        b = nb;
+        return e;
+    };
+    CKB(grow4(bp->box_lo));
+    CKB(grow4(bp->box_hi));
+    CKB(grow4(bp->pend_lo));
+    CKB(grow4(bp->pend_hi));
+    CKB(growu(bp->pend_seq, SEQ_NONE));
+    CKB(growu(bp->upd_seq, SEQ_NONE));
+    CKB(growu(bp->win, 0));
+    CKB(growu(bp->d_attached, ST_VACANT));
+    bp->slots_cap = bp->box_lo.cap;
+    return NCB_OK;
+}
+
+extern "C" {
+
+int ncb_bp_create(ncb_ctx* ctx, float margin, ncb_bp** out) {
+    if (!ctx || !out) return NCB_ERR_ARG;
+    if (!(margin >= 0.f)) {
+        ctx->err = "The loosening margin must be positive.";  // aabb.rs:181-184
+        return NCB_ERR_ARG;
+    }
+    ncb_bp* bp = new ncb_bp;
+    bp->owner = ctx;
+    bp->margin = margin;
+    ncb_ctx* w = new ncb_ctx;
+    w->device = ctx->device;
+    w->stream = ctx->stream;
+    w->sm_count = ctx->sm_count;
+    bp->work = w;
+    *out = bp;
+    return NCB_OK;
+}
+
+void ncb_bp_destroy(ncb_bp* bp) {
+    if (!bp) return;
+    cudaSetDevice(bp->owner->device);
+    cudaStreamSynchronize(bp->owner->stream);
+    ncb_ctx* w = bp->work;
+    w->aabb_lo.release(), w->aabb_hi.release(), w->keys_a.release(), w->keys_b.release(), w->idx_a.release(), w->idx_b.release();
+    w->cub_tmp.release(), w->leaf_lo.release(), w->leaf_hi.release(), w->nodes.release(), w->parent.release(), w->flags.release();
+    w->pairs_raw.release(), w->keys_raw.release(), w->counters.release();
+    if (w->h_counters) cudaFreeHost(w->h_counters);
+    delete w;
+    bp->box_lo.release(), bp->box_hi.release(), bp->pend_lo.release(), bp->pend_hi.release();
+    bp->pend_seq.release(), bp->upd_seq.release(), bp->win.release(), bp->d_attached.release();
+    bp->stage_f.release(), bp->stage_u.release(), bp->alive.release(), bp->groups_dev.release();
+    bp->keys_old.release(), bp->keys_new.release(), bp->keys_tmp.release(), bp->cub_tmp.release();
+    bp->ev_a.release(), bp->ev_b.release(), bp->ev_sorted.release(), bp->ev_u32.release(), bp->counters.release();
+    delete bp;
+}
+
+int ncb_bp_create_proxies(ncb_bp* bp, uint32_t n, const float* aabb_minmax, uint32_t* out_handles) {
+    if (!bp || (n && (!aabb_minmax || !out_handles))) return NCB_ERR_ARG;
+    CKB(cudaSetDevice(bp->owner->device));
+    if (n == 0) return NCB_OK;
+    for (uint32_t i = 0; i < n; ++i) {  // Slab::insert
+        size_t key = bp->next;
+        if (key == bp->next_free.size()) {
+            bp->next_free.push_back(-2);
+            bp->attached.push_back(0);
+            bp->next = key + 1;
+        } else {
+            bp->next = (size_t)bp->next_free[key];
+            bp->next_free[key] = -2;
+            bp->attached[key] = 0;
+        }
+        bp->len++;
+        out_handles[i] = (uint32_t)key;
+    }
+    int r = bp_grow(bp, bp->next_free.size());
+    if (r) return r;
+    cudaStream_t s = bp->owner->stream;
+    CKB(bp->stage_f.reserve(6 * (size_t)n));
+    CKB(bp->stage_u.reserve(n));
+    CKB(cudaMemcpyAsync(bp->stage_f.p, aabb_minmax, 24 * (size_t)n, cudaMemcpyHostToDevice, s));
+    CKB(cudaMemcpyAsync(bp->stage_u.p, out_handles, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+    k_bp_stage_create<<<(n + 255) / 256, 256, 0, s>>>(bp->stage_u.p, bp->stage_f.p, n, bp->seq, bp->pend_lo.p, bp->pend_hi.p, bp->pend_seq.p,
+                                                      bp->d_attached.p);
+    CKB(cudaGetLastError());
+    CKB(cudaStreamSynchronize(s));  // the staging buffers are reused by the next call
+    bp->seq += n;
+    return NCB_OK;
+}
+
+int ncb_bp_set_bounding_volumes(ncb_bp* bp, uint32_t n, const uint32_t* handles, const float* aabb_minmax) {
+    if (!bp || (n && (!handles || !aabb_minmax))) return NCB_ERR_ARG;
+    CKB(cudaSetDevice(bp->owner->device));
+    if (n == 0) return NCB_OK;
+    for (uint32_t i = 0; i < n; ++i)
+        if (handles[i] >= bp->next_free.size() || bp->next_free[handles[i]] != -2) {
+            bp->err = bp->owner->err = "Attempting to set the bounding volume of an object that does not exist.";  // :345
+            return NCB_ERR_ARG;
+        }
+    cudaStream_t s = bp->owner->stream;
+    CKB(bp->stage_f.reserve(6 * (size_t)n));
+    CKB(bp->stage_u.reserve(n));
+    CKB(cudaMemcpyAsync(bp->stage_f.p, aabb_minmax, 24 * (size_t)n, cudaMemcpyHostToDevice, s));
+    CKB(cudaMemcpyAsync(bp->stage_u.p, handles, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+    unsigned g = (n + 255) / 256;
+    k_bp_clear_win<<<g, 256, 0, s>>>(bp->stage_u.p, n, bp->win.p);
+    k_bp_stage_set1<<<g, 256, 0, s>>>(bp->stage_u.p, bp->stage_f.p, n, bp->seq, bp->box_lo.p, bp->box_hi.p, bp->d_attached.p, bp->win.p,
+                                      bp->pend_seq.p);
+    k_bp_stage_set2<<<g, 256, 0, s>>>(bp->stage_u.p, bp->stage_f.p, n, bp->margin, bp->win.p, bp->pend_lo.p, bp->pend_hi.p);
+    CKB(cudaGetLastError());
+    CKB(cudaStreamSynchronize(s));
+    bp->seq += n;
+    return NCB_OK;
+}
+
+static int bp_sort_keys(ncb_bp* bp, unsigned long long* in, unsigned long long* out, uint32_t n) {
+    if (n == 0) return NCB_OK;
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, in, out, (int)n, 0, 64);
+    CKB(bp->cub_tmp.reserve(bytes + 256));
+    bytes = bp->cub_tmp.cap;
+    CKB(cub::DeviceRadixSort::SortKeys(bp->cub_tmp.p, bytes, in, out, (int)n, 0, 64, bp->owner->stream));
+    return NCB_OK;
+}
+
+// Sorts the n events of `ev` (deterministic output order) in place.
+static int bp_sort_events(ncb_bp* bp, DevBuf<unsigned long long>& ev, uint32_t n) {
+    if (n < 2) return NCB_OK;
+    CKB(bp->ev_sorted.reserve(ev.cap));
+    int r = bp_sort_keys(bp, ev.p, bp->ev_sorted.p, n);
+    if (r) return r;
+    std::swap(ev, bp->ev_sorted);
+    return NCB_OK;
+}
+
+// BroadPhase::remove (:284-323): every interference of a removed proxy is dropped and reported (the reference calls
+// its removal handler with the two proxies' data; here: the pair, smaller handle first); events land in the
+// "stopped" list of ncb_bp_events.
+int ncb_bp_remove(ncb_bp* bp, uint32_t n, const uint32_t* handles, uint32_t* n_removed) {
+    if (!bp || (n && !handles)) return NCB_ERR_ARG;
+    CKB(cudaSetDevice(bp->owner->device));
+    if (n_removed) *n_removed = 0;
+    bp->n_started = bp->n_stopped = 0;
+    if (n == 0) return NCB_OK;
+    std::vector<uint8_t> seen(bp->next_free.size(), 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (handles[i] >= bp->next_free.size() || bp->next_free[handles[i]] != -2 || seen[handles[i]]) {
+            bp->err = bp->owner->err = "Attempting to remove an object that does not exist.";  // :297
+            return NCB_ERR_ARG;
+        }
+        seen[handles[i]] = 1;
+    }
+    cudaStream_t s = bp->owner->stream;
+    CKB(bp->stage_u.reserve(n));
+    CKB(bp->counters.reserve(4));
+    CKB(cudaMemcpyAsync(bp->stage_u.p, handles, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+    k_bp_set_flags<<<(n + 255) / 256, 256, 0, s>>>(bp->stage_u.p, n, ST_REMOVING, bp->d_attached.p);
+    uint32_t nr = 0;
+    if (bp->n_old) {
+        CKB(cudaMemsetAsync(bp->counters.p, 0, 16, s));
+        CKB(bp->ev_b.reserve(bp->n_old));
+        k_bp_mark_removed<<<(bp->n_old + 255) / 256, 256, 0, s>>>(bp->keys_old.p, bp->n_old, bp->d_attached.p, bp->ev_b.p, bp->counters.p);
+        CKB(cudaGetLastError());
+        CKB(cudaMemcpyAsync(&nr, bp->counters.p, 4, cudaMemcpyDeviceToHost, s));
+        CKB(cudaStreamSynchronize(s));
+        if (nr) {
+            CKB(bp->keys_tmp.reserve(bp->n_old));
+            int r = bp_sort_keys(bp, bp->keys_old.p, bp->keys_tmp.p, bp->n_old);  // dropped keys (~0) go last
+            if (r) return r;
+            std::swap(bp->keys_old, bp->keys_tmp);
+            bp->n_old -= nr;
+            r = bp_sort_events(bp, bp->ev_b, nr);
+            if (r) return r;
+        }
+    }
+    k_bp_set_flags<<<(n + 255) / 256, 256, 0, s>>>(bp->stage_u.p, n, ST_VACANT, bp->d_attached.p);
+    CKB(cudaGetLastError());
+    CKB(cudaStreamSynchronize(s));
+    for (uint32_t i = 0; i < n; ++i) {  // Slab::remove, in argument order
+        uint32_t h = handles[i];
+        if (bp->attached[h]) bp->n_attached--;
+        bp->attached[h] = 0;
+        bp->next_free[h] = (int64_t)bp->next;
+        bp->next = h;
+        bp->len--;
+    }
+    bp->n_stopped = nr;
+    if (n_removed) *n_removed = nr;
+    return NCB_OK;
+}
+
+// BroadPhase::update (:174-259).  groups: 3 words per handle slot (membership, whitelist, blacklist) or NULL —
+// the `allow_proximity` filter of the reference's handler, evaluated like CollisionGroups::can_interact_with_groups.
+int ncb_bp_update(ncb_bp* bp, const uint32_t* groups, uint32_t n_group_slots, uint32_t* n_started, uint32_t* n_stopped) {
+    if (!bp) return NCB_ERR_ARG;
+    CKB(cudaSetDevice(bp->owner->device));
+    cudaStream_t s = bp->owner->stream;
+    ncb_ctx* w = bp->work;
+    w->stream = s;
+    bp->n_started = bp->n_stopped = 0;
+    if (n_started) *n_started = 0;
+    if (n_stopped) *n_stopped = 0;
+    uint32_t slots = (uint32_t)bp->next_free.size();
+    if (slots == 0) return NCB_OK;
+    if (groups && n_group_slots < slots) {
+        bp->err = bp->owner->err = "ncb_bp_update: groups must cover every handle slot";
+        return NCB_ERR_ARG;
+    }
+    bool any_pending = bp->seq != 0;
+    if (!any_pending) return NCB_OK;  // no leaf was updated: the reference neither queries nor purges
+    // 1. apply pending boxes; every occupied slot is attached afterwards
+    k_bp_apply<<<(slots + 255) / 256, 256, 0, s>>>(slots, bp->box_lo.p, bp->box_hi.p, bp->pend_lo.p, bp->pend_hi.p, bp->pend_seq.p, bp->upd_seq.p,
+                                                   bp->d_attached.p);
+    CKB(cudaGetLastError());
+    std::vector<uint32_t> alive;
+    alive.reserve(bp->len);
+    for (uint32_t h = 0; h < slots; ++h)
+        if (bp->next_free[h] == -2) {
+            bp->attached[h] = 1;
+            alive.push_back(h);
+        }
+    bp->n_attached = (uint32_t)alive.size();
+    bp->seq = 0;
+    uint32_t m = (uint32_t)alive.size();
+    uint32_t n_new = 0;
+    if (m >= 2) {
+        // 2. LBVH over the attached proxies, leaf ids = handles
+        CKB(bp->alive.reserve(m));
+        CKB(cudaMemcpyAsync(bp->alive.p, alive.data(), 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+        CKB(w->aabb_lo.reserve(m));
+        CKB(w->aabb_hi.reserve(m));
+        CKB(w->keys_a.reserve(m));
+        CKB(w->keys_b.reserve(m));
+        CKB(w->idx_a.reserve(m));
+        CKB(w->idx_b.reserve(m));
+        CKB(w->leaf_lo.reserve(m));
+        CKB(w->leaf_hi.reserve(m));
+        CKB(w->nodes.reserve(4 * (size_t)m));
+        CKB(w->parent.reserve(2 * (size_t)m));
+        CKB(w->flags.reserve(m));
+        CKB(w->cub_tmp.reserve(lbvh_temp_bytes(m) + 256));
+        CKB(w->counters.reserve(1));
+        if (!w->h_counters) CKB(cudaMallocHost((void**)&w->h_counters, sizeof(DevCounters)));
+        const uint32_t* dgroups = nullptr;
+        if (groups) {
+            CKB(bp->groups_dev.reserve(3 * (size_t)slots));
+            CKB(cudaMemcpyAsync(bp->groups_dev.p, groups, 12 * (size_t)slots, cudaMemcpyHostToDevice, s));
+            dgroups = bp->groups_dev.p;
+        }
+        k_bp_gather<<<(m + 255) / 256, 256, 0, s>>>(bp->alive.p, m, bp->box_lo.p, bp->box_hi.p, w->aabb_lo.p, w->aabb_hi.p);
+        CKB(cudaGetLastError());
+        size_t cap_pairs = w->pairs_raw.cap ? w->pairs_raw.cap : (size_t)8 * m + 1024;
+        for (int attempt = 0; attempt < 3; ++attempt) {
+            CKB(w->pairs_raw.reserve(cap_pairs));
+            CKB(w->keys_raw.reserve(w->pairs_raw.cap));
+            DevCounters z;
+            memset(&z, 0, sizeof z);
+            for (int k = 0; k < 3; ++k) z.bounds[k] = 0x7f7fffff, z.bounds[3 + k] = (int)0x80800000;
+            *w->h_counters = z;
+            CKB(cudaMemcpyAsync(w->counters.p, w->h_counters, sizeof z, cudaMemcpyHostToDevice, s));
+            CKB(launch_lbvh_build(w, m, bp->alive.p));
+            CKB(launch_pair_search(w, m, dgroups, 0, m, (uint32_t)w->pairs_raw.cap));
+            CKB(cudaMemcpyAsync(w->h_counters, w->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
+            CKB(cudaStreamSynchronize(s));
+            n_new = w->h_counters->n_pairs;
+            if (n_new <= w->pairs_raw.cap) break;
+            cap_pairs = (size_t)n_new + n_new / 8 + 1024;
+        }
+        // 3. sorted 64-bit keys
+        if (n_new) {
+            CKB(bp->keys_tmp.reserve(n_new));
+            CKB(bp->keys_new.reserve(n_new));
+            k_bp_keys<<<(n_new + 255) / 256, 256, 0, s>>>(w->pairs_raw.p, n_new, bp->keys_tmp.p);
+            CKB(cudaGetLastError());
+            int r = bp_sort_keys(bp, bp->keys_tmp.p, bp->keys_new.p, n_new);
+            if (r) return r;
+        }
+    }
+    // 4. started = new \ old, stopped = old \ new
+    CKB(bp->counters.reserve(4));
+    CKB(cudaMemsetAsync(bp->counters.p, 0, 16, s));
+    if (n_new) {
+        CKB(bp->ev_a.reserve(n_new));
+        k_bp_diff<<<(n_new + 255) / 256, 256, 0, s>>>(bp->keys_new.p, n_new, bp->keys_old.p, bp->n_old, 1, bp->upd_seq.p, bp->ev_a.p, bp->counters.p);
+    }
+    if (bp->n_old) {
+        CKB(bp->ev_b.reserve(bp->n_old));
+        k_bp_diff<<<(bp->n_old + 255) / 256, 256, 0, s>>>(bp->keys_old.p, bp->n_old, bp->keys_new.p, n_new, 0, bp->upd_seq.p, bp->ev_b.p,
+                                                          bp->counters.p + 1);
+    }
+    CKB(cudaGetLastError());
+    uint32_t cnt[2] = {0, 0};
+    CKB(cudaMemcpyAsync(cnt, bp->counters.p, 8, cudaMemcpyDeviceToHost, s));
+    CKB(cudaStreamSynchronize(s));
+    int r = bp_sort_events(bp, bp->ev_a, cnt[0]);
+    if (r) return r;
+    r = bp_sort_events(bp, bp->ev_b, cnt[1]);
+    if (r) return r;
+    std::swap(bp->keys_old, bp->keys_new);
+    bp->n_old = n_new;
+    bp->n_started = cnt[0];
+    bp->n_stopped = cnt[1];
+    if (n_started) *n_started = cnt[0];
+    if (n_stopped) *n_stopped = cnt[1];
+    return NCB_OK;
+}
+
+static int bp_fetch(ncb_bp* bp, const unsigned long long* ev, uint32_t n, uint32_t* out) {
+    if (!n || !out) return NCB_OK;
+    cudaStream_t s = bp->owner->stream;
+    CKB(bp->ev_u32.reserve(2 * (size_t)n));
+    k_bp_unpack<<<(n + 255) / 256, 256, 0, s>>>(ev, n, bp->ev_u32.p);
+    CKB(cudaGetLastError());
+    CKB(cudaMemcpyAsync(out, bp->ev_u32.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
+    CKB(cudaStreamSynchronize(s));
+    return NCB_OK;
+}
+
+// Events of the last update() / remove(): started[2 * n_started] in interference_started argument order,
+// stopped[2 * n_stopped] in interference_stopped order.  Either pointer may be NULL.
+int ncb_bp_events(ncb_bp* bp, uint32_t* started, uint32_t* stopped) {
+    if (!bp) return NCB_ERR_ARG;
+    CKB(cudaSetDevice(bp->owner->device));
+    int r = bp_fetch(bp, bp->ev_a.p, bp->n_started, started);
+    if (r) return r;
+    return bp_fetch(bp, bp->ev_b.p, bp->n_stopped, stopped);
+}
+
+int ncb_bp_num_interferences(ncb_bp* bp, uint32_t* n) {
+    if (!bp || !n) return NCB_ERR_ARG;
+    *n = bp->n_old;
+    return NCB_OK;
+}
+
+// The current interference set, sorted, (smaller handle, larger handle) per pair; cap in pairs.
+int ncb_bp_pairs(ncb_bp* bp, uint32_t* pairs, uint32_t cap, uint32_t* n) {
+    if (!bp) return NCB_ERR_ARG;
+    CKB(cudaSetDevice(bp->owner->device));
+    if (n) *n = bp->n_old;
+    uint32_t w = bp->n_old < cap ? bp->n_old : cap;
+    int r = bp_fetch(bp, bp->keys_old.p, w, pairs);
+    if (r) return r;
+    return bp->n_old > cap && pairs ? 1 : NCB_OK;
+}
+
+// BroadPhase::proxy (:262-273): 1 and the stored box when the proxy is attached, 0 otherwise
+int ncb_bp_proxy(ncb_bp* bp, uint32_t handle, float* minmax) {
+    if (!bp || !minmax) return NCB_ERR_ARG;
+    if (handle >= bp->next_free.size() || bp->next_free[handle] != -2 || !bp->attached[handle]) return 0;
+    CKB(cudaSetDevice(bp->owner->device));
+    float4 lo, hi;
+    CKB(cudaMemcpyAsync(&lo, bp->box_lo.p + handle, 16, cudaMemcpyDeviceToHost, bp->owner->stream));
+    CKB(cudaMemcpyAsync(&hi, bp->box_hi.p + handle, 16, cudaMemcpyDeviceToHost, bp->owner->stream));
+    CKB(cudaStreamSynchronize(bp->owner->stream));
+    minmax[0] = lo.x, minmax[1] = lo.y, minmax[2] = lo.z, minmax[3] = hi.x, minmax[4] = hi.y, minmax[5] = hi.z;
+    return 1;
+}
+
+}  // extern "C"

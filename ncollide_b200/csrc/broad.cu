@@ -172,13 +172,13 @@ __global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ lo, c
 
 // Gather the boxes into Morton order; lo.w <- handle, hi.w keeps the shape type.
 __global__ void __launch_bounds__(256) k_gather_leaves(const float4* __restrict__ lo, const float4* __restrict__ hi,
-                                                       const uint32_t* __restrict__ idx, uint32_t n, float4* __restrict__ llo,
-                                                       float4* __restrict__ lhi) {
+                                                       const uint32_t* __restrict__ idx, const uint32_t* __restrict__ handle_map,
+                                                       uint32_t n, float4* __restrict__ llo, float4* __restrict__ lhi) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t h = __ldg(&idx[i]);
     float4 a = __ldg(&lo[h]), b = __ldg(&hi[h]);
-    a.w = __uint_as_float(h);
+    a.w = __uint_as_float(handle_map ? __ldg(&handle_map[h]) : h);  // the id pairs are reported with
     llo[i] = a;
     lhi[i] = b;
 }
@@ -272,7 +272,7 @@ size_t lbvh_temp_bytes(uint32_t n) {
 }
 
 // Builds the LBVH over c->aabb_lo/hi[0..n).  Needs c->counters zeroed (bounds initialised) by the caller.
-cudaError_t launch_lbvh_build(ncb_ctx* c, uint32_t n, const uint32_t*) {
+cudaError_t launch_lbvh_build(ncb_ctx* c, uint32_t n, const uint32_t* handle_map) {
     cudaStream_t s = c->stream;
     if (n == 0) return cudaSuccess;
     int gs = c->sm_count * 4;
@@ -283,7 +283,7 @@ cudaError_t launch_lbvh_build(ncb_ctx* c, uint32_t n, const uint32_t*) {
     cudaError_t e = cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, c->keys_a.p, c->keys_b.p, c->idx_a.p, c->idx_b.p, (int)n, 0, 31, s);
     if (e != cudaSuccess) return e;
     timer_mark(c, "morton_sort", 6);
-    k_gather_leaves<<<nb, 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, c->idx_b.p, n, c->leaf_lo.p, c->leaf_hi.p);
+    k_gather_leaves<<<nb, 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, c->idx_b.p, handle_map, n, c->leaf_lo.p, c->leaf_hi.p);
     e = cudaMemsetAsync(c->flags.p, 0, (size_t)n * sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
     k_karras<<<nb, 256, 0, s>>>(c->keys_b.p, n, c->counters.p, c->nodes.p, c->parent.p);

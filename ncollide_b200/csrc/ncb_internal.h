@@ -173,7 +173,8 @@ inline void timer_mark(ncb_ctx* c, const char* name, uint32_t launches) {
 
 // broad.cu
 cudaError_t launch_aabbs(ncb_ctx* c, const DevObjects& o, float margin, int fat, uint32_t begin, uint32_t end);
-cudaError_t launch_lbvh_build(ncb_ctx* c, uint32_t n, const uint32_t* type_or_null);
+// handle_map (optional): leaf ids reported in pairs are handle_map[index] instead of the index into aabb_lo / aabb_hi
+cudaError_t launch_lbvh_build(ncb_ctx* c, uint32_t n, const uint32_t* handle_map);
 cudaError_t launch_pair_search(ncb_ctx* c, uint32_t n, const uint32_t* groups, uint32_t q_begin, uint32_t q_end, uint32_t cap_pairs);
 cudaError_t launch_pair_sort(ncb_ctx* c, uint32_t cap_pairs, uint32_t* index_out);
 size_t lbvh_temp_bytes(uint32_t n);

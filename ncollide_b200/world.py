@@ -1,8 +1,9 @@
 """Host-side mirror of the reference's pipeline interface for the hot path, over the C ABI (include/ncb200.h).
 
   * ``CollisionWorld``   pipeline/world.rs:28-119   (``new(margin)``, ``add``, ``update``, ``contact_pairs``)
-  * ``BroadPhase``       pipeline/broad_phase/broad_phase.rs:41-86 (``create_proxy``, ``deferred_set_bounding_volume``,
-                         ``update(handler)`` with is_interference_allowed / interference_started)
+  * ``BroadPhase``       pipeline/broad_phase/broad_phase.rs:41-99 (``create_proxy``, ``remove``, ``proxy``,
+                         ``deferred_set_bounding_volume``, ``update(handler)`` with interference_started / _stopped,
+                         persistent over updates like DBVTBroadPhase)
   * ``NarrowPhase``      contact_generator/contact_manifold_generator.rs:10-36 (batched ``generate_contacts``)
   * ``TriMesh``          shape/trimesh.rs:100-197 + query/ray/ray_trimesh.rs:22-50 (batched ``toi_and_normal_with_ray``)
 
@@ -304,49 +305,147 @@ class BroadPhaseInterferenceHandler:
 
 
 class BroadPhase:
-    """Mirror of the ``BroadPhase`` trait for a fresh proxy set: ``create_proxy`` queues (bv, data),
-    ``deferred_set_bounding_volume`` loosens by the margin like DBVTBroadPhase (dbvt_broad_phase.rs:325-347),
-    ``update(handler)`` runs the device pair search and replays is_interference_allowed / interference_started
-    in the reference's argument order (later proxy first)."""
+    """The ``BroadPhase`` trait (pipeline/broad_phase/broad_phase.rs:68-99) over the device persistent broad phase
+    (``ncb_bp_*``, csrc/bp_persistent.cu), a drop-in for ``DBVTBroadPhase::new(margin)``:
+    ``create_proxy`` / ``remove`` / ``deferred_set_bounding_volume`` / ``update(handler)`` / ``proxy`` /
+    ``num_interferences`` with the reference's handle recycling, loosening rule and handler argument order.
+
+    Collision groups (``groups=(membership, whitelist, blacklist)`` per proxy) are filtered on the device; an
+    arbitrary ``handler.is_interference_allowed`` is applied on the host to the started events (its answer must be
+    stable for a pair, as it is for the reference's collision-world handler)."""
 
     def __init__(self, margin, ctx=None, device=0):
         self.margin = np.float32(margin)
         self.ctx = ctx or Context(device)
-        self._bv, self._data = [], []
-        self.pairs = set()
+        self._lib = self.ctx.lib
+        h = C.c_void_p()
+        self.ctx.check(self._lib.ncb_bp_create(self.ctx.h, C.c_float(float(margin)), C.byref(h)), "ncb_bp_create")
+        self._h = h
+        self._data = {}
+        self._groups = np.zeros((0, 3), dtype=np.uint32)
+        self._any_groups = False
+        self._vetoed = set()
+        self._pending_set = ([], [])
 
-    def create_proxy(self, bv, data):
-        self._bv.append(np.asarray(bv, dtype=np.float32).reshape(6))
-        self._data.append(data)
-        return len(self._bv) - 1
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ncb_bp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- proxies ---------------------------------------------------------------------------------------------
+    def create_proxies(self, bvs, datas=None, groups=None):
+        self._flush_sets()
+        bvs = as_f32(bvs).reshape(-1, 6)
+        n = len(bvs)
+        out = np.zeros(n, dtype=np.uint32)
+        self.ctx.check(self._lib.ncb_bp_create_proxies(self._h, C.c_uint32(n), ptr(bvs), ptr(out)), "ncb_bp_create_proxies")
+        top = int(out.max()) + 1 if n else 0
+        if top > len(self._groups):
+            g = np.zeros((max(top, 2 * len(self._groups)), 3), dtype=np.uint32)
+            g[:, 0] = g[:, 1] = 0x3FFFFFFF  # CollisionGroups::new(): member of all, whitelist all (collision_groups.rs:39-46)
+            g[: len(self._groups)] = self._groups
+            self._groups = g
+        self._groups[out, 0] = self._groups[out, 1] = 0x3FFFFFFF
+        self._groups[out, 2] = 0
+        if groups is not None:
+            self._groups[out] = as_u32(groups).reshape(n, 3)
+            self._any_groups = True
+        for k, hnd in enumerate(out.tolist()):
+            self._data[hnd] = datas[k] if datas is not None else hnd
+        return out
+
+    def create_proxy(self, bv, data=None, groups=None):
+        g = None if groups is None else np.asarray(groups, dtype=np.uint32).reshape(1, 3)
+        return int(self.create_proxies(np.asarray(bv, dtype=np.float32).reshape(1, 6), [data], g)[0])
+
+    def remove(self, handles, removal_handler=None):
+        self._flush_sets()
+        handles = as_u32(handles).reshape(-1)
+        n = C.c_uint32()
+        self.ctx.check(self._lib.ncb_bp_remove(self._h, C.c_uint32(len(handles)), ptr(handles), C.byref(n)), "ncb_bp_remove")
+        ev = np.zeros((n.value, 2), dtype=np.uint32)
+        if n.value:
+            self.ctx.check(self._lib.ncb_bp_events(self._h, None, ptr(ev)), "ncb_bp_events")
+        for a, b in ev.tolist():
+            if (a, b) in self._vetoed:
+                self._vetoed.discard((a, b))
+            elif removal_handler is not None:
+                removal_handler(self._data[a], self._data[b])
+        for hnd in handles.tolist():
+            self._data.pop(hnd, None)
+        return ev
 
     def proxy(self, handle):
-        if handle < 0 or handle >= len(self._bv):
-            return None
-        return self._bv[handle], self._data[handle]
+        self._flush_sets()
+        mm = np.zeros(6, dtype=np.float32)
+        r = self._lib.ncb_bp_proxy(self._h, C.c_uint32(int(handle)), ptr(mm))
+        self.ctx.check(min(r, 0), "ncb_bp_proxy")
+        return (mm, self._data[int(handle)]) if r == 1 else None
 
     def deferred_set_bounding_volume(self, handle, bv):
-        if handle < 0 or handle >= len(self._bv):
-            raise RuntimeError("Attempting to set the bounding volume of an object that does not exist.")
-        b = np.asarray(bv, dtype=np.float32).reshape(6).copy()
-        b[:3] = b[:3] + (-self.margin)
-        b[3:] = b[3:] + self.margin
-        self._bv[handle] = b
+        # queued on the host and sent as one batch (order kept) before the next call that needs it
+        self._pending_set[0].append(int(handle))
+        self._pending_set[1].append(np.asarray(bv, dtype=np.float32).reshape(6))
+
+    def deferred_set_bounding_volumes(self, handles, bvs):
+        self._flush_sets()
+        handles, bvs = as_u32(handles).reshape(-1), as_f32(bvs).reshape(-1, 6)
+        self.ctx.check(self._lib.ncb_bp_set_bounding_volumes(self._h, C.c_uint32(len(handles)), ptr(handles), ptr(bvs)),
+                       "ncb_bp_set_bounding_volumes")
+
+    def _flush_sets(self):
+        hs, bs = self._pending_set
+        if hs:
+            self._pending_set = ([], [])
+            self.deferred_set_bounding_volumes(np.array(hs, dtype=np.uint32), np.stack(bs))
 
     def num_interferences(self):
-        return len(self.pairs)
+        n = C.c_uint32()
+        self.ctx.check(self._lib.ncb_bp_num_interferences(self._h, C.byref(n)), "ncb_bp_num_interferences")
+        return n.value - len(self._vetoed)
+
+    def pairs(self):
+        n = self.num_interferences() + len(self._vetoed)
+        out = np.zeros((n, 2), dtype=np.uint32)
+        cnt = C.c_uint32()
+        self.ctx.check(self._lib.ncb_bp_pairs(self._h, ptr(out), C.c_uint32(n), C.byref(cnt)), "ncb_bp_pairs")
+        if self._vetoed:
+            keep = [tuple(p) not in self._vetoed for p in out.tolist()]
+            out = out[np.array(keep, dtype=bool)]
+        return out
+
+    def update_events(self):
+        """One ``update``; returns (started[k,2], stopped[m,2]) handle arrays without going through a handler."""
+        self._flush_sets()
+        ns, nst = C.c_uint32(), C.c_uint32()
+        g = self._groups if self._any_groups else None
+        self.ctx.check(self._lib.ncb_bp_update(self._h, ptr(g), C.c_uint32(0 if g is None else len(g)), C.byref(ns), C.byref(nst)),
+                       "ncb_bp_update")
+        started = np.zeros((ns.value, 2), dtype=np.uint32)
+        stopped = np.zeros((nst.value, 2), dtype=np.uint32)
+        if ns.value or nst.value:
+            self.ctx.check(self._lib.ncb_bp_events(self._h, ptr(started) if ns.value else None, ptr(stopped) if nst.value else None),
+                           "ncb_bp_events")
+        return started, stopped
 
     def update(self, handler):
-        if not self._bv:
-            return
-        cand = self.ctx.broad_phase(np.stack(self._bv))
-        for a, b in cand[np.lexsort((cand[:, 1], cand[:, 0]))]:
-            a, b = int(a), int(b)
+        started, stopped = self.update_events()
+        for a, b in started.tolist():
             if handler.is_interference_allowed(self._data[a], self._data[b]):
-                key = (min(a, b), max(a, b))
-                if key not in self.pairs:
-                    self.pairs.add(key)
-                    handler.interference_started(self._data[a], self._data[b])
+                handler.interference_started(self._data[a], self._data[b])
+            else:
+                self._vetoed.add((min(a, b), max(a, b)))
+        for a, b in stopped.tolist():
+            if (a, b) in self._vetoed:
+                self._vetoed.discard((a, b))
+            else:
+                handler.interference_stopped(self._data[a], self._data[b])
 
 
 class TriMesh:

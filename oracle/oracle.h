@@ -63,7 +63,20 @@ void orc_world_update_timed(const orc_objects* objs, real margin, double* times,
  * objects 0 and 1 of objs; returns 1 and fills out when a contact exists. */
 int orc_query_contact(const orc_objects* objs, real prediction, orc_contact* out);
 
-/* Convex hull tables: see hull.cpp. */
+/* Multi-step DBVTBroadPhase (reference-faithful: two DBVTs, slab handles, pair hash map, purge, activation states).
+ * Events are returned instead of calling a BroadPhaseInterferenceHandler: started = (re-inserted leaf, leaf it met),
+ * stopped = SortedPair order. groups: 3 u32 per handle (indexed by handle) or NULL (only a != b is required). */
+typedef struct orc_bp orc_bp;
+orc_bp* orc_bp_create(real margin);
+void orc_bp_destroy(orc_bp*);
+uint32_t orc_bp_create_proxy(orc_bp*, const real* minmax);
+int orc_bp_set_bounding_volume(orc_bp*, uint32_t handle, const real* minmax);
+int orc_bp_remove(orc_bp*, uint32_t n, const uint32_t* handles, uint32_t* removed_pairs, uint64_t cap, uint64_t* n_removed);
+void orc_bp_update(orc_bp*, const uint32_t* groups, uint32_t* started, uint64_t cap_s, uint64_t* n_started, uint32_t* stopped,
+                   uint64_t cap_p, uint64_t* n_stopped);
+uint64_t orc_bp_num_interferences(const orc_bp*);
+int orc_bp_proxy(const orc_bp*, uint32_t handle, real* minmax);
+uint64_t orc_bp_pairs(const orc_bp*, uint32_t* out, uint64_t cap);
 
 /* TriMesh ray casting. */
 typedef struct orc_trimesh orc_trimesh;

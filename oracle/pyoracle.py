@@ -157,6 +157,9 @@ class Oracle:
     def trimesh(self, verts, tris):
         return OracleTriMesh(self, verts, tris)
 
+    def broad_phase_persistent(self, margin):
+        return OracleBroadPhase(self, margin)
+
     def aabb_toi_with_ray(self, minmax, origin, direction, max_toi, solid):
         mm = np.ascontiguousarray(minmax, dtype=self.dtype)
         o = np.ascontiguousarray(origin, dtype=self.dtype)
@@ -194,5 +197,71 @@ class OracleTriMesh:
     def __del__(self):
         try:
             self.o.lib.orc_trimesh_destroy(self.h)
+        except Exception:
+            pass
+
+
+class OracleBroadPhase:
+    """Reference-faithful multi-step DBVTBroadPhase (oracle/bp_persistent.cpp)."""
+
+    def __init__(self, oracle, margin):
+        self.o = oracle
+        L = oracle.lib
+        L.orc_bp_create.restype = C.c_void_p
+        L.orc_bp_create_proxy.restype = C.c_uint32
+        L.orc_bp_num_interferences.restype = C.c_uint64
+        L.orc_bp_pairs.restype = C.c_uint64
+        self.h = C.c_void_p(L.orc_bp_create(oracle.creal(margin)))
+
+    def create_proxy(self, bv):
+        a = np.ascontiguousarray(bv, dtype=self.o.dtype)
+        return int(self.o.lib.orc_bp_create_proxy(self.h, C.c_void_p(a.ctypes.data)))
+
+    def deferred_set_bounding_volume(self, handle, bv):
+        a = np.ascontiguousarray(bv, dtype=self.o.dtype)
+        r = self.o.lib.orc_bp_set_bounding_volume(self.h, C.c_uint32(handle), C.c_void_p(a.ctypes.data))
+        if r != 0:
+            raise RuntimeError("Attempting to set the bounding volume of an object that does not exist.")
+
+    def remove(self, handles):
+        hs = np.ascontiguousarray(handles, dtype=np.uint32)
+        cap = max(16 * len(hs) + 1024, 4096)
+        while True:
+            out = np.zeros((cap, 2), dtype=np.uint32)
+            n = C.c_uint64()
+            # the call mutates state: size the buffer generously up front instead of retrying
+            r = self.o.lib.orc_bp_remove(self.h, C.c_uint32(len(hs)), C.c_void_p(hs.ctypes.data), C.c_void_p(out.ctypes.data), C.c_uint64(cap), C.byref(n))
+            if r != 0:
+                raise RuntimeError("Attempting to remove an object that does not exist.")
+            return out[: min(n.value, cap)].copy()
+
+    def update(self, groups=None, cap=None):
+        cap = cap or 1 << 22
+        st = np.zeros((cap, 2), dtype=np.uint32)
+        sp = np.zeros((cap, 2), dtype=np.uint32)
+        ns, np_ = C.c_uint64(), C.c_uint64()
+        g = np.ascontiguousarray(groups, dtype=np.uint32) if groups is not None else None
+        self.o.lib.orc_bp_update(self.h, C.c_void_p(g.ctypes.data) if g is not None else None, C.c_void_p(st.ctypes.data), C.c_uint64(cap), C.byref(ns),
+                                 C.c_void_p(sp.ctypes.data), C.c_uint64(cap), C.byref(np_))
+        assert ns.value <= cap and np_.value <= cap
+        return st[: ns.value].copy(), sp[: np_.value].copy()
+
+    def num_interferences(self):
+        return int(self.o.lib.orc_bp_num_interferences(self.h))
+
+    def proxy(self, handle):
+        out = np.zeros(6, dtype=self.o.dtype)
+        r = self.o.lib.orc_bp_proxy(self.h, C.c_uint32(handle), C.c_void_p(out.ctypes.data))
+        return out if r else None
+
+    def pairs(self):
+        n = self.num_interferences()
+        out = np.zeros((max(n, 1), 2), dtype=np.uint32)
+        self.o.lib.orc_bp_pairs(self.h, C.c_void_p(out.ctypes.data), C.c_uint64(n))
+        return out[:n]
+
+    def __del__(self):
+        try:
+            self.o.lib.orc_bp_destroy(self.h)
         except Exception:
             pass

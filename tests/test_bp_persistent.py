@@ -1,0 +1,123 @@
+"""Persistent broad phase (BroadPhase trait over several updates).
+
+CPU: the reference-faithful oracle (two DBVTs, slab, pending queue, purge — oracle/bp_persistent.cpp) is pinned on the
+reference's own example and checked against the tree-free set semantics the device path relies on.
+GPU: the device broad phase (ncb_bp_*) against the oracle, event by event."""
+import numpy as np
+import pytest
+
+from bp_scenario import DeviceAdapter, OracleAdapter, SetModel, assert_same_log, run_scenario
+
+F32 = np.float32
+
+
+def ball_box(c, r=0.5):
+    c = np.asarray(c, dtype=F32)
+    return np.concatenate([c - F32(r), c + F32(r)])
+
+
+def example_kat(make):
+    # build/ncollide3d/examples/dbvt_broad_phase3d.rs:38-60
+    bp = make(0.02)
+    hs = bp.create([ball_box(p) for p in [(0, 0, 0), (0, 0.5, 0), (0.5, 0, 0), (0.5, 0.5, 0)]], [(0x3FFFFFFF, 0x3FFFFFFF, 0)] * 4)
+    assert hs == [0, 1, 2, 3]
+    assert bp.proxy(0) is None  # not attached before the first update
+    started, stopped = bp.update()
+    assert bp.num() == 6 and len(started) == 6 and len(stopped) == 0
+    assert all(a > b for a, b in started.tolist())  # the proxy inserted later comes first
+    gone = bp.remove(np.array([0, 1], dtype=np.uint32))
+    assert len(gone) == 5
+    started, stopped = bp.update()
+    assert bp.num() == 1 and len(started) == 0 and len(stopped) == 0
+    # create_proxy stores the box as given; deferred_set_bounding_volume stores it loosened by the margin
+    assert np.array_equal(bp.proxy(2), ball_box((0.5, 0, 0)))
+    moved = ball_box((0.5, 0.0, 3.0))
+    bp.set_bvs(np.array([2], dtype=np.uint32), moved.reshape(1, 6))
+    started, stopped = bp.update()
+    assert stopped.tolist() == [[2, 3]] and bp.num() == 0
+    want = moved.copy()
+    want[:3] += -F32(0.02)
+    want[3:] += F32(0.02)
+    assert np.array_equal(bp.proxy(2), want)
+    # a move that stays inside the stored box changes nothing
+    bp.set_bvs(np.array([2], dtype=np.uint32), (moved + F32(0.01)).reshape(1, 6))
+    bp.update()
+    assert np.array_equal(bp.proxy(2), want)
+    # freed handles are reused, last freed first
+    assert bp.create([ball_box((9, 9, 9))], [(0x3FFFFFFF, 0x3FFFFFFF, 0)]) == [1]
+    assert bp.create([ball_box((9, 9, 9))], [(0x3FFFFFFF, 0x3FFFFFFF, 0)]) == [0]
+    started, _ = bp.update()
+    assert started.tolist() == [[0, 1]] and bp.num() == 1
+    with pytest.raises(RuntimeError):
+        bp.set_bvs(np.array([17], dtype=np.uint32), moved.reshape(1, 6))
+
+
+def test_oracle_example_kat(oracle):
+    example_kat(lambda m: OracleAdapter(oracle, m))
+
+
+def test_set_model_example_kat():
+    example_kat(SetModel)
+
+
+@pytest.mark.parametrize("seed,groups", [(1, True), (2, False), (3, True)])
+def test_oracle_matches_set_semantics(oracle, seed, groups):
+    a = run_scenario(OracleAdapter(oracle, 0.05), seed, n0=250, steps=11, use_groups=groups)
+    b = run_scenario(SetModel(0.05), seed, n0=250, steps=11, use_groups=groups)
+    assert sum(len(r["started"]) for r in a) > 300 and sum(len(r["stopped"]) for r in a) > 30
+    assert_same_log(a, b, "oracle vs set model")
+
+
+@pytest.mark.gpu
+def test_device_example_kat():
+    from ncollide_b200.world import Context
+
+    ctx = Context(0)
+    example_kat(lambda m: DeviceAdapter(ctx, m))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n0,steps,groups", [(1, 250, 11, True), (2, 250, 11, False), (5, 4000, 8, True), (6, 20000, 6, False)])
+def test_device_matches_oracle(oracle, seed, n0, steps, groups):
+    from ncollide_b200.world import Context
+
+    ctx = Context(0)
+    side = 10.0 * (n0 / 300.0) ** (1 / 3)
+    a = run_scenario(OracleAdapter(oracle, 0.05), seed, n0=n0, steps=steps, side=side, use_groups=groups)
+    b = run_scenario(DeviceAdapter(ctx, 0.05), seed, n0=n0, steps=steps, side=side, use_groups=groups)
+    assert_same_log(a, b, "device vs oracle")
+
+
+@pytest.mark.gpu
+def test_device_handler_mirror():
+    """BroadPhase.update(handler) replays the events through the reference's handler trait."""
+    from ncollide_b200.world import BroadPhase, BroadPhaseInterferenceHandler, Context
+
+    class H(BroadPhaseInterferenceHandler):
+        def __init__(self):
+            self.started, self.stopped = [], []
+
+        def is_interference_allowed(self, a, b):
+            return not (a == "c" or b == "c")
+
+        def interference_started(self, a, b):
+            self.started.append((a, b))
+
+        def interference_stopped(self, a, b):
+            self.stopped.append((a, b))
+
+    bp = BroadPhase(0.02, ctx=Context(0))
+    ha = bp.create_proxy(ball_box((0, 0, 0)), "a")
+    hb = bp.create_proxy(ball_box((0.5, 0, 0)), "b")
+    hc = bp.create_proxy(ball_box((0, 0.5, 0)), "c")
+    h = H()
+    bp.update(h)
+    assert h.started == [("b", "a")] and bp.num_interferences() == 1
+    bp.deferred_set_bounding_volume(hb, ball_box((5, 0, 0)))
+    bp.deferred_set_bounding_volume(hc, ball_box((5, 0.5, 0)))
+    bp.update(h)
+    assert h.stopped == [("a", "b")] and bp.num_interferences() == 0
+    assert bp.proxy(ha)[1] == "a"
+    with pytest.raises(Exception):
+        bp.deferred_set_bounding_volume(99, ball_box((0, 0, 0)))
+        bp.update(h)
