@@ -190,7 +190,7 @@ int ncb_trimesh_ray_cast_device(ncb_mesh* mesh, const float* pose_tq_host, uint3
  * Handles are slab keys handed out LIFO like the reference's (`slab` crate).  Boxes are 6 floats (mins, maxs).
  * After each ncb_bp_update the interference set equals the reference's: { (i, j) : stored boxes intersect (inclusive),
  * groups allow }, where a stored box changes only when a new box is not contained in it (then: new.loosened(margin)).
- * The collision groups of a handle must not change while it is alive (the reference's world re-creates the proxy). */
+ * When the groups of a live handle change, call ncb_bp_recompute_with for it (as glue/update.rs:85 does). */
 typedef struct ncb_bp ncb_bp;
 /* DBVTBroadPhase::new(margin) (dbvt_broad_phase.rs:75-88) */
 int ncb_bp_create(ncb_ctx* ctx, float margin, ncb_bp** out);
@@ -200,6 +200,10 @@ int ncb_bp_create_proxies(ncb_bp* bp, uint32_t n, const float* aabb_minmax, uint
 /* BroadPhase::deferred_set_bounding_volume (:325-347) for n (handle, box) entries, in order.  NCB_ERR_ARG when a
  * handle does not exist (the reference panics). */
 int ncb_bp_set_bounding_volumes(ncb_bp* bp, uint32_t n, const uint32_t* handles, const float* aabb_minmax);
+/* BroadPhase::deferred_recompute_all_proximities_with (:349-363) / deferred_recompute_all_proximities (:365-386):
+ * the way the reference's world tells the broad phase that a proxy's groups (or the pair filter) changed. */
+int ncb_bp_recompute_with(ncb_bp* bp, uint32_t n, const uint32_t* handles);
+int ncb_bp_recompute_all(ncb_bp* bp);
 /* BroadPhase::remove (:282-323).  The dropped interferences are readable as the "stopped" list of ncb_bp_events. */
 int ncb_bp_remove(ncb_bp* bp, uint32_t n, const uint32_t* handles, uint32_t* n_removed);
 /* BroadPhase::update (:174-259).  groups = 3 words per handle slot (membership, whitelist, blacklist) or NULL. */
@@ -212,6 +216,11 @@ int ncb_bp_events(ncb_bp* bp, uint32_t* started, uint32_t* stopped);
 int ncb_bp_num_interferences(ncb_bp* bp, uint32_t* n);
 /* The current interference set, sorted, (smaller, larger) handle per pair; cap in pairs; returns 1 when truncated. */
 int ncb_bp_pairs(ncb_bp* bp, uint32_t* pairs, uint32_t cap, uint32_t* n);
+/* Batched BroadPhase::interferences_with_bounding_volume (kind 0; 6 floats per query: mins, maxs), interferences_with_ray
+ * (kind 1; 7 floats: origin, dir, max_toi) and interferences_with_point (kind 2; 3 floats) (:388-432), against the boxes
+ * stored by the last ncb_bp_update, removed proxies excluded.  out[2 * k] = (query index, handle), sorted; cap in
+ * entries; *n_out = entries found; returns 1 when truncated.  Reuses the event buffer: read ncb_bp_events first. */
+int ncb_bp_query(ncb_bp* bp, int kind, uint32_t n_queries, const float* queries, uint32_t* out, uint32_t cap, uint32_t* n_out);
 /* BroadPhase::proxy (:262-273): returns 1 and the stored (loosened) box when the proxy is attached, else 0. */
 int ncb_bp_proxy(ncb_bp* bp, uint32_t handle, float* minmax);
 

@@ -20,6 +20,9 @@
 using namespace ncb;
 
 #define SEQ_NONE 0xffffffffu
+#define LEAF_BIT 0x80000000u  // child word of an LBVH node record (broad.cu)
+#define SEQ_BACK0 0x80000000u   // entries pushed at the back of the reference's queue: SEQ_BACK0 + k
+#define SEQ_FRONT0 0x7fffffffu  // entries pushed at its front (recompute_*): SEQ_FRONT0 - k
 enum : uint32_t { ST_DETACHED = 0, ST_ATTACHED = 1, ST_REMOVING = 2, ST_VACANT = 3 };
 
 struct ncb_bp {
@@ -31,7 +34,8 @@ struct ncb_bp {
     std::vector<uint8_t> attached;   // host mirror: 0 detached (pending), 1 attached
     size_t next = 0, len = 0;
     uint32_t n_attached = 0;
-    uint32_t seq = 0;  // pending entries issued since the last update
+    uint32_t seq = 0;    // back entries issued since the last update
+    uint32_t front = 0;  // front entries issued since the last update
     // device state, indexed by handle slot
     DevBuf<float4> box_lo, box_hi, pend_lo, pend_hi;
     DevBuf<uint32_t> pend_seq, upd_seq, win, d_attached;
@@ -44,6 +48,8 @@ struct ncb_bp {
     DevBuf<unsigned long long> ev_a, ev_b, ev_sorted;  // started / stopped events as (first << 32 | second)
     DevBuf<uint32_t> ev_u32, counters;
     uint32_t n_old = 0;
+    uint32_t tree_n = 0, tree_outliers = 0;  // leaves of the LBVH built by the last update() (0: none yet)
+    DevBuf<float> q_in;
     uint32_t n_started = 0, n_stopped = 0;  // events of the last update() / remove()
     std::string err;
 };
@@ -97,6 +103,21 @@ __global__ void k_bp_stage_set2(const uint32_t* __restrict__ handles, const floa
     const float* s = mm + 6 * (size_t)i;
     pend_lo[h] = make_float4(s[0] + (-margin), s[1] + (-margin), s[2] + (-margin), 0.f);
     pend_hi[h] = make_float4(s[3] + margin, s[4] + margin, s[5] + margin, 0.f);
+}
+// deferred_recompute_all_proximities_with (:349-363): an attached proxy is queued at the FRONT with its stored box;
+// a box already queued for it stays the one applied (it sits later in the queue)
+__global__ void k_bp_recompute_with(const uint32_t* __restrict__ handles, uint32_t n, uint32_t front0, const float4* __restrict__ box_lo,
+                                    const float4* __restrict__ box_hi, const uint32_t* __restrict__ d_attached, float4* pend_lo, float4* pend_hi,
+                                    uint32_t* pend_seq) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t h = handles ? handles[i] : i;
+    if (d_attached[h] != ST_ATTACHED) return;
+    if (pend_seq[h] == SEQ_NONE) {
+        pend_lo[h] = box_lo[h];
+        pend_hi[h] = box_hi[h];
+    }
+    atomicMin(&pend_seq[h], front0 - i);
 }
 __global__ void k_bp_clear_win(const uint32_t* __restrict__ handles, uint32_t n, uint32_t* win) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -187,6 +208,101 @@ __global__ void k_bp_set_flags(const uint32_t* __restrict__ handles, uint32_t n,
     d_attached[handles[i]] = v;
 }
 
+
+// ---- interferences_with_bounding_volume / _ray / _point (:388-432) on the LBVH of the last update -------------------
+struct BpQuery {
+    float a[7];
+};
+template <int KIND>
+__device__ __forceinline__ bool bp_query_test(const BpQuery& q, const float* inv, float4 lo, float4 hi) {
+    if (KIND == 0)  // AABB::intersects (aabb.rs:156-158)
+        return lo.x <= q.a[3] && lo.y <= q.a[4] && lo.z <= q.a[5] && hi.x >= q.a[0] && hi.y >= q.a[1] && hi.z >= q.a[2];
+    if (KIND == 2) {  // AABB::contains_local_point (aabb.rs:138-146)
+        if (q.a[0] < lo.x || q.a[0] > hi.x) return false;
+        if (q.a[1] < lo.y || q.a[1] > hi.y) return false;
+        if (q.a[2] < lo.z || q.a[2] > hi.z) return false;
+        return true;
+    }
+    // AABB::toi_with_ray(.., solid).is_some() (ray_aabb.rs:13-50); inv[i] = 1 / dir[i] as the reference computes it per box
+    float tmin = 0.f, tmax = q.a[6];
+    const float mn[3] = {lo.x, lo.y, lo.z}, mx[3] = {hi.x, hi.y, hi.z};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (q.a[3 + i] == 0.f) {
+            if (q.a[i] < mn[i] || q.a[i] > mx[i]) return false;
+        } else {
+            float near = (mn[i] - q.a[i]) * inv[i], far = (mx[i] - q.a[i]) * inv[i];
+            if (near > far) {
+                float t = near;
+                near = far;
+                far = t;
+            }
+            tmin = fmaxf(tmin, near);
+            tmax = fminf(tmax, far);
+            if (tmin > tmax) return false;
+        }
+    }
+    return true;
+}
+
+__device__ __forceinline__ void bp_query_emit(uint32_t qi, uint32_t handle, const uint32_t* __restrict__ d_attached, unsigned long long* out,
+                                              uint32_t cap, uint32_t* counter) {
+    if (d_attached[handle] != ST_ATTACHED) return;  // removed since the tree was built
+    uint32_t slot = atomicAdd(counter, 1u);
+    if (slot < cap) out[slot] = ((unsigned long long)qi << 32) | handle;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128) k_bp_query(const float* __restrict__ qin, uint32_t nq, const float4* __restrict__ llo,
+                                                  const float4* __restrict__ lhi, const float4* __restrict__ nodes, uint32_t n, uint32_t nout,
+                                                  const uint32_t* __restrict__ d_attached, unsigned long long* out, uint32_t cap,
+                                                  uint32_t* counter) {
+    const int W = KIND == 0 ? 6 : (KIND == 1 ? 7 : 3);
+    uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    BpQuery q;
+    for (int k = 0; k < W; ++k) q.a[k] = qin[(size_t)W * qi + k];
+    float inv[3] = {0.f, 0.f, 0.f};
+    if (KIND == 1)
+        for (int k = 0; k < 3; ++k) inv[k] = 1.0f / q.a[3 + k];
+    uint32_t m = n - nout;
+    if (m >= 2) {
+        uint32_t stack[64];
+        int sp = 0;
+        uint32_t node = 0;
+        for (;;) {
+            const float4* rec = nodes + 4 * (size_t)node;
+            float4 Llo = __ldg(rec + 0), Lhi = __ldg(rec + 1), Rlo = __ldg(rec + 2), Rhi = __ldg(rec + 3);
+            uint32_t left = __float_as_uint(Llo.w), right = __float_as_uint(Lhi.w);
+            bool goL = bp_query_test<KIND>(q, inv, Llo, Lhi), goR = bp_query_test<KIND>(q, inv, Rlo, Rhi);
+            if (goL && (left & LEAF_BIT)) {
+                bp_query_emit(qi, __float_as_uint(__ldg(&llo[left & ~LEAF_BIT].w)), d_attached, out, cap, counter);
+                goL = false;
+            }
+            if (goR && (right & LEAF_BIT)) {
+                bp_query_emit(qi, __float_as_uint(__ldg(&llo[right & ~LEAF_BIT].w)), d_attached, out, cap, counter);
+                goR = false;
+            }
+            if (goL) {
+                if (goR && sp < 64) stack[sp++] = right;
+                node = left;
+            } else if (goR) {
+                node = right;
+            } else {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+        }
+    } else if (m == 1) {
+        float4 lo = __ldg(&llo[0]), hi = __ldg(&lhi[0]);
+        if (bp_query_test<KIND>(q, inv, lo, hi)) bp_query_emit(qi, __float_as_uint(lo.w), d_attached, out, cap, counter);
+    }
+    for (uint32_t o = m; o < n; ++o) {  // leaves kept out of the tree (planes, huge boxes)
+        float4 lo = __ldg(&llo[o]), hi = __ldg(&lhi[o]);
+        if (bp_query_test<KIND>(q, inv, lo, hi)) bp_query_emit(qi, __float_as_uint(lo.w), d_attached, out, cap, counter);
+    }
+}
+
 }  // namespace
 
 #define CKB(call)                                                                                         \
@@ -272,7 +388,7 @@ void ncb_bp_destroy(ncb_bp* bp) {
     bp->pend_seq.release(), bp->upd_seq.release(), bp->win.release(), bp->d_attached.release();
     bp->stage_f.release(), bp->stage_u.release(), bp->alive.release(), bp->groups_dev.release();
     bp->keys_old.release(), bp->keys_new.release(), bp->keys_tmp.release(), bp->cub_tmp.release();
-    bp->ev_a.release(), bp->ev_b.release(), bp->ev_sorted.release(), bp->ev_u32.release(), bp->counters.release();
+    bp->q_in.release(), bp->ev_a.release(), bp->ev_b.release(), bp->ev_sorted.release(), bp->ev_u32.release(), bp->counters.release();
     delete bp;
 }
 
@@ -301,7 +417,7 @@ int ncb_bp_create_proxies(ncb_bp* bp, uint32_t n, const float* aabb_minmax, uint
     CKB(bp->stage_u.reserve(n));
     CKB(cudaMemcpyAsync(bp->stage_f.p, aabb_minmax, 24 * (size_t)n, cudaMemcpyHostToDevice, s));
     CKB(cudaMemcpyAsync(bp->stage_u.p, out_handles, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
-    k_bp_stage_create<<<(n + 255) / 256, 256, 0, s>>>(bp->stage_u.p, bp->stage_f.p, n, bp->seq, bp->pend_lo.p, bp->pend_hi.p, bp->pend_seq.p,
+    k_bp_stage_create<<<(n + 255) / 256, 256, 0, s>>>(bp->stage_u.p, bp->stage_f.p, n, SEQ_BACK0 + bp->seq, bp->pend_lo.p, bp->pend_hi.p, bp->pend_seq.p,
                                                       bp->d_attached.p);
     CKB(cudaGetLastError());
     CKB(cudaStreamSynchronize(s));  // the staging buffers are reused by the next call
@@ -325,12 +441,48 @@ int ncb_bp_set_bounding_volumes(ncb_bp* bp, uint32_t n, const uint32_t* handles,
     CKB(cudaMemcpyAsync(bp->stage_u.p, handles, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
     unsigned g = (n + 255) / 256;
     k_bp_clear_win<<<g, 256, 0, s>>>(bp->stage_u.p, n, bp->win.p);
-    k_bp_stage_set1<<<g, 256, 0, s>>>(bp->stage_u.p, bp->stage_f.p, n, bp->seq, bp->box_lo.p, bp->box_hi.p, bp->d_attached.p, bp->win.p,
+    k_bp_stage_set1<<<g, 256, 0, s>>>(bp->stage_u.p, bp->stage_f.p, n, SEQ_BACK0 + bp->seq, bp->box_lo.p, bp->box_hi.p, bp->d_attached.p, bp->win.p,
                                       bp->pend_seq.p);
     k_bp_stage_set2<<<g, 256, 0, s>>>(bp->stage_u.p, bp->stage_f.p, n, bp->margin, bp->win.p, bp->pend_lo.p, bp->pend_hi.p);
     CKB(cudaGetLastError());
     CKB(cudaStreamSynchronize(s));
     bp->seq += n;
+    return NCB_OK;
+}
+
+// BroadPhase::deferred_recompute_all_proximities_with (:349-363) for n handles, in order (unknown or not yet
+// attached handles are ignored like in the reference).
+int ncb_bp_recompute_with(ncb_bp* bp, uint32_t n, const uint32_t* handles) {
+    if (!bp || (n && !handles)) return NCB_ERR_ARG;
+    CKB(cudaSetDevice(bp->owner->device));
+    std::vector<uint32_t> ok;
+    ok.reserve(n);
+    for (uint32_t i = 0; i < n; ++i)
+        if (handles[i] < bp->next_free.size() && bp->next_free[handles[i]] == -2 && bp->attached[handles[i]]) ok.push_back(handles[i]);
+    if (ok.empty()) return NCB_OK;
+    cudaStream_t s = bp->owner->stream;
+    uint32_t m = (uint32_t)ok.size();
+    CKB(bp->stage_u.reserve(m));
+    CKB(cudaMemcpyAsync(bp->stage_u.p, ok.data(), 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+    k_bp_recompute_with<<<(m + 255) / 256, 256, 0, s>>>(bp->stage_u.p, m, SEQ_FRONT0 - bp->front, bp->box_lo.p, bp->box_hi.p, bp->d_attached.p,
+                                                        bp->pend_lo.p, bp->pend_hi.p, bp->pend_seq.p);
+    CKB(cudaGetLastError());
+    CKB(cudaStreamSynchronize(s));
+    bp->front += m;
+    return NCB_OK;
+}
+
+// BroadPhase::deferred_recompute_all_proximities (:365-386): every attached proxy, in slab order.
+int ncb_bp_recompute_all(ncb_bp* bp) {
+    if (!bp) return NCB_ERR_ARG;
+    CKB(cudaSetDevice(bp->owner->device));
+    uint32_t slots = (uint32_t)bp->next_free.size();
+    if (slots == 0) return NCB_OK;
+    cudaStream_t s = bp->owner->stream;
+    k_bp_recompute_with<<<(slots + 255) / 256, 256, 0, s>>>(nullptr, slots, SEQ_FRONT0 - bp->front, bp->box_lo.p, bp->box_hi.p, bp->d_attached.p,
+                                                            bp->pend_lo.p, bp->pend_hi.p, bp->pend_seq.p);
+    CKB(cudaGetLastError());
+    bp->front += slots;
     return NCB_OK;
 }
 
@@ -427,7 +579,7 @@ int ncb_bp_update(ncb_bp* bp, const uint32_t* groups, uint32_t n_group_slots, ui
         bp->err = bp->owner->err = "ncb_bp_update: groups must cover every handle slot";
         return NCB_ERR_ARG;
     }
-    bool any_pending = bp->seq != 0;
+    bool any_pending = bp->seq != 0 || bp->front != 0;
     if (!any_pending) return NCB_OK;  // no leaf was updated: the reference neither queries nor purges
     // 1. apply pending boxes; every occupied slot is attached afterwards
     k_bp_apply<<<(slots + 255) / 256, 256, 0, s>>>(slots, bp->box_lo.p, bp->box_hi.p, bp->pend_lo.p, bp->pend_hi.p, bp->pend_seq.p, bp->upd_seq.p,
@@ -441,9 +593,21 @@ int ncb_bp_update(ncb_bp* bp, const uint32_t* groups, uint32_t n_group_slots, ui
             alive.push_back(h);
         }
     bp->n_attached = (uint32_t)alive.size();
-    bp->seq = 0;
+    bp->seq = bp->front = 0;
     uint32_t m = (uint32_t)alive.size();
     uint32_t n_new = 0;
+    bp->tree_n = 0;
+    if (m == 1) {  // a single leaf: no internal node; keep it where the queries look for it
+        CKB(bp->alive.reserve(1));
+        CKB(cudaMemcpyAsync(bp->alive.p, alive.data(), 4, cudaMemcpyHostToDevice, s));
+        CKB(w->leaf_lo.reserve(1));
+        CKB(w->leaf_hi.reserve(1));
+        k_bp_gather<<<1, 32, 0, s>>>(bp->alive.p, 1, bp->box_lo.p, bp->box_hi.p, w->leaf_lo.p, w->leaf_hi.p);
+        k_bp_fill<<<1, 32, 0, s>>>(reinterpret_cast<uint32_t*>(w->leaf_lo.p) + 3, alive[0], 1);
+        CKB(cudaGetLastError());
+        bp->tree_n = 1;
+        bp->tree_outliers = 1;  // scanned linearly
+    }
     if (m >= 2) {
         // 2. LBVH over the attached proxies, leaf ids = handles
         CKB(bp->alive.reserve(m));
@@ -484,6 +648,8 @@ int ncb_bp_update(ncb_bp* bp, const uint32_t* groups, uint32_t n_group_slots, ui
             CKB(cudaMemcpyAsync(w->h_counters, w->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
             CKB(cudaStreamSynchronize(s));
             n_new = w->h_counters->n_pairs;
+            bp->tree_n = m;
+            bp->tree_outliers = w->h_counters->n_outliers;
             if (n_new <= w->pairs_raw.cap) break;
             cap_pairs = (size_t)n_new + n_new / 8 + 1024;
         }
@@ -545,6 +711,52 @@ int ncb_bp_events(ncb_bp* bp, uint32_t* started, uint32_t* stopped) {
     int r = bp_fetch(bp, bp->ev_a.p, bp->n_started, started);
     if (r) return r;
     return bp_fetch(bp, bp->ev_b.p, bp->n_stopped, stopped);
+}
+
+// Batched BroadPhase::interferences_with_bounding_volume (kind 0, 6 floats per query: mins, maxs), _with_ray (kind 1,
+// 7 floats: origin, dir, max_toi) and _with_point (kind 2, 3 floats) (:388-432).  out[2 * k] = (query index, handle),
+// sorted; cap in entries; *n_out = entries found; returns 1 when truncated.
+int ncb_bp_query(ncb_bp* bp, int kind, uint32_t n_queries, const float* queries, uint32_t* out, uint32_t cap, uint32_t* n_out) {
+    if (!bp || kind < 0 || kind > 2 || (n_queries && !queries)) return NCB_ERR_ARG;
+    CKB(cudaSetDevice(bp->owner->device));
+    if (n_out) *n_out = 0;
+    if (n_queries == 0 || bp->tree_n == 0) return NCB_OK;
+    cudaStream_t s = bp->owner->stream;
+    ncb_ctx* w = bp->work;
+    const int W = kind == 0 ? 6 : (kind == 1 ? 7 : 3);
+    CKB(bp->q_in.reserve((size_t)W * n_queries));
+    CKB(cudaMemcpyAsync(bp->q_in.p, queries, 4 * (size_t)W * n_queries, cudaMemcpyHostToDevice, s));
+    CKB(bp->counters.reserve(4));
+    size_t want = bp->ev_a.cap ? bp->ev_a.cap : (size_t)16 * n_queries + 1024;
+    uint32_t found = 0;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        CKB(bp->ev_a.reserve(want));
+        CKB(cudaMemsetAsync(bp->counters.p, 0, 16, s));
+        unsigned g = (n_queries + 127) / 128;
+        uint32_t c = (uint32_t)bp->ev_a.cap;
+        if (kind == 0)
+            k_bp_query<0><<<g, 128, 0, s>>>(bp->q_in.p, n_queries, w->leaf_lo.p, w->leaf_hi.p, w->nodes.p, bp->tree_n, bp->tree_outliers,
+                                            bp->d_attached.p, bp->ev_a.p, c, bp->counters.p);
+        else if (kind == 1)
+            k_bp_query<1><<<g, 128, 0, s>>>(bp->q_in.p, n_queries, w->leaf_lo.p, w->leaf_hi.p, w->nodes.p, bp->tree_n, bp->tree_outliers,
+                                            bp->d_attached.p, bp->ev_a.p, c, bp->counters.p);
+        else
+            k_bp_query<2><<<g, 128, 0, s>>>(bp->q_in.p, n_queries, w->leaf_lo.p, w->leaf_hi.p, w->nodes.p, bp->tree_n, bp->tree_outliers,
+                                            bp->d_attached.p, bp->ev_a.p, c, bp->counters.p);
+        CKB(cudaGetLastError());
+        CKB(cudaMemcpyAsync(&found, bp->counters.p, 4, cudaMemcpyDeviceToHost, s));
+        CKB(cudaStreamSynchronize(s));
+        if (found <= bp->ev_a.cap) break;
+        want = (size_t)found + 1024;
+    }
+    bp->n_started = 0;  // the event buffer was reused
+    int r = bp_sort_events(bp, bp->ev_a, found);
+    if (r) return r;
+    if (n_out) *n_out = found;
+    uint32_t wr = found < cap ? found : cap;
+    r = bp_fetch(bp, bp->ev_a.p, wr, out);
+    if (r) return r;
+    return (out && found > cap) ? 1 : NCB_OK;
 }
 
 int ncb_bp_num_interferences(ncb_bp* bp, uint32_t* n) {

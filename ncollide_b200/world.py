@@ -399,6 +399,21 @@ class BroadPhase:
         self.ctx.check(self._lib.ncb_bp_set_bounding_volumes(self._h, C.c_uint32(len(handles)), ptr(handles), ptr(bvs)),
                        "ncb_bp_set_bounding_volumes")
 
+    def deferred_recompute_all_proximities_with(self, handles):
+        self._flush_sets()
+        handles = as_u32(np.atleast_1d(handles)).reshape(-1)
+        self.ctx.check(self._lib.ncb_bp_recompute_with(self._h, C.c_uint32(len(handles)), ptr(handles)), "ncb_bp_recompute_with")
+
+    def deferred_recompute_all_proximities(self):
+        self._flush_sets()
+        self.ctx.check(self._lib.ncb_bp_recompute_all(self._h), "ncb_bp_recompute_all")
+
+    def set_groups(self, handle, groups):
+        """Changes the collision groups of a live proxy and re-queues it (glue/update.rs:83-86)."""
+        self._groups[int(handle)] = np.asarray(groups, dtype=np.uint32).reshape(3)
+        self._any_groups = True
+        self.deferred_recompute_all_proximities_with([handle])
+
     def _flush_sets(self):
         hs, bs = self._pending_set
         if hs:
@@ -419,6 +434,40 @@ class BroadPhase:
             keep = [tuple(p) not in self._vetoed for p in out.tolist()]
             out = out[np.array(keep, dtype=bool)]
         return out
+
+    def _query(self, kind, q, width):
+        self._flush_sets()
+        q = as_f32(q).reshape(-1, width)
+        cap = max(64 * len(q), 4096)
+        while True:
+            out = np.zeros((cap, 2), dtype=np.uint32)
+            n = C.c_uint32()
+            r = self.ctx.check(self._lib.ncb_bp_query(self._h, C.c_int(kind), C.c_uint32(len(q)), ptr(q), ptr(out), C.c_uint32(cap), C.byref(n)),
+                               "ncb_bp_query")
+            if r == 0:
+                return out[: n.value]
+            cap = n.value
+
+    def interferences_with_bounding_volumes(self, bvs):
+        """Batched ``interferences_with_bounding_volume``: [K,2] rows (query index, handle), sorted."""
+        return self._query(0, bvs, 6)
+
+    def interferences_with_rays(self, origins, dirs, max_toi):
+        o, d = as_f32(origins).reshape(-1, 3), as_f32(dirs).reshape(-1, 3)
+        t = np.broadcast_to(np.asarray(max_toi, dtype=np.float32).reshape(-1, 1), (len(o), 1))
+        return self._query(1, np.concatenate([o, d, t], axis=1), 7)
+
+    def interferences_with_points(self, points):
+        return self._query(2, points, 3)
+
+    def interferences_with_bounding_volume(self, bv):
+        return [self._data[h] for h in self.interferences_with_bounding_volumes(np.asarray(bv).reshape(1, 6))[:, 1].tolist()]
+
+    def interferences_with_ray(self, origin, direction, max_toi):
+        return [self._data[h] for h in self.interferences_with_rays(origin, direction, max_toi)[:, 1].tolist()]
+
+    def interferences_with_point(self, point):
+        return [self._data[h] for h in self.interferences_with_points(np.asarray(point).reshape(1, 3))[:, 1].tolist()]
 
     def update_events(self):
         """One ``update``; returns (started[k,2], stopped[m,2]) handle arrays without going through a handler."""

@@ -192,7 +192,55 @@ struct Dbvt {
             }
         }
     }
+    // the same walk with any bounding-volume predicate (ray / point collectors, query/visitors/*.rs)
+    template <typename Pred>
+    void visit_pred(const Pred& pred, std::vector<uint32_t>& collector, std::vector<NodeId>& stack) const {
+        if (empty()) return;
+        stack.clear();
+        stack.push_back(root);
+        while (!stack.empty()) {
+            NodeId node = stack.back();
+            stack.pop_back();
+            if (!node.leaf) {
+                const Internal& n = internals[node.id];
+                if (pred(n.bv)) {
+                    stack.push_back(n.left);
+                    stack.push_back(n.right);
+                }
+            } else {
+                const Leaf& l = leaves[node.id];
+                if (pred(l.bv)) collector.push_back(l.data);
+            }
+        }
+    }
 };
+
+// AABB::toi_with_ray(.., solid = true).is_some()  (query/ray/ray_aabb.rs:13-50, ray.rs:157-159)
+static bool bb_intersects_ray(const BBox& b, V3 o, V3 d, real max_toi) {
+    real tmin = 0, tmax = max_toi;
+    const real oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    const real mn[3] = {b.mins.x, b.mins.y, b.mins.z}, mx[3] = {b.maxs.x, b.maxs.y, b.maxs.z};
+    for (int i = 0; i < 3; ++i) {
+        if (dd[i] == real(0)) {
+            if (oo[i] < mn[i] || oo[i] > mx[i]) return false;
+        } else {
+            real denom = real(1) / dd[i];
+            real near = (mn[i] - oo[i]) * denom, far = (mx[i] - oo[i]) * denom;
+            if (near > far) std::swap(near, far);
+            tmin = std::fmax(tmin, near);
+            tmax = std::fmin(tmax, far);
+            if (tmin > tmax) return false;
+        }
+    }
+    return true;
+}
+// AABB::contains_local_point (bounding_volume/aabb.rs:138-146)
+static bool bb_contains_point(const BBox& b, V3 p) {
+    if (p.x < b.mins.x || p.x > b.maxs.x) return false;
+    if (p.y < b.mins.y || p.y > b.maxs.y) return false;
+    if (p.z < b.mins.z || p.z > b.maxs.z) return false;
+    return true;
+}
 
 enum StatusKind { ON_STATIC, ON_DYNAMIC, DETACHED, DELETED };
 struct Proxy {
@@ -382,6 +430,50 @@ void orc_bp_update(orc_bp* b, const uint32_t* groups, uint32_t* started, uint64_
     }
     if (n_started) *n_started = ns;
     if (n_stopped) *n_stopped = np;
+}
+
+// :349-363.  Attached proxies are re-queued at the FRONT of the pending queue with their stored box.
+void orc_bp_recompute_with(orc_bp* b, uint32_t h) {
+    if (!b->proxies.contains(h)) return;
+    const Proxy& p = b->proxies[h];
+    if (p.status != ON_STATIC && p.status != ON_DYNAMIC) return;
+    b->proxies_to_update.push_front({h, b->bv_of(p)});
+}
+
+// :365-386.  Every attached proxy, in slab order, each pushed in front of the previous one; purge_all stays set.
+void orc_bp_recompute_all(orc_bp* b) {
+    for (size_t k = 0; k < b->proxies.items.size(); ++k) {
+        if (!b->proxies.contains(k)) continue;
+        const Proxy& p = b->proxies[k];
+        if (p.status != ON_STATIC && p.status != ON_DYNAMIC) continue;
+        b->proxies_to_update.push_front({(uint32_t)k, b->bv_of(p)});
+    }
+    b->purge_all = true;
+}
+
+// interferences_with_bounding_volume / _ray / _point (:388-432): dynamic tree first, then the static tree.
+// kind 0: q = 6 reals (mins, maxs); 1: q = 7 reals (origin, dir, max_toi); 2: q = 3 reals.  Returns the count.
+uint64_t orc_bp_query(orc_bp* b, int kind, const real* q, uint32_t* out, uint64_t cap) {
+    b->collector.clear();
+    if (kind == 0) {
+        BBox bv{{q[0], q[1], q[2]}, {q[3], q[4], q[5]}};
+        auto pred = [&](const BBox& x) { return bb_intersects(x, bv); };
+        b->tree.visit_pred(pred, b->collector, b->stack);
+        b->stree.visit_pred(pred, b->collector, b->stack);
+    } else if (kind == 1) {
+        V3 o = v3(q[0], q[1], q[2]), d = v3(q[3], q[4], q[5]);
+        real max_toi = q[6];
+        auto pred = [&](const BBox& x) { return bb_intersects_ray(x, o, d, max_toi); };
+        b->tree.visit_pred(pred, b->collector, b->stack);
+        b->stree.visit_pred(pred, b->collector, b->stack);
+    } else {
+        V3 p = v3(q[0], q[1], q[2]);
+        auto pred = [&](const BBox& x) { return bb_contains_point(x, p); };
+        b->tree.visit_pred(pred, b->collector, b->stack);
+        b->stree.visit_pred(pred, b->collector, b->stack);
+    }
+    for (size_t k = 0; k < b->collector.size() && k < cap; ++k) out[k] = b->collector[k];
+    return b->collector.size();
 }
 
 uint64_t orc_bp_num_interferences(const orc_bp* b) { return b->pairs.size(); }

@@ -74,6 +74,9 @@ int orc_bp_set_bounding_volume(orc_bp*, uint32_t handle, const real* minmax);
 int orc_bp_remove(orc_bp*, uint32_t n, const uint32_t* handles, uint32_t* removed_pairs, uint64_t cap, uint64_t* n_removed);
 void orc_bp_update(orc_bp*, const uint32_t* groups, uint32_t* started, uint64_t cap_s, uint64_t* n_started, uint32_t* stopped,
                    uint64_t cap_p, uint64_t* n_stopped);
+void orc_bp_recompute_with(orc_bp*, uint32_t handle);
+void orc_bp_recompute_all(orc_bp*);
+uint64_t orc_bp_query(orc_bp*, int kind, const real* q, uint32_t* out, uint64_t cap);
 uint64_t orc_bp_num_interferences(const orc_bp*);
 int orc_bp_proxy(const orc_bp*, uint32_t handle, real* minmax);
 uint64_t orc_bp_pairs(const orc_bp*, uint32_t* out, uint64_t cap);

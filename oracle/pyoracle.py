@@ -246,6 +246,32 @@ class OracleBroadPhase:
         assert ns.value <= cap and np_.value <= cap
         return st[: ns.value].copy(), sp[: np_.value].copy()
 
+    def deferred_recompute_all_proximities_with(self, handle):
+        self.o.lib.orc_bp_recompute_with(self.h, C.c_uint32(handle))
+
+    def deferred_recompute_all_proximities(self):
+        self.o.lib.orc_bp_recompute_all(self.h)
+
+    def _query(self, kind, q):
+        q = np.ascontiguousarray(q, dtype=self.o.dtype)
+        self.o.lib.orc_bp_query.restype = C.c_uint64
+        cap = 4096
+        while True:
+            out = np.zeros(cap, dtype=np.uint32)
+            n = self.o.lib.orc_bp_query(self.h, C.c_int(kind), C.c_void_p(q.ctypes.data), C.c_void_p(out.ctypes.data), C.c_uint64(cap))
+            if n <= cap:
+                return out[:n].copy()
+            cap = int(n)
+
+    def interferences_with_bounding_volume(self, bv):
+        return self._query(0, bv)
+
+    def interferences_with_ray(self, origin, direction, max_toi):
+        return self._query(1, np.concatenate([np.asarray(origin).reshape(3), np.asarray(direction).reshape(3), [max_toi]]))
+
+    def interferences_with_point(self, point):
+        return self._query(2, point)
+
     def num_interferences(self):
         return int(self.o.lib.orc_bp_num_interferences(self.h))
 

@@ -43,6 +43,17 @@ class OracleAdapter:
     def update(self):
         return self.bp.update(self.groups if len(self.groups) else None)
 
+    def set_groups(self, h, g, requeue=True):
+        self.groups[h] = g
+        if requeue:
+            self.bp.deferred_recompute_all_proximities_with(int(h))
+
+    def recompute_all(self):
+        self.bp.deferred_recompute_all_proximities()
+
+    def query(self, kind, q):
+        return QUERY_IMPL[type(self).__name__](self, kind, q)
+
     def num(self):
         return self.bp.num_interferences()
 
@@ -72,6 +83,19 @@ class DeviceAdapter:
     def update(self):
         return self.bp.update_events()
 
+    def set_groups(self, h, g, requeue=True):
+        if requeue:
+            self.bp.set_groups(h, g)
+        else:
+            self.bp._groups[int(h)] = g
+            self.bp._any_groups = True
+
+    def recompute_all(self):
+        self.bp.deferred_recompute_all_proximities()
+
+    def query(self, kind, q):
+        return QUERY_IMPL[type(self).__name__](self, kind, q)
+
     def num(self):
         return self.bp.num_interferences()
 
@@ -94,6 +118,7 @@ class SetModel:
         self.groups = np.zeros((0, 3), dtype=np.uint32)
         self.pending = {}  # handle -> [first seq, box]; survives removal like the reference's queue
         self.seq = 0
+        self.front = 0
         self.set = set()
 
     def _slot(self):
@@ -111,6 +136,27 @@ class SetModel:
         else:
             self.pending[h] = [self.seq, box]
         self.seq += 1
+
+    def _push_front(self, h):
+        if not (self.occupied[h] and self.attached[h]):
+            return
+        self.front += 1
+        if h in self.pending:
+            self.pending[h][0] = min(self.pending[h][0], -self.front)
+        else:
+            self.pending[h] = [-self.front, self.box[h].copy()]
+
+    def set_groups(self, h, g, requeue=True):
+        self.groups[h] = g
+        if requeue:
+            self._push_front(int(h))
+
+    def recompute_all(self):
+        for h in range(len(self.occupied)):
+            self._push_front(h)
+
+    def query(self, kind, q):
+        return _model_query(self, kind, q)
 
     def create(self, bvs, groups):
         out = []
@@ -159,7 +205,7 @@ class SetModel:
                 self.box[h] = box
                 self.attached[h] = True
         self.pending = {}
-        self.seq = 0
+        self.seq = self.front = 0
         if not upd:
             return np.zeros((0, 2), np.uint32), np.zeros((0, 2), np.uint32)
         alive = [h for h in range(len(self.occupied)) if self.occupied[h]]
@@ -191,12 +237,70 @@ class SetModel:
         return np.array(sorted(self.set), dtype=np.uint32).reshape(-1, 2)
 
 
+def _oracle_query(self, kind, q):
+    rows = []
+    for i, r in enumerate(q):
+        if kind == 0:
+            hs = self.bp.interferences_with_bounding_volume(r)
+        elif kind == 1:
+            hs = self.bp.interferences_with_ray(r[:3], r[3:6], r[6])
+        else:
+            hs = self.bp.interferences_with_point(r)
+        rows += [(i, int(h)) for h in hs]
+    return np.array(rows, dtype=np.uint32).reshape(-1, 2)
+
+
+def _device_query(self, kind, q):
+    if kind == 0:
+        return self.bp.interferences_with_bounding_volumes(q)
+    if kind == 1:
+        return self.bp.interferences_with_rays(q[:, :3], q[:, 3:6], q[:, 6])
+    return self.bp.interferences_with_points(q)
+
+
+def _model_query(self, kind, q):
+    rows = []
+    hs = [h for h in range(len(self.occupied)) if self.occupied[h] and self.attached[h]]
+    for i, r in enumerate(q):
+        for h in hs:
+            b = self.box[h]
+            if kind == 0:
+                ok = np.all(b[:3] <= r[3:6]) and np.all(b[3:] >= r[:3])
+            elif kind == 2:
+                ok = not (np.any(r < b[:3]) or np.any(r > b[3:]))
+            else:
+                ok = _slab(b, r[:3], r[3:6], r[6])
+            if ok:
+                rows.append((i, h))
+    return np.array(rows, dtype=np.uint32).reshape(-1, 2)
+
+
+def _slab(b, o, d, max_toi):
+    tmin, tmax = F32(0), F32(max_toi)
+    for i in range(3):
+        if d[i] == 0:
+            if o[i] < b[i] or o[i] > b[3 + i]:
+                return False
+        else:
+            inv = F32(1) / d[i]
+            near, far = (b[i] - o[i]) * inv, (b[3 + i] - o[i]) * inv
+            if near > far:
+                near, far = far, near
+            tmin, tmax = max(tmin, near), min(tmax, far)
+            if tmin > tmax:
+                return False
+    return True
+
+
+QUERY_IMPL = {"OracleAdapter": _oracle_query, "DeviceAdapter": _device_query, "SetModel": _model_query}
+
+
 def sort_rows(a):
     a = np.asarray(a, dtype=np.uint32).reshape(-1, 2)
     return a[np.lexsort((a[:, 1], a[:, 0]))]
 
 
-def run_scenario(impl, seed, n0=300, steps=12, side=10.0, use_groups=True):
+def run_scenario(impl, seed, n0=300, steps=12, side=10.0, use_groups=True, n_queries=0):
     """Returns a list of per-step records (dicts of numpy arrays / ints)."""
     rng = np.random.default_rng(seed)
 
@@ -267,6 +371,17 @@ def run_scenario(impl, seed, n0=300, steps=12, side=10.0, use_groups=True):
                 (h2,) = impl.create(nb2, rand_groups(1))
                 assert h2 == hn[1], "slab handles are recycled LIFO"
                 live[h2] = nb2[0]
+        if use_groups and step % 4 == 2:
+            # the groups of a few attached proxies change; the world re-queues them (glue/update.rs:83-86)
+            hs = [h for h in sorted(live) if impl.proxy(h) is not None]
+            for h in rng.choice(np.array(hs), size=min(12, len(hs)), replace=False).tolist():
+                impl.set_groups(h, rand_groups(1)[0])
+        if use_groups and step == steps - 2:
+            # pair filter replaced: groups change silently, then deferred_recompute_all_proximities (world.rs:216)
+            hs = [h for h in sorted(live) if impl.proxy(h) is not None]
+            for h in rng.choice(np.array(hs), size=min(30, len(hs)), replace=False).tolist():
+                impl.set_groups(h, rand_groups(1)[0], requeue=False)
+            impl.recompute_all()
         started, stopped = impl.update()
         rec["started"] = sort_rows(started)
         rec["stopped"] = sort_rows(stopped)
@@ -276,6 +391,24 @@ def run_scenario(impl, seed, n0=300, steps=12, side=10.0, use_groups=True):
         sample = sorted(live)[:: max(1, len(live) // 40)]
         rec["proxy"] = np.array([impl.proxy(h) for h in sample], dtype=F32)
         rec["live"] = len(live)
+        if n_queries:
+            # world-level queries between updates: after a removal, so the tree of the last update is stale for it
+            hs = np.array(sorted(h for h in live if impl.proxy(h) is not None), dtype=np.uint32)
+            gone = impl.remove(hs[:: max(1, len(hs) // 7)][:5])
+            for h in hs[:: max(1, len(hs) // 7)][:5].tolist():
+                del live[h]
+            rec["removed2"] = sort_rows(gone)
+            qb = rand_boxes(n_queries)
+            o = rng.uniform(0, side, size=(n_queries, 3)).astype(F32)
+            d = rng.normal(0, 1, size=(n_queries, 3)).astype(F32)
+            d[::5, 0] = 0  # axis-parallel rays exercise the zero-direction branch
+            d[::7, 1:] = 0
+            t = rng.uniform(1.0, 2 * side, size=(n_queries, 1)).astype(F32)
+            t[::3] = np.finfo(F32).max
+            pts = np.concatenate([rng.uniform(0, side, size=(n_queries - 4, 3)).astype(F32), qb[:4, :3]])  # on a box corner
+            rec["q_aabb"] = sort_rows(impl.query(0, qb))
+            rec["q_ray"] = sort_rows(impl.query(1, np.concatenate([o, d, t], axis=1)))
+            rec["q_point"] = sort_rows(impl.query(2, pts))
         log.append(rec)
     return log
 
@@ -283,7 +416,7 @@ def run_scenario(impl, seed, n0=300, steps=12, side=10.0, use_groups=True):
 def assert_same_log(a, b, what=""):
     assert len(a) == len(b)
     for t, (x, y) in enumerate(zip(a, b)):
-        for k in ("removed", "started", "stopped", "pairs"):
+        for k in ("removed", "started", "stopped", "pairs") + tuple(q for q in ("removed2", "q_aabb", "q_ray", "q_point") if q in x):
             assert np.array_equal(x[k], y[k]), f"{what} step {t}: {k} differ ({len(x[k])} vs {len(y[k])})"
         assert x["num"] == y["num"], f"{what} step {t}: num_interferences"
         assert np.array_equal(x["proxy"].view(np.uint32), y["proxy"].view(np.uint32)), f"{what} step {t}: proxy boxes"

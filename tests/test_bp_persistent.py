@@ -68,6 +68,14 @@ def test_oracle_matches_set_semantics(oracle, seed, groups):
     assert_same_log(a, b, "oracle vs set model")
 
 
+def test_oracle_queries_match_brute_force(oracle):
+    # interferences_with_{bounding_volume,ray,point} through the two DBVTs == a scan of the stored boxes
+    a = run_scenario(OracleAdapter(oracle, 0.05), 4, n0=200, steps=6, n_queries=24)
+    b = run_scenario(SetModel(0.05), 4, n0=200, steps=6, n_queries=24)
+    assert sum(len(r["q_ray"]) for r in a) > 50 and sum(len(r["q_point"]) for r in a) > 5
+    assert_same_log(a, b, "oracle vs set model")
+
+
 @pytest.mark.gpu
 def test_device_example_kat():
     from ncollide_b200.world import Context
@@ -83,8 +91,8 @@ def test_device_matches_oracle(oracle, seed, n0, steps, groups):
 
     ctx = Context(0)
     side = 10.0 * (n0 / 300.0) ** (1 / 3)
-    a = run_scenario(OracleAdapter(oracle, 0.05), seed, n0=n0, steps=steps, side=side, use_groups=groups)
-    b = run_scenario(DeviceAdapter(ctx, 0.05), seed, n0=n0, steps=steps, side=side, use_groups=groups)
+    a = run_scenario(OracleAdapter(oracle, 0.05), seed, n0=n0, steps=steps, side=side, use_groups=groups, n_queries=64)
+    b = run_scenario(DeviceAdapter(ctx, 0.05), seed, n0=n0, steps=steps, side=side, use_groups=groups, n_queries=64)
     assert_same_log(a, b, "device vs oracle")
 
 
