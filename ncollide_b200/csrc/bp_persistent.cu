@@ -34,6 +34,7 @@ struct ncb_bp {
     std::vector<uint8_t> attached;   // host mirror: 0 detached (pending), 1 attached
     size_t next = 0, len = 0;
     uint32_t n_attached = 0;
+    bool slab_dirty = true;  // proxies were created / removed since `alive` was uploaded
     uint32_t seq = 0;    // back entries issued since the last update
     uint32_t front = 0;  // front entries issued since the last update
     // device state, indexed by handle slot
@@ -410,6 +411,7 @@ int ncb_bp_create_proxies(ncb_bp* bp, uint32_t n, const float* aabb_minmax, uint
         bp->len++;
         out_handles[i] = (uint32_t)key;
     }
+    bp->slab_dirty = true;
     int r = bp_grow(bp, bp->next_free.size());
     if (r) return r;
     cudaStream_t s = bp->owner->stream;
@@ -557,6 +559,7 @@ int ncb_bp_remove(ncb_bp* bp, uint32_t n, const uint32_t* handles, uint32_t* n_r
         bp->next = h;
         bp->len--;
     }
+    bp->slab_dirty = true;
     bp->n_stopped = nr;
     if (n_removed) *n_removed = nr;
     return NCB_OK;
@@ -585,33 +588,35 @@ int ncb_bp_update(ncb_bp* bp, const uint32_t* groups, uint32_t n_group_slots, ui
     k_bp_apply<<<(slots + 255) / 256, 256, 0, s>>>(slots, bp->box_lo.p, bp->box_hi.p, bp->pend_lo.p, bp->pend_hi.p, bp->pend_seq.p, bp->upd_seq.p,
                                                    bp->d_attached.p);
     CKB(cudaGetLastError());
-    std::vector<uint32_t> alive;
-    alive.reserve(bp->len);
-    for (uint32_t h = 0; h < slots; ++h)
-        if (bp->next_free[h] == -2) {
-            bp->attached[h] = 1;
-            alive.push_back(h);
-        }
-    bp->n_attached = (uint32_t)alive.size();
+    if (bp->slab_dirty) {
+        std::vector<uint32_t> alive;
+        alive.reserve(bp->len);
+        for (uint32_t h = 0; h < slots; ++h)
+            if (bp->next_free[h] == -2) {
+                bp->attached[h] = 1;
+                alive.push_back(h);
+            }
+        bp->n_attached = (uint32_t)alive.size();
+        CKB(bp->alive.reserve(alive.size() + 1));
+        if (!alive.empty()) CKB(cudaMemcpyAsync(bp->alive.p, alive.data(), 4 * alive.size(), cudaMemcpyHostToDevice, s));
+        CKB(cudaStreamSynchronize(s));  // `alive` is a local
+        bp->slab_dirty = false;
+    }
     bp->seq = bp->front = 0;
-    uint32_t m = (uint32_t)alive.size();
+    uint32_t m = bp->n_attached;
     uint32_t n_new = 0;
     bp->tree_n = 0;
     if (m == 1) {  // a single leaf: no internal node; keep it where the queries look for it
-        CKB(bp->alive.reserve(1));
-        CKB(cudaMemcpyAsync(bp->alive.p, alive.data(), 4, cudaMemcpyHostToDevice, s));
         CKB(w->leaf_lo.reserve(1));
         CKB(w->leaf_hi.reserve(1));
         k_bp_gather<<<1, 32, 0, s>>>(bp->alive.p, 1, bp->box_lo.p, bp->box_hi.p, w->leaf_lo.p, w->leaf_hi.p);
-        k_bp_fill<<<1, 32, 0, s>>>(reinterpret_cast<uint32_t*>(w->leaf_lo.p) + 3, alive[0], 1);
+        CKB(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(w->leaf_lo.p) + 3, bp->alive.p, 4, cudaMemcpyDeviceToDevice, s));
         CKB(cudaGetLastError());
         bp->tree_n = 1;
         bp->tree_outliers = 1;  // scanned linearly
     }
     if (m >= 2) {
         // 2. LBVH over the attached proxies, leaf ids = handles
-        CKB(bp->alive.reserve(m));
-        CKB(cudaMemcpyAsync(bp->alive.p, alive.data(), 4 * (size_t)m, cudaMemcpyHostToDevice, s));
         CKB(w->aabb_lo.reserve(m));
         CKB(w->aabb_hi.reserve(m));
         CKB(w->keys_a.reserve(m));
