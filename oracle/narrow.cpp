@@ -433,18 +433,72 @@ static void support_feature_toward(const Shape& s, const Iso& m, V3 dir, real an
 }
 
 // ---------------------------------------------------------------------------------------------
-// ContactManifold (contact_manifold.rs), fresh manifold, DistanceBased(0.02)
+// ContactManifold (contact_manifold.rs:14-236): Slab<(TrackedContact, usize)> + DistanceBased(0.02) cache,
+// persistence = 1.  A fresh manifold (no save_cache_and_clear before) behaves like the one-shot case.
 // ---------------------------------------------------------------------------------------------
 struct Tracked {
     Contact c;
     uint32_t f1, f2;
+    uint32_t id = 0;  // insertion counter of this manifold: stable exactly as long as the reference's ContactId is
 };
 struct Manifold {
-    std::vector<Tracked> contacts;
+    struct Slot {
+        Tracked t;
+        size_t remaining = 0;    // the `usize` of the tuple
+        bool occupied = false;
+        int64_t next_free = -1;  // slab free-list link
+    };
+    // slab::Slab: vacant entries form a LIFO free list; `next` == entries.len() when the list is empty
+    std::vector<Slot> slab;
+    size_t slab_next = 0;
     std::vector<std::pair<V3, size_t>> cache;
-    size_t deepest = 0;
+    size_t deepest = 0, ncontacts = 0;
+    static constexpr size_t persistence = 1;
+    uint32_t next_id = 0;
+
+    size_t slab_insert(const Tracked& t, size_t remaining) {
+        size_t key = slab_next;
+        if (key == slab.size()) {
+            slab.push_back(Slot{});
+            slab_next = key + 1;
+        } else {
+            slab_next = (size_t)slab[key].next_free;
+        }
+        slab[key].t = t;
+        slab[key].remaining = remaining;
+        slab[key].occupied = true;
+        return key;
+    }
+    void slab_remove(size_t key) {
+        slab[key].occupied = false;
+        slab[key].next_free = (int64_t)slab_next;
+        slab_next = key;
+    }
+    size_t len() const { return ncontacts; }
+    // contacts(): slab order, entries with remaining == persistence (:59-68)
+    template <typename F>
+    void for_each_contact(F f) const {
+        for (size_t i = 0; i < slab.size(); ++i)
+            if (slab[i].occupied && slab[i].remaining == persistence) f(slab[i].t, i);
+    }
+    void save_cache_and_clear() {  // :134-156
+        std::vector<std::pair<V3, size_t>> kept;
+        for (auto& c : cache)
+            if (slab[c.second].remaining != 0) kept.push_back(c);
+        cache.swap(kept);
+        deepest = 0;
+        ncontacts = 0;
+        for (size_t i = 0; i < slab.size(); ++i) {  // Slab::retain visits the keys in increasing order
+            if (!slab[i].occupied) continue;
+            if (slab[i].remaining == 0)
+                slab_remove(i);
+            else
+                slab[i].remaining -= 1;
+        }
+    }
     void push(const Contact& c, uint32_t f1, uint32_t f2, V3 tracking_pt) {  // :165-236
         const real threshold = real(0.02);
+        bool is_deepest = ncontacts == 0 || c.depth > slab[deepest].t.c.depth;
         size_t closest = cache.size();
         real closest_dist = threshold * threshold;
         for (size_t i = 0; i < cache.size(); ++i) {
@@ -454,16 +508,25 @@ struct Manifold {
                 closest = i;
             }
         }
-        bool is_deepest = contacts.empty() || c.depth > contacts[deepest].c.depth;
         if (closest == cache.size()) {
-            contacts.push_back({c, f1, f2});
-            cache.push_back({tracking_pt, contacts.size() - 1});
-            if (is_deepest) deepest = contacts.size() - 1;
+            Tracked t{c, f1, f2, 0};
+            t.id = ++next_id;  // narrow_phase.rs:85-89 hands a fresh id to every contact whose id is null
+            size_t i = slab_insert(t, persistence);
+            cache.push_back({tracking_pt, i});
+            ncontacts += 1;
+            if (is_deepest) deepest = i;
         } else {
             size_t ci = cache[closest].second;
             if (is_deepest) deepest = ci;
-            if (c.depth <= contacts[ci].c.depth) return;
-            contacts[ci] = {c, f1, f2};
+            Slot& sl = slab[ci];
+            if (sl.remaining == persistence) {
+                if (c.depth <= sl.t.c.depth) return;  // keep the contact already in cache because it is deeper
+            } else {
+                ncontacts += 1;
+                sl.remaining = persistence;
+            }
+            sl.t.c = c;  // the TrackedContact keeps its id
+            sl.t.f1 = f1, sl.t.f2 = f2;
             cache[closest].first = tracking_pt;
         }
     }
@@ -756,12 +819,23 @@ static bool feature_ok_for_manifold(const Feature& ft, uint32_t f) {
     }
 }
 
-// convex_polyhedron_convex_polyhedron_manifold_generator.rs:83-167 (fresh generator: last_gjk_dir = None)
+// convex_polyhedron_convex_polyhedron_manifold_generator.rs:83-167.  last_gjk_dir: the generator's persistent
+// direction (nullptr / !*has_dir = fresh generator, None); updated like :106 and :139.
 static void gen_convex_convex(const Iso& ma, const Shape& a, const Iso& mb, const Shape& b, real pred_linear, real ang1, real ang2,
-                              Manifold& mf, GJKStats* st) {
+                              Manifold& mf, GJKStats* st, V3* last_gjk_dir = nullptr, bool* has_dir = nullptr) {
     Support ga = as_support(a), gb = as_support(b);
     VoronoiSimplex simplex;
-    GJKResult r = contact_support_map_support_map_with_params(ma, ga, mb, gb, pred_linear, simplex, nullptr, st);
+    const V3* init = (last_gjk_dir && has_dir && *has_dir) ? last_gjk_dir : nullptr;
+    V3 init_copy;
+    if (init) {
+        init_copy = *init;
+        init = &init_copy;
+    }
+    GJKResult r = contact_support_map_support_map_with_params(ma, ga, mb, gb, pred_linear, simplex, init, st);
+    if (last_gjk_dir && has_dir && (r.kind == GJK_CLOSEST_POINTS || r.kind == GJK_NO_INTERSECTION)) {
+        *last_gjk_dir = r.dir;
+        *has_dir = true;
+    }
     std::vector<NewContact> new_contacts;
     Feature m1, m2;
     if (r.kind == GJK_CLOSEST_POINTS) {
@@ -788,7 +862,8 @@ static void gen_convex_convex(const Iso& ma, const Shape& a, const Iso& mb, cons
 // default_contact_dispatcher.rs:27-97
 enum Algo : uint8_t { A_NONE = 0, A_BALL_BALL, A_PLANE_BALL, A_PLANE_CONVEX, A_BALL_CONVEX, A_CONVEX_CONVEX };
 
-static uint8_t generate_contacts(const Objects& o, uint32_t i1, uint32_t i2, Manifold& mf, GJKStats* st) {
+static uint8_t generate_contacts(const Objects& o, uint32_t i1, uint32_t i2, Manifold& mf, GJKStats* st, V3* last_gjk_dir = nullptr,
+                                 bool* has_dir = nullptr) {
     Shape a = get_shape(o, i1), b = get_shape(o, i2);
     Iso ma = o.iso(i1), mb = o.iso(i2);
     // query_type.rs:39-51
@@ -818,7 +893,7 @@ static uint8_t generate_contacts(const Objects& o, uint32_t i1, uint32_t i2, Man
         gen_ball_convex(mb, b.radius, ma, a, linear, true, mf, st);
         return A_BALL_CONVEX;
     } else if (is_convex_polyhedron(a) && is_convex_polyhedron(b)) {
-        gen_convex_convex(ma, a, mb, b, linear, ang1, ang2, mf, st);
+        gen_convex_convex(ma, a, mb, b, linear, ang1, ang2, mf, st, last_gjk_dir, has_dir);
         return A_CONVEX_CONVEX;
     }
     return A_NONE;  // e.g. plane x plane: pair kept by the broad phase, no interaction edge
@@ -865,10 +940,10 @@ uint64_t orc_narrow_phase(const orc_objects* objs, uint64_t n_pairs, const uint3
         uint8_t algo = generate_contacts(o, pairs[2 * p], pairs[2 * p + 1], mf, &st);
         if (algo_out) algo_out[p] = algo;
         if (manifold_off) manifold_off[p] = (uint32_t)nc;
-        for (auto& t : mf.contacts) {
+        mf.for_each_contact([&](const Tracked& t, size_t) {
             if (nc < cap && out) write_contact(&out[nc], t);
             nc++;
-        }
+        });
     }
     if (manifold_off) manifold_off[n_pairs] = (uint32_t)nc;
     if (stats) {
@@ -892,8 +967,8 @@ void orc_world_update_timed(const orc_objects* objs, real margin, double* times,
     for (uint64_t p = 0; p < np; ++p) {
         Manifold mf;
         generate_contacts(o, pairs[2 * p], pairs[2 * p + 1], mf, nullptr);
-        nc += mf.contacts.size();
-        n_with += !mf.contacts.empty();
+        nc += mf.len();
+        n_with += mf.len() != 0;
     }
     auto t3 = clk::now();
     times[0] = std::chrono::duration<double>(t1 - t0).count();
@@ -946,9 +1021,11 @@ int orc_query_contact(const orc_objects* objs, real prediction, orc_contact* out
             have = true;
         }
     }
-    if (!have && !mf.contacts.empty()) {
-        c = mf.contacts[0].c;
-        have = true;
+    if (!have && mf.len() != 0) {
+        mf.for_each_contact([&](const Tracked& t, size_t) {
+            if (!have) c = t.c;
+            have = true;
+        });
     }
     if (have) {
         Tracked t = {c, FID_UNKNOWN, FID_UNKNOWN};
@@ -956,5 +1033,169 @@ int orc_query_contact(const orc_objects* objs, real prediction, orc_contact* out
     }
     return have ? 1 : 0;
 }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Stepping world: CollisionWorld::update over several steps (pipeline/world.rs:104-119, glue/update.rs:65-138,
+// narrow_phase.rs:56-104,168-278): persistent broad phase (bp_persistent.cpp), interaction edges created /
+// removed by its started / stopped callbacks with the callback's argument order, per-edge generator state
+// (last_gjk_dir) and ContactManifold cache, contact events, update flags.
+// ---------------------------------------------------------------------------------------------
+#include <map>
+
+namespace orc {
+AABB shape_aabb(const Objects& o, uint32_t i);
+struct Edge {
+    uint32_t h1, h2;
+    uint8_t algo;
+    Manifold manifold;
+    V3 last_gjk_dir{0, 0, 0};
+    bool has_dir = false;
+};
+}  // namespace orc
+
+struct orc_sim {
+    Objects o;
+    std::vector<real> pos, rot;
+    std::vector<uint8_t> flags;  // 1 = POSITION_CHANGED (| everything, for a new object)
+    orc_bp* bp = nullptr;
+    std::map<uint64_t, Edge> edges;  // key = min << 32 | max (iteration order is not observable: events are sorted)
+    std::vector<uint32_t> events;    // (h1, h2, started)
+    bool first = true;
+};
+
+static uint8_t dispatch_algo(const Objects& o, uint32_t i1, uint32_t i2) {  // default_contact_dispatcher.rs:27-97
+    uint32_t a = o.shape_type[i1], b = o.shape_type[i2];
+    if (a == BALL && b == BALL) return A_BALL_BALL;
+    if ((a == PLANE && b == BALL) || (a == BALL && b == PLANE)) return A_PLANE_BALL;
+    if (a == PLANE && b == PLANE) return A_NONE;
+    if (a == PLANE || b == PLANE) return A_PLANE_CONVEX;
+    if (a == BALL || b == BALL) return A_BALL_CONVEX;
+    return A_CONVEX_CONVEX;
+}
+
+extern "C" {
+
+orc_sim* orc_sim_create(const orc_objects* objs, real margin) {
+    orc_sim* s = new orc_sim;
+    s->o = make_objects(objs);
+    s->pos.assign(objs->pos, objs->pos + 3 * (size_t)objs->n);
+    s->rot.assign(objs->rot, objs->rot + 4 * (size_t)objs->n);
+    s->o.pos = s->pos.data();
+    s->o.rot = s->rot.data();
+    s->flags.assign(objs->n, 1);
+    s->bp = orc_bp_create(margin);
+    // CollisionWorld::add -> glue::create_proxies (glue/setup.rs:20-36): proxy box = compute_swept_aabb()
+    for (uint32_t i = 0; i < s->o.n; ++i) {
+        AABB a = shape_aabb(s->o, i);
+        real ql = s->o.query_limit[i];
+        real mm[6] = {a.mins.x + (-ql), a.mins.y + (-ql), a.mins.z + (-ql), a.maxs.x + ql, a.maxs.y + ql, a.maxs.z + ql};
+        uint32_t h = orc_bp_create_proxy(s->bp, mm);
+        (void)h;
+    }
+    return s;
+}
+void orc_sim_destroy(orc_sim* s) {
+    if (!s) return;
+    orc_bp_destroy(s->bp);
+    delete s;
+}
+// CollisionObject::set_position for n objects (handles == NULL: objects 0..n-1)
+void orc_sim_set_positions(orc_sim* s, uint32_t n, const uint32_t* handles, const real* pos, const real* rot) {
+    for (uint32_t k = 0; k < n; ++k) {
+        uint32_t h = handles ? handles[k] : k;
+        for (int d = 0; d < 3; ++d) s->pos[3 * (size_t)h + d] = pos[3 * (size_t)k + d];
+        for (int d = 0; d < 4; ++d) s->rot[4 * (size_t)h + d] = rot[4 * (size_t)k + d];
+        s->flags[h] = 1;
+    }
+}
+
+void orc_sim_step(orc_sim* s) {
+    const Objects& o = s->o;
+    s->events.clear();  // narrow_phase.clear_events()
+    // perform_broad_phase (glue/update.rs:65-99)
+    for (uint32_t i = 0; i < o.n; ++i) {
+        if (!s->flags[i]) continue;
+        AABB a = shape_aabb(o, i);
+        real ql = o.query_limit[i];
+        real mm[6] = {a.mins.x + (-ql), a.mins.y + (-ql), a.mins.z + (-ql), a.maxs.x + ql, a.maxs.y + ql, a.maxs.z + ql};
+        orc_bp_set_bounding_volume(s->bp, i, mm);
+        // a new object also has SHAPE_CHANGED etc. set: deferred_recompute_all_proximities_with, a no-op on a detached proxy
+        if (s->first) orc_bp_recompute_with(s->bp, i);
+    }
+    uint64_t cap = 1 << 16, ns = 0, np = 0;
+    std::vector<uint32_t> st, sp;
+    // the call mutates state, so size the buffers from the upper bounds first
+    cap = std::max<uint64_t>(cap, 64ull * o.n + 1024);
+    st.resize(2 * cap), sp.resize(2 * cap);
+    orc_bp_update(s->bp, o.groups, st.data(), cap, &ns, sp.data(), cap, &np);
+    if (ns > cap || np > cap) abort();
+    // interference_started -> handle_interaction(.., true) (narrow_phase.rs:216-247)
+    for (uint64_t k = 0; k < ns; ++k) {
+        uint32_t b1 = st[2 * k], b2 = st[2 * k + 1];
+        uint64_t key = ((uint64_t)std::min(b1, b2) << 32) | std::max(b1, b2);
+        if (s->edges.count(key)) continue;
+        uint8_t algo = dispatch_algo(o, b1, b2);
+        if (algo == A_NONE) continue;
+        Edge e;
+        e.h1 = b1, e.h2 = b2, e.algo = algo;
+        s->edges.emplace(key, std::move(e));
+    }
+    // interference_stopped -> handle_interaction(.., false) (:248-277)
+    for (uint64_t k = 0; k < np; ++k) {
+        uint64_t key = ((uint64_t)sp[2 * k] << 32) | sp[2 * k + 1];
+        auto it = s->edges.find(key);
+        if (it == s->edges.end()) continue;
+        if (it->second.manifold.len() != 0) s->events.insert(s->events.end(), {it->second.h1, it->second.h2, 0u});
+        s->edges.erase(it);
+    }
+    // perform_narrow_phase -> NarrowPhase::update (:168-197) -> update_contact (:56-104)
+    for (auto& kv : s->edges) {
+        Edge& e = kv.second;
+        if (!s->flags[e.h1] && !s->flags[e.h2]) continue;
+        bool had = e.manifold.len() != 0;
+        e.manifold.save_cache_and_clear();
+        generate_contacts(o, e.h1, e.h2, e.manifold, nullptr, &e.last_gjk_dir, &e.has_dir);
+        bool has = e.manifold.len() != 0;
+        if (!has && had) s->events.insert(s->events.end(), {e.h1, e.h2, 0u});
+        if (has && !had) s->events.insert(s->events.end(), {e.h1, e.h2, 1u});
+    }
+    std::fill(s->flags.begin(), s->flags.end(), 0);
+    s->first = false;
+}
+
+uint64_t orc_sim_num_pairs(const orc_sim* s) { return s->edges.size(); }
+uint64_t orc_sim_num_contacts(const orc_sim* s) {
+    uint64_t n = 0;
+    for (auto& kv : s->edges) n += kv.second.manifold.len();
+    return n;
+}
+// Edges sorted by (min handle, max handle): pairs = (h1, h2) in the edge's own orientation; manifold_off has n + 1 entries;
+// ids[k] = insertion counter << 8 | slab slot of contact k inside its manifold.
+void orc_sim_fetch(const orc_sim* s, uint32_t* pairs, uint8_t* algo, uint32_t* manifold_off, orc_contact* contacts, uint32_t* ids) {
+    uint64_t p = 0, nc = 0;
+    for (auto& kv : s->edges) {
+        const Edge& e = kv.second;
+        pairs[2 * p] = e.h1, pairs[2 * p + 1] = e.h2;
+        algo[p] = e.algo;
+        manifold_off[p] = (uint32_t)nc;
+        e.manifold.for_each_contact([&](const Tracked& t, size_t slot) {
+            write_contact(&contacts[nc], t);
+            ids[nc] = (t.id << 8) | (uint32_t)slot;
+            nc++;
+        });
+        p++;
+    }
+    manifold_off[p] = (uint32_t)nc;
+}
+// ContactEvents of the last step as (h1, h2, 1 = Started / 0 = Stopped) triples, in emission order.
+uint64_t orc_sim_events(const orc_sim* s, uint32_t* out, uint64_t cap) {
+    uint64_t n = s->events.size() / 3;
+    for (uint64_t k = 0; k < n && k < cap; ++k)
+        for (int d = 0; d < 3; ++d) out[3 * k + d] = s->events[3 * k + d];
+    return n;
+}
+uint64_t orc_sim_bp_num_interferences(const orc_sim* s) { return orc_bp_num_interferences(s->bp); }
 
 }  // extern "C"

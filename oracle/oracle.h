@@ -81,6 +81,20 @@ uint64_t orc_bp_num_interferences(const orc_bp*);
 int orc_bp_proxy(const orc_bp*, uint32_t handle, real* minmax);
 uint64_t orc_bp_pairs(const orc_bp*, uint32_t* out, uint64_t cap);
 
+/* Stepping world: CollisionWorld::update over several steps (persistent broad phase, interaction edges in the callback
+ * orientation, GJK warm start, ContactManifold cache, contact events).  The shape arrays / hull library of objs must
+ * outlive the sim; positions are copied.  Results are listed by edges sorted on (min handle, max handle). */
+typedef struct orc_sim orc_sim;
+orc_sim* orc_sim_create(const orc_objects* objs, real margin);
+void orc_sim_destroy(orc_sim*);
+void orc_sim_set_positions(orc_sim*, uint32_t n, const uint32_t* handles, const real* pos, const real* rot);
+void orc_sim_step(orc_sim*);
+uint64_t orc_sim_num_pairs(const orc_sim*);
+uint64_t orc_sim_num_contacts(const orc_sim*);
+void orc_sim_fetch(const orc_sim*, uint32_t* pairs, uint8_t* algo, uint32_t* manifold_off, orc_contact* contacts, uint32_t* ids);
+uint64_t orc_sim_events(const orc_sim*, uint32_t* out, uint64_t cap);
+uint64_t orc_sim_bp_num_interferences(const orc_sim*);
+
 /* TriMesh ray casting. */
 typedef struct orc_trimesh orc_trimesh;
 orc_trimesh* orc_trimesh_create(uint32_t n_verts, const real* xyz, uint32_t n_tris, const uint32_t* idx);

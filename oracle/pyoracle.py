@@ -160,6 +160,9 @@ class Oracle:
     def broad_phase_persistent(self, margin):
         return OracleBroadPhase(self, margin)
 
+    def sim(self, scene):
+        return OracleSim(self, scene)
+
     def aabb_toi_with_ray(self, minmax, origin, direction, max_toi, solid):
         mm = np.ascontiguousarray(minmax, dtype=self.dtype)
         o = np.ascontiguousarray(origin, dtype=self.dtype)
@@ -167,6 +170,50 @@ class Oracle:
         t = self.creal(0)
         self.lib.orc_aabb_toi_with_ray(C.c_void_p(mm.ctypes.data), C.c_void_p(o.ctypes.data), C.c_void_p(d.ctypes.data), self.creal(max_toi), C.c_int(int(solid)), C.byref(t))
         return None if t.value < 0 else t.value
+
+
+class OracleSim:
+    """Reference-faithful stepping CollisionWorld (oracle/narrow.cpp, orc_sim_*)."""
+
+    def __init__(self, oracle, scene):
+        self.o = oracle
+        L = oracle.lib
+        L.orc_sim_create.restype = C.c_void_p
+        for f in ("orc_sim_num_pairs", "orc_sim_num_contacts", "orc_sim_events", "orc_sim_bp_num_interferences"):
+            getattr(L, f).restype = C.c_uint64
+        self._objs, self._keep = oracle._objects(scene)
+        self.h = C.c_void_p(L.orc_sim_create(C.byref(self._objs), oracle.creal(scene.margin)))
+
+    def set_positions(self, handles, pos, rot):
+        hs = None if handles is None else np.ascontiguousarray(handles, dtype=np.uint32)
+        p = np.ascontiguousarray(pos, dtype=self.o.dtype)
+        r = np.ascontiguousarray(rot, dtype=self.o.dtype)
+        self.o.lib.orc_sim_set_positions(self.h, C.c_uint32(len(p)), C.c_void_p(hs.ctypes.data) if hs is not None else None,
+                                         C.c_void_p(p.ctypes.data), C.c_void_p(r.ctypes.data))
+
+    def step(self):
+        """One CollisionWorld::update.  Returns dict(pairs[P,2] (h1, h2), algo[P], off[P+1], contacts, ids, events[E,3])."""
+        L = self.o.lib
+        L.orc_sim_step(self.h)
+        P, Cn = int(L.orc_sim_num_pairs(self.h)), int(L.orc_sim_num_contacts(self.h))
+        pairs = np.zeros((P, 2), dtype=np.uint32)
+        algo = np.zeros(P, dtype=np.uint8)
+        off = np.zeros(P + 1, dtype=np.uint32)
+        contacts = np.zeros(max(Cn, 1), dtype=self.o.contact_dtype)
+        ids = np.zeros(max(Cn, 1), dtype=np.uint32)
+        L.orc_sim_fetch(self.h, C.c_void_p(pairs.ctypes.data), C.c_void_p(algo.ctypes.data), C.c_void_p(off.ctypes.data),
+                        C.c_void_p(contacts.ctypes.data), C.c_void_p(ids.ctypes.data))
+        ne = int(L.orc_sim_events(self.h, None, C.c_uint64(0)))
+        ev = np.zeros((max(ne, 1), 3), dtype=np.uint32)
+        L.orc_sim_events(self.h, C.c_void_p(ev.ctypes.data), C.c_uint64(ne))
+        return {"pairs": pairs, "algo": algo, "off": off, "contacts": contacts[:Cn], "ids": ids[:Cn], "events": ev[:ne],
+                "bp_pairs": int(L.orc_sim_bp_num_interferences(self.h))}
+
+    def __del__(self):
+        try:
+            self.o.lib.orc_sim_destroy(self.h)
+        except Exception:
+            pass
 
 
 class OracleTriMesh:
