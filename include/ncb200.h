@@ -224,6 +224,26 @@ int ncb_bp_query(ncb_bp* bp, int kind, uint32_t n_queries, const float* queries,
 /* BroadPhase::proxy (:262-273): returns 1 and the stored (loosened) box when the proxy is attached, else 0. */
 int ncb_bp_proxy(ncb_bp* bp, uint32_t handle, float* minmax);
 
+/* ---- Stepping world: CollisionWorld::update over several steps ------------------------------- */
+/* Replaces world.rs:104-119 + glue/update.rs:65-138 + narrow_phase.rs:56-104,168-278 for a fixed object set (the one
+ * given to ncb_set_objects; object handle = index): persistent broad phase, interaction pairs created / removed by its
+ * started / stopped callbacks (object order = callback argument order), only pairs with a moved object regenerated,
+ * GJK warm start (last_gjk_dir), ContactManifold cache with stable contact ids, ContactEvents. */
+typedef struct ncb_sim ncb_sim;
+int ncb_sim_create(ncb_ctx* ctx, float margin, ncb_sim** out);
+void ncb_sim_destroy(ncb_sim* sim);
+/* CollisionObject::set_position (collision_object.rs:215-222) for m objects; handles == NULL means objects 0..m-1. */
+int ncb_sim_set_positions(ncb_sim* sim, uint32_t m, const uint32_t* handles, const float* pos, const float* rot);
+/* CollisionWorld::update.  counts: n_pairs, n_contacts, epa_overflow (+ manifold-cache overflows), ref_panics,
+ * n_epa_pairs, n_manifold_jobs (= pairs regenerated in this step). */
+int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts);
+int ncb_sim_sizes(ncb_sim* sim, uint32_t* n_pairs, uint32_t* n_contacts, uint32_t* n_events);
+/* Results of the last step, arrays sized from ncb_sim_sizes (NULL = not wanted): pairs[2 P] sorted by (min, max) handle in
+ * the pair's own object order; algo / manifold_start / manifold_count [P]; contacts[C]; contact_ids[C] (stable per pair as
+ * long as the reference's ContactId is); events[3 E] = (object1, object2, 1 Started | 0 Stopped), sorted. */
+int ncb_sim_fetch(ncb_sim* sim, uint32_t* pairs, uint8_t* algo, uint32_t* manifold_start, uint8_t* manifold_count, ncb_contact* contacts,
+                  uint32_t* contact_ids, uint32_t* events);
+
 const char* ncb_version(void);
 
 #ifdef __cplusplus

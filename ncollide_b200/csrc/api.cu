@@ -29,7 +29,7 @@ static thread_local std::string g_create_err;
         }                        \
     } while (0)
 
-static DevObjects dev_objects(ncb_ctx* c) {
+DevObjects dev_objects(ncb_ctx* c) {
     DevObjects o;
     o.n = c->n;
     o.pos = c->pos.p;
@@ -44,7 +44,7 @@ static DevObjects dev_objects(ncb_ctx* c) {
     return o;
 }
 
-static int reserve_broad(ncb_ctx* ctx, uint32_t n) {
+int reserve_broad(ncb_ctx* ctx, uint32_t n) {
     CK(ctx->aabb_lo.reserve(n));
     CK(ctx->aabb_hi.reserve(n));
     CK(ctx->keys_a.reserve(n));
@@ -60,7 +60,7 @@ static int reserve_broad(ncb_ctx* ctx, uint32_t n) {
     CK(ctx->counters.reserve(1));
     return NCB_OK;
 }
-static int reserve_pairs(ncb_ctx* ctx, size_t cap) {
+int reserve_pairs(ncb_ctx* ctx, size_t cap) {
     CK(ctx->pairs_raw.reserve(cap));
     CK(ctx->pairs.reserve(cap));
     CK(ctx->keys_raw.reserve(cap));
@@ -72,7 +72,7 @@ static int reserve_pairs(ncb_ctx* ctx, size_t cap) {
     return NCB_OK;
 }
 
-static int reset_counters(ncb_ctx* ctx) {
+int reset_counters(ncb_ctx* ctx) {
     DevCounters z;
     memset(&z, 0, sizeof z);
     for (int k = 0; k < 3; ++k) {
@@ -350,7 +350,7 @@ int ncb_compute_aabbs(ncb_ctx* ctx, float margin, int mode, float* out_minmax) {
     return NCB_OK;
 }
 
-static int read_counters(ncb_ctx* ctx) {
+extern "C++" int read_counters(ncb_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->last_counters = *ctx->h_counters;

@@ -19,41 +19,7 @@
 
 using namespace ncb;
 
-#define SEQ_NONE 0xffffffffu
-#define LEAF_BIT 0x80000000u  // child word of an LBVH node record (broad.cu)
-#define SEQ_BACK0 0x80000000u   // entries pushed at the back of the reference's queue: SEQ_BACK0 + k
-#define SEQ_FRONT0 0x7fffffffu  // entries pushed at its front (recompute_*): SEQ_FRONT0 - k
-enum : uint32_t { ST_DETACHED = 0, ST_ATTACHED = 1, ST_REMOVING = 2, ST_VACANT = 3 };
-
-struct ncb_bp {
-    ncb_ctx* owner = nullptr;
-    ncb_ctx* work = nullptr;  // private LBVH / pair buffers
-    float margin = 0.f;
-    // host slab (LIFO reuse like the `slab` crate)
-    std::vector<int64_t> next_free;  // -2 occupied, else next vacant
-    std::vector<uint8_t> attached;   // host mirror: 0 detached (pending), 1 attached
-    size_t next = 0, len = 0;
-    uint32_t n_attached = 0;
-    bool slab_dirty = true;  // proxies were created / removed since `alive` was uploaded
-    uint32_t seq = 0;    // back entries issued since the last update
-    uint32_t front = 0;  // front entries issued since the last update
-    // device state, indexed by handle slot
-    DevBuf<float4> box_lo, box_hi, pend_lo, pend_hi;
-    DevBuf<uint32_t> pend_seq, upd_seq, win, d_attached;
-    size_t slots_cap = 0;
-    // staging
-    DevBuf<float> stage_f;
-    DevBuf<uint32_t> stage_u, alive, groups_dev;
-    DevBuf<unsigned long long> keys_old, keys_new, keys_tmp;
-    DevBuf<uint8_t> cub_tmp;
-    DevBuf<unsigned long long> ev_a, ev_b, ev_sorted;  // started / stopped events as (first << 32 | second)
-    DevBuf<uint32_t> ev_u32, counters;
-    uint32_t n_old = 0;
-    uint32_t tree_n = 0, tree_outliers = 0;  // leaves of the LBVH built by the last update() (0: none yet)
-    DevBuf<float> q_in;
-    uint32_t n_started = 0, n_stopped = 0;  // events of the last update() / remove()
-    std::string err;
-};
+#include "bp_internal.h"
 
 namespace {
 
@@ -570,6 +536,25 @@ int ncb_bp_remove(ncb_bp* bp, uint32_t n, const uint32_t* handles, uint32_t* n_r
 int ncb_bp_update(ncb_bp* bp, const uint32_t* groups, uint32_t n_group_slots, uint32_t* n_started, uint32_t* n_stopped) {
     if (!bp) return NCB_ERR_ARG;
     CKB(cudaSetDevice(bp->owner->device));
+    uint32_t slots = (uint32_t)bp->next_free.size();
+    const uint32_t* dgroups = nullptr;
+    if (groups && slots) {
+        if (n_group_slots < slots) {
+            bp->err = bp->owner->err = "ncb_bp_update: groups must cover every handle slot";
+            return NCB_ERR_ARG;
+        }
+        CKB(bp->groups_dev.reserve(3 * (size_t)slots));
+        CKB(cudaMemcpyAsync(bp->groups_dev.p, groups, 12 * (size_t)slots, cudaMemcpyHostToDevice, bp->owner->stream));
+        dgroups = bp->groups_dev.p;
+    }
+    return bp_update_impl(bp, dgroups, n_started, n_stopped);
+}
+
+}  // extern "C"
+
+// d_groups: device pointer, 3 words per handle slot, or nullptr
+int bp_update_impl(ncb_bp* bp, const uint32_t* d_groups, uint32_t* n_started, uint32_t* n_stopped) {
+    CKB(cudaSetDevice(bp->owner->device));
     cudaStream_t s = bp->owner->stream;
     ncb_ctx* w = bp->work;
     w->stream = s;
@@ -578,10 +563,6 @@ int ncb_bp_update(ncb_bp* bp, const uint32_t* groups, uint32_t n_group_slots, ui
     if (n_stopped) *n_stopped = 0;
     uint32_t slots = (uint32_t)bp->next_free.size();
     if (slots == 0) return NCB_OK;
-    if (groups && n_group_slots < slots) {
-        bp->err = bp->owner->err = "ncb_bp_update: groups must cover every handle slot";
-        return NCB_ERR_ARG;
-    }
     bool any_pending = bp->seq != 0 || bp->front != 0;
     if (!any_pending) return NCB_OK;  // no leaf was updated: the reference neither queries nor purges
     // 1. apply pending boxes; every occupied slot is attached afterwards
@@ -631,12 +612,7 @@ int ncb_bp_update(ncb_bp* bp, const uint32_t* groups, uint32_t n_group_slots, ui
         CKB(w->cub_tmp.reserve(lbvh_temp_bytes(m) + 256));
         CKB(w->counters.reserve(1));
         if (!w->h_counters) CKB(cudaMallocHost((void**)&w->h_counters, sizeof(DevCounters)));
-        const uint32_t* dgroups = nullptr;
-        if (groups) {
-            CKB(bp->groups_dev.reserve(3 * (size_t)slots));
-            CKB(cudaMemcpyAsync(bp->groups_dev.p, groups, 12 * (size_t)slots, cudaMemcpyHostToDevice, s));
-            dgroups = bp->groups_dev.p;
-        }
+        const uint32_t* dgroups = d_groups;
         k_bp_gather<<<(m + 255) / 256, 256, 0, s>>>(bp->alive.p, m, bp->box_lo.p, bp->box_hi.p, w->aabb_lo.p, w->aabb_hi.p);
         CKB(cudaGetLastError());
         size_t cap_pairs = w->pairs_raw.cap ? w->pairs_raw.cap : (size_t)8 * m + 1024;
@@ -696,6 +672,68 @@ int ncb_bp_update(ncb_bp* bp, const uint32_t* groups, uint32_t n_group_slots, ui
     if (n_stopped) *n_stopped = cnt[1];
     return NCB_OK;
 }
+
+// ---- device-side staging for the stepping world: boxes of ALL objects as float4 arrays indexed by handle ------------
+namespace {
+__global__ void k_bp_stage_create_f4(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n, uint32_t seq0, float4* pend_lo,
+                                     float4* pend_hi, uint32_t* pend_seq, uint32_t* d_attached) {
+    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n) return;
+    float4 a = lo[h], b = hi[h];
+    pend_lo[h] = make_float4(a.x, a.y, a.z, 0.f);
+    pend_hi[h] = make_float4(b.x, b.y, b.z, 0.f);
+    pend_seq[h] = min(pend_seq[h], seq0 + h);
+    d_attached[h] = ST_DETACHED;
+}
+// deferred_set_bounding_volume for every object with a set `moved` flag, in handle order (glue/update.rs:77-83)
+__global__ void k_bp_stage_set_f4(const float4* __restrict__ lo, const float4* __restrict__ hi, const uint8_t* __restrict__ moved, uint32_t n,
+                                  uint32_t seq0, float margin, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
+                                  const uint32_t* __restrict__ d_attached, float4* pend_lo, float4* pend_hi, uint32_t* pend_seq) {
+    uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n || (moved && !moved[h])) return;
+    float4 a = lo[h], b = hi[h];
+    if (d_attached[h] == ST_ATTACHED) {
+        float4 slo = box_lo[h], shi = box_hi[h];
+        bool contains = slo.x <= a.x && slo.y <= a.y && slo.z <= a.z && shi.x >= b.x && shi.y >= b.y && shi.z >= b.z;
+        if (contains) return;
+    }
+    pend_lo[h] = make_float4(a.x + (-margin), a.y + (-margin), a.z + (-margin), 0.f);
+    pend_hi[h] = make_float4(b.x + margin, b.y + margin, b.z + margin, 0.f);
+    pend_seq[h] = min(pend_seq[h], seq0 + h);
+}
+}  // namespace
+
+int bp_create_all_device(ncb_bp* bp, uint32_t n, const float4* lo, const float4* hi) {
+    if (!bp->next_free.empty()) {
+        bp->err = bp->owner->err = "bp_create_all_device: the broad phase must be empty";
+        return NCB_ERR_STATE;
+    }
+    CKB(cudaSetDevice(bp->owner->device));
+    bp->next_free.assign(n, -2);
+    bp->attached.assign(n, 0);
+    bp->next = n, bp->len = n;
+    bp->slab_dirty = true;
+    int r = bp_grow(bp, n);
+    if (r) return r;
+    if (n == 0) return NCB_OK;
+    k_bp_stage_create_f4<<<(n + 255) / 256, 256, 0, bp->owner->stream>>>(lo, hi, n, SEQ_BACK0 + bp->seq, bp->pend_lo.p, bp->pend_hi.p, bp->pend_seq.p,
+                                                                         bp->d_attached.p);
+    CKB(cudaGetLastError());
+    bp->seq += n;
+    return NCB_OK;
+}
+
+int bp_set_moved_device(ncb_bp* bp, uint32_t n, const float4* lo, const float4* hi, const uint8_t* moved) {
+    CKB(cudaSetDevice(bp->owner->device));
+    if (n == 0) return NCB_OK;
+    k_bp_stage_set_f4<<<(n + 255) / 256, 256, 0, bp->owner->stream>>>(lo, hi, moved, n, SEQ_BACK0 + bp->seq, bp->margin, bp->box_lo.p, bp->box_hi.p,
+                                                                      bp->d_attached.p, bp->pend_lo.p, bp->pend_hi.p, bp->pend_seq.p);
+    CKB(cudaGetLastError());
+    bp->seq += n;
+    return NCB_OK;
+}
+
+extern "C" {
 
 static int bp_fetch(ncb_bp* bp, const unsigned long long* ev, uint32_t n, uint32_t* out) {
     if (!n || !out) return NCB_OK;

@@ -313,13 +313,34 @@ struct ManifoldContact {
     float depth;
     uint32_t f1, f2;
 };
-struct Manifold {
+// P = false: a fresh manifold (one-shot update).  P = true: the persistent manifold of a stepping world — the reference's
+// Slab<(TrackedContact, usize)> + DistanceBased cache with persistence 1 (contact_manifold.rs:14-236): entries are kept in
+// CACHE order; `slot` is the slab key (free slots are reused LIFO), `live` = "remaining == persistence", `id` = insertion
+// counter of this manifold (stable exactly as long as the reference's ContactId is).
+template <bool P>
+struct ManifoldT {
     ManifoldContact c[MANIFOLD_MAX];
     V3 track[MANIFOLD_MAX];
     int n;
     int deepest;
 };
-NCB_HD void manifold_push(Manifold& mf, V3 w1, V3 w2, V3 n, float depth, uint32_t f1, uint32_t f2, V3 tracking_pt) {
+template <>
+struct ManifoldT<true> {
+    ManifoldContact c[PM_CAP];
+    V3 track[PM_CAP];
+    uint8_t slot[PM_CAP], live[PM_CAP];
+    uint32_t id[PM_CAP];
+    uint8_t free_stack[PM_CAP];
+    int n, deepest;
+    int nfree, slab_len, had_live;
+    uint32_t next_id;
+    bool overflow;
+};
+typedef ManifoldT<false> Manifold;
+typedef ManifoldT<true> PManifold;
+
+template <bool P>
+NCB_HD void manifold_push(ManifoldT<P>& mf, V3 w1, V3 w2, V3 n, float depth, uint32_t f1, uint32_t f2, V3 tracking_pt) {
     const float threshold = 0.02f;
     int closest = mf.n;
     float closest_dist = threshold * threshold;
@@ -331,22 +352,45 @@ NCB_HD void manifold_push(Manifold& mf, V3 w1, V3 w2, V3 n, float depth, uint32_
         }
     }
     if (closest == mf.n) {
-        if (mf.n < MANIFOLD_MAX) {
-            ManifoldContact& c = mf.c[mf.n];
-            c.w1 = w1, c.w2 = w2, c.n = n, c.depth = depth, c.f1 = f1, c.f2 = f2;
-            mf.track[mf.n] = tracking_pt;
-            mf.n++;
+        if constexpr (P) {
+            if (mf.n < PM_CAP) {
+                ManifoldContact& c = mf.c[mf.n];
+                c.w1 = w1, c.w2 = w2, c.n = n, c.depth = depth, c.f1 = f1, c.f2 = f2;
+                mf.track[mf.n] = tracking_pt;
+                mf.slot[mf.n] = mf.nfree > 0 ? mf.free_stack[--mf.nfree] : (uint8_t)mf.slab_len++;  // Slab::insert
+                mf.live[mf.n] = 1;
+                mf.id[mf.n] = ++mf.next_id;
+                mf.n++;
+            } else {
+                mf.overflow = true;
+            }
+        } else {
+            if (mf.n < MANIFOLD_MAX) {
+                ManifoldContact& c = mf.c[mf.n];
+                c.w1 = w1, c.w2 = w2, c.n = n, c.depth = depth, c.f1 = f1, c.f2 = f2;
+                mf.track[mf.n] = tracking_pt;
+                mf.n++;
+            }
         }
     } else {
         ManifoldContact& c = mf.c[closest];
-        if (depth <= c.depth) return;
+        if constexpr (P) {
+            if (mf.live[closest]) {
+                if (depth <= c.depth) return;  // the contact already in the cache is deeper
+            } else {
+                mf.live[closest] = 1;  // a contact of the previous step is matched: it keeps its slot and its id
+            }
+        } else {
+            if (depth <= c.depth) return;
+        }
         c.w1 = w1, c.w2 = w2, c.n = n, c.depth = depth, c.f1 = f1, c.f2 = f2;
         mf.track[closest] = tracking_pt;
     }
 }
 
 // ---- generators -----------------------------------------------------------------------------------------------
-NCB_HD void gen_ball_ball(const Iso& ma, float r1, const Iso& mb, float r2, float prediction, Manifold& mf) {
+template <bool P>
+NCB_HD void gen_ball_ball(const Iso& ma, float r1, const Iso& mb, float r2, float prediction, ManifoldT<P>& mf) {
     V3 c1 = ma.t, c2 = mb.t;
     V3 delta = c2 - c1;
     float d2 = norm_squared(delta);
@@ -357,7 +401,8 @@ NCB_HD void gen_ball_ball(const Iso& ma, float r1, const Iso& mb, float r2, floa
         manifold_push(mf, c1 + normal * r1, c2 + normal * (-r2), normal, sum_radius - sqrtf(d2), FACE0, FACE0, v3(0.f, 0.f, 0.f));
     }
 }
-NCB_HD void gen_plane_ball(const Iso& m1, V3 plane_n, const Iso& m2, float radius, float prediction, bool flip, Manifold& mf) {
+template <bool P>
+NCB_HD void gen_plane_ball(const Iso& m1, V3 plane_n, const Iso& m2, float radius, float prediction, bool flip, ManifoldT<P>& mf) {
     V3 n = iso_mul_vec(m1, plane_n);
     V3 pc = m1.t, bc = m2.t;
     float dist = dot(bc - pc, n);
@@ -371,8 +416,9 @@ NCB_HD void gen_plane_ball(const Iso& m1, V3 plane_n, const Iso& m2, float radiu
             manifold_push(mf, world2, world1, -n, depth, FACE0, FACE0, v3(0.f, 0.f, 0.f));
     }
 }
+template <bool P>
 __device__ __noinline__ void gen_plane_convex(const Iso& m1, V3 plane_n, const Iso& m2, const Shape& cp, float prediction, bool flip,
-                                              Manifold& mf, Feature& feat) {
+                                              ManifoldT<P>& mf, Feature& feat) {
     V3 n = iso_mul_vec(m1, plane_n);
     V3 pc = m1.t;
     support_face_toward(cp, m2, -n, feat);
@@ -501,8 +547,9 @@ NCB_HD uint32_t hull_project_feature(const HullView& H, const Iso& m_in, V3 poin
 }
 
 // (m1, ball) (m2, convex polyhedron)
+template <bool P>
 NCB_HD void gen_ball_convex_finish(V3 ball_center, float radius, const Shape& cp, bool inside, V3 world2, uint32_t f2, float prediction,
-                                   bool flip, Manifold& mf) {
+                                   bool flip, ManifoldT<P>& mf) {
     V3 dpt = world2 - ball_center;
     float depth, dist;
     V3 normal, dir;
@@ -614,16 +661,18 @@ struct ClipCand {
     V3 w1, w2;
     uint32_t f1, f2;
 };
-struct ClipCtx {
+template <bool P>
+struct ClipCtxT {
     const Iso* ma;
-    Manifold* mf;
+    ManifoldT<P>* mf;
     const Feature *m1, *m2;
     V3 normal;
     int n_new;   // candidates within the prediction distance so far (buffered + already flushed)
     int n_buf;
     ClipCand buf[CLIP_CAND_MAX];
 };
-NCB_HD void clip_flush(ClipCtx& cc) {
+template <bool P>
+NCB_HD void clip_flush(ClipCtxT<P>& cc) {
     for (int k = 0; k < cc.n_buf; ++k) {
         const ClipCand& c = cc.buf[k];
         if (!feature_ok_for_manifold(*cc.m1, c.f1)) continue;
@@ -634,7 +683,8 @@ NCB_HD void clip_flush(ClipCtx& cc) {
     }
     cc.n_buf = 0;
 }
-NCB_HD void clip_emit(ClipCtx& cc, V3 w1, V3 w2, V3 normal, float prediction, uint32_t f1, uint32_t f2) {
+template <bool P>
+NCB_HD void clip_emit(ClipCtxT<P>& cc, V3 w1, V3 w2, V3 normal, float prediction, uint32_t f1, uint32_t f2) {
     float depth = -dot(normal, w2 - w1);  // Contact::new_wo_depth
     if (-depth <= prediction) {
         cc.n_new++;
@@ -646,7 +696,8 @@ NCB_HD void clip_emit(ClipCtx& cc, V3 w1, V3 w2, V3 normal, float prediction, ui
 
 // ConvexPolygonalFeature::clip (convex_polygonal_feature3.rs:217-338); candidates go straight into the manifold
 // in the reference's order (the reference buffers them in a Vec and pushes them afterwards: same result).
-__device__ __noinline__ void clip(const Feature& self, const Feature& other, V3 normal, float prediction, ClipCtx& cc) {
+template <bool P>
+__device__ __noinline__ void clip(const Feature& self, const Feature& other, V3 normal, float prediction, ClipCtxT<P>& cc) {
     if (self.nv <= 2 && other.nv <= 2) return;
     V3 b0, b1;
     orthonormal_basis(normal, b0, b1);
@@ -703,8 +754,9 @@ __device__ __noinline__ void clip(const Feature& self, const Feature& other, V3 
 
 // ConvexPolyhedronConvexPolyhedronManifoldGenerator::generate_contacts after the GJK/EPA result is known
 // (convex_polyhedron_convex_polyhedron_manifold_generator.rs:112-161).
+template <bool P>
 __device__ __noinline__ void convex_convex_manifold(const Iso& ma, const Shape& a, const Iso& mb, const Shape& b, float linear, float2 ang1,
-                                                    float2 ang2, V3 p1, V3 p2, V3 dir, Manifold& mf, Feature& m1, Feature& m2) {
+                                                    float2 ang2, V3 p1, V3 p2, V3 dir, ManifoldT<P>& mf, Feature& m1, Feature& m2) {
     float depth = -dot(dir, p2 - p1);
     {
         // the two feature extractions are independent: issue the cuboid one first and the hull one second whatever the
@@ -726,7 +778,7 @@ __device__ __noinline__ void convex_convex_manifold(const Iso& ma, const Shape& 
             support_feature_toward(sb, ib, -da, angb, fb);
         }
     }
-    ClipCtx cc;
+    ClipCtxT<P> cc;
     cc.ma = &ma;
     cc.mf = &mf;
     cc.m1 = &m1;
@@ -781,7 +833,86 @@ NCB_HD void write_manifold(const Manifold& mf, bool valid, uint32_t pair_slot, u
     }
 }
 
+// ---- persistent manifold / generator state of a stepping world (indexed by state slot = pair_index[p]) ----------
+// header: 8 words  [0] n | nfree << 8 | slab_len << 16   [1] next_id   [2..7] free stack (one byte per entry)
+// entry : 4 float4 [w1, depth] [w2, f1] [normal, f2] [tracking point, slot | live << 8 | id << 9], in cache order
+__device__ __forceinline__ void pm_load_and_age(const PersistArgs& ps, uint32_t slot, PManifold& mf) {
+    const uint32_t* hdr = ps.pm_hdr + (size_t)slot * PM_HDR_WORDS;
+    uint32_t w0 = hdr[0];
+    int n0 = (int)(w0 & 0xffu);
+    mf.nfree = (int)((w0 >> 8) & 0xffu);
+    mf.slab_len = (int)((w0 >> 16) & 0xffu);
+    mf.next_id = hdr[1];
+    for (int k = 0; k < PM_CAP / 4; ++k) {
+        uint32_t w = hdr[2 + k];
+        mf.free_stack[4 * k] = (uint8_t)w, mf.free_stack[4 * k + 1] = (uint8_t)(w >> 8);
+        mf.free_stack[4 * k + 2] = (uint8_t)(w >> 16), mf.free_stack[4 * k + 3] = (uint8_t)(w >> 24);
+    }
+    mf.n = 0, mf.deepest = 0, mf.had_live = 0, mf.overflow = false;
+    // ContactManifold::save_cache_and_clear (contact_manifold.rs:134-156): contacts of the previous update stay in the
+    // cache as match candidates (live -> stale); contacts that were already stale leave the cache and the slab
+    uint32_t stale_slots = 0;
+    const float4* e = ps.pm_entry + (size_t)slot * PM_CAP * PM_ENTRY_F4;
+    for (int i = 0; i < n0; ++i) {
+        float4 d = e[4 * i + 3];
+        uint32_t meta = __float_as_uint(d.w);
+        if ((meta >> 8) & 1u) {
+            float4 a = e[4 * i], b = e[4 * i + 1], c = e[4 * i + 2];
+            ManifoldContact& mc = mf.c[mf.n];
+            mc.w1 = v3(a.x, a.y, a.z), mc.depth = a.w;
+            mc.w2 = v3(b.x, b.y, b.z), mc.f1 = __float_as_uint(b.w);
+            mc.n = v3(c.x, c.y, c.z), mc.f2 = __float_as_uint(c.w);
+            mf.track[mf.n] = v3(d.x, d.y, d.z);
+            mf.slot[mf.n] = (uint8_t)meta;
+            mf.live[mf.n] = 0;
+            mf.id[mf.n] = meta >> 9;
+            mf.n++;
+            mf.had_live++;
+        } else {
+            stale_slots |= 1u << (meta & 0xffu);
+        }
+    }
+    while (stale_slots) {  // Slab::retain visits the keys in increasing order; every removal pushes its key on the free list
+        int sl = __ffs(stale_slots) - 1;
+        stale_slots &= stale_slots - 1;
+        mf.free_stack[mf.nfree++] = (uint8_t)sl;
+    }
+}
+__device__ __forceinline__ void pm_store(const PersistArgs& ps, uint32_t slot, const PManifold& mf, uint32_t h1, uint32_t h2) {
+    uint32_t* hdr = ps.pm_hdr + (size_t)slot * PM_HDR_WORDS;
+    hdr[0] = (uint32_t)mf.n | ((uint32_t)mf.nfree << 8) | ((uint32_t)mf.slab_len << 16);
+    hdr[1] = mf.next_id;
+    for (int k = 0; k < PM_CAP / 4; ++k)
+        hdr[2 + k] = (uint32_t)mf.free_stack[4 * k] | ((uint32_t)mf.free_stack[4 * k + 1] << 8) | ((uint32_t)mf.free_stack[4 * k + 2] << 16) |
+                     ((uint32_t)mf.free_stack[4 * k + 3] << 24);
+    float4* e = ps.pm_entry + (size_t)slot * PM_CAP * PM_ENTRY_F4;
+    int has = 0;
+    for (int i = 0; i < mf.n; ++i) {
+        const ManifoldContact& mc = mf.c[i];
+        e[4 * i] = make_float4(mc.w1.x, mc.w1.y, mc.w1.z, mc.depth);
+        e[4 * i + 1] = make_float4(mc.w2.x, mc.w2.y, mc.w2.z, __uint_as_float(mc.f1));
+        e[4 * i + 2] = make_float4(mc.n.x, mc.n.y, mc.n.z, __uint_as_float(mc.f2));
+        uint32_t meta = (uint32_t)mf.slot[i] | ((uint32_t)mf.live[i] << 8) | (mf.id[i] << 9);
+        e[4 * i + 3] = make_float4(mf.track[i].x, mf.track[i].y, mf.track[i].z, __uint_as_float(meta));
+        has += mf.live[i];
+    }
+    if (mf.overflow) atomicAdd(ps.pm_overflow, 1u);
+    // NarrowPhase::update_contact (narrow_phase.rs:92-103): ContactEvent::Started / Stopped
+    if ((mf.had_live > 0) != (has > 0)) {
+        uint32_t k = atomicAdd(ps.n_events, 1u);
+        if (k < ps.cap_events) ps.events[k] = ((has > 0) ? (1ull << 63) : 0ull) | ((unsigned long long)h1 << 32) | h2;
+    }
+}
+// An updated pair whose generator pushes nothing (separated shapes) still went through save_cache_and_clear.
+__device__ __noinline__ void pm_age_only(const PersistArgs& ps, uint32_t slot, uint32_t h1, uint32_t h2) {
+    if ((ps.pm_hdr[(size_t)slot * PM_HDR_WORDS] & 0xffu) == 0) return;
+    PManifold mf;
+    pm_load_and_age(ps, slot, mf);
+    pm_store(ps, slot, mf, h1, h2);
+}
+
 struct NarrowArgs {
+    PersistArgs ps;
     DevObjects o;
     DevHulls H;
     const uint2* pairs;
@@ -832,6 +963,7 @@ NCB_HD void cp_store(uint32_t* q, uint32_t slot, uint32_t p, V3 p1, V3 p2, V3 di
 #ifndef NCB_GJK_MINBLOCKS
 #define NCB_GJK_MINBLOCKS 6
 #endif
+template <bool PS>
 __global__ void __launch_bounds__(128, NCB_GJK_MINBLOCKS) k_cc_gjk(NarrowArgs A) {
     const int KEY = CCQ;
     uint32_t seg_begin = A.cnt->key_start[K_CUBOID_CUBOID];
@@ -853,11 +985,21 @@ __global__ void __launch_bounds__(128, NCB_GJK_MINBLOCKS) k_cc_gjk(NarrowArgs A)
             Support ga = as_support(a), gb = as_support(b);
             // contact_support_map_support_map_with_params, init_dir = None (fresh generator)
             V3 d0;
-            if (!unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
+            uint32_t out_index = 0;
+            bool warm = false;
+            if constexpr (PS) {  // the generator's last_gjk_dir (convex_polyhedron_convex_polyhedron_manifold_generator.rs:98)
+                out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
+                float4 pd = A.ps.dir[out_index];
+                if (pd.w != 0.f) d0 = v3(pd.x, pd.y, pd.z), warm = true;
+            }
+            if (!warm && !unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
             simplex_init(s, cso_from_shapes(ma, ga, mb, gb, d0));
             r = gjk_closest_points(ma, ga, mb, gb, linear, s, p1, p2, dir);
-            if (r == GJK_NO_INTERSECTION) {
-                uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
+            if constexpr (PS) {
+                if (r != GJK_INTERSECTION) A.ps.dir[out_index] = make_float4(dir.x, dir.y, dir.z, 1.f);  // :106 / :139
+                if (r == GJK_NO_INTERSECTION) pm_age_only(A.ps, out_index, i1, i2);
+            } else if (r == GJK_NO_INTERSECTION) {
+                out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
                 A.manifold_start[out_index] = 0;
                 A.manifold_count[out_index] = 0;
             }
@@ -886,6 +1028,7 @@ __global__ void __launch_bounds__(128, NCB_GJK_MINBLOCKS) k_cc_gjk(NarrowArgs A)
 #ifndef NCB_EPA_MINBLOCKS
 #define NCB_EPA_MINBLOCKS 16
 #endif
+template <bool PS>
 __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) {
     const int KEY = CCQ;
     const uint32_t seg_end = A.cnt->epa_cursor[KEY];
@@ -936,13 +1079,22 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) 
         bool ok = active && status == EPA_DONE_OK;
         bool fail = active && status == EPA_DONE_FAIL;
         uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], ok);
-        if (ok) cp_store(A.cp_queue, slot, p, p1, p2, n);
+        if (ok) {
+            cp_store(A.cp_queue, slot, p, p1, p2, n);
+            if constexpr (PS) A.ps.dir[A.pair_index ? __ldg(&A.pair_index[p]) : p] = make_float4(n.x, n.y, n.z, 1.f);
+        }
         if (fail) {
             if (e.overflow) atomicAdd(&A.cnt->epa_overflow, 1u);
             if (e.panicked) atomicAdd(&A.cnt->ref_panics, 1u);
             uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
-            A.manifold_start[out_index] = 0;
-            A.manifold_count[out_index] = 0;
+            if constexpr (PS) {  // NoIntersection(x axis) (contact_support_map_support_map.rs:76)
+                A.ps.dir[out_index] = make_float4(1.f, 0.f, 0.f, 1.f);
+                uint2 pr = __ldg(&A.pairs[p]);
+                pm_age_only(A.ps, out_index, pr.x, pr.y);
+            } else {
+                A.manifold_start[out_index] = 0;
+                A.manifold_count[out_index] = 0;
+            }
         }
         if (ok || fail) active = false;
         if (exhausted && __all_sync(0xffffffffu, !active)) break;
@@ -952,25 +1104,27 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) 
 #ifndef NCB_MAN_MINBLOCKS
 #define NCB_MAN_MINBLOCKS 6
 #endif
+template <bool PS>
 __global__ void __launch_bounds__(128, NCB_MAN_MINBLOCKS) k_cc_manifold(NarrowArgs A) {
     const int KEY = CCQ;
     uint32_t seg_begin = A.cnt->key_start[KEY];
     uint32_t seg_end = A.cnt->cp_cursor[KEY];
     uint32_t stride = gridDim.x * blockDim.x;
-    Manifold mf;
+    ManifoldT<PS> mf;
     for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
         uint32_t w = base + threadIdx.x;
         bool valid = w < seg_end;
         mf.n = 0;
         mf.deepest = 0;
-        uint32_t p = 0;
+        uint32_t p = 0, i1 = 0, i2 = 0;
         if (valid) {
             const uint32_t* q = A.cp_queue + (size_t)w * CP_REC_WORDS;
             const float* f = reinterpret_cast<const float*>(q);
             p = q[0];
             V3 p1 = v3(f[1], f[2], f[3]), p2 = v3(f[4], f[5], f[6]), dir = v3(f[7], f[8], f[9]);
             uint2 pr = __ldg(&A.pairs[p]);
-            uint32_t i1 = pr.x, i2 = pr.y;
+            i1 = pr.x, i2 = pr.y;
+            if constexpr (PS) pm_load_and_age(A.ps, A.pair_index ? __ldg(&A.pair_index[p]) : p, mf);
             uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
             Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
             float linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
@@ -980,18 +1134,22 @@ __global__ void __launch_bounds__(128, NCB_MAN_MINBLOCKS) k_cc_manifold(NarrowAr
             convex_convex_manifold(ma, a, mb, b, linear, ang1, ang2, p1, p2, dir, mf, f1, f2);
         }
         uint32_t out_index = valid ? (A.pair_index ? __ldg(&A.pair_index[p]) : p) : 0;
-        write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+        if constexpr (PS) {
+            if (valid) pm_store(A.ps, out_index, mf, i1, i2);
+        } else {
+            write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+        }
     }
 }
 
 // One persistent kernel per key; the segment bounds are read from the device counters.
-template <int KEY>
+template <int KEY, bool PS>
 __global__ void __launch_bounds__(128) k_narrow(NarrowArgs A) {
     uint32_t seg_begin = A.cnt->key_start[KEY];
     uint32_t seg_end = seg_begin + A.cnt->key_hist[KEY];
     uint32_t stride = gridDim.x * blockDim.x;
     // local-memory working set, only instantiated for the keys that need it
-    Manifold mf;
+    ManifoldT<PS> mf;
     for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
         uint32_t p = base + threadIdx.x;
         bool valid = p < seg_end;
@@ -999,9 +1157,11 @@ __global__ void __launch_bounds__(128) k_narrow(NarrowArgs A) {
         Simplex bh_simplex;
         mf.n = 0;
         mf.deepest = 0;
+        uint32_t i1 = 0, i2 = 0;
         if (valid) {
             uint2 pr = __ldg(&A.pairs[p]);
-            uint32_t i1 = pr.x, i2 = pr.y;
+            i1 = pr.x, i2 = pr.y;
+            if constexpr (PS) pm_load_and_age(A.ps, A.pair_index ? __ldg(&A.pair_index[p]) : p, mf);
             uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
             Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
             float linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
@@ -1063,23 +1223,28 @@ __global__ void __launch_bounds__(128) k_narrow(NarrowArgs A) {
             }
         }
         uint32_t out_index = valid ? (A.pair_index ? __ldg(&A.pair_index[p]) : p) : 0;
-        write_manifold(mf, valid && !deferred, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+        if constexpr (PS) {
+            if (valid && !deferred) pm_store(A.ps, out_index, mf, i1, i2);  // deferred pairs are loaded again by k_bh_epa
+        } else {
+            write_manifold(mf, valid && !deferred, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+        }
     }
 }
 
 // Ball x hull pairs whose ball centre is inside the hull: EPA::project_origin + the rest of the generator.
+template <bool PS>
 __global__ void __launch_bounds__(64) k_bh_epa(NarrowArgs A) {
     uint32_t seg_begin = A.cnt->key_start[K_BALL_HULL];
     uint32_t seg_end = A.cnt->epa_cursor[K_BALL_HULL];
     uint32_t stride = gridDim.x * blockDim.x;
     EpaState e;
-    Manifold mf;
+    ManifoldT<PS> mf;
     for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
         uint32_t w = base + threadIdx.x;
         bool valid = w < seg_end;
         mf.n = 0;
         mf.deepest = 0;
-        uint32_t p = 0;
+        uint32_t p = 0, h1 = 0, h2 = 0;
         if (valid) {
             const uint32_t* q = A.epa_queue + (size_t)w * EPA_REC_WORDS;
             const float* f = reinterpret_cast<const float*>(q);
@@ -1093,6 +1258,8 @@ __global__ void __launch_bounds__(64) k_bh_epa(NarrowArgs A) {
             }
             uint2 pr = __ldg(&A.pairs[p]);
             uint32_t i1 = pr.x, i2 = pr.y;
+            h1 = i1, h2 = i2;
+            if constexpr (PS) pm_load_and_age(A.ps, A.pair_index ? __ldg(&A.pair_index[p]) : p, mf);
             uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
             Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
             float linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
@@ -1116,7 +1283,11 @@ __global__ void __launch_bounds__(64) k_bh_epa(NarrowArgs A) {
             gen_ball_convex_finish(mball.t, ball.radius, cp, true, world2, f2, linear, flip, mf);
         }
         uint32_t out_index = valid ? (A.pair_index ? __ldg(&A.pair_index[p]) : p) : 0;
-        write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+        if constexpr (PS) {
+            if (valid) pm_store(A.ps, out_index, mf, h1, h2);
+        } else {
+            write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+        }
     }
 }
 
@@ -1131,9 +1302,12 @@ __global__ void __launch_bounds__(256) k_narrow_none(NarrowArgs A) {
     }
 }
 
-cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, uint32_t cap_pairs,
-                                uint32_t cap_contacts) {
+template <bool PS>
+static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, uint32_t cap_pairs,
+                                         uint32_t cap_contacts, const PersistArgs* ps) {
     NarrowArgs A;
+    memset(&A.ps, 0, sizeof A.ps);
+    if (ps) A.ps = *ps;
     A.o = o;
     A.H = c->hulls;
     A.pairs = pairs;
@@ -1165,24 +1339,33 @@ cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pa
         cudaEventRecord(c->ev_fork, s);
         cudaStreamWaitEvent(s2, c->ev_fork, 0);
     }
-    k_narrow<K_BALL_HULL><<<sm * 8, 128, 0, s2>>>(A);
-    k_bh_epa<<<sm * 4, 64, 0, s2>>>(A);
-    k_narrow<K_BALL_CUBOID><<<sm * 8, 128, 0, s2>>>(A);
-    k_narrow<K_BALL_BALL><<<sm * 8, 128, 0, s2>>>(A);
-    k_narrow<K_PLANE_BALL><<<sm * 2, 128, 0, s2>>>(A);
-    k_narrow<K_PLANE_CUBOID><<<sm * 2, 128, 0, s2>>>(A);
-    k_narrow<K_PLANE_HULL><<<sm * 2, 128, 0, s2>>>(A);
-    k_narrow_none<<<sm, 256, 0, s2>>>(A);
+    k_narrow<K_BALL_HULL, PS><<<sm * 8, 128, 0, s2>>>(A);
+    k_bh_epa<PS><<<sm * 4, 64, 0, s2>>>(A);
+    k_narrow<K_BALL_CUBOID, PS><<<sm * 8, 128, 0, s2>>>(A);
+    k_narrow<K_BALL_BALL, PS><<<sm * 8, 128, 0, s2>>>(A);
+    k_narrow<K_PLANE_BALL, PS><<<sm * 2, 128, 0, s2>>>(A);
+    k_narrow<K_PLANE_CUBOID, PS><<<sm * 2, 128, 0, s2>>>(A);
+    k_narrow<K_PLANE_HULL, PS><<<sm * 2, 128, 0, s2>>>(A);
+    if (!PS) k_narrow_none<<<sm, 256, 0, s2>>>(A);
     if (c->side_stream) cudaEventRecord(c->ev_join, s2);
-    k_cc_gjk<<<sm * gjk_bpsm, 128, 0, s>>>(A);
+    k_cc_gjk<PS><<<sm * gjk_bpsm, 128, 0, s>>>(A);
     timer_mark(c, "cc_gjk", 1);
-    k_cc_epa<<<sm * epa_bpsm, 64, 0, s>>>(A);
+    k_cc_epa<PS><<<sm * epa_bpsm, 64, 0, s>>>(A);
     timer_mark(c, "cc_epa", 1);
-    k_cc_manifold<<<sm * man_bpsm, 128, 0, s>>>(A);
+    k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
     timer_mark(c, "cc_manifold", 1);
     if (c->side_stream) cudaStreamWaitEvent(s, c->ev_join, 0);
     timer_mark(c, "narrow_other_join", 7);
     return cudaGetLastError();
+}
+cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, uint32_t cap_pairs,
+                                uint32_t cap_contacts) {
+    return launch_narrow_phase_t<false>(c, o, pairs, pair_index, cap_pairs, cap_contacts, nullptr);
+}
+// Stepping world: the manifolds / generator directions live in the persistent arrays of `ps`, indexed by pair_index[p].
+cudaError_t launch_narrow_phase_persistent(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, uint32_t cap_pairs,
+                                           const PersistArgs& ps) {
+    return launch_narrow_phase_t<true>(c, o, pairs, pair_index, cap_pairs, 0, &ps);
 }
 
 // Classify caller-provided pairs (ncb_generate_contacts): key per pair from the two shape types.

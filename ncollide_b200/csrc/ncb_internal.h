@@ -67,6 +67,20 @@ struct DevCounters {
     int bounds[6];             // ordered-int encoded min xyz / max xyz of AABB centres
 };
 
+// Persistent narrow-phase state of a stepping world (sim.cu), indexed by state slot.
+#define PM_CAP 24        // cache entries (live + stale) of one persistent manifold
+#define PM_HDR_WORDS 8   // 2 + PM_CAP / 4
+#define PM_ENTRY_F4 4    // float4 per entry
+struct PersistArgs {
+    float4* dir;        // last_gjk_dir (xyz) + valid flag (w) per slot
+    uint32_t* pm_hdr;   // PM_HDR_WORDS per slot
+    float4* pm_entry;   // PM_CAP * PM_ENTRY_F4 per slot
+    unsigned long long* events;  // started << 63 | h1 << 32 | h2
+    uint32_t* n_events;
+    uint32_t cap_events;
+    uint32_t* pm_overflow;
+};
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -149,6 +163,13 @@ struct ncb_ctx {
     ncb::DevCounters* h_counters = nullptr;  // pinned
 };
 
+// api.cu helpers shared with sim.cu
+ncb::DevObjects dev_objects(ncb_ctx* c);
+int reserve_broad(ncb_ctx* ctx, uint32_t n);
+int reserve_pairs(ncb_ctx* ctx, size_t cap);
+int reset_counters(ncb_ctx* ctx);
+int read_counters(ncb_ctx* ctx);
+
 namespace ncb {
 
 // ---- stage timers (CUDA events on the context's stream, only when ncb_profile_enable(ctx, 1)) ----------------
@@ -182,4 +203,6 @@ size_t lbvh_temp_bytes(uint32_t n);
 cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, uint32_t cap_pairs,
                                 uint32_t cap_contacts);
 cudaError_t launch_classify_pairs(ncb_ctx* c, const uint2* pairs, uint32_t n);
+cudaError_t launch_narrow_phase_persistent(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, uint32_t cap_pairs,
+                                           const PersistArgs& ps);
 }  // namespace ncb

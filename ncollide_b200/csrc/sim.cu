@@ -1,0 +1,488 @@
+// Stepping world: CollisionWorld::update over several steps with the reference's temporal coherence.
+//
+// Replaces (reference, file:line): pipeline/world.rs:104-119 (update), pipeline/glue/update.rs:65-138 (perform_broad_phase /
+// perform_narrow_phase), pipeline/narrow_phase/narrow_phase.rs:56-104 (update_contact: save_cache_and_clear, generate,
+// ContactEvents), :168-197 (update: only pairs with a changed object), :200-278 (handle_interaction: edges created /
+// removed by the broad phase callbacks, in the callback's argument order),
+// contact_generator/convex_polyhedron_convex_polyhedron_manifold_generator.rs:25-33,98,106,139 (last_gjk_dir),
+// query/contact/contact_manifold.rs:134-236 (manifold cache), pipeline/object/collision_object.rs:215-222 (set_position flags).
+//
+// State per interference pair lives in a slot (stable while the pair exists): orientation (h1, h2), dispatcher key,
+// last_gjk_dir, persistent manifold.  The sorted pair list of the persistent broad phase (bp_persistent.cu) maps to slots.
+#include <cub/cub.cuh>
+#include <cstring>
+#include "bp_internal.h"
+
+using namespace ncb;
+
+struct ncb_sim {
+    ncb_ctx* ctx = nullptr;
+    ncb_bp* bp = nullptr;
+    float margin = 0.f;
+    uint32_t n = 0;
+    bool first = true;
+    DevBuf<uint8_t> moved;
+    DevBuf<uint32_t> stage_h;
+    DevBuf<float> stage_p, stage_r;
+    // pair table, sorted-key order
+    DevBuf<unsigned long long> keys_prev;
+    uint32_t n_prev = 0;
+    DevBuf<uint32_t> slot_prev, slot_new, raw_slot;
+    // slot-indexed state
+    size_t slot_cap = 0;
+    uint32_t next_slot_bound = 0;  // host upper bound of the bump allocator
+    DevBuf<uint2> slot_pair;
+    DevBuf<uint8_t> slot_key;
+    DevBuf<float4> slot_dir;
+    DevBuf<uint32_t> pm_hdr;
+    DevBuf<float4> pm_entry;
+    DevBuf<uint32_t> free_slots;
+    DevBuf<uint32_t> cnt;  // [0] n_free (signed) [1] next_slot [2] n_events [3] pm_overflow
+    DevBuf<unsigned long long> events, events_sorted;
+    DevBuf<uint8_t> cub_tmp;
+    // export of the last step
+    DevBuf<uint32_t> exp_count, exp_start, exp_ids, exp_events;
+    DevBuf<ncb_contact> exp_contacts;
+    DevBuf<uint2> exp_pairs;
+    DevBuf<uint8_t> exp_algo, exp_mcount;
+    uint32_t n_pairs = 0, n_contacts = 0, n_events = 0, n_active = 0, pm_overflow = 0;
+    ncb_update_counts last = {};
+};
+
+#define CKS(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            char b__[512];                                                                                \
+            snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            sim->ctx->err = b__;                                                                          \
+            return NCB_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+namespace {
+
+__device__ __constant__ uint8_t c_sim_key[16] = {K_BALL_BALL,   K_BALL_CUBOID,  K_BALL_HULL,  K_PLANE_BALL,   K_BALL_CUBOID, K_CUBOID_CUBOID,
+                                                 K_CUBOID_HULL, K_PLANE_CUBOID, K_BALL_HULL,  K_CUBOID_HULL,  K_HULL_HULL,   K_PLANE_HULL,
+                                                 K_PLANE_BALL,  K_PLANE_CUBOID, K_PLANE_HULL, K_NONE};
+__device__ __constant__ uint8_t c_sim_algo[16] = {NCB_ALGO_BALL_BALL,     NCB_ALGO_PLANE_BALL,  NCB_ALGO_PLANE_CONVEX,  NCB_ALGO_PLANE_CONVEX,
+                                                  NCB_ALGO_BALL_CONVEX,   NCB_ALGO_BALL_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_CONVEX_CONVEX,
+                                                  NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_NONE,        0, 0, 0, 0, 0, 0};
+
+__device__ int sim_find(const unsigned long long* __restrict__ keys, uint32_t n, unsigned long long k) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (keys[mid] < k)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return (lo < n && keys[lo] == k) ? (int)lo : -1;
+}
+__device__ int pm_live_count(const uint32_t* __restrict__ pm_hdr, const float4* __restrict__ pm_entry, uint32_t slot) {
+    int n0 = (int)(pm_hdr[(size_t)slot * PM_HDR_WORDS] & 0xffu), live = 0;
+    const float4* e = pm_entry + (size_t)slot * PM_CAP * PM_ENTRY_F4;
+    for (int i = 0; i < n0; ++i) live += (__float_as_uint(e[4 * i + 3].w) >> 8) & 1u;
+    return live;
+}
+
+// CollisionObject::set_position for a batch (collision_object.rs:215-222)
+__global__ void k_sim_scatter_poses(const uint32_t* __restrict__ handles, const float* __restrict__ pos, const float* __restrict__ rot, uint32_t m,
+                                    float* dpos, float4* drot, uint8_t* moved) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    uint32_t h = handles ? handles[k] : k;
+    dpos[3 * (size_t)h] = pos[3 * (size_t)k], dpos[3 * (size_t)h + 1] = pos[3 * (size_t)k + 1], dpos[3 * (size_t)h + 2] = pos[3 * (size_t)k + 2];
+    drot[h] = make_float4(rot[4 * (size_t)k], rot[4 * (size_t)k + 1], rot[4 * (size_t)k + 2], rot[4 * (size_t)k + 3]);
+    moved[h] = 1;
+}
+// interference_stopped -> handle_interaction(.., false) (narrow_phase.rs:248-277): the edge goes, Stopped if it had contacts
+__global__ void k_sim_release(const unsigned long long* __restrict__ prev, uint32_t n_prev, const unsigned long long* __restrict__ cur, uint32_t n_cur,
+                              const uint32_t* __restrict__ slot_prev, const uint2* __restrict__ slot_pair, const uint32_t* __restrict__ pm_hdr,
+                              const float4* __restrict__ pm_entry, uint32_t* free_slots, uint32_t* cnt, unsigned long long* events, uint32_t cap_events) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_prev) return;
+    if (sim_find(cur, n_cur, prev[j]) >= 0) return;
+    uint32_t slot = slot_prev[j];
+    if (pm_live_count(pm_hdr, pm_entry, slot) > 0) {
+        uint2 pr = slot_pair[slot];
+        uint32_t k = atomicAdd(&cnt[2], 1u);
+        if (k < cap_events) events[k] = ((unsigned long long)pr.x << 32) | pr.y;
+    }
+    free_slots[atomicAdd(&cnt[0], 1u)] = slot;
+}
+// interference_started -> handle_interaction(.., true) (:216-247): a new edge in the callback's argument order, fresh generator
+__global__ void k_sim_assign(const unsigned long long* __restrict__ cur, uint32_t n_cur, const unsigned long long* __restrict__ prev, uint32_t n_prev,
+                             const uint32_t* __restrict__ slot_prev, uint32_t* slot_new, const uint32_t* __restrict__ upd_seq,
+                             const uint32_t* __restrict__ type, const uint32_t* __restrict__ free_slots, uint32_t* cnt, uint2* slot_pair,
+                             uint8_t* slot_key, float4* slot_dir, uint32_t* pm_hdr) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cur) return;
+    unsigned long long k = cur[i];
+    int j = sim_find(prev, n_prev, k);
+    if (j >= 0) {
+        slot_new[i] = slot_prev[j];
+        return;
+    }
+    int idx = atomicAdd(reinterpret_cast<int*>(&cnt[0]), -1) - 1;
+    uint32_t slot = idx >= 0 ? free_slots[idx] : atomicAdd(&cnt[1], 1u);
+    uint32_t lo = (uint32_t)(k >> 32), hi = (uint32_t)k;
+    uint32_t sl = upd_seq[lo], sh = upd_seq[hi];
+    bool hi_first = (sh != SEQ_NONE) && (sl == SEQ_NONE || sh > sl);
+    uint32_t h1 = hi_first ? hi : lo, h2 = hi_first ? lo : hi;
+    slot_new[i] = slot;
+    slot_pair[slot] = make_uint2(h1, h2);
+    slot_key[slot] = c_sim_key[(type[h1] & 3) * 4 + (type[h2] & 3)];
+    slot_dir[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int w = 0; w < PM_HDR_WORDS; ++w) pm_hdr[(size_t)slot * PM_HDR_WORDS + w] = 0;
+}
+__global__ void k_sim_fix_free(uint32_t* cnt) {
+    if ((int)cnt[0] < 0) cnt[0] = 0;
+}
+// NarrowPhase::update (:168-197): only the edges with a changed endpoint are regenerated
+__global__ void k_sim_active(const uint32_t* __restrict__ slot_new, uint32_t n_cur, const uint2* __restrict__ slot_pair, const uint8_t* __restrict__ slot_key,
+                             const uint8_t* __restrict__ moved, uint2* pairs_raw, uint8_t* keys_raw, uint32_t* raw_slot, DevCounters* cnt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cur) return;
+    uint32_t slot = slot_new[i];
+    uint2 pr = slot_pair[slot];
+    uint8_t key = slot_key[slot];
+    if (key == K_NONE || !(moved[pr.x] | moved[pr.y])) return;
+    uint32_t k = atomicAdd(&cnt->n_pairs, 1u);
+    pairs_raw[k] = pr;
+    keys_raw[k] = key;
+    raw_slot[k] = slot;
+}
+__global__ void k_sim_compose(uint32_t* pair_index, const uint32_t* __restrict__ raw_slot, const DevCounters* __restrict__ cnt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt->n_pairs) return;
+    pair_index[i] = raw_slot[pair_index[i]];
+}
+__global__ void k_sim_count(const uint32_t* __restrict__ slot_new, uint32_t n_cur, const uint32_t* __restrict__ pm_hdr, const float4* __restrict__ pm_entry,
+                            uint32_t* count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cur) return;
+    count[i] = (uint32_t)pm_live_count(pm_hdr, pm_entry, slot_new[i]);
+}
+// ContactManifold::contacts(): slab order, live entries (contact_manifold.rs:59-68)
+__global__ void k_sim_export(const uint32_t* __restrict__ slot_new, uint32_t n_cur, const uint2* __restrict__ slot_pair, const uint8_t* __restrict__ slot_key,
+                             const uint32_t* __restrict__ pm_hdr, const float4* __restrict__ pm_entry, const uint32_t* __restrict__ start,
+                             uint2* out_pairs, uint8_t* out_algo, uint8_t* out_count, ncb_contact* contacts, uint32_t* ids) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cur) return;
+    uint32_t slot = slot_new[i];
+    out_pairs[i] = slot_pair[slot];
+    out_algo[i] = c_sim_algo[slot_key[slot]];
+    int n0 = (int)(pm_hdr[(size_t)slot * PM_HDR_WORDS] & 0xffu);
+    const float4* e = pm_entry + (size_t)slot * PM_CAP * PM_ENTRY_F4;
+    uint32_t dst = start[i], done = 0;
+    int written = 0;
+    for (;;) {  // selection by increasing slab slot
+        int best = -1;
+        uint32_t best_slot = 0xffffffffu;
+        for (int k = 0; k < n0; ++k) {
+            uint32_t meta = __float_as_uint(e[4 * k + 3].w);
+            if (!((meta >> 8) & 1u) || ((done >> k) & 1u)) continue;
+            if ((meta & 0xffu) < best_slot) best_slot = meta & 0xffu, best = k;
+        }
+        if (best < 0) break;
+        done |= 1u << best;
+        float4 a = e[4 * best], b = e[4 * best + 1], c = e[4 * best + 2];
+        uint32_t meta = __float_as_uint(e[4 * best + 3].w);
+        ncb_contact o;
+        o.world1[0] = a.x, o.world1[1] = a.y, o.world1[2] = a.z;
+        o.world2[0] = b.x, o.world2[1] = b.y, o.world2[2] = b.z;
+        o.normal[0] = c.x, o.normal[1] = c.y, o.normal[2] = c.z;
+        o.depth = a.w;
+        o.f1 = __float_as_uint(b.w), o.f2 = __float_as_uint(c.w);
+        o.pair = i;
+        contacts[dst] = o;
+        ids[dst] = ((meta >> 9) << 8) | (meta & 0xffu);
+        dst++, written++;
+    }
+    out_count[i] = (uint8_t)written;
+}
+__global__ void k_sim_unpack_events(const unsigned long long* __restrict__ ev, uint32_t n, uint32_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long k = ev[i];
+    out[3 * i] = (uint32_t)(k >> 32) & 0x7fffffffu;
+    out[3 * i + 1] = (uint32_t)k;
+    out[3 * i + 2] = (uint32_t)(k >> 63);
+}
+
+template <typename T>
+cudaError_t grow_keep(DevBuf<T>& b, size_t want, size_t keep, cudaStream_t s) {
+    if (want <= b.cap) return cudaSuccess;
+    DevBuf<T> nb;
+    cudaError_t e = nb.reserve(want + want / 2);
+    if (e != cudaSuccess) return e;
+    if (b.p && keep) e = cudaMemcpyAsync(nb.p, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
+    cudaStreamSynchronize(s);
+    b.release();
+    b = nb;
+    return e;
+}
+
+}  // namespace
+
+static int sim_grow_slots(ncb_sim* sim, size_t want) {
+    if (want <= sim->slot_cap) return NCB_OK;
+    cudaStream_t s = sim->ctx->stream;
+    size_t keep = sim->slot_cap;
+    CKS(grow_keep(sim->slot_pair, want, keep, s));
+    CKS(grow_keep(sim->slot_key, want, keep, s));
+    CKS(grow_keep(sim->slot_dir, want, keep, s));
+    CKS(grow_keep(sim->pm_hdr, want * PM_HDR_WORDS, keep * PM_HDR_WORDS, s));
+    CKS(grow_keep(sim->pm_entry, want * PM_CAP * PM_ENTRY_F4, keep * PM_CAP * PM_ENTRY_F4, s));
+    CKS(grow_keep(sim->free_slots, want, keep, s));
+    size_t cap = sim->slot_pair.cap;
+    cap = std::min(cap, (size_t)sim->slot_key.cap);
+    cap = std::min(cap, (size_t)sim->slot_dir.cap);
+    cap = std::min(cap, sim->pm_hdr.cap / PM_HDR_WORDS);
+    cap = std::min(cap, sim->pm_entry.cap / (PM_CAP * PM_ENTRY_F4));
+    cap = std::min(cap, (size_t)sim->free_slots.cap);
+    sim->slot_cap = cap;
+    return NCB_OK;
+}
+
+extern "C" {
+
+int ncb_sim_create(ncb_ctx* ctx, float margin, ncb_sim** out) {
+    if (!ctx || !out) return NCB_ERR_ARG;
+    if (ctx->n == 0) {
+        ctx->err = "ncb_sim_create: call ncb_set_objects first";
+        return NCB_ERR_STATE;
+    }
+    ncb_sim* sim = new ncb_sim;
+    sim->ctx = ctx;
+    sim->margin = margin;
+    sim->n = ctx->n;
+    int r = ncb_bp_create(ctx, margin, &sim->bp);
+    if (r) {
+        delete sim;
+        return r;
+    }
+    CKS(cudaSetDevice(ctx->device));
+    CKS(sim->moved.reserve(sim->n));
+    CKS(cudaMemsetAsync(sim->moved.p, 1, sim->n, ctx->stream));  // a new object has every update flag set
+    CKS(sim->cnt.reserve(8));
+    CKS(cudaMemsetAsync(sim->cnt.p, 0, 32, ctx->stream));
+    *out = sim;
+    return NCB_OK;
+}
+
+void ncb_sim_destroy(ncb_sim* sim) {
+    if (!sim) return;
+    cudaSetDevice(sim->ctx->device);
+    cudaStreamSynchronize(sim->ctx->stream);
+    ncb_bp_destroy(sim->bp);
+    sim->moved.release(), sim->stage_h.release(), sim->stage_p.release(), sim->stage_r.release();
+    sim->keys_prev.release(), sim->slot_prev.release(), sim->slot_new.release(), sim->raw_slot.release();
+    sim->slot_pair.release(), sim->slot_key.release(), sim->slot_dir.release(), sim->pm_hdr.release(), sim->pm_entry.release();
+    sim->free_slots.release(), sim->cnt.release(), sim->events.release(), sim->events_sorted.release(), sim->cub_tmp.release();
+    sim->exp_count.release(), sim->exp_start.release(), sim->exp_ids.release(), sim->exp_events.release(), sim->exp_contacts.release();
+    sim->exp_pairs.release(), sim->exp_algo.release(), sim->exp_mcount.release();
+    delete sim;
+}
+
+// CollisionObject::set_position for m objects (handles == NULL: objects 0..m-1); marks them for the next step.
+int ncb_sim_set_positions(ncb_sim* sim, uint32_t m, const uint32_t* handles, const float* pos, const float* rot) {
+    if (!sim || (m && (!pos || !rot))) return NCB_ERR_ARG;
+    CKS(cudaSetDevice(sim->ctx->device));
+    if (m == 0) return NCB_OK;
+    if (m > sim->n && !handles) return NCB_ERR_ARG;
+    if (handles)
+        for (uint32_t k = 0; k < m; ++k)
+            if (handles[k] >= sim->n) {
+                sim->ctx->err = "ncb_sim_set_positions: unknown object handle";
+                return NCB_ERR_ARG;
+            }
+    cudaStream_t s = sim->ctx->stream;
+    CKS(sim->stage_p.reserve(3 * (size_t)m));
+    CKS(sim->stage_r.reserve(4 * (size_t)m));
+    CKS(cudaMemcpyAsync(sim->stage_p.p, pos, 12 * (size_t)m, cudaMemcpyHostToDevice, s));
+    CKS(cudaMemcpyAsync(sim->stage_r.p, rot, 16 * (size_t)m, cudaMemcpyHostToDevice, s));
+    const uint32_t* dh = nullptr;
+    if (handles) {
+        CKS(sim->stage_h.reserve(m));
+        CKS(cudaMemcpyAsync(sim->stage_h.p, handles, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+        dh = sim->stage_h.p;
+    }
+    k_sim_scatter_poses<<<(m + 255) / 256, 256, 0, s>>>(dh, sim->stage_p.p, sim->stage_r.p, m, sim->ctx->pos.p, sim->ctx->rot.p, sim->moved.p);
+    CKS(cudaGetLastError());
+    CKS(cudaStreamSynchronize(s));  // staging buffers are reused
+    return NCB_OK;
+}
+
+// CollisionWorld::update (world.rs:104-119)
+int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
+    if (!sim) return NCB_ERR_ARG;
+    ncb_ctx* ctx = sim->ctx;
+    CKS(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    uint32_t n = sim->n;
+    if (ctx->n != n) {
+        ctx->err = "ncb_sim_step: the object set changed since ncb_sim_create";
+        return NCB_ERR_STATE;
+    }
+    // ---- perform_broad_phase (glue/update.rs:65-99): swept AABB = shape AABB loosened by the query limit
+    int r = reserve_broad(ctx, n);
+    if (r) return r;
+    DevObjects objs = dev_objects(ctx);
+    CKS(launch_aabbs(ctx, objs, sim->margin, 1, 0, n));
+    if (sim->first) {
+        r = bp_create_all_device(sim->bp, n, ctx->aabb_lo.p, ctx->aabb_hi.p);  // CollisionWorld::add -> create_proxies
+        if (r) return r;
+    }
+    r = bp_set_moved_device(sim->bp, n, ctx->aabb_lo.p, ctx->aabb_hi.p, sim->moved.p);
+    if (r) return r;
+    uint32_t ns = 0, nst = 0;
+    r = bp_update_impl(sim->bp, ctx->has_groups ? ctx->groups.p : nullptr, &ns, &nst);
+    if (r) return r;
+    uint32_t n_cur = sim->bp->n_old;
+    const unsigned long long* cur = sim->bp->keys_old.p;
+    // ---- interaction edges follow the started / stopped callbacks
+    r = sim_grow_slots(sim, (size_t)sim->next_slot_bound + ns + 16);
+    if (r) return r;
+    sim->next_slot_bound += ns;
+    uint32_t cap_events = sim->n_prev + n_cur + 16;
+    CKS(sim->events.reserve(cap_events));
+    CKS(sim->slot_new.reserve(n_cur + 1));
+    CKS(sim->raw_slot.reserve(n_cur + 1));
+    CKS(cudaMemsetAsync(sim->cnt.p + 2, 0, 8, s));
+    if (sim->n_prev)
+        k_sim_release<<<(sim->n_prev + 255) / 256, 256, 0, s>>>(sim->keys_prev.p, sim->n_prev, cur, n_cur, sim->slot_prev.p, sim->slot_pair.p, sim->pm_hdr.p,
+                                                                sim->pm_entry.p, sim->free_slots.p, sim->cnt.p, sim->events.p, cap_events);
+    if (n_cur)
+        k_sim_assign<<<(n_cur + 255) / 256, 256, 0, s>>>(cur, n_cur, sim->keys_prev.p, sim->n_prev, sim->slot_prev.p, sim->slot_new.p, sim->bp->upd_seq.p,
+                                                         ctx->type.p, sim->free_slots.p, sim->cnt.p, sim->slot_pair.p, sim->slot_key.p, sim->slot_dir.p,
+                                                         sim->pm_hdr.p);
+    k_sim_fix_free<<<1, 1, 0, s>>>(sim->cnt.p);
+    CKS(cudaGetLastError());
+    CKS(sim->keys_prev.reserve(n_cur + 1));
+    if (n_cur) CKS(cudaMemcpyAsync(sim->keys_prev.p, cur, 8 * (size_t)n_cur, cudaMemcpyDeviceToDevice, s));
+    std::swap(sim->slot_prev, sim->slot_new);  // slot_prev now describes the current pair list
+    sim->n_prev = n_cur;
+    // ---- perform_narrow_phase: regenerate the edges with a changed endpoint
+    size_t cap_pairs = (size_t)n_cur + 1024;
+    r = reserve_pairs(ctx, cap_pairs);
+    if (r) return r;
+    CKS(ctx->pair_index.reserve(cap_pairs));
+    r = reset_counters(ctx);
+    if (r) return r;
+    if (n_cur) {
+        k_sim_active<<<(n_cur + 255) / 256, 256, 0, s>>>(sim->slot_prev.p, n_cur, sim->slot_pair.p, sim->slot_key.p, sim->moved.p, ctx->pairs_raw.p,
+                                                         ctx->keys_raw.p, sim->raw_slot.p, ctx->counters.p);
+        CKS(launch_pair_sort(ctx, (uint32_t)cap_pairs, ctx->pair_index.p));
+        k_sim_compose<<<(n_cur + 255) / 256, 256, 0, s>>>(ctx->pair_index.p, sim->raw_slot.p, ctx->counters.p);
+        PersistArgs ps;
+        ps.dir = sim->slot_dir.p;
+        ps.pm_hdr = sim->pm_hdr.p;
+        ps.pm_entry = sim->pm_entry.p;
+        ps.events = sim->events.p;
+        ps.n_events = sim->cnt.p + 2;
+        ps.cap_events = cap_events;
+        ps.pm_overflow = sim->cnt.p + 3;
+        CKS(launch_narrow_phase_persistent(ctx, objs, ctx->pairs.p, ctx->pair_index.p, (uint32_t)cap_pairs, ps));
+    }
+    // ---- export: pairs in sorted order, live contacts in slab order
+    CKS(sim->exp_count.reserve(n_cur + 1));
+    CKS(sim->exp_start.reserve(n_cur + 1));
+    CKS(sim->exp_pairs.reserve(n_cur + 1));
+    CKS(sim->exp_algo.reserve(n_cur + 1));
+    CKS(sim->exp_mcount.reserve(n_cur + 1));
+    uint32_t total = 0;
+    if (n_cur) {
+        k_sim_count<<<(n_cur + 255) / 256, 256, 0, s>>>(sim->slot_prev.p, n_cur, sim->pm_hdr.p, sim->pm_entry.p, sim->exp_count.p);
+        size_t bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, bytes, sim->exp_count.p, sim->exp_start.p, (int)n_cur);
+        CKS(sim->cub_tmp.reserve(bytes + 256));
+        bytes = sim->cub_tmp.cap;
+        CKS(cub::DeviceScan::ExclusiveSum(sim->cub_tmp.p, bytes, sim->exp_count.p, sim->exp_start.p, (int)n_cur, s));
+        uint32_t last_start = 0, last_count = 0;
+        CKS(cudaMemcpyAsync(&last_start, sim->exp_start.p + (n_cur - 1), 4, cudaMemcpyDeviceToHost, s));
+        CKS(cudaMemcpyAsync(&last_count, sim->exp_count.p + (n_cur - 1), 4, cudaMemcpyDeviceToHost, s));
+        CKS(cudaStreamSynchronize(s));
+        total = last_start + last_count;
+        CKS(sim->exp_contacts.reserve(total + 1));
+        CKS(sim->exp_ids.reserve(total + 1));
+        k_sim_export<<<(n_cur + 255) / 256, 256, 0, s>>>(sim->slot_prev.p, n_cur, sim->slot_pair.p, sim->slot_key.p, sim->pm_hdr.p, sim->pm_entry.p,
+                                                         sim->exp_start.p, sim->exp_pairs.p, sim->exp_algo.p, sim->exp_mcount.p, sim->exp_contacts.p,
+                                                         sim->exp_ids.p);
+        CKS(cudaGetLastError());
+    }
+    // ---- counters, events (sorted for a deterministic order), flags cleared (world.rs:115-118)
+    uint32_t hc[4] = {0, 0, 0, 0};
+    CKS(cudaMemcpyAsync(hc, sim->cnt.p, 16, cudaMemcpyDeviceToHost, s));
+    r = read_counters(ctx);
+    if (r) return r;
+    sim->next_slot_bound = hc[1];
+    sim->n_events = hc[2] < cap_events ? hc[2] : cap_events;
+    sim->pm_overflow = hc[3];
+    if (sim->n_events > 1) {
+        CKS(sim->events_sorted.reserve(sim->events.cap));
+        size_t bytes = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, bytes, sim->events.p, sim->events_sorted.p, (int)sim->n_events, 0, 64);
+        CKS(sim->cub_tmp.reserve(bytes + 256));
+        bytes = sim->cub_tmp.cap;
+        CKS(cub::DeviceRadixSort::SortKeys(sim->cub_tmp.p, bytes, sim->events.p, sim->events_sorted.p, (int)sim->n_events, 0, 64, s));
+        std::swap(sim->events, sim->events_sorted);
+    }
+    CKS(cudaMemsetAsync(sim->moved.p, 0, n, s));
+    CKS(cudaStreamSynchronize(s));
+    sim->first = false;
+    sim->n_pairs = n_cur;
+    sim->n_contacts = total;
+    sim->n_active = ctx->last_counters.n_pairs;
+    if (counts) {
+        memset(counts, 0, sizeof *counts);
+        counts->n_pairs = n_cur;
+        counts->n_contacts = total;
+        counts->epa_overflow = ctx->last_counters.epa_overflow + sim->pm_overflow;
+        counts->ref_panics = ctx->last_counters.ref_panics;
+        counts->n_epa_pairs = ctx->last_counters.epa_cursor[K_CUBOID_CUBOID] - ctx->last_counters.key_start[K_CUBOID_CUBOID];
+        counts->n_manifold_jobs = sim->n_active;  // pairs regenerated in this step
+    }
+    return NCB_OK;
+}
+
+// Sizes of the last step: pairs, contacts, contact events.
+int ncb_sim_sizes(ncb_sim* sim, uint32_t* n_pairs, uint32_t* n_contacts, uint32_t* n_events) {
+    if (!sim) return NCB_ERR_ARG;
+    if (n_pairs) *n_pairs = sim->n_pairs;
+    if (n_contacts) *n_contacts = sim->n_contacts;
+    if (n_events) *n_events = sim->n_events;
+    return NCB_OK;
+}
+
+// Results of the last step; every array is sized from ncb_sim_sizes (NULL = not wanted).
+//   pairs[2 * P]   (object1, object2) of every interference pair, sorted by (min handle, max handle); object order = the
+//                  argument order of the interference_started callback that created the pair
+//   algo[P], manifold_start[P], manifold_count[P], contacts[C] as ncb_world_fetch; contact_ids[C] = insertion counter << 8 |
+//                  slab slot, stable per pair exactly as long as the reference's ContactId is
+//   events[3 * E]  (object1, object2, 1 = ContactEvent::Started / 0 = Stopped), sorted
+int ncb_sim_fetch(ncb_sim* sim, uint32_t* pairs, uint8_t* algo, uint32_t* manifold_start, uint8_t* manifold_count, ncb_contact* contacts,
+                  uint32_t* contact_ids, uint32_t* events) {
+    if (!sim) return NCB_ERR_ARG;
+    CKS(cudaSetDevice(sim->ctx->device));
+    cudaStream_t s = sim->ctx->stream;
+    uint32_t P = sim->n_pairs, Cn = sim->n_contacts, E = sim->n_events;
+    if (pairs && P) CKS(cudaMemcpyAsync(pairs, sim->exp_pairs.p, 8 * (size_t)P, cudaMemcpyDeviceToHost, s));
+    if (algo && P) CKS(cudaMemcpyAsync(algo, sim->exp_algo.p, P, cudaMemcpyDeviceToHost, s));
+    if (manifold_start && P) CKS(cudaMemcpyAsync(manifold_start, sim->exp_start.p, 4 * (size_t)P, cudaMemcpyDeviceToHost, s));
+    if (manifold_count && P) CKS(cudaMemcpyAsync(manifold_count, sim->exp_mcount.p, P, cudaMemcpyDeviceToHost, s));
+    if (contacts && Cn) CKS(cudaMemcpyAsync(contacts, sim->exp_contacts.p, sizeof(ncb_contact) * (size_t)Cn, cudaMemcpyDeviceToHost, s));
+    if (contact_ids && Cn) CKS(cudaMemcpyAsync(contact_ids, sim->exp_ids.p, 4 * (size_t)Cn, cudaMemcpyDeviceToHost, s));
+    if (events && E) {
+        CKS(sim->exp_events.reserve(3 * (size_t)E));
+        k_sim_unpack_events<<<(E + 255) / 256, 256, 0, s>>>(sim->events.p, E, sim->exp_events.p);
+        CKS(cudaGetLastError());
+        CKS(cudaMemcpyAsync(events, sim->exp_events.p, 12 * (size_t)E, cudaMemcpyDeviceToHost, s));
+    }
+    CKS(cudaStreamSynchronize(s));
+    return NCB_OK;
+}
+
+}  // extern "C"

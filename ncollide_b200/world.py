@@ -497,6 +497,60 @@ class BroadPhase:
                 handler.interference_stopped(self._data[a], self._data[b])
 
 
+class SteppingWorld:
+    """``CollisionWorld`` stepped over time (``set_position`` on some objects, then ``update``) with the reference's temporal
+    coherence: persistent broad phase, pairs in callback orientation, GJK warm start, manifold cache with stable contact
+    ids, contact events (``ncb_sim_*``, csrc/sim.cu).  The object set is the scene given at construction."""
+
+    def __init__(self, ctx: Context, scene: WorldScene):
+        self.ctx = ctx
+        ctx.set_scene(scene)
+        ctx.n = scene.n
+        h = C.c_void_p()
+        ctx.check(ctx.lib.ncb_sim_create(ctx.h, C.c_float(scene.margin), C.byref(h)), "ncb_sim_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx.lib.ncb_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_positions(self, handles, pos, rot):
+        hs = None if handles is None else as_u32(handles).reshape(-1)
+        p, r = as_f32(pos).reshape(-1, 3), as_f32(rot).reshape(-1, 4)
+        self.ctx.check(self.ctx.lib.ncb_sim_set_positions(self._h, C.c_uint32(len(p)), ptr(hs), ptr(p), ptr(r)), "ncb_sim_set_positions")
+
+    def update(self, fetch=True):
+        """One ``CollisionWorld::update``.  Returns dict(pairs, algo, off, contacts, ids, events, counts)."""
+        c = _ffi.UpdateCountsC()
+        self.ctx.check(self.ctx.lib.ncb_sim_step(self._h, C.byref(c)), "ncb_sim_step")
+        counts = self.ctx._counts(c)
+        if not fetch:
+            return {"counts": counts}
+        P, Cn, E = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self.ctx.check(self.ctx.lib.ncb_sim_sizes(self._h, C.byref(P), C.byref(Cn), C.byref(E)), "ncb_sim_sizes")
+        P, Cn, E = P.value, Cn.value, E.value
+        pairs = np.zeros((P, 2), dtype=np.uint32)
+        algo = np.zeros(P, dtype=np.uint8)
+        start = np.zeros(P, dtype=np.uint32)
+        count = np.zeros(P, dtype=np.uint8)
+        contacts = np.zeros(Cn, dtype=CONTACT_DTYPE)
+        ids = np.zeros(Cn, dtype=np.uint32)
+        events = np.zeros((E, 3), dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.ncb_sim_fetch(self._h, ptr(pairs), ptr(algo), ptr(start), ptr(count), ptr(contacts), ptr(ids), ptr(events)),
+                       "ncb_sim_fetch")
+        off = np.concatenate([start, [Cn]]).astype(np.uint32) if P else np.zeros(1, dtype=np.uint32)
+        return {"pairs": pairs, "algo": algo, "off": off, "count": count, "contacts": contacts, "ids": ids, "events": events, "counts": counts}
+
+    step = update
+
+
 class TriMesh:
     """``TriMesh::new(points, indices, None)`` + batched ``RayCast::toi_and_normal_with_ray``."""
 

@@ -129,3 +129,79 @@ def test_device_handler_mirror():
     with pytest.raises(Exception):
         bp.deferred_set_bounding_volume(99, ball_box((0, 0, 0)))
         bp.update(h)
+
+
+# ---- stepping world (persistent narrow phase on top of the persistent broad phase) -----------------------------------
+RTOL, ATOL = 1e-4, 1e-5
+
+
+class DeviceSimAdapter:
+    def __init__(self, ctx, scene):
+        from ncollide_b200.world import SteppingWorld
+
+        self.w = SteppingWorld(ctx, scene)
+
+    def set_positions(self, handles, pos, rot):
+        self.w.set_positions(handles, pos, rot)
+
+    def step(self):
+        r = self.w.update()
+        keep = r["algo"] != 0  # plane x plane: a broad-phase pair without an interaction edge
+        cnt = np.diff(r["off"].astype(np.int64))
+        assert np.array_equal(cnt, r["count"].astype(np.int64))
+        sel = np.repeat(keep, cnt)
+        off = np.concatenate([[0], np.cumsum(cnt[keep])]).astype(np.uint32)
+        return {"pairs": r["pairs"][keep], "algo": r["algo"][keep], "off": off, "contacts": r["contacts"][sel], "ids": r["ids"][sel],
+                "events": r["events"], "counts": r["counts"], "bp_pairs": len(r["pairs"])}
+
+
+def compare_sim_logs(dev, orc):
+    assert len(dev) == len(orc)
+    for t, (a, b) in enumerate(zip(dev, orc)):
+        assert a["bp_pairs"] == b["bp_pairs"], f"step {t}: broad-phase pair count"
+        assert np.array_equal(a["pairs"], b["pairs"]), f"step {t}: pairs / orientation"
+        assert np.array_equal(a["algo"], b["algo"]), f"step {t}: algo"
+        assert np.array_equal(a["off"], b["off"]), f"step {t}: manifold sizes ({int(np.sum(a['off'] != b['off']))} differ)"
+        assert np.array_equal(a["ids"], b["ids"]), f"step {t}: contact ids"
+        for f in ("f1", "f2"):
+            assert np.array_equal(a["contacts"][f], b["contacts"][f]), f"step {t}: {f}"
+        for f in ("world1", "world2", "normal", "depth"):
+            assert np.allclose(a["contacts"][f], b["contacts"][f], rtol=RTOL, atol=ATOL), f"step {t}: {f}"
+        ea = a["events"][np.lexsort((a["events"][:, 1], a["events"][:, 0], a["events"][:, 2]))] if len(a["events"]) else a["events"]
+        eb = b["events"][np.lexsort((b["events"][:, 1], b["events"][:, 0], b["events"][:, 2]))] if len(b["events"]) else b["events"]
+        assert np.array_equal(ea, eb), f"step {t}: contact events"
+        assert a["counts"]["epa_overflow"] == 0 and a["counts"]["ref_panics"] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,kinds,side,plane,seed", [(1500, (1, 1, 1), 7.0, False, 3), (4000, (1, 1, 1), 10.0, True, 4), (3000, (0, 1, 1), 8.0, False, 5),
+                                                      (20000, (1, 1, 1), 18.0, False, 6)])
+def test_stepping_world_matches_oracle(oracle, n, kinds, side, plane, seed):
+    from ncollide_b200.scenes import make_world_scene
+    from ncollide_b200.world import Context
+    from sim_scenario import drive
+
+    s = make_world_scene(n, 20 + seed, kinds, side=side, n_hulls=32, plane=plane, angular=0.02 if seed == 5 else 0.0, name="sim")
+    dev = drive(DeviceSimAdapter(Context(0), s), s, steps=7, seed=seed)
+    orc = drive(oracle.sim(s), s, steps=7, seed=seed)
+    assert sum(len(r["events"]) for r in orc[1:]) > 10
+    compare_sim_logs(dev, orc)
+
+
+@pytest.mark.gpu
+def test_stepping_world_first_step_equals_fresh_update(oracle):
+    from ncollide_b200.scenes import make_world_scene
+    from ncollide_b200.world import Context, SteppingWorld
+
+    s = make_world_scene(5000, 31, (1, 1, 1), side=11.0, n_hulls=32, plane=True, name="sim_first")
+    ctx = Context(0)
+    fresh = ctx.world_update(s)
+    r = SteppingWorld(ctx, s).update()
+    order = np.lexsort((np.maximum(fresh.pairs[:, 0], fresh.pairs[:, 1]), np.minimum(fresh.pairs[:, 0], fresh.pairs[:, 1])))
+    assert np.array_equal(r["pairs"], fresh.pairs[order])
+    assert np.array_equal(r["algo"], fresh.pair_algo[order])
+    assert np.array_equal(r["count"], fresh.manifold_count[order])
+    got = r["contacts"]
+    want = np.concatenate([fresh.contacts_of(p) for p in order]) if len(order) else fresh.contacts
+    for f in ("world1", "world2", "normal", "depth", "f1", "f2"):
+        assert np.array_equal(got[f], want[f]), f
