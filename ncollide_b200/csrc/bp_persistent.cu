@@ -12,6 +12,9 @@
 // started = new \ old, stopped = old \ new.  interference_started(a, b) gets the re-inserted leaf first (the later
 // one in update order when both moved); interference_stopped gets SortedPair order (smaller handle first).
 #include <cub/cub.cuh>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -563,6 +566,15 @@ int bp_update_impl(ncb_bp* bp, const uint32_t* d_groups, uint32_t* n_started, ui
     if (n_stopped) *n_stopped = 0;
     uint32_t slots = (uint32_t)bp->next_free.size();
     if (slots == 0) return NCB_OK;
+    static const bool prof = getenv("NCB_SIM_PROFILE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!prof) return;
+        cudaStreamSynchronize(s);
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bp]    %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
     bool any_pending = bp->seq != 0 || bp->front != 0;
     if (!any_pending) return NCB_OK;  // no leaf was updated: the reference neither queries nor purges
     // 1. apply pending boxes; every occupied slot is attached afterwards
@@ -583,6 +595,7 @@ int bp_update_impl(ncb_bp* bp, const uint32_t* d_groups, uint32_t* n_started, ui
         CKB(cudaStreamSynchronize(s));  // `alive` is a local
         bp->slab_dirty = false;
     }
+    mark("apply+alive");
     bp->seq = bp->front = 0;
     uint32_t m = bp->n_attached;
     uint32_t n_new = 0;
@@ -634,6 +647,7 @@ int bp_update_impl(ncb_bp* bp, const uint32_t* d_groups, uint32_t* n_started, ui
             if (n_new <= w->pairs_raw.cap) break;
             cap_pairs = (size_t)n_new + n_new / 8 + 1024;
         }
+        mark("lbvh+pairs");
         // 3. sorted 64-bit keys
         if (n_new) {
             CKB(bp->keys_tmp.reserve(n_new));
@@ -644,6 +658,7 @@ int bp_update_impl(ncb_bp* bp, const uint32_t* d_groups, uint32_t* n_started, ui
             if (r) return r;
         }
     }
+    mark("sort_keys");
     // 4. started = new \ old, stopped = old \ new
     CKB(bp->counters.reserve(4));
     CKB(cudaMemsetAsync(bp->counters.p, 0, 16, s));
@@ -664,6 +679,7 @@ int bp_update_impl(ncb_bp* bp, const uint32_t* d_groups, uint32_t* n_started, ui
     if (r) return r;
     r = bp_sort_events(bp, bp->ev_b, cnt[1]);
     if (r) return r;
+    mark("diff+events");
     std::swap(bp->keys_old, bp->keys_new);
     bp->n_old = n_new;
     bp->n_started = cnt[0];

@@ -10,6 +10,9 @@
 // State per interference pair lives in a slot (stable while the pair exists): orientation (h1, h2), dispatcher key,
 // last_gjk_dir, persistent manifold.  The sorted pair list of the persistent broad phase (bp_persistent.cu) maps to slots.
 #include <cub/cub.cuh>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "bp_internal.h"
 
@@ -327,6 +330,16 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
         ctx->err = "ncb_sim_step: the object set changed since ncb_sim_create";
         return NCB_ERR_STATE;
     }
+    // NCB_SIM_PROFILE=1: wall time per phase (with a stream synchronisation at every phase boundary) on stderr
+    static const bool prof = getenv("NCB_SIM_PROFILE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!prof) return;
+        cudaStreamSynchronize(s);
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sim] %-14s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
     // ---- perform_broad_phase (glue/update.rs:65-99): swept AABB = shape AABB loosened by the query limit
     int r = reserve_broad(ctx, n);
     if (r) return r;
@@ -338,9 +351,11 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
     }
     r = bp_set_moved_device(sim->bp, n, ctx->aabb_lo.p, ctx->aabb_hi.p, sim->moved.p);
     if (r) return r;
+    mark("aabb+stage");
     uint32_t ns = 0, nst = 0;
     r = bp_update_impl(sim->bp, ctx->has_groups ? ctx->groups.p : nullptr, &ns, &nst);
     if (r) return r;
+    mark("bp_update");
     uint32_t n_cur = sim->bp->n_old;
     const unsigned long long* cur = sim->bp->keys_old.p;
     // ---- interaction edges follow the started / stopped callbacks
@@ -365,6 +380,7 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
     if (n_cur) CKS(cudaMemcpyAsync(sim->keys_prev.p, cur, 8 * (size_t)n_cur, cudaMemcpyDeviceToDevice, s));
     std::swap(sim->slot_prev, sim->slot_new);  // slot_prev now describes the current pair list
     sim->n_prev = n_cur;
+    mark("pair_table");
     // ---- perform_narrow_phase: regenerate the edges with a changed endpoint
     size_t cap_pairs = (size_t)n_cur + 1024;
     r = reserve_pairs(ctx, cap_pairs);
@@ -387,6 +403,7 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
         ps.pm_overflow = sim->cnt.p + 3;
         CKS(launch_narrow_phase_persistent(ctx, objs, ctx->pairs.p, ctx->pair_index.p, (uint32_t)cap_pairs, ps));
     }
+    mark("narrow");
     // ---- export: pairs in sorted order, live contacts in slab order
     CKS(sim->exp_count.reserve(n_cur + 1));
     CKS(sim->exp_start.reserve(n_cur + 1));
@@ -413,6 +430,7 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
                                                          sim->exp_ids.p);
         CKS(cudaGetLastError());
     }
+    mark("export");
     // ---- counters, events (sorted for a deterministic order), flags cleared (world.rs:115-118)
     uint32_t hc[4] = {0, 0, 0, 0};
     CKS(cudaMemcpyAsync(hc, sim->cnt.p, 16, cudaMemcpyDeviceToHost, s));
@@ -432,6 +450,7 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
     }
     CKS(cudaMemsetAsync(sim->moved.p, 0, n, s));
     CKS(cudaStreamSynchronize(s));
+    mark("finish");
     sim->first = false;
     sim->n_pairs = n_cur;
     sim->n_contacts = total;

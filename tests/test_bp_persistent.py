@@ -195,6 +195,7 @@ def test_stepping_world_first_step_equals_fresh_update(oracle):
 
     s = make_world_scene(5000, 31, (1, 1, 1), side=11.0, n_hulls=32, plane=True, name="sim_first")
     ctx = Context(0)
+    ctx.set_scene(s)
     fresh = ctx.world_update(s)
     r = SteppingWorld(ctx, s).update()
     order = np.lexsort((np.maximum(fresh.pairs[:, 0], fresh.pairs[:, 1]), np.minimum(fresh.pairs[:, 0], fresh.pairs[:, 1])))
