@@ -470,10 +470,10 @@ static int bp_sort_keys(ncb_bp* bp, unsigned long long* in, unsigned long long* 
 // Sorts the n events of `ev` (deterministic output order) in place.
 static int bp_sort_events(ncb_bp* bp, DevBuf<unsigned long long>& ev, uint32_t n) {
     if (n < 2) return NCB_OK;
-    CKB(bp->ev_sorted.reserve(ev.cap));
+    CKB(bp->ev_sorted.reserve(n));
     int r = bp_sort_keys(bp, ev.p, bp->ev_sorted.p, n);
     if (r) return r;
-    std::swap(ev, bp->ev_sorted);
+    CKB(cudaMemcpyAsync(ev.p, bp->ev_sorted.p, 8 * (size_t)n, cudaMemcpyDeviceToDevice, bp->owner->stream));  // keeps both capacities stable
     return NCB_OK;
 }
 

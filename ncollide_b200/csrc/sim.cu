@@ -33,7 +33,8 @@ struct ncb_sim {
     DevBuf<uint32_t> slot_prev, slot_new, raw_slot;
     // slot-indexed state
     size_t slot_cap = 0;
-    uint32_t next_slot_bound = 0;  // host upper bound of the bump allocator
+    uint32_t next_slot_bound = 0;  // host copy of the bump allocator
+    uint32_t n_free_host = 0;      // host copy of the free-list length
     DevBuf<uint2> slot_pair;
     DevBuf<uint8_t> slot_key;
     DevBuf<float4> slot_dir;
@@ -359,9 +360,11 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
     uint32_t n_cur = sim->bp->n_old;
     const unsigned long long* cur = sim->bp->keys_old.p;
     // ---- interaction edges follow the started / stopped callbacks
-    r = sim_grow_slots(sim, (size_t)sim->next_slot_bound + ns + 16);
-    if (r) return r;
-    sim->next_slot_bound += ns;
+    {
+        uint32_t avail = sim->n_free_host + nst;  // slots released by this step's stopped pairs come back first
+        r = sim_grow_slots(sim, (size_t)sim->next_slot_bound + (ns > avail ? ns - avail : 0) + 16);
+        if (r) return r;
+    }
     uint32_t cap_events = sim->n_prev + n_cur + 16;
     CKS(sim->events.reserve(cap_events));
     CKS(sim->slot_new.reserve(n_cur + 1));
@@ -436,17 +439,18 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
     CKS(cudaMemcpyAsync(hc, sim->cnt.p, 16, cudaMemcpyDeviceToHost, s));
     r = read_counters(ctx);
     if (r) return r;
+    sim->n_free_host = hc[0];
     sim->next_slot_bound = hc[1];
     sim->n_events = hc[2] < cap_events ? hc[2] : cap_events;
     sim->pm_overflow = hc[3];
     if (sim->n_events > 1) {
-        CKS(sim->events_sorted.reserve(sim->events.cap));
+        CKS(sim->events_sorted.reserve(sim->n_events));
         size_t bytes = 0;
         cub::DeviceRadixSort::SortKeys(nullptr, bytes, sim->events.p, sim->events_sorted.p, (int)sim->n_events, 0, 64);
         CKS(sim->cub_tmp.reserve(bytes + 256));
         bytes = sim->cub_tmp.cap;
         CKS(cub::DeviceRadixSort::SortKeys(sim->cub_tmp.p, bytes, sim->events.p, sim->events_sorted.p, (int)sim->n_events, 0, 64, s));
-        std::swap(sim->events, sim->events_sorted);
+        CKS(cudaMemcpyAsync(sim->events.p, sim->events_sorted.p, 8 * (size_t)sim->n_events, cudaMemcpyDeviceToDevice, s));
     }
     CKS(cudaMemsetAsync(sim->moved.p, 0, n, s));
     CKS(cudaStreamSynchronize(s));

@@ -40,7 +40,8 @@ if __name__ == "__main__":
     s = config_scene(3, n)
     ctx = Context(0)
     first, times, info = run(lambda sc: SteppingWorld(ctx, sc), s, steps, frac, True)
-    dev = {"n": n, "first_update_ms": 1e3 * first, "step_ms_median": 1e3 * float(np.median(times)), "counts": info["counts"]}
+    dev = {"n": n, "first_update_ms": 1e3 * first, "step_ms_median": 1e3 * float(np.median(times)), "step_ms_all": [round(1e3 * t, 2) for t in times],
+           "counts": info["counts"]}
     from oracle.pyoracle import Oracle
 
     sc = config_scene(3, n_cpu)
