@@ -166,6 +166,10 @@ void* ncb_device_ptr(ncb_ctx* ctx, int which);
 /* Split update for multi-GPU: stage 0 = AABBs of objects [obj_begin, obj_end) only; stage 1 = everything after the
  * AABBs (LBVH + pair search for query slice + narrow phase). */
 int ncb_world_update_stage(ncb_ctx* ctx, int stage, float margin, uint32_t begin, uint32_t end, ncb_update_counts* counts);
+/* Multi-GPU stage 1 with spatial ownership: after stage 0 + the all-gather of the AABB arrays (ncb_device_ptr 0 / 1), rank
+ * `rank` of `world` selects the objects it owns (equal-count Morton ranges) plus the ghosts around them, builds its LBVH
+ * over those only and reports its share of the pairs + their contacts.  Every pair is reported by exactly one rank. */
+int ncb_world_update_sharded(ncb_ctx* ctx, float margin, int rank, int world, ncb_update_counts* counts);
 
 /* Per-stage device times of the last ncb_world_update_device, measured with CUDA events on the context's stream
  * when enabled.  names/ms are arrays of at least 16 entries; returns the number of stages filled. */

@@ -456,8 +456,11 @@ int ncb_generate_contacts(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* pairs,
 }
 
 // ---- fused hot path ----------------------------------------------------------------------------------------
-static int update_after_aabbs(ncb_ctx* ctx, uint32_t q_begin, uint32_t q_end) {
-    uint32_t n = ctx->n;
+// n_local / handle_map / my_rank: the spatially sharded variant runs on the selected (owned + ghost) boxes that the caller
+// put in ctx->aabb_lo / aabb_hi, reports global handles through handle_map and filters pairs by ownership.
+static int update_after_aabbs(ncb_ctx* ctx, uint32_t q_begin, uint32_t q_end, uint32_t n_local = 0xffffffffu, const uint32_t* handle_map = nullptr,
+                              int my_rank = -1) {
+    uint32_t n = n_local == 0xffffffffu ? ctx->n : n_local;
     // capacities: grow-on-overflow, remembered across calls
     size_t cap_pairs = ctx->cap_pairs_hint ? ctx->cap_pairs_hint : (size_t)6 * n + 1024;
     size_t cap_contacts = ctx->cap_contacts_hint ? ctx->cap_contacts_hint : (size_t)6 * n + 1024;
@@ -468,8 +471,8 @@ static int update_after_aabbs(ncb_ctx* ctx, uint32_t q_begin, uint32_t q_end) {
         r = reset_counters(ctx);
         if (r) return r;
         if (!ctx->timer_external || attempt > 0) timer_begin(ctx);
-        CK(launch_lbvh_build(ctx, n, nullptr));
-        CK(launch_pair_search(ctx, n, ctx->has_groups ? ctx->groups.p : nullptr, q_begin, q_end, (uint32_t)cap_pairs));
+        CK(launch_lbvh_build(ctx, n, handle_map));
+        CK(launch_pair_search(ctx, n, ctx->has_groups ? ctx->groups.p : nullptr, q_begin, q_end, (uint32_t)cap_pairs, my_rank));
         timer_mark(ctx, "pair_search", 2);
         CK(launch_pair_sort(ctx, (uint32_t)cap_pairs, nullptr));
         timer_mark(ctx, "pair_sort", 3);
@@ -518,6 +521,50 @@ int ncb_world_update_stage(ncb_ctx* ctx, int stage, float margin, uint32_t begin
     }
     int r = update_after_aabbs(ctx, begin, end);
     ctx->timer_external = false;
+    if (r) return r;
+    fill_counts(ctx, counts);
+    return NCB_OK;
+}
+
+// Stage 1 of a multi-GPU update with SPATIAL ownership (see launch_shard_select): every rank holds all fat AABBs (stage 0 +
+// all-gather), selects the objects it owns plus the ghosts around them, builds its LBVH over those only and reports the
+// pairs it is responsible for.  The union over the ranks is the full pair set, every pair exactly once.
+int ncb_world_update_sharded(ncb_ctx* ctx, float margin, int rank, int world, ncb_update_counts* counts) {
+    (void)margin;
+    if (!ctx || rank < 0 || world < 1 || rank >= world || world > SHARD_MAX_RANKS) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t n = ctx->n;
+    if (n == 0 || world == 1) return ncb_world_update_stage(ctx, 1, margin, 0, 0xffffffffu, counts);
+    cudaStream_t s = ctx->stream;
+    CK(ctx->shard.reserve(1));
+    CK(ctx->shard_bins.reserve(n));
+    size_t cap = ctx->shard_sel.cap ? ctx->shard_sel.cap : (size_t)n / world + n / 8 + 4096;
+    int r = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CK(ctx->shard_sel.reserve(cap));
+        CK(ctx->shard_lo.reserve(cap));
+        CK(ctx->shard_hi.reserve(cap));
+        cap = std::min(ctx->shard_sel.cap, std::min(ctx->shard_lo.cap, ctx->shard_hi.cap));
+        r = reset_counters(ctx);
+        if (r) return r;
+        if (!ctx->timer_external) timer_begin(ctx);
+        CK(launch_shard_select(ctx, n, rank, world, ctx->shard.p, ctx->shard_bins.p, (uint32_t)cap, ctx->shard_sel.p, ctx->shard_lo.p, ctx->shard_hi.p));
+        uint32_t mo[2] = {0, 0};
+        CK(cudaMemcpyAsync(mo, &ctx->shard.p->m, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        ctx->shard_m = mo[0], ctx->shard_owned = mo[1];
+        if (mo[0] <= cap) break;
+        cap = (size_t)mo[0] + mo[0] / 8 + 4096;
+    }
+    timer_mark(ctx, "shard_select", 5);
+    // the selected boxes stand in for the object boxes during the local build / search
+    std::swap(ctx->aabb_lo, ctx->shard_lo);
+    std::swap(ctx->aabb_hi, ctx->shard_hi);
+    ctx->timer_external = true;
+    r = update_after_aabbs(ctx, 0, 0xffffffffu, ctx->shard_m, ctx->shard_sel.p, rank);
+    ctx->timer_external = false;
+    std::swap(ctx->aabb_lo, ctx->shard_lo);
+    std::swap(ctx->aabb_hi, ctx->shard_hi);
     if (r) return r;
     fill_counts(ctx, counts);
     return NCB_OK;

@@ -293,6 +293,138 @@ cudaError_t launch_lbvh_build(ncb_ctx* c, uint32_t n, const uint32_t* handle_map
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Spatial sharding over several GPUs (after the all-gather of the fat AABBs every rank holds all N boxes):
+// a rank OWNS the objects whose Morton code falls in its range of 4096 top-bit bins (ranges hold equal object counts)
+// and takes as GHOSTS the other objects whose box meets the union box of its owned objects; its LBVH and pair search
+// then run on owned + ghost objects only (about N / ranks + a surface layer) instead of all N.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t morton_of(float4 a, float4 b, const DevCounters* __restrict__ cnt) {
+    if (is_outlier(a, b)) return 0x40000000u;
+    float bx = o2f(cnt->bounds[0]), by = o2f(cnt->bounds[1]), bz = o2f(cnt->bounds[2]);
+    float ex = o2f(cnt->bounds[3]) - bx, ey = o2f(cnt->bounds[4]) - by, ez = o2f(cnt->bounds[5]) - bz;
+    float e = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-20f));
+    float s = 1023.0f / e;
+    float cx = ((a.x + b.x) * 0.5f - bx) * s, cy = ((a.y + b.y) * 0.5f - by) * s, cz = ((a.z + b.z) * 0.5f - bz) * s;
+    uint32_t ux = (uint32_t)fminf(fmaxf(cx, 0.0f), 1023.0f);
+    uint32_t uy = (uint32_t)fminf(fmaxf(cy, 0.0f), 1023.0f);
+    uint32_t uz = (uint32_t)fminf(fmaxf(cz, 0.0f), 1023.0f);
+    return (expand_bits10(ux) << 2) | (expand_bits10(uy) << 1) | expand_bits10(uz);
+}
+__global__ void __launch_bounds__(256) k_shard_hist(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n,
+                                                    const DevCounters* __restrict__ cnt, uint32_t* __restrict__ bins, ShardScratch* sh) {
+    __shared__ uint32_t h[SHARD_BINS];
+    for (int k = threadIdx.x; k < SHARD_BINS; k += blockDim.x) h[k] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t key = morton_of(__ldg(&lo[i]), __ldg(&hi[i]), cnt);
+        uint32_t bin = key >= 0x40000000u ? SHARD_BINS : (key >> 18);
+        bins[i] = bin;
+        if (bin < SHARD_BINS) atomicAdd(&h[bin], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < SHARD_BINS; k += blockDim.x)
+        if (h[k]) atomicAdd(&sh->hist[k], h[k]);
+}
+// rank r owns the bins [split[r], split[r + 1]); outliers (bin SHARD_BINS) belong to the last rank
+__global__ void k_shard_split(ShardScratch* sh, int world) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t total = 0;
+    for (int k = 0; k < SHARD_BINS; ++k) total += sh->hist[k];
+    uint32_t acc = 0;
+    int r = 1;
+    sh->split[0] = 0;
+    for (int k = 0; k < SHARD_BINS && r < world; ++k) {
+        acc += sh->hist[k];
+        while (r < world && (unsigned long long)acc * world >= (unsigned long long)total * r) sh->split[r++] = k + 1;
+    }
+    for (; r < world; ++r) sh->split[r] = SHARD_BINS;
+    sh->split[world] = SHARD_BINS + 1;
+}
+__device__ __forceinline__ int shard_owner(const ShardScratch* __restrict__ sh, int world, uint32_t bin) {
+    int r = 0;
+    while (r + 1 < world && bin >= sh->split[r + 1]) ++r;
+    return r;
+}
+__global__ void __launch_bounds__(256) k_shard_region(const float4* __restrict__ lo, const float4* __restrict__ hi, const uint32_t* __restrict__ bins,
+                                                      uint32_t n, ShardScratch* sh, int rank) {
+    float mn[3] = {NCB_FMAX, NCB_FMAX, NCB_FMAX}, mx[3] = {-NCB_FMAX, -NCB_FMAX, -NCB_FMAX};
+    uint32_t b0 = sh->split[rank], b1 = sh->split[rank + 1];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t bin = __ldg(&bins[i]);
+        if (bin < b0 || bin >= b1 || bin >= SHARD_BINS) continue;  // infinite boxes do not shape the region
+        float4 a = __ldg(&lo[i]), b = __ldg(&hi[i]);
+        mn[0] = fminf(mn[0], a.x), mn[1] = fminf(mn[1], a.y), mn[2] = fminf(mn[2], a.z);
+        mx[0] = fmaxf(mx[0], b.x), mx[1] = fmaxf(mx[1], b.y), mx[2] = fmaxf(mx[2], b.z);
+    }
+    for (int off = 16; off; off >>= 1)
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], off));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], off));
+        }
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(&sh->region[k], f2o(mn[k]));
+            atomicMax(&sh->region[3 + k], f2o(mx[k]));
+        }
+}
+__global__ void __launch_bounds__(256) k_shard_select(const float4* __restrict__ lo, const float4* __restrict__ hi, const uint32_t* __restrict__ bins,
+                                                      uint32_t n, ShardScratch* sh, int rank, int world, uint32_t cap, uint32_t* __restrict__ sel,
+                                                      float4* __restrict__ loc_lo, float4* __restrict__ loc_hi) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool take = false;
+    float4 a, b;
+    int owner = 0;
+    if (i < n) {
+        a = __ldg(&lo[i]), b = __ldg(&hi[i]);
+        uint32_t bin = __ldg(&bins[i]);
+        owner = shard_owner(sh, world, bin);
+        if (owner == rank) {
+            take = true;
+        } else {
+            float rl[3] = {o2f(sh->region[0]), o2f(sh->region[1]), o2f(sh->region[2])};
+            float rh[3] = {o2f(sh->region[3]), o2f(sh->region[4]), o2f(sh->region[5])};
+            // inclusive like AABB::intersects: a ghost must be present whenever a pair with an owned object can exist
+            take = a.x <= rh[0] && a.y <= rh[1] && a.z <= rh[2] && b.x >= rl[0] && b.y >= rl[1] && b.z >= rl[2];
+        }
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, take);
+    if (mask == 0) return;
+    int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) {
+        base = atomicAdd(&sh->m, (uint32_t)__popc(mask));
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!take) return;
+    if (owner == rank) atomicAdd(&sh->n_owned, 1u);
+    uint32_t k = base + __popc(mask & ((1u << lane) - 1));
+    if (k >= cap) return;
+    sel[k] = i;
+    loc_lo[k] = a;
+    b.w = __uint_as_float((__float_as_uint(b.w) & 0xffu) | ((uint32_t)owner << 8));
+    loc_hi[k] = b;
+}
+
+// Needs c->counters reset by the caller; leaves the global bounds in c->counters (reset again before the local build).
+cudaError_t launch_shard_select(ncb_ctx* c, uint32_t n, int rank, int world, ShardScratch* sh, uint32_t* bins, uint32_t cap, uint32_t* sel,
+                                float4* loc_lo, float4* loc_hi) {
+    cudaStream_t s = c->stream;
+    int gs = c->sm_count * 4;
+    uint32_t nb = (n + 255) / 256;
+    ShardScratch z;
+    memset(&z, 0, sizeof z);
+    for (int k = 0; k < 3; ++k) z.region[k] = 0x7f7fffff, z.region[3 + k] = (int)0x80800000;
+    cudaError_t e = cudaMemcpyAsync(sh, &z, sizeof z, cudaMemcpyHostToDevice, s);  // pageable source: copied before the call returns
+    if (e != cudaSuccess) return e;
+    k_bounds<<<min((uint32_t)gs, nb), 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, n, c->counters.p);
+    k_shard_hist<<<min((uint32_t)gs, nb), 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, n, c->counters.p, bins, sh);
+    k_shard_split<<<1, 32, 0, s>>>(sh, world);
+    k_shard_region<<<min((uint32_t)gs, nb), 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, bins, n, sh, rank);
+    k_shard_select<<<nb, 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, bins, n, sh, rank, world, cap, sel, loc_lo, loc_hi);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // K5: pair search.  One thread per query leaf, in Morton order (neighbouring lanes traverse neighbouring boxes).
 // A query at sorted position i reports only leaves at positions j > i, so each unordered pair is emitted once;
 // it is oriented (larger handle, smaller handle) = the argument order of interference_started.
@@ -314,6 +446,17 @@ __device__ __forceinline__ bool groups_allow(const uint32_t* __restrict__ g, uin
     uint32_t m1 = __ldg(&g[3 * a]), w1 = __ldg(&g[3 * a + 1]), b1 = __ldg(&g[3 * a + 2]);
     uint32_t m2 = __ldg(&g[3 * b]), w2 = __ldg(&g[3 * b + 1]), b2 = __ldg(&g[3 * b + 2]);
     return (m1 & b2) == 0 && (m2 & b1) == 0 && (m1 & w2) != 0 && (m2 & w1) != 0;
+}
+
+// Spatially sharded update (several GPUs): hi.w of a leaf carries `type | owner rank << 8`.  A rank reports a pair when it
+// owns both objects, or owns one of them and has the lower rank of the two owners (both owners see the pair: the other
+// object is a ghost there).  my_rank < 0: no filter.
+__device__ __forceinline__ bool shard_allow(int my_rank, uint32_t tq, uint32_t tj) {
+    if (my_rank < 0) return true;
+    uint32_t me = (uint32_t)my_rank, oq = tq >> 8, oj = tj >> 8;
+    if (oq != me && oj != me) return false;
+    if (oq == oj) return true;
+    return me < (oq == me ? oj : oq);
 }
 
 // Warp-aggregated append: one atomicAdd per converged group of emitting lanes.
@@ -348,7 +491,7 @@ __device__ __forceinline__ bool boxes_intersect(float4 alo, float4 ahi, float4 b
 __global__ void __launch_bounds__(128) k_pair_search(const float4* __restrict__ llo, const float4* __restrict__ lhi,
                                                      const float4* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ groups,
                                                      uint32_t q_begin, uint32_t q_end, uint2* __restrict__ pairs,
-                                                     uint8_t* __restrict__ keys, uint32_t cap, DevCounters* cnt) {
+                                                     uint8_t* __restrict__ keys, uint32_t cap, DevCounters* cnt, int my_rank) {
     uint32_t m = n - cnt->n_outliers;
     uint32_t i = q_begin + blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = i < m && i < q_end && m >= 2;
@@ -374,7 +517,7 @@ __global__ void __launch_bounds__(128) k_pair_search(const float4* __restrict__ 
                     buf[nb++] = j;
                 else {
                     uint32_t hj = __float_as_uint(__ldg(&llo[j].w)), tj = __float_as_uint(__ldg(&lhi[j].w));
-                    if (groups_allow(groups, hq, hj)) emit_pair(hq, tq, hj, tj, pairs, keys, cap, cnt);
+                    if (shard_allow(my_rank, tq, tj) && groups_allow(groups, hq, hj)) emit_pair(hq, tq, hj, tj, pairs, keys, cap, cnt);
                 }
                 goL = false;
             }
@@ -384,7 +527,7 @@ __global__ void __launch_bounds__(128) k_pair_search(const float4* __restrict__ 
                     buf[nb++] = j;
                 else {
                     uint32_t hj = __float_as_uint(__ldg(&llo[j].w)), tj = __float_as_uint(__ldg(&lhi[j].w));
-                    if (groups_allow(groups, hq, hj)) emit_pair(hq, tq, hj, tj, pairs, keys, cap, cnt);
+                    if (shard_allow(my_rank, tq, tj) && groups_allow(groups, hq, hj)) emit_pair(hq, tq, hj, tj, pairs, keys, cap, cnt);
                 }
                 goR = false;
             }
@@ -408,7 +551,7 @@ __global__ void __launch_bounds__(128) k_pair_search(const float4* __restrict__ 
         if (k < nb) {
             uint32_t j = buf[k];
             uint32_t hj = __float_as_uint(__ldg(&llo[j].w)), tj = __float_as_uint(__ldg(&lhi[j].w));
-            if (groups_allow(groups, hq, hj)) {
+            if (shard_allow(my_rank, tq, tj) && groups_allow(groups, hq, hj)) {
                 hjs[na] = hj;
                 tjs[na] = (uint8_t)tj;
                 na++;
@@ -446,7 +589,7 @@ __global__ void __launch_bounds__(128) k_pair_search(const float4* __restrict__ 
 __global__ void __launch_bounds__(256) k_pair_outliers(const float4* __restrict__ llo, const float4* __restrict__ lhi, uint32_t n,
                                                        const uint32_t* __restrict__ groups, uint32_t q_begin, uint32_t q_end,
                                                        uint2* __restrict__ pairs, uint8_t* __restrict__ keys, uint32_t cap,
-                                                       DevCounters* cnt) {
+                                                       DevCounters* cnt, int my_rank) {
     uint32_t nout = cnt->n_outliers;
     if (nout == 0) return;
     uint32_t m = n - nout;
@@ -458,21 +601,21 @@ __global__ void __launch_bounds__(256) k_pair_outliers(const float4* __restrict_
         float4 blo = __ldg(&llo[o]), bhi = __ldg(&lhi[o]);
         if (boxes_intersect(alo, ahi, blo, bhi)) {
             uint32_t hb = __float_as_uint(blo.w), tb = __float_as_uint(bhi.w);
-            if (groups_allow(groups, ha, hb)) emit_pair(ha, ta, hb, tb, pairs, keys, cap, cnt);
+            if (shard_allow(my_rank, ta, tb) && groups_allow(groups, ha, hb)) emit_pair(ha, ta, hb, tb, pairs, keys, cap, cnt);
         }
     }
 }
 
-cudaError_t launch_pair_search(ncb_ctx* c, uint32_t n, const uint32_t* groups, uint32_t q_begin, uint32_t q_end, uint32_t cap_pairs) {
+cudaError_t launch_pair_search(ncb_ctx* c, uint32_t n, const uint32_t* groups, uint32_t q_begin, uint32_t q_end, uint32_t cap_pairs, int my_rank) {
     if (n == 0) return cudaSuccess;
     cudaStream_t s = c->stream;
     q_end = min(q_end, n);
     if (q_end <= q_begin) return cudaSuccess;
     uint32_t nq = q_end - q_begin;
     k_pair_search<<<(nq + 127) / 128, 128, 0, s>>>(c->leaf_lo.p, c->leaf_hi.p, c->nodes.p, n, groups, q_begin, q_end, c->pairs_raw.p,
-                                                   c->keys_raw.p, cap_pairs, c->counters.p);
+                                                   c->keys_raw.p, cap_pairs, c->counters.p, my_rank);
     k_pair_outliers<<<(nq + 255) / 256, 256, 0, s>>>(c->leaf_lo.p, c->leaf_hi.p, n, groups, q_begin, q_end, c->pairs_raw.p,
-                                                     c->keys_raw.p, cap_pairs, c->counters.p);
+                                                     c->keys_raw.p, cap_pairs, c->counters.p, my_rank);
     return cudaGetLastError();
 }
 

@@ -81,6 +81,16 @@ struct PersistArgs {
     uint32_t* pm_overflow;
 };
 
+// Scratch of the spatial shard selection (broad.cu)
+#define SHARD_BINS 4096
+#define SHARD_MAX_RANKS 16
+struct ShardScratch {
+    uint32_t hist[SHARD_BINS];
+    uint32_t split[SHARD_MAX_RANKS + 1];
+    int region[6];  // ordered-int encoded union of the owned fat boxes
+    uint32_t m, n_owned;
+};
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -161,6 +171,11 @@ struct ncb_ctx {
     ncb::StageTimer timer;
     bool timer_external = false;  // stage 0 (AABBs) already started the timer of this update
     ncb::DevCounters* h_counters = nullptr;  // pinned
+    // spatial sharding (several GPUs)
+    ncb::DevBuf<ncb::ShardScratch> shard;
+    ncb::DevBuf<uint32_t> shard_bins, shard_sel;
+    ncb::DevBuf<float4> shard_lo, shard_hi;
+    uint32_t shard_m = 0, shard_owned = 0;
 };
 
 // api.cu helpers shared with sim.cu
@@ -196,7 +211,9 @@ inline void timer_mark(ncb_ctx* c, const char* name, uint32_t launches) {
 cudaError_t launch_aabbs(ncb_ctx* c, const DevObjects& o, float margin, int fat, uint32_t begin, uint32_t end);
 // handle_map (optional): leaf ids reported in pairs are handle_map[index] instead of the index into aabb_lo / aabb_hi
 cudaError_t launch_lbvh_build(ncb_ctx* c, uint32_t n, const uint32_t* handle_map);
-cudaError_t launch_pair_search(ncb_ctx* c, uint32_t n, const uint32_t* groups, uint32_t q_begin, uint32_t q_end, uint32_t cap_pairs);
+cudaError_t launch_pair_search(ncb_ctx* c, uint32_t n, const uint32_t* groups, uint32_t q_begin, uint32_t q_end, uint32_t cap_pairs, int my_rank = -1);
+cudaError_t launch_shard_select(ncb_ctx* c, uint32_t n, int rank, int world, ShardScratch* sh, uint32_t* bins, uint32_t cap, uint32_t* sel,
+                                float4* loc_lo, float4* loc_hi);
 cudaError_t launch_pair_sort(ncb_ctx* c, uint32_t cap_pairs, uint32_t* index_out);
 size_t lbvh_temp_bytes(uint32_t n);
 // narrow.cu

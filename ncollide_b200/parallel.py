@@ -1,6 +1,7 @@
 """Multi-GPU plumbing for the world update: one process per GPU, objects
-block-partitioned, fat AABBs all-gathered (NCCL on GPU; gloo in the CPU tests), LBVH replicated, broad-phase QUERY
-leaves and the narrow phase of the resulting pairs split per rank.  torch.distributed is plumbing only."""
+block-partitioned for the AABB computation, fat AABBs all-gathered (NCCL on GPU; gloo in the CPU tests), then every rank
+selects the objects it owns spatially (equal-count Morton ranges) plus the ghosts around them, builds its own LBVH over
+those and runs the pair search + narrow phase of its share of the pairs.  torch.distributed is plumbing only."""
 from __future__ import annotations
 
 import ctypes as C
@@ -45,8 +46,13 @@ class ShardedWorld:
     per step each rank computes the AABBs of its block, all-gathers them, builds the replicated LBVH and processes
     its slice of the Morton order."""
 
-    def __init__(self, ctx, scene, world, rank, device):
+    def __init__(self, ctx, scene, world, rank, device, spatial=None):
+        import os
+
         self.ctx, self.scene, self.world, self.rank, self.device = ctx, scene, world, rank, device
+        # spatial = True: ownership by Morton range + ghosts, local LBVH (ncb_world_update_sharded);
+        # spatial = False: replicated LBVH, query slices of the Morton order (the first design; NCB_SHARD=slices)
+        self.spatial = (os.environ.get("NCB_SHARD", "spatial") != "slices") if spatial is None else spatial
         self.n = scene.n
         self.obj_begin, self.obj_end = shard_range(self.n, world, rank)
         self.q_begin, self.q_end = shard_range(self.n, world, rank)
@@ -83,5 +89,8 @@ class ShardedWorld:
         if self.world > 1:
             for t in self.aabb_tensors():
                 all_gather_rows(t, self.obj_begin, self.obj_end, self.world)
-        self.ctx.check(lib.ncb_world_update_stage(h, 1, m, C.c_uint32(self.q_begin), C.c_uint32(self.q_end), C.byref(counts_c)), "stage 1")
+        if self.spatial and self.world > 1:
+            self.ctx.check(lib.ncb_world_update_sharded(h, m, C.c_int(self.rank), C.c_int(self.world), C.byref(counts_c)), "sharded stage 1")
+        else:
+            self.ctx.check(lib.ncb_world_update_stage(h, 1, m, C.c_uint32(self.q_begin), C.c_uint32(self.q_end), C.byref(counts_c)), "stage 1")
         return self.ctx._counts(counts_c)

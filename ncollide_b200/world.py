@@ -151,6 +151,13 @@ class Context:
         )
         return self._counts(c)
 
+    def world_update_sharded(self, margin, rank, world):
+        """AABBs of all objects (stage 0) + ``ncb_world_update_sharded``: the share of rank `rank` of `world`."""
+        self.check(self.lib.ncb_world_update_stage(self.h, 0, C.c_float(margin), C.c_uint32(0), C.c_uint32(0xFFFFFFFF), None), "stage 0")
+        c = _ffi.UpdateCountsC()
+        self.check(self.lib.ncb_world_update_sharded(self.h, C.c_float(margin), C.c_int(rank), C.c_int(world), C.byref(c)), "ncb_world_update_sharded")
+        return self._counts(c)
+
     def world_fetch(self, counts):
         P, Cn = counts["n_pairs"], counts["n_contacts"]
         pairs = np.zeros((P, 2), dtype=np.uint32)

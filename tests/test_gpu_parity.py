@@ -364,6 +364,32 @@ def test_query_slices_partition_the_pair_set(ctx, oracle):
             assert np.array_equal(a[name], b[name])
 
 
+@pytest.mark.parametrize("world,mk", [(2, lambda: config_scene(3, 7001)), (4, lambda: config_scene(2, 9000)), (8, lambda: config_scene(5, 30000)),
+                                      (3, lambda: make_world_scene(5000, 91, (1, 1, 1), side=4.0, n_hulls=16, name="tiny_dense"))])
+def test_spatial_shards_partition_the_pair_set(ctx, world, mk):
+    """Multi-GPU spatial sharding on one device: rank r of `world` selects owned + ghost objects, builds its own LBVH and
+    reports its share; the union over the ranks is the full pair set, no pair twice, manifolds identical."""
+    s = mk()
+    ctx.set_scene(s)
+    full = ctx.world_fetch(ctx.world_update_device(s.margin))
+    per_pair, total, owned = {}, 0, []
+    for rank in range(world):
+        r = ctx.world_fetch(ctx.world_update_sharded(s.margin, rank, world))
+        assert np.all(r.pairs[:, 0] > r.pairs[:, 1])
+        total += len(r.pairs)
+        for i, p in enumerate(map(tuple, r.pairs.tolist())):
+            assert p not in per_pair, "pair reported by two ranks"
+            per_pair[p] = r.contacts_of(i)[["world1", "world2", "normal", "depth", "f1", "f2"]].copy()
+    assert total == len(full.pairs), "a pair was reported by two ranks or by none"
+    assert np.array_equal(canon(np.array(list(per_pair), dtype=np.uint32)), canon(full.pairs))
+    for i, p in enumerate(map(tuple, full.pairs.tolist())):
+        a = full.contacts_of(i)[["world1", "world2", "normal", "depth", "f1", "f2"]]
+        b = per_pair[p]
+        assert len(a) == len(b)
+        for name in ("world1", "world2", "normal", "depth", "f1", "f2"):
+            assert np.array_equal(a[name], b[name])
+
+
 def test_golden_fixtures_on_device(ctx):
     """tests/golden/*.npz (oracle outputs, see make_golden.py) reproduced by the device."""
     import glob
