@@ -294,7 +294,7 @@ cudaError_t launch_lbvh_build(ncb_ctx* c, uint32_t n, const uint32_t* handle_map
 
 // ------------------------------------------------------------------------------------------------------------
 // Spatial sharding over several GPUs (after the all-gather of the fat AABBs every rank holds all N boxes):
-// a rank OWNS the objects whose Morton code falls in its range of 4096 top-bit bins (ranges hold equal object counts)
+// a rank OWNS the objects whose Morton code falls in its range of SHARD_BINS top-bit bins (ranges hold equal object counts)
 // and takes as GHOSTS the other objects whose box meets the union box of its owned objects; its LBVH and pair search
 // then run on owned + ghost objects only (about N / ranks + a surface layer) instead of all N.
 // ------------------------------------------------------------------------------------------------------------
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256) k_shard_hist(const float4* __restrict__ l
     __syncthreads();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t key = morton_of(__ldg(&lo[i]), __ldg(&hi[i]), cnt);
-        uint32_t bin = key >= 0x40000000u ? SHARD_BINS : (key >> 18);
+        uint32_t bin = key >= 0x40000000u ? SHARD_BINS : (key >> 20);  // top 10 of the 30 code bits
         bins[i] = bin;
         if (bin < SHARD_BINS) atomicAdd(&h[bin], 1u);
     }
@@ -361,11 +361,20 @@ __global__ void __launch_bounds__(256) k_shard_region(const float4* __restrict__
             mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], off));
             mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], off));
         }
-    if ((threadIdx.x & 31) == 0)
-        for (int k = 0; k < 3; ++k) {
-            atomicMin(&sh->region[k], f2o(mn[k]));
-            atomicMax(&sh->region[3 + k], f2o(mx[k]));
-        }
+    __shared__ float s_mn[8][3], s_mx[8][3];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int k = 0; k < 3; ++k) s_mn[warp][k] = mn[k], s_mx[warp][k] = mx[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            for (int k = 0; k < 3; ++k) mn[k] = fminf(mn[k], s_mn[w][k]), mx[k] = fmaxf(mx[k], s_mx[w][k]);
+        if (mn[0] <= mx[0])
+            for (int k = 0; k < 3; ++k) {
+                atomicMin(&sh->region[k], f2o(mn[k]));
+                atomicMax(&sh->region[3 + k], f2o(mx[k]));
+            }
+    }
 }
 __global__ void __launch_bounds__(256) k_shard_select(const float4* __restrict__ lo, const float4* __restrict__ hi, const uint32_t* __restrict__ bins,
                                                       uint32_t n, ShardScratch* sh, int rank, int world, uint32_t cap, uint32_t* __restrict__ sel,
@@ -387,17 +396,27 @@ __global__ void __launch_bounds__(256) k_shard_select(const float4* __restrict__
             take = a.x <= rh[0] && a.y <= rh[1] && a.z <= rh[2] && b.x >= rl[0] && b.y >= rl[1] && b.z >= rl[2];
         }
     }
+    // one allocation per CTA: warp counts -> shared prefix -> a single atomicAdd
+    __shared__ uint32_t s_cnt[8], s_own[8], s_base;
     unsigned mask = __ballot_sync(0xffffffffu, take);
-    if (mask == 0) return;
-    int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane == leader) {
-        base = atomicAdd(&sh->m, (uint32_t)__popc(mask));
+    unsigned own = __ballot_sync(0xffffffffu, take && owner == rank);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) s_cnt[warp] = __popc(mask), s_own[warp] = __popc(own);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0, town = 0;
+        for (int w = 0; w < 8; ++w) {
+            uint32_t c = s_cnt[w];
+            s_cnt[w] = tot;
+            tot += c;
+            town += s_own[w];
+        }
+        s_base = tot ? atomicAdd(&sh->m, tot) : 0;
+        if (town) atomicAdd(&sh->n_owned, town);
     }
-    base = __shfl_sync(0xffffffffu, base, leader);
+    __syncthreads();
     if (!take) return;
-    if (owner == rank) atomicAdd(&sh->n_owned, 1u);
-    uint32_t k = base + __popc(mask & ((1u << lane) - 1));
+    uint32_t k = s_base + s_cnt[warp] + __popc(mask & ((1u << lane) - 1));
     if (k >= cap) return;
     sel[k] = i;
     loc_lo[k] = a;
@@ -417,7 +436,7 @@ cudaError_t launch_shard_select(ncb_ctx* c, uint32_t n, int rank, int world, Sha
     cudaError_t e = cudaMemcpyAsync(sh, &z, sizeof z, cudaMemcpyHostToDevice, s);  // pageable source: copied before the call returns
     if (e != cudaSuccess) return e;
     k_bounds<<<min((uint32_t)gs, nb), 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, n, c->counters.p);
-    k_shard_hist<<<min((uint32_t)gs, nb), 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, n, c->counters.p, bins, sh);
+    k_shard_hist<<<min((uint32_t)c->sm_count * 2, nb), 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, n, c->counters.p, bins, sh);
     k_shard_split<<<1, 32, 0, s>>>(sh, world);
     k_shard_region<<<min((uint32_t)gs, nb), 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, bins, n, sh, rank);
     k_shard_select<<<nb, 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, bins, n, sh, rank, world, cap, sel, loc_lo, loc_hi);

@@ -82,7 +82,7 @@ struct PersistArgs {
 };
 
 // Scratch of the spatial shard selection (broad.cu)
-#define SHARD_BINS 4096
+#define SHARD_BINS 1024
 #define SHARD_MAX_RANKS 16
 struct ShardScratch {
     uint32_t hist[SHARD_BINS];
