@@ -150,6 +150,92 @@ static inline GJKResult gjk_closest_points(const Iso& m1, const Support& g1, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// gjk::cast_ray -> minkowski_ray_cast (query/algorithms/gjk.rs:180-365) with g2 = ConstantOrigin, m2 = identity.
+// Returns true + (toi, normal) on a hit.  The simplex must have been reset by the caller (ray_support_map.rs:28-29).
+// ------------------------------------------------------------------------------------------------
+static inline bool ray_toi_with_plane(V3 center, V3 normal, V3 origin, V3 dir, real* t_out) {  // ray_plane.rs:9-42
+    V3 dpos = center - origin;
+    real denom = dot(normal, dir);
+    if (relative_eq(denom, real(0))) return false;
+    real t = dot(normal, dpos) / denom;
+    if (t >= real(0)) {
+        *t_out = t;
+        return true;
+    }
+    return false;
+}
+static inline bool minkowski_ray_cast(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, V3 ray_origin, V3 ray_dir, real max_toi,
+                                      VoronoiSimplex& simplex, real* toi_out, V3* normal_out) {
+    const real _eps_tol = EPS * real(10);
+    const real _eps_rel = std::sqrt(_eps_tol);
+    real ray_length = norm(ray_dir);
+    if (relative_eq(ray_length, real(0))) return false;
+    real ltoi = 0;
+    V3 curr_origin = ray_origin, curr_dir = ray_dir / ray_length;
+    V3 dir0 = -curr_dir;
+    V3 ldir = dir0;
+    CSOPoint sp0 = cso_from_shapes(m1, g1, m2, g2, dir0);
+    sp0.point = sp0.point + (-curr_origin);
+    simplex.reset(sp0);
+    V3 proj = simplex.project_origin_and_reduce();
+    real max_bound = FMAX;
+    V3 dir;
+    int niter = 0;
+    bool last_chance = false;
+    for (;;) {
+        real old_max_bound = max_bound;
+        real dist;
+        if (unit_try_new_and_get(-proj, _eps_tol, &dir, &dist))
+            max_bound = dist;
+        else {
+            *toi_out = ltoi / ray_length, *normal_out = ldir;
+            return true;
+        }
+        CSOPoint support_point;
+        if (max_bound >= old_max_bound) {
+            last_chance = true;
+            V3 p = proj + curr_origin;  // CSOPoint::single_point
+            support_point = CSOPoint{p, p, v3(0, 0, 0)};
+        } else {
+            support_point = cso_from_shapes(m1, g1, m2, g2, dir);
+        }
+        if (last_chance && ltoi > real(0)) {
+            *toi_out = ltoi / ray_length, *normal_out = ldir;
+            return true;
+        }
+        real t;
+        if (ray_toi_with_plane(support_point.point, dir, curr_origin, curr_dir, &t)) {
+            if (dot(dir, curr_dir) < real(0) && t > real(0)) {
+                ldir = dir;
+                ltoi += t;
+                if (ltoi / ray_length > max_toi) return false;
+                V3 shift = curr_dir * t;
+                curr_origin = curr_origin + shift;
+                max_bound = FMAX;
+                for (int i = 0; i < simplex.dim + 1; ++i) simplex.vertices[i].point = simplex.vertices[i].point + (-shift);
+                last_chance = false;
+            }
+        } else if (dot(dir, curr_dir) > _eps_tol) {
+            return false;
+        }
+        if (last_chance) return false;
+        real min_bound = -dot(dir, support_point.point - curr_origin);
+        if (max_bound - min_bound <= _eps_rel * max_bound) return false;  // feature improved_fixed_point_support is off
+        CSOPoint tp = support_point;
+        tp.point = tp.point + (-curr_origin);
+        (void)simplex.add_point(tp, _eps_tol);
+        proj = simplex.project_origin_and_reduce();
+        if (simplex.dim == 3) {
+            if (min_bound >= _eps_tol) return false;
+            *toi_out = ltoi / ray_length, *normal_out = ldir;
+            return true;
+        }
+        niter += 1;
+        if (niter == 10000) return false;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // EPA (epa3.rs)
 // ------------------------------------------------------------------------------------------------
 struct EpaFaceId {

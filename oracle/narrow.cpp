@@ -12,6 +12,7 @@
 //   query/closest_points/closest_points_segment_segment.rs:62-141,
 //   query/contact/contact_manifold.rs:165-236 (distance-based tracking, 0.02),
 //   pipeline/narrow_phase/narrow_phase.rs:56-104,168-197, pipeline/object/query_type.rs:39-51.
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <vector>
@@ -1197,5 +1198,214 @@ uint64_t orc_sim_events(const orc_sim* s, uint32_t* out, uint64_t cap) {
     return n;
 }
 uint64_t orc_sim_bp_num_interferences(const orc_sim* s) { return orc_bp_num_interferences(s->bp); }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// World ray queries (pipeline/glue/query.rs:13-77,183-224): broad-phase candidates (interferences_with_ray on the stored
+// boxes) -> collision-groups test against the query's groups -> shape.toi_and_normal_with_ray(position, ray, max_toi, true).
+// Shape ray casts: query/ray/ray_ball.rs:77-142, ray_cuboid.rs + ray_aabb.rs:52-75,183-300, ray_plane.rs:44-79,
+// ray_support_map.rs:15-35,139-160 + gjk.rs:180-365 (ConvexHull).  solid = true only (what the world queries use).
+// ---------------------------------------------------------------------------------------------
+namespace orc {
+struct RayHit {
+    bool hit = false;
+    real toi = 0;
+    V3 normal{0, 0, 0};
+    uint32_t feature = FID_UNKNOWN;
+};
+static RayHit ray_cast_ball(V3 center, real radius, V3 o, V3 d, real max_toi) {
+    RayHit h;
+    V3 dcenter = o - center;
+    real a = norm_squared(d), b = dot(dcenter, d), c = norm_squared(dcenter) - radius * radius;
+    bool inside = false, some = false;
+    real t = 0;
+    if (a == real(0)) {
+        if (c > real(0)) return h;
+        inside = true, some = true, t = 0;
+    } else if (c > real(0) && b > real(0)) {
+        return h;
+    } else {
+        real delta = b * b - a * c;
+        if (delta < real(0)) return h;
+        t = (-b - std::sqrt(delta)) / a;
+        if (t <= real(0)) {
+            inside = true, t = 0;  // solid
+        }
+        some = true;
+    }
+    if (!some || !(t <= max_toi)) return h;
+    V3 pos = o + d * t - center;
+    V3 normal = normalize(pos);
+    h.hit = true, h.toi = t, h.normal = inside ? -normal : normal, h.feature = FACE0;
+    return h;
+}
+static RayHit ray_cast_cuboid(V3 he, const Iso& m, V3 o_w, V3 d_w, real max_toi) {
+    RayHit h;
+    V3 o = iso_inv_point(m, o_w), d = iso_inv_vec(m, d_w);
+    const real oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z}, mn[3] = {-he.x, -he.y, -he.z}, mx[3] = {he.x, he.y, he.z};
+    // clip_line (ray_aabb.rs:183-279)
+    real tmax = FMAX, tmin = -FMAX;
+    int near_side = 0, far_side = 0;
+    bool near_diag = false, far_diag = false;
+    for (int i = 0; i < 3; ++i) {
+        if (dd[i] == real(0)) {
+            if (oo[i] < mn[i] || oo[i] > mx[i]) return h;
+        } else {
+            real denom = real(1) / dd[i];
+            real near = (mn[i] - oo[i]) * denom, far = (mx[i] - oo[i]) * denom;
+            bool flip = false;
+            if (near > far) {
+                flip = true;
+                std::swap(near, far);
+            }
+            if (near > tmin) {
+                tmin = near;
+                near_side = flip ? -(i + 1) : (i + 1);
+                near_diag = false;
+            } else if (near == tmin) {
+                near_diag = true;
+            }
+            if (far < tmax) {
+                tmax = far;
+                far_side = !flip ? -(i + 1) : (i + 1);
+                far_diag = false;
+            } else if (far == tmax) {
+                far_diag = true;
+            }
+            if (tmax < real(0) || tmin > tmax) return h;
+        }
+    }
+    V3 near_n{0, 0, 0};
+    if (near_diag)
+        near_n = -normalize(d);
+    else if (near_side != 0) {
+        real* c = &near_n.x;
+        if (near_side < 0)
+            c[-near_side - 1] = real(1);
+        else
+            c[near_side - 1] = -real(1);
+    }
+    // ray_aabb (:282-300), solid = true
+    real t;
+    V3 n;
+    int side;
+    if (tmin < real(0)) {
+        t = 0, n = v3(0, 0, 0), side = far_side;
+    } else if (tmin <= max_toi) {
+        t = tmin, n = near_n, side = near_side;
+    } else {
+        return h;
+    }
+    h.hit = true, h.toi = t, h.normal = iso_mul_vec(m, n);
+    h.feature = (F_FACE << 30) | (uint32_t)(side < 0 ? (-side - 1 + 3) : (side - 1));
+    return h;
+}
+static RayHit ray_cast_plane(V3 pn, const Iso& m, V3 o_w, V3 d_w, real max_toi) {
+    RayHit h;
+    V3 o = iso_inv_point(m, o_w), d = iso_inv_vec(m, d_w);
+    V3 dpos = -o;
+    real dot_normal_dpos = dot(pn, dpos);
+    if (dot_normal_dpos > real(0)) {  // solid: inside the half-space
+        h.hit = true, h.toi = 0, h.normal = v3(0, 0, 0), h.feature = FACE0;
+        return h;
+    }
+    real t = dot_normal_dpos / dot(pn, d);
+    if (t >= real(0) && t <= max_toi) {
+        V3 n = dot_normal_dpos > real(0) ? -pn : pn;
+        h.hit = true, h.toi = t, h.normal = iso_mul_vec(m, n), h.feature = FACE0;
+    }
+    return h;
+}
+static RayHit ray_cast_hull(const Hull& H, const Iso& m, V3 o_w, V3 d_w, real max_toi) {
+    RayHit h;
+    V3 o = iso_inv_point(m, o_w), d = iso_inv_vec(m, d_w);
+    Support g;
+    g.kind = Support::S_HULL;
+    g.hull = H;
+    Support origin;
+    origin.kind = Support::S_ORIGIN;
+    Iso id = iso_identity();
+    VoronoiSimplex simplex;
+    V3 supp = g.support_point(id, -d);
+    V3 p = supp - o;
+    simplex.reset(CSOPoint{p, p, v3(0, 0, 0)});  // overwritten by minkowski_ray_cast's own reset, like the reference
+    real toi;
+    V3 normal;
+    if (!minkowski_ray_cast(id, g, id, origin, o, d, max_toi, simplex, &toi, &normal)) return h;
+    h.hit = true, h.toi = toi, h.normal = iso_mul_vec(m, normal), h.feature = FID_UNKNOWN;
+    return h;
+}
+static RayHit shape_ray_cast(const Objects& o, uint32_t i, V3 ro, V3 rd, real max_toi) {
+    Shape s = get_shape(o, i);
+    Iso m = o.iso(i);
+    switch (s.type) {
+        case BALL: return ray_cast_ball(m.t, s.radius, ro, rd, max_toi);
+        case CUBOID: return ray_cast_cuboid(s.he, m, ro, rd, max_toi);
+        case HULL: return ray_cast_hull(s.hull, m, ro, rd, max_toi);
+        default: return ray_cast_plane(s.he, m, ro, rd, max_toi);
+    }
+}
+}  // namespace orc
+
+extern "C" {
+
+// One shape ray cast (RayCast::toi_and_normal_with_ray, solid = true) against object i; out = toi, normal xyz.
+int orc_shape_ray_cast(const orc_objects* objs, uint32_t i, const real* origin, const real* dir, real max_toi, real* out, uint32_t* feature) {
+    Objects o = make_objects(objs);
+    RayHit h = shape_ray_cast(o, i, v3(origin[0], origin[1], origin[2]), v3(dir[0], dir[1], dir[2]), max_toi);
+    if (!h.hit) return 0;
+    out[0] = h.toi, out[1] = h.normal.x, out[2] = h.normal.y, out[3] = h.normal.z;
+    *feature = h.feature;
+    return 1;
+}
+
+// glue::interferences_with_ray (first_only = 0: every hit, rows sorted by (ray, handle)) / first_interference_with_ray
+// (first_only = 1: smallest toi, ties -> smallest handle).  rays: 7 reals (origin, dir, max_toi); groups: the query's
+// CollisionGroups (3 words) or NULL.  Rows: idx[2k] = (ray, handle), val[4k] = (toi, normal), feat[k].  Returns the row count.
+uint64_t orc_sim_ray_cast(orc_sim* s, uint64_t n_rays, const real* rays, const uint32_t* groups, int first_only, uint32_t* idx, real* val,
+                          uint32_t* feat, uint64_t cap) {
+    const Objects& o = s->o;
+    uint64_t rows = 0;
+    std::vector<uint32_t> cand(o.n + 1);
+    for (uint64_t r = 0; r < n_rays; ++r) {
+        const real* q = rays + 7 * r;
+        uint64_t nc = orc_bp_query(s->bp, 1, q, cand.data(), cand.size());
+        std::sort(cand.begin(), cand.begin() + nc);
+        V3 ro = v3(q[0], q[1], q[2]), rd = v3(q[3], q[4], q[5]);
+        bool have = false;
+        RayHit best;
+        uint32_t best_h = 0;
+        for (uint64_t k = 0; k < nc; ++k) {
+            uint32_t h = cand[k];
+            if (groups && o.groups) {
+                uint32_t m1 = o.groups[3 * h], w1 = o.groups[3 * h + 1], b1 = o.groups[3 * h + 2];
+                uint32_t m2 = groups[0], w2 = groups[1], b2 = groups[2];
+                if (!((m1 & b2) == 0 && (m2 & b1) == 0 && (m1 & w2) != 0 && (m2 & w1) != 0)) continue;
+            }
+            RayHit hit = shape_ray_cast(o, h, ro, rd, q[6]);
+            if (!hit.hit) continue;
+            if (first_only) {
+                if (!have || hit.toi < best.toi) best = hit, best_h = h, have = true;
+            } else {
+                if (rows < cap) {
+                    idx[2 * rows] = (uint32_t)r, idx[2 * rows + 1] = h;
+                    val[4 * rows] = hit.toi, val[4 * rows + 1] = hit.normal.x, val[4 * rows + 2] = hit.normal.y, val[4 * rows + 3] = hit.normal.z;
+                    feat[rows] = hit.feature;
+                }
+                rows++;
+            }
+        }
+        if (first_only && have) {
+            if (rows < cap) {
+                idx[2 * rows] = (uint32_t)r, idx[2 * rows + 1] = best_h;
+                val[4 * rows] = best.toi, val[4 * rows + 1] = best.normal.x, val[4 * rows + 2] = best.normal.y, val[4 * rows + 3] = best.normal.z;
+                feat[rows] = best.feature;
+            }
+            rows++;
+        }
+    }
+    return rows;
+}
 
 }  // extern "C"

@@ -163,6 +163,17 @@ class Oracle:
     def sim(self, scene):
         return OracleSim(self, scene)
 
+    def shape_ray_cast(self, scene, i, origin, direction, max_toi):
+        """RayCast::toi_and_normal_with_ray(position_i, ray, max_toi, solid = true) -> (toi, normal, feature) or None."""
+        o, keep = self._objects(scene)
+        ro = np.ascontiguousarray(origin, dtype=self.dtype)
+        rd = np.ascontiguousarray(direction, dtype=self.dtype)
+        out = np.zeros(4, dtype=self.dtype)
+        feat = C.c_uint32()
+        r = self.lib.orc_shape_ray_cast(C.byref(o), C.c_uint32(i), C.c_void_p(ro.ctypes.data), C.c_void_p(rd.ctypes.data), self.creal(max_toi),
+                                        C.c_void_p(out.ctypes.data), C.byref(feat))
+        return (out[0], out[1:4].copy(), feat.value) if r else None
+
     def aabb_toi_with_ray(self, minmax, origin, direction, max_toi, solid):
         mm = np.ascontiguousarray(minmax, dtype=self.dtype)
         o = np.ascontiguousarray(origin, dtype=self.dtype)
@@ -208,6 +219,26 @@ class OracleSim:
         L.orc_sim_events(self.h, C.c_void_p(ev.ctypes.data), C.c_uint64(ne))
         return {"pairs": pairs, "algo": algo, "off": off, "contacts": contacts[:Cn], "ids": ids[:Cn], "events": ev[:ne],
                 "bp_pairs": int(L.orc_sim_bp_num_interferences(self.h))}
+
+    def ray_cast(self, origins, dirs, max_toi, groups=None, first_only=False):
+        """glue::interferences_with_ray / first_interference_with_ray.  Returns (idx[K,2] (ray, handle), toi[K], normal[K,3], feature[K])."""
+        o = np.ascontiguousarray(origins, dtype=self.o.dtype).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, dtype=self.o.dtype).reshape(-1, 3)
+        t = np.broadcast_to(np.asarray(max_toi, dtype=self.o.dtype).reshape(-1, 1), (len(o), 1))
+        rays = np.ascontiguousarray(np.concatenate([o, d, t], axis=1))
+        g = None if groups is None else np.ascontiguousarray(groups, dtype=np.uint32)
+        self.o.lib.orc_sim_ray_cast.restype = C.c_uint64
+        cap = max(64 * len(o), 4096)
+        while True:
+            idx = np.zeros((cap, 2), dtype=np.uint32)
+            val = np.zeros((cap, 4), dtype=self.o.dtype)
+            feat = np.zeros(cap, dtype=np.uint32)
+            n = self.o.lib.orc_sim_ray_cast(self.h, C.c_uint64(len(o)), C.c_void_p(rays.ctypes.data), C.c_void_p(g.ctypes.data) if g is not None else None,
+                                            C.c_int(int(first_only)), C.c_void_p(idx.ctypes.data), C.c_void_p(val.ctypes.data),
+                                            C.c_void_p(feat.ctypes.data), C.c_uint64(cap))
+            if n <= cap:
+                return idx[:n], val[:n, 0].copy(), val[:n, 1:4].copy(), feat[:n]
+            cap = int(n)
 
     def __del__(self):
         try:
