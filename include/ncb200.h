@@ -248,6 +248,16 @@ int ncb_sim_sizes(ncb_sim* sim, uint32_t* n_pairs, uint32_t* n_contacts, uint32_
 int ncb_sim_fetch(ncb_sim* sim, uint32_t* pairs, uint8_t* algo, uint32_t* manifold_start, uint8_t* manifold_count, ncb_contact* contacts,
                   uint32_t* contact_ids, uint32_t* events);
 
+/* World ray queries: glue::interferences_with_ray (first_only = 0) / first_interference_with_ray
+ * (first_only = 1) (pipeline/glue/query.rs:13-77,183-224) against the state of the last ncb_sim_step.  rays[7 n] = origin,
+ * dir, max_toi; groups = the query's CollisionGroups (membership, whitelist, blacklist) or NULL.  Candidates come from the
+ * broad phase's stored boxes, each is tested with its shape's RayCast::toi_and_normal_with_ray(position, ray, max_toi,
+ * solid = true) (ball, cuboid, plane, convex hull through the GJK ray cast).  Rows sorted by (ray, handle): idx[2 k] =
+ * (ray, handle), val[4 k] = (toi, normal), feat[k] = feature id; first_only keeps the smallest toi per ray (ties: smallest
+ * handle).  cap in rows; *n_out = rows found; returns 1 when truncated. */
+int ncb_sim_ray_cast(ncb_sim* sim, uint32_t n_rays, const float* rays, const uint32_t* groups, int first_only, uint32_t* idx, float* val,
+                     uint32_t* feat, uint32_t cap, uint32_t* n_out);
+
 const char* ncb_version(void);
 
 #ifdef __cplusplus

@@ -47,3 +47,18 @@ struct ncb_bp {
 int bp_create_all_device(ncb_bp* bp, uint32_t n, const float4* lo, const float4* hi);
 int bp_set_moved_device(ncb_bp* bp, uint32_t n, const float4* lo, const float4* hi, const uint8_t* moved);
 int bp_update_impl(ncb_bp* bp, const uint32_t* d_groups, uint32_t* n_started, uint32_t* n_stopped);
+
+// world-level ray queries (query.cu)
+struct WorldQueryBufs {
+    DevBuf<float> rays;
+    DevBuf<unsigned long long> keys, keys_sorted;
+    DevBuf<float4> vals, out_val;
+    DevBuf<uint32_t> feats, counter, order_in, order_out, out_idx, out_feat;
+    DevBuf<uint8_t> cub_tmp;
+    void release() {
+        rays.release(), keys.release(), keys_sorted.release(), vals.release(), out_val.release(), feats.release(), counter.release();
+        order_in.release(), order_out.release(), out_idx.release(), out_feat.release(), cub_tmp.release();
+    }
+};
+int world_ray_cast(ncb_ctx* ctx, ncb_bp* bp, WorldQueryBufs& B, uint32_t n_rays, const float* rays, const uint32_t* groups, int first_only,
+                   uint32_t* idx, float* val, uint32_t* feat, uint32_t cap, uint32_t* n_out);

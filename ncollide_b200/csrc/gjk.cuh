@@ -128,7 +128,7 @@ NCB_HD V3 proj_segment(V3 a, V3 b, V3 p, Loc& loc) {
 }
 
 // solid = true variant only (the one the simplex and EPA use)
-__device__ __noinline__ V3 proj_triangle(V3 a, V3 b, V3 c, V3 p, Loc& loc) {
+static __device__ __noinline__ V3 proj_triangle(V3 a, V3 b, V3 c, V3 p, Loc& loc) {
     V3 ab = b - a, ac = c - a, ap = p - a;
     float ab_ap = dot(ab, ap), ac_ap = dot(ac, ap);
     if (ab_ap <= 0.f && ac_ap <= 0.f) {
@@ -212,7 +212,7 @@ NCB_HD bool tetra_face(int i, V3 a, V3 b, V3 c, V3 ap, V3 bp, V3 cp, V3 ab, V3 a
     }
     return false;
 }
-__device__ __noinline__ V3 proj_tetrahedron(V3 a, V3 b, V3 c, V3 d, V3 p, Loc& loc) {
+static __device__ __noinline__ V3 proj_tetrahedron(V3 a, V3 b, V3 c, V3 d, V3 p, Loc& loc) {
     V3 ab = b - a, ac = c - a, ad = d - a, ap = p - a;
     float ap_ab = dot(ap, ab), ap_ac = dot(ap, ac), ap_ad = dot(ap, ad);
     if (ap_ab <= 0.f && ap_ac <= 0.f && ap_ad <= 0.f) {
@@ -307,7 +307,7 @@ NCB_HD bool simplex_add_point(Simplex& s, const CSOPoint& pt) {
     s.v[s.dim] = pt;
     return true;
 }
-__device__ __noinline__ V3 simplex_project_origin_and_reduce(Simplex& s) {
+static __device__ __noinline__ V3 simplex_project_origin_and_reduce(Simplex& s) {
     const V3 O = v3(0.f, 0.f, 0.f);
     Loc loc;
     if (s.dim == 0) {
@@ -413,7 +413,7 @@ NCB_HD void gjk_result(const Simplex& s, bool prev, V3& p1, V3& p2) {
 enum { GJK_INTERSECTION = 0, GJK_CLOSEST_POINTS = 1, GJK_NO_INTERSECTION = 3 };
 
 // gjk::closest_points with exact_dist = true
-__device__ __noinline__ int gjk_closest_points(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, float max_dist,
+static __device__ __noinline__ int gjk_closest_points(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, float max_dist,
                                                Simplex& s, V3& p1, V3& p2, V3& out_dir) {
     const float eps_tol = NCB_EPS * 10.0f;
     const float eps_rel = sqrtf(eps_tol);
@@ -571,7 +571,7 @@ NCB_HD bool heap_pop(EpaState& e, EpaHeapItem& out) {
 }
 
 // Face::new (epa3.rs:93-114): normal + "projection of the origin lies inside the face".  false on overflow.
-__device__ __noinline__ bool epa_face_new(EpaState& e, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t a0, uint32_t a1, uint32_t a2,
+static __device__ __noinline__ bool epa_face_new(EpaState& e, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t a0, uint32_t a1, uint32_t a2,
                                           bool& proj_inside) {
     if (e.nfaces >= EPA_MAX_FACES) {
         e.overflow = true;
@@ -590,7 +590,7 @@ __device__ __noinline__ bool epa_face_new(EpaState& e, uint32_t p0, uint32_t p1,
     return true;
 }
 // Face::closest_points (epa3.rs:116-126) with the barycentric coordinates recomputed as Face::new computed them.
-__device__ __noinline__ void epa_face_closest_points(const EpaState& e, uint32_t f, V3& p1, V3& p2) {
+static __device__ __noinline__ void epa_face_closest_points(const EpaState& e, uint32_t f, V3& p1, V3& p2) {
     uint32_t i0 = f_pt(e, f, 0), i1 = f_pt(e, f, 1), i2 = f_pt(e, f, 2);
     Loc loc;
     proj_triangle(e.vpoint[i0], e.vpoint[i1], e.vpoint[i2], v3(0.f, 0.f, 0.f), loc);
@@ -617,7 +617,7 @@ NCB_HD bool epa_can_be_seen_by(const EpaState& e, uint32_t f, uint32_t point, ui
     return relative_eq(norm_squared(cross(p1p2, p1p3)), 0.f, eps_tol * eps_tol);
 }
 // compute_silhouette (epa3.rs:432-454): the recursion becomes a LIFO of (face, opp) visits in the same order.
-__device__ __noinline__ void epa_compute_silhouette3(EpaState& e, uint32_t point, uint32_t id0, uint32_t opp0, uint32_t id1, uint32_t opp1,
+static __device__ __noinline__ void epa_compute_silhouette3(EpaState& e, uint32_t point, uint32_t id0, uint32_t opp0, uint32_t id1, uint32_t opp1,
                                                      uint32_t id2, uint32_t opp2) {
     int sp = 0;
     e.stk_face[sp] = (uint8_t)id2, e.stk_opp[sp] = (uint8_t)opp2, sp++;
@@ -661,7 +661,7 @@ enum { EPA_CONTINUE = 0, EPA_DONE_OK = 1, EPA_DONE_FAIL = 2 };
     }
 
 // EPA::closest_points, part 1 (epa3.rs:219-328): initial polytope from the GJK simplex.
-__device__ __noinline__ int epa_init(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, int sdim,
+static __device__ __noinline__ int epa_init(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, int sdim,
                                      const CSOPoint* sv, V3& out1, V3& out2, V3& out_n) {
     e.nverts = e.nfaces = e.nheap = e.nsil = 0;
     e.niter = 0;
@@ -717,7 +717,7 @@ __device__ __noinline__ int epa_init(EpaState& e, const Iso& m1, const Support& 
 }
 
 // EPA::closest_points, part 2: ONE turn of `while let Some(face_id) = self.heap.pop()` (epa3.rs:330-425).
-__device__ __noinline__ int epa_step(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, V3& out1, V3& out2,
+static __device__ __noinline__ int epa_step(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, V3& out1, V3& out2,
                                      V3& out_n) {
     const float eps_tol = NCB_EPS * 100.0f;
     EpaHeapItem face_id;
@@ -807,7 +807,7 @@ __device__ __noinline__ int epa_step(EpaState& e, const Iso& m1, const Support& 
 #undef NCB_EPA_PUSH
 
 // EPA::closest_points (epa3.rs:219-430).  false = None (also on capacity overflow, flagged in e.overflow).
-__device__ __noinline__ bool epa_closest_points(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2,
+static __device__ __noinline__ bool epa_closest_points(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2,
                                                 int sdim, const CSOPoint* sv, V3& out1, V3& out2, V3& out_n) {
     int st = epa_init(e, m1, g1, m2, g2, sdim, sv, out1, out2, out_n);
     while (st == EPA_CONTINUE) st = epa_step(e, m1, g1, m2, g2, out1, out2, out_n);
@@ -816,7 +816,7 @@ __device__ __noinline__ bool epa_closest_points(EpaState& e, const Iso& m1, cons
 
 // contact_support_map_support_map_with_params (init_dir = None: fresh generator).
 // Returns GJK_CLOSEST_POINTS / GJK_NO_INTERSECTION.
-__device__ __noinline__ int contact_sm_sm(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2,
+static __device__ __noinline__ int contact_sm_sm(EpaState& e, const Iso& m1, const Support& g1, const Iso& m2, const Support& g2,
                                           float prediction, V3& p1, V3& p2, V3& dir_out, uint32_t* epa_overflow, uint32_t* ref_panics) {
     V3 dir;
     if (!unit_try_new(m2.t - m1.t, NCB_EPS, dir)) dir = v3(1.f, 0.f, 0.f);

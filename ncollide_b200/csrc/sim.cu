@@ -51,6 +51,7 @@ struct ncb_sim {
     DevBuf<uint8_t> exp_algo, exp_mcount;
     uint32_t n_pairs = 0, n_contacts = 0, n_events = 0, n_active = 0, pm_overflow = 0;
     ncb_update_counts last = {};
+    WorldQueryBufs qbufs;
 };
 
 #define CKS(call)                                                                                         \
@@ -288,6 +289,7 @@ void ncb_sim_destroy(ncb_sim* sim) {
     sim->free_slots.release(), sim->cnt.release(), sim->events.release(), sim->events_sorted.release(), sim->cub_tmp.release();
     sim->exp_count.release(), sim->exp_start.release(), sim->exp_ids.release(), sim->exp_events.release(), sim->exp_contacts.release();
     sim->exp_pairs.release(), sim->exp_algo.release(), sim->exp_mcount.release();
+    sim->qbufs.release();
     delete sim;
 }
 
@@ -506,6 +508,16 @@ int ncb_sim_fetch(ncb_sim* sim, uint32_t* pairs, uint8_t* algo, uint32_t* manifo
     }
     CKS(cudaStreamSynchronize(s));
     return NCB_OK;
+}
+
+// glue::interferences_with_ray (first_only = 0) / first_interference_with_ray (first_only = 1) (glue/query.rs:13-77,183-224)
+// against the boxes stored by the last ncb_sim_step: rays[7 * n] = origin, dir, max_toi; groups = the query's CollisionGroups
+// (membership, whitelist, blacklist) or NULL.  Rows sorted by (ray, handle): idx[2 k] = (ray, handle), val[4 k] = (toi,
+// normal), feat[k]; cap in rows; *n_out = rows found; returns 1 when truncated.  solid = true like the reference's queries.
+int ncb_sim_ray_cast(ncb_sim* sim, uint32_t n_rays, const float* rays, const uint32_t* groups, int first_only, uint32_t* idx, float* val,
+                     uint32_t* feat, uint32_t cap, uint32_t* n_out) {
+    if (!sim || (n_rays && !rays)) return NCB_ERR_ARG;
+    return world_ray_cast(sim->ctx, sim->bp, sim->qbufs, n_rays, rays, groups, first_only, idx, val, feat, cap, n_out);
 }
 
 }  // extern "C"

@@ -557,6 +557,26 @@ class SteppingWorld:
 
     step = update
 
+    def ray_cast(self, origins, dirs, max_toi, groups=None, first_only=False):
+        """``interferences_with_ray`` / ``first_interference_with_ray`` for a batch of rays (glue/query.rs:13-77,183-224).
+        Returns (idx[K,2] (ray, handle), toi[K], normal[K,3], feature[K]), rows sorted by (ray, handle)."""
+        o, d = as_f32(origins).reshape(-1, 3), as_f32(dirs).reshape(-1, 3)
+        t = np.broadcast_to(np.asarray(max_toi, dtype=np.float32).reshape(-1, 1), (len(o), 1))
+        rays = np.ascontiguousarray(np.concatenate([o, d, t], axis=1), dtype=np.float32)
+        g = None if groups is None else as_u32(groups).reshape(3)
+        cap = max(16 * len(o), 4096)
+        while True:
+            idx = np.zeros((cap, 2), dtype=np.uint32)
+            val = np.zeros((cap, 4), dtype=np.float32)
+            feat = np.zeros(cap, dtype=np.uint32)
+            n = C.c_uint32()
+            r = self.ctx.check(self.ctx.lib.ncb_sim_ray_cast(self._h, C.c_uint32(len(o)), ptr(rays), ptr(g), C.c_int(int(first_only)), ptr(idx), ptr(val),
+                                                             ptr(feat), C.c_uint32(cap), C.byref(n)), "ncb_sim_ray_cast")
+            if r == 0:
+                k = n.value
+                return idx[:k], val[:k, 0].copy(), val[:k, 1:4].copy(), feat[:k]
+            cap = n.value
+
 
 class TriMesh:
     """``TriMesh::new(points, indices, None)`` + batched ``RayCast::toi_and_normal_with_ray``."""

@@ -128,3 +128,48 @@ def test_world_ray_cast_oracle_consistency(oracle):
         assert tt == toi[m].min() and h == idx[m, 1][toi[m] == tt].min()
     assert set(idx1[:, 0].tolist()) == set(idx[:, 0].tolist())
     assert np.all(toi <= t[idx[:, 0]])
+
+
+# ---- device ----------------------------------------------------------------------------------------------------------
+RTOL, ATOL = 1e-4, 1e-5
+
+
+@pytest.mark.gpu
+def test_world_ray_kats_device():
+    from ncollide_b200.world import Context, SteppingWorld
+
+    ctx = Context(0)
+    world_kats(lambda s: SteppingWorld(ctx, s))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,kinds,side,plane,seed", [(1200, (1, 1, 1), 6.0, True, 41), (6000, (1, 1, 1), 12.0, False, 42), (3000, (0, 1, 1), 8.0, False, 43)])
+def test_world_ray_cast_matches_oracle(oracle, n, kinds, side, plane, seed):
+    from ncollide_b200.world import Context, SteppingWorld
+    from sim_scenario import step_poses
+
+    s = make_world_scene(n, seed, kinds, side=side, n_hulls=24, plane=plane, name="q")
+    rng = np.random.default_rng(seed)
+    s.groups[rng.random(n + (1 if plane else 0)) < 0.2] = (1 << 3, 0x3FFFFFFF, 0)  # a fifth of the objects in group 3 only
+    dev, orc = SteppingWorld(Context(0), s), oracle.sim(s)
+    dev.step(), orc.step()
+    pos, rot = s.pos.copy(), s.rot.copy()
+    for rnd in range(2):
+        if rnd == 1:  # queries see the boxes / poses of the latest update
+            idx = step_poses(s, pos, rot, rng, 0.5)
+            for w in (dev, orc):
+                w.set_positions(idx, pos[idx], rot[idx])
+                w.step()
+        o, d, t = random_rays(rng, 1500, side)
+        for groups in (None, [1 << 3, 1 << 3, 0], [1, 0x3FFFFFFF, 1 << 3]):
+            for first in (False, True):
+                a = dev.ray_cast(o, d, t, groups=groups, first_only=first)
+                b = orc.ray_cast(o, d, t, groups=groups, first_only=first)
+                if first:  # tie class: equal toi on two objects may pick either in the reference; both sides use the smallest handle
+                    assert np.array_equal(a[0], b[0])
+                else:
+                    assert np.array_equal(a[0], b[0]), f"hit sets differ ({len(a[0])} vs {len(b[0])})"
+                assert np.array_equal(a[3], b[3])
+                assert np.allclose(a[1], b[1], rtol=RTOL, atol=ATOL)
+                assert np.allclose(a[2], b[2], rtol=RTOL, atol=ATOL)
+        assert len(b[0]) > 100
