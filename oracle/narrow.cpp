@@ -1298,7 +1298,8 @@ static RayHit ray_cast_cuboid(V3 he, const Iso& m, V3 o_w, V3 d_w, real max_toi)
         return h;
     }
     h.hit = true, h.toi = t, h.normal = iso_mul_vec(m, n);
-    h.feature = (F_FACE << 30) | (uint32_t)(side < 0 ? (-side - 1 + 3) : (side - 1));
+    // side == 0 (zero direction, origin inside): Face(0usize - 1) wraps in a release build of the reference; ids are 30 bits here
+    h.feature = (F_FACE << 30) | ((uint32_t)(side < 0 ? (-side - 1 + 3) : (side - 1)) & 0x3fffffffu);
     return h;
 }
 static RayHit ray_cast_plane(V3 pn, const Iso& m, V3 o_w, V3 d_w, real max_toi) {

@@ -161,7 +161,8 @@ def test_world_ray_cast_matches_oracle(oracle, n, kinds, side, plane, seed):
                 w.set_positions(idx, pos[idx], rot[idx])
                 w.step()
         o, d, t = random_rays(rng, 1500, side)
-        for groups in (None, [1 << 3, 1 << 3, 0], [1, 0x3FFFFFFF, 1 << 3]):
+        sizes = []
+        for groups in (None, [1 << 4, 1 << 4, 0], [1, 0x3FFFFFFF, 1 << 3]):
             for first in (False, True):
                 a = dev.ray_cast(o, d, t, groups=groups, first_only=first)
                 b = orc.ray_cast(o, d, t, groups=groups, first_only=first)
@@ -172,4 +173,5 @@ def test_world_ray_cast_matches_oracle(oracle, n, kinds, side, plane, seed):
                 assert np.array_equal(a[3], b[3])
                 assert np.allclose(a[1], b[1], rtol=RTOL, atol=ATOL)
                 assert np.allclose(a[2], b[2], rtol=RTOL, atol=ATOL)
-        assert len(b[0]) > 100
+                sizes.append(len(b[0]))
+        assert sizes[0] > 1000 and 0 < sizes[2] < sizes[0] and sizes[4] == 0  # all / without the group-3-only objects / none
