@@ -258,6 +258,13 @@ int ncb_sim_fetch(ncb_sim* sim, uint32_t* pairs, uint8_t* algo, uint32_t* manifo
 int ncb_sim_ray_cast(ncb_sim* sim, uint32_t n_rays, const float* rays, const uint32_t* groups, int first_only, uint32_t* idx, float* val,
                      uint32_t* feat, uint32_t cap, uint32_t* n_out);
 
+/* glue::interferences_with_aabb (kind 0; 6 floats per query: mins, maxs) / interferences_with_point (kind 2; 3 floats)
+ * (pipeline/glue/query.rs:79-181): candidates from the stored boxes, the query's collision groups, and for points the shape's
+ * PointQuery::contains_point (ball, cuboid, plane, convex hull through gjk::project_origin).  idx[2 k] = (query, handle),
+ * sorted; cap in rows; returns 1 when truncated. */
+int ncb_sim_query(ncb_sim* sim, int kind, uint32_t n_queries, const float* queries, const uint32_t* groups, uint32_t* idx, uint32_t cap,
+                  uint32_t* n_out);
+
 const char* ncb_version(void);
 
 #ifdef __cplusplus

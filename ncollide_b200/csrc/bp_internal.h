@@ -62,3 +62,5 @@ struct WorldQueryBufs {
 };
 int world_ray_cast(ncb_ctx* ctx, ncb_bp* bp, WorldQueryBufs& B, uint32_t n_rays, const float* rays, const uint32_t* groups, int first_only,
                    uint32_t* idx, float* val, uint32_t* feat, uint32_t cap, uint32_t* n_out);
+int world_query(ncb_ctx* ctx, ncb_bp* bp, WorldQueryBufs& B, int kind, uint32_t n_q, const float* q, const uint32_t* groups, uint32_t* idx,
+                uint32_t cap, uint32_t* n_out);

@@ -346,6 +346,97 @@ __global__ void __launch_bounds__(128) k_world_ray_cast(QueryArgs A) {
     }
 }
 
+// ---- glue::interferences_with_point (KIND 2) / interferences_with_aabb (KIND 0) (glue/query.rs:79-181) ------------------
+template <int KIND>
+__device__ __forceinline__ bool box_test(const float* q, float4 lo, float4 hi) {
+    if (KIND == 0)  // AABB::intersects
+        return lo.x <= q[3] && lo.y <= q[4] && lo.z <= q[5] && hi.x >= q[0] && hi.y >= q[1] && hi.z >= q[2];
+    if (q[0] < lo.x || q[0] > hi.x) return false;  // AABB::contains_local_point
+    if (q[1] < lo.y || q[1] > hi.y) return false;
+    if (q[2] < lo.z || q[2] > hi.z) return false;
+    return true;
+}
+template <int KIND>
+__device__ __forceinline__ void visit_leaf_q(const QueryArgs& A, uint32_t qi, const float* q, uint32_t handle) {
+    if (A.d_attached[handle] != ST_ATTACHED) return;
+    if (A.use_groups && A.o.groups) {
+        uint32_t m1 = __ldg(&A.o.groups[3 * handle]), w1 = __ldg(&A.o.groups[3 * handle + 1]), b1 = __ldg(&A.o.groups[3 * handle + 2]);
+        if (!((m1 & A.qg[2]) == 0 && (A.qg[0] & b1) == 0 && (m1 & A.qg[1]) != 0 && (A.qg[0] & w1) != 0)) return;
+    }
+    if (KIND == 2) {  // PointQuery::contains_point of the shape
+        uint32_t type = __ldg(&A.o.type[handle]);
+        Shape sh = load_shape(A.o, A.H, handle, type);
+        Iso m = load_iso(A.o, handle);
+        V3 pt = v3(q[0], q[1], q[2]);
+        bool inside;
+        if (type == NCB_SHAPE_BALL) {
+            inside = norm_squared(iso_inv_point(m, pt)) <= sh.radius * sh.radius;
+        } else if (type == NCB_SHAPE_CUBOID) {
+            V3 l = iso_inv_point(m, pt);
+            inside = !(l.x < -sh.he.x || l.x > sh.he.x || l.y < -sh.he.y || l.y > sh.he.y || l.z < -sh.he.z || l.z > sh.he.z);
+        } else if (type == NCB_SHAPE_CONVEX_HULL) {
+            HullProjSetup u = hull_proj_setup(sh.hull, m, pt);
+            Simplex s;
+            V3 proj;
+            inside = hull_project_gjk(u, pt, s, proj) != GJK_CLOSEST_POINTS;
+        } else {
+            inside = dot(sh.he, iso_inv_point(m, pt)) <= 0.f;
+        }
+        if (!inside) return;
+    }
+    uint32_t k = atomicAdd(A.counter, 1u);
+    if (k < A.cap) A.keys[k] = ((unsigned long long)qi << 32) | handle;
+}
+template <int KIND>
+__global__ void __launch_bounds__(128) k_world_query(QueryArgs A) {
+    const int W = KIND == 0 ? 6 : 3;
+    uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= A.n_rays) return;
+    float q[6];
+    for (int k = 0; k < W; ++k) q[k] = A.rays[(size_t)W * qi + k];
+    uint32_t m = A.n - A.nout;
+    if (m >= 2) {
+        uint32_t stack[64];
+        int sp = 0;
+        uint32_t node = 0;
+        for (;;) {
+            const float4* rec = A.nodes + 4 * (size_t)node;
+            float4 Llo = __ldg(rec + 0), Lhi = __ldg(rec + 1), Rlo = __ldg(rec + 2), Rhi = __ldg(rec + 3);
+            uint32_t left = __float_as_uint(Llo.w), right = __float_as_uint(Lhi.w);
+            bool goL = box_test<KIND>(q, Llo, Lhi), goR = box_test<KIND>(q, Rlo, Rhi);
+            if (goL && (left & LEAF_BIT)) {
+                visit_leaf_q<KIND>(A, qi, q, __float_as_uint(__ldg(&A.llo[left & ~LEAF_BIT].w)));
+                goL = false;
+            }
+            if (goR && (right & LEAF_BIT)) {
+                visit_leaf_q<KIND>(A, qi, q, __float_as_uint(__ldg(&A.llo[right & ~LEAF_BIT].w)));
+                goR = false;
+            }
+            if (goL) {
+                if (goR && sp < 64) stack[sp++] = right;
+                node = left;
+            } else if (goR) {
+                node = right;
+            } else {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+        }
+    } else if (m == 1) {
+        float4 lo = __ldg(&A.llo[0]), hi = __ldg(&A.lhi[0]);
+        if (box_test<KIND>(q, lo, hi)) visit_leaf_q<KIND>(A, qi, q, __float_as_uint(lo.w));
+    }
+    for (uint32_t o = m; o < A.n; ++o) {
+        float4 lo = __ldg(&A.llo[o]), hi = __ldg(&A.lhi[o]);
+        if (box_test<KIND>(q, lo, hi)) visit_leaf_q<KIND>(A, qi, q, __float_as_uint(lo.w));
+    }
+}
+__global__ void k_unpack_keys(const unsigned long long* __restrict__ keys, uint32_t n, uint32_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[2 * i] = (uint32_t)(keys[i] >> 32), out[2 * i + 1] = (uint32_t)keys[i];
+}
+
 __global__ void k_iota(uint32_t* p, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;
@@ -435,6 +526,60 @@ int world_ray_cast(ncb_ctx* ctx, ncb_bp* bp, WorldQueryBufs& B, uint32_t n_rays,
     if (idx && wr) CKQ(cudaMemcpyAsync(idx, B.out_idx.p, 8 * (size_t)wr, cudaMemcpyDeviceToHost, s));
     if (val && wr) CKQ(cudaMemcpyAsync(val, B.out_val.p, 16 * (size_t)wr, cudaMemcpyDeviceToHost, s));
     if (feat && wr) CKQ(cudaMemcpyAsync(feat, B.out_feat.p, 4 * (size_t)wr, cudaMemcpyDeviceToHost, s));
+    CKQ(cudaStreamSynchronize(s));
+    return found > cap ? 1 : NCB_OK;
+}
+
+// kind 0: interferences_with_aabb (6 floats per query), kind 2: interferences_with_point (3 floats).  Rows (query, handle) sorted.
+int world_query(ncb_ctx* ctx, ncb_bp* bp, WorldQueryBufs& B, int kind, uint32_t n_q, const float* q, const uint32_t* groups, uint32_t* idx,
+                uint32_t cap, uint32_t* n_out) {
+    CKQ(cudaSetDevice(ctx->device));
+    if (n_out) *n_out = 0;
+    if (n_q == 0 || bp->tree_n == 0) return NCB_OK;
+    cudaStream_t s = ctx->stream;
+    ncb_ctx* w = bp->work;
+    const int W = kind == 0 ? 6 : 3;
+    CKQ(B.rays.reserve((size_t)W * n_q));
+    CKQ(cudaMemcpyAsync(B.rays.p, q, 4 * (size_t)W * n_q, cudaMemcpyHostToDevice, s));
+    CKQ(B.counter.reserve(4));
+    size_t want = B.keys.cap ? B.keys.cap : (size_t)8 * n_q + 1024;
+    uint32_t found = 0;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        CKQ(B.keys.reserve(want));
+        CKQ(cudaMemsetAsync(B.counter.p, 0, 16, s));
+        QueryArgs A;
+        A.rays = B.rays.p, A.n_rays = n_q;
+        A.llo = w->leaf_lo.p, A.lhi = w->leaf_hi.p, A.nodes = w->nodes.p;
+        A.n = bp->tree_n, A.nout = bp->tree_outliers;
+        A.d_attached = bp->d_attached.p;
+        A.o = dev_objects(ctx), A.H = ctx->hulls;
+        A.use_groups = groups != nullptr;
+        for (int k = 0; k < 3; ++k) A.qg[k] = groups ? groups[k] : 0;
+        A.keys = B.keys.p, A.vals = nullptr, A.feats = nullptr, A.cap = (uint32_t)B.keys.cap, A.counter = B.counter.p;
+        unsigned g = (n_q + 127) / 128;
+        if (kind == 0)
+            k_world_query<0><<<g, 128, 0, s>>>(A);
+        else
+            k_world_query<2><<<g, 128, 0, s>>>(A);
+        CKQ(cudaGetLastError());
+        CKQ(cudaMemcpyAsync(&found, B.counter.p, 4, cudaMemcpyDeviceToHost, s));
+        CKQ(cudaStreamSynchronize(s));
+        if (found <= B.keys.cap) break;
+        want = (size_t)found + 1024;
+    }
+    if (n_out) *n_out = found;
+    if (found == 0) return NCB_OK;
+    CKQ(B.keys_sorted.reserve(found));
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, B.keys.p, B.keys_sorted.p, (int)found, 0, 64);
+    CKQ(B.cub_tmp.reserve(bytes + 256));
+    bytes = B.cub_tmp.cap;
+    CKQ(cub::DeviceRadixSort::SortKeys(B.cub_tmp.p, bytes, B.keys.p, B.keys_sorted.p, (int)found, 0, 64, s));
+    CKQ(B.out_idx.reserve(2 * (size_t)found));
+    k_unpack_keys<<<(found + 255) / 256, 256, 0, s>>>(B.keys_sorted.p, found, B.out_idx.p);
+    CKQ(cudaGetLastError());
+    uint32_t wr = found < cap ? found : cap;
+    if (idx && wr) CKQ(cudaMemcpyAsync(idx, B.out_idx.p, 8 * (size_t)wr, cudaMemcpyDeviceToHost, s));
     CKQ(cudaStreamSynchronize(s));
     return found > cap ? 1 : NCB_OK;
 }

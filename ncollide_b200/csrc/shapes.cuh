@@ -43,4 +43,36 @@ NCB_HD Support as_support(const Shape& s) {
     return g;
 }
 
+// ConvexHull::project_point_with_feature (point_support_map.rs:15-53 with solid = false, :97-116), in two parts so that
+// the rare "point inside the hull" case (EPA) can be deferred to its own compacted kernel.
+struct HullProjSetup {
+    Iso m;  // Translation::from(-point) * m
+    Support shape, origin;
+};
+NCB_HD HullProjSetup hull_proj_setup(const HullView& H, const Iso& m_in, V3 point) {
+    HullProjSetup u;
+    u.m = m_in;
+    u.m.t = (-point) + m_in.t;
+    u.shape.kind = 1;
+    u.shape.hull = H;
+    u.origin.kind = 2;
+    return u;
+}
+NCB_HD Iso iso_id() {
+    Iso id;
+    id.t = v3(0.f, 0.f, 0.f);
+    id.q = Quat{0.f, 0.f, 0.f, 1.f};
+    return id;
+}
+// gjk::project_origin: GJK_CLOSEST_POINTS (outside, proj set) or GJK_INTERSECTION (inside: simplex s feeds EPA)
+static __device__ __noinline__ int hull_project_gjk(const HullProjSetup& u, V3 point, Simplex& s, V3& proj) {
+    Iso id = iso_id();
+    V3 dir;
+    if (!unit_try_new(-u.m.t, NCB_EPS, dir)) dir = v3(1.f, 0.f, 0.f);
+    simplex_init(s, cso_from_shapes(u.m, u.shape, id, u.origin, dir));
+    V3 p1, p2, d;
+    int r = gjk_closest_points(u.m, u.shape, id, u.origin, NCB_FMAX, s, p1, p2, d);
+    if (r == GJK_CLOSEST_POINTS) proj = p1 + point;
+    return r == GJK_CLOSEST_POINTS ? GJK_CLOSEST_POINTS : GJK_INTERSECTION;
+}
 }  // namespace ncb

@@ -520,4 +520,13 @@ int ncb_sim_ray_cast(ncb_sim* sim, uint32_t n_rays, const float* rays, const uin
     return world_ray_cast(sim->ctx, sim->bp, sim->qbufs, n_rays, rays, groups, first_only, idx, val, feat, cap, n_out);
 }
 
+// glue::interferences_with_aabb (kind 0; 6 floats per query: mins, maxs) / interferences_with_point (kind 2; 3 floats)
+// (glue/query.rs:79-181): broad-phase candidates on the stored boxes, the query's collision groups, and for points the
+// shape's PointQuery::contains_point.  idx[2 k] = (query, handle), sorted; cap in rows; returns 1 when truncated.
+int ncb_sim_query(ncb_sim* sim, int kind, uint32_t n_queries, const float* queries, const uint32_t* groups, uint32_t* idx, uint32_t cap,
+                  uint32_t* n_out) {
+    if (!sim || (kind != 0 && kind != 2) || (n_queries && !queries)) return NCB_ERR_ARG;
+    return world_query(sim->ctx, sim->bp, sim->qbufs, kind, n_queries, queries, groups, idx, cap, n_out);
+}
+
 }  // extern "C"

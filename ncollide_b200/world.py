@@ -557,6 +557,21 @@ class SteppingWorld:
 
     step = update
 
+    def query(self, kind, q, groups=None):
+        """kind 0: ``interferences_with_aabb`` (q[n,6]); kind 2: ``interferences_with_point`` (q[n,3]) (glue/query.rs:79-181).
+        Returns rows (query, handle), sorted."""
+        q = as_f32(q).reshape(-1, 6 if kind == 0 else 3)
+        g = None if groups is None else as_u32(groups).reshape(3)
+        cap = max(16 * len(q), 4096)
+        while True:
+            idx = np.zeros((cap, 2), dtype=np.uint32)
+            n = C.c_uint32()
+            r = self.ctx.check(self.ctx.lib.ncb_sim_query(self._h, C.c_int(kind), C.c_uint32(len(q)), ptr(q), ptr(g), ptr(idx), C.c_uint32(cap),
+                                                          C.byref(n)), "ncb_sim_query")
+            if r == 0:
+                return idx[: n.value]
+            cap = n.value
+
     def ray_cast(self, origins, dirs, max_toi, groups=None, first_only=False):
         """``interferences_with_ray`` / ``first_interference_with_ray`` for a batch of rays (glue/query.rs:13-77,183-224).
         Returns (idx[K,2] (ray, handle), toi[K], normal[K,3], feature[K]), rows sorted by (ray, handle)."""

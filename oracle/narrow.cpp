@@ -1409,4 +1409,47 @@ uint64_t orc_sim_ray_cast(orc_sim* s, uint64_t n_rays, const real* rays, const u
     return rows;
 }
 
+// glue::interferences_with_point (kind 2: candidates whose stored box contains the point, collision-groups test, then
+// shape.contains_point(position, point); glue/query.rs:79-131) and interferences_with_aabb (kind 0: stored box intersects,
+// collision-groups test; :133-181).  q: 3 / 6 reals per query.  Rows (query, handle) sorted.  Returns the row count.
+uint64_t orc_sim_query(orc_sim* s, int kind, uint64_t n, const real* q, const uint32_t* groups, uint32_t* idx, uint64_t cap) {
+    const Objects& o = s->o;
+    uint64_t rows = 0;
+    std::vector<uint32_t> cand(o.n + 1);
+    const int W = kind == 0 ? 6 : 3;
+    for (uint64_t r = 0; r < n; ++r) {
+        const real* qq = q + W * r;
+        uint64_t nc = orc_bp_query(s->bp, kind, qq, cand.data(), cand.size());
+        std::sort(cand.begin(), cand.begin() + nc);
+        for (uint64_t k = 0; k < nc; ++k) {
+            uint32_t h = cand[k];
+            if (groups && o.groups) {
+                uint32_t m1 = o.groups[3 * h], w1 = o.groups[3 * h + 1], b1 = o.groups[3 * h + 2];
+                if (!((m1 & groups[2]) == 0 && (groups[0] & b1) == 0 && (m1 & groups[1]) != 0 && (groups[0] & w1) != 0)) continue;
+            }
+            if (kind == 2) {
+                V3 pt = v3(qq[0], qq[1], qq[2]);
+                Shape sh = get_shape(o, h);
+                Iso m = o.iso(h);
+                bool inside;
+                if (sh.type == BALL) {  // point_ball.rs:45-47
+                    inside = norm_squared(iso_inv_point(m, pt)) <= sh.radius * sh.radius;
+                } else if (sh.type == CUBOID) {  // point_cuboid.rs -> AABB::contains_local_point
+                    V3 l = iso_inv_point(m, pt);
+                    inside = !(l.x < -sh.he.x || l.x > sh.he.x || l.y < -sh.he.y || l.y > sh.he.y || l.z < -sh.he.z || l.z > sh.he.z);
+                } else if (sh.type == HULL) {  // point_support_map.rs:15-53: inside <=> gjk::project_origin finds no projection
+                    V3 proj;
+                    hull_project_point(sh.hull, m, pt, &inside, &proj, nullptr);
+                } else {  // point_plane.rs:8-19
+                    inside = dot(sh.he, iso_inv_point(m, pt)) <= real(0);
+                }
+                if (!inside) continue;
+            }
+            if (rows < cap) idx[2 * rows] = (uint32_t)r, idx[2 * rows + 1] = h;
+            rows++;
+        }
+    }
+    return rows;
+}
+
 }  // extern "C"

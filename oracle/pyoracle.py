@@ -220,6 +220,20 @@ class OracleSim:
         return {"pairs": pairs, "algo": algo, "off": off, "contacts": contacts[:Cn], "ids": ids[:Cn], "events": ev[:ne],
                 "bp_pairs": int(L.orc_sim_bp_num_interferences(self.h))}
 
+    def query(self, kind, q, groups=None):
+        """kind 0: interferences_with_aabb (q[n,6]); kind 2: interferences_with_point (q[n,3]).  Rows (query, handle)."""
+        q = np.ascontiguousarray(q, dtype=self.o.dtype)
+        g = None if groups is None else np.ascontiguousarray(groups, dtype=np.uint32)
+        self.o.lib.orc_sim_query.restype = C.c_uint64
+        cap = max(64 * len(q), 4096)
+        while True:
+            idx = np.zeros((cap, 2), dtype=np.uint32)
+            n = self.o.lib.orc_sim_query(self.h, C.c_int(kind), C.c_uint64(len(q)), C.c_void_p(q.ctypes.data),
+                                         C.c_void_p(g.ctypes.data) if g is not None else None, C.c_void_p(idx.ctypes.data), C.c_uint64(cap))
+            if n <= cap:
+                return idx[:n]
+            cap = int(n)
+
     def ray_cast(self, origins, dirs, max_toi, groups=None, first_only=False):
         """glue::interferences_with_ray / first_interference_with_ray.  Returns (idx[K,2] (ray, handle), toi[K], normal[K,3], feature[K])."""
         o = np.ascontiguousarray(origins, dtype=self.o.dtype).reshape(-1, 3)

