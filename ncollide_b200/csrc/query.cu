@@ -218,8 +218,9 @@ __device__ __noinline__ RayHit ray_cast_hull(const HullView& H, const Iso& m, V3
     }
 }
 
-__device__ __forceinline__ bool slab_hit(const float* q, const float* inv, float4 lo, float4 hi) {  // ray_aabb.rs:13-50
-    float tmin = 0.f, tmax = q[6];
+__device__ __forceinline__ bool slab_hit(const float* q, const float* inv, float4 lo, float4 hi, float& tmin) {  // ray_aabb.rs:13-50
+    tmin = 0.f;
+    float tmax = q[6];
     const float mn[3] = {lo.x, lo.y, lo.z}, mx[3] = {hi.x, hi.y, hi.z};
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -290,6 +291,10 @@ __device__ __forceinline__ void visit_leaf(const QueryArgs& A, uint32_t ri, cons
     }
 }
 
+// FIRST: once a hit is known, boxes entered later than it cannot hold a closer hit (a stored box contains its shape), so the
+// slab test's upper bound shrinks to the best toi (plus a rounding guard) — the pruning the reference's best-first search does.
+#define SHRINK()                                                                  \
+    if (FIRST && best.hit) q[6] = fminf(q[6], best.toi * 1.00001f + 1e-6f)
 template <bool FIRST>
 __global__ void __launch_bounds__(128) k_world_ray_cast(QueryArgs A) {
     uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
@@ -301,6 +306,7 @@ __global__ void __launch_bounds__(128) k_world_ray_cast(QueryArgs A) {
     best.hit = false;
     uint32_t best_h = 0;
     uint32_t m = A.n - A.nout;
+    float te;
     if (m >= 2) {
         uint32_t stack[64];
         int sp = 0;
@@ -309,17 +315,25 @@ __global__ void __launch_bounds__(128) k_world_ray_cast(QueryArgs A) {
             const float4* rec = A.nodes + 4 * (size_t)node;
             float4 Llo = __ldg(rec + 0), Lhi = __ldg(rec + 1), Rlo = __ldg(rec + 2), Rhi = __ldg(rec + 3);
             uint32_t left = __float_as_uint(Llo.w), right = __float_as_uint(Lhi.w);
-            bool goL = slab_hit(q, inv, Llo, Lhi), goR = slab_hit(q, inv, Rlo, Rhi);
+            float tl, tr;
+            bool goL = slab_hit(q, inv, Llo, Lhi, tl), goR = slab_hit(q, inv, Rlo, Rhi, tr);
             if (goL && (left & LEAF_BIT)) {
                 visit_leaf<FIRST>(A, ri, q, __float_as_uint(__ldg(&A.llo[left & ~LEAF_BIT].w)), best, best_h);
+                SHRINK();
                 goL = false;
+                if (FIRST && goR) goR = tr <= q[6];
             }
             if (goR && (right & LEAF_BIT)) {
                 visit_leaf<FIRST>(A, ri, q, __float_as_uint(__ldg(&A.llo[right & ~LEAF_BIT].w)), best, best_h);
+                SHRINK();
                 goR = false;
             }
-            if (goL) {
-                if (goR && sp < 64) stack[sp++] = right;
+            if (goL && goR) {
+                // FIRST: the child entered sooner is walked first, so that its hits prune the other one
+                bool right_first = FIRST && tr < tl;
+                if (sp < 64) stack[sp++] = right_first ? left : right;
+                node = right_first ? right : left;
+            } else if (goL) {
                 node = left;
             } else if (goR) {
                 node = right;
@@ -330,11 +344,14 @@ __global__ void __launch_bounds__(128) k_world_ray_cast(QueryArgs A) {
         }
     } else if (m == 1) {
         float4 lo = __ldg(&A.llo[0]), hi = __ldg(&A.lhi[0]);
-        if (slab_hit(q, inv, lo, hi)) visit_leaf<FIRST>(A, ri, q, __float_as_uint(lo.w), best, best_h);
+        if (slab_hit(q, inv, lo, hi, te)) visit_leaf<FIRST>(A, ri, q, __float_as_uint(lo.w), best, best_h);
     }
     for (uint32_t o = m; o < A.n; ++o) {
         float4 lo = __ldg(&A.llo[o]), hi = __ldg(&A.lhi[o]);
-        if (slab_hit(q, inv, lo, hi)) visit_leaf<FIRST>(A, ri, q, __float_as_uint(lo.w), best, best_h);
+        if (slab_hit(q, inv, lo, hi, te)) {
+            visit_leaf<FIRST>(A, ri, q, __float_as_uint(lo.w), best, best_h);
+            SHRINK();
+        }
     }
     if (FIRST && best.hit) {
         uint32_t k = atomicAdd(A.counter, 1u);

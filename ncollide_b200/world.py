@@ -579,11 +579,11 @@ class SteppingWorld:
         t = np.broadcast_to(np.asarray(max_toi, dtype=np.float32).reshape(-1, 1), (len(o), 1))
         rays = np.ascontiguousarray(np.concatenate([o, d, t], axis=1), dtype=np.float32)
         g = None if groups is None else as_u32(groups).reshape(3)
-        cap = max(16 * len(o), 4096)
+        cap = len(o) if first_only else max(4 * len(o), 4096)
         while True:
-            idx = np.zeros((cap, 2), dtype=np.uint32)
-            val = np.zeros((cap, 4), dtype=np.float32)
-            feat = np.zeros(cap, dtype=np.uint32)
+            idx = np.empty((cap, 2), dtype=np.uint32)
+            val = np.empty((cap, 4), dtype=np.float32)
+            feat = np.empty(cap, dtype=np.uint32)
             n = C.c_uint32()
             r = self.ctx.check(self.ctx.lib.ncb_sim_ray_cast(self._h, C.c_uint32(len(o)), ptr(rays), ptr(g), C.c_int(int(first_only)), ptr(idx), ptr(val),
                                                              ptr(feat), C.c_uint32(cap), C.byref(n)), "ncb_sim_ray_cast")
