@@ -80,7 +80,7 @@ def make_world_scene(
     rng = np.random.default_rng(seed)
     fb, fc, fh = fractions
     nb = int(round(n * fb / (fb + fc + fh)))
-    nc = int(round(n * fc / (fb + fc + fh)))
+    nc = min(int(round(n * fc / (fb + fc + fh))), n - nb)
     nh = n - nb - nc
     types = np.concatenate([np.full(nb, BALL), np.full(nc, CUBOID), np.full(nh, HULL)]).astype(np.uint32)
     rng.shuffle(types)

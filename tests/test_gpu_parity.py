@@ -112,6 +112,53 @@ def test_world_update_parity(ctx, oracle, mk):
     assert sum(res.counts["n_algo"].values()) == len(res.pairs)
 
 
+def _adversarial_scenes():
+    """Configurations that stress degenerate branches: exact coincidence, axis-aligned face contact, touching at depth 0,
+    far-from-origin coordinates, a dense clump, tiny / huge shapes side by side."""
+    F = np.float32
+    out = []
+    # 1. everything at one point (all pairs; GJK starts from a zero direction, EPA from degenerate simplices)
+    s = make_world_scene(60, 301, (1, 1, 1), side=1.0, n_hulls=8, name="coincident")
+    s.pos[:] = F(0.25)
+    out.append(s)
+    # 2. an axis-aligned lattice of unit cubes and balls exactly touching (depth 0, parallel faces, shared edges / corners)
+    s = make_world_scene(343, 302, (1, 1, 0), side=1.0, name="lattice")
+    g = np.stack(np.meshgrid(*[np.arange(7)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(F)
+    s.pos[:] = g
+    s.rot[:] = (0, 0, 0, 1)
+    s.shape_param[:, :3] = F(0.5)
+    out.append(s)
+    # 3. the same lattice slightly compressed (everything interpenetrates by the same amount)
+    s2 = make_world_scene(343, 302, (1, 1, 0), side=1.0, name="lattice_compressed")
+    s2.pos[:] = g * F(0.9)
+    s2.rot[:] = (0, 0, 0, 1)
+    s2.shape_param[:, :3] = F(0.5)
+    out.append(s2)
+    # 4. far from the origin (cancellation in every difference)
+    s = make_world_scene(1500, 303, (1, 1, 1), side=6.0, n_hulls=16, name="far_away")
+    s.pos[:] = (s.pos + np.array([4096.0, -2048.0, 8192.0], dtype=F)).astype(F)
+    out.append(s)
+    # 5. a dense clump: ~40 neighbours per object, deep penetrations, many EPA expansions
+    out.append(make_world_scene(1200, 304, (1, 1, 1), side=2.2, n_hulls=32, name="clump"))
+    # 6. mixed scales: 1e-2 .. 5 (prediction and the 0.02 manifold threshold are absolute)
+    s = make_world_scene(1500, 305, (1, 1, 0), side=8.0, name="scales")
+    k = np.random.default_rng(305).choice([0.02, 0.2, 1.0, 5.0], size=s.n).astype(F)
+    s.shape_param[:, :3] = (s.shape_param[:, :3] * k[:, None]).astype(F)
+    out.append(s)
+    return out
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_adversarial_scenes_parity(ctx, oracle, k):
+    s = _adversarial_scenes()[k]
+    ctx.set_hulls(s.hulls)
+    res = ctx.world_update(s)
+    assert res.counts["epa_overflow"] == 0, s.name
+    want = oracle.broad_phase(oracle.compute_aabbs(s), s.groups, mode=1)
+    assert np.array_equal(canon(res.pairs), canon(want)), s.name
+    compare_manifolds(res, s, oracle, s.name)
+
+
 def test_world_update_is_deterministic_as_a_set(ctx):
     s = config_scene(3, 5000)
     ctx.set_hulls(s.hulls)
