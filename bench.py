@@ -334,7 +334,8 @@ def run_native(args):
         e2e_ms = float(t.item())
     e2e_value = (n_total / 1e6) / (e2e_ms / 1e3)
     n_up = n_total
-    h2d = n_up * (12 + 16 + 4 + 16 + 12 + 4 + 4) + 8 if world == 1 else n_per * 28
+    # pos, rot, type, param, groups, query_limit per object + the (cos, sin) table of the angular prediction
+    h2d = n_up * (12 + 16 + 4 + 16 + 12 + 4) + 8 if world == 1 else n_per * 28
     d2h = counts["n_pairs"] * (8 + 1 + 4 + 1) + counts["n_contacts"] * 52 + 256
 
     # ---- secondary figure: batched TriMesh ray casting (configs[3]) ---------------------------------------

@@ -112,6 +112,12 @@ int ncb_create(int device, ncb_ctx** out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_counters, sizeof(DevCounters));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_snap, 2 * sizeof(DevCounters));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_pairs, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = c->snap.reserve(1);
     if (e == cudaSuccess && !getenv("NCB_NO_SIDE_STREAM")) {
         e = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
@@ -148,6 +154,12 @@ void ncb_destroy(ncb_ctx* c) {
     if (c->timer.created)
         for (int i = 0; i <= StageTimer::MAX; ++i) cudaEventDestroy(c->timer.ev[i]);
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_pairs) cudaEventDestroy(c->ev_pairs);
+    if (c->ev_snap) cudaEventDestroy(c->ev_snap);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->h_snap) cudaFreeHost(c->h_snap);
+    c->snap.release();
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -258,9 +270,23 @@ int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* o) {
     CK(ctx->qlimit.reserve(n));
     CK(ctx->ang.reserve(n));
     CK(ctx->ang_cs.reserve(n));
+    // the large copies go first; the host work below (angular prediction table) overlaps with them
+    if (n) {
+        CK(cudaMemcpyAsync(ctx->pos.p, o->pos, 12 * (size_t)n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->rot.p, o->rot, 16 * (size_t)n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->type.p, o->shape_type, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->param.p, o->shape_param, 16 * (size_t)n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->qlimit.p, o->query_limit, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+    }
+    ctx->has_groups = o->groups != nullptr;
+    if (o->groups && n) {
+        CK(ctx->groups.reserve(3 * (size_t)n));
+        CK(cudaMemcpyAsync(ctx->groups.p, o->groups, 12 * (size_t)n, cudaMemcpyHostToDevice, s));
+    }
     // cos/sin of the angular prediction: the reference evaluates them with libm (f32::cos / f32::sin in
     // Cuboid::support_feature_toward, cuboid.rs:317,331 and ConvexHull::support_feature_id_toward_eps, convex.rs:389);
-    // CUDA's cosf/sinf are not the same function, so they are evaluated here, once per distinct value.
+    // CUDA's cosf/sinf are not the same function, so they are evaluated here, once per distinct value.  Only this table
+    // goes to the device (the raw angles are not read by any kernel).
     bool uniform_ang = true;
     for (uint32_t i = 1; i < n && uniform_ang; ++i) uniform_ang = o->ang_pred[i] == o->ang_pred[0];
     ctx->ang_stride = uniform_ang ? 0u : 1u;
@@ -279,20 +305,7 @@ int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* o) {
             ctx->h_ang_cs[i] = cs;
         }
     }
-    if (n) {
-        CK(cudaMemcpyAsync(ctx->ang_cs.p, ctx->h_ang_cs.data(), 8 * ctx->h_ang_cs.size(), cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->pos.p, o->pos, 12 * (size_t)n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->rot.p, o->rot, 16 * (size_t)n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->type.p, o->shape_type, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->param.p, o->shape_param, 16 * (size_t)n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->qlimit.p, o->query_limit, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->ang.p, o->ang_pred, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
-    }
-    ctx->has_groups = o->groups != nullptr;
-    if (o->groups && n) {
-        CK(ctx->groups.reserve(3 * (size_t)n));
-        CK(cudaMemcpyAsync(ctx->groups.p, o->groups, 12 * (size_t)n, cudaMemcpyHostToDevice, s));
-    }
+    if (n) CK(cudaMemcpyAsync(ctx->ang_cs.p, ctx->h_ang_cs.data(), 8 * ctx->h_ang_cs.size(), cudaMemcpyHostToDevice, s));
     ctx->n = n;
     CK(reserve_broad(ctx, n) == NCB_OK ? cudaSuccess : cudaErrorMemoryAllocation);
     return NCB_OK;
@@ -476,7 +489,35 @@ static int update_after_aabbs(ncb_ctx* ctx, uint32_t q_begin, uint32_t q_end, ui
         timer_mark(ctx, "pair_search", 2);
         CK(launch_pair_sort(ctx, (uint32_t)cap_pairs, nullptr));
         timer_mark(ctx, "pair_sort", 3);
+        if (ctx->early.active) CK(cudaEventRecord(ctx->ev_pairs, ctx->stream));
         CK(launch_narrow_phase(ctx, dev_objects(ctx), ctx->pairs.p, nullptr, (uint32_t)cap_pairs, (uint32_t)cap_contacts));
+        if (ctx->early.active) {
+            // Everything of this update is enqueued.  While the narrow phase runs, the copy stream ships what is already
+            // final: the sorted pair list (+ algorithm per pair) once the pair sort is done, then the contacts written by
+            // the kernels that finished before the convex-convex EPA / manifold phases (counter snapshot in ctx->snap).
+            ncb_ctx::EarlyFetch& ef = ctx->early;
+            ef.pairs_done = ef.contacts_done = 0;
+            cudaStream_t cs = ctx->copy_stream;
+            CK(cudaStreamWaitEvent(cs, ctx->ev_pairs, 0));
+            CK(cudaMemcpyAsync(&ctx->h_snap[0], ctx->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, cs));
+            CK(cudaStreamSynchronize(cs));
+            uint32_t np = ctx->h_snap[0].n_pairs;
+            if (np <= cap_pairs) {
+                uint32_t wp = np < ef.cap_pairs ? np : ef.cap_pairs;
+                if (ef.pairs && wp) CK(cudaMemcpyAsync(ef.pairs, ctx->pairs.p, 8 * (size_t)wp, cudaMemcpyDeviceToHost, cs));
+                if (ef.algo && wp) CK(cudaMemcpyAsync(ef.algo, ctx->pair_algo.p, wp, cudaMemcpyDeviceToHost, cs));
+                ef.pairs_done = wp;
+                CK(cudaStreamWaitEvent(cs, ctx->ev_snap, 0));
+                CK(cudaMemcpyAsync(&ctx->h_snap[1], ctx->snap.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, cs));
+                CK(cudaStreamSynchronize(cs));
+                uint32_t n1 = ctx->h_snap[1].n_contacts;
+                if (n1 <= cap_contacts) {
+                    uint32_t wc = n1 < ef.cap_contacts ? n1 : ef.cap_contacts;
+                    if (ef.contacts && wc) CK(cudaMemcpyAsync(ef.contacts, ctx->contacts.p, sizeof(ncb_contact) * (size_t)wc, cudaMemcpyDeviceToHost, cs));
+                    ef.contacts_done = wc;
+                }
+            }
+        }
         r = read_counters(ctx);
         if (r) return r;
         const DevCounters& c = ctx->last_counters;
@@ -598,9 +639,35 @@ int ncb_world_update(ncb_ctx* ctx, const ncb_objects* objs, float margin, uint32
                      ncb_update_counts* counts) {
     int r = ncb_set_objects(ctx, objs);
     if (r) return r;
+    // results are copied back while the narrow phase is still running (see update_after_aabbs); NCB_NO_EARLY_FETCH=1 disables it
+    static const bool early_ok = getenv("NCB_NO_EARLY_FETCH") == nullptr;
+    ctx->early.active = early_ok && ctx->copy_stream != nullptr;
+    ctx->early.pairs = pairs, ctx->early.algo = pair_algo, ctx->early.contacts = contacts;
+    ctx->early.cap_pairs = cap_pairs, ctx->early.cap_contacts = cap_contacts;
+    ctx->early.pairs_done = ctx->early.contacts_done = 0;
     r = ncb_world_update_device(ctx, margin, 0, 0xffffffffu, counts);
-    if (r) return r;
-    return ncb_world_fetch(ctx, pairs, cap_pairs, pair_algo, manifold_start, manifold_count, contacts, cap_contacts);
+    bool was_early = ctx->early.active;
+    ctx->early.active = false;
+    if (r) {
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        return r;
+    }
+    if (!was_early) return ncb_world_fetch(ctx, pairs, cap_pairs, pair_algo, manifold_start, manifold_count, contacts, cap_contacts);
+    // the rest: contacts written by the convex-convex manifold kernels, per-pair manifold ranges, anything the early copies skipped
+    cudaStream_t s = ctx->stream;
+    uint32_t np = ctx->last_n_pairs, nc = ctx->last_n_contacts;
+    uint32_t wp = np < cap_pairs ? np : cap_pairs, wc = nc < cap_contacts ? nc : cap_contacts;
+    uint32_t pd = ctx->early.pairs_done, cd = ctx->early.contacts_done;
+    if (pd > wp) pd = wp;
+    if (cd > wc) cd = wc;
+    if (pairs && wp > pd) CK(cudaMemcpyAsync(pairs + 2 * (size_t)pd, ctx->pairs.p + pd, 8 * (size_t)(wp - pd), cudaMemcpyDeviceToHost, s));
+    if (pair_algo && wp > pd) CK(cudaMemcpyAsync(pair_algo + pd, ctx->pair_algo.p + pd, wp - pd, cudaMemcpyDeviceToHost, s));
+    if (manifold_start && wp) CK(cudaMemcpyAsync(manifold_start, ctx->manifold_start.p, 4 * (size_t)wp, cudaMemcpyDeviceToHost, s));
+    if (manifold_count && wp) CK(cudaMemcpyAsync(manifold_count, ctx->manifold_count.p, wp, cudaMemcpyDeviceToHost, s));
+    if (contacts && wc > cd) CK(cudaMemcpyAsync(contacts + cd, ctx->contacts.p + cd, sizeof(ncb_contact) * (size_t)(wc - cd), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    CK(cudaStreamSynchronize(s));
+    return ((pairs && np > cap_pairs) || (contacts && nc > cap_contacts)) ? 1 : NCB_OK;
 }
 
 void* ncb_device_ptr(ncb_ctx* ctx, int which) {

@@ -1282,11 +1282,20 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     if (c->side_stream) cudaEventRecord(c->ev_join, s2);
     k_cc_gjk<PS><<<sm * gjk_bpsm, 128, 0, s>>>(A);
     timer_mark(c, "cc_gjk", 1);
+    // ncb_world_update (host buffers): the side chain joins here; from this point until k_cc_manifold no kernel allocates
+    // contact slots, so a snapshot of the counters tells which contacts are final and they are copied to the host while
+    // the EPA / manifold phases run.
+    const bool early = !PS && c->early.active;
+    if (early) {
+        if (c->side_stream) cudaStreamWaitEvent(s, c->ev_join, 0);
+        cudaMemcpyAsync(c->snap.p, c->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToDevice, s);
+        cudaEventRecord(c->ev_snap, s);
+    }
     k_cc_epa<PS><<<sm * epa_bpsm, 64, 0, s>>>(A);
     timer_mark(c, "cc_epa", 1);
     k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
     timer_mark(c, "cc_manifold", 1);
-    if (c->side_stream) cudaStreamWaitEvent(s, c->ev_join, 0);
+    if (!early && c->side_stream) cudaStreamWaitEvent(s, c->ev_join, 0);  // device-only updates: the side chain may run to the end
     timer_mark(c, "narrow_other_join", 7);
     return cudaGetLastError();
 }

@@ -171,6 +171,19 @@ struct ncb_ctx {
     ncb::StageTimer timer;
     bool timer_external = false;  // stage 0 (AABBs) already started the timer of this update
     ncb::DevCounters* h_counters = nullptr;  // pinned
+    // overlapped result fetch of ncb_world_update (api.cu): copy stream, events, counter snapshots
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_pairs = nullptr, ev_snap = nullptr, ev_copy = nullptr;
+    ncb::DevBuf<ncb::DevCounters> snap;      // device copy of the counters taken before the convex-convex manifold kernels
+    ncb::DevCounters* h_snap = nullptr;      // pinned, 2 entries
+    struct EarlyFetch {
+        bool active = false;
+        uint32_t* pairs = nullptr;
+        uint8_t* algo = nullptr;
+        ncb_contact* contacts = nullptr;
+        uint32_t cap_pairs = 0, cap_contacts = 0;
+        uint32_t pairs_done = 0, contacts_done = 0;  // rows already on their way to the host
+    } early;
     // spatial sharding (several GPUs)
     ncb::DevBuf<ncb::ShardScratch> shard;
     ncb::DevBuf<uint32_t> shard_bins, shard_sel;
