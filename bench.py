@@ -312,6 +312,8 @@ def run_native(args):
         else:
             # every rank uploads the poses of its own block, steps, and reads its own results back
             sharded.upload_own_poses(pin_scene.pos, pin_scene.rot)
+            ctx.check(lib.ncb_world_fetch_early(h, _ffi.ptr(pin_out["pairs"]), C.c_uint32(len(pin_out["pairs"])), _ffi.ptr(pin_out["algo"]),
+                                                _ffi.ptr(pin_out["contacts"]), C.c_uint32(len(pin_out["contacts"]))), "fetch_early")
             step_device()
             ctx.check(lib.ncb_world_fetch(h, _ffi.ptr(pin_out["pairs"]), C.c_uint32(len(pin_out["pairs"])), _ffi.ptr(pin_out["algo"]),
                                           _ffi.ptr(pin_out["start"]), _ffi.ptr(pin_out["count"]), _ffi.ptr(pin_out["contacts"]),

@@ -170,6 +170,10 @@ int ncb_world_update_stage(ncb_ctx* ctx, int stage, float margin, uint32_t begin
  * `rank` of `world` selects the objects it owns (equal-count Morton ranges) plus the ghosts around them, builds its LBVH
  * over those only and reports its share of the pairs + their contacts.  Every pair is reported by exactly one rank. */
 int ncb_world_update_sharded(ncb_ctx* ctx, float margin, int rank, int world, ncb_update_counts* counts);
+/* Arms an overlapped fetch for the NEXT device update: while its narrow phase runs, the sorted pairs (+ algorithm) and the
+ * contacts that are already final are copied into these host buffers (pinned memory recommended); ncb_world_fetch with the
+ * same buffers then only copies the rest.  ncb_world_update does this by itself. */
+int ncb_world_fetch_early(ncb_ctx* ctx, uint32_t* pairs, uint32_t cap_pairs, uint8_t* pair_algo, ncb_contact* contacts, uint32_t cap_contacts);
 
 /* Per-stage device times of the last ncb_world_update_device, measured with CUDA events on the context's stream
  * when enabled.  names/ms are arrays of at least 16 entries; returns the number of stages filled. */

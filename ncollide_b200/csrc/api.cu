@@ -535,6 +535,8 @@ static int update_after_aabbs(ncb_ctx* ctx, uint32_t q_begin, uint32_t q_end, ui
         if (!over) {
             ctx->last_n_pairs = c.n_pairs;
             ctx->last_n_contacts = c.n_contacts;
+            ctx->early.valid = ctx->early.active;
+            ctx->early.active = false;
             return NCB_OK;
         }
     }
@@ -618,6 +620,20 @@ int ncb_world_update_device(ncb_ctx* ctx, float margin, uint32_t q_begin, uint32
     return ncb_world_update_stage(ctx, 1, margin, q_begin, q_end, counts);
 }
 
+// Arms the overlapped result fetch for the NEXT device update (ncb_world_update_device / _stage(1) / _sharded): while its
+// narrow phase runs, the sorted pairs (+ algorithm) and the contacts that are already final are copied into these host
+// buffers; ncb_world_fetch with the same buffers then copies only the rest.  ncb_world_update does this by itself.
+int ncb_world_fetch_early(ncb_ctx* ctx, uint32_t* pairs, uint32_t cap_pairs, uint8_t* pair_algo, ncb_contact* contacts, uint32_t cap_contacts) {
+    if (!ctx) return NCB_ERR_ARG;
+    static const bool early_ok = getenv("NCB_NO_EARLY_FETCH") == nullptr;
+    ctx->early.active = early_ok && ctx->copy_stream != nullptr;
+    ctx->early.pairs = pairs, ctx->early.algo = pair_algo, ctx->early.contacts = contacts;
+    ctx->early.cap_pairs = cap_pairs, ctx->early.cap_contacts = cap_contacts;
+    ctx->early.pairs_done = ctx->early.contacts_done = 0;
+    ctx->early.valid = false;
+    return NCB_OK;
+}
+
 int ncb_world_fetch(ncb_ctx* ctx, uint32_t* pairs, uint32_t cap_pairs, uint8_t* pair_algo, uint32_t* manifold_start,
                     uint8_t* manifold_count, ncb_contact* contacts, uint32_t cap_contacts) {
     if (!ctx) return NCB_ERR_ARG;
@@ -625,11 +641,22 @@ int ncb_world_fetch(ncb_ctx* ctx, uint32_t* pairs, uint32_t cap_pairs, uint8_t* 
     cudaStream_t s = ctx->stream;
     uint32_t np = ctx->last_n_pairs, nc = ctx->last_n_contacts;
     uint32_t wp = np < cap_pairs ? np : cap_pairs, wc = nc < cap_contacts ? nc : cap_contacts;
-    if (pairs && wp) CK(cudaMemcpyAsync(pairs, ctx->pairs.p, 8 * (size_t)wp, cudaMemcpyDeviceToHost, s));
-    if (pair_algo && wp) CK(cudaMemcpyAsync(pair_algo, ctx->pair_algo.p, wp, cudaMemcpyDeviceToHost, s));
+    // rows an armed early fetch already put on their way into exactly these buffers
+    uint32_t pd = 0, cd = 0;
+    if (ctx->early.valid) {
+        if (pairs == ctx->early.pairs && pair_algo == ctx->early.algo) pd = ctx->early.pairs_done;
+        if (contacts == ctx->early.contacts) cd = ctx->early.contacts_done;
+        ctx->early.valid = false;
+    }
+    ctx->early.active = false;
+    if (pd > wp) pd = wp;
+    if (cd > wc) cd = wc;
+    if (pairs && wp > pd) CK(cudaMemcpyAsync(pairs + 2 * (size_t)pd, ctx->pairs.p + pd, 8 * (size_t)(wp - pd), cudaMemcpyDeviceToHost, s));
+    if (pair_algo && wp > pd) CK(cudaMemcpyAsync(pair_algo + pd, ctx->pair_algo.p + pd, wp - pd, cudaMemcpyDeviceToHost, s));
     if (manifold_start && wp) CK(cudaMemcpyAsync(manifold_start, ctx->manifold_start.p, 4 * (size_t)wp, cudaMemcpyDeviceToHost, s));
     if (manifold_count && wp) CK(cudaMemcpyAsync(manifold_count, ctx->manifold_count.p, wp, cudaMemcpyDeviceToHost, s));
-    if (contacts && wc) CK(cudaMemcpyAsync(contacts, ctx->contacts.p, sizeof(ncb_contact) * (size_t)wc, cudaMemcpyDeviceToHost, s));
+    if (contacts && wc > cd) CK(cudaMemcpyAsync(contacts + cd, ctx->contacts.p + cd, sizeof(ncb_contact) * (size_t)(wc - cd), cudaMemcpyDeviceToHost, s));
+    if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(s));
     return ((pairs && np > cap_pairs) || (contacts && nc > cap_contacts)) ? 1 : NCB_OK;
 }
@@ -640,34 +667,15 @@ int ncb_world_update(ncb_ctx* ctx, const ncb_objects* objs, float margin, uint32
     int r = ncb_set_objects(ctx, objs);
     if (r) return r;
     // results are copied back while the narrow phase is still running (see update_after_aabbs); NCB_NO_EARLY_FETCH=1 disables it
-    static const bool early_ok = getenv("NCB_NO_EARLY_FETCH") == nullptr;
-    ctx->early.active = early_ok && ctx->copy_stream != nullptr;
-    ctx->early.pairs = pairs, ctx->early.algo = pair_algo, ctx->early.contacts = contacts;
-    ctx->early.cap_pairs = cap_pairs, ctx->early.cap_contacts = cap_contacts;
-    ctx->early.pairs_done = ctx->early.contacts_done = 0;
+    r = ncb_world_fetch_early(ctx, pairs, cap_pairs, pair_algo, contacts, cap_contacts);
+    if (r) return r;
     r = ncb_world_update_device(ctx, margin, 0, 0xffffffffu, counts);
-    bool was_early = ctx->early.active;
-    ctx->early.active = false;
     if (r) {
+        ctx->early.active = ctx->early.valid = false;
         if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
         return r;
     }
-    if (!was_early) return ncb_world_fetch(ctx, pairs, cap_pairs, pair_algo, manifold_start, manifold_count, contacts, cap_contacts);
-    // the rest: contacts written by the convex-convex manifold kernels, per-pair manifold ranges, anything the early copies skipped
-    cudaStream_t s = ctx->stream;
-    uint32_t np = ctx->last_n_pairs, nc = ctx->last_n_contacts;
-    uint32_t wp = np < cap_pairs ? np : cap_pairs, wc = nc < cap_contacts ? nc : cap_contacts;
-    uint32_t pd = ctx->early.pairs_done, cd = ctx->early.contacts_done;
-    if (pd > wp) pd = wp;
-    if (cd > wc) cd = wc;
-    if (pairs && wp > pd) CK(cudaMemcpyAsync(pairs + 2 * (size_t)pd, ctx->pairs.p + pd, 8 * (size_t)(wp - pd), cudaMemcpyDeviceToHost, s));
-    if (pair_algo && wp > pd) CK(cudaMemcpyAsync(pair_algo + pd, ctx->pair_algo.p + pd, wp - pd, cudaMemcpyDeviceToHost, s));
-    if (manifold_start && wp) CK(cudaMemcpyAsync(manifold_start, ctx->manifold_start.p, 4 * (size_t)wp, cudaMemcpyDeviceToHost, s));
-    if (manifold_count && wp) CK(cudaMemcpyAsync(manifold_count, ctx->manifold_count.p, wp, cudaMemcpyDeviceToHost, s));
-    if (contacts && wc > cd) CK(cudaMemcpyAsync(contacts + cd, ctx->contacts.p + cd, sizeof(ncb_contact) * (size_t)(wc - cd), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(ctx->copy_stream));
-    CK(cudaStreamSynchronize(s));
-    return ((pairs && np > cap_pairs) || (contacts && nc > cap_contacts)) ? 1 : NCB_OK;
+    return ncb_world_fetch(ctx, pairs, cap_pairs, pair_algo, manifold_start, manifold_count, contacts, cap_contacts);
 }
 
 void* ncb_device_ptr(ncb_ctx* ctx, int which) {

@@ -177,7 +177,8 @@ struct ncb_ctx {
     ncb::DevBuf<ncb::DevCounters> snap;      // device copy of the counters taken before the convex-convex manifold kernels
     ncb::DevCounters* h_snap = nullptr;      // pinned, 2 entries
     struct EarlyFetch {
-        bool active = false;
+        bool active = false;  // armed for the next update
+        bool valid = false;   // the last update filled pairs_done / contacts_done
         uint32_t* pairs = nullptr;
         uint8_t* algo = nullptr;
         ncb_contact* contacts = nullptr;
