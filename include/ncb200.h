@@ -102,7 +102,8 @@ typedef struct ncb_update_counts {
     uint32_t n_contacts;       /* contacts over all manifolds */
     uint32_t n_contact_pairs;  /* pairs whose manifold is not empty */
     uint32_t n_algo[6];        /* pairs per NCB_ALGO_* */
-    uint32_t epa_overflow;     /* pairs whose EPA exceeded the fixed device capacity (result = "no contact"; 0 expected) */
+    uint32_t epa_overflow;     /* pairs that exceeded a fixed device capacity: EPA polytope (result = "no contact") or more than
+                                * 32 distinct contacts in one manifold (extra contacts dropped); 0 expected, tests assert it */
     uint32_t ref_panics;       /* pairs on which the reference itself would have panicked (assert / unwrap) */
     uint32_t n_epa_pairs;      /* convex-convex pairs that needed EPA (GJK found the origin inside the CSO) */
     uint32_t n_manifold_jobs;  /* convex-convex pairs that reached feature clipping */

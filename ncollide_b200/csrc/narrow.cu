@@ -286,7 +286,7 @@ struct ManifoldT {
     ManifoldContact c[MANIFOLD_MAX];
     V3 track[MANIFOLD_MAX];
     int n;
-    int deepest;
+    int deepest;  // >= 0; set to -1 when a contact had to be dropped (capacity), reported through the overflow counter
 };
 template <>
 struct ManifoldT<true> {
@@ -334,6 +334,8 @@ NCB_HD void manifold_push(ManifoldT<P>& mf, V3 w1, V3 w2, V3 n, float depth, uin
                 c.w1 = w1, c.w2 = w2, c.n = n, c.depth = depth, c.f1 = f1, c.f2 = f2;
                 mf.track[mf.n] = tracking_pt;
                 mf.n++;
+            } else {
+                mf.deepest = -1;
             }
         }
     } else {
@@ -731,6 +733,7 @@ NCB_HD void write_manifold(const Manifold& mf, bool valid, uint32_t pair_slot, u
                            uint32_t cap_contacts, uint32_t* __restrict__ manifold_start, uint8_t* __restrict__ manifold_count,
                            DevCounters* cnt) {
     // all 32 lanes call this (valid = false for idle lanes)
+    if (valid && mf.deepest < 0) atomicAdd(&cnt->epa_overflow, 1u);  // more than MANIFOLD_MAX distinct contacts: never silent
     uint32_t n = valid ? (uint32_t)mf.n : 0u;
     uint32_t incl = n;
     int lane = threadIdx.x & 31;

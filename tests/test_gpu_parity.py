@@ -159,6 +159,48 @@ def test_adversarial_scenes_parity(ctx, oracle, k):
     compare_manifolds(res, s, oracle, s.name)
 
 
+def _prism(k, r=1.0, h=0.25):
+    a = np.arange(k) * 2 * np.pi / k
+    ring = np.stack([r * np.cos(a), r * np.sin(a)], 1)
+    pts = np.concatenate([np.c_[ring, np.full(k, -h)], np.c_[ring, np.full(k, h)]]).astype(np.float32)
+    return ConvexHull.try_from_points(pts)
+
+
+@pytest.mark.parametrize("k", [8, 12, 16])
+def test_large_faces_and_many_contacts(ctx, oracle, k):
+    """Capacity edges: k-gon prisms stacked face to face (16-vertex faces = the device maximum; up to 2k + k^2 clip candidates,
+    16-19 distinct contacts per manifold), also against a cuboid and a ball; and a stepping world on the same bodies, whose
+    manifold cache holds the previous contacts as well."""
+    from test_oracle_kat import scene_of
+
+    lib = HullLibrary([_prism(k)])
+    q = (0, 0, float(np.sin(0.1)), float(np.cos(0.1)))
+    s = scene_of([(HULL, [0], (0, 0, 0)), (HULL, [0], (0.05, 0.02, 0.45), q), (CUBOID, [0.8, 0.8, 0.2], (0.1, 0, -0.4), q), (BALL, [0.5], (0.2, 0.1, 1.1))],
+                 hulls=lib)
+    ctx.set_hulls(s.hulls)
+    res = ctx.world_update(s)
+    assert res.counts["epa_overflow"] == 0
+    assert len(res.pairs) >= 3 and res.manifold_count.max() >= 12
+    compare_manifolds(res, s, oracle, f"prism{k}")
+    # stepping: small motions keep the stacks in contact; overflow of the persistent cache would be counted
+    from ncollide_b200.world import SteppingWorld
+
+    dev, orc = SteppingWorld(ctx, s), oracle.sim(s)
+    pos, rot = s.pos.copy(), s.rot.copy()
+    for t in range(4):
+        if t:
+            pos[1] += np.array([0.004, -0.003, 0.001], dtype=np.float32)
+            for w in (dev, orc):
+                w.set_positions([1], pos[1:2], rot[1:2])
+        a, b = dev.step(), orc.step()
+        assert a["counts"]["epa_overflow"] == 0, "persistent manifold cache overflow"
+        keep = a["algo"] != 0
+        assert np.array_equal(a["pairs"][keep], b["pairs"]) and np.array_equal(a["count"][keep], np.diff(b["off"]))
+        assert np.array_equal(a["ids"], b["ids"])
+        for f in ("world1", "world2", "normal", "depth"):
+            assert np.allclose(a["contacts"][f], b["contacts"][f], rtol=RTOL, atol=ATOL)
+
+
 def test_world_update_is_deterministic_as_a_set(ctx):
     s = config_scene(3, 5000)
     ctx.set_hulls(s.hulls)
