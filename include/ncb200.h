@@ -243,6 +243,12 @@ int ncb_sim_create(ncb_ctx* ctx, float margin, ncb_sim** out);
 void ncb_sim_destroy(ncb_sim* sim);
 /* CollisionObject::set_position (collision_object.rs:215-222) for m objects; handles == NULL means objects 0..m-1. */
 int ncb_sim_set_positions(ncb_sim* sim, uint32_t m, const uint32_t* handles, const float* pos, const float* rot);
+/* CollisionWorld::remove (world.rs:129-144) / CollisionWorld::add (world.rs:64-96) between updates (after the first
+ * ncb_sim_step).  Removed objects and their pairs disappear without events (glue/setup.rs:50-62); handles are recycled
+ * last-freed-first like the reference's slabs, so ncb_sim_add returns the handles the reference would hand out.  New objects
+ * refer to the hull library already set with ncb_set_hulls. */
+int ncb_sim_remove(ncb_sim* sim, uint32_t m, const uint32_t* handles);
+int ncb_sim_add(ncb_sim* sim, const ncb_objects* objs, uint32_t* out_handles);
 /* CollisionWorld::update.  counts: n_pairs, n_contacts, epa_overflow (+ manifold-cache overflows), ref_panics,
  * n_epa_pairs, n_manifold_jobs (= pairs regenerated in this step). */
 int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts);

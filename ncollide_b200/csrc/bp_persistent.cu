@@ -739,6 +739,51 @@ int bp_create_all_device(ncb_bp* bp, uint32_t n, const float4* lo, const float4*
     return NCB_OK;
 }
 
+namespace {
+__global__ void k_bp_stage_create_listed(const uint32_t* __restrict__ handles, uint32_t m, const float4* __restrict__ lo, const float4* __restrict__ hi,
+                                         uint32_t seq0, float4* pend_lo, float4* pend_hi, uint32_t* pend_seq, uint32_t* d_attached) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    uint32_t h = handles[k];
+    float4 a = lo[h], b = hi[h];
+    pend_lo[h] = make_float4(a.x, a.y, a.z, 0.f);
+    pend_hi[h] = make_float4(b.x, b.y, b.z, 0.f);
+    pend_seq[h] = min(pend_seq[h], seq0 + k);
+    d_attached[h] = ST_DETACHED;
+}
+}  // namespace
+
+// create_proxy for m new objects whose handles the caller predicted from its own slab: the proxy slab must hand out the same
+// handles (both recycle last-freed-first); boxes are read from the float4 arrays indexed by handle.
+int bp_create_listed_device(ncb_bp* bp, uint32_t m, const uint32_t* handles_host, const uint32_t* handles_dev, const float4* lo, const float4* hi) {
+    CKB(cudaSetDevice(bp->owner->device));
+    for (uint32_t i = 0; i < m; ++i) {  // Slab::insert
+        size_t key = bp->next;
+        if (key == bp->next_free.size()) {
+            bp->next_free.push_back(-2);
+            bp->attached.push_back(0);
+            bp->next = key + 1;
+        } else {
+            bp->next = (size_t)bp->next_free[key];
+            bp->next_free[key] = -2;
+            bp->attached[key] = 0;
+        }
+        bp->len++;
+        if (key != handles_host[i]) {
+            bp->err = bp->owner->err = "bp_create_listed_device: proxy slab and object slab are out of step";
+            return NCB_ERR_STATE;
+        }
+    }
+    bp->slab_dirty = true;
+    int r = bp_grow(bp, bp->next_free.size());
+    if (r) return r;
+    k_bp_stage_create_listed<<<(m + 255) / 256, 256, 0, bp->owner->stream>>>(handles_dev, m, lo, hi, SEQ_BACK0 + bp->seq, bp->pend_lo.p, bp->pend_hi.p,
+                                                                            bp->pend_seq.p, bp->d_attached.p);
+    CKB(cudaGetLastError());
+    bp->seq += m;
+    return NCB_OK;
+}
+
 int bp_set_moved_device(ncb_bp* bp, uint32_t n, const float4* lo, const float4* hi, const uint8_t* moved) {
     CKB(cudaSetDevice(bp->owner->device));
     if (n == 0) return NCB_OK;

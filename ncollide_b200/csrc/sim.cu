@@ -24,7 +24,12 @@ struct ncb_sim {
     float margin = 0.f;
     uint32_t n = 0;
     bool first = true;
+    std::vector<uint8_t> alive;          // host mirror of the object slab
+    std::vector<uint32_t> free_handles;  // vacant object handles, reused last-freed-first (CollisionObjectSlab)
     DevBuf<uint8_t> moved;
+    DevBuf<uint8_t> sel_flags;
+    DevBuf<unsigned long long> keys_tmp;
+    DevBuf<uint32_t> slot_tmp, sel_count;
     DevBuf<uint32_t> stage_h;
     DevBuf<float> stage_p, stage_r;
     // pair table, sorted-key order
@@ -217,6 +222,48 @@ __global__ void k_sim_unpack_events(const unsigned long long* __restrict__ ev, u
     out[3 * i + 2] = (uint32_t)(k >> 63);
 }
 
+// ---- CollisionWorld::remove / add between updates ------------------------------------------------------------------------
+// pairs of a removed object leave the pair table silently (glue/setup.rs:56-58): flag them, release their slots
+__global__ void k_sim_flag_removed(const unsigned long long* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ d_attached,
+                                   const uint32_t* __restrict__ slots, uint8_t* keep, uint32_t* free_slots, uint32_t* cnt) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long k = keys[i];
+    bool gone = d_attached[(uint32_t)(k >> 32)] == ST_VACANT || d_attached[(uint32_t)k] == ST_VACANT;
+    keep[i] = gone ? 0 : 1;
+    if (gone) free_slots[atomicAdd(&cnt[0], 1u)] = slots[i];
+}
+__global__ void k_sim_clear_moved(const uint32_t* __restrict__ handles, uint32_t n, uint8_t* moved, uint8_t v) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) moved[handles[i]] = v;
+}
+// new objects: scatter their records into the object arrays
+__global__ void k_sim_scatter_objects(const uint32_t* __restrict__ handles, uint32_t m, const float* __restrict__ pos, const float* __restrict__ rot,
+                                      const uint32_t* __restrict__ type, const float* __restrict__ param, const uint32_t* __restrict__ groups,
+                                      const float* __restrict__ qlimit, const float2* __restrict__ ang_cs, float* dpos, float4* drot, uint32_t* dtype,
+                                      float4* dparam, uint32_t* dgroups, float* dqlimit, float2* dang_cs, uint8_t* moved) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    uint32_t h = handles[k];
+    for (int d = 0; d < 3; ++d) dpos[3 * (size_t)h + d] = pos[3 * (size_t)k + d];
+    drot[h] = make_float4(rot[4 * (size_t)k], rot[4 * (size_t)k + 1], rot[4 * (size_t)k + 2], rot[4 * (size_t)k + 3]);
+    dtype[h] = type[k];
+    dparam[h] = make_float4(param[4 * (size_t)k], param[4 * (size_t)k + 1], param[4 * (size_t)k + 2], param[4 * (size_t)k + 3]);
+    if (dgroups)
+        for (int d = 0; d < 3; ++d) dgroups[3 * (size_t)h + d] = groups ? groups[3 * (size_t)k + d] : (d < 2 ? 0x3FFFFFFFu : 0u);
+    dqlimit[h] = qlimit[k];
+    if (dang_cs) dang_cs[h] = ang_cs[k];
+    moved[h] = 1;
+}
+__global__ void k_sim_fill_groups(uint32_t* g, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) g[3 * (size_t)i] = g[3 * (size_t)i + 1] = 0x3FFFFFFFu, g[3 * (size_t)i + 2] = 0u;
+}
+__global__ void k_sim_fill_f2(float2* p, float2 v, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 template <typename T>
 cudaError_t grow_keep(DevBuf<T>& b, size_t want, size_t keep, cudaStream_t s) {
     if (want <= b.cap) return cudaSuccess;
@@ -270,6 +317,7 @@ int ncb_sim_create(ncb_ctx* ctx, float margin, ncb_sim** out) {
         return r;
     }
     CKS(cudaSetDevice(ctx->device));
+    sim->alive.assign(sim->n, 1);
     CKS(sim->moved.reserve(sim->n));
     CKS(cudaMemsetAsync(sim->moved.p, 1, sim->n, ctx->stream));  // a new object has every update flag set
     CKS(sim->cnt.reserve(8));
@@ -286,6 +334,7 @@ void ncb_sim_destroy(ncb_sim* sim) {
     sim->moved.release(), sim->stage_h.release(), sim->stage_p.release(), sim->stage_r.release();
     sim->keys_prev.release(), sim->slot_prev.release(), sim->slot_new.release(), sim->raw_slot.release();
     sim->slot_pair.release(), sim->slot_key.release(), sim->slot_dir.release(), sim->pm_hdr.release(), sim->pm_entry.release();
+    sim->sel_flags.release(), sim->keys_tmp.release(), sim->slot_tmp.release(), sim->sel_count.release();
     sim->free_slots.release(), sim->cnt.release(), sim->events.release(), sim->events_sorted.release(), sim->cub_tmp.release();
     sim->exp_count.release(), sim->exp_start.release(), sim->exp_ids.release(), sim->exp_events.release(), sim->exp_contacts.release();
     sim->exp_pairs.release(), sim->exp_algo.release(), sim->exp_mcount.release();
@@ -301,7 +350,7 @@ int ncb_sim_set_positions(ncb_sim* sim, uint32_t m, const uint32_t* handles, con
     if (m > sim->n && !handles) return NCB_ERR_ARG;
     if (handles)
         for (uint32_t k = 0; k < m; ++k)
-            if (handles[k] >= sim->n) {
+            if (handles[k] >= sim->n || !sim->alive[handles[k]]) {
                 sim->ctx->err = "ncb_sim_set_positions: unknown object handle";
                 return NCB_ERR_ARG;
             }
@@ -471,6 +520,164 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
         counts->n_manifold_jobs = sim->n_active;  // pairs regenerated in this step
     }
     return NCB_OK;
+}
+
+// CollisionWorld::remove (world.rs:129-144) between updates: the objects leave the world, their proxies leave the broad
+// phase, their pairs disappear without events (glue/setup.rs:50-62); the handles are recycled last-freed-first by ncb_sim_add.
+int ncb_sim_remove(ncb_sim* sim, uint32_t m, const uint32_t* handles) {
+    if (!sim || (m && !handles)) return NCB_ERR_ARG;
+    if (m == 0) return NCB_OK;
+    ncb_ctx* ctx = sim->ctx;
+    CKS(cudaSetDevice(ctx->device));
+    if (sim->first) {
+        ctx->err = "ncb_sim_remove: call ncb_sim_step once before removing objects";
+        return NCB_ERR_STATE;
+    }
+    std::vector<uint8_t> seen(sim->n, 0);
+    for (uint32_t k = 0; k < m; ++k) {
+        if (handles[k] >= sim->n || !sim->alive[handles[k]] || seen[handles[k]]) {
+            ctx->err = "ncb_sim_remove: unknown object handle";
+            return NCB_ERR_ARG;
+        }
+        seen[handles[k]] = 1;
+    }
+    cudaStream_t s = ctx->stream;
+    uint32_t nr = 0;
+    int r = ncb_bp_remove(sim->bp, m, handles, &nr);  // same order => the proxy slab recycles in lockstep with the object slab
+    if (r < 0) return r;
+    for (uint32_t k = 0; k < m; ++k) {
+        sim->alive[handles[k]] = 0;
+        sim->free_handles.push_back(handles[k]);
+    }
+    CKS(sim->stage_h.reserve(m));
+    CKS(cudaMemcpyAsync(sim->stage_h.p, handles, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+    k_sim_clear_moved<<<(m + 255) / 256, 256, 0, s>>>(sim->stage_h.p, m, sim->moved.p, 0);
+    if (sim->n_prev) {
+        // compact the pair table: entries of removed objects go, their state slots return to the free list
+        uint32_t np = sim->n_prev;
+        CKS(sim->sel_flags.reserve(np));
+        CKS(sim->keys_tmp.reserve(np));
+        CKS(sim->slot_tmp.reserve(np));
+        CKS(sim->sel_count.reserve(4));
+        k_sim_flag_removed<<<(np + 255) / 256, 256, 0, s>>>(sim->keys_prev.p, np, sim->bp->d_attached.p, sim->slot_prev.p, sim->sel_flags.p,
+                                                            sim->free_slots.p, sim->cnt.p);
+        size_t b1 = 0, b2 = 0;
+        cub::DeviceSelect::Flagged(nullptr, b1, sim->keys_prev.p, sim->sel_flags.p, sim->keys_tmp.p, sim->sel_count.p, (int)np);
+        cub::DeviceSelect::Flagged(nullptr, b2, sim->slot_prev.p, sim->sel_flags.p, sim->slot_tmp.p, sim->sel_count.p, (int)np);
+        CKS(sim->cub_tmp.reserve(std::max(b1, b2) + 256));
+        size_t bytes = sim->cub_tmp.cap;
+        CKS(cub::DeviceSelect::Flagged(sim->cub_tmp.p, bytes, sim->keys_prev.p, sim->sel_flags.p, sim->keys_tmp.p, sim->sel_count.p, (int)np, s));
+        bytes = sim->cub_tmp.cap;
+        CKS(cub::DeviceSelect::Flagged(sim->cub_tmp.p, bytes, sim->slot_prev.p, sim->sel_flags.p, sim->slot_tmp.p, sim->sel_count.p, (int)np, s));
+        uint32_t kept = 0, hc0 = 0;
+        CKS(cudaMemcpyAsync(&kept, sim->sel_count.p, 4, cudaMemcpyDeviceToHost, s));
+        CKS(cudaMemcpyAsync(&hc0, sim->cnt.p, 4, cudaMemcpyDeviceToHost, s));
+        CKS(cudaStreamSynchronize(s));
+        if (kept) {
+            CKS(cudaMemcpyAsync(sim->keys_prev.p, sim->keys_tmp.p, 8 * (size_t)kept, cudaMemcpyDeviceToDevice, s));
+            CKS(cudaMemcpyAsync(sim->slot_prev.p, sim->slot_tmp.p, 4 * (size_t)kept, cudaMemcpyDeviceToDevice, s));
+        }
+        sim->n_prev = kept;
+        sim->n_free_host = hc0;
+    }
+    CKS(cudaGetLastError());
+    CKS(cudaStreamSynchronize(s));
+    return NCB_OK;
+}
+
+// CollisionWorld::add (world.rs:64-96) between updates for the objects of `objs` (hulls refer to the library already set):
+// handles come from the object slab (last freed first, else appended) and are returned in out_handles; each proxy is created
+// with the object's swept AABB; the object takes part in the next ncb_sim_step with every update flag set.
+int ncb_sim_add(ncb_sim* sim, const ncb_objects* objs, uint32_t* out_handles) {
+    if (!sim || !objs || !out_handles) return NCB_ERR_ARG;
+    ncb_ctx* ctx = sim->ctx;
+    CKS(cudaSetDevice(ctx->device));
+    uint32_t m = objs->n;
+    if (m == 0) return NCB_OK;
+    if (!(objs->pos && objs->rot && objs->shape_type && objs->shape_param && objs->query_limit && objs->ang_pred)) return NCB_ERR_ARG;
+    if (sim->first) {
+        ctx->err = "ncb_sim_add: call ncb_sim_step once before adding objects (the initial set comes from ncb_set_objects)";
+        return NCB_ERR_STATE;
+    }
+    cudaStream_t s = ctx->stream;
+    // handles
+    uint32_t old_n = sim->n, new_n = old_n;
+    std::vector<uint32_t> fh = sim->free_handles;
+    for (uint32_t k = 0; k < m; ++k) {
+        if (!fh.empty()) {
+            out_handles[k] = fh.back();
+            fh.pop_back();
+        } else {
+            out_handles[k] = new_n++;
+        }
+    }
+    // grow the object arrays (contents kept)
+    if (new_n > old_n) {
+        CKS(grow_keep(ctx->pos, 3 * (size_t)new_n, 3 * (size_t)old_n, s));
+        CKS(grow_keep(ctx->rot, new_n, old_n, s));
+        CKS(grow_keep(ctx->type, new_n, old_n, s));
+        CKS(grow_keep(ctx->param, new_n, old_n, s));
+        CKS(grow_keep(ctx->qlimit, new_n, old_n, s));
+        if (ctx->has_groups) CKS(grow_keep(ctx->groups, 3 * (size_t)new_n, 3 * (size_t)old_n, s));
+        if (ctx->ang_stride) CKS(grow_keep(ctx->ang_cs, new_n, old_n, s));
+        CKS(grow_keep(sim->moved, new_n, old_n, s));
+        CKS(cudaMemsetAsync(sim->moved.p + old_n, 0, new_n - old_n, s));
+    }
+    if (objs->groups && !ctx->has_groups) {  // the world used default groups so far: materialise them
+        CKS(ctx->groups.reserve(3 * (size_t)new_n));
+        k_sim_fill_groups<<<(new_n + 255) / 256, 256, 0, s>>>(ctx->groups.p, new_n);
+        ctx->has_groups = true;
+    }
+    // angular prediction table: (cos, sin) from the host libm like ncb_set_objects; a uniform table is expanded on the first deviation
+    std::vector<float2> cs(m);
+    bool same = ctx->ang_stride == 0;
+    for (uint32_t k = 0; k < m; ++k) {
+        cs[k] = make_float2(cosf(objs->ang_pred[k]), sinf(objs->ang_pred[k]));
+        if (ctx->ang_stride == 0 && !ctx->h_ang_cs.empty() && (cs[k].x != ctx->h_ang_cs[0].x || cs[k].y != ctx->h_ang_cs[0].y)) same = false;
+    }
+    if (ctx->ang_stride == 0 && !same) {
+        CKS(ctx->ang_cs.reserve(new_n));
+        k_sim_fill_f2<<<(new_n + 255) / 256, 256, 0, s>>>(ctx->ang_cs.p, ctx->h_ang_cs[0], new_n);
+        ctx->ang_stride = 1;
+    }
+    // stage + scatter
+    DevBuf<float> d_pos, d_rot, d_param, d_ql;
+    DevBuf<uint32_t> d_type, d_groups, d_h;
+    DevBuf<float2> d_cs;
+    CKS(d_pos.reserve(3 * (size_t)m));
+    CKS(d_rot.reserve(4 * (size_t)m));
+    CKS(d_param.reserve(4 * (size_t)m));
+    CKS(d_ql.reserve(m));
+    CKS(d_type.reserve(m));
+    CKS(d_h.reserve(m));
+    CKS(d_cs.reserve(m));
+    CKS(cudaMemcpyAsync(d_pos.p, objs->pos, 12 * (size_t)m, cudaMemcpyHostToDevice, s));
+    CKS(cudaMemcpyAsync(d_rot.p, objs->rot, 16 * (size_t)m, cudaMemcpyHostToDevice, s));
+    CKS(cudaMemcpyAsync(d_param.p, objs->shape_param, 16 * (size_t)m, cudaMemcpyHostToDevice, s));
+    CKS(cudaMemcpyAsync(d_ql.p, objs->query_limit, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+    CKS(cudaMemcpyAsync(d_type.p, objs->shape_type, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+    CKS(cudaMemcpyAsync(d_h.p, out_handles, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+    CKS(cudaMemcpyAsync(d_cs.p, cs.data(), 8 * (size_t)m, cudaMemcpyHostToDevice, s));
+    if (objs->groups) {
+        CKS(d_groups.reserve(3 * (size_t)m));
+        CKS(cudaMemcpyAsync(d_groups.p, objs->groups, 12 * (size_t)m, cudaMemcpyHostToDevice, s));
+    }
+    k_sim_scatter_objects<<<(m + 255) / 256, 256, 0, s>>>(d_h.p, m, d_pos.p, d_rot.p, d_type.p, d_param.p, objs->groups ? d_groups.p : nullptr, d_ql.p, d_cs.p,
+                                                          ctx->pos.p, ctx->rot.p, ctx->type.p, ctx->param.p, ctx->has_groups ? ctx->groups.p : nullptr,
+                                                          ctx->qlimit.p, ctx->ang_stride ? ctx->ang_cs.p : nullptr, sim->moved.p);
+    CKS(cudaGetLastError());
+    ctx->n = sim->n = new_n;
+    sim->alive.resize(new_n, 0);
+    for (uint32_t k = 0; k < m; ++k) sim->alive[out_handles[k]] = 1;
+    sim->free_handles = fh;
+    // proxies: swept AABB of the new objects at their current pose (glue/setup.rs:27-30)
+    int r = reserve_broad(ctx, new_n);
+    if (r) return r;
+    CKS(launch_aabbs(ctx, dev_objects(ctx), sim->margin, 1, 0, new_n));
+    r = bp_create_listed_device(sim->bp, m, out_handles, d_h.p, ctx->aabb_lo.p, ctx->aabb_hi.p);
+    CKS(cudaStreamSynchronize(s));
+    d_pos.release(), d_rot.release(), d_param.release(), d_ql.release(), d_type.release(), d_groups.release(), d_h.release(), d_cs.release();
+    return r;
 }
 
 // Sizes of the last step: pairs, contacts, contact events.

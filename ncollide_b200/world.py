@@ -533,6 +533,19 @@ class SteppingWorld:
         p, r = as_f32(pos).reshape(-1, 3), as_f32(rot).reshape(-1, 4)
         self.ctx.check(self.ctx.lib.ncb_sim_set_positions(self._h, C.c_uint32(len(p)), ptr(hs), ptr(p), ptr(r)), "ncb_sim_set_positions")
 
+    def remove(self, handles):
+        """``CollisionWorld::remove``: the objects and their pairs disappear (no events); handles are recycled by ``add``."""
+        hs = as_u32(handles).reshape(-1)
+        self.ctx.check(self.ctx.lib.ncb_sim_remove(self._h, C.c_uint32(len(hs)), ptr(hs)), "ncb_sim_remove")
+
+    def add(self, scene: WorldScene):
+        """``CollisionWorld::add`` for every object of `scene` (same hull library as the world); returns their handles."""
+        oc, keep = _ffi.pack_objects(scene)
+        out = np.zeros(scene.n, dtype=np.uint32)
+        self.ctx.check(self.ctx.lib.ncb_sim_add(self._h, C.byref(oc), ptr(out)), "ncb_sim_add")
+        self.ctx.n = max(self.ctx.n, int(out.max()) + 1) if len(out) else self.ctx.n
+        return out
+
     def update(self, fetch=True):
         """One ``CollisionWorld::update``.  Returns dict(pairs, algo, off, contacts, ids, events, counts)."""
         c = _ffi.UpdateCountsC()

@@ -1058,8 +1058,17 @@ struct Edge {
 
 struct orc_sim {
     Objects o;
-    std::vector<real> pos, rot;
+    std::vector<real> pos, rot, param, qlimit, ang;  // the sim owns the per-object arrays (objects can be added later)
+    std::vector<uint32_t> type, groups;
     std::vector<uint8_t> flags;  // 1 = POSITION_CHANGED (| everything, for a new object)
+    std::vector<uint8_t> alive;
+    std::vector<uint32_t> free_handles;  // CollisionObjectSlab: vacant keys, reused last-freed-first
+    void rebind() {
+        o.n = (uint32_t)alive.size();
+        o.pos = pos.data(), o.rot = rot.data(), o.shape_type = type.data(), o.shape_param = param.data();
+        o.groups = groups.empty() ? nullptr : groups.data();
+        o.query_limit = qlimit.data(), o.ang_pred = ang.data();
+    }
     orc_bp* bp = nullptr;
     std::map<uint64_t, Edge> edges;  // key = min << 32 | max (iteration order is not observable: events are sorted)
     std::vector<uint32_t> events;    // (h1, h2, started)
@@ -1081,11 +1090,17 @@ extern "C" {
 orc_sim* orc_sim_create(const orc_objects* objs, real margin) {
     orc_sim* s = new orc_sim;
     s->o = make_objects(objs);
-    s->pos.assign(objs->pos, objs->pos + 3 * (size_t)objs->n);
-    s->rot.assign(objs->rot, objs->rot + 4 * (size_t)objs->n);
-    s->o.pos = s->pos.data();
-    s->o.rot = s->rot.data();
-    s->flags.assign(objs->n, 1);
+    size_t n0 = objs->n;
+    s->pos.assign(objs->pos, objs->pos + 3 * n0);
+    s->rot.assign(objs->rot, objs->rot + 4 * n0);
+    s->type.assign(objs->shape_type, objs->shape_type + n0);
+    s->param.assign(objs->shape_param, objs->shape_param + 4 * n0);
+    if (objs->groups) s->groups.assign(objs->groups, objs->groups + 3 * n0);
+    s->qlimit.assign(objs->query_limit, objs->query_limit + n0);
+    s->ang.assign(objs->ang_pred, objs->ang_pred + n0);
+    s->flags.assign(n0, 1);
+    s->alive.assign(n0, 1);
+    s->rebind();
     s->bp = orc_bp_create(margin);
     // CollisionWorld::add -> glue::create_proxies (glue/setup.rs:20-36): proxy box = compute_swept_aabb()
     for (uint32_t i = 0; i < s->o.n; ++i) {
@@ -1108,7 +1123,7 @@ void orc_sim_set_positions(orc_sim* s, uint32_t n, const uint32_t* handles, cons
         uint32_t h = handles ? handles[k] : k;
         for (int d = 0; d < 3; ++d) s->pos[3 * (size_t)h + d] = pos[3 * (size_t)k + d];
         for (int d = 0; d < 4; ++d) s->rot[4 * (size_t)h + d] = rot[4 * (size_t)k + d];
-        s->flags[h] = 1;
+        if (h < s->alive.size() && s->alive[h] && s->flags[h] == 0) s->flags[h] = 1;
     }
 }
 
@@ -1117,13 +1132,13 @@ void orc_sim_step(orc_sim* s) {
     s->events.clear();  // narrow_phase.clear_events()
     // perform_broad_phase (glue/update.rs:65-99)
     for (uint32_t i = 0; i < o.n; ++i) {
-        if (!s->flags[i]) continue;
+        if (!s->alive[i] || !s->flags[i]) continue;
         AABB a = shape_aabb(o, i);
         real ql = o.query_limit[i];
         real mm[6] = {a.mins.x + (-ql), a.mins.y + (-ql), a.mins.z + (-ql), a.maxs.x + ql, a.maxs.y + ql, a.maxs.z + ql};
         orc_bp_set_bounding_volume(s->bp, i, mm);
         // a new object also has SHAPE_CHANGED etc. set: deferred_recompute_all_proximities_with, a no-op on a detached proxy
-        if (s->first) orc_bp_recompute_with(s->bp, i);
+        if (s->flags[i] == 2 || s->first) orc_bp_recompute_with(s->bp, i);
     }
     uint64_t cap = 1 << 16, ns = 0, np = 0;
     std::vector<uint32_t> st, sp;
@@ -1164,6 +1179,65 @@ void orc_sim_step(orc_sim* s) {
     }
     std::fill(s->flags.begin(), s->flags.end(), 0);
     s->first = false;
+}
+
+// CollisionWorld::remove (world.rs:129-144): per handle, objects.remove + glue::remove_proxies (glue/setup.rs:50-62): the
+// broad phase drops the proxy and its pairs WITHOUT notifying anybody, the interaction-graph node goes with its edges.
+int orc_sim_remove(orc_sim* s, uint32_t n, const uint32_t* handles) {
+    for (uint32_t k = 0; k < n; ++k) {
+        uint32_t h = handles[k];
+        if (h >= s->alive.size() || !s->alive[h]) return -1;
+        s->alive[h] = 0;
+        s->flags[h] = 0;
+        s->free_handles.push_back(h);
+        if (orc_bp_remove(s->bp, 1, &h, nullptr, 0, nullptr) != 0) return -1;
+        for (auto it = s->edges.begin(); it != s->edges.end();) {
+            if (it->second.h1 == h || it->second.h2 == h)
+                it = s->edges.erase(it);
+            else
+                ++it;
+        }
+    }
+    return 0;
+}
+// CollisionWorld::add (world.rs:64-96) for the n objects of `objs` (same hull library): handles come from the slab
+// (last freed first, else appended); the proxy is created with the swept AABB; every update flag is set.
+int orc_sim_add(orc_sim* s, const orc_objects* objs, uint32_t* out_handles) {
+    for (uint32_t k = 0; k < objs->n; ++k) {
+        uint32_t h;
+        if (!s->free_handles.empty()) {
+            h = s->free_handles.back();
+            s->free_handles.pop_back();
+        } else {
+            h = (uint32_t)s->alive.size();
+            s->alive.push_back(0), s->flags.push_back(0), s->type.push_back(0), s->qlimit.push_back(0), s->ang.push_back(0);
+            s->pos.resize(s->pos.size() + 3), s->rot.resize(s->rot.size() + 4), s->param.resize(s->param.size() + 4);
+            if (!s->groups.empty() || objs->groups) {
+                size_t old = s->groups.size() / 3;
+                s->groups.resize(3 * s->alive.size());
+                for (size_t i = old; i < s->alive.size(); ++i) s->groups[3 * i] = s->groups[3 * i + 1] = 0x3FFFFFFFu, s->groups[3 * i + 2] = 0;
+            }
+        }
+        for (int d = 0; d < 3; ++d) s->pos[3 * (size_t)h + d] = objs->pos[3 * (size_t)k + d];
+        for (int d = 0; d < 4; ++d) s->rot[4 * (size_t)h + d] = objs->rot[4 * (size_t)k + d];
+        for (int d = 0; d < 4; ++d) s->param[4 * (size_t)h + d] = objs->shape_param[4 * (size_t)k + d];
+        s->type[h] = objs->shape_type[k];
+        s->qlimit[h] = objs->query_limit[k];
+        s->ang[h] = objs->ang_pred[k];
+        if (!s->groups.empty()) {
+            for (int d = 0; d < 3; ++d) s->groups[3 * (size_t)h + d] = objs->groups ? objs->groups[3 * (size_t)k + d] : (d < 2 ? 0x3FFFFFFFu : 0u);
+        }
+        s->alive[h] = 1;
+        s->flags[h] = 2;
+        s->rebind();
+        AABB a = shape_aabb(s->o, h);
+        real ql = s->o.query_limit[h];
+        real mm[6] = {a.mins.x + (-ql), a.mins.y + (-ql), a.mins.z + (-ql), a.maxs.x + ql, a.maxs.y + ql, a.maxs.z + ql};
+        uint32_t ph = orc_bp_create_proxy(s->bp, mm);
+        if (ph != h) return -1;  // object slab and proxy slab evolve in lockstep
+        if (out_handles) out_handles[k] = h;
+    }
+    return 0;
 }
 
 uint64_t orc_sim_num_pairs(const orc_sim* s) { return s->edges.size(); }

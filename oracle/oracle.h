@@ -89,6 +89,8 @@ orc_sim* orc_sim_create(const orc_objects* objs, real margin);
 void orc_sim_destroy(orc_sim*);
 void orc_sim_set_positions(orc_sim*, uint32_t n, const uint32_t* handles, const real* pos, const real* rot);
 void orc_sim_step(orc_sim*);
+int orc_sim_remove(orc_sim*, uint32_t n, const uint32_t* handles);
+int orc_sim_add(orc_sim*, const orc_objects* objs, uint32_t* out_handles);
 uint64_t orc_sim_num_pairs(const orc_sim*);
 uint64_t orc_sim_num_contacts(const orc_sim*);
 void orc_sim_fetch(const orc_sim*, uint32_t* pairs, uint8_t* algo, uint32_t* manifold_off, orc_contact* contacts, uint32_t* ids);

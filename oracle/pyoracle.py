@@ -202,6 +202,19 @@ class OracleSim:
         self.o.lib.orc_sim_set_positions(self.h, C.c_uint32(len(p)), C.c_void_p(hs.ctypes.data) if hs is not None else None,
                                          C.c_void_p(p.ctypes.data), C.c_void_p(r.ctypes.data))
 
+    def remove(self, handles):
+        hs = np.ascontiguousarray(handles, dtype=np.uint32)
+        if self.o.lib.orc_sim_remove(self.h, C.c_uint32(len(hs)), C.c_void_p(hs.ctypes.data)) != 0:
+            raise RuntimeError("orc_sim_remove: unknown handle")
+
+    def add(self, scene):
+        """CollisionWorld::add for every object of `scene` (same hull library); returns the handles."""
+        objs, keep = self.o._objects(scene)
+        out = np.zeros(scene.n, dtype=np.uint32)
+        if self.o.lib.orc_sim_add(self.h, C.byref(objs), C.c_void_p(out.ctypes.data)) != 0:
+            raise RuntimeError("orc_sim_add failed")
+        return out
+
     def step(self):
         """One CollisionWorld::update.  Returns dict(pairs[P,2] (h1, h2), algo[P], off[P+1], contacts, ids, events[E,3])."""
         L = self.o.lib

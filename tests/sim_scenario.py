@@ -36,3 +36,43 @@ def drive(sim, scene, steps, seed, frac=0.4):
         r["moved"] = moved
         log.append(r)
     return log
+
+
+def drive_add_remove(sim, scene, extra, steps, seed):
+    """Like `drive`, with objects removed and added between updates: step 2 removes a tenth of the world, step 3 adds the
+    objects of `extra` (recycled handles first), step 5 removes some of the new ones and moves others."""
+    rng = np.random.default_rng(seed)
+    n0 = scene.n
+    pos = np.concatenate([scene.pos, extra.pos]).copy()  # indexed by handle once handles are known
+    rot = np.concatenate([scene.rot, extra.rot]).copy()
+    alive = np.zeros(n0 + extra.n, dtype=bool)
+    alive[:n0] = True
+    pos_h = {h: scene.pos[h].copy() for h in range(n0)}
+    rot_h = {h: scene.rot[h].copy() for h in range(n0)}
+    log, new_handles = [], None
+    for t in range(steps):
+        if t == 2:
+            gone = np.sort(rng.choice(n0, size=n0 // 10, replace=False)).astype(np.uint32)
+            sim.remove(gone)
+            for h in gone.tolist():
+                del pos_h[h], rot_h[h]
+        if t == 3:
+            new_handles = np.asarray(sim.add(extra)).astype(np.uint32)
+            for k, h in enumerate(new_handles.tolist()):
+                pos_h[h], rot_h[h] = extra.pos[k].copy(), extra.rot[k].copy()
+        if t == 5:
+            sim.remove(new_handles[::3])
+            for h in new_handles[::3].tolist():
+                del pos_h[h], rot_h[h]
+        if t in (1, 4, 5, 6):
+            hs = np.array(sorted(pos_h), dtype=np.uint32)
+            idx = hs[rng.random(len(hs)) < 0.3]
+            p = np.array([pos_h[h] for h in idx.tolist()], dtype=F32) + rng.normal(0, 0.01, size=(len(idx), 3)).astype(F32)
+            r = np.array([rot_h[h] for h in idx.tolist()], dtype=F32)
+            for h, pp in zip(idx.tolist(), p):
+                pos_h[h] = pp
+            sim.set_positions(idx, p, r)
+        r = sim.step()
+        r["new_handles"] = new_handles
+        log.append(r)
+    return log

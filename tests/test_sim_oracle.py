@@ -3,7 +3,7 @@ import numpy as np
 
 from ncollide_b200.scenes import make_world_scene
 from ncollide_b200.shapes import CUBOID
-from sim_scenario import drive, step_poses
+from sim_scenario import drive, drive_add_remove, step_poses
 from test_oracle_kat import scene_of
 
 F32 = np.float32
@@ -94,3 +94,20 @@ def test_stepping_invariants(oracle):
         ib = {(tuple(b["pairs"][p]), int(i)) for p in range(len(b["pairs"])) for i in b["ids"][b["off"][p] : b["off"][p + 1]]}
         kept += len(ia & ib)
     assert kept > 100
+
+
+def test_add_and_remove_between_updates(oracle):
+    # CollisionWorld::remove / add (world.rs:64-96,129-144): handles are recycled last-freed-first, removed objects take their
+    # pairs with them without contact events, new objects interact from the next update on
+    s = make_world_scene(800, 23, (1, 1, 1), side=5.5, n_hulls=16, name="sim_addrm")
+    extra = make_world_scene(120, 24, (1, 1, 1), side=5.5, hull_library=s.hulls, name="extra")
+    log = drive_add_remove(oracle.sim(s), s, extra, steps=7, seed=9)
+    gone = set(range(s.n)) - set(np.unique(log[2]["pairs"]).tolist()) - set()
+    assert len(gone) >= s.n // 10
+    nh = log[3]["new_handles"]
+    assert len(set(nh.tolist())) == extra.n and (nh < s.n).sum() == s.n // 10 and nh.max() == s.n + extra.n - s.n // 10 - 1
+    assert np.isin(nh, log[3]["pairs"]).sum() > 30  # the new objects collide
+    # no Stopped event names a removed object
+    removed_first = set(range(s.n)) - set(np.unique(np.concatenate([log[1]["pairs"].ravel(), nh])).tolist())
+    for ev in log[2]["events"].tolist():
+        assert ev[0] not in removed_first and ev[1] not in removed_first
