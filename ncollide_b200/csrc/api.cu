@@ -68,6 +68,7 @@ int reserve_pairs(ncb_ctx* ctx, size_t cap) {
     CK(ctx->manifold_start.reserve(cap));
     CK(ctx->manifold_count.reserve(cap));
     CK(ctx->epa_queue.reserve(26 * cap));
+    CK(ctx->epa_long.reserve(cap));
     CK(ctx->cp_queue.reserve(10 * cap));
     return NCB_OK;
 }

@@ -862,6 +862,8 @@ struct NarrowArgs {
     uint32_t* epa_queue;   // EPA_REC_WORDS per record
     uint32_t* cp_queue;    // CP_REC_WORDS per record
     int epa_refill_min;    // idle lanes needed before a warp refills (batched initialisation)
+    uint32_t* epa_long;    // two-pass EPA: queue indices deferred to the second pass
+    int epa_pass1_steps;   // expansion steps a pair may take in the first pass
 };
 
 // ---- convex x convex in three compacted phases -------------------------------------------------------------------
@@ -963,15 +965,20 @@ __global__ void __launch_bounds__(128, NCB_GJK_MINBLOCKS) k_cc_gjk(NarrowArgs A)
 #ifndef NCB_EPA_MINBLOCKS
 #define NCB_EPA_MINBLOCKS 16
 #endif
-template <bool PS>
+// PASS 0: one pass over the whole queue.  A whole-warp batch lasts as long as its slowest pair (up to ~12 expansion steps while
+// the average is ~4), so with PASS 1 / 2 the work is split: PASS 1 gives every pair at most A.epa_pass1_steps steps and defers
+// the unfinished ones (their queue index goes to A.epa_long), PASS 2 restarts those among their peers.  A restarted pair repeats
+// exactly the same arithmetic, so results do not depend on the split.
+template <bool PS, int PASS>
 __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) {
     const int KEY = CCQ;
-    const uint32_t seg_end = A.cnt->epa_cursor[KEY];
-    uint32_t* fetch = &A.cnt->epa_fetch[KEY];
+    const uint32_t seg_end = PASS == 2 ? A.cnt->epa_long_n : A.cnt->epa_cursor[KEY];
+    uint32_t* fetch = PASS == 2 ? &A.cnt->epa_long_fetch : &A.cnt->epa_fetch[KEY];
     const int lane = threadIdx.x & 31;
     EpaState e;
     bool active = false, exhausted = false;
-    uint32_t p = 0;
+    uint32_t p = 0, wq = 0;
+    int steps = 0;
     Iso ma, mb;
     Support ga, gb;
     V3 p1, p2, n;
@@ -988,7 +995,9 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) 
             if (!active) {
                 uint32_t w = base + __popc(idle & ((1u << lane) - 1));
                 if (w < seg_end) {
-                    const uint32_t* q = A.epa_queue + (size_t)w * EPA_REC_WORDS;
+                    wq = PASS == 2 ? __ldg(&A.epa_long[w]) : w;
+                    steps = 0;
+                    const uint32_t* q = A.epa_queue + (size_t)wq * EPA_REC_WORDS;
                     const float* f = reinterpret_cast<const float*>(q);
                     p = q[0];
                     int sdim = (int)q[1];
@@ -1010,6 +1019,15 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) 
             }
         } else if (active) {
             status = epa_step(e, ma, ga, mb, gb, p1, p2, n);
+            steps++;
+        }
+        if (PASS == 1) {  // all lanes take part in the aggregated append
+            bool defer = active && status == EPA_CONTINUE && steps >= A.epa_pass1_steps;
+            uint32_t ls = queue_append(&A.cnt->epa_long_n, defer);
+            if (defer) {
+                A.epa_long[ls] = wq;
+                active = false;
+            }
         }
         bool ok = active && status == EPA_DONE_OK;
         bool fail = active && status == EPA_DONE_FAIL;
@@ -1257,6 +1275,9 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     A.epa_refill_min = refill_min;
     A.epa_queue = c->epa_queue.p;
     A.cp_queue = c->cp_queue.p;
+    A.epa_long = c->epa_long.p;
+    static int pass1 = getenv("NCB_EPA_PASS1") ? atoi(getenv("NCB_EPA_PASS1")) : 0;
+    A.epa_pass1_steps = pass1;
     {
         float one_degree = (float)(3.14159265358979323846 / 180.0);
         A.one_degree_cs = make_float2(cosf(one_degree), sinf(one_degree));
@@ -1294,7 +1315,12 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
         cudaMemcpyAsync(c->snap.p, c->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToDevice, s);
         cudaEventRecord(c->ev_snap, s);
     }
-    k_cc_epa<PS><<<sm * epa_bpsm, 64, 0, s>>>(A);
+    if (A.epa_pass1_steps > 0) {
+        k_cc_epa<PS, 1><<<sm * epa_bpsm, 64, 0, s>>>(A);
+        k_cc_epa<PS, 2><<<sm * epa_bpsm, 64, 0, s>>>(A);
+    } else {
+        k_cc_epa<PS, 0><<<sm * epa_bpsm, 64, 0, s>>>(A);
+    }
     timer_mark(c, "cc_epa", 1);
     k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
     timer_mark(c, "cc_manifold", 1);

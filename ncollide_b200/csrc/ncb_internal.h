@@ -65,6 +65,8 @@ struct DevCounters {
     uint32_t epa_fetch[16];    // per key: next EPA queue entry to hand to an idle lane (dynamic fetch)
     uint32_t gjk_fetch[16];    // per key: next pair of the key segment to hand to an idle lane
     int bounds[6];             // ordered-int encoded min xyz / max xyz of AABB centres
+    uint32_t epa_long_n;       // two-pass EPA: entries deferred to the second pass
+    uint32_t epa_long_fetch;
 };
 
 // Persistent narrow-phase state of a stepping world (sim.cu), indexed by state slot.
@@ -161,6 +163,7 @@ struct ncb_ctx {
     ncb::DevBuf<uint32_t> manifold_start;
     ncb::DevBuf<uint8_t> manifold_count;
     ncb::DevBuf<uint32_t> pair_index;
+    ncb::DevBuf<uint32_t> epa_long;              // two-pass EPA: EPA-queue indices of the pairs that need many expansion steps
     ncb::DevBuf<uint32_t> epa_queue;             // 26 words per record
     ncb::DevBuf<uint32_t> cp_queue;              // 10 words per record
 
