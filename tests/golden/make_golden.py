@@ -66,6 +66,29 @@ def main():
             d["c_" + n] = c[n]
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         print(name, s.n, "objects", len(pairs), "pairs", len(c), "contacts")
+    # stepping world: 5 updates of a 400-object world driven by tests/sim_scenario.drive, then world queries
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from sim_scenario import drive
+
+    s = make_world_scene(400, 1010, (1, 1, 1), side=4.6, n_hulls=10, plane=True)
+    sim = o.sim(s)
+    log = drive(sim, s, steps=5, seed=1010)
+    d = scene_to_dict(s)
+    for t, r in enumerate(log):
+        for k in ("pairs", "algo", "off", "ids", "events"):
+            d[f"s{t}_{k}"] = r[k]
+        for n in ("world1", "world2", "normal", "depth", "f1", "f2"):
+            d[f"s{t}_c_{n}"] = r["contacts"][n]
+    rng = np.random.default_rng(1011)
+    ro = rng.uniform(-1, 5.6, size=(300, 3)).astype(np.float32)
+    rd = rng.normal(size=(300, 3)).astype(np.float32)
+    idx, toi, normal, feat = sim.ray_cast(ro, rd, 30.0)
+    idx1, toi1, normal1, feat1 = sim.ray_cast(ro, rd, 30.0, first_only=True)
+    pts = rng.uniform(0, 4.6, size=(300, 3)).astype(np.float32)
+    d.update(q_ro=ro, q_rd=rd, q_idx=idx, q_toi=toi, q_normal=normal, q_feat=feat, q_first_idx=idx1, q_first_toi=toi1, q_pts=pts,
+             q_point_rows=sim.query(2, pts))
+    np.savez_compressed(os.path.join(HERE, "sim_mixed_plane_400.npz"), **d)
+    print("sim", [len(r["pairs"]) for r in log], "pairs per step,", len(idx), "ray hits")
     for kind in ("terrain", "soup"):
         rs = make_ray_scene(kind, 2000, 600, seed=1004)
         om = o.trimesh(rs.verts, rs.tris)

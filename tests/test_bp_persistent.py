@@ -232,3 +232,21 @@ def test_stepping_world_add_remove_matches_oracle(oracle, n, kinds, seed):
     orc = drive_add_remove(oracle.sim(s), s, extra, steps=7, seed=seed)
     assert np.array_equal(dev[3]["new_handles"], orc[3]["new_handles"])
     compare_sim_logs(dev, orc)
+
+
+@pytest.mark.gpu
+def test_sim_golden_fixture_device():
+    """The committed stepping-world fixture (5 updates + ray / point queries) reproduced by the device."""
+    from ncollide_b200.world import Context
+    from test_sim_oracle import _load_sim_golden, check_against_sim_golden
+
+    z, s = _load_sim_golden()
+
+    class A(DeviceSimAdapter):
+        def ray_cast(self, *a, **k):
+            return self.w.ray_cast(*a, **k)
+
+        def query(self, *a, **k):
+            return self.w.query(*a, **k)
+
+    check_against_sim_golden(A(Context(0), s), z, s, exact=False)

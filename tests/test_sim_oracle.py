@@ -111,3 +111,40 @@ def test_add_and_remove_between_updates(oracle):
     removed_first = set(range(s.n)) - set(np.unique(np.concatenate([log[1]["pairs"].ravel(), nh])).tolist())
     for ev in log[2]["events"].tolist():
         assert ev[0] not in removed_first and ev[1] not in removed_first
+
+
+def _load_sim_golden():
+    import os
+
+    from golden.make_golden import scene_from_npz
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "sim_mixed_plane_400.npz"))
+    return z, scene_from_npz(z)
+
+
+def check_against_sim_golden(sim, z, s, exact):
+    """Replays tests/golden/sim_mixed_plane_400.npz (5 updates + world queries, made by make_golden.py from the oracle)."""
+    log = drive(sim, s, steps=5, seed=1010)
+    for t, r in enumerate(log):
+        for k in ("pairs", "algo", "off", "ids"):
+            assert np.array_equal(r[k], z[f"s{t}_{k}"]), (t, k)
+        ev = lambda e: e[np.lexsort((e[:, 1], e[:, 0], e[:, 2]))] if len(e) else e
+        assert np.array_equal(ev(r["events"]), ev(z[f"s{t}_events"])), (t, "events")
+        for n in ("f1", "f2"):
+            assert np.array_equal(r["contacts"][n], z[f"s{t}_c_{n}"]), (t, n)
+        for n in ("world1", "world2", "normal", "depth"):
+            if exact:
+                assert np.array_equal(r["contacts"][n], z[f"s{t}_c_{n}"]), (t, n)
+            else:
+                assert np.allclose(r["contacts"][n], z[f"s{t}_c_{n}"], rtol=1e-4, atol=1e-5), (t, n)
+    idx, toi, normal, feat = sim.ray_cast(z["q_ro"], z["q_rd"], 30.0)
+    assert np.array_equal(idx, z["q_idx"]) and np.array_equal(feat, z["q_feat"])
+    assert np.allclose(toi, z["q_toi"], rtol=1e-4, atol=1e-5) and np.allclose(normal, z["q_normal"], rtol=1e-4, atol=1e-5)
+    idx1, toi1, _, _ = sim.ray_cast(z["q_ro"], z["q_rd"], 30.0, first_only=True)
+    assert np.array_equal(idx1, z["q_first_idx"]) and np.allclose(toi1, z["q_first_toi"], rtol=1e-4, atol=1e-5)
+    assert np.array_equal(sim.query(2, z["q_pts"]), z["q_point_rows"])
+
+
+def test_sim_golden_fixture_oracle(oracle):
+    z, s = _load_sim_golden()
+    check_against_sim_golden(oracle.sim(s), z, s, exact=True)
