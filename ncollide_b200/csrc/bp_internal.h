@@ -47,7 +47,7 @@ struct ncb_bp {
 int bp_create_all_device(ncb_bp* bp, uint32_t n, const float4* lo, const float4* hi);
 int bp_create_listed_device(ncb_bp* bp, uint32_t m, const uint32_t* handles_host, const uint32_t* handles_dev, const float4* lo, const float4* hi);
 int bp_set_moved_device(ncb_bp* bp, uint32_t n, const float4* lo, const float4* hi, const uint8_t* moved);
-int bp_update_impl(ncb_bp* bp, const uint32_t* d_groups, uint32_t* n_started, uint32_t* n_stopped);
+int bp_update_impl(ncb_bp* bp, const uint32_t* d_groups, uint32_t* n_started, uint32_t* n_stopped, bool want_events = true);
 
 // world-level ray queries (query.cu)
 struct WorldQueryBufs {

@@ -550,13 +550,13 @@ int ncb_bp_update(ncb_bp* bp, const uint32_t* groups, uint32_t n_group_slots, ui
         CKB(cudaMemcpyAsync(bp->groups_dev.p, groups, 12 * (size_t)slots, cudaMemcpyHostToDevice, bp->owner->stream));
         dgroups = bp->groups_dev.p;
     }
-    return bp_update_impl(bp, dgroups, n_started, n_stopped);
+    return bp_update_impl(bp, dgroups, n_started, n_stopped, true);
 }
 
 }  // extern "C"
 
 // d_groups: device pointer, 3 words per handle slot, or nullptr
-int bp_update_impl(ncb_bp* bp, const uint32_t* d_groups, uint32_t* n_started, uint32_t* n_stopped) {
+int bp_update_impl(ncb_bp* bp, const uint32_t* d_groups, uint32_t* n_started, uint32_t* n_stopped, bool want_events) {
     CKB(cudaSetDevice(bp->owner->device));
     cudaStream_t s = bp->owner->stream;
     ncb_ctx* w = bp->work;
@@ -659,6 +659,11 @@ int bp_update_impl(ncb_bp* bp, const uint32_t* d_groups, uint32_t* n_started, ui
         }
     }
     mark("sort_keys");
+    if (!want_events) {  // the stepping world diffs the sorted key lists itself (sim.cu)
+        std::swap(bp->keys_old, bp->keys_new);
+        bp->n_old = n_new;
+        return NCB_OK;
+    }
     // 4. started = new \ old, stopped = old \ new
     CKB(bp->counters.reserve(4));
     CKB(cudaMemsetAsync(bp->counters.p, 0, 16, s));

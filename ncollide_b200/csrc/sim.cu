@@ -404,16 +404,17 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
     r = bp_set_moved_device(sim->bp, n, ctx->aabb_lo.p, ctx->aabb_hi.p, sim->moved.p);
     if (r) return r;
     mark("aabb+stage");
-    uint32_t ns = 0, nst = 0;
-    r = bp_update_impl(sim->bp, ctx->has_groups ? ctx->groups.p : nullptr, &ns, &nst);
+    // no event lists wanted: started / stopped pairs are found below by diffing the sorted key lists against the pair table
+    r = bp_update_impl(sim->bp, ctx->has_groups ? ctx->groups.p : nullptr, nullptr, nullptr, false);
     if (r) return r;
     mark("bp_update");
     uint32_t n_cur = sim->bp->n_old;
     const unsigned long long* cur = sim->bp->keys_old.p;
     // ---- interaction edges follow the started / stopped callbacks
     {
-        uint32_t avail = sim->n_free_host + nst;  // slots released by this step's stopped pairs come back first
-        r = sim_grow_slots(sim, (size_t)sim->next_slot_bound + (ns > avail ? ns - avail : 0) + 16);
+        // started - stopped == n_cur - n_prev, and the stopped pairs release their slots before the started ones take theirs
+        uint32_t net = n_cur > sim->n_prev ? n_cur - sim->n_prev : 0;
+        r = sim_grow_slots(sim, (size_t)sim->next_slot_bound + (net > sim->n_free_host ? net - sim->n_free_host : 0) + 16);
         if (r) return r;
     }
     uint32_t cap_events = sim->n_prev + n_cur + 16;
