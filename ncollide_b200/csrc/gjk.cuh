@@ -412,53 +412,60 @@ NCB_HD void gjk_result(const Simplex& s, bool prev, V3& p1, V3& p2) {
 
 enum { GJK_INTERSECTION = 0, GJK_CLOSEST_POINTS = 1, GJK_NO_INTERSECTION = 3 };
 
-// gjk::closest_points with exact_dist = true
+// gjk::closest_points with exact_dist = true, preceded by the caller's `simplex.reset(CSOPoint::from_shapes(.., init_dir))`
+// (contact_support_map_support_map.rs:52-63): the first support evaluation shares the loop's code (one copy of the two support
+// maps in the instruction stream instead of two) and the three ClosestPoints exits share one witness computation.
 static __device__ __noinline__ int gjk_closest_points(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, float max_dist,
-                                               Simplex& s, V3& p1, V3& p2, V3& out_dir) {
+                                                      V3 init_dir, Simplex& s, V3& p1, V3& p2, V3& out_dir) {
     const float eps_tol = NCB_EPS * 10.0f;
     const float eps_rel = sqrtf(eps_tol);
-    V3 proj = simplex_project_origin_and_reduce(s);
-    V3 old_dir;
-    {
-        V3 pd;
-        if (!unit_try_new(proj, 0.f, pd)) return GJK_INTERSECTION;
-        old_dir = -pd;
-    }
+    V3 proj = v3(0.f, 0.f, 0.f), old_dir = v3(0.f, 0.f, 0.f);
     float max_bound = NCB_FMAX;
-    V3 dir;
+    V3 dir = init_dir;
     int niter = 0;
+    bool first = true;
+    bool res_prev = false;
     for (;;) {
-        float old_max_bound = max_bound;
-        float dist;
-        if (!unit_try_new_and_get(-proj, eps_tol, dir, dist)) return GJK_INTERSECTION;
-        max_bound = dist;
-        if (max_bound >= old_max_bound) {
-            gjk_result(s, true, p1, p2);
-            out_dir = old_dir;
-            return GJK_CLOSEST_POINTS;
+        if (!first) {
+            float old_max_bound = max_bound;
+            float dist;
+            if (!unit_try_new_and_get(-proj, eps_tol, dir, dist)) return GJK_INTERSECTION;
+            max_bound = dist;
+            if (max_bound >= old_max_bound) {
+                res_prev = true;
+                out_dir = old_dir;
+                break;
+            }
         }
         CSOPoint cso = cso_from_shapes(m1, g1, m2, g2, dir);
+        if (first) {
+            simplex_init(s, cso);
+            proj = simplex_project_origin_and_reduce(s);
+            V3 pd;
+            if (!unit_try_new(proj, 0.f, pd)) return GJK_INTERSECTION;
+            old_dir = -pd;
+            first = false;
+            continue;
+        }
         float min_bound = -dot(dir, cso.point);
         if (min_bound > max_dist) {
             out_dir = dir;
             return GJK_NO_INTERSECTION;
         } else if (max_bound - min_bound <= eps_rel * max_bound) {
-            gjk_result(s, false, p1, p2);
             out_dir = dir;
-            return GJK_CLOSEST_POINTS;
+            break;
         }
         if (!simplex_add_point(s, cso)) {
-            gjk_result(s, false, p1, p2);
             out_dir = dir;
-            return GJK_CLOSEST_POINTS;
+            break;
         }
         old_dir = dir;
         proj = simplex_project_origin_and_reduce(s);
         if (s.dim == 3) {
             if (min_bound >= eps_tol) {
-                gjk_result(s, true, p1, p2);
+                res_prev = true;
                 out_dir = old_dir;
-                return GJK_CLOSEST_POINTS;
+                break;
             }
             return GJK_INTERSECTION;
         }
@@ -468,6 +475,8 @@ static __device__ __noinline__ int gjk_closest_points(const Iso& m1, const Suppo
             return GJK_NO_INTERSECTION;
         }
     }
+    gjk_result(s, res_prev, p1, p2);
+    return GJK_CLOSEST_POINTS;
 }
 
 // ---- EPA ----------------------------------------------------------------------------------------------------
@@ -821,8 +830,7 @@ static __device__ __noinline__ int contact_sm_sm(EpaState& e, const Iso& m1, con
     V3 dir;
     if (!unit_try_new(m2.t - m1.t, NCB_EPS, dir)) dir = v3(1.f, 0.f, 0.f);
     Simplex s;
-    simplex_init(s, cso_from_shapes(m1, g1, m2, g2, dir));
-    int r = gjk_closest_points(m1, g1, m2, g2, prediction, s, p1, p2, dir_out);
+    int r = gjk_closest_points(m1, g1, m2, g2, prediction, dir, s, p1, p2, dir_out);
     if (r != GJK_INTERSECTION) return r;
     if (epa_closest_points(e, m1, g1, m2, g2, s.dim, s.v, p1, p2, dir_out)) return GJK_CLOSEST_POINTS;
     if (e.overflow) atomicAdd(epa_overflow, 1u);

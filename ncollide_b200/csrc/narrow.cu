@@ -930,8 +930,7 @@ __global__ void __launch_bounds__(128, NCB_GJK_MINBLOCKS) k_cc_gjk(NarrowArgs A)
                 if (pd.w != 0.f) d0 = v3(pd.x, pd.y, pd.z), warm = true;
             }
             if (!warm && !unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
-            simplex_init(s, cso_from_shapes(ma, ga, mb, gb, d0));
-            r = gjk_closest_points(ma, ga, mb, gb, linear, s, p1, p2, dir);
+            r = gjk_closest_points(ma, ga, mb, gb, linear, d0, s, p1, p2, dir);
             if constexpr (PS) {
                 if (r != GJK_INTERSECTION) A.ps.dir[out_index] = make_float4(dir.x, dir.y, dir.z, 1.f);  // :106 / :139
                 if (r == GJK_NO_INTERSECTION) pm_age_only(A.ps, out_index, i1, i2);

@@ -69,9 +69,8 @@ static __device__ __noinline__ int hull_project_gjk(const HullProjSetup& u, V3 p
     Iso id = iso_id();
     V3 dir;
     if (!unit_try_new(-u.m.t, NCB_EPS, dir)) dir = v3(1.f, 0.f, 0.f);
-    simplex_init(s, cso_from_shapes(u.m, u.shape, id, u.origin, dir));
     V3 p1, p2, d;
-    int r = gjk_closest_points(u.m, u.shape, id, u.origin, NCB_FMAX, s, p1, p2, d);
+    int r = gjk_closest_points(u.m, u.shape, id, u.origin, NCB_FMAX, dir, s, p1, p2, d);
     if (r == GJK_CLOSEST_POINTS) proj = p1 + point;
     return r == GJK_CLOSEST_POINTS ? GJK_CLOSEST_POINTS : GJK_INTERSECTION;
 }
