@@ -1053,6 +1053,67 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) 
     }
 }
 
+#include "epa_coop.cuh"
+
+// EPA over the compacted queue, eight lanes per pair (epa_coop.cuh).  Pairs that do not fit the shared-memory capacities are
+// appended to A.epa_long and finished by k_cc_epa<PS, 2>.
+template <bool PS>
+__global__ void __launch_bounds__(CE_PAIRS * CE_G) k_cc_epa_coop(NarrowArgs A) {
+    __shared__ CoopEpa pool[CE_PAIRS];
+    const int KEY = CCQ;
+    const uint32_t seg_end = A.cnt->epa_cursor[KEY];
+    uint32_t* fetch = &A.cnt->epa_fetch[KEY];
+    const int gl = threadIdx.x & 7;
+    CoopEpa& e = pool[threadIdx.x >> 3];
+    for (;;) {
+        uint32_t w = 0;
+        if (gl == 0) w = atomicAdd(fetch, 1u);
+        w = ce_bcast(w, 0);
+        if (w >= seg_end) break;
+        const uint32_t* q = A.epa_queue + (size_t)w * EPA_REC_WORDS;
+        const float* f = reinterpret_cast<const float*>(q);
+        uint32_t p = q[0];
+        int sdim = (int)q[1];
+        CSOPoint sv[4];
+        for (int i = 0; i < 4; ++i) {
+            sv[i].orig1 = v3(f[2 + 6 * i + 0], f[2 + 6 * i + 1], f[2 + 6 * i + 2]);
+            sv[i].orig2 = v3(f[2 + 6 * i + 3], f[2 + 6 * i + 4], f[2 + 6 * i + 5]);
+            sv[i].point = sv[i].orig1 - sv[i].orig2;  // bit-identical to the value GJK computed (CSOPoint::new)
+        }
+        uint2 pr = __ldg(&A.pairs[p]);
+        uint32_t i1 = pr.x, i2 = pr.y;
+        uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
+        Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
+        Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+        SlimSupport ga, gb;
+        ga.kind = t1 == NCB_SHAPE_CUBOID ? 0 : 1, ga.he = a.he, ga.nv = a.hull.nv, ga.pts = a.hull.pts;
+        gb.kind = t2 == NCB_SHAPE_CUBOID ? 0 : 1, gb.he = b.he, gb.nv = b.hull.nv, gb.pts = b.hull.pts;
+        V3 p1, p2, n;
+        bool panicked = false;
+        int st = ce_run(e, ma, ga, mb, gb, sdim, sv, p1, p2, n, panicked);
+        if (gl == 0) {
+            uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
+            if (st == CE_OK) {
+                uint32_t slot = atomicAdd(&A.cnt->cp_cursor[KEY], 1u);
+                cp_store(A.cp_queue, slot, p, p1, p2, n);
+                if constexpr (PS) A.ps.dir[out_index] = make_float4(n.x, n.y, n.z, 1.f);
+            } else if (st == CE_DEFER) {
+                A.epa_long[atomicAdd(&A.cnt->epa_long_n, 1u)] = w;
+            } else {
+                if (panicked) atomicAdd(&A.cnt->ref_panics, 1u);
+                if constexpr (PS) {
+                    A.ps.dir[out_index] = make_float4(1.f, 0.f, 0.f, 1.f);
+                    pm_age_only(A.ps, out_index, i1, i2);
+                } else {
+                    A.manifold_start[out_index] = 0;
+                    A.manifold_count[out_index] = 0;
+                }
+            }
+        }
+        ce_sync();
+    }
+}
+
 #ifndef NCB_MAN_MINBLOCKS
 #define NCB_MAN_MINBLOCKS 6
 #endif
@@ -1314,7 +1375,12 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
         cudaMemcpyAsync(c->snap.p, c->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToDevice, s);
         cudaEventRecord(c->ev_snap, s);
     }
-    if (A.epa_pass1_steps > 0) {
+    static int epa_coop = getenv("NCB_EPA_COOP") ? atoi(getenv("NCB_EPA_COOP")) : 0;
+    static int epac_bpsm = getenv("NCB_EPAC_BPSM") ? atoi(getenv("NCB_EPAC_BPSM")) : 5;
+    if (epa_coop) {
+        k_cc_epa_coop<PS><<<sm * epac_bpsm, CE_PAIRS * CE_G, 0, s>>>(A);
+        k_cc_epa<PS, 2><<<sm * 2, 64, 0, s>>>(A);  // the few pairs beyond the shared-memory capacities
+    } else if (A.epa_pass1_steps > 0) {
         k_cc_epa<PS, 1><<<sm * epa_bpsm, 64, 0, s>>>(A);
         k_cc_epa<PS, 2><<<sm * epa_bpsm, 64, 0, s>>>(A);
     } else {
