@@ -515,6 +515,19 @@ def test_golden_fixtures_on_device(ctx):
         mesh.close()
 
 
+def test_full_size_cfg1_cfg2_parity(ctx, oracle):
+    """BASELINE.json configs[0] (1,000 balls) and configs[1] (100,000 balls / cuboids + one plane) at their full sizes."""
+    for cfg, n in ((1, 1000), (2, 100_000)):
+        s = config_scene(cfg)
+        assert s.n in (n, n + 1)
+        ctx.set_hulls(s.hulls)
+        res = ctx.world_update(s)
+        assert res.counts["epa_overflow"] == 0 and res.counts["ref_panics"] == 0
+        want = oracle.broad_phase(oracle.compute_aabbs(s), s.groups, mode=0)
+        assert np.array_equal(canon(res.pairs), canon(want)), f"cfg{cfg} pair set"
+        compare_manifolds(res, s, oracle, f"cfg{cfg} full size")
+
+
 def test_full_size_1M_world_update_parity(ctx, oracle):
     """BASELINE.json configs[2] at its full size: 1,000,000 mixed balls / cuboids / hulls.  The canonical pair set must be
     bit-exact against the reference-faithful DBVT broad phase of the oracle, and every manifold within tolerance."""
