@@ -81,6 +81,10 @@ def make_world_scene(
     fb, fc, fh = fractions
     nb = int(round(n * fb / (fb + fc + fh)))
     nc = min(int(round(n * fc / (fb + fc + fh))), n - nb)
+    if fh == 0:  # no hulls asked for: rounding must not create one
+        if fc == 0:
+            nb = n
+        nc = n - nb
     nh = n - nb - nc
     types = np.concatenate([np.full(nb, BALL), np.full(nc, CUBOID), np.full(nh, HULL)]).astype(np.uint32)
     rng.shuffle(types)
