@@ -1,4 +1,5 @@
-/* ncb200 — C ABI of the B200-native collision hot path (one CollisionWorld::update step + TriMesh ray casting).
+/* ncb200 — C ABI of the B200-native collision hot path (one CollisionWorld::update step + TriMesh ray casting), widened to
+ * the persistent BroadPhase (ncb_bp_*), the stepping CollisionWorld (ncb_sim_*) and its world queries.
  *
  * This is the drop-in boundary: plain pointers and sizes, no C++ / torch types, no unwinding.
  * Every entry point names the reference (dimforge/ncollide, paths relative to the reference root) item it
