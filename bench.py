@@ -408,6 +408,14 @@ def run_native(args):
                          "C++ restatement of the reference, single thread like the reference, not the Rust binary",
                "host_cores_available": os.cpu_count(), "pairs": c[0], "contacts": c[1]}
 
+    # ---- widened rows, N = 1 only, reported beside the headline; never allowed to break the line ----
+    widened = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            widened = bench_widened(ctx, scene)
+        except Exception as ex:  # noqa: BLE001
+            widened = {"error": repr(ex)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -416,7 +424,9 @@ def run_native(args):
                 "workload": f"configs[2]: {n_per} mixed balls/cuboids/convex hulls (<=32 verts) per GPU, fresh-world update "
                             "(AABBs -> LBVH -> pair search -> contact manifolds)",
                 "n_objects_total": n_total, "pairs": tot_pairs, "contacts": tot_contacts, "contact_pairs": tot_contact_pairs,
-                "parallelism": "single GPU" if world == 1 else f"{world} ranks: AABB block per rank + NCCL all-gather, replicated LBVH, query slices",
+                "parallelism": "single GPU" if world == 1 else (
+                    f"{world} ranks: AABB block per rank + NCCL all-gather, "
+                    + ("replicated LBVH, query slices" if os.environ.get("NCB_SHARD") == "slices" else "spatial ownership (Morton ranges + ghosts), local LBVH per rank")),
                 "l2": "256 MiB flush between timed iterations; working set > L2",
                 "seed": 1003,
             },
@@ -431,6 +441,7 @@ def run_native(args):
             "clocks": clocks,
             "counts": {k: v for k, v in counts.items() if k != "n_algo"} | {"n_algo": counts["n_algo"]},
             "rays": rays,
+            "widened": widened,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -494,6 +505,49 @@ def world_total_bytes(n, counts, scene):
     return float(sum(stage_bytes(k, n, counts, scene) for k in names))
 
 
+
+def bench_widened(ctx, scene):
+    """Stepping world (CollisionWorld::update over several steps, 10 % of the poses set per step) and world ray queries
+    (first_interference_with_ray) on the same scene, through the C ABI with host buffers; wall clock."""
+    from ncollide_b200.world import SteppingWorld
+
+    rng = np.random.default_rng(11)
+    n = scene.n
+    w = SteppingWorld(ctx, scene)
+    t0 = time.perf_counter()
+    w.update(fetch=False)
+    first_ms = (time.perf_counter() - t0) * 1e3
+    pos, rot = scene.pos.copy(), scene.rot.copy()
+    times = []
+    info = None
+    for _ in range(8):
+        idx = np.sort(rng.choice(n, size=max(1, n // 10), replace=False)).astype(np.uint32)
+        pos[idx] = (pos[idx] + rng.normal(0, 0.004, size=(len(idx), 3))).astype(np.float32)
+        t0 = time.perf_counter()
+        w.set_positions(idx, pos[idx], rot[idx])
+        info = w.update(fetch=False)
+        times.append((time.perf_counter() - t0) * 1e3)
+    side = float(scene.pos.max())
+    n_rays = min(n, 1_000_000)
+    ro = rng.uniform(0, side, size=(n_rays, 3)).astype(np.float32)
+    rd = rng.normal(size=(n_rays, 3)).astype(np.float32)
+    rt = []
+    rows = 0
+    for _ in range(3):
+        t0 = time.perf_counter()
+        hit = w.ray_cast(ro, rd, 20.0, first_only=True)
+        rt.append((time.perf_counter() - t0) * 1e3)
+        rows = len(hit[0])
+    w.close()
+    return {
+        "stepping_world": {"workload": f"{n} objects, {n // 10} poses set per update (ncb_sim_set_positions + ncb_sim_step)",
+                           "ms_per_update": statistics.median(times[2:]), "first_update_ms": first_ms, "pairs": info["counts"]["n_pairs"],
+                           "contacts": info["counts"]["n_contacts"], "pairs_regenerated": info["counts"]["n_manifold_jobs"]},
+        "world_ray_queries": {"workload": f"{n_rays} rays, first_interference_with_ray within 20 units, {n}-object world (ncb_sim_ray_cast)",
+                              "ms": min(rt[1:]), "Mrays_per_s": n_rays / (min(rt[1:]) / 1e3) / 1e6, "hits": rows},
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -503,6 +557,7 @@ def main():
     ap.add_argument("--n-objects", type=int, default=0, help="objects per GPU (default 1,000,000)")
     ap.add_argument("--no-rays", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the stepping-world / world-query figures")
     ap.add_argument("--rays-only", action="store_true", help="debug: only the ray-casting sub-benchmark, prints its dict")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
