@@ -1144,6 +1144,7 @@ void orc_sim_step(orc_sim* s) {
     std::vector<uint32_t> st, sp;
     // the call mutates state, so size the buffers from the upper bounds first
     cap = std::max<uint64_t>(cap, 64ull * o.n + 1024);
+    cap = std::max<uint64_t>(cap, std::min<uint64_t>((uint64_t)o.n * o.n / 2 + 1024, 1ull << 26));  // dense small worlds: every pair can start at once
     st.resize(2 * cap), sp.resize(2 * cap);
     orc_bp_update(s->bp, o.groups, st.data(), cap, &ns, sp.data(), cap, &np);
     if (ns > cap || np > cap) abort();
