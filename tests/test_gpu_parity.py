@@ -504,9 +504,12 @@ def test_early_fetch_with_staged_updates(ctx):
         P, Cn = c.n_pairs, c.n_contacts
         assert P == len(ref.pairs) and Cn == len(ref.contacts)
         # the pair order after the key sort is deterministic up to atomics inside one key segment: compare per pair
-        got = {tuple(p): bufs["contacts"][st : st + k][["world1", "world2", "normal", "depth", "f1", "f2"]].tobytes()
+        def key(c):  # per-field bytes: a multi-field view still carries the `pair` back-reference, which depends on the pair order
+            return b"".join(np.ascontiguousarray(c[f]).tobytes() for f in ("world1", "world2", "normal", "depth", "f1", "f2"))
+
+        got = {tuple(p): key(bufs["contacts"][st : st + k])
                for p, st, k in zip(bufs["pairs"][:P].tolist(), bufs["start"][:P].tolist(), bufs["count"][:P].tolist())}
-        want = {tuple(p): ref.contacts_of(i)[["world1", "world2", "normal", "depth", "f1", "f2"]].tobytes() for i, p in enumerate(ref.pairs.tolist())}
+        want = {tuple(p): key(ref.contacts_of(i)) for i, p in enumerate(ref.pairs.tolist())}
         assert got == want, mode
         assert np.array_equal(np.sort(bufs["algo"][:P]), np.sort(ref.pair_algo))
 
