@@ -47,6 +47,15 @@ extern "C" {
 #define NCB_ALGO_PLANE_CONVEX 3u
 #define NCB_ALGO_BALL_CONVEX 4u
 #define NCB_ALGO_CONVEX_CONVEX 5u
+/* The pair involves a GeometricQueryType::Proximity object: a ProximityDetector ran instead of a contact generator
+ * (DefaultProximityDispatcher::get_proximity_algorithm, proximity_detector/default_proximity_dispatcher.rs:19-47). */
+#define NCB_ALGO_PROXIMITY 6u
+
+/* query::Proximity (query/proximity/proximity.rs:4-12) as a byte; NCB_PROXIMITY_NONE: not a proximity pair / no detector. */
+#define NCB_PROXIMITY_INTERSECTING 0u
+#define NCB_PROXIMITY_WITHIN_MARGIN 1u
+#define NCB_PROXIMITY_DISJOINT 2u
+#define NCB_PROXIMITY_NONE 255u
 
 typedef struct ncb_ctx ncb_ctx;
 typedef struct ncb_mesh ncb_mesh;
@@ -108,6 +117,8 @@ typedef struct ncb_update_counts {
     uint32_t ref_panics;       /* pairs on which the reference itself would have panicked (assert / unwrap) */
     uint32_t n_epa_pairs;      /* convex-convex pairs that needed EPA (GJK found the origin inside the CSO) */
     uint32_t n_manifold_jobs;  /* convex-convex pairs that reached feature clipping */
+    uint32_t n_proximity_pairs; /* pairs handled by a proximity detector (NCB_ALGO_PROXIMITY) */
+    uint32_t n_proximity[3];    /* of those: Intersecting, WithinMargin, Disjoint */
 } ncb_update_counts;
 
 /* ---- context ------------------------------------------------------------------------------------------------ */
@@ -130,6 +141,12 @@ int ncb_set_positions(ncb_ctx* ctx, uint32_t n, const float* pos, const float* r
  * all-gathered on the device buffers returned by ncb_device_ptr(ctx, 4 / 5)). pos / rot point at the block. */
 int ncb_set_positions_range(ncb_ctx* ctx, uint32_t begin, uint32_t count, const float* pos, const float* rot);
 
+/* GeometricQueryType per object (pipeline/object/query_type.rs:8-37): kinds[i] = 0 Contacts(query_limit, ang_pred) or
+ * 1 Proximity(query_limit) — a sensor.  A pair with at least one sensor gets a Proximity status instead of a contact manifold
+ * (NarrowPhase::handle_interaction, narrow_phase.rs:226-247).  kinds == NULL (or all 0): every object is Contacts, the state
+ * after ncb_set_objects.  n must equal the object count. */
+int ncb_set_query_types(ncb_ctx* ctx, uint32_t n, const uint8_t* kinds);
+
 /* ---- stage entry points (each mirrors one reference routine, host buffers in/out) ---------------------------- */
 /* mode 0: bounding_volume::aabb(shape, position) (shape/shape.rs aabb, bounding_volume/aabb_*.rs);
  * mode 1: CollisionObjectRef::compute_aabb = mode 0 loosened by query_limit (collision_object.rs:89-93);
@@ -148,6 +165,13 @@ int ncb_generate_contacts(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* pairs,
                           uint32_t cap_contacts, uint32_t* n_contacts, uint32_t* manifold_start, uint8_t* manifold_count,
                           uint8_t* algo);
 
+/* ProximityDetector::update with fresh detectors for a batch of (object1, object2) pairs over the objects set by
+ * ncb_set_objects (proximity_detector/proximity_detector.rs:10-30; ball x ball, plane x support map, support map x support map
+ * through GJK with exact_dist = false; balls are support maps here).  margins[p] or, when NULL, query_limit[o1] + query_limit[o2]
+ * (narrow_phase.rs:138).  out[p] = NCB_PROXIMITY_* (NONE for plane x plane).  With one explicit margin per pair this is
+ * query::proximity(m1, g1, m2, g2, margin) (query/proximity/proximity_shape_shape.rs:8-33). */
+int ncb_proximity(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* pairs, const float* margins, uint8_t* out);
+
 /* ---- fused hot path ------------------------------------------------------------------------------------------ */
 /* One fresh-world CollisionWorld::update (pipeline/world.rs:104-119 -> glue/update.rs:117-135) over the objects
  * currently on the device; results stay on the device.  q_begin/q_end restrict the broad-phase QUERY leaves to a
@@ -156,6 +180,10 @@ int ncb_world_update_device(ncb_ctx* ctx, float margin, uint32_t q_begin, uint32
 /* Copy the results of the last update to host buffers (any pointer may be NULL). */
 int ncb_world_fetch(ncb_ctx* ctx, uint32_t* pairs, uint32_t cap_pairs, uint8_t* pair_algo, uint32_t* manifold_start,
                     uint8_t* manifold_count, ncb_contact* contacts, uint32_t cap_contacts);
+/* Proximity status of every pair of the last update, in the order of ncb_world_fetch's pairs: NCB_PROXIMITY_* for
+ * NCB_ALGO_PROXIMITY pairs, NCB_PROXIMITY_NONE for the others.  On a fresh world every status other than Disjoint is what
+ * the reference reports as ProximityEvent(o1, o2, Disjoint, status) (narrow_phase.rs:108-121).  All NONE without sensors. */
+int ncb_world_fetch_proximity(ncb_ctx* ctx, uint8_t* prox, uint32_t cap_pairs);
 /* Host-buffer convenience = ncb_set_objects + ncb_world_update_device + ncb_world_fetch (the end-to-end call). */
 int ncb_world_update(ncb_ctx* ctx, const ncb_objects* objs, float margin, uint32_t* pairs, uint32_t cap_pairs,
                      uint8_t* pair_algo, uint32_t* manifold_start, uint8_t* manifold_count, ncb_contact* contacts,

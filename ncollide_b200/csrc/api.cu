@@ -152,6 +152,7 @@ void ncb_destroy(ncb_ctx* c) {
     c->pairs_raw.release(), c->pairs.release(), c->keys_raw.release(), c->pair_algo.release(), c->counters.release();
     c->contacts.release(), c->manifold_start.release(), c->manifold_count.release(), c->pair_index.release();
     c->epa_queue.release(), c->cp_queue.release();
+    c->qkind.release(), c->prox.release();
     if (c->timer.created)
         for (int i = 0; i <= StageTimer::MAX; ++i) cudaEventDestroy(c->timer.ev[i]);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -307,8 +308,27 @@ int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* o) {
         }
     }
     if (n) CK(cudaMemcpyAsync(ctx->ang_cs.p, ctx->h_ang_cs.data(), 8 * ctx->h_ang_cs.size(), cudaMemcpyHostToDevice, s));
+    if (n != ctx->n) ctx->has_prox = false;  // query types belong to an object set: a different count resets them to Contacts
     ctx->n = n;
     CK(reserve_broad(ctx, n) == NCB_OK ? cudaSuccess : cudaErrorMemoryAllocation);
+    return NCB_OK;
+}
+
+int ncb_set_query_types(ncb_ctx* ctx, uint32_t n, const uint8_t* kinds) {
+    if (!ctx) return NCB_ERR_ARG;
+    REQUIRE(n == ctx->n, NCB_ERR_ARG, "ncb_set_query_types: n differs from the object count");
+    CK(cudaSetDevice(ctx->device));
+    bool any = false;
+    for (uint32_t i = 0; kinds && i < n; ++i) {
+        REQUIRE(kinds[i] <= 1, NCB_ERR_ARG, "ncb_set_query_types: kind must be 0 (Contacts) or 1 (Proximity)");
+        any = any || kinds[i] != 0;
+    }
+    ctx->has_prox = any;
+    if (any) {
+        CK(ctx->qkind.reserve(n));
+        CK(cudaMemcpyAsync(ctx->qkind.p, kinds, n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));  // the caller's array may go away
+    }
     return NCB_OK;
 }
 
@@ -426,6 +446,31 @@ static void fill_counts(ncb_ctx* ctx, ncb_update_counts* counts) {
     counts->n_algo[NCB_ALGO_NONE] = c.key_hist[K_NONE];
     counts->n_epa_pairs = c.epa_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID];
     counts->n_manifold_jobs = c.cp_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID];
+    counts->n_proximity_pairs = c.key_hist[K_PROX_BALL_BALL] + c.key_hist[K_PROX_PLANE] + c.key_hist[K_PROX_SM];
+    for (int k = 0; k < 3; ++k) counts->n_proximity[k] = c.prox_hist[k];
+}
+
+int ncb_proximity(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* pairs, const float* margins, uint8_t* out) {
+    if (!ctx || (n_pairs && (!pairs || !out))) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n_pairs == 0) return NCB_OK;
+    REQUIRE(ctx->n > 0, NCB_ERR_STATE, "ncb_proximity: call ncb_set_objects first");
+    for (uint32_t p = 0; p < 2 * n_pairs; ++p) REQUIRE(pairs[p] < ctx->n, NCB_ERR_ARG, "ncb_proximity: object index out of range");
+    cudaStream_t s = ctx->stream;
+    CK(ctx->pairs_raw.reserve(n_pairs));
+    CK(ctx->prox.reserve(n_pairs));
+    CK(cudaMemcpyAsync(ctx->pairs_raw.p, pairs, 8 * (size_t)n_pairs, cudaMemcpyHostToDevice, s));
+    const float* d_margins = nullptr;
+    if (margins) {
+        // the margins ride in the manifold_start buffer (same element size), unused by this call
+        CK(ctx->manifold_start.reserve(n_pairs));
+        CK(cudaMemcpyAsync(ctx->manifold_start.p, margins, 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, s));
+        d_margins = reinterpret_cast<const float*>(ctx->manifold_start.p);
+    }
+    CK(launch_proximity_batch(ctx, dev_objects(ctx), ctx->pairs_raw.p, n_pairs, d_margins, ctx->prox.p));
+    CK(cudaMemcpyAsync(out, ctx->prox.p, n_pairs, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return NCB_OK;
 }
 
 int ncb_generate_contacts(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* pairs, ncb_contact* out_contacts, uint32_t cap_contacts,
@@ -488,6 +533,11 @@ static int update_after_aabbs(ncb_ctx* ctx, uint32_t q_begin, uint32_t q_end, ui
         CK(launch_lbvh_build(ctx, n, handle_map));
         CK(launch_pair_search(ctx, n, ctx->has_groups ? ctx->groups.p : nullptr, q_begin, q_end, (uint32_t)cap_pairs, my_rank));
         timer_mark(ctx, "pair_search", 2);
+        if (ctx->has_prox) {  // sensors: their pairs move to the proximity keys; statuses default to NONE
+            CK(ctx->prox.reserve(cap_pairs));
+            CK(cudaMemsetAsync(ctx->prox.p, 0xff, cap_pairs, ctx->stream));
+            CK(launch_prox_rekey(ctx, (uint32_t)cap_pairs));
+        }
         CK(launch_pair_sort(ctx, (uint32_t)cap_pairs, nullptr));
         timer_mark(ctx, "pair_sort", 3);
         if (ctx->early.active) CK(cudaEventRecord(ctx->ev_pairs, ctx->stream));
@@ -660,6 +710,21 @@ int ncb_world_fetch(ncb_ctx* ctx, uint32_t* pairs, uint32_t cap_pairs, uint8_t* 
     if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(s));
     return ((pairs && np > cap_pairs) || (contacts && nc > cap_contacts)) ? 1 : NCB_OK;
+}
+
+int ncb_world_fetch_proximity(ncb_ctx* ctx, uint8_t* prox, uint32_t cap_pairs) {
+    if (!ctx || (cap_pairs && !prox)) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t np = ctx->last_n_pairs;
+    uint32_t wp = np < cap_pairs ? np : cap_pairs;
+    if (wp == 0) return np > cap_pairs ? 1 : NCB_OK;
+    if (!ctx->has_prox || !ctx->prox.p) {
+        memset(prox, 0xff, wp);
+    } else {
+        CK(cudaMemcpyAsync(prox, ctx->prox.p, wp, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return np > cap_pairs ? 1 : NCB_OK;
 }
 
 int ncb_world_update(ncb_ctx* ctx, const ncb_objects* objs, float margin, uint32_t* pairs, uint32_t cap_pairs, uint8_t* pair_algo,

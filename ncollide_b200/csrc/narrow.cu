@@ -1363,6 +1363,7 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     k_narrow<K_PLANE_CUBOID, PS><<<sm * 2, 128, 0, s2>>>(A);
     k_narrow<K_PLANE_HULL, PS><<<sm * 2, 128, 0, s2>>>(A);
     if (!PS) k_narrow_none<<<sm, 256, 0, s2>>>(A);
+    if (!PS && c->has_prox && c->prox.p) launch_proximity_segments(c, o, pairs, pair_index, s2);  // sensor pairs (proximity.cu)
     if (c->side_stream) cudaEventRecord(c->ev_join, s2);
     k_cc_gjk<PS><<<sm * gjk_bpsm, 128, 0, s>>>(A);
     timer_mark(c, "cc_gjk", 1);

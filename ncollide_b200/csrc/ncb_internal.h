@@ -20,7 +20,11 @@ enum PairKey : uint32_t {
     K_CUBOID_HULL = 7,
     K_HULL_HULL = 8,
     K_NONE = 9,
-    K_COUNT = 10
+    // pairs with a GeometricQueryType::Proximity object (proximity.cu); adjacent, after every contact key
+    K_PROX_BALL_BALL = 10,
+    K_PROX_PLANE = 11,
+    K_PROX_SM = 12,
+    K_COUNT = 13
 };
 
 struct DevHulls {
@@ -67,6 +71,7 @@ struct DevCounters {
     int bounds[6];             // ordered-int encoded min xyz / max xyz of AABB centres
     uint32_t epa_long_n;       // two-pass EPA: entries deferred to the second pass
     uint32_t epa_long_fetch;
+    uint32_t prox_hist[4];     // proximity pairs per status (Intersecting, WithinMargin, Disjoint)
 };
 
 // Persistent narrow-phase state of a stepping world (sim.cu), indexed by state slot.
@@ -143,6 +148,10 @@ struct ncb_ctx {
     ncb::DevBuf<uint32_t> type, groups;
     std::vector<float2> h_ang_cs;
     uint32_t ang_stride = 1;
+    // GeometricQueryType per object (ncb_set_query_types): 1 = Proximity(query_limit).  has_prox = at least one sensor.
+    ncb::DevBuf<uint8_t> qkind;
+    bool has_prox = false;
+    ncb::DevBuf<uint8_t> prox;                   // Proximity status per sorted pair (255 for contact pairs)
     // hulls
     ncb::DevHulls hulls = {};
     std::vector<void*> hull_allocs;
@@ -237,6 +246,10 @@ size_t lbvh_temp_bytes(uint32_t n);
 cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, uint32_t cap_pairs,
                                 uint32_t cap_contacts);
 cudaError_t launch_classify_pairs(ncb_ctx* c, const uint2* pairs, uint32_t n);
+// proximity.cu
+cudaError_t launch_prox_rekey(ncb_ctx* c, uint32_t cap_pairs);
+cudaError_t launch_proximity_segments(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, cudaStream_t s);
+cudaError_t launch_proximity_batch(ncb_ctx* c, const DevObjects& o, const uint2* pairs, uint32_t n, const float* margins, uint8_t* out);
 cudaError_t launch_narrow_phase_persistent(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, uint32_t cap_pairs,
                                            const PersistArgs& ps);
 }  // namespace ncb

@@ -307,6 +307,10 @@ int ncb_sim_create(ncb_ctx* ctx, float margin, ncb_sim** out) {
         ctx->err = "ncb_sim_create: call ncb_set_objects first";
         return NCB_ERR_STATE;
     }
+    if (ctx->has_prox) {
+        ctx->err = "ncb_sim_create: proximity sensors (ncb_set_query_types) are only supported by the fresh-world update";
+        return NCB_ERR_UNSUPPORTED;
+    }
     ncb_sim* sim = new ncb_sim;
     sim->ctx = ctx;
     sim->margin = margin;

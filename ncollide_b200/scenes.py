@@ -28,10 +28,25 @@ class WorldScene:
     hulls: HullLibrary
     margin: float = 0.02
     name: str = ""
+    # GeometricQueryType per object (pipeline/object/query_type.rs:8-37): None / 0 = Contacts(query_limit, ang_pred),
+    # 1 = Proximity(query_limit) — a sensor: its pairs get a Proximity status instead of a contact manifold.
+    query_kind: np.ndarray | None = None  # [N] u8
 
     @property
     def n(self):
         return len(self.pos)
+
+
+def with_sensors(scene, fraction, seed, margin=None):
+    """Marks a seeded random `fraction` of the objects as GeometricQueryType::Proximity(margin) (margin None: keep query_limit)."""
+    rng = np.random.default_rng(seed)
+    kind = (rng.random(scene.n) < fraction).astype(np.uint8)
+    scene.query_kind = np.ascontiguousarray(kind)
+    if margin is not None:
+        ql = scene.query_limit.copy()
+        ql[kind != 0] = F32(margin)
+        scene.query_limit = np.ascontiguousarray(ql)
+    return scene
 
 
 def random_unit_quaternions(rng, n):

@@ -22,7 +22,15 @@ from ._ffi import CONTACT_DTYPE, NcbError, as_f32, as_u32, ptr
 from .scenes import DEFAULT_GROUPS, WorldScene
 from .shapes import HullLibrary
 
-ALGO_NAMES = ["none", "ball_ball", "plane_ball", "plane_convex", "ball_convex", "convex_convex"]
+ALGO_NAMES = ["none", "ball_ball", "plane_ball", "plane_convex", "ball_convex", "convex_convex", "proximity"]
+ALGO_PROXIMITY = 6
+
+
+class Proximity:
+    """query/proximity/proximity.rs:4-12 (NONE: the pair has no proximity detector / is a contact pair)."""
+
+    Intersecting, WithinMargin, Disjoint, NONE = 0, 1, 2, 255
+    NAMES = {0: "Intersecting", 1: "WithinMargin", 2: "Disjoint", 255: "None"}
 
 
 @dataclass
@@ -33,6 +41,7 @@ class UpdateResult:
     manifold_count: np.ndarray  # [P] u8
     contacts: np.ndarray  # [C] CONTACT_DTYPE
     counts: dict
+    proximity: np.ndarray | None = None  # [P] u8 Proximity status (255 for contact pairs); None when the world has no sensor
 
     def contacts_of(self, p):
         s = int(self.manifold_start[p])
@@ -77,9 +86,16 @@ class Context:
         self.check(self.lib.ncb_set_objects(self.h, C.byref(oc)), "ncb_set_objects")
         self.n = oc.n
 
+    def set_query_types(self, kinds):
+        """GeometricQueryType per object: 0 Contacts, 1 Proximity (ncb_set_query_types); None = all Contacts."""
+        k = None if kinds is None else np.ascontiguousarray(kinds, dtype=np.uint8)
+        self.check(self.lib.ncb_set_query_types(self.h, C.c_uint32(self.n), ptr(k)), "ncb_set_query_types")
+        self.has_sensors = k is not None and bool(k.any())
+
     def set_scene(self, scene: WorldScene):
         self.set_hulls(scene.hulls)
         self.set_objects(scene)
+        self.set_query_types(getattr(scene, "query_kind", None))
 
     def set_positions(self, pos, rot):
         pos, rot = as_f32(pos), as_f32(rot)
@@ -129,6 +145,21 @@ class Context:
                 return UpdateResult(pairs, algo, start, count, out[: nc.value].copy(), {"n_contacts": nc.value})
             cap = int(nc.value) + 16
 
+    def proximity(self, pairs, margins=None):
+        """ProximityDetector::update with fresh detectors for (object1, object2) pairs (ncb_proximity) -> u8 statuses."""
+        pairs = as_u32(pairs).reshape(-1, 2)
+        out = np.zeros(len(pairs), dtype=np.uint8)
+        m = None if margins is None else as_f32(margins)
+        if m is not None and len(m) != len(pairs):
+            raise ValueError("one margin per pair")
+        self.check(self.lib.ncb_proximity(self.h, C.c_uint32(len(pairs)), ptr(pairs), ptr(m), ptr(out)), "ncb_proximity")
+        return out
+
+    def world_fetch_proximity(self, n_pairs):
+        out = np.zeros(n_pairs, dtype=np.uint8)
+        self.check(self.lib.ncb_world_fetch_proximity(self.h, ptr(out), C.c_uint32(n_pairs)), "ncb_world_fetch_proximity")
+        return out
+
     # -- fused update -----------------------------------------------------------------------------------
     @staticmethod
     def _counts(c):
@@ -136,7 +167,8 @@ class Context:
             "n_pairs": c.n_pairs,
             "n_contacts": c.n_contacts,
             "n_contact_pairs": c.n_contact_pairs,
-            "n_algo": {ALGO_NAMES[i]: c.n_algo[i] for i in range(6)},
+            "n_algo": {**{ALGO_NAMES[i]: c.n_algo[i] for i in range(6)}, "proximity": c.n_proximity_pairs},
+            "n_proximity": {"intersecting": c.n_proximity[0], "within_margin": c.n_proximity[1], "disjoint": c.n_proximity[2]},
             "epa_overflow": c.epa_overflow,
             "ref_panics": c.ref_panics,
             "n_epa_pairs": c.n_epa_pairs,
@@ -169,12 +201,19 @@ class Context:
             self.lib.ncb_world_fetch(self.h, ptr(pairs), C.c_uint32(P), ptr(algo), ptr(start), ptr(count), ptr(contacts), C.c_uint32(Cn)),
             "ncb_world_fetch",
         )
-        return UpdateResult(pairs, algo, start, count, contacts, counts)
+        prox = self.world_fetch_proximity(P) if getattr(self, "has_sensors", False) else None
+        return UpdateResult(pairs, algo, start, count, contacts, counts, prox)
 
     def world_update(self, scene: WorldScene, bufs=None):
         """The end-to-end host-buffer call (ncb_world_update): uploads the objects, runs the step, copies results back."""
         oc, keep = _ffi.pack_objects(scene)
         n = oc.n
+        qk = getattr(scene, "query_kind", None)
+        if qk is not None or getattr(self, "has_sensors", False):
+            # query types belong to the object set: install the set first so that they can be attached to it
+            self.check(self.lib.ncb_set_objects(self.h, C.byref(oc)), "ncb_set_objects")
+            self.n = n
+            self.set_query_types(qk)
         self.n = n
         if bufs is None:
             bufs = self.alloc_result_buffers(max(8 * n, 1024), max(8 * n, 1024))
@@ -189,7 +228,8 @@ class Context:
             )
             if r == 0:
                 P, Cn = c.n_pairs, c.n_contacts
-                return UpdateResult(bufs["pairs"][:P], bufs["algo"][:P], bufs["start"][:P], bufs["count"][:P], bufs["contacts"][:Cn], self._counts(c))
+                prox = self.world_fetch_proximity(P) if getattr(self, "has_sensors", False) else None
+                return UpdateResult(bufs["pairs"][:P], bufs["algo"][:P], bufs["start"][:P], bufs["count"][:P], bufs["contacts"][:Cn], self._counts(c), prox)
             bufs = self.alloc_result_buffers(c.n_pairs + 16, c.n_contacts + 16)
 
     @staticmethod
@@ -217,11 +257,15 @@ class Context:
 
 
 class GeometricQueryType:
-    """pipeline/object/query_type.rs:13-19 — only Contacts(linear, angular) is on the path."""
+    """pipeline/object/query_type.rs:8-37: Contacts(linear, angular) or Proximity(margin) (a sensor)."""
 
     @staticmethod
     def Contacts(linear, angular):
         return ("contacts", float(linear), float(angular))
+
+    @staticmethod
+    def Proximity(margin):
+        return ("proximity", float(margin), 0.0)
 
 
 class CollisionWorld:
@@ -235,6 +279,7 @@ class CollisionWorld:
         self.margin = float(margin)
         self.ctx = ctx or Context(device)
         self._pos, self._rot, self._type, self._param, self._groups, self._ql, self._ang = [], [], [], [], [], [], []
+        self._kind = []
         self._hulls = []
         self._hull_ids = {}
         self.result = None
@@ -242,8 +287,10 @@ class CollisionWorld:
 
     def add(self, position, shape, groups=None, query_type=None, data=None):
         """position = (translation xyz, quaternion ijkw); returns the object handle."""
-        if query_type is None or query_type[0] != "contacts":
-            raise ValueError("only GeometricQueryType::Contacts is supported on the accelerated path")
+        if query_type is None or query_type[0] not in ("contacts", "proximity"):
+            raise ValueError("query_type must be GeometricQueryType.Contacts(..) or GeometricQueryType.Proximity(..)")
+        if query_type[1] < 0:
+            raise ValueError("The proximity margin / contact prediction must be positive or null.")  # the reference asserts it
         t, q = position
         self._pos.append(np.asarray(t, dtype=np.float32))
         self._rot.append(np.asarray(q, dtype=np.float32))
@@ -259,6 +306,7 @@ class CollisionWorld:
         self._groups.append(np.asarray(groups if groups is not None else DEFAULT_GROUPS, dtype=np.uint32))
         self._ql.append(query_type[1])
         self._ang.append(query_type[2])
+        self._kind.append(1 if query_type[0] == "proximity" else 0)
         self._dirty = True
         return len(self._pos) - 1
 
@@ -274,6 +322,7 @@ class CollisionWorld:
             ang_pred=np.array(self._ang, dtype=np.float32),
             hulls=HullLibrary(self._hulls),
             margin=self.margin,
+            query_kind=np.array(self._kind, dtype=np.uint8) if any(self._kind) else None,
         )
 
     def update(self):
@@ -290,12 +339,31 @@ class CollisionWorld:
         if r is None:
             return
         for p in range(len(r.pairs)):
-            if r.pair_algo[p] == 0:
+            if r.pair_algo[p] == 0 or r.pair_algo[p] == ALGO_PROXIMITY:
                 continue
             c = r.contacts_of(p)
-            if effective_only and len(c) == 0:
+            # InteractionGraph::is_interaction_effective (interaction_graph.rs:390-398): deepest contact with depth >= 0
+            if effective_only and (len(c) == 0 or not (c["depth"].max() >= 0)):
                 continue
             yield int(r.pairs[p, 0]), int(r.pairs[p, 1]), ALGO_NAMES[r.pair_algo[p]], c
+
+
+    def proximity_pairs(self, effective_only=True):
+        """Iterator of (handle1, handle2, status) over the proximity interactions — world.rs:433-445 (`proximity_pairs`);
+        effective_only keeps the Intersecting pairs only (interaction_graph.rs:399)."""
+        r = self.result
+        if r is None or r.proximity is None:
+            return
+        for p in np.nonzero(r.pair_algo == ALGO_PROXIMITY)[0]:
+            st = int(r.proximity[p])
+            if effective_only and st != Proximity.Intersecting:
+                continue
+            yield int(r.pairs[p, 0]), int(r.pairs[p, 1]), st
+
+    def proximity_events(self):
+        """ProximityEvents of the (fresh-world) update: (collider1, collider2, prev_status = Disjoint, new_status) for every
+        proximity pair whose status is not Disjoint (narrow_phase.rs:108-121; a new interaction starts as Disjoint)."""
+        return [(a, b, Proximity.Disjoint, st) for a, b, st in self.proximity_pairs(effective_only=False) if st != Proximity.Disjoint]
 
 
 class BroadPhaseInterferenceHandler:

@@ -249,6 +249,7 @@ static Objects make_objects(const orc_objects* o) {
     r.query_limit = o->query_limit;
     r.ang_pred = o->ang_pred;
     r.hulls = reinterpret_cast<const HullLibrary*>(o->hulls);
+    r.query_kind = o->query_kind;
     return r;
 }
 

@@ -32,7 +32,7 @@ struct Support {
                 }
                 return hull.pt(best);
             }
-            case S_BALL:  // ball.rs: local_support_point_toward(normalize(dir)) = dir * radius
+            case S_BALL:  // ball.rs:41-48: local_support_point_toward(normalize(dir)) = dir * radius
                 return normalize(dir) * radius;
             default:
                 return v3(0, 0, 0);
@@ -40,8 +40,13 @@ struct Support {
     }
     V3 support_point(const Iso& m, V3 dir) const {  // support_map.rs:26-29
         if (kind == S_ORIGIN) return v3(0, 0, 0);
+        if (kind == S_BALL) return m.t + normalize(dir) * radius;  // Ball overrides it (ball.rs:31-38): the rotation is not applied
         V3 ld = iso_inv_vec(m, dir);
         return iso_mul_point(m, local_support_point(ld));
+    }
+    V3 support_point_toward(const Iso& m, V3 unit_dir) const {  // support_map.rs:32-35; ball.rs:36-38 (no normalisation)
+        if (kind == S_BALL) return m.t + unit_dir * radius;
+        return support_point(m, unit_dir);
     }
 };
 
@@ -84,9 +89,10 @@ struct GJKStats {
     uint32_t gjk_iters = 0, epa_iters = 0, epa_max_verts = 0, epa_max_faces = 0, epa_max_heap = 0, epa_calls = 0, epa_fail = 0;
 };
 
-// gjk.rs:76-177 with exact_dist = true (the only mode the path uses)
+// gjk.rs:76-177.  exact_dist = true is what the contact generators use; exact_dist = false (the proximity detectors,
+// proximity_support_map_support_map.rs:68) stops as soon as the origin is proven closer than max_dist but outside.
 static inline GJKResult gjk_closest_points(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, real max_dist,
-                                           VoronoiSimplex& simplex, GJKStats* st) {
+                                           VoronoiSimplex& simplex, GJKStats* st, bool exact_dist = true) {
     const real _eps_tol = gjk_eps_tol();
     const real _eps_rel = std::sqrt(_eps_tol);
     GJKResult res;
@@ -111,6 +117,7 @@ static inline GJKResult gjk_closest_points(const Iso& m1, const Support& g1, con
             return {GJK_INTERSECTION, {}, {}, {}};
 
         if (max_bound >= old_max_bound) {
+            if (!exact_dist) return {GJK_PROXIMITY, {}, {}, old_dir};
             res.kind = GJK_CLOSEST_POINTS;
             gjk_result(simplex, true, &res.p1, &res.p2);
             res.dir = old_dir;
@@ -120,13 +127,17 @@ static inline GJKResult gjk_closest_points(const Iso& m1, const Support& g1, con
         real min_bound = -dot(dir, cso_point.point);
         if (min_bound > max_dist) {
             return {GJK_NO_INTERSECTION, {}, {}, dir};
+        } else if (!exact_dist && min_bound > real(0) && max_bound <= max_dist) {
+            return {GJK_PROXIMITY, {}, {}, old_dir};
         } else if (max_bound - min_bound <= _eps_rel * max_bound) {
+            if (!exact_dist) return {GJK_PROXIMITY, {}, {}, dir};
             res.kind = GJK_CLOSEST_POINTS;
             gjk_result(simplex, false, &res.p1, &res.p2);
             res.dir = dir;
             return res;
         }
         if (!simplex.add_point(cso_point, _eps_tol)) {
+            if (!exact_dist) return {GJK_PROXIMITY, {}, {}, dir};
             res.kind = GJK_CLOSEST_POINTS;
             gjk_result(simplex, false, &res.p1, &res.p2);
             res.dir = dir;
@@ -136,6 +147,7 @@ static inline GJKResult gjk_closest_points(const Iso& m1, const Support& g1, con
         proj = simplex.project_origin_and_reduce();
         if (simplex.dim == 3) {
             if (min_bound >= _eps_tol) {
+                if (!exact_dist) return {GJK_PROXIMITY, {}, {}, old_dir};
                 res.kind = GJK_CLOSEST_POINTS;
                 gjk_result(simplex, true, &res.p1, &res.p2);
                 res.dir = old_dir;

@@ -900,6 +900,68 @@ static uint8_t generate_contacts(const Objects& o, uint32_t i1, uint32_t i2, Man
     return A_NONE;  // e.g. plane x plane: pair kept by the broad phase, no interaction edge
 }
 
+// ---------------------------------------------------------------------------------------------
+// Proximity detectors: default_proximity_dispatcher.rs:19-47, ball_ball_proximity_detector.rs:24-43 +
+// proximity_ball_ball.rs:8-36, plane_support_map_proximity_detector.rs:37-67 + proximity_plane_support_map.rs:9-47,
+// support_map_support_map_proximity_detector.rs:31-61 + proximity_support_map_support_map.rs:36-75 (GJK, exact_dist = false).
+// Proximity as a byte: Intersecting = 0, WithinMargin = 1, Disjoint = 2 (proximity.rs:4-12); 255 = no detector.
+// ---------------------------------------------------------------------------------------------
+enum : uint8_t { PROX_INTERSECTING = 0, PROX_WITHIN_MARGIN = 1, PROX_DISJOINT = 2, PROX_NONE = 255 };
+static const uint8_t A_PROXIMITY = 6;
+
+static uint8_t proximity_ball_ball(V3 c1, real r1, V3 c2, real r2, real margin) {
+    V3 delta_pos = c2 - c1;
+    real distance_squared = norm_squared(delta_pos);
+    real sum_radius = r1 + r2;
+    real sum_radius_with_error = sum_radius + margin;
+    if (distance_squared <= sum_radius_with_error * sum_radius_with_error)
+        return distance_squared <= sum_radius * sum_radius ? PROX_INTERSECTING : PROX_WITHIN_MARGIN;
+    return PROX_DISJOINT;
+}
+static uint8_t proximity_plane_support_map(const Iso& mplane, V3 plane_n, const Iso& mother, const Support& other, real margin) {
+    V3 plane_normal = iso_mul_vec(mplane, plane_n);
+    V3 plane_center = mplane.t;
+    V3 deepest = other.support_point_toward(mother, -plane_normal);
+    real distance = dot(plane_normal, plane_center - deepest);
+    if (distance >= -margin) return distance >= real(0) ? PROX_INTERSECTING : PROX_WITHIN_MARGIN;
+    return PROX_DISJOINT;
+}
+// sep_axis / has_axis: SupportMapSupportMapProximityDetector::sep_axis (None on a fresh detector and after Intersecting)
+static uint8_t proximity_support_map_support_map(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, real margin, V3* sep_axis,
+                                                 bool* has_axis) {
+    V3 dir;
+    if (has_axis && *has_axis)
+        dir = *sep_axis;
+    else if (!unit_try_new(m2.t - m1.t, EPS, &dir))
+        dir = v3(1, 0, 0);
+    VoronoiSimplex simplex;
+    simplex.reset(cso_from_shapes(m1, g1, m2, g2, dir));
+    GJKResult r = gjk_closest_points(m1, g1, m2, g2, margin, simplex, nullptr, false);
+    uint8_t res;
+    V3 out_dir = dir;
+    if (r.kind == GJK_INTERSECTION)
+        res = PROX_INTERSECTING;
+    else if (r.kind == GJK_PROXIMITY)
+        res = PROX_WITHIN_MARGIN, out_dir = r.dir;
+    else
+        res = PROX_DISJOINT, out_dir = r.dir;
+    if (has_axis) {
+        *has_axis = res != PROX_INTERSECTING;
+        if (*has_axis) *sep_axis = out_dir;
+    }
+    return res;
+}
+// ProximityDetector::update of the detector the default dispatcher picks for (a, b).
+static uint8_t proximity_update(const Objects& o, uint32_t i1, uint32_t i2, real margin, V3* sep_axis = nullptr, bool* has_axis = nullptr) {
+    Shape a = get_shape(o, i1), b = get_shape(o, i2);
+    Iso ma = o.iso(i1), mb = o.iso(i2);
+    if (a.type == BALL && b.type == BALL) return proximity_ball_ball(ma.t, a.radius, mb.t, b.radius, margin);
+    if (a.type == PLANE && b.type != PLANE) return proximity_plane_support_map(ma, a.he, mb, as_support(b), margin);
+    if (b.type == PLANE && a.type != PLANE) return proximity_plane_support_map(mb, b.he, ma, as_support(a), margin);
+    if (a.type != PLANE && b.type != PLANE) return proximity_support_map_support_map(ma, as_support(a), mb, as_support(b), margin, sep_axis, has_axis);
+    return PROX_NONE;
+}
+
 }  // namespace orc
 
 using namespace orc;
@@ -915,6 +977,7 @@ static Objects make_objects(const orc_objects* o) {
     r.query_limit = o->query_limit;
     r.ang_pred = o->ang_pred;
     r.hulls = reinterpret_cast<const HullLibrary*>(o->hulls);
+    r.query_kind = o->query_kind;
     return r;
 }
 
@@ -994,7 +1057,7 @@ int orc_query_contact(const orc_objects* objs, real prediction, orc_contact* out
         // contact_plane_support_map.rs:7-27
         V3 n = iso_mul_vec(m1, a.he);
         Support g = as_support(b);
-        V3 deepest = g.support_point(m2, -n);
+        V3 deepest = g.support_point_toward(m2, -n);
         real distance = dot(n, m1.t - deepest);
         if (distance > -prediction) {
             c = {deepest + n * distance, deepest, n, distance};
@@ -1003,7 +1066,7 @@ int orc_query_contact(const orc_objects* objs, real prediction, orc_contact* out
     } else if (b.type == PLANE && a.type != PLANE) {
         V3 n = iso_mul_vec(m2, b.he);
         Support g = as_support(a);
-        V3 deepest = g.support_point(m1, -n);
+        V3 deepest = g.support_point_toward(m1, -n);
         real distance = dot(n, m2.t - deepest);
         if (distance > -prediction) {
             c = {deepest, deepest + n * distance, -n, distance};
@@ -1035,6 +1098,55 @@ int orc_query_contact(const orc_objects* objs, real prediction, orc_contact* out
     return have ? 1 : 0;
 }
 
+void orc_proximity(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, const real* margins, uint8_t* out) {
+    Objects o = make_objects(objs);
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
+        real margin = margins ? margins[p] : o.query_limit[i1] + o.query_limit[i2];
+        out[p] = proximity_update(o, i1, i2, margin);
+    }
+}
+void orc_proximity_warm(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, const real* margins, real* axis_io, uint8_t* out) {
+    Objects o = make_objects(objs);
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
+        real margin = margins ? margins[p] : o.query_limit[i1] + o.query_limit[i2];
+        V3 axis = v3(axis_io[4 * p], axis_io[4 * p + 1], axis_io[4 * p + 2]);
+        bool has_axis = axis_io[4 * p + 3] != real(0);
+        out[p] = proximity_update(o, i1, i2, margin, &axis, &has_axis);
+        axis_io[4 * p] = axis.x, axis_io[4 * p + 1] = axis.y, axis_io[4 * p + 2] = axis.z, axis_io[4 * p + 3] = has_axis ? real(1) : real(0);
+    }
+}
+int orc_query_proximity(const orc_objects* objs, real margin) {
+    Objects o = make_objects(objs);
+    return proximity_update(o, 0, 1, margin);
+}
+uint64_t orc_narrow_phase_kinds(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, orc_contact* out, uint64_t cap,
+                                uint32_t* manifold_off, uint8_t* algo_out, uint8_t* prox_out) {
+    Objects o = make_objects(objs);
+    uint64_t nc = 0;
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
+        if (manifold_off) manifold_off[p] = (uint32_t)nc;
+        if (o.is_proximity(i1) || o.is_proximity(i2)) {  // narrow_phase.rs:226-247
+            uint8_t st = proximity_update(o, i1, i2, o.query_limit[i1] + o.query_limit[i2]);
+            if (prox_out) prox_out[p] = st;
+            if (algo_out) algo_out[p] = st == PROX_NONE ? A_NONE : A_PROXIMITY;
+            continue;
+        }
+        Manifold mf;
+        uint8_t algo = generate_contacts(o, i1, i2, mf, nullptr);
+        if (algo_out) algo_out[p] = algo;
+        if (prox_out) prox_out[p] = PROX_NONE;
+        mf.for_each_contact([&](const Tracked& t, size_t) {
+            if (nc < cap && out) write_contact(&out[nc], t);
+            nc++;
+        });
+    }
+    if (manifold_off) manifold_off[n_pairs] = (uint32_t)nc;
+    return nc;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------
@@ -1053,6 +1165,11 @@ struct Edge {
     Manifold manifold;
     V3 last_gjk_dir{0, 0, 0};
     bool has_dir = false;
+    // Interaction::Proximity(detector, status) (interaction_graph.rs): status + the detector's sep_axis
+    bool is_prox = false;
+    uint8_t prox = 2;  // Proximity::Disjoint
+    V3 sep_axis{0, 0, 0};
+    bool has_axis = false;
 };
 }  // namespace orc
 
@@ -1060,6 +1177,8 @@ struct orc_sim {
     Objects o;
     std::vector<real> pos, rot, param, qlimit, ang;  // the sim owns the per-object arrays (objects can be added later)
     std::vector<uint32_t> type, groups;
+    std::vector<uint8_t> qkind;  // empty = all Contacts
+    std::vector<uint32_t> prox_events;  // (h1, h2, prev, new)
     std::vector<uint8_t> flags;  // 1 = POSITION_CHANGED (| everything, for a new object)
     std::vector<uint8_t> alive;
     std::vector<uint32_t> free_handles;  // CollisionObjectSlab: vacant keys, reused last-freed-first
@@ -1068,6 +1187,7 @@ struct orc_sim {
         o.pos = pos.data(), o.rot = rot.data(), o.shape_type = type.data(), o.shape_param = param.data();
         o.groups = groups.empty() ? nullptr : groups.data();
         o.query_limit = qlimit.data(), o.ang_pred = ang.data();
+        o.query_kind = qkind.empty() ? nullptr : qkind.data();
     }
     orc_bp* bp = nullptr;
     std::map<uint64_t, Edge> edges;  // key = min << 32 | max (iteration order is not observable: events are sorted)
@@ -1098,6 +1218,7 @@ orc_sim* orc_sim_create(const orc_objects* objs, real margin) {
     if (objs->groups) s->groups.assign(objs->groups, objs->groups + 3 * n0);
     s->qlimit.assign(objs->query_limit, objs->query_limit + n0);
     s->ang.assign(objs->ang_pred, objs->ang_pred + n0);
+    if (objs->query_kind) s->qkind.assign(objs->query_kind, objs->query_kind + n0);
     s->flags.assign(n0, 1);
     s->alive.assign(n0, 1);
     s->rebind();
@@ -1130,6 +1251,7 @@ void orc_sim_set_positions(orc_sim* s, uint32_t n, const uint32_t* handles, cons
 void orc_sim_step(orc_sim* s) {
     const Objects& o = s->o;
     s->events.clear();  // narrow_phase.clear_events()
+    s->prox_events.clear();
     // perform_broad_phase (glue/update.rs:65-99)
     for (uint32_t i = 0; i < o.n; ++i) {
         if (!s->alive[i] || !s->flags[i]) continue;
@@ -1154,9 +1276,10 @@ void orc_sim_step(orc_sim* s) {
         uint64_t key = ((uint64_t)std::min(b1, b2) << 32) | std::max(b1, b2);
         if (s->edges.count(key)) continue;
         uint8_t algo = dispatch_algo(o, b1, b2);
-        if (algo == A_NONE) continue;
+        if (algo == A_NONE) continue;  // plane x plane: neither dispatcher has an algorithm
         Edge e;
         e.h1 = b1, e.h2 = b2, e.algo = algo;
+        if (o.is_proximity(b1) || o.is_proximity(b2)) e.is_prox = true, e.algo = A_PROXIMITY;  // narrow_phase.rs:240-246
         s->edges.emplace(key, std::move(e));
     }
     // interference_stopped -> handle_interaction(.., false) (:248-277)
@@ -1164,13 +1287,23 @@ void orc_sim_step(orc_sim* s) {
         uint64_t key = ((uint64_t)sp[2 * k] << 32) | sp[2 * k + 1];
         auto it = s->edges.find(key);
         if (it == s->edges.end()) continue;
-        if (it->second.manifold.len() != 0) s->events.insert(s->events.end(), {it->second.h1, it->second.h2, 0u});
+        if (it->second.is_prox) {  // narrow_phase.rs:266-274
+            if (it->second.prox != PROX_DISJOINT)
+                s->prox_events.insert(s->prox_events.end(), {it->second.h1, it->second.h2, (uint32_t)it->second.prox, (uint32_t)PROX_DISJOINT});
+        } else if (it->second.manifold.len() != 0)
+            s->events.insert(s->events.end(), {it->second.h1, it->second.h2, 0u});
         s->edges.erase(it);
     }
     // perform_narrow_phase -> NarrowPhase::update (:168-197) -> update_contact (:56-104)
     for (auto& kv : s->edges) {
         Edge& e = kv.second;
         if (!s->flags[e.h1] && !s->flags[e.h2]) continue;
+        if (e.is_prox) {  // update_proximity (narrow_phase.rs:123-143)
+            uint8_t np_ = proximity_update(o, e.h1, e.h2, o.query_limit[e.h1] + o.query_limit[e.h2], &e.sep_axis, &e.has_axis);
+            if (np_ != e.prox) s->prox_events.insert(s->prox_events.end(), {e.h1, e.h2, (uint32_t)e.prox, (uint32_t)np_});
+            e.prox = np_;
+            continue;
+        }
         bool had = e.manifold.len() != 0;
         e.manifold.save_cache_and_clear();
         generate_contacts(o, e.h1, e.h2, e.manifold, nullptr, &e.last_gjk_dir, &e.has_dir);
@@ -1212,6 +1345,7 @@ int orc_sim_add(orc_sim* s, const orc_objects* objs, uint32_t* out_handles) {
         } else {
             h = (uint32_t)s->alive.size();
             s->alive.push_back(0), s->flags.push_back(0), s->type.push_back(0), s->qlimit.push_back(0), s->ang.push_back(0);
+            if (!s->qkind.empty()) s->qkind.push_back(0);
             s->pos.resize(s->pos.size() + 3), s->rot.resize(s->rot.size() + 4), s->param.resize(s->param.size() + 4);
             if (!s->groups.empty() || objs->groups) {
                 size_t old = s->groups.size() / 3;
@@ -1225,6 +1359,8 @@ int orc_sim_add(orc_sim* s, const orc_objects* objs, uint32_t* out_handles) {
         s->type[h] = objs->shape_type[k];
         s->qlimit[h] = objs->query_limit[k];
         s->ang[h] = objs->ang_pred[k];
+        if (objs->query_kind && objs->query_kind[k] && s->qkind.empty()) s->qkind.assign(s->alive.size(), 0);
+        if (!s->qkind.empty()) s->qkind[h] = objs->query_kind ? objs->query_kind[k] : 0;
         if (!s->groups.empty()) {
             for (int d = 0; d < 3; ++d) s->groups[3 * (size_t)h + d] = objs->groups ? objs->groups[3 * (size_t)k + d] : (d < 2 ? 0x3FFFFFFFu : 0u);
         }
@@ -1270,6 +1406,16 @@ uint64_t orc_sim_events(const orc_sim* s, uint32_t* out, uint64_t cap) {
     uint64_t n = s->events.size() / 3;
     for (uint64_t k = 0; k < n && k < cap; ++k)
         for (int d = 0; d < 3; ++d) out[3 * k + d] = s->events[3 * k + d];
+    return n;
+}
+void orc_sim_fetch_proximity(const orc_sim* s, uint8_t* prox) {
+    uint64_t p = 0;
+    for (auto& kv : s->edges) prox[p++] = kv.second.is_prox ? kv.second.prox : (uint8_t)PROX_NONE;
+}
+uint64_t orc_sim_proximity_events(const orc_sim* s, uint32_t* out, uint64_t cap) {
+    uint64_t n = s->prox_events.size() / 4;
+    for (uint64_t k = 0; k < n && k < cap; ++k)
+        for (int d = 0; d < 4; ++d) out[4 * k + d] = s->prox_events[4 * k + d];
     return n;
 }
 uint64_t orc_sim_bp_num_interferences(const orc_sim* s) { return orc_bp_num_interferences(s->bp); }

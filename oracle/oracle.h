@@ -38,6 +38,7 @@ typedef struct orc_objects {
     const real* query_limit;
     const real* ang_pred;
     const orc_hull_library* hulls;
+    const uint8_t* query_kind; /* per object: 0 = GeometricQueryType::Contacts, 1 = Proximity(query_limit); NULL = all Contacts */
 } orc_objects;
 
 typedef struct orc_contact {
@@ -54,6 +55,25 @@ uint64_t orc_broad_phase(uint32_t n, const real* aabb_minmax, const uint32_t* gr
  * algorithm per pair.  Returns the number of contacts (may exceed cap). */
 uint64_t orc_narrow_phase(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, orc_contact* out, uint64_t cap,
                           uint32_t* manifold_off, uint8_t* algo_out, uint32_t* stats);
+
+/* Proximity (query/proximity/proximity.rs:4-12) as a byte; ORC_PROX_NONE = the dispatcher has no detector (plane x plane). */
+#define ORC_PROX_INTERSECTING 0
+#define ORC_PROX_WITHIN_MARGIN 1
+#define ORC_PROX_DISJOINT 2
+#define ORC_PROX_NONE 255
+#define ORC_ALGO_PROXIMITY 6
+/* ProximityDetector::update with FRESH detectors (default_proximity_dispatcher.rs:19-47 and the four detectors) for a batch
+ * of (object1, object2) pairs; margins == NULL: query_limit[o1] + query_limit[o2] (narrow_phase.rs:131-139). */
+void orc_proximity(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, const real* margins, uint8_t* out);
+/* Same with the detector state carried by the caller: axis_io[4 p] = sep_axis xyz + a "Some" flag, read and written back
+ * (SupportMapSupportMapProximityDetector::sep_axis, support_map_support_map_proximity_detector.rs:53-57). */
+void orc_proximity_warm(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, const real* margins, real* axis_io, uint8_t* out);
+/* query::proximity(m1, g1, m2, g2, margin) (proximity_shape_shape.rs:8-33) for objects 0 and 1. */
+int orc_query_proximity(const orc_objects* objs, real margin);
+/* orc_narrow_phase for a world whose objects carry query kinds: pairs with a Proximity object go to the proximity detectors
+ * (narrow_phase.rs:226-247): algo = ORC_ALGO_PROXIMITY, no contacts, prox_out[p] = status; other pairs: prox_out[p] = 255. */
+uint64_t orc_narrow_phase_kinds(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, orc_contact* out, uint64_t cap,
+                                uint32_t* manifold_off, uint8_t* algo_out, uint8_t* prox_out);
 
 /* One reference-faithful fresh-world CollisionWorld::update (DBVT broad phase + narrow phase); returns
  * seconds spent in [aabb, broad, narrow] through times[3]; n_pairs / n_contacts through counts[2]. */
@@ -95,6 +115,10 @@ uint64_t orc_sim_num_pairs(const orc_sim*);
 uint64_t orc_sim_num_contacts(const orc_sim*);
 void orc_sim_fetch(const orc_sim*, uint32_t* pairs, uint8_t* algo, uint32_t* manifold_off, orc_contact* contacts, uint32_t* ids);
 uint64_t orc_sim_events(const orc_sim*, uint32_t* out, uint64_t cap);
+/* Proximity status per edge (same order as orc_sim_fetch; 255 for contact edges) and the ProximityEvents of the last step as
+ * (h1, h2, prev, new) rows in emission order. */
+void orc_sim_fetch_proximity(const orc_sim*, uint8_t* prox);
+uint64_t orc_sim_proximity_events(const orc_sim*, uint32_t* out, uint64_t cap);
 uint64_t orc_sim_bp_num_interferences(const orc_sim*);
 uint64_t orc_sim_query(orc_sim*, int kind, uint64_t n, const real* q, const uint32_t* groups, uint32_t* idx, uint64_t cap);
 int orc_shape_ray_cast(const orc_objects* objs, uint32_t i, const real* origin, const real* dir, real max_toi, real* out, uint32_t* feature);

@@ -48,6 +48,7 @@ class _Objects(C.Structure):
         ("query_limit", C.c_void_p),
         ("ang_pred", C.c_void_p),
         ("hulls", C.c_void_p),
+        ("query_kind", C.c_void_p),
     ]
 
 
@@ -96,6 +97,8 @@ class Oracle:
         o.query_limit = arr(scene.query_limit, self.dtype)
         o.ang_pred = arr(scene.ang_pred, self.dtype)
         o.hulls = C.addressof(hl)
+        qk = getattr(scene, "query_kind", None)
+        o.query_kind = arr(qk, np.uint8) if qk is not None else None
         return o, keep
 
     # -- API -----------------------------------------------------------------------------------
@@ -139,6 +142,53 @@ class Oracle:
             )
             if nc <= cap:
                 return out[:nc].copy(), off, algo, stats
+            cap = int(nc)
+
+    def proximity(self, scene, pairs, margins=None):
+        """ProximityDetector::update with fresh detectors per (object1, object2) pair -> u8 status (0 Intersecting, 1 WithinMargin,
+        2 Disjoint, 255 no detector).  margins None: query_limit[o1] + query_limit[o2]."""
+        o, keep = self._objects(scene)
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        out = np.zeros(len(pairs), dtype=np.uint8)
+        m = None if margins is None else np.ascontiguousarray(margins, dtype=self.dtype)
+        self.lib.orc_proximity(C.byref(o), C.c_uint64(len(pairs)), C.c_void_p(pairs.ctypes.data), C.c_void_p(m.ctypes.data) if m is not None else None,
+                               C.c_void_p(out.ctypes.data))
+        return out
+
+    def proximity_warm(self, scene, pairs, margins, axis_io):
+        """proximity() with the detectors' sep_axis carried in axis_io[P,4] (xyz + Some flag), updated in place."""
+        o, keep = self._objects(scene)
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        out = np.zeros(len(pairs), dtype=np.uint8)
+        m = None if margins is None else np.ascontiguousarray(margins, dtype=self.dtype)
+        assert axis_io.dtype == self.dtype and axis_io.flags.c_contiguous and axis_io.shape == (len(pairs), 4)
+        self.lib.orc_proximity_warm(C.byref(o), C.c_uint64(len(pairs)), C.c_void_p(pairs.ctypes.data), C.c_void_p(m.ctypes.data) if m is not None else None,
+                                    C.c_void_p(axis_io.ctypes.data), C.c_void_p(out.ctypes.data))
+        return out
+
+    def query_proximity(self, scene, margin):
+        """query::proximity between objects 0 and 1."""
+        o, keep = self._objects(scene)
+        return int(self.lib.orc_query_proximity(C.byref(o), self.creal(margin)))
+
+    def narrow_phase_kinds(self, scene, pairs):
+        """Narrow phase honouring scene.query_kind.  Returns (contacts, manifold_off[P+1], algo[P], prox[P])."""
+        o, keep = self._objects(scene)
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        P = len(pairs)
+        cap = max(4 * P, 64)
+        off = np.zeros(P + 1, dtype=np.uint32)
+        algo = np.zeros(P, dtype=np.uint8)
+        prox = np.zeros(P, dtype=np.uint8)
+        self.lib.orc_narrow_phase_kinds.restype = C.c_uint64
+        while True:
+            out = np.zeros(cap, dtype=self.contact_dtype)
+            nc = self.lib.orc_narrow_phase_kinds(
+                C.byref(o), C.c_uint64(P), C.c_void_p(pairs.ctypes.data), C.c_void_p(out.ctypes.data), C.c_uint64(cap),
+                C.c_void_p(off.ctypes.data), C.c_void_p(algo.ctypes.data), C.c_void_p(prox.ctypes.data),
+            )
+            if nc <= cap:
+                return out[:nc].copy(), off, algo, prox
             cap = int(nc)
 
     def world_update_timed(self, scene):
@@ -190,7 +240,7 @@ class OracleSim:
         self.o = oracle
         L = oracle.lib
         L.orc_sim_create.restype = C.c_void_p
-        for f in ("orc_sim_num_pairs", "orc_sim_num_contacts", "orc_sim_events", "orc_sim_bp_num_interferences"):
+        for f in ("orc_sim_num_pairs", "orc_sim_num_contacts", "orc_sim_events", "orc_sim_bp_num_interferences", "orc_sim_proximity_events"):
             getattr(L, f).restype = C.c_uint64
         self._objs, self._keep = oracle._objects(scene)
         self.h = C.c_void_p(L.orc_sim_create(C.byref(self._objs), oracle.creal(scene.margin)))
@@ -230,8 +280,13 @@ class OracleSim:
         ne = int(L.orc_sim_events(self.h, None, C.c_uint64(0)))
         ev = np.zeros((max(ne, 1), 3), dtype=np.uint32)
         L.orc_sim_events(self.h, C.c_void_p(ev.ctypes.data), C.c_uint64(ne))
+        prox = np.zeros(max(P, 1), dtype=np.uint8)
+        L.orc_sim_fetch_proximity(self.h, C.c_void_p(prox.ctypes.data))
+        npe = int(L.orc_sim_proximity_events(self.h, None, C.c_uint64(0)))
+        pev = np.zeros((max(npe, 1), 4), dtype=np.uint32)
+        L.orc_sim_proximity_events(self.h, C.c_void_p(pev.ctypes.data), C.c_uint64(npe))
         return {"pairs": pairs, "algo": algo, "off": off, "contacts": contacts[:Cn], "ids": ids[:Cn], "events": ev[:ne],
-                "bp_pairs": int(L.orc_sim_bp_num_interferences(self.h))}
+                "prox": prox[:P], "prox_events": pev[:npe], "bp_pairs": int(L.orc_sim_bp_num_interferences(self.h))}
 
     def query(self, kind, q, groups=None):
         """kind 0: interferences_with_aabb (q[n,6]); kind 2: interferences_with_point (q[n,3]).  Rows (query, handle)."""

@@ -89,6 +89,8 @@ struct Objects {
     const real* query_limit;  // GeometricQueryType::Contacts(linear, _)
     const real* ang_pred;     // GeometricQueryType::Contacts(_, angular)
     const HullLibrary* hulls;
+    const uint8_t* query_kind = nullptr;  // 1 = GeometricQueryType::Proximity(query_limit); null = all Contacts
+    bool is_proximity(uint32_t i) const { return query_kind && query_kind[i] != 0; }
     Iso iso(uint32_t i) const {
         return Iso{{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]}, {rot[4 * i], rot[4 * i + 1], rot[4 * i + 2], rot[4 * i + 3]}};
     }

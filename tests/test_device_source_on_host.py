@@ -1,0 +1,81 @@
+"""The per-pair DEVICE functions of csrc/proximity.cu (+ the GJK / simplex code of gjk.cuh they call), compiled for the host
+by g++ through tests/host_shim/cuda_runtime.h, against the oracle.  This checks the device SOURCE (logic, f32 operation
+order, no FMA contraction) where no GPU exists; the compiled kernels themselves are checked by tests/test_proximity.py -m gpu.
+Test infrastructure only: nothing in ncollide_b200/ uses the shim."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from ncollide_b200 import _ffi
+from ncollide_b200.scenes import make_world_scene, random_unit_quaternions
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+F = np.float32
+
+
+@pytest.fixture(scope="module")
+def shim():
+    out = os.path.join(HERE, "host_shim", "_build", "libprox_host.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    subprocess.check_call([
+        "g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-DNCB_HOST_SHIM",
+        "-I", os.path.join(HERE, "host_shim"), "-I", os.path.join(ROOT, "ncollide_b200", "csrc"),
+        "-shared", "-o", out, os.path.join(HERE, "host_shim", "proximity_host.cpp"),
+    ])
+    return C.CDLL(out)
+
+
+def shim_proximity(lib, scene, pairs, margins=None, axis_io=None):
+    oc, keep = _ffi.pack_objects(scene)
+    hc, keep2 = _ffi.pack_hull_library(scene.hulls)
+    pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+    out = np.zeros(len(pairs), dtype=np.uint8)
+    m = None if margins is None else np.ascontiguousarray(margins, dtype=F)
+    lib.shim_proximity(C.byref(oc), C.byref(hc), C.c_uint64(len(pairs)), _ffi.ptr(pairs), _ffi.ptr(m), _ffi.ptr(axis_io), _ffi.ptr(out))
+    return out
+
+
+SCENES = [
+    lambda: make_world_scene(3000, 61, (1, 1, 1), side=8.0, plane=True, n_hulls=48, linear=0.1),
+    lambda: make_world_scene(2000, 62, (0, 1, 1), side=4.0, n_hulls=24, linear=0.0),
+    lambda: make_world_scene(2000, 63, (1, 0, 0), side=6.0, linear=0.2),
+]
+
+
+@pytest.mark.parametrize("mk", SCENES)
+def test_device_proximity_source_matches_oracle(shim, oracle, mk):
+    s = mk()
+    fat = oracle.compute_aabbs(s)
+    bp = oracle.broad_phase(fat, s.groups)
+    rng = np.random.default_rng(17)
+    extra = rng.integers(0, s.n, size=(20000, 2)).astype(np.uint32)
+    pairs = np.concatenate([bp, bp[:, ::-1], extra[extra[:, 0] != extra[:, 1]]])
+    got, want = shim_proximity(shim, s, pairs), oracle.proximity(s, pairs)
+    assert np.array_equal(got, want), int((got != want).sum())
+    margins = rng.uniform(0, 2.5, size=len(pairs)).astype(F)
+    got, want = shim_proximity(shim, s, pairs, margins), oracle.proximity(s, pairs, margins)
+    assert np.array_equal(got, want), int((got != want).sum())
+    assert set(want.tolist()) >= {0, 1, 2}
+
+
+def test_device_proximity_source_warm_start_matches_oracle(shim, oracle):
+    """The detector's sep_axis carried over several updates while the objects move (the stepping-world use)."""
+    s = make_world_scene(1500, 64, (1, 1, 1), side=5.0, n_hulls=24, linear=0.15)
+    fat = oracle.compute_aabbs(s)
+    pairs = oracle.broad_phase(fat, s.groups)
+    rng = np.random.default_rng(23)
+    ax_d = np.zeros((len(pairs), 4), dtype=F)
+    ax_o = np.zeros((len(pairs), 4), dtype=F)
+    seen = set()
+    for step in range(5):
+        got, want = shim_proximity(shim, s, pairs, None, ax_d), oracle.proximity_warm(s, pairs, None, ax_o)
+        assert np.array_equal(got, want), (step, int((got != want).sum()))
+        assert np.array_equal(ax_d.view(np.uint32), ax_o.view(np.uint32)), step
+        seen |= set(want.tolist())
+        s.pos = np.ascontiguousarray((s.pos + rng.normal(0, 0.08, size=s.pos.shape)).astype(F))
+        s.rot = random_unit_quaternions(rng, s.n) if step == 2 else s.rot
+    assert seen >= {0, 1, 2} and ax_o[:, 3].any()

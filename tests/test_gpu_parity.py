@@ -64,7 +64,11 @@ def test_broad_phase_pair_set_bit_exact(ctx, oracle, mk):
 
 def compare_manifolds(res, s, oracle, label):
     """res: UpdateResult for pairs res.pairs; oracle narrow phase is run on the same pairs in the same order."""
-    oc, ooff, oalgo, ostats = oracle.narrow_phase(s, res.pairs)
+    if getattr(s, "query_kind", None) is not None:  # world with proximity sensors (tests/test_proximity.py)
+        oc, ooff, oalgo, oprox = oracle.narrow_phase_kinds(s, res.pairs)
+        assert res.proximity is not None and np.array_equal(res.proximity, oprox), f"{label}: proximity statuses differ"
+    else:
+        oc, ooff, oalgo, ostats = oracle.narrow_phase(s, res.pairs)
     assert np.array_equal(res.pair_algo, oalgo), f"{label}: dispatched algorithm differs"
     ocount = np.diff(ooff)
     bad = np.nonzero(res.manifold_count != ocount)[0]

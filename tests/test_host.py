@@ -62,7 +62,7 @@ def test_contact_struct_layout_matches_header():
 
     assert CONTACT_DTYPE.itemsize == 52
     assert [CONTACT_DTYPE.fields[n][1] for n in ("world1", "world2", "normal", "depth", "f1", "f2", "pair")] == [0, 12, 24, 36, 40, 44, 48]
-    assert ctypes.sizeof(UpdateCountsC) == 4 * 13
+    assert ctypes.sizeof(UpdateCountsC) == 4 * 17  # 13 + n_proximity_pairs + n_proximity[3]
 
 
 # ---- scenes / shapes -------------------------------------------------------------------------------------------
