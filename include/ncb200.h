@@ -278,6 +278,8 @@ int ncb_sim_set_positions(ncb_sim* sim, uint32_t m, const uint32_t* handles, con
  * refer to the hull library already set with ncb_set_hulls. */
 int ncb_sim_remove(ncb_sim* sim, uint32_t m, const uint32_t* handles);
 int ncb_sim_add(ncb_sim* sim, const ncb_objects* objs, uint32_t* out_handles);
+/* ncb_sim_add with a GeometricQueryType per new object: kinds[k] = 0 Contacts / 1 Proximity(query_limit) (NULL = all Contacts). */
+int ncb_sim_add_with_query_types(ncb_sim* sim, const ncb_objects* objs, const uint8_t* kinds, uint32_t* out_handles);
 /* CollisionWorld::update.  counts: n_pairs, n_contacts, epa_overflow (+ manifold-cache overflows), ref_panics,
  * n_epa_pairs, n_manifold_jobs (= pairs regenerated in this step). */
 int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts);
@@ -287,6 +289,14 @@ int ncb_sim_sizes(ncb_sim* sim, uint32_t* n_pairs, uint32_t* n_contacts, uint32_
  * long as the reference's ContactId is); events[3 E] = (object1, object2, 1 Started | 0 Stopped), sorted. */
 int ncb_sim_fetch(ncb_sim* sim, uint32_t* pairs, uint8_t* algo, uint32_t* manifold_start, uint8_t* manifold_count, ncb_contact* contacts,
                   uint32_t* contact_ids, uint32_t* events);
+
+/* Proximity interactions of a stepping world: objects marked with ncb_set_query_types before ncb_sim_create
+ * (or added with ncb_sim_add_with_query_types) are sensors; their pairs carry Interaction::Proximity(detector, status) — status
+ * Disjoint on a new pair, the support-map detector's separating axis kept between updates — and emit ProximityEvents
+ * (narrow_phase.rs:108-143,226-247,266-274).  prox[P] = status per pair in ncb_sim_fetch's order (NCB_PROXIMITY_NONE for contact
+ * pairs); events[4 E] = (collider1, collider2, prev_status, new_status), sorted; cap_events in rows; *n_events = rows that exist;
+ * returns 1 when the events were truncated.  Any pointer may be NULL. */
+int ncb_sim_fetch_proximity(ncb_sim* sim, uint8_t* prox, uint32_t* events, uint32_t cap_events, uint32_t* n_events);
 
 /* World ray queries: glue::interferences_with_ray (first_only = 0) / first_interference_with_ray
  * (first_only = 1) (pipeline/glue/query.rs:13-77,183-224) against the state of the last ncb_sim_step.  rays[7 n] = origin,

@@ -249,6 +249,8 @@ cudaError_t launch_classify_pairs(ncb_ctx* c, const uint2* pairs, uint32_t n);
 // proximity.cu
 cudaError_t launch_prox_rekey(ncb_ctx* c, uint32_t cap_pairs);
 cudaError_t launch_proximity_segments(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, cudaStream_t s);
+cudaError_t launch_proximity_persistent(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* slot_of, float4* slot_dir,
+                                        uint8_t* slot_prox, uint4* events, uint32_t* n_events, uint32_t cap_events);
 cudaError_t launch_proximity_batch(ncb_ctx* c, const DevObjects& o, const uint2* pairs, uint32_t n, const float* margins, uint8_t* out);
 cudaError_t launch_narrow_phase_persistent(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, uint32_t cap_pairs,
                                            const PersistArgs& ps);

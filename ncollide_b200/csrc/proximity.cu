@@ -207,6 +207,32 @@ __global__ void __launch_bounds__(128) k_proximity(DevObjects o, DevHulls H, con
     if (threadIdx.x < 3 && hist[threadIdx.x]) atomicAdd(&cnt->prox_hist[threadIdx.x], hist[threadIdx.x]);
 }
 
+// Stepping world (sim.cu): the detector state of a pair lives in its state slot — the status (Interaction::Proximity's second
+// field, Disjoint on a new edge) and the support-map detector's sep_axis (slot_dir: xyz + "Some" flag).  update_proximity
+// (narrow_phase.rs:123-143): run the detector, emit ProximityEvent(h1, h2, prev, new) when the status changed, store it.
+__global__ void __launch_bounds__(128) k_proximity_persist(DevObjects o, DevHulls H, const uint2* __restrict__ pairs, const uint32_t* __restrict__ slot_of,
+                                                           const DevCounters* __restrict__ cnt, float4* __restrict__ slot_dir, uint8_t* __restrict__ slot_prox,
+                                                           uint4* __restrict__ events, uint32_t* n_events, uint32_t cap_events) {
+    uint32_t seg_begin = cnt->key_start[K_PROX_BALL_BALL];
+    uint32_t seg_end = cnt->key_start[K_PROX_SM] + cnt->key_hist[K_PROX_SM];
+    for (uint32_t p = seg_begin + blockIdx.x * blockDim.x + threadIdx.x; p < seg_end; p += gridDim.x * blockDim.x) {
+        uint2 pr = __ldg(&pairs[p]);
+        uint32_t slot = __ldg(&slot_of[p]);
+        float margin = __ldg(&o.qlimit[pr.x]) + __ldg(&o.qlimit[pr.y]);
+        float4 d = slot_dir[slot];
+        V3 axis = v3(d.x, d.y, d.z);
+        bool has_axis = d.w != 0.f;
+        uint8_t st = proximity_pair(o, H, pr.x, pr.y, margin, axis, has_axis);
+        uint8_t prev = slot_prox[slot];
+        if (st != prev) {
+            uint32_t k = atomicAdd(n_events, 1u);
+            if (k < cap_events) events[k] = make_uint4(pr.x, pr.y, prev, st);
+            slot_prox[slot] = st;
+        }
+        slot_dir[slot] = make_float4(axis.x, axis.y, axis.z, has_axis ? 1.f : 0.f);
+    }
+}
+
 // Stage entry: caller-provided pairs, fresh detectors, no sorting.
 __global__ void __launch_bounds__(128) k_proximity_batch(DevObjects o, DevHulls H, const uint2* __restrict__ pairs, uint32_t n,
                                                          const float* __restrict__ margins, uint8_t* __restrict__ out) {
@@ -229,6 +255,12 @@ cudaError_t launch_prox_rekey(ncb_ctx* c, uint32_t cap_pairs) {
 }
 cudaError_t launch_proximity_segments(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, cudaStream_t s) {
     k_proximity<<<c->sm_count * 4, 128, 0, s>>>(o, c->hulls, pairs, pair_index, c->counters.p, c->manifold_start.p, c->manifold_count.p, c->prox.p);
+    return cudaGetLastError();
+}
+cudaError_t launch_proximity_persistent(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* slot_of, float4* slot_dir,
+                                        uint8_t* slot_prox, uint4* events, uint32_t* n_events, uint32_t cap_events) {
+    k_proximity_persist<<<c->sm_count * 4, 128, 0, c->stream>>>(o, c->hulls, pairs, slot_of, c->counters.p, slot_dir, slot_prox, events, n_events,
+                                                                 cap_events);
     return cudaGetLastError();
 }
 cudaError_t launch_proximity_batch(ncb_ctx* c, const DevObjects& o, const uint2* pairs, uint32_t n, const float* margins, uint8_t* out) {

@@ -10,6 +10,7 @@
 // State per interference pair lives in a slot (stable while the pair exists): orientation (h1, h2), dispatcher key,
 // last_gjk_dir, persistent manifold.  The sorted pair list of the persistent broad phase (bp_persistent.cu) maps to slots.
 #include <cub/cub.cuh>
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -42,11 +43,15 @@ struct ncb_sim {
     uint32_t n_free_host = 0;      // host copy of the free-list length
     DevBuf<uint2> slot_pair;
     DevBuf<uint8_t> slot_key;
-    DevBuf<float4> slot_dir;
+    DevBuf<float4> slot_dir;             // last_gjk_dir of a contact pair / sep_axis of a proximity pair (xyz + valid flag)
+    DevBuf<uint8_t> slot_prox;           // Proximity status of a proximity pair (Interaction::Proximity(_, status))
     DevBuf<uint32_t> pm_hdr;
     DevBuf<float4> pm_entry;
     DevBuf<uint32_t> free_slots;
-    DevBuf<uint32_t> cnt;  // [0] n_free (signed) [1] next_slot [2] n_events [3] pm_overflow
+    DevBuf<uint32_t> cnt;  // [0] n_free (signed) [1] next_slot [2] n_events [3] pm_overflow [4] n_prox_events
+    DevBuf<uint4> prox_events;  // ProximityEvent rows (h1, h2, prev, new) of the last step
+    DevBuf<uint8_t> exp_prox;
+    uint32_t n_prox_events = 0;
     DevBuf<unsigned long long> events, events_sorted;
     DevBuf<uint8_t> cub_tmp;
     // export of the last step
@@ -77,7 +82,9 @@ __device__ __constant__ uint8_t c_sim_key[16] = {K_BALL_BALL,   K_BALL_CUBOID,  
                                                  K_PLANE_BALL,  K_PLANE_CUBOID, K_PLANE_HULL, K_NONE};
 __device__ __constant__ uint8_t c_sim_algo[16] = {NCB_ALGO_BALL_BALL,     NCB_ALGO_PLANE_BALL,  NCB_ALGO_PLANE_CONVEX,  NCB_ALGO_PLANE_CONVEX,
                                                   NCB_ALGO_BALL_CONVEX,   NCB_ALGO_BALL_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_CONVEX_CONVEX,
-                                                  NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_NONE,        0, 0, 0, 0, 0, 0};
+                                                  NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_NONE,        NCB_ALGO_PROXIMITY, NCB_ALGO_PROXIMITY,
+                                                  NCB_ALGO_PROXIMITY,     0,                    0, 0};
+__device__ __forceinline__ bool is_prox_key(uint8_t k) { return k >= K_PROX_BALL_BALL && k <= K_PROX_SM; }
 
 __device__ int sim_find(const unsigned long long* __restrict__ keys, uint32_t n, unsigned long long k) {
     uint32_t lo = 0, hi = n;
@@ -110,12 +117,21 @@ __global__ void k_sim_scatter_poses(const uint32_t* __restrict__ handles, const 
 // interference_stopped -> handle_interaction(.., false) (narrow_phase.rs:248-277): the edge goes, Stopped if it had contacts
 __global__ void k_sim_release(const unsigned long long* __restrict__ prev, uint32_t n_prev, const unsigned long long* __restrict__ cur, uint32_t n_cur,
                               const uint32_t* __restrict__ slot_prev, const uint2* __restrict__ slot_pair, const uint32_t* __restrict__ pm_hdr,
-                              const float4* __restrict__ pm_entry, uint32_t* free_slots, uint32_t* cnt, unsigned long long* events, uint32_t cap_events) {
+                              const float4* __restrict__ pm_entry, uint32_t* free_slots, uint32_t* cnt, unsigned long long* events, uint32_t cap_events,
+                              const uint8_t* __restrict__ slot_key, const uint8_t* __restrict__ slot_prox, uint4* prox_events) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_prev) return;
     if (sim_find(cur, n_cur, prev[j]) >= 0) return;
     uint32_t slot = slot_prev[j];
-    if (pm_live_count(pm_hdr, pm_entry, slot) > 0) {
+    if (is_prox_key(slot_key[slot])) {
+        // a proximity edge goes: ProximityEvent(h1, h2, prev, Disjoint) unless it was Disjoint already (narrow_phase.rs:266-274)
+        uint8_t st = slot_prox[slot];
+        if (st != NCB_PROXIMITY_DISJOINT) {
+            uint2 pr = slot_pair[slot];
+            uint32_t k = atomicAdd(&cnt[4], 1u);
+            if (k < cap_events) prox_events[k] = make_uint4(pr.x, pr.y, st, NCB_PROXIMITY_DISJOINT);
+        }
+    } else if (pm_live_count(pm_hdr, pm_entry, slot) > 0) {
         uint2 pr = slot_pair[slot];
         uint32_t k = atomicAdd(&cnt[2], 1u);
         if (k < cap_events) events[k] = ((unsigned long long)pr.x << 32) | pr.y;
@@ -126,7 +142,7 @@ __global__ void k_sim_release(const unsigned long long* __restrict__ prev, uint3
 __global__ void k_sim_assign(const unsigned long long* __restrict__ cur, uint32_t n_cur, const unsigned long long* __restrict__ prev, uint32_t n_prev,
                              const uint32_t* __restrict__ slot_prev, uint32_t* slot_new, const uint32_t* __restrict__ upd_seq,
                              const uint32_t* __restrict__ type, const uint32_t* __restrict__ free_slots, uint32_t* cnt, uint2* slot_pair,
-                             uint8_t* slot_key, float4* slot_dir, uint32_t* pm_hdr) {
+                             uint8_t* slot_key, float4* slot_dir, uint32_t* pm_hdr, const uint8_t* __restrict__ qkind, uint8_t* slot_prox) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cur) return;
     unsigned long long k = cur[i];
@@ -143,7 +159,13 @@ __global__ void k_sim_assign(const unsigned long long* __restrict__ cur, uint32_
     uint32_t h1 = hi_first ? hi : lo, h2 = hi_first ? lo : hi;
     slot_new[i] = slot;
     slot_pair[slot] = make_uint2(h1, h2);
-    slot_key[slot] = c_sim_key[(type[h1] & 3) * 4 + (type[h2] & 3)];
+    uint32_t t1 = type[h1] & 3, t2 = type[h2] & 3;
+    uint8_t key = c_sim_key[t1 * 4 + t2];
+    if (qkind && key != K_NONE && (qkind[h1] | qkind[h2])) {  // (_, Proximity) | (Proximity, _): a proximity detector (narrow_phase.rs:240-246)
+        key = (t1 == NCB_SHAPE_BALL && t2 == NCB_SHAPE_BALL) ? K_PROX_BALL_BALL : ((t1 == NCB_SHAPE_PLANE || t2 == NCB_SHAPE_PLANE) ? K_PROX_PLANE : K_PROX_SM);
+        slot_prox[slot] = NCB_PROXIMITY_DISJOINT;
+    }
+    slot_key[slot] = key;
     slot_dir[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int w = 0; w < PM_HDR_WORDS; ++w) pm_hdr[(size_t)slot * PM_HDR_WORDS + w] = 0;
 }
@@ -222,6 +244,14 @@ __global__ void k_sim_unpack_events(const unsigned long long* __restrict__ ev, u
     out[3 * i + 2] = (uint32_t)(k >> 63);
 }
 
+__global__ void k_sim_export_prox(const uint32_t* __restrict__ slot_new, uint32_t n_cur, const uint8_t* __restrict__ slot_key,
+                                  const uint8_t* __restrict__ slot_prox, uint8_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cur) return;
+    uint32_t slot = slot_new[i];
+    out[i] = is_prox_key(slot_key[slot]) ? slot_prox[slot] : (uint8_t)NCB_PROXIMITY_NONE;
+}
+
 // ---- CollisionWorld::remove / add between updates ------------------------------------------------------------------------
 // pairs of a removed object leave the pair table silently (glue/setup.rs:56-58): flag them, release their slots
 __global__ void k_sim_flag_removed(const unsigned long long* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ d_attached,
@@ -255,6 +285,10 @@ __global__ void k_sim_scatter_objects(const uint32_t* __restrict__ handles, uint
     if (dang_cs) dang_cs[h] = ang_cs[k];
     moved[h] = 1;
 }
+__global__ void k_sim_scatter_kinds(const uint32_t* __restrict__ handles, uint32_t m, const uint8_t* __restrict__ kinds, uint8_t* qkind) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < m) qkind[handles[k]] = kinds ? kinds[k] : 0;
+}
 __global__ void k_sim_fill_groups(uint32_t* g, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) g[3 * (size_t)i] = g[3 * (size_t)i + 1] = 0x3FFFFFFFu, g[3 * (size_t)i + 2] = 0u;
@@ -286,12 +320,14 @@ static int sim_grow_slots(ncb_sim* sim, size_t want) {
     CKS(grow_keep(sim->slot_pair, want, keep, s));
     CKS(grow_keep(sim->slot_key, want, keep, s));
     CKS(grow_keep(sim->slot_dir, want, keep, s));
+    CKS(grow_keep(sim->slot_prox, want, keep, s));
     CKS(grow_keep(sim->pm_hdr, want * PM_HDR_WORDS, keep * PM_HDR_WORDS, s));
     CKS(grow_keep(sim->pm_entry, want * PM_CAP * PM_ENTRY_F4, keep * PM_CAP * PM_ENTRY_F4, s));
     CKS(grow_keep(sim->free_slots, want, keep, s));
     size_t cap = sim->slot_pair.cap;
     cap = std::min(cap, (size_t)sim->slot_key.cap);
     cap = std::min(cap, (size_t)sim->slot_dir.cap);
+    cap = std::min(cap, (size_t)sim->slot_prox.cap);
     cap = std::min(cap, sim->pm_hdr.cap / PM_HDR_WORDS);
     cap = std::min(cap, sim->pm_entry.cap / (PM_CAP * PM_ENTRY_F4));
     cap = std::min(cap, (size_t)sim->free_slots.cap);
@@ -306,10 +342,6 @@ int ncb_sim_create(ncb_ctx* ctx, float margin, ncb_sim** out) {
     if (ctx->n == 0) {
         ctx->err = "ncb_sim_create: call ncb_set_objects first";
         return NCB_ERR_STATE;
-    }
-    if (ctx->has_prox) {
-        ctx->err = "ncb_sim_create: proximity sensors (ncb_set_query_types) are only supported by the fresh-world update";
-        return NCB_ERR_UNSUPPORTED;
     }
     ncb_sim* sim = new ncb_sim;
     sim->ctx = ctx;
@@ -338,6 +370,7 @@ void ncb_sim_destroy(ncb_sim* sim) {
     sim->moved.release(), sim->stage_h.release(), sim->stage_p.release(), sim->stage_r.release();
     sim->keys_prev.release(), sim->slot_prev.release(), sim->slot_new.release(), sim->raw_slot.release();
     sim->slot_pair.release(), sim->slot_key.release(), sim->slot_dir.release(), sim->pm_hdr.release(), sim->pm_entry.release();
+    sim->slot_prox.release(), sim->prox_events.release(), sim->exp_prox.release();
     sim->sel_flags.release(), sim->keys_tmp.release(), sim->slot_tmp.release(), sim->sel_count.release();
     sim->free_slots.release(), sim->cnt.release(), sim->events.release(), sim->events_sorted.release(), sim->cub_tmp.release();
     sim->exp_count.release(), sim->exp_start.release(), sim->exp_ids.release(), sim->exp_events.release(), sim->exp_contacts.release();
@@ -425,14 +458,16 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
     CKS(sim->events.reserve(cap_events));
     CKS(sim->slot_new.reserve(n_cur + 1));
     CKS(sim->raw_slot.reserve(n_cur + 1));
-    CKS(cudaMemsetAsync(sim->cnt.p + 2, 0, 8, s));
+    CKS(sim->prox_events.reserve(cap_events));
+    CKS(cudaMemsetAsync(sim->cnt.p + 2, 0, 12, s));
     if (sim->n_prev)
         k_sim_release<<<(sim->n_prev + 255) / 256, 256, 0, s>>>(sim->keys_prev.p, sim->n_prev, cur, n_cur, sim->slot_prev.p, sim->slot_pair.p, sim->pm_hdr.p,
-                                                                sim->pm_entry.p, sim->free_slots.p, sim->cnt.p, sim->events.p, cap_events);
+                                                                sim->pm_entry.p, sim->free_slots.p, sim->cnt.p, sim->events.p, cap_events, sim->slot_key.p,
+                                                                sim->slot_prox.p, sim->prox_events.p);
     if (n_cur)
         k_sim_assign<<<(n_cur + 255) / 256, 256, 0, s>>>(cur, n_cur, sim->keys_prev.p, sim->n_prev, sim->slot_prev.p, sim->slot_new.p, sim->bp->upd_seq.p,
                                                          ctx->type.p, sim->free_slots.p, sim->cnt.p, sim->slot_pair.p, sim->slot_key.p, sim->slot_dir.p,
-                                                         sim->pm_hdr.p);
+                                                         sim->pm_hdr.p, ctx->has_prox ? ctx->qkind.p : nullptr, sim->slot_prox.p);
     k_sim_fix_free<<<1, 1, 0, s>>>(sim->cnt.p);
     CKS(cudaGetLastError());
     CKS(sim->keys_prev.reserve(n_cur + 1));
@@ -461,6 +496,9 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
         ps.cap_events = cap_events;
         ps.pm_overflow = sim->cnt.p + 3;
         CKS(launch_narrow_phase_persistent(ctx, objs, ctx->pairs.p, ctx->pair_index.p, (uint32_t)cap_pairs, ps));
+        if (ctx->has_prox)  // update_proximity for the sensor pairs with a changed endpoint (their three key segments)
+            CKS(launch_proximity_persistent(ctx, objs, ctx->pairs.p, ctx->pair_index.p, sim->slot_dir.p, sim->slot_prox.p, sim->prox_events.p, sim->cnt.p + 4,
+                                            cap_events));
     }
     mark("narrow");
     // ---- export: pairs in sorted order, live contacts in slab order
@@ -469,6 +507,7 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
     CKS(sim->exp_pairs.reserve(n_cur + 1));
     CKS(sim->exp_algo.reserve(n_cur + 1));
     CKS(sim->exp_mcount.reserve(n_cur + 1));
+    CKS(sim->exp_prox.reserve(n_cur + 1));
     uint32_t total = 0;
     if (n_cur) {
         k_sim_count<<<(n_cur + 255) / 256, 256, 0, s>>>(sim->slot_prev.p, n_cur, sim->pm_hdr.p, sim->pm_entry.p, sim->exp_count.p);
@@ -487,18 +526,20 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
         k_sim_export<<<(n_cur + 255) / 256, 256, 0, s>>>(sim->slot_prev.p, n_cur, sim->slot_pair.p, sim->slot_key.p, sim->pm_hdr.p, sim->pm_entry.p,
                                                          sim->exp_start.p, sim->exp_pairs.p, sim->exp_algo.p, sim->exp_mcount.p, sim->exp_contacts.p,
                                                          sim->exp_ids.p);
+        k_sim_export_prox<<<(n_cur + 255) / 256, 256, 0, s>>>(sim->slot_prev.p, n_cur, sim->slot_key.p, sim->slot_prox.p, sim->exp_prox.p);
         CKS(cudaGetLastError());
     }
     mark("export");
     // ---- counters, events (sorted for a deterministic order), flags cleared (world.rs:115-118)
-    uint32_t hc[4] = {0, 0, 0, 0};
-    CKS(cudaMemcpyAsync(hc, sim->cnt.p, 16, cudaMemcpyDeviceToHost, s));
+    uint32_t hc[5] = {0, 0, 0, 0, 0};
+    CKS(cudaMemcpyAsync(hc, sim->cnt.p, 20, cudaMemcpyDeviceToHost, s));
     r = read_counters(ctx);
     if (r) return r;
     sim->n_free_host = hc[0];
     sim->next_slot_bound = hc[1];
     sim->n_events = hc[2] < cap_events ? hc[2] : cap_events;
     sim->pm_overflow = hc[3];
+    sim->n_prox_events = hc[4] < cap_events ? hc[4] : cap_events;
     if (sim->n_events > 1) {
         CKS(sim->events_sorted.reserve(sim->n_events));
         size_t bytes = 0;
@@ -523,6 +564,8 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
         counts->ref_panics = ctx->last_counters.ref_panics;
         counts->n_epa_pairs = ctx->last_counters.epa_cursor[K_CUBOID_CUBOID] - ctx->last_counters.key_start[K_CUBOID_CUBOID];
         counts->n_manifold_jobs = sim->n_active;  // pairs regenerated in this step
+        const DevCounters& lc = ctx->last_counters;
+        counts->n_proximity_pairs = lc.key_hist[K_PROX_BALL_BALL] + lc.key_hist[K_PROX_PLANE] + lc.key_hist[K_PROX_SM];  // proximity pairs updated
     }
     return NCB_OK;
 }
@@ -593,13 +636,21 @@ int ncb_sim_remove(ncb_sim* sim, uint32_t m, const uint32_t* handles) {
 // CollisionWorld::add (world.rs:64-96) between updates for the objects of `objs` (hulls refer to the library already set):
 // handles come from the object slab (last freed first, else appended) and are returned in out_handles; each proxy is created
 // with the object's swept AABB; the object takes part in the next ncb_sim_step with every update flag set.
-int ncb_sim_add(ncb_sim* sim, const ncb_objects* objs, uint32_t* out_handles) {
+int ncb_sim_add(ncb_sim* sim, const ncb_objects* objs, uint32_t* out_handles) { return ncb_sim_add_with_query_types(sim, objs, nullptr, out_handles); }
+
+// Same; kinds[k] = 0 Contacts / 1 Proximity per new object (NULL: all Contacts), see ncb_set_query_types.
+int ncb_sim_add_with_query_types(ncb_sim* sim, const ncb_objects* objs, const uint8_t* kinds, uint32_t* out_handles) {
     if (!sim || !objs || !out_handles) return NCB_ERR_ARG;
     ncb_ctx* ctx = sim->ctx;
     CKS(cudaSetDevice(ctx->device));
     uint32_t m = objs->n;
     if (m == 0) return NCB_OK;
     if (!(objs->pos && objs->rot && objs->shape_type && objs->shape_param && objs->query_limit && objs->ang_pred)) return NCB_ERR_ARG;
+    for (uint32_t k = 0; kinds && k < m; ++k)
+        if (kinds[k] > 1) {
+            ctx->err = "ncb_sim_add_with_query_types: kind must be 0 (Contacts) or 1 (Proximity)";
+            return NCB_ERR_ARG;
+        }
     if (sim->first) {
         ctx->err = "ncb_sim_add: call ncb_sim_step once before adding objects (the initial set comes from ncb_set_objects)";
         return NCB_ERR_STATE;
@@ -671,6 +722,30 @@ int ncb_sim_add(ncb_sim* sim, const ncb_objects* objs, uint32_t* out_handles) {
                                                           ctx->pos.p, ctx->rot.p, ctx->type.p, ctx->param.p, ctx->has_groups ? ctx->groups.p : nullptr,
                                                           ctx->qlimit.p, ctx->ang_stride ? ctx->ang_cs.p : nullptr, sim->moved.p);
     CKS(cudaGetLastError());
+    {
+        // query types of the new objects (a recycled handle must not inherit the kind of its previous owner)
+        bool any_kind = false;
+        for (uint32_t k = 0; kinds && k < m; ++k) any_kind = any_kind || kinds[k] != 0;
+        if (any_kind && !ctx->has_prox) {  // first sensor of this world
+            CKS(ctx->qkind.reserve(new_n));
+            CKS(cudaMemsetAsync(ctx->qkind.p, 0, new_n, s));
+            ctx->has_prox = true;
+        } else if (ctx->has_prox && new_n > old_n) {
+            CKS(grow_keep(ctx->qkind, new_n, old_n, s));
+            CKS(cudaMemsetAsync(ctx->qkind.p + old_n, 0, new_n - old_n, s));
+        }
+        if (ctx->has_prox) {
+            DevBuf<uint8_t> d_k;
+            if (kinds) {
+                CKS(d_k.reserve(m));
+                CKS(cudaMemcpyAsync(d_k.p, kinds, m, cudaMemcpyHostToDevice, s));
+            }
+            k_sim_scatter_kinds<<<(m + 255) / 256, 256, 0, s>>>(d_h.p, m, kinds ? d_k.p : nullptr, ctx->qkind.p);
+            CKS(cudaGetLastError());
+            CKS(cudaStreamSynchronize(s));
+            d_k.release();
+        }
+    }
     ctx->n = sim->n = new_n;
     sim->alive.resize(new_n, 0);
     for (uint32_t k = 0; k < m; ++k) sim->alive[out_handles[k]] = 1;
@@ -720,6 +795,29 @@ int ncb_sim_fetch(ncb_sim* sim, uint32_t* pairs, uint8_t* algo, uint32_t* manifo
     }
     CKS(cudaStreamSynchronize(s));
     return NCB_OK;
+}
+
+// Proximity side of the last step: prox[P] = status per pair in the order of ncb_sim_fetch (NCB_PROXIMITY_NONE for contact pairs);
+// events[4 * E] = ProximityEvent rows (collider1, collider2, prev_status, new_status), sorted; cap_events in rows; *n_events = rows
+// that exist; returns 1 when events were truncated.  Any pointer may be NULL.
+int ncb_sim_fetch_proximity(ncb_sim* sim, uint8_t* prox, uint32_t* events, uint32_t cap_events, uint32_t* n_events) {
+    if (!sim) return NCB_ERR_ARG;
+    CKS(cudaSetDevice(sim->ctx->device));
+    cudaStream_t s = sim->ctx->stream;
+    uint32_t P = sim->n_pairs, E = sim->n_prox_events;
+    if (n_events) *n_events = E;
+    if (prox && P) CKS(cudaMemcpyAsync(prox, sim->exp_prox.p, P, cudaMemcpyDeviceToHost, s));
+    std::vector<uint4> ev;
+    if (events && E) {
+        ev.resize(E);
+        CKS(cudaMemcpyAsync(ev.data(), sim->prox_events.p, sizeof(uint4) * (size_t)E, cudaMemcpyDeviceToHost, s));
+    }
+    CKS(cudaStreamSynchronize(s));
+    if (events && E) {
+        std::sort(ev.begin(), ev.end(), [](const uint4& a, const uint4& b) { return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z); });
+        for (uint32_t k = 0; k < E && k < cap_events; ++k) events[4 * k] = ev[k].x, events[4 * k + 1] = ev[k].y, events[4 * k + 2] = ev[k].z, events[4 * k + 3] = ev[k].w;
+    }
+    return (events && E > cap_events) ? 1 : NCB_OK;
 }
 
 // glue::interferences_with_ray (first_only = 0) / first_interference_with_ray (first_only = 1) (glue/query.rs:13-77,183-224)

@@ -610,7 +610,9 @@ class SteppingWorld:
         """``CollisionWorld::add`` for every object of `scene` (same hull library as the world); returns their handles."""
         oc, keep = _ffi.pack_objects(scene)
         out = np.zeros(scene.n, dtype=np.uint32)
-        self.ctx.check(self.ctx.lib.ncb_sim_add(self._h, C.byref(oc), ptr(out)), "ncb_sim_add")
+        qk = getattr(scene, "query_kind", None)
+        qk = None if qk is None else np.ascontiguousarray(qk, dtype=np.uint8)
+        self.ctx.check(self.ctx.lib.ncb_sim_add_with_query_types(self._h, C.byref(oc), ptr(qk), ptr(out)), "ncb_sim_add_with_query_types")
         self.ctx.n = max(self.ctx.n, int(out.max()) + 1) if len(out) else self.ctx.n
         return out
 
@@ -634,7 +636,15 @@ class SteppingWorld:
         self.ctx.check(self.ctx.lib.ncb_sim_fetch(self._h, ptr(pairs), ptr(algo), ptr(start), ptr(count), ptr(contacts), ptr(ids), ptr(events)),
                        "ncb_sim_fetch")
         off = np.concatenate([start, [Cn]]).astype(np.uint32) if P else np.zeros(1, dtype=np.uint32)
-        return {"pairs": pairs, "algo": algo, "off": off, "count": count, "contacts": contacts, "ids": ids, "events": events, "counts": counts}
+        # proximity side (sensors): status per pair + ProximityEvents (collider1, collider2, prev, new)
+        prox = np.full(P, 255, dtype=np.uint8)
+        ne = C.c_uint32()
+        self.ctx.check(self.ctx.lib.ncb_sim_fetch_proximity(self._h, ptr(prox) if P else None, None, C.c_uint32(0), C.byref(ne)), "ncb_sim_fetch_proximity")
+        pev = np.zeros((ne.value, 4), dtype=np.uint32)
+        if ne.value:
+            self.ctx.check(self.ctx.lib.ncb_sim_fetch_proximity(self._h, None, ptr(pev), C.c_uint32(ne.value), C.byref(ne)), "ncb_sim_fetch_proximity")
+        return {"pairs": pairs, "algo": algo, "off": off, "count": count, "contacts": contacts, "ids": ids, "events": events, "counts": counts,
+                "prox": prox, "prox_events": pev}
 
     step = update
 

@@ -152,7 +152,7 @@ class DeviceSimAdapter:
         sel = np.repeat(keep, cnt)
         off = np.concatenate([[0], np.cumsum(cnt[keep])]).astype(np.uint32)
         return {"pairs": r["pairs"][keep], "algo": r["algo"][keep], "off": off, "contacts": r["contacts"][sel], "ids": r["ids"][sel],
-                "events": r["events"], "counts": r["counts"], "bp_pairs": len(r["pairs"])}
+                "events": r["events"], "counts": r["counts"], "bp_pairs": len(r["pairs"]), "prox": r["prox"][keep], "prox_events": r["prox_events"]}
 
 
 def compare_sim_logs(dev, orc):

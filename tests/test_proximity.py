@@ -238,7 +238,8 @@ def test_collision_world_mirror_with_sensor(oracle):
     cube = w.add(((0, 0, 0), ident), Cuboid((1, 1, 1)), query_type=GeometricQueryType.Contacts(0.02, 0.0))
     s1 = w.add(((1.2, 0, 0), ident), Ball(0.5), query_type=GeometricQueryType.Proximity(0.25))   # intersecting
     s2 = w.add(((0, 1.7, 0), ident), Ball(0.5), query_type=GeometricQueryType.Proximity(0.25))   # within margin
-    s3 = w.add(((0, 0, -1.76), ident), Ball(0.5), query_type=GeometricQueryType.Proximity(0.25))  # boxes meet, disjoint
+    # margin of a pair = sum of the two query limits = 0.25 + 0.02 (narrow_phase.rs:138): 0.28 away is Disjoint, the boxes still meet
+    s3 = w.add(((0, 0, -1.78), ident), Ball(0.5), query_type=GeometricQueryType.Proximity(0.25))
     b = w.add(((-1.4, 0, 0), ident), Ball(0.5), query_type=GeometricQueryType.Contacts(0.02, 0.0))  # a real contact
     w.update()
     prox = {(a, c): st for a, c, st in w.proximity_pairs(effective_only=False)}
@@ -247,3 +248,56 @@ def test_collision_world_mirror_with_sensor(oracle):
     assert sorted(w.proximity_events()) == sorted([(s1, cube, Proximity.Disjoint, Proximity.Intersecting), (s2, cube, Proximity.Disjoint, Proximity.WithinMargin)])
     contacts = list(w.contact_pairs())
     assert len(contacts) == 1 and contacts[0][:2] == (b, cube)
+
+
+def _sim_compare(dev, orc):
+    """Per step: same pairs / orientation / algorithm / proximity status; ProximityEvents equal as sorted rows; contact side
+    through the stepping-world comparison of tests/test_bp_persistent.py."""
+    from test_bp_persistent import compare_sim_logs
+
+    compare_sim_logs(dev, orc)
+    n_ev = 0
+    for t, (d, o) in enumerate(zip(dev, orc)):
+        assert np.array_equal(d["prox"], o["prox"]), f"step {t}: proximity statuses differ on {int((d['prox'] != o['prox']).sum())} pairs"
+        de = d["prox_events"][np.lexsort(d["prox_events"].T[::-1])] if len(d["prox_events"]) else d["prox_events"]
+        oe = o["prox_events"][np.lexsort(o["prox_events"].T[::-1])] if len(o["prox_events"]) else o["prox_events"]
+        assert np.array_equal(de, oe), f"step {t}: proximity events differ ({len(de)} vs {len(oe)})"
+        n_ev += len(oe) if t > 0 else 0
+    return n_ev
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,kinds,side,plane,seed,frac", [(1500, (1, 1, 1), 6.5, False, 3, 0.3), (4000, (1, 1, 1), 9.5, True, 4, 0.5),
+                                                          (2500, (0, 1, 1), 7.0, False, 5, 1.0)])
+def test_stepping_world_with_sensors_matches_oracle(oracle, n, kinds, side, plane, seed, frac):
+    from ncollide_b200.world import Context
+    from sim_scenario import drive
+    from test_bp_persistent import DeviceSimAdapter
+
+    s = with_sensors(make_world_scene(n, 70 + seed, kinds, side=side, n_hulls=32, plane=plane, name="sim_sensors"), frac, seed, margin=0.12)
+    dev = drive(DeviceSimAdapter(Context(0), s), s, steps=7, seed=seed)
+    orc = drive(oracle.sim(s), s, steps=7, seed=seed)
+    assert _sim_compare(dev, orc) > 10  # status changes after the first step: the warm-started detectors and the stop events
+
+
+@pytest.mark.gpu
+def test_stepping_world_add_remove_with_sensors_matches_oracle(oracle):
+    from ncollide_b200.world import Context
+    from sim_scenario import drive_add_remove
+    from test_bp_persistent import DeviceSimAdapterAR
+
+    n, seed = 1500, 11
+    side = 5.5 * (n / 800.0) ** (1 / 3)
+    s = with_sensors(make_world_scene(n, 80, (1, 1, 1), side=side, n_hulls=16, name="sim_addrm_sensors"), 0.3, 5, margin=0.1)
+    extra = with_sensors(make_world_scene(n // 6, 81, (1, 1, 1), side=side, hull_library=s.hulls, name="extra"), 0.5, 6, margin=0.1)
+    dev = drive_add_remove(DeviceSimAdapterAR(Context(0), s), s, extra, steps=7, seed=seed)
+    orc = drive_add_remove(oracle.sim(s), s, extra, steps=7, seed=seed)
+    assert np.array_equal(dev[3]["new_handles"], orc[3]["new_handles"])
+    _sim_compare(dev, orc)
+    # sensors added to a world that had none
+    s2 = make_world_scene(n, 82, (1, 1, 1), side=side, n_hulls=16, name="no_sensors_then_some")
+    extra2 = with_sensors(make_world_scene(n // 6, 83, (1, 1, 1), side=side, hull_library=s2.hulls, name="extra2"), 0.6, 7, margin=0.1)
+    dev = drive_add_remove(DeviceSimAdapterAR(Context(0), s2), s2, extra2, steps=7, seed=seed)
+    orc = drive_add_remove(oracle.sim(s2), s2, extra2, steps=7, seed=seed)
+    _sim_compare(dev, orc)
+    assert sum(int((r["algo"] == 6).sum()) for r in orc) > 0
