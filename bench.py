@@ -415,6 +415,10 @@ def run_native(args):
             widened = bench_widened(ctx, scene)
         except Exception as ex:  # noqa: BLE001
             widened = {"error": repr(ex)[:200]}
+        try:
+            widened["proximity_sensors"] = bench_proximity(ctx, scene)
+        except Exception as ex:  # noqa: BLE001
+            widened["proximity_sensors"] = {"error": repr(ex)[:200]}
 
     if rank == 0:
         line = {
@@ -546,6 +550,47 @@ def bench_widened(ctx, scene):
         "world_ray_queries": {"workload": f"{n_rays} rays, first_interference_with_ray within 20 units, {n}-object world (ncb_sim_ray_cast)",
                               "ms": min(rt[1:]), "Mrays_per_s": n_rays / (min(rt[1:]) / 1e3) / 1e6, "hits": rows},
     }
+
+
+def bench_proximity(ctx, scene, fraction=0.2, reps=6):
+    """Widened row N4 (proximity-only interactions): the same scene with a seeded `fraction` of the objects turned into
+    GeometricQueryType::Proximity sensors.  Fresh-world update on the device (wall clock around ncb_world_update_device, which
+    ends with the counter read-back) next to the same update without sensors, and the batched detector entry (ncb_proximity)
+    on the update's own sensor pairs with host buffers."""
+    import copy
+
+    from ncollide_b200.scenes import with_sensors
+
+    s = with_sensors(copy.copy(scene), fraction, 5)
+    out = {"workload": f"{s.n} objects, {int(s.query_kind.sum())} of them Proximity sensors (margin = their query limit), fresh-world update"}
+
+    def timed():
+        ts, c = [], None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            c = ctx.world_update_device(s.margin)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        return statistics.median(ts[2:]), c
+
+    ctx.set_scene(scene)
+    out["ms_per_update_without_sensors"], c0 = timed()
+    ctx.set_scene(s)
+    out["ms_per_update"], c = timed()
+    res = ctx.world_fetch(c)
+    sel = res.pair_algo == 6
+    out.update({"pairs": c["n_pairs"], "proximity_pairs": c["n_algo"]["proximity"], "statuses": c["n_proximity"], "contacts": c["n_contacts"],
+                "contacts_without_sensors": c0["n_contacts"]})
+    pp = np.ascontiguousarray(res.pairs[sel])
+    ts = []
+    for _ in range(4):
+        t0 = time.perf_counter()
+        st = ctx.proximity(pp)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    assert np.array_equal(st, res.proximity[sel]), "ncb_proximity disagrees with the world update on the same pairs"
+    out["batch_entry"] = {"pairs": int(len(pp)), "ms": min(ts[1:]), "Mpairs_per_s": len(pp) / (min(ts[1:]) / 1e3) / 1e6,
+                          "note": "ncb_proximity, host buffers (8 B in + 1 B out per pair), unsorted pairs"}
+    ctx.set_scene(scene)  # back to a sensor-free world
+    return out
 
 
 def main():

@@ -1,5 +1,6 @@
 /* ncb200 — C ABI of the B200-native collision hot path (one CollisionWorld::update step + TriMesh ray casting), widened to
- * the persistent BroadPhase (ncb_bp_*), the stepping CollisionWorld (ncb_sim_*) and its world queries.
+ * the persistent BroadPhase (ncb_bp_*), the stepping CollisionWorld (ncb_sim_*), its world queries and
+ * proximity-only interactions (GeometricQueryType::Proximity sensors, the 3-D half of N4).
  *
  * This is the drop-in boundary: plain pointers and sizes, no C++ / torch types, no unwinding.
  * Every entry point names the reference (dimforge/ncollide, paths relative to the reference root) item it
@@ -85,7 +86,8 @@ typedef struct ncb_hull_library {
 } ncb_hull_library;
 
 /* SoA collision objects = what CollisionObject holds on the path (pipeline/object/collision_object.rs:62-113):
- * position (Isometry3: translation + unit quaternion i,j,k,w), shape, CollisionGroups, GeometricQueryType::Contacts. */
+ * position (Isometry3: translation + unit quaternion i,j,k,w), shape, CollisionGroups, GeometricQueryType (Contacts here;
+ * ncb_set_query_types turns objects into Proximity sensors, query_limit then holds the proximity margin). */
 typedef struct ncb_objects {
     uint32_t n;
     const float* pos;           /* 3 per object */
@@ -93,7 +95,7 @@ typedef struct ncb_objects {
     const uint32_t* shape_type; /* NCB_SHAPE_* */
     const float* shape_param;   /* 4 per object: radius | half extents | (float)hull id | plane normal */
     const uint32_t* groups;     /* 3 per object: membership, whitelist, blacklist; NULL = CollisionGroups::new() */
-    const float* query_limit;   /* Contacts(linear, _) */
+    const float* query_limit;   /* Contacts(linear, _) or Proximity(margin): GeometricQueryType::query_limit() */
     const float* ang_pred;      /* Contacts(_, angular) */
 } ncb_objects;
 
@@ -111,7 +113,7 @@ typedef struct ncb_update_counts {
     uint32_t n_pairs;          /* broad-phase pairs (DBVTBroadPhase::num_interferences) */
     uint32_t n_contacts;       /* contacts over all manifolds */
     uint32_t n_contact_pairs;  /* pairs whose manifold is not empty */
-    uint32_t n_algo[6];        /* pairs per NCB_ALGO_* */
+    uint32_t n_algo[6];        /* pairs per NCB_ALGO_NONE .. NCB_ALGO_CONVEX_CONVEX (NCB_ALGO_PROXIMITY: n_proximity_pairs below) */
     uint32_t epa_overflow;     /* pairs that exceeded a fixed device capacity: EPA polytope (result = "no contact") or more than
                                 * 32 distinct contacts in one manifold (extra contacts dropped); 0 expected, tests assert it */
     uint32_t ref_panics;       /* pairs on which the reference itself would have panicked (assert / unwrap) */

@@ -446,7 +446,7 @@ static void fill_counts(ncb_ctx* ctx, ncb_update_counts* counts) {
     counts->n_algo[NCB_ALGO_NONE] = c.key_hist[K_NONE];
     counts->n_epa_pairs = c.epa_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID];
     counts->n_manifold_jobs = c.cp_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID];
-    counts->n_proximity_pairs = c.key_hist[K_PROX_BALL_BALL] + c.key_hist[K_PROX_PLANE] + c.key_hist[K_PROX_SM];
+    counts->n_proximity_pairs = c.key_hist[K_PROX_BALL_BALL] + c.key_hist[K_PROX_PLANE] + c.key_hist[K_PROX_SM] + c.key_hist[K_PROX_SM_HULL];
     for (int k = 0; k < 3; ++k) counts->n_proximity[k] = c.prox_hist[k];
 }
 

@@ -459,7 +459,7 @@ __device__ __constant__ uint8_t c_key_table[16] = {
 __device__ __constant__ uint8_t c_algo_of_key[16] = {NCB_ALGO_BALL_BALL,     NCB_ALGO_PLANE_BALL,  NCB_ALGO_PLANE_CONVEX,  NCB_ALGO_PLANE_CONVEX,
                                                      NCB_ALGO_BALL_CONVEX,   NCB_ALGO_BALL_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_CONVEX_CONVEX,
                                                      NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_NONE,        NCB_ALGO_PROXIMITY, NCB_ALGO_PROXIMITY,
-                                                     NCB_ALGO_PROXIMITY,     0,                    0, 0};
+                                                     NCB_ALGO_PROXIMITY,     NCB_ALGO_PROXIMITY,   0, 0};
 
 __device__ __forceinline__ bool groups_allow(const uint32_t* __restrict__ g, uint32_t a, uint32_t b) {
     if (!g) return true;

@@ -23,8 +23,9 @@ enum PairKey : uint32_t {
     // pairs with a GeometricQueryType::Proximity object (proximity.cu); adjacent, after every contact key
     K_PROX_BALL_BALL = 10,
     K_PROX_PLANE = 11,
-    K_PROX_SM = 12,
-    K_COUNT = 13
+    K_PROX_SM = 12,       // support map x support map without a hull operand (ball / cuboid): O(1) support functions
+    K_PROX_SM_HULL = 13,  // ... with at least one convex hull (vertex scans)
+    K_COUNT = 14
 };
 
 struct DevHulls {

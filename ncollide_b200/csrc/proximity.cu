@@ -15,9 +15,9 @@
 //                                                        normalises the direction; support_point_toward does not)
 //   query::proximity                                     query/proximity/proximity_shape_shape.rs:8-33
 //
-// World path: after the pair search a small pass re-keys the pairs that involve a sensor (three extra key segments: ball x
-// ball, plane x support map, support map x support map), the counting sort groups them, and ONE persistent kernel runs the
-// three segments (contiguous in the sorted pair array) one pair per thread; the contact kernels never see those pairs.
+// World path: after the pair search a small pass re-keys the pairs that involve a sensor (four extra key segments: ball x
+// ball, plane x support map, support map x support map without / with a hull operand), the counting sort groups them, and ONE persistent kernel runs the
+// four segments (contiguous in the sorted pair array) one pair per thread; the contact kernels never see those pairs.
 // The kernels run only when ncb_set_query_types marked at least one sensor: a world without sensors takes the old path.
 #include "gjk.cuh"
 #include "ncb_internal.h"
@@ -46,10 +46,21 @@ NCB_HD V3 prox_support_point_toward(const Support& g, const Iso& m, V3 unit_dir)
     if (g.kind == 3) return m.t + unit_dir * g.he.x;
     return support_point(g, m, unit_dir);
 }
-NCB_HD CSOPoint prox_cso(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, V3 dir) {  // cso_point.rs:70-85
+// CSOPoint::from_shapes (cso_point.rs:70-85).  As in gjk.cuh, the two independent support evaluations are issued in a canonical
+// order (the vertex-scanning hull operand second) so that lanes holding (x, hull) and (hull, x) pairs run the scan together;
+// each operand still sees its own isometry and direction, the values are unchanged.
+NCB_HD CSOPoint prox_cso(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, V3 dir) {
     CSOPoint c;
-    c.orig1 = prox_support_point(g1, m1, dir);
-    c.orig2 = prox_support_point(g2, m2, -dir);
+    bool swap = g1.kind == 1 && g2.kind != 1;
+    const Support& ga = swap ? g2 : g1;
+    const Support& gb = swap ? g1 : g2;
+    const Iso& ia = swap ? m2 : m1;
+    const Iso& ib = swap ? m1 : m2;
+    V3 da = swap ? -dir : dir;
+    V3 sa = prox_support_point(ga, ia, da);
+    V3 sb = prox_support_point(gb, ib, -da);
+    c.orig1 = swap ? sb : sa;
+    c.orig2 = swap ? sa : sb;
     c.point = c.orig1 - c.orig2;
     return c;
 }
@@ -177,12 +188,13 @@ __global__ void __launch_bounds__(256) k_prox_rekey(const uint2* __restrict__ pa
         uint32_t t1 = __ldg(&type[pr.x]) & 3u, t2 = __ldg(&type[pr.y]) & 3u;
         uint8_t k = (t1 == NCB_SHAPE_BALL && t2 == NCB_SHAPE_BALL) ? K_PROX_BALL_BALL
                     : (t1 == NCB_SHAPE_PLANE || t2 == NCB_SHAPE_PLANE) ? K_PROX_PLANE
-                                                                       : K_PROX_SM;
+                    : (t1 == NCB_SHAPE_CONVEX_HULL || t2 == NCB_SHAPE_CONVEX_HULL) ? K_PROX_SM_HULL
+                                                                                   : K_PROX_SM;
         keys[p] = k;
     }
 }
 
-// The three proximity key segments are adjacent: one persistent launch, warps mostly inside a single segment.
+// The four proximity key segments are adjacent: one persistent launch, warps mostly inside a single segment.
 __global__ void __launch_bounds__(128) k_proximity(DevObjects o, DevHulls H, const uint2* __restrict__ pairs, const uint32_t* __restrict__ pair_index,
                                                    DevCounters* cnt, uint32_t* __restrict__ manifold_start, uint8_t* __restrict__ manifold_count,
                                                    uint8_t* __restrict__ prox) {
@@ -190,7 +202,7 @@ __global__ void __launch_bounds__(128) k_proximity(DevObjects o, DevHulls H, con
     if (threadIdx.x < 4) hist[threadIdx.x] = 0;
     __syncthreads();
     uint32_t seg_begin = cnt->key_start[K_PROX_BALL_BALL];
-    uint32_t seg_end = cnt->key_start[K_PROX_SM] + cnt->key_hist[K_PROX_SM];
+    uint32_t seg_end = cnt->key_start[K_PROX_SM_HULL] + cnt->key_hist[K_PROX_SM_HULL];
     for (uint32_t p = seg_begin + blockIdx.x * blockDim.x + threadIdx.x; p < seg_end; p += gridDim.x * blockDim.x) {
         uint2 pr = __ldg(&pairs[p]);
         float margin = __ldg(&o.qlimit[pr.x]) + __ldg(&o.qlimit[pr.y]);  // narrow_phase.rs:138
@@ -214,7 +226,7 @@ __global__ void __launch_bounds__(128) k_proximity_persist(DevObjects o, DevHull
                                                            const DevCounters* __restrict__ cnt, float4* __restrict__ slot_dir, uint8_t* __restrict__ slot_prox,
                                                            uint4* __restrict__ events, uint32_t* n_events, uint32_t cap_events) {
     uint32_t seg_begin = cnt->key_start[K_PROX_BALL_BALL];
-    uint32_t seg_end = cnt->key_start[K_PROX_SM] + cnt->key_hist[K_PROX_SM];
+    uint32_t seg_end = cnt->key_start[K_PROX_SM_HULL] + cnt->key_hist[K_PROX_SM_HULL];
     for (uint32_t p = seg_begin + blockIdx.x * blockDim.x + threadIdx.x; p < seg_end; p += gridDim.x * blockDim.x) {
         uint2 pr = __ldg(&pairs[p]);
         uint32_t slot = __ldg(&slot_of[p]);
@@ -254,12 +266,12 @@ cudaError_t launch_prox_rekey(ncb_ctx* c, uint32_t cap_pairs) {
     return cudaGetLastError();
 }
 cudaError_t launch_proximity_segments(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, cudaStream_t s) {
-    k_proximity<<<c->sm_count * 4, 128, 0, s>>>(o, c->hulls, pairs, pair_index, c->counters.p, c->manifold_start.p, c->manifold_count.p, c->prox.p);
+    k_proximity<<<c->sm_count * 8, 128, 0, s>>>(o, c->hulls, pairs, pair_index, c->counters.p, c->manifold_start.p, c->manifold_count.p, c->prox.p);
     return cudaGetLastError();
 }
 cudaError_t launch_proximity_persistent(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* slot_of, float4* slot_dir,
                                         uint8_t* slot_prox, uint4* events, uint32_t* n_events, uint32_t cap_events) {
-    k_proximity_persist<<<c->sm_count * 4, 128, 0, c->stream>>>(o, c->hulls, pairs, slot_of, c->counters.p, slot_dir, slot_prox, events, n_events,
+    k_proximity_persist<<<c->sm_count * 8, 128, 0, c->stream>>>(o, c->hulls, pairs, slot_of, c->counters.p, slot_dir, slot_prox, events, n_events,
                                                                  cap_events);
     return cudaGetLastError();
 }

@@ -83,8 +83,8 @@ __device__ __constant__ uint8_t c_sim_key[16] = {K_BALL_BALL,   K_BALL_CUBOID,  
 __device__ __constant__ uint8_t c_sim_algo[16] = {NCB_ALGO_BALL_BALL,     NCB_ALGO_PLANE_BALL,  NCB_ALGO_PLANE_CONVEX,  NCB_ALGO_PLANE_CONVEX,
                                                   NCB_ALGO_BALL_CONVEX,   NCB_ALGO_BALL_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_CONVEX_CONVEX,
                                                   NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_NONE,        NCB_ALGO_PROXIMITY, NCB_ALGO_PROXIMITY,
-                                                  NCB_ALGO_PROXIMITY,     0,                    0, 0};
-__device__ __forceinline__ bool is_prox_key(uint8_t k) { return k >= K_PROX_BALL_BALL && k <= K_PROX_SM; }
+                                                  NCB_ALGO_PROXIMITY,     NCB_ALGO_PROXIMITY,   0, 0};
+__device__ __forceinline__ bool is_prox_key(uint8_t k) { return k >= K_PROX_BALL_BALL && k <= K_PROX_SM_HULL; }
 
 __device__ int sim_find(const unsigned long long* __restrict__ keys, uint32_t n, unsigned long long k) {
     uint32_t lo = 0, hi = n;
@@ -162,7 +162,10 @@ __global__ void k_sim_assign(const unsigned long long* __restrict__ cur, uint32_
     uint32_t t1 = type[h1] & 3, t2 = type[h2] & 3;
     uint8_t key = c_sim_key[t1 * 4 + t2];
     if (qkind && key != K_NONE && (qkind[h1] | qkind[h2])) {  // (_, Proximity) | (Proximity, _): a proximity detector (narrow_phase.rs:240-246)
-        key = (t1 == NCB_SHAPE_BALL && t2 == NCB_SHAPE_BALL) ? K_PROX_BALL_BALL : ((t1 == NCB_SHAPE_PLANE || t2 == NCB_SHAPE_PLANE) ? K_PROX_PLANE : K_PROX_SM);
+        key = (t1 == NCB_SHAPE_BALL && t2 == NCB_SHAPE_BALL) ? K_PROX_BALL_BALL
+              : (t1 == NCB_SHAPE_PLANE || t2 == NCB_SHAPE_PLANE) ? K_PROX_PLANE
+              : (t1 == NCB_SHAPE_CONVEX_HULL || t2 == NCB_SHAPE_CONVEX_HULL) ? K_PROX_SM_HULL
+                                                                             : K_PROX_SM;
         slot_prox[slot] = NCB_PROXIMITY_DISJOINT;
     }
     slot_key[slot] = key;
@@ -496,7 +499,7 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
         ps.cap_events = cap_events;
         ps.pm_overflow = sim->cnt.p + 3;
         CKS(launch_narrow_phase_persistent(ctx, objs, ctx->pairs.p, ctx->pair_index.p, (uint32_t)cap_pairs, ps));
-        if (ctx->has_prox)  // update_proximity for the sensor pairs with a changed endpoint (their three key segments)
+        if (ctx->has_prox)  // update_proximity for the sensor pairs with a changed endpoint (their four key segments)
             CKS(launch_proximity_persistent(ctx, objs, ctx->pairs.p, ctx->pair_index.p, sim->slot_dir.p, sim->slot_prox.p, sim->prox_events.p, sim->cnt.p + 4,
                                             cap_events));
     }
@@ -565,7 +568,7 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
         counts->n_epa_pairs = ctx->last_counters.epa_cursor[K_CUBOID_CUBOID] - ctx->last_counters.key_start[K_CUBOID_CUBOID];
         counts->n_manifold_jobs = sim->n_active;  // pairs regenerated in this step
         const DevCounters& lc = ctx->last_counters;
-        counts->n_proximity_pairs = lc.key_hist[K_PROX_BALL_BALL] + lc.key_hist[K_PROX_PLANE] + lc.key_hist[K_PROX_SM];  // proximity pairs updated
+        counts->n_proximity_pairs = lc.key_hist[K_PROX_BALL_BALL] + lc.key_hist[K_PROX_PLANE] + lc.key_hist[K_PROX_SM] + lc.key_hist[K_PROX_SM_HULL];  // updated
     }
     return NCB_OK;
 }
