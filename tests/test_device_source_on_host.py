@@ -79,3 +79,17 @@ def test_device_proximity_source_warm_start_matches_oracle(shim, oracle):
         s.pos = np.ascontiguousarray((s.pos + rng.normal(0, 0.08, size=s.pos.shape)).astype(F))
         s.rot = random_unit_quaternions(rng, s.n) if step == 2 else s.rot
     assert seen >= {0, 1, 2} and ax_o[:, 3].any()
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_device_proximity_source_on_adversarial_scenes(shim, oracle, k):
+    """Degenerate placements (everything coincident, exactly touching lattices, far from the origin, a dense clump, mixed scales):
+    zero start directions, origin-on-simplex exits, ties.  All pairs of the broad phase, margins 0 / pair margins / large."""
+    from test_gpu_parity import _adversarial_scenes
+
+    s = _adversarial_scenes()[k]
+    pairs = oracle.broad_phase(oracle.compute_aabbs(s), s.groups)
+    pairs = np.concatenate([pairs, pairs[:, ::-1]])
+    for margins in (None, np.zeros(len(pairs), dtype=F), np.full(len(pairs), 0.5, dtype=F)):
+        got, want = shim_proximity(shim, s, pairs, margins), oracle.proximity(s, pairs, margins)
+        assert np.array_equal(got, want), (s.name, int((got != want).sum()))

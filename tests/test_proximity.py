@@ -187,6 +187,27 @@ def test_device_proximity_batch_matches_oracle(ctx, oracle, mk):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("k", range(6))
+def test_device_proximity_on_adversarial_scenes(ctx, oracle, k):
+    """Coincident objects, exactly touching lattices, far-away coordinates, a dense clump, mixed scales: every broad-phase pair in
+    both orders as a batch, and the world update with every second object a sensor."""
+    from test_gpu_parity import _adversarial_scenes, canon, compare_manifolds
+
+    s = _adversarial_scenes()[k]
+    ctx.set_scene(s)
+    pairs = oracle.broad_phase(oracle.compute_aabbs(s), s.groups)
+    pairs = np.concatenate([pairs, pairs[:, ::-1]])
+    for margins in (None, np.zeros(len(pairs), dtype=F), np.full(len(pairs), 0.5, dtype=F)):
+        got, want = ctx.proximity(pairs, margins), oracle.proximity(s, pairs, margins)
+        assert np.array_equal(got, want), (s.name, int((got != want).sum()))
+    s.query_kind = (np.arange(s.n) % 2).astype(np.uint8)
+    res = ctx.world_update(s)
+    assert res.counts["epa_overflow"] == 0
+    assert np.array_equal(canon(res.pairs), canon(oracle.broad_phase(oracle.compute_aabbs(s), s.groups, mode=1)))
+    compare_manifolds(res, s, oracle, s.name + "/sensors")
+
+
+@pytest.mark.gpu
 def test_device_proximity_reference_example(ctx):
     for pos, st in {(1, 1, 1): INTERSECTING, (2, 2, 2): WITHIN_MARGIN, (3, 3, 3): DISJOINT}.items():
         s = two_shapes(BALL, [1, 0, 0, 0], pos, CUBOID, [1, 1, 1, 0], (0, 0, 0))
