@@ -24,6 +24,8 @@ HULL_FIELDS = HullLibrary.FIELDS
 
 def scene_to_dict(s):
     d = {k: getattr(s, k) for k in ("pos", "rot", "shape_type", "shape_param", "groups", "query_limit", "ang_pred")}
+    if getattr(s, "query_kind", None) is not None:
+        d["query_kind"] = s.query_kind
     d["margin"] = np.float32(s.margin)
     d["hull_n"] = np.uint32(s.hulls.n_hulls)
     for f in HULL_FIELDS:
@@ -44,7 +46,38 @@ def scene_from_npz(z):
     return WorldScene(
         pos=z["pos"], rot=z["rot"], shape_type=z["shape_type"], shape_param=z["shape_param"], groups=z["groups"],
         query_limit=z["query_limit"], ang_pred=z["ang_pred"], hulls=lib, margin=float(z["margin"]),
+        query_kind=z["query_kind"] if "query_kind" in z else None,
     )
+
+
+def make_proximity(o):
+    """prox_mixed_plane_400.npz: a 400-object world with a plane and 35 % Proximity sensors — the fresh-world
+    narrow phase (algorithm, manifold sizes, contacts, proximity status per pair), the batched detectors with random explicit
+    margins, and 5 stepping-world updates (statuses + ProximityEvents per step)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from ncollide_b200.scenes import with_sensors
+    from sim_scenario import drive
+
+    s = with_sensors(make_world_scene(400, 1020, (1, 1, 1), side=4.4, n_hulls=10, plane=True), 0.35, 1021, margin=0.1)
+    d = scene_to_dict(s)
+    fat = o.compute_aabbs(s)
+    pairs = o.broad_phase(fat, s.groups, 0)
+    c, off, algo, prox = o.narrow_phase_kinds(s, pairs)
+    d.update(fat_aabbs=fat, pairs=pairs, manifold_off=off, algo=algo, prox=prox)
+    for n in ("world1", "world2", "normal", "depth", "f1", "f2"):
+        d["c_" + n] = c[n]
+    rng = np.random.default_rng(1022)
+    bp = rng.integers(0, s.n, size=(3000, 2)).astype(np.uint32)
+    bp = bp[bp[:, 0] != bp[:, 1]]
+    bm = rng.uniform(0, 1.5, size=len(bp)).astype(np.float32)
+    d.update(batch_pairs=bp, batch_margins=bm, batch_prox=o.proximity(s, bp, bm))
+    log = drive(o.sim(s), s, steps=5, seed=1020)
+    for t, r in enumerate(log):
+        for k in ("pairs", "algo", "off", "prox", "prox_events", "events"):
+            d[f"s{t}_{k}"] = r[k]
+    np.savez_compressed(os.path.join(HERE, "prox_mixed_plane_400.npz"), **d)
+    print("prox", s.n, "objects", len(pairs), "pairs", int((algo == 6).sum()), "proximity pairs", np.bincount(prox[algo == 6], minlength=3).tolist(),
+          "statuses;", [len(r["prox_events"]) for r in log], "proximity events per step")
 
 
 def main():
@@ -89,6 +122,7 @@ def main():
              q_point_rows=sim.query(2, pts))
     np.savez_compressed(os.path.join(HERE, "sim_mixed_plane_400.npz"), **d)
     print("sim", [len(r["pairs"]) for r in log], "pairs per step,", len(idx), "ray hits")
+    make_proximity(o)
     for kind in ("terrain", "soup"):
         rs = make_ray_scene(kind, 2000, 600, seed=1004)
         om = o.trimesh(rs.verts, rs.tris)

@@ -93,3 +93,13 @@ def test_device_proximity_source_on_adversarial_scenes(shim, oracle, k):
     for margins in (None, np.zeros(len(pairs), dtype=F), np.full(len(pairs), 0.5, dtype=F)):
         got, want = shim_proximity(shim, s, pairs, margins), oracle.proximity(s, pairs, margins)
         assert np.array_equal(got, want), (s.name, int((got != want).sum()))
+
+
+def test_device_proximity_source_reproduces_the_golden_fixture(shim):
+    """tests/golden/prox_mixed_plane_400.npz (oracle-made, committed): the device source must give the same statuses."""
+    from test_proximity import _load_prox_golden
+
+    z, s = _load_prox_golden()
+    sel = z["algo"] == 6
+    assert np.array_equal(shim_proximity(shim, s, z["pairs"][sel]), z["prox"][sel])
+    assert np.array_equal(shim_proximity(shim, s, z["batch_pairs"], z["batch_margins"]), z["batch_prox"])

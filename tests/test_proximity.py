@@ -151,6 +151,71 @@ def test_stepping_world_first_step_equals_fresh_world_with_sensors(oracle):
     assert np.all(r["prox_events"][:, 2] == DISJOINT)
 
 
+# ---- golden fixture (tests/golden/prox_mixed_plane_400.npz, made by tests/golden/make_golden.py from the oracle) --------------
+def _load_prox_golden():
+    import os
+
+    from golden.make_golden import scene_from_npz
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "prox_mixed_plane_400.npz"))
+    return z, scene_from_npz(z)
+
+
+def check_sim_against_prox_golden(sim, z, s):
+    from sim_scenario import drive
+
+    log = drive(sim, s, steps=5, seed=1020)
+    for t, r in enumerate(log):
+        assert np.array_equal(r["pairs"], z[f"s{t}_pairs"]) and np.array_equal(r["algo"], z[f"s{t}_algo"]), t
+        assert np.array_equal(r["off"], z[f"s{t}_off"]) and np.array_equal(r["prox"], z[f"s{t}_prox"]), t
+        for k in ("prox_events", "events"):
+            a, b = np.asarray(r[k]), z[f"s{t}_{k}"]
+            a = a[np.lexsort(a.T[::-1])] if len(a) else a
+            b = b[np.lexsort(b.T[::-1])] if len(b) else b
+            assert np.array_equal(a, b), (t, k)
+
+
+def test_prox_golden_fixture_oracle(oracle):
+    z, s = _load_prox_golden()
+    assert s.query_kind is not None and s.query_kind.any()
+    fat = oracle.compute_aabbs(s)
+    assert np.array_equal(fat, z["fat_aabbs"])
+    pairs = oracle.broad_phase(fat, s.groups, 0)
+    assert np.array_equal(pairs, z["pairs"])
+    c, off, algo, prox = oracle.narrow_phase_kinds(s, pairs)
+    assert np.array_equal(off, z["manifold_off"]) and np.array_equal(algo, z["algo"]) and np.array_equal(prox, z["prox"])
+    for name in ("world1", "world2", "normal", "depth", "f1", "f2"):
+        assert np.array_equal(c[name], z["c_" + name]), name
+    assert np.array_equal(oracle.proximity(s, z["batch_pairs"], z["batch_margins"]), z["batch_prox"])
+    check_sim_against_prox_golden(oracle.sim(s), z, s)
+
+
+@pytest.mark.gpu
+def test_prox_golden_fixture_device():
+    from ncollide_b200.world import Context
+    from test_bp_persistent import DeviceSimAdapter
+    from test_gpu_parity import canon
+
+    z, s = _load_prox_golden()
+    c = Context(0)
+    c.set_hulls(s.hulls)
+    r = c.world_update(s)
+    assert np.array_equal(canon(r.pairs), canon(z["pairs"]))
+    order = {tuple(p): i for i, p in enumerate(map(tuple, z["pairs"].tolist()))}
+    j = np.array([order[tuple(p)] for p in r.pairs.tolist()])
+    assert np.array_equal(r.pair_algo, z["algo"][j]) and np.array_equal(r.proximity, z["prox"][j])
+    assert np.array_equal(r.manifold_count, np.diff(z["manifold_off"])[j])
+    for i in np.nonzero(r.manifold_count)[0]:
+        sl = slice(z["manifold_off"][j[i]], z["manifold_off"][j[i] + 1])
+        got = r.contacts_of(i)
+        assert np.array_equal(got["f1"], z["c_f1"][sl]) and np.array_equal(got["f2"], z["c_f2"][sl])
+        for name in ("world1", "world2", "normal", "depth"):
+            assert np.allclose(got[name], z["c_" + name][sl], rtol=1e-4, atol=1e-5), (i, name)
+    c.set_scene(s)
+    assert np.array_equal(c.proximity(z["batch_pairs"], z["batch_margins"]), z["batch_prox"])
+    check_sim_against_prox_golden(DeviceSimAdapter(Context(0), s), z, s)
+
+
 # ---- GPU ---------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def ctx():
