@@ -1098,6 +1098,27 @@ int orc_query_contact(const orc_objects* objs, real prediction, orc_contact* out
     return have ? 1 : 0;
 }
 
+// contact_support_map_support_map (contact_support_map_support_map.rs:12-79) with a fresh simplex for a batch of cuboid / hull
+// pairs: out[10 p] = p1, p2, normal, kind (0 = no contact within the prediction, 1 = closest points / penetration).
+void orc_contact_sm_sm(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, const real* predictions, real* out, uint32_t* stats) {
+    Objects o = make_objects(objs);
+    GJKStats st;
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
+        Shape a = get_shape(o, i1), b = get_shape(o, i2);
+        real prediction = predictions ? predictions[p] : o.query_limit[i1] + o.query_limit[i2];
+        VoronoiSimplex simplex;
+        GJKResult r = contact_support_map_support_map_with_params(o.iso(i1), as_support(a), o.iso(i2), as_support(b), prediction, simplex, nullptr, &st);
+        real* d = out + 10 * p;
+        for (int k = 0; k < 10; ++k) d[k] = 0;
+        if (r.kind == GJK_CLOSEST_POINTS) {
+            for (int k = 0; k < 3; ++k) d[k] = r.p1[k], d[3 + k] = r.p2[k], d[6 + k] = r.dir[k];
+            d[9] = 1;
+        }
+    }
+    if (stats) stats[0] = st.gjk_iters, stats[1] = st.epa_iters, stats[2] = st.epa_calls, stats[3] = st.epa_fail;
+}
+
 void orc_proximity(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, const real* margins, uint8_t* out) {
     Objects o = make_objects(objs);
     for (uint64_t p = 0; p < n_pairs; ++p) {

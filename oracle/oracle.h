@@ -56,6 +56,11 @@ uint64_t orc_broad_phase(uint32_t n, const real* aabb_minmax, const uint32_t* gr
 uint64_t orc_narrow_phase(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, orc_contact* out, uint64_t cap,
                           uint32_t* manifold_off, uint8_t* algo_out, uint32_t* stats);
 
+/* contact_support_map_support_map (query/contact/contact_support_map_support_map.rs:12-79: GJK, then EPA when penetrating) with a
+ * fresh simplex for a batch of cuboid / hull pairs; predictions == NULL: query_limit sums.  out[10 p] = p1, p2, normal, found flag;
+ * stats[4] = GJK iterations, EPA iterations, EPA calls, EPA failures. */
+void orc_contact_sm_sm(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, const real* predictions, real* out, uint32_t* stats);
+
 /* Proximity (query/proximity/proximity.rs:4-12) as a byte; ORC_PROX_NONE = the dispatcher has no detector (plane x plane). */
 #define ORC_PROX_INTERSECTING 0
 #define ORC_PROX_WITHIN_MARGIN 1

@@ -144,6 +144,17 @@ class Oracle:
                 return out[:nc].copy(), off, algo, stats
             cap = int(nc)
 
+    def contact_sm_sm(self, scene, pairs, predictions=None):
+        """contact_support_map_support_map for cuboid / hull pairs -> (out[P,10] = p1, p2, normal, found; stats[4])."""
+        o, keep = self._objects(scene)
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        out = np.zeros((len(pairs), 10), dtype=self.dtype)
+        stats = np.zeros(4, dtype=np.uint32)
+        m = None if predictions is None else np.ascontiguousarray(predictions, dtype=self.dtype)
+        self.lib.orc_contact_sm_sm(C.byref(o), C.c_uint64(len(pairs)), C.c_void_p(pairs.ctypes.data), C.c_void_p(m.ctypes.data) if m is not None else None,
+                                   C.c_void_p(out.ctypes.data), C.c_void_p(stats.ctypes.data))
+        return out, stats
+
     def proximity(self, scene, pairs, margins=None):
         """ProximityDetector::update with fresh detectors per (object1, object2) pair -> u8 status (0 Intersecting, 1 WithinMargin,
         2 Disjoint, 255 no detector).  margins None: query_limit[o1] + query_limit[o2]."""

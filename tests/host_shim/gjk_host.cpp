@@ -1,0 +1,58 @@
+// TEST INFRASTRUCTURE ONLY — compiles the device GJK / EPA of ncollide_b200/csrc/gjk.cuh (the functions k_cc_gjk / k_cc_epa /
+// k_bh_epa run per pair: gjk_closest_points, epa_init, epa_step, the Voronoi simplex) for the host through
+// tests/host_shim/cuda_runtime.h, so that their logic and f32 operation order can be checked against the oracle without a GPU.
+#include "shapes.cuh"
+
+using namespace ncb;
+
+static DevHulls hulls_from(const ncb_hull_library* L) {
+    DevHulls H;
+    std::memset(&H, 0, sizeof H);
+    if (!L) return H;
+    H.n_hulls = L->n_hulls;
+    H.vert_off = L->vert_off, H.face_off = L->face_off, H.edge_off = L->edge_off, H.fadj_off = L->fadj_off, H.vadj_off = L->vadj_off;
+    H.points = L->points;
+    H.vert_first_adj = L->vert_first_adj, H.vert_num_adj = L->vert_num_adj;
+    H.face_first = L->face_first, H.face_num = L->face_num;
+    H.face_normal = L->face_normal;
+    H.vaf = L->vertices_adj_to_face, H.eaf = L->edges_adj_to_face;
+    H.edge_vertices = L->edge_vertices, H.edge_faces = L->edge_faces;
+    H.edge_dir = L->edge_dir;
+    H.fav = L->faces_adj_to_vertex, H.eav = L->edges_adj_to_vertex;
+    return H;
+}
+
+extern "C" {
+// contact_sm_sm (GJK, then EPA when the origin is inside the CSO) for cuboid / hull pairs.
+// out[10 p] = p1, p2, normal, found flag; flags[0] += EPA capacity overflows, flags[1] += reference panics, flags[2] = EPA calls.
+void shim_contact_sm_sm(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_pairs, const uint32_t* pairs, const float* predictions,
+                        float* out, uint32_t* flags) {
+    DevObjects o;
+    std::memset(&o, 0, sizeof o);
+    o.n = objs->n;
+    o.pos = objs->pos;
+    o.rot = reinterpret_cast<const float4*>(objs->rot);
+    o.type = objs->shape_type;
+    o.param = reinterpret_cast<const float4*>(objs->shape_param);
+    o.qlimit = objs->query_limit;
+    DevHulls H = hulls_from(lib);
+    EpaState* e = new EpaState;
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
+        Shape a = load_shape(o, H, i1, o.type[i1]), b = load_shape(o, H, i2, o.type[i2]);
+        Iso ma = load_iso(o, i1), mb = load_iso(o, i2);
+        float prediction = predictions ? predictions[p] : o.qlimit[i1] + o.qlimit[i2];
+        V3 p1 = v3(0.f, 0.f, 0.f), p2 = p1, n = p1;
+        uint32_t before = flags[0] + flags[1];
+        (void)before;
+        int r = contact_sm_sm(*e, ma, as_support(a), mb, as_support(b), prediction, p1, p2, n, &flags[0], &flags[1]);
+        float* d = out + 10 * p;
+        for (int k = 0; k < 10; ++k) d[k] = 0.f;
+        if (r == GJK_CLOSEST_POINTS) {
+            d[0] = p1.x, d[1] = p1.y, d[2] = p1.z, d[3] = p2.x, d[4] = p2.y, d[5] = p2.z, d[6] = n.x, d[7] = n.y, d[8] = n.z;
+            d[9] = 1.f;
+        }
+    }
+    delete e;
+}
+}

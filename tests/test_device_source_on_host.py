@@ -17,16 +17,25 @@ ROOT = os.path.dirname(HERE)
 F = np.float32
 
 
-@pytest.fixture(scope="module")
-def shim():
-    out = os.path.join(HERE, "host_shim", "_build", "libprox_host.so")
+def _build_shim(name, src):
+    out = os.path.join(HERE, "host_shim", "_build", name)
     os.makedirs(os.path.dirname(out), exist_ok=True)
     subprocess.check_call([
         "g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-DNCB_HOST_SHIM",
         "-I", os.path.join(HERE, "host_shim"), "-I", os.path.join(ROOT, "ncollide_b200", "csrc"),
-        "-shared", "-o", out, os.path.join(HERE, "host_shim", "proximity_host.cpp"),
+        "-shared", "-o", out, os.path.join(HERE, "host_shim", src),
     ])
     return C.CDLL(out)
+
+
+@pytest.fixture(scope="module")
+def shim():
+    return _build_shim("libprox_host.so", "proximity_host.cpp")
+
+
+@pytest.fixture(scope="module")
+def gjk_shim():
+    return _build_shim("libgjk_host.so", "gjk_host.cpp")
 
 
 def shim_proximity(lib, scene, pairs, margins=None, axis_io=None):
@@ -103,3 +112,61 @@ def test_device_proximity_source_reproduces_the_golden_fixture(shim):
     sel = z["algo"] == 6
     assert np.array_equal(shim_proximity(shim, s, z["pairs"][sel]), z["prox"][sel])
     assert np.array_equal(shim_proximity(shim, s, z["batch_pairs"], z["batch_margins"]), z["batch_prox"])
+
+
+# ---- the device GJK / EPA of gjk.cuh (what k_cc_gjk / k_cc_epa run per pair) -----------------------------------------------------
+def shim_contact_sm_sm(lib, scene, pairs, predictions=None):
+    oc, keep = _ffi.pack_objects(scene)
+    hc, keep2 = _ffi.pack_hull_library(scene.hulls)
+    pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+    out = np.zeros((len(pairs), 10), dtype=F)
+    flags = np.zeros(4, dtype=np.uint32)
+    m = None if predictions is None else np.ascontiguousarray(predictions, dtype=F)
+    lib.shim_contact_sm_sm(C.byref(oc), C.byref(hc), C.c_uint64(len(pairs)), _ffi.ptr(pairs), _ffi.ptr(m), _ffi.ptr(out), _ffi.ptr(flags))
+    return out, flags
+
+
+def _convex_pairs(oracle, s):
+    pairs = oracle.broad_phase(oracle.compute_aabbs(s), s.groups)
+    t = s.shape_type
+    keep = (t[pairs[:, 0]] != 0) & (t[pairs[:, 1]] != 0) & (t[pairs[:, 0]] != 3) & (t[pairs[:, 1]] != 3)  # cuboid / hull operands
+    return pairs[keep]
+
+
+GJK_SCENES = [
+    lambda: make_world_scene(3000, 71, (0, 1, 1), side=7.0, n_hulls=48, linear=0.02),
+    lambda: make_world_scene(1500, 72, (0, 1, 1), side=3.0, n_hulls=24, linear=0.05),   # dense: deep penetrations, long EPA runs
+    lambda: make_world_scene(2000, 73, (0, 1, 0), side=5.0, linear=0.02),               # cuboids only: parallel faces, degenerate simplices
+]
+
+
+@pytest.mark.parametrize("mk", GJK_SCENES)
+def test_device_gjk_epa_source_matches_oracle(gjk_shim, oracle, mk):
+    """contact_support_map_support_map through the device's gjk_closest_points + epa_init / epa_step (fixed-capacity polytope,
+    packed topology, deferred heap pushes) against the oracle's std-container restatement: same found / not found, same points and
+    normals BIT FOR BIT — the device follows the reference's iteration path, not just its maths."""
+    s = mk()
+    pairs = _convex_pairs(oracle, s)
+    pairs = np.concatenate([pairs, pairs[:, ::-1]])
+    assert len(pairs) > 2000
+    got, flags = shim_contact_sm_sm(gjk_shim, s, pairs)
+    want, stats = oracle.contact_sm_sm(s, pairs)
+    assert flags[0] == 0 and flags[1] == 0, "EPA capacity overflow / reference panic"
+    assert np.array_equal(got[:, 9], want[:, 9]), int((got[:, 9] != want[:, 9]).sum())
+    assert stats[2] > 100 and stats[3] == 0  # EPA ran and never failed
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), int((got.view(np.uint32) != want.view(np.uint32)).any(axis=1).sum())
+
+
+@pytest.mark.parametrize("k", [0, 2, 3, 4])
+def test_device_gjk_epa_source_on_adversarial_scenes(gjk_shim, oracle, k):
+    from test_gpu_parity import _adversarial_scenes
+
+    s = _adversarial_scenes()[k]
+    pairs = _convex_pairs(oracle, s)
+    if len(pairs) == 0:
+        pytest.skip("no convex pairs")
+    got, flags = shim_contact_sm_sm(gjk_shim, s, pairs)
+    want, stats = oracle.contact_sm_sm(s, pairs)
+    assert flags[0] == 0
+    assert np.array_equal(got[:, 9], want[:, 9])
+    assert np.allclose(got, want, rtol=1e-4, atol=1e-5)
