@@ -13,7 +13,9 @@
 //   Cuboid / ConvexHull features              shape/cuboid.rs:185-405,502-563, shape/convex.rs:388-540
 //   ConvexPolygonalFeature::clip / add_contact_to_manifold   shape/convex_polygonal_feature3.rs:217-401
 //   ContactManifold::push (DistanceBased 0.02) query/contact/contact_manifold.rs:165-236
+#ifndef NCB_HOST_SHIM  // tests/host_shim compiles the per-pair functions of this file for the host (test infrastructure)
 #include <cooperative_groups.h>
+#endif
 #include <cmath>
 #include <cstdlib>
 #include "gjk.cuh"
@@ -728,6 +730,7 @@ __device__ __noinline__ void convex_convex_manifold(const Iso& ma, const Shape& 
     }
 }
 
+#ifndef NCB_HOST_SHIM  // everything below is warp-level / kernel code: CUDA only
 // ---- result write-out: warp-aggregated allocation of contact slots --------------------------------------------
 NCB_HD void write_manifold(const Manifold& mf, bool valid, uint32_t pair_slot, uint32_t out_index, ncb_contact* __restrict__ contacts,
                            uint32_t cap_contacts, uint32_t* __restrict__ manifold_start, uint8_t* __restrict__ manifold_count,
@@ -1421,5 +1424,7 @@ cudaError_t launch_classify_pairs(ncb_ctx* c, const uint2* pairs, uint32_t n) {
     k_classify_pairs<<<(n + 255) / 256, 256, 0, c->stream>>>(pairs, n, c->type.p, c->keys_raw.p, c->counters.p);
     return cudaGetLastError();
 }
+
+#endif  // NCB_HOST_SHIM
 
 }  // namespace ncb

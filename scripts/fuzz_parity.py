@@ -48,6 +48,12 @@ def random_scene(rng, seed):
         s.groups[:, 0] = (1 << rng.integers(0, 4, size=m)).astype(np.uint32)
         s.groups[:, 1] = rng.integers(1, 16, size=m).astype(np.uint32)
         s.groups[:, 2] = np.where(rng.random(m) < 0.2, 1 << rng.integers(0, 4, size=m), 0).astype(np.uint32)
+    if os.environ.get("FUZZ_SENSORS", "1") != "0" and rng.random() < 0.4:  # some objects are Proximity sensors
+        s.query_kind = (rng.random(s.n) < rng.choice([0.1, 0.5, 1.0])).astype(np.uint8)
+        if not s.query_kind.any():
+            s.query_kind = None
+        else:
+            s.query_limit = np.where(s.query_kind != 0, F(rng.choice([0.0, 0.05, 0.3])), s.query_limit).astype(F)
     return s
 
 
@@ -55,7 +61,12 @@ def compare(res, s, orc):
     want = orc.broad_phase(orc.compute_aabbs(s), s.groups, mode=1)
     if not np.array_equal(canon(res.pairs), canon(want)):
         return "pair set"
-    oc, ooff, oalgo, _ = orc.narrow_phase(s, res.pairs)
+    if getattr(s, "query_kind", None) is not None:
+        oc, ooff, oalgo, oprox = orc.narrow_phase_kinds(s, res.pairs)
+        if res.proximity is None or not np.array_equal(res.proximity, oprox):
+            return "proximity statuses"
+    else:
+        oc, ooff, oalgo, _ = orc.narrow_phase(s, res.pairs)
     if not np.array_equal(res.pair_algo, oalgo):
         return "algo"
     if not np.array_equal(res.manifold_count, np.diff(ooff)):
@@ -93,7 +104,8 @@ def main():
             bad.append((seed, why))
             os.makedirs("gpurun_out", exist_ok=True)
             np.savez_compressed(f"gpurun_out/fuzz_bad_{seed}.npz", pos=s.pos, rot=s.rot, shape_type=s.shape_type, shape_param=s.shape_param,
-                                groups=s.groups, query_limit=s.query_limit, ang_pred=s.ang_pred, margin=s.margin)
+                                groups=s.groups, query_limit=s.query_limit, ang_pred=s.ang_pred, margin=s.margin,
+                                query_kind=s.query_kind if s.query_kind is not None else np.zeros(0, np.uint8))
             if len(bad) >= 10:
                 break
         seed += 1

@@ -34,6 +34,11 @@ def shim():
 
 
 @pytest.fixture(scope="module")
+def narrow_shim():
+    return _build_shim("libnarrow_host.so", "narrow_host.cpp")
+
+
+@pytest.fixture(scope="module")
 def gjk_shim():
     return _build_shim("libgjk_host.so", "gjk_host.cpp")
 
@@ -170,3 +175,82 @@ def test_device_gjk_epa_source_on_adversarial_scenes(gjk_shim, oracle, k):
     assert flags[0] == 0
     assert np.array_equal(got[:, 9], want[:, 9])
     assert np.allclose(got, want, rtol=1e-4, atol=1e-5)
+
+
+# ---- the whole fresh-world narrow phase of narrow.cu, one pair after the other --------------------------------------------------
+def shim_narrow_phase(lib, scene, pairs):
+    oc, keep = _ffi.pack_objects(scene)
+    hc, keep2 = _ffi.pack_hull_library(scene.hulls)
+    pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+    P = len(pairs)
+    off = np.zeros(P + 1, dtype=np.uint32)
+    algo = np.zeros(P, dtype=np.uint8)
+    flags = np.zeros(4, dtype=np.uint32)
+    lib.shim_narrow_phase.restype = C.c_uint64
+    cap = max(4 * P, 64)
+    while True:
+        out = np.zeros(cap, dtype=_ffi.CONTACT_DTYPE)
+        flags[:] = 0
+        nc = lib.shim_narrow_phase(C.byref(oc), C.byref(hc), C.c_uint64(P), _ffi.ptr(pairs), _ffi.ptr(out), C.c_uint64(cap), _ffi.ptr(off), _ffi.ptr(algo),
+                                   _ffi.ptr(flags))
+        if nc <= cap:
+            return out[:nc], off, algo, flags
+        cap = int(nc)
+
+
+def compare_narrow(got, want, label):
+    (dc, doff, dalgo, flags), (oc, ooff, oalgo, _) = got, want
+    assert flags[0] == 0 and flags[1] == 0, f"{label}: capacity overflow / reference panic"
+    assert np.array_equal(dalgo, oalgo), f"{label}: dispatched algorithm"
+    assert np.array_equal(doff, ooff), f"{label}: manifold sizes differ on {int((np.diff(doff) != np.diff(ooff)).sum())} pairs"
+    assert np.array_equal(dc["f1"], oc["f1"]) and np.array_equal(dc["f2"], oc["f2"]), f"{label}: feature ids"
+    inexact = 0
+    for name in ("world1", "world2", "normal", "depth"):
+        assert np.allclose(dc[name], oc[name], rtol=1e-4, atol=1e-5), f"{label}: {name}"
+        inexact += int((dc[name].view(np.uint32) != oc[name].view(np.uint32)).sum())
+    return inexact
+
+
+NARROW_SCENES = [
+    lambda: make_world_scene(4000, 81, (1, 1, 1), side=9.5, plane=True, n_hulls=48),
+    lambda: make_world_scene(2500, 82, (1, 1, 1), side=6.0, n_hulls=32, angular=0.05, linear=0.05),
+    lambda: make_world_scene(2000, 83, (0, 1, 1), side=4.5, n_hulls=24, angular=0.02),
+    lambda: make_world_scene(2000, 84, (1, 1, 0), side=5.0, plane=True),
+]
+
+
+@pytest.mark.parametrize("mk", NARROW_SCENES)
+def test_device_narrow_phase_source_matches_oracle(narrow_shim, oracle, mk):
+    """All five contact generators (features, clipping, manifold with the 0.02 dedup) from the device source vs the oracle on the
+    broad-phase pairs in the reference's callback orientation: algorithm, manifold sizes, feature ids exact; contacts bit-exact."""
+    s = mk()
+    pairs = oracle.broad_phase(oracle.compute_aabbs(s), s.groups, mode=0)
+    assert len(pairs) > 3000
+    inexact = compare_narrow(shim_narrow_phase(narrow_shim, s, pairs), oracle.narrow_phase(s, pairs), "scene")
+    assert inexact == 0, f"{inexact} contact fields within tolerance but not bit-exact"
+
+
+@pytest.mark.parametrize("k", range(6))
+def test_device_narrow_phase_source_on_adversarial_scenes(narrow_shim, oracle, k):
+    from test_gpu_parity import _adversarial_scenes
+
+    s = _adversarial_scenes()[k]
+    pairs = oracle.broad_phase(oracle.compute_aabbs(s), s.groups, mode=0)
+    compare_narrow(shim_narrow_phase(narrow_shim, s, pairs), oracle.narrow_phase(s, pairs), s.name)
+
+
+def test_device_narrow_phase_source_reproduces_the_golden_fixtures(narrow_shim):
+    import glob
+
+    from golden.make_golden import scene_from_npz
+
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "world_*.npz")))
+    assert files
+    for f in files:
+        z = np.load(f)
+        s = scene_from_npz(z)
+        dc, doff, dalgo, flags = shim_narrow_phase(narrow_shim, s, z["pairs"])
+        assert np.array_equal(doff, z["manifold_off"]) and np.array_equal(dalgo, z["algo"]), f
+        assert np.array_equal(dc["f1"], z["c_f1"]) and np.array_equal(dc["f2"], z["c_f2"]), f
+        for name in ("world1", "world2", "normal", "depth"):
+            assert np.allclose(dc[name], z["c_" + name], rtol=1e-4, atol=1e-5), (f, name)
