@@ -151,6 +151,26 @@ def test_stepping_world_first_step_equals_fresh_world_with_sensors(oracle):
     assert np.all(r["prox_events"][:, 2] == DISJOINT)
 
 
+def test_collision_world_mirror_builds_sensor_scenes_without_a_gpu():
+    """Host logic of the mirror: GeometricQueryType.Proximity(margin) -> query_kind / query_limit of the scene it uploads."""
+    from ncollide_b200.shapes import Ball, Cuboid
+    from ncollide_b200.world import CollisionWorld, GeometricQueryType
+
+    ident = (0, 0, 0, 1)
+    w = CollisionWorld(0.02, ctx=object())  # no device work happens before update()
+    w.add(((0, 0, 0), ident), Cuboid((1, 1, 1)), query_type=GeometricQueryType.Contacts(0.02, 0.0))
+    assert w.scene().query_kind is None  # no sensor: the sensor-free path
+    w.add(((2, 0, 0), ident), Ball(0.5), query_type=GeometricQueryType.Proximity(0.3))
+    s = w.scene()
+    assert s.query_kind.tolist() == [0, 1] and s.query_kind.dtype == np.uint8
+    assert np.allclose(s.query_limit, [0.02, 0.3])
+    with pytest.raises(ValueError):  # the reference asserts margin >= 0 in every proximity query
+        w.add(((0, 0, 0), ident), Ball(0.5), query_type=GeometricQueryType.Proximity(-0.1))
+    with pytest.raises(ValueError):
+        w.add(((0, 0, 0), ident), Ball(0.5), query_type=None)
+    assert list(w.proximity_pairs()) == [] and w.proximity_events() == []  # before any update
+
+
 # ---- golden fixture (tests/golden/prox_mixed_plane_400.npz, made by tests/golden/make_golden.py from the oracle) --------------
 def _load_prox_golden():
     import os
