@@ -12,7 +12,7 @@ namespace orc {
 
 // A support-mapped operand: cuboid, convex hull, ball (for one-shot queries) or ConstantOrigin.
 struct Support {
-    enum Kind { S_CUBOID, S_HULL, S_BALL, S_ORIGIN } kind;
+    enum Kind { S_CUBOID, S_HULL, S_BALL, S_ORIGIN, S_CYLINDER } kind;  // S_CYLINDER: only for the reference's cylinder / cuboid KAT
     V3 he;
     real radius;
     Hull hull;
@@ -31,6 +31,13 @@ struct Support {
                     }
                 }
                 return hull.pt(best);
+            }
+            case S_CYLINDER: {  // cylinder.rs:47-62 (half_height in he.x)
+                V3 vres = v3(dir.x, 0, dir.z);
+                real n = norm(vres);
+                vres = n == real(0) ? v3(0, 0, 0) : (vres / n) * radius;
+                vres.y = std::copysign(he.x, dir.y);
+                return vres;
             }
             case S_BALL:  // ball.rs:41-48: local_support_point_toward(normalize(dir)) = dir * radius
                 return normalize(dir) * radius;

@@ -1119,6 +1119,31 @@ void orc_contact_sm_sm(const orc_objects* objs, uint64_t n_pairs, const uint32_t
     if (stats) stats[0] = st.gjk_iters, stats[1] = st.epa_iters, stats[2] = st.epa_calls, stats[3] = st.epa_fail;
 }
 
+// The reference's issue-#157 test (build/ncollide3d/tests/geometry/cylinder_cuboid_contact.rs): Cylinder(half_height, radius) at t1
+// vs Cuboid(he) at t2, identity rotations.  out[0] = distance_support_map_support_map (distance_support_map_support_map.rs:8-53),
+// out[1] = proximity_support_map_support_map(margin) as ORC_PROX_*, out[2] = contact_support_map_support_map(prediction).is_some().
+void orc_kat_cylinder_cuboid(real half_height, real radius, const real* t1, const real* he, const real* t2, real margin, real prediction,
+                             real* out) {
+    Iso m1{{t1[0], t1[1], t1[2]}, {0, 0, 0, 1}}, m2{{t2[0], t2[1], t2[2]}, {0, 0, 0, 1}};
+    Support g1, g2;
+    g1.kind = Support::S_CYLINDER, g1.he = v3(half_height, 0, 0), g1.radius = radius;
+    g2.kind = Support::S_CUBOID, g2.he = v3(he[0], he[1], he[2]), g2.radius = 0;
+    {
+        V3 dir;
+        if (!unit_try_new(m1.t - m2.t, EPS, &dir)) dir = v3(1, 0, 0);
+        VoronoiSimplex simplex;
+        simplex.reset(cso_from_shapes(m1, g1, m2, g2, dir));
+        GJKResult r = gjk_closest_points(m1, g1, m2, g2, FMAX, simplex, nullptr, true);
+        out[0] = r.kind == GJK_CLOSEST_POINTS ? norm(r.p1 - r.p2) : real(0);
+    }
+    out[1] = proximity_support_map_support_map(m1, g1, m2, g2, margin, nullptr, nullptr);
+    {
+        VoronoiSimplex simplex;
+        GJKResult r = contact_support_map_support_map_with_params(m1, g1, m2, g2, prediction, simplex, nullptr, nullptr);
+        out[2] = r.kind == GJK_CLOSEST_POINTS ? real(1) : real(0);
+    }
+}
+
 void orc_proximity(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, const real* margins, uint8_t* out) {
     Objects o = make_objects(objs);
     for (uint64_t p = 0; p < n_pairs; ++p) {

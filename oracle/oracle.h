@@ -61,6 +61,11 @@ uint64_t orc_narrow_phase(const orc_objects* objs, uint64_t n_pairs, const uint3
  * stats[4] = GJK iterations, EPA iterations, EPA calls, EPA failures. */
 void orc_contact_sm_sm(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, const real* predictions, real* out, uint32_t* stats);
 
+/* The reference's cylinder / cuboid known-answer test (tests/geometry/cylinder_cuboid_contact.rs): out[3] = distance, proximity
+ * status, contact.is_some(), through the same GJK / EPA restatement with a Cylinder support map (shape/cylinder.rs:47-62). */
+void orc_kat_cylinder_cuboid(real half_height, real radius, const real* t1, const real* he, const real* t2, real margin, real prediction,
+                             real* out);
+
 /* Proximity (query/proximity/proximity.rs:4-12) as a byte; ORC_PROX_NONE = the dispatcher has no detector (plane x plane). */
 #define ORC_PROX_INTERSECTING 0
 #define ORC_PROX_WITHIN_MARGIN 1

@@ -155,6 +155,14 @@ class Oracle:
                                    C.c_void_p(out.ctypes.data), C.c_void_p(stats.ctypes.data))
         return out, stats
 
+    def kat_cylinder_cuboid(self, half_height, radius, t1, he, t2, margin, prediction):
+        """(distance, proximity status, contact found) of the reference's cylinder_cuboid_contact test."""
+        a = [np.ascontiguousarray(x, dtype=self.dtype) for x in (t1, he, t2)]
+        out = np.zeros(3, dtype=self.dtype)
+        self.lib.orc_kat_cylinder_cuboid(self.creal(half_height), self.creal(radius), C.c_void_p(a[0].ctypes.data), C.c_void_p(a[1].ctypes.data),
+                                         C.c_void_p(a[2].ctypes.data), self.creal(margin), self.creal(prediction), C.c_void_p(out.ctypes.data))
+        return float(out[0]), int(out[1]), bool(out[2])
+
     def proximity(self, scene, pairs, margins=None):
         """ProximityDetector::update with fresh detectors per (object1, object2) pair -> u8 status (0 Intersecting, 1 WithinMargin,
         2 Disjoint, 255 no detector).  margins None: query_limit[o1] + query_limit[o2]."""

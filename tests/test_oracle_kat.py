@@ -165,3 +165,23 @@ def test_triangle_aabb_matches_rotated_points(oracle):
     tm = oracle.trimesh(verts, np.array([[0, 1, 2]], dtype=np.uint32))
     toi, face, n = tm.ray_cast(np.array([[0, 0.5, 10]], dtype=F32), np.array([[0, 0, -1]], dtype=F32))
     assert toi[0] > 0 and face[0] in (0, 1)
+
+
+@pytest.mark.parametrize("which", ["oracle64", "oracle"])
+def test_cylinder_cuboid_contact_issue_157(which, request):
+    """build/ncollide3d/tests/geometry/cylinder_cuboid_contact.rs (f64 in the reference): a cylinder overlapping a thin cuboid by
+    0.02 -> distance_support_map_support_map == 0.0, proximity_support_map_support_map(.., 0.1) == Intersecting,
+    contact_support_map_support_map(.., 10.0).is_some().  Pins the GJK restatement in both of its modes (exact_dist = true for the
+    distance / contact queries, false for the proximity query) and the hand-over to EPA; the Cylinder support map exists in the
+    oracle for this test only."""
+    orc = request.getfixturevalue(which)
+    dist, prox, contact = orc.kat_cylinder_cuboid(0.925, 0.5, (10.97, 0.925, 61.02), (0.05, 0.75, 0.5), (11.50, 0.75, 60.5), 0.1, 10.0)
+    assert dist == 0.0
+    assert prox == 0  # Proximity::Intersecting
+    assert contact
+    # moved apart along x (not in the reference's test; analytic): the cylinder axis is 0.53 in x and 0.02 in z away from the cuboid's
+    # vertical edge -> distance sqrt(0.53^2 + 0.02^2) - 0.5; WithinMargin for margin 0.1, Disjoint for margin 0.01
+    dist, prox, contact = orc.kat_cylinder_cuboid(0.925, 0.5, (10.92, 0.925, 61.02), (0.05, 0.75, 0.5), (11.50, 0.75, 60.5), 0.1, 10.0)
+    assert abs(dist - (np.hypot(0.53, 0.02) - 0.5)) < 1e-4 and prox == 1 and contact
+    dist, prox, contact = orc.kat_cylinder_cuboid(0.925, 0.5, (10.92, 0.925, 61.02), (0.05, 0.75, 0.5), (11.50, 0.75, 60.5), 0.01, 0.01)
+    assert prox == 2 and not contact
