@@ -1,0 +1,43 @@
+"""Proximity sensors through the spatially sharded multi-GPU update (ncb_world_update_sharded), replayed rank by rank on one
+device like tests/test_gpu_parity.py::test_spatial_shards_partition_the_pair_set.
+
+Written after the round's GPU budget was spent: the sensor path re-keys pairs by GLOBAL handle with replicated query kinds, so the
+sharded update should need nothing else, but this file has not run on hardware yet.  It is therefore marked xfail(strict=False):
+a pass shows up as XPASS, a failure cannot hide the verified tests.  Remove the marker once it has been seen green."""
+import numpy as np
+import pytest
+
+from ncollide_b200.scenes import config_scene, make_world_scene, with_sensors
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet run on a GPU (round-1 budget exhausted)")]
+
+
+def canon(pairs):
+    p = np.sort(np.asarray(pairs, dtype=np.uint32).reshape(-1, 2), axis=1)
+    return p[np.lexsort((p[:, 1], p[:, 0]))]
+
+
+@pytest.mark.parametrize("world,mk", [(2, lambda: config_scene(3, 7001)), (4, lambda: make_world_scene(6000, 92, (1, 1, 1), side=9.0, plane=True, n_hulls=24))])
+def test_sharded_update_with_sensors(oracle, world, mk):
+    from ncollide_b200.world import Context
+
+    s = with_sensors(mk(), 0.3, 17, margin=0.1)
+    ctx = Context(0)
+    ctx.set_scene(s)
+    full = ctx.world_fetch(ctx.world_update_device(s.margin))
+    want = {tuple(p): (int(a), int(st), int(c)) for p, a, st, c in zip(full.pairs.tolist(), full.pair_algo, full.proximity, full.manifold_count)}
+    assert (full.pair_algo == 6).any()
+    seen = {}
+    for rank in range(world):
+        c = ctx.world_update_sharded(s.margin, rank, world)
+        r = ctx.world_fetch(c)
+        assert r.proximity is not None
+        assert c["n_algo"]["proximity"] == int((r.pair_algo == 6).sum())
+        for p, a, st, cnt in zip(map(tuple, r.pairs.tolist()), r.pair_algo, r.proximity, r.manifold_count):
+            assert p not in seen, "pair reported by two ranks"
+            seen[p] = (int(a), int(st), int(cnt))
+    assert seen == want, "union of the ranks' (algorithm, proximity status, manifold size) differs from the single-GPU update"
+    # and the single-GPU statuses are the oracle's
+    o_c, o_off, o_algo, o_prox = oracle.narrow_phase_kinds(s, full.pairs)
+    assert np.array_equal(full.proximity, o_prox) and np.array_equal(full.pair_algo, o_algo)
+    ctx.close()
