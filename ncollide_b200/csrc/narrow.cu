@@ -730,7 +730,7 @@ __device__ __noinline__ void convex_convex_manifold(const Iso& ma, const Shape& 
     }
 }
 
-#ifndef NCB_HOST_SHIM  // everything below is warp-level / kernel code: CUDA only
+#ifndef NCB_HOST_SHIM  // warp-level code: CUDA only
 // ---- result write-out: warp-aggregated allocation of contact slots --------------------------------------------
 NCB_HD void write_manifold(const Manifold& mf, bool valid, uint32_t pair_slot, uint32_t out_index, ncb_contact* __restrict__ contacts,
                            uint32_t cap_contacts, uint32_t* __restrict__ manifold_start, uint8_t* __restrict__ manifold_count,
@@ -770,6 +770,8 @@ NCB_HD void write_manifold(const Manifold& mf, bool valid, uint32_t pair_slot, u
         contacts[dst] = o;
     }
 }
+
+#endif  // NCB_HOST_SHIM (write_manifold)
 
 // ---- persistent manifold / generator state of a stepping world (indexed by state slot = pair_index[p]) ----------
 // header: 8 words  [0] n | nfree << 8 | slab_len << 16   [1] next_id   [2..7] free stack (one byte per entry)
@@ -849,6 +851,7 @@ __device__ __noinline__ void pm_age_only(const PersistArgs& ps, uint32_t slot, u
     pm_store(ps, slot, mf, h1, h2);
 }
 
+#ifndef NCB_HOST_SHIM  // kernels, work queues and launchers: CUDA only
 struct NarrowArgs {
     PersistArgs ps;
     DevObjects o;

@@ -1454,6 +1454,55 @@ uint64_t orc_sim_events(const orc_sim* s, uint32_t* out, uint64_t cap) {
         for (int d = 0; d < 3; ++d) out[3 * k + d] = s->events[3 * k + d];
     return n;
 }
+// ---- a bare set of Interaction::Contact edges driven by the caller (no broad phase): NarrowPhase::update_contact
+// (narrow_phase.rs:56-104) on the listed edges, with the generator state (last_gjk_dir) and the ContactManifold cache kept per edge.
+struct orc_edges {
+    std::vector<Edge> e;
+};
+orc_edges* orc_edges_create(uint64_t n, const uint32_t* pairs) {
+    orc_edges* E = new orc_edges;
+    E->e.resize(n);
+    for (uint64_t i = 0; i < n; ++i) E->e[i].h1 = pairs[2 * i], E->e[i].h2 = pairs[2 * i + 1], E->e[i].algo = A_NONE;
+    return E;
+}
+void orc_edges_destroy(orc_edges* E) { delete E; }
+// events: (h1, h2, 1 Started / 0 Stopped) rows in emission order; returns their number
+uint64_t orc_edges_update(orc_edges* E, const orc_objects* objs, uint64_t n_update, const uint32_t* which, uint32_t* events, uint64_t cap) {
+    Objects o = make_objects(objs);
+    uint64_t ne = 0;
+    for (uint64_t k = 0; k < n_update; ++k) {
+        Edge& e = E->e[which[k]];
+        bool had = e.manifold.len() != 0;
+        e.manifold.save_cache_and_clear();
+        e.algo = generate_contacts(o, e.h1, e.h2, e.manifold, nullptr, &e.last_gjk_dir, &e.has_dir);
+        bool has = e.manifold.len() != 0;
+        if (has != had) {
+            if (ne < cap) events[3 * ne] = e.h1, events[3 * ne + 1] = e.h2, events[3 * ne + 2] = has ? 1u : 0u;
+            ne++;
+        }
+    }
+    return ne;
+}
+// manifold_off[n + 1]; contacts in ContactManifold::contacts() order; ids = insertion counter << 8 | slab slot; dirs[4 i] = the
+// generator's last_gjk_dir + a "Some" flag.  Returns the number of contacts (may exceed cap).
+uint64_t orc_edges_fetch(const orc_edges* E, uint32_t* manifold_off, orc_contact* contacts, uint32_t* ids, uint64_t cap, real* dirs) {
+    uint64_t nc = 0, n = E->e.size();
+    for (uint64_t i = 0; i < n; ++i) {
+        const Edge& e = E->e[i];
+        manifold_off[i] = (uint32_t)nc;
+        e.manifold.for_each_contact([&](const Tracked& t, size_t slot) {
+            if (nc < cap) {
+                write_contact(&contacts[nc], t);
+                ids[nc] = (t.id << 8) | (uint32_t)slot;
+            }
+            nc++;
+        });
+        if (dirs) dirs[4 * i] = e.last_gjk_dir.x, dirs[4 * i + 1] = e.last_gjk_dir.y, dirs[4 * i + 2] = e.last_gjk_dir.z, dirs[4 * i + 3] = e.has_dir ? 1 : 0;
+    }
+    manifold_off[n] = (uint32_t)nc;
+    return nc;
+}
+
 void orc_sim_fetch_proximity(const orc_sim* s, uint8_t* prox) {
     uint64_t p = 0;
     for (auto& kv : s->edges) prox[p++] = kv.second.is_prox ? kv.second.prox : (uint8_t)PROX_NONE;

@@ -125,6 +125,13 @@ uint64_t orc_sim_num_pairs(const orc_sim*);
 uint64_t orc_sim_num_contacts(const orc_sim*);
 void orc_sim_fetch(const orc_sim*, uint32_t* pairs, uint8_t* algo, uint32_t* manifold_off, orc_contact* contacts, uint32_t* ids);
 uint64_t orc_sim_events(const orc_sim*, uint32_t* out, uint64_t cap);
+/* A bare set of contact edges driven by the caller (no broad phase): NarrowPhase::update_contact on the listed edges, generator
+ * state (last_gjk_dir) and ContactManifold cache kept per edge — what a state slot of the device's stepping world holds. */
+typedef struct orc_edges orc_edges;
+orc_edges* orc_edges_create(uint64_t n, const uint32_t* pairs);
+void orc_edges_destroy(orc_edges*);
+uint64_t orc_edges_update(orc_edges*, const orc_objects* objs, uint64_t n_update, const uint32_t* which, uint32_t* events, uint64_t cap);
+uint64_t orc_edges_fetch(const orc_edges*, uint32_t* manifold_off, orc_contact* contacts, uint32_t* ids, uint64_t cap, real* dirs);
 /* Proximity status per edge (same order as orc_sim_fetch; 255 for contact edges) and the ProximityEvents of the last step as
  * (h1, h2, prev, new) rows in emission order. */
 void orc_sim_fetch_proximity(const orc_sim*, uint8_t* prox);

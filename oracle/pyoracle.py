@@ -232,6 +232,9 @@ class Oracle:
     def sim(self, scene):
         return OracleSim(self, scene)
 
+    def edges(self, pairs):
+        return OracleEdges(self, pairs)
+
     def shape_ray_cast(self, scene, i, origin, direction, max_toi):
         """RayCast::toi_and_normal_with_ray(position_i, ray, max_toi, solid = true) -> (toi, normal, feature) or None."""
         o, keep = self._objects(scene)
@@ -250,6 +253,47 @@ class Oracle:
         t = self.creal(0)
         self.lib.orc_aabb_toi_with_ray(C.c_void_p(mm.ctypes.data), C.c_void_p(o.ctypes.data), C.c_void_p(d.ctypes.data), self.creal(max_toi), C.c_int(int(solid)), C.byref(t))
         return None if t.value < 0 else t.value
+
+
+class OracleEdges:
+    """A caller-driven set of contact edges (orc_edges_*): update_contact on chosen edges, state kept per edge."""
+
+    def __init__(self, oracle, pairs):
+        self.o = oracle
+        L = oracle.lib
+        L.orc_edges_create.restype = C.c_void_p
+        L.orc_edges_update.restype = C.c_uint64
+        L.orc_edges_fetch.restype = C.c_uint64
+        self.pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        self.h = C.c_void_p(L.orc_edges_create(C.c_uint64(len(self.pairs)), C.c_void_p(self.pairs.ctypes.data)))
+
+    def __del__(self):
+        try:
+            self.o.lib.orc_edges_destroy(self.h)
+        except Exception:
+            pass
+
+    def update(self, scene, which):
+        o, keep = self.o._objects(scene)
+        which = np.ascontiguousarray(which, dtype=np.uint32)
+        ev = np.zeros((max(len(which), 1), 3), dtype=np.uint32)
+        ne = self.o.lib.orc_edges_update(self.h, C.byref(o), C.c_uint64(len(which)), C.c_void_p(which.ctypes.data), C.c_void_p(ev.ctypes.data),
+                                         C.c_uint64(len(ev)))
+        return ev[:ne]
+
+    def fetch(self):
+        P = len(self.pairs)
+        off = np.zeros(P + 1, dtype=np.uint32)
+        dirs = np.zeros((P, 4), dtype=self.o.dtype)
+        cap = max(8 * P, 64)
+        while True:
+            c = np.zeros(cap, dtype=self.o.contact_dtype)
+            ids = np.zeros(cap, dtype=np.uint32)
+            nc = self.o.lib.orc_edges_fetch(self.h, C.c_void_p(off.ctypes.data), C.c_void_p(c.ctypes.data), C.c_void_p(ids.ctypes.data), C.c_uint64(cap),
+                                            C.c_void_p(dirs.ctypes.data))
+            if nc <= cap:
+                return c[:nc], off, ids[:nc], dirs
+            cap = int(nc)
 
 
 class OracleSim:

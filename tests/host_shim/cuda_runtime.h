@@ -32,6 +32,7 @@ static inline uint32_t __float_as_uint(float f) { uint32_t i; std::memcpy(&i, &f
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline float __uint_as_float(uint32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
+static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 using std::isinf;
 using std::isnan;
 using std::signbit;

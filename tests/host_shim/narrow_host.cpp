@@ -145,4 +145,169 @@ uint64_t shim_narrow_phase(const ncb_objects* objs, const ncb_hull_library* lib,
     delete mfp;
     return nc;
 }
+
+// Stepping world, per pair: what k_narrow<KEY, true>, k_bh_epa<true>, k_cc_gjk<true> -> k_cc_epa<true> -> k_cc_manifold<true> do for ONE
+// updated pair whose persistent state lives in slot `slots[k]` of dir / pm_hdr / pm_entry (same calls, same order: load + age the
+// manifold cache, warm-started GJK, generate, store back, contact events).
+void shim_persist_update(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_update, const uint32_t* pairs, const uint32_t* slots,
+                         float* dir, uint32_t* pm_hdr, float* pm_entry, unsigned long long* events, uint32_t* n_events, uint32_t cap_events,
+                         uint32_t* pm_overflow, uint32_t* flags) {
+    DevObjects o;
+    std::memset(&o, 0, sizeof o);
+    o.n = objs->n;
+    o.pos = objs->pos;
+    o.rot = reinterpret_cast<const float4*>(objs->rot);
+    o.type = objs->shape_type;
+    o.param = reinterpret_cast<const float4*>(objs->shape_param);
+    o.qlimit = objs->query_limit;
+    DevHulls H = hulls_from(lib);
+    const float one_degree = (float)(3.14159265358979323846 / 180.0);
+    const float2 one_degree_cs = make_float2(cosf(one_degree), sinf(one_degree));
+    PersistArgs ps;
+    ps.dir = reinterpret_cast<float4*>(dir);
+    ps.pm_hdr = pm_hdr;
+    ps.pm_entry = reinterpret_cast<float4*>(pm_entry);
+    ps.events = events;
+    ps.n_events = n_events;
+    ps.cap_events = cap_events;
+    ps.pm_overflow = pm_overflow;
+    EpaState* e = new EpaState;
+    PManifold* mfp = new PManifold;
+    PManifold& mf = *mfp;
+    for (uint64_t k = 0; k < n_update; ++k) {
+        uint32_t i1 = pairs[2 * k], i2 = pairs[2 * k + 1], slot = slots[k];
+        uint32_t t1 = o.type[i1] & 3u, t2 = o.type[i2] & 3u;
+        Iso ma = load_iso(o, i1), mb = load_iso(o, i2);
+        float linear = o.qlimit[i1] + o.qlimit[i2];
+        Shape a = load_shape(o, H, i1, t1), b = load_shape(o, H, i2, t2);
+        bool a_ball = t1 == NCB_SHAPE_BALL, b_ball = t2 == NCB_SHAPE_BALL, a_plane = t1 == NCB_SHAPE_PLANE, b_plane = t2 == NCB_SHAPE_PLANE;
+        if (a_plane && b_plane) continue;  // K_NONE: no edge
+        bool convex_convex = !a_ball && !b_ball && !a_plane && !b_plane;
+        if (!convex_convex) {  // k_narrow<KEY, true> (+ k_bh_epa<true>)
+            pm_load_and_age(ps, slot, mf);
+            if (a_ball && b_ball) {
+                gen_ball_ball(ma, a.radius, mb, b.radius, linear, mf);
+            } else if ((a_plane && b_ball) || (a_ball && b_plane)) {
+                if (a_plane)
+                    gen_plane_ball(ma, a.he, mb, b.radius, linear, false, mf);
+                else
+                    gen_plane_ball(mb, b.he, ma, a.radius, linear, true, mf);
+            } else if (a_plane || b_plane) {
+                Feature feat;
+                if (a_plane)
+                    gen_plane_convex(ma, a.he, mb, b, linear, false, mf, feat);
+                else
+                    gen_plane_convex(mb, b.he, ma, a, linear, true, mf, feat);
+            } else {
+                bool flip = !a_ball;
+                const Shape& ball = flip ? b : a;
+                const Shape& cp = flip ? a : b;
+                const Iso& mball = flip ? mb : ma;
+                const Iso& mcp = flip ? ma : mb;
+                if (cp.type == NCB_SHAPE_CUBOID) {
+                    bool inside;
+                    V3 world2;
+                    uint32_t f2;
+                    cuboid_project_point_with_feature(cp.he, mcp, mball.t, inside, world2, f2);
+                    gen_ball_convex_finish(mball.t, ball.radius, cp, inside, world2, f2, linear, flip, mf);
+                } else {
+                    HullProjSetup u = hull_proj_setup(cp.hull, mcp, mball.t);
+                    V3 world2;
+                    Simplex s;
+                    if (hull_project_gjk(u, mball.t, s, world2) == GJK_CLOSEST_POINTS) {
+                        uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, false, world2, one_degree_cs);
+                        gen_ball_convex_finish(mball.t, ball.radius, cp, false, world2, f2, linear, flip, mf);
+                    } else {
+                        Iso id = iso_id();
+                        V3 p1, p2, d;
+                        if (epa_closest_points(*e, u.m, u.shape, id, u.origin, s.dim, s.v, p1, p2, d))
+                            world2 = p1 + mball.t;
+                        else {
+                            flags[0] += e->overflow, flags[1] += e->panicked;
+                            world2 = mball.t;
+                        }
+                        uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, true, world2, one_degree_cs);
+                        gen_ball_convex_finish(mball.t, ball.radius, cp, true, world2, f2, linear, flip, mf);
+                    }
+                }
+            }
+            pm_store(ps, slot, mf, i1, i2);
+            continue;
+        }
+        // k_cc_gjk<true>
+        Support ga = as_support(a), gb = as_support(b);
+        V3 d0;
+        bool warm = false;
+        float4 pd = ps.dir[slot];
+        if (pd.w != 0.f) d0 = v3(pd.x, pd.y, pd.z), warm = true;
+        if (!warm && !unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
+        V3 p1, p2, dirv;
+        Simplex s;
+        int r = gjk_closest_points(ma, ga, mb, gb, linear, d0, s, p1, p2, dirv);
+        if (r != GJK_INTERSECTION) ps.dir[slot] = make_float4(dirv.x, dirv.y, dirv.z, 1.f);
+        if (r == GJK_NO_INTERSECTION) {
+            pm_age_only(ps, slot, i1, i2);
+            continue;
+        }
+        if (r == GJK_INTERSECTION) {  // k_cc_epa<true>
+            if (epa_closest_points(*e, ma, ga, mb, gb, s.dim, s.v, p1, p2, dirv)) {
+                ps.dir[slot] = make_float4(dirv.x, dirv.y, dirv.z, 1.f);
+            } else {
+                flags[0] += e->overflow, flags[1] += e->panicked;
+                ps.dir[slot] = make_float4(1.f, 0.f, 0.f, 1.f);
+                pm_age_only(ps, slot, i1, i2);
+                continue;
+            }
+        }
+        // k_cc_manifold<true>
+        pm_load_and_age(ps, slot, mf);
+        float a1 = objs->ang_pred[i1], a2 = objs->ang_pred[i2];
+        float2 ang1 = make_float2(cosf(a1), sinf(a1)), ang2 = make_float2(cosf(a2), sinf(a2));
+        Feature f1, f2;
+        convex_convex_manifold(ma, a, mb, b, linear, ang1, ang2, p1, p2, dirv, mf, f1, f2);
+        pm_store(ps, slot, mf, i1, i2);
+    }
+    delete e;
+    delete mfp;
+}
+
+// k_sim_export for the listed slots: live contacts in slab order, ids = insertion counter << 8 | slab slot.
+uint64_t shim_persist_export(uint64_t n, const uint32_t* slots, const uint32_t* pm_hdr, const float* pm_entry_f, uint32_t* manifold_off,
+                             ncb_contact* contacts, uint32_t* ids, uint64_t cap) {
+    const float4* pm_entry = reinterpret_cast<const float4*>(pm_entry_f);
+    uint64_t nc = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t slot = slots[i];
+        manifold_off[i] = (uint32_t)nc;
+        int n0 = (int)(pm_hdr[(size_t)slot * PM_HDR_WORDS] & 0xffu);
+        const float4* e = pm_entry + (size_t)slot * PM_CAP * PM_ENTRY_F4;
+        uint32_t done = 0;
+        for (;;) {
+            int best = -1;
+            uint32_t best_slot = 0xffffffffu;
+            for (int k = 0; k < n0; ++k) {
+                uint32_t meta = __float_as_uint(e[4 * k + 3].w);
+                if (!((meta >> 8) & 1u) || ((done >> k) & 1u)) continue;
+                if ((meta & 0xffu) < best_slot) best_slot = meta & 0xffu, best = k;
+            }
+            if (best < 0) break;
+            done |= 1u << best;
+            if (nc < cap) {
+                float4 a = e[4 * best], b = e[4 * best + 1], c = e[4 * best + 2];
+                uint32_t meta = __float_as_uint(e[4 * best + 3].w);
+                ncb_contact& w = contacts[nc];
+                w.world1[0] = a.x, w.world1[1] = a.y, w.world1[2] = a.z;
+                w.world2[0] = b.x, w.world2[1] = b.y, w.world2[2] = b.z;
+                w.normal[0] = c.x, w.normal[1] = c.y, w.normal[2] = c.z;
+                w.depth = a.w;
+                w.f1 = __float_as_uint(b.w), w.f2 = __float_as_uint(c.w);
+                w.pair = (uint32_t)i;
+                ids[nc] = ((meta >> 9) << 8) | (meta & 0xffu);
+            }
+            nc++;
+        }
+    }
+    manifold_off[n] = (uint32_t)nc;
+    return nc;
+}
 }

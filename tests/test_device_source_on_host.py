@@ -254,3 +254,91 @@ def test_device_narrow_phase_source_reproduces_the_golden_fixtures(narrow_shim):
         assert np.array_equal(dc["f1"], z["c_f1"]) and np.array_equal(dc["f2"], z["c_f2"]), f
         for name in ("world1", "world2", "normal", "depth"):
             assert np.allclose(dc[name], z["c_" + name], rtol=1e-4, atol=1e-5), (f, name)
+
+
+# ---- stepping world, per pair: persistent manifold cache + GJK warm start (pm_load_and_age / manifold_push<true> / pm_store) ----
+class ShimEdges:
+    """The device's per-pair persistent state (slot = pair index) driven through tests/host_shim/narrow_host.cpp."""
+
+    def __init__(self, lib, pairs):
+        self.lib, self.pairs = lib, np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        P = len(self.pairs)
+        self.dir = np.zeros((P, 4), dtype=F)
+        self.hdr = np.zeros((P, 8), dtype=np.uint32)         # PM_HDR_WORDS
+        self.entry = np.zeros((P, 24 * 4, 4), dtype=F)       # PM_CAP * PM_ENTRY_F4 float4
+        self.flags = np.zeros(4, dtype=np.uint32)
+        self.overflow = np.zeros(1, dtype=np.uint32)
+
+    def update(self, scene, which):
+        oc, keep = _ffi.pack_objects(scene)
+        hc, keep2 = _ffi.pack_hull_library(scene.hulls)
+        which = np.ascontiguousarray(which, dtype=np.uint32)
+        pr = np.ascontiguousarray(self.pairs[which])
+        ev = np.zeros(len(which) + 1, dtype=np.uint64)
+        nev = np.zeros(1, dtype=np.uint32)
+        self.lib.shim_persist_update(C.byref(oc), C.byref(hc), C.c_uint64(len(which)), _ffi.ptr(pr), _ffi.ptr(which), _ffi.ptr(self.dir), _ffi.ptr(self.hdr),
+                                     _ffi.ptr(self.entry), _ffi.ptr(ev), _ffi.ptr(nev), C.c_uint32(len(ev)), _ffi.ptr(self.overflow), _ffi.ptr(self.flags))
+        ev = ev[: int(nev[0])]
+        return np.stack([(ev >> np.uint64(32)) & np.uint64(0x7FFFFFFF), ev & np.uint64(0xFFFFFFFF), ev >> np.uint64(63)], axis=1).astype(np.uint32)
+
+    def fetch(self):
+        P = len(self.pairs)
+        slots = np.arange(P, dtype=np.uint32)
+        off = np.zeros(P + 1, dtype=np.uint32)
+        self.lib.shim_persist_export.restype = C.c_uint64
+        cap = max(8 * P, 64)
+        while True:
+            c = np.zeros(cap, dtype=_ffi.CONTACT_DTYPE)
+            ids = np.zeros(cap, dtype=np.uint32)
+            nc = self.lib.shim_persist_export(C.c_uint64(P), _ffi.ptr(slots), _ffi.ptr(self.hdr), _ffi.ptr(self.entry), _ffi.ptr(off), _ffi.ptr(c), _ffi.ptr(ids),
+                                              C.c_uint64(cap))
+            if nc <= cap:
+                return c[:nc], off, ids[:nc], self.dir
+            cap = int(nc)
+
+
+def _sorted_rows(a):
+    a = np.asarray(a).reshape(-1, 3)
+    return a[np.lexsort(a.T[::-1])] if len(a) else a
+
+
+@pytest.mark.parametrize("n,kinds,side,plane,ang,seed", [(1500, (1, 1, 1), 6.5, True, 0.0, 3), (1500, (0, 1, 1), 5.5, False, 0.02, 5), (1200, (1, 1, 0), 5.0, True, 0.0, 7)])
+def test_device_persistent_manifold_source_matches_oracle(narrow_shim, oracle, n, kinds, side, plane, ang, seed):
+    """Seven updates of a fixed edge set while the objects jitter / jump / rotate: after every update the device's persistent
+    manifolds (contacts in slab order, contact ids, feature ids), the generators' warm-start directions and the contact events
+    equal the oracle's ContactManifold cache — values bit for bit."""
+    from sim_scenario import step_poses
+
+    s = make_world_scene(n, 90 + seed, kinds, side=side, n_hulls=24, plane=plane, angular=ang)
+    pairs = oracle.broad_phase(oracle.compute_aabbs(s), s.groups, mode=0)
+    t = s.shape_type
+    pairs = pairs[~((t[pairs[:, 0]] == 3) & (t[pairs[:, 1]] == 3))]
+    dev, orc = ShimEdges(narrow_shim, pairs), oracle.edges(pairs)
+    rng = np.random.default_rng(seed)
+    n_events = n_kept_ids = 0
+    prev_ids = None
+    for step in range(7):
+        if step == 0:
+            which = np.arange(len(pairs), dtype=np.uint32)
+        elif step == 3:
+            which = np.zeros(0, dtype=np.uint32)  # an idle update
+        else:
+            idx = step_poses(s, s.pos, s.rot, rng, 0.4)
+            moved = np.zeros(s.n, dtype=bool)
+            moved[idx] = True
+            which = np.nonzero(moved[pairs[:, 0]] | moved[pairs[:, 1]])[0].astype(np.uint32)
+        ed, eo = dev.update(s, which), orc.update(s, which)
+        assert dev.flags[0] == 0 and dev.flags[1] == 0 and dev.overflow[0] == 0
+        assert np.array_equal(_sorted_rows(ed), _sorted_rows(eo)), f"step {step}: contact events"
+        n_events += len(eo) if step else 0
+        (dc, doff, dids, ddir), (oc, ooff, oids, odir) = dev.fetch(), orc.fetch()
+        assert np.array_equal(doff, ooff), f"step {step}: manifold sizes differ on {int((np.diff(doff) != np.diff(ooff)).sum())} edges"
+        assert np.array_equal(dids, oids), f"step {step}: contact ids"
+        for name in ("f1", "f2", "world1", "world2", "normal", "depth"):
+            assert np.array_equal(dc[name].view(np.uint32), oc[name].view(np.uint32)), f"step {step}: {name}"
+        has = odir[:, 3] != 0
+        assert np.array_equal(ddir[:, 3] != 0, has) and np.array_equal(ddir[has].view(np.uint32), odir[has].view(np.uint32)), f"step {step}: last_gjk_dir"
+        if prev_ids is not None:
+            n_kept_ids += len(np.intersect1d(prev_ids, (np.repeat(np.arange(len(pairs)), np.diff(ooff)).astype(np.uint64) << np.uint64(32)) | oids))
+        prev_ids = (np.repeat(np.arange(len(pairs)), np.diff(ooff)).astype(np.uint64) << np.uint64(32)) | oids
+    assert n_events > 5 and n_kept_ids > 100  # contacts started / stopped, and contacts that kept their id across updates
