@@ -16,7 +16,42 @@ sys.path.insert(0, "scripts")
 os.environ["FUZZ_SENSORS"] = "0"
 from fuzz_parity import random_scene  # noqa: E402
 from oracle.pyoracle import Oracle  # noqa: E402
-from test_device_source_on_host import _build_shim, compare_narrow, shim_contact_sm_sm, shim_narrow_phase, shim_proximity  # noqa: E402
+from sim_scenario import step_poses  # noqa: E402
+from test_device_source_on_host import ShimEdges, _build_shim, _sorted_rows, compare_narrow, shim_contact_sm_sm, shim_narrow_phase, shim_proximity  # noqa: E402
+
+
+def persist_rounds(nar, orc, s, cb, rng, steps=4):
+    """A fixed edge set over `steps` updates (stepping-world per-pair state).  Returns (edge updates, None) or (.., reason)."""
+    t = s.shape_type
+    cb = cb[~((t[cb[:, 0]] == 3) & (t[cb[:, 1]] == 3))]
+    if len(cb) == 0:
+        return 0, None
+    dev, ref = ShimEdges(nar, cb), orc.edges(cb)
+    n = 0
+    for step in range(steps):
+        if step == 0:
+            which = np.arange(len(cb), dtype=np.uint32)
+        else:
+            idx = step_poses(s, s.pos, s.rot, rng, 0.5)
+            moved = np.zeros(s.n, dtype=bool)
+            moved[idx] = True
+            which = np.nonzero(moved[cb[:, 0]] | moved[cb[:, 1]])[0].astype(np.uint32)
+        ed, eo = dev.update(s, which), ref.update(s, which)
+        n += len(which)
+        if dev.flags[0] or dev.flags[1] or dev.overflow[0]:
+            return n, f"step {step}: overflow / panic {dev.flags[:2].tolist()} {int(dev.overflow[0])}"
+        if not np.array_equal(_sorted_rows(ed), _sorted_rows(eo)):
+            return n, f"step {step}: events"
+        (dc, doff, dids, ddir), (oc, ooff, oids, odir) = dev.fetch(), ref.fetch()
+        if not (np.array_equal(doff, ooff) and np.array_equal(dids, oids)):
+            return n, f"step {step}: manifold sizes / ids"
+        for name in ("f1", "f2", "world1", "world2", "normal", "depth"):
+            if not np.array_equal(dc[name].view(np.uint32), oc[name].view(np.uint32)):
+                return n, f"step {step}: {name}"
+        has = odir[:, 3] != 0
+        if not (np.array_equal(ddir[:, 3] != 0, has) and np.array_equal(ddir[has].view(np.uint32), odir[has].view(np.uint32))):
+            return n, f"step {step}: last_gjk_dir"
+    return n, None
 
 F = np.float32
 
@@ -26,7 +61,7 @@ def main():
     seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 50_000
     prox, gjk, orc = _build_shim("libprox_host.so", "proximity_host.cpp"), _build_shim("libgjk_host.so", "gjk_host.cpp"), Oracle()
     nar = _build_shim("libnarrow_host.so", "narrow_host.cpp")
-    n_narrow = n_contacts = narrow_inexact = 0
+    n_narrow = n_contacts = narrow_inexact = n_persist = 0
     t0 = time.time()
     n_scenes = n_prox = n_gjk = n_epa = 0
     inexact = 0
@@ -62,10 +97,16 @@ def main():
                 narrow_inexact += compare_narrow(got, want, f"seed {seed}")
             except AssertionError as ex:
                 bad.append((seed, "narrow phase", str(ex)[:120]))
+            if seed % 4 == 0:  # stepping-world state per pair over a few updates (moves the scene: last check of this world)
+                k, why = persist_rounds(nar, orc, s, cb, rng)
+                n_persist += k
+                if why:
+                    bad.append((seed, "persistent manifold", why))
         n_scenes += 1
         seed += 1
     print(json.dumps({"scenes": n_scenes, "proximity_pairs": n_prox, "gjk_pairs": n_gjk, "epa_runs": n_epa, "gjk_rows_not_bit_exact": inexact,
                       "narrow_phase_pairs": n_narrow, "contacts": n_contacts, "contact_fields_not_bit_exact": narrow_inexact,
+                      "persistent_edge_updates": n_persist,
                       "mismatches": bad, "seconds": round(time.time() - t0, 1), "seed0": seed0}))
 
 
