@@ -9,7 +9,9 @@
 // One thread per ray walks the LBVH with the reference's slab test (monotone under box inclusion, so the candidate set
 // equals the one the two DBVTs produce), filters candidates by the query's collision groups, and runs the shape's ray cast.
 // "all" mode appends (ray, handle, toi, normal, feature) rows; "first" mode keeps the smallest toi (ties: smallest handle).
+#ifndef NCB_HOST_SHIM  // tests/host_shim compiles the per-shape functions of this file for the host (test infrastructure)
 #include <cub/cub.cuh>
+#endif
 #include "bp_internal.h"
 #include "shapes.cuh"
 
@@ -218,6 +220,7 @@ __device__ __noinline__ RayHit ray_cast_hull(const HullView& H, const Iso& m, V3
     }
 }
 
+#ifndef NCB_HOST_SHIM  // traversal kernels and host entry points: CUDA only
 __device__ __forceinline__ bool slab_hit(const float* q, const float* inv, float4 lo, float4 hi, float& tmin) {  // ray_aabb.rs:13-50
     tmin = 0.f;
     float tmax = q[6];
@@ -600,3 +603,6 @@ int world_query(ncb_ctx* ctx, ncb_bp* bp, WorldQueryBufs& B, int kind, uint32_t 
     CKQ(cudaStreamSynchronize(s));
     return found > cap ? 1 : NCB_OK;
 }
+#else
+}  // namespace (host shim: only the per-shape ray casts above)
+#endif  // NCB_HOST_SHIM

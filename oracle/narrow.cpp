@@ -1677,6 +1677,40 @@ int orc_shape_ray_cast(const orc_objects* objs, uint32_t i, const real* origin, 
     return 1;
 }
 
+// The same for a batch: ray k (7 reals: origin, dir, max_toi) against object which[k]; out[4 k] = toi, normal; feat[k]; hit[k].
+void orc_shape_ray_cast_batch(const orc_objects* objs, uint64_t n, const uint32_t* which, const real* rays, real* out, uint32_t* feat, uint8_t* hit) {
+    Objects o = make_objects(objs);
+    for (uint64_t k = 0; k < n; ++k) {
+        const real* q = rays + 7 * k;
+        RayHit h = shape_ray_cast(o, which[k], v3(q[0], q[1], q[2]), v3(q[3], q[4], q[5]), q[6]);
+        hit[k] = h.hit ? 1 : 0;
+        out[4 * k] = h.hit ? h.toi : 0, out[4 * k + 1] = h.hit ? h.normal.x : 0, out[4 * k + 2] = h.hit ? h.normal.y : 0, out[4 * k + 3] = h.hit ? h.normal.z : 0;
+        feat[k] = h.hit ? h.feature : 0u;
+    }
+}
+// PointQuery::contains_point(position, point) of object which[k] for point k (point_ball.rs:45-47, point_cuboid.rs, point_plane.rs:8-19,
+// point_support_map.rs:15-53 for hulls).
+static bool shape_contains_point(const Objects& o, uint32_t h, V3 pt) {
+    Shape sh = get_shape(o, h);
+    Iso m = o.iso(h);
+    if (sh.type == BALL) return norm_squared(iso_inv_point(m, pt)) <= sh.radius * sh.radius;
+    if (sh.type == CUBOID) {
+        V3 l = iso_inv_point(m, pt);
+        return !(l.x < -sh.he.x || l.x > sh.he.x || l.y < -sh.he.y || l.y > sh.he.y || l.z < -sh.he.z || l.z > sh.he.z);
+    }
+    if (sh.type == HULL) {
+        bool inside;
+        V3 proj;
+        hull_project_point(sh.hull, m, pt, &inside, &proj, nullptr);
+        return inside;
+    }
+    return dot(sh.he, iso_inv_point(m, pt)) <= real(0);
+}
+void orc_shape_contains_point_batch(const orc_objects* objs, uint64_t n, const uint32_t* which, const real* pts, uint8_t* inside) {
+    Objects o = make_objects(objs);
+    for (uint64_t k = 0; k < n; ++k) inside[k] = shape_contains_point(o, which[k], v3(pts[3 * k], pts[3 * k + 1], pts[3 * k + 2])) ? 1 : 0;
+}
+
 // glue::interferences_with_ray (first_only = 0: every hit, rows sorted by (ray, handle)) / first_interference_with_ray
 // (first_only = 1: smallest toi, ties -> smallest handle).  rays: 7 reals (origin, dir, max_toi); groups: the query's
 // CollisionGroups (3 words) or NULL.  Rows: idx[2k] = (ray, handle), val[4k] = (toi, normal), feat[k].  Returns the row count.
@@ -1744,22 +1778,7 @@ uint64_t orc_sim_query(orc_sim* s, int kind, uint64_t n, const real* q, const ui
                 if (!((m1 & groups[2]) == 0 && (groups[0] & b1) == 0 && (m1 & groups[1]) != 0 && (groups[0] & w1) != 0)) continue;
             }
             if (kind == 2) {
-                V3 pt = v3(qq[0], qq[1], qq[2]);
-                Shape sh = get_shape(o, h);
-                Iso m = o.iso(h);
-                bool inside;
-                if (sh.type == BALL) {  // point_ball.rs:45-47
-                    inside = norm_squared(iso_inv_point(m, pt)) <= sh.radius * sh.radius;
-                } else if (sh.type == CUBOID) {  // point_cuboid.rs -> AABB::contains_local_point
-                    V3 l = iso_inv_point(m, pt);
-                    inside = !(l.x < -sh.he.x || l.x > sh.he.x || l.y < -sh.he.y || l.y > sh.he.y || l.z < -sh.he.z || l.z > sh.he.z);
-                } else if (sh.type == HULL) {  // point_support_map.rs:15-53: inside <=> gjk::project_origin finds no projection
-                    V3 proj;
-                    hull_project_point(sh.hull, m, pt, &inside, &proj, nullptr);
-                } else {  // point_plane.rs:8-19
-                    inside = dot(sh.he, iso_inv_point(m, pt)) <= real(0);
-                }
-                if (!inside) continue;
+                if (!shape_contains_point(o, h, v3(qq[0], qq[1], qq[2]))) continue;
             }
             if (rows < cap) idx[2 * rows] = (uint32_t)r, idx[2 * rows + 1] = h;
             rows++;

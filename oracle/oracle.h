@@ -139,6 +139,8 @@ uint64_t orc_sim_proximity_events(const orc_sim*, uint32_t* out, uint64_t cap);
 uint64_t orc_sim_bp_num_interferences(const orc_sim*);
 uint64_t orc_sim_query(orc_sim*, int kind, uint64_t n, const real* q, const uint32_t* groups, uint32_t* idx, uint64_t cap);
 int orc_shape_ray_cast(const orc_objects* objs, uint32_t i, const real* origin, const real* dir, real max_toi, real* out, uint32_t* feature);
+void orc_shape_ray_cast_batch(const orc_objects* objs, uint64_t n, const uint32_t* which, const real* rays, real* out, uint32_t* feat, uint8_t* hit);
+void orc_shape_contains_point_batch(const orc_objects* objs, uint64_t n, const uint32_t* which, const real* pts, uint8_t* inside);
 uint64_t orc_sim_ray_cast(orc_sim*, uint64_t n_rays, const real* rays, const uint32_t* groups, int first_only, uint32_t* idx, real* val,
                           uint32_t* feat, uint64_t cap);
 

@@ -246,6 +246,27 @@ class Oracle:
                                         C.c_void_p(out.ctypes.data), C.byref(feat))
         return (out[0], out[1:4].copy(), feat.value) if r else None
 
+    def shape_ray_cast_batch(self, scene, which, rays):
+        """rays[K,7] (origin, dir, max_toi) against objects which[K] -> (hit[K] u8, out[K,4] = toi + normal, feature[K])."""
+        o, keep = self._objects(scene)
+        which = np.ascontiguousarray(which, dtype=np.uint32)
+        rays = np.ascontiguousarray(rays, dtype=self.dtype).reshape(-1, 7)
+        out = np.zeros((len(which), 4), dtype=self.dtype)
+        feat = np.zeros(len(which), dtype=np.uint32)
+        hit = np.zeros(len(which), dtype=np.uint8)
+        self.lib.orc_shape_ray_cast_batch(C.byref(o), C.c_uint64(len(which)), C.c_void_p(which.ctypes.data), C.c_void_p(rays.ctypes.data),
+                                          C.c_void_p(out.ctypes.data), C.c_void_p(feat.ctypes.data), C.c_void_p(hit.ctypes.data))
+        return hit, out, feat
+
+    def shape_contains_point_batch(self, scene, which, pts):
+        o, keep = self._objects(scene)
+        which = np.ascontiguousarray(which, dtype=np.uint32)
+        pts = np.ascontiguousarray(pts, dtype=self.dtype).reshape(-1, 3)
+        inside = np.zeros(len(which), dtype=np.uint8)
+        self.lib.orc_shape_contains_point_batch(C.byref(o), C.c_uint64(len(which)), C.c_void_p(which.ctypes.data), C.c_void_p(pts.ctypes.data),
+                                                C.c_void_p(inside.ctypes.data))
+        return inside
+
     def aabb_toi_with_ray(self, minmax, origin, direction, max_toi, solid):
         mm = np.ascontiguousarray(minmax, dtype=self.dtype)
         o = np.ascontiguousarray(origin, dtype=self.dtype)

@@ -34,6 +34,11 @@ def shim():
 
 
 @pytest.fixture(scope="module")
+def query_shim():
+    return _build_shim("libquery_host.so", "query_host.cpp")
+
+
+@pytest.fixture(scope="module")
 def narrow_shim():
     return _build_shim("libnarrow_host.so", "narrow_host.cpp")
 
@@ -342,3 +347,50 @@ def test_device_persistent_manifold_source_matches_oracle(narrow_shim, oracle, n
             n_kept_ids += len(np.intersect1d(prev_ids, (np.repeat(np.arange(len(pairs)), np.diff(ooff)).astype(np.uint64) << np.uint64(32)) | oids))
         prev_ids = (np.repeat(np.arange(len(pairs)), np.diff(ooff)).astype(np.uint64) << np.uint64(32)) | oids
     assert n_events > 5 and n_kept_ids > 100  # contacts started / stopped, and contacts that kept their id across updates
+
+
+# ---- world queries: per-shape ray casts and point containment of query.cu -----------------------------------------------------------
+def _rays_at_objects(s, rng, k):
+    """k rays per call aimed at random objects: origins on a shell around the object (some inside it), directions towards it with
+    jitter (some pointing away), a mix of max_toi values."""
+    which = rng.integers(0, s.n, size=k).astype(np.uint32)
+    c = s.pos[which]
+    off = rng.normal(size=(k, 3))
+    off /= np.linalg.norm(off, axis=1, keepdims=True)
+    r = rng.choice([0.0, 0.2, 0.8, 2.0, 6.0], size=k)[:, None]
+    o = (c + off * r).astype(F)
+    d = (-off + rng.normal(0, 0.35, size=(k, 3))).astype(F)
+    d[rng.random(k) < 0.1] *= F(-1)
+    d[rng.random(k) < 0.3] *= F(3.7)  # the reference does not require unit directions
+    t = rng.choice([0.5, 3.0, 1e3, np.finfo(np.float32).max], size=k).astype(F)
+    return which, np.ascontiguousarray(np.concatenate([o, d, t[:, None]], axis=1), dtype=F)
+
+
+@pytest.mark.parametrize("seed,plane", [(1, True), (2, False), (3, True)])
+def test_device_shape_ray_casts_and_point_queries_match_oracle(query_shim, oracle, seed, plane):
+    """RayCast::toi_and_normal_with_ray(solid = true) per shape (ball, cuboid with the reference's face ids, plane, hull through the
+    GJK ray cast) and PointQuery::contains_point: hit / miss, feature ids and inside flags exact, toi and normals bit for bit."""
+    s = make_world_scene(600, 100 + seed, (1, 1, 1), side=6.0, n_hulls=32, plane=plane)
+    rng = np.random.default_rng(seed)
+    which, rays = _rays_at_objects(s, rng, 30000)
+    if plane:
+        which[:2000] = s.n - 1  # the plane
+    oc, keep = _ffi.pack_objects(s)
+    hc, keep2 = _ffi.pack_hull_library(s.hulls)
+    out = np.zeros((len(which), 4), dtype=F)
+    feat = np.zeros(len(which), dtype=np.uint32)
+    hit = np.zeros(len(which), dtype=np.uint8)
+    query_shim.shim_shape_ray_cast(C.byref(oc), C.byref(hc), C.c_uint64(len(which)), _ffi.ptr(which), _ffi.ptr(rays), _ffi.ptr(out), _ffi.ptr(feat), _ffi.ptr(hit))
+    ohit, oout, ofeat = oracle.shape_ray_cast_batch(s, which, rays)
+    assert np.array_equal(hit, ohit), int((hit != ohit).sum())
+    assert 0.2 < hit.mean() < 0.95
+    assert np.array_equal(feat, ofeat)
+    assert np.array_equal(out.view(np.uint32), oout.view(np.uint32)), int((out.view(np.uint32) != oout.view(np.uint32)).any(axis=1).sum())
+    for t in range(4):
+        assert hit[s.shape_type[which] == t].any() or (t == 3 and not plane)
+    # points: near / inside the objects
+    pts = (s.pos[which] + rng.normal(0, 0.3, size=(len(which), 3))).astype(F)
+    inside = np.zeros(len(which), dtype=np.uint8)
+    query_shim.shim_shape_contains_point(C.byref(oc), C.byref(hc), C.c_uint64(len(which)), _ffi.ptr(which), _ffi.ptr(pts), _ffi.ptr(inside))
+    want = oracle.shape_contains_point_batch(s, which, pts)
+    assert np.array_equal(inside, want) and 0.1 < want.mean() < 0.9
