@@ -8,7 +8,7 @@ import numpy as np
 
 sys.path.insert(0, ".")
 sys.path.insert(0, "tests")
-from ncollide_b200.scenes import make_world_scene  # noqa: E402
+from ncollide_b200.scenes import make_world_scene, with_sensors  # noqa: E402
 from ncollide_b200.world import Context, SteppingWorld  # noqa: E402
 from oracle.pyoracle import Oracle  # noqa: E402
 from sim_scenario import drive, drive_add_remove  # noqa: E402
@@ -37,7 +37,7 @@ class Dev:
         sel = np.repeat(keep, cnt)
         off = np.concatenate([[0], np.cumsum(cnt[keep])]).astype(np.uint32)
         return {"pairs": r["pairs"][keep], "algo": r["algo"][keep], "off": off, "contacts": r["contacts"][sel], "ids": r["ids"][sel],
-                "events": r["events"], "counts": r["counts"], "bp_pairs": len(r["pairs"])}
+                "events": r["events"], "counts": r["counts"], "bp_pairs": len(r["pairs"]), "prox": r["prox"][keep], "prox_events": r["prox_events"]}
 
 
 def ev_sorted(e):
@@ -53,6 +53,11 @@ def same(dev, orc):
                 return f"step {t}: {k}"
         if not np.array_equal(ev_sorted(a["events"]), ev_sorted(b["events"])):
             return f"step {t}: events"
+        if not np.array_equal(a["prox"], b["prox"]):  # proximity sensors
+            return f"step {t}: proximity statuses"
+        pa, pb = np.asarray(a["prox_events"]).reshape(-1, 4), np.asarray(b["prox_events"]).reshape(-1, 4)
+        if not np.array_equal(pa[np.lexsort(pa.T[::-1])] if len(pa) else pa, pb[np.lexsort(pb.T[::-1])] if len(pb) else pb):
+            return f"step {t}: proximity events"
         for f in ("f1", "f2"):
             if not np.array_equal(a["contacts"][f], b["contacts"][f]):
                 return f"step {t}: {f}"
@@ -81,10 +86,17 @@ def main():
         s = make_world_scene(n, seed, kinds, side=side, n_hulls=int(rng.integers(2, 16)), plane=bool(rng.random() < 0.3),
                              linear=float(rng.choice([0.0, 0.02, 0.1])), angular=float(rng.choice([0.0, 0.02, 0.2])),
                              margin=float(rng.choice([0.0, 0.02, 0.08])))
+        sensors = rng.random() < 0.4
+        if sensors:
+            with_sensors(s, float(rng.choice([0.1, 0.5, 1.0])), seed + 7, margin=float(rng.choice([0.0, 0.05, 0.3])))
+            if not s.query_kind.any():
+                s.query_kind = None
         if rng.random() < 0.5:
             extra_kinds = kinds if hull_kinds else (kinds[0], kinds[1], 0)
             extra = make_world_scene(max(6, n // 5), seed + 1, extra_kinds, side=side, hull_library=s.hulls,
                                      linear=float(s.query_limit[0]), angular=float(rng.choice([0.0, 0.05])), margin=s.margin)
+            if sensors or rng.random() < 0.2:  # sensors among the added objects (also into a world that had none)
+                with_sensors(extra, 0.5, seed + 9, margin=0.1)
             if s.n // 10 >= 1:
                 a = drive_add_remove(Dev(ctx, s), s, extra, steps=7, seed=seed)
                 b = drive_add_remove(orc.sim(s), s, extra, steps=7, seed=seed)
