@@ -206,3 +206,40 @@ def test_golden_fixtures_match_the_oracle(oracle):
         om = oracle.trimesh(z["verts"], z["tris"])
         t, face, n = om.ray_cast(z["origins"], z["dirs"], mode=0)
         assert np.array_equal(t, z["toi"]) and np.array_equal(face, z["face"]) and np.array_equal(n, z["normal"])
+
+
+# ---- bench.py contract (the reference arm runs on the CPU, so its JSON line can be checked here) ----------------------------------
+def test_bench_reference_arm_json_contract():
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--n-objects", "3000"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, "exactly ONE JSON line"
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
+    for k in ("metric", "value", "unit", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["vs_baseline"] is None and d["dtype"] == "f32" and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0
+
+
+def test_bench_native_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: the native arm must fail loudly (non-zero exit, no JSON metric line) when no CUDA device is usable."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--n-objects", "2000", "--no-rays", "--no-cpu",
+                        "--no-extras"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode != 0
+    assert not any(ln.startswith("{") and '"value"' in ln for ln in r.stdout.splitlines())
