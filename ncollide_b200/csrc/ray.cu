@@ -15,7 +15,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#ifndef NCB_HOST_SHIM  // tests/host_shim compiles slab_toi / ray_triangle for the host (test infrastructure)
 #include <cub/cub.cuh>
+#endif
 #include "ncb_internal.h"
 #include "vec.cuh"
 
@@ -38,6 +40,7 @@ struct ncb_mesh {
 namespace ncb {
 
 #define LEAF_BIT 0x80000000u
+#ifndef NCB_HOST_SHIM  // kernels and TMA helpers: CUDA only
 
 __global__ void __launch_bounds__(256) k_tri_aabb(const float* __restrict__ verts, const uint32_t* __restrict__ tris, uint32_t nt,
                                                   float4* __restrict__ lo, float4* __restrict__ hi) {
@@ -154,6 +157,8 @@ __global__ void __launch_bounds__(256) k_pack_tris(const float* __restrict__ ver
     out[3 * (size_t)pos + 2] = make_float4(verts[3 * ic], verts[3 * ic + 1], verts[3 * ic + 2], 0.f);
 }
 
+#endif  // NCB_HOST_SHIM
+
 // AABB::toi_with_ray(identity, ray, max_toi, solid = true) (ray_aabb.rs:13-50): returns tmin or -1 (miss).
 // `inv` holds 1 / dir per axis, computed once per ray: the reference recomputes the same IEEE quotient for every box.
 NCB_HD float slab_toi(float4 lo, float4 hi, V3 o, V3 d, V3 inv, float max_toi) {
@@ -233,6 +238,7 @@ NCB_HD bool ray_triangle(V3 a, V3 b, V3 c, V3 o, V3 dir, float& toi, V3& n_out, 
     return true;
 }
 
+#ifndef NCB_HOST_SHIM  // the traversal kernel and the host entry points: CUDA only
 struct RayArgs {
     const float4* nodes;
     const float4* leaf_lo;
@@ -582,3 +588,6 @@ int ncb_trimesh_ray_cast(ncb_mesh* m, const float* pose, uint32_t n_rays, const 
 }
 
 }  // extern "C"
+#else
+}  // namespace ncb (host shim: only slab_toi / ray_triangle above)
+#endif  // NCB_HOST_SHIM

@@ -34,6 +34,11 @@ def shim():
 
 
 @pytest.fixture(scope="module")
+def ray_shim():
+    return _build_shim("libray_host.so", "ray_host.cpp")
+
+
+@pytest.fixture(scope="module")
 def query_shim():
     return _build_shim("libquery_host.so", "query_host.cpp")
 
@@ -394,3 +399,27 @@ def test_device_shape_ray_casts_and_point_queries_match_oracle(query_shim, oracl
     query_shim.shim_shape_contains_point(C.byref(oc), C.byref(hc), C.c_uint64(len(which)), _ffi.ptr(which), _ffi.ptr(pts), _ffi.ptr(inside))
     want = oracle.shape_contains_point_batch(s, which, pts)
     assert np.array_equal(inside, want) and 0.1 < want.mean() < 0.9
+
+
+# ---- TriMesh ray casting: slab_toi / ray_triangle of ray.cu with the device's hit semantics, without the tree ------------------------
+@pytest.mark.parametrize("kind,posed", [("terrain", False), ("soup", False), ("soup", True)])
+def test_device_trimesh_ray_primitives_match_oracle(ray_shim, oracle, kind, posed):
+    """Minimum toi over {triangle AABB entered, triangle hit, toi <= max_toi}, ties -> smallest face, back faces as face + T, normalised
+    normal: the device's per-ray arithmetic against the oracle's brute-force mode — faces exact, toi and normals bit for bit."""
+    from ncollide_b200.scenes import make_ray_scene
+
+    rs = make_ray_scene(kind, 3000, 2500, seed=1204, random_pose=posed)
+    pose = rs.pose if posed else None
+    for max_toi in (np.finfo(np.float32).max, 12.0):
+        n = len(rs.origins)
+        toi = np.zeros(n, dtype=F)
+        face = np.zeros(n, dtype=np.uint32)
+        normal = np.zeros((n, 3), dtype=F)
+        ray_shim.shim_trimesh_ray_cast(C.c_uint32(len(rs.tris)), _ffi.ptr(rs.verts), _ffi.ptr(rs.tris), _ffi.ptr(np.ascontiguousarray(pose, dtype=F)) if posed else None,
+                                       C.c_uint64(n), _ffi.ptr(rs.origins), _ffi.ptr(rs.dirs), C.c_float(max_toi), _ffi.ptr(toi), _ffi.ptr(face), _ffi.ptr(normal))
+        otoi, oface, onormal = oracle.trimesh(rs.verts, rs.tris).ray_cast(rs.origins, rs.dirs, max_toi=max_toi, pose=pose, mode=1)
+        hit = otoi >= 0
+        assert hit.sum() >= 30
+        assert np.array_equal(face[hit], oface[hit]) and np.array_equal(toi >= 0, hit)
+        assert np.array_equal(toi[hit].view(np.uint32), otoi[hit].view(np.uint32))
+        assert np.array_equal(normal[hit].view(np.uint32), onormal[hit].view(np.uint32))
