@@ -55,4 +55,37 @@ void shim_contact_sm_sm(const ncb_objects* objs, const ncb_hull_library* lib, ui
     }
     delete e;
 }
+
+// Work statistics of the device EPA per penetrating pair (design data for kernel restructuring, scripts/epa_work_stats.py):
+// stats[4 k] = expansion steps, vertices, faces (incl. deleted), heap entries at the end of pair k's EPA run; 0s when GJK did not reach EPA.
+void shim_epa_work_stats(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_pairs, const uint32_t* pairs, uint32_t* stats) {
+    DevObjects o;
+    std::memset(&o, 0, sizeof o);
+    o.n = objs->n;
+    o.pos = objs->pos;
+    o.rot = reinterpret_cast<const float4*>(objs->rot);
+    o.type = objs->shape_type;
+    o.param = reinterpret_cast<const float4*>(objs->shape_param);
+    o.qlimit = objs->query_limit;
+    DevHulls H = hulls_from(lib);
+    EpaState* e = new EpaState;
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
+        Shape a = load_shape(o, H, i1, o.type[i1]), b = load_shape(o, H, i2, o.type[i2]);
+        Iso ma = load_iso(o, i1), mb = load_iso(o, i2);
+        Support ga = as_support(a), gb = as_support(b);
+        V3 d0;
+        if (!unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
+        V3 p1, p2, dir;
+        Simplex s;
+        uint32_t* st = stats + 4 * p;
+        st[0] = st[1] = st[2] = st[3] = 0;
+        if (gjk_closest_points(ma, ga, mb, gb, o.qlimit[i1] + o.qlimit[i2], d0, s, p1, p2, dir) != GJK_INTERSECTION) continue;
+        int status = epa_init(*e, ma, ga, mb, gb, s.dim, s.v, p1, p2, dir);
+        uint32_t steps = 0;
+        while (status == EPA_CONTINUE) status = epa_step(*e, ma, ga, mb, gb, p1, p2, dir), steps++;
+        st[0] = steps + 1, st[1] = (uint32_t)e->nverts, st[2] = (uint32_t)e->nfaces, st[3] = (uint32_t)e->nheap;
+    }
+    delete e;
+}
 }
