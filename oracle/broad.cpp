@@ -53,6 +53,18 @@ AABB shape_aabb(const Objects& o, uint32_t i) {
             }
             return a;
         }
+        case CAPSULE: {  // aabb_support_map.rs:35-45 -> aabb_utils.rs:9-31 (support points along +-x, +-y, +-z) with capsule.rs:72-85
+            real hh = o.shape_param[4 * i], r = o.shape_param[4 * i + 1];
+            auto support = [&](V3 dir) {
+                V3 ld = iso_inv_vec(m, dir);
+                V3 d = normalize(ld);
+                return iso_mul_point(m, v3(0, std::copysign(hh, d.y), 0) + d * r);
+            };
+            AABB a;
+            a.maxs = v3(support(v3(1, 0, 0)).x, support(v3(0, 1, 0)).y, support(v3(0, 0, 1)).z);
+            a.mins = v3(support(v3(-1, 0, 0)).x, support(v3(0, -1, 0)).y, support(v3(0, 0, -1)).z);
+            return a;
+        }
         default: {  // PLANE
             real mx = FMAX * real(0.5);
             return {v3(-mx, -mx, -mx), v3(mx, mx, mx)};

@@ -12,7 +12,8 @@ namespace orc {
 
 // A support-mapped operand: cuboid, convex hull, ball (for one-shot queries) or ConstantOrigin.
 struct Support {
-    enum Kind { S_CUBOID, S_HULL, S_BALL, S_ORIGIN, S_CYLINDER } kind;  // S_CYLINDER: only for the reference's cylinder / cuboid KAT
+    // S_CYLINDER: only for the reference's cylinder / cuboid KAT.  S_SEGMENT / S_CAPSULE: half_height in he.x (capsule radius in radius).
+    enum Kind { S_CUBOID, S_HULL, S_BALL, S_ORIGIN, S_CYLINDER, S_SEGMENT, S_CAPSULE } kind;
     V3 he;
     real radius;
     Hull hull;
@@ -39,6 +40,14 @@ struct Support {
                 vres.y = std::copysign(he.x, dir.y);
                 return vres;
             }
+            case S_SEGMENT: {  // segment.rs:182-190 with a = (0, -hh, 0), b = (0, hh, 0)
+                V3 a = v3(0, -he.x, 0), b = v3(0, he.x, 0);
+                return dot(a, dir) > dot(b, dir) ? a : b;
+            }
+            case S_CAPSULE: {  // capsule.rs:72-85: local_support_point_toward(normalize(dir))
+                V3 d = normalize(dir);
+                return v3(0, std::copysign(he.x, d.y), 0) + d * radius;
+            }
             case S_BALL:  // ball.rs:41-48: local_support_point_toward(normalize(dir)) = dir * radius
                 return normalize(dir) * radius;
             default:
@@ -53,6 +62,10 @@ struct Support {
     }
     V3 support_point_toward(const Iso& m, V3 unit_dir) const {  // support_map.rs:32-35; ball.rs:36-38 (no normalisation)
         if (kind == S_BALL) return m.t + unit_dir * radius;
+        if (kind == S_CAPSULE) {  // capsule.rs:79-84 through the default support_point_toward: the local direction is not re-normalised
+            V3 ld = iso_inv_vec(m, unit_dir);
+            return iso_mul_point(m, v3(0, std::copysign(he.x, ld.y), 0) + ld * radius);
+        }
         return support_point(m, unit_dir);
     }
 };

@@ -390,13 +390,117 @@ static V3 hull_feature_normal(const Hull& H, uint32_t f) {  // convex.rs:463-485
 }
 
 // ---------------------------------------------------------------------------------------------
+// Segment as a ConvexPolyhedron (segment.rs:152-375, dim3), for the segment of a Capsule: a = (0, -hh, 0), b = (0, hh, 0)
+// (capsule.rs:53-61).  Groundwork for SURVEY §8f N3 (capsule generators); oracle only so far.
+// ---------------------------------------------------------------------------------------------
+static void segment_support_face_toward(real hh, const Iso& m, Feature& out) {  // segment.rs:286-299
+    out.clear();
+    out.push(v3(0, -hh, 0), fid(F_VERTEX, 0));
+    out.push(v3(0, hh, 0), fid(F_VERTEX, 1));
+    out.edges_id.push_back(fid(F_EDGE, 0));
+    out.feature_id = fid(F_EDGE, 0);
+    out.transform_by(m);
+}
+static void segment_support_feature_toward(real hh, const Iso& m, V3 dir, real eps, Feature& out) {  // segment.rs:301-341
+    out.clear();
+    V3 a = iso_mul_point(m, v3(0, -hh, 0)), b = iso_mul_point(m, v3(0, hh, 0));  // self.transformed(transform)
+    real ceps = std::sin(eps);
+    V3 seg_dir;
+    if (!unit_try_new(b - a, EPS, &seg_dir)) return;
+    real cang = dot(dir, seg_dir);
+    if (cang > ceps) {
+        out.feature_id = fid(F_VERTEX, 1);
+        out.push(b, fid(F_VERTEX, 1));
+    } else if (cang < -ceps) {
+        out.feature_id = fid(F_VERTEX, 0);
+        out.push(a, fid(F_VERTEX, 0));
+    } else {
+        out.push(a, fid(F_VERTEX, 0));
+        out.push(b, fid(F_VERTEX, 1));
+        out.edges_id.push_back(fid(F_EDGE, 0));
+        out.feature_id = fid(F_EDGE, 0);
+    }
+}
+static V3 segment_feature_normal(real hh, uint32_t f) {  // segment.rs:237-284
+    V3 direction;
+    if (!unit_try_new(v3(0, hh, 0) - v3(0, -hh, 0), EPS, &direction)) return v3(0, 1, 0);
+    switch (fid_kind(f)) {
+        case F_VERTEX:
+            return fid_id(f) == 0 ? direction : -direction;
+        case F_EDGE: {
+            int iamin = 0;  // first component of smallest absolute value
+            for (int k = 1; k < 3; ++k)
+                if (std::fabs(direction[k]) < std::fabs(direction[iamin])) iamin = k;
+            V3 normal = v3(0, 0, 0);
+            normal[iamin] = 1;
+            normal = normal - direction * direction[iamin];
+            return normalize(normal);
+        }
+        default: {  // Face(id): the 2-D formula, z left at 0
+            V3 dir = fid_id(f) == 0 ? v3(direction.y, -direction.x, 0) : v3(-direction.y, direction.x, 0);
+            return dir;
+        }
+    }
+}
+// PointQuery::project_point_with_feature for Segment (point_segment.rs:14-40,50-91)
+static void segment_project_point_with_feature(real hh, const Iso& m, V3 pt, bool* inside, V3* proj_out, uint32_t* feature) {
+    V3 a = v3(0, -hh, 0), b = v3(0, hh, 0);
+    V3 ls_pt = iso_inv_point(m, pt);
+    V3 ab = b - a, ap = ls_pt - a;
+    real ab_ap = dot(ab, ap), sqnab = norm_squared(ab);
+    V3 proj;
+    if (ab_ap <= 0) {
+        *feature = fid(F_VERTEX, 0);
+        proj = iso_mul_point(m, a);
+    } else if (ab_ap >= sqnab) {
+        *feature = fid(F_VERTEX, 1);
+        proj = iso_mul_point(m, b);
+    } else {
+        real u = ab_ap / sqnab;
+        *feature = fid(F_EDGE, 0);
+        proj = iso_mul_point(m, a + ab * u);
+    }
+    *inside = relative_eq_v3(proj, pt);
+    *proj_out = proj;
+}
+
+// ContactPreprocessor of a capsule (capsule.rs:87-132): the sub-detector works on the capsule's segment with the prediction enlarged
+// by the radius; every contact it produces is moved out to the capsule's surface and its segment feature is renamed.
+struct Preproc {
+    bool active = false;
+    real radius = 0;
+    // returns false when the contact must be ignored
+    bool process(Contact& c, uint32_t& f1, uint32_t& f2, bool is_first) const {
+        if (!active) return true;
+        uint32_t f = is_first ? f1 : f2, actual;
+        switch (fid_kind(f)) {
+            case F_VERTEX: actual = fid(F_FACE, fid_id(f)); break;
+            case F_EDGE: actual = fid(F_FACE, 2); break;
+            case F_FACE: actual = fid(F_FACE, 2 + fid_id(f)); break;
+            default: return false;
+        }
+        if (is_first) {
+            f1 = actual;
+            c.world1 = c.world1 + c.normal * radius;
+            c.depth += radius;
+        } else {
+            f2 = actual;
+            c.world2 = c.world2 - c.normal * radius;
+            c.depth += radius;
+        }
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // Shapes
 // ---------------------------------------------------------------------------------------------
 struct Shape {
     uint32_t type;
     real radius;
-    V3 he;      // cuboid half extents / plane normal
+    V3 he;      // cuboid half extents / plane normal / (half_height, radius, 0) of a capsule
     Hull hull;
+    real hh = 0;  // capsule / segment half height
 };
 static Shape get_shape(const Objects& o, uint32_t i) {
     Shape s;
@@ -404,6 +508,7 @@ static Shape get_shape(const Objects& o, uint32_t i) {
     s.radius = o.shape_param[4 * i];
     s.he = o.p3(i);
     if (s.type == HULL) s.hull = hull_view(o.hulls, o.hull_id(i));
+    if (s.type == CAPSULE) s.hh = o.shape_param[4 * i], s.radius = o.shape_param[4 * i + 1];
     return s;
 }
 static Support as_support(const Shape& s) {
@@ -415,20 +520,30 @@ static Support as_support(const Shape& s) {
     else if (s.type == HULL) {
         g.kind = Support::S_HULL;
         g.hull = s.hull;
+    } else if (s.type == SEGMENT) {
+        g.kind = Support::S_SEGMENT;
+        g.he = v3(s.hh, 0, 0);
+    } else if (s.type == CAPSULE) {
+        g.kind = Support::S_CAPSULE;
+        g.he = v3(s.hh, 0, 0);
     } else
         g.kind = Support::S_BALL;
     return g;
 }
-static bool is_convex_polyhedron(const Shape& s) { return s.type == CUBOID || s.type == HULL; }
+static bool is_convex_polyhedron(const Shape& s) { return s.type == CUBOID || s.type == HULL || s.type == SEGMENT; }
 static void support_face_toward(const Shape& s, const Iso& m, V3 dir, Feature& out) {
     if (s.type == CUBOID)
         cuboid_support_face_toward(s.he, m, dir, out);
+    else if (s.type == SEGMENT)
+        segment_support_face_toward(s.hh, m, out);
     else
         hull_support_face_toward(s.hull, m, dir, out);
 }
 static void support_feature_toward(const Shape& s, const Iso& m, V3 dir, real angle, Feature& out) {
     if (s.type == CUBOID)
         cuboid_support_feature_toward(s.he, m, dir, angle, out);
+    else if (s.type == SEGMENT)
+        segment_support_feature_toward(s.hh, m, dir, angle, out);
     else
         hull_support_feature_toward(s.hull, m, dir, angle, out);
 }
@@ -496,6 +611,12 @@ struct Manifold {
             else
                 slab[i].remaining -= 1;
         }
+    }
+    // preprocessor1 / preprocessor2 of :171-181 (only the capsule's exists on the path); a rejected contact is dropped
+    void push(Contact c, uint32_t f1, uint32_t f2, V3 tracking_pt, const Preproc* pp1, const Preproc* pp2) {
+        if (pp1 && !pp1->process(c, f1, f2, true)) return;
+        if (pp2 && !pp2->process(c, f1, f2, false)) return;
+        push(c, f1, f2, tracking_pt);
     }
     void push(const Contact& c, uint32_t f1, uint32_t f2, V3 tracking_pt) {  // :165-236
         const real threshold = real(0.02);
@@ -570,7 +691,9 @@ static void gen_plane_ball(const Iso& m1, V3 plane_n, const Iso& m2, real radius
 }
 
 // plane_convex_polyhedron_manifold_generator.rs:29-81
-static void gen_plane_convex(const Iso& m1, V3 plane_n, const Iso& m2, const Shape& cp, real prediction, bool flip, Manifold& mf) {
+// pp1 / pp2: the preprocessors of (m1, plane) / (m2, cp) as do_update_to receives them
+static void gen_plane_convex(const Iso& m1, V3 plane_n, const Iso& m2, const Shape& cp, real prediction, bool flip, Manifold& mf,
+                             const Preproc* pp1 = nullptr, const Preproc* pp2 = nullptr) {
     V3 n = iso_mul_vec(m1, plane_n);
     V3 pc = m1.t;
     Feature feat;
@@ -584,9 +707,9 @@ static void gen_plane_convex(const Iso& m1, V3 plane_n, const Iso& m2, const Sha
             V3 local2 = iso_inv_point(m2, world2);
             uint32_t f2 = feat.vertices_id[i];
             if (!flip)
-                mf.push({world1, world2, n, -dist}, FACE0, f2, local2);
+                mf.push({world1, world2, n, -dist}, FACE0, f2, local2, pp1, pp2);
             else
-                mf.push({world2, world1, -n, -dist}, f2, FACE0, local2);
+                mf.push({world2, world1, -n, -dist}, f2, FACE0, local2, pp2, pp1);
         }
     }
 }
@@ -637,13 +760,15 @@ static void hull_project_point_with_feature(const Hull& H, const Iso& m, V3 poin
 
 // ball_convex_polyhedron_manifold_generator.rs:28-122.  (m1, ball) (m2, convex polyhedron)
 static void gen_ball_convex(const Iso& m1, real radius, const Iso& m2, const Shape& cp, real prediction, bool flip, Manifold& mf,
-                            GJKStats* st) {
+                            GJKStats* st, const Preproc* pp1 = nullptr, const Preproc* pp2 = nullptr) {
     V3 ball_center = m1.t;
     bool inside;
     V3 world2;
     uint32_t f2;
     if (cp.type == CUBOID)
         cuboid_project_point_with_feature(cp.he, m2, ball_center, &inside, &world2, &f2);
+    else if (cp.type == SEGMENT)
+        segment_project_point_with_feature(cp.hh, m2, ball_center, &inside, &world2, &f2);
     else
         hull_project_point_with_feature(cp.hull, m2, ball_center, &inside, &world2, &f2, st);
     V3 dpt = world2 - ball_center;
@@ -661,15 +786,15 @@ static void gen_ball_convex(const Iso& m1, real radius, const Iso& m2, const Sha
     } else {
         if (f2 == FID_UNKNOWN) return;
         depth = radius;
-        normal = -(cp.type == CUBOID ? cuboid_feature_normal(f2) : hull_feature_normal(cp.hull, f2));
+        normal = -(cp.type == CUBOID ? cuboid_feature_normal(f2) : (cp.type == SEGMENT ? segment_feature_normal(cp.hh, f2) : hull_feature_normal(cp.hull, f2)));
     }
     if (depth >= -prediction) {
         V3 world1 = ball_center + normal * radius;
         // geometry of f2: an Edge feature needs cp.edge(f2) (cannot fail); nothing else can reject the contact
         if (!flip)
-            mf.push({world1, world2, normal, depth}, FACE0, f2, v3(0, 0, 0));
+            mf.push({world1, world2, normal, depth}, FACE0, f2, v3(0, 0, 0), pp1, pp2);
         else
-            mf.push({world2, world1, -normal, depth}, f2, FACE0, v3(0, 0, 0));
+            mf.push({world2, world1, -normal, depth}, f2, FACE0, v3(0, 0, 0), pp2, pp1);
     }
 }
 
@@ -823,7 +948,8 @@ static bool feature_ok_for_manifold(const Feature& ft, uint32_t f) {
 // convex_polyhedron_convex_polyhedron_manifold_generator.rs:83-167.  last_gjk_dir: the generator's persistent
 // direction (nullptr / !*has_dir = fresh generator, None); updated like :106 and :139.
 static void gen_convex_convex(const Iso& ma, const Shape& a, const Iso& mb, const Shape& b, real pred_linear, real ang1, real ang2,
-                              Manifold& mf, GJKStats* st, V3* last_gjk_dir = nullptr, bool* has_dir = nullptr) {
+                              Manifold& mf, GJKStats* st, V3* last_gjk_dir = nullptr, bool* has_dir = nullptr, const Preproc* pp1 = nullptr,
+                              const Preproc* pp2 = nullptr) {
     Support ga = as_support(a), gb = as_support(b);
     VoronoiSimplex simplex;
     const V3* init = (last_gjk_dir && has_dir && *has_dir) ? last_gjk_dir : nullptr;
@@ -856,12 +982,13 @@ static void gen_convex_convex(const Iso& ma, const Shape& a, const Iso& mb, cons
         if (!feature_ok_for_manifold(m1, nc.f1)) continue;
         if (!feature_ok_for_manifold(m2, nc.f2)) continue;
         V3 local1 = iso_inv_point(ma, nc.c.world1);
-        mf.push(nc.c, nc.f1, nc.f2, local1);
+        mf.push(nc.c, nc.f1, nc.f2, local1, pp1, pp2);
     }
 }
 
 // default_contact_dispatcher.rs:27-97
-enum Algo : uint8_t { A_NONE = 0, A_BALL_BALL, A_PLANE_BALL, A_PLANE_CONVEX, A_BALL_CONVEX, A_CONVEX_CONVEX };
+enum Algo : uint8_t { A_NONE = 0, A_BALL_BALL, A_PLANE_BALL, A_PLANE_CONVEX, A_BALL_CONVEX, A_CONVEX_CONVEX, A_PROXIMITY_RESERVED,
+                      A_CAPSULE_CAPSULE = 7, A_CAPSULE_SHAPE = 8 };
 
 static uint8_t generate_contacts(const Objects& o, uint32_t i1, uint32_t i2, Manifold& mf, GJKStats* st, V3* last_gjk_dir = nullptr,
                                  bool* has_dir = nullptr) {
@@ -870,34 +997,56 @@ static uint8_t generate_contacts(const Objects& o, uint32_t i1, uint32_t i2, Man
     // query_type.rs:39-51
     real linear = o.query_limit[i1] + o.query_limit[i2];
     real ang1 = o.ang_pred[i1], ang2 = o.ang_pred[i2];
+    // CapsuleCapsuleManifoldGenerator (capsule_capsule_manifold_generator.rs:24-55) / CapsuleShapeManifoldGenerator
+    // (capsule_shape_manifold_generator.rs:23-75): the capsule is replaced by its segment, the linear prediction grows by the radius,
+    // the capsule's preprocessor is attached on that side, and the sub-detector the dispatcher picks for (segment, other) /
+    // (other, segment) runs with the shapes in their original order (`flip` only restores that order).
+    Preproc ppa, ppb;
+    uint8_t capsule_algo = A_NONE;
+    if (a.type == CAPSULE || b.type == CAPSULE) {
+        capsule_algo = (a.type == CAPSULE && b.type == CAPSULE) ? A_CAPSULE_CAPSULE : A_CAPSULE_SHAPE;
+        if (a.type == CAPSULE) {
+            ppa.active = true, ppa.radius = a.radius;
+            linear = linear + a.radius;
+            a.type = SEGMENT;
+        }
+        if (b.type == CAPSULE) {
+            ppb.active = true, ppb.radius = b.radius;
+            linear = linear + b.radius;
+            b.type = SEGMENT;
+        }
+    }
+    const Preproc* pa = ppa.active ? &ppa : nullptr;
+    const Preproc* pb = ppb.active ? &ppb : nullptr;
     bool a_ball = a.type == BALL, b_ball = b.type == BALL, a_plane = a.type == PLANE, b_plane = b.type == PLANE;
     bool a_sm = a.type != PLANE, b_sm = b.type != PLANE;  // is_support_map
+    uint8_t algo = A_NONE;
     if (a_ball && b_ball) {
         gen_ball_ball(ma, a.radius, mb, b.radius, linear, mf);
-        return A_BALL_BALL;
+        algo = A_BALL_BALL;
     } else if (a_plane && b_ball) {
         gen_plane_ball(ma, a.he, mb, b.radius, linear, false, mf);
-        return A_PLANE_BALL;
+        algo = A_PLANE_BALL;
     } else if (a_ball && b_plane) {
         gen_plane_ball(mb, b.he, ma, a.radius, linear, true, mf);
-        return A_PLANE_BALL;
+        algo = A_PLANE_BALL;
     } else if (a_plane && b_sm) {
-        gen_plane_convex(ma, a.he, mb, b, linear, false, mf);
-        return A_PLANE_CONVEX;
+        gen_plane_convex(ma, a.he, mb, b, linear, false, mf, pa, pb);
+        algo = A_PLANE_CONVEX;
     } else if (b_plane && a_sm) {
-        gen_plane_convex(mb, b.he, ma, a, linear, true, mf);
-        return A_PLANE_CONVEX;
+        gen_plane_convex(mb, b.he, ma, a, linear, true, mf, pb, pa);
+        algo = A_PLANE_CONVEX;
     } else if (a_ball && is_convex_polyhedron(b)) {
-        gen_ball_convex(ma, a.radius, mb, b, linear, false, mf, st);
-        return A_BALL_CONVEX;
+        gen_ball_convex(ma, a.radius, mb, b, linear, false, mf, st, pa, pb);
+        algo = A_BALL_CONVEX;
     } else if (b_ball && is_convex_polyhedron(a)) {
-        gen_ball_convex(mb, b.radius, ma, a, linear, true, mf, st);
-        return A_BALL_CONVEX;
+        gen_ball_convex(mb, b.radius, ma, a, linear, true, mf, st, pb, pa);
+        algo = A_BALL_CONVEX;
     } else if (is_convex_polyhedron(a) && is_convex_polyhedron(b)) {
-        gen_convex_convex(ma, a, mb, b, linear, ang1, ang2, mf, st, last_gjk_dir, has_dir);
-        return A_CONVEX_CONVEX;
+        gen_convex_convex(ma, a, mb, b, linear, ang1, ang2, mf, st, last_gjk_dir, has_dir, pa, pb);
+        algo = A_CONVEX_CONVEX;
     }
-    return A_NONE;  // e.g. plane x plane: pair kept by the broad phase, no interaction edge
+    return capsule_algo != A_NONE ? capsule_algo : algo;  // A_NONE e.g. plane x plane: pair kept by the broad phase, no interaction edge
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1634,12 +1783,17 @@ static RayHit ray_cast_plane(V3 pn, const Iso& m, V3 o_w, V3 d_w, real max_toi) 
     }
     return h;
 }
+static RayHit ray_cast_support_map(const Support& g, const Iso& m, V3 o_w, V3 d_w, real max_toi);
 static RayHit ray_cast_hull(const Hull& H, const Iso& m, V3 o_w, V3 d_w, real max_toi) {
-    RayHit h;
-    V3 o = iso_inv_point(m, o_w), d = iso_inv_vec(m, d_w);
     Support g;
     g.kind = Support::S_HULL;
     g.hull = H;
+    return ray_cast_support_map(g, m, o_w, d_w, max_toi);
+}
+// ray_support_map.rs:15-35,114-137 (ConvexHull and Capsule share it): gjk::cast_ray in the shape's local frame, solid = true
+static RayHit ray_cast_support_map(const Support& g, const Iso& m, V3 o_w, V3 d_w, real max_toi) {
+    RayHit h;
+    V3 o = iso_inv_point(m, o_w), d = iso_inv_vec(m, d_w);
     Support origin;
     origin.kind = Support::S_ORIGIN;
     Iso id = iso_identity();
@@ -1660,6 +1814,7 @@ static RayHit shape_ray_cast(const Objects& o, uint32_t i, V3 ro, V3 rd, real ma
         case BALL: return ray_cast_ball(m.t, s.radius, ro, rd, max_toi);
         case CUBOID: return ray_cast_cuboid(s.he, m, ro, rd, max_toi);
         case HULL: return ray_cast_hull(s.hull, m, ro, rd, max_toi);
+        case CAPSULE: return ray_cast_support_map(as_support(s), m, ro, rd, max_toi);
         default: return ray_cast_plane(s.he, m, ro, rd, max_toi);
     }
 }
@@ -1703,6 +1858,16 @@ static bool shape_contains_point(const Objects& o, uint32_t h, V3 pt) {
         V3 proj;
         hull_project_point(sh.hull, m, pt, &inside, &proj, nullptr);
         return inside;
+    }
+    if (sh.type == CAPSULE) {  // point_capsule.rs:6-33 (contains_point = project_point(.., solid = true).is_inside)
+        bool seg_inside;
+        V3 proj;
+        uint32_t f;
+        segment_project_point_with_feature(sh.hh, m, pt, &seg_inside, &proj, &f);
+        V3 dir;
+        real dist;
+        if (unit_try_new_and_get(pt - proj, EPS, &dir, &dist)) return dist <= sh.radius;
+        return true;
     }
     return dot(sh.he, iso_inv_point(m, pt)) <= real(0);
 }

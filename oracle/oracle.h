@@ -3,6 +3,8 @@
  * used to check the CUDA path and as bench.py's cpu_baseline.  The product never links this.
  * The Rust reference cannot be built in this image (no rustc/cargo; nalgebra not vendored), so this
  * is a restatement ("port"), pinned against the reference's own known-answer tests (tests/test_oracle_kat.py).
+ * PARITY UNPINNED for shape_type 4 (Capsule: half_height, radius in shape_param; groundwork for SURVEY.md §8f N3): the reference has
+ * no test that involves a capsule; that part is checked against closed-form geometry only (tests/test_oracle_capsule.py).
  */
 #ifndef ORC_ORACLE_H
 #define ORC_ORACLE_H
@@ -32,7 +34,7 @@ typedef struct orc_objects {
     uint32_t n;
     const real* pos;         /* 3 per object */
     const real* rot;         /* 4 per object, (i,j,k,w) */
-    const uint32_t* shape_type; /* 0 ball, 1 cuboid, 2 convex hull, 3 plane */
+    const uint32_t* shape_type; /* 0 ball, 1 cuboid, 2 convex hull, 3 plane, 4 capsule (oracle only so far) */
     const real* shape_param; /* 4 per object: r | half extents | hull id bits | plane normal */
     const uint32_t* groups;   /* 3 per object or NULL */
     const real* query_limit;

@@ -9,7 +9,9 @@
 
 namespace orc {
 
-enum ShapeType : uint32_t { BALL = 0, CUBOID = 1, HULL = 2, PLANE = 3 };
+// CAPSULE (oracle only so far: groundwork for SURVEY §8f N3): shape_param = (half_height, radius), axis = local y (capsule.rs:10-17).
+// SEGMENT never appears in a scene: it is the capsule's segment handed to the sub-detectors (capsule.rs:53-61).
+enum ShapeType : uint32_t { BALL = 0, CUBOID = 1, HULL = 2, PLANE = 3, CAPSULE = 4, SEGMENT = 5 };
 
 // FeatureId (shape/feature_id.rs): kind in the top 2 bits, id in the low 30.
 enum : uint32_t { F_VERTEX = 0u, F_EDGE = 1u, F_FACE = 2u, F_UNKNOWN = 3u };
