@@ -280,6 +280,12 @@ int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* o) {
         CK(cudaMemcpyAsync(ctx->param.p, o->shape_param, 16 * (size_t)n, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->qlimit.p, o->query_limit, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
     }
+    {
+        // only the four shapes of the path exist on the device (a larger id would be masked into one of them): fail loudly
+        uint32_t any = 0;
+        for (uint32_t i = 0; i < n; ++i) any |= o->shape_type[i];
+        REQUIRE((any & ~3u) == 0, NCB_ERR_UNSUPPORTED, "ncb_set_objects: shape_type must be NCB_SHAPE_BALL / CUBOID / CONVEX_HULL / PLANE");
+    }
     ctx->has_groups = o->groups != nullptr;
     if (o->groups && n) {
         CK(ctx->groups.reserve(3 * (size_t)n));

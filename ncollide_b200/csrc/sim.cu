@@ -649,6 +649,11 @@ int ncb_sim_add_with_query_types(ncb_sim* sim, const ncb_objects* objs, const ui
     uint32_t m = objs->n;
     if (m == 0) return NCB_OK;
     if (!(objs->pos && objs->rot && objs->shape_type && objs->shape_param && objs->query_limit && objs->ang_pred)) return NCB_ERR_ARG;
+    for (uint32_t k = 0; k < m; ++k)
+        if (objs->shape_type[k] > NCB_SHAPE_PLANE) {
+            ctx->err = "ncb_sim_add: shape_type must be NCB_SHAPE_BALL / CUBOID / CONVEX_HULL / PLANE";
+            return NCB_ERR_UNSUPPORTED;
+        }
     for (uint32_t k = 0; kinds && k < m; ++k)
         if (kinds[k] > 1) {
             ctx->err = "ncb_sim_add_with_query_types: kind must be 0 (Contacts) or 1 (Proximity)";

@@ -1392,6 +1392,8 @@ struct orc_sim {
 
 static uint8_t dispatch_algo(const Objects& o, uint32_t i1, uint32_t i2) {  // default_contact_dispatcher.rs:27-97
     uint32_t a = o.shape_type[i1], b = o.shape_type[i2];
+    if (a == CAPSULE && b == CAPSULE) return A_CAPSULE_CAPSULE;
+    if (a == CAPSULE || b == CAPSULE) return A_CAPSULE_SHAPE;
     if (a == BALL && b == BALL) return A_BALL_BALL;
     if ((a == PLANE && b == BALL) || (a == BALL && b == PLANE)) return A_PLANE_BALL;
     if (a == PLANE && b == PLANE) return A_NONE;

@@ -218,3 +218,36 @@ def test_world_with_capsules_is_consistent(oracle):
     assert np.allclose(np.linalg.norm(c["normal"], axis=1), 1, atol=1e-5)
     assert np.allclose(-np.einsum("ij,ij->i", c["normal"], c["world2"] - c["world1"]), c["depth"], atol=2e-4)
     assert np.all(c["depth"] >= -0.0401 - 1e-5)
+
+
+def test_stepping_world_with_capsules(oracle):
+    """The oracle's stepping world accepts capsules: step 1 equals the fresh-world narrow phase on the same pairs, later steps keep
+    contact ids for resting capsule contacts."""
+    import sys, os
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    from sim_scenario import drive
+
+    rng = np.random.default_rng(8)
+    n = 300
+    q = random_unit_quaternions(rng, n)
+    objs = []
+    for i in range(n):
+        t = (BALL, CUBOID, CAPSULE)[i % 3]
+        param = {BALL: [rng.uniform(0.25, 0.5)], CUBOID: list(rng.uniform(0.25, 0.5, 3)), CAPSULE: [rng.uniform(0.2, 0.5), rng.uniform(0.15, 0.3)]}[t]
+        objs.append((t, param, rng.uniform(0, 4.0, 3), q[i]))
+    s = scene_of(objs, ql=0.02)
+    s.margin = 0.02
+    s.groups = None
+    log = drive(oracle.sim(s), s, steps=5, seed=4)
+    r0 = log[0]
+    c, off, algo, _ = oracle.narrow_phase(s, r0["pairs"])
+    assert np.array_equal(algo, r0["algo"]) and np.array_equal(off, r0["off"]) and (algo >= 7).sum() > 50
+    for name in ("world1", "world2", "normal", "depth", "f1", "f2"):
+        assert np.array_equal(c[name], r0["contacts"][name])
+    kept = 0
+    for a, b in zip(log[:-1], log[1:]):
+        ka = {(tuple(p), i) for p, lo, hi in zip(a["pairs"].tolist(), a["off"][:-1], a["off"][1:]) for i in a["ids"][lo:hi].tolist()}
+        kb = {(tuple(p), i) for p, lo, hi in zip(b["pairs"].tolist(), b["off"][:-1], b["off"][1:]) for i in b["ids"][lo:hi].tolist()}
+        kept += len(ka & kb)
+    assert kept > 100

@@ -41,3 +41,18 @@ def test_sharded_update_with_sensors(oracle, world, mk):
     o_c, o_off, o_algo, o_prox = oracle.narrow_phase_kinds(s, full.pairs)
     assert np.array_equal(full.proximity, o_prox) and np.array_equal(full.pair_algo, o_algo)
     ctx.close()
+
+
+def test_device_rejects_shapes_it_does_not_know():
+    """shape_type 4 (capsule: oracle groundwork only) must be refused at the boundary, not masked into another shape."""
+    from ncollide_b200._ffi import NcbError
+    from ncollide_b200.world import Context
+
+    s = make_world_scene(50, 1, (1, 1, 0), side=3.0)
+    ctx = Context(0)
+    ctx.set_scene(s)  # fine
+    s.shape_type = s.shape_type.copy()
+    s.shape_type[7] = 4
+    with pytest.raises(NcbError, match="shape_type"):
+        ctx.set_objects(s)
+    ctx.close()
