@@ -135,7 +135,8 @@ int ncb_synchronize(ncb_ctx* ctx);
 /* ---- shapes and objects -------------------------------------------------------------------------------------- */
 /* ConvexHull tables (host pointers), copied to the device once. */
 int ncb_set_hulls(ncb_ctx* ctx, const ncb_hull_library* lib);
-/* CollisionWorld::add for a whole world (pipeline/world.rs:66-96): host SoA -> device. */
+/* CollisionWorld::add for a whole world (pipeline/world.rs:66-96): host SoA -> device.  NCB_ERR_UNSUPPORTED when a shape_type is not
+ * one of the four NCB_SHAPE_* values (capsules, composite shapes: SURVEY.md §8f N3, not on the device yet). */
 int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* objs);
 /* CollisionObject::set_position for all objects (pipeline/object/collision_object.rs:186-190). */
 int ncb_set_positions(ncb_ctx* ctx, uint32_t n, const float* pos, const float* rot);
