@@ -19,6 +19,7 @@ F32 = np.float32
 EPS = np.finfo(np.float32).eps
 
 BALL, CUBOID, HULL, PLANE = 0, 1, 2, 3
+CAPSULE = 4  # known to the oracle only so far; the device boundary refuses it with NCB_ERR_UNSUPPORTED
 
 
 def _dot(a, b):
@@ -53,6 +54,19 @@ class Ball:
 
     def param(self):
         return np.array([self.radius, 0, 0, 0], dtype=F32)
+
+
+class Capsule:
+    """``Capsule::new(half_height, radius)`` (shape/capsule.rs:19-30), principal axis = local y.  Not on the device yet: a world
+    that contains one fails loudly in ``ncb_set_objects`` (no silent fallback); the CPU oracle handles it (tests/test_oracle_capsule.py)."""
+
+    type_id = CAPSULE
+
+    def __init__(self, half_height, radius):
+        self.half_height, self.radius = F32(half_height), F32(radius)
+
+    def param(self):
+        return np.array([self.half_height, self.radius, 0, 0], dtype=F32)
 
 
 class Cuboid:
