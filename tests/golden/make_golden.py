@@ -80,6 +80,29 @@ def make_proximity(o):
           "statuses;", [len(r["prox_events"]) for r in log], "proximity events per step")
 
 
+def make_capsules(o):
+    """capsule_mixed_plane_300.npz (SURVEY §8f N3 groundwork): balls / cuboids / capsules and a plane — fat AABBs, pairs, the two capsule
+    generators' manifolds.  Oracle output like everything else here; the capsule part of the oracle is checked against closed-form
+    geometry only (tests/test_oracle_capsule.py), the reference has no capsule test."""
+    rng = np.random.default_rng(1030)
+    n = 300
+    s = make_world_scene(n, 1030, (1, 1, 0), side=4.2, plane=True)
+    cap = np.arange(n) % 3 == 2
+    s.shape_type[:n][cap] = 4
+    s.shape_param[:n][cap, 0] = rng.uniform(0.2, 0.5, size=int(cap.sum())).astype(np.float32)
+    s.shape_param[:n][cap, 1] = rng.uniform(0.15, 0.3, size=int(cap.sum())).astype(np.float32)
+    s.shape_param[:n][cap, 2] = 0
+    d = scene_to_dict(s)
+    fat = o.compute_aabbs(s)
+    pairs = o.broad_phase(fat, s.groups, 0)
+    c, off, algo, _ = o.narrow_phase(s, pairs)
+    d.update(fat_aabbs=fat, pairs=pairs, manifold_off=off, algo=algo)
+    for k in ("world1", "world2", "normal", "depth", "f1", "f2"):
+        d["c_" + k] = c[k]
+    np.savez_compressed(os.path.join(HERE, "capsule_mixed_plane_300.npz"), **d)
+    print("capsules", s.n, "objects", len(pairs), "pairs", int((algo >= 7).sum()), "capsule pairs", len(c), "contacts")
+
+
 def main():
     from oracle.pyoracle import Oracle
 
@@ -123,6 +146,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "sim_mixed_plane_400.npz"), **d)
     print("sim", [len(r["pairs"]) for r in log], "pairs per step,", len(idx), "ray hits")
     make_proximity(o)
+    make_capsules(o)
     for kind in ("terrain", "soup"):
         rs = make_ray_scene(kind, 2000, 600, seed=1004)
         om = o.trimesh(rs.verts, rs.tris)

@@ -251,3 +251,23 @@ def test_stepping_world_with_capsules(oracle):
         kb = {(tuple(p), i) for p, lo, hi in zip(b["pairs"].tolist(), b["off"][:-1], b["off"][1:]) for i in b["ids"][lo:hi].tolist()}
         kept += len(ka & kb)
     assert kept > 100
+
+
+def test_capsule_golden_fixture(oracle):
+    """tests/golden/capsule_mixed_plane_300.npz (made by tests/golden/make_golden.py): guards the capsule restatement against drift and
+    is the fixture the device path will have to reproduce."""
+    import os
+
+    from golden.make_golden import scene_from_npz
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "capsule_mixed_plane_300.npz"))
+    s = scene_from_npz(z)
+    assert (s.shape_type == CAPSULE).sum() == 100
+    fat = oracle.compute_aabbs(s)
+    assert np.array_equal(fat, z["fat_aabbs"])
+    pairs = oracle.broad_phase(fat, s.groups, 0)
+    assert np.array_equal(pairs, z["pairs"])
+    c, off, algo, _ = oracle.narrow_phase(s, pairs)
+    assert np.array_equal(off, z["manifold_off"]) and np.array_equal(algo, z["algo"]) and (algo >= 7).sum() > 100
+    for name in ("world1", "world2", "normal", "depth", "f1", "f2"):
+        assert np.array_equal(c[name], z["c_" + name]), name
