@@ -1,9 +1,12 @@
-"""Proximity sensors through the spatially sharded multi-GPU update (ncb_world_update_sharded), replayed rank by rank on one
-device like tests/test_gpu_parity.py::test_spatial_shards_partition_the_pair_set.
+"""GPU tests written after the round's GPU budget was spent (they have never run on hardware):
 
-Written after the round's GPU budget was spent: the sensor path re-keys pairs by GLOBAL handle with replicated query kinds, so the
-sharded update should need nothing else, but this file has not run on hardware yet.  It is therefore marked xfail(strict=False):
-a pass shows up as XPASS, a failure cannot hide the verified tests.  Remove the marker once it has been seen green."""
+  * proximity sensors through the spatially sharded multi-GPU update (ncb_world_update_sharded), replayed rank by rank on one device
+    like tests/test_gpu_parity.py::test_spatial_shards_partition_the_pair_set — the sensor path re-keys pairs by GLOBAL handle with
+    replicated query kinds, so the sharded update should need nothing else;
+  * the boundary refusing shape types the device does not know.
+
+They are marked xfail(strict=False): a pass shows up as XPASS, a failure cannot hide the verified tests (the file also sorts last).
+Remove the marker once they have been seen green."""
 import numpy as np
 import pytest
 
