@@ -1255,6 +1255,9 @@ void orc_contact_sm_sm(const orc_objects* objs, uint64_t n_pairs, const uint32_t
     for (uint64_t p = 0; p < n_pairs; ++p) {
         uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
         Shape a = get_shape(o, i1), b = get_shape(o, i2);
+        // a capsule takes part through its segment, as in the capsule generators (capsule_capsule_manifold_generator.rs:35-36)
+        if (a.type == CAPSULE) a.type = SEGMENT;
+        if (b.type == CAPSULE) b.type = SEGMENT;
         real prediction = predictions ? predictions[p] : o.query_limit[i1] + o.query_limit[i2];
         VoronoiSimplex simplex;
         GJKResult r = contact_support_map_support_map_with_params(o.iso(i1), as_support(a), o.iso(i2), as_support(b), prediction, simplex, nullptr, &st);

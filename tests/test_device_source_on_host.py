@@ -430,3 +430,50 @@ def test_device_trimesh_ray_primitives_match_oracle(ray_shim, oracle, kind, pose
         assert np.array_equal(face[hit], oface[hit]) and np.array_equal(toi >= 0, hit)
         assert np.array_equal(toi[hit].view(np.uint32), otoi[hit].view(np.uint32))
         assert np.array_equal(normal[hit].view(np.uint32), onormal[hit].view(np.uint32))
+
+
+def test_device_gjk_epa_handles_segments_as_two_point_hulls(gjk_shim, oracle):
+    """Plan check for the capsule device path: the segment of a capsule is given to the EXISTING device GJK / EPA as a
+    2-point hull [b, a] — in that order the hull scan's first-maximum rule is the segment's own support rule — and must reproduce the
+    oracle's contact_support_map_support_map on (segment, segment) and (segment, cuboid) pairs bit for bit."""
+    from ncollide_b200.scenes import WorldScene
+
+    rng = np.random.default_rng(31)
+    n = 400
+    s = make_world_scene(n, 131, (0, 1, 0), side=3.2, linear=0.05)  # cuboids; every second one becomes a capsule
+    cap = np.arange(n) % 2 == 0
+    hh = rng.uniform(0.2, 0.6, size=n).astype(F)
+    s_or = WorldScene(pos=s.pos, rot=s.rot, shape_type=np.where(cap, 4, s.shape_type).astype(np.uint32), shape_param=s.shape_param.copy(),
+                      groups=None, query_limit=s.query_limit, ang_pred=s.ang_pred, hulls=s.hulls, margin=s.margin)
+    s_or.shape_param[cap, 0] = hh[cap]
+    s_or.shape_param[cap, 1] = F(0.1)
+    s_or.shape_param[cap, 2:] = 0
+
+    class Lib:  # only the vertex tables are read by the support function
+        FIELDS = s.hulls.FIELDS
+
+    lib = Lib()
+    ids = np.cumsum(cap) - 1
+    lib.n_hulls = int(cap.sum())
+    for f in Lib.FIELDS:
+        setattr(lib, f, np.zeros(1, dtype=np.float32 if f in ("points", "face_normal", "edge_dir") else np.uint32))
+    lib.vert_off = (2 * np.arange(lib.n_hulls + 1)).astype(np.uint32)
+    for f in ("face_off", "edge_off", "fadj_off", "vadj_off"):
+        setattr(lib, f, np.zeros(lib.n_hulls + 1, dtype=np.uint32))
+    pts = np.zeros((lib.n_hulls, 2, 3), dtype=F)
+    pts[:, 0, 1] = hh[cap]    # b first
+    pts[:, 1, 1] = -hh[cap]   # then a
+    lib.points = np.ascontiguousarray(pts.reshape(-1, 3))
+    s_dev = WorldScene(pos=s.pos, rot=s.rot, shape_type=np.where(cap, 2, s.shape_type).astype(np.uint32), shape_param=s.shape_param.copy(),
+                       groups=None, query_limit=s.query_limit, ang_pred=s.ang_pred, hulls=lib, margin=s.margin)
+    s_dev.shape_param[cap, 0] = ids[cap].astype(F)
+    pairs = rng.integers(0, n, size=(30000, 2)).astype(np.uint32)
+    pairs = pairs[(pairs[:, 0] != pairs[:, 1]) & (cap[pairs[:, 0]] | cap[pairs[:, 1]])]
+    d = np.linalg.norm(s.pos[pairs[:, 0]] - s.pos[pairs[:, 1]], axis=1)
+    pairs = pairs[d < 1.0]
+    assert len(pairs) > 800
+    got, flags = shim_contact_sm_sm(gjk_shim, s_dev, pairs)
+    want, stats = oracle.contact_sm_sm(s_or, pairs)
+    assert flags[0] == 0 and flags[1] == 0
+    assert np.array_equal(got[:, 9], want[:, 9]) and 0.1 < want[:, 9].mean() < 1.0 and stats[2] > 50
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), int((got.view(np.uint32) != want.view(np.uint32)).any(axis=1).sum())
