@@ -4,6 +4,7 @@
 // k_cc_epa -> k_cc_manifold (same calls in the same order; the work queues between the phases only carry these values across
 // kernels).  Compared against the oracle by tests/test_device_source_on_host.py.  The product never links this.
 #include "narrow.cu"
+#include "capsule.cuh"
 
 using namespace ncb;
 
@@ -24,11 +25,151 @@ static DevHulls hulls_from(const ncb_hull_library* L) {
     return H;
 }
 
+// One fresh-world pair without capsules: the bodies of k_narrow<KEY>, k_bh_epa, k_cc_gjk -> k_cc_epa -> k_cc_manifold.
+static uint8_t fresh_pair(const DevObjects& o, const DevHulls& H, const ncb_objects* objs, float2 one_degree_cs, EpaState* e, Manifold& mf, uint32_t* flags,
+                          uint32_t i1, uint32_t i2) {
+    static const uint8_t algo_of[4][4] = {{NCB_ALGO_BALL_BALL, NCB_ALGO_BALL_CONVEX, NCB_ALGO_BALL_CONVEX, NCB_ALGO_PLANE_BALL},
+                                          {NCB_ALGO_BALL_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_PLANE_CONVEX},
+                                          {NCB_ALGO_BALL_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_PLANE_CONVEX},
+                                          {NCB_ALGO_PLANE_BALL, NCB_ALGO_PLANE_CONVEX, NCB_ALGO_PLANE_CONVEX, NCB_ALGO_NONE}};
+    uint32_t t1 = o.type[i1] & 3u, t2 = o.type[i2] & 3u;
+    Iso ma = load_iso(o, i1), mb = load_iso(o, i2);
+    float linear = o.qlimit[i1] + o.qlimit[i2];
+    Shape a = load_shape(o, H, i1, t1), b = load_shape(o, H, i2, t2);
+    uint8_t al = algo_of[t1][t2];
+    if (al == NCB_ALGO_BALL_BALL) {
+        gen_ball_ball(ma, a.radius, mb, b.radius, linear, mf);
+    } else if (al == NCB_ALGO_PLANE_BALL) {
+        if (t1 == NCB_SHAPE_PLANE)
+            gen_plane_ball(ma, a.he, mb, b.radius, linear, false, mf);
+        else
+            gen_plane_ball(mb, b.he, ma, a.radius, linear, true, mf);
+    } else if (al == NCB_ALGO_PLANE_CONVEX) {
+        Feature feat;
+        if (t1 == NCB_SHAPE_PLANE)
+            gen_plane_convex(ma, a.he, mb, b, linear, false, mf, feat);
+        else
+            gen_plane_convex(mb, b.he, ma, a, linear, true, mf, feat);
+    } else if (al == NCB_ALGO_BALL_CONVEX) {
+        bool flip = t1 != NCB_SHAPE_BALL;
+        const Shape& ball = flip ? b : a;
+        const Shape& cp = flip ? a : b;
+        const Iso& mball = flip ? mb : ma;
+        const Iso& mcp = flip ? ma : mb;
+        if (cp.type == NCB_SHAPE_CUBOID) {
+            bool inside;
+            V3 world2;
+            uint32_t f2;
+            cuboid_project_point_with_feature(cp.he, mcp, mball.t, inside, world2, f2);
+            gen_ball_convex_finish(mball.t, ball.radius, cp, inside, world2, f2, linear, flip, mf);
+        } else {
+            HullProjSetup u = hull_proj_setup(cp.hull, mcp, mball.t);
+            V3 world2;
+            Simplex s;
+            if (hull_project_gjk(u, mball.t, s, world2) == GJK_CLOSEST_POINTS) {
+                uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, false, world2, one_degree_cs);
+                gen_ball_convex_finish(mball.t, ball.radius, cp, false, world2, f2, linear, flip, mf);
+            } else {  // k_bh_epa: the ball centre is inside the hull
+                Iso id = iso_id();
+                V3 p1, p2, d;
+                if (epa_closest_points(*e, u.m, u.shape, id, u.origin, s.dim, s.v, p1, p2, d))
+                    world2 = p1 + mball.t;
+                else {
+                    flags[0] += e->overflow, flags[1] += e->panicked;
+                    world2 = mball.t;
+                }
+                uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, true, world2, one_degree_cs);
+                gen_ball_convex_finish(mball.t, ball.radius, cp, true, world2, f2, linear, flip, mf);
+            }
+        }
+    } else if (al == NCB_ALGO_CONVEX_CONVEX) {
+        Support ga = as_support(a), gb = as_support(b);
+        V3 d0;
+        if (!unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
+        V3 p1, p2, dir;
+        Simplex s;
+        int r = gjk_closest_points(ma, ga, mb, gb, linear, d0, s, p1, p2, dir);  // k_cc_gjk
+        if (r == GJK_INTERSECTION) {                                              // k_cc_epa
+            if (epa_closest_points(*e, ma, ga, mb, gb, s.dim, s.v, p1, p2, dir))
+                r = GJK_CLOSEST_POINTS;
+            else {
+                flags[0] += e->overflow, flags[1] += e->panicked;
+                r = GJK_NO_INTERSECTION;
+            }
+        }
+        if (r == GJK_CLOSEST_POINTS) {                                            // k_cc_manifold
+            float a1 = objs->ang_pred[i1], a2 = objs->ang_pred[i2];
+            float2 ang1 = make_float2(cosf(a1), sinf(a1)), ang2 = make_float2(cosf(a2), sinf(a2));
+            Feature f1, f2;
+            convex_convex_manifold(ma, a, mb, b, linear, ang1, ang2, p1, p2, dir, mf, f1, f2);
+        }
+    }
+    return al;
+}
+
+// A pair with at least one capsule (shape_type 4, param = half_height, radius): the staged device functions of capsule.cuh, called the
+// way the kernels will call them.  seg_pts: 6 floats per OBJECT (b then a of the capsule's segment; unused for other shapes).
+static uint8_t capsule_pair(const DevObjects& o, const DevHulls& H, const ncb_objects* objs, const float* seg_pts, EpaState* e, Manifold& mf, uint32_t* flags,
+                            uint32_t i1, uint32_t i2) {
+    uint32_t t1 = o.type[i1], t2 = o.type[i2];
+    bool a_cap = t1 == 4, b_cap = t2 == 4;
+    Iso ma = load_iso(o, i1), mb = load_iso(o, i2);
+    float linear = o.qlimit[i1] + o.qlimit[i2];
+    CapOperand a, b;
+    std::memset(&a, 0, sizeof a);
+    std::memset(&b, 0, sizeof b);
+    if (a_cap) {
+        a.is_segment = true, a.hh = o.param[i1].x, a.seg_pts = seg_pts + 6 * (size_t)i1, a.pre.active = true, a.pre.radius = o.param[i1].y;
+        linear = linear + a.pre.radius;
+    } else
+        a.shape = load_shape(o, H, i1, t1);
+    if (b_cap) {
+        b.is_segment = true, b.hh = o.param[i2].x, b.seg_pts = seg_pts + 6 * (size_t)i2, b.pre.active = true, b.pre.radius = o.param[i2].y;
+        linear = linear + b.pre.radius;
+    } else
+        b.shape = load_shape(o, H, i2, t2);
+    uint8_t algo = (a_cap && b_cap) ? 7 : 8;  // CapsuleCapsule / CapsuleShape
+    if (!a_cap && t1 == NCB_SHAPE_BALL) {
+        gen_ball_segment(ma, a.shape.radius, mb, b.hh, linear, false, b.pre, mf);
+    } else if (!b_cap && t2 == NCB_SHAPE_BALL) {
+        gen_ball_segment(mb, b.shape.radius, ma, a.hh, linear, true, a.pre, mf);
+    } else if (!a_cap && t1 == NCB_SHAPE_PLANE) {
+        Feature feat;
+        gen_plane_segment(ma, a.shape.he, mb, b.hh, linear, false, b.pre, mf, feat);
+    } else if (!b_cap && t2 == NCB_SHAPE_PLANE) {
+        Feature feat;
+        gen_plane_segment(mb, b.shape.he, ma, a.hh, linear, true, a.pre, mf, feat);
+    } else {
+        Support ga = cap_support(a), gb = cap_support(b);
+        V3 d0;
+        if (!unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
+        V3 p1, p2, dir;
+        Simplex s;
+        int r = gjk_closest_points(ma, ga, mb, gb, linear, d0, s, p1, p2, dir);
+        if (r == GJK_INTERSECTION) {
+            if (epa_closest_points(*e, ma, ga, mb, gb, s.dim, s.v, p1, p2, dir))
+                r = GJK_CLOSEST_POINTS;
+            else {
+                flags[0] += e->overflow, flags[1] += e->panicked;
+                r = GJK_NO_INTERSECTION;
+            }
+        }
+        if (r == GJK_CLOSEST_POINTS) {
+            float a1 = objs->ang_pred[i1], a2 = objs->ang_pred[i2];
+            float2 ang1 = make_float2(cosf(a1), sinf(a1)), ang2 = make_float2(cosf(a2), sinf(a2));
+            Feature f1, f2;
+            if (!capsule_convex_manifold(ma, a, mb, b, linear, ang1, ang2, p1, p2, dir, mf, f1, f2)) flags[0] += 1;
+        }
+    }
+    return algo;
+}
+
 extern "C" {
-// Returns the number of contacts (may exceed cap).  manifold_off[n_pairs + 1]; algo[p] = NCB_ALGO_*; flags[0] += EPA capacity
-// overflows / dropped contacts, flags[1] += reference panics.
-uint64_t shim_narrow_phase(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_pairs, const uint32_t* pairs, ncb_contact* out,
-                           uint64_t cap, uint32_t* manifold_off, uint8_t* algo, uint32_t* flags) {
+// Returns the number of contacts (may exceed cap).  manifold_off[n_pairs + 1]; algo[p] = NCB_ALGO_* (7 / 8: the capsule generators);
+// flags[0] += EPA capacity overflows / dropped contacts, flags[1] += reference panics.  seg_pts: NULL, or 6 floats per object for
+// worlds with capsules (shape_type 4).
+uint64_t shim_narrow_phase_ex(const ncb_objects* objs, const ncb_hull_library* lib, const float* seg_pts, uint64_t n_pairs, const uint32_t* pairs,
+                              ncb_contact* out, uint64_t cap, uint32_t* manifold_off, uint8_t* algo, uint32_t* flags) {
     DevObjects o;
     std::memset(&o, 0, sizeof o);
     o.n = objs->n;
@@ -41,90 +182,16 @@ uint64_t shim_narrow_phase(const ncb_objects* objs, const ncb_hull_library* lib,
     // what ncb_set_objects / launch_narrow_phase_t prepare on the host with libm
     const float one_degree = (float)(3.14159265358979323846 / 180.0);
     const float2 one_degree_cs = make_float2(cosf(one_degree), sinf(one_degree));
-    static const uint8_t algo_of[4][4] = {{NCB_ALGO_BALL_BALL, NCB_ALGO_BALL_CONVEX, NCB_ALGO_BALL_CONVEX, NCB_ALGO_PLANE_BALL},
-                                          {NCB_ALGO_BALL_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_PLANE_CONVEX},
-                                          {NCB_ALGO_BALL_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_PLANE_CONVEX},
-                                          {NCB_ALGO_PLANE_BALL, NCB_ALGO_PLANE_CONVEX, NCB_ALGO_PLANE_CONVEX, NCB_ALGO_NONE}};
     EpaState* e = new EpaState;
     Manifold* mfp = new Manifold;
     Manifold& mf = *mfp;
     uint64_t nc = 0;
     for (uint64_t p = 0; p < n_pairs; ++p) {
         uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
-        uint32_t t1 = o.type[i1] & 3u, t2 = o.type[i2] & 3u;
         mf.n = 0;
         mf.deepest = 0;
-        Iso ma = load_iso(o, i1), mb = load_iso(o, i2);
-        float linear = o.qlimit[i1] + o.qlimit[i2];
-        Shape a = load_shape(o, H, i1, t1), b = load_shape(o, H, i2, t2);
-        uint8_t al = algo_of[t1][t2];
-        if (al == NCB_ALGO_BALL_BALL) {
-            gen_ball_ball(ma, a.radius, mb, b.radius, linear, mf);
-        } else if (al == NCB_ALGO_PLANE_BALL) {
-            if (t1 == NCB_SHAPE_PLANE)
-                gen_plane_ball(ma, a.he, mb, b.radius, linear, false, mf);
-            else
-                gen_plane_ball(mb, b.he, ma, a.radius, linear, true, mf);
-        } else if (al == NCB_ALGO_PLANE_CONVEX) {
-            Feature feat;
-            if (t1 == NCB_SHAPE_PLANE)
-                gen_plane_convex(ma, a.he, mb, b, linear, false, mf, feat);
-            else
-                gen_plane_convex(mb, b.he, ma, a, linear, true, mf, feat);
-        } else if (al == NCB_ALGO_BALL_CONVEX) {
-            bool flip = t1 != NCB_SHAPE_BALL;
-            const Shape& ball = flip ? b : a;
-            const Shape& cp = flip ? a : b;
-            const Iso& mball = flip ? mb : ma;
-            const Iso& mcp = flip ? ma : mb;
-            if (cp.type == NCB_SHAPE_CUBOID) {
-                bool inside;
-                V3 world2;
-                uint32_t f2;
-                cuboid_project_point_with_feature(cp.he, mcp, mball.t, inside, world2, f2);
-                gen_ball_convex_finish(mball.t, ball.radius, cp, inside, world2, f2, linear, flip, mf);
-            } else {
-                HullProjSetup u = hull_proj_setup(cp.hull, mcp, mball.t);
-                V3 world2;
-                Simplex s;
-                if (hull_project_gjk(u, mball.t, s, world2) == GJK_CLOSEST_POINTS) {
-                    uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, false, world2, one_degree_cs);
-                    gen_ball_convex_finish(mball.t, ball.radius, cp, false, world2, f2, linear, flip, mf);
-                } else {  // k_bh_epa: the ball centre is inside the hull
-                    Iso id = iso_id();
-                    V3 p1, p2, d;
-                    if (epa_closest_points(*e, u.m, u.shape, id, u.origin, s.dim, s.v, p1, p2, d))
-                        world2 = p1 + mball.t;
-                    else {
-                        flags[0] += e->overflow, flags[1] += e->panicked;
-                        world2 = mball.t;
-                    }
-                    uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, true, world2, one_degree_cs);
-                    gen_ball_convex_finish(mball.t, ball.radius, cp, true, world2, f2, linear, flip, mf);
-                }
-            }
-        } else if (al == NCB_ALGO_CONVEX_CONVEX) {
-            Support ga = as_support(a), gb = as_support(b);
-            V3 d0;
-            if (!unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
-            V3 p1, p2, dir;
-            Simplex s;
-            int r = gjk_closest_points(ma, ga, mb, gb, linear, d0, s, p1, p2, dir);  // k_cc_gjk
-            if (r == GJK_INTERSECTION) {                                              // k_cc_epa
-                if (epa_closest_points(*e, ma, ga, mb, gb, s.dim, s.v, p1, p2, dir))
-                    r = GJK_CLOSEST_POINTS;
-                else {
-                    flags[0] += e->overflow, flags[1] += e->panicked;
-                    r = GJK_NO_INTERSECTION;
-                }
-            }
-            if (r == GJK_CLOSEST_POINTS) {                                            // k_cc_manifold
-                float a1 = objs->ang_pred[i1], a2 = objs->ang_pred[i2];
-                float2 ang1 = make_float2(cosf(a1), sinf(a1)), ang2 = make_float2(cosf(a2), sinf(a2));
-                Feature f1, f2;
-                convex_convex_manifold(ma, a, mb, b, linear, ang1, ang2, p1, p2, dir, mf, f1, f2);
-            }
-        }
+        uint8_t al = (o.type[i1] == 4 || o.type[i2] == 4) ? capsule_pair(o, H, objs, seg_pts, e, mf, flags, i1, i2)
+                                                          : fresh_pair(o, H, objs, one_degree_cs, e, mf, flags, i1, i2);
         if (mf.deepest < 0) flags[0] += 1;  // more than MANIFOLD_MAX distinct contacts
         algo[p] = al;
         manifold_off[p] = (uint32_t)nc;
@@ -144,6 +211,10 @@ uint64_t shim_narrow_phase(const ncb_objects* objs, const ncb_hull_library* lib,
     delete e;
     delete mfp;
     return nc;
+}
+uint64_t shim_narrow_phase(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_pairs, const uint32_t* pairs, ncb_contact* out,
+                           uint64_t cap, uint32_t* manifold_off, uint8_t* algo, uint32_t* flags) {
+    return shim_narrow_phase_ex(objs, lib, nullptr, n_pairs, pairs, out, cap, manifold_off, algo, flags);
 }
 
 // Stepping world, per pair: what k_narrow<KEY, true>, k_bh_epa<true>, k_cc_gjk<true> -> k_cc_epa<true> -> k_cc_manifold<true> do for ONE

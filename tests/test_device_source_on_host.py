@@ -477,3 +477,71 @@ def test_device_gjk_epa_handles_segments_as_two_point_hulls(gjk_shim, oracle):
     assert flags[0] == 0 and flags[1] == 0
     assert np.array_equal(got[:, 9], want[:, 9]) and 0.1 < want[:, 9].mean() < 1.0 and stats[2] > 50
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), int((got.view(np.uint32) != want.view(np.uint32)).any(axis=1).sum())
+
+
+# ---- capsules: the STAGED device functions of csrc/capsule.cuh (no kernel calls them yet) --------------------------------------------
+def shim_narrow_phase_capsules(lib, scene, pairs):
+    """scene.shape_type may contain 4 (capsule: shape_param = half_height, radius)."""
+    oc, keep = _ffi.pack_objects(scene)
+    hc, keep2 = _ffi.pack_hull_library(scene.hulls)
+    pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+    seg = np.zeros((scene.n, 6), dtype=F)  # the 2-point hull [b, a] of every capsule's segment
+    cap = scene.shape_type == 4
+    seg[cap, 1] = scene.shape_param[cap, 0]
+    seg[cap, 4] = -scene.shape_param[cap, 0]
+    P = len(pairs)
+    off = np.zeros(P + 1, dtype=np.uint32)
+    algo = np.zeros(P, dtype=np.uint8)
+    flags = np.zeros(4, dtype=np.uint32)
+    lib.shim_narrow_phase_ex.restype = C.c_uint64
+    cap_c = max(4 * P, 64)
+    while True:
+        out = np.zeros(cap_c, dtype=_ffi.CONTACT_DTYPE)
+        flags[:] = 0
+        nc = lib.shim_narrow_phase_ex(C.byref(oc), C.byref(hc), _ffi.ptr(seg), C.c_uint64(P), _ffi.ptr(pairs), _ffi.ptr(out), C.c_uint64(cap_c), _ffi.ptr(off),
+                                      _ffi.ptr(algo), _ffi.ptr(flags))
+        if nc <= cap_c:
+            return out[:nc], off, algo, flags
+        cap_c = int(nc)
+
+
+def _capsule_scene(n, seed, kinds, side, plane, ang=0.0):
+    s = make_world_scene(n, seed, kinds, side=side, n_hulls=24, plane=plane, angular=ang)
+    rng = np.random.default_rng(seed + 1)
+    cap = np.zeros(s.n, dtype=bool)
+    cap[:n] = np.arange(n) % 3 == 1
+    s.shape_type[cap] = 4
+    s.shape_param[cap, 0] = rng.uniform(0.2, 0.5, size=int(cap.sum())).astype(F)
+    s.shape_param[cap, 1] = rng.uniform(0.15, 0.3, size=int(cap.sum())).astype(F)
+    s.shape_param[cap, 2:] = 0
+    return s
+
+
+@pytest.mark.parametrize("n,kinds,side,plane,ang,seed", [(2400, (1, 1, 1), 8.0, True, 0.0, 141), (1800, (0, 1, 1), 5.5, False, 0.03, 142), (1500, (1, 1, 0), 5.0, True, 0.0, 143)])
+def test_staged_capsule_device_source_matches_oracle(narrow_shim, oracle, n, kinds, side, plane, ang, seed):
+    """Worlds with capsules through csrc/capsule.cuh (segment features, the capsule's contact preprocessor, the capsule generators on top
+    of the existing GJK / EPA / clipping / manifold code) against the oracle: algorithm, manifold sizes, feature ids exact, contacts
+    bit for bit — for capsule x {capsule, ball, cuboid, hull, plane} in both orders, and unchanged results for the other pairs."""
+    s = _capsule_scene(n, seed, kinds, side, plane, ang)
+    pairs = oracle.broad_phase(oracle.compute_aabbs(s), s.groups, mode=0)
+    both = np.concatenate([pairs, pairs[:, ::-1]])
+    got, want = shim_narrow_phase_capsules(narrow_shim, s, both), oracle.narrow_phase(s, both)
+    assert (want[2] == 7).sum() > 100 and (want[2] == 8).sum() > 500
+    inexact = compare_narrow(got, want, "capsules")
+    assert inexact == 0, f"{inexact} contact fields within tolerance but not bit-exact"
+    t = s.shape_type
+    for other in set(t[t != 4].tolist()):
+        sel = ((t[both[:, 0]] == 4) & (t[both[:, 1]] == other)) | ((t[both[:, 0]] == other) & (t[both[:, 1]] == 4))
+        assert np.diff(want[1])[sel].sum() > 0, f"no contact between a capsule and shape {other}"
+
+
+def test_staged_capsule_device_source_reproduces_the_golden_fixture(narrow_shim):
+    from golden.make_golden import scene_from_npz
+
+    z = np.load(os.path.join(HERE, "golden", "capsule_mixed_plane_300.npz"))
+    s = scene_from_npz(z)
+    dc, doff, dalgo, flags = shim_narrow_phase_capsules(narrow_shim, s, z["pairs"])
+    assert flags[0] == 0 and flags[1] == 0
+    assert np.array_equal(doff, z["manifold_off"]) and np.array_equal(dalgo, z["algo"])
+    for name in ("f1", "f2", "world1", "world2", "normal", "depth"):
+        assert np.array_equal(dc[name].view(np.uint32), z["c_" + name].view(np.uint32)), name
