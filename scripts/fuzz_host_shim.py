@@ -2,6 +2,7 @@
 csrc/gjk.cuh, the contact generators / clipping / manifold of csrc/narrow.cu), compiled for the host through tests/host_shim/, against the oracle on many small random worlds (sizes, densities,
 margins, degenerate placements, scales, far-away coordinates: the generator of scripts/fuzz_parity.py).
 python scripts/fuzz_host_shim.py [seconds] [seed0]  ->  one JSON summary line.  Test infrastructure only."""
+import copy
 import ctypes as C
 import json
 import os
@@ -17,7 +18,8 @@ os.environ["FUZZ_SENSORS"] = "0"
 from fuzz_parity import random_scene  # noqa: E402
 from oracle.pyoracle import Oracle  # noqa: E402
 from sim_scenario import step_poses  # noqa: E402
-from test_device_source_on_host import ShimEdges, _build_shim, _sorted_rows, compare_narrow, shim_contact_sm_sm, shim_narrow_phase, shim_proximity  # noqa: E402
+from test_device_source_on_host import (ShimEdges, _build_shim, _sorted_rows, compare_narrow, shim_contact_sm_sm, shim_narrow_phase,  # noqa: E402
+                                        shim_narrow_phase_capsules, shim_proximity)
 
 
 def persist_rounds(nar, orc, s, cb, rng, steps=4):
@@ -61,7 +63,7 @@ def main():
     seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 50_000
     prox, gjk, orc = _build_shim("libprox_host.so", "proximity_host.cpp"), _build_shim("libgjk_host.so", "gjk_host.cpp"), Oracle()
     nar = _build_shim("libnarrow_host.so", "narrow_host.cpp")
-    n_narrow = n_contacts = narrow_inexact = n_persist = 0
+    n_narrow = n_contacts = narrow_inexact = n_persist = n_capsule_pairs = capsule_inexact = 0
     t0 = time.time()
     n_scenes = n_prox = n_gjk = n_epa = 0
     inexact = 0
@@ -97,6 +99,23 @@ def main():
                 narrow_inexact += compare_narrow(got, want, f"seed {seed}")
             except AssertionError as ex:
                 bad.append((seed, "narrow phase", str(ex)[:120]))
+            if seed % 3 == 0:  # a third of the balls / cuboids / hulls become capsules: the staged device functions of csrc/capsule.cuh
+                sc = copy.copy(s)
+                sc.shape_type, sc.shape_param = s.shape_type.copy(), s.shape_param.copy()
+                pick = (sc.shape_type != 3) & (rng.random(sc.n) < 0.35)
+                sc.shape_type[pick] = 4
+                sc.shape_param[pick, 0] = rng.uniform(0.05, 0.6, size=int(pick.sum())).astype(F)
+                sc.shape_param[pick, 1] = rng.uniform(0.02, 0.35, size=int(pick.sum())).astype(F)
+                sc.shape_param[pick, 2:] = 0
+                cbc = orc.broad_phase(orc.compute_aabbs(sc), sc.groups, mode=0)
+                if len(cbc):
+                    cbc = np.concatenate([cbc, cbc[:, ::-1]])
+                    got, want = shim_narrow_phase_capsules(nar, sc, cbc), orc.narrow_phase(sc, cbc)
+                    n_capsule_pairs += int((want[2] >= 7).sum())
+                    try:
+                        capsule_inexact += compare_narrow(got, want, f"seed {seed} capsules")
+                    except AssertionError as ex:
+                        bad.append((seed, "capsules", str(ex)[:120]))
             if seed % 4 == 0:  # stepping-world state per pair over a few updates (moves the scene: last check of this world)
                 k, why = persist_rounds(nar, orc, s, cb, rng)
                 n_persist += k
@@ -107,6 +126,7 @@ def main():
     print(json.dumps({"scenes": n_scenes, "proximity_pairs": n_prox, "gjk_pairs": n_gjk, "epa_runs": n_epa, "gjk_rows_not_bit_exact": inexact,
                       "narrow_phase_pairs": n_narrow, "contacts": n_contacts, "contact_fields_not_bit_exact": narrow_inexact,
                       "persistent_edge_updates": n_persist,
+                      "capsule_pairs": n_capsule_pairs, "capsule_contact_fields_not_bit_exact": capsule_inexact,
                       "mismatches": bad, "seconds": round(time.time() - t0, 1), "seed0": seed0}))
 
 
