@@ -217,10 +217,25 @@ uint64_t shim_narrow_phase(const ncb_objects* objs, const ncb_hull_library* lib,
     return shim_narrow_phase_ex(objs, lib, nullptr, n_pairs, pairs, out, cap, manifold_off, algo, flags);
 }
 
+// capsule_aabb of capsule.cuh for the capsules of a scene (mode 0: the shape's AABB); out: 6 floats per object, untouched for other shapes
+void shim_capsule_aabbs(const ncb_objects* objs, float* out) {
+    for (uint32_t i = 0; i < objs->n; ++i) {
+        if (objs->shape_type[i] != 4) continue;
+        Iso m;
+        m.t = v3(objs->pos[3 * i], objs->pos[3 * i + 1], objs->pos[3 * i + 2]);
+        m.q = Quat{objs->rot[4 * i], objs->rot[4 * i + 1], objs->rot[4 * i + 2], objs->rot[4 * i + 3]};
+        V3 mins, maxs;
+        capsule_aabb(m, objs->shape_param[4 * i], objs->shape_param[4 * i + 1], mins, maxs);
+        float* d = out + 6 * (size_t)i;
+        d[0] = mins.x, d[1] = mins.y, d[2] = mins.z, d[3] = maxs.x, d[4] = maxs.y, d[5] = maxs.z;
+    }
+}
+
 // Stepping world, per pair: what k_narrow<KEY, true>, k_bh_epa<true>, k_cc_gjk<true> -> k_cc_epa<true> -> k_cc_manifold<true> do for ONE
 // updated pair whose persistent state lives in slot `slots[k]` of dir / pm_hdr / pm_entry (same calls, same order: load + age the
 // manifold cache, warm-started GJK, generate, store back, contact events).
-void shim_persist_update(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_update, const uint32_t* pairs, const uint32_t* slots,
+void shim_persist_update_ex(const ncb_objects* objs, const ncb_hull_library* lib, const float* seg_pts, uint64_t n_update, const uint32_t* pairs,
+                            const uint32_t* slots,
                          float* dir, uint32_t* pm_hdr, float* pm_entry, unsigned long long* events, uint32_t* n_events, uint32_t cap_events,
                          uint32_t* pm_overflow, uint32_t* flags) {
     DevObjects o;
@@ -247,6 +262,71 @@ void shim_persist_update(const ncb_objects* objs, const ncb_hull_library* lib, u
     PManifold& mf = *mfp;
     for (uint64_t k = 0; k < n_update; ++k) {
         uint32_t i1 = pairs[2 * k], i2 = pairs[2 * k + 1], slot = slots[k];
+        if (o.type[i1] == 4 || o.type[i2] == 4) {  // a capsule pair: the staged functions of capsule.cuh with the persistent manifold
+            uint32_t c1 = o.type[i1], c2 = o.type[i2];
+            bool a_cap = c1 == 4, b_cap = c2 == 4;
+            Iso ma = load_iso(o, i1), mb = load_iso(o, i2);
+            float linear = o.qlimit[i1] + o.qlimit[i2];
+            CapOperand a, b;
+            std::memset(&a, 0, sizeof a);
+            std::memset(&b, 0, sizeof b);
+            if (a_cap) {
+                a.is_segment = true, a.hh = o.param[i1].x, a.seg_pts = seg_pts + 6 * (size_t)i1, a.pre.active = true, a.pre.radius = o.param[i1].y;
+                linear = linear + a.pre.radius;
+            } else
+                a.shape = load_shape(o, H, i1, c1);
+            if (b_cap) {
+                b.is_segment = true, b.hh = o.param[i2].x, b.seg_pts = seg_pts + 6 * (size_t)i2, b.pre.active = true, b.pre.radius = o.param[i2].y;
+                linear = linear + b.pre.radius;
+            } else
+                b.shape = load_shape(o, H, i2, c2);
+            bool simple = (!a_cap && (c1 == NCB_SHAPE_BALL || c1 == NCB_SHAPE_PLANE)) || (!b_cap && (c2 == NCB_SHAPE_BALL || c2 == NCB_SHAPE_PLANE));
+            if (simple) {
+                pm_load_and_age(ps, slot, mf);
+                Feature feat;
+                if (!a_cap && c1 == NCB_SHAPE_BALL)
+                    gen_ball_segment(ma, a.shape.radius, mb, b.hh, linear, false, b.pre, mf);
+                else if (!b_cap && c2 == NCB_SHAPE_BALL)
+                    gen_ball_segment(mb, b.shape.radius, ma, a.hh, linear, true, a.pre, mf);
+                else if (!a_cap)
+                    gen_plane_segment(ma, a.shape.he, mb, b.hh, linear, false, b.pre, mf, feat);
+                else
+                    gen_plane_segment(mb, b.shape.he, ma, a.hh, linear, true, a.pre, mf, feat);
+                pm_store(ps, slot, mf, i1, i2);
+                continue;
+            }
+            Support ga = cap_support(a), gb = cap_support(b);
+            V3 d0;
+            bool warm = false;
+            float4 pd = ps.dir[slot];
+            if (pd.w != 0.f) d0 = v3(pd.x, pd.y, pd.z), warm = true;
+            if (!warm && !unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
+            V3 p1, p2, dirv;
+            Simplex s;
+            int r = gjk_closest_points(ma, ga, mb, gb, linear, d0, s, p1, p2, dirv);
+            if (r != GJK_INTERSECTION) ps.dir[slot] = make_float4(dirv.x, dirv.y, dirv.z, 1.f);
+            if (r == GJK_NO_INTERSECTION) {
+                pm_age_only(ps, slot, i1, i2);
+                continue;
+            }
+            if (r == GJK_INTERSECTION) {
+                if (epa_closest_points(*e, ma, ga, mb, gb, s.dim, s.v, p1, p2, dirv)) {
+                    ps.dir[slot] = make_float4(dirv.x, dirv.y, dirv.z, 1.f);
+                } else {
+                    flags[0] += e->overflow, flags[1] += e->panicked;
+                    ps.dir[slot] = make_float4(1.f, 0.f, 0.f, 1.f);
+                    pm_age_only(ps, slot, i1, i2);
+                    continue;
+                }
+            }
+            pm_load_and_age(ps, slot, mf);
+            float a1 = objs->ang_pred[i1], a2 = objs->ang_pred[i2];
+            float2 ang1 = make_float2(cosf(a1), sinf(a1)), ang2 = make_float2(cosf(a2), sinf(a2));
+            Feature f1, f2;
+            if (!capsule_convex_manifold(ma, a, mb, b, linear, ang1, ang2, p1, p2, dirv, mf, f1, f2)) flags[0] += 1;
+            pm_store(ps, slot, mf, i1, i2);
+            continue;
+        }
         uint32_t t1 = o.type[i1] & 3u, t2 = o.type[i2] & 3u;
         Iso ma = load_iso(o, i1), mb = load_iso(o, i2);
         float linear = o.qlimit[i1] + o.qlimit[i2];
@@ -340,6 +420,12 @@ void shim_persist_update(const ncb_objects* objs, const ncb_hull_library* lib, u
     }
     delete e;
     delete mfp;
+}
+
+void shim_persist_update(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_update, const uint32_t* pairs, const uint32_t* slots,
+                         float* dir, uint32_t* pm_hdr, float* pm_entry, unsigned long long* events, uint32_t* n_events, uint32_t cap_events,
+                         uint32_t* pm_overflow, uint32_t* flags) {
+    shim_persist_update_ex(objs, lib, nullptr, n_update, pairs, slots, dir, pm_hdr, pm_entry, events, n_events, cap_events, pm_overflow, flags);
 }
 
 // k_sim_export for the listed slots: live contacts in slab order, ids = insertion counter << 8 | slab slot.

@@ -286,8 +286,13 @@ class ShimEdges:
         pr = np.ascontiguousarray(self.pairs[which])
         ev = np.zeros(len(which) + 1, dtype=np.uint64)
         nev = np.zeros(1, dtype=np.uint32)
-        self.lib.shim_persist_update(C.byref(oc), C.byref(hc), C.c_uint64(len(which)), _ffi.ptr(pr), _ffi.ptr(which), _ffi.ptr(self.dir), _ffi.ptr(self.hdr),
-                                     _ffi.ptr(self.entry), _ffi.ptr(ev), _ffi.ptr(nev), C.c_uint32(len(ev)), _ffi.ptr(self.overflow), _ffi.ptr(self.flags))
+        seg = np.zeros((scene.n, 6), dtype=F)  # capsules (shape_type 4): the 2-point hull [b, a] of the segment
+        cap = scene.shape_type == 4
+        seg[cap, 1] = scene.shape_param[cap, 0]
+        seg[cap, 4] = -scene.shape_param[cap, 0]
+        self.lib.shim_persist_update_ex(C.byref(oc), C.byref(hc), _ffi.ptr(seg), C.c_uint64(len(which)), _ffi.ptr(pr), _ffi.ptr(which), _ffi.ptr(self.dir),
+                                        _ffi.ptr(self.hdr), _ffi.ptr(self.entry), _ffi.ptr(ev), _ffi.ptr(nev), C.c_uint32(len(ev)), _ffi.ptr(self.overflow),
+                                        _ffi.ptr(self.flags))
         ev = ev[: int(nev[0])]
         return np.stack([(ev >> np.uint64(32)) & np.uint64(0x7FFFFFFF), ev & np.uint64(0xFFFFFFFF), ev >> np.uint64(63)], axis=1).astype(np.uint32)
 
@@ -545,3 +550,47 @@ def test_staged_capsule_device_source_reproduces_the_golden_fixture(narrow_shim)
     assert np.array_equal(doff, z["manifold_off"]) and np.array_equal(dalgo, z["algo"])
     for name in ("f1", "f2", "world1", "world2", "normal", "depth"):
         assert np.array_equal(dc[name].view(np.uint32), z["c_" + name].view(np.uint32)), name
+
+
+def test_staged_capsule_aabb_matches_oracle(narrow_shim, oracle):
+    s = _capsule_scene(3000, 151, (1, 1, 1), 9.0, False)
+    oc, keep = _ffi.pack_objects(s)
+    out = np.zeros((s.n, 6), dtype=F)
+    narrow_shim.shim_capsule_aabbs(C.byref(oc), _ffi.ptr(out))
+    cap = s.shape_type == 4
+    want = oracle.compute_aabbs(s, mode=0)
+    assert cap.sum() == 1000 and np.array_equal(out[cap].view(np.uint32), want[cap].view(np.uint32))
+
+
+def test_staged_capsule_persistent_state_matches_oracle(narrow_shim, oracle):
+    """Stepping-world state per pair with capsules: the capsule generators instantiated with the persistent manifold (load + age, warm
+    started GJK on the segment hulls, store, contact events) over six updates against the oracle's caller-driven edges."""
+    from sim_scenario import step_poses
+
+    s = _capsule_scene(1200, 161, (1, 1, 1), 5.8, True)
+    pairs = oracle.broad_phase(oracle.compute_aabbs(s), s.groups, mode=0)
+    t = s.shape_type
+    pairs = pairs[~((t[pairs[:, 0]] == 3) & (t[pairs[:, 1]] == 3))]
+    dev, orc = ShimEdges(narrow_shim, pairs), oracle.edges(pairs)
+    rng = np.random.default_rng(5)
+    n_events = 0
+    for step in range(6):
+        if step == 0:
+            which = np.arange(len(pairs), dtype=np.uint32)
+        else:
+            idx = step_poses(s, s.pos, s.rot, rng, 0.4)
+            moved = np.zeros(s.n, dtype=bool)
+            moved[idx] = True
+            which = np.nonzero(moved[pairs[:, 0]] | moved[pairs[:, 1]])[0].astype(np.uint32)
+        ed, eo = dev.update(s, which), orc.update(s, which)
+        assert dev.flags[0] == 0 and dev.flags[1] == 0 and dev.overflow[0] == 0
+        assert np.array_equal(_sorted_rows(ed), _sorted_rows(eo)), f"step {step}: contact events"
+        n_events += len(eo) if step else 0
+        (dc, doff, dids, ddir), (oc, ooff, oids, odir) = dev.fetch(), orc.fetch()
+        assert np.array_equal(doff, ooff) and np.array_equal(dids, oids), f"step {step}: manifold sizes / contact ids"
+        for name in ("f1", "f2", "world1", "world2", "normal", "depth"):
+            assert np.array_equal(dc[name].view(np.uint32), oc[name].view(np.uint32)), f"step {step}: {name}"
+        has = odir[:, 3] != 0
+        assert np.array_equal(ddir[:, 3] != 0, has) and np.array_equal(ddir[has].view(np.uint32), odir[has].view(np.uint32)), f"step {step}: last_gjk_dir"
+    capsule_edges = (t[pairs[:, 0]] == 4) | (t[pairs[:, 1]] == 4)
+    assert n_events > 5 and np.diff(ooff)[capsule_edges].sum() > 100
