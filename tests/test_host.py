@@ -243,3 +243,20 @@ def test_bench_native_arm_refuses_to_run_without_a_gpu():
                         "--no-extras"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode != 0
     assert not any(ln.startswith("{") and '"value"' in ln for ln in r.stdout.splitlines())
+
+
+def test_staged_capsule_header_compiles_as_device_code():
+    """ncollide_b200/csrc/capsule.cuh is staged (no kernel includes it yet): make sure nvcc accepts it as sm_100a device code together
+    with the narrow-phase translation unit, both manifold flavours instantiated."""
+    import shutil
+    import subprocess
+    import tempfile
+
+    nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else shutil.which("nvcc")
+    if not nvcc:
+        pytest.skip("nvcc not found")
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "--fmad=false", "-std=c++17", "-I", os.path.join(ROOT, "ncollide_b200", "csrc"),
+                            "-c", os.path.join(ROOT, "tests", "host_shim", "capsule_device_compile_check.cu"), "-o", os.path.join(d, "check.o")],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-1500:]
