@@ -867,9 +867,8 @@ struct NarrowArgs {
     float2 one_degree_cs;  // cos / sin of (pi / 180) as f32, from the host libm (convex.rs:543)
     uint32_t* epa_queue;   // EPA_REC_WORDS per record
     uint32_t* cp_queue;    // CP_REC_WORDS per record
-    int epa_refill_min;    // idle lanes needed before a warp refills (batched initialisation)
-    uint32_t* epa_long;    // two-pass EPA: queue indices deferred to the second pass
-    int epa_pass1_steps;   // expansion steps a pair may take in the first pass
+    int epa_refill_min;    // idle lanes needed before a warp of k_cc_epa_s refills (batched initialisation)
+    uint32_t* epa_long;    // EPA-queue indices of the pairs that did not fit the compact polytope store (overflow queue)
 };
 
 // ---- convex x convex in three compacted phases -------------------------------------------------------------------
@@ -964,16 +963,111 @@ __global__ void __launch_bounds__(128, NCB_GJK_MINBLOCKS) k_cc_gjk(NarrowArgs A)
 
 // EPA over the compacted queue.  Lanes are independent workers: an idle lane fetches the next queue entry and builds
 // its initial polytope; a busy lane executes ONE expansion step per turn of the outer loop.  All busy lanes therefore
-// run the same code (one step) regardless of how many steps their pair needs; refills are batched (>= REFILL_MIN idle
+// run the same code (one step) regardless of how many steps their pair needs; refills are batched (>= refill_min idle
 // lanes) so that the initialisation path is not paid on every turn.
+//
+// k_cc_epa_s (the default): the polytope lives in SHARED memory (EpaCompact: 133 lane-strided words per pair, face normals
+// recomputed), 6 CTAs of 64 threads per SM; the operands are kept slim (kind, half extents | vertex array) in registers.  Round 1's
+// kernel kept a 7.4 KB polytope per thread in local memory: 32 warps x 55 KB of touched lines per SM overflowed L1 and, over 148
+// SMs, L2, and ncu counted 3.0 GB of DRAM traffic for 82 MB of algorithmic bytes.  Here the expansion loop touches no global or local
+// memory except the hull vertices (L1-resident library) and 24 B of cold support points per new vertex.
+// A pair that does not fit the compact capacities (1 % on cfg3) or starts from a flat simplex goes to the overflow queue
+// (A.epa_long) and is restarted on the big local-memory store by k_cc_epa<PS, 2> right after.
+//
+// k_cc_epa<PS, PASS>: PASS 0 = one pass over the whole queue on the big store (round 1's kernel, NCB_EPA_SHARED=0);
+// PASS 2 = the overflow queue.
+#define EPAS_THREADS 64
+#ifndef NCB_EPAS_MINBLOCKS
+#define NCB_EPAS_MINBLOCKS 6
+#endif
+typedef EpaCompact<EPAS_THREADS> EpaShared;
+
+NCB_HD void epa_rec_load(const uint32_t* q, uint32_t& p, int& sdim, CSOPoint* sv) {
+    const float* f = reinterpret_cast<const float*>(q);
+    p = q[0];
+    sdim = (int)q[1];
+    for (int i = 0; i < 4; ++i) {
+        sv[i].orig1 = v3(f[2 + 6 * i + 0], f[2 + 6 * i + 1], f[2 + 6 * i + 2]);
+        sv[i].orig2 = v3(f[2 + 6 * i + 3], f[2 + 6 * i + 4], f[2 + 6 * i + 5]);
+        sv[i].point = sv[i].orig1 - sv[i].orig2;  // bit-identical to the value GJK computed (CSOPoint::new)
+    }
+}
+
+template <bool PS>
+__global__ void __launch_bounds__(EPAS_THREADS, NCB_EPAS_MINBLOCKS) k_cc_epa_s(NarrowArgs A) {
+    extern __shared__ uint32_t epa_smem[];
+    const int KEY = CCQ;
+    const uint32_t seg_end = A.cnt->epa_cursor[KEY];
+    uint32_t* fetch = &A.cnt->epa_fetch[KEY];
+    const int lane = threadIdx.x & 31;
+    EpaShared e;
+    e.base = epa_smem + threadIdx.x;
+    bool active = false, exhausted = false;
+    uint32_t p = 0, wq = 0;
+    Iso ma, mb;
+    SupportS ga, gb;
+    V3 p1, p2, n;
+    for (;;) {
+        int status = EPA_CONTINUE;
+        uint32_t res_face = EPA_RES_DIRECT;
+        unsigned idle = __ballot_sync(0xffffffffu, !active);
+        bool refill = !exhausted && (idle == 0xffffffffu || __popc(idle) >= A.epa_refill_min);
+        if (refill) {  // warp-uniform
+            uint32_t base = 0;
+            int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + __popc(idle) >= seg_end) exhausted = true;  // nothing left after this batch
+            if (!active) {
+                wq = base + __popc(idle & ((1u << lane) - 1));
+                if (wq < seg_end) {
+                    int sdim;
+                    CSOPoint sv[4];
+                    epa_rec_load(A.epa_queue + (size_t)wq * EPA_REC_WORDS, p, sdim, sv);
+                    uint2 pr = __ldg(&A.pairs[p]);
+                    uint32_t i1 = pr.x, i2 = pr.y;
+                    uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
+                    ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
+                    ga = load_slim_support(A.o, A.H, i1, t1), gb = load_slim_support(A.o, A.H, i2, t2);
+                    active = true;
+                    status = epa_init_t<true>(e, ma, ga, mb, gb, sdim, sv, p1, p2, n, res_face);
+                }
+            }
+        } else if (active) {
+            status = epa_step_t(e, ma, ga, mb, gb, res_face);
+        }
+        bool ok = active && status == EPA_DONE_OK;
+        bool defer = active && status == EPA_DONE_FAIL && e.overflow;
+        bool fail = active && status == EPA_DONE_FAIL && !e.overflow;
+        if (ok && res_face != EPA_RES_DIRECT) epa_result_from_face(e, res_face, p1, p2, n);
+        uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], ok);
+        if (ok) {
+            cp_store(A.cp_queue, slot, p, p1, p2, n);
+            if constexpr (PS) A.ps.dir[A.pair_index ? __ldg(&A.pair_index[p]) : p] = make_float4(n.x, n.y, n.z, 1.f);
+        }
+        slot = queue_append(&A.cnt->epa_long_n, defer);
+        if (defer) A.epa_long[slot] = wq;
+        if (fail) {
+            if (e.panicked) atomicAdd(&A.cnt->ref_panics, 1u);
+            uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
+            if constexpr (PS) {  // NoIntersection(x axis) (contact_support_map_support_map.rs:76)
+                A.ps.dir[out_index] = make_float4(1.f, 0.f, 0.f, 1.f);
+                uint2 pr = __ldg(&A.pairs[p]);
+                pm_age_only(A.ps, out_index, pr.x, pr.y);
+            } else {
+                A.manifold_start[out_index] = 0;
+                A.manifold_count[out_index] = 0;
+            }
+        }
+        if (ok || defer || fail) active = false;
+        if (exhausted && __all_sync(0xffffffffu, !active)) break;
+    }
+}
+
 #define EPA_REFILL_MIN 32
 #ifndef NCB_EPA_MINBLOCKS
 #define NCB_EPA_MINBLOCKS 16
 #endif
-// PASS 0: one pass over the whole queue.  A whole-warp batch lasts as long as its slowest pair (up to ~12 expansion steps while
-// the average is ~4), so with PASS 1 / 2 the work is split: PASS 1 gives every pair at most A.epa_pass1_steps steps and defers
-// the unfinished ones (their queue index goes to A.epa_long), PASS 2 restarts those among their peers.  A restarted pair repeats
-// exactly the same arithmetic, so results do not depend on the split.
 template <bool PS, int PASS>
 __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) {
     const int KEY = CCQ;
@@ -983,14 +1077,13 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) 
     EpaState e;
     bool active = false, exhausted = false;
     uint32_t p = 0, wq = 0;
-    int steps = 0;
     Iso ma, mb;
     Support ga, gb;
     V3 p1, p2, n;
     for (;;) {
         int status = EPA_CONTINUE;
         unsigned idle = __ballot_sync(0xffffffffu, !active);
-        bool refill = !exhausted && (idle == 0xffffffffu || __popc(idle) >= A.epa_refill_min);
+        bool refill = !exhausted && (idle == 0xffffffffu || __popc(idle) >= EPA_REFILL_MIN);
         if (refill) {  // warp-uniform
             uint32_t base = 0;
             int leader = __ffs(idle) - 1;
@@ -1001,17 +1094,9 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) 
                 uint32_t w = base + __popc(idle & ((1u << lane) - 1));
                 if (w < seg_end) {
                     wq = PASS == 2 ? __ldg(&A.epa_long[w]) : w;
-                    steps = 0;
-                    const uint32_t* q = A.epa_queue + (size_t)wq * EPA_REC_WORDS;
-                    const float* f = reinterpret_cast<const float*>(q);
-                    p = q[0];
-                    int sdim = (int)q[1];
+                    int sdim;
                     CSOPoint sv[4];
-                    for (int i = 0; i < 4; ++i) {
-                        sv[i].orig1 = v3(f[2 + 6 * i + 0], f[2 + 6 * i + 1], f[2 + 6 * i + 2]);
-                        sv[i].orig2 = v3(f[2 + 6 * i + 3], f[2 + 6 * i + 4], f[2 + 6 * i + 5]);
-                        sv[i].point = sv[i].orig1 - sv[i].orig2;  // bit-identical to the value GJK computed (CSOPoint::new)
-                    }
+                    epa_rec_load(A.epa_queue + (size_t)wq * EPA_REC_WORDS, p, sdim, sv);
                     uint2 pr = __ldg(&A.pairs[p]);
                     uint32_t i1 = pr.x, i2 = pr.y;
                     uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
@@ -1024,15 +1109,6 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) 
             }
         } else if (active) {
             status = epa_step(e, ma, ga, mb, gb, p1, p2, n);
-            steps++;
-        }
-        if (PASS == 1) {  // all lanes take part in the aggregated append
-            bool defer = active && status == EPA_CONTINUE && steps >= A.epa_pass1_steps;
-            uint32_t ls = queue_append(&A.cnt->epa_long_n, defer);
-            if (defer) {
-                A.epa_long[ls] = wq;
-                active = false;
-            }
         }
         bool ok = active && status == EPA_DONE_OK;
         bool fail = active && status == EPA_DONE_FAIL;
@@ -1056,67 +1132,6 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) 
         }
         if (ok || fail) active = false;
         if (exhausted && __all_sync(0xffffffffu, !active)) break;
-    }
-}
-
-#include "epa_coop.cuh"
-
-// EPA over the compacted queue, eight lanes per pair (epa_coop.cuh).  Pairs that do not fit the shared-memory capacities are
-// appended to A.epa_long and finished by k_cc_epa<PS, 2>.
-template <bool PS>
-__global__ void __launch_bounds__(CE_PAIRS * CE_G) k_cc_epa_coop(NarrowArgs A) {
-    __shared__ CoopEpa pool[CE_PAIRS];
-    const int KEY = CCQ;
-    const uint32_t seg_end = A.cnt->epa_cursor[KEY];
-    uint32_t* fetch = &A.cnt->epa_fetch[KEY];
-    const int gl = threadIdx.x & 7;
-    CoopEpa& e = pool[threadIdx.x >> 3];
-    for (;;) {
-        uint32_t w = 0;
-        if (gl == 0) w = atomicAdd(fetch, 1u);
-        w = ce_bcast(w, 0);
-        if (w >= seg_end) break;
-        const uint32_t* q = A.epa_queue + (size_t)w * EPA_REC_WORDS;
-        const float* f = reinterpret_cast<const float*>(q);
-        uint32_t p = q[0];
-        int sdim = (int)q[1];
-        CSOPoint sv[4];
-        for (int i = 0; i < 4; ++i) {
-            sv[i].orig1 = v3(f[2 + 6 * i + 0], f[2 + 6 * i + 1], f[2 + 6 * i + 2]);
-            sv[i].orig2 = v3(f[2 + 6 * i + 3], f[2 + 6 * i + 4], f[2 + 6 * i + 5]);
-            sv[i].point = sv[i].orig1 - sv[i].orig2;  // bit-identical to the value GJK computed (CSOPoint::new)
-        }
-        uint2 pr = __ldg(&A.pairs[p]);
-        uint32_t i1 = pr.x, i2 = pr.y;
-        uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
-        Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
-        Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
-        SlimSupport ga, gb;
-        ga.kind = t1 == NCB_SHAPE_CUBOID ? 0 : 1, ga.he = a.he, ga.nv = a.hull.nv, ga.pts = a.hull.pts;
-        gb.kind = t2 == NCB_SHAPE_CUBOID ? 0 : 1, gb.he = b.he, gb.nv = b.hull.nv, gb.pts = b.hull.pts;
-        V3 p1, p2, n;
-        bool panicked = false;
-        int st = ce_run(e, ma, ga, mb, gb, sdim, sv, p1, p2, n, panicked);
-        if (gl == 0) {
-            uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
-            if (st == CE_OK) {
-                uint32_t slot = atomicAdd(&A.cnt->cp_cursor[KEY], 1u);
-                cp_store(A.cp_queue, slot, p, p1, p2, n);
-                if constexpr (PS) A.ps.dir[out_index] = make_float4(n.x, n.y, n.z, 1.f);
-            } else if (st == CE_DEFER) {
-                A.epa_long[atomicAdd(&A.cnt->epa_long_n, 1u)] = w;
-            } else {
-                if (panicked) atomicAdd(&A.cnt->ref_panics, 1u);
-                if constexpr (PS) {
-                    A.ps.dir[out_index] = make_float4(1.f, 0.f, 0.f, 1.f);
-                    pm_age_only(A.ps, out_index, i1, i2);
-                } else {
-                    A.manifold_start[out_index] = 0;
-                    A.manifold_count[out_index] = 0;
-                }
-            }
-        }
-        ce_sync();
     }
 }
 
@@ -1265,16 +1280,9 @@ __global__ void __launch_bounds__(64) k_bh_epa(NarrowArgs A) {
         mf.deepest = 0;
         uint32_t p = 0, h1 = 0, h2 = 0;
         if (valid) {
-            const uint32_t* q = A.epa_queue + (size_t)w * EPA_REC_WORDS;
-            const float* f = reinterpret_cast<const float*>(q);
-            p = q[0];
-            int sdim = (int)q[1];
+            int sdim;
             CSOPoint sv[4];
-            for (int i = 0; i < 4; ++i) {
-                sv[i].orig1 = v3(f[2 + 6 * i + 0], f[2 + 6 * i + 1], f[2 + 6 * i + 2]);
-                sv[i].orig2 = v3(f[2 + 6 * i + 3], f[2 + 6 * i + 4], f[2 + 6 * i + 5]);
-                sv[i].point = sv[i].orig1 - sv[i].orig2;
-            }
+            epa_rec_load(A.epa_queue + (size_t)w * EPA_REC_WORDS, p, sdim, sv);
             uint2 pr = __ldg(&A.pairs[p]);
             uint32_t i1 = pr.x, i2 = pr.y;
             h1 = i1, h2 = i2;
@@ -1337,13 +1345,11 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     A.manifold_count = c->manifold_count.p;
     A.cnt = c->counters.p;
     A.cap_pairs = cap_pairs;
-    static int refill_min = getenv("NCB_EPA_REFILL") ? atoi(getenv("NCB_EPA_REFILL")) : EPA_REFILL_MIN;
+    static int refill_min = getenv("NCB_EPA_REFILL") ? atoi(getenv("NCB_EPA_REFILL")) : 16;
     A.epa_refill_min = refill_min;
     A.epa_queue = c->epa_queue.p;
     A.cp_queue = c->cp_queue.p;
     A.epa_long = c->epa_long.p;
-    static int pass1 = getenv("NCB_EPA_PASS1") ? atoi(getenv("NCB_EPA_PASS1")) : 0;
-    A.epa_pass1_steps = pass1;
     {
         float one_degree = (float)(3.14159265358979323846 / 180.0);
         A.one_degree_cs = make_float2(cosf(one_degree), sinf(one_degree));
@@ -1382,14 +1388,17 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
         cudaMemcpyAsync(c->snap.p, c->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToDevice, s);
         cudaEventRecord(c->ev_snap, s);
     }
-    static int epa_coop = getenv("NCB_EPA_COOP") ? atoi(getenv("NCB_EPA_COOP")) : 0;
-    static int epac_bpsm = getenv("NCB_EPAC_BPSM") ? atoi(getenv("NCB_EPAC_BPSM")) : 5;
-    if (epa_coop) {
-        k_cc_epa_coop<PS><<<sm * epac_bpsm, CE_PAIRS * CE_G, 0, s>>>(A);
-        k_cc_epa<PS, 2><<<sm * 2, 64, 0, s>>>(A);  // the few pairs beyond the shared-memory capacities
-    } else if (A.epa_pass1_steps > 0) {
-        k_cc_epa<PS, 1><<<sm * epa_bpsm, 64, 0, s>>>(A);
-        k_cc_epa<PS, 2><<<sm * epa_bpsm, 64, 0, s>>>(A);
+    static int epa_shared = getenv("NCB_EPA_SHARED") ? atoi(getenv("NCB_EPA_SHARED")) : 1;
+    static int epas_bpsm = getenv("NCB_EPAS_BPSM") ? atoi(getenv("NCB_EPAS_BPSM")) : NCB_EPAS_MINBLOCKS;
+    if (epa_shared) {
+        const size_t smem = (size_t)EpaShared::WORDS * EPAS_THREADS * sizeof(uint32_t);
+        static bool attr_set[2] = {false, false};
+        if (!attr_set[PS]) {
+            cudaFuncSetAttribute(k_cc_epa_s<PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set[PS] = true;
+        }
+        k_cc_epa_s<PS><<<sm * epas_bpsm, EPAS_THREADS, smem, s>>>(A);
+        k_cc_epa<PS, 2><<<sm * 2, 64, 0, s>>>(A);  // the pairs beyond the compact capacities
     } else {
         k_cc_epa<PS, 0><<<sm * epa_bpsm, 64, 0, s>>>(A);
     }

@@ -43,6 +43,23 @@ NCB_HD Support as_support(const Shape& s) {
     return g;
 }
 
+// The slim operand of the EPA kernels straight from the object arrays (no HullView with its 13 table pointers).
+NCB_HD SupportS load_slim_support(const DevObjects& o, const DevHulls& H, uint32_t i, uint32_t type) {
+    SupportS g;
+    float4 p = __ldg(&o.param[i]);
+    g.kind = type == NCB_SHAPE_CUBOID ? 0 : 1;
+    g.he = v3(p.x, p.y, p.z);
+    g.nverts = 0;
+    g.pts = nullptr;
+    if (type == NCB_SHAPE_CONVEX_HULL) {
+        uint32_t h = (uint32_t)p.x;
+        uint32_t v0 = __ldg(H.vert_off + h);
+        g.nverts = __ldg(H.vert_off + h + 1) - v0;
+        g.pts = H.points + 3 * (size_t)v0;
+    }
+    return g;
+}
+
 // ConvexHull::project_point_with_feature (point_support_map.rs:15-53 with solid = false, :97-116), in two parts so that
 // the rare "point inside the hull" case (EPA) can be deferred to its own compacted kernel.
 struct HullProjSetup {

@@ -23,7 +23,7 @@ cv = np.ascontiguousarray(pairs[(t[pairs[:, 0]] != 0) & (t[pairs[:, 1]] != 0)])
 lib = _build_shim("libgjk_host.so", "gjk_host.cpp")
 oc, keep = _ffi.pack_objects(s)
 hc, keep2 = _ffi.pack_hull_library(s.hulls)
-st = np.zeros((len(cv), 4), dtype=np.uint32)
+st = np.zeros((len(cv), 8), dtype=np.uint32)
 lib.shim_epa_work_stats(C.byref(oc), C.byref(hc), C.c_uint64(len(cv)), _ffi.ptr(cv), _ffi.ptr(st))
 e = st[st[:, 0] > 0]
 
@@ -37,7 +37,11 @@ out = {
     "steps": {"mean": float(e[:, 0].mean()), "percentiles": pct(e[:, 0]), "share_of_all_steps_in_the_longest_10pct_of_pairs":
               float(np.sort(e[:, 0])[int(0.9 * len(e)):].sum() / e[:, 0].sum())},
     "vertices_at_exit": pct(e[:, 1]), "faces_at_exit": pct(e[:, 2]), "heap_entries_at_exit": pct(e[:, 3]),
+    "peak_heap": pct(e[:, 4]), "peak_silhouette": pct(e[:, 5]), "peak_flood_stack": pct(e[:, 6]),
+    "simplex_dim_plus_1": {str(k): float((e[:, 7] == k).mean()) for k in (1, 2, 3, 4)},
     "capacities": {"EPA_MAX_VERTS": 48, "EPA_MAX_FACES": 192, "EPA_MAX_HEAP": 160},
+    "compact_store": {"capacities": {"verts": 16, "faces": 48, "heap": 24, "silhouette": 16, "flood_stack": 12},
+                      "fits": float(((e[:, 1] <= 16) & (e[:, 2] <= 48) & (e[:, 4] <= 24) & (e[:, 5] <= 16) & (e[:, 6] <= 12) & (e[:, 7] == 4)).mean())},
     "fits": {f"<= {v} verts and <= {f} faces": float(((e[:, 1] <= v) & (e[:, 2] <= f)).mean()) for v, f in ((8, 16), (12, 32), (16, 48), (24, 80), (32, 128))},
 }
 print(json.dumps(out))

@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY — compiles the device GJK / EPA of ncollide_b200/csrc/gjk.cuh (the functions k_cc_gjk / k_cc_epa /
 // k_bh_epa run per pair: gjk_closest_points, epa_init, epa_step, the Voronoi simplex) for the host through
 // tests/host_shim/cuda_runtime.h, so that their logic and f32 operation order can be checked against the oracle without a GPU.
+#define NCB_EPA_STATS  // peak heap / silhouette / flood-stack sizes for scripts/epa_work_stats.py (this test library only)
 #include "shapes.cuh"
 
 using namespace ncb;
@@ -57,7 +58,8 @@ void shim_contact_sm_sm(const ncb_objects* objs, const ncb_hull_library* lib, ui
 }
 
 // Work statistics of the device EPA per penetrating pair (design data for kernel restructuring, scripts/epa_work_stats.py):
-// stats[4 k] = expansion steps, vertices, faces (incl. deleted), heap entries at the end of pair k's EPA run; 0s when GJK did not reach EPA.
+// stats[8 k] = expansion steps, vertices, faces (incl. deleted), heap entries at the end of pair k's EPA run, then the PEAK heap size,
+// silhouette length and flood-stack depth, and the simplex dimension + 1; 0s when GJK did not reach EPA.
 void shim_epa_work_stats(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_pairs, const uint32_t* pairs, uint32_t* stats) {
     DevObjects o;
     std::memset(&o, 0, sizeof o);
@@ -78,14 +80,80 @@ void shim_epa_work_stats(const ncb_objects* objs, const ncb_hull_library* lib, u
         if (!unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
         V3 p1, p2, dir;
         Simplex s;
-        uint32_t* st = stats + 4 * p;
-        st[0] = st[1] = st[2] = st[3] = 0;
+        uint32_t* st = stats + 8 * p;
+        for (int k = 0; k < 8; ++k) st[k] = 0;
         if (gjk_closest_points(ma, ga, mb, gb, o.qlimit[i1] + o.qlimit[i2], d0, s, p1, p2, dir) != GJK_INTERSECTION) continue;
         int status = epa_init(*e, ma, ga, mb, gb, s.dim, s.v, p1, p2, dir);
         uint32_t steps = 0;
         while (status == EPA_CONTINUE) status = epa_step(*e, ma, ga, mb, gb, p1, p2, dir), steps++;
         st[0] = steps + 1, st[1] = (uint32_t)e->nverts, st[2] = (uint32_t)e->nfaces, st[3] = (uint32_t)e->nheap;
+        st[4] = (uint32_t)e->peak_heap, st[5] = (uint32_t)e->peak_sil, st[6] = (uint32_t)e->peak_stk, st[7] = (uint32_t)s.dim + 1;
     }
     delete e;
+}
+
+// The same as shim_contact_sm_sm, but EPA runs on the COMPACT polytope store of epa.cuh (the shared-memory layout of k_cc_epa_s, here
+// backed by a host array with the kernel's lane stride) with the slim operands; a pair that exceeds a compact capacity is restarted
+// on the big store exactly as the kernel's overflow queue does.  flags[3] += pairs that were restarted.
+void shim_contact_sm_sm_compact(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_pairs, const uint32_t* pairs,
+                                const float* predictions, float* out, uint32_t* flags) {
+    DevObjects o;
+    std::memset(&o, 0, sizeof o);
+    o.n = objs->n;
+    o.pos = objs->pos;
+    o.rot = reinterpret_cast<const float4*>(objs->rot);
+    o.type = objs->shape_type;
+    o.param = reinterpret_cast<const float4*>(objs->shape_param);
+    o.qlimit = objs->query_limit;
+    DevHulls H = hulls_from(lib);
+    EpaState* big = new EpaState;
+    typedef EpaCompact<64> Compact;
+    uint32_t* words = new uint32_t[Compact::WORDS * 64];
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
+        Shape a = load_shape(o, H, i1, o.type[i1]), b = load_shape(o, H, i2, o.type[i2]);
+        Iso ma = load_iso(o, i1), mb = load_iso(o, i2);
+        Support ga = as_support(a), gb = as_support(b);
+        float prediction = predictions ? predictions[p] : o.qlimit[i1] + o.qlimit[i2];
+        V3 p1 = v3(0.f, 0.f, 0.f), p2 = p1, n = p1;
+        V3 dir;
+        if (!unit_try_new(mb.t - ma.t, NCB_EPS, dir)) dir = v3(1.f, 0.f, 0.f);
+        Simplex s;
+        int r = gjk_closest_points(ma, ga, mb, gb, prediction, dir, s, p1, p2, n);
+        if (r == GJK_INTERSECTION) {
+            flags[2]++;
+            Compact e;
+            e.base = words + (p % 64);  // any lane of the CTA
+            SupportS sa = slim_support(ga), sb = slim_support(gb);
+            uint32_t res_face;
+            int st = epa_init_t<true>(e, ma, sa, mb, sb, s.dim, s.v, p1, p2, n, res_face);
+            while (st == EPA_CONTINUE) st = epa_step_t(e, ma, sa, mb, sb, res_face);
+            if (st == EPA_DONE_OK) {
+                if (res_face != EPA_RES_DIRECT) epa_result_from_face(e, res_face, p1, p2, n);
+                r = GJK_CLOSEST_POINTS;
+            } else if (e.overflow) {
+                flags[3]++;
+                if (epa_closest_points(*big, ma, ga, mb, gb, s.dim, s.v, p1, p2, n))
+                    r = GJK_CLOSEST_POINTS;
+                else {
+                    if (big->overflow) flags[0]++;
+                    if (big->panicked) flags[1]++;
+                    r = GJK_NO_INTERSECTION;
+                }
+            } else {
+                if (e.panicked) flags[1]++;
+                r = GJK_NO_INTERSECTION;
+            }
+            if (r == GJK_NO_INTERSECTION) n = v3(1.f, 0.f, 0.f);
+        }
+        float* d = out + 10 * p;
+        for (int k = 0; k < 10; ++k) d[k] = 0.f;
+        if (r == GJK_CLOSEST_POINTS) {
+            d[0] = p1.x, d[1] = p1.y, d[2] = p1.z, d[3] = p2.x, d[4] = p2.y, d[5] = p2.z, d[6] = n.x, d[7] = n.y, d[8] = n.z;
+            d[9] = 1.f;
+        }
+    }
+    delete big;
+    delete[] words;
 }
 }

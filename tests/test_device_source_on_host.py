@@ -130,14 +130,15 @@ def test_device_proximity_source_reproduces_the_golden_fixture(shim):
 
 
 # ---- the device GJK / EPA of gjk.cuh (what k_cc_gjk / k_cc_epa run per pair) -----------------------------------------------------
-def shim_contact_sm_sm(lib, scene, pairs, predictions=None):
+def shim_contact_sm_sm(lib, scene, pairs, predictions=None, compact=False):
     oc, keep = _ffi.pack_objects(scene)
     hc, keep2 = _ffi.pack_hull_library(scene.hulls)
     pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
     out = np.zeros((len(pairs), 10), dtype=F)
     flags = np.zeros(4, dtype=np.uint32)
     m = None if predictions is None else np.ascontiguousarray(predictions, dtype=F)
-    lib.shim_contact_sm_sm(C.byref(oc), C.byref(hc), C.c_uint64(len(pairs)), _ffi.ptr(pairs), _ffi.ptr(m), _ffi.ptr(out), _ffi.ptr(flags))
+    fn = lib.shim_contact_sm_sm_compact if compact else lib.shim_contact_sm_sm
+    fn(C.byref(oc), C.byref(hc), C.c_uint64(len(pairs)), _ffi.ptr(pairs), _ffi.ptr(m), _ffi.ptr(out), _ffi.ptr(flags))
     return out, flags
 
 
@@ -155,32 +156,38 @@ GJK_SCENES = [
 ]
 
 
+@pytest.mark.parametrize("compact", [False, True])
 @pytest.mark.parametrize("mk", GJK_SCENES)
-def test_device_gjk_epa_source_matches_oracle(gjk_shim, oracle, mk):
+def test_device_gjk_epa_source_matches_oracle(gjk_shim, oracle, mk, compact):
     """contact_support_map_support_map through the device's gjk_closest_points + epa_init / epa_step (fixed-capacity polytope,
     packed topology, deferred heap pushes) against the oracle's std-container restatement: same found / not found, same points and
-    normals BIT FOR BIT — the device follows the reference's iteration path, not just its maths."""
+    normals BIT FOR BIT — the device follows the reference's iteration path, not just its maths.
+    compact: EPA on the shared-memory polytope store of k_cc_epa_s (16 / 48 / 24 capacities, one packed word per face, face normals
+    recomputed, slim operands), pairs beyond its capacities restarted on the big store like the kernel's overflow queue does."""
     s = mk()
     pairs = _convex_pairs(oracle, s)
     pairs = np.concatenate([pairs, pairs[:, ::-1]])
     assert len(pairs) > 2000
-    got, flags = shim_contact_sm_sm(gjk_shim, s, pairs)
+    got, flags = shim_contact_sm_sm(gjk_shim, s, pairs, compact=compact)
     want, stats = oracle.contact_sm_sm(s, pairs)
     assert flags[0] == 0 and flags[1] == 0, "EPA capacity overflow / reference panic"
+    if compact:
+        assert flags[3] < 0.1 * flags[2], "the compact store is sized for (almost) every pair"
     assert np.array_equal(got[:, 9], want[:, 9]), int((got[:, 9] != want[:, 9]).sum())
     assert stats[2] > 100 and stats[3] == 0  # EPA ran and never failed
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), int((got.view(np.uint32) != want.view(np.uint32)).any(axis=1).sum())
 
 
+@pytest.mark.parametrize("compact", [False, True])
 @pytest.mark.parametrize("k", [0, 2, 3, 4])
-def test_device_gjk_epa_source_on_adversarial_scenes(gjk_shim, oracle, k):
+def test_device_gjk_epa_source_on_adversarial_scenes(gjk_shim, oracle, k, compact):
     from test_gpu_parity import _adversarial_scenes
 
     s = _adversarial_scenes()[k]
     pairs = _convex_pairs(oracle, s)
     if len(pairs) == 0:
         pytest.skip("no convex pairs")
-    got, flags = shim_contact_sm_sm(gjk_shim, s, pairs)
+    got, flags = shim_contact_sm_sm(gjk_shim, s, pairs, compact=compact)
     want, stats = oracle.contact_sm_sm(s, pairs)
     assert flags[0] == 0
     assert np.array_equal(got[:, 9], want[:, 9])
