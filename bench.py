@@ -34,13 +34,91 @@ UNIT = "updates/s (1M-shape worlds)"
 N_PER_GPU = 1_000_000
 
 
-def measured_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+def workload_config(n_per, world):
+    """The `config` object: names the workload only, so both arms (native and --impl reference) print the same one."""
+    return {
+        "workload": f"configs[2]: {n_per} mixed balls/cuboids/convex hulls (<=32 verts) per GPU, fresh-world update "
+                    "(AABBs -> broad-phase pair search -> contact manifolds)",
+        "n_objects_total": n_per * world,
+        "seed": 1003,
+        "l2": "native arm: 256 MiB flush between timed iterations, working set > L2; reference arm: host memory",
+        "parallelism": ("native arm: single GPU" if world == 1 else
+                        f"native arm: {world} ranks, AABB block per rank + NCCL all-gather, spatial ownership (Morton ranges + ghosts), local LBVH per rank")
+                       + "; reference arm: 1 host thread (the reference is single-threaded)",
+    }
+
+
+STAGE_KERNEL = {"cc_epa": "k_cc_epa", "cc_gjk": "k_cc_gjk", "cc_manifold": "k_cc_manifold", "pair_search": "k_pair_search",
+                "narrow_other_join": "k_narrow"}
+
+
+def source_hash():
+    """Hash of the CUDA sources: a committed ncu traffic figure is only used when it was captured from this code."""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "ncollide_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(f.encode())
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/r2_traffic.json), refused
+    (None) when the capture was made from other kernel sources than the ones in the tree."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
-        return json.load(open(p)).get(kernel)
+        d = json.load(open(p))
+        if d.get("source_hash") != source_hash():
+            return None, "committed capture is stale (kernel sources changed since): refused"
+        return d["kernels"].get(key), f"profiles/r2_traffic.json ({d.get('captured')})"
     except Exception:
-        return None
+        return None, "no capture"
+
+
+def live_traffic(regex, child_args, timeout=240):
+    """One `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` pass over one launch of every kernel matching `regex`, in a child
+    process that replays this bench's workload (after the timed region: nothing timed runs under the profiler).
+    Returns total DRAM bytes over the matched kernels of ONE step, or None when ncu is not usable here."""
+    import shutil
+
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    log = os.path.join("/tmp", f"ncb_traffic_{os.getpid()}.csv")
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", f"regex:{regex}",
+           "--csv", "--log-file", log, sys.executable, os.path.join(ROOT, "bench.py"), "--traffic-child"] + child_args
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        if r.returncode != 0 or not os.path.exists(log):
+            return None, f"ncu child failed (rc {r.returncode})"
+        import csv
+
+        rows = list(csv.reader(l for l in open(log) if l.startswith('"')))
+        hdr = rows[0]
+        ik, im, iv, iu, iid = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("ID")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        per_launch = {}
+        for row in rows[1:]:
+            if row[im] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v = float(row[iv].replace(",", "")) * scale.get(row[iu], 1.0)
+                per_launch.setdefault((row[iid], row[ik]), 0.0)
+                per_launch[(row[iid], row[ik])] += v
+        if not per_launch:
+            return None, "no matching launch in the ncu log"
+        # the child runs TRAFFIC_CHILD_STEPS identical steps: keep the launches of the last one
+        names = [k[1] for k in per_launch]
+        n_kernels = len(set(names))
+        last = list(per_launch.items())[-n_kernels:]
+        return float(sum(v for _, v in last)), f"live: ncu dram__bytes_read.sum + dram__bytes_write.sum over {[k[1][:40] for k, _ in last]}, one step"
+    except Exception as ex:  # noqa: BLE001
+        return None, f"ncu child: {repr(ex)[:120]}"
+    finally:
+        try:
+            os.remove(log)
+        except OSError:
+            pass
 
 
 def measured_peaks():
@@ -109,9 +187,34 @@ class ClockSampler:
         }
 
 
+RAY_CPU_SAMPLE = 250_000
+
+
+def rays_cpu_baseline(n_tris=1_000_000, n_rays=RAY_CPU_SAMPLE, kind="terrain"):
+    """Timing analogue of the reference's build/ncollide3d/benches/query/ray.rs for a TriMesh: the oracle's reference-faithful BVT
+    (median-split build, BinaryHeap best-first search, ray_trimesh.rs:22-50) on ONE host thread, full-size mesh, a sample of the rays."""
+    from ncollide_b200.scenes import make_ray_scene
+    from oracle.pyoracle import Oracle
+
+    orc = Oracle()
+    rs = make_ray_scene(kind, n_tris, n_rays, seed=1004)
+    t0 = time.perf_counter()
+    mesh = orc.trimesh(rs.verts, rs.tris)
+    build_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    toi, _face, _n = mesh.ray_cast(rs.origins, rs.dirs, mode=0)
+    cast_s = time.perf_counter() - t0
+    return {"value": n_rays / cast_s / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
+            "sample": f"{n_rays} of {n_tris} rays vs the full {len(rs.tris)}-triangle {kind} TriMesh (BVT build {build_s:.2f} s not timed, like the "
+                      "reference's bench); C++ restatement of the reference's BVT best-first ray cast, single thread, not the Rust binary",
+            "hit_fraction": float((toi >= 0).mean()), "host_cores_available": os.cpu_count()}
+
+
 def run_reference(args):
     """CPU arm: reference-faithful DBVT broad phase + narrow phase of the oracle, single thread (the reference is
-    single-threaded: no thread / rayon / atomic use anywhere in its src/)."""
+    single-threaded: no thread / rayon / atomic use anywhere in its src/), on the native arm's config: every step is one full
+    1M-object update (6-7 s), so the driver's --steps 20 --warmup 5 takes under three minutes.  At N > 1 the native arm's world has
+    N x 1M objects; the CPU sample stays one 1M-object world per step (value is in 1M-shape world updates per second either way)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -120,12 +223,9 @@ def run_reference(args):
 
     orc = Oracle()
     total_steps = args.steps + args.warmup
-    # ~10 s per 1M-object step on one core: bound the sample so the whole run stays within a few minutes
-    n = args.n_objects or N_PER_GPU
-    budget_s = 200.0
-    est = 10.0 * n / 1e6
-    if est * total_steps > budget_s:
-        n = max(20_000, int(n * budget_s / (est * total_steps)))
+    n_per = args.n_objects or N_PER_GPU
+    world = max(1, args.gpus)
+    n = n_per  # the sample: one GPU's share of the workload
     scene = config_scene(3, n)
     times = []
     counts = None
@@ -135,17 +235,27 @@ def run_reference(args):
             times.append(sum(t))
     ms = 1e3 * sum(times) / len(times)
     value = (n / 1e6) / (ms / 1e3)
+    rays = None
+    if not args.no_rays:
+        n_tris = 1_000_000 if not args.n_objects else max(1000, args.n_objects)
+        rc = rays_cpu_baseline(n_tris, min(RAY_CPU_SAMPLE, n_tris))
+        rays = {"metric": "Mrays/s vs TriMesh", "value": rc["value"], "unit": "Mrays/s", "cpu_baseline": rc,
+                "workload": f"{n_tris} rays per GPU vs {n_tris}-triangle terrain TriMesh, identity pose (first hit + TOI + normal)"}
+    sample = (f"every step is one full {n}-object cfg3 update" if world == 1 else
+              f"every step is one {n}-object cfg3 update = one GPU's share of the {n * world}-object world") + \
+        "; C++ restatement of the reference (DBVT + per-pair generators), not the Rust binary"
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg3 mixed balls/cuboids/hulls fresh-world update, {n} objects (sample of the 1M-object workload, same density)",
-                   "n_objects": n, "pairs": counts[0], "contacts": counts[1]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{n} of 1000000 objects per step, same density; C++ restatement of the reference (DBVT + per-pair generators), not the Rust binary"},
+        "config": workload_config(n_per, world),
+        "same_config": True,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "counts": {"n_pairs": counts[0], "n_contacts": counts[1], "n_contact_pairs": counts[2]},
         "contact_pairs_per_sec": counts[2] / (ms / 1e3),
         "host_cores_available": os.cpu_count(),
+        "rays": rays,
     }
     print(json.dumps(line))
     return 0
@@ -286,7 +396,7 @@ def run_native(args):
         ach = dom_bytes / (dom_ms / 1e3) / 1e9
         roofline = {
             "bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": measured_traffic(dom_name) if (n_per == N_PER_GPU) else None,
+            "traffic": None, "traffic_source": None,
             "peak_kind": f"{peak_kind} copy bandwidth", "kernel_ms": dom_ms, "algorithmic_bytes": dom_bytes,
             "share_of_step": dom_ms / max(sum(stage_acc.values()), 1e-9),
             "whole_step": {"algorithmic_bytes": total_bytes, "achieved": total_bytes / (ms_step / 1e3) / 1e9,
@@ -300,15 +410,15 @@ def run_native(args):
         t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
         keep.append(t)
         pin_out[k] = t.numpy().view(a.dtype).reshape(a.shape)
-    oc, okeep = _ffi.pack_objects(pin_scene)
 
     def step_e2e():
         if world == 1:
-            r = lib.ncb_world_update(
-                h, C.byref(oc), C.c_float(scene.margin), _ffi.ptr(pin_out["pairs"]), C.c_uint32(len(pin_out["pairs"])), _ffi.ptr(pin_out["algo"]),
-                _ffi.ptr(pin_out["start"]), _ffi.ptr(pin_out["count"]), _ffi.ptr(pin_out["contacts"]), C.c_uint32(len(pin_out["contacts"])),
-                C.byref(counts_c))
-            ctx.check(r, "ncb_world_update")
+            # the objects persist in the world (world.rs:64-96); a step sets the poses and updates (world.rs:104-119)
+            r = lib.ncb_world_update_poses(
+                h, C.c_uint32(n_total), _ffi.ptr(pin_scene.pos), _ffi.ptr(pin_scene.rot), C.c_float(scene.margin), _ffi.ptr(pin_out["pairs"]),
+                C.c_uint32(len(pin_out["pairs"])), _ffi.ptr(pin_out["algo"]), _ffi.ptr(pin_out["start"]), _ffi.ptr(pin_out["count"]),
+                _ffi.ptr(pin_out["contacts"]), C.c_uint32(len(pin_out["contacts"])), C.byref(counts_c))
+            ctx.check(r, "ncb_world_update_poses")
         else:
             # every rank uploads the poses of its own block, steps, and reads its own results back
             sharded.upload_own_poses(pin_scene.pos, pin_scene.rot)
@@ -336,57 +446,80 @@ def run_native(args):
         e2e_ms = float(t.item())
     e2e_value = (n_total / 1e6) / (e2e_ms / 1e3)
     n_up = n_total
-    # pos, rot, type, param, groups, query_limit per object + the (cos, sin) table of the angular prediction
-    h2d = n_up * (12 + 16 + 4 + 16 + 12 + 4) + 8 if world == 1 else n_per * 28
+    # per step: the poses (pos 12 B + rot 16 B per object); shapes / groups / query limits persist on the device like the objects of a
+    # CollisionWorld persist between updates
+    h2d = n_up * 28 if world == 1 else n_per * 28
     d2h = counts["n_pairs"] * (8 + 1 + 4 + 1) + counts["n_contacts"] * 52 + 256
 
-    # ---- secondary figure: batched TriMesh ray casting (configs[3]) ---------------------------------------
+    # ---- secondary figure: batched TriMesh ray casting (configs[3] / SURVEY §8d cfg 4a + 4b) ---------------
     rays = None
     if not args.no_rays:
         n_tris, n_rays = (1_000_000, 1_000_000) if (not args.n_objects or args.rays_only) else (max(1000, args.n_objects), max(1000, args.n_objects))
-        rs = make_ray_scene("terrain", n_tris, n_rays * world, seed=1004)
-        mesh = ctx.trimesh(rs.verts, rs.tris)
-        lo, hi = rank * n_rays, (rank + 1) * n_rays
-        d_o = torch.from_numpy(rs.origins[lo:hi]).to(dev)
-        d_d = torch.from_numpy(rs.dirs[lo:hi]).to(dev)
-        d_toi = torch.empty(n_rays, dtype=torch.float32, device=dev)
-        d_face = torch.empty(n_rays, dtype=torch.int32, device=dev)
-        d_n = torch.empty((n_rays, 3), dtype=torch.float32, device=dev)
         fmax = float(np.finfo(np.float32).max)
+        variants = {}
+        for kind, posed in (("terrain", False), ("terrain", True), ("soup", False), ("soup", True)):
+            rs = make_ray_scene(kind, n_tris, n_rays * world, seed=1004, random_pose=posed)
+            mesh = ctx.trimesh(rs.verts, rs.tris)
+            lo, hi = rank * n_rays, (rank + 1) * n_rays
+            origins, dirs = rs.origins[lo:hi], rs.dirs[lo:hi]
+            pose_arg = None
+            if posed:  # the rays move with the mesh, so the posed cast answers the same question as the identity one
+                from ncollide_b200.scenes import transform_rays
 
-        def ray_step():
-            ctx.check(lib.ncb_trimesh_ray_cast_device(mesh.h, None, C.c_uint32(n_rays), C.c_void_p(d_o.data_ptr()), C.c_void_p(d_d.data_ptr()),
-                                                      C.c_float(fmax), C.c_void_p(d_toi.data_ptr()), C.c_void_p(d_face.data_ptr()),
-                                                      C.c_void_p(d_n.data_ptr())), "ray_cast_device")
+                origins, dirs = transform_rays(rs.pose, origins, dirs)
+                pose_arg = np.ascontiguousarray(rs.pose, dtype=np.float32)
+            d_o = torch.from_numpy(origins).to(dev)
+            d_d = torch.from_numpy(dirs).to(dev)
+            d_toi = torch.empty(n_rays, dtype=torch.float32, device=dev)
+            d_face = torch.empty(n_rays, dtype=torch.int32, device=dev)
+            d_n = torch.empty((n_rays, 3), dtype=torch.float32, device=dev)
 
-        rms, _ = timed_steps(ray_step, max(args.steps, 5), 3)
-        rms_mean = sum(rms) / len(rms)
-        if dist is not None:
-            t = torch.tensor([rms_mean], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            rms_mean = float(t.item())
-        T, V = len(rs.tris), len(rs.verts)
-        ray_bytes = n_rays * (24 + 8 + 12) + V * 12 + T * 12 + (2 * T - 1) * 32
-        # end to end with host buffers
-        toi_h = np.zeros(n_rays, np.float32)
-        t0 = time.perf_counter()
-        mesh.toi_and_normal_with_ray(None, rs.origins[lo:hi], rs.dirs[lo:hi])
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            mesh.toi_and_normal_with_ray(None, rs.origins[lo:hi], rs.dirs[lo:hi])
-        barrier()
-        ray_e2e_ms = (time.perf_counter() - t0) * 1e3 / 3
-        rays = {
-            "metric": "Mrays/s vs TriMesh", "value": n_rays * world / (rms_mean / 1e3) / 1e6, "unit": "Mrays/s", "ms_per_batch": rms_mean,
-            "workload": f"{n_rays} rays per GPU vs {T}-triangle terrain TriMesh (first hit + TOI + normal)",
-            "hit_fraction": float((d_toi >= 0).float().mean().item()),
-            "roofline": {"bound": "hbm", "achieved": ray_bytes / (rms_mean / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": ray_bytes / (rms_mean / 1e3) / 1e9 / peak, "algorithmic_bytes": ray_bytes,
-                         "traffic": measured_traffic("k_ray_cast") if n_rays == 1_000_000 else None},
-            "e2e": {"value": n_rays * world / (ray_e2e_ms / 1e3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * 20},
-        }
-        mesh.close()
+            def ray_step():
+                ctx.check(lib.ncb_trimesh_ray_cast_device(mesh.h, _ffi.ptr(pose_arg), C.c_uint32(n_rays), C.c_void_p(d_o.data_ptr()),
+                                                          C.c_void_p(d_d.data_ptr()), C.c_float(fmax), C.c_void_p(d_toi.data_ptr()),
+                                                          C.c_void_p(d_face.data_ptr()), C.c_void_p(d_n.data_ptr())), "ray_cast_device")
+
+            rms, _ = timed_steps(ray_step, max(args.steps, 5), 3)
+            rms_mean = sum(rms) / len(rms)
+            if dist is not None:
+                t = torch.tensor([rms_mean], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                rms_mean = float(t.item())
+            T, V = len(rs.tris), len(rs.verts)
+            ray_bytes = n_rays * (24 + 8 + 12) + V * 12 + T * 12 + (2 * T - 1) * 32
+            # end to end with host buffers (pinned, like the world update's)
+            o_t, o_h = pinned(origins)
+            d_t, d_h = pinned(dirs)
+            keep.extend([o_t, d_t])
+            mesh.toi_and_normal_with_ray(pose_arg, o_h, d_h)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                mesh.toi_and_normal_with_ray(pose_arg, o_h, d_h)
+            barrier()
+            ray_e2e_ms = (time.perf_counter() - t0) * 1e3 / 3
+            if dist is not None:
+                t = torch.tensor([ray_e2e_ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ray_e2e_ms = float(t.item())
+            name = f"{kind}_{'random_pose' if posed else 'identity'}"
+            variants[name] = {
+                "value": n_rays * world / (rms_mean / 1e3) / 1e6, "unit": "Mrays/s", "ms_per_batch": rms_mean,
+                "workload": f"{n_rays} rays per GPU vs {T}-triangle {kind} TriMesh, {'one random mesh pose' if posed else 'identity pose'} (first hit + TOI + normal)",
+                "hit_fraction": float((d_toi >= 0).float().mean().item()),
+                "roofline": {"bound": "hbm", "achieved": ray_bytes / (rms_mean / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": ray_bytes / (rms_mean / 1e3) / 1e9 / peak, "algorithmic_bytes": ray_bytes},
+                "e2e": {"value": n_rays * world / (ray_e2e_ms / 1e3) / 1e6, "unit": "Mrays/s", "ms_per_batch": ray_e2e_ms,
+                        "h2d_bytes_per_step": n_rays * 24, "d2h_bytes_per_step": n_rays * 20},
+            }
+            mesh.close()
+            del d_o, d_d, d_toi, d_face, d_n
+        head = variants["terrain_identity"]
+        rays = {"metric": "Mrays/s vs TriMesh", **head, "variants": {k: v for k, v in variants.items() if k != "terrain_identity"}}
+        tr, tr_src = committed_traffic("k_ray_cast")
+        rays["roofline"]["traffic"], rays["roofline"]["traffic_source"] = (tr, tr_src) if n_rays == 1_000_000 else (None, None)
+        if rank == 0 and world == 1 and not args.no_cpu:
+            rays["cpu_baseline"] = rays_cpu_baseline(n_tris, min(RAY_CPU_SAMPLE, n_rays))
         if args.rays_only:
             if rank == 0:
                 print(json.dumps(rays))
@@ -408,6 +541,17 @@ def run_native(args):
                          "C++ restatement of the reference, single thread like the reference, not the Rust binary",
                "host_cores_available": os.cpu_count(), "pairs": c[0], "contacts": c[1]}
 
+    # ---- DRAM traffic of the dominant stage's kernels: one ncu pass in a child process (nothing timed runs under the profiler) ----
+    if rank == 0 and world == 1 and roofline and n_per == N_PER_GPU:
+        key = STAGE_KERNEL.get(dom_name)
+        tr, src = (None, "not measured")
+        if key and not args.no_traffic:
+            tr, src = live_traffic(key, [])
+        if tr is None and key:
+            tr2, src2 = committed_traffic(key)
+            tr, src = tr2, (src2 if tr2 is not None else f"{src}; {src2}")
+        roofline["traffic"], roofline["traffic_source"] = tr, src
+
     # ---- widened rows, N = 1 only, reported beside the headline; never allowed to break the line ----
     widened = None
     if rank == 0 and world == 1 and not args.no_extras:
@@ -424,22 +568,17 @@ def run_native(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": f"configs[2]: {n_per} mixed balls/cuboids/convex hulls (<=32 verts) per GPU, fresh-world update "
-                            "(AABBs -> LBVH -> pair search -> contact manifolds)",
-                "n_objects_total": n_total, "pairs": tot_pairs, "contacts": tot_contacts, "contact_pairs": tot_contact_pairs,
-                "parallelism": "single GPU" if world == 1 else (
-                    f"{world} ranks: AABB block per rank + NCCL all-gather, "
-                    + ("replicated LBVH, query slices" if os.environ.get("NCB_SHARD") == "slices" else "spatial ownership (Morton ranges + ghosts), local LBVH per rank")),
-                "l2": "256 MiB flush between timed iterations; working set > L2",
-                "seed": 1003,
-            },
+            "config": workload_config(n_per, world),
+            "pairs": tot_pairs, "contacts": tot_contacts, "contact_pairs": tot_contact_pairs,
             "contact_pairs_per_sec": tot_contact_pairs / (ms_step / 1e3),
             "broad_phase_pairs_per_sec": tot_pairs / (ms_step / 1e3),
             "stages_ms": stages,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "call": "ncb_world_update_poses: pinned host poses in (set_position on every object), update, every pair / manifold / contact "
+                            "out to pinned host buffers" if world == 1 else "per rank: ncb_set_positions_range + NCCL pose all-gather + "
+                            "ncb_world_update_stage / _sharded + ncb_world_fetch of the rank's own pairs and contacts"},
             "gpu_launches": int(launches_total * args.steps),
             "gpu_launches_per_step": int(launches_total),
             "clocks": clocks,
@@ -451,6 +590,28 @@ def run_native(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+TRAFFIC_CHILD_STEPS = 3
+
+
+def run_traffic_child(args):
+    """The workload's device-resident steps and nothing else (the parent runs this under ncu)."""
+    import ctypes as C
+
+    from ncollide_b200 import _ffi
+    from ncollide_b200.scenes import config_scene
+    from ncollide_b200.world import Context
+
+    ctx = Context(0)
+    scene = config_scene(3, args.n_objects or N_PER_GPU)
+    ctx.set_hulls(scene.hulls)
+    ctx.set_objects(scene)
+    counts_c = _ffi.UpdateCountsC()
+    for _ in range(TRAFFIC_CHILD_STEPS):
+        ctx.check(ctx.lib.ncb_world_update_device(ctx.h, C.c_float(scene.margin), C.c_uint32(0), C.c_uint32(0xFFFFFFFF), C.byref(counts_c)), "update")
     ctx.close()
     return 0
 
@@ -604,10 +765,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the stepping-world / world-query figures")
     ap.add_argument("--rays-only", action="store_true", help="debug: only the ray-casting sub-benchmark, prints its dict")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child that measures the dominant kernel's DRAM traffic")
+    ap.add_argument("--traffic-child", action="store_true", help="internal: replay the workload's device steps (run under ncu by the parent)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.traffic_child:
+        return run_traffic_child(args)
     return run_native(args)
 
 

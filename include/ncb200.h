@@ -191,6 +191,13 @@ int ncb_world_fetch_proximity(ncb_ctx* ctx, uint8_t* prox, uint32_t cap_pairs);
 int ncb_world_update(ncb_ctx* ctx, const ncb_objects* objs, float margin, uint32_t* pairs, uint32_t cap_pairs,
                      uint8_t* pair_algo, uint32_t* manifold_start, uint8_t* manifold_count, ncb_contact* contacts,
                      uint32_t cap_contacts, ncb_update_counts* counts);
+/* The end-to-end call of a world whose objects persist (pipeline/world.rs:64-119: `add` once, then per step
+ * `CollisionObject::set_position` on the objects + `CollisionWorld::update`): uploads only the n poses (28 B per object, host
+ * pointers, pinned memory recommended), updates, and returns the results like ncb_world_update.  Shapes, groups and query limits are
+ * the ones of the last ncb_set_objects.  = ncb_set_positions + ncb_world_fetch_early + ncb_world_update_device + ncb_world_fetch. */
+int ncb_world_update_poses(ncb_ctx* ctx, uint32_t n, const float* pos, const float* rot, float margin, uint32_t* pairs, uint32_t cap_pairs,
+                           uint8_t* pair_algo, uint32_t* manifold_start, uint8_t* manifold_count, ncb_contact* contacts,
+                           uint32_t cap_contacts, ncb_update_counts* counts);
 
 /* Device pointers of internal buffers, for multi-GPU plumbing (NCCL all-gather of AABBs) and zero-copy consumers.
  * which: 0 aabb_lo (float4 per object: mins, w unused) 1 aabb_hi, 2 pairs (uint2), 3 contacts (ncb_contact),

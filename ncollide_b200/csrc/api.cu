@@ -123,6 +123,9 @@ int ncb_create(int device, ncb_ctx** out) {
         e = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->over_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_epa, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_over, cudaEventDisableTiming);
     }
     if (e != cudaSuccess) {
         g_create_err = cudaGetErrorString(e);
@@ -165,6 +168,9 @@ void ncb_destroy(ncb_ctx* c) {
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->over_stream) cudaStreamDestroy(c->over_stream);
+    if (c->ev_epa) cudaEventDestroy(c->ev_epa);
+    if (c->ev_over) cudaEventDestroy(c->ev_over);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -451,7 +457,7 @@ static void fill_counts(ncb_ctx* ctx, ncb_update_counts* counts) {
     counts->n_algo[NCB_ALGO_CONVEX_CONVEX] = c.key_hist[K_CUBOID_CUBOID] + c.key_hist[K_CUBOID_HULL] + c.key_hist[K_HULL_HULL];
     counts->n_algo[NCB_ALGO_NONE] = c.key_hist[K_NONE];
     counts->n_epa_pairs = c.epa_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID];
-    counts->n_manifold_jobs = c.cp_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID];
+    counts->n_manifold_jobs = c.cp_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID] + c.cp_over_n;
     counts->n_proximity_pairs = c.key_hist[K_PROX_BALL_BALL] + c.key_hist[K_PROX_PLANE] + c.key_hist[K_PROX_SM] + c.key_hist[K_PROX_SM_HULL];
     for (int k = 0; k < 3; ++k) counts->n_proximity[k] = c.prox_hist[k];
 }
@@ -739,6 +745,23 @@ int ncb_world_update(ncb_ctx* ctx, const ncb_objects* objs, float margin, uint32
     int r = ncb_set_objects(ctx, objs);
     if (r) return r;
     // results are copied back while the narrow phase is still running (see update_after_aabbs); NCB_NO_EARLY_FETCH=1 disables it
+    r = ncb_world_fetch_early(ctx, pairs, cap_pairs, pair_algo, contacts, cap_contacts);
+    if (r) return r;
+    r = ncb_world_update_device(ctx, margin, 0, 0xffffffffu, counts);
+    if (r) {
+        ctx->early.active = ctx->early.valid = false;
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        return r;
+    }
+    return ncb_world_fetch(ctx, pairs, cap_pairs, pair_algo, manifold_start, manifold_count, contacts, cap_contacts);
+}
+
+int ncb_world_update_poses(ncb_ctx* ctx, uint32_t n, const float* pos, const float* rot, float margin, uint32_t* pairs, uint32_t cap_pairs,
+                           uint8_t* pair_algo, uint32_t* manifold_start, uint8_t* manifold_count, ncb_contact* contacts,
+                           uint32_t cap_contacts, ncb_update_counts* counts) {
+    if (!ctx || (n && (!pos || !rot))) return NCB_ERR_ARG;
+    int r = ncb_set_positions(ctx, n, pos, rot);
+    if (r) return r;
     r = ncb_world_fetch_early(ctx, pairs, cap_pairs, pair_algo, contacts, cap_contacts);
     if (r) return r;
     r = ncb_world_update_device(ctx, margin, 0, 0xffffffffu, counts);

@@ -298,7 +298,7 @@ static int bp_grow(ncb_bp* bp, size_t slots) {
         if (b.p && bp->slots_cap) e = cudaMemcpyAsync(nb.p, b.p, bp->slots_cap * sizeof(float4), cudaMemcpyDeviceToDevice, s);
         cudaStreamSynchronize(s);
         b.release();
-        b = nb;
+        b = std::move(nb);
         return e;
     };
     auto growu = [&](DevBuf<uint32_t>& b, uint32_t fill) -> cudaError_t {
@@ -309,7 +309,7 @@ static int bp_grow(ncb_bp* bp, size_t slots) {
         if (b.p && bp->slots_cap) e = cudaMemcpyAsync(nb.p, b.p, bp->slots_cap * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
         cudaStreamSynchronize(s);
         b.release();
-        b = nb;
+        b = std::move(nb);
         return e;
     };
     CKB(grow4(bp->box_lo));

@@ -972,10 +972,7 @@ __global__ void __launch_bounds__(128, NCB_GJK_MINBLOCKS) k_cc_gjk(NarrowArgs A)
 // SMs, L2, and ncu counted 3.0 GB of DRAM traffic for 82 MB of algorithmic bytes.  Here the expansion loop touches no global or local
 // memory except the hull vertices (L1-resident library) and 24 B of cold support points per new vertex.
 // A pair that does not fit the compact capacities (1 % on cfg3) or starts from a flat simplex goes to the overflow queue
-// (A.epa_long) and is restarted on the big local-memory store by k_cc_epa<PS, 2> right after.
-//
-// k_cc_epa<PS, PASS>: PASS 0 = one pass over the whole queue on the big store (round 1's kernel, NCB_EPA_SHARED=0);
-// PASS 2 = the overflow queue.
+// (A.epa_long) and is restarted on the big local-memory store by k_cc_epa_big.
 #define EPAS_THREADS 64
 #ifndef NCB_EPAS_MINBLOCKS
 #define NCB_EPAS_MINBLOCKS 6
@@ -1064,36 +1061,45 @@ __global__ void __launch_bounds__(EPAS_THREADS, NCB_EPAS_MINBLOCKS) k_cc_epa_s(N
     }
 }
 
-#define EPA_REFILL_MIN 32
+// The overflow queue on the big local-memory store.  A restarted pair is a chain of 10-20 dependent expansion steps (~0.2 ms alone),
+// and there are only a few thousand such pairs, so the kernel spreads them over as many WARPS as possible (one or a few lanes per
+// warp, `lanes` below) and runs on its own stream next to k_cc_manifold: its latency is hidden instead of ending the phase.
+// Its closest-point records go to the END of the convex-convex segment of the manifold queue (slot seg_end - 1 - k), which the
+// main records, growing from the start, cannot reach (records <= pairs of the segment); k_cc_manifold<PS, 1> consumes them.
 #ifndef NCB_EPA_MINBLOCKS
 #define NCB_EPA_MINBLOCKS 16
 #endif
-template <bool PS, int PASS>
-__global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) {
+template <bool PS>
+__global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa_big(NarrowArgs A) {
     const int KEY = CCQ;
-    const uint32_t seg_end = PASS == 2 ? A.cnt->epa_long_n : A.cnt->epa_cursor[KEY];
-    uint32_t* fetch = PASS == 2 ? &A.cnt->epa_long_fetch : &A.cnt->epa_fetch[KEY];
+    const uint32_t seg_end = A.cnt->epa_long_n;
+    if (seg_end == 0) return;
+    const uint32_t cp_end = A.cnt->key_start[K_HULL_HULL] + A.cnt->key_hist[K_HULL_HULL];
+    uint32_t* fetch = &A.cnt->epa_long_fetch;
     const int lane = threadIdx.x & 31;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t lanes = min(32u, (seg_end + nwarps - 1) / nwarps);
+    const bool usable = (uint32_t)lane < lanes;
     EpaState e;
     bool active = false, exhausted = false;
-    uint32_t p = 0, wq = 0;
+    uint32_t p = 0;
     Iso ma, mb;
     Support ga, gb;
     V3 p1, p2, n;
     for (;;) {
         int status = EPA_CONTINUE;
-        unsigned idle = __ballot_sync(0xffffffffu, !active);
-        bool refill = !exhausted && (idle == 0xffffffffu || __popc(idle) >= EPA_REFILL_MIN);
+        unsigned idle = __ballot_sync(0xffffffffu, usable && !active);
+        bool refill = !exhausted && idle != 0;
         if (refill) {  // warp-uniform
             uint32_t base = 0;
             int leader = __ffs(idle) - 1;
             if (lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, leader);
             if (base + __popc(idle) >= seg_end) exhausted = true;  // nothing left after this batch
-            if (!active) {
+            if (usable && !active) {
                 uint32_t w = base + __popc(idle & ((1u << lane) - 1));
                 if (w < seg_end) {
-                    wq = PASS == 2 ? __ldg(&A.epa_long[w]) : w;
+                    uint32_t wq = __ldg(&A.epa_long[w]);
                     int sdim;
                     CSOPoint sv[4];
                     epa_rec_load(A.epa_queue + (size_t)wq * EPA_REC_WORDS, p, sdim, sv);
@@ -1112,9 +1118,9 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) 
         }
         bool ok = active && status == EPA_DONE_OK;
         bool fail = active && status == EPA_DONE_FAIL;
-        uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], ok);
+        uint32_t k = queue_append(&A.cnt->cp_over_n, ok);
         if (ok) {
-            cp_store(A.cp_queue, slot, p, p1, p2, n);
+            cp_store(A.cp_queue, cp_end - 1 - k, p, p1, p2, n);
             if constexpr (PS) A.ps.dir[A.pair_index ? __ldg(&A.pair_index[p]) : p] = make_float4(n.x, n.y, n.z, 1.f);
         }
         if (fail) {
@@ -1138,11 +1144,13 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa(NarrowArgs A) 
 #ifndef NCB_MAN_MINBLOCKS
 #define NCB_MAN_MINBLOCKS 6
 #endif
-template <bool PS>
+// PART 0: the records of k_cc_gjk / k_cc_epa_s (from the start of the segment); PART 1: those of k_cc_epa_big (at its end).
+template <bool PS, int PART>
 __global__ void __launch_bounds__(128, NCB_MAN_MINBLOCKS) k_cc_manifold(NarrowArgs A) {
     const int KEY = CCQ;
-    uint32_t seg_begin = A.cnt->key_start[KEY];
-    uint32_t seg_end = A.cnt->cp_cursor[KEY];
+    const uint32_t cc_end = A.cnt->key_start[K_HULL_HULL] + A.cnt->key_hist[K_HULL_HULL];
+    uint32_t seg_begin = PART == 0 ? A.cnt->key_start[KEY] : cc_end - A.cnt->cp_over_n;
+    uint32_t seg_end = PART == 0 ? A.cnt->cp_cursor[KEY] : cc_end;
     uint32_t stride = gridDim.x * blockDim.x;
     ManifoldT<PS> mf;
     for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
@@ -1358,7 +1366,7 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     int sm = c->sm_count;
     // tuning knobs (CTAs per SM of the persistent kernels); defaults chosen from ncu runs, see profiles/
     static int gjk_bpsm = getenv("NCB_GJK_BPSM") ? atoi(getenv("NCB_GJK_BPSM")) : 6;
-    static int epa_bpsm = getenv("NCB_EPA_BPSM") ? atoi(getenv("NCB_EPA_BPSM")) : 16;
+    static int epa_bpsm = getenv("NCB_EPA_BPSM") ? atoi(getenv("NCB_EPA_BPSM")) : 16;  // overflow kernel (k_cc_epa_big)
     static int man_bpsm = getenv("NCB_MAN_BPSM") ? atoi(getenv("NCB_MAN_BPSM")) : 6;
     // Two independent chains: the convex-convex phases on the context's stream, everything else on a side stream
     // (each persistent kernel alone leaves most issue slots idle; together they overlap).
@@ -1388,9 +1396,8 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
         cudaMemcpyAsync(c->snap.p, c->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToDevice, s);
         cudaEventRecord(c->ev_snap, s);
     }
-    static int epa_shared = getenv("NCB_EPA_SHARED") ? atoi(getenv("NCB_EPA_SHARED")) : 1;
     static int epas_bpsm = getenv("NCB_EPAS_BPSM") ? atoi(getenv("NCB_EPAS_BPSM")) : NCB_EPAS_MINBLOCKS;
-    if (epa_shared) {
+    {
         const size_t smem = (size_t)EpaShared::WORDS * EPAS_THREADS * sizeof(uint32_t);
         static bool attr_set[2] = {false, false};
         if (!attr_set[PS]) {
@@ -1398,13 +1405,21 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
             attr_set[PS] = true;
         }
         k_cc_epa_s<PS><<<sm * epas_bpsm, EPAS_THREADS, smem, s>>>(A);
-        k_cc_epa<PS, 2><<<sm * 2, 64, 0, s>>>(A);  // the pairs beyond the compact capacities
-    } else {
-        k_cc_epa<PS, 0><<<sm * epa_bpsm, 64, 0, s>>>(A);
     }
     timer_mark(c, "cc_epa", 1);
-    k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
+    // the overflow pairs (beyond the compact capacities) run beside the manifold kernel of everything else
+    cudaStream_t s3 = c->over_stream ? c->over_stream : s;
+    if (c->over_stream) {
+        cudaEventRecord(c->ev_epa, s);
+        cudaStreamWaitEvent(s3, c->ev_epa, 0);
+    }
+    k_cc_epa_big<PS><<<sm * epa_bpsm, 64, 0, s3>>>(A);
+    if (c->over_stream) cudaEventRecord(c->ev_over, s3);
+    k_cc_manifold<PS, 0><<<sm * man_bpsm, 128, 0, s>>>(A);
     timer_mark(c, "cc_manifold", 1);
+    if (c->over_stream) cudaStreamWaitEvent(s, c->ev_over, 0);
+    k_cc_manifold<PS, 1><<<sm, 128, 0, s>>>(A);
+    timer_mark(c, "cc_overflow_tail", 2);
     if (!early && c->side_stream) cudaStreamWaitEvent(s, c->ev_join, 0);  // device-only updates: the side chain may run to the end
     timer_mark(c, "narrow_other_join", 7);
     return cudaGetLastError();

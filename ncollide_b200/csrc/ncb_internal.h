@@ -70,8 +70,9 @@ struct DevCounters {
     uint32_t epa_fetch[16];    // per key: next EPA queue entry to hand to an idle lane (dynamic fetch)
     uint32_t gjk_fetch[16];    // per key: next pair of the key segment to hand to an idle lane
     int bounds[6];             // ordered-int encoded min xyz / max xyz of AABB centres
-    uint32_t epa_long_n;       // two-pass EPA: entries deferred to the second pass
+    uint32_t epa_long_n;       // EPA overflow queue: pairs that did not fit the compact (shared-memory) polytope store
     uint32_t epa_long_fetch;
+    uint32_t cp_over_n;        // closest-point records appended by the overflow EPA kernel (stored from the END of the segment)
     uint32_t prox_hist[4];     // proximity pairs per status (Intersecting, WithinMargin, Disjoint)
 };
 
@@ -118,6 +119,19 @@ struct DevBuf {
         p = nullptr;
         cap = 0;
     }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr, o.cap = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p, cap = o.cap;
+            o.p = nullptr, o.cap = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }  // every buffer of a context / a temporary goes with its owner (error returns included)
 };
 
 struct StageTimer {
@@ -137,6 +151,8 @@ struct ncb_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t side_stream = nullptr;  // second chain of the narrow phase (fork / join with events)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t over_stream = nullptr;  // EPA overflow pairs, beside the convex-convex manifold kernel
+    cudaEvent_t ev_epa = nullptr, ev_over = nullptr;
     std::string err;
     int sm_count = 148;
 
@@ -173,7 +189,7 @@ struct ncb_ctx {
     ncb::DevBuf<uint32_t> manifold_start;
     ncb::DevBuf<uint8_t> manifold_count;
     ncb::DevBuf<uint32_t> pair_index;
-    ncb::DevBuf<uint32_t> epa_long;              // two-pass EPA: EPA-queue indices of the pairs that need many expansion steps
+    ncb::DevBuf<uint32_t> epa_long;              // EPA overflow queue: EPA-queue indices of the pairs beyond the compact store's capacities
     ncb::DevBuf<uint32_t> epa_queue;             // 26 words per record
     ncb::DevBuf<uint32_t> cp_queue;              // 10 words per record
 

@@ -310,7 +310,7 @@ cudaError_t grow_keep(DevBuf<T>& b, size_t want, size_t keep, cudaStream_t s) {
     if (b.p && keep) e = cudaMemcpyAsync(nb.p, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
     cudaStreamSynchronize(s);
     b.release();
-    b = nb;
+    b = std::move(nb);
     return e;
 }
 

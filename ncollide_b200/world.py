@@ -232,6 +232,28 @@ class Context:
                 return UpdateResult(bufs["pairs"][:P], bufs["algo"][:P], bufs["start"][:P], bufs["count"][:P], bufs["contacts"][:Cn], self._counts(c), prox)
             bufs = self.alloc_result_buffers(c.n_pairs + 16, c.n_contacts + 16)
 
+    def world_update_poses(self, pos, rot, margin, bufs=None):
+        """``set_position`` on every object + ``CollisionWorld::update`` (world.rs:104-119) for a world whose objects are already on
+        the device (``set_objects``): uploads the poses only, runs the step, copies the results back (ncb_world_update_poses)."""
+        pos, rot = as_f32(pos).reshape(-1, 3), as_f32(rot).reshape(-1, 4)
+        n = len(pos)
+        if bufs is None:
+            bufs = self.alloc_result_buffers(max(8 * n, 1024), max(8 * n, 1024))
+        while True:
+            c = _ffi.UpdateCountsC()
+            r = self.check(
+                self.lib.ncb_world_update_poses(
+                    self.h, C.c_uint32(n), ptr(pos), ptr(rot), C.c_float(margin), ptr(bufs["pairs"]), C.c_uint32(len(bufs["pairs"])),
+                    ptr(bufs["algo"]), ptr(bufs["start"]), ptr(bufs["count"]), ptr(bufs["contacts"]), C.c_uint32(len(bufs["contacts"])), C.byref(c),
+                ),
+                "ncb_world_update_poses",
+            )
+            if r == 0:
+                P, Cn = c.n_pairs, c.n_contacts
+                prox = self.world_fetch_proximity(P) if getattr(self, "has_sensors", False) else None
+                return UpdateResult(bufs["pairs"][:P], bufs["algo"][:P], bufs["start"][:P], bufs["count"][:P], bufs["contacts"][:Cn], self._counts(c), prox)
+            bufs = self.alloc_result_buffers(c.n_pairs + 16, c.n_contacts + 16)
+
     @staticmethod
     def alloc_result_buffers(cap_pairs, cap_contacts):
         return {

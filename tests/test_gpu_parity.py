@@ -116,6 +116,24 @@ def test_world_update_parity(ctx, oracle, mk):
     assert sum(res.counts["n_algo"].values()) == len(res.pairs)
 
 
+def test_world_update_poses_equals_world_update(ctx, oracle):
+    """ncb_world_update_poses (objects persist, only the poses travel) returns what ncb_world_update returns for the same world."""
+    s = config_scene(3, 5000)
+    ctx.set_hulls(s.hulls)
+    a = ctx.world_update(s)
+    rng = np.random.default_rng(5)
+    s2 = config_scene(3, 5000)
+    s2.pos = (s.pos + rng.normal(0, 0.05, size=s.pos.shape)).astype(np.float32)
+    b = ctx.world_update_poses(s2.pos, s2.rot, s2.margin)
+    want = ctx.world_update(s2)
+    assert np.array_equal(b.pairs, want.pairs) and np.array_equal(b.manifold_count, want.manifold_count)
+    assert np.array_equal(b.pair_algo, want.pair_algo)
+    key = lambda r: np.sort(r.contacts, order=["pair", "f1", "f2", "depth"])  # noqa: E731
+    assert np.array_equal(key(b), key(want))
+    assert not np.array_equal(a.pairs, b.pairs)
+    compare_manifolds(b, s2, oracle, "poses")
+
+
 def _adversarial_scenes():
     """Configurations that stress degenerate branches: exact coincidence, axis-aligned face contact, touching at depth 0,
     far-from-origin coordinates, a dense clump, tiny / huge shapes side by side."""

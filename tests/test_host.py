@@ -1,6 +1,7 @@
 """CPU-only tests: the C-ABI library builds, loads and exports what include/ncb200.h declares; the product never
 touches the oracle and fails loudly without a GPU; host-side mirrors (hull tables, scenes); oracle self-consistency."""
 import os
+import sys
 import re
 
 import numpy as np
@@ -228,6 +229,22 @@ def test_bench_reference_arm_json_contract():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["value"] > 0
+    assert d["same_config"] is True and d["config"]["n_objects_total"] == 3000
+    rc = d["rays"]["cpu_baseline"]  # the Mrays/s half of the metric has its CPU baseline in both arms
+    assert rc["kind"] == "port" and rc["cores"] == 1 and rc["unit"] == "Mrays/s" and rc["value"] > 0 and 0 < rc["hit_fraction"] <= 1
+
+
+def test_bench_config_is_the_same_object_in_both_arms():
+    sys_path = sys.path[:]
+    try:
+        sys.path.insert(0, ROOT)
+        import bench
+    finally:
+        sys.path[:] = sys_path
+    a, b = bench.workload_config(1_000_000, 1), bench.workload_config(1_000_000, 1)
+    assert a == b and a["n_objects_total"] == 1_000_000
+    assert bench.workload_config(1_000_000, 8)["n_objects_total"] == 8_000_000
+    assert len(bench.source_hash()) == 16
 
 
 def test_bench_native_arm_refuses_to_run_without_a_gpu():

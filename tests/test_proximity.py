@@ -211,7 +211,6 @@ def test_prox_golden_fixture_oracle(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: not yet run on hardware (its logic was replayed on oracle data)")
 def test_prox_golden_fixture_device():
     from ncollide_b200.world import Context
     from test_bp_persistent import DeviceSimAdapter

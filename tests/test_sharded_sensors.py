@@ -1,18 +1,15 @@
-"""GPU tests written after the round's GPU budget was spent (they have never run on hardware):
+"""GPU tests of two boundary behaviours (first seen green on the driver's B200 box at the end of round 1):
 
   * proximity sensors through the spatially sharded multi-GPU update (ncb_world_update_sharded), replayed rank by rank on one device
     like tests/test_gpu_parity.py::test_spatial_shards_partition_the_pair_set — the sensor path re-keys pairs by GLOBAL handle with
-    replicated query kinds, so the sharded update should need nothing else;
-  * the boundary refusing shape types the device does not know.
-
-They are marked xfail(strict=False): a pass shows up as XPASS, a failure cannot hide the verified tests (the file also sorts last).
-Remove the marker once they have been seen green."""
+    replicated query kinds;
+  * the boundary refusing shape types the device does not know."""
 import numpy as np
 import pytest
 
 from ncollide_b200.scenes import config_scene, make_world_scene, with_sensors
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet run on a GPU (round-1 budget exhausted)")]
+pytestmark = pytest.mark.gpu
 
 
 def canon(pairs):
