@@ -202,6 +202,21 @@ def make_soup(t, seed, side=100.0, jitter=0.5):
     return np.ascontiguousarray(verts), np.ascontiguousarray(tris)
 
 
+def transform_rays(pose, origins, dirs):
+    """Moves rays given in the mesh's local frame into world space with the mesh pose (t xyz, q ijkw): a posed cast of the moved
+    rays answers the same question as the identity-pose cast of the original ones."""
+    t, q = np.asarray(pose[:3], dtype=np.float64), np.asarray(pose[3:], dtype=np.float64)
+
+    def rot(v):
+        qv = q[:3]
+        tt = 2 * np.cross(qv, v)
+        return v + q[3] * tt + np.cross(qv, tt)
+
+    o = (rot(np.asarray(origins, dtype=np.float64)) + t).astype(F32)
+    d = rot(np.asarray(dirs, dtype=np.float64)).astype(F32)
+    return np.ascontiguousarray(o), np.ascontiguousarray(d)
+
+
 def make_ray_scene(kind, n_tris, n_rays, seed=1004, random_pose=False):
     rng = np.random.default_rng(seed + 17)
     if kind == "terrain":
