@@ -33,6 +33,7 @@ extern "C" {
 #define NCB_SHAPE_CUBOID 1u
 #define NCB_SHAPE_CONVEX_HULL 2u
 #define NCB_SHAPE_PLANE 3u
+#define NCB_SHAPE_CAPSULE 4u /* shape/capsule.rs: shape_param = (half_height, radius, -, -), axis = local y */
 
 /* FeatureId (shape/feature_id.rs): kind in bits 31..30 (0 vertex, 1 edge, 2 face, 3 unknown), id in bits 29..0. */
 #define NCB_FEATURE_VERTEX 0u
@@ -51,6 +52,8 @@ extern "C" {
 /* The pair involves a GeometricQueryType::Proximity object: a ProximityDetector ran instead of a contact generator
  * (DefaultProximityDispatcher::get_proximity_algorithm, proximity_detector/default_proximity_dispatcher.rs:19-47). */
 #define NCB_ALGO_PROXIMITY 6u
+#define NCB_ALGO_CAPSULE_CAPSULE 7u /* CapsuleCapsuleManifoldGenerator (capsule_capsule_manifold_generator.rs) */
+#define NCB_ALGO_CAPSULE_SHAPE 8u   /* CapsuleShapeManifoldGenerator (capsule_shape_manifold_generator.rs) */
 
 /* query::Proximity (query/proximity/proximity.rs:4-12) as a byte; NCB_PROXIMITY_NONE: not a proximity pair / no detector. */
 #define NCB_PROXIMITY_INTERSECTING 0u
@@ -121,6 +124,9 @@ typedef struct ncb_update_counts {
     uint32_t n_manifold_jobs;  /* convex-convex pairs that reached feature clipping */
     uint32_t n_proximity_pairs; /* pairs handled by a proximity detector (NCB_ALGO_PROXIMITY) */
     uint32_t n_proximity[3];    /* of those: Intersecting, WithinMargin, Disjoint */
+    uint32_t n_capsule_pairs[2]; /* pairs per NCB_ALGO_CAPSULE_CAPSULE, NCB_ALGO_CAPSULE_SHAPE */
+    uint32_t stack_overflow;    /* BVH traversals that ran out of their fixed stack (a subtree was skipped): 0 expected, tests assert it */
+    uint32_t n_epa_restarts;    /* EPA pairs beyond the shared-memory polytope capacities, restarted on the large store (not an error) */
 } ncb_update_counts;
 
 /* ---- context ------------------------------------------------------------------------------------------------ */
@@ -132,11 +138,16 @@ int ncb_set_stream(ncb_ctx* ctx, void* cuda_stream);
 void* ncb_get_stream(ncb_ctx* ctx);
 int ncb_synchronize(ncb_ctx* ctx);
 
+/* BVH walks of the query entry points (TriMesh ray casts, world / broad-phase queries) use a fixed 64-entry stack; a walk that runs
+ * out of it skips a subtree and is counted here (cumulative over the context's life, plus the pair search of the last update /
+ * ncb_broad_phase, which an update also reports in ncb_update_counts.stack_overflow).  The LBVH's depth bound (30 Morton bits + 32 tie-break bits) keeps both at 0; tests assert it. */
+int ncb_traversal_overflows(ncb_ctx* ctx, uint32_t* out);
+
 /* ---- shapes and objects -------------------------------------------------------------------------------------- */
 /* ConvexHull tables (host pointers), copied to the device once. */
 int ncb_set_hulls(ncb_ctx* ctx, const ncb_hull_library* lib);
 /* CollisionWorld::add for a whole world (pipeline/world.rs:66-96): host SoA -> device.  NCB_ERR_UNSUPPORTED when a shape_type is not
- * one of the four NCB_SHAPE_* values (capsules, composite shapes: SURVEY.md §8f N3, not on the device yet). */
+ * one of the NCB_SHAPE_* values. */
 int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* objs);
 /* CollisionObject::set_position for all objects (pipeline/object/collision_object.rs:186-190). */
 int ncb_set_positions(ncb_ctx* ctx, uint32_t n, const float* pos, const float* rot);
@@ -147,7 +158,8 @@ int ncb_set_positions_range(ncb_ctx* ctx, uint32_t begin, uint32_t count, const 
 /* GeometricQueryType per object (pipeline/object/query_type.rs:8-37): kinds[i] = 0 Contacts(query_limit, ang_pred) or
  * 1 Proximity(query_limit) — a sensor.  A pair with at least one sensor gets a Proximity status instead of a contact manifold
  * (NarrowPhase::handle_interaction, narrow_phase.rs:226-247).  kinds == NULL (or all 0): every object is Contacts, the state
- * after ncb_set_objects.  n must equal the object count. */
+ * after EVERY ncb_set_objects (ncb_world_update, which re-uploads the world, keeps the kinds when the object count is unchanged).
+ * n must equal the object count.  NCB_ERR_UNSUPPORTED for a world with capsules (their proximity detectors are not on the device). */
 int ncb_set_query_types(ncb_ctx* ctx, uint32_t n, const uint8_t* kinds);
 
 /* ---- stage entry points (each mirrors one reference routine, host buffers in/out) ---------------------------- */

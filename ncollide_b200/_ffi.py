@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libncb200.so")
 
 EXPORTED_SYMBOLS = [
-    "ncb_version", "ncb_create", "ncb_destroy", "ncb_last_error", "ncb_set_stream", "ncb_get_stream", "ncb_synchronize",
+    "ncb_version", "ncb_create", "ncb_destroy", "ncb_last_error", "ncb_set_stream", "ncb_get_stream", "ncb_synchronize", "ncb_traversal_overflows",
     "ncb_set_hulls", "ncb_set_objects", "ncb_set_positions", "ncb_set_positions_range", "ncb_compute_aabbs", "ncb_broad_phase", "ncb_generate_contacts",
     "ncb_world_update_device", "ncb_world_fetch", "ncb_world_update", "ncb_world_update_poses", "ncb_device_ptr", "ncb_world_update_stage", "ncb_world_update_sharded", "ncb_world_fetch_early",
     "ncb_profile_enable", "ncb_profile_get", "ncb_trimesh_create", "ncb_trimesh_destroy", "ncb_trimesh_ray_cast",
@@ -58,6 +58,9 @@ class UpdateCountsC(C.Structure):
         ("n_manifold_jobs", C.c_uint32),
         ("n_proximity_pairs", C.c_uint32),
         ("n_proximity", C.c_uint32 * 3),
+        ("n_capsule_pairs", C.c_uint32 * 2),
+        ("stack_overflow", C.c_uint32),
+        ("n_epa_restarts", C.c_uint32),
     ]
 
 

@@ -41,6 +41,7 @@ DevObjects dev_objects(ncb_ctx* c) {
     o.ang = c->ang.p;
     o.ang_cs = c->ang_cs.p;
     o.ang_stride = c->ang_stride;
+    o.cap_pts = c->has_capsules ? c->cap_pts.p : nullptr;
     return o;
 }
 
@@ -123,7 +124,11 @@ int ncb_create(int device, ncb_ctx** out) {
         e = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->over_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = the numerically lowest = highest priority
+            e = cudaStreamCreateWithPriority(&c->over_stream, cudaStreamNonBlocking, hi);
+        }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_epa, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_over, cudaEventDisableTiming);
     }
@@ -271,6 +276,19 @@ int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* o) {
     REQUIRE(n == 0 || (o->pos && o->rot && o->shape_type && o->shape_param && o->query_limit && o->ang_pred), NCB_ERR_ARG,
             "ncb_set_objects: null array");
     cudaStream_t s = ctx->stream;
+    // validate before any device state is touched: only the shapes of the path exist on the device (an unknown id would be
+    // dispatched as something else), and a hull object must name a hull of the uploaded library
+    bool has_capsules = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t t = o->shape_type[i];
+        REQUIRE(t <= NCB_SHAPE_CAPSULE, NCB_ERR_UNSUPPORTED, "ncb_set_objects: shape_type must be NCB_SHAPE_BALL / CUBOID / CONVEX_HULL / PLANE / CAPSULE");
+        has_capsules = has_capsules || t == NCB_SHAPE_CAPSULE;
+        if (t == NCB_SHAPE_CONVEX_HULL) {
+            float h = o->shape_param[4 * (size_t)i];
+            REQUIRE(h >= 0.f && h < (float)ctx->hulls.n_hulls && h == (float)(uint32_t)h, NCB_ERR_ARG,
+                    "ncb_set_objects: convex-hull object names a hull id that is not in the uploaded library (ncb_set_hulls)");
+        }
+    }
     CK(ctx->pos.reserve(3 * (size_t)n));
     CK(ctx->rot.reserve(n));
     CK(ctx->type.reserve(n));
@@ -286,12 +304,11 @@ int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* o) {
         CK(cudaMemcpyAsync(ctx->param.p, o->shape_param, 16 * (size_t)n, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->qlimit.p, o->query_limit, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
     }
-    {
-        // only the four shapes of the path exist on the device (a larger id would be masked into one of them): fail loudly
-        uint32_t any = 0;
-        for (uint32_t i = 0; i < n; ++i) any |= o->shape_type[i];
-        REQUIRE((any & ~3u) == 0, NCB_ERR_UNSUPPORTED, "ncb_set_objects: shape_type must be NCB_SHAPE_BALL / CUBOID / CONVEX_HULL / PLANE");
+    if (has_capsules) {  // the capsule segments as 2-point hulls [b, a] for GJK / EPA (capsule.cuh)
+        CK(ctx->cap_pts.reserve(6 * (size_t)n));
+        CK(launch_fill_cap_pts(ctx, n));
     }
+    ctx->has_capsules = has_capsules;
     ctx->has_groups = o->groups != nullptr;
     if (o->groups && n) {
         CK(ctx->groups.reserve(3 * (size_t)n));
@@ -320,7 +337,7 @@ int ncb_set_objects(ncb_ctx* ctx, const ncb_objects* o) {
         }
     }
     if (n) CK(cudaMemcpyAsync(ctx->ang_cs.p, ctx->h_ang_cs.data(), 8 * ctx->h_ang_cs.size(), cudaMemcpyHostToDevice, s));
-    if (n != ctx->n) ctx->has_prox = false;  // query types belong to an object set: a different count resets them to Contacts
+    ctx->has_prox = false;  // query types belong to an object set: every object is Contacts after ncb_set_objects (ncb200.h)
     ctx->n = n;
     CK(reserve_broad(ctx, n) == NCB_OK ? cudaSuccess : cudaErrorMemoryAllocation);
     return NCB_OK;
@@ -335,6 +352,7 @@ int ncb_set_query_types(ncb_ctx* ctx, uint32_t n, const uint8_t* kinds) {
         REQUIRE(kinds[i] <= 1, NCB_ERR_ARG, "ncb_set_query_types: kind must be 0 (Contacts) or 1 (Proximity)");
         any = any || kinds[i] != 0;
     }
+    REQUIRE(!(any && ctx->has_capsules), NCB_ERR_UNSUPPORTED, "ncb_set_query_types: sensors in a world with capsules are not supported on the device");
     ctx->has_prox = any;
     if (any) {
         CK(ctx->qkind.reserve(n));
@@ -366,6 +384,20 @@ int ncb_set_positions_range(ncb_ctx* ctx, uint32_t begin, uint32_t count, const 
     return NCB_OK;
 }
 
+// ---- capsule segments ----------------------------------------------------------------------------------------
+__global__ void k_fill_cap_pts(const uint32_t* __restrict__ type, const float4* __restrict__ param, uint32_t n, float* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float hh = (type[i] & NCB_TYPE_MASK) == NCB_SHAPE_CAPSULE ? param[i].x : 0.f;
+    float* d = out + 6 * (size_t)i;  // b = (0, hh, 0) then a = (0, -hh, 0): Segment::local_support_point as a first-maximum scan
+    d[0] = 0.f, d[1] = hh, d[2] = 0.f, d[3] = 0.f, d[4] = -hh, d[5] = 0.f;
+}
+extern "C++" cudaError_t launch_fill_cap_pts(ncb_ctx* ctx, uint32_t n) {
+    if (n == 0) return cudaSuccess;
+    k_fill_cap_pts<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->type.p, ctx->param.p, n, ctx->cap_pts.p);
+    return cudaGetLastError();
+}
+
 // ---- stage entry points ------------------------------------------------------------------------------------
 __global__ void k_unpack_aabb(const float4* lo, const float4* hi, uint32_t n, float* out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -393,6 +425,26 @@ int ncb_compute_aabbs(ncb_ctx* ctx, float margin, int mode, float* out_minmax) {
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out_minmax, tmp, 24 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return NCB_OK;
+}
+
+extern "C++" uint32_t* trav_overflow_counter(ncb_ctx* ctx) {
+    if (!ctx->trav_overflow.p) {
+        if (ctx->trav_overflow.reserve(4) != cudaSuccess) return nullptr;
+        cudaMemsetAsync(ctx->trav_overflow.p, 0, 16, ctx->stream);
+    }
+    return ctx->trav_overflow.p;
+}
+
+int ncb_traversal_overflows(ncb_ctx* ctx, uint32_t* out) {
+    if (!ctx || !out) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    *out = ctx->last_counters.stack_overflow;  // pair search of the last update / ncb_broad_phase
+    if (!ctx->trav_overflow.p) return NCB_OK;
+    uint32_t q = 0;
+    CK(cudaMemcpyAsync(&q, ctx->trav_overflow.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out += q;
     return NCB_OK;
 }
 
@@ -457,9 +509,13 @@ static void fill_counts(ncb_ctx* ctx, ncb_update_counts* counts) {
     counts->n_algo[NCB_ALGO_CONVEX_CONVEX] = c.key_hist[K_CUBOID_CUBOID] + c.key_hist[K_CUBOID_HULL] + c.key_hist[K_HULL_HULL];
     counts->n_algo[NCB_ALGO_NONE] = c.key_hist[K_NONE];
     counts->n_epa_pairs = c.epa_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID];
-    counts->n_manifold_jobs = c.cp_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID] + c.cp_over_n;
+    counts->n_manifold_jobs = c.cp_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID] + c.epa_long_ok;
     counts->n_proximity_pairs = c.key_hist[K_PROX_BALL_BALL] + c.key_hist[K_PROX_PLANE] + c.key_hist[K_PROX_SM] + c.key_hist[K_PROX_SM_HULL];
     for (int k = 0; k < 3; ++k) counts->n_proximity[k] = c.prox_hist[k];
+    counts->n_capsule_pairs[0] = c.key_hist[K_CAPSULE_CAPSULE];
+    counts->n_capsule_pairs[1] = c.key_hist[K_CAPSULE_BALL] + c.key_hist[K_CAPSULE_PLANE] + c.key_hist[K_CAPSULE_CUBOID] + c.key_hist[K_CAPSULE_HULL];
+    counts->stack_overflow = c.stack_overflow;
+    counts->n_epa_restarts = c.epa_long_n;
 }
 
 int ncb_proximity(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* pairs, const float* margins, uint8_t* out) {
@@ -492,6 +548,7 @@ int ncb_generate_contacts(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* pairs,
     *n_contacts = 0;
     if (n_pairs == 0) return NCB_OK;
     REQUIRE(ctx->n > 0, NCB_ERR_STATE, "ncb_generate_contacts: call ncb_set_objects first");
+    for (uint32_t p = 0; p < 2 * n_pairs; ++p) REQUIRE(pairs[p] < ctx->n, NCB_ERR_ARG, "ncb_generate_contacts: object index out of range");
     cudaStream_t s = ctx->stream;
     int r = reserve_pairs(ctx, n_pairs);
     if (r) return r;
@@ -742,8 +799,13 @@ int ncb_world_fetch_proximity(ncb_ctx* ctx, uint8_t* prox, uint32_t cap_pairs) {
 int ncb_world_update(ncb_ctx* ctx, const ncb_objects* objs, float margin, uint32_t* pairs, uint32_t cap_pairs, uint8_t* pair_algo,
                      uint32_t* manifold_start, uint8_t* manifold_count, ncb_contact* contacts, uint32_t cap_contacts,
                      ncb_update_counts* counts) {
+    if (!ctx || !objs) return NCB_ERR_ARG;
+    // the query types installed with ncb_set_query_types survive this call when the object count is unchanged (the call re-uploads
+    // the world it was given before); ncb_set_objects alone resets them
+    const bool keep_kinds = ctx->has_prox && objs->n == ctx->n;
     int r = ncb_set_objects(ctx, objs);
     if (r) return r;
+    if (keep_kinds) ctx->has_prox = true;
     // results are copied back while the narrow phase is still running (see update_after_aabbs); NCB_NO_EARLY_FETCH=1 disables it
     r = ncb_world_fetch_early(ctx, pairs, cap_pairs, pair_algo, contacts, cap_contacts);
     if (r) return r;

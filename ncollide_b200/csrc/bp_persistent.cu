@@ -226,7 +226,7 @@ template <int KIND>
 __global__ void __launch_bounds__(128) k_bp_query(const float* __restrict__ qin, uint32_t nq, const float4* __restrict__ llo,
                                                   const float4* __restrict__ lhi, const float4* __restrict__ nodes, uint32_t n, uint32_t nout,
                                                   const uint32_t* __restrict__ d_attached, unsigned long long* out, uint32_t cap,
-                                                  uint32_t* counter) {
+                                                  uint32_t* counter, uint32_t* trav_overflow) {
     const int W = KIND == 0 ? 6 : (KIND == 1 ? 7 : 3);
     uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
@@ -254,7 +254,12 @@ __global__ void __launch_bounds__(128) k_bp_query(const float* __restrict__ qin,
                 goR = false;
             }
             if (goL) {
-                if (goR && sp < 64) stack[sp++] = right;
+                if (goR) {
+                    if (sp < 64)
+                        stack[sp++] = right;
+                    else
+                        atomicAdd(trav_overflow, 1u);
+                }
                 node = left;
             } else if (goR) {
                 node = right;
@@ -845,13 +850,13 @@ int ncb_bp_query(ncb_bp* bp, int kind, uint32_t n_queries, const float* queries,
         uint32_t c = (uint32_t)bp->ev_a.cap;
         if (kind == 0)
             k_bp_query<0><<<g, 128, 0, s>>>(bp->q_in.p, n_queries, w->leaf_lo.p, w->leaf_hi.p, w->nodes.p, bp->tree_n, bp->tree_outliers,
-                                            bp->d_attached.p, bp->ev_a.p, c, bp->counters.p);
+                                            bp->d_attached.p, bp->ev_a.p, c, bp->counters.p, trav_overflow_counter(bp->owner));
         else if (kind == 1)
             k_bp_query<1><<<g, 128, 0, s>>>(bp->q_in.p, n_queries, w->leaf_lo.p, w->leaf_hi.p, w->nodes.p, bp->tree_n, bp->tree_outliers,
-                                            bp->d_attached.p, bp->ev_a.p, c, bp->counters.p);
+                                            bp->d_attached.p, bp->ev_a.p, c, bp->counters.p, trav_overflow_counter(bp->owner));
         else
             k_bp_query<2><<<g, 128, 0, s>>>(bp->q_in.p, n_queries, w->leaf_lo.p, w->leaf_hi.p, w->nodes.p, bp->tree_n, bp->tree_outliers,
-                                            bp->d_attached.p, bp->ev_a.p, c, bp->counters.p);
+                                            bp->d_attached.p, bp->ev_a.p, c, bp->counters.p, trav_overflow_counter(bp->owner));
         CKB(cudaGetLastError());
         CKB(cudaMemcpyAsync(&found, bp->counters.p, 4, cudaMemcpyDeviceToHost, s));
         CKB(cudaStreamSynchronize(s));

@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(256) k_aabb(DevObjects o, DevHulls H, float ma
             mins = vmin(mins, w);
             maxs = vmax(maxs, w);
         }
+    } else if (type == NCB_SHAPE_CAPSULE) {
+        capsule_aabb(Iso{t, q}, p4.x, p4.y, mins, maxs);
     } else {
         float mx = NCB_FMAX * 0.5f;
         mins = v3(-mx, -mx, -mx);
@@ -448,19 +450,6 @@ cudaError_t launch_shard_select(ncb_ctx* c, uint32_t n, int rank, int world, Sha
 // A query at sorted position i reports only leaves at positions j > i, so each unordered pair is emitted once;
 // it is oriented (larger handle, smaller handle) = the argument order of interference_started.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __constant__ uint8_t c_key_table[16] = {
-    // [t1 * 4 + t2], t = ball, cuboid, hull, plane
-    K_BALL_BALL,   K_BALL_CUBOID,   K_BALL_HULL,   K_PLANE_BALL,    //
-    K_BALL_CUBOID, K_CUBOID_CUBOID, K_CUBOID_HULL, K_PLANE_CUBOID,  //
-    K_BALL_HULL,   K_CUBOID_HULL,   K_HULL_HULL,   K_PLANE_HULL,    //
-    K_PLANE_BALL,  K_PLANE_CUBOID,  K_PLANE_HULL,  K_NONE};
-
-// NCB_ALGO_* per key
-__device__ __constant__ uint8_t c_algo_of_key[16] = {NCB_ALGO_BALL_BALL,     NCB_ALGO_PLANE_BALL,  NCB_ALGO_PLANE_CONVEX,  NCB_ALGO_PLANE_CONVEX,
-                                                     NCB_ALGO_BALL_CONVEX,   NCB_ALGO_BALL_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_CONVEX_CONVEX,
-                                                     NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_NONE,        NCB_ALGO_PROXIMITY, NCB_ALGO_PROXIMITY,
-                                                     NCB_ALGO_PROXIMITY,     NCB_ALGO_PROXIMITY,   0, 0};
-
 __device__ __forceinline__ bool groups_allow(const uint32_t* __restrict__ g, uint32_t a, uint32_t b) {
     if (!g) return true;
     uint32_t m1 = __ldg(&g[3 * a]), w1 = __ldg(&g[3 * a + 1]), b1 = __ldg(&g[3 * a + 2]);
@@ -495,7 +484,7 @@ __device__ __forceinline__ void emit_pair(uint32_t ha, uint32_t ta, uint32_t hb,
             h1 = hb, t1 = tb, h2 = ha, t2 = ta;
         }
         pairs[slot] = make_uint2(h1, h2);
-        keys[slot] = c_key_table[(t1 & 3) * 4 + (t2 & 3)];
+        keys[slot] = (uint8_t)pair_key(t1, t2);
     }
 }
 
@@ -552,7 +541,12 @@ __global__ void __launch_bounds__(128) k_pair_search(const float4* __restrict__ 
                 goR = false;
             }
             if (goL) {
-                if (goR && sp < 64) stack[sp++] = right;
+                if (goR) {
+                    if (sp < 64)
+                        stack[sp++] = right;
+                    else
+                        atomicAdd(&cnt->stack_overflow, 1u);  // a subtree would be skipped: never silent (Karras depth <= 62 keeps it 0)
+                }
                 node = left;
             } else if (goR) {
                 node = right;
@@ -599,7 +593,7 @@ __global__ void __launch_bounds__(128) k_pair_search(const float4* __restrict__ 
                 h1 = hb, t1 = tb, h2 = hq, t2 = tq;
             }
             pairs[slot] = make_uint2(h1, h2);
-            keys[slot] = c_key_table[(t1 & 3) * 4 + (t2 & 3)];
+            keys[slot] = (uint8_t)pair_key(t1, t2);
         }
     }
 }
@@ -644,18 +638,18 @@ cudaError_t launch_pair_search(ncb_ctx* c, uint32_t n, const uint32_t* groups, u
 // persistent grid-stride kernels read n_pairs from the counters, so the host never synchronises mid-update.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_key_hist(const uint8_t* __restrict__ keys, uint32_t cap, DevCounters* cnt) {
-    __shared__ uint32_t h[16];
-    if (threadIdx.x < 16) h[threadIdx.x] = 0;
+    __shared__ uint32_t h[K_MAX];
+    if (threadIdx.x < K_MAX) h[threadIdx.x] = 0;
     __syncthreads();
     uint32_t np = min(cnt->n_pairs, cap);
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) atomicAdd(&h[keys[p] & 15], 1u);
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) atomicAdd(&h[keys[p] & (K_MAX - 1)], 1u);
     __syncthreads();
-    if (threadIdx.x < 16 && h[threadIdx.x]) atomicAdd(&cnt->key_hist[threadIdx.x], h[threadIdx.x]);
+    if (threadIdx.x < K_MAX && h[threadIdx.x]) atomicAdd(&cnt->key_hist[threadIdx.x], h[threadIdx.x]);
 }
 __global__ void k_key_scan(DevCounters* cnt) {
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < K_MAX; ++k) {
             cnt->key_start[k] = acc;
             cnt->key_cursor[k] = acc;
             cnt->epa_cursor[k] = acc;
@@ -674,7 +668,7 @@ __global__ void __launch_bounds__(256) k_key_scatter(const uint2* __restrict__ p
     for (uint32_t base = blockIdx.x * blockDim.x; base < np; base += stride) {
         uint32_t p = base + threadIdx.x;
         bool valid = p < np;
-        uint32_t key = valid ? (kin[p] & 15) : 31;
+        uint32_t key = valid ? (kin[p] & (K_MAX - 1)) : 0xffu;
         unsigned peers = __match_any_sync(0xffffffffu, key);
         if (valid) {
             int lane = threadIdx.x & 31;
@@ -684,7 +678,7 @@ __global__ void __launch_bounds__(256) k_key_scatter(const uint2* __restrict__ p
             b = __shfl_sync(peers, b, leader);
             uint32_t dst = b + __popc(peers & ((1u << lane) - 1));
             pout[dst] = pin[p];
-            algo_out[dst] = c_algo_of_key[key];
+            algo_out[dst] = (uint8_t)algo_of_key(key);
             if (index_out) index_out[dst] = p;
         }
     }

@@ -1,7 +1,6 @@
-// Capsules, per pair — STAGED: these device functions are complete and checked bit for bit against the oracle
-// on the CPU (tests/host_shim/narrow_host.cpp, tests/test_device_source_on_host.py), but no kernel calls them yet.  What is left
-// for the device path is plumbing (a third shape-type bit, pair keys for the capsule segments of the sorted pair array, the two
-// segment end points of every capsule in a global table); until then ncb_set_objects refuses capsules (NCB_ERR_UNSUPPORTED).
+// Capsules, per pair: the CapsuleCapsule / CapsuleShape contact generators as device functions, run by k_capsule
+// (narrow.cu) over the five capsule key segments of the sorted pair array, one pair per thread.  The per-pair functions are also
+// compiled for the host and checked bit for bit against the oracle (tests/host_shim/narrow_host.cpp).
 // Include after the definitions of narrow.cu (Feature, clip, manifold_push, gjk.cuh).
 //
 // Replaces (reference, file:line):
@@ -14,23 +13,11 @@
 // The capsule is replaced by its segment, the linear prediction grows by the radius, and every contact the sub-detector produces
 // goes through the capsule's ContactPreprocessor before ContactManifold::push.  GJK / EPA need no new support kind: the segment is
 // the 2-point "hull" [b, a] (in that order the hull scan's first-maximum rule returns `a` exactly when a.dir > b.dir, which is
-// Segment::local_support_point); `seg_pts` points at those six floats (b then a) in GLOBAL memory (HullView reads through __ldg).
+// Segment::local_support_point); `seg_pts` points at those six floats (b then a) in GLOBAL memory (HullView reads through __ldg):
+// DevObjects::cap_pts holds them for every object of a world with capsules (k_fill_cap_pts).
 #pragma once
 
 namespace ncb {
-
-// Capsule as a SupportMap (capsule.rs:72-85): support_point(m, dir) = m * local_support_point_toward(normalize(m^-1 dir))
-NCB_HD V3 capsule_support_point(const Iso& m, float hh, float radius, V3 dir) {
-    V3 d = normalize(iso_inv_vec(m, dir));
-    return iso_mul_point(m, v3(0.f, copysignf(hh, d.y), 0.f) + d * radius);
-}
-// AABB of a capsule (aabb_support_map.rs:35-45 -> aabb_utils.rs:9-31): the support points along +-x, +-y, +-z
-NCB_HD void capsule_aabb(const Iso& m, float hh, float radius, V3& mins, V3& maxs) {
-    maxs = v3(capsule_support_point(m, hh, radius, v3(1.f, 0.f, 0.f)).x, capsule_support_point(m, hh, radius, v3(0.f, 1.f, 0.f)).y,
-              capsule_support_point(m, hh, radius, v3(0.f, 0.f, 1.f)).z);
-    mins = v3(capsule_support_point(m, hh, radius, v3(-1.f, 0.f, 0.f)).x, capsule_support_point(m, hh, radius, v3(0.f, -1.f, 0.f)).y,
-              capsule_support_point(m, hh, radius, v3(0.f, 0.f, -1.f)).z);
-}
 
 // ContactPreprocessor of a capsule side (capsule.rs:98-132); active = false: no preprocessor on that side
 struct CapsulePre {
@@ -270,6 +257,91 @@ NCB_HD void gen_plane_segment(const Iso& mplane, V3 plane_n, const Iso& mseg, fl
                 manifold_push_pp(mf, world2, world1, -n, -dist, f2, FACE0, local2, seg_pre, none);
         }
     }
+}
+
+// One pair with at least one capsule, from the object arrays to its manifold: what k_capsule runs per thread.
+//   PS = false: `mf` (cleared by the caller) receives the contacts; the caller writes it out.
+//   PS = true : the stepping world's state slot `slot` is loaded (aged), updated and stored here (warm-started GJK direction incl.).
+// CapsuleCapsule: both operands become segments; CapsuleShape: the capsule becomes a segment and the sub-detector is the one the
+// dispatcher picks for (segment, other) — ball / plane / convex polyhedron generators — with the capsule's ContactPreprocessor on
+// the segment's side and the linear prediction grown by the radius (capsule_shape_manifold_generator.rs:37-75).
+template <bool PS>
+__device__ __noinline__ void capsule_pair(const DevObjects& o, const DevHulls& H, const PersistArgs& ps, uint32_t slot, EpaState& e, ManifoldT<PS>& mf,
+                                          uint32_t i1, uint32_t i2, uint32_t* epa_overflow, uint32_t* ref_panics) {
+    uint32_t t1 = __ldg(&o.type[i1]) & NCB_TYPE_MASK, t2 = __ldg(&o.type[i2]) & NCB_TYPE_MASK;
+    bool a_cap = t1 == NCB_SHAPE_CAPSULE, b_cap = t2 == NCB_SHAPE_CAPSULE;
+    Iso ma = load_iso(o, i1), mb = load_iso(o, i2);
+    float linear = __ldg(&o.qlimit[i1]) + __ldg(&o.qlimit[i2]);
+    CapOperand a, b;
+    a.shape = Shape{}, b.shape = Shape{};
+    a.is_segment = a_cap, b.is_segment = b_cap;
+    a.hh = b.hh = 0.f;
+    a.seg_pts = b.seg_pts = nullptr;
+    a.pre.active = b.pre.active = false;
+    a.pre.radius = b.pre.radius = 0.f;
+    if (a_cap) {
+        float4 p = __ldg(&o.param[i1]);
+        a.hh = p.x, a.seg_pts = o.cap_pts + 6 * (size_t)i1, a.pre.active = true, a.pre.radius = p.y;
+        a.shape.type = NCB_SHAPE_CAPSULE;
+        linear = linear + a.pre.radius;
+    } else
+        a.shape = load_shape(o, H, i1, t1);
+    if (b_cap) {
+        float4 p = __ldg(&o.param[i2]);
+        b.hh = p.x, b.seg_pts = o.cap_pts + 6 * (size_t)i2, b.pre.active = true, b.pre.radius = p.y;
+        b.shape.type = NCB_SHAPE_CAPSULE;
+        linear = linear + b.pre.radius;
+    } else
+        b.shape = load_shape(o, H, i2, t2);
+    bool simple = (!a_cap && (t1 == NCB_SHAPE_BALL || t1 == NCB_SHAPE_PLANE)) || (!b_cap && (t2 == NCB_SHAPE_BALL || t2 == NCB_SHAPE_PLANE));
+    if (simple) {
+        if constexpr (PS) pm_load_and_age(ps, slot, mf);
+        Feature feat;
+        if (!a_cap && t1 == NCB_SHAPE_BALL)
+            gen_ball_segment(ma, a.shape.radius, mb, b.hh, linear, false, b.pre, mf);
+        else if (!b_cap && t2 == NCB_SHAPE_BALL)
+            gen_ball_segment(mb, b.shape.radius, ma, a.hh, linear, true, a.pre, mf);
+        else if (!a_cap)
+            gen_plane_segment(ma, a.shape.he, mb, b.hh, linear, false, b.pre, mf, feat);
+        else
+            gen_plane_segment(mb, b.shape.he, ma, a.hh, linear, true, a.pre, mf, feat);
+        if constexpr (PS) pm_store(ps, slot, mf, i1, i2);
+        return;
+    }
+    Support ga = cap_support(a), gb = cap_support(b);
+    V3 d0;
+    bool warm = false;
+    if constexpr (PS) {
+        float4 pd = ps.dir[slot];
+        if (pd.w != 0.f) d0 = v3(pd.x, pd.y, pd.z), warm = true;
+    }
+    if (!warm && !unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
+    V3 p1, p2, dir;
+    Simplex s;
+    int r = gjk_closest_points(ma, ga, mb, gb, linear, d0, s, p1, p2, dir);
+    if constexpr (PS) {
+        if (r != GJK_INTERSECTION) ps.dir[slot] = make_float4(dir.x, dir.y, dir.z, 1.f);
+    }
+    if (r == GJK_INTERSECTION) {
+        if (epa_closest_points(e, ma, ga, mb, gb, s.dim, s.v, p1, p2, dir)) {
+            r = GJK_CLOSEST_POINTS;
+            if constexpr (PS) ps.dir[slot] = make_float4(dir.x, dir.y, dir.z, 1.f);
+        } else {
+            if (e.overflow) atomicAdd(epa_overflow, 1u);
+            if (e.panicked) atomicAdd(ref_panics, 1u);
+            r = GJK_NO_INTERSECTION;
+            if constexpr (PS) ps.dir[slot] = make_float4(1.f, 0.f, 0.f, 1.f);
+        }
+    }
+    if (r == GJK_NO_INTERSECTION) {
+        if constexpr (PS) pm_age_only(ps, slot, i1, i2);
+        return;
+    }
+    if constexpr (PS) pm_load_and_age(ps, slot, mf);
+    float2 ang1 = __ldg(&o.ang_cs[i1 * o.ang_stride]), ang2 = __ldg(&o.ang_cs[i2 * o.ang_stride]);
+    Feature f1, f2;
+    if (!capsule_convex_manifold(ma, a, mb, b, linear, ang1, ang2, p1, p2, dir, mf, f1, f2)) atomicAdd(epa_overflow, 1u);
+    if constexpr (PS) pm_store(ps, slot, mf, i1, i2);
 }
 
 }  // namespace ncb

@@ -851,6 +851,10 @@ __device__ __noinline__ void pm_age_only(const PersistArgs& ps, uint32_t slot, u
     pm_store(ps, slot, mf, h1, h2);
 }
 
+}  // namespace ncb
+#include "capsule.cuh"
+namespace ncb {
+
 #ifndef NCB_HOST_SHIM  // kernels, work queues and launchers: CUDA only
 struct NarrowArgs {
     PersistArgs ps;
@@ -1062,27 +1066,26 @@ __global__ void __launch_bounds__(EPAS_THREADS, NCB_EPAS_MINBLOCKS) k_cc_epa_s(N
 }
 
 // The overflow queue on the big local-memory store.  A restarted pair is a chain of 10-20 dependent expansion steps (~0.2 ms alone),
-// and there are only a few thousand such pairs, so the kernel spreads them over as many WARPS as possible (one or a few lanes per
-// warp, `lanes` below) and runs on its own stream next to k_cc_manifold: its latency is hidden instead of ending the phase.
-// Its closest-point records go to the END of the convex-convex segment of the manifold queue (slot seg_end - 1 - k), which the
-// main records, growing from the start, cannot reach (records <= pairs of the segment); k_cc_manifold<PS, 1> consumes them.
+// and there are only a few thousand such pairs, so the kernel spreads them over its warps (a few lanes per warp, `lanes` below),
+// finishes each pair completely (EPA, then features + clipping + manifold in the same thread: no queue, no follow-up launch) and
+// runs on its own high-priority stream NEXT TO k_cc_manifold with a small grid (2 CTAs of 64 threads per SM leave the manifold kernel
+// its registers): its latency is hidden behind the manifold kernel of the other 99 % instead of ending the phase.
 #ifndef NCB_EPA_MINBLOCKS
 #define NCB_EPA_MINBLOCKS 16
 #endif
 template <bool PS>
 __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa_big(NarrowArgs A) {
-    const int KEY = CCQ;
     const uint32_t seg_end = A.cnt->epa_long_n;
     if (seg_end == 0) return;
-    const uint32_t cp_end = A.cnt->key_start[K_HULL_HULL] + A.cnt->key_hist[K_HULL_HULL];
     uint32_t* fetch = &A.cnt->epa_long_fetch;
     const int lane = threadIdx.x & 31;
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
     const uint32_t lanes = min(32u, (seg_end + nwarps - 1) / nwarps);
     const bool usable = (uint32_t)lane < lanes;
     EpaState e;
+    ManifoldT<PS> mf;
     bool active = false, exhausted = false;
-    uint32_t p = 0;
+    uint32_t p = 0, i1 = 0, i2 = 0;
     Iso ma, mb;
     Support ga, gb;
     V3 p1, p2, n;
@@ -1104,7 +1107,7 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa_big(NarrowArgs
                     CSOPoint sv[4];
                     epa_rec_load(A.epa_queue + (size_t)wq * EPA_REC_WORDS, p, sdim, sv);
                     uint2 pr = __ldg(&A.pairs[p]);
-                    uint32_t i1 = pr.x, i2 = pr.y;
+                    i1 = pr.x, i2 = pr.y;
                     uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
                     ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
                     Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
@@ -1118,24 +1121,33 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa_big(NarrowArgs
         }
         bool ok = active && status == EPA_DONE_OK;
         bool fail = active && status == EPA_DONE_FAIL;
-        uint32_t k = queue_append(&A.cnt->cp_over_n, ok);
-        if (ok) {
-            cp_store(A.cp_queue, cp_end - 1 - k, p, p1, p2, n);
-            if constexpr (PS) A.ps.dir[A.pair_index ? __ldg(&A.pair_index[p]) : p] = make_float4(n.x, n.y, n.z, 1.f);
+        uint32_t out_index = (ok || fail) ? (A.pair_index ? __ldg(&A.pair_index[p]) : p) : 0;
+        mf.n = 0;
+        mf.deepest = 0;
+        if (ok) {  // the body of k_cc_manifold for this pair
+            atomicAdd(&A.cnt->epa_long_ok, 1u);
+            if constexpr (PS) {
+                A.ps.dir[out_index] = make_float4(n.x, n.y, n.z, 1.f);
+                pm_load_and_age(A.ps, out_index, mf);
+            }
+            uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
+            float linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
+            Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
+            float2 ang1 = __ldg(&A.o.ang_cs[i1 * A.o.ang_stride]), ang2 = __ldg(&A.o.ang_cs[i2 * A.o.ang_stride]);
+            Feature f1, f2;
+            convex_convex_manifold(ma, a, mb, b, linear, ang1, ang2, p1, p2, n, mf, f1, f2);
+            if constexpr (PS) pm_store(A.ps, out_index, mf, i1, i2);
         }
         if (fail) {
             if (e.overflow) atomicAdd(&A.cnt->epa_overflow, 1u);
             if (e.panicked) atomicAdd(&A.cnt->ref_panics, 1u);
-            uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
             if constexpr (PS) {  // NoIntersection(x axis) (contact_support_map_support_map.rs:76)
                 A.ps.dir[out_index] = make_float4(1.f, 0.f, 0.f, 1.f);
-                uint2 pr = __ldg(&A.pairs[p]);
-                pm_age_only(A.ps, out_index, pr.x, pr.y);
-            } else {
-                A.manifold_start[out_index] = 0;
-                A.manifold_count[out_index] = 0;
+                pm_age_only(A.ps, out_index, i1, i2);
             }
         }
+        // an Err pair writes its empty manifold through the same call (mf.n == 0)
+        if constexpr (!PS) write_manifold(mf, ok || fail, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
         if (ok || fail) active = false;
         if (exhausted && __all_sync(0xffffffffu, !active)) break;
     }
@@ -1144,13 +1156,11 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa_big(NarrowArgs
 #ifndef NCB_MAN_MINBLOCKS
 #define NCB_MAN_MINBLOCKS 6
 #endif
-// PART 0: the records of k_cc_gjk / k_cc_epa_s (from the start of the segment); PART 1: those of k_cc_epa_big (at its end).
-template <bool PS, int PART>
+template <bool PS>
 __global__ void __launch_bounds__(128, NCB_MAN_MINBLOCKS) k_cc_manifold(NarrowArgs A) {
     const int KEY = CCQ;
-    const uint32_t cc_end = A.cnt->key_start[K_HULL_HULL] + A.cnt->key_hist[K_HULL_HULL];
-    uint32_t seg_begin = PART == 0 ? A.cnt->key_start[KEY] : cc_end - A.cnt->cp_over_n;
-    uint32_t seg_end = PART == 0 ? A.cnt->cp_cursor[KEY] : cc_end;
+    uint32_t seg_begin = A.cnt->key_start[KEY];
+    uint32_t seg_end = A.cnt->cp_cursor[KEY];
     uint32_t stride = gridDim.x * blockDim.x;
     ManifoldT<PS> mf;
     for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
@@ -1337,6 +1347,30 @@ __global__ void __launch_bounds__(256) k_narrow_none(NarrowArgs A) {
     }
 }
 
+// Pairs with a capsule: the five capsule key segments are adjacent, one launch walks them all (one pair per thread, the whole
+// generator in the thread: capsule.cuh).  Worlds without capsules never launch it.
+template <bool PS>
+__global__ void __launch_bounds__(64) k_capsule(NarrowArgs A) {
+    uint32_t seg_begin = A.cnt->key_start[K_CAPSULE_BALL];
+    uint32_t seg_end = A.cnt->key_start[K_CAPSULE_HULL] + A.cnt->key_hist[K_CAPSULE_HULL];
+    uint32_t stride = gridDim.x * blockDim.x;
+    EpaState e;
+    ManifoldT<PS> mf;
+    for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
+        uint32_t p = base + threadIdx.x;
+        bool valid = p < seg_end;
+        mf.n = 0;
+        mf.deepest = 0;
+        uint32_t out_index = 0;
+        if (valid) {
+            uint2 pr = __ldg(&A.pairs[p]);
+            out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
+            capsule_pair<PS>(A.o, A.H, A.ps, out_index, e, mf, pr.x, pr.y, &A.cnt->epa_overflow, &A.cnt->ref_panics);
+        }
+        if constexpr (!PS) write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+    }
+}
+
 template <bool PS>
 static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, uint32_t cap_pairs,
                                          uint32_t cap_contacts, const PersistArgs* ps) {
@@ -1366,7 +1400,7 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     int sm = c->sm_count;
     // tuning knobs (CTAs per SM of the persistent kernels); defaults chosen from ncu runs, see profiles/
     static int gjk_bpsm = getenv("NCB_GJK_BPSM") ? atoi(getenv("NCB_GJK_BPSM")) : 6;
-    static int epa_bpsm = getenv("NCB_EPA_BPSM") ? atoi(getenv("NCB_EPA_BPSM")) : 16;  // overflow kernel (k_cc_epa_big)
+    static int epa_bpsm = getenv("NCB_EPA_BPSM") ? atoi(getenv("NCB_EPA_BPSM")) : 2;  // overflow kernel (k_cc_epa_big): small on purpose
     static int man_bpsm = getenv("NCB_MAN_BPSM") ? atoi(getenv("NCB_MAN_BPSM")) : 6;
     // Two independent chains: the convex-convex phases on the context's stream, everything else on a side stream
     // (each persistent kernel alone leaves most issue slots idle; together they overlap).
@@ -1383,6 +1417,7 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     k_narrow<K_PLANE_CUBOID, PS><<<sm * 2, 128, 0, s2>>>(A);
     k_narrow<K_PLANE_HULL, PS><<<sm * 2, 128, 0, s2>>>(A);
     if (!PS) k_narrow_none<<<sm, 256, 0, s2>>>(A);
+    if (c->has_capsules) k_capsule<PS><<<sm * 8, 64, 0, s2>>>(A);
     if (!PS && c->has_prox && c->prox.p) launch_proximity_segments(c, o, pairs, pair_index, s2);  // sensor pairs (proximity.cu)
     if (c->side_stream) cudaEventRecord(c->ev_join, s2);
     k_cc_gjk<PS><<<sm * gjk_bpsm, 128, 0, s>>>(A);
@@ -1407,7 +1442,7 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
         k_cc_epa_s<PS><<<sm * epas_bpsm, EPAS_THREADS, smem, s>>>(A);
     }
     timer_mark(c, "cc_epa", 1);
-    // the overflow pairs (beyond the compact capacities) run beside the manifold kernel of everything else
+    // the overflow pairs (beyond the compact capacities) run beside the manifold kernel of everything else, EPA to manifold
     cudaStream_t s3 = c->over_stream ? c->over_stream : s;
     if (c->over_stream) {
         cudaEventRecord(c->ev_epa, s);
@@ -1415,11 +1450,9 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     }
     k_cc_epa_big<PS><<<sm * epa_bpsm, 64, 0, s3>>>(A);
     if (c->over_stream) cudaEventRecord(c->ev_over, s3);
-    k_cc_manifold<PS, 0><<<sm * man_bpsm, 128, 0, s>>>(A);
-    timer_mark(c, "cc_manifold", 1);
+    k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
     if (c->over_stream) cudaStreamWaitEvent(s, c->ev_over, 0);
-    k_cc_manifold<PS, 1><<<sm, 128, 0, s>>>(A);
-    timer_mark(c, "cc_overflow_tail", 2);
+    timer_mark(c, "cc_manifold", 2);
     if (!early && c->side_stream) cudaStreamWaitEvent(s, c->ev_join, 0);  // device-only updates: the side chain may run to the end
     timer_mark(c, "narrow_other_join", 7);
     return cudaGetLastError();
@@ -1435,16 +1468,13 @@ cudaError_t launch_narrow_phase_persistent(ncb_ctx* c, const DevObjects& o, cons
 }
 
 // Classify caller-provided pairs (ncb_generate_contacts): key per pair from the two shape types.
-__device__ __constant__ uint8_t c_key_table2[16] = {K_BALL_BALL,   K_BALL_CUBOID,   K_BALL_HULL,   K_PLANE_BALL,   K_BALL_CUBOID, K_CUBOID_CUBOID,
-                                                    K_CUBOID_HULL, K_PLANE_CUBOID,  K_BALL_HULL,   K_CUBOID_HULL,  K_HULL_HULL,   K_PLANE_HULL,
-                                                    K_PLANE_BALL,  K_PLANE_CUBOID,  K_PLANE_HULL,  K_NONE};
 __global__ void __launch_bounds__(256) k_classify_pairs(const uint2* __restrict__ pairs, uint32_t n, const uint32_t* __restrict__ type,
                                                         uint8_t* __restrict__ keys, DevCounters* cnt) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p == 0) cnt->n_pairs = n;
     if (p >= n) return;
     uint2 pr = pairs[p];
-    keys[p] = c_key_table2[(type[pr.x] & 3) * 4 + (type[pr.y] & 3)];
+    keys[p] = (uint8_t)pair_key(type[pr.x], type[pr.y]);
 }
 cudaError_t launch_classify_pairs(ncb_ctx* c, const uint2* pairs, uint32_t n) {
     if (n == 0) return cudaSuccess;

@@ -20,13 +20,61 @@ enum PairKey : uint32_t {
     K_CUBOID_HULL = 7,
     K_HULL_HULL = 8,
     K_NONE = 9,
-    // pairs with a GeometricQueryType::Proximity object (proximity.cu); adjacent, after every contact key
+    // pairs with a GeometricQueryType::Proximity object (proximity.cu); adjacent
     K_PROX_BALL_BALL = 10,
     K_PROX_PLANE = 11,
     K_PROX_SM = 12,       // support map x support map without a hull operand (ball / cuboid): O(1) support functions
     K_PROX_SM_HULL = 13,  // ... with at least one convex hull (vertex scans)
-    K_COUNT = 14
+    // pairs with a capsule (capsule.cuh; CapsuleCapsule / CapsuleShape generators); adjacent, one kernel runs the five segments
+    K_CAPSULE_BALL = 14,
+    K_CAPSULE_PLANE = 15,
+    K_CAPSULE_CAPSULE = 16,
+    K_CAPSULE_CUBOID = 17,
+    K_CAPSULE_HULL = 18,
+    K_COUNT = 19,
+    K_MAX = 32  // size of the per-key counter arrays
 };
+#define NCB_TYPE_MASK 7u  // shape types travel in 3 bits (leaf records, key tables)
+
+// The contact dispatcher as a table (default_contact_dispatcher.rs:27-97): key of a pair from its two shape types.
+// Types: 0 ball, 1 cuboid, 2 convex hull, 3 plane, 4 capsule; anything else has no generator.
+__host__ __device__ inline uint32_t pair_key(uint32_t t1, uint32_t t2) {
+    t1 &= NCB_TYPE_MASK, t2 &= NCB_TYPE_MASK;
+    if (t1 > 4 || t2 > 4) return K_NONE;
+    if (t1 == 4 || t2 == 4) {  // CapsuleCapsule, then CapsuleShape on whatever the other shape is (dispatcher :64-78)
+        uint32_t other = t1 == 4 ? t2 : t1;
+        return other == 0 ? K_CAPSULE_BALL : other == 1 ? K_CAPSULE_CUBOID : other == 2 ? K_CAPSULE_HULL : other == 3 ? K_CAPSULE_PLANE : K_CAPSULE_CAPSULE;
+    }
+    uint32_t lo = t1 < t2 ? t1 : t2, hi = t1 < t2 ? t2 : t1;
+    if (hi == 3) return lo == 0 ? K_PLANE_BALL : lo == 1 ? K_PLANE_CUBOID : lo == 2 ? K_PLANE_HULL : K_NONE;
+    if (lo == 0) return hi == 0 ? K_BALL_BALL : hi == 1 ? K_BALL_CUBOID : K_BALL_HULL;
+    if (lo == 1) return hi == 1 ? K_CUBOID_CUBOID : K_CUBOID_HULL;
+    return K_HULL_HULL;
+}
+// NCB_ALGO_* of a key
+__host__ __device__ inline uint32_t algo_of_key(uint32_t key) {
+    switch (key) {
+        case K_BALL_BALL: return NCB_ALGO_BALL_BALL;
+        case K_PLANE_BALL: return NCB_ALGO_PLANE_BALL;
+        case K_PLANE_CUBOID:
+        case K_PLANE_HULL: return NCB_ALGO_PLANE_CONVEX;
+        case K_BALL_CUBOID:
+        case K_BALL_HULL: return NCB_ALGO_BALL_CONVEX;
+        case K_CUBOID_CUBOID:
+        case K_CUBOID_HULL:
+        case K_HULL_HULL: return NCB_ALGO_CONVEX_CONVEX;
+        case K_PROX_BALL_BALL:
+        case K_PROX_PLANE:
+        case K_PROX_SM:
+        case K_PROX_SM_HULL: return NCB_ALGO_PROXIMITY;
+        case K_CAPSULE_CAPSULE: return NCB_ALGO_CAPSULE_CAPSULE;
+        case K_CAPSULE_BALL:
+        case K_CAPSULE_PLANE:
+        case K_CAPSULE_CUBOID:
+        case K_CAPSULE_HULL: return NCB_ALGO_CAPSULE_SHAPE;
+        default: return NCB_ALGO_NONE;
+    }
+}
 
 struct DevHulls {
     uint32_t n_hulls;
@@ -52,6 +100,7 @@ struct DevObjects {
     const float* ang;
     const float2* ang_cs;    // (cos, sin) of ang, evaluated on the host with libm like the reference does
     uint32_t ang_stride;     // 1: one entry per object; 0: every object has the same angular prediction (entry 0)
+    const float* cap_pts;    // worlds with capsules: 6 floats per OBJECT, the capsule segment as the 2-point hull [b, a] (else nullptr)
 };
 
 // Counters living in one device allocation (zeroed per update with one memset).
@@ -62,17 +111,18 @@ struct DevCounters {
     uint32_t epa_overflow;
     uint32_t ref_panics;
     uint32_t n_outliers;       // objects kept out of the LBVH (planes / non-finite boxes)
-    uint32_t key_hist[16];     // pairs per PairKey
-    uint32_t key_start[16];    // exclusive scan of key_hist
-    uint32_t key_cursor[16];   // scatter cursors
-    uint32_t epa_cursor[16];   // per key: end of the EPA work queue (starts at key_start[key])
-    uint32_t cp_cursor[16];    // per key: end of the closest-points (manifold) work queue
-    uint32_t epa_fetch[16];    // per key: next EPA queue entry to hand to an idle lane (dynamic fetch)
-    uint32_t gjk_fetch[16];    // per key: next pair of the key segment to hand to an idle lane
+    uint32_t key_hist[K_MAX];     // pairs per PairKey
+    uint32_t key_start[K_MAX];    // exclusive scan of key_hist
+    uint32_t key_cursor[K_MAX];   // scatter cursors
+    uint32_t epa_cursor[K_MAX];   // per key: end of the EPA work queue (starts at key_start[key])
+    uint32_t cp_cursor[K_MAX];    // per key: end of the closest-points (manifold) work queue
+    uint32_t epa_fetch[K_MAX];    // per key: next EPA queue entry to hand to an idle lane (dynamic fetch)
+    uint32_t gjk_fetch[K_MAX];    // per key: next pair of the key segment to hand to an idle lane
     int bounds[6];             // ordered-int encoded min xyz / max xyz of AABB centres
     uint32_t epa_long_n;       // EPA overflow queue: pairs that did not fit the compact (shared-memory) polytope store
     uint32_t epa_long_fetch;
-    uint32_t cp_over_n;        // closest-point records appended by the overflow EPA kernel (stored from the END of the segment)
+    uint32_t epa_long_ok;      // overflow pairs whose EPA succeeded (they reach clipping inside k_cc_epa_big)
+    uint32_t stack_overflow;   // BVH traversals (pair search, ray casts, queries) that ran out of their 64-entry stack: must stay 0
     uint32_t prox_hist[4];     // proximity pairs per status (Intersecting, WithinMargin, Disjoint)
 };
 
@@ -163,6 +213,9 @@ struct ncb_ctx {
     ncb::DevBuf<float4> rot, param;
     ncb::DevBuf<float2> ang_cs;
     ncb::DevBuf<uint32_t> type, groups;
+    ncb::DevBuf<uint32_t> trav_overflow;         // query / ray traversals that ran out of stack (cumulative; ncb_traversal_overflows)
+    ncb::DevBuf<float> cap_pts;                  // capsule segments as 2-point hulls, 6 floats per object (only with capsules)
+    bool has_capsules = false;
     std::vector<float2> h_ang_cs;
     uint32_t ang_stride = 1;
     // GeometricQueryType per object (ncb_set_query_types): 1 = Proximity(query_limit).  has_prox = at least one sensor.
@@ -227,6 +280,8 @@ int reserve_broad(ncb_ctx* ctx, uint32_t n);
 int reserve_pairs(ncb_ctx* ctx, size_t cap);
 int reset_counters(ncb_ctx* ctx);
 int read_counters(ncb_ctx* ctx);
+uint32_t* trav_overflow_counter(ncb_ctx* ctx);
+cudaError_t launch_fill_cap_pts(ncb_ctx* ctx, uint32_t n);  // ctx->cap_pts from ctx->type / ctx->param (worlds with capsules)  // device counter of skipped subtrees in query / ray traversals (allocated on first use)
 
 namespace ncb {
 

@@ -259,6 +259,7 @@ struct QueryArgs {
     uint32_t* feats;
     uint32_t cap;
     uint32_t* counter;
+    uint32_t* trav_overflow;
 };
 
 template <bool FIRST>
@@ -334,7 +335,10 @@ __global__ void __launch_bounds__(128) k_world_ray_cast(QueryArgs A) {
             if (goL && goR) {
                 // FIRST: the child entered sooner is walked first, so that its hits prune the other one
                 bool right_first = FIRST && tr < tl;
-                if (sp < 64) stack[sp++] = right_first ? left : right;
+                if (sp < 64)
+                    stack[sp++] = right_first ? left : right;
+                else
+                    atomicAdd(A.trav_overflow, 1u);
                 node = right_first ? right : left;
             } else if (goL) {
                 node = left;
@@ -433,7 +437,12 @@ __global__ void __launch_bounds__(128) k_world_query(QueryArgs A) {
                 goR = false;
             }
             if (goL) {
-                if (goR && sp < 64) stack[sp++] = right;
+                if (goR) {
+                    if (sp < 64)
+                        stack[sp++] = right;
+                    else
+                        atomicAdd(A.trav_overflow, 1u);
+                }
                 node = left;
             } else if (goR) {
                 node = right;
@@ -491,6 +500,10 @@ int world_ray_cast(ncb_ctx* ctx, ncb_bp* bp, WorldQueryBufs& B, uint32_t n_rays,
     CKQ(cudaSetDevice(ctx->device));
     if (n_out) *n_out = 0;
     if (n_rays == 0 || bp->tree_n == 0) return NCB_OK;
+    if (ctx->has_capsules) {
+        ctx->err = "world ray queries: the capsule ray cast is not on the device (worlds with capsules support updates only)";
+        return NCB_ERR_UNSUPPORTED;
+    }
     cudaStream_t s = ctx->stream;
     ncb_ctx* w = bp->work;
     CKQ(B.rays.reserve(7 * (size_t)n_rays));
@@ -513,7 +526,7 @@ int world_ray_cast(ncb_ctx* ctx, ncb_bp* bp, WorldQueryBufs& B, uint32_t n_rays,
         A.o = dev_objects(ctx), A.H = ctx->hulls;
         A.use_groups = groups != nullptr;
         for (int k = 0; k < 3; ++k) A.qg[k] = groups ? groups[k] : 0;
-        A.keys = B.keys.p, A.vals = B.vals.p, A.feats = B.feats.p, A.cap = c, A.counter = B.counter.p;
+        A.keys = B.keys.p, A.vals = B.vals.p, A.feats = B.feats.p, A.cap = c, A.counter = B.counter.p, A.trav_overflow = trav_overflow_counter(ctx);
         unsigned g = (n_rays + 127) / 128;
         if (first_only)
             k_world_ray_cast<true><<<g, 128, 0, s>>>(A);
@@ -556,6 +569,10 @@ int world_query(ncb_ctx* ctx, ncb_bp* bp, WorldQueryBufs& B, int kind, uint32_t 
     CKQ(cudaSetDevice(ctx->device));
     if (n_out) *n_out = 0;
     if (n_q == 0 || bp->tree_n == 0) return NCB_OK;
+    if (kind == 2 && ctx->has_capsules) {
+        ctx->err = "world point queries: capsule point containment is not on the device (worlds with capsules support updates only)";
+        return NCB_ERR_UNSUPPORTED;
+    }
     cudaStream_t s = ctx->stream;
     ncb_ctx* w = bp->work;
     const int W = kind == 0 ? 6 : 3;
@@ -575,7 +592,7 @@ int world_query(ncb_ctx* ctx, ncb_bp* bp, WorldQueryBufs& B, int kind, uint32_t 
         A.o = dev_objects(ctx), A.H = ctx->hulls;
         A.use_groups = groups != nullptr;
         for (int k = 0; k < 3; ++k) A.qg[k] = groups ? groups[k] : 0;
-        A.keys = B.keys.p, A.vals = nullptr, A.feats = nullptr, A.cap = (uint32_t)B.keys.cap, A.counter = B.counter.p;
+        A.keys = B.keys.p, A.vals = nullptr, A.feats = nullptr, A.cap = (uint32_t)B.keys.cap, A.counter = B.counter.p, A.trav_overflow = trav_overflow_counter(ctx);
         unsigned g = (n_q + 127) / 128;
         if (kind == 0)
             k_world_query<0><<<g, 128, 0, s>>>(A);

@@ -256,6 +256,7 @@ struct RayArgs {
     float* toi;
     uint32_t* face;
     float* normal;
+    uint32_t* trav_overflow;
 };
 
 template <bool TILE>
@@ -346,6 +347,8 @@ __global__ void __launch_bounds__(128) k_ray_cast(RayArgs A) {
                     stack[sp] = farn;
                     stack_t[sp] = fart;
                     sp++;
+                } else {
+                    atomicAdd(A.trav_overflow, 1u);
                 }
                 node = nearn;
             } else if (goL) {
@@ -522,6 +525,7 @@ int ncb_trimesh_ray_cast_device(ncb_mesh* m, const float* pose, uint32_t n_rays,
     A.toi = d_toi;
     A.face = d_face;
     A.normal = d_normal;
+    A.trav_overflow = trav_overflow_counter(ctx);
     A.top_tile = (m->use_tile && m->n_tris >= 2) ? m->top_tile.p : nullptr;
     A.perm = nullptr;
     if (m->sort_rays && n_rays >= 4096) {

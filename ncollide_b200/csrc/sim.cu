@@ -77,13 +77,6 @@ struct ncb_sim {
 
 namespace {
 
-__device__ __constant__ uint8_t c_sim_key[16] = {K_BALL_BALL,   K_BALL_CUBOID,  K_BALL_HULL,  K_PLANE_BALL,   K_BALL_CUBOID, K_CUBOID_CUBOID,
-                                                 K_CUBOID_HULL, K_PLANE_CUBOID, K_BALL_HULL,  K_CUBOID_HULL,  K_HULL_HULL,   K_PLANE_HULL,
-                                                 K_PLANE_BALL,  K_PLANE_CUBOID, K_PLANE_HULL, K_NONE};
-__device__ __constant__ uint8_t c_sim_algo[16] = {NCB_ALGO_BALL_BALL,     NCB_ALGO_PLANE_BALL,  NCB_ALGO_PLANE_CONVEX,  NCB_ALGO_PLANE_CONVEX,
-                                                  NCB_ALGO_BALL_CONVEX,   NCB_ALGO_BALL_CONVEX, NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_CONVEX_CONVEX,
-                                                  NCB_ALGO_CONVEX_CONVEX, NCB_ALGO_NONE,        NCB_ALGO_PROXIMITY, NCB_ALGO_PROXIMITY,
-                                                  NCB_ALGO_PROXIMITY,     NCB_ALGO_PROXIMITY,   0, 0};
 __device__ __forceinline__ bool is_prox_key(uint8_t k) { return k >= K_PROX_BALL_BALL && k <= K_PROX_SM_HULL; }
 
 __device__ int sim_find(const unsigned long long* __restrict__ keys, uint32_t n, unsigned long long k) {
@@ -159,8 +152,8 @@ __global__ void k_sim_assign(const unsigned long long* __restrict__ cur, uint32_
     uint32_t h1 = hi_first ? hi : lo, h2 = hi_first ? lo : hi;
     slot_new[i] = slot;
     slot_pair[slot] = make_uint2(h1, h2);
-    uint32_t t1 = type[h1] & 3, t2 = type[h2] & 3;
-    uint8_t key = c_sim_key[t1 * 4 + t2];
+    uint32_t t1 = type[h1] & NCB_TYPE_MASK, t2 = type[h2] & NCB_TYPE_MASK;
+    uint8_t key = (uint8_t)pair_key(t1, t2);
     if (qkind && key != K_NONE && (qkind[h1] | qkind[h2])) {  // (_, Proximity) | (Proximity, _): a proximity detector (narrow_phase.rs:240-246)
         key = (t1 == NCB_SHAPE_BALL && t2 == NCB_SHAPE_BALL) ? K_PROX_BALL_BALL
               : (t1 == NCB_SHAPE_PLANE || t2 == NCB_SHAPE_PLANE) ? K_PROX_PLANE
@@ -208,7 +201,7 @@ __global__ void k_sim_export(const uint32_t* __restrict__ slot_new, uint32_t n_c
     if (i >= n_cur) return;
     uint32_t slot = slot_new[i];
     out_pairs[i] = slot_pair[slot];
-    out_algo[i] = c_sim_algo[slot_key[slot]];
+    out_algo[i] = (uint8_t)algo_of_key(slot_key[slot]);
     int n0 = (int)(pm_hdr[(size_t)slot * PM_HDR_WORDS] & 0xffu);
     const float4* e = pm_entry + (size_t)slot * PM_CAP * PM_ENTRY_F4;
     uint32_t dst = start[i], done = 0;
@@ -649,11 +642,30 @@ int ncb_sim_add_with_query_types(ncb_sim* sim, const ncb_objects* objs, const ui
     uint32_t m = objs->n;
     if (m == 0) return NCB_OK;
     if (!(objs->pos && objs->rot && objs->shape_type && objs->shape_param && objs->query_limit && objs->ang_pred)) return NCB_ERR_ARG;
-    for (uint32_t k = 0; k < m; ++k)
-        if (objs->shape_type[k] > NCB_SHAPE_PLANE) {
-            ctx->err = "ncb_sim_add: shape_type must be NCB_SHAPE_BALL / CUBOID / CONVEX_HULL / PLANE";
+    bool add_capsules = false;
+    for (uint32_t k = 0; k < m; ++k) {
+        uint32_t t = objs->shape_type[k];
+        if (t > NCB_SHAPE_CAPSULE) {
+            ctx->err = "ncb_sim_add: shape_type must be NCB_SHAPE_BALL / CUBOID / CONVEX_HULL / PLANE / CAPSULE";
             return NCB_ERR_UNSUPPORTED;
         }
+        add_capsules = add_capsules || t == NCB_SHAPE_CAPSULE;
+        if (t == NCB_SHAPE_CONVEX_HULL) {
+            float h = objs->shape_param[4 * (size_t)k];
+            if (!(h >= 0.f && h < (float)ctx->hulls.n_hulls && h == (float)(uint32_t)h)) {
+                ctx->err = "ncb_sim_add: convex-hull object names a hull id that is not in the uploaded library (ncb_set_hulls)";
+                return NCB_ERR_ARG;
+            }
+        }
+    }
+    {
+        bool any_kind = ctx->has_prox;
+        for (uint32_t k = 0; kinds && k < m; ++k) any_kind = any_kind || kinds[k] != 0;
+        if (any_kind && (add_capsules || ctx->has_capsules)) {
+            ctx->err = "ncb_sim_add: sensors in a world with capsules are not supported on the device";
+            return NCB_ERR_UNSUPPORTED;
+        }
+    }
     for (uint32_t k = 0; kinds && k < m; ++k)
         if (kinds[k] > 1) {
             ctx->err = "ncb_sim_add_with_query_types: kind must be 0 (Contacts) or 1 (Proximity)";
@@ -753,6 +765,11 @@ int ncb_sim_add_with_query_types(ncb_sim* sim, const ncb_objects* objs, const ui
             CKS(cudaStreamSynchronize(s));
             d_k.release();
         }
+    }
+    if (add_capsules || ctx->has_capsules) {  // capsule segments as 2-point hulls, for every object of the (grown) world
+        CKS(ctx->cap_pts.reserve(6 * (size_t)new_n));
+        CKS(launch_fill_cap_pts(ctx, new_n));
+        ctx->has_capsules = true;
     }
     ctx->n = sim->n = new_n;
     sim->alive.resize(new_n, 0);

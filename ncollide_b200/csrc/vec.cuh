@@ -128,4 +128,18 @@ NCB_HD void orthonormal_basis(V3 v, V3& first, V3& second) {
     second = a;
 }
 
+// Capsule as a SupportMap (capsule.rs:72-85): support_point(m, dir) = m * local_support_point_toward(normalize(m^-1 dir)),
+// hh = half height along local y.
+NCB_HD V3 capsule_support_point(const Iso& m, float hh, float radius, V3 dir) {
+    V3 d = normalize(iso_inv_vec(m, dir));
+    return iso_mul_point(m, v3(0.f, copysignf(hh, d.y), 0.f) + d * radius);
+}
+// AABB of a capsule (aabb_support_map.rs:35-45 -> aabb_utils.rs:9-31): the support points along +-x, +-y, +-z
+NCB_HD void capsule_aabb(const Iso& m, float hh, float radius, V3& mins, V3& maxs) {
+    maxs = v3(capsule_support_point(m, hh, radius, v3(1.f, 0.f, 0.f)).x, capsule_support_point(m, hh, radius, v3(0.f, 1.f, 0.f)).y,
+              capsule_support_point(m, hh, radius, v3(0.f, 0.f, 1.f)).z);
+    mins = v3(capsule_support_point(m, hh, radius, v3(-1.f, 0.f, 0.f)).x, capsule_support_point(m, hh, radius, v3(0.f, -1.f, 0.f)).y,
+              capsule_support_point(m, hh, radius, v3(0.f, 0.f, -1.f)).z);
+}
+
 }  // namespace ncb

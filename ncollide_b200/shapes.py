@@ -19,7 +19,7 @@ F32 = np.float32
 EPS = np.finfo(np.float32).eps
 
 BALL, CUBOID, HULL, PLANE = 0, 1, 2, 3
-CAPSULE = 4  # known to the oracle only so far; the device boundary refuses it with NCB_ERR_UNSUPPORTED
+CAPSULE = 4  # CapsuleCapsule / CapsuleShape contact generators on the device (csrc/capsule.cuh)
 
 
 def _dot(a, b):
@@ -57,8 +57,8 @@ class Ball:
 
 
 class Capsule:
-    """``Capsule::new(half_height, radius)`` (shape/capsule.rs:19-30), principal axis = local y.  Not on the device yet: a world
-    that contains one fails loudly in ``ncb_set_objects`` (no silent fallback); the CPU oracle handles it (tests/test_oracle_capsule.py)."""
+    """``Capsule::new(half_height, radius)`` (shape/capsule.rs:19-30), principal axis = local y.  Contact generation runs on the
+    device (k_capsule); sensors and world ray / point queries in a world with capsules are refused loudly (NCB_ERR_UNSUPPORTED)."""
 
     type_id = CAPSULE
 

@@ -22,7 +22,7 @@ from ._ffi import CONTACT_DTYPE, NcbError, as_f32, as_u32, ptr
 from .scenes import DEFAULT_GROUPS, WorldScene
 from .shapes import HullLibrary
 
-ALGO_NAMES = ["none", "ball_ball", "plane_ball", "plane_convex", "ball_convex", "convex_convex", "proximity"]
+ALGO_NAMES = ["none", "ball_ball", "plane_ball", "plane_convex", "ball_convex", "convex_convex", "proximity", "capsule_capsule", "capsule_shape"]
 ALGO_PROXIMITY = 6
 
 
@@ -104,6 +104,12 @@ class Context:
     def synchronize(self):
         self.check(self.lib.ncb_synchronize(self.h), "ncb_synchronize")
 
+    def traversal_overflows(self):
+        """Query / ray BVH walks that ran out of their fixed stack since the context was created (must be 0)."""
+        out = C.c_uint32(0)
+        self.check(self.lib.ncb_traversal_overflows(self.h, C.byref(out)), "ncb_traversal_overflows")
+        return int(out.value)
+
     # -- stage entry points ---------------------------------------------------------------------------
     def compute_aabbs(self, margin, mode=2):
         """mode 0: shape AABB, 1: + query_limit (compute_aabb), 2: + margin (what the broad phase stores)."""
@@ -167,12 +173,15 @@ class Context:
             "n_pairs": c.n_pairs,
             "n_contacts": c.n_contacts,
             "n_contact_pairs": c.n_contact_pairs,
-            "n_algo": {**{ALGO_NAMES[i]: c.n_algo[i] for i in range(6)}, "proximity": c.n_proximity_pairs},
+            "n_algo": {**{ALGO_NAMES[i]: c.n_algo[i] for i in range(6)}, "proximity": c.n_proximity_pairs,
+                       "capsule_capsule": c.n_capsule_pairs[0], "capsule_shape": c.n_capsule_pairs[1]},
             "n_proximity": {"intersecting": c.n_proximity[0], "within_margin": c.n_proximity[1], "disjoint": c.n_proximity[2]},
             "epa_overflow": c.epa_overflow,
             "ref_panics": c.ref_panics,
             "n_epa_pairs": c.n_epa_pairs,
             "n_manifold_jobs": c.n_manifold_jobs,
+            "stack_overflow": c.stack_overflow,
+            "n_epa_restarts": c.n_epa_restarts,
         }
 
     def world_update_device(self, margin, q_begin=0, q_end=0xFFFFFFFF):

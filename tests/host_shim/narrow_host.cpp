@@ -107,61 +107,18 @@ static uint8_t fresh_pair(const DevObjects& o, const DevHulls& H, const ncb_obje
     return al;
 }
 
-// A pair with at least one capsule (shape_type 4, param = half_height, radius): the staged device functions of capsule.cuh, called the
-// way the kernels will call them.  seg_pts: 6 floats per OBJECT (b then a of the capsule's segment; unused for other shapes).
-static uint8_t capsule_pair(const DevObjects& o, const DevHulls& H, const ncb_objects* objs, const float* seg_pts, EpaState* e, Manifold& mf, uint32_t* flags,
-                            uint32_t i1, uint32_t i2) {
-    uint32_t t1 = o.type[i1], t2 = o.type[i2];
-    bool a_cap = t1 == 4, b_cap = t2 == 4;
-    Iso ma = load_iso(o, i1), mb = load_iso(o, i2);
-    float linear = o.qlimit[i1] + o.qlimit[i2];
-    CapOperand a, b;
-    std::memset(&a, 0, sizeof a);
-    std::memset(&b, 0, sizeof b);
-    if (a_cap) {
-        a.is_segment = true, a.hh = o.param[i1].x, a.seg_pts = seg_pts + 6 * (size_t)i1, a.pre.active = true, a.pre.radius = o.param[i1].y;
-        linear = linear + a.pre.radius;
-    } else
-        a.shape = load_shape(o, H, i1, t1);
-    if (b_cap) {
-        b.is_segment = true, b.hh = o.param[i2].x, b.seg_pts = seg_pts + 6 * (size_t)i2, b.pre.active = true, b.pre.radius = o.param[i2].y;
-        linear = linear + b.pre.radius;
-    } else
-        b.shape = load_shape(o, H, i2, t2);
-    uint8_t algo = (a_cap && b_cap) ? 7 : 8;  // CapsuleCapsule / CapsuleShape
-    if (!a_cap && t1 == NCB_SHAPE_BALL) {
-        gen_ball_segment(ma, a.shape.radius, mb, b.hh, linear, false, b.pre, mf);
-    } else if (!b_cap && t2 == NCB_SHAPE_BALL) {
-        gen_ball_segment(mb, b.shape.radius, ma, a.hh, linear, true, a.pre, mf);
-    } else if (!a_cap && t1 == NCB_SHAPE_PLANE) {
-        Feature feat;
-        gen_plane_segment(ma, a.shape.he, mb, b.hh, linear, false, b.pre, mf, feat);
-    } else if (!b_cap && t2 == NCB_SHAPE_PLANE) {
-        Feature feat;
-        gen_plane_segment(mb, b.shape.he, ma, a.hh, linear, true, a.pre, mf, feat);
-    } else {
-        Support ga = cap_support(a), gb = cap_support(b);
-        V3 d0;
-        if (!unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
-        V3 p1, p2, dir;
-        Simplex s;
-        int r = gjk_closest_points(ma, ga, mb, gb, linear, d0, s, p1, p2, dir);
-        if (r == GJK_INTERSECTION) {
-            if (epa_closest_points(*e, ma, ga, mb, gb, s.dim, s.v, p1, p2, dir))
-                r = GJK_CLOSEST_POINTS;
-            else {
-                flags[0] += e->overflow, flags[1] += e->panicked;
-                r = GJK_NO_INTERSECTION;
-            }
-        }
-        if (r == GJK_CLOSEST_POINTS) {
-            float a1 = objs->ang_pred[i1], a2 = objs->ang_pred[i2];
-            float2 ang1 = make_float2(cosf(a1), sinf(a1)), ang2 = make_float2(cosf(a2), sinf(a2));
-            Feature f1, f2;
-            if (!capsule_convex_manifold(ma, a, mb, b, linear, ang1, ang2, p1, p2, dir, mf, f1, f2)) flags[0] += 1;
-        }
-    }
-    return algo;
+// A pair with at least one capsule (shape_type 4, param = half_height, radius): capsule_pair<false> of capsule.cuh, the function
+// k_capsule runs per thread.  seg_pts: 6 floats per OBJECT (b then a of the capsule's segment; unused for other shapes).
+static uint8_t capsule_pair_host(DevObjects o, const DevHulls& H, const ncb_objects* objs, const float* seg_pts, const float2* ang_cs, EpaState* e,
+                                 Manifold& mf, uint32_t* flags, uint32_t i1, uint32_t i2) {
+    (void)objs;
+    o.cap_pts = seg_pts;
+    o.ang_cs = ang_cs;
+    o.ang_stride = 1;
+    PersistArgs none;
+    std::memset(&none, 0, sizeof none);
+    capsule_pair<false>(o, H, none, 0, *e, mf, i1, i2, &flags[0], &flags[1]);
+    return (o.type[i1] == 4 && o.type[i2] == 4) ? 7 : 8;  // CapsuleCapsule / CapsuleShape
 }
 
 extern "C" {
@@ -186,11 +143,13 @@ uint64_t shim_narrow_phase_ex(const ncb_objects* objs, const ncb_hull_library* l
     Manifold* mfp = new Manifold;
     Manifold& mf = *mfp;
     uint64_t nc = 0;
+    float2* ang_cs = new float2[objs->n ? objs->n : 1];  // ncb_set_objects' (cos, sin) table of the angular predictions
+    for (uint32_t i = 0; i < objs->n; ++i) ang_cs[i] = make_float2(cosf(objs->ang_pred[i]), sinf(objs->ang_pred[i]));
     for (uint64_t p = 0; p < n_pairs; ++p) {
         uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
         mf.n = 0;
         mf.deepest = 0;
-        uint8_t al = (o.type[i1] == 4 || o.type[i2] == 4) ? capsule_pair(o, H, objs, seg_pts, e, mf, flags, i1, i2)
+        uint8_t al = (o.type[i1] == 4 || o.type[i2] == 4) ? capsule_pair_host(o, H, objs, seg_pts, ang_cs, e, mf, flags, i1, i2)
                                                           : fresh_pair(o, H, objs, one_degree_cs, e, mf, flags, i1, i2);
         if (mf.deepest < 0) flags[0] += 1;  // more than MANIFOLD_MAX distinct contacts
         algo[p] = al;
@@ -210,6 +169,7 @@ uint64_t shim_narrow_phase_ex(const ncb_objects* objs, const ncb_hull_library* l
     manifold_off[n_pairs] = (uint32_t)nc;
     delete e;
     delete mfp;
+    delete[] ang_cs;
     return nc;
 }
 uint64_t shim_narrow_phase(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_pairs, const uint32_t* pairs, ncb_contact* out,
@@ -249,6 +209,11 @@ void shim_persist_update_ex(const ncb_objects* objs, const ncb_hull_library* lib
     DevHulls H = hulls_from(lib);
     const float one_degree = (float)(3.14159265358979323846 / 180.0);
     const float2 one_degree_cs = make_float2(cosf(one_degree), sinf(one_degree));
+    float2* ang_cs_tab = new float2[objs->n ? objs->n : 1];
+    for (uint32_t i = 0; i < objs->n; ++i) ang_cs_tab[i] = make_float2(cosf(objs->ang_pred[i]), sinf(objs->ang_pred[i]));
+    o.cap_pts = seg_pts;
+    o.ang_cs = ang_cs_tab;
+    o.ang_stride = 1;
     PersistArgs ps;
     ps.dir = reinterpret_cast<float4*>(dir);
     ps.pm_hdr = pm_hdr;
@@ -262,69 +227,8 @@ void shim_persist_update_ex(const ncb_objects* objs, const ncb_hull_library* lib
     PManifold& mf = *mfp;
     for (uint64_t k = 0; k < n_update; ++k) {
         uint32_t i1 = pairs[2 * k], i2 = pairs[2 * k + 1], slot = slots[k];
-        if (o.type[i1] == 4 || o.type[i2] == 4) {  // a capsule pair: the staged functions of capsule.cuh with the persistent manifold
-            uint32_t c1 = o.type[i1], c2 = o.type[i2];
-            bool a_cap = c1 == 4, b_cap = c2 == 4;
-            Iso ma = load_iso(o, i1), mb = load_iso(o, i2);
-            float linear = o.qlimit[i1] + o.qlimit[i2];
-            CapOperand a, b;
-            std::memset(&a, 0, sizeof a);
-            std::memset(&b, 0, sizeof b);
-            if (a_cap) {
-                a.is_segment = true, a.hh = o.param[i1].x, a.seg_pts = seg_pts + 6 * (size_t)i1, a.pre.active = true, a.pre.radius = o.param[i1].y;
-                linear = linear + a.pre.radius;
-            } else
-                a.shape = load_shape(o, H, i1, c1);
-            if (b_cap) {
-                b.is_segment = true, b.hh = o.param[i2].x, b.seg_pts = seg_pts + 6 * (size_t)i2, b.pre.active = true, b.pre.radius = o.param[i2].y;
-                linear = linear + b.pre.radius;
-            } else
-                b.shape = load_shape(o, H, i2, c2);
-            bool simple = (!a_cap && (c1 == NCB_SHAPE_BALL || c1 == NCB_SHAPE_PLANE)) || (!b_cap && (c2 == NCB_SHAPE_BALL || c2 == NCB_SHAPE_PLANE));
-            if (simple) {
-                pm_load_and_age(ps, slot, mf);
-                Feature feat;
-                if (!a_cap && c1 == NCB_SHAPE_BALL)
-                    gen_ball_segment(ma, a.shape.radius, mb, b.hh, linear, false, b.pre, mf);
-                else if (!b_cap && c2 == NCB_SHAPE_BALL)
-                    gen_ball_segment(mb, b.shape.radius, ma, a.hh, linear, true, a.pre, mf);
-                else if (!a_cap)
-                    gen_plane_segment(ma, a.shape.he, mb, b.hh, linear, false, b.pre, mf, feat);
-                else
-                    gen_plane_segment(mb, b.shape.he, ma, a.hh, linear, true, a.pre, mf, feat);
-                pm_store(ps, slot, mf, i1, i2);
-                continue;
-            }
-            Support ga = cap_support(a), gb = cap_support(b);
-            V3 d0;
-            bool warm = false;
-            float4 pd = ps.dir[slot];
-            if (pd.w != 0.f) d0 = v3(pd.x, pd.y, pd.z), warm = true;
-            if (!warm && !unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
-            V3 p1, p2, dirv;
-            Simplex s;
-            int r = gjk_closest_points(ma, ga, mb, gb, linear, d0, s, p1, p2, dirv);
-            if (r != GJK_INTERSECTION) ps.dir[slot] = make_float4(dirv.x, dirv.y, dirv.z, 1.f);
-            if (r == GJK_NO_INTERSECTION) {
-                pm_age_only(ps, slot, i1, i2);
-                continue;
-            }
-            if (r == GJK_INTERSECTION) {
-                if (epa_closest_points(*e, ma, ga, mb, gb, s.dim, s.v, p1, p2, dirv)) {
-                    ps.dir[slot] = make_float4(dirv.x, dirv.y, dirv.z, 1.f);
-                } else {
-                    flags[0] += e->overflow, flags[1] += e->panicked;
-                    ps.dir[slot] = make_float4(1.f, 0.f, 0.f, 1.f);
-                    pm_age_only(ps, slot, i1, i2);
-                    continue;
-                }
-            }
-            pm_load_and_age(ps, slot, mf);
-            float a1 = objs->ang_pred[i1], a2 = objs->ang_pred[i2];
-            float2 ang1 = make_float2(cosf(a1), sinf(a1)), ang2 = make_float2(cosf(a2), sinf(a2));
-            Feature f1, f2;
-            if (!capsule_convex_manifold(ma, a, mb, b, linear, ang1, ang2, p1, p2, dirv, mf, f1, f2)) flags[0] += 1;
-            pm_store(ps, slot, mf, i1, i2);
+        if (o.type[i1] == 4 || o.type[i2] == 4) {  // a capsule pair: capsule_pair<true>, the function k_capsule<true> runs per thread
+            capsule_pair<true>(o, H, ps, slot, *e, mf, i1, i2, &flags[0], &flags[1]);
             continue;
         }
         uint32_t t1 = o.type[i1] & 3u, t2 = o.type[i2] & 3u;
@@ -420,6 +324,7 @@ void shim_persist_update_ex(const ncb_objects* objs, const ncb_hull_library* lib
     }
     delete e;
     delete mfp;
+    delete[] ang_cs_tab;
 }
 
 void shim_persist_update(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_update, const uint32_t* pairs, const uint32_t* slots,

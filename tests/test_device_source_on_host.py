@@ -530,8 +530,8 @@ def _capsule_scene(n, seed, kinds, side, plane, ang=0.0):
 
 
 @pytest.mark.parametrize("n,kinds,side,plane,ang,seed", [(2400, (1, 1, 1), 8.0, True, 0.0, 141), (1800, (0, 1, 1), 5.5, False, 0.03, 142), (1500, (1, 1, 0), 5.0, True, 0.0, 143)])
-def test_staged_capsule_device_source_matches_oracle(narrow_shim, oracle, n, kinds, side, plane, ang, seed):
-    """Worlds with capsules through csrc/capsule.cuh (segment features, the capsule's contact preprocessor, the capsule generators on top
+def test_capsule_device_source_matches_oracle(narrow_shim, oracle, n, kinds, side, plane, ang, seed):
+    """Worlds with capsules through csrc/capsule.cuh (capsule_pair, the function k_capsule runs per thread: segment features, the capsule's contact preprocessor, the capsule generators on top
     of the existing GJK / EPA / clipping / manifold code) against the oracle: algorithm, manifold sizes, feature ids exact, contacts
     bit for bit — for capsule x {capsule, ball, cuboid, hull, plane} in both orders, and unchanged results for the other pairs."""
     s = _capsule_scene(n, seed, kinds, side, plane, ang)
@@ -547,7 +547,7 @@ def test_staged_capsule_device_source_matches_oracle(narrow_shim, oracle, n, kin
         assert np.diff(want[1])[sel].sum() > 0, f"no contact between a capsule and shape {other}"
 
 
-def test_staged_capsule_device_source_reproduces_the_golden_fixture(narrow_shim):
+def test_capsule_device_source_reproduces_the_golden_fixture(narrow_shim):
     from golden.make_golden import scene_from_npz
 
     z = np.load(os.path.join(HERE, "golden", "capsule_mixed_plane_300.npz"))
@@ -559,7 +559,7 @@ def test_staged_capsule_device_source_reproduces_the_golden_fixture(narrow_shim)
         assert np.array_equal(dc[name].view(np.uint32), z["c_" + name].view(np.uint32)), name
 
 
-def test_staged_capsule_aabb_matches_oracle(narrow_shim, oracle):
+def test_capsule_aabb_matches_oracle(narrow_shim, oracle):
     s = _capsule_scene(3000, 151, (1, 1, 1), 9.0, False)
     oc, keep = _ffi.pack_objects(s)
     out = np.zeros((s.n, 6), dtype=F)
@@ -569,7 +569,7 @@ def test_staged_capsule_aabb_matches_oracle(narrow_shim, oracle):
     assert cap.sum() == 1000 and np.array_equal(out[cap].view(np.uint32), want[cap].view(np.uint32))
 
 
-def test_staged_capsule_persistent_state_matches_oracle(narrow_shim, oracle):
+def test_capsule_persistent_state_matches_oracle(narrow_shim, oracle):
     """Stepping-world state per pair with capsules: the capsule generators instantiated with the persistent manifold (load + age, warm
     started GJK on the segment hulls, store, contact events) over six updates against the oracle's caller-driven edges."""
     from sim_scenario import step_poses

@@ -106,7 +106,7 @@ def test_world_update_parity(ctx, oracle, mk):
     s = mk()
     ctx.set_hulls(s.hulls)
     res = ctx.world_update(s)
-    assert res.counts["epa_overflow"] == 0
+    assert res.counts["epa_overflow"] == 0 and res.counts["stack_overflow"] == 0
     fat = oracle.compute_aabbs(s)
     want = oracle.broad_phase(fat, s.groups, mode=1)
     assert np.array_equal(canon(res.pairs), canon(want)), "pair set"
@@ -136,6 +136,31 @@ def test_world_update_poses_equals_world_update(ctx, oracle):
     assert len(b.contacts) == len(want.contacts) and b.counts["n_contact_pairs"] == want.counts["n_contact_pairs"]
     assert not np.array_equal(canon(a.pairs), canon(b.pairs))
     compare_manifolds(b, s2, oracle, "poses")
+
+
+def test_deep_tree_coincident_boxes(ctx, oracle):
+    """120 000 boxes of which 100 000 share a few dozen distinct positions (identical Morton codes: the LBVH splits them on the tie-break
+    bits, its deepest shape) and 20 000 sit within a few ulps of them.  The pair search must neither lose a pair nor run out of its
+    traversal stack; groups keep the pair count finite (every object only collides with its own small group)."""
+    rng = np.random.default_rng(99)
+    n, n_sites = 120_000, 40
+    sites = rng.uniform(0, 50, size=(n_sites, 3)).astype(np.float32)
+    which = rng.integers(0, n_sites, size=n)
+    lo = sites[which].copy()
+    near = np.arange(n) >= 100_000
+    lo[near] += (rng.integers(1, 5, size=(int(near.sum()), 3)) * np.spacing(lo[near])).astype(np.float32)  # 1..4 ulps away
+    fat = np.concatenate([lo, lo + np.float32(0.25)], axis=1).astype(np.float32)
+    # 30 collision groups, membership = whitelist = one group
+    g = (np.arange(n) % 30).astype(np.uint32)
+    groups = np.stack([1 << g, 1 << g, np.zeros(n, np.uint32)], axis=1).astype(np.uint32)
+    # thin out: only every 8th object keeps its group, the others get a private "no collision" whitelist
+    lonely = (np.arange(n) // 30) % 8 != 0
+    groups[lonely, 1] = 0
+    got = ctx.broad_phase(fat, groups)
+    want = oracle.broad_phase(fat, groups, mode=1)
+    assert len(want) > 20_000
+    assert np.array_equal(canon(got), canon(want))
+    assert ctx.traversal_overflows() == 0, "a BVH walk ran out of its traversal stack"
 
 
 def _adversarial_scenes():
@@ -386,6 +411,7 @@ def check_rays(ctx, oracle, rs, brute, pose=None):
     hit = same & (rtoi >= 0)
     assert close(normal[hit], rnormal[hit])
     assert (face[toi >= 0] % T < T).all()
+    assert ctx.traversal_overflows() == 0, "a ray walk ran out of its stack"
     mesh.close()
     return len(diff), int((toi >= 0).sum())
 

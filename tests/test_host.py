@@ -63,7 +63,7 @@ def test_contact_struct_layout_matches_header():
 
     assert CONTACT_DTYPE.itemsize == 52
     assert [CONTACT_DTYPE.fields[n][1] for n in ("world1", "world2", "normal", "depth", "f1", "f2", "pair")] == [0, 12, 24, 36, 40, 44, 48]
-    assert ctypes.sizeof(UpdateCountsC) == 4 * 17  # 13 + n_proximity_pairs + n_proximity[3]
+    assert ctypes.sizeof(UpdateCountsC) == 4 * 21  # 13 + n_proximity_pairs + n_proximity[3] + n_capsule_pairs[2] + stack_overflow + n_epa_restarts
 
 
 # ---- scenes / shapes -------------------------------------------------------------------------------------------
@@ -260,20 +260,3 @@ def test_bench_native_arm_refuses_to_run_without_a_gpu():
                         "--no-extras"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode != 0
     assert not any(ln.startswith("{") and '"value"' in ln for ln in r.stdout.splitlines())
-
-
-def test_staged_capsule_header_compiles_as_device_code():
-    """ncollide_b200/csrc/capsule.cuh is staged (no kernel includes it yet): make sure nvcc accepts it as sm_100a device code together
-    with the narrow-phase translation unit, both manifold flavours instantiated."""
-    import shutil
-    import subprocess
-    import tempfile
-
-    nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else shutil.which("nvcc")
-    if not nvcc:
-        pytest.skip("nvcc not found")
-    with tempfile.TemporaryDirectory() as d:
-        r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "--fmad=false", "-std=c++17", "-I", os.path.join(ROOT, "ncollide_b200", "csrc"),
-                            "-c", os.path.join(ROOT, "tests", "host_shim", "capsule_device_compile_check.cu"), "-o", os.path.join(d, "check.o")],
-                           capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stderr[-1500:]

@@ -44,7 +44,8 @@ def test_sharded_update_with_sensors(oracle, world, mk):
 
 
 def test_device_rejects_shapes_it_does_not_know():
-    """shape_type 4 (capsule: oracle groundwork only) must be refused at the boundary, not masked into another shape."""
+    """A shape_type the device has no generator for (5 and up: composite shapes) must be refused at the boundary, not masked into
+    another shape; so must a convex-hull object that names a hull outside the uploaded library."""
     from ncollide_b200._ffi import NcbError
     from ncollide_b200.world import Context
 
@@ -52,7 +53,15 @@ def test_device_rejects_shapes_it_does_not_know():
     ctx = Context(0)
     ctx.set_scene(s)  # fine
     s.shape_type = s.shape_type.copy()
-    s.shape_type[7] = 4
+    s.shape_type[7] = 5
     with pytest.raises(NcbError, match="shape_type"):
         ctx.set_objects(s)
+    s.shape_type[7] = 2  # a convex hull ...
+    s.shape_param[7, 0] = 1.0e6  # ... that is not in the library
+    with pytest.raises(NcbError, match="hull id"):
+        ctx.set_objects(s)
+    bad = np.array([[0, s.n + 5]], dtype=np.uint32)
+    ctx.set_scene(make_world_scene(50, 1, (1, 1, 0), side=3.0))
+    with pytest.raises(NcbError, match="out of range"):
+        ctx.generate_contacts(bad)
     ctx.close()
