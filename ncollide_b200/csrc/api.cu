@@ -70,6 +70,7 @@ int reserve_pairs(ncb_ctx* ctx, size_t cap) {
     CK(ctx->manifold_count.reserve(cap));
     CK(ctx->epa_queue.reserve(26 * cap));
     CK(ctx->epa_long.reserve(cap));
+    CK(ctx->epa_pool.reserve((size_t)448 * std::max<size_t>(4096, cap / 128)));  // EpaFlex::B_WORDS per slot
     CK(ctx->cp_queue.reserve(10 * cap));
     return NCB_OK;
 }
@@ -124,13 +125,6 @@ int ncb_create(int device, ncb_ctx** out) {
         e = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
-        if (e == cudaSuccess) {
-            int lo = 0, hi = 0;
-            cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = the numerically lowest = highest priority
-            e = cudaStreamCreateWithPriority(&c->over_stream, cudaStreamNonBlocking, hi);
-        }
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_epa, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_over, cudaEventDisableTiming);
     }
     if (e != cudaSuccess) {
         g_create_err = cudaGetErrorString(e);
@@ -173,9 +167,6 @@ void ncb_destroy(ncb_ctx* c) {
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
-    if (c->over_stream) cudaStreamDestroy(c->over_stream);
-    if (c->ev_epa) cudaEventDestroy(c->ev_epa);
-    if (c->ev_over) cudaEventDestroy(c->ev_over);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }

@@ -4,14 +4,14 @@
 // fixed arrays + explicit stack); query/contact/contact_support_map_support_map.rs:38-79; utils/ccw_face_normal.rs:26.
 //
 // The algorithm is written ONCE, over a polytope store `S`; two stores exist:
-//   EpaState    48 vertices / 192 faces / 160 heap entries in per-thread arrays (local memory), face normals stored.  It takes the
-//               pairs that do not fit the compact store (1 % of cfg3's pairs) and the rare ball-centre-inside-hull pairs.
-//   EpaCompact  16 vertices / 48 faces / 24 heap entries in 133 lane-strided words of SHARED memory (vertex points, ONE packed
-//               topology word per face, the heap, silhouette and flood stack); face normals are RECOMPUTED from the three vertices
-//               whenever they are needed (same inputs, same operations, same bits as when Face::new computed them), which is what
-//               makes the state small enough for 384 pairs per SM to be resident next to each other.  A pair that exceeds any
-//               capacity is flagged (`overflow`) and restarted by the caller on an EpaState: the restart repeats the same
-//               arithmetic, so results do not depend on which store ran.
+//   EpaState    48 vertices / 192 faces / 160 heap entries in per-thread arrays (local memory), face normals stored: the rare
+//               ball-centre-inside-hull pairs, capsule pairs, and the last resort for a pair beyond EpaFlex's big slot.
+//   EpaFlex     the store of k_cc_epa_s: 16 vertices / 48 faces / 20 heap entries in 143 lane-strided words of SHARED memory (vertex
+//               points, one packed topology word + one byte per face, the heap, silhouette and flood stack); face normals are
+//               RECOMPUTED from the three vertices whenever they are needed (same inputs, same operations, same bits as when
+//               Face::new computed them), which is what makes the state small enough for 384 pairs per SM to be resident next to each
+//               other.  A pair that exceeds a capacity restarts in the same lane on a 32 / 160 / 96 slot of a global pool (same
+//               layout, same code); the restart repeats the same arithmetic, so results do not depend on where a pair ran.
 // Both follow the reference's iteration path exactly (same heap sift order as Rust's BinaryHeap, same flood order, same exits);
 // tests/host_shim compiles both for the host and compares them with the oracle bit for bit.
 #pragma once
@@ -93,67 +93,83 @@ struct EpaState : EpaScalars {
 };
 static_assert(EPA_MAX_FACES <= 255 && EPA_MAX_VERTS <= 255, "ids are packed in 8 bits");
 
-// The compact store.  Word w of the lane lives at base[w * STRIDE] (STRIDE = threads per CTA, base = shared-memory array + thread
-// index): whatever index a lane computes, its bank is its lane id, so the divergent accesses of an expansion step are conflict free.
-// Face word: pts0 | pts1 << 4 | pts2 << 8 | adj0 << 12 | adj1 << 18 | adj2 << 24 | deleted << 30.
-template <int STRIDE>
-struct EpaCompact : EpaScalars {
-    enum { MAXV = 16, MAXF = 48, MAXH = 24, MAXSIL = 16, MAXSTK = 12, ADJ_MASK = 63 };
-    enum {
-        W_VP = 0,
-        W_TP = W_VP + 3 * MAXV,
-        W_HD = W_TP + MAXF,
-        W_HI = W_HD + MAXH,
-        W_SIL = W_HI + MAXH / 4,
-        W_STK = W_SIL + MAXSIL / 4,
-        WORDS = W_STK + MAXSTK / 4
-    };
+// The flexible store of k_cc_epa_s: ONE layout, two places.
+//   compact  16 vertices / 48 faces / 20 heap entries in 143 words of SHARED memory; word w of the lane lives at base[w * stride] with
+//            stride = threads per CTA and base = shared array + thread index: whatever index a lane computes, its bank is its lane id,
+//            so the divergent accesses of an expansion step are conflict free.  99 % of cfg3's EPA runs fit.
+//   big      32 vertices / 160 faces / 96 heap entries in a slot of a GLOBAL pool (stride 1), taken by a lane whose pair outgrew the
+//            compact capacities; the lane restarts its pair there, inside the same kernel, so the long runs overlap with everybody
+//            else's work instead of forming a second phase.
+// The code is the same for both (generic addressing, per-lane capacities and offsets in registers).
+// Face record: word = pts0 | pts1 << 5 | pts2 << 10 | deleted << 15 | adj0 << 16 | adj1 << 24, byte = adj2.
+struct EpaFlex : EpaScalars {
+    enum { ADJ_MASK = 0xff };
+    enum { C_MAXV = 16, C_MAXF = 48, C_MAXH = 20, C_MAXSIL = 12, C_MAXSTK = 8 };      // compact (cfg3 peaks: silhouette 10, stack 7)
+    enum { B_MAXV = 32, B_MAXF = 160, B_MAXH = 96, B_MAXSIL = 32, B_MAXSTK = 32 };    // big
     static const bool STORED_NORMALS = false;
+    enum { C_WORDS = 3 * C_MAXV + C_MAXF + C_MAXF / 4 + C_MAXH + C_MAXH / 4 + C_MAXSIL / 2 + C_MAXSTK / 2 };
+    enum { B_WORDS = 3 * B_MAXV + B_MAXF + B_MAXF / 4 + B_MAXH + B_MAXH / 4 + B_MAXSIL / 2 + B_MAXSTK / 2 };
     uint32_t* base;
-    V3 vorig1[MAXV], vorig2[MAXV];  // cold: written once per vertex, three of each read for the result (local memory)
+    int stride;
+    int MAXV, MAXF, MAXH, MAXSIL, MAXSTK;          // this lane's capacities
+    int o_tw, o_tb, o_hd, o_hi, o_sil, o_stk;      // word offsets: face words, face bytes, heap keys, heap ids, silhouette, flood stack
+    bool big;
+    V3 vorig1[B_MAXV], vorig2[B_MAXV];  // cold: written once per vertex, three of each read for the result (local memory)
 
-    NCB_HD uint32_t& w(int i) const { return base[i * STRIDE]; }
-    NCB_HD uint8_t& b(int w0, int i) const { return reinterpret_cast<uint8_t*>(base + (w0 + (i >> 2)) * STRIDE)[i & 3]; }
-    NCB_HD V3 vp(uint32_t i) const {
-        return v3(__uint_as_float(w(W_VP + 3 * i)), __uint_as_float(w(W_VP + 3 * i + 1)), __uint_as_float(w(W_VP + 3 * i + 2)));
+    NCB_HD void layout(uint32_t* b, int st, int v, int f, int h, int sil, int stk, bool is_big) {
+        base = b, stride = st, big = is_big;
+        MAXV = v, MAXF = f, MAXH = h, MAXSIL = sil, MAXSTK = stk;
+        o_tw = 3 * v, o_tb = o_tw + f, o_hd = o_tb + f / 4, o_hi = o_hd + h, o_sil = o_hi + h / 4, o_stk = o_sil + sil / 2;
     }
-    NCB_HD void set_vp(uint32_t i, V3 p) {
-        w(W_VP + 3 * i) = __float_as_uint(p.x), w(W_VP + 3 * i + 1) = __float_as_uint(p.y), w(W_VP + 3 * i + 2) = __float_as_uint(p.z);
-    }
+    NCB_HD void layout_compact(uint32_t* b, int st) { layout(b, st, C_MAXV, C_MAXF, C_MAXH, C_MAXSIL, C_MAXSTK, false); }
+    NCB_HD void layout_big(uint32_t* b) { layout(b, 1, B_MAXV, B_MAXF, B_MAXH, B_MAXSIL, B_MAXSTK, true); }
+
+    NCB_HD uint32_t& w(int i) const { return base[i * stride]; }
+    NCB_HD uint8_t& b(int w0, int i) const { return reinterpret_cast<uint8_t*>(base + (w0 + (i >> 2)) * stride)[i & 3]; }
+    NCB_HD V3 vp(uint32_t i) const { return v3(__uint_as_float(w(3 * i)), __uint_as_float(w(3 * i + 1)), __uint_as_float(w(3 * i + 2))); }
+    NCB_HD void set_vp(uint32_t i, V3 p) { w(3 * i) = __float_as_uint(p.x), w(3 * i + 1) = __float_as_uint(p.y), w(3 * i + 2) = __float_as_uint(p.z); }
     NCB_HD V3 o1(uint32_t i) const { return vorig1[i]; }
     NCB_HD V3 o2(uint32_t i) const { return vorig2[i]; }
     NCB_HD void set_orig(uint32_t i, V3 a, V3 c) { vorig1[i] = a, vorig2[i] = c; }
     NCB_HD void f_init(uint32_t f, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t a0, uint32_t a1, uint32_t a2) {
-        w(W_TP + f) = p0 | (p1 << 4) | (p2 << 8) | (a0 << 12) | (a1 << 18) | (a2 << 24);
+        w(o_tw + f) = p0 | (p1 << 5) | (p2 << 10) | (a0 << 16) | (a1 << 24);
+        b(o_tb, f) = (uint8_t)a2;
     }
     NCB_HD void f_pts(uint32_t f, uint32_t& p0, uint32_t& p1, uint32_t& p2) const {
-        uint32_t t = w(W_TP + f);
-        p0 = t & 15u, p1 = (t >> 4) & 15u, p2 = (t >> 8) & 15u;
+        uint32_t t = w(o_tw + f);
+        p0 = t & 31u, p1 = (t >> 5) & 31u, p2 = (t >> 10) & 31u;
     }
     NCB_HD void f_adjs(uint32_t f, uint32_t& a0, uint32_t& a1, uint32_t& a2) const {
-        uint32_t t = w(W_TP + f);
-        a0 = (t >> 12) & 63u, a1 = (t >> 18) & 63u, a2 = (t >> 24) & 63u;
+        uint32_t t = w(o_tw + f);
+        a0 = (t >> 16) & 0xffu, a1 = t >> 24, a2 = b(o_tb, f);
     }
-    NCB_HD bool f_deleted(uint32_t f) const { return (w(W_TP + f) >> 30) != 0; }
-    NCB_HD void f_set_deleted(uint32_t f) { w(W_TP + f) |= 0x40000000u; }
+    NCB_HD bool f_deleted(uint32_t f) const { return (w(o_tw + f) >> 15) & 1u; }
+    NCB_HD void f_set_deleted(uint32_t f) { w(o_tw + f) |= 0x8000u; }
     NCB_HD void f_set_adj(uint32_t f, uint32_t k, uint32_t v) {
-        uint32_t sh = 12 + 6 * k;
-        w(W_TP + f) = (w(W_TP + f) & ~(63u << sh)) | (v << sh);
+        if (k == 2) {
+            b(o_tb, f) = (uint8_t)v;
+        } else {
+            uint32_t sh = 16 + 8 * k;
+            w(o_tw + f) = (w(o_tw + f) & ~(0xffu << sh)) | (v << sh);
+        }
     }
     NCB_HD V3 stored_normal(uint32_t) const { return v3(0.f, 0.f, 0.f); }
     NCB_HD void set_normal(uint32_t, V3) {}
-    NCB_HD float hd(int i) const { return __uint_as_float(w(W_HD + i)); }
-    NCB_HD uint32_t hi(int i) const { return b(W_HI, i); }
-    NCB_HD void hset(int i, float d, uint32_t id) { w(W_HD + i) = __float_as_uint(d), b(W_HI, i) = (uint8_t)id; }
-    NCB_HD void sil_set(int k, uint32_t f, uint32_t opp) { b(W_SIL, k) = (uint8_t)(f | (opp << 6)); }
+    NCB_HD float hd(int i) const { return __uint_as_float(w(o_hd + i)); }
+    NCB_HD uint32_t hi(int i) const { return b(o_hi, i); }
+    NCB_HD void hset(int i, float d, uint32_t id) { w(o_hd + i) = __float_as_uint(d), b(o_hi, i) = (uint8_t)id; }
+    // silhouette / flood-stack entries: face id (8 bits) and opp (2 bits) in separate byte planes would cost two accesses; faces < 256
+    // and opp < 3 do not fit one byte together, so an entry is 16 bits: [face | opp << 8] in halves of the words
+    NCB_HD uint16_t& h16(int w0, int i) const { return reinterpret_cast<uint16_t*>(base + (w0 + (i >> 1)) * stride)[i & 1]; }
+    NCB_HD void sil_set(int k, uint32_t f, uint32_t opp) { h16(o_sil, k) = (uint16_t)(f | (opp << 8)); }
     NCB_HD void sil_get(int k, uint32_t& f, uint32_t& opp) const {
-        uint32_t v = b(W_SIL, k);
-        f = v & 63u, opp = v >> 6;
+        uint32_t v = h16(o_sil, k);
+        f = v & 0xffu, opp = v >> 8;
     }
-    NCB_HD void stk_set(int k, uint32_t f, uint32_t opp) { b(W_STK, k) = (uint8_t)(f | (opp << 6)); }
+    NCB_HD void stk_set(int k, uint32_t f, uint32_t opp) { h16(o_stk, k) = (uint16_t)(f | (opp << 8)); }
     NCB_HD void stk_get(int k, uint32_t& f, uint32_t& opp) const {
-        uint32_t v = b(W_STK, k);
-        f = v & 63u, opp = v >> 6;
+        uint32_t v = h16(o_stk, k);
+        f = v & 0xffu, opp = v >> 8;
     }
 };
 
@@ -192,7 +208,7 @@ NCB_HD void epa_heap_sift_up(S& e, int pos) {
 }
 template <class S>
 NCB_HD void epa_heap_push(S& e, uint32_t id, float nd) {
-    if (e.nheap >= S::MAXH) {
+    if (e.nheap >= e.MAXH) {
         e.overflow = true;
         return;
     }
@@ -242,7 +258,7 @@ NCB_HD bool epa_heap_pop(S& e, EpaHeapItem& out) {
 template <class S>
 NCB_HD bool epa_face_new(S& e, uint32_t p0, uint32_t p1, uint32_t p2, V3 A, V3 B, V3 C, uint32_t a0, uint32_t a1, uint32_t a2,
                          bool& proj_inside, V3& normal) {
-    if (e.nfaces >= S::MAXF) {
+    if (e.nfaces >= e.MAXF) {
         e.overflow = true;
         return false;
     }
@@ -312,7 +328,7 @@ NCB_HD void epa_compute_silhouette3(S& e, V3 pt, uint32_t id0, uint32_t opp0, ui
         e.stk_get(sp, id, opp);
         if (e.f_deleted(id)) continue;
         if (!epa_can_be_seen_by(e, id, pt, opp)) {
-            if (e.nsil >= S::MAXSIL) {
+            if (e.nsil >= e.MAXSIL) {
                 e.overflow = true;
                 return;
             }
@@ -331,7 +347,7 @@ NCB_HD void epa_compute_silhouette3(S& e, V3 pt, uint32_t id0, uint32_t opp0, ui
             uint32_t o1 = epa_next_ccw(e, adj1, epa_sel3(adj_pt_id1, i0, i1, i2));
             uint32_t o2 = epa_next_ccw(e, adj2, epa_sel3(adj_pt_id2, i0, i1, i2));
             if (e.panicked) return;
-            if (sp + 2 > S::MAXSTK) {
+            if (sp + 2 > e.MAXSTK) {
                 e.overflow = true;
                 return;
             }
@@ -369,9 +385,10 @@ NCB_HD void epa_result_from_face(const S& e, uint32_t f, V3& out1, V3& out2, V3&
 // pushes them on the heap in face order; here face k is pushed right after it is built (building a face does not read the heap
 // and a push does not read the faces, and a failing FaceId::new ends the run whichever faces exist), so one face constructor in
 // a loop serves both the tetrahedron (4 faces) and the flat (2 faces) start.
-// TETRA_ONLY: a segment / triangle simplex (0.007 % of cfg3's EPA pairs) is handed to the caller's overflow path instead.
+// NO_SEGMENT: a segment simplex (its third vertex needs one more support evaluation; never seen on cfg3, where 0.007 % of the EPA
+// pairs start from a triangle and the rest from a tetrahedron) is handed to the caller's overflow path instead of being built here.
 #define EPA_FACE_SPEC(p0, p1, p2, a0, a1, a2) ((p0) | ((p1) << 4) | ((p2) << 8) | ((a0) << 12) | ((a1) << 16) | ((a2) << 20))
-template <bool TETRA_ONLY, class S, class G>
+template <bool NO_SEGMENT, class S, class G>
 NCB_HD int epa_init_t(S& e, const Iso& m1, const G& g1, const Iso& m2, const G& g2, int sdim, const CSOPoint* sv, V3& out1, V3& out2,
                       V3& out_n, uint32_t& res_face) {
     res_face = EPA_RES_DIRECT;
@@ -396,16 +413,17 @@ NCB_HD int epa_init_t(S& e, const Iso& m1, const G& g1, const Iso& m2, const G& 
         bool flip = dot(cross(dp1, dp2), dp3) > 0.f;
         epa_push_vertex(e, c0), epa_push_vertex(e, flip ? c2 : c1), epa_push_vertex(e, flip ? c1 : c2), epa_push_vertex(e, c3);
     } else {
-        if (TETRA_ONLY) {
-            e.overflow = true;
-            return EPA_DONE_FAIL;
-        }
         CSOPoint c0 = sv[0], c1 = sv[1], c2 = sv[2];
         if (sdim == 1) {
-            V3 dpt = c1.point - c0.point;
-            V3 first, second;
-            orthonormal_basis(dpt, first, second);
-            c2 = cso_from_shapes(m1, g1, m2, g2, first);
+            if constexpr (NO_SEGMENT) {
+                e.overflow = true;
+                return EPA_DONE_FAIL;
+            } else {
+                V3 dpt = c1.point - c0.point;
+                V3 first, second;
+                orthonormal_basis(dpt, first, second);
+                c2 = cso_from_shapes(m1, g1, m2, g2, first);
+            }
         }
         epa_push_vertex(e, c0), epa_push_vertex(e, c1), epa_push_vertex(e, c2);
     }
@@ -457,7 +475,7 @@ NCB_HD int epa_step_t(S& e, const Iso& m1, const G& g1, const Iso& m2, const G& 
     e.f_pts(fid, fp0, fp1, fp2);
     e.f_adjs(fid, fa0, fa1, fa2);
     V3 fnorm = epa_face_normal(e, fid);
-    if (e.nverts >= S::MAXV) {
+    if (e.nverts >= e.MAXV) {
         e.overflow = true;
         return EPA_DONE_FAIL;
     }

@@ -430,6 +430,12 @@ NCB_HD void gjk_result(const Simplex& s, bool prev, V3& p1, V3& p2) {
 }
 
 enum { GJK_INTERSECTION = 0, GJK_CLOSEST_POINTS = 1, GJK_NO_INTERSECTION = 3 };
+#ifdef NCB_EPA_STATS  // host-side work statistics only (tests/host_shim/gjk_host.cpp, scripts/epa_work_stats.py)
+static int g_gjk_support_evals = 0;
+#define NCB_GJK_COUNT() (++g_gjk_support_evals)
+#else
+#define NCB_GJK_COUNT()
+#endif
 
 // gjk::closest_points with exact_dist = true, preceded by the caller's `simplex.reset(CSOPoint::from_shapes(.., init_dir))`
 // (contact_support_map_support_map.rs:52-63): the first support evaluation shares the loop's code (one copy of the two support
@@ -457,6 +463,7 @@ static __device__ __noinline__ int gjk_closest_points(const Iso& m1, const Suppo
             }
         }
         CSOPoint cso = cso_from_shapes(m1, g1, m2, g2, dir);
+        NCB_GJK_COUNT();
         if (first) {
             simplex_init(s, cso);
             proj = simplex_project_origin_and_reduce(s);

@@ -872,7 +872,9 @@ struct NarrowArgs {
     uint32_t* epa_queue;   // EPA_REC_WORDS per record
     uint32_t* cp_queue;    // CP_REC_WORDS per record
     int epa_refill_min;    // idle lanes needed before a warp of k_cc_epa_s refills (batched initialisation)
-    uint32_t* epa_long;    // EPA-queue indices of the pairs that did not fit the compact polytope store (overflow queue)
+    uint32_t* epa_long;    // last-resort queue: EPA-queue indices of the pairs k_cc_epa_s could not finish (k_cc_epa_big)
+    uint32_t* epa_pool;    // EpaFlex::B_WORDS words per slot: big polytope stores of k_cc_epa_s
+    uint32_t epa_pool_slots;
 };
 
 // ---- convex x convex in three compacted phases -------------------------------------------------------------------
@@ -970,18 +972,19 @@ __global__ void __launch_bounds__(128, NCB_GJK_MINBLOCKS) k_cc_gjk(NarrowArgs A)
 // run the same code (one step) regardless of how many steps their pair needs; refills are batched (>= refill_min idle
 // lanes) so that the initialisation path is not paid on every turn.
 //
-// k_cc_epa_s (the default): the polytope lives in SHARED memory (EpaCompact: 133 lane-strided words per pair, face normals
+// k_cc_epa_s: the polytope lives in SHARED memory (EpaFlex, compact layout: 143 lane-strided words per pair, face normals
 // recomputed), 6 CTAs of 64 threads per SM; the operands are kept slim (kind, half extents | vertex array) in registers.  Round 1's
 // kernel kept a 7.4 KB polytope per thread in local memory: 32 warps x 55 KB of touched lines per SM overflowed L1 and, over 148
 // SMs, L2, and ncu counted 3.0 GB of DRAM traffic for 82 MB of algorithmic bytes.  Here the expansion loop touches no global or local
 // memory except the hull vertices (L1-resident library) and 24 B of cold support points per new vertex.
-// A pair that does not fit the compact capacities (1 % on cfg3) or starts from a flat simplex goes to the overflow queue
-// (A.epa_long) and is restarted on the big local-memory store by k_cc_epa_big.
+// A pair that outgrows the compact capacities (1 % on cfg3) takes a slot of a global pool (EpaFlex, big layout) and RESTARTS IN ITS
+// LANE: same code, generic loads, and its long run (10-20 dependent steps, ~0.2 ms) overlaps with the rest of the queue instead of
+// forming a second phase (a separate overflow kernel cost 0.4-0.6 ms of tail, measured: profiles/r2_epa_overflow.txt).  Beyond the
+// big slot, or when the pool is exhausted, or for a segment simplex, the pair goes to the last-resort queue (k_cc_epa_big).
 #define EPAS_THREADS 64
 #ifndef NCB_EPAS_MINBLOCKS
 #define NCB_EPAS_MINBLOCKS 6
 #endif
-typedef EpaCompact<EPAS_THREADS> EpaShared;
 
 NCB_HD void epa_rec_load(const uint32_t* q, uint32_t& p, int& sdim, CSOPoint* sv) {
     const float* f = reinterpret_cast<const float*>(q);
@@ -994,6 +997,7 @@ NCB_HD void epa_rec_load(const uint32_t* q, uint32_t& p, int& sdim, CSOPoint* sv
     }
 }
 
+static_assert(EpaFlex::B_WORDS == 448, "api.cu sizes the slot pool with this figure");
 template <bool PS>
 __global__ void __launch_bounds__(EPAS_THREADS, NCB_EPAS_MINBLOCKS) k_cc_epa_s(NarrowArgs A) {
     extern __shared__ uint32_t epa_smem[];
@@ -1001,9 +1005,9 @@ __global__ void __launch_bounds__(EPAS_THREADS, NCB_EPAS_MINBLOCKS) k_cc_epa_s(N
     const uint32_t seg_end = A.cnt->epa_cursor[KEY];
     uint32_t* fetch = &A.cnt->epa_fetch[KEY];
     const int lane = threadIdx.x & 31;
-    EpaShared e;
-    e.base = epa_smem + threadIdx.x;
-    bool active = false, exhausted = false;
+    EpaFlex e;
+    e.layout_compact(epa_smem + threadIdx.x, EPAS_THREADS);
+    bool active = false, exhausted = false, restart = false;
     uint32_t p = 0, wq = 0;
     Iso ma, mb;
     SupportS ga, gb;
@@ -1012,41 +1016,62 @@ __global__ void __launch_bounds__(EPAS_THREADS, NCB_EPAS_MINBLOCKS) k_cc_epa_s(N
         int status = EPA_CONTINUE;
         uint32_t res_face = EPA_RES_DIRECT;
         unsigned idle = __ballot_sync(0xffffffffu, !active);
-        bool refill = !exhausted && (idle == 0xffffffffu || __popc(idle) >= A.epa_refill_min);
+        unsigned again = __ballot_sync(0xffffffffu, restart);
+        bool refill = (!exhausted && (idle == 0xffffffffu || __popc(idle) >= A.epa_refill_min)) || again != 0;
         if (refill) {  // warp-uniform
-            uint32_t base = 0;
-            int leader = __ffs(idle) - 1;
-            if (lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (base + __popc(idle) >= seg_end) exhausted = true;  // nothing left after this batch
-            if (!active) {
-                wq = base + __popc(idle & ((1u << lane) - 1));
-                if (wq < seg_end) {
-                    int sdim;
-                    CSOPoint sv[4];
-                    epa_rec_load(A.epa_queue + (size_t)wq * EPA_REC_WORDS, p, sdim, sv);
-                    uint2 pr = __ldg(&A.pairs[p]);
-                    uint32_t i1 = pr.x, i2 = pr.y;
-                    uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
-                    ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
-                    ga = load_slim_support(A.o, A.H, i1, t1), gb = load_slim_support(A.o, A.H, i2, t2);
-                    active = true;
-                    status = epa_init_t<true>(e, ma, ga, mb, gb, sdim, sv, p1, p2, n, res_face);
+            bool init = restart;
+            if (!exhausted && idle != 0) {  // warp-uniform: hand the next queue entries to the idle lanes
+                uint32_t base = 0;
+                int leader = __ffs(idle) - 1;
+                if (lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (base + __popc(idle) >= seg_end) exhausted = true;  // nothing left after this batch
+                if (!active) {
+                    wq = base + __popc(idle & ((1u << lane) - 1));
+                    if (wq < seg_end) {
+                        init = true;
+                        e.layout_compact(epa_smem + threadIdx.x, EPAS_THREADS);  // (a lane that ran a big pair returns to its own words)
+                    }
                 }
+            }
+            if (init) {
+                int sdim;
+                CSOPoint sv[4];
+                epa_rec_load(A.epa_queue + (size_t)wq * EPA_REC_WORDS, p, sdim, sv);
+                uint2 pr = __ldg(&A.pairs[p]);
+                uint32_t i1 = pr.x, i2 = pr.y;
+                uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
+                ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
+                ga = load_slim_support(A.o, A.H, i1, t1), gb = load_slim_support(A.o, A.H, i2, t2);
+                active = true;
+                restart = false;
+                status = epa_init_t<true>(e, ma, ga, mb, gb, sdim, sv, p1, p2, n, res_face);
             }
         } else if (active) {
             status = epa_step_t(e, ma, ga, mb, gb, res_face);
         }
         bool ok = active && status == EPA_DONE_OK;
-        bool defer = active && status == EPA_DONE_FAIL && e.overflow;
+        bool over = active && status == EPA_DONE_FAIL && e.overflow;
         bool fail = active && status == EPA_DONE_FAIL && !e.overflow;
+        bool defer = false;
+        if (over) {
+            defer = true;
+            if (!e.big) {  // outgrew the compact store: restart on a slot of the global pool (next turn, through the init path)
+                uint32_t slot = atomicAdd(&A.cnt->epa_long_n, 1u);
+                if (slot < A.epa_pool_slots) {
+                    e.layout_big(A.epa_pool + (size_t)slot * EpaFlex::B_WORDS);
+                    restart = true;
+                    defer = false;
+                }
+            }
+        }
         if (ok && res_face != EPA_RES_DIRECT) epa_result_from_face(e, res_face, p1, p2, n);
         uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], ok);
         if (ok) {
             cp_store(A.cp_queue, slot, p, p1, p2, n);
             if constexpr (PS) A.ps.dir[A.pair_index ? __ldg(&A.pair_index[p]) : p] = make_float4(n.x, n.y, n.z, 1.f);
         }
-        slot = queue_append(&A.cnt->epa_long_n, defer);
+        slot = queue_append(&A.cnt->epa_defer_n, defer);
         if (defer) A.epa_long[slot] = wq;
         if (fail) {
             if (e.panicked) atomicAdd(&A.cnt->ref_panics, 1u);
@@ -1065,17 +1090,15 @@ __global__ void __launch_bounds__(EPAS_THREADS, NCB_EPAS_MINBLOCKS) k_cc_epa_s(N
     }
 }
 
-// The overflow queue on the big local-memory store.  A restarted pair is a chain of 10-20 dependent expansion steps (~0.2 ms alone),
-// and there are only a few thousand such pairs, so the kernel spreads them over its warps (a few lanes per warp, `lanes` below),
-// finishes each pair completely (EPA, then features + clipping + manifold in the same thread: no queue, no follow-up launch) and
-// runs on its own high-priority stream NEXT TO k_cc_manifold with a small grid (2 CTAs of 64 threads per SM leave the manifold kernel
-// its registers): its latency is hidden behind the manifold kernel of the other 99 % instead of ending the phase.
+// The last-resort queue on the big local-memory store (48 / 192 / 160): pairs beyond EpaFlex's big slot, pairs that found the slot
+// pool exhausted, segment simplices.  Empty on every scene measured so far (the kernel then returns at once); a pair that does get
+// here is finished completely in its thread (EPA, then features + clipping + manifold: no queue, no follow-up launch).
 #ifndef NCB_EPA_MINBLOCKS
 #define NCB_EPA_MINBLOCKS 16
 #endif
 template <bool PS>
 __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa_big(NarrowArgs A) {
-    const uint32_t seg_end = A.cnt->epa_long_n;
+    const uint32_t seg_end = A.cnt->epa_defer_n;
     if (seg_end == 0) return;
     uint32_t* fetch = &A.cnt->epa_long_fetch;
     const int lane = threadIdx.x & 31;
@@ -1392,6 +1415,8 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     A.epa_queue = c->epa_queue.p;
     A.cp_queue = c->cp_queue.p;
     A.epa_long = c->epa_long.p;
+    A.epa_pool = c->epa_pool.p;
+    A.epa_pool_slots = (uint32_t)(c->epa_pool.cap / EpaFlex::B_WORDS);
     {
         float one_degree = (float)(3.14159265358979323846 / 180.0);
         A.one_degree_cs = make_float2(cosf(one_degree), sinf(one_degree));
@@ -1433,7 +1458,7 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     }
     static int epas_bpsm = getenv("NCB_EPAS_BPSM") ? atoi(getenv("NCB_EPAS_BPSM")) : NCB_EPAS_MINBLOCKS;
     {
-        const size_t smem = (size_t)EpaShared::WORDS * EPAS_THREADS * sizeof(uint32_t);
+        const size_t smem = (size_t)EpaFlex::C_WORDS * EPAS_THREADS * sizeof(uint32_t);
         static bool attr_set[2] = {false, false};
         if (!attr_set[PS]) {
             cudaFuncSetAttribute(k_cc_epa_s<PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1442,16 +1467,8 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
         k_cc_epa_s<PS><<<sm * epas_bpsm, EPAS_THREADS, smem, s>>>(A);
     }
     timer_mark(c, "cc_epa", 1);
-    // the overflow pairs (beyond the compact capacities) run beside the manifold kernel of everything else, EPA to manifold
-    cudaStream_t s3 = c->over_stream ? c->over_stream : s;
-    if (c->over_stream) {
-        cudaEventRecord(c->ev_epa, s);
-        cudaStreamWaitEvent(s3, c->ev_epa, 0);
-    }
-    k_cc_epa_big<PS><<<sm * epa_bpsm, 64, 0, s3>>>(A);
-    if (c->over_stream) cudaEventRecord(c->ev_over, s3);
     k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
-    if (c->over_stream) cudaStreamWaitEvent(s, c->ev_over, 0);
+    k_cc_epa_big<PS><<<sm * epa_bpsm, 64, 0, s>>>(A);  // last resort, normally an empty queue
     timer_mark(c, "cc_manifold", 2);
     if (!early && c->side_stream) cudaStreamWaitEvent(s, c->ev_join, 0);  // device-only updates: the side chain may run to the end
     timer_mark(c, "narrow_other_join", 7);

@@ -119,7 +119,8 @@ struct DevCounters {
     uint32_t epa_fetch[K_MAX];    // per key: next EPA queue entry to hand to an idle lane (dynamic fetch)
     uint32_t gjk_fetch[K_MAX];    // per key: next pair of the key segment to hand to an idle lane
     int bounds[6];             // ordered-int encoded min xyz / max xyz of AABB centres
-    uint32_t epa_long_n;       // EPA overflow queue: pairs that did not fit the compact (shared-memory) polytope store
+    uint32_t epa_long_n;       // EPA pairs that outgrew the compact (shared-memory) polytope store and restarted on a pool slot
+    uint32_t epa_defer_n;      // last-resort queue of k_cc_epa_big (beyond the big slot / pool exhausted / segment simplex)
     uint32_t epa_long_fetch;
     uint32_t epa_long_ok;      // overflow pairs whose EPA succeeded (they reach clipping inside k_cc_epa_big)
     uint32_t stack_overflow;   // BVH traversals (pair search, ray casts, queries) that ran out of their 64-entry stack: must stay 0
@@ -201,8 +202,6 @@ struct ncb_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t side_stream = nullptr;  // second chain of the narrow phase (fork / join with events)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    cudaStream_t over_stream = nullptr;  // EPA overflow pairs, beside the convex-convex manifold kernel
-    cudaEvent_t ev_epa = nullptr, ev_over = nullptr;
     std::string err;
     int sm_count = 148;
 
@@ -242,7 +241,8 @@ struct ncb_ctx {
     ncb::DevBuf<uint32_t> manifold_start;
     ncb::DevBuf<uint8_t> manifold_count;
     ncb::DevBuf<uint32_t> pair_index;
-    ncb::DevBuf<uint32_t> epa_long;              // EPA overflow queue: EPA-queue indices of the pairs beyond the compact store's capacities
+    ncb::DevBuf<uint32_t> epa_long;              // last-resort EPA queue (k_cc_epa_big)
+    ncb::DevBuf<uint32_t> epa_pool;              // big polytope slots of k_cc_epa_s (EpaFlex::B_WORDS words each)
     ncb::DevBuf<uint32_t> epa_queue;             // 26 words per record
     ncb::DevBuf<uint32_t> cp_queue;              // 10 words per record
 

@@ -92,9 +92,10 @@ void shim_epa_work_stats(const ncb_objects* objs, const ncb_hull_library* lib, u
     delete e;
 }
 
-// The same as shim_contact_sm_sm, but EPA runs on the COMPACT polytope store of epa.cuh (the shared-memory layout of k_cc_epa_s, here
-// backed by a host array with the kernel's lane stride) with the slim operands; a pair that exceeds a compact capacity is restarted
-// on the big store exactly as the kernel's overflow queue does.  flags[3] += pairs that were restarted.
+// The same as shim_contact_sm_sm, but EPA runs the way k_cc_epa_s runs it: on the flexible polytope store of epa.cuh in its compact
+// layout (the shared-memory words of a lane, here a host array with the kernel's lane stride) with the slim operands; a pair that
+// exceeds a compact capacity restarts on the big layout (a pool slot), and beyond that on the local-memory store, exactly like the
+// kernel.  flags[3] += pairs that restarted on the big layout, flags[2] = EPA calls.
 void shim_contact_sm_sm_compact(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_pairs, const uint32_t* pairs,
                                 const float* predictions, float* out, uint32_t* flags) {
     DevObjects o;
@@ -106,9 +107,9 @@ void shim_contact_sm_sm_compact(const ncb_objects* objs, const ncb_hull_library*
     o.param = reinterpret_cast<const float4*>(objs->shape_param);
     o.qlimit = objs->query_limit;
     DevHulls H = hulls_from(lib);
-    EpaState* big = new EpaState;
-    typedef EpaCompact<64> Compact;
-    uint32_t* words = new uint32_t[Compact::WORDS * 64];
+    EpaState* last = new EpaState;
+    uint32_t* words = new uint32_t[EpaFlex::C_WORDS * 64];
+    uint32_t* slot = new uint32_t[EpaFlex::B_WORDS];
     for (uint64_t p = 0; p < n_pairs; ++p) {
         uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
         Shape a = load_shape(o, H, i1, o.type[i1]), b = load_shape(o, H, i2, o.type[i2]);
@@ -122,29 +123,34 @@ void shim_contact_sm_sm_compact(const ncb_objects* objs, const ncb_hull_library*
         int r = gjk_closest_points(ma, ga, mb, gb, prediction, dir, s, p1, p2, n);
         if (r == GJK_INTERSECTION) {
             flags[2]++;
-            Compact e;
-            e.base = words + (p % 64);  // any lane of the CTA
+            EpaFlex e;
             SupportS sa = slim_support(ga), sb = slim_support(gb);
-            uint32_t res_face;
-            int st = epa_init_t<true>(e, ma, sa, mb, sb, s.dim, s.v, p1, p2, n, res_face);
-            while (st == EPA_CONTINUE) st = epa_step_t(e, ma, sa, mb, sb, res_face);
+            int st = EPA_DONE_FAIL;
+            for (int mode = 0; mode < 2; ++mode) {  // compact, then (restart) big
+                if (mode == 0)
+                    e.layout_compact(words + (p % 64), 64);  // any lane of the CTA
+                else
+                    e.layout_big(slot), flags[3]++;
+                uint32_t res_face;
+                st = epa_init_t<true>(e, ma, sa, mb, sb, s.dim, s.v, p1, p2, n, res_face);
+                while (st == EPA_CONTINUE) st = epa_step_t(e, ma, sa, mb, sb, res_face);
+                if (st == EPA_DONE_OK && res_face != EPA_RES_DIRECT) epa_result_from_face(e, res_face, p1, p2, n);
+                if (!(st == EPA_DONE_FAIL && e.overflow)) break;
+            }
             if (st == EPA_DONE_OK) {
-                if (res_face != EPA_RES_DIRECT) epa_result_from_face(e, res_face, p1, p2, n);
                 r = GJK_CLOSEST_POINTS;
-            } else if (e.overflow) {
-                flags[3]++;
-                if (epa_closest_points(*big, ma, ga, mb, gb, s.dim, s.v, p1, p2, n))
+            } else if (e.overflow) {  // last resort (k_cc_epa_big)
+                if (epa_closest_points(*last, ma, ga, mb, gb, s.dim, s.v, p1, p2, n))
                     r = GJK_CLOSEST_POINTS;
                 else {
-                    if (big->overflow) flags[0]++;
-                    if (big->panicked) flags[1]++;
+                    if (last->overflow) flags[0]++;
+                    if (last->panicked) flags[1]++;
                     r = GJK_NO_INTERSECTION;
                 }
             } else {
                 if (e.panicked) flags[1]++;
                 r = GJK_NO_INTERSECTION;
             }
-            if (r == GJK_NO_INTERSECTION) n = v3(1.f, 0.f, 0.f);
         }
         float* d = out + 10 * p;
         for (int k = 0; k < 10; ++k) d[k] = 0.f;
@@ -153,7 +159,35 @@ void shim_contact_sm_sm_compact(const ncb_objects* objs, const ncb_hull_library*
             d[9] = 1.f;
         }
     }
-    delete big;
+    delete last;
     delete[] words;
+    delete[] slot;
+}
+
+// GJK work per convex pair: stats[3 k] = support-point evaluations (loop turns incl. the initial one), exit kind (GJK_*), simplex
+// dimension + 1 at the exit.  Design data for restructuring k_cc_gjk (scripts/gjk_work_stats.py).
+void shim_gjk_work_stats(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_pairs, const uint32_t* pairs, uint32_t* stats) {
+    DevObjects o;
+    std::memset(&o, 0, sizeof o);
+    o.n = objs->n;
+    o.pos = objs->pos;
+    o.rot = reinterpret_cast<const float4*>(objs->rot);
+    o.type = objs->shape_type;
+    o.param = reinterpret_cast<const float4*>(objs->shape_param);
+    o.qlimit = objs->query_limit;
+    DevHulls H = hulls_from(lib);
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+        uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
+        Shape a = load_shape(o, H, i1, o.type[i1]), b = load_shape(o, H, i2, o.type[i2]);
+        Iso ma = load_iso(o, i1), mb = load_iso(o, i2);
+        Support ga = as_support(a), gb = as_support(b);
+        V3 d0;
+        if (!unit_try_new(mb.t - ma.t, NCB_EPS, d0)) d0 = v3(1.f, 0.f, 0.f);
+        V3 p1, p2, dir;
+        Simplex s;
+        g_gjk_support_evals = 0;
+        int r = gjk_closest_points(ma, ga, mb, gb, o.qlimit[i1] + o.qlimit[i2], d0, s, p1, p2, dir);
+        stats[3 * p] = (uint32_t)g_gjk_support_evals, stats[3 * p + 1] = (uint32_t)r, stats[3 * p + 2] = (uint32_t)s.dim + 1;
+    }
 }
 }
