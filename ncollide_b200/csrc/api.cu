@@ -69,8 +69,7 @@ int reserve_pairs(ncb_ctx* ctx, size_t cap) {
     CK(ctx->manifold_start.reserve(cap));
     CK(ctx->manifold_count.reserve(cap));
     CK(ctx->epa_queue.reserve(26 * cap));
-    CK(ctx->epa_long.reserve(cap));
-    CK(ctx->epa_pool.reserve((size_t)448 * std::max<size_t>(4096, cap / 128)));  // EpaFlex::B_WORDS per slot
+    CK(ctx->epa_long.reserve(2 * cap));
     CK(ctx->cp_queue.reserve(10 * cap));
     return NCB_OK;
 }
@@ -500,7 +499,7 @@ static void fill_counts(ncb_ctx* ctx, ncb_update_counts* counts) {
     counts->n_algo[NCB_ALGO_CONVEX_CONVEX] = c.key_hist[K_CUBOID_CUBOID] + c.key_hist[K_CUBOID_HULL] + c.key_hist[K_HULL_HULL];
     counts->n_algo[NCB_ALGO_NONE] = c.key_hist[K_NONE];
     counts->n_epa_pairs = c.epa_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID];
-    counts->n_manifold_jobs = c.cp_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID] + c.epa_long_ok;
+    counts->n_manifold_jobs = c.cp_cursor[K_CUBOID_CUBOID] - c.key_start[K_CUBOID_CUBOID];
     counts->n_proximity_pairs = c.key_hist[K_PROX_BALL_BALL] + c.key_hist[K_PROX_PLANE] + c.key_hist[K_PROX_SM] + c.key_hist[K_PROX_SM_HULL];
     for (int k = 0; k < 3; ++k) counts->n_proximity[k] = c.prox_hist[k];
     counts->n_capsule_pairs[0] = c.key_hist[K_CAPSULE_CAPSULE];

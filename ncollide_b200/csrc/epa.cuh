@@ -5,13 +5,13 @@
 //
 // The algorithm is written ONCE, over a polytope store `S`; two stores exist:
 //   EpaState    48 vertices / 192 faces / 160 heap entries in per-thread arrays (local memory), face normals stored: the rare
-//               ball-centre-inside-hull pairs, capsule pairs, and the last resort for a pair beyond EpaFlex's big slot.
-//   EpaFlex     the store of k_cc_epa_s: 16 vertices / 48 faces / 20 heap entries in 143 lane-strided words of SHARED memory (vertex
-//               points, one packed topology word + one byte per face, the heap, silhouette and flood stack); face normals are
-//               RECOMPUTED from the three vertices whenever they are needed (same inputs, same operations, same bits as when
-//               Face::new computed them), which is what makes the state small enough for 384 pairs per SM to be resident next to each
-//               other.  A pair that exceeds a capacity restarts in the same lane on a 32 / 160 / 96 slot of a global pool (same
-//               layout, same code); the restart repeats the same arithmetic, so results do not depend on where a pair ran.
+//               ball-centre-inside-hull pairs, capsule pairs, and the last resort for a pair beyond the second tier.
+//   EpaSmem     lane-strided words of SHARED memory (vertex points, packed topology, the heap, silhouette and flood stack); face
+//               normals are RECOMPUTED from the three vertices whenever they are needed (same inputs, same operations, same bits as
+//               when Face::new computed them), which is what makes the state small enough for 384 pairs per SM to be resident next
+//               to each other.  Two sizes: EpaTier1 (16 / 48 / 24, k_cc_epa_s) for 99 % of the pairs, EpaTier2 (32 / 160 / 96,
+//               k_cc_epa_t2) for those that outgrow it.  A pair that exceeds a capacity is flagged (`overflow`) and restarted on the
+//               next tier: the restart repeats the same arithmetic, so results do not depend on which store ran.
 // Both follow the reference's iteration path exactly (same heap sift order as Rust's BinaryHeap, same flood order, same exits);
 // tests/host_shim compiles both for the host and compares them with the oracle bit for bit.
 #pragma once
@@ -93,85 +93,116 @@ struct EpaState : EpaScalars {
 };
 static_assert(EPA_MAX_FACES <= 255 && EPA_MAX_VERTS <= 255, "ids are packed in 8 bits");
 
-// The flexible store of k_cc_epa_s: ONE layout, two places.
-//   compact  16 vertices / 48 faces / 20 heap entries in 143 words of SHARED memory; word w of the lane lives at base[w * stride] with
-//            stride = threads per CTA and base = shared array + thread index: whatever index a lane computes, its bank is its lane id,
-//            so the divergent accesses of an expansion step are conflict free.  99 % of cfg3's EPA runs fit.
-//   big      32 vertices / 160 faces / 96 heap entries in a slot of a GLOBAL pool (stride 1), taken by a lane whose pair outgrew the
-//            compact capacities; the lane restarts its pair there, inside the same kernel, so the long runs overlap with everybody
-//            else's work instead of forming a second phase.
-// The code is the same for both (generic addressing, per-lane capacities and offsets in registers).
-// Face record: word = pts0 | pts1 << 5 | pts2 << 10 | deleted << 15 | adj0 << 16 | adj1 << 24, byte = adj2.
-struct EpaFlex : EpaScalars {
-    enum { ADJ_MASK = 0xff };
-    enum { C_MAXV = 16, C_MAXF = 48, C_MAXH = 20, C_MAXSIL = 12, C_MAXSTK = 8 };      // compact (cfg3 peaks: silhouette 10, stack 7)
-    enum { B_MAXV = 32, B_MAXF = 160, B_MAXH = 96, B_MAXSIL = 32, B_MAXSTK = 32 };    // big
+// The shared-memory store.  Word w of the lane lives at base[w * STRIDE] (STRIDE = threads per CTA, base = shared-memory array +
+// thread index): whatever index a lane computes, its bank is its lane id, so the divergent accesses of an expansion step are
+// conflict free; all offsets are compile-time constants.
+//   WIDE = false (k_cc_epa_s, first tier):  one word per face = pts0 | pts1 << 4 | pts2 << 8 | adj0 << 12 | adj1 << 18 | adj2 << 24 |
+//                                           deleted << 30 (<= 16 vertices, <= 64 faces); silhouette / stack entries in one byte.
+//   WIDE = true  (k_cc_epa_t2, second tier): two words per face = [pts0 | pts1 << 8 | pts2 << 16 | deleted << 24] [adj0 | adj1 << 8 |
+//                                           adj2 << 16]; silhouette / stack entries in 16 bits.
+template <int STRIDE, int V, int F, int H, int SIL, int STK, bool WIDE>
+struct EpaSmem : EpaScalars {
+    enum { MAXV = V, MAXF = F, MAXH = H, MAXSIL = SIL, MAXSTK = STK, ADJ_MASK = WIDE ? 0xff : 63 };
+    enum { EB = WIDE ? 2 : 1 };  // bytes per silhouette / stack entry
+    enum {
+        W_VP = 0,
+        W_TP = W_VP + 3 * MAXV,
+        W_HD = W_TP + (WIDE ? 2 : 1) * MAXF,
+        W_HI = W_HD + MAXH,
+        W_SIL = W_HI + (MAXH + 3) / 4,
+        W_STK = W_SIL + (MAXSIL * EB + 3) / 4,
+        WORDS = W_STK + (MAXSTK * EB + 3) / 4
+    };
+    static_assert(WIDE || (MAXV <= 16 && MAXF <= 64), "narrow face word: 4-bit vertex ids, 6-bit face ids");
+    static_assert(MAXV <= 255 && MAXF <= 255, "8-bit ids");
     static const bool STORED_NORMALS = false;
-    enum { C_WORDS = 3 * C_MAXV + C_MAXF + C_MAXF / 4 + C_MAXH + C_MAXH / 4 + C_MAXSIL / 2 + C_MAXSTK / 2 };
-    enum { B_WORDS = 3 * B_MAXV + B_MAXF + B_MAXF / 4 + B_MAXH + B_MAXH / 4 + B_MAXSIL / 2 + B_MAXSTK / 2 };
     uint32_t* base;
-    int stride;
-    int MAXV, MAXF, MAXH, MAXSIL, MAXSTK;          // this lane's capacities
-    int o_tw, o_tb, o_hd, o_hi, o_sil, o_stk;      // word offsets: face words, face bytes, heap keys, heap ids, silhouette, flood stack
-    bool big;
-    V3 vorig1[B_MAXV], vorig2[B_MAXV];  // cold: written once per vertex, three of each read for the result (local memory)
+    V3 vorig1[MAXV], vorig2[MAXV];  // cold: written once per vertex, three of each read for the result (local memory)
 
-    NCB_HD void layout(uint32_t* b, int st, int v, int f, int h, int sil, int stk, bool is_big) {
-        base = b, stride = st, big = is_big;
-        MAXV = v, MAXF = f, MAXH = h, MAXSIL = sil, MAXSTK = stk;
-        o_tw = 3 * v, o_tb = o_tw + f, o_hd = o_tb + f / 4, o_hi = o_hd + h, o_sil = o_hi + h / 4, o_stk = o_sil + sil / 2;
+    NCB_HD uint32_t& w(int i) const { return base[i * STRIDE]; }
+    NCB_HD uint8_t& b(int w0, int i) const { return reinterpret_cast<uint8_t*>(base + (w0 + (i >> 2)) * STRIDE)[i & 3]; }
+    NCB_HD uint16_t& h(int w0, int i) const { return reinterpret_cast<uint16_t*>(base + (w0 + (i >> 1)) * STRIDE)[i & 1]; }
+    NCB_HD V3 vp(uint32_t i) const {
+        return v3(__uint_as_float(w(W_VP + 3 * i)), __uint_as_float(w(W_VP + 3 * i + 1)), __uint_as_float(w(W_VP + 3 * i + 2)));
     }
-    NCB_HD void layout_compact(uint32_t* b, int st) { layout(b, st, C_MAXV, C_MAXF, C_MAXH, C_MAXSIL, C_MAXSTK, false); }
-    NCB_HD void layout_big(uint32_t* b) { layout(b, 1, B_MAXV, B_MAXF, B_MAXH, B_MAXSIL, B_MAXSTK, true); }
-
-    NCB_HD uint32_t& w(int i) const { return base[i * stride]; }
-    NCB_HD uint8_t& b(int w0, int i) const { return reinterpret_cast<uint8_t*>(base + (w0 + (i >> 2)) * stride)[i & 3]; }
-    NCB_HD V3 vp(uint32_t i) const { return v3(__uint_as_float(w(3 * i)), __uint_as_float(w(3 * i + 1)), __uint_as_float(w(3 * i + 2))); }
-    NCB_HD void set_vp(uint32_t i, V3 p) { w(3 * i) = __float_as_uint(p.x), w(3 * i + 1) = __float_as_uint(p.y), w(3 * i + 2) = __float_as_uint(p.z); }
+    NCB_HD void set_vp(uint32_t i, V3 p) {
+        w(W_VP + 3 * i) = __float_as_uint(p.x), w(W_VP + 3 * i + 1) = __float_as_uint(p.y), w(W_VP + 3 * i + 2) = __float_as_uint(p.z);
+    }
     NCB_HD V3 o1(uint32_t i) const { return vorig1[i]; }
     NCB_HD V3 o2(uint32_t i) const { return vorig2[i]; }
     NCB_HD void set_orig(uint32_t i, V3 a, V3 c) { vorig1[i] = a, vorig2[i] = c; }
     NCB_HD void f_init(uint32_t f, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t a0, uint32_t a1, uint32_t a2) {
-        w(o_tw + f) = p0 | (p1 << 5) | (p2 << 10) | (a0 << 16) | (a1 << 24);
-        b(o_tb, f) = (uint8_t)a2;
+        if (WIDE) {
+            w(W_TP + 2 * f) = p0 | (p1 << 8) | (p2 << 16);
+            w(W_TP + 2 * f + 1) = a0 | (a1 << 8) | (a2 << 16);
+        } else {
+            w(W_TP + f) = p0 | (p1 << 4) | (p2 << 8) | (a0 << 12) | (a1 << 18) | (a2 << 24);
+        }
     }
     NCB_HD void f_pts(uint32_t f, uint32_t& p0, uint32_t& p1, uint32_t& p2) const {
-        uint32_t t = w(o_tw + f);
-        p0 = t & 31u, p1 = (t >> 5) & 31u, p2 = (t >> 10) & 31u;
+        if (WIDE) {
+            uint32_t t = w(W_TP + 2 * f);
+            p0 = t & 0xffu, p1 = (t >> 8) & 0xffu, p2 = (t >> 16) & 0xffu;
+        } else {
+            uint32_t t = w(W_TP + f);
+            p0 = t & 15u, p1 = (t >> 4) & 15u, p2 = (t >> 8) & 15u;
+        }
     }
     NCB_HD void f_adjs(uint32_t f, uint32_t& a0, uint32_t& a1, uint32_t& a2) const {
-        uint32_t t = w(o_tw + f);
-        a0 = (t >> 16) & 0xffu, a1 = t >> 24, a2 = b(o_tb, f);
-    }
-    NCB_HD bool f_deleted(uint32_t f) const { return (w(o_tw + f) >> 15) & 1u; }
-    NCB_HD void f_set_deleted(uint32_t f) { w(o_tw + f) |= 0x8000u; }
-    NCB_HD void f_set_adj(uint32_t f, uint32_t k, uint32_t v) {
-        if (k == 2) {
-            b(o_tb, f) = (uint8_t)v;
+        if (WIDE) {
+            uint32_t t = w(W_TP + 2 * f + 1);
+            a0 = t & 0xffu, a1 = (t >> 8) & 0xffu, a2 = (t >> 16) & 0xffu;
         } else {
-            uint32_t sh = 16 + 8 * k;
-            w(o_tw + f) = (w(o_tw + f) & ~(0xffu << sh)) | (v << sh);
+            uint32_t t = w(W_TP + f);
+            a0 = (t >> 12) & 63u, a1 = (t >> 18) & 63u, a2 = (t >> 24) & 63u;
+        }
+    }
+    NCB_HD bool f_deleted(uint32_t f) const { return WIDE ? (w(W_TP + 2 * f) >> 24) != 0 : (w(W_TP + f) >> 30) != 0; }
+    NCB_HD void f_set_deleted(uint32_t f) {
+        if (WIDE)
+            w(W_TP + 2 * f) |= 0x01000000u;
+        else
+            w(W_TP + f) |= 0x40000000u;
+    }
+    NCB_HD void f_set_adj(uint32_t f, uint32_t k, uint32_t v) {
+        if (WIDE) {
+            w(W_TP + 2 * f + 1) = (w(W_TP + 2 * f + 1) & ~(0xffu << (8 * k))) | (v << (8 * k));
+        } else {
+            uint32_t sh = 12 + 6 * k;
+            w(W_TP + f) = (w(W_TP + f) & ~(63u << sh)) | (v << sh);
         }
     }
     NCB_HD V3 stored_normal(uint32_t) const { return v3(0.f, 0.f, 0.f); }
     NCB_HD void set_normal(uint32_t, V3) {}
-    NCB_HD float hd(int i) const { return __uint_as_float(w(o_hd + i)); }
-    NCB_HD uint32_t hi(int i) const { return b(o_hi, i); }
-    NCB_HD void hset(int i, float d, uint32_t id) { w(o_hd + i) = __float_as_uint(d), b(o_hi, i) = (uint8_t)id; }
-    // silhouette / flood-stack entries: face id (8 bits) and opp (2 bits) in separate byte planes would cost two accesses; faces < 256
-    // and opp < 3 do not fit one byte together, so an entry is 16 bits: [face | opp << 8] in halves of the words
-    NCB_HD uint16_t& h16(int w0, int i) const { return reinterpret_cast<uint16_t*>(base + (w0 + (i >> 1)) * stride)[i & 1]; }
-    NCB_HD void sil_set(int k, uint32_t f, uint32_t opp) { h16(o_sil, k) = (uint16_t)(f | (opp << 8)); }
-    NCB_HD void sil_get(int k, uint32_t& f, uint32_t& opp) const {
-        uint32_t v = h16(o_sil, k);
-        f = v & 0xffu, opp = v >> 8;
+    NCB_HD float hd(int i) const { return __uint_as_float(w(W_HD + i)); }
+    NCB_HD uint32_t hi(int i) const { return b(W_HI, i); }
+    NCB_HD void hset(int i, float d, uint32_t id) { w(W_HD + i) = __float_as_uint(d), b(W_HI, i) = (uint8_t)id; }
+    NCB_HD void ent_set(int w0, int k, uint32_t f, uint32_t opp) {
+        if (WIDE)
+            h(w0, k) = (uint16_t)(f | (opp << 8));
+        else
+            b(w0, k) = (uint8_t)(f | (opp << 6));
     }
-    NCB_HD void stk_set(int k, uint32_t f, uint32_t opp) { h16(o_stk, k) = (uint16_t)(f | (opp << 8)); }
-    NCB_HD void stk_get(int k, uint32_t& f, uint32_t& opp) const {
-        uint32_t v = h16(o_stk, k);
-        f = v & 0xffu, opp = v >> 8;
+    NCB_HD void ent_get(int w0, int k, uint32_t& f, uint32_t& opp) const {
+        if (WIDE) {
+            uint32_t v = h(w0, k);
+            f = v & 0xffu, opp = v >> 8;
+        } else {
+            uint32_t v = b(w0, k);
+            f = v & 63u, opp = v >> 6;
+        }
     }
+    NCB_HD void sil_set(int k, uint32_t f, uint32_t opp) { ent_set(W_SIL, k, f, opp); }
+    NCB_HD void sil_get(int k, uint32_t& f, uint32_t& opp) const { ent_get(W_SIL, k, f, opp); }
+    NCB_HD void stk_set(int k, uint32_t f, uint32_t opp) { ent_set(W_STK, k, f, opp); }
+    NCB_HD void stk_get(int k, uint32_t& f, uint32_t& opp) const { ent_get(W_STK, k, f, opp); }
 };
+// first tier: 99 % of cfg3's EPA runs (133 words = 532 B per pair; 6 CTAs of 64 threads per SM)
+template <int STRIDE>
+using EpaTier1 = EpaSmem<STRIDE, 16, 48, 24, 16, 12, false>;
+// second tier: the pairs that outgrew the first one, restarted (584 words per pair; 3 CTAs of 32 threads per SM, one wave)
+template <int STRIDE>
+using EpaTier2 = EpaSmem<STRIDE, 32, 160, 96, 32, 32, true>;
 
 NCB_HD V3 epa_sel3(uint32_t k, V3 a, V3 b, V3 c) { return k == 0 ? a : (k == 1 ? b : c); }
 NCB_HD uint32_t epa_sel3(uint32_t k, uint32_t a, uint32_t b, uint32_t c) { return k == 0 ? a : (k == 1 ? b : c); }

@@ -872,9 +872,7 @@ struct NarrowArgs {
     uint32_t* epa_queue;   // EPA_REC_WORDS per record
     uint32_t* cp_queue;    // CP_REC_WORDS per record
     int epa_refill_min;    // idle lanes needed before a warp of k_cc_epa_s refills (batched initialisation)
-    uint32_t* epa_long;    // last-resort queue: EPA-queue indices of the pairs k_cc_epa_s could not finish (k_cc_epa_big)
-    uint32_t* epa_pool;    // EpaFlex::B_WORDS words per slot: big polytope stores of k_cc_epa_s
-    uint32_t epa_pool_slots;
+    uint32_t* epa_long;    // [0, cap_pairs): EPA-queue indices tier 1 deferred to tier 2; [cap_pairs, 2 cap_pairs): tier 2 to the last resort
 };
 
 // ---- convex x convex in three compacted phases -------------------------------------------------------------------
@@ -972,16 +970,23 @@ __global__ void __launch_bounds__(128, NCB_GJK_MINBLOCKS) k_cc_gjk(NarrowArgs A)
 // run the same code (one step) regardless of how many steps their pair needs; refills are batched (>= refill_min idle
 // lanes) so that the initialisation path is not paid on every turn.
 //
-// k_cc_epa_s: the polytope lives in SHARED memory (EpaFlex, compact layout: 143 lane-strided words per pair, face normals
-// recomputed), 6 CTAs of 64 threads per SM; the operands are kept slim (kind, half extents | vertex array) in registers.  Round 1's
-// kernel kept a 7.4 KB polytope per thread in local memory: 32 warps x 55 KB of touched lines per SM overflowed L1 and, over 148
-// SMs, L2, and ncu counted 3.0 GB of DRAM traffic for 82 MB of algorithmic bytes.  Here the expansion loop touches no global or local
-// memory except the hull vertices (L1-resident library) and 24 B of cold support points per new vertex.
-// A pair that outgrows the compact capacities (1 % on cfg3) takes a slot of a global pool (EpaFlex, big layout) and RESTARTS IN ITS
-// LANE: same code, generic loads, and its long run (10-20 dependent steps, ~0.2 ms) overlaps with the rest of the queue instead of
-// forming a second phase (a separate overflow kernel cost 0.4-0.6 ms of tail, measured: profiles/r2_epa_overflow.txt).  Beyond the
-// big slot, or when the pool is exhausted, or for a segment simplex, the pair goes to the last-resort queue (k_cc_epa_big).
+// Three tiers, one after the other on the stream, each restarting what the previous one could not hold (a restart repeats the same
+// arithmetic, so the result does not depend on the tier):
+//   k_cc_epa_tier<PS, 1>  the whole EPA queue; polytope in SHARED memory (EpaTier1: 16 / 48 / 24 in 133 lane-strided words, face
+//                         normals recomputed), 6 CTAs of 64 threads per SM, operands slim (kind, half extents | vertex array) in
+//                         registers.  Round 1's kernel kept a 7.4 KB polytope per thread in local memory: 32 warps x 55 KB of touched
+//                         lines per SM overflowed L1 and, over 148 SMs, L2, and ncu counted 3.0 GB of DRAM traffic for 82 MB of
+//                         algorithmic bytes; here the expansion loop touches no global or local memory except the hull vertices
+//                         (L1-resident library) and 24 B of cold support points per new vertex (0.13 GB of DRAM traffic).
+//   k_cc_epa_tier<PS, 2>  the 1 % that outgrew tier 1 (queue A.epa_long): EpaTier2 (32 / 160 / 96) in shared memory, CTAs of one
+//                         warp, the pairs spread over all warps (a few lanes each): what is left is the latency of the longest runs.
+//   k_cc_epa_big          last resort on the local-memory store (48 / 192 / 160): beyond tier 2, segment simplices.  Empty on every
+//                         scene measured so far (it then returns at once).
+// Handling the 1 % inside the tier-1 kernel was measured and rejected (profiles/r2_epa_overflow.txt): with generic addressing and
+// per-lane capacities the kernel executes 29 % more instructions, and a lane whose polytope lives in global memory slows its
+// whole warp down (0.79 -> 1.49 ms).
 #define EPAS_THREADS 64
+#define EPAT2_THREADS 32
 #ifndef NCB_EPAS_MINBLOCKS
 #define NCB_EPAS_MINBLOCKS 6
 #endif
@@ -997,17 +1002,37 @@ NCB_HD void epa_rec_load(const uint32_t* q, uint32_t& p, int& sdim, CSOPoint* sv
     }
 }
 
-static_assert(EpaFlex::B_WORDS == 448, "api.cu sizes the slot pool with this figure");
-template <bool PS>
-__global__ void __launch_bounds__(EPAS_THREADS, NCB_EPAS_MINBLOCKS) k_cc_epa_s(NarrowArgs A) {
+template <int TIER>
+struct EpaTierTraits;
+template <>
+struct EpaTierTraits<1> {
+    enum { THREADS = EPAS_THREADS, MINBLOCKS = NCB_EPAS_MINBLOCKS };
+    typedef EpaTier1<EPAS_THREADS> Store;
+};
+template <>
+struct EpaTierTraits<2> {
+    enum { THREADS = EPAT2_THREADS, MINBLOCKS = 3 };
+    typedef EpaTier2<EPAT2_THREADS> Store;
+};
+
+template <bool PS, int TIER>
+__global__ void __launch_bounds__(EpaTierTraits<TIER>::THREADS, EpaTierTraits<TIER>::MINBLOCKS) k_cc_epa_tier(NarrowArgs A) {
     extern __shared__ uint32_t epa_smem[];
+    typedef typename EpaTierTraits<TIER>::Store Store;
     const int KEY = CCQ;
-    const uint32_t seg_end = A.cnt->epa_cursor[KEY];
-    uint32_t* fetch = &A.cnt->epa_fetch[KEY];
+    // tier 1 walks the EPA queue itself; tier 2 the list of queue indices tier 1 deferred
+    const uint32_t seg_end = TIER == 1 ? A.cnt->epa_cursor[KEY] : A.cnt->epa_long_n;
+    uint32_t* fetch = TIER == 1 ? &A.cnt->epa_fetch[KEY] : &A.cnt->epa_long_fetch;
+    if (TIER == 2 && seg_end == 0) return;
     const int lane = threadIdx.x & 31;
-    EpaFlex e;
-    e.layout_compact(epa_smem + threadIdx.x, EPAS_THREADS);
-    bool active = false, exhausted = false, restart = false;
+    // tier 2: a handful of pairs, long runs: spread them over the warps of the grid instead of filling the first warps
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t lanes = TIER == 1 ? 32u : min(32u, (seg_end + nwarps - 1) / nwarps);
+    const bool usable = (uint32_t)lane < lanes;
+    const int refill_min = TIER == 1 ? A.epa_refill_min : 1;
+    Store e;
+    e.base = epa_smem + threadIdx.x;
+    bool active = false, exhausted = false;
     uint32_t p = 0, wq = 0;
     Iso ma, mb;
     SupportS ga, gb;
@@ -1015,64 +1040,46 @@ __global__ void __launch_bounds__(EPAS_THREADS, NCB_EPAS_MINBLOCKS) k_cc_epa_s(N
     for (;;) {
         int status = EPA_CONTINUE;
         uint32_t res_face = EPA_RES_DIRECT;
-        unsigned idle = __ballot_sync(0xffffffffu, !active);
-        unsigned again = __ballot_sync(0xffffffffu, restart);
-        bool refill = (!exhausted && (idle == 0xffffffffu || __popc(idle) >= A.epa_refill_min)) || again != 0;
+        unsigned idle = __ballot_sync(0xffffffffu, usable && !active);
+        unsigned all_idle = __ballot_sync(0xffffffffu, !active);
+        bool refill = !exhausted && idle != 0 && (all_idle == 0xffffffffu || __popc(idle) >= refill_min);
         if (refill) {  // warp-uniform
-            bool init = restart;
-            if (!exhausted && idle != 0) {  // warp-uniform: hand the next queue entries to the idle lanes
-                uint32_t base = 0;
-                int leader = __ffs(idle) - 1;
-                if (lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (base + __popc(idle) >= seg_end) exhausted = true;  // nothing left after this batch
-                if (!active) {
-                    wq = base + __popc(idle & ((1u << lane) - 1));
-                    if (wq < seg_end) {
-                        init = true;
-                        e.layout_compact(epa_smem + threadIdx.x, EPAS_THREADS);  // (a lane that ran a big pair returns to its own words)
-                    }
+            uint32_t base = 0;
+            int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(fetch, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + __popc(idle) >= seg_end) exhausted = true;  // nothing left after this batch
+            if (usable && !active) {
+                uint32_t w = base + __popc(idle & ((1u << lane) - 1));
+                if (w < seg_end) {
+                    wq = TIER == 1 ? w : __ldg(&A.epa_long[w]);
+                    int sdim;
+                    CSOPoint sv[4];
+                    epa_rec_load(A.epa_queue + (size_t)wq * EPA_REC_WORDS, p, sdim, sv);
+                    uint2 pr = __ldg(&A.pairs[p]);
+                    uint32_t i1 = pr.x, i2 = pr.y;
+                    uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
+                    ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
+                    ga = load_slim_support(A.o, A.H, i1, t1), gb = load_slim_support(A.o, A.H, i2, t2);
+                    active = true;
+                    status = epa_init_t<true>(e, ma, ga, mb, gb, sdim, sv, p1, p2, n, res_face);
                 }
-            }
-            if (init) {
-                int sdim;
-                CSOPoint sv[4];
-                epa_rec_load(A.epa_queue + (size_t)wq * EPA_REC_WORDS, p, sdim, sv);
-                uint2 pr = __ldg(&A.pairs[p]);
-                uint32_t i1 = pr.x, i2 = pr.y;
-                uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
-                ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
-                ga = load_slim_support(A.o, A.H, i1, t1), gb = load_slim_support(A.o, A.H, i2, t2);
-                active = true;
-                restart = false;
-                status = epa_init_t<true>(e, ma, ga, mb, gb, sdim, sv, p1, p2, n, res_face);
             }
         } else if (active) {
             status = epa_step_t(e, ma, ga, mb, gb, res_face);
         }
         bool ok = active && status == EPA_DONE_OK;
-        bool over = active && status == EPA_DONE_FAIL && e.overflow;
+        bool defer = active && status == EPA_DONE_FAIL && e.overflow;
         bool fail = active && status == EPA_DONE_FAIL && !e.overflow;
-        bool defer = false;
-        if (over) {
-            defer = true;
-            if (!e.big) {  // outgrew the compact store: restart on a slot of the global pool (next turn, through the init path)
-                uint32_t slot = atomicAdd(&A.cnt->epa_long_n, 1u);
-                if (slot < A.epa_pool_slots) {
-                    e.layout_big(A.epa_pool + (size_t)slot * EpaFlex::B_WORDS);
-                    restart = true;
-                    defer = false;
-                }
-            }
-        }
         if (ok && res_face != EPA_RES_DIRECT) epa_result_from_face(e, res_face, p1, p2, n);
         uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], ok);
         if (ok) {
             cp_store(A.cp_queue, slot, p, p1, p2, n);
             if constexpr (PS) A.ps.dir[A.pair_index ? __ldg(&A.pair_index[p]) : p] = make_float4(n.x, n.y, n.z, 1.f);
         }
-        slot = queue_append(&A.cnt->epa_defer_n, defer);
-        if (defer) A.epa_long[slot] = wq;
+        // tier 1 defers to tier 2 (A.epa_long), tier 2 to the last resort (the second half of the same array)
+        slot = queue_append(TIER == 1 ? &A.cnt->epa_long_n : &A.cnt->epa_defer_n, defer);
+        if (defer) A.epa_long[(TIER == 1 ? 0u : A.cap_pairs) + slot] = wq;
         if (fail) {
             if (e.panicked) atomicAdd(&A.cnt->ref_panics, 1u);
             uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
@@ -1090,25 +1097,24 @@ __global__ void __launch_bounds__(EPAS_THREADS, NCB_EPAS_MINBLOCKS) k_cc_epa_s(N
     }
 }
 
-// The last-resort queue on the big local-memory store (48 / 192 / 160): pairs beyond EpaFlex's big slot, pairs that found the slot
-// pool exhausted, segment simplices.  Empty on every scene measured so far (the kernel then returns at once); a pair that does get
-// here is finished completely in its thread (EPA, then features + clipping + manifold: no queue, no follow-up launch).
+// The last-resort queue on the big local-memory store (48 / 192 / 160): pairs beyond tier 2, segment simplices.  Empty on every
+// scene measured so far (the kernel then returns at once).
 #ifndef NCB_EPA_MINBLOCKS
 #define NCB_EPA_MINBLOCKS 16
 #endif
 template <bool PS>
 __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa_big(NarrowArgs A) {
+    const int KEY = CCQ;
     const uint32_t seg_end = A.cnt->epa_defer_n;
     if (seg_end == 0) return;
-    uint32_t* fetch = &A.cnt->epa_long_fetch;
+    uint32_t* fetch = &A.cnt->epa_defer_fetch;
     const int lane = threadIdx.x & 31;
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
     const uint32_t lanes = min(32u, (seg_end + nwarps - 1) / nwarps);
     const bool usable = (uint32_t)lane < lanes;
     EpaState e;
-    ManifoldT<PS> mf;
     bool active = false, exhausted = false;
-    uint32_t p = 0, i1 = 0, i2 = 0;
+    uint32_t p = 0;
     Iso ma, mb;
     Support ga, gb;
     V3 p1, p2, n;
@@ -1125,12 +1131,12 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa_big(NarrowArgs
             if (usable && !active) {
                 uint32_t w = base + __popc(idle & ((1u << lane) - 1));
                 if (w < seg_end) {
-                    uint32_t wq = __ldg(&A.epa_long[w]);
+                    uint32_t wq = __ldg(&A.epa_long[A.cap_pairs + w]);
                     int sdim;
                     CSOPoint sv[4];
                     epa_rec_load(A.epa_queue + (size_t)wq * EPA_REC_WORDS, p, sdim, sv);
                     uint2 pr = __ldg(&A.pairs[p]);
-                    i1 = pr.x, i2 = pr.y;
+                    uint32_t i1 = pr.x, i2 = pr.y;
                     uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
                     ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
                     Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
@@ -1144,33 +1150,24 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa_big(NarrowArgs
         }
         bool ok = active && status == EPA_DONE_OK;
         bool fail = active && status == EPA_DONE_FAIL;
-        uint32_t out_index = (ok || fail) ? (A.pair_index ? __ldg(&A.pair_index[p]) : p) : 0;
-        mf.n = 0;
-        mf.deepest = 0;
-        if (ok) {  // the body of k_cc_manifold for this pair
-            atomicAdd(&A.cnt->epa_long_ok, 1u);
-            if constexpr (PS) {
-                A.ps.dir[out_index] = make_float4(n.x, n.y, n.z, 1.f);
-                pm_load_and_age(A.ps, out_index, mf);
-            }
-            uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
-            float linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
-            Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
-            float2 ang1 = __ldg(&A.o.ang_cs[i1 * A.o.ang_stride]), ang2 = __ldg(&A.o.ang_cs[i2 * A.o.ang_stride]);
-            Feature f1, f2;
-            convex_convex_manifold(ma, a, mb, b, linear, ang1, ang2, p1, p2, n, mf, f1, f2);
-            if constexpr (PS) pm_store(A.ps, out_index, mf, i1, i2);
+        uint32_t slot = queue_append(&A.cnt->cp_cursor[KEY], ok);
+        if (ok) {
+            cp_store(A.cp_queue, slot, p, p1, p2, n);
+            if constexpr (PS) A.ps.dir[A.pair_index ? __ldg(&A.pair_index[p]) : p] = make_float4(n.x, n.y, n.z, 1.f);
         }
         if (fail) {
             if (e.overflow) atomicAdd(&A.cnt->epa_overflow, 1u);
             if (e.panicked) atomicAdd(&A.cnt->ref_panics, 1u);
+            uint32_t out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
             if constexpr (PS) {  // NoIntersection(x axis) (contact_support_map_support_map.rs:76)
                 A.ps.dir[out_index] = make_float4(1.f, 0.f, 0.f, 1.f);
-                pm_age_only(A.ps, out_index, i1, i2);
+                uint2 pr = __ldg(&A.pairs[p]);
+                pm_age_only(A.ps, out_index, pr.x, pr.y);
+            } else {
+                A.manifold_start[out_index] = 0;
+                A.manifold_count[out_index] = 0;
             }
         }
-        // an Err pair writes its empty manifold through the same call (mf.n == 0)
-        if constexpr (!PS) write_manifold(mf, ok || fail, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
         if (ok || fail) active = false;
         if (exhausted && __all_sync(0xffffffffu, !active)) break;
     }
@@ -1415,8 +1412,6 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     A.epa_queue = c->epa_queue.p;
     A.cp_queue = c->cp_queue.p;
     A.epa_long = c->epa_long.p;
-    A.epa_pool = c->epa_pool.p;
-    A.epa_pool_slots = (uint32_t)(c->epa_pool.cap / EpaFlex::B_WORDS);
     {
         float one_degree = (float)(3.14159265358979323846 / 180.0);
         A.one_degree_cs = make_float2(cosf(one_degree), sinf(one_degree));
@@ -1458,18 +1453,21 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     }
     static int epas_bpsm = getenv("NCB_EPAS_BPSM") ? atoi(getenv("NCB_EPAS_BPSM")) : NCB_EPAS_MINBLOCKS;
     {
-        const size_t smem = (size_t)EpaFlex::C_WORDS * EPAS_THREADS * sizeof(uint32_t);
+        const size_t smem1 = (size_t)EpaTierTraits<1>::Store::WORDS * EPAS_THREADS * sizeof(uint32_t);
+        const size_t smem2 = (size_t)EpaTierTraits<2>::Store::WORDS * EPAT2_THREADS * sizeof(uint32_t);
         static bool attr_set[2] = {false, false};
         if (!attr_set[PS]) {
-            cudaFuncSetAttribute(k_cc_epa_s<PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_cc_epa_tier<PS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+            cudaFuncSetAttribute(k_cc_epa_tier<PS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
             attr_set[PS] = true;
         }
-        k_cc_epa_s<PS><<<sm * epas_bpsm, EPAS_THREADS, smem, s>>>(A);
+        k_cc_epa_tier<PS, 1><<<sm * epas_bpsm, EPAS_THREADS, smem1, s>>>(A);
+        k_cc_epa_tier<PS, 2><<<sm * 3, EPAT2_THREADS, smem2, s>>>(A);
+        k_cc_epa_big<PS><<<sm * epa_bpsm, 64, 0, s>>>(A);  // last resort, normally an empty queue
     }
-    timer_mark(c, "cc_epa", 1);
+    timer_mark(c, "cc_epa", 3);
     k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
-    k_cc_epa_big<PS><<<sm * epa_bpsm, 64, 0, s>>>(A);  // last resort, normally an empty queue
-    timer_mark(c, "cc_manifold", 2);
+    timer_mark(c, "cc_manifold", 1);
     if (!early && c->side_stream) cudaStreamWaitEvent(s, c->ev_join, 0);  // device-only updates: the side chain may run to the end
     timer_mark(c, "narrow_other_join", 7);
     return cudaGetLastError();

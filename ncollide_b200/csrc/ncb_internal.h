@@ -119,10 +119,10 @@ struct DevCounters {
     uint32_t epa_fetch[K_MAX];    // per key: next EPA queue entry to hand to an idle lane (dynamic fetch)
     uint32_t gjk_fetch[K_MAX];    // per key: next pair of the key segment to hand to an idle lane
     int bounds[6];             // ordered-int encoded min xyz / max xyz of AABB centres
-    uint32_t epa_long_n;       // EPA pairs that outgrew the compact (shared-memory) polytope store and restarted on a pool slot
-    uint32_t epa_defer_n;      // last-resort queue of k_cc_epa_big (beyond the big slot / pool exhausted / segment simplex)
+    uint32_t epa_long_n;       // EPA pairs that outgrew the first-tier (shared-memory) polytope store: queue of the second tier
     uint32_t epa_long_fetch;
-    uint32_t epa_long_ok;      // overflow pairs whose EPA succeeded (they reach clipping inside k_cc_epa_big)
+    uint32_t epa_defer_n;      // pairs beyond the second tier / segment simplices: queue of the last resort (k_cc_epa_big)
+    uint32_t epa_defer_fetch;
     uint32_t stack_overflow;   // BVH traversals (pair search, ray casts, queries) that ran out of their 64-entry stack: must stay 0
     uint32_t prox_hist[4];     // proximity pairs per status (Intersecting, WithinMargin, Disjoint)
 };
@@ -241,8 +241,7 @@ struct ncb_ctx {
     ncb::DevBuf<uint32_t> manifold_start;
     ncb::DevBuf<uint8_t> manifold_count;
     ncb::DevBuf<uint32_t> pair_index;
-    ncb::DevBuf<uint32_t> epa_long;              // last-resort EPA queue (k_cc_epa_big)
-    ncb::DevBuf<uint32_t> epa_pool;              // big polytope slots of k_cc_epa_s (EpaFlex::B_WORDS words each)
+    ncb::DevBuf<uint32_t> epa_long;              // EPA queue indices deferred to the second tier / to the last resort (2 x cap_pairs)
     ncb::DevBuf<uint32_t> epa_queue;             // 26 words per record
     ncb::DevBuf<uint32_t> cp_queue;              // 10 words per record
 

@@ -23,6 +23,15 @@ static DevHulls hulls_from(const ncb_hull_library* L) {
     return H;
 }
 
+template <class Store>
+static int run_tier(Store& e, const Iso& ma, const SupportS& sa, const Iso& mb, const SupportS& sb, const Simplex& s, V3& p1, V3& p2, V3& n) {
+    uint32_t res_face;
+    int st = epa_init_t<true>(e, ma, sa, mb, sb, s.dim, s.v, p1, p2, n, res_face);
+    while (st == EPA_CONTINUE) st = epa_step_t(e, ma, sa, mb, sb, res_face);
+    if (st == EPA_DONE_OK && res_face != EPA_RES_DIRECT) epa_result_from_face(e, res_face, p1, p2, n);
+    return st;
+}
+
 extern "C" {
 // contact_sm_sm (GJK, then EPA when the origin is inside the CSO) for cuboid / hull pairs.
 // out[10 p] = p1, p2, normal, found flag; flags[0] += EPA capacity overflows, flags[1] += reference panics, flags[2] = EPA calls.
@@ -92,10 +101,10 @@ void shim_epa_work_stats(const ncb_objects* objs, const ncb_hull_library* lib, u
     delete e;
 }
 
-// The same as shim_contact_sm_sm, but EPA runs the way k_cc_epa_s runs it: on the flexible polytope store of epa.cuh in its compact
-// layout (the shared-memory words of a lane, here a host array with the kernel's lane stride) with the slim operands; a pair that
-// exceeds a compact capacity restarts on the big layout (a pool slot), and beyond that on the local-memory store, exactly like the
-// kernel.  flags[3] += pairs that restarted on the big layout, flags[2] = EPA calls.
+// The same as shim_contact_sm_sm, but EPA runs the way the tiered kernels run it: on the shared-memory polytope store of epa.cuh
+// (first tier: the words of one lane of a 64-thread CTA, here a host array with the kernel's lane stride; second tier: one lane of a
+// 32-thread CTA) with the slim operands; a pair that exceeds a capacity restarts on the next tier, and beyond the second one on the
+// local-memory store, exactly like the kernels.  flags[3] += pairs that restarted on the second tier, flags[2] = EPA calls.
 void shim_contact_sm_sm_compact(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_pairs, const uint32_t* pairs,
                                 const float* predictions, float* out, uint32_t* flags) {
     DevObjects o;
@@ -108,8 +117,10 @@ void shim_contact_sm_sm_compact(const ncb_objects* objs, const ncb_hull_library*
     o.qlimit = objs->query_limit;
     DevHulls H = hulls_from(lib);
     EpaState* last = new EpaState;
-    uint32_t* words = new uint32_t[EpaFlex::C_WORDS * 64];
-    uint32_t* slot = new uint32_t[EpaFlex::B_WORDS];
+    typedef EpaTier1<64> T1;
+    typedef EpaTier2<32> T2;
+    uint32_t* words1 = new uint32_t[T1::WORDS * 64];
+    uint32_t* words2 = new uint32_t[T2::WORDS * 32];
     for (uint64_t p = 0; p < n_pairs; ++p) {
         uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
         Shape a = load_shape(o, H, i1, o.type[i1]), b = load_shape(o, H, i2, o.type[i2]);
@@ -123,23 +134,21 @@ void shim_contact_sm_sm_compact(const ncb_objects* objs, const ncb_hull_library*
         int r = gjk_closest_points(ma, ga, mb, gb, prediction, dir, s, p1, p2, n);
         if (r == GJK_INTERSECTION) {
             flags[2]++;
-            EpaFlex e;
             SupportS sa = slim_support(ga), sb = slim_support(gb);
-            int st = EPA_DONE_FAIL;
-            for (int mode = 0; mode < 2; ++mode) {  // compact, then (restart) big
-                if (mode == 0)
-                    e.layout_compact(words + (p % 64), 64);  // any lane of the CTA
-                else
-                    e.layout_big(slot), flags[3]++;
-                uint32_t res_face;
-                st = epa_init_t<true>(e, ma, sa, mb, sb, s.dim, s.v, p1, p2, n, res_face);
-                while (st == EPA_CONTINUE) st = epa_step_t(e, ma, sa, mb, sb, res_face);
-                if (st == EPA_DONE_OK && res_face != EPA_RES_DIRECT) epa_result_from_face(e, res_face, p1, p2, n);
-                if (!(st == EPA_DONE_FAIL && e.overflow)) break;
+            T1 e1;
+            e1.base = words1 + (p % 64);  // any lane of the CTA
+            int st = run_tier(e1, ma, sa, mb, sb, s, p1, p2, n);
+            bool overflow = st == EPA_DONE_FAIL && e1.overflow, panicked = e1.panicked;
+            if (overflow) {
+                flags[3]++;
+                T2 e2;
+                e2.base = words2 + (p % 32);
+                st = run_tier(e2, ma, sa, mb, sb, s, p1, p2, n);
+                overflow = st == EPA_DONE_FAIL && e2.overflow, panicked = e2.panicked;
             }
             if (st == EPA_DONE_OK) {
                 r = GJK_CLOSEST_POINTS;
-            } else if (e.overflow) {  // last resort (k_cc_epa_big)
+            } else if (overflow) {  // last resort (k_cc_epa_big)
                 if (epa_closest_points(*last, ma, ga, mb, gb, s.dim, s.v, p1, p2, n))
                     r = GJK_CLOSEST_POINTS;
                 else {
@@ -148,7 +157,7 @@ void shim_contact_sm_sm_compact(const ncb_objects* objs, const ncb_hull_library*
                     r = GJK_NO_INTERSECTION;
                 }
             } else {
-                if (e.panicked) flags[1]++;
+                if (panicked) flags[1]++;
                 r = GJK_NO_INTERSECTION;
             }
         }
@@ -160,8 +169,8 @@ void shim_contact_sm_sm_compact(const ncb_objects* objs, const ncb_hull_library*
         }
     }
     delete last;
-    delete[] words;
-    delete[] slot;
+    delete[] words1;
+    delete[] words2;
 }
 
 // GJK work per convex pair: stats[3 k] = support-point evaluations (loop turns incl. the initial one), exit kind (GJK_*), simplex
