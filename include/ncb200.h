@@ -112,6 +112,20 @@ typedef struct ncb_contact {
     uint32_t pair; /* index into the pair array of the same call */
 } ncb_contact;
 
+/* query::ContactKinematic (query/contact/contact_kinematic.rs:57-66) of a contact, besides the two feature ids that ncb_contact
+ * carries: the tracked local points (local1 / local2, `approx.point`), the NeighborhoodGeometry of each side (geometry: 0 Point,
+ * 1 Line(dir), 2 Plane(dir); dir in the object's local frame, zero for Point) and the dilations (margin1 / margin2).  Together with
+ * ncb_contact this is what ContactManifold::push receives (contact_manifold.rs:165-171).  Produced on request (ncb_set_kinematics). */
+typedef struct ncb_kinematic {
+    float local1[3], local2[3];
+    float dir1[3], dir2[3];
+    float dilation1, dilation2;
+    uint32_t geometry1, geometry2;
+} ncb_kinematic;
+#define NCB_GEOMETRY_POINT 0u
+#define NCB_GEOMETRY_LINE 1u
+#define NCB_GEOMETRY_PLANE 2u
+
 typedef struct ncb_update_counts {
     uint32_t n_pairs;          /* broad-phase pairs (DBVTBroadPhase::num_interferences) */
     uint32_t n_contacts;       /* contacts over all manifolds */
@@ -142,6 +156,15 @@ int ncb_synchronize(ncb_ctx* ctx);
  * out of it skips a subtree and is counted here (cumulative over the context's life, plus the pair search of the last update /
  * ncb_broad_phase, which an update also reports in ncb_update_counts.stack_overflow).  The LBVH's depth bound (30 Morton bits + 32 tie-break bits) keeps both at 0; tests assert it. */
 int ncb_traversal_overflows(ncb_ctx* ctx, uint32_t* out);
+
+/* on != 0: fresh-world updates (ncb_world_update*, ncb_generate_contacts) also produce the ContactKinematic of every contact, in an
+ * array aligned with the contacts (ncb_world_fetch_kinematics).  Off by default (64 more bytes per contact).  The stepping world
+ * (ncb_sim_*) does not produce kinematics: the reference keeps the kinematic of a cached contact across updates, which would have to
+ * be stored with every entry of the persistent manifolds. */
+int ncb_set_kinematics(ncb_ctx* ctx, int on);
+/* The kinematics of the last update's / ncb_generate_contacts' contacts, same order as the contacts.  NCB_ERR_STATE if they were not
+ * requested before that call. */
+int ncb_world_fetch_kinematics(ncb_ctx* ctx, ncb_kinematic* out, uint32_t cap_contacts);
 
 /* ---- shapes and objects -------------------------------------------------------------------------------------- */
 /* ConvexHull tables (host pointers), copied to the device once. */

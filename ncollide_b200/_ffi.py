@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libncb200.so")
 
 EXPORTED_SYMBOLS = [
-    "ncb_version", "ncb_create", "ncb_destroy", "ncb_last_error", "ncb_set_stream", "ncb_get_stream", "ncb_synchronize", "ncb_traversal_overflows",
+    "ncb_version", "ncb_create", "ncb_destroy", "ncb_last_error", "ncb_set_stream", "ncb_get_stream", "ncb_synchronize", "ncb_traversal_overflows", "ncb_set_kinematics", "ncb_world_fetch_kinematics",
     "ncb_set_hulls", "ncb_set_objects", "ncb_set_positions", "ncb_set_positions_range", "ncb_compute_aabbs", "ncb_broad_phase", "ncb_generate_contacts",
     "ncb_world_update_device", "ncb_world_fetch", "ncb_world_update", "ncb_world_update_poses", "ncb_device_ptr", "ncb_world_update_stage", "ncb_world_update_sharded", "ncb_world_fetch_early",
     "ncb_profile_enable", "ncb_profile_get", "ncb_trimesh_create", "ncb_trimesh_destroy", "ncb_trimesh_ray_cast",
@@ -69,6 +69,11 @@ CONTACT_DTYPE = np.dtype(
      ("f1", np.uint32), ("f2", np.uint32), ("pair", np.uint32)]
 )
 assert CONTACT_DTYPE.itemsize == 52
+KINEMATIC_DTYPE = np.dtype(
+    [("local1", np.float32, 3), ("local2", np.float32, 3), ("dir1", np.float32, 3), ("dir2", np.float32, 3),
+     ("dil1", np.float32), ("dil2", np.float32), ("g1", np.uint32), ("g2", np.uint32)]
+)
+assert KINEMATIC_DTYPE.itemsize == 64
 
 _lib = None
 

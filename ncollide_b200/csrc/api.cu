@@ -114,12 +114,13 @@ int ncb_create(int device, ncb_ctx** out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_counters, sizeof(DevCounters));
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_snap, 2 * sizeof(DevCounters));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_snap, sizeof(DevCounters));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_snap_n, (1 + NCB_MAN_PARTS) * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_pairs, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming);
+    for (int k = 0; k <= NCB_MAN_PARTS && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->ev_snap[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = c->snap.reserve(1);
+    if (e == cudaSuccess) e = c->snap.reserve(1 + NCB_MAN_PARTS);
     if (e == cudaSuccess && !getenv("NCB_NO_SIDE_STREAM")) {
         e = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
@@ -159,7 +160,9 @@ void ncb_destroy(ncb_ctx* c) {
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_pairs) cudaEventDestroy(c->ev_pairs);
-    if (c->ev_snap) cudaEventDestroy(c->ev_snap);
+    for (int k = 0; k <= NCB_MAN_PARTS; ++k)
+        if (c->ev_snap[k]) cudaEventDestroy(c->ev_snap[k]);
+    if (c->h_snap_n) cudaFreeHost(c->h_snap_n);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->h_snap) cudaFreeHost(c->h_snap);
     c->snap.release();
@@ -426,6 +429,24 @@ extern "C++" uint32_t* trav_overflow_counter(ncb_ctx* ctx) {
     return ctx->trav_overflow.p;
 }
 
+int ncb_set_kinematics(ncb_ctx* ctx, int on) {
+    if (!ctx) return NCB_ERR_ARG;
+    ctx->want_kinematics = on != 0;
+    if (!on) ctx->have_kinematics = false;
+    return NCB_OK;
+}
+int ncb_world_fetch_kinematics(ncb_ctx* ctx, ncb_kinematic* out, uint32_t cap_contacts) {
+    if (!ctx || (cap_contacts && !out)) return NCB_ERR_ARG;
+    REQUIRE(ctx->have_kinematics, NCB_ERR_STATE, "ncb_world_fetch_kinematics: call ncb_set_kinematics(ctx, 1) before the update");
+    CK(cudaSetDevice(ctx->device));
+    uint32_t nc = ctx->last_n_contacts, w = nc < cap_contacts ? nc : cap_contacts;
+    if (w) {
+        CK(cudaMemcpyAsync(out, ctx->kinematics.p, sizeof(ncb_kinematic) * (size_t)w, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return nc > cap_contacts ? 1 : NCB_OK;
+}
+
 int ncb_traversal_overflows(ncb_ctx* ctx, uint32_t* out) {
     if (!ctx || !out) return NCB_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -546,6 +567,8 @@ int ncb_generate_contacts(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* pairs,
     CK(ctx->counters.reserve(1));
     size_t capc = cap_contacts ? cap_contacts : 1;
     CK(ctx->contacts.reserve(capc));
+    if (ctx->want_kinematics) CK(ctx->kinematics.reserve(capc));
+    ctx->have_kinematics = false;
     r = reset_counters(ctx);
     if (r) return r;
     CK(cudaMemcpyAsync(ctx->pairs_raw.p, pairs, 8 * (size_t)n_pairs, cudaMemcpyHostToDevice, s));
@@ -556,6 +579,8 @@ int ncb_generate_contacts(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* pairs,
     if (r) return r;
     uint32_t nc = ctx->last_counters.n_contacts;
     *n_contacts = nc;
+    ctx->last_n_contacts = nc < cap_contacts ? nc : cap_contacts;
+    ctx->have_kinematics = ctx->want_kinematics;
     uint32_t w = nc < cap_contacts ? nc : cap_contacts;
     if (out_contacts && w) CK(cudaMemcpyAsync(out_contacts, ctx->contacts.p, sizeof(ncb_contact) * (size_t)w, cudaMemcpyDeviceToHost, s));
     if (manifold_start) CK(cudaMemcpyAsync(manifold_start, ctx->manifold_start.p, 4 * (size_t)n_pairs, cudaMemcpyDeviceToHost, s));
@@ -586,6 +611,8 @@ static int update_after_aabbs(ncb_ctx* ctx, uint32_t q_begin, uint32_t q_end, ui
         int r = reserve_pairs(ctx, cap_pairs);
         if (r) return r;
         CK(ctx->contacts.reserve(cap_contacts));
+        if (ctx->want_kinematics) CK(ctx->kinematics.reserve(cap_contacts));
+        ctx->have_kinematics = false;
         r = reset_counters(ctx);
         if (r) return r;
         if (!ctx->timer_external || attempt > 0) timer_begin(ctx);
@@ -603,28 +630,34 @@ static int update_after_aabbs(ncb_ctx* ctx, uint32_t q_begin, uint32_t q_end, ui
         CK(launch_narrow_phase(ctx, dev_objects(ctx), ctx->pairs.p, nullptr, (uint32_t)cap_pairs, (uint32_t)cap_contacts));
         if (ctx->early.active) {
             // Everything of this update is enqueued.  While the narrow phase runs, the copy stream ships what is already
-            // final: the sorted pair list (+ algorithm per pair) once the pair sort is done, then the contacts written by
-            // the kernels that finished before the convex-convex EPA / manifold phases (counter snapshot in ctx->snap).
+            // final: the sorted pair list (+ algorithm per pair) once the pair sort is done, the contacts written by the
+            // kernels that finished before the convex-convex EPA / manifold phases (snapshot 0), then the contacts of each
+            // part of the manifold kernel while the next part computes (snapshots 1 .. NCB_MAN_PARTS); ncb_world_fetch is
+            // left with the per-pair manifold index.  Contact slots are allocated with one atomic counter, so what a
+            // snapshot covers is a contiguous, final prefix of the contact array.
             ncb_ctx::EarlyFetch& ef = ctx->early;
             ef.pairs_done = ef.contacts_done = 0;
             cudaStream_t cs = ctx->copy_stream;
             CK(cudaStreamWaitEvent(cs, ctx->ev_pairs, 0));
-            CK(cudaMemcpyAsync(&ctx->h_snap[0], ctx->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, cs));
+            CK(cudaMemcpyAsync(ctx->h_snap, ctx->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, cs));
             CK(cudaStreamSynchronize(cs));
-            uint32_t np = ctx->h_snap[0].n_pairs;
+            uint32_t np = ctx->h_snap->n_pairs;
             if (np <= cap_pairs) {
                 uint32_t wp = np < ef.cap_pairs ? np : ef.cap_pairs;
                 if (ef.pairs && wp) CK(cudaMemcpyAsync(ef.pairs, ctx->pairs.p, 8 * (size_t)wp, cudaMemcpyDeviceToHost, cs));
                 if (ef.algo && wp) CK(cudaMemcpyAsync(ef.algo, ctx->pair_algo.p, wp, cudaMemcpyDeviceToHost, cs));
                 ef.pairs_done = wp;
-                CK(cudaStreamWaitEvent(cs, ctx->ev_snap, 0));
-                CK(cudaMemcpyAsync(&ctx->h_snap[1], ctx->snap.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, cs));
-                CK(cudaStreamSynchronize(cs));
-                uint32_t n1 = ctx->h_snap[1].n_contacts;
-                if (n1 <= cap_contacts) {
-                    uint32_t wc = n1 < ef.cap_contacts ? n1 : ef.cap_contacts;
-                    if (ef.contacts && wc) CK(cudaMemcpyAsync(ef.contacts, ctx->contacts.p, sizeof(ncb_contact) * (size_t)wc, cudaMemcpyDeviceToHost, cs));
-                    ef.contacts_done = wc;
+                for (int k = 0; k <= NCB_MAN_PARTS; ++k) {
+                    CK(cudaStreamWaitEvent(cs, ctx->ev_snap[k], 0));
+                    CK(cudaMemcpyAsync(&ctx->h_snap_n[k], ctx->snap.p + k, sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+                    CK(cudaStreamSynchronize(cs));
+                    uint32_t nk = ctx->h_snap_n[k];
+                    if (nk > cap_contacts) break;  // the contact array overflowed: this attempt is repeated with a larger one
+                    uint32_t wc = nk < ef.cap_contacts ? nk : ef.cap_contacts;
+                    if (ef.contacts && wc > ef.contacts_done)
+                        CK(cudaMemcpyAsync(ef.contacts + ef.contacts_done, ctx->contacts.p + ef.contacts_done,
+                                           sizeof(ncb_contact) * (size_t)(wc - ef.contacts_done), cudaMemcpyDeviceToHost, cs));
+                    if (wc > ef.contacts_done) ef.contacts_done = wc;
                 }
             }
         }
@@ -645,6 +678,7 @@ static int update_after_aabbs(ncb_ctx* ctx, uint32_t q_begin, uint32_t q_end, ui
         if (!over) {
             ctx->last_n_pairs = c.n_pairs;
             ctx->last_n_contacts = c.n_contacts;
+            ctx->have_kinematics = ctx->want_kinematics;
             ctx->early.valid = ctx->early.active;
             ctx->early.active = false;
             return NCB_OK;

@@ -25,7 +25,7 @@ struct CapsulePre {
     float radius;
 };
 // returns false when the contact must be ignored (FeatureId::Unknown)
-NCB_HD bool capsule_preprocess(const CapsulePre& pp, V3& w1, V3& w2, V3 n, float& depth, uint32_t& f1, uint32_t& f2, bool is_first) {
+NCB_HD bool capsule_preprocess(const CapsulePre& pp, V3& w1, V3& w2, V3 n, float& depth, uint32_t& f1, uint32_t& f2, bool is_first, Kin* kin) {
     if (!pp.active) return true;
     uint32_t f = is_first ? f1 : f2, actual;
     uint32_t kind = FID_KIND(f);
@@ -39,10 +39,12 @@ NCB_HD bool capsule_preprocess(const CapsulePre& pp, V3& w1, V3& w2, V3 n, float
         return false;
     if (is_first) {
         f1 = actual;
+        if (kin) kin->dil1 = pp.radius;  // kinematic.set_dilation1
         w1 = w1 + n * pp.radius;
         depth += pp.radius;
     } else {
         f2 = actual;
+        if (kin) kin->dil2 = pp.radius;
         w2 = w2 - n * pp.radius;
         depth += pp.radius;
     }
@@ -51,10 +53,10 @@ NCB_HD bool capsule_preprocess(const CapsulePre& pp, V3& w1, V3& w2, V3 n, float
 // ContactManifold::push(contact, kinematic, tracking_pt, preprocessor1, preprocessor2) (contact_manifold.rs:165-181)
 template <bool P>
 NCB_HD void manifold_push_pp(ManifoldT<P>& mf, V3 w1, V3 w2, V3 n, float depth, uint32_t f1, uint32_t f2, V3 tracking_pt, const CapsulePre& pp1,
-                             const CapsulePre& pp2) {
-    if (!capsule_preprocess(pp1, w1, w2, n, depth, f1, f2, true)) return;
-    if (!capsule_preprocess(pp2, w1, w2, n, depth, f1, f2, false)) return;
-    manifold_push(mf, w1, w2, n, depth, f1, f2, tracking_pt);
+                             const CapsulePre& pp2, Kin* kin = nullptr) {
+    if (!capsule_preprocess(pp1, w1, w2, n, depth, f1, f2, true, kin)) return;
+    if (!capsule_preprocess(pp2, w1, w2, n, depth, f1, f2, false, kin)) return;
+    manifold_push(mf, w1, w2, n, depth, f1, f2, tracking_pt, kin);
 }
 
 // ---- Segment a = (0, -hh, 0), b = (0, hh, 0) as a ConvexPolyhedron (segment.rs, dim3) -----------------------------------------
@@ -165,7 +167,9 @@ NCB_HD void clip_flush_pp(ClipCtxT<P>& cc, const CapsulePre& pp1, const CapsuleP
         if (!feature_ok_for_manifold(*cc.m2, c.f2)) continue;
         float depth = -dot(cc.normal, c.w2 - c.w1);
         V3 local1 = iso_inv_point(*cc.ma, c.w1);
-        manifold_push_pp(*cc.mf, c.w1, c.w2, cc.normal, depth, c.f1, c.f2, local1, pp1, pp2);
+        Kin kin = kin_zero();
+        if (cc.mf->wants_kin()) kin = kin_from_features(*cc.m1, *cc.m2, *cc.ma, *cc.mb, c.w1, c.w2, c.f1, c.f2, local1);
+        manifold_push_pp(*cc.mf, c.w1, c.w2, cc.normal, depth, c.f1, c.f2, local1, pp1, pp2, &kin);
     }
     cc.n_buf = 0;
 }
@@ -185,6 +189,7 @@ __device__ __noinline__ bool capsule_convex_manifold(const Iso& ma, const CapOpe
     }
     ClipCtxT<P> cc;
     cc.ma = &ma;
+    cc.mb = &mb;
     cc.mf = &mf;
     cc.m1 = &m1;
     cc.m2 = &m2;
@@ -195,8 +200,12 @@ __device__ __noinline__ bool capsule_convex_manifold(const Iso& ma, const CapOpe
     bool spilled = cc.n_new != cc.n_buf;
     clip_flush_pp(cc, a.pre, b.pre);
     if (cc.n_new == 0) {
-        if (feature_ok_for_manifold(m1, m1.feature_id) && feature_ok_for_manifold(m2, m2.feature_id))
-            manifold_push_pp(mf, p1, p2, dir, depth, m1.feature_id, m2.feature_id, iso_inv_point(ma, p1), a.pre, b.pre);
+        if (feature_ok_for_manifold(m1, m1.feature_id) && feature_ok_for_manifold(m2, m2.feature_id)) {
+            V3 local1 = iso_inv_point(ma, p1);
+            Kin k = kin_zero();
+            if (mf.wants_kin()) k = kin_from_features(m1, m2, ma, mb, p1, p2, m1.feature_id, m2.feature_id, local1);
+            manifold_push_pp(mf, p1, p2, dir, depth, m1.feature_id, m2.feature_id, local1, a.pre, b.pre, &k);
+        }
     }
     return !spilled;
 }
@@ -230,10 +239,12 @@ NCB_HD void gen_ball_segment(const Iso& mball, float radius, const Iso& mseg, fl
     }
     if (depth >= -prediction) {
         V3 world1 = ball_center + normal * radius;
+        Kin k = kin_zero();
+        if (mf.wants_kin()) k = kin_ball_polyhedron(radius, mseg, world2, normal, f2, v3(0.f, -hh, 0.f), v3(0.f, hh, 0.f), flip);  // Segment::edge = (a, b)
         if (!flip)
-            manifold_push_pp(mf, world1, world2, normal, depth, FACE0, f2, v3(0.f, 0.f, 0.f), none, seg_pre);
+            manifold_push_pp(mf, world1, world2, normal, depth, FACE0, f2, v3(0.f, 0.f, 0.f), none, seg_pre, &k);
         else
-            manifold_push_pp(mf, world2, world1, -normal, depth, f2, FACE0, v3(0.f, 0.f, 0.f), seg_pre, none);
+            manifold_push_pp(mf, world2, world1, -normal, depth, f2, FACE0, v3(0.f, 0.f, 0.f), seg_pre, none, &k);
     }
 }
 // PlaneConvexPolyhedronManifoldGenerator with the capsule's segment (plane_convex_polyhedron_manifold_generator.rs:29-81)
@@ -251,10 +262,18 @@ NCB_HD void gen_plane_segment(const Iso& mplane, V3 plane_n, const Iso& mseg, fl
             V3 world1 = world2 + (-n * dist);
             V3 local2 = iso_inv_point(mseg, world2);
             uint32_t f2 = feat.vid[i];
+            Kin k = kin_zero();
+            if (mf.wants_kin()) {
+                V3 local1 = iso_inv_point(mplane, world1);
+                if (!flip)
+                    k.local1 = local1, k.g1 = G_PLANE, k.dir1 = plane_n, k.local2 = local2;
+                else
+                    k.local1 = local2, k.local2 = local1, k.g2 = G_PLANE, k.dir2 = plane_n;
+            }
             if (!flip)
-                manifold_push_pp(mf, world1, world2, n, -dist, FACE0, f2, local2, none, seg_pre);
+                manifold_push_pp(mf, world1, world2, n, -dist, FACE0, f2, local2, none, seg_pre, &k);
             else
-                manifold_push_pp(mf, world2, world1, -n, -dist, f2, FACE0, local2, seg_pre, none);
+                manifold_push_pp(mf, world2, world1, -n, -dist, f2, FACE0, local2, seg_pre, none, &k);
         }
     }
 }

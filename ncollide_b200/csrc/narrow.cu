@@ -279,6 +279,22 @@ struct ManifoldContact {
     float depth;
     uint32_t f1, f2;
 };
+// ContactKinematic of a contact (query/contact/contact_kinematic.rs:57-66) besides its two feature ids: the tracked local points,
+// the NeighborhoodGeometry of each side (g: 0 Point, 1 Line(dir), 2 Plane(dir)) and the dilations.  Only produced when the caller
+// asked for it (ncb_set_kinematics): a fresh manifold then carries a side array, one entry per contact slot.
+enum { G_POINT = 0, G_LINE = 1, G_PLANE = 2 };
+struct Kin {
+    V3 local1, local2, dir1, dir2;
+    float dil1, dil2;
+    uint32_t g1, g2;
+};
+NCB_HD Kin kin_zero() {
+    Kin k;
+    k.local1 = k.local2 = k.dir1 = k.dir2 = v3(0.f, 0.f, 0.f);
+    k.dil1 = k.dil2 = 0.f;
+    k.g1 = k.g2 = G_POINT;
+    return k;
+}
 // P = false: a fresh manifold (one-shot update).  P = true: the persistent manifold of a stepping world — the reference's
 // Slab<(TrackedContact, usize)> + DistanceBased cache with persistence 1 (contact_manifold.rs:14-236): entries are kept in
 // CACHE order; `slot` is the slab key (free slots are reused LIFO), `live` = "remaining == persistence", `id` = insertion
@@ -289,6 +305,8 @@ struct ManifoldT {
     V3 track[MANIFOLD_MAX];
     int n;
     int deepest;  // >= 0; set to -1 when a contact had to be dropped (capacity), reported through the overflow counter
+    Kin* kin = nullptr;  // nullptr, or MANIFOLD_MAX entries aligned with c[] (kinematics wanted)
+    NCB_HD bool wants_kin() const { return kin != nullptr; }
 };
 template <>
 struct ManifoldT<true> {
@@ -301,12 +319,15 @@ struct ManifoldT<true> {
     int nfree, slab_len, had_live;
     uint32_t next_id;
     bool overflow;
+    // the stepping world does not keep kinematics (they would have to live in every cache entry): documented in ncb200.h
+    NCB_HD bool wants_kin() const { return false; }
 };
 typedef ManifoldT<false> Manifold;
 typedef ManifoldT<true> PManifold;
 
 template <bool P>
-NCB_HD void manifold_push(ManifoldT<P>& mf, V3 w1, V3 w2, V3 n, float depth, uint32_t f1, uint32_t f2, V3 tracking_pt) {
+NCB_HD void manifold_push(ManifoldT<P>& mf, V3 w1, V3 w2, V3 n, float depth, uint32_t f1, uint32_t f2, V3 tracking_pt,
+                          const Kin* kin = nullptr) {
     const float threshold = 0.02f;
     int closest = mf.n;
     float closest_dist = threshold * threshold;
@@ -335,6 +356,7 @@ NCB_HD void manifold_push(ManifoldT<P>& mf, V3 w1, V3 w2, V3 n, float depth, uin
                 ManifoldContact& c = mf.c[mf.n];
                 c.w1 = w1, c.w2 = w2, c.n = n, c.depth = depth, c.f1 = f1, c.f2 = f2;
                 mf.track[mf.n] = tracking_pt;
+                if (mf.kin && kin) mf.kin[mf.n] = *kin;
                 mf.n++;
             } else {
                 mf.deepest = -1;
@@ -350,6 +372,7 @@ NCB_HD void manifold_push(ManifoldT<P>& mf, V3 w1, V3 w2, V3 n, float depth, uin
             }
         } else {
             if (depth <= c.depth) return;
+            if (mf.kin && kin) mf.kin[closest] = *kin;  // c.0.kinematic = kinematic (contact_manifold.rs:229)
         }
         c.w1 = w1, c.w2 = w2, c.n = n, c.depth = depth, c.f1 = f1, c.f2 = f2;
         mf.track[closest] = tracking_pt;
@@ -366,7 +389,9 @@ NCB_HD void gen_ball_ball(const Iso& ma, float r1, const Iso& mb, float r2, floa
     float sre = sum_radius + prediction;
     if (d2 < sre * sre) {
         V3 normal = d2 != 0.f ? normalize(delta) : v3(1.f, 0.f, 0.f);
-        manifold_push(mf, c1 + normal * r1, c2 + normal * (-r2), normal, sum_radius - sqrtf(d2), FACE0, FACE0, v3(0.f, 0.f, 0.f));
+        Kin k = kin_zero();  // both sides (Face(0), origin, Point), dilated by the radii (ball_ball_manifold_generator.rs:46-58)
+        k.dil1 = r1, k.dil2 = r2;
+        manifold_push(mf, c1 + normal * r1, c2 + normal * (-r2), normal, sum_radius - sqrtf(d2), FACE0, FACE0, v3(0.f, 0.f, 0.f), &k);
     }
 }
 template <bool P>
@@ -378,10 +403,18 @@ NCB_HD void gen_plane_ball(const Iso& m1, V3 plane_n, const Iso& m2, float radiu
     if (depth > -prediction) {
         V3 world1 = bc + n * (-dist);
         V3 world2 = bc + n * (-radius);
+        Kin k = kin_zero();  // plane side (Face(0), local1, Plane(plane.normal)), ball side (Face(0), origin, Point) + dilation (:53-75)
+        if (mf.wants_kin()) {
+            V3 local1 = iso_inv_point(m1, world1);
+            if (!flip)
+                k.local1 = local1, k.g1 = G_PLANE, k.dir1 = plane_n, k.dil2 = radius;
+            else
+                k.local2 = local1, k.g2 = G_PLANE, k.dir2 = plane_n, k.dil1 = radius;
+        }
         if (!flip)
-            manifold_push(mf, world1, world2, n, depth, FACE0, FACE0, v3(0.f, 0.f, 0.f));
+            manifold_push(mf, world1, world2, n, depth, FACE0, FACE0, v3(0.f, 0.f, 0.f), &k);
         else
-            manifold_push(mf, world2, world1, -n, depth, FACE0, FACE0, v3(0.f, 0.f, 0.f));
+            manifold_push(mf, world2, world1, -n, depth, FACE0, FACE0, v3(0.f, 0.f, 0.f), &k);
     }
 }
 template <bool P>
@@ -397,10 +430,18 @@ __device__ __noinline__ void gen_plane_convex(const Iso& m1, V3 plane_n, const I
             V3 world1 = world2 + (-n * dist);
             V3 local2 = iso_inv_point(m2, world2);
             uint32_t f2 = feat.vid[i];
+            Kin k = kin_zero();  // plane side (Face(0), local1, Plane(plane.normal)), polyhedron side (vertex id, local2, Point) (:57-72)
+            if (mf.wants_kin()) {
+                V3 local1 = iso_inv_point(m1, world1);
+                if (!flip)
+                    k.local1 = local1, k.g1 = G_PLANE, k.dir1 = plane_n, k.local2 = local2;
+                else
+                    k.local1 = local2, k.local2 = local1, k.g2 = G_PLANE, k.dir2 = plane_n;
+            }
             if (!flip)
-                manifold_push(mf, world1, world2, n, -dist, FACE0, f2, local2);
+                manifold_push(mf, world1, world2, n, -dist, FACE0, f2, local2, &k);
             else
-                manifold_push(mf, world2, world1, -n, -dist, f2, FACE0, local2);
+                manifold_push(mf, world2, world1, -n, -dist, f2, FACE0, local2, &k);
         }
     }
 }
@@ -483,9 +524,41 @@ NCB_HD uint32_t hull_project_feature(const HullView& H, const Iso& m_in, V3 poin
 }
 
 // (m1, ball) (m2, convex polyhedron)
+// ConvexPolyhedron::edge(id) in local coordinates (cuboid.rs:163-183, convex.rs:430-441)
+NCB_HD void shape_edge(const Shape& cp, uint32_t f, V3& p1, V3& p2) {
+    uint32_t eid = FID_ID(f);
+    if (cp.type == NCB_SHAPE_CUBOID) {
+        uint32_t edge_i = eid & 3u, vertex_i = eid >> 2;
+        V3 res = cp.he;
+        for (uint32_t i = 0; i < 3; ++i)
+            if (i != edge_i && (vertex_i & (1u << i))) vset(res, (int)i, -vget(res, (int)i));
+        p1 = res;
+        vset(res, (int)edge_i, -vget(res, (int)edge_i));
+        p2 = res;
+    } else {
+        p1 = cp.hull.pt(__ldg(cp.hull.edge_vertices + 2 * eid)), p2 = cp.hull.pt(__ldg(cp.hull.edge_vertices + 2 * eid + 1));
+    }
+}
+// kinematic of a ball x polyhedron contact (ball_convex_polyhedron_manifold_generator.rs:76-114): the ball side is (Face(0), origin,
+// Point) dilated by the radius; the polyhedron side is local2 with the geometry of feature f2 (edge end points e0, e1 in local space)
+NCB_HD Kin kin_ball_polyhedron(float radius, const Iso& mcp, V3 world2, V3 normal, uint32_t f2, V3 e0, V3 e1, bool flip) {
+    Kin k = kin_zero();
+    V3 local2 = iso_inv_point(mcp, world2);
+    uint32_t g2 = G_POINT;
+    V3 d2 = v3(0.f, 0.f, 0.f);
+    if (FID_KIND(f2) == NCB_FEATURE_FACE)
+        g2 = G_PLANE, d2 = iso_inv_vec(mcp, -normal);
+    else if (FID_KIND(f2) == NCB_FEATURE_EDGE)
+        g2 = G_LINE, d2 = normalize(e1 - e0);
+    if (!flip)
+        k.dil1 = radius, k.local2 = local2, k.g2 = g2, k.dir2 = d2;
+    else
+        k.dil2 = radius, k.local1 = local2, k.g1 = g2, k.dir1 = d2;
+    return k;
+}
 template <bool P>
-NCB_HD void gen_ball_convex_finish(V3 ball_center, float radius, const Shape& cp, bool inside, V3 world2, uint32_t f2, float prediction,
-                                   bool flip, ManifoldT<P>& mf) {
+NCB_HD void gen_ball_convex_finish(V3 ball_center, float radius, const Shape& cp, const Iso& mcp, bool inside, V3 world2, uint32_t f2,
+                                   float prediction, bool flip, ManifoldT<P>& mf) {
     V3 dpt = world2 - ball_center;
     float depth, dist;
     V3 normal, dir;
@@ -504,10 +577,16 @@ NCB_HD void gen_ball_convex_finish(V3 ball_center, float radius, const Shape& cp
     }
     if (depth >= -prediction) {
         V3 world1 = ball_center + normal * radius;
+        Kin k = kin_zero();
+        if (mf.wants_kin()) {
+            V3 e0 = v3(0.f, 0.f, 0.f), e1 = e0;
+            if (FID_KIND(f2) == NCB_FEATURE_EDGE) shape_edge(cp, f2, e0, e1);
+            k = kin_ball_polyhedron(radius, mcp, world2, normal, f2, e0, e1, flip);
+        }
         if (!flip)
-            manifold_push(mf, world1, world2, normal, depth, FACE0, f2, v3(0.f, 0.f, 0.f));
+            manifold_push(mf, world1, world2, normal, depth, FACE0, f2, v3(0.f, 0.f, 0.f), &k);
         else
-            manifold_push(mf, world2, world1, -normal, depth, f2, FACE0, v3(0.f, 0.f, 0.f));
+            manifold_push(mf, world2, world1, -normal, depth, f2, FACE0, v3(0.f, 0.f, 0.f), &k);
     }
 }
 
@@ -589,6 +668,34 @@ NCB_HD bool feature_ok_for_manifold(const Feature& ft, uint32_t f) {
     return false;
 }
 
+// NeighborhoodGeometry of feature f of the polygonal feature ft in the local frame of m (add_contact_to_manifold,
+// convex_polygonal_feature3.rs:356-397); f passed feature_ok_for_manifold
+NCB_HD void feature_geometry(const Feature& ft, uint32_t f, const Iso& m, uint32_t& g, V3& dir) {
+    g = G_POINT, dir = v3(0.f, 0.f, 0.f);
+    uint32_t kind = FID_KIND(f);
+    if (kind == NCB_FEATURE_FACE) {
+        g = G_PLANE, dir = iso_inv_vec(m, ft.normal);
+    } else if (kind == NCB_FEATURE_EDGE) {
+        for (int i1 = 0; i1 < ft.nv; ++i1) {
+            if (i1 < ft.ne && ft.eid[i1] == f) {
+                int i2 = (i1 + 1) % ft.nv;
+                V3 d = v3(0.f, 0.f, 0.f);
+                unit_try_new(ft.v[i2] - ft.v[i1], NCB_EPS, d);
+                g = G_LINE, dir = iso_inv_vec(m, d);
+                return;
+            }
+        }
+    }
+}
+NCB_HD Kin kin_from_features(const Feature& m1, const Feature& m2, const Iso& ma, const Iso& mb, V3 w1, V3 w2, uint32_t f1, uint32_t f2, V3 local1) {
+    Kin k = kin_zero();
+    k.local1 = local1;
+    k.local2 = iso_inv_point(mb, w2);
+    feature_geometry(m1, f1, ma, k.g1, k.dir1);
+    feature_geometry(m2, f2, mb, k.g2, k.dir2);
+    return k;
+}
+
 // Candidates found by clip() are buffered and handed to the manifold afterwards, like the reference's `new_contacts`
 // Vec (convex_polyhedron_convex_polyhedron_manifold_generator.rs:147-161).  Besides mirroring the reference, this keeps
 // the (rare, lane-dependent) manifold work out of clip's nested loops so that lanes stay converged in both parts.
@@ -599,7 +706,7 @@ struct ClipCand {
 };
 template <bool P>
 struct ClipCtxT {
-    const Iso* ma;
+    const Iso *ma, *mb;
     ManifoldT<P>* mf;
     const Feature *m1, *m2;
     V3 normal;
@@ -615,7 +722,9 @@ NCB_HD void clip_flush(ClipCtxT<P>& cc) {
         if (!feature_ok_for_manifold(*cc.m2, c.f2)) continue;
         float depth = -dot(cc.normal, c.w2 - c.w1);  // Contact::new_wo_depth
         V3 local1 = iso_inv_point(*cc.ma, c.w1);
-        manifold_push(*cc.mf, c.w1, c.w2, cc.normal, depth, c.f1, c.f2, local1);
+        Kin kin = kin_zero();
+        if (cc.mf->wants_kin()) kin = kin_from_features(*cc.m1, *cc.m2, *cc.ma, *cc.mb, c.w1, c.w2, c.f1, c.f2, local1);
+        manifold_push(*cc.mf, c.w1, c.w2, cc.normal, depth, c.f1, c.f2, local1, &kin);
     }
     cc.n_buf = 0;
 }
@@ -716,6 +825,7 @@ __device__ __noinline__ void convex_convex_manifold(const Iso& ma, const Shape& 
     }
     ClipCtxT<P> cc;
     cc.ma = &ma;
+    cc.mb = &mb;
     cc.mf = &mf;
     cc.m1 = &m1;
     cc.m2 = &m2;
@@ -725,8 +835,12 @@ __device__ __noinline__ void convex_convex_manifold(const Iso& ma, const Shape& 
     clip(m1, m2, dir, linear, cc);
     clip_flush(cc);
     if (cc.n_new == 0) {
-        if (feature_ok_for_manifold(m1, m1.feature_id) && feature_ok_for_manifold(m2, m2.feature_id))
-            manifold_push(mf, p1, p2, dir, depth, m1.feature_id, m2.feature_id, iso_inv_point(ma, p1));
+        if (feature_ok_for_manifold(m1, m1.feature_id) && feature_ok_for_manifold(m2, m2.feature_id)) {
+            V3 local1 = iso_inv_point(ma, p1);
+            Kin k = kin_zero();
+            if (mf.wants_kin()) k = kin_from_features(m1, m2, ma, mb, p1, p2, m1.feature_id, m2.feature_id, local1);
+            manifold_push(mf, p1, p2, dir, depth, m1.feature_id, m2.feature_id, local1, &k);
+        }
     }
 }
 
@@ -734,7 +848,7 @@ __device__ __noinline__ void convex_convex_manifold(const Iso& ma, const Shape& 
 // ---- result write-out: warp-aggregated allocation of contact slots --------------------------------------------
 NCB_HD void write_manifold(const Manifold& mf, bool valid, uint32_t pair_slot, uint32_t out_index, ncb_contact* __restrict__ contacts,
                            uint32_t cap_contacts, uint32_t* __restrict__ manifold_start, uint8_t* __restrict__ manifold_count,
-                           DevCounters* cnt) {
+                           DevCounters* cnt, ncb_kinematic* __restrict__ kin_out = nullptr) {
     // all 32 lanes call this (valid = false for idle lanes)
     if (valid && mf.deepest < 0) atomicAdd(&cnt->epa_overflow, 1u);  // more than MANIFOLD_MAX distinct contacts: never silent
     uint32_t n = valid ? (uint32_t)mf.n : 0u;
@@ -768,6 +882,17 @@ NCB_HD void write_manifold(const Manifold& mf, bool valid, uint32_t pair_slot, u
         o.f1 = c.f1, o.f2 = c.f2;
         o.pair = out_index;
         contacts[dst] = o;
+        if (kin_out && mf.kin) {
+            const Kin& q = mf.kin[k];
+            ncb_kinematic w;
+            w.local1[0] = q.local1.x, w.local1[1] = q.local1.y, w.local1[2] = q.local1.z;
+            w.local2[0] = q.local2.x, w.local2[1] = q.local2.y, w.local2[2] = q.local2.z;
+            w.dir1[0] = q.dir1.x, w.dir1[1] = q.dir1.y, w.dir1[2] = q.dir1.z;
+            w.dir2[0] = q.dir2.x, w.dir2[1] = q.dir2.y, w.dir2[2] = q.dir2.z;
+            w.dilation1 = q.dil1, w.dilation2 = q.dil2;
+            w.geometry1 = q.g1, w.geometry2 = q.g2;
+            kin_out[dst] = w;
+        }
     }
 }
 
@@ -863,6 +988,7 @@ struct NarrowArgs {
     const uint2* pairs;
     const uint32_t* pair_index;  // optional: original index of each sorted pair
     ncb_contact* contacts;
+    ncb_kinematic* kin_out;  // nullptr: kinematics not wanted (ncb_set_kinematics)
     uint32_t cap_contacts;
     uint32_t* manifold_start;
     uint8_t* manifold_count;
@@ -872,6 +998,7 @@ struct NarrowArgs {
     uint32_t* epa_queue;   // EPA_REC_WORDS per record
     uint32_t* cp_queue;    // CP_REC_WORDS per record
     int epa_refill_min;    // idle lanes needed before a warp of k_cc_epa_s refills (batched initialisation)
+    int man_part, man_parts;  // k_cc_manifold walks part man_part of man_parts equal parts of the manifold queue
     uint32_t* epa_long;    // [0, cap_pairs): EPA-queue indices tier 1 deferred to tier 2; [cap_pairs, 2 cap_pairs): tier 2 to the last resort
 };
 
@@ -1181,8 +1308,16 @@ __global__ void __launch_bounds__(128, NCB_MAN_MINBLOCKS) k_cc_manifold(NarrowAr
     const int KEY = CCQ;
     uint32_t seg_begin = A.cnt->key_start[KEY];
     uint32_t seg_end = A.cnt->cp_cursor[KEY];
+    if (A.man_parts > 1) {
+        uint32_t len = seg_end - seg_begin, per = (len + A.man_parts - 1) / A.man_parts;
+        uint32_t b = seg_begin + min(len, per * (uint32_t)A.man_part);
+        seg_end = seg_begin + min(len, per * (uint32_t)(A.man_part + 1));
+        seg_begin = b;
+    }
     uint32_t stride = gridDim.x * blockDim.x;
     ManifoldT<PS> mf;
+    Kin kin_side[PS ? 1 : MANIFOLD_MAX];  // only touched when kinematics are wanted
+    if constexpr (!PS) mf.kin = A.kin_out ? kin_side : nullptr;
     for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
         uint32_t w = base + threadIdx.x;
         bool valid = w < seg_end;
@@ -1209,7 +1344,7 @@ __global__ void __launch_bounds__(128, NCB_MAN_MINBLOCKS) k_cc_manifold(NarrowAr
         if constexpr (PS) {
             if (valid) pm_store(A.ps, out_index, mf, i1, i2);
         } else {
-            write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+            write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt, A.kin_out);
         }
     }
 }
@@ -1222,6 +1357,8 @@ __global__ void __launch_bounds__(128) k_narrow(NarrowArgs A) {
     uint32_t stride = gridDim.x * blockDim.x;
     // local-memory working set, only instantiated for the keys that need it
     ManifoldT<PS> mf;
+    Kin kin_side[PS ? 1 : MANIFOLD_MAX];  // only touched when kinematics are wanted
+    if constexpr (!PS) mf.kin = A.kin_out ? kin_side : nullptr;
     for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
         uint32_t p = base + threadIdx.x;
         bool valid = p < seg_end;
@@ -1263,7 +1400,7 @@ __global__ void __launch_bounds__(128) k_narrow(NarrowArgs A) {
                 V3 world2;
                 uint32_t f2;
                 cuboid_project_point_with_feature(cp.he, mcp, mball.t, inside, world2, f2);
-                gen_ball_convex_finish(mball.t, ball.radius, cp, inside, world2, f2, linear, flip, mf);
+                gen_ball_convex_finish(mball.t, ball.radius, cp, mcp, inside, world2, f2, linear, flip, mf);
             } else if (KEY == K_BALL_HULL) {
                 Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
                 bool flip = t1 != NCB_SHAPE_BALL;
@@ -1275,7 +1412,7 @@ __global__ void __launch_bounds__(128) k_narrow(NarrowArgs A) {
                 V3 world2;
                 if (hull_project_gjk(u, mball.t, bh_simplex, world2) == GJK_CLOSEST_POINTS) {
                     uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, false, world2, A.one_degree_cs);
-                    gen_ball_convex_finish(mball.t, ball.radius, cp, false, world2, f2, linear, flip, mf);
+                    gen_ball_convex_finish(mball.t, ball.radius, cp, mcp, false, world2, f2, linear, flip, mf);
                 } else {
                     deferred = true;  // ball centre inside the hull: EPA, in k_bh_epa
                 }
@@ -1298,7 +1435,7 @@ __global__ void __launch_bounds__(128) k_narrow(NarrowArgs A) {
         if constexpr (PS) {
             if (valid && !deferred) pm_store(A.ps, out_index, mf, i1, i2);  // deferred pairs are loaded again by k_bh_epa
         } else {
-            write_manifold(mf, valid && !deferred, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+            write_manifold(mf, valid && !deferred, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt, A.kin_out);
         }
     }
 }
@@ -1311,6 +1448,8 @@ __global__ void __launch_bounds__(64) k_bh_epa(NarrowArgs A) {
     uint32_t stride = gridDim.x * blockDim.x;
     EpaState e;
     ManifoldT<PS> mf;
+    Kin kin_side[PS ? 1 : MANIFOLD_MAX];  // only touched when kinematics are wanted
+    if constexpr (!PS) mf.kin = A.kin_out ? kin_side : nullptr;
     for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
         uint32_t w = base + threadIdx.x;
         bool valid = w < seg_end;
@@ -1345,13 +1484,13 @@ __global__ void __launch_bounds__(64) k_bh_epa(NarrowArgs A) {
                 world2 = mball.t;
             }
             uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, true, world2, A.one_degree_cs);
-            gen_ball_convex_finish(mball.t, ball.radius, cp, true, world2, f2, linear, flip, mf);
+            gen_ball_convex_finish(mball.t, ball.radius, cp, mcp, true, world2, f2, linear, flip, mf);
         }
         uint32_t out_index = valid ? (A.pair_index ? __ldg(&A.pair_index[p]) : p) : 0;
         if constexpr (PS) {
             if (valid) pm_store(A.ps, out_index, mf, h1, h2);
         } else {
-            write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+            write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt, A.kin_out);
         }
     }
 }
@@ -1376,6 +1515,8 @@ __global__ void __launch_bounds__(64) k_capsule(NarrowArgs A) {
     uint32_t stride = gridDim.x * blockDim.x;
     EpaState e;
     ManifoldT<PS> mf;
+    Kin kin_side[PS ? 1 : MANIFOLD_MAX];  // only touched when kinematics are wanted
+    if constexpr (!PS) mf.kin = A.kin_out ? kin_side : nullptr;
     for (uint32_t base = seg_begin + blockIdx.x * blockDim.x; base < seg_end; base += stride) {
         uint32_t p = base + threadIdx.x;
         bool valid = p < seg_end;
@@ -1387,7 +1528,7 @@ __global__ void __launch_bounds__(64) k_capsule(NarrowArgs A) {
             out_index = A.pair_index ? __ldg(&A.pair_index[p]) : p;
             capsule_pair<PS>(A.o, A.H, A.ps, out_index, e, mf, pr.x, pr.y, &A.cnt->epa_overflow, &A.cnt->ref_panics);
         }
-        if constexpr (!PS) write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt);
+        if constexpr (!PS) write_manifold(mf, valid, p, out_index, A.contacts, A.cap_contacts, A.manifold_start, A.manifold_count, A.cnt, A.kin_out);
     }
 }
 
@@ -1402,11 +1543,13 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     A.pairs = pairs;
     A.pair_index = pair_index;
     A.contacts = c->contacts.p;
+    A.kin_out = (!PS && c->want_kinematics) ? c->kinematics.p : nullptr;
     A.cap_contacts = cap_contacts;
     A.manifold_start = c->manifold_start.p;
     A.manifold_count = c->manifold_count.p;
     A.cnt = c->counters.p;
     A.cap_pairs = cap_pairs;
+    A.man_part = 0, A.man_parts = 1;
     static int refill_min = getenv("NCB_EPA_REFILL") ? atoi(getenv("NCB_EPA_REFILL")) : 16;
     A.epa_refill_min = refill_min;
     A.epa_queue = c->epa_queue.p;
@@ -1448,8 +1591,8 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
     const bool early = !PS && c->early.active;
     if (early) {
         if (c->side_stream) cudaStreamWaitEvent(s, c->ev_join, 0);
-        cudaMemcpyAsync(c->snap.p, c->counters.p, sizeof(DevCounters), cudaMemcpyDeviceToDevice, s);
-        cudaEventRecord(c->ev_snap, s);
+        cudaMemcpyAsync(c->snap.p, &c->counters.p->n_contacts, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
+        cudaEventRecord(c->ev_snap[0], s);
     }
     static int epas_bpsm = getenv("NCB_EPAS_BPSM") ? atoi(getenv("NCB_EPAS_BPSM")) : NCB_EPAS_MINBLOCKS;
     {
@@ -1466,8 +1609,21 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
         k_cc_epa_big<PS><<<sm * epa_bpsm, 64, 0, s>>>(A);  // last resort, normally an empty queue
     }
     timer_mark(c, "cc_epa", 3);
-    k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
-    timer_mark(c, "cc_manifold", 1);
+    if (early) {
+        // the manifold queue in NCB_MAN_PARTS parts, a snapshot of the contact counter after each: the copy stream ships the
+        // contacts of a finished part while the next one computes (api.cu, update_after_aabbs)
+        for (int part = 0; part < NCB_MAN_PARTS; ++part) {
+            A.man_part = part, A.man_parts = NCB_MAN_PARTS;
+            k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
+            cudaMemcpyAsync(c->snap.p + 1 + part, &c->counters.p->n_contacts, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
+            cudaEventRecord(c->ev_snap[1 + part], s);
+        }
+        timer_mark(c, "cc_manifold", NCB_MAN_PARTS);
+    } else {
+        A.man_part = 0, A.man_parts = 1;
+        k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
+        timer_mark(c, "cc_manifold", 1);
+    }
     if (!early && c->side_stream) cudaStreamWaitEvent(s, c->ev_join, 0);  // device-only updates: the side chain may run to the end
     timer_mark(c, "narrow_other_join", 7);
     return cudaGetLastError();

@@ -142,6 +142,10 @@ struct PersistArgs {
 };
 
 // Scratch of the spatial shard selection (broad.cu)
+// The convex-convex manifold kernel runs in this many parts when results are shipped to the host while the update runs
+// (ncb_world_update / ncb_world_fetch_early): the contacts of part k leave while part k + 1 computes.
+#define NCB_MAN_PARTS 4
+
 #define SHARD_BINS 1024
 #define SHARD_MAX_RANKS 16
 struct ShardScratch {
@@ -238,6 +242,8 @@ struct ncb_ctx {
     ncb::DevBuf<ncb::DevCounters> counters;
     // narrow phase
     ncb::DevBuf<ncb_contact> contacts;
+    ncb::DevBuf<ncb_kinematic> kinematics;       // aligned with contacts; only with want_kinematics (ncb_set_kinematics)
+    bool want_kinematics = false, have_kinematics = false;
     ncb::DevBuf<uint32_t> manifold_start;
     ncb::DevBuf<uint8_t> manifold_count;
     ncb::DevBuf<uint32_t> pair_index;
@@ -254,9 +260,13 @@ struct ncb_ctx {
     ncb::DevCounters* h_counters = nullptr;  // pinned
     // overlapped result fetch of ncb_world_update (api.cu): copy stream, events, counter snapshots
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_pairs = nullptr, ev_snap = nullptr, ev_copy = nullptr;
-    ncb::DevBuf<ncb::DevCounters> snap;      // device copy of the counters taken before the convex-convex manifold kernels
-    ncb::DevCounters* h_snap = nullptr;      // pinned, 2 entries
+    cudaEvent_t ev_pairs = nullptr, ev_copy = nullptr;
+    // counter snapshots of an update that ships its results while it runs: [0] before the convex-convex EPA / manifold phases
+    // (everything the other kernels wrote is final), [1 .. NCB_MAN_PARTS] after each part of the manifold kernel
+    cudaEvent_t ev_snap[1 + NCB_MAN_PARTS] = {};
+    ncb::DevBuf<uint32_t> snap;              // n_contacts per snapshot (device)
+    ncb::DevCounters* h_snap = nullptr;      // pinned: [0] the counters after the pair sort; h_snap_n: the snapshots above
+    uint32_t* h_snap_n = nullptr;
     struct EarlyFetch {
         bool active = false;  // armed for the next update
         bool valid = false;   // the last update filled pairs_done / contacts_done

@@ -104,6 +104,17 @@ class Context:
     def synchronize(self):
         self.check(self.lib.ncb_synchronize(self.h), "ncb_synchronize")
 
+    def set_kinematics(self, on=True):
+        """Ask fresh-world updates / generate_contacts for the ContactKinematic of every contact (``fetch_kinematics``)."""
+        self.check(self.lib.ncb_set_kinematics(self.h, C.c_int(1 if on else 0)), "ncb_set_kinematics")
+
+    def fetch_kinematics(self, n_contacts):
+        """ContactKinematic records (local1, local2, NeighborhoodGeometry per side, dilations) aligned with the contacts of the last
+        update / generate_contacts call."""
+        out = np.zeros(n_contacts, dtype=_ffi.KINEMATIC_DTYPE)
+        self.check(self.lib.ncb_world_fetch_kinematics(self.h, ptr(out), C.c_uint32(n_contacts)), "ncb_world_fetch_kinematics")
+        return out
+
     def traversal_overflows(self):
         """Query / ray BVH walks that ran out of their fixed stack since the context was created (must be 0)."""
         out = C.c_uint32(0)

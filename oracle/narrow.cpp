@@ -481,10 +481,12 @@ struct Preproc {
         }
         if (is_first) {
             f1 = actual;
+            c.k.dil1 = radius;  // kinematic.set_dilation1
             c.world1 = c.world1 + c.normal * radius;
             c.depth += radius;
         } else {
             f2 = actual;
+            c.k.dil2 = radius;
             c.world2 = c.world2 - c.normal * radius;
             c.depth += radius;
         }
@@ -670,6 +672,7 @@ static void gen_ball_ball(const Iso& ma, real r1, const Iso& mb, real r2, real p
     if (d2 < sre * sre) {
         V3 normal = d2 != 0 ? normalize(delta) : v3(1, 0, 0);
         Contact c = {c1 + normal * r1, c2 + normal * (-r2), normal, sum_radius - std::sqrt(d2)};
+        c.k.dil1 = r1, c.k.dil2 = r2;  // both approximations: (Face(0), origin, Point) (ball_ball_manifold_generator.rs:46-58)
         mf.push(c, FACE0, FACE0, v3(0, 0, 0));
     }
 }
@@ -683,10 +686,16 @@ static void gen_plane_ball(const Iso& m1, V3 plane_n, const Iso& m2, real radius
     if (depth > -prediction) {
         V3 world1 = bc + n * (-dist);
         V3 world2 = bc + n * (-radius);
-        if (!flip)
-            mf.push({world1, world2, n, depth}, FACE0, FACE0, v3(0, 0, 0));
-        else
-            mf.push({world2, world1, -n, depth}, FACE0, FACE0, v3(0, 0, 0));
+        V3 local1 = iso_inv_point(m1, world1);  // plane side: (Face(0), local1, Plane(plane.normal)); ball side: (Face(0), origin, Point)
+        if (!flip) {
+            Contact c = {world1, world2, n, depth};
+            c.k.local1 = local1, c.k.g1 = G_PLANE, c.k.dir1 = plane_n, c.k.dil2 = radius;
+            mf.push(c, FACE0, FACE0, v3(0, 0, 0));
+        } else {
+            Contact c = {world2, world1, -n, depth};
+            c.k.local2 = local1, c.k.g2 = G_PLANE, c.k.dir2 = plane_n, c.k.dil1 = radius;
+            mf.push(c, FACE0, FACE0, v3(0, 0, 0));
+        }
     }
 }
 
@@ -704,12 +713,18 @@ static void gen_plane_convex(const Iso& m1, V3 plane_n, const Iso& m2, const Sha
         real dist = dot(dpt, n);
         if (dist <= prediction) {
             V3 world1 = world2 + (-n * dist);
+            V3 local1 = iso_inv_point(m1, world1);
             V3 local2 = iso_inv_point(m2, world2);
             uint32_t f2 = feat.vertices_id[i];
-            if (!flip)
-                mf.push({world1, world2, n, -dist}, FACE0, f2, local2, pp1, pp2);
-            else
-                mf.push({world2, world1, -n, -dist}, f2, FACE0, local2, pp2, pp1);
+            if (!flip) {
+                Contact c = {world1, world2, n, -dist};
+                c.k.local1 = local1, c.k.g1 = G_PLANE, c.k.dir1 = plane_n, c.k.local2 = local2;  // approx2 = Point
+                mf.push(c, FACE0, f2, local2, pp1, pp2);
+            } else {
+                Contact c = {world2, world1, -n, -dist};
+                c.k.local1 = local2, c.k.local2 = local1, c.k.g2 = G_PLANE, c.k.dir2 = plane_n;
+                mf.push(c, f2, FACE0, local2, pp2, pp1);
+            }
         }
     }
 }
@@ -758,6 +773,24 @@ static void hull_project_point_with_feature(const Hull& H, const Iso& m, V3 poin
         *feature = FID_UNKNOWN;
 }
 
+// ConvexPolyhedron::edge(id) in LOCAL coordinates: cuboid.rs:163-183, convex.rs:430-441, segment.rs:203-205
+static void shape_edge(const Shape& cp, uint32_t f, V3* p1, V3* p2) {
+    uint32_t eid = fid_id(f);
+    if (cp.type == CUBOID) {
+        real res[3] = {cp.he.x, cp.he.y, cp.he.z};
+        uint32_t edge_i = eid & 3u, vertex_i = eid >> 2;
+        for (uint32_t i = 0; i < 3; ++i)
+            if (i != edge_i && (vertex_i & (1u << i))) res[i] = -res[i];
+        *p1 = v3(res[0], res[1], res[2]);
+        res[edge_i] = -res[edge_i];
+        *p2 = v3(res[0], res[1], res[2]);
+    } else if (cp.type == SEGMENT) {
+        *p1 = v3(0, -cp.hh, 0), *p2 = v3(0, cp.hh, 0);
+    } else {
+        *p1 = cp.hull.pt(cp.hull.edge_vertices[2 * eid]), *p2 = cp.hull.pt(cp.hull.edge_vertices[2 * eid + 1]);
+    }
+}
+
 // ball_convex_polyhedron_manifold_generator.rs:28-122.  (m1, ball) (m2, convex polyhedron)
 static void gen_ball_convex(const Iso& m1, real radius, const Iso& m2, const Shape& cp, real prediction, bool flip, Manifold& mf,
                             GJKStats* st, const Preproc* pp1 = nullptr, const Preproc* pp2 = nullptr) {
@@ -790,11 +823,26 @@ static void gen_ball_convex(const Iso& m1, real radius, const Iso& m2, const Sha
     }
     if (depth >= -prediction) {
         V3 world1 = ball_center + normal * radius;
-        // geometry of f2: an Edge feature needs cp.edge(f2) (cannot fail); nothing else can reject the contact
-        if (!flip)
-            mf.push({world1, world2, normal, depth}, FACE0, f2, v3(0, 0, 0), pp1, pp2);
-        else
-            mf.push({world2, world1, -normal, depth}, f2, FACE0, v3(0, 0, 0), pp2, pp1);
+        // ball side: (Face(0), origin, Point) + dilation; polyhedron side: local2 and the geometry of f2 (:80-114)
+        V3 local2 = iso_inv_point(m2, world2);
+        uint32_t g2 = G_POINT;
+        V3 d2 = v3(0, 0, 0);
+        if (fid_kind(f2) == F_FACE) {
+            g2 = G_PLANE, d2 = iso_inv_vec(m2, -normal);
+        } else if (fid_kind(f2) == F_EDGE) {
+            V3 e0, e1;
+            shape_edge(cp, f2, &e0, &e1);
+            g2 = G_LINE, d2 = normalize(e1 - e0);
+        }
+        if (!flip) {
+            Contact c = {world1, world2, normal, depth};
+            c.k.dil1 = radius, c.k.local2 = local2, c.k.g2 = g2, c.k.dir2 = d2;
+            mf.push(c, FACE0, f2, v3(0, 0, 0), pp1, pp2);
+        } else {
+            Contact c = {world2, world1, -normal, depth};
+            c.k.dil2 = radius, c.k.local1 = local2, c.k.g1 = g2, c.k.dir1 = d2;
+            mf.push(c, f2, FACE0, v3(0, 0, 0), pp2, pp1);
+        }
     }
 }
 
@@ -945,6 +993,20 @@ static bool feature_ok_for_manifold(const Feature& ft, uint32_t f) {
     }
 }
 
+// NeighborhoodGeometry of feature f of the polygonal feature ft, in the local frame of m (add_contact_to_manifold,
+// convex_polygonal_feature3.rs:356-397); f passed feature_ok_for_manifold
+static void feature_geometry(const Feature& ft, uint32_t f, const Iso& m, uint32_t* g, V3* dir) {
+    *g = G_POINT, *dir = v3(0, 0, 0);
+    if (fid_kind(f) == F_FACE) {
+        *g = G_PLANE, *dir = iso_inv_vec(m, ft.normal);  // inverse_transform_unit_vector(self.normal.unwrap())
+    } else if (fid_kind(f) == F_EDGE) {
+        V3 a = v3(0, 0, 0), b = a, d = a;
+        ft.edge(f, &a, &b);
+        unit_try_new(b - a, EPS, &d);  // Segment::direction
+        *g = G_LINE, *dir = iso_inv_vec(m, d);
+    }
+}
+
 // convex_polyhedron_convex_polyhedron_manifold_generator.rs:83-167.  last_gjk_dir: the generator's persistent
 // direction (nullptr / !*has_dir = fresh generator, None); updated like :106 and :139.
 static void gen_convex_convex(const Iso& ma, const Shape& a, const Iso& mb, const Shape& b, real pred_linear, real ang1, real ang2,
@@ -982,6 +1044,11 @@ static void gen_convex_convex(const Iso& ma, const Shape& a, const Iso& mb, cons
         if (!feature_ok_for_manifold(m1, nc.f1)) continue;
         if (!feature_ok_for_manifold(m2, nc.f2)) continue;
         V3 local1 = iso_inv_point(ma, nc.c.world1);
+        // ConvexPolygonalFeature::add_contact_to_manifold (convex_polygonal_feature3.rs:340-401)
+        nc.c.k.local1 = local1;
+        nc.c.k.local2 = iso_inv_point(mb, nc.c.world2);
+        feature_geometry(m1, nc.f1, ma, &nc.c.k.g1, &nc.c.k.dir1);
+        feature_geometry(m2, nc.f2, mb, &nc.c.k.g2, &nc.c.k.dir2);
         mf.push(nc.c, nc.f1, nc.f2, local1, pp1, pp2);
     }
 }
@@ -1141,10 +1208,18 @@ static void write_contact(orc_contact* d, const Tracked& t) {
     d->f2 = t.f2;
 }
 
+static void write_kinematic(orc_kinematic* d, const Tracked& t) {
+    const Kin& k = t.c.k;
+    for (int i = 0; i < 3; ++i) d->local1[i] = k.local1[i], d->local2[i] = k.local2[i], d->dir1[i] = k.dir1[i], d->dir2[i] = k.dir2[i];
+    d->dil1 = k.dil1, d->dil2 = k.dil2;
+    d->g1 = k.g1, d->g2 = k.g2;
+}
+
 extern "C" {
 
-uint64_t orc_narrow_phase(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, orc_contact* out, uint64_t cap,
-                          uint32_t* manifold_off, uint8_t* algo_out, uint32_t* stats) {
+// kin_out (optional, same capacity as out): the ContactKinematic of every contact (contact_kinematic.rs:57-66)
+uint64_t orc_narrow_phase_kin(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, orc_contact* out, orc_kinematic* kin_out,
+                              uint64_t cap, uint32_t* manifold_off, uint8_t* algo_out, uint32_t* stats) {
     Objects o = make_objects(objs);
     uint64_t nc = 0;
     GJKStats st;
@@ -1155,6 +1230,7 @@ uint64_t orc_narrow_phase(const orc_objects* objs, uint64_t n_pairs, const uint3
         if (manifold_off) manifold_off[p] = (uint32_t)nc;
         mf.for_each_contact([&](const Tracked& t, size_t) {
             if (nc < cap && out) write_contact(&out[nc], t);
+            if (nc < cap && kin_out) write_kinematic(&kin_out[nc], t);
             nc++;
         });
     }
@@ -1164,6 +1240,10 @@ uint64_t orc_narrow_phase(const orc_objects* objs, uint64_t n_pairs, const uint3
         stats[4] = st.epa_max_heap, stats[5] = st.epa_calls, stats[6] = st.epa_fail;
     }
     return nc;
+}
+uint64_t orc_narrow_phase(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, orc_contact* out, uint64_t cap,
+                          uint32_t* manifold_off, uint8_t* algo_out, uint32_t* stats) {
+    return orc_narrow_phase_kin(objs, n_pairs, pairs, out, nullptr, cap, manifold_off, algo_out, stats);
 }
 
 void orc_world_update_timed(const orc_objects* objs, real margin, double* times, uint64_t* counts) {

@@ -48,6 +48,13 @@ typedef struct orc_contact {
     uint32_t f1, f2;
 } orc_contact;
 
+/* ContactKinematic of a contact (query/contact/contact_kinematic.rs:57-66): tracked local points, NeighborhoodGeometry per side
+ * (g: 0 Point, 1 Line(dir), 2 Plane(dir)), dilations (margin1 / margin2).  The feature ids are in orc_contact. */
+typedef struct orc_kinematic {
+    real local1[3], local2[3], dir1[3], dir2[3], dil1, dil2;
+    uint32_t g1, g2;
+} orc_kinematic;
+
 void orc_compute_aabbs(const orc_objects* objs, real margin, int mode, real* out_minmax);
 uint64_t orc_broad_phase(uint32_t n, const real* aabb_minmax, const uint32_t* groups, int mode, uint32_t* out_pairs,
                          uint64_t cap);
@@ -55,6 +62,8 @@ uint64_t orc_broad_phase(uint32_t n, const real* aabb_minmax, const uint32_t* gr
 /* Narrow phase for the given (object1, object2) pairs, object1 being the first argument of
  * generate_contacts.  manifold_off has n_pairs+1 entries.  algo_out (optional) gets the dispatched
  * algorithm per pair.  Returns the number of contacts (may exceed cap). */
+uint64_t orc_narrow_phase_kin(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, orc_contact* out, orc_kinematic* kin_out,
+                              uint64_t cap, uint32_t* manifold_off, uint8_t* algo_out, uint32_t* stats);
 uint64_t orc_narrow_phase(const orc_objects* objs, uint64_t n_pairs, const uint32_t* pairs, orc_contact* out, uint64_t cap,
                           uint32_t* manifold_off, uint8_t* algo_out, uint32_t* stats);
 

@@ -144,6 +144,32 @@ class Oracle:
                 return out[:nc].copy(), off, algo, stats
             cap = int(nc)
 
+    def narrow_phase_kinematics(self, scene, pairs):
+        """narrow_phase + the ContactKinematic of every contact (local1, local2, NeighborhoodGeometry kind + direction per side, dilations).
+        Returns (contacts, kinematics, manifold_off, algo)."""
+        o, keep = self._objects(scene)
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        P = len(pairs)
+        cap = max(4 * P, 64)
+        off = np.zeros(P + 1, dtype=np.uint32)
+        algo = np.zeros(P, dtype=np.uint8)
+        kd = self.kinematic_dtype()
+        self.lib.orc_narrow_phase_kin.restype = C.c_uint64
+        while True:
+            out = np.zeros(cap, dtype=self.contact_dtype)
+            kin = np.zeros(cap, dtype=kd)
+            nc = self.lib.orc_narrow_phase_kin(
+                C.byref(o), C.c_uint64(P), C.c_void_p(pairs.ctypes.data), C.c_void_p(out.ctypes.data), C.c_void_p(kin.ctypes.data), C.c_uint64(cap),
+                C.c_void_p(off.ctypes.data), C.c_void_p(algo.ctypes.data), None,
+            )
+            if nc <= cap:
+                return out[:nc].copy(), kin[:nc].copy(), off, algo
+            cap = int(nc)
+
+    def kinematic_dtype(self):
+        r = self.dtype
+        return np.dtype([("local1", r, 3), ("local2", r, 3), ("dir1", r, 3), ("dir2", r, 3), ("dil1", r), ("dil2", r), ("g1", np.uint32), ("g2", np.uint32)])
+
     def contact_sm_sm(self, scene, pairs, predictions=None):
         """contact_support_map_support_map for cuboid / hull pairs -> (out[P,10] = p1, p2, normal, found; stats[4])."""
         o, keep = self._objects(scene)

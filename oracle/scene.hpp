@@ -108,9 +108,25 @@ struct ContactOut {
     uint32_t f1, f2;
 };
 
+// query/contact/contact_kinematic.rs:57-66: NeighborhoodGeometry (kind + direction / normal) and tracked local point per side,
+// and the dilations (margin1 / margin2)
+enum { G_POINT = 0, G_LINE = 1, G_PLANE = 2 };
+struct Kin {
+    V3 local1{0, 0, 0}, local2{0, 0, 0};
+    V3 dir1{0, 0, 0}, dir2{0, 0, 0};
+    real dil1 = 0, dil2 = 0;
+    uint32_t g1 = G_POINT, g2 = G_POINT;
+};
+// what the C interface returns per contact (oracle.h: orc_kinematic)
+struct KinOut {
+    real local1[3], local2[3], dir1[3], dir2[3], dil1, dil2;
+    uint32_t g1, g2;
+};
+
 struct Contact {
     V3 world1, world2, normal;
     real depth;
+    Kin k;  // the ContactKinematic pushed with the contact (contact_manifold.rs:165-171)
 };
 
 }  // namespace orc

@@ -61,14 +61,14 @@ static uint8_t fresh_pair(const DevObjects& o, const DevHulls& H, const ncb_obje
             V3 world2;
             uint32_t f2;
             cuboid_project_point_with_feature(cp.he, mcp, mball.t, inside, world2, f2);
-            gen_ball_convex_finish(mball.t, ball.radius, cp, inside, world2, f2, linear, flip, mf);
+            gen_ball_convex_finish(mball.t, ball.radius, cp, mcp, inside, world2, f2, linear, flip, mf);
         } else {
             HullProjSetup u = hull_proj_setup(cp.hull, mcp, mball.t);
             V3 world2;
             Simplex s;
             if (hull_project_gjk(u, mball.t, s, world2) == GJK_CLOSEST_POINTS) {
                 uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, false, world2, one_degree_cs);
-                gen_ball_convex_finish(mball.t, ball.radius, cp, false, world2, f2, linear, flip, mf);
+                gen_ball_convex_finish(mball.t, ball.radius, cp, mcp, false, world2, f2, linear, flip, mf);
             } else {  // k_bh_epa: the ball centre is inside the hull
                 Iso id = iso_id();
                 V3 p1, p2, d;
@@ -79,7 +79,7 @@ static uint8_t fresh_pair(const DevObjects& o, const DevHulls& H, const ncb_obje
                     world2 = mball.t;
                 }
                 uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, true, world2, one_degree_cs);
-                gen_ball_convex_finish(mball.t, ball.radius, cp, true, world2, f2, linear, flip, mf);
+                gen_ball_convex_finish(mball.t, ball.radius, cp, mcp, true, world2, f2, linear, flip, mf);
             }
         }
     } else if (al == NCB_ALGO_CONVEX_CONVEX) {
@@ -125,8 +125,9 @@ extern "C" {
 // Returns the number of contacts (may exceed cap).  manifold_off[n_pairs + 1]; algo[p] = NCB_ALGO_* (7 / 8: the capsule generators);
 // flags[0] += EPA capacity overflows / dropped contacts, flags[1] += reference panics.  seg_pts: NULL, or 6 floats per object for
 // worlds with capsules (shape_type 4).
-uint64_t shim_narrow_phase_ex(const ncb_objects* objs, const ncb_hull_library* lib, const float* seg_pts, uint64_t n_pairs, const uint32_t* pairs,
-                              ncb_contact* out, uint64_t cap, uint32_t* manifold_off, uint8_t* algo, uint32_t* flags) {
+// kin_out (optional): the ContactKinematic of every contact (ncb_set_kinematics), aligned with out
+uint64_t shim_narrow_phase_kin(const ncb_objects* objs, const ncb_hull_library* lib, const float* seg_pts, uint64_t n_pairs, const uint32_t* pairs,
+                               ncb_contact* out, ncb_kinematic* kin_out, uint64_t cap, uint32_t* manifold_off, uint8_t* algo, uint32_t* flags) {
     DevObjects o;
     std::memset(&o, 0, sizeof o);
     o.n = objs->n;
@@ -142,6 +143,8 @@ uint64_t shim_narrow_phase_ex(const ncb_objects* objs, const ncb_hull_library* l
     EpaState* e = new EpaState;
     Manifold* mfp = new Manifold;
     Manifold& mf = *mfp;
+    Kin* kin_side = new Kin[MANIFOLD_MAX];
+    mf.kin = kin_out ? kin_side : nullptr;
     uint64_t nc = 0;
     float2* ang_cs = new float2[objs->n ? objs->n : 1];  // ncb_set_objects' (cos, sin) table of the angular predictions
     for (uint32_t i = 0; i < objs->n; ++i) ang_cs[i] = make_float2(cosf(objs->ang_pred[i]), sinf(objs->ang_pred[i]));
@@ -164,13 +167,28 @@ uint64_t shim_narrow_phase_ex(const ncb_objects* objs, const ncb_hull_library* l
             w.depth = c.depth;
             w.f1 = c.f1, w.f2 = c.f2;
             w.pair = (uint32_t)p;
+            if (kin_out) {
+                const Kin& q = kin_side[k];
+                ncb_kinematic& z = kin_out[nc];
+                z.local1[0] = q.local1.x, z.local1[1] = q.local1.y, z.local1[2] = q.local1.z;
+                z.local2[0] = q.local2.x, z.local2[1] = q.local2.y, z.local2[2] = q.local2.z;
+                z.dir1[0] = q.dir1.x, z.dir1[1] = q.dir1.y, z.dir1[2] = q.dir1.z;
+                z.dir2[0] = q.dir2.x, z.dir2[1] = q.dir2.y, z.dir2[2] = q.dir2.z;
+                z.dilation1 = q.dil1, z.dilation2 = q.dil2;
+                z.geometry1 = q.g1, z.geometry2 = q.g2;
+            }
         }
     }
     manifold_off[n_pairs] = (uint32_t)nc;
     delete e;
     delete mfp;
+    delete[] kin_side;
     delete[] ang_cs;
     return nc;
+}
+uint64_t shim_narrow_phase_ex(const ncb_objects* objs, const ncb_hull_library* lib, const float* seg_pts, uint64_t n_pairs, const uint32_t* pairs,
+                              ncb_contact* out, uint64_t cap, uint32_t* manifold_off, uint8_t* algo, uint32_t* flags) {
+    return shim_narrow_phase_kin(objs, lib, seg_pts, n_pairs, pairs, out, nullptr, cap, manifold_off, algo, flags);
 }
 uint64_t shim_narrow_phase(const ncb_objects* objs, const ncb_hull_library* lib, uint64_t n_pairs, const uint32_t* pairs, ncb_contact* out,
                            uint64_t cap, uint32_t* manifold_off, uint8_t* algo, uint32_t* flags) {
@@ -264,14 +282,14 @@ void shim_persist_update_ex(const ncb_objects* objs, const ncb_hull_library* lib
                     V3 world2;
                     uint32_t f2;
                     cuboid_project_point_with_feature(cp.he, mcp, mball.t, inside, world2, f2);
-                    gen_ball_convex_finish(mball.t, ball.radius, cp, inside, world2, f2, linear, flip, mf);
+                    gen_ball_convex_finish(mball.t, ball.radius, cp, mcp, inside, world2, f2, linear, flip, mf);
                 } else {
                     HullProjSetup u = hull_proj_setup(cp.hull, mcp, mball.t);
                     V3 world2;
                     Simplex s;
                     if (hull_project_gjk(u, mball.t, s, world2) == GJK_CLOSEST_POINTS) {
                         uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, false, world2, one_degree_cs);
-                        gen_ball_convex_finish(mball.t, ball.radius, cp, false, world2, f2, linear, flip, mf);
+                        gen_ball_convex_finish(mball.t, ball.radius, cp, mcp, false, world2, f2, linear, flip, mf);
                     } else {
                         Iso id = iso_id();
                         V3 p1, p2, d;
@@ -282,7 +300,7 @@ void shim_persist_update_ex(const ncb_objects* objs, const ncb_hull_library* lib
                             world2 = mball.t;
                         }
                         uint32_t f2 = hull_project_feature(cp.hull, mcp, mball.t, true, world2, one_degree_cs);
-                        gen_ball_convex_finish(mball.t, ball.radius, cp, true, world2, f2, linear, flip, mf);
+                        gen_ball_convex_finish(mball.t, ball.radius, cp, mcp, true, world2, f2, linear, flip, mf);
                     }
                 }
             }

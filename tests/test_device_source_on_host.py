@@ -247,6 +247,88 @@ def test_device_narrow_phase_source_matches_oracle(narrow_shim, oracle, mk):
     assert inexact == 0, f"{inexact} contact fields within tolerance but not bit-exact"
 
 
+def shim_narrow_phase_kinematics(lib, scene, pairs):
+    """The harness with ncb_set_kinematics on: contacts + ContactKinematic records (capsule worlds included)."""
+    oc, keep = _ffi.pack_objects(scene)
+    hc, keep2 = _ffi.pack_hull_library(scene.hulls)
+    pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+    seg = np.zeros((scene.n, 6), dtype=F)
+    cap = scene.shape_type == 4
+    seg[cap, 1] = scene.shape_param[cap, 0]
+    seg[cap, 4] = -scene.shape_param[cap, 0]
+    P = len(pairs)
+    off = np.zeros(P + 1, dtype=np.uint32)
+    algo = np.zeros(P, dtype=np.uint8)
+    flags = np.zeros(4, dtype=np.uint32)
+    lib.shim_narrow_phase_kin.restype = C.c_uint64
+    cap_c = max(4 * P, 64)
+    while True:
+        out = np.zeros(cap_c, dtype=_ffi.CONTACT_DTYPE)
+        kin = np.zeros(cap_c, dtype=_ffi.KINEMATIC_DTYPE)
+        flags[:] = 0
+        nc = lib.shim_narrow_phase_kin(C.byref(oc), C.byref(hc), _ffi.ptr(seg), C.c_uint64(P), _ffi.ptr(pairs), _ffi.ptr(out), _ffi.ptr(kin),
+                                       C.c_uint64(cap_c), _ffi.ptr(off), _ffi.ptr(algo), _ffi.ptr(flags))
+        if nc <= cap_c:
+            return out[:nc], kin[:nc], off, algo
+        cap_c = int(nc)
+
+
+def compare_kinematics(dk, ok, label):
+    """ContactKinematic records: geometry kinds and dilations exact, local points / directions bit for bit."""
+    assert len(dk) == len(ok), label
+    assert np.array_equal(dk["g1"], ok["g1"]) and np.array_equal(dk["g2"], ok["g2"]), f"{label}: NeighborhoodGeometry kinds"
+    for name in ("local1", "local2", "dir1", "dir2", "dil1", "dil2"):
+        a, b = np.ascontiguousarray(dk[name]), np.ascontiguousarray(ok[name])
+        assert np.allclose(a, b, rtol=1e-4, atol=1e-5), f"{label}: {name}"
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{label}: {name} within tolerance but not bit-exact"
+
+
+@pytest.mark.parametrize("mk", NARROW_SCENES + [lambda: _capsule_scene(2400, 141, (1, 1, 1), 8.0, True), lambda: _capsule_scene(1800, 142, (0, 1, 1), 5.5, False, 0.03)])
+def test_device_contact_kinematics_match_oracle(narrow_shim, oracle, mk):
+    """ContactKinematic (local1 / local2, NeighborhoodGeometry per side, dilations: contact_kinematic.rs:57-66) as the device source
+    produces it with ncb_set_kinematics on, against the oracle's restatement of every generator's kinematic (ball-ball, plane-ball,
+    plane-polyhedron, ball-polyhedron, add_contact_to_manifold for polyhedron pairs, the capsule preprocessor's dilation): bit for
+    bit, both operand orders; the contacts themselves are unchanged by the request."""
+    s = mk()
+    pairs = oracle.broad_phase(oracle.compute_aabbs(s), s.groups, mode=0)
+    both = np.concatenate([pairs, pairs[:, ::-1]])
+    dc, dk, doff, dalgo = shim_narrow_phase_kinematics(narrow_shim, s, both)
+    oc, ok, ooff, oalgo = oracle.narrow_phase_kinematics(s, both)
+    assert np.array_equal(doff, ooff) and np.array_equal(dalgo, oalgo)
+    for name in ("world1", "world2", "normal", "depth", "f1", "f2"):
+        assert np.array_equal(np.ascontiguousarray(dc[name]).view(np.uint32), np.ascontiguousarray(oc[name]).view(np.uint32)), name
+    compare_kinematics(dk, ok, "kinematics")
+    assert (ok["g1"] == 1).any() and (ok["g1"] == 2).any() and (ok["g2"] == 1).any() and (ok["g2"] == 2).any()
+    # sanity of the restatement itself: Plane / Line directions are unit vectors, and the tracked local points, moved to world space
+    # and dilated along the normal, are the contact points: world1 = m1 * local1 + n * dilation1, world2 = m2 * local2 - n * dilation2
+    for g, d in (("g1", "dir1"), ("g2", "dir2")):
+        sel = ok[g] != 0
+        assert np.allclose(np.linalg.norm(ok[d][sel], axis=1), 1.0, atol=1e-5)
+    pair_of = np.repeat(np.arange(len(both)), np.diff(ooff))
+
+    def to_world(obj, local):
+        q, t = s.rot[obj].astype(np.float64), s.pos[obj].astype(np.float64)
+        qv = q[:, :3]
+        tt = 2 * np.cross(qv, local)
+        return local + q[:, 3:4] * tt + np.cross(qv, tt) + t
+
+    n = oc["normal"].astype(np.float64)
+    w1 = to_world(both[pair_of, 0], ok["local1"].astype(np.float64)) + n * ok["dil1"][:, None]
+    w2 = to_world(both[pair_of, 1], ok["local2"].astype(np.float64)) - n * ok["dil2"][:, None]
+    assert np.allclose(w1, oc["world1"], atol=2e-5) and np.allclose(w2, oc["world2"], atol=2e-5)
+    # a Plane geometry is (within the angular tolerances of the support features) the contact normal seen from the object
+    def to_world_vec(obj, v):
+        q = s.rot[obj].astype(np.float64)
+        qv = q[:, :3]
+        tt = 2 * np.cross(qv, v)
+        return v + q[:, 3:4] * tt + np.cross(qv, tt)
+
+    p1 = ok["g1"] == 2
+    assert (np.einsum("ij,ij->i", to_world_vec(both[pair_of, 0], ok["dir1"].astype(np.float64))[p1], n[p1]) > 0.3).all()  # the support FACE toward the normal (cuboid: >= 1 / sqrt 3)
+    p2 = ok["g2"] == 2
+    assert (np.einsum("ij,ij->i", to_world_vec(both[pair_of, 1], ok["dir2"].astype(np.float64))[p2], n[p2]) < -0.3).all()
+
+
 @pytest.mark.parametrize("k", range(6))
 def test_device_narrow_phase_source_on_adversarial_scenes(narrow_shim, oracle, k):
     from test_gpu_parity import _adversarial_scenes

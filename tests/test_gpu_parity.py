@@ -138,6 +138,35 @@ def test_world_update_poses_equals_world_update(ctx, oracle):
     compare_manifolds(b, s2, oracle, "poses")
 
 
+@pytest.mark.parametrize("mk", [SCENES[1], SCENES[3], SCENES[4]])
+def test_contact_kinematics_match_oracle(ctx, oracle, mk):
+    """ncb_set_kinematics: every contact of a fresh-world update comes with its ContactKinematic (local1 / local2, NeighborhoodGeometry
+    kind + direction per side, dilations); compared with the oracle's restatement of each generator's kinematic.  The contacts
+    themselves must not change when kinematics are requested."""
+    s = mk()
+    ctx.set_hulls(s.hulls)
+    plain = ctx.world_update(s)
+    ctx.set_kinematics(True)
+    try:
+        res = ctx.world_update(s)
+        kin = ctx.fetch_kinematics(len(res.contacts))
+    finally:
+        ctx.set_kinematics(False)
+    assert len(res.contacts) == len(plain.contacts) and res.counts["n_contact_pairs"] == plain.counts["n_contact_pairs"]
+    oc, ok, ooff, oalgo = oracle.narrow_phase_kinematics(s, res.pairs)
+    assert np.array_equal(res.manifold_count, np.diff(ooff)) and np.array_equal(res.pair_algo, oalgo)
+    idx = np.concatenate([np.arange(a, a + c) for a, c in zip(res.manifold_start, res.manifold_count)]).astype(np.int64)
+    dk, dc = kin[idx], res.contacts[idx]
+    assert np.array_equal(dc["f1"], oc["f1"]) and np.array_equal(dc["f2"], oc["f2"])
+    assert np.array_equal(dk["g1"], ok["g1"]) and np.array_equal(dk["g2"], ok["g2"]), "NeighborhoodGeometry kinds"
+    for name in ("local1", "local2", "dir1", "dir2", "dil1", "dil2"):
+        assert np.allclose(dk[name], ok[name], rtol=RTOL, atol=ATOL), name
+    assert (ok["g1"] == 1).any() and (ok["g1"] == 2).any()
+    with pytest.raises(Exception, match="ncb_set_kinematics"):
+        ctx.world_update(s)
+        ctx.fetch_kinematics(4)
+
+
 def test_deep_tree_coincident_boxes(ctx, oracle):
     """120 000 boxes of which 100 000 share a few dozen distinct positions (identical Morton codes: the LBVH splits them on the tie-break
     bits, its deepest shape) and 20 000 sit within a few ulps of them.  The pair search must neither lose a pair nor run out of its
