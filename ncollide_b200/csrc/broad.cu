@@ -446,6 +446,250 @@ cudaError_t launch_shard_select(ncb_ctx* c, uint32_t n, int rank, int world, Sha
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Routed sharding (several GPUs, second design): instead of all-gathering every fat AABB and letting every rank scan
+// all N of them, each rank ROUTES the objects of its own block to the ranks that need them.  Per step and rank:
+//   0  bounds of the own block's AABB centres                         -> all-reduce (max of [-min, max], 6 floats)
+//   1  Morton bin per own object + 1024-bin histogram                 -> all-reduce (sum)
+//   2  equal-count bin ranges (owner per bin); own objects appended to the send bucket of their owner;
+//      union box of what goes to each owner                            -> all-to-all (owned records), all-reduce (regions)
+//   3  own objects whose box meets the region of another rank          -> all-to-all (ghost records)
+//   4  received records unpacked into the local box arrays (+ poses scattered into the replicated pose arrays)
+// then the local LBVH build / pair search / narrow phase of the first design (ownership rule unchanged: a pair is reported
+// by the rank that owns both objects, or owns one and has the lower rank of the two owners).  Every rank receives about
+// N / ranks + ghosts records instead of N; nothing is scanned N times.  Bucket capacities are fixed per call (equal splits,
+// so the collectives need no host-side counts); slot 0 of a bucket carries its record count.
+// Record: float4 (lo.xyz, handle) (hi.xyz, type | owner << 8) [ (pos.xyz, rot.i) (rot.j, rot.k, rot.w, -) with poses ].
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_route_pack_bounds(const DevCounters* cnt, float* out) {
+    if (threadIdx.x < 3) {
+        out[threadIdx.x] = -o2f(cnt->bounds[threadIdx.x]);
+        out[3 + threadIdx.x] = o2f(cnt->bounds[3 + threadIdx.x]);
+    }
+}
+__device__ __forceinline__ uint32_t route_bin(float4 a, float4 b, const float* __restrict__ gb) {
+    if (is_outlier(a, b)) return SHARD_BINS;
+    float bx = -gb[0], by = -gb[1], bz = -gb[2];
+    float ex = gb[3] - bx, ey = gb[4] - by, ez = gb[5] - bz;
+    float e = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-20f));
+    float s = 1023.0f / e;
+    float cx = ((a.x + b.x) * 0.5f - bx) * s, cy = ((a.y + b.y) * 0.5f - by) * s, cz = ((a.z + b.z) * 0.5f - bz) * s;
+    uint32_t ux = (uint32_t)fminf(fmaxf(cx, 0.0f), 1023.0f);
+    uint32_t uy = (uint32_t)fminf(fmaxf(cy, 0.0f), 1023.0f);
+    uint32_t uz = (uint32_t)fminf(fmaxf(cz, 0.0f), 1023.0f);
+    return ((expand_bits10(ux) << 2) | (expand_bits10(uy) << 1) | expand_bits10(uz)) >> 20;  // top 10 of the 30 code bits
+}
+__global__ void __launch_bounds__(256) k_route_hist(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t begin, uint32_t end,
+                                                    const float* __restrict__ gb, uint32_t* __restrict__ bins, int* __restrict__ hist) {
+    __shared__ uint32_t h[SHARD_BINS];
+    for (int k = threadIdx.x; k < SHARD_BINS; k += blockDim.x) h[k] = 0;
+    __syncthreads();
+    for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
+        uint32_t bin = route_bin(__ldg(&lo[i]), __ldg(&hi[i]), gb);
+        bins[i - begin] = bin;
+        if (bin < SHARD_BINS) atomicAdd(&h[bin], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < SHARD_BINS; k += blockDim.x)
+        if (h[k]) atomicAdd(&hist[k], (int)h[k]);
+}
+__global__ void k_route_split(const int* __restrict__ hist, int world, uint32_t* __restrict__ split) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long total = 0;
+    for (int k = 0; k < SHARD_BINS; ++k) total += (uint32_t)hist[k];
+    unsigned long long acc = 0;
+    int r = 1;
+    split[0] = 0;
+    for (int k = 0; k < SHARD_BINS && r < world; ++k) {
+        acc += (uint32_t)hist[k];
+        while (r < world && acc * world >= total * r) split[r++] = k + 1;
+    }
+    for (; r < world; ++r) split[r] = SHARD_BINS;
+    split[world] = SHARD_BINS + 1;  // outliers (bin SHARD_BINS) belong to the last rank
+}
+__device__ __forceinline__ int route_owner(const uint32_t* __restrict__ split, int world, uint32_t bin) {
+    int r = 0;
+    while (r + 1 < world && bin >= split[r + 1]) ++r;
+    return r;
+}
+// stage 2: own objects -> the bucket of their owner; union box of the (finite) boxes per owner
+__global__ void __launch_bounds__(256) k_route_owned(const float4* __restrict__ lo, const float4* __restrict__ hi, const float* __restrict__ pos,
+                                                     const float4* __restrict__ rot, uint32_t begin, uint32_t end, const uint32_t* __restrict__ bins,
+                                                     const uint32_t* __restrict__ split, int world, uint32_t cap, int recw, float4* __restrict__ send,
+                                                     uint32_t* __restrict__ counts, int* __restrict__ region) {
+    __shared__ int s_reg[SHARD_MAX_RANKS][6];
+    for (int k = threadIdx.x; k < SHARD_MAX_RANKS * 6; k += blockDim.x) (&s_reg[0][0])[k] = (k % 6) < 3 ? 0x7f7fffff : (int)0x80800000;
+    __syncthreads();
+    uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < end) {
+        float4 a = __ldg(&lo[i]), b = __ldg(&hi[i]);
+        uint32_t bin = __ldg(&bins[i - begin]);
+        int owner = route_owner(split, world, bin);
+        unsigned peers = __match_any_sync(__activemask(), owner);
+        int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&counts[owner], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        uint32_t k = base + __popc(peers & ((1u << lane) - 1));
+        if (k + 1 < cap) {  // slot 0 is the header
+            float4* r = send + ((size_t)owner * cap + 1 + k) * recw;
+            a.w = __uint_as_float(i);
+            b.w = __uint_as_float((__float_as_uint(b.w) & 0xffu) | ((uint32_t)owner << 8));
+            r[0] = a, r[1] = b;
+            if (recw == 4) {
+                float4 q = __ldg(&rot[i]);
+                r[2] = make_float4(pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2], q.x);
+                r[3] = make_float4(q.y, q.z, q.w, 0.f);
+            }
+        }
+        if (bin < SHARD_BINS) {  // infinite boxes do not shape a region
+            atomicMin(&s_reg[owner][0], f2o(a.x)), atomicMin(&s_reg[owner][1], f2o(a.y)), atomicMin(&s_reg[owner][2], f2o(a.z));
+            atomicMax(&s_reg[owner][3], f2o(b.x)), atomicMax(&s_reg[owner][4], f2o(b.y)), atomicMax(&s_reg[owner][5], f2o(b.z));
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < world * 6; k += blockDim.x) {
+        int v = (&s_reg[0][0])[k];
+        if ((k % 6) < 3) {
+            if (v != 0x7f7fffff) atomicMin(&region[k], v);
+        } else if (v != (int)0x80800000) {
+            atomicMax(&region[k], v);
+        }
+    }
+}
+// bucket headers (slot 0 = record count, may exceed the capacity: the receiver clamps and flags) + regions as [-min, max] floats
+__global__ void k_route_finish(const uint32_t* __restrict__ counts, int world, uint32_t cap, int recw, float4* __restrict__ send,
+                               const int* __restrict__ region, float* __restrict__ region_f) {
+    int t = threadIdx.x;
+    if (t < world) send[(size_t)t * cap * recw] = make_float4(__uint_as_float(counts[t]), 0.f, 0.f, 0.f);
+    if (region_f && t < world * 6) region_f[t] = (t % 6) < 3 ? -o2f(region[t]) : o2f(region[t]);
+}
+// stage 3: ghosts = own objects whose box meets the region of a rank that does not own them (inclusive test, like AABB::intersects)
+__global__ void __launch_bounds__(256) k_route_ghosts(const float4* __restrict__ lo, const float4* __restrict__ hi, const float* __restrict__ pos,
+                                                      const float4* __restrict__ rot, uint32_t begin, uint32_t end, const uint32_t* __restrict__ bins,
+                                                      const uint32_t* __restrict__ split, const float* __restrict__ region_f, int world, uint32_t cap,
+                                                      int recw, float4* __restrict__ send, uint32_t* __restrict__ counts) {
+    __shared__ float s_r[SHARD_MAX_RANKS][6];
+    for (int k = threadIdx.x; k < world * 6; k += blockDim.x) (&s_r[0][0])[k] = (k % 6) < 3 ? -region_f[k] : region_f[k];
+    __syncthreads();
+    uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    float4 a = __ldg(&lo[i]), b = __ldg(&hi[i]);
+    int owner = route_owner(split, world, __ldg(&bins[i - begin]));
+    for (int q = 0; q < world; ++q) {
+        if (q == owner) continue;
+        bool take = a.x <= s_r[q][3] && a.y <= s_r[q][4] && a.z <= s_r[q][5] && b.x >= s_r[q][0] && b.y >= s_r[q][1] && b.z >= s_r[q][2];
+        if (!take) continue;
+        uint32_t k = atomicAdd(&counts[q], 1u);
+        if (k + 1 < cap) {
+            float4* r = send + ((size_t)q * cap + 1 + k) * recw;
+            float4 a2 = a, b2 = b;
+            a2.w = __uint_as_float(i);
+            b2.w = __uint_as_float((__float_as_uint(b.w) & 0xffu) | ((uint32_t)owner << 8));
+            r[0] = a2, r[1] = b2;
+            if (recw == 4) {
+                float4 qq = __ldg(&rot[i]);
+                r[2] = make_float4(pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2], qq.x);
+                r[3] = make_float4(qq.y, qq.z, qq.w, 0.f);
+            }
+        }
+    }
+}
+// stage 4: the 2 * world received buckets (owned, then ghosts) -> compact local arrays; sh->m = records, sh->n_owned = owned ones.
+// A bucket whose header exceeds its capacity was truncated by its sender: flagged in sh->split[0] (overflow), the step is repeated.
+__global__ void __launch_bounds__(256) k_route_unpack(const float4* __restrict__ recv_o, const float4* __restrict__ recv_g, int world, uint32_t cap_o,
+                                                      uint32_t cap_g, int recw, uint32_t cap_local, uint32_t* __restrict__ sel,
+                                                      float4* __restrict__ loc_lo, float4* __restrict__ loc_hi, float* __restrict__ pos,
+                                                      float4* __restrict__ rot, ShardScratch* sh) {
+    __shared__ uint32_t s_off[2 * SHARD_MAX_RANKS + 1], s_cnt[2 * SHARD_MAX_RANKS];
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0, owned = 0, need_o = 0, need_g = 0;
+        for (int bk = 0; bk < 2 * world; ++bk) {
+            bool ghost = bk >= world;
+            const float4* hdr = ghost ? recv_g + (size_t)(bk - world) * cap_g * recw : recv_o + (size_t)bk * cap_o * recw;
+            uint32_t c = __float_as_uint(hdr->x), cap = (ghost ? cap_g : cap_o) - 1;
+            if (ghost) need_g = max(need_g, c + 1); else need_o = max(need_o, c + 1);
+            c = min(c, cap);
+            s_off[bk] = acc, s_cnt[bk] = c;
+            acc += c;
+            if (!ghost) owned += c;
+        }
+        s_off[2 * world] = acc;
+        if (blockIdx.x == 0 && blockIdx.y == 0) {
+            sh->m = acc, sh->n_owned = owned;
+            sh->split[0] = need_o, sh->split[1] = need_g;  // capacities this step would have needed (host: grow + repeat when larger)
+        }
+    }
+    __syncthreads();
+    int bk = blockIdx.y;
+    bool ghost = bk >= world;
+    uint32_t cap = ghost ? cap_g : cap_o;
+    const float4* bucket = ghost ? recv_g + (size_t)(bk - world) * cap_g * recw : recv_o + (size_t)bk * cap_o * recw;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < s_cnt[bk]; k += gridDim.x * blockDim.x) {
+        const float4* r = bucket + (size_t)(1 + k) * recw;
+        uint32_t dst = s_off[bk] + k;
+        if (dst >= cap_local) continue;
+        float4 a = r[0], b = r[1];
+        uint32_t handle = __float_as_uint(a.w);
+        sel[dst] = handle;
+        loc_lo[dst] = a, loc_hi[dst] = b;
+        if (recw == 4) {
+            float4 p = r[2], q = r[3];
+            pos[3 * (size_t)handle] = p.x, pos[3 * (size_t)handle + 1] = p.y, pos[3 * (size_t)handle + 2] = p.z;
+            rot[handle] = make_float4(p.w, q.x, q.y, q.z);
+        }
+    }
+    (void)cap;
+}
+
+cudaError_t launch_route_stage(ncb_ctx* c, int stage, int rank, int world, uint32_t begin, uint32_t end, RouteBufs& R) {
+    (void)rank;
+    cudaStream_t s = c->stream;
+    uint32_t n_own = end - begin, nb = (n_own + 255) / 256;
+    int gs = c->sm_count * 4;
+    switch (stage) {
+        case 0: {  // bounds of the own block (needs counters reset by the caller)
+            if (n_own) k_bounds<<<min((uint32_t)gs, nb), 256, 0, s>>>(c->aabb_lo.p + begin, c->aabb_hi.p + begin, n_own, c->counters.p);
+            k_route_pack_bounds<<<1, 32, 0, s>>>(c->counters.p, R.bounds.p);
+            break;
+        }
+        case 1: {
+            cudaMemsetAsync(R.hist.p, 0, SHARD_BINS * sizeof(int), s);
+            if (n_own) k_route_hist<<<min((uint32_t)c->sm_count * 2, nb), 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, begin, end, R.bounds.p, R.bins.p, R.hist.p);
+            break;
+        }
+        case 2: {
+            int z[SHARD_MAX_RANKS * 6];
+            for (int k = 0; k < SHARD_MAX_RANKS * 6; ++k) z[k] = (k % 6) < 3 ? 0x7f7fffff : (int)0x80800000;
+            cudaMemcpyAsync(R.region_i.p, z, sizeof z, cudaMemcpyHostToDevice, s);
+            cudaMemsetAsync(R.counts.p, 0, 2 * SHARD_MAX_RANKS * sizeof(uint32_t), s);
+            k_route_split<<<1, 32, 0, s>>>(R.hist.p, world, R.split.p);
+            if (n_own)
+                k_route_owned<<<nb, 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, c->pos.p, c->rot.p, begin, end, R.bins.p, R.split.p, world, R.cap_o, R.recw,
+                                                 R.send_o.p, R.counts.p, R.region_i.p);
+            k_route_finish<<<1, 128, 0, s>>>(R.counts.p, world, R.cap_o, R.recw, R.send_o.p, R.region_i.p, R.region_f.p);
+            break;
+        }
+        case 3: {
+            if (n_own)
+                k_route_ghosts<<<nb, 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, c->pos.p, c->rot.p, begin, end, R.bins.p, R.split.p, R.region_f.p, world,
+                                                  R.cap_g, R.recw, R.send_g.p, R.counts.p + SHARD_MAX_RANKS);
+            k_route_finish<<<1, 128, 0, s>>>(R.counts.p + SHARD_MAX_RANKS, world, R.cap_g, R.recw, R.send_g.p, nullptr, nullptr);
+            break;
+        }
+        default: break;
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_route_unpack(ncb_ctx* c, int world, RouteBufs& R, uint32_t cap_local, ShardScratch* sh, uint32_t* sel, float4* loc_lo,
+                                float4* loc_hi) {
+    uint32_t per = max(R.cap_o, R.cap_g);
+    dim3 grid(min((per + 255) / 256, (uint32_t)c->sm_count * 2), 2 * world);
+    k_route_unpack<<<grid, 256, 0, c->stream>>>(R.recv_o.p, R.recv_g.p, world, R.cap_o, R.cap_g, R.recw, cap_local, sel, loc_lo, loc_hi, c->pos.p,
+                                                c->rot.p, sh);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // K5: pair search.  One thread per query leaf, in Morton order (neighbouring lanes traverse neighbouring boxes).
 // A query at sorted position i reports only leaves at positions j > i, so each unordered pair is emitted once;
 // it is oriented (larger handle, smaller handle) = the argument order of interference_started.

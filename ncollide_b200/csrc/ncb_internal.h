@@ -189,6 +189,20 @@ struct DevBuf {
     ~DevBuf() { release(); }  // every buffer of a context / a temporary goes with its owner (error returns included)
 };
 
+// Buffers of the routed multi-GPU sharding (broad.cu): what the collectives of ncollide_b200/parallel.py read and write.
+struct RouteBufs {
+    DevBuf<float> bounds;      // 8 floats: [-min xyz, max xyz] of the own block's AABB centres (all-reduce max)
+    DevBuf<int> hist;          // SHARD_BINS counts of the own block (all-reduce sum)
+    DevBuf<uint32_t> split;    // world + 1 bin boundaries
+    DevBuf<uint32_t> bins;     // bin per own object
+    DevBuf<int> region_i;      // SHARD_MAX_RANKS x 6 ordered ints: union box of what this rank sends to each owner
+    DevBuf<float> region_f;    // the same as [-min, max] floats (all-reduce max) = the owned region of every rank
+    DevBuf<uint32_t> counts;   // [0, MAX_RANKS): owned records per destination, [MAX_RANKS, 2 MAX_RANKS): ghost records
+    DevBuf<float4> send_o, recv_o, send_g, recv_g;  // world buckets of cap records of recw float4 (slot 0 = header)
+    uint32_t cap_o = 0, cap_g = 0;
+    int recw = 2;              // 2: boxes only; 4: boxes + poses
+};
+
 struct StageTimer {
     static const int MAX = 24;
     bool enabled = false;
@@ -281,6 +295,7 @@ struct ncb_ctx {
     ncb::DevBuf<uint32_t> shard_bins, shard_sel;
     ncb::DevBuf<float4> shard_lo, shard_hi;
     uint32_t shard_m = 0, shard_owned = 0;
+    ncb::RouteBufs route;
 };
 
 // api.cu helpers shared with sim.cu
@@ -322,6 +337,8 @@ cudaError_t launch_pair_search(ncb_ctx* c, uint32_t n, const uint32_t* groups, u
 cudaError_t launch_shard_select(ncb_ctx* c, uint32_t n, int rank, int world, ShardScratch* sh, uint32_t* bins, uint32_t cap, uint32_t* sel,
                                 float4* loc_lo, float4* loc_hi);
 cudaError_t launch_pair_sort(ncb_ctx* c, uint32_t cap_pairs, uint32_t* index_out);
+cudaError_t launch_route_stage(ncb_ctx* c, int stage, int rank, int world, uint32_t begin, uint32_t end, RouteBufs& R);
+cudaError_t launch_route_unpack(ncb_ctx* c, int world, RouteBufs& R, uint32_t cap_local, ShardScratch* sh, uint32_t* sel, float4* loc_lo, float4* loc_hi);
 size_t lbvh_temp_bytes(uint32_t n);
 // narrow.cu
 cudaError_t launch_narrow_phase(ncb_ctx* c, const DevObjects& o, const uint2* pairs, const uint32_t* pair_index, uint32_t cap_pairs,
