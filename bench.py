@@ -43,7 +43,8 @@ def workload_config(n_per, world):
         "seed": 1003,
         "l2": "native arm: 256 MiB flush between timed iterations, working set > L2; reference arm: host memory",
         "parallelism": ("native arm: single GPU" if world == 1 else
-                        f"native arm: {world} ranks, AABB block per rank + NCCL all-gather, spatial ownership (Morton ranges + ghosts), local LBVH per rank")
+                        f"native arm: {world} ranks, AABB block per rank, routed spatial ownership (Morton-bin owners + ghosts through NCCL all-to-all; "
+                        "NCB_SHARD=spatial selects the all-gather design), local LBVH per rank")
                        + "; reference arm: 1 host thread (the reference is single-threaded)",
     }
 
@@ -424,7 +425,7 @@ def run_native(args):
             sharded.upload_own_poses(pin_scene.pos, pin_scene.rot)
             ctx.check(lib.ncb_world_fetch_early(h, _ffi.ptr(pin_out["pairs"]), C.c_uint32(len(pin_out["pairs"])), _ffi.ptr(pin_out["algo"]),
                                                 _ffi.ptr(pin_out["contacts"]), C.c_uint32(len(pin_out["contacts"]))), "fetch_early")
-            step_device()
+            sharded.step(counts_c, with_poses=True)  # routed mode: the poses travel with the records (no pose all-gather)
             ctx.check(lib.ncb_world_fetch(h, _ffi.ptr(pin_out["pairs"]), C.c_uint32(len(pin_out["pairs"])), _ffi.ptr(pin_out["algo"]),
                                           _ffi.ptr(pin_out["start"]), _ffi.ptr(pin_out["count"]), _ffi.ptr(pin_out["contacts"]),
                                           C.c_uint32(len(pin_out["contacts"]))), "fetch")
@@ -577,8 +578,9 @@ def run_native(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "call": "ncb_world_update_poses: pinned host poses in (set_position on every object), update, every pair / manifold / contact "
-                            "out to pinned host buffers" if world == 1 else "per rank: ncb_set_positions_range + NCCL pose all-gather + "
-                            "ncb_world_update_stage / _sharded + ncb_world_fetch of the rank's own pairs and contacts"},
+                            "out to pinned host buffers" if world == 1 else f"per rank: ncb_set_positions_range (own block) + {sharded.mode} sharded update "
+                            "(routed: poses travel with the NCCL all-to-all records; spatial / slices: NCCL pose all-gather) + ncb_world_fetch of the "
+                            "rank's own pairs and contacts"},
             "gpu_launches": int(launches_total * args.steps),
             "gpu_launches_per_step": int(launches_total),
             "clocks": clocks,

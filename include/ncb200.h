@@ -27,6 +27,7 @@ extern "C" {
 #define NCB_ERR_ARG (-2)
 #define NCB_ERR_STATE (-3)
 #define NCB_ERR_UNSUPPORTED (-4)
+#define NCB_ROUTE_REPEAT 2 /* ncb_world_update_routed stage 4: bucket capacities were raised, repeat from stage 2 */
 
 /* shape_type values (shape/ball.rs, shape/cuboid.rs, shape/convex.rs, shape/plane.rs) */
 #define NCB_SHAPE_BALL 0u
@@ -147,7 +148,8 @@ typedef struct ncb_update_counts {
 int ncb_create(int device, ncb_ctx** out);
 void ncb_destroy(ncb_ctx* ctx);
 const char* ncb_last_error(const ncb_ctx* ctx); /* NULL ctx: error of the last failed ncb_create on this thread */
-/* Use the caller's CUDA stream (cudaStream_t as void*) instead of the context's own; NULL restores it. */
+/* Use the caller's CUDA stream (cudaStream_t as void*) instead of the context's own; NULL restores the context's own stream (to share
+ * the legacy default stream pass cudaStreamLegacy, i.e. (void*)0x1).  Work already enqueued on the outgoing stream is waited for. */
 int ncb_set_stream(ncb_ctx* ctx, void* cuda_stream);
 void* ncb_get_stream(ncb_ctx* ctx);
 int ncb_synchronize(ncb_ctx* ctx);
@@ -245,6 +247,22 @@ int ncb_world_update_stage(ncb_ctx* ctx, int stage, float margin, uint32_t begin
  * `rank` of `world` selects the objects it owns (equal-count Morton ranges) plus the ghosts around them, builds its LBVH
  * over those only and reports its share of the pairs + their contacts.  Every pair is reported by exactly one rank. */
 int ncb_world_update_sharded(ncb_ctx* ctx, float margin, int rank, int world, ncb_update_counts* counts);
+/* Multi-GPU update with ROUTED spatial ownership (the default of ncollide_b200/parallel.py): no all-gather of all boxes; every rank
+ * sends each object of its own block [begin, end) to the rank that owns its Morton bin and, as a ghost, to the ranks whose region its
+ * fat box meets (pipeline/broad_phase/dbvt_broad_phase.rs:174-259 sees the same pair set: every intersecting pair has both boxes on
+ * the rank that reports it).  The caller runs one collective on the device buffers of ncb_route_buffer between the stages:
+ *   stage 0: AABBs + centre bounds of the own block          -> all-reduce MAX of buffer 0
+ *   stage 1: Morton bins + histogram                          -> all-reduce SUM of buffer 1
+ *   stage 2: owner buckets + per-owner regions                -> all-to-all buffer 2 -> 3 (world equal parts), all-reduce MAX of buffer 4
+ *   stage 3: ghost buckets                                    -> all-to-all buffer 5 -> 6
+ *   stage 4: unpack, local LBVH, pair search, narrow phase; fills counts.  NCB_ROUTE_REPEAT: a bucket was too small on some rank;
+ *            every rank has raised its capacities identically, repeat from stage 2.
+ * with_poses != 0: records also carry the poses (a rank needs only the poses of its own block before stage 0). */
+int ncb_world_update_routed(ncb_ctx* ctx, int stage, float margin, int rank, int world, uint32_t begin, uint32_t end, int with_poses,
+                            ncb_update_counts* counts);
+/* Device buffers of the routed update, for the caller's collectives.  which: 0 bounds (6 f32), 1 histogram (1024 i32), 2 / 3 owner
+ * buckets send / recv, 4 regions (6 * world f32), 5 / 6 ghost buckets send / recv; *bytes = the extent the collective covers. */
+void* ncb_route_buffer(ncb_ctx* ctx, int which, int world, uint64_t* bytes);
 /* Arms an overlapped fetch for the NEXT device update: while its narrow phase runs, the sorted pairs (+ algorithm) and the
  * contacts that are already final are copied into these host buffers (pinned memory recommended); ncb_world_fetch with the
  * same buffers then only copies the rest.  ncb_world_update does this by itself. */

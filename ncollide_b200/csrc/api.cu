@@ -177,7 +177,14 @@ const char* ncb_last_error(const ncb_ctx* c) { return c ? c->err.c_str() : g_cre
 
 int ncb_set_stream(ncb_ctx* ctx, void* s) {
     if (!ctx) return NCB_ERR_ARG;
-    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    cudaStream_t next = s ? (cudaStream_t)s : ctx->own_stream;
+    if (next != ctx->stream) {
+        // work already enqueued on the outgoing stream (uploads of ncb_set_objects / ncb_set_hulls, their fill kernels) must be
+        // complete before anything on the new stream reads it: the two streams are not ordered with each other
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->stream = next;
     return NCB_OK;
 }
 void* ncb_get_stream(ncb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -755,6 +762,131 @@ int ncb_world_update_sharded(ncb_ctx* ctx, float margin, int rank, int world, nc
     if (r) return r;
     fill_counts(ctx, counts);
     return NCB_OK;
+}
+
+// Multi-GPU update with ROUTED spatial ownership (see the routed-sharding block of broad.cu): nothing is all-gathered; every rank
+// sends each object of its own block [begin, end) to the rank that owns its Morton bin, and as a ghost to the ranks whose region
+// its box meets.  The caller performs one collective on the buffers of ncb_route_buffer between the stages:
+//   stage 0 (AABBs + centre bounds of the own block)   -> all-reduce MAX  of buffer 0 (6 floats)
+//   stage 1 (bins + histogram)                          -> all-reduce SUM  of buffer 1 (SHARD_BINS ints)
+//   stage 2 (owner buckets + regions)                   -> all-to-all      buffer 2 -> 3, all-reduce MAX of buffer 4 (6 * world floats)
+//   stage 3 (ghost buckets)                             -> all-to-all      buffer 5 -> 6
+//   stage 4 (unpack, local LBVH, pair search, narrow phase; fills counts).  Returns NCB_ROUTE_REPEAT when a bucket was too
+//            small somewhere: the capacities have been raised (identically on every rank), repeat from stage 2.
+// with_poses != 0: the records also carry the poses (the end-to-end arm: a rank uploads the poses of its own block only).
+int ncb_world_update_routed(ncb_ctx* ctx, int stage, float margin, int rank, int world, uint32_t begin, uint32_t end, int with_poses,
+                            ncb_update_counts* counts) {
+    if (!ctx || rank < 0 || world < 1 || rank >= world || world > SHARD_MAX_RANKS || stage < 0 || stage > 4) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t n = ctx->n;
+    if (end > n) end = n;
+    if (begin > end) begin = end;
+    ncb::RouteBufs& R = ctx->route;
+    cudaStream_t s = ctx->stream;
+    uint32_t n_own = end - begin;
+    if (stage == 0) {
+        R.recw = with_poses ? 4 : 2;
+        CK(R.bounds.reserve(8));
+        CK(R.hist.reserve(SHARD_BINS));
+        CK(R.split.reserve(SHARD_MAX_RANKS + 1));
+        CK(R.bins.reserve(n_own ? n_own : 1));
+        CK(R.region_i.reserve(SHARD_MAX_RANKS * 6));
+        CK(R.region_f.reserve(SHARD_MAX_RANKS * 6));
+        CK(R.counts.reserve(2 * SHARD_MAX_RANKS));
+        CK(ctx->shard.reserve(1));
+        CK(ctx->counters.reserve(1));
+        int r = reset_counters(ctx);
+        if (r) return r;
+        timer_begin(ctx);
+        ctx->timer_external = true;
+        CK(launch_aabbs(ctx, dev_objects(ctx), margin, 2, begin, end));
+        timer_mark(ctx, "aabb", 1);
+        CK(launch_route_stage(ctx, 0, rank, world, begin, end, R));
+        return NCB_OK;
+    }
+    if (stage == 1) {
+        CK(launch_route_stage(ctx, 1, rank, world, begin, end, R));
+        return NCB_OK;
+    }
+    if (stage == 2) {
+        // bucket capacities (records incl. the header slot), the same on every rank: derived from the largest block and from
+        // requirements that every rank sees identically (stage 4)
+        uint32_t blk = (n + world - 1) / world;
+        static const char* slack_env = getenv("NCB_ROUTE_SLACK");  // tests: a tiny slack forces the grow-and-repeat path
+        uint32_t slack = slack_env ? (uint32_t)atoi(slack_env) : 2048;
+        if (!R.cap_o) R.cap_o = blk / world + blk / (4 * world) + slack;
+        if (!R.cap_g) R.cap_g = blk / (4 * world) + slack;
+        if (R.cap_o < 2) R.cap_o = 2;
+        if (R.cap_g < 2) R.cap_g = 2;
+        size_t w = (size_t)R.recw;
+        CK(R.send_o.reserve((size_t)world * R.cap_o * w));
+        CK(R.recv_o.reserve((size_t)world * R.cap_o * w));
+        CK(R.send_g.reserve((size_t)world * R.cap_g * w));
+        CK(R.recv_g.reserve((size_t)world * R.cap_g * w));
+        CK(launch_route_stage(ctx, 2, rank, world, begin, end, R));
+        return NCB_OK;
+    }
+    if (stage == 3) {
+        CK(launch_route_stage(ctx, 3, rank, world, begin, end, R));
+        timer_mark(ctx, "route", 5);
+        return NCB_OK;
+    }
+    // stage 4
+    size_t cap_local = (size_t)world * ((size_t)R.cap_o + R.cap_g);
+    CK(ctx->shard_sel.reserve(cap_local));
+    CK(ctx->shard_lo.reserve(cap_local));
+    CK(ctx->shard_hi.reserve(cap_local));
+    CK(launch_route_unpack(ctx, world, R, (uint32_t)cap_local, ctx->shard.p, ctx->shard_sel.p, ctx->shard_lo.p, ctx->shard_hi.p));
+    uint32_t tail[SHARD_MAX_RANKS + 1 + 6 + 2];
+    CK(cudaMemcpyAsync(tail, &ctx->shard.p->split[0], sizeof tail, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    uint32_t need_o = tail[0], need_g = tail[1];
+    ctx->shard_m = tail[SHARD_MAX_RANKS + 1 + 6], ctx->shard_owned = tail[SHARD_MAX_RANKS + 1 + 6 + 1];
+    if (need_o > R.cap_o || need_g > R.cap_g) {
+        if (need_o > R.cap_o) R.cap_o = need_o + need_o / 8 + 1024;
+        if (need_g > R.cap_g) R.cap_g = need_g + need_g / 8 + 1024;
+        return NCB_ROUTE_REPEAT;
+    }
+    timer_mark(ctx, "route_unpack", 7);
+    if (ctx->shard_m == 0) {
+        ctx->timer_external = false;
+        memset(&ctx->last_counters, 0, sizeof ctx->last_counters);
+        ctx->last_n_pairs = ctx->last_n_contacts = 0;
+        ctx->early.active = ctx->early.valid = false;
+        fill_counts(ctx, counts);
+        return NCB_OK;
+    }
+    std::swap(ctx->aabb_lo, ctx->shard_lo);
+    std::swap(ctx->aabb_hi, ctx->shard_hi);
+    int r = update_after_aabbs(ctx, 0, 0xffffffffu, ctx->shard_m, ctx->shard_sel.p, rank);
+    ctx->timer_external = false;
+    std::swap(ctx->aabb_lo, ctx->shard_lo);
+    std::swap(ctx->aabb_hi, ctx->shard_hi);
+    if (r) return r;
+    fill_counts(ctx, counts);
+    return NCB_OK;
+}
+
+// Buffers of the routed update for the caller's collectives: which = 0 bounds (6 f32), 1 histogram (SHARD_BINS i32), 2 / 3 owner
+// buckets send / recv, 4 regions (6 * SHARD_MAX_RANKS f32; the first 6 * world are used), 5 / 6 ghost buckets send / recv.
+// *bytes = the extent a collective covers (for 2 / 3 / 5 / 6: world equal parts).  Valid after the stage that precedes the collective.
+void* ncb_route_buffer(ncb_ctx* ctx, int which, int world, uint64_t* bytes) {
+    if (!ctx) return nullptr;
+    ncb::RouteBufs& R = ctx->route;
+    uint64_t b = 0;
+    void* p = nullptr;
+    switch (which) {
+        case 0: p = R.bounds.p, b = 6 * sizeof(float); break;
+        case 1: p = R.hist.p, b = SHARD_BINS * sizeof(int); break;
+        case 2: p = R.send_o.p, b = (uint64_t)world * R.cap_o * R.recw * sizeof(float4); break;
+        case 3: p = R.recv_o.p, b = (uint64_t)world * R.cap_o * R.recw * sizeof(float4); break;
+        case 4: p = R.region_f.p, b = (uint64_t)world * 6 * sizeof(float); break;
+        case 5: p = R.send_g.p, b = (uint64_t)world * R.cap_g * R.recw * sizeof(float4); break;
+        case 6: p = R.recv_g.p, b = (uint64_t)world * R.cap_g * R.recw * sizeof(float4); break;
+        default: break;
+    }
+    if (bytes) *bytes = b;
+    return p;
 }
 
 int ncb_world_update_device(ncb_ctx* ctx, float margin, uint32_t q_begin, uint32_t q_end, ncb_update_counts* counts) {

@@ -560,7 +560,11 @@ __global__ void __launch_bounds__(256) k_route_owned(const float4* __restrict__ 
 __global__ void k_route_finish(const uint32_t* __restrict__ counts, int world, uint32_t cap, int recw, float4* __restrict__ send,
                                const int* __restrict__ region, float* __restrict__ region_f) {
     int t = threadIdx.x;
-    if (t < world) send[(size_t)t * cap * recw] = make_float4(__uint_as_float(counts[t]), 0.f, 0.f, 0.f);
+    // header.y: the largest bucket of this sender.  Every receiver sees it from every sender, so all ranks derive the same
+    // capacity requirement (the collectives use one capacity for all buckets of all ranks) without another collective.
+    uint32_t mx = 0;
+    for (int q = 0; q < world; ++q) mx = max(mx, counts[q]);
+    if (t < world) send[(size_t)t * cap * recw] = make_float4(__uint_as_float(counts[t]), __uint_as_float(mx), 0.f, 0.f);
     if (region_f && t < world * 6) region_f[t] = (t % 6) < 3 ? -o2f(region[t]) : o2f(region[t]);
 }
 // stage 3: ghosts = own objects whose box meets the region of a rank that does not own them (inclusive test, like AABB::intersects)
@@ -606,8 +610,8 @@ __global__ void __launch_bounds__(256) k_route_unpack(const float4* __restrict__
         for (int bk = 0; bk < 2 * world; ++bk) {
             bool ghost = bk >= world;
             const float4* hdr = ghost ? recv_g + (size_t)(bk - world) * cap_g * recw : recv_o + (size_t)bk * cap_o * recw;
-            uint32_t c = __float_as_uint(hdr->x), cap = (ghost ? cap_g : cap_o) - 1;
-            if (ghost) need_g = max(need_g, c + 1); else need_o = max(need_o, c + 1);
+            uint32_t c = __float_as_uint(hdr->x), big = __float_as_uint(hdr->y), cap = (ghost ? cap_g : cap_o) - 1;
+            if (ghost) need_g = max(need_g, big + 1); else need_o = max(need_o, big + 1);
             c = min(c, cap);
             s_off[bk] = acc, s_cnt[bk] = c;
             acc += c;
