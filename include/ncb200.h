@@ -263,6 +263,19 @@ int ncb_world_update_routed(ncb_ctx* ctx, int stage, float margin, int rank, int
 /* Device buffers of the routed update, for the caller's collectives.  which: 0 bounds (6 f32), 1 histogram (1024 i32), 2 / 3 owner
  * buckets send / recv, 4 regions (6 * world f32), 5 / 6 ghost buckets send / recv; *bytes = the extent the collective covers. */
 void* ncb_route_buffer(ncb_ctx* ctx, int which, int world, uint64_t* bytes);
+/* Peer-memory exchange for the routed update (NVLink P2P instead of NCCL inside the step).  ncb_route_p2p_alloc allocates this rank's
+ * receive buffers (buckets of largest-block + 1 records: they cannot overflow) and exports them: `handles` receives 3 cudaIpcMemHandle_t
+ * (3 x 64 bytes) for peers in other processes, `ptrs` 3 raw device pointers for peers inside this process (either may be NULL).  The
+ * caller gathers every rank's handles (any transport; done once) and calls ncb_route_p2p_connect with world x 3 handles in rank order
+ * (or handles_all NULL and world x 3 raw pointers when all ranks live in one process).  From then on the routing kernels store records
+ * straight into the owner's bucket on the peer GPU, the small arrays (bounds, histogram, regions) go to per-sender slots, a
+ * system-scope flag per sender closes each round, and ncb_world_update_routed(stage = -1) runs a whole step in one call with no
+ * collective and no host work between the stages (stages 0..4 remain callable one by one: every rank must have been given stage s
+ * before any rank is given stage s + 1 when the ranks share a stream).  A peer that does not arrive within ~2 s makes the step
+ * return NCB_ERR_STATE instead of hanging. */
+int ncb_route_p2p_alloc(ncb_ctx* ctx, int rank, int world, uint32_t n_total, void* handles, uint64_t* ptrs);
+int ncb_route_p2p_connect(ncb_ctx* ctx, const void* handles_all, const uint64_t* ptrs_all);
+int ncb_route_p2p_close(ncb_ctx* ctx);
 /* Arms an overlapped fetch for the NEXT device update: while its narrow phase runs, the sorted pairs (+ algorithm) and the
  * contacts that are already final are copied into these host buffers (pinned memory recommended); ncb_world_fetch with the
  * same buffers then only copies the rest.  ncb_world_update does this by itself. */

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libncb200.so")
 EXPORTED_SYMBOLS = [
     "ncb_version", "ncb_create", "ncb_destroy", "ncb_last_error", "ncb_set_stream", "ncb_get_stream", "ncb_synchronize", "ncb_traversal_overflows", "ncb_set_kinematics", "ncb_world_fetch_kinematics",
     "ncb_set_hulls", "ncb_set_objects", "ncb_set_positions", "ncb_set_positions_range", "ncb_compute_aabbs", "ncb_broad_phase", "ncb_generate_contacts",
-    "ncb_world_update_device", "ncb_world_fetch", "ncb_world_update", "ncb_world_update_poses", "ncb_device_ptr", "ncb_world_update_stage", "ncb_world_update_sharded", "ncb_world_update_routed", "ncb_route_buffer", "ncb_world_fetch_early",
+    "ncb_world_update_device", "ncb_world_fetch", "ncb_world_update", "ncb_world_update_poses", "ncb_device_ptr", "ncb_world_update_stage", "ncb_world_update_sharded", "ncb_world_update_routed", "ncb_route_buffer", "ncb_route_p2p_alloc", "ncb_route_p2p_connect", "ncb_route_p2p_close", "ncb_world_fetch_early",
     "ncb_profile_enable", "ncb_profile_get", "ncb_trimesh_create", "ncb_trimesh_destroy", "ncb_trimesh_ray_cast",
     "ncb_trimesh_ray_cast_device",
     "ncb_bp_create", "ncb_bp_destroy", "ncb_bp_create_proxies", "ncb_bp_set_bounding_volumes", "ncb_bp_remove", "ncb_bp_update",

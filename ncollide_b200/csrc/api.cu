@@ -142,10 +142,12 @@ static void free_hulls(ncb_ctx* c) {
     memset(&c->hulls, 0, sizeof c->hulls);
 }
 
+static void p2p_close(ncb_ctx* ctx);
 void ncb_destroy(ncb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    p2p_close(c);  // unmap the peers' buffers (the own ones go with the context)
     free_hulls(c);
     c->ang_cs.release();
     c->pos.release(), c->qlimit.release(), c->ang.release(), c->rot.release(), c->param.release(), c->type.release(), c->groups.release();
@@ -774,16 +776,17 @@ int ncb_world_update_sharded(ncb_ctx* ctx, float margin, int rank, int world, nc
 //   stage 4 (unpack, local LBVH, pair search, narrow phase; fills counts).  Returns NCB_ROUTE_REPEAT when a bucket was too
 //            small somewhere: the capacities have been raised (identically on every rank), repeat from stage 2.
 // with_poses != 0: the records also carry the poses (the end-to-end arm: a rank uploads the poses of its own block only).
-int ncb_world_update_routed(ncb_ctx* ctx, int stage, float margin, int rank, int world, uint32_t begin, uint32_t end, int with_poses,
-                            ncb_update_counts* counts) {
-    if (!ctx || rank < 0 || world < 1 || rank >= world || world > SHARD_MAX_RANKS || stage < 0 || stage > 4) return NCB_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
+static int routed_stage(ncb_ctx* ctx, int stage, float margin, int rank, int world, uint32_t begin, uint32_t end, int with_poses,
+                        ncb_update_counts* counts) {
     uint32_t n = ctx->n;
-    if (end > n) end = n;
-    if (begin > end) begin = end;
     ncb::RouteBufs& R = ctx->route;
     cudaStream_t s = ctx->stream;
     uint32_t n_own = end - begin;
+    const bool p2p = R.p2p;
+    if (p2p) {
+        REQUIRE(R.p2p_rank == rank && R.p2p_world == world, NCB_ERR_ARG, "ncb_world_update_routed: rank / world differ from ncb_route_p2p_alloc");
+        REQUIRE(n_own + 1 <= R.p2p_cap, NCB_ERR_STATE, "ncb_world_update_routed: the block outgrew the peer buffers (ncb_route_p2p_alloc again)");
+    }
     if (stage == 0) {
         R.recw = with_poses ? 4 : 2;
         CK(R.bounds.reserve(8));
@@ -802,47 +805,73 @@ int ncb_world_update_routed(ncb_ctx* ctx, int stage, float margin, int rank, int
         CK(launch_aabbs(ctx, dev_objects(ctx), margin, 2, begin, end));
         timer_mark(ctx, "aabb", 1);
         CK(launch_route_stage(ctx, 0, rank, world, begin, end, R));
+        if (p2p) {
+            R.epoch++;
+            CK(launch_p2p_push(ctx, R, R.bounds.p, 6, 0, 1));
+        }
         return NCB_OK;
     }
     if (stage == 1) {
+        if (p2p) CK(launch_p2p_wait_reduce(ctx, R, 1, 0, 6, 0, R.bounds.p));
         CK(launch_route_stage(ctx, 1, rank, world, begin, end, R));
+        if (p2p) CK(launch_p2p_push(ctx, R, R.hist.p, SHARD_BINS, 1, 2));
         return NCB_OK;
     }
     if (stage == 2) {
-        // bucket capacities (records incl. the header slot), the same on every rank: derived from the largest block and from
-        // requirements that every rank sees identically (stage 4)
-        uint32_t blk = (n + world - 1) / world;
-        static const char* slack_env = getenv("NCB_ROUTE_SLACK");  // tests: a tiny slack forces the grow-and-repeat path
-        uint32_t slack = slack_env ? (uint32_t)atoi(slack_env) : 2048;
-        if (!R.cap_o) R.cap_o = blk / world + blk / (4 * world) + slack;
-        if (!R.cap_g) R.cap_g = blk / (4 * world) + slack;
-        if (R.cap_o < 2) R.cap_o = 2;
-        if (R.cap_g < 2) R.cap_g = 2;
-        size_t w = (size_t)R.recw;
-        CK(R.send_o.reserve((size_t)world * R.cap_o * w));
-        CK(R.recv_o.reserve((size_t)world * R.cap_o * w));
-        CK(R.send_g.reserve((size_t)world * R.cap_g * w));
-        CK(R.recv_g.reserve((size_t)world * R.cap_g * w));
+        if (p2p) {
+            CK(launch_p2p_wait_reduce(ctx, R, 2, 1, SHARD_BINS, 1, R.hist.p));
+        } else {
+            // bucket capacities (records incl. the header slot), the same on every rank: derived from the largest block and from
+            // requirements that every rank sees identically (stage 4)
+            uint32_t blk = (n + world - 1) / world;
+            static const char* slack_env = getenv("NCB_ROUTE_SLACK");  // tests: a tiny slack forces the grow-and-repeat path
+            uint32_t slack = slack_env ? (uint32_t)atoi(slack_env) : 2048;
+            if (!R.cap_o) R.cap_o = blk / world + blk / (4 * world) + slack;
+            if (!R.cap_g) R.cap_g = blk / (4 * world) + slack;
+            if (R.cap_o < 2) R.cap_o = 2;
+            if (R.cap_g < 2) R.cap_g = 2;
+            size_t w = (size_t)R.recw;
+            CK(R.send_o.reserve((size_t)world * R.cap_o * w));
+            CK(R.recv_o.reserve((size_t)world * R.cap_o * w));
+            CK(R.send_g.reserve((size_t)world * R.cap_g * w));
+            CK(R.recv_g.reserve((size_t)world * R.cap_g * w));
+        }
         CK(launch_route_stage(ctx, 2, rank, world, begin, end, R));
+        if (p2p) CK(launch_p2p_push(ctx, R, R.region_f.p, 6 * (uint32_t)world, 2, 3));
         return NCB_OK;
     }
     if (stage == 3) {
+        if (p2p) CK(launch_p2p_wait_reduce(ctx, R, 3, 2, 6 * (uint32_t)world, 0, R.region_f.p));
         CK(launch_route_stage(ctx, 3, rank, world, begin, end, R));
+        if (p2p) CK(launch_p2p_push(ctx, R, nullptr, 0, 2, 4));
         timer_mark(ctx, "route", 5);
         return NCB_OK;
     }
     // stage 4
-    size_t cap_local = (size_t)world * ((size_t)R.cap_o + R.cap_g);
+    if (p2p) CK(launch_p2p_wait_reduce(ctx, R, 4, 0, 0, -1, nullptr));
+    uint32_t cap_o = p2p ? R.p2p_cap : R.cap_o, cap_g = p2p ? R.p2p_cap : R.cap_g;
+    size_t cap_local = p2p ? (size_t)n : (size_t)world * ((size_t)cap_o + cap_g);  // a rank never holds an object twice
     CK(ctx->shard_sel.reserve(cap_local));
     CK(ctx->shard_lo.reserve(cap_local));
     CK(ctx->shard_hi.reserve(cap_local));
     CK(launch_route_unpack(ctx, world, R, (uint32_t)cap_local, ctx->shard.p, ctx->shard_sel.p, ctx->shard_lo.p, ctx->shard_hi.p));
     uint32_t tail[SHARD_MAX_RANKS + 1 + 6 + 2];
+    uint32_t p2p_err = 0;
     CK(cudaMemcpyAsync(tail, &ctx->shard.p->split[0], sizeof tail, cudaMemcpyDeviceToHost, s));
+    if (p2p) CK(cudaMemcpyAsync(&p2p_err, R.p2p_meta.p + P2P_ERR_OFF, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (p2p_err) {
+        ctx->timer_external = false;
+        ctx->err = "routed update: a peer did not reach the exchange within the time limit";
+        return NCB_ERR_STATE;
+    }
     uint32_t need_o = tail[0], need_g = tail[1];
     ctx->shard_m = tail[SHARD_MAX_RANKS + 1 + 6], ctx->shard_owned = tail[SHARD_MAX_RANKS + 1 + 6 + 1];
-    if (need_o > R.cap_o || need_g > R.cap_g) {
+    if (need_o > cap_o || need_g > cap_g) {
+        if (p2p) {
+            ctx->err = "routed update: a peer bucket overflowed";
+            return NCB_ERR_STATE;
+        }
         if (need_o > R.cap_o) R.cap_o = need_o + need_o / 8 + 1024;
         if (need_g > R.cap_g) R.cap_g = need_g + need_g / 8 + 1024;
         return NCB_ROUTE_REPEAT;
@@ -864,6 +893,101 @@ int ncb_world_update_routed(ncb_ctx* ctx, int stage, float margin, int rank, int
     std::swap(ctx->aabb_hi, ctx->shard_hi);
     if (r) return r;
     fill_counts(ctx, counts);
+    return NCB_OK;
+}
+
+int ncb_world_update_routed(ncb_ctx* ctx, int stage, float margin, int rank, int world, uint32_t begin, uint32_t end, int with_poses,
+                            ncb_update_counts* counts) {
+    if (!ctx || rank < 0 || world < 1 || rank >= world || world > SHARD_MAX_RANKS || stage < -1 || stage > 4) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (end > ctx->n) end = ctx->n;
+    if (begin > end) begin = end;
+    if (stage >= 0) return routed_stage(ctx, stage, margin, rank, world, begin, end, with_poses, counts);
+    // stage -1: the whole step in one call; only with the peer-memory exchange (nothing for the caller to do between the stages)
+    REQUIRE(ctx->route.p2p, NCB_ERR_STATE, "ncb_world_update_routed(stage -1) needs ncb_route_p2p_connect");
+    for (int st = 0; st <= 4; ++st) {
+        int r = routed_stage(ctx, st, margin, rank, world, begin, end, with_poses, counts);
+        if (r) return r;
+    }
+    return NCB_OK;
+}
+
+// ---- peer-memory exchange set-up -------------------------------------------------------------------------------------------
+// Allocates this rank's receive buffers (owner buckets, ghost buckets: world x (largest block + 1) records of 64 B, so they can
+// never overflow) and its meta / flag words, and exports them: `handles` receives 3 cudaIpcMemHandle_t (3 x 64 B) for peers in other
+// processes, `ptrs` the 3 raw device pointers for peers inside this process.
+int ncb_route_p2p_alloc(ncb_ctx* ctx, int rank, int world, uint32_t n_total, void* handles, uint64_t* ptrs) {
+    if (!ctx || rank < 0 || world < 1 || rank >= world || world > SHARD_MAX_RANKS) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ncb::RouteBufs& R = ctx->route;
+    uint32_t blk = (n_total + world - 1) / world;
+    R.p2p = false;
+    R.p2p_rank = rank, R.p2p_world = world, R.p2p_cap = blk + 1, R.epoch = 0;
+    size_t recs = (size_t)world * R.p2p_cap * 4;
+    CK(R.p2p_recv_o.reserve(recs));
+    CK(R.p2p_recv_g.reserve(recs));
+    CK(R.p2p_meta.reserve(P2P_META_WORDS));
+    CK(cudaMemsetAsync(R.p2p_meta.p, 0, P2P_META_WORDS * sizeof(uint32_t), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    void* base[3] = {R.p2p_recv_o.p, R.p2p_recv_g.p, R.p2p_meta.p};
+    for (int k = 0; k < 3; ++k) {
+        if (ptrs) ptrs[k] = (uint64_t)(uintptr_t)base[k];
+        if (handles) CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handles + k, base[k]));
+    }
+    return NCB_OK;
+}
+
+static void p2p_close(ncb_ctx* ctx) {
+    ncb::RouteBufs& R = ctx->route;
+    for (int q = 0; q < SHARD_MAX_RANKS; ++q) {
+        void* mapped[3] = {R.peer_recv_o[q], R.peer_recv_g[q], R.peer_meta[q]};
+        for (int k = 0; k < 3; ++k)
+            if (R.peer_opened[q][k] && mapped[k]) cudaIpcCloseMemHandle(mapped[k]);
+        R.peer_recv_o[q] = R.peer_recv_g[q] = nullptr;
+        R.peer_meta[q] = nullptr;
+        R.peer_opened[q][0] = R.peer_opened[q][1] = R.peer_opened[q][2] = false;
+    }
+    R.p2p = false;
+}
+
+// Connects to the peers: handles_all = world x 3 cudaIpcMemHandle_t in rank order (peers in other processes), or NULL with ptrs_all =
+// world x 3 raw device pointers (all ranks live in this process: the replay tests).  The own rank always uses its local pointers.
+int ncb_route_p2p_connect(ncb_ctx* ctx, const void* handles_all, const uint64_t* ptrs_all) {
+    if (!ctx || (!handles_all && !ptrs_all)) return NCB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ncb::RouteBufs& R = ctx->route;
+    REQUIRE(R.p2p_world > 0 && R.p2p_meta.p, NCB_ERR_STATE, "ncb_route_p2p_connect: call ncb_route_p2p_alloc first");
+    p2p_close(ctx);
+    for (int q = 0; q < R.p2p_world; ++q) {
+        void* got[3] = {nullptr, nullptr, nullptr};
+        if (q == R.p2p_rank) {
+            got[0] = R.p2p_recv_o.p, got[1] = R.p2p_recv_g.p, got[2] = R.p2p_meta.p;
+        } else if (handles_all) {
+            for (int k = 0; k < 3; ++k) {
+                cudaError_t e = cudaIpcOpenMemHandle(&got[k], ((const cudaIpcMemHandle_t*)handles_all)[q * 3 + k], cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    ctx->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+                    p2p_close(ctx);
+                    return NCB_ERR_CUDA;
+                }
+                R.peer_opened[q][k] = true;
+                if (k == 0) R.peer_recv_o[q] = (float4*)got[0];  // recorded at once so that a later failure closes it
+                if (k == 1) R.peer_recv_g[q] = (float4*)got[1];
+                if (k == 2) R.peer_meta[q] = (uint32_t*)got[2];
+            }
+        } else {
+            for (int k = 0; k < 3; ++k) got[k] = (void*)(uintptr_t)ptrs_all[q * 3 + k];
+        }
+        R.peer_recv_o[q] = (float4*)got[0], R.peer_recv_g[q] = (float4*)got[1], R.peer_meta[q] = (uint32_t*)got[2];
+    }
+    R.p2p = true;
+    return NCB_OK;
+}
+
+int ncb_route_p2p_close(ncb_ctx* ctx) {
+    if (!ctx) return NCB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    p2p_close(ctx);
     return NCB_OK;
 }
 

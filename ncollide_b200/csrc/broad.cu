@@ -514,7 +514,7 @@ __device__ __forceinline__ int route_owner(const uint32_t* __restrict__ split, i
 // stage 2: own objects -> the bucket of their owner; union box of the (finite) boxes per owner
 __global__ void __launch_bounds__(256) k_route_owned(const float4* __restrict__ lo, const float4* __restrict__ hi, const float* __restrict__ pos,
                                                      const float4* __restrict__ rot, uint32_t begin, uint32_t end, const uint32_t* __restrict__ bins,
-                                                     const uint32_t* __restrict__ split, int world, uint32_t cap, int recw, float4* __restrict__ send,
+                                                     const uint32_t* __restrict__ split, int world, uint32_t cap, int recw, RouteDst dst,
                                                      uint32_t* __restrict__ counts, int* __restrict__ region) {
     __shared__ int s_reg[SHARD_MAX_RANKS][6];
     for (int k = threadIdx.x; k < SHARD_MAX_RANKS * 6; k += blockDim.x) (&s_reg[0][0])[k] = (k % 6) < 3 ? 0x7f7fffff : (int)0x80800000;
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(256) k_route_owned(const float4* __restrict__ 
         base = __shfl_sync(peers, base, leader);
         uint32_t k = base + __popc(peers & ((1u << lane) - 1));
         if (k + 1 < cap) {  // slot 0 is the header
-            float4* r = send + ((size_t)owner * cap + 1 + k) * recw;
+            float4* r = dst.p[owner] + (size_t)(1 + k) * recw;
             a.w = __uint_as_float(i);
             b.w = __uint_as_float((__float_as_uint(b.w) & 0xffu) | ((uint32_t)owner << 8));
             r[0] = a, r[1] = b;
@@ -557,21 +557,21 @@ __global__ void __launch_bounds__(256) k_route_owned(const float4* __restrict__ 
     }
 }
 // bucket headers (slot 0 = record count, may exceed the capacity: the receiver clamps and flags) + regions as [-min, max] floats
-__global__ void k_route_finish(const uint32_t* __restrict__ counts, int world, uint32_t cap, int recw, float4* __restrict__ send,
-                               const int* __restrict__ region, float* __restrict__ region_f) {
+__global__ void k_route_finish(const uint32_t* __restrict__ counts, int world, RouteDst dst, const int* __restrict__ region,
+                               float* __restrict__ region_f) {
     int t = threadIdx.x;
     // header.y: the largest bucket of this sender.  Every receiver sees it from every sender, so all ranks derive the same
     // capacity requirement (the collectives use one capacity for all buckets of all ranks) without another collective.
     uint32_t mx = 0;
     for (int q = 0; q < world; ++q) mx = max(mx, counts[q]);
-    if (t < world) send[(size_t)t * cap * recw] = make_float4(__uint_as_float(counts[t]), __uint_as_float(mx), 0.f, 0.f);
+    if (t < world) dst.p[t][0] = make_float4(__uint_as_float(counts[t]), __uint_as_float(mx), 0.f, 0.f);
     if (region_f && t < world * 6) region_f[t] = (t % 6) < 3 ? -o2f(region[t]) : o2f(region[t]);
 }
 // stage 3: ghosts = own objects whose box meets the region of a rank that does not own them (inclusive test, like AABB::intersects)
 __global__ void __launch_bounds__(256) k_route_ghosts(const float4* __restrict__ lo, const float4* __restrict__ hi, const float* __restrict__ pos,
                                                       const float4* __restrict__ rot, uint32_t begin, uint32_t end, const uint32_t* __restrict__ bins,
                                                       const uint32_t* __restrict__ split, const float* __restrict__ region_f, int world, uint32_t cap,
-                                                      int recw, float4* __restrict__ send, uint32_t* __restrict__ counts) {
+                                                      int recw, RouteDst dst, uint32_t* __restrict__ counts) {
     __shared__ float s_r[SHARD_MAX_RANKS][6];
     for (int k = threadIdx.x; k < world * 6; k += blockDim.x) (&s_r[0][0])[k] = (k % 6) < 3 ? -region_f[k] : region_f[k];
     __syncthreads();
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(256) k_route_ghosts(const float4* __restrict__
         if (!take) continue;
         uint32_t k = atomicAdd(&counts[q], 1u);
         if (k + 1 < cap) {
-            float4* r = send + ((size_t)q * cap + 1 + k) * recw;
+            float4* r = dst.p[q] + (size_t)(1 + k) * recw;
             float4 a2 = a, b2 = b;
             a2.w = __uint_as_float(i);
             b2.w = __uint_as_float((__float_as_uint(b.w) & 0xffu) | ((uint32_t)owner << 8));
@@ -610,7 +610,8 @@ __global__ void __launch_bounds__(256) k_route_unpack(const float4* __restrict__
         for (int bk = 0; bk < 2 * world; ++bk) {
             bool ghost = bk >= world;
             const float4* hdr = ghost ? recv_g + (size_t)(bk - world) * cap_g * recw : recv_o + (size_t)bk * cap_o * recw;
-            uint32_t c = __float_as_uint(hdr->x), big = __float_as_uint(hdr->y), cap = (ghost ? cap_g : cap_o) - 1;
+            float4 hv = __ldcg(hdr);
+            uint32_t c = __float_as_uint(hv.x), big = __float_as_uint(hv.y), cap = (ghost ? cap_g : cap_o) - 1;
             if (ghost) need_g = max(need_g, big + 1); else need_o = max(need_o, big + 1);
             c = min(c, cap);
             s_off[bk] = acc, s_cnt[bk] = c;
@@ -632,12 +633,12 @@ __global__ void __launch_bounds__(256) k_route_unpack(const float4* __restrict__
         const float4* r = bucket + (size_t)(1 + k) * recw;
         uint32_t dst = s_off[bk] + k;
         if (dst >= cap_local) continue;
-        float4 a = r[0], b = r[1];
+        float4 a = __ldcg(&r[0]), b = __ldcg(&r[1]);  // L2 reads: a peer may have written the bucket over NVLink
         uint32_t handle = __float_as_uint(a.w);
         sel[dst] = handle;
         loc_lo[dst] = a, loc_hi[dst] = b;
         if (recw == 4) {
-            float4 p = r[2], q = r[3];
+            float4 p = __ldcg(&r[2]), q = __ldcg(&r[3]);
             pos[3 * (size_t)handle] = p.x, pos[3 * (size_t)handle + 1] = p.y, pos[3 * (size_t)handle + 2] = p.z;
             rot[handle] = make_float4(p.w, q.x, q.y, q.z);
         }
@@ -645,11 +646,24 @@ __global__ void __launch_bounds__(256) k_route_unpack(const float4* __restrict__
     (void)cap;
 }
 
+static RouteDst route_dst(const RouteBufs& R, int world, bool ghosts) {
+    RouteDst d;
+    for (int q = 0; q < SHARD_MAX_RANKS; ++q) d.p[q] = nullptr;
+    for (int q = 0; q < world; ++q) {
+        if (R.p2p)  // my bucket inside peer q's receive buffer
+            d.p[q] = (ghosts ? R.peer_recv_g[q] : R.peer_recv_o[q]) + (size_t)R.p2p_rank * R.p2p_cap * R.recw;
+        else
+            d.p[q] = (ghosts ? R.send_g.p + (size_t)q * R.cap_g * R.recw : R.send_o.p + (size_t)q * R.cap_o * R.recw);
+    }
+    return d;
+}
+
 cudaError_t launch_route_stage(ncb_ctx* c, int stage, int rank, int world, uint32_t begin, uint32_t end, RouteBufs& R) {
     (void)rank;
     cudaStream_t s = c->stream;
     uint32_t n_own = end - begin, nb = (n_own + 255) / 256;
     int gs = c->sm_count * 4;
+    uint32_t cap_o = R.p2p ? R.p2p_cap : R.cap_o, cap_g = R.p2p ? R.p2p_cap : R.cap_g;
     switch (stage) {
         case 0: {  // bounds of the own block (needs counters reset by the caller)
             if (n_own) k_bounds<<<min((uint32_t)gs, nb), 256, 0, s>>>(c->aabb_lo.p + begin, c->aabb_hi.p + begin, n_own, c->counters.p);
@@ -667,29 +681,91 @@ cudaError_t launch_route_stage(ncb_ctx* c, int stage, int rank, int world, uint3
             cudaMemcpyAsync(R.region_i.p, z, sizeof z, cudaMemcpyHostToDevice, s);
             cudaMemsetAsync(R.counts.p, 0, 2 * SHARD_MAX_RANKS * sizeof(uint32_t), s);
             k_route_split<<<1, 32, 0, s>>>(R.hist.p, world, R.split.p);
+            RouteDst d = route_dst(R, world, false);
             if (n_own)
-                k_route_owned<<<nb, 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, c->pos.p, c->rot.p, begin, end, R.bins.p, R.split.p, world, R.cap_o, R.recw,
-                                                 R.send_o.p, R.counts.p, R.region_i.p);
-            k_route_finish<<<1, 128, 0, s>>>(R.counts.p, world, R.cap_o, R.recw, R.send_o.p, R.region_i.p, R.region_f.p);
+                k_route_owned<<<nb, 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, c->pos.p, c->rot.p, begin, end, R.bins.p, R.split.p, world, cap_o, R.recw, d,
+                                                 R.counts.p, R.region_i.p);
+            k_route_finish<<<1, 128, 0, s>>>(R.counts.p, world, d, R.region_i.p, R.region_f.p);
             break;
         }
         case 3: {
+            RouteDst d = route_dst(R, world, true);
             if (n_own)
                 k_route_ghosts<<<nb, 256, 0, s>>>(c->aabb_lo.p, c->aabb_hi.p, c->pos.p, c->rot.p, begin, end, R.bins.p, R.split.p, R.region_f.p, world,
-                                                  R.cap_g, R.recw, R.send_g.p, R.counts.p + SHARD_MAX_RANKS);
-            k_route_finish<<<1, 128, 0, s>>>(R.counts.p + SHARD_MAX_RANKS, world, R.cap_g, R.recw, R.send_g.p, nullptr, nullptr);
+                                                  cap_g, R.recw, d, R.counts.p + SHARD_MAX_RANKS);
+            k_route_finish<<<1, 128, 0, s>>>(R.counts.p + SHARD_MAX_RANKS, world, d, nullptr, nullptr);
             break;
         }
         default: break;
     }
     return cudaGetLastError();
 }
+
+// ---- peer-memory rounds: push a small array into every peer's meta slot and raise my flag there; wait for all flags; reduce ----
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// One CTA per peer.  Everything this rank stored for the round (records written by the kernels before this one on the stream, the
+// words copied here) is ordered before the flag by the system-scope fence + release store.
+__global__ void __launch_bounds__(256) k_p2p_push(const uint32_t* __restrict__ src, uint32_t words, RoutePeers peers, int slot, int rank,
+                                                  uint32_t value) {
+    uint32_t* m = peers.meta[blockIdx.x];
+    uint32_t* dst = m + ((size_t)slot * SHARD_MAX_RANKS + rank) * P2P_SLOT_WORDS;
+    for (uint32_t t = threadIdx.x; t < words; t += blockDim.x) dst[t] = src[t];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(m + P2P_FLAGS_OFF + rank, value);
+}
+// Waits until every sender has raised its flag to `value` (flags only grow), then reduces the senders' slots: op 0 = float max,
+// 1 = int sum, < 0 = nothing to reduce.  A peer that does not arrive within ~2 s sets the error word instead of hanging the GPU.
+__global__ void __launch_bounds__(256) k_p2p_wait_reduce(uint32_t* __restrict__ meta, int world, uint32_t value, int slot, uint32_t words, int op,
+                                                         uint32_t* __restrict__ out) {
+    if (threadIdx.x < (unsigned)world) {
+        const uint32_t* f = meta + P2P_FLAGS_OFF + threadIdx.x;
+        long long t0 = clock64();
+        while ((int)(ld_acquire_sys(f) - value) < 0) {
+            if (clock64() - t0 > 4000000000ll) {
+                atomicExch(meta + P2P_ERR_OFF, 1u);
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    if (op < 0) return;
+    for (uint32_t t = threadIdx.x; t < words; t += blockDim.x) {
+        if (op == 0) {
+            float v = -NCB_FMAX;
+            for (int q = 0; q < world; ++q) v = fmaxf(v, __uint_as_float(__ldcg(meta + ((size_t)slot * SHARD_MAX_RANKS + q) * P2P_SLOT_WORDS + t)));
+            out[t] = __float_as_uint(v);
+        } else {
+            uint32_t v = 0;
+            for (int q = 0; q < world; ++q) v += __ldcg(meta + ((size_t)slot * SHARD_MAX_RANKS + q) * P2P_SLOT_WORDS + t);
+            out[t] = v;
+        }
+    }
+}
+cudaError_t launch_p2p_push(ncb_ctx* c, RouteBufs& R, const void* src, uint32_t words, int slot, int round) {
+    RoutePeers peers;
+    for (int q = 0; q < SHARD_MAX_RANKS; ++q) peers.meta[q] = q < R.p2p_world ? R.peer_meta[q] : nullptr;
+    k_p2p_push<<<R.p2p_world, 256, 0, c->stream>>>((const uint32_t*)src, words, peers, slot, R.p2p_rank, 4 * R.epoch + (uint32_t)round);
+    return cudaGetLastError();
+}
+cudaError_t launch_p2p_wait_reduce(ncb_ctx* c, RouteBufs& R, int round, int slot, uint32_t words, int op, void* out) {
+    k_p2p_wait_reduce<<<1, 256, 0, c->stream>>>(R.p2p_meta.p, R.p2p_world, 4 * R.epoch + (uint32_t)round, slot, words, op, (uint32_t*)out);
+    return cudaGetLastError();
+}
 cudaError_t launch_route_unpack(ncb_ctx* c, int world, RouteBufs& R, uint32_t cap_local, ShardScratch* sh, uint32_t* sel, float4* loc_lo,
                                 float4* loc_hi) {
-    uint32_t per = max(R.cap_o, R.cap_g);
+    uint32_t cap_o = R.p2p ? R.p2p_cap : R.cap_o, cap_g = R.p2p ? R.p2p_cap : R.cap_g;
+    const float4* ro = R.p2p ? R.p2p_recv_o.p : R.recv_o.p;
+    const float4* rg = R.p2p ? R.p2p_recv_g.p : R.recv_g.p;
+    uint32_t per = max(cap_o, cap_g);
     dim3 grid(min((per + 255) / 256, (uint32_t)c->sm_count * 2), 2 * world);
-    k_route_unpack<<<grid, 256, 0, c->stream>>>(R.recv_o.p, R.recv_g.p, world, R.cap_o, R.cap_g, R.recw, cap_local, sel, loc_lo, loc_hi, c->pos.p,
-                                                c->rot.p, sh);
+    k_route_unpack<<<grid, 256, 0, c->stream>>>(ro, rg, world, cap_o, cap_g, R.recw, cap_local, sel, loc_lo, loc_hi, c->pos.p, c->rot.p, sh);
     return cudaGetLastError();
 }
 

@@ -201,6 +201,31 @@ struct RouteBufs {
     DevBuf<float4> send_o, recv_o, send_g, recv_g;  // world buckets of cap records of recw float4 (slot 0 = header)
     uint32_t cap_o = 0, cap_g = 0;
     int recw = 2;              // 2: boxes only; 4: boxes + poses
+    // Peer-memory exchange (NVLink P2P, no NCCL in the step): every rank's recv buffers, meta slots and flags are mapped into all
+    // peers (CUDA IPC between processes, raw pointers inside one process); the routing kernels store records straight into the
+    // owner's bucket, small arrays (bounds, histogram, regions) go to a per-sender meta slot, and a system-scope flag per sender
+    // closes each of the four rounds of a step.
+    bool p2p = false;
+    int p2p_rank = 0, p2p_world = 0;
+    uint32_t p2p_cap = 0;              // records per bucket (incl. the header slot) = largest block + 1: cannot overflow
+    uint32_t epoch = 0;                // steps so far; the flag value of round r (1..4) of a step is 4 * epoch + r
+    DevBuf<float4> p2p_recv_o, p2p_recv_g;
+    DevBuf<uint32_t> p2p_meta;
+    float4* peer_recv_o[SHARD_MAX_RANKS] = {};
+    float4* peer_recv_g[SHARD_MAX_RANKS] = {};
+    uint32_t* peer_meta[SHARD_MAX_RANKS] = {};
+    bool peer_opened[SHARD_MAX_RANKS][3] = {};  // mapped with cudaIpcOpenMemHandle (to be closed)
+};
+// meta buffer of the peer-memory exchange, in 32-bit words: three slots (bounds, histogram, regions) per sender, then flags
+#define P2P_SLOT_WORDS 1024
+#define P2P_FLAGS_OFF (3 * SHARD_MAX_RANKS * P2P_SLOT_WORDS)
+#define P2P_ERR_OFF (P2P_FLAGS_OFF + 32)
+#define P2P_META_WORDS (P2P_ERR_OFF + 32)
+struct RouteDst {
+    float4* p[SHARD_MAX_RANKS];  // where the bucket for destination q starts (local send buffer, or the peer's recv buffer)
+};
+struct RoutePeers {
+    uint32_t* meta[SHARD_MAX_RANKS];
 };
 
 struct StageTimer {
@@ -338,6 +363,8 @@ cudaError_t launch_shard_select(ncb_ctx* c, uint32_t n, int rank, int world, Sha
                                 float4* loc_lo, float4* loc_hi);
 cudaError_t launch_pair_sort(ncb_ctx* c, uint32_t cap_pairs, uint32_t* index_out);
 cudaError_t launch_route_stage(ncb_ctx* c, int stage, int rank, int world, uint32_t begin, uint32_t end, RouteBufs& R);
+cudaError_t launch_p2p_push(ncb_ctx* c, RouteBufs& R, const void* src, uint32_t words, int slot, int round);
+cudaError_t launch_p2p_wait_reduce(ncb_ctx* c, RouteBufs& R, int round, int slot, uint32_t words, int op, void* out);
 cudaError_t launch_route_unpack(ncb_ctx* c, int world, RouteBufs& R, uint32_t cap_local, ShardScratch* sh, uint32_t* sel, float4* loc_lo, float4* loc_hi);
 size_t lbvh_temp_bytes(uint32_t n);
 // narrow.cu

@@ -75,7 +75,9 @@ def run_plans_lockstep(plans):
     while any(o is not None for o in ops):
         kind = ops[0][0]
         assert all(o is not None and o[0] == kind for o in ops), "ranks disagree on the collective sequence"
-        if kind in ("all_reduce_max", "all_reduce_sum"):
+        if kind == "p2p_round":  # peer-memory exchange: nothing to perform, the ranks only have to advance stage by stage
+            pass
+        elif kind in ("all_reduce_max", "all_reduce_sum"):
             stack = torch.stack([o[1] for o in ops])
             red = stack.max(dim=0).values if kind == "all_reduce_max" else stack.sum(dim=0)
             for o in ops:
@@ -116,21 +118,75 @@ class ShardedWorld:
         import torch
 
         self.ctx, self.scene, self.world, self.rank, self.device = ctx, scene, world, rank, device
-        # "routed" (default) / "spatial" (all-gather + select; NCB_SHARD=spatial) / "slices" (replicated LBVH; NCB_SHARD=slices)
+        # "p2p" (default): routed ownership, records stored straight into the owner's buffers over NVLink peer memory, no NCCL in the
+        #     step (falls back to "routed" on every rank when the peer mapping cannot be set up);
+        # "routed": the same ownership with NCCL all-to-all / all-reduce between the stages (NCB_SHARD=routed);
+        # "spatial": all-gather + select (NCB_SHARD=spatial); "slices": replicated LBVH (NCB_SHARD=slices)
         if mode is None:
-            mode = os.environ.get("NCB_SHARD", "routed")
+            mode = os.environ.get("NCB_SHARD", "p2p")
             if spatial is not None:
                 mode = "spatial" if spatial else "slices"
-        assert mode in ("routed", "spatial", "slices")
+        assert mode in ("p2p", "routed", "spatial", "slices")
         self.mode = mode
+        self.p2p_connected = False
         self.spatial = mode == "spatial"
         self.n = scene.n
+        self._route_views = {}
         self.obj_begin, self.obj_end = shard_range(self.n, world, rank)
         self.q_begin, self.q_end = shard_range(self.n, world, rank)
         if torch.device(device).type == "cuda":
             # torch's default stream has handle 0, which ncb_set_stream reads as "the context's own stream": name the legacy
             # default stream explicitly (cudaStreamLegacy == 0x1) so that both sides really share it
             ctx.lib.ncb_set_stream(ctx.h, C.c_void_p(torch.cuda.current_stream(device).cuda_stream or 1))
+
+    # -- peer-memory exchange set-up -------------------------------------------------------------------------
+    def p2p_alloc(self):
+        """Allocates + exports this rank's receive buffers: (192 bytes of IPC handles, 3 raw device pointers)."""
+        import numpy as np
+
+        handles = np.zeros(3 * 64, dtype=np.uint8)
+        ptrs = np.zeros(3, dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.ncb_route_p2p_alloc(self.ctx.h, C.c_int(self.rank), C.c_int(self.world), C.c_uint32(self.n),
+                                                        C.c_void_p(handles.ctypes.data), C.c_void_p(ptrs.ctypes.data)), "ncb_route_p2p_alloc")
+        return handles, ptrs
+
+    def connect_p2p(self, group=None):
+        """Multi-process set-up (once): all-gathers the IPC handles with torch.distributed and maps the peers' buffers.  Every rank
+        learns whether ALL ranks succeeded; otherwise all fall back to the NCCL-routed mode together."""
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        ok = 1
+        try:
+            handles, _ = self.p2p_alloc()
+        except Exception:  # noqa: BLE001
+            handles, ok = np.zeros(3 * 64, dtype=np.uint8), 0
+        mine = torch.from_numpy(handles).to(self.device)
+        everyone = torch.empty(self.world * 3 * 64, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        if ok:
+            all_h = np.ascontiguousarray(everyone.cpu().numpy())
+            if self.ctx.lib.ncb_route_p2p_connect(self.ctx.h, C.c_void_p(all_h.ctypes.data), None) != 0:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.p2p_connected = bool(flag.item())
+        if not self.p2p_connected:
+            self.ctx.lib.ncb_route_p2p_close(self.ctx.h)
+            self.mode = "routed"
+        return self.p2p_connected
+
+    @staticmethod
+    def connect_p2p_local(ranks):
+        """All ranks inside ONE process (replay tests): raw device pointers instead of IPC handles."""
+        import numpy as np
+
+        ptrs = np.concatenate([sw.p2p_alloc()[1] for sw in ranks]).astype(np.uint64)
+        for sw in ranks:
+            sw.ctx.check(sw.ctx.lib.ncb_route_p2p_connect(sw.ctx.h, None, C.c_void_p(ptrs.ctypes.data)), "ncb_route_p2p_connect")
+            sw.p2p_connected = True
+            sw.mode = "p2p"
 
     def aabb_tensors(self):
         import torch
@@ -154,7 +210,12 @@ class ShardedWorld:
         p = self.ctx.lib.ncb_route_buffer(self.ctx.h, C.c_int(which), C.c_int(self.world), C.byref(nbytes))
         if not p:
             raise RuntimeError(f"ncb_route_buffer({which}) is not allocated yet")
-        return torch.as_tensor(_CudaArray(p, (nbytes.value // 4,), typestr), device=self.device)
+        key = (which, int(p), nbytes.value, typestr)  # the views are reused from step to step (buffers only move when they grow)
+        t = self._route_views.get(which)
+        if t is None or t[0] != key:
+            t = (key, torch.as_tensor(_CudaArray(p, (nbytes.value // 4,), typestr), device=self.device))
+            self._route_views[which] = t
+        return t[1]
 
     def upload_own_poses(self, pos, rot, gather=None):
         """End-to-end input path: this rank uploads the poses of ITS block from host memory.  In the all-gather modes the blocks are
@@ -166,7 +227,7 @@ class ShardedWorld:
         pb, rb = as_f32(pos[b:e]), as_f32(rot[b:e])
         self.ctx.check(self.ctx.lib.ncb_set_positions_range(self.ctx.h, C.c_uint32(b), C.c_uint32(e - b), ptr(pb), ptr(rb)), "set_positions_range")
         if gather is None:
-            gather = self.mode != "routed"
+            gather = self.mode not in ("routed", "p2p")
         if self.world > 1 and gather:
             for t in self.pose_tensors():
                 all_gather_rows(t, b, e, self.world)
@@ -177,6 +238,12 @@ class ShardedWorld:
         lib, h = self.ctx.lib, self.ctx.h
         args = (C.c_float(self.scene.margin), C.c_int(self.rank), C.c_int(self.world), C.c_uint32(self.obj_begin), C.c_uint32(self.obj_end),
                 C.c_int(1 if with_poses else 0))
+        if self.mode == "p2p" and self.p2p_connected:  # the exchange happens inside the stages; the driver only keeps the ranks in step
+            for stage in range(4):
+                self.ctx.check(lib.ncb_world_update_routed(h, stage, *args, None), f"routed stage {stage}")
+                yield ("p2p_round",)
+            self.ctx.check(lib.ncb_world_update_routed(h, 4, *args, C.byref(counts_c)), "routed stage 4")
+            return self.ctx._counts(counts_c)
         self.ctx.check(lib.ncb_world_update_routed(h, 0, *args, None), "routed stage 0")
         yield ("all_reduce_max", self.route_tensor(0))
         self.ctx.check(lib.ncb_world_update_routed(h, 1, *args, None), "routed stage 1")
@@ -195,6 +262,13 @@ class ShardedWorld:
 
     def step(self, counts_c, with_poses=False):
         lib, h, m = self.ctx.lib, self.ctx.h, C.c_float(self.scene.margin)
+        if self.mode == "p2p" and self.world > 1:
+            if not self.p2p_connected:
+                self.connect_p2p()  # first step: one handle exchange; may switch every rank to "routed"
+            if self.p2p_connected:  # the whole step in one call: no collective, no host work between the stages
+                self.ctx.check(lib.ncb_world_update_routed(h, -1, m, C.c_int(self.rank), C.c_int(self.world), C.c_uint32(self.obj_begin),
+                                                           C.c_uint32(self.obj_end), C.c_int(1 if with_poses else 0), C.byref(counts_c)), "routed (p2p)")
+                return self.ctx._counts(counts_c)
         if self.mode == "routed" and self.world > 1:
             plan = self.routed_plan(counts_c, with_poses)
             try:

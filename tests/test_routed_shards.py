@@ -34,7 +34,7 @@ def canon(p):
     return p[np.lexsort((p[:, 1], p[:, 0]))]
 
 
-def _replay(s, world, with_poses, full_ctx):
+def _replay(s, world, with_poses, full_ctx, p2p=False):
     import torch
 
     from ncollide_b200.world import Context
@@ -53,9 +53,11 @@ def _replay(s, world, with_poses, full_ctx):
                 pos[b:e], rot[b:e] = s.pos[b:e], s.rot[b:e]
                 c.set_positions(pos, rot)
             ctxs.append(c)
-            sws.append(ShardedWorld(c, s, world, r, torch.device("cuda", 0), mode="routed"))
+            sws.append(ShardedWorld(c, s, world, r, torch.device("cuda", 0), mode="p2p" if p2p else "routed"))
             counts.append(_ffi.UpdateCountsC())
-        for _step in range(2):  # the second step runs on the remembered capacities
+        if p2p:
+            ShardedWorld.connect_p2p_local(sws)
+        for _step in range(3 if p2p else 2):  # later steps run on the remembered capacities / the next flag epochs
             res = run_plans_lockstep([sw.routed_plan(cc, with_poses) for sw, cc in zip(sws, counts)])
             per_pair, total = {}, 0
             for r in range(world):
@@ -89,6 +91,19 @@ def _replay(s, world, with_poses, full_ctx):
 ])
 def test_routed_shards_partition_the_pair_set(ctx, world, mk, with_poses):
     _replay(mk(), world, with_poses, ctx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,mk,with_poses", [
+    (2, lambda: config_scene(3, 7001), True),
+    (8, lambda: config_scene(3, 40000), True),
+    (5, lambda: config_scene(5, 30000), False),
+    (4, lambda: make_world_scene(3000, 92, (1, 1, 1), side=12.0, n_hulls=16, plane=True, name="with_plane"), True),
+])
+def test_routed_shards_over_peer_memory(ctx, world, mk, with_poses):
+    """The same partition property with the peer-memory exchange (records stored straight into the owner's buffers, flag rounds instead
+    of collectives); all ranks live in this process, so the peers are mapped by raw pointer and advance stage by stage."""
+    _replay(mk(), world, with_poses, ctx, p2p=True)
 
 
 @pytest.mark.gpu
