@@ -43,8 +43,8 @@ def workload_config(n_per, world):
         "seed": 1003,
         "l2": "native arm: 256 MiB flush between timed iterations, working set > L2; reference arm: host memory",
         "parallelism": ("native arm: single GPU" if world == 1 else
-                        f"native arm: {world} ranks, AABB block per rank, routed spatial ownership (Morton-bin owners + ghosts through NCCL all-to-all; "
-                        "NCB_SHARD=spatial selects the all-gather design), local LBVH per rank")
+                        f"native arm: {world} ranks, AABB block per rank, routed spatial ownership (Morton-bin owners + ghosts; records stored into "
+                        "the owner's buffers over NVLink peer memory, or NCCL all-to-all: see the line's `sharding`), local LBVH per rank")
                        + "; reference arm: 1 host thread (the reference is single-threaded)",
     }
 
@@ -565,11 +565,56 @@ def run_native(args):
         except Exception as ex:  # noqa: BLE001
             widened["proximity_sensors"] = {"error": repr(ex)[:200]}
 
+    # ---- secondary worlds (after everything else: they replace the world on the device) -----------------------------------
+    #   strong scaling: ONE fixed 8 M-object cfg3 world at every N (the driver's N = 1, 2, 4, 8 runs give the curve);
+    #   config 5 at full size: 16 M convex shapes, only when 8 GPUs are present (BASELINE.json configs[4]).
+    secondary = None
+    if not args.no_secondary and n_per == N_PER_GPU:
+        secondary = {}
+        jobs = [("strong_scaling_8M", 3, 8_000_000)] + ([("cfg5_16M", 5, 16_000_000)] if world == 8 else [])
+        for name, cfg, n_sec in jobs:
+            try:
+                t_sec = time.perf_counter()
+                sc = config_scene(cfg, n_sec)
+                ctx.set_hulls(sc.hulls)
+                ctx.set_objects(sc)
+                ctx.synchronize()
+                sw = ShardedWorld(ctx, sc, world, rank, dev)
+                cc = _ffi.UpdateCountsC()
+
+                def sec_step():
+                    if world == 1:
+                        ctx.check(lib.ncb_world_update_device(h, C.c_float(sc.margin), C.c_uint32(0), C.c_uint32(0xFFFFFFFF), C.byref(cc)), "update")
+                        return ctx._counts(cc)
+                    return sw.step(cc)
+
+                sms, scounts = timed_steps(sec_step, 5, 3)
+                sms_mean = sum(sms) / len(sms)
+                tot = [scounts["n_pairs"], scounts["n_contacts"], scounts["n_contact_pairs"], scounts["epa_overflow"]]
+                if dist is not None:
+                    t = torch.tensor([sms_mean], device=dev, dtype=torch.float64)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    sms_mean = float(t.item())
+                    agg = torch.tensor(tot, device=dev, dtype=torch.int64)
+                    dist.all_reduce(agg)
+                    tot = [int(x) for x in agg.tolist()]
+                secondary[name] = {
+                    "workload": f"{sc.name}: {n_sec} objects in ONE world over {world} GPU(s), fresh-world update, device-resident inputs",
+                    "scaling": "strong" if name.startswith("strong") else "config 5 (full size)",
+                    "ms_per_update": sms_mean, "updates_per_s": 1e3 / sms_mean, "steps": 5, "warmup": 3,
+                    "pairs": tot[0], "contacts": tot[1], "contact_pairs": tot[2], "contact_pairs_per_sec": tot[2] / (sms_mean / 1e3),
+                    "epa_overflow": tot[3], "sharding": sw.mode if world > 1 else "single GPU",
+                    "wall_s_incl_scene_build": round(time.perf_counter() - t_sec, 1),
+                }
+            except Exception as ex:  # noqa: BLE001  (never allowed to break the headline line)
+                secondary[name] = {"error": repr(ex)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(n_per, world),
+            "sharding": sharded.mode if world > 1 else "single GPU",
             "pairs": tot_pairs, "contacts": tot_contacts, "contact_pairs": tot_contact_pairs,
             "contact_pairs_per_sec": tot_contact_pairs / (ms_step / 1e3),
             "broad_phase_pairs_per_sec": tot_pairs / (ms_step / 1e3),
@@ -587,6 +632,7 @@ def run_native(args):
             "counts": {k: v for k, v in counts.items() if k != "n_algo"} | {"n_algo": counts["n_algo"]},
             "rays": rays,
             "widened": widened,
+            "secondary": secondary,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -766,6 +812,7 @@ def main():
     ap.add_argument("--no-rays", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the stepping-world / world-query figures")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the strong-scaling (8 M objects) and config-5 (16 M, 8 GPUs) worlds")
     ap.add_argument("--rays-only", action="store_true", help="debug: only the ray-casting sub-benchmark, prints its dict")
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu child that measures the dominant kernel's DRAM traffic")
     ap.add_argument("--traffic-child", action="store_true", help="internal: replay the workload's device steps (run under ncu by the parent)")

@@ -157,6 +157,9 @@ class ShardedWorld:
         import torch
         import torch.distributed as dist
 
+        # peers may still have this rank's previous buffers mapped: every rank unmaps first, and only then may anyone reallocate
+        self.ctx.lib.ncb_route_p2p_close(self.ctx.h)
+        dist.barrier(group=group)
         ok = 1
         try:
             handles, _ = self.p2p_alloc()
