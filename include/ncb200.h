@@ -295,6 +295,15 @@ void ncb_trimesh_destroy(ncb_mesh* mesh);
  * for a back-face hit (ray_trimesh.rs:41-45); normal (optional) in world space. */
 int ncb_trimesh_ray_cast(ncb_mesh* mesh, const float* pose_tq, uint32_t n_rays, const float* origins, const float* dirs,
                          float max_toi, float* toi, uint32_t* face, float* normal);
+/* TriMesh::uvs (shape/trimesh.rs, `uvs: Option<Vec<Point2<N>>>`): 2 floats per vertex, NULL clears them. */
+int ncb_trimesh_set_uvs(ncb_mesh* mesh, const float* uvs);
+/* RayCast::toi_and_normal_and_uv_with_ray for a batch (query/ray/ray_trimesh.rs:52-94; barycentric coordinates of
+ * query/ray/ray_triangle.rs:92-114): like ncb_trimesh_ray_cast, plus uv (2 floats per ray, optional; zeros for a miss or when the mesh has
+ * no uvs, where the reference falls back to toi_and_normal_with_ray) and max_tois (one limit per ray, optional; NULL = max_toi for all:
+ * `Ray` casts of query/ray/ray.rs:125-160 each carry their own max_toi).  Host buffers; the batch is pipelined in chunks (upload | cast |
+ * download on three streams), so pinned buffers make the call cost about max(copies, kernel). */
+int ncb_trimesh_ray_cast_uv(ncb_mesh* mesh, const float* pose_tq, uint32_t n_rays, const float* origins, const float* dirs, float max_toi,
+                            const float* max_tois, float* toi, uint32_t* face, float* normal, float* uv);
 /* Same with device-resident rays / results (pointers are device pointers); asynchronous on the context's stream. */
 int ncb_trimesh_ray_cast_device(ncb_mesh* mesh, const float* pose_tq_host, uint32_t n_rays, const float* d_origins,
                                 const float* d_dirs, float max_toi, float* d_toi, uint32_t* d_face, float* d_normal);

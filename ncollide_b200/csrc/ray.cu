@@ -35,6 +35,15 @@ struct ncb_mesh {
     int use_tile = 0, sort_rays = 0;
     ncb::DevBuf<float> d_in;   // staging for the host-buffer entry point
     ncb::DevBuf<float> d_out;
+    ncb::DevBuf<float4> nodes4;  // 4-wide BVH: 8 float4 per binary node id (children of its two children), see k_build_bvh4
+    ncb::DevBuf<float> uvs;      // per-vertex texture coordinates (TriMesh::uvs), optional
+    int use_wide = 1;
+    // host-buffer entry: the batch is cut into chunks that run [upload, cast, download] on a small pool of streams, so the copy
+    // engines and the SMs work on different chunks at the same time and the casts of neighbouring chunks overlap
+    static const int N_STREAMS = 4;
+    cudaStream_t chunk_stream[N_STREAMS] = {};
+    cudaEvent_t ev_begin = nullptr, ev_end[N_STREAMS] = {};
+    bool pipeline_ready = false;
 };
 
 namespace ncb {
@@ -206,7 +215,7 @@ NCB_HD float slab_toi(float4 lo, float4 hi, V3 o, V3 d, V3 inv, float max_toi) {
 }
 
 // ray_intersection_with_triangle; side: 0 front, 1 back
-NCB_HD bool ray_triangle(V3 a, V3 b, V3 c, V3 o, V3 dir, float& toi, V3& n_out, int& side) {
+NCB_HD bool ray_triangle(V3 a, V3 b, V3 c, V3 o, V3 dir, float& toi, V3& n_out, int& side, float* vw = nullptr) {
     V3 ab = b - a, ac = c - a;
     V3 n = cross(ab, ac);
     float d = dot(n, dir);
@@ -226,6 +235,7 @@ NCB_HD bool ray_triangle(V3 a, V3 b, V3 c, V3 o, V3 dir, float& toi, V3& n_out, 
         float invd = 1.f / d;
         toi = -t * invd;
         n_out = -n;  // normalised by the caller only for the winning hit
+        if (vw) vw[0] = v * invd, vw[1] = w * invd;
     } else {
         v = dot(ac, e);
         if (v < 0.f || v > d) return false;
@@ -234,6 +244,7 @@ NCB_HD bool ray_triangle(V3 a, V3 b, V3 c, V3 o, V3 dir, float& toi, V3& n_out, 
         float invd = 1.f / d;
         toi = t * invd;
         n_out = n;
+        if (vw) vw[0] = v * invd, vw[1] = w * invd;
     }
     return true;
 }
@@ -257,7 +268,191 @@ struct RayArgs {
     uint32_t* face;
     float* normal;
     uint32_t* trav_overflow;
+    const float4* nodes4;     // 4-wide nodes (k_ray_cast4)
+    const float* max_tois;    // nullptr: max_toi for every ray
+    const float* uvs;         // per-vertex uv (with tris): toi_and_normal_and_uv_with_ray
+    const uint32_t* tris;
+    float* uv_out;            // 2 floats per ray
 };
+
+// The best hit of a ray while its traversal runs, and the triangle test of a leaf (shared by the binary and the 4-wide kernel).
+struct RayBest {
+    float toi;
+    uint32_t face;
+    int side;
+    V3 n;
+    float v, w;
+    bool have;
+};
+template <bool UV>
+__device__ __forceinline__ void ray_test_leaf(const float4* __restrict__ tri_packed, uint32_t leaf_pos, V3 o, V3 d, float max_toi, RayBest& B) {
+    // one 48 B record per leaf, in leaf (Morton) order: a.xyz | face id, b.xyz, c.xyz  (no index -> vertex chain)
+    const float4* tp = tri_packed + 3 * (size_t)leaf_pos;
+    float4 pa = __ldg(tp), pb = __ldg(tp + 1), pc = __ldg(tp + 2);
+    uint32_t t = __float_as_uint(pa.w);
+    V3 a = v3(pa.x, pa.y, pa.z), b = v3(pb.x, pb.y, pb.z), c = v3(pc.x, pc.y, pc.z);
+    float toi, vw[2];
+    V3 n;
+    int side;
+    if (ray_triangle(a, b, c, o, d, toi, n, side, UV ? vw : nullptr) && toi <= max_toi) {
+        if (!B.have || toi < B.toi || (toi == B.toi && t < B.face)) {
+            B.have = true, B.toi = toi, B.face = t, B.side = side, B.n = n;
+            if (UV) B.v = vw[0], B.w = vw[1];
+        }
+    }
+}
+// RayCast for TriMesh, the tail of toi_and_normal(_and_uv)_with_ray (ray_trimesh.rs:39-49, 74-93)
+__device__ __forceinline__ void ray_write_hit(const RayArgs& A, uint32_t r, const RayBest& B) {
+    if (B.have) {
+        A.toi[r] = B.toi;
+        A.face[r] = B.side == 1 ? B.face + A.n_tris : B.face;  // ray_trimesh.rs:41-45
+        if (A.normal) {
+            V3 n = normalize(B.n);
+            if (B.n.x == 0.f && B.n.y == 0.f && B.n.z == 0.f) n = B.n;
+            // -n.normalize() == (-n).normalize() component-wise (division by the same norm)
+            if (A.has_pose) n = iso_mul_vec(A.pose, n);
+            A.normal[3 * r] = n.x, A.normal[3 * r + 1] = n.y, A.normal[3 * r + 2] = n.z;
+        }
+        if (A.uv_out) {
+            float ux = 0.f, uy = 0.f;
+            if (A.uvs) {  // uv1 * (1 - v - w) + uv2 * v + uv3 * w, evaluated like ray_trimesh.rs:83-84 / ray_triangle.rs:113
+                uint32_t i0 = __ldg(A.tris + 3 * (size_t)B.face), i1 = __ldg(A.tris + 3 * (size_t)B.face + 1), i2 = __ldg(A.tris + 3 * (size_t)B.face + 2);
+                float b0 = (-B.v - B.w) + 1.f, b1 = B.v, b2 = B.w;
+                ux = (__ldg(A.uvs + 2 * i0) * b0 + __ldg(A.uvs + 2 * i1) * b1) + __ldg(A.uvs + 2 * i2) * b2;
+                uy = (__ldg(A.uvs + 2 * i0 + 1) * b0 + __ldg(A.uvs + 2 * i1 + 1) * b1) + __ldg(A.uvs + 2 * i2 + 1) * b2;
+            }
+            A.uv_out[2 * r] = ux, A.uv_out[2 * r + 1] = uy;
+        }
+    } else {
+        A.toi[r] = -1.f;
+        A.face[r] = 0xffffffffu;
+        if (A.normal) A.normal[3 * r] = A.normal[3 * r + 1] = A.normal[3 * r + 2] = 0.f;
+        if (A.uv_out) A.uv_out[2 * r] = A.uv_out[2 * r + 1] = 0.f;
+    }
+}
+
+// ---- 4-wide BVH ------------------------------------------------------------------------------------------------------
+// One 128 B record per binary node id b: the (up to four) children of b's two children, as structure-of-arrays
+// [lo.x x4][lo.y x4][lo.z x4][hi.x x4][hi.y x4][hi.z x4][ids x4][unused]; a child of b that is a leaf takes one slot itself.
+// A ray visits half as many (dependent) node fetches as in the binary tree and tests four boxes per fetch.  The boxes that are
+// tested are a subset of the binary tree's boxes and the slab test is monotone under box inclusion, so the set of leaves whose
+// triangle is tested after pruning, and with it the hit (min toi, ties -> smallest face), is the same as before.
+// Only records of nodes reachable by grandchild steps from the root are ever read.
+#define EMPTY_CHILD 0xffffffffu
+__global__ void __launch_bounds__(256) k_build_bvh4(const float4* __restrict__ nodes, uint32_t n_tris, float4* __restrict__ nodes4) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b + 1 >= n_tris) return;  // n_tris - 1 internal nodes
+    float lo[4][3], hi[4][3];
+    uint32_t id[4];
+    int k = 0;
+    const float4* rec = nodes + 4 * (size_t)b;
+    float4 c_lo[2] = {rec[0], rec[2]}, c_hi[2] = {rec[1], rec[3]};
+    uint32_t c_id[2] = {__float_as_uint(rec[0].w), __float_as_uint(rec[1].w)};
+    for (int c = 0; c < 2; ++c) {
+        if (c_id[c] & LEAF_BIT) {
+            lo[k][0] = c_lo[c].x, lo[k][1] = c_lo[c].y, lo[k][2] = c_lo[c].z, hi[k][0] = c_hi[c].x, hi[k][1] = c_hi[c].y, hi[k][2] = c_hi[c].z;
+            id[k++] = c_id[c];
+        } else {
+            const float4* g = nodes + 4 * (size_t)c_id[c];
+            float4 g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3];
+            lo[k][0] = g0.x, lo[k][1] = g0.y, lo[k][2] = g0.z, hi[k][0] = g1.x, hi[k][1] = g1.y, hi[k][2] = g1.z;
+            id[k++] = __float_as_uint(g0.w);
+            lo[k][0] = g2.x, lo[k][1] = g2.y, lo[k][2] = g2.z, hi[k][0] = g3.x, hi[k][1] = g3.y, hi[k][2] = g3.z;
+            id[k++] = __float_as_uint(g1.w);
+        }
+    }
+    for (; k < 4; ++k) {
+        for (int a = 0; a < 3; ++a) lo[k][a] = NCB_FMAX, hi[k][a] = -NCB_FMAX;
+        id[k] = EMPTY_CHILD;
+    }
+    float4* out = nodes4 + 8 * (size_t)b;
+    for (int a = 0; a < 3; ++a) {
+        out[a] = make_float4(lo[0][a], lo[1][a], lo[2][a], lo[3][a]);
+        out[3 + a] = make_float4(hi[0][a], hi[1][a], hi[2][a], hi[3][a]);
+    }
+    out[6] = make_float4(__uint_as_float(id[0]), __uint_as_float(id[1]), __uint_as_float(id[2]), __uint_as_float(id[3]));
+    out[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <bool UV>
+__global__ void __launch_bounds__(128) k_ray_cast4(RayArgs A) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= A.n_rays) return;
+    V3 o = v3(__ldg(A.origins + 3 * r), __ldg(A.origins + 3 * r + 1), __ldg(A.origins + 3 * r + 2));
+    V3 d = v3(__ldg(A.dirs + 3 * r), __ldg(A.dirs + 3 * r + 1), __ldg(A.dirs + 3 * r + 2));
+    if (A.has_pose) {  // ray.inverse_transform_by(m)
+        o = iso_inv_point(A.pose, o);
+        d = iso_inv_vec(A.pose, d);
+    }
+    const float max_toi = A.max_tois ? __ldg(A.max_tois + r) : A.max_toi;
+    const V3 inv = v3(1.f / d.x, 1.f / d.y, 1.f / d.z);  // only read on axes where d != 0
+    RayBest B;
+    B.toi = NCB_FMAX, B.face = 0xffffffffu, B.side = 0, B.n = v3(0.f, 0.f, 0.f), B.v = B.w = 0.f, B.have = false;
+    if (A.n_tris == 1) {
+        float4 lo = __ldg(&A.leaf_lo[0]), hi = __ldg(&A.leaf_hi[0]);
+        if (slab_toi(lo, hi, o, d, inv, max_toi) >= 0.f) ray_test_leaf<UV>(A.tri_packed, 0, o, d, max_toi, B);
+    } else if (A.n_tris >= 2) {
+        uint32_t stack[64];
+        float stack_t[64];
+        int sp = 0;
+        uint32_t node = 0;
+        for (;;) {
+            const float4* rec = A.nodes4 + 8 * (size_t)node;
+            float4 lx = __ldg(rec), ly = __ldg(rec + 1), lz = __ldg(rec + 2), hx = __ldg(rec + 3), hy = __ldg(rec + 4), hz = __ldg(rec + 5);
+            float4 idw = __ldg(rec + 6);
+            uint32_t id[4] = {__float_as_uint(idw.x), __float_as_uint(idw.y), __float_as_uint(idw.z), __float_as_uint(idw.w)};
+            float t[4];
+            t[0] = slab_toi(make_float4(lx.x, ly.x, lz.x, 0.f), make_float4(hx.x, hy.x, hz.x, 0.f), o, d, inv, max_toi);
+            t[1] = slab_toi(make_float4(lx.y, ly.y, lz.y, 0.f), make_float4(hx.y, hy.y, hz.y, 0.f), o, d, inv, max_toi);
+            t[2] = id[2] == EMPTY_CHILD ? -1.f : slab_toi(make_float4(lx.z, ly.z, lz.z, 0.f), make_float4(hx.z, hy.z, hz.z, 0.f), o, d, inv, max_toi);
+            t[3] = id[3] == EMPTY_CHILD ? -1.f : slab_toi(make_float4(lx.w, ly.w, lz.w, 0.f), make_float4(hx.w, hy.w, hz.w, 0.f), o, d, inv, max_toi);
+            // leaves at once (their triangles may lower the bound for the internal children)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (t[k] >= 0.f && (id[k] & LEAF_BIT)) {
+                    if (!(B.have && t[k] > B.toi)) ray_test_leaf<UV>(A.tri_packed, id[k] & ~LEAF_BIT, o, d, max_toi, B);
+                    t[k] = -1.f;
+                }
+            // internal children still worth a visit, nearest first
+            uint32_t cn[4];
+            float ct[4];
+            int nc = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (t[k] >= 0.f && !(B.have && t[k] > B.toi)) {
+                    int j = nc++;
+                    while (j > 0 && ct[j - 1] > t[k]) {
+                        ct[j] = ct[j - 1], cn[j] = cn[j - 1];
+                        --j;
+                    }
+                    ct[j] = t[k], cn[j] = id[k];
+                }
+            if (nc > 0) {
+                for (int j = nc - 1; j >= 1; --j) {  // farthest first, so that the nearest of them is popped first
+                    if (sp < 64) {
+                        stack[sp] = cn[j], stack_t[sp] = ct[j];
+                        sp++;
+                    } else {
+                        atomicAdd(A.trav_overflow, 1u);
+                    }
+                }
+                node = cn[0];
+            } else {
+                bool found = false;
+                while (sp > 0) {
+                    sp--;
+                    if (!(B.have && stack_t[sp] > B.toi)) {
+                        node = stack[sp];
+                        found = true;
+                        break;
+                    }
+                }
+                if (!found) break;
+            }
+        }
+    }
+    ray_write_hit(A, r, B);
+}
 
 template <bool TILE>
 __global__ void __launch_bounds__(128) k_ray_cast(RayArgs A) {
@@ -278,33 +473,13 @@ __global__ void __launch_bounds__(128) k_ray_cast(RayArgs A) {
         o = iso_inv_point(A.pose, o);
         d = iso_inv_vec(A.pose, d);
     }
-    const float max_toi = A.max_toi;
+    const float max_toi = A.max_tois ? __ldg(A.max_tois + r) : A.max_toi;
     const V3 inv = v3(1.f / d.x, 1.f / d.y, 1.f / d.z);  // only read on axes where d != 0
-    float best = NCB_FMAX;  // best accepted toi so far (bounded by max_toi through the triangle test)
-    uint32_t best_face = 0xffffffffu;
-    int best_side = 0;
-    V3 best_n = v3(0.f, 0.f, 0.f);
-    bool have = false;
-
-    auto test_leaf = [&](uint32_t leaf_pos) {
-        // one 48 B record per leaf, in leaf (Morton) order: a.xyz | face id, b.xyz, c.xyz  (no index -> vertex chain)
-        const float4* tp = A.tri_packed + 3 * (size_t)leaf_pos;
-        float4 pa = __ldg(tp), pb = __ldg(tp + 1), pc = __ldg(tp + 2);
-        uint32_t t = __float_as_uint(pa.w);
-        V3 a = v3(pa.x, pa.y, pa.z), b = v3(pb.x, pb.y, pb.z), c = v3(pc.x, pc.y, pc.z);
-        float toi;
-        V3 n;
-        int side;
-        if (ray_triangle(a, b, c, o, d, toi, n, side) && toi <= max_toi) {
-            if (!have || toi < best || (toi == best && t < best_face)) {
-                have = true;
-                best = toi;
-                best_face = t;
-                best_side = side;
-                best_n = n;
-            }
-        }
-    };
+    RayBest B;
+    B.toi = NCB_FMAX, B.face = 0xffffffffu, B.side = 0, B.n = v3(0.f, 0.f, 0.f), B.v = B.w = 0.f, B.have = false;
+    float& best = B.toi;  // best accepted toi so far (bounded by max_toi through the triangle test)
+    bool& have = B.have;
+    auto test_leaf = [&](uint32_t leaf_pos) { ray_test_leaf<true>(A.tri_packed, leaf_pos, o, d, max_toi, B); };
 
     if (A.n_tris == 1) {
         float4 lo = __ldg(&A.leaf_lo[0]), hi = __ldg(&A.leaf_hi[0]);
@@ -369,21 +544,7 @@ __global__ void __launch_bounds__(128) k_ray_cast(RayArgs A) {
             }
         }
     }
-    if (have) {
-        A.toi[r] = best;
-        A.face[r] = best_side == 1 ? best_face + A.n_tris : best_face;  // ray_trimesh.rs:41-45
-        if (A.normal) {
-            V3 n = normalize(best_n);
-            if (best_n.x == 0.f && best_n.y == 0.f && best_n.z == 0.f) n = best_n;
-            // -n.normalize() == (-n).normalize() component-wise (division by the same norm)
-            if (A.has_pose) n = iso_mul_vec(A.pose, n);
-            A.normal[3 * r] = n.x, A.normal[3 * r + 1] = n.y, A.normal[3 * r + 2] = n.z;
-        }
-    } else {
-        A.toi[r] = -1.f;
-        A.face[r] = 0xffffffffu;
-        if (A.normal) A.normal[3 * r] = A.normal[3 * r + 1] = A.normal[3 * r + 2] = 0.f;
-    }
+    ray_write_hit(A, r, B);
     }  // ray loop
 }
 
@@ -455,6 +616,11 @@ int ncb_trimesh_create(ncb_ctx* ctx, uint32_t n_verts, const float* xyz, uint32_
         if ((e = m->tri_packed.reserve(3 * (size_t)n)) != cudaSuccess) return fail("alloc packed triangles");
         k_pack_tris<<<(n + 255) / 256, 256, 0, s>>>(m->verts.p, m->tris.p, b->leaf_lo.p, n, m->tri_packed.p);
         if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_pack_tris");
+        if (n >= 2) {
+            if ((e = m->nodes4.reserve(8 * (size_t)(n - 1))) != cudaSuccess) return fail("alloc 4-wide nodes");
+            k_build_bvh4<<<(n + 255) / 256, 256, 0, s>>>(b->nodes.p, n, m->nodes4.p);
+            if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_build_bvh4");
+        }
         if ((e = m->top_tile.reserve(TOP_SLOTS * 4)) != cudaSuccess) return fail("alloc top tile");
         if (n >= 2) k_build_top_tile<<<1, 256, 0, s>>>(b->nodes.p, n, m->top_tile.p);
         if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_build_top_tile");
@@ -472,6 +638,7 @@ int ncb_trimesh_create(ncb_ctx* ctx, uint32_t n_verts, const float* xyz, uint32_
         m->bounds[3] = fmaxf(rec[1].x, rec[3].x), m->bounds[4] = fmaxf(rec[1].y, rec[3].y), m->bounds[5] = fmaxf(rec[1].z, rec[3].z);
         if (const char* v = getenv("NCB_RAY_TILE")) m->use_tile = atoi(v);
         if (const char* v = getenv("NCB_RAY_SORT")) m->sort_rays = atoi(v);
+        if (const char* v = getenv("NCB_RAY_WIDE")) m->use_wide = atoi(v);
     }
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail("sync");
     if (n_tris) {
@@ -497,16 +664,36 @@ void ncb_trimesh_destroy(ncb_mesh* m) {
         delete b;
     }
     m->verts.release(), m->tris.release(), m->d_in.release(), m->d_out.release(), m->tri_packed.release(), m->top_tile.release();
+    m->nodes4.release(), m->uvs.release();
+    for (int k = 0; k < ncb_mesh::N_STREAMS; ++k) {
+        if (m->chunk_stream[k]) cudaStreamDestroy(m->chunk_stream[k]);
+        if (m->ev_end[k]) cudaEventDestroy(m->ev_end[k]);
+    }
+    if (m->ev_begin) cudaEventDestroy(m->ev_begin);
     m->rkeys_a.release(), m->rkeys_b.release(), m->ridx_a.release(), m->ridx_b.release(), m->rsort_tmp.release();
     delete m;
 }
 
-int ncb_trimesh_ray_cast_device(ncb_mesh* m, const float* pose, uint32_t n_rays, const float* d_origins, const float* d_dirs, float max_toi,
-                                float* d_toi, uint32_t* d_face, float* d_normal) {
-    if (!m || (n_rays && (!d_origins || !d_dirs || !d_toi || !d_face))) return NCB_ERR_ARG;
+// TriMesh::uvs (shape/trimesh.rs: `uvs: Option<Vec<Point2<N>>>`): per-vertex texture coordinates, or NULL to clear them.
+int ncb_trimesh_set_uvs(ncb_mesh* m, const float* uvs) {
+    if (!m) return NCB_ERR_ARG;
     ncb_ctx* ctx = m->owner;
     CKM(cudaSetDevice(ctx->device));
-    if (n_rays == 0) return NCB_OK;
+    if (!uvs) {
+        m->uvs.release();
+        return NCB_OK;
+    }
+    CKM(m->uvs.reserve(2 * (size_t)m->n_verts + 2));
+    CKM(cudaMemcpyAsync(m->uvs.p, uvs, 8 * (size_t)m->n_verts, cudaMemcpyHostToDevice, ctx->stream));
+    CKM(cudaStreamSynchronize(ctx->stream));
+    return NCB_OK;
+}
+
+// One kernel launch over device-resident rays [0, n_rays) on `stream`.
+static int launch_ray_cast(ncb_mesh* m, const float* pose, uint32_t n_rays, const float* d_origins, const float* d_dirs, float max_toi,
+                           const float* d_max_tois, float* d_toi, uint32_t* d_face, float* d_normal, float* d_uv, cudaStream_t stream,
+                           bool allow_sort) {
+    ncb_ctx* ctx = m->owner;
     RayArgs A;
     A.nodes = m->bvh->nodes.p;
     A.leaf_lo = m->bvh->leaf_lo.p;
@@ -528,7 +715,22 @@ int ncb_trimesh_ray_cast_device(ncb_mesh* m, const float* pose, uint32_t n_rays,
     A.trav_overflow = trav_overflow_counter(ctx);
     A.top_tile = (m->use_tile && m->n_tris >= 2) ? m->top_tile.p : nullptr;
     A.perm = nullptr;
-    if (m->sort_rays && n_rays >= 4096) {
+    A.nodes4 = m->nodes4.p;
+    A.max_tois = d_max_tois;
+    A.uvs = m->uvs.p;
+    A.tris = m->tris.p;
+    A.uv_out = d_uv;
+    if (m->use_wide && !A.top_tile && !(allow_sort && m->sort_rays)) {
+        // Default: the 4-wide tree, one CTA per 128 rays (profiles/r2_ray_variants.txt).
+        uint32_t grid = (n_rays + 127) / 128;
+        if (d_uv)
+            k_ray_cast4<true><<<grid, 128, 0, stream>>>(A);
+        else
+            k_ray_cast4<false><<<grid, 128, 0, stream>>>(A);
+        CKM(cudaGetLastError());
+        return NCB_OK;
+    }
+    if (allow_sort && m->sort_rays && n_rays >= 4096) {
         size_t n = n_rays;
         CKM(m->rkeys_a.reserve(n));
         CKM(m->rkeys_b.reserve(n));
@@ -542,53 +744,106 @@ int ncb_trimesh_ray_cast_device(ncb_mesh* m, const float* pose, uint32_t n_rays,
         float ex = m->bounds[3] - m->bounds[0], ey = m->bounds[4] - m->bounds[1], ez = m->bounds[5] - m->bounds[2];
         float bx = m->bounds[0] - 0.5f * ex, by = m->bounds[1] - 0.5f * ey, bz = m->bounds[2] - 0.5f * ez;
         float sx = 1023.f / fmaxf(2.f * ex, 1e-20f), sy = 1023.f / fmaxf(2.f * ey, 1e-20f), sz = 1023.f / fmaxf(2.f * ez, 1e-20f);
-        k_ray_keys<<<(n_rays + 255) / 256, 256, 0, ctx->stream>>>(d_origins, d_dirs, n_rays, A.pose, A.has_pose, bx, by, bz, sx, sy, sz,
-                                                                 m->rkeys_a.p, m->ridx_a.p);
+        k_ray_keys<<<(n_rays + 255) / 256, 256, 0, stream>>>(d_origins, d_dirs, n_rays, A.pose, A.has_pose, bx, by, bz, sx, sy, sz,
+                                                            m->rkeys_a.p, m->ridx_a.p);
         bytes = m->rsort_tmp.cap;
-        CKM(cub::DeviceRadixSort::SortPairs(m->rsort_tmp.p, bytes, m->rkeys_a.p, m->rkeys_b.p, m->ridx_a.p, m->ridx_b.p, (int)n_rays, 0, 32,
-                                            ctx->stream));
+        CKM(cub::DeviceRadixSort::SortPairs(m->rsort_tmp.p, bytes, m->rkeys_a.p, m->rkeys_b.p, m->ridx_a.p, m->ridx_b.p, (int)n_rays, 0, 32, stream));
         A.perm = m->ridx_b.p;
     }
-    // Measured on B200, 1M rays vs 1M-triangle terrain (profiles/r1_ray_variants.txt): one CTA per 128 rays 0.753 ms;
-    // persistent CTAs (12 / SM, grid stride) 0.951 ms (ray costs vary, the hardware CTA scheduler balances better);
+    // Binary-tree variants, measured on B200, 1M rays vs 1M-triangle terrain (profiles/r1_ray_variants.txt): one CTA per 128 rays
+    // 0.753 ms; persistent CTAs (12 / SM, grid stride) 0.951 ms (ray costs vary, the hardware CTA scheduler balances better);
     // TMA-staged top tile 0.827 ms (the top levels are L1-resident anyway); Morton-sorted rays 0.79 ms (sort not repaid).
-    // Defaults follow the measurement; NCB_RAY_BPSM / NCB_RAY_TILE / NCB_RAY_SORT select the other variants.
+    // NCB_RAY_WIDE=0 / NCB_RAY_BPSM / NCB_RAY_TILE / NCB_RAY_SORT select them.
     static int ray_bpsm = getenv("NCB_RAY_BPSM") ? atoi(getenv("NCB_RAY_BPSM")) : 0;
     uint32_t need = (n_rays + 127) / 128;
     uint32_t grid = ray_bpsm > 0 ? (uint32_t)(ctx->sm_count * ray_bpsm) : need;
     if (grid > need) grid = need;
     if (A.top_tile)
-        k_ray_cast<true><<<grid, 128, 0, ctx->stream>>>(A);
+        k_ray_cast<true><<<grid, 128, 0, stream>>>(A);
     else
-        k_ray_cast<false><<<grid, 128, 0, ctx->stream>>>(A);
+        k_ray_cast<false><<<grid, 128, 0, stream>>>(A);
     CKM(cudaGetLastError());
     return NCB_OK;
 }
 
-int ncb_trimesh_ray_cast(ncb_mesh* m, const float* pose, uint32_t n_rays, const float* origins, const float* dirs, float max_toi, float* toi,
-                         uint32_t* face, float* normal) {
+int ncb_trimesh_ray_cast_device(ncb_mesh* m, const float* pose, uint32_t n_rays, const float* d_origins, const float* d_dirs, float max_toi,
+                                float* d_toi, uint32_t* d_face, float* d_normal) {
+    if (!m || (n_rays && (!d_origins || !d_dirs || !d_toi || !d_face))) return NCB_ERR_ARG;
+    ncb_ctx* ctx = m->owner;
+    CKM(cudaSetDevice(ctx->device));
+    if (n_rays == 0) return NCB_OK;
+    return launch_ray_cast(m, pose, n_rays, d_origins, d_dirs, max_toi, nullptr, d_toi, d_face, d_normal, nullptr, ctx->stream, true);
+}
+
+// Host buffers in, host buffers out (RayCast::toi_and_normal_and_uv_with_ray for a batch; uv NULL = toi_and_normal_with_ray).
+// The batch runs as a pipeline of up to 16 chunks on three streams: while chunk k is cast, chunk k + 1 is uploaded and the results of
+// chunk k - 1 are downloaded (PCIe is full duplex), so with pinned host buffers the call costs about max(copies, kernel) instead of
+// their sum.  max_tois: per-ray limits (NULL: max_toi for every ray).
+int ncb_trimesh_ray_cast_uv(ncb_mesh* m, const float* pose, uint32_t n_rays, const float* origins, const float* dirs, float max_toi,
+                            const float* max_tois, float* toi, uint32_t* face, float* normal, float* uv) {
     if (!m || (n_rays && (!origins || !dirs || !toi || !face))) return NCB_ERR_ARG;
     ncb_ctx* ctx = m->owner;
     CKM(cudaSetDevice(ctx->device));
     if (n_rays == 0) return NCB_OK;
     cudaStream_t s = ctx->stream;
     size_t n = n_rays;
-    CKM(m->d_in.reserve(6 * n));
-    CKM(m->d_out.reserve(5 * n));
+    CKM(m->d_in.reserve(7 * n));
+    CKM(m->d_out.reserve(7 * n));
+    if (!m->pipeline_ready) {
+        for (int k = 0; k < ncb_mesh::N_STREAMS; ++k) {
+            CKM(cudaStreamCreateWithFlags(&m->chunk_stream[k], cudaStreamNonBlocking));
+            CKM(cudaEventCreateWithFlags(&m->ev_end[k], cudaEventDisableTiming));
+        }
+        CKM(cudaEventCreateWithFlags(&m->ev_begin, cudaEventDisableTiming));
+        m->pipeline_ready = true;
+    }
     float* d_o = m->d_in.p;
     float* d_d = m->d_in.p + 3 * n;
+    float* d_mt = m->d_in.p + 6 * n;
     float* d_toi = m->d_out.p;
     uint32_t* d_face = reinterpret_cast<uint32_t*>(m->d_out.p + n);
     float* d_n = m->d_out.p + 2 * n;
-    CKM(cudaMemcpyAsync(d_o, origins, 12 * n, cudaMemcpyHostToDevice, s));
-    CKM(cudaMemcpyAsync(d_d, dirs, 12 * n, cudaMemcpyHostToDevice, s));
-    int r = ncb_trimesh_ray_cast_device(m, pose, n_rays, d_o, d_d, max_toi, d_toi, d_face, normal ? d_n : nullptr);
-    if (r) return r;
-    CKM(cudaMemcpyAsync(toi, d_toi, 4 * n, cudaMemcpyDeviceToHost, s));
-    CKM(cudaMemcpyAsync(face, d_face, 4 * n, cudaMemcpyDeviceToHost, s));
-    if (normal) CKM(cudaMemcpyAsync(normal, d_n, 12 * n, cudaMemcpyDeviceToHost, s));
-    CKM(cudaStreamSynchronize(s));
+    float* d_uv = m->d_out.p + 5 * n;
+    // A cast has a latency floor (a ray is a chain of dependent node fetches), so chunks must be large enough to fill the GPU and
+    // their casts must overlap: chunks of 256 k rays on 4 streams (profiles/r2_ray_variants.txt).
+    static int chunk_rays = getenv("NCB_RAY_CHUNK") ? atoi(getenv("NCB_RAY_CHUNK")) : 262144;
+    uint32_t per = (uint32_t)(chunk_rays > 0 ? chunk_rays : 262144);
+    per = (per + 127) & ~127u;
+    uint32_t n_chunks = (n_rays + per - 1) / per;
+    if (n_chunks > 32) {
+        per = ((n_rays + 31) / 32 + 127) & ~127u;
+        n_chunks = (n_rays + per - 1) / per;
+    }
+    // the staging buffers may still be read by earlier work of the context's stream (ncb_trimesh_ray_cast_device is asynchronous)
+    CKM(cudaEventRecord(m->ev_begin, s));
+    int used = (int)std::min<uint32_t>(n_chunks, ncb_mesh::N_STREAMS);
+    for (int j = 0; j < used; ++j) CKM(cudaStreamWaitEvent(m->chunk_stream[j], m->ev_begin, 0));
+    int rc = NCB_OK;
+    for (uint32_t k = 0; k < n_chunks && rc == NCB_OK; ++k) {
+        cudaStream_t cs = m->chunk_stream[k % ncb_mesh::N_STREAMS];
+        size_t off = (size_t)k * per, cnt = std::min<size_t>(per, n - off);
+        CKM(cudaMemcpyAsync(d_o + 3 * off, origins + 3 * off, 12 * cnt, cudaMemcpyHostToDevice, cs));
+        CKM(cudaMemcpyAsync(d_d + 3 * off, dirs + 3 * off, 12 * cnt, cudaMemcpyHostToDevice, cs));
+        if (max_tois) CKM(cudaMemcpyAsync(d_mt + off, max_tois + off, 4 * cnt, cudaMemcpyHostToDevice, cs));
+        rc = launch_ray_cast(m, pose, (uint32_t)cnt, d_o + 3 * off, d_d + 3 * off, max_toi, max_tois ? d_mt + off : nullptr, d_toi + off,
+                             d_face + off, normal ? d_n + 3 * off : nullptr, uv ? d_uv + 2 * off : nullptr, cs, false);
+        if (rc) break;
+        CKM(cudaMemcpyAsync(toi + off, d_toi + off, 4 * cnt, cudaMemcpyDeviceToHost, cs));
+        CKM(cudaMemcpyAsync(face + off, d_face + off, 4 * cnt, cudaMemcpyDeviceToHost, cs));
+        if (normal) CKM(cudaMemcpyAsync(normal + 3 * off, d_n + 3 * off, 12 * cnt, cudaMemcpyDeviceToHost, cs));
+        if (uv) CKM(cudaMemcpyAsync(uv + 2 * off, d_uv + 2 * off, 8 * cnt, cudaMemcpyDeviceToHost, cs));
+    }
+    for (int j = 0; j < used; ++j) {  // the context's stream continues after the chunks (later device casts reuse nothing of this call)
+        cudaStreamSynchronize(m->chunk_stream[j]);
+    }
+    if (rc) return rc;
+    CKM(cudaGetLastError());
     return NCB_OK;
+}
+
+int ncb_trimesh_ray_cast(ncb_mesh* m, const float* pose, uint32_t n_rays, const float* origins, const float* dirs, float max_toi, float* toi,
+                         uint32_t* face, float* normal) {
+    return ncb_trimesh_ray_cast_uv(m, pose, n_rays, origins, dirs, max_toi, nullptr, toi, face, normal, nullptr);
 }
 
 }  // extern "C"

@@ -741,21 +741,47 @@ class TriMesh:
         self.h = h
         self.n_tris = len(self.tris)
 
-    def toi_and_normal_with_ray(self, pose, origins, dirs, max_toi=None, want_normals=True):
-        """pose: None or 7 floats (t xyz, q ijkw).  Returns (toi [-1 = None], face [i or i+T], normals)."""
+    def set_uvs(self, uvs):
+        """``TriMesh::new(points, indices, Some(uvs))``: per-vertex texture coordinates (None clears them)."""
+        u = as_f32(uvs).reshape(-1, 2) if uvs is not None else None
+        if u is not None and len(u) != len(self.verts):
+            raise ValueError("one uv per vertex")
+        self.ctx.check(self.ctx.lib.ncb_trimesh_set_uvs(self.h, ptr(u)), "ncb_trimesh_set_uvs")
+        self.has_uvs = u is not None
+
+    def toi_and_normal_with_ray(self, pose, origins, dirs, max_toi=None, want_normals=True, out=None):
+        """pose: None or 7 floats (t xyz, q ijkw).  max_toi: None, one value, or one per ray.  `out`: optional dict of preallocated
+        (e.g. pinned) result arrays "toi" / "face" / "normal".  Returns (toi [-1 = None], face [i or i+T], normals)."""
+        toi, face, normal, _ = self._cast(pose, origins, dirs, max_toi, want_normals, False, out)
+        return toi, face, normal
+
+    def toi_and_normal_and_uv_with_ray(self, pose, origins, dirs, max_toi=None, out=None):
+        """``RayCast::toi_and_normal_and_uv_with_ray`` (ray_trimesh.rs:52-94): also the interpolated uv of the hit point."""
+        return self._cast(pose, origins, dirs, max_toi, True, True, out)
+
+    def _cast(self, pose, origins, dirs, max_toi, want_normals, want_uv, out):
         o, d = as_f32(origins).reshape(-1, 3), as_f32(dirs).reshape(-1, 3)
         n = len(o)
-        toi = np.zeros(n, dtype=np.float32)
-        face = np.zeros(n, dtype=np.uint32)
-        normal = np.zeros((n, 3), dtype=np.float32) if want_normals else None
+        out = out or {}
+        toi = out.get("toi") if out.get("toi") is not None else np.zeros(n, dtype=np.float32)
+        face = out.get("face") if out.get("face") is not None else np.zeros(n, dtype=np.uint32)
+        normal = (out.get("normal") if out.get("normal") is not None else np.zeros((n, 3), dtype=np.float32)) if want_normals else None
+        uv = (out.get("uv") if out.get("uv") is not None else np.zeros((n, 2), dtype=np.float32)) if want_uv else None
         p = as_f32(pose) if pose is not None else None
+        per_ray = None
         if max_toi is None:
             max_toi = np.finfo(np.float32).max
+        elif np.ndim(max_toi) > 0:
+            per_ray = as_f32(max_toi).reshape(-1)
+            if len(per_ray) != n:
+                raise ValueError("one max_toi per ray")
+            max_toi = 0.0
         self.ctx.check(
-            self.ctx.lib.ncb_trimesh_ray_cast(self.h, ptr(p), C.c_uint32(n), ptr(o), ptr(d), C.c_float(max_toi), ptr(toi), ptr(face), ptr(normal)),
-            "ncb_trimesh_ray_cast",
+            self.ctx.lib.ncb_trimesh_ray_cast_uv(self.h, ptr(p), C.c_uint32(n), ptr(o), ptr(d), C.c_float(max_toi), ptr(per_ray), ptr(toi), ptr(face),
+                                                 ptr(normal), ptr(uv)),
+            "ncb_trimesh_ray_cast_uv",
         )
-        return toi, face, normal
+        return toi, face, normal, uv
 
     def close(self):
         if getattr(self, "h", None) and getattr(self.ctx, "h", None):

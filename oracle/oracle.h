@@ -161,6 +161,8 @@ orc_trimesh* orc_trimesh_create(uint32_t n_verts, const real* xyz, uint32_t n_tr
 void orc_trimesh_destroy(orc_trimesh*);
 /* mode 0: reference-faithful BVT best-first search; mode 1: brute force, global min toi over accepted hits,
  * ties -> smallest face index.  pose = t(3) q(4) or NULL for identity.  toi < 0 => miss. face = i or i+T (back face). */
+void orc_trimesh_ray_cast_uv(const orc_trimesh*, const real* pose, uint64_t n_rays, const real* origins, const real* dirs, real max_toi,
+                             const real* max_tois, const real* uvs, int mode, real* toi, uint32_t* face, real* normal, real* uv_out);
 void orc_trimesh_ray_cast(const orc_trimesh*, const real* pose, uint64_t n_rays, const real* origins, const real* dirs,
                           real max_toi, int mode, real* toi, uint32_t* face, real* normal);
 void orc_aabb_toi_with_ray(const real* minmax, const real* origin, const real* dir, real max_toi, int solid, real* toi);

@@ -464,6 +464,29 @@ class OracleTriMesh:
         )
         return toi, face, normal
 
+    def ray_cast_uv(self, origins, dirs, uvs=None, max_toi=None, pose=None, mode=0):
+        """toi_and_normal_and_uv_with_ray; max_toi: None, a scalar, or one per ray.  Returns (toi, face, normal, uv)."""
+        dt = self.o.dtype
+        o = np.ascontiguousarray(origins, dtype=dt)
+        d = np.ascontiguousarray(dirs, dtype=dt)
+        n = len(o)
+        toi = np.zeros(n, dtype=dt)
+        face = np.zeros(n, dtype=np.uint32)
+        normal = np.zeros((n, 3), dtype=dt)
+        uv = np.zeros((n, 2), dtype=dt)
+        per = None
+        if max_toi is None:
+            max_toi = np.finfo(dt).max
+        elif np.ndim(max_toi) > 0:
+            per = np.ascontiguousarray(max_toi, dtype=dt)
+            max_toi = 0.0
+        p = np.ascontiguousarray(pose, dtype=dt) if pose is not None else None
+        u = np.ascontiguousarray(uvs, dtype=dt) if uvs is not None else None
+        vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None  # noqa: E731
+        self.o.lib.orc_trimesh_ray_cast_uv(self.h, vp(p), C.c_uint64(n), vp(o), vp(d), self.o.creal(max_toi), vp(per), vp(u), C.c_int(mode),
+                                           vp(toi), vp(face), vp(normal), vp(uv))
+        return toi, face, normal, uv
+
     def __del__(self):
         try:
             self.o.lib.orc_trimesh_destroy(self.h)

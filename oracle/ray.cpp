@@ -38,7 +38,7 @@ static bool aabb_toi_with_ray(const Box& b, V3 origin, V3 dir, real max_toi, boo
 }
 
 // ray_triangle.rs:32-114.  fid: 0 front, 1 back.
-static bool ray_triangle(V3 a, V3 b, V3 c, V3 origin, V3 dir, real* toi, V3* normal, int* fid) {
+static bool ray_triangle(V3 a, V3 b, V3 c, V3 origin, V3 dir, real* toi, V3* normal, int* fid, V3* bary = nullptr) {
     V3 ab = b - a, ac = c - a;
     V3 n = cross(ab, ac);
     real d = dot(n, dir);
@@ -58,6 +58,8 @@ static bool ray_triangle(V3 a, V3 b, V3 c, V3 origin, V3 dir, real* toi, V3* nor
         real invd = real(1) / d;
         *toi = -t * invd;
         *normal = -normalize(n);
+        v = v * invd;
+        w = w * invd;
     } else {
         v = dot(ac, e);
         if (v < 0 || v > d) return false;
@@ -66,7 +68,10 @@ static bool ray_triangle(V3 a, V3 b, V3 c, V3 origin, V3 dir, real* toi, V3* nor
         real invd = real(1) / d;
         *toi = t * invd;
         *normal = normalize(n);
+        v = v * invd;
+        w = w * invd;
     }
+    if (bary) *bary = v3(-v - w + real(1), v, w);  // ray_triangle.rs:113
     return true;
 }
 
@@ -195,6 +200,7 @@ struct Hit {
     real toi = 0;
     V3 normal = {0, 0, 0};
     int fid = 0;
+    V3 bary = {0, 0, 0};  // TriMeshRayToiAndNormalAndUVsVisitor's third result (ray_trimesh.rs:199-240)
 };
 
 // TriMeshRayToiAndNormalVisitor::visit (ray_trimesh.rs:156-190)
@@ -209,13 +215,15 @@ static int visit(const orc_trimesh* m, real best, const Box& bv, const uint32_t*
         real ttoi;
         V3 n;
         int f;
-        if (ray_triangle(a, b, c, o, d, &ttoi, &n, &f) && ttoi <= max_toi) {
+        V3 bary;
+        if (ray_triangle(a, b, c, o, d, &ttoi, &n, &f, &bary) && ttoi <= max_toi) {
             *cost = ttoi;
             result->some = true;
             result->tri = t;
             result->toi = ttoi;
             result->normal = n;
             result->fid = f;
+            result->bary = bary;
         }
     }
     return 1;  // Continue
@@ -300,8 +308,10 @@ orc_trimesh* orc_trimesh_create(uint32_t n_verts, const real* xyz, uint32_t n_tr
 }
 void orc_trimesh_destroy(orc_trimesh* m) { delete m; }
 
-void orc_trimesh_ray_cast(const orc_trimesh* m, const real* pose, uint64_t n_rays, const real* origins, const real* dirs, real max_toi,
-                          int mode, real* toi, uint32_t* face, real* normal) {
+// toi_and_normal_and_uv_with_ray (ray_trimesh.rs:52-94) for a batch; uvs == NULL: toi_and_normal_with_ray (the reference's own
+// fall-back, :59-61).  max_tois: one max_toi per ray (NULL: max_toi).  uv_out: 2 reals per ray.
+void orc_trimesh_ray_cast_uv(const orc_trimesh* m, const real* pose, uint64_t n_rays, const real* origins, const real* dirs, real max_toi_all,
+                             const real* max_tois, const real* uvs, int mode, real* toi, uint32_t* face, real* normal, real* uv_out) {
     Iso iso = iso_identity();
     if (pose) iso = Iso{{pose[0], pose[1], pose[2]}, {pose[3], pose[4], pose[5], pose[6]}};
     Heap queue;
@@ -310,6 +320,7 @@ void orc_trimesh_ray_cast(const orc_trimesh* m, const real* pose, uint64_t n_ray
         V3 d = v3(dirs[3 * r], dirs[3 * r + 1], dirs[3 * r + 2]);
         // ray.inverse_transform_by(m) (ray.rs:36-41)
         V3 lo = iso_inv_point(iso, o), ld = iso_inv_vec(iso, d);
+        real max_toi = max_tois ? max_tois[r] : max_toi_all;
         Hit h;
         if (mode == 0) {
             h = best_first(m, lo, ld, max_toi, queue);
@@ -321,13 +332,15 @@ void orc_trimesh_ray_cast(const orc_trimesh* m, const real* pose, uint64_t n_ray
                 real tt;
                 V3 n;
                 int f;
-                if (ray_triangle(a, b, c, lo, ld, &tt, &n, &f) && tt <= max_toi) {
+                V3 bary;
+                if (ray_triangle(a, b, c, lo, ld, &tt, &n, &f, &bary) && tt <= max_toi) {
                     if (!h.some || tt < h.toi) {
                         h.some = true;
                         h.tri = t;
                         h.toi = tt;
                         h.normal = n;
                         h.fid = f;
+                        h.bary = bary;
                     }
                 }
             }
@@ -337,12 +350,26 @@ void orc_trimesh_ray_cast(const orc_trimesh* m, const real* pose, uint64_t n_ray
             face[r] = h.fid == 1 ? h.tri + m->ntris : h.tri;  // ray_trimesh.rs:41-45
             V3 wn = iso_mul_vec(iso, h.normal);                // :47
             if (normal) normal[3 * r] = wn.x, normal[3 * r + 1] = wn.y, normal[3 * r + 2] = wn.z;
+            if (uv_out) {
+                real ux = 0, uy = 0;
+                if (uvs) {  // ray_trimesh.rs:76-84
+                    uint32_t i0 = m->idx[3 * h.tri], i1 = m->idx[3 * h.tri + 1], i2 = m->idx[3 * h.tri + 2];
+                    ux = uvs[2 * i0] * h.bary.x + uvs[2 * i1] * h.bary.y + uvs[2 * i2] * h.bary.z;
+                    uy = uvs[2 * i0 + 1] * h.bary.x + uvs[2 * i1 + 1] * h.bary.y + uvs[2 * i2 + 1] * h.bary.z;
+                }
+                uv_out[2 * r] = ux, uv_out[2 * r + 1] = uy;
+            }
         } else {
             toi[r] = -1;
             face[r] = 0xffffffffu;
             if (normal) normal[3 * r] = normal[3 * r + 1] = normal[3 * r + 2] = 0;
+            if (uv_out) uv_out[2 * r] = uv_out[2 * r + 1] = 0;
         }
     }
+}
+void orc_trimesh_ray_cast(const orc_trimesh* m, const real* pose, uint64_t n_rays, const real* origins, const real* dirs, real max_toi,
+                          int mode, real* toi, uint32_t* face, real* normal) {
+    orc_trimesh_ray_cast_uv(m, pose, n_rays, origins, dirs, max_toi, nullptr, nullptr, mode, toi, face, normal, nullptr);
 }
 
 void orc_aabb_toi_with_ray(const real* mm, const real* origin, const real* dir, real max_toi, int solid, real* toi) {
