@@ -125,6 +125,8 @@ int ncb_create(int device, ncb_ctx** out) {
         e = cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_tier1, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_tier2, cudaEventDisableTiming);
     }
     if (e != cudaSuccess) {
         g_create_err = cudaGetErrorString(e);
@@ -171,6 +173,8 @@ void ncb_destroy(ncb_ctx* c) {
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_tier1) cudaEventDestroy(c->ev_tier1);
+    if (c->ev_tier2) cudaEventDestroy(c->ev_tier2);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }

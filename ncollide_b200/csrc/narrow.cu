@@ -1300,15 +1300,23 @@ __global__ void __launch_bounds__(64, NCB_EPA_MINBLOCKS) k_cc_epa_big(NarrowArgs
     }
 }
 
+__global__ void k_snap_manifold_split(DevCounters* cnt) { cnt->man_split = cnt->cp_cursor[CCQ]; }
+
 #ifndef NCB_MAN_MINBLOCKS
 #define NCB_MAN_MINBLOCKS 6
 #endif
 template <bool PS>
 __global__ void __launch_bounds__(128, NCB_MAN_MINBLOCKS) k_cc_manifold(NarrowArgs A) {
     const int KEY = CCQ;
+    // The queue has two ranges: [key_start, man_split) was complete when the first EPA tier finished and is processed in
+    // man_parts parts (part index < man_parts) while the later EPA tiers still append beyond it; [man_split, cp_cursor) is the
+    // tail they produced (part index == man_parts, launched after they finished).
     uint32_t seg_begin = A.cnt->key_start[KEY];
-    uint32_t seg_end = A.cnt->cp_cursor[KEY];
-    if (A.man_parts > 1) {
+    uint32_t seg_end = A.cnt->man_split;
+    if (A.man_part >= A.man_parts) {
+        seg_begin = seg_end;
+        seg_end = A.cnt->cp_cursor[KEY];
+    } else if (A.man_parts > 1) {
         uint32_t len = seg_end - seg_begin, per = (len + A.man_parts - 1) / A.man_parts;
         uint32_t b = seg_begin + min(len, per * (uint32_t)A.man_part);
         seg_end = seg_begin + min(len, per * (uint32_t)(A.man_part + 1));
@@ -1605,24 +1613,45 @@ static cudaError_t launch_narrow_phase_t(ncb_ctx* c, const DevObjects& o, const 
             attr_set[PS] = true;
         }
         k_cc_epa_tier<PS, 1><<<sm * epas_bpsm, EPAS_THREADS, smem1, s>>>(A);
-        k_cc_epa_tier<PS, 2><<<sm * 3, EPAT2_THREADS, smem2, s>>>(A);
-        k_cc_epa_big<PS><<<sm * epa_bpsm, 64, 0, s>>>(A);  // last resort, normally an empty queue
-    }
-    timer_mark(c, "cc_epa", 3);
-    if (early) {
-        // the manifold queue in NCB_MAN_PARTS parts, a snapshot of the contact counter after each: the copy stream ships the
-        // contacts of a finished part while the next one computes (api.cu, update_after_aabbs)
-        for (int part = 0; part < NCB_MAN_PARTS; ++part) {
-            A.man_part = part, A.man_parts = NCB_MAN_PARTS;
-            k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
-            cudaMemcpyAsync(c->snap.p + 1 + part, &c->counters.p->n_contacts, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
-            cudaEventRecord(c->ev_snap[1 + part], s);
+        // The later tiers hold ~1 % of the pairs in a few long runs (0.22 ms at 4 % occupancy).  NCB_EPA_TIERS_ASIDE=1 runs them on
+        // the side stream, followed there by a short manifold launch for what they append, beside the main manifold kernel (which
+        // works through what the queue held when tier 1 finished, man_split).  Measured and left off (profiles/r2_epa_tiers_aside.txt):
+        // the persistent manifold grid fills every SM, so the side chain only starts when it drains, and every extra launch of
+        // these kernels costs the latency of one pair's run (~0.15 ms): 3.77 ms per step instead of 3.65.
+        static const bool aside_ok = getenv("NCB_EPA_TIERS_ASIDE") != nullptr;
+        const bool aside = aside_ok && c->side_stream && !early;
+        cudaStream_t st = aside ? c->side_stream : s;
+        if (aside) {
+            k_snap_manifold_split<<<1, 1, 0, s>>>(A.cnt);
+            cudaEventRecord(c->ev_tier1, s);
+            cudaStreamWaitEvent(st, c->ev_tier1, 0);
         }
-        timer_mark(c, "cc_manifold", NCB_MAN_PARTS);
-    } else {
-        A.man_part = 0, A.man_parts = 1;
-        k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
-        timer_mark(c, "cc_manifold", 1);
+        k_cc_epa_tier<PS, 2><<<sm * 3, EPAT2_THREADS, smem2, st>>>(A);
+        k_cc_epa_big<PS><<<sm * epa_bpsm, 64, 0, st>>>(A);  // last resort, normally an empty queue
+        if (aside) {
+            A.man_part = 1, A.man_parts = 1;  // the tail: [man_split, cp_cursor)
+            k_cc_manifold<PS><<<sm * 2, 128, 0, st>>>(A);
+            cudaEventRecord(c->ev_tier2, st);
+        } else {
+            k_snap_manifold_split<<<1, 1, 0, s>>>(A.cnt);  // everything is in the queue: no tail
+        }
+        timer_mark(c, "cc_epa", aside ? 2 : 4);
+        if (early) {
+            // the manifold queue in NCB_MAN_PARTS parts, a snapshot of the contact counter after each: the copy stream ships the
+            // contacts of a finished part while the next one computes (api.cu, update_after_aabbs)
+            for (int part = 0; part < NCB_MAN_PARTS; ++part) {
+                A.man_part = part, A.man_parts = NCB_MAN_PARTS;
+                k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
+                cudaMemcpyAsync(c->snap.p + 1 + part, &c->counters.p->n_contacts, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
+                cudaEventRecord(c->ev_snap[1 + part], s);
+            }
+            timer_mark(c, "cc_manifold", NCB_MAN_PARTS);
+        } else {
+            A.man_part = 0, A.man_parts = 1;
+            k_cc_manifold<PS><<<sm * man_bpsm, 128, 0, s>>>(A);
+            if (aside) cudaStreamWaitEvent(s, c->ev_tier2, 0);
+            timer_mark(c, "cc_manifold", aside ? 4 : 1);
+        }
     }
     if (!early && c->side_stream) cudaStreamWaitEvent(s, c->ev_join, 0);  // device-only updates: the side chain may run to the end
     timer_mark(c, "narrow_other_join", 7);

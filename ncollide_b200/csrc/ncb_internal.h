@@ -125,6 +125,7 @@ struct DevCounters {
     uint32_t epa_defer_fetch;
     uint32_t stack_overflow;   // BVH traversals (pair search, ray casts, queries) that ran out of their 64-entry stack: must stay 0
     uint32_t prox_hist[4];     // proximity pairs per status (Intersecting, WithinMargin, Disjoint)
+    uint32_t man_split;        // end of the manifold queue when the first EPA tier finished: what lies beyond comes from the later tiers
 };
 
 // Persistent narrow-phase state of a stepping world (sim.cu), indexed by state slot.
@@ -245,6 +246,7 @@ struct ncb_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t side_stream = nullptr;  // second chain of the narrow phase (fork / join with events)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_tier1 = nullptr, ev_tier2 = nullptr;  // later EPA tiers run on the side stream beside the manifold kernel
     std::string err;
     int sm_count = 148;
 
