@@ -365,6 +365,12 @@ int ncb_sim_remove(ncb_sim* sim, uint32_t m, const uint32_t* handles);
 int ncb_sim_add(ncb_sim* sim, const ncb_objects* objs, uint32_t* out_handles);
 /* ncb_sim_add with a GeometricQueryType per new object: kinds[k] = 0 Contacts / 1 Proximity(query_limit) (NULL = all Contacts). */
 int ncb_sim_add_with_query_types(ncb_sim* sim, const ncb_objects* objs, const uint8_t* kinds, uint32_t* out_handles);
+/* CollisionObject::set_collision_groups (pipeline/object/collision_object.rs:246-250) for a batch of live objects; groups = 3 words
+ * per handle (membership, whitelist, blacklist; collision_groups.rs:26-37).  Sets COLLISION_GROUPS_CHANGED: the next ncb_sim_step
+ * redispatches the objects in the broad phase (glue/update.rs:83-86: pairs that are no longer allowed stop — with a
+ * ContactEvent::Stopped / ProximityEvent if they were touching —, newly allowed ones start) and updates their pairs in the narrow
+ * phase (collision_object.rs:33-43). */
+int ncb_sim_set_collision_groups(ncb_sim* sim, uint32_t n, const uint32_t* handles, const uint32_t* groups);
 /* CollisionWorld::update.  counts: n_pairs, n_contacts, epa_overflow (+ manifold-cache overflows), ref_panics,
  * n_epa_pairs, n_manifold_jobs (= pairs regenerated in this step). */
 int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts);

@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = [
     "ncb_profile_enable", "ncb_profile_get", "ncb_trimesh_create", "ncb_trimesh_destroy", "ncb_trimesh_ray_cast",
     "ncb_trimesh_ray_cast_device", "ncb_trimesh_ray_cast_uv", "ncb_trimesh_set_uvs",
     "ncb_bp_create", "ncb_bp_destroy", "ncb_bp_create_proxies", "ncb_bp_set_bounding_volumes", "ncb_bp_remove", "ncb_bp_update",
-    "ncb_sim_create", "ncb_sim_destroy", "ncb_sim_set_positions", "ncb_sim_step", "ncb_sim_sizes", "ncb_sim_fetch", "ncb_sim_remove", "ncb_sim_add", "ncb_sim_ray_cast", "ncb_sim_query",
+    "ncb_sim_create", "ncb_sim_destroy", "ncb_sim_set_positions", "ncb_sim_set_collision_groups", "ncb_sim_step", "ncb_sim_sizes", "ncb_sim_fetch", "ncb_sim_remove", "ncb_sim_add", "ncb_sim_ray_cast", "ncb_sim_query",
     "ncb_set_query_types", "ncb_proximity", "ncb_world_fetch_proximity", "ncb_sim_fetch_proximity", "ncb_sim_add_with_query_types",
     "ncb_bp_events", "ncb_bp_query", "ncb_bp_recompute_with", "ncb_bp_recompute_all", "ncb_bp_num_interferences", "ncb_bp_pairs", "ncb_bp_proxy",
 ]

@@ -27,6 +27,7 @@ struct ncb_sim {
     bool first = true;
     std::vector<uint8_t> alive;          // host mirror of the object slab
     std::vector<uint32_t> free_handles;  // vacant object handles, reused last-freed-first (CollisionObjectSlab)
+    std::vector<uint32_t> groups_changed;  // objects with COLLISION_GROUPS_CHANGED since the last update (collision_object.rs:10-25)
     DevBuf<uint8_t> moved;
     DevBuf<uint8_t> sel_flags;
     DevBuf<unsigned long long> keys_tmp;
@@ -404,6 +405,46 @@ int ncb_sim_set_positions(ncb_sim* sim, uint32_t m, const uint32_t* handles, con
     return NCB_OK;
 }
 
+// CollisionObject::set_collision_groups (collision_object.rs:246-250) on a batch of live objects: sets COLLISION_GROUPS_CHANGED.  The
+// next update then asks the broad phase to recompute all proximities of the object (needs_broad_phase_redispatch, glue/update.rs:83-86:
+// pairs that are no longer allowed stop, newly allowed ones start) and the narrow phase to update the object's pairs
+// (needs_narrow_phase_update); the bounding volume is not touched.  groups: 3 words per handle (membership, whitelist, blacklist).
+__global__ void k_sim_scatter_groups(const uint32_t* __restrict__ handles, const uint32_t* __restrict__ g, uint32_t m, uint32_t* dgroups,
+                                     uint8_t* moved) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    uint32_t h = handles[k];
+    dgroups[3 * (size_t)h] = g[3 * k], dgroups[3 * (size_t)h + 1] = g[3 * k + 1], dgroups[3 * (size_t)h + 2] = g[3 * k + 2];
+    moved[h] = 1;  // the object's pairs take part in the next narrow-phase update; its stored box stays (the same box is re-submitted)
+}
+int ncb_sim_set_collision_groups(ncb_sim* sim, uint32_t m, const uint32_t* handles, const uint32_t* groups) {
+    if (!sim || (m && (!handles || !groups))) return NCB_ERR_ARG;
+    ncb_ctx* ctx = sim->ctx;
+    CKS(cudaSetDevice(ctx->device));
+    if (m == 0) return NCB_OK;
+    for (uint32_t k = 0; k < m; ++k)
+        if (handles[k] >= sim->n || !sim->alive[handles[k]]) {
+            ctx->err = "ncb_sim_set_collision_groups: unknown object handle";
+            return NCB_ERR_ARG;
+        }
+    cudaStream_t s = ctx->stream;
+    if (!ctx->has_groups) {  // the world used default groups so far: materialise them
+        CKS(ctx->groups.reserve(3 * (size_t)sim->n));
+        k_sim_fill_groups<<<(sim->n + 255) / 256, 256, 0, s>>>(ctx->groups.p, sim->n);
+        ctx->has_groups = true;
+    }
+    CKS(sim->stage_h.reserve(m));
+    CKS(sim->stage_p.reserve(3 * (size_t)m));
+    CKS(cudaMemcpyAsync(sim->stage_h.p, handles, 4 * (size_t)m, cudaMemcpyHostToDevice, s));
+    CKS(cudaMemcpyAsync(sim->stage_p.p, groups, 12 * (size_t)m, cudaMemcpyHostToDevice, s));
+    k_sim_scatter_groups<<<(m + 255) / 256, 256, 0, s>>>(sim->stage_h.p, reinterpret_cast<const uint32_t*>(sim->stage_p.p), m, ctx->groups.p,
+                                                         sim->moved.p);
+    CKS(cudaGetLastError());
+    CKS(cudaStreamSynchronize(s));  // staging buffers are reused
+    sim->groups_changed.insert(sim->groups_changed.end(), handles, handles + m);
+    return NCB_OK;
+}
+
 // CollisionWorld::update (world.rs:104-119)
 int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
     if (!sim) return NCB_ERR_ARG;
@@ -436,6 +477,19 @@ int ncb_sim_step(ncb_sim* sim, ncb_update_counts* counts) {
     }
     r = bp_set_moved_device(sim->bp, n, ctx->aabb_lo.p, ctx->aabb_hi.p, sim->moved.p);
     if (r) return r;
+    if (!sim->groups_changed.empty()) {
+        // objects.foreach visits the objects in handle order and pushes each redispatch to the FRONT of the update queue
+        std::sort(sim->groups_changed.begin(), sim->groups_changed.end());
+        sim->groups_changed.erase(std::unique(sim->groups_changed.begin(), sim->groups_changed.end()), sim->groups_changed.end());
+        std::vector<uint32_t> live;
+        for (uint32_t h : sim->groups_changed)
+            if (h < sim->n && sim->alive[h]) live.push_back(h);
+        sim->groups_changed.clear();
+        if (!live.empty()) {
+            r = ncb_bp_recompute_with(sim->bp, (uint32_t)live.size(), live.data());
+            if (r) return r;
+        }
+    }
     mark("aabb+stage");
     // no event lists wanted: started / stopped pairs are found below by diffing the sorted key lists against the pair table
     r = bp_update_impl(sim->bp, ctx->has_groups ? ctx->groups.p : nullptr, nullptr, nullptr, false);

@@ -643,6 +643,14 @@ class SteppingWorld:
         p, r = as_f32(pos).reshape(-1, 3), as_f32(rot).reshape(-1, 4)
         self.ctx.check(self.ctx.lib.ncb_sim_set_positions(self._h, C.c_uint32(len(p)), ptr(hs), ptr(p), ptr(r)), "ncb_sim_set_positions")
 
+    def set_collision_groups(self, handles, groups):
+        """``CollisionObject::set_collision_groups`` on live objects (groups[k] = membership, whitelist, blacklist): the next update
+        redispatches them in the broad phase and updates their pairs (``ncb_sim_set_collision_groups``)."""
+        hs, g = as_u32(handles).reshape(-1), as_u32(groups).reshape(-1, 3)
+        if len(hs) != len(g):
+            raise ValueError("one (membership, whitelist, blacklist) row per handle")
+        self.ctx.check(self.ctx.lib.ncb_sim_set_collision_groups(self._h, C.c_uint32(len(hs)), ptr(hs), ptr(g)), "ncb_sim_set_collision_groups")
+
     def remove(self, handles):
         """``CollisionWorld::remove``: the objects and their pairs disappear (no events); handles are recycled by ``add``."""
         hs = as_u32(handles).reshape(-1)

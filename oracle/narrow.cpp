@@ -1524,7 +1524,7 @@ void orc_sim_set_positions(orc_sim* s, uint32_t n, const uint32_t* handles, cons
         uint32_t h = handles ? handles[k] : k;
         for (int d = 0; d < 3; ++d) s->pos[3 * (size_t)h + d] = pos[3 * (size_t)k + d];
         for (int d = 0; d < 4; ++d) s->rot[4 * (size_t)h + d] = rot[4 * (size_t)k + d];
-        if (h < s->alive.size() && s->alive[h] && s->flags[h] == 0) s->flags[h] = 1;
+        if (h < s->alive.size() && s->alive[h] && !(s->flags[h] & 2)) s->flags[h] |= 1;
     }
 }
 
@@ -1535,12 +1535,15 @@ void orc_sim_step(orc_sim* s) {
     // perform_broad_phase (glue/update.rs:65-99)
     for (uint32_t i = 0; i < o.n; ++i) {
         if (!s->alive[i] || !s->flags[i]) continue;
-        AABB a = shape_aabb(o, i);
-        real ql = o.query_limit[i];
-        real mm[6] = {a.mins.x + (-ql), a.mins.y + (-ql), a.mins.z + (-ql), a.maxs.x + ql, a.maxs.y + ql, a.maxs.z + ql};
-        orc_bp_set_bounding_volume(s->bp, i, mm);
-        // a new object also has SHAPE_CHANGED etc. set: deferred_recompute_all_proximities_with, a no-op on a detached proxy
-        if (s->flags[i] == 2 || s->first) orc_bp_recompute_with(s->bp, i);
+        // flags: 1 POSITION_CHANGED, 2 a new object (every flag), 4 COLLISION_GROUPS_CHANGED (collision_object.rs:10-59)
+        if (s->flags[i] & 3) {  // needs_bounding_volume_update
+            AABB a = shape_aabb(o, i);
+            real ql = o.query_limit[i];
+            real mm[6] = {a.mins.x + (-ql), a.mins.y + (-ql), a.mins.z + (-ql), a.maxs.x + ql, a.maxs.y + ql, a.maxs.z + ql};
+            orc_bp_set_bounding_volume(s->bp, i, mm);
+        }
+        // needs_broad_phase_redispatch: a new object also has SHAPE_CHANGED etc. set (a no-op on a detached proxy); changed groups
+        if ((s->flags[i] & 6) || s->first) orc_bp_recompute_with(s->bp, i);
     }
     uint64_t cap = 1 << 16, ns = 0, np = 0;
     std::vector<uint32_t> st, sp;
@@ -1593,6 +1596,23 @@ void orc_sim_step(orc_sim* s) {
     }
     std::fill(s->flags.begin(), s->flags.end(), 0);
     s->first = false;
+}
+
+// CollisionObject::set_collision_groups (collision_object.rs:246-250)
+int orc_sim_set_collision_groups(orc_sim* s, uint32_t n, const uint32_t* handles, const uint32_t* groups) {
+    for (uint32_t k = 0; k < n; ++k)
+        if (handles[k] >= s->alive.size() || !s->alive[handles[k]]) return -1;
+    if (s->groups.empty()) {  // CollisionGroups::new() for everybody so far
+        s->groups.resize(3 * s->alive.size());
+        for (size_t i = 0; i < s->alive.size(); ++i) s->groups[3 * i] = s->groups[3 * i + 1] = 0x3FFFFFFFu, s->groups[3 * i + 2] = 0;
+        s->rebind();
+    }
+    for (uint32_t k = 0; k < n; ++k) {
+        uint32_t h = handles[k];
+        for (int d = 0; d < 3; ++d) s->groups[3 * (size_t)h + d] = groups[3 * (size_t)k + d];
+        s->flags[h] |= 4;
+    }
+    return 0;
 }
 
 // CollisionWorld::remove (world.rs:129-144): per handle, objects.remove + glue::remove_proxies (glue/setup.rs:50-62): the

@@ -130,6 +130,7 @@ orc_sim* orc_sim_create(const orc_objects* objs, real margin);
 void orc_sim_destroy(orc_sim*);
 void orc_sim_set_positions(orc_sim*, uint32_t n, const uint32_t* handles, const real* pos, const real* rot);
 void orc_sim_step(orc_sim*);
+int orc_sim_set_collision_groups(orc_sim*, uint32_t n, const uint32_t* handles, const uint32_t* groups);
 int orc_sim_remove(orc_sim*, uint32_t n, const uint32_t* handles);
 int orc_sim_add(orc_sim*, const orc_objects* objs, uint32_t* out_handles);
 uint64_t orc_sim_num_pairs(const orc_sim*);

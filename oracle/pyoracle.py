@@ -362,6 +362,14 @@ class OracleSim:
         self.o.lib.orc_sim_set_positions(self.h, C.c_uint32(len(p)), C.c_void_p(hs.ctypes.data) if hs is not None else None,
                                          C.c_void_p(p.ctypes.data), C.c_void_p(r.ctypes.data))
 
+    def set_collision_groups(self, handles, groups):
+        hs = np.ascontiguousarray(handles, dtype=np.uint32).reshape(-1)
+        g = np.ascontiguousarray(groups, dtype=np.uint32).reshape(-1, 3)
+        assert len(g) == len(hs)
+        r = self.o.lib.orc_sim_set_collision_groups(self.h, C.c_uint32(len(hs)), C.c_void_p(hs.ctypes.data), C.c_void_p(g.ctypes.data))
+        if r != 0:
+            raise ValueError("unknown object handle")
+
     def remove(self, handles):
         hs = np.ascontiguousarray(handles, dtype=np.uint32)
         if self.o.lib.orc_sim_remove(self.h, C.c_uint32(len(hs)), C.c_void_p(hs.ctypes.data)) != 0:

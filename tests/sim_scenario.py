@@ -76,3 +76,35 @@ def drive_add_remove(sim, scene, extra, steps, seed):
         r["new_handles"] = new_handles
         log.append(r)
     return log
+
+
+def drive_group_changes(sim, scene, steps, seed):
+    """Like `drive`, with CollisionObject::set_collision_groups on live objects between updates: objects leave the default groups
+    (pairs stop, with ContactEvent::Stopped when they were touching), come back (pairs start again), and some do both while moving."""
+    rng = np.random.default_rng(seed)
+    pos, rot = scene.pos.copy(), scene.rot.copy()
+    n = scene.n
+    ALL = 0x3FFFFFFF
+    groups = np.tile(np.array([ALL, ALL, 0], dtype=np.uint32), (n, 1))
+    log = []
+    for t in range(steps):
+        if t in (1, 4):  # a tenth of the world stops talking to group 1 members; a few become group-1 members only
+            a = np.sort(rng.choice(n, size=n // 10, replace=False)).astype(np.uint32)
+            groups[a] = np.array([ALL, ALL & ~2, 0], dtype=np.uint32)
+            b = np.sort(rng.choice(n, size=n // 10, replace=False)).astype(np.uint32)
+            groups[b] = np.array([2, ALL, 0], dtype=np.uint32)
+            hs = np.unique(np.concatenate([a, b]))
+            sim.set_collision_groups(hs, groups[hs])
+        if t in (2, 5):  # half of the changed objects return to the default groups
+            changed = np.nonzero((groups[:, 0] != ALL) | (groups[:, 1] != ALL))[0].astype(np.uint32)
+            back = changed[rng.random(len(changed)) < 0.5]
+            groups[back] = np.array([ALL, ALL, 0], dtype=np.uint32)
+            if len(back):
+                sim.set_collision_groups(back, groups[back])
+        if t in (1, 3, 5, 6):
+            idx = step_poses(scene, pos, rot, rng, 0.3)
+            sim.set_positions(idx, pos[idx], rot[idx])
+        r = sim.step()
+        r["groups"] = groups.copy()
+        log.append(r)
+    return log

@@ -131,6 +131,81 @@ def test_device_handler_mirror():
         bp.update(h)
 
 
+@pytest.mark.gpu
+def test_user_pair_filter_over_steps():
+    """An arbitrary BroadPhasePairFilter (broad_phase_pair_filter.rs:5-16, applied through is_interference_allowed,
+    glue/update.rs:29-41) on top of the device broad phase, over random moves / removals: after every update the pairs the
+    handler has been told about (started minus stopped) are exactly {stored boxes intersect AND the filter allows the pair},
+    and num_interferences / pairs() agree."""
+    from ncollide_b200.world import BroadPhase, BroadPhaseInterferenceHandler, Context
+
+    rng = np.random.default_rng(77)
+
+    def allowed(a, b):  # deterministic, symmetric, vetoes about a third of the pairs
+        lo, hi = min(a, b), max(a, b)
+        return (lo * 2654435761 + hi * 40503) % 3 != 0
+
+    class H(BroadPhaseInterferenceHandler):
+        def __init__(self):
+            self.live = set()
+            self.calls = 0
+
+        def is_interference_allowed(self, a, b):
+            self.calls += 1
+            return allowed(a, b)
+
+        def interference_started(self, a, b):
+            key = (min(a, b), max(a, b))
+            assert allowed(a, b) and key not in self.live
+            self.live.add(key)
+
+        def interference_stopped(self, a, b):
+            key = (min(a, b), max(a, b))
+            assert key in self.live, "a vetoed pair must never be reported as stopped"
+            self.live.discard(key)
+
+    bp = BroadPhase(0.05, ctx=Context(0))
+    n, side = 600, 9.0
+    centres = (rng.random((n, 3)) * side).astype(F32)
+    handles = bp.create_proxies(np.stack([ball_box(c) for c in centres]), list(range(n)))  # user data = index
+    # user data must be the HANDLE here (the filter sees the data): handles are 0..n-1 in creation order on a fresh broad phase
+    assert handles.tolist() == list(range(n))
+    alive = set(range(n))
+    h = H()
+    for step in range(6):
+        bp.update(h)
+        ids = sorted(alive)
+        boxes = np.stack([bp.proxy(i)[0] for i in ids])
+        want = set()
+        for ai, a in enumerate(ids):
+            hit = np.all(boxes[ai, :3] <= boxes[:, 3:], axis=1) & np.all(boxes[:, :3] <= boxes[ai, 3:], axis=1)
+            for bi in np.nonzero(hit)[0]:
+                b = ids[bi]
+                if a < b and allowed(a, b):
+                    want.add((a, b))
+        assert h.live == want, f"step {step}: {len(h.live ^ want)} pairs differ"
+        assert bp.num_interferences() == len(want)
+        got = {(min(a, b), max(a, b)) for a, b in bp.pairs().tolist()}
+        assert got == want
+        # move a third of the proxies, remove a few
+        move = rng.choice(ids, size=len(ids) // 3, replace=False)
+        centres[move] += rng.normal(0, 0.6, size=(len(move), 3)).astype(F32)
+        bp.deferred_set_bounding_volumes(move, np.stack([ball_box(centres[i]) for i in move]))
+        gone = rng.choice(ids, size=10, replace=False)
+
+        class R:
+            def __init__(self, live):
+                self.live = live
+
+            def __call__(self, a, b):
+                self.live.discard((min(a, b), max(a, b)))
+
+        bp.remove(gone, R(h.live))
+        alive -= set(int(g) for g in gone)
+    assert h.calls > 0 and len(h.live) > 100
+    bp.close()
+
+
 # ---- stepping world (persistent narrow phase on top of the persistent broad phase) -----------------------------------
 RTOL, ATOL = 1e-4, 1e-5
 
@@ -212,8 +287,54 @@ class DeviceSimAdapterAR(DeviceSimAdapter):
     def remove(self, handles):
         self.w.remove(handles)
 
+    def set_collision_groups(self, handles, groups):
+        self.w.set_collision_groups(handles, groups)
+
     def add(self, scene):
         return self.w.add(scene)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,kinds,seed", [(900, (1, 1, 1), 12), (4000, (1, 1, 1), 13)])
+def test_stepping_world_group_changes_match_oracle(oracle, n, kinds, seed):
+    """CollisionObject::set_collision_groups on live objects (COLLISION_GROUPS_CHANGED -> broad-phase redispatch + narrow-phase
+    update, glue/update.rs:76-87): pairs, orientation, manifolds, contact ids and events equal the oracle's step by step."""
+    from ncollide_b200.scenes import make_world_scene
+    from ncollide_b200.world import Context
+    from sim_scenario import drive_group_changes
+
+    s = make_world_scene(n, 40 + seed, kinds, side=7.0 * (n / 900.0) ** (1 / 3), n_hulls=32, name="sim_groups")
+    dev = drive_group_changes(DeviceSimAdapterAR(Context(0), s), s, steps=7, seed=seed)
+    orc = drive_group_changes(oracle.sim(s), s, steps=7, seed=seed)
+    assert len(orc[1]["pairs"]) < len(orc[0]["pairs"]) and len(orc[2]["pairs"]) > len(orc[1]["pairs"])
+    assert sum(len(r["events"]) for r in orc[1:]) > 10
+    compare_sim_logs(dev, orc)
+
+
+def test_oracle_group_changes_follow_the_filter(oracle):
+    """ORACLE check (CPU): after every update of a world whose objects change groups, the edge set is exactly
+    {stored broad-phase boxes intersect AND CollisionGroups::can_interact_with_groups} (collision_groups.rs:353-359)."""
+    from ncollide_b200.scenes import make_world_scene
+    from sim_scenario import drive_group_changes
+
+    s = make_world_scene(700, 51, (1, 1, 1), side=6.5, n_hulls=16, name="sim_groups_cpu")
+    log = drive_group_changes(oracle.sim(s), s, steps=7, seed=14)
+
+    def allowed(g, a, b):
+        if a == b:
+            return bool(g[a][2] & g[a][0])  # never queried here
+        return bool(g[a][0] & g[b][1]) and bool(g[b][0] & g[a][1]) and not (g[a][0] & g[b][2]) and not (g[b][0] & g[a][2])
+
+    seen_drop = False
+    for t, r in enumerate(log):
+        g = r["groups"]
+        for a, b in r["pairs"].tolist():
+            assert allowed(g, a, b), f"step {t}: pair ({a}, {b}) is not allowed by its groups"
+        if t > 0 and len(r["pairs"]) < len(log[0]["pairs"]):
+            seen_drop = True
+    assert seen_drop
+    # stopped pairs that were touching produce ContactEvent::Stopped in the step their groups change
+    assert any(len(r["events"]) and (np.asarray(r["events"])[:, 2] == 0).any() for r in log[1:])
 
 
 @pytest.mark.gpu
