@@ -440,7 +440,9 @@ static int g_gjk_support_evals = 0;
 // gjk::closest_points with exact_dist = true, preceded by the caller's `simplex.reset(CSOPoint::from_shapes(.., init_dir))`
 // (contact_support_map_support_map.rs:52-63): the first support evaluation shares the loop's code (one copy of the two support
 // maps in the instruction stream instead of two) and the three ClosestPoints exits share one witness computation.
-static __device__ __noinline__ int gjk_closest_points(const Iso& m1, const Support& g1, const Iso& m2, const Support& g2, float max_dist,
+// G: Support, or SupportS (kind, half extents | vertex array: all a support evaluation reads; k_cc_gjk keeps its operands that slim).
+template <class G>
+static __device__ __noinline__ int gjk_closest_points(const Iso& m1, const G& g1, const Iso& m2, const G& g2, float max_dist,
                                                       V3 init_dir, Simplex& s, V3& p1, V3& p2, V3& out_dir) {
     const float eps_tol = NCB_EPS * 10.0f;
     const float eps_rel = sqrtf(eps_tol);

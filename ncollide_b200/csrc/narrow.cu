@@ -1054,8 +1054,8 @@ __global__ void __launch_bounds__(128, NCB_GJK_MINBLOCKS) k_cc_gjk(NarrowArgs A)
             uint32_t t1 = __ldg(&A.o.type[i1]), t2 = __ldg(&A.o.type[i2]);
             Iso ma = load_iso(A.o, i1), mb = load_iso(A.o, i2);
             float linear = __ldg(&A.o.qlimit[i1]) + __ldg(&A.o.qlimit[i2]);
-            Shape a = load_shape(A.o, A.H, i1, t1), b = load_shape(A.o, A.H, i2, t2);
-            Support ga = as_support(a), gb = as_support(b);
+            // GJK only evaluates support points: slim operands (kind, half extents | vertex array) instead of the full hull views
+            SupportS ga = load_slim_support(A.o, A.H, i1, t1), gb = load_slim_support(A.o, A.H, i2, t2);
             // contact_support_map_support_map_with_params, init_dir = None (fresh generator)
             V3 d0;
             uint32_t out_index = 0;
