@@ -637,10 +637,18 @@ static int update_after_aabbs(ncb_ctx* ctx, uint32_t q_begin, uint32_t q_end, ui
             CK(cudaMemsetAsync(ctx->prox.p, 0xff, cap_pairs, ctx->stream));
             CK(launch_prox_rekey(ctx, (uint32_t)cap_pairs));
         }
-        CK(launch_pair_sort(ctx, (uint32_t)cap_pairs, nullptr));
-        timer_mark(ctx, "pair_sort", 3);
+        // sharded updates read their narrow-phase operands from compact rank-local arrays (broad.cu: k_gather_local_objects)
+        static const bool local_ops_ok = getenv("NCB_SHARD_GLOBAL_OPERANDS") == nullptr;
+        const bool local_ops = local_ops_ok && handle_map != nullptr && n < ctx->n;
+        DevObjects objs = dev_objects(ctx);
+        if (local_ops) {
+            CK(ctx->pairs_local.reserve(cap_pairs));
+            CK(launch_gather_local_objects(ctx, handle_map, n, dev_objects(ctx), &objs));
+        }
+        CK(launch_pair_sort(ctx, (uint32_t)cap_pairs, nullptr, local_ops ? ctx->local_of.p : nullptr, local_ops ? ctx->pairs_local.p : nullptr));
+        timer_mark(ctx, "pair_sort", local_ops ? 4 : 3);
         if (ctx->early.active) CK(cudaEventRecord(ctx->ev_pairs, ctx->stream));
-        CK(launch_narrow_phase(ctx, dev_objects(ctx), ctx->pairs.p, nullptr, (uint32_t)cap_pairs, (uint32_t)cap_contacts));
+        CK(launch_narrow_phase(ctx, objs, local_ops ? ctx->pairs_local.p : ctx->pairs.p, nullptr, (uint32_t)cap_pairs, (uint32_t)cap_contacts));
         if (ctx->early.active) {
             // Everything of this update is enqueued.  While the narrow phase runs, the copy stream ships what is already
             // final: the sorted pair list (+ algorithm per pair) once the pair sort is done, the contacts written by the

@@ -323,6 +323,12 @@ struct ncb_ctx {
     ncb::DevBuf<float4> shard_lo, shard_hi;
     uint32_t shard_m = 0, shard_owned = 0;
     ncb::RouteBufs route;
+    // sharded updates: compact copies of the attributes of the objects this rank holds, indexed by local id (broad.cu)
+    ncb::DevBuf<float> loc_pos, loc_qlimit, loc_cap;
+    ncb::DevBuf<float4> loc_rot, loc_param;
+    ncb::DevBuf<uint32_t> loc_type, local_of;
+    ncb::DevBuf<float2> loc_ang_cs;
+    ncb::DevBuf<uint2> pairs_local;
 };
 
 // api.cu helpers shared with sim.cu
@@ -363,7 +369,8 @@ cudaError_t launch_lbvh_build(ncb_ctx* c, uint32_t n, const uint32_t* handle_map
 cudaError_t launch_pair_search(ncb_ctx* c, uint32_t n, const uint32_t* groups, uint32_t q_begin, uint32_t q_end, uint32_t cap_pairs, int my_rank = -1);
 cudaError_t launch_shard_select(ncb_ctx* c, uint32_t n, int rank, int world, ShardScratch* sh, uint32_t* bins, uint32_t cap, uint32_t* sel,
                                 float4* loc_lo, float4* loc_hi);
-cudaError_t launch_pair_sort(ncb_ctx* c, uint32_t cap_pairs, uint32_t* index_out);
+cudaError_t launch_pair_sort(ncb_ctx* c, uint32_t cap_pairs, uint32_t* index_out, const uint32_t* local_of = nullptr, uint2* pairs_local = nullptr);
+cudaError_t launch_gather_local_objects(ncb_ctx* c, const uint32_t* sel, uint32_t m, const DevObjects& g, DevObjects* out);
 cudaError_t launch_route_stage(ncb_ctx* c, int stage, int rank, int world, uint32_t begin, uint32_t end, RouteBufs& R);
 cudaError_t launch_p2p_push(ncb_ctx* c, RouteBufs& R, const void* src, uint32_t words, int slot, int round);
 cudaError_t launch_p2p_wait_reduce(ncb_ctx* c, RouteBufs& R, int round, int slot, uint32_t words, int op, void* out);
