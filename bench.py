@@ -632,8 +632,8 @@ def run_native(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "call": "ncb_world_update_poses: pinned host poses in (set_position on every object), update, every pair / manifold / contact "
                             "out to pinned host buffers" if world == 1 else f"per rank: ncb_set_positions_range (own block) + {sharded.mode} sharded update "
-                            "(routed: poses travel with the NCCL all-to-all records; spatial / slices: NCCL pose all-gather) + ncb_world_fetch of the "
-                            "rank's own pairs and contacts"},
+                            "(p2p / routed: the poses travel inside the routed records, over NVLink peer memory / NCCL all-to-all; spatial / "
+                            "slices: NCCL pose all-gather) + ncb_world_fetch of the rank's own pairs and contacts"},
             "gpu_launches": int(launches_total * args.steps),
             "gpu_launches_per_step": int(launches_total),
             "clocks": clocks,
