@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libncb200.so")
-SOURCES = ["api.cu", "broad.cu", "narrow.cu", "ray.cu", "bp_persistent.cu", "sim.cu", "query.cu", "proximity.cu"]
+SOURCES = ["api.cu", "broad.cu", "narrow.cu", "ray.cu", "bp_persistent.cu", "sim.cu", "query.cu", "proximity.cu", "dim2.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "--fmad=false", "-std=c++17",

@@ -1,0 +1,665 @@
+// ncollide2d on the device, first slice (the 2-D build): batched `query::contact` between 2-D balls, cuboids and
+// convex polygons — one thread per pair, fixed capacities, no recursion, no heap allocation.
+//
+// Replaces (reference, file:line; the 2-D crate is the same tree built with feature "dim2"):
+//   query::contact dispatch               query/contact/contact_shape_shape.rs:15-60
+//   contact_ball_ball                     query/contact/contact_ball_ball.rs:8-38
+//   contact_ball_convex_polyhedron (+ flipped)  query/contact/contact_ball_convex_polyhedron.rs:12-92 with Cuboid::project_point_with_feature
+//                                         (query/point/point_cuboid.rs:17-26 -> point_aabb.rs:14-135) and the 2-D feature normals (shape/cuboid.rs:469-503)
+//   contact_support_map_support_map       query/contact/contact_support_map_support_map.rs:9-79
+//   gjk::closest_points (DIM = 2)         query/algorithms/gjk.rs:76-177,367-388
+//   VoronoiSimplex (2-D)                  query/algorithms/voronoi_simplex2.rs:20-168, query/point/point_segment.rs:52-91,
+//                                         query/point/point_triangle.rs:60-250 (dim2 branches)
+//   EPA (2-D)                             query/algorithms/epa2.rs:15-378 (Vec + std BinaryHeap -> fixed arrays, same sift order)
+//   support maps                          shape/ball.rs:29-48, shape/cuboid.rs:137-145, shape/convex_polygon.rs + utils/point_cloud_support_point.rs:6-24
+// Same arithmetic contract as the 3-D path: --fmad=false, IEEE division / sqrt, nalgebra's evaluation order
+// (UnitComplex * v = (re x - im y, im x + re y); Isometry2 * p = rotation * p + translation).
+// Not in this slice: ball x polygon (ConvexPolygon::project_point_with_feature), the manifold generators / ConvexPolygonalFeature2,
+// the 2-D broad phase and world.  ncb2d_contact answers NCB_ERR_UNSUPPORTED for a ball x polygon pair.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "ncb_internal.h"
+#include "vec.cuh"  // NCB_EPS / NCB_FMAX only: the 2-D types are this file's own
+
+namespace ncb {
+namespace d2 {
+
+struct W2 {
+    float x, y;
+};
+__device__ __forceinline__ W2 w2(float x, float y) { return W2{x, y}; }
+__device__ __forceinline__ W2 operator+(W2 a, W2 b) { return W2{a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ W2 operator-(W2 a, W2 b) { return W2{a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ W2 operator-(W2 a) { return W2{-a.x, -a.y}; }
+__device__ __forceinline__ W2 operator*(W2 a, float s) { return W2{a.x * s, a.y * s}; }
+__device__ __forceinline__ W2 operator/(W2 a, float s) { return W2{a.x / s, a.y / s}; }
+__device__ __forceinline__ float dot(W2 a, W2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ float perp(W2 a, W2 b) { return a.x * b.y - a.y * b.x; }
+__device__ __forceinline__ float nsq(W2 a) { return dot(a, a); }
+// Unit::try_new_and_get: succeeds iff norm_squared > min_norm^2
+__device__ __forceinline__ bool unit_get(W2 a, float min_norm, W2& u, float& n) {
+    float sq = nsq(a);
+    if (!(sq > min_norm * min_norm)) return false;
+    n = sqrtf(sq);
+    u = a / n;
+    return true;
+}
+__device__ __forceinline__ bool unit(W2 a, float min_norm, W2& u) {
+    float n;
+    return unit_get(a, min_norm, u, n);
+}
+__device__ __forceinline__ W2 normalized(W2 a) { return a / sqrtf(nsq(a)); }
+
+struct Pose2 {
+    W2 t;
+    float re, im;
+};
+__device__ __forceinline__ W2 rotate(const Pose2& m, W2 v) { return W2{m.re * v.x - m.im * v.y, m.im * v.x + m.re * v.y}; }
+__device__ __forceinline__ W2 unrotate(const Pose2& m, W2 v) { return W2{m.re * v.x + m.im * v.y, -m.im * v.x + m.re * v.y}; }
+__device__ __forceinline__ W2 to_world(const Pose2& m, W2 p) { return rotate(m, p) + m.t; }
+__device__ __forceinline__ W2 to_local(const Pose2& m, W2 p) { return unrotate(m, p - m.t); }
+
+#define D2_BALL 0u
+#define D2_CUBOID 1u
+#define D2_POLYGON 2u
+struct Operand2 {
+    uint32_t kind;
+    float a, b;          // radius | half extents
+    const float* pts;    // polygon vertices (x, y)
+    uint32_t npts;
+    Pose2 m;
+};
+
+__device__ W2 support(const Operand2& g, W2 dir) {
+    if (g.kind == D2_BALL) return g.m.t + normalized(dir) * g.a;  // support_point_toward(m, Unit::new_normalize(dir)): the rotation plays no part
+    W2 ld = unrotate(g.m, dir), lp;
+    if (g.kind == D2_CUBOID) {
+        lp = w2(copysignf(g.a, ld.x), copysignf(g.b, ld.y));
+    } else {
+        uint32_t arg = 0;
+        float best = __ldg(g.pts) * ld.x + __ldg(g.pts + 1) * ld.y;
+        for (uint32_t i = 1; i < g.npts; ++i) {
+            float d = __ldg(g.pts + 2 * i) * ld.x + __ldg(g.pts + 2 * i + 1) * ld.y;
+            if (d > best) best = d, arg = i;  // first maximum
+        }
+        lp = w2(__ldg(g.pts + 2 * arg), __ldg(g.pts + 2 * arg + 1));
+    }
+    return to_world(g.m, lp);
+}
+
+// CSOPoint::from_shapes as three parallel arrays (point = orig1 - orig2)
+struct MinkowskiPt {
+    W2 p, o1, o2;
+};
+__device__ __forceinline__ MinkowskiPt minkowski(const Operand2& g1, const Operand2& g2, W2 dir) {
+    MinkowskiPt c;
+    c.o1 = support(g1, dir);
+    c.o2 = support(g2, -dir);
+    c.p = c.o1 - c.o2;
+    return c;
+}
+
+#define TOL10 (NCB_EPS * 10.0f)    // gjk::eps_tol()
+#define TOL100 (NCB_EPS * 100.0f)  // epa2's _eps_tol
+
+// VoronoiSimplex of dimension <= 2
+struct Tri2 {
+    MinkowskiPt v[3];
+    float bary[2], old_bary[2];
+    int old_idx[3];
+    int dim, old_dim;
+};
+__device__ __forceinline__ void tri_swap(Tri2& s, int a, int b) {
+    MinkowskiPt t = s.v[a];
+    s.v[a] = s.v[b];
+    s.v[b] = t;
+    int u = s.old_idx[a];
+    s.old_idx[a] = s.old_idx[b];
+    s.old_idx[b] = u;
+}
+__device__ bool tri_add(Tri2& s, const MinkowskiPt& c) {
+    s.old_dim = s.dim;
+    s.old_bary[0] = s.bary[0], s.old_bary[1] = s.bary[1];
+    s.old_idx[0] = 0, s.old_idx[1] = 1, s.old_idx[2] = 2;
+    for (int i = 0; i <= s.dim; ++i)
+        if (nsq(s.v[i].p - c.p) < TOL10) return false;
+    s.dim += 1;
+    s.v[s.dim] = c;
+    return true;
+}
+// project_origin_and_reduce: projection of the origin on the simplex, which shrinks to the sub-simplex that carries it
+__device__ W2 tri_project(Tri2& s) {
+    const W2 O = w2(0.f, 0.f);
+    if (s.dim == 0) {
+        s.bary[0] = 1.f;
+        return s.v[0].p;
+    }
+    W2 a = s.v[0].p, b = s.v[1].p;
+    W2 ab = b - a, ap = O - a;
+    float ab_ap = dot(ab, ap);
+    if (s.dim == 1) {
+        float len2 = nsq(ab);
+        if (ab_ap <= 0.f) {
+            s.bary[0] = 1.f, s.dim = 0;
+            return a;
+        }
+        if (ab_ap >= len2) {
+            s.bary[0] = 1.f;
+            tri_swap(s, 0, 1);
+            s.dim = 0;
+            return b;
+        }
+        float u = ab_ap / len2;
+        s.bary[0] = 1.f - u, s.bary[1] = u;
+        return a + ab * u;
+    }
+    W2 c = s.v[2].p, ac = c - a;
+    float ac_ap = dot(ac, ap);
+    if (ab_ap <= 0.f && ac_ap <= 0.f) {
+        s.bary[0] = 1.f, s.dim = 0;
+        return a;
+    }
+    W2 bp = O - b;
+    float ab_bp = dot(ab, bp), ac_bp = dot(ac, bp);
+    if (ab_bp >= 0.f && ac_bp <= ab_bp) {
+        tri_swap(s, 0, 1);
+        s.bary[0] = 1.f, s.dim = 0;
+        return b;
+    }
+    W2 cp = O - c;
+    float ab_cp = dot(ab, cp), ac_cp = dot(ac, cp);
+    if (ac_cp >= 0.f && ab_cp <= ac_cp) {
+        tri_swap(s, 0, 2);
+        s.bary[0] = 1.f, s.dim = 0;
+        return c;
+    }
+    W2 bc = c - b;
+    float n = perp(ab, ac);
+    if (n * perp(ab, ap) < 0.f && ab_ap >= 0.f && ab_bp <= 0.f) {  // edge ab
+        float v = ab_ap / nsq(ab);
+        s.bary[0] = 1.f - v, s.bary[1] = v, s.dim = 1;
+        return a + ab * v;
+    }
+    if (-n * perp(ac, cp) < 0.f && ac_ap >= 0.f && ac_cp <= 0.f) {  // edge ac: vertices (a, c) stay, in that order
+        float w = ac_ap / nsq(ac);
+        tri_swap(s, 1, 2);
+        s.bary[0] = 1.f - w, s.bary[1] = w, s.dim = 1;
+        return a + ac * w;
+    }
+    if (n * perp(bc, bp) < 0.f && ac_bp - ab_bp >= 0.f && ab_cp - ac_cp >= 0.f) {  // edge bc: becomes (c, b)
+        float w = dot(bc, bp) / nsq(bc);
+        tri_swap(s, 0, 2);
+        s.bary[0] = w, s.bary[1] = 1.f - w, s.dim = 1;
+        return b + bc * w;
+    }
+    return O;  // inside the triangle (solid): dimension stays 2
+}
+__device__ void witness(const Tri2& s, bool old, W2& p1, W2& p2) {
+    W2 r1 = w2(0.f, 0.f), r2 = w2(0.f, 0.f);
+    int n = old ? s.old_dim : s.dim;
+    for (int i = 0; i <= n; ++i) {
+        float k = old ? s.old_bary[i] : s.bary[i];
+        const MinkowskiPt& q = s.v[old ? s.old_idx[i] : i];
+        r1 = r1 + q.o1 * k;
+        r2 = r2 + q.o2 * k;
+    }
+    p1 = r1, p2 = r2;
+}
+
+enum { G_INSIDE = 0, G_POINTS = 1, G_APART = 3 };
+__device__ int gjk2(const Operand2& g1, const Operand2& g2, float max_dist, Tri2& s, W2& p1, W2& p2, W2& axis) {
+    const float rel = sqrtf(TOL10);
+    W2 proj = tri_project(s), u;
+    if (!unit(proj, 0.f, u)) return G_INSIDE;
+    W2 prev_dir = -u, dir;
+    float upper = NCB_FMAX;
+    for (int it = 0;; ++it) {
+        float prev_upper = upper, len;
+        if (!unit_get(-proj, TOL10, dir, len)) return G_INSIDE;
+        upper = len;
+        if (upper >= prev_upper) {
+            witness(s, true, p1, p2);
+            axis = prev_dir;
+            return G_POINTS;
+        }
+        MinkowskiPt c = minkowski(g1, g2, dir);
+        float lower = -dot(dir, c.p);
+        if (lower > max_dist) {
+            axis = dir;
+            return G_APART;
+        }
+        if (upper - lower <= rel * upper || !tri_add(s, c)) {
+            witness(s, false, p1, p2);
+            axis = dir;
+            return G_POINTS;
+        }
+        prev_dir = dir;
+        proj = tri_project(s);
+        if (s.dim == 2) {
+            if (lower >= TOL10) {
+                witness(s, true, p1, p2);
+                axis = prev_dir;
+                return G_POINTS;
+            }
+            return G_INSIDE;
+        }
+        if (it + 1 == 10000) {
+            axis = w2(1.f, 0.f);
+            return G_APART;
+        }
+    }
+}
+
+// ---- EPA in the plane: the polytope is a polygon, its faces are edges ---------------------------------------------------------
+#define E2_VERTS 72
+#define E2_FACES 140
+#define E2_HEAP 140
+struct Poly2 {
+    MinkowskiPt v[E2_VERTS];
+    // face f: end points fa[f] -> fb[f], outward normal, projection of the origin, its barycentric coordinates, deleted flag
+    uint8_t fa[E2_FACES], fb[E2_FACES], dead[E2_FACES];
+    W2 fn[E2_FACES], fproj[E2_FACES];
+    float fbary[E2_FACES][2];
+    int nv, nf;
+    // Rust BinaryHeap<FaceId> (max-heap on neg_dist)
+    uint8_t hid[E2_HEAP];
+    float hkey[E2_HEAP];
+    int nh;
+    bool overflow;
+};
+__device__ void heap_up(Poly2& e, int start, int pos) {
+    uint8_t id = e.hid[pos];
+    float key = e.hkey[pos];
+    while (pos > start) {
+        int parent = (pos - 1) / 2;
+        if (key <= e.hkey[parent]) break;
+        e.hid[pos] = e.hid[parent], e.hkey[pos] = e.hkey[parent];
+        pos = parent;
+    }
+    e.hid[pos] = id, e.hkey[pos] = key;
+}
+__device__ void heap_push(Poly2& e, int id, float key) {
+    if (e.nh >= E2_HEAP) {
+        e.overflow = true;
+        return;
+    }
+    e.hid[e.nh] = (uint8_t)id, e.hkey[e.nh] = key;
+    e.nh++;
+    heap_up(e, 0, e.nh - 1);
+}
+__device__ bool heap_pop(Poly2& e, int& id, float& key) {
+    if (e.nh == 0) return false;
+    e.nh--;
+    uint8_t lid = e.hid[e.nh];
+    float lkey = e.hkey[e.nh];
+    if (e.nh > 0) {
+        id = e.hid[0], key = e.hkey[0];
+        e.hid[0] = lid, e.hkey[0] = lkey;
+        int end = e.nh, pos = 0, child = 1;  // sift_down_to_bottom(0), then sift_up
+        while (end >= 2 && child <= end - 2) {
+            if (e.hkey[child] <= e.hkey[child + 1]) child += 1;
+            e.hid[pos] = e.hid[child], e.hkey[pos] = e.hkey[child];
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        if (child == end - 1) {
+            e.hid[pos] = e.hid[child], e.hkey[pos] = e.hkey[child];
+            pos = child;
+        }
+        e.hid[pos] = lid, e.hkey[pos] = lkey;
+        heap_up(e, 0, pos);
+    } else {
+        id = lid, key = lkey;
+    }
+    return true;
+}
+// Face::new / new_with_proj: appends nothing, fills slot f; returns whether the origin projects inside the segment
+__device__ bool face_make(Poly2& e, int f, int a, int b, bool project) {
+    W2 pa = e.v[a].p, pb = e.v[b].p, ab = pb - pa;
+    bool inside = false;
+    W2 pr = w2(0.f, 0.f);
+    float c0 = 0.f, c1 = 0.f;
+    if (project) {
+        float t = dot(ab, -pa), len2 = nsq(ab);
+        if (len2 != 0.f && !(t < -TOL10 || t > len2 + TOL10)) {
+            float k = t / len2;
+            pr = pa + ab * k;
+            c0 = 1.f - k, c1 = k;
+            inside = true;
+        }
+    } else {
+        c0 = 1.f;  // the segment simplex case: proj = origin, bcoords = [1, 0]
+    }
+    e.fa[f] = (uint8_t)a, e.fb[f] = (uint8_t)b;
+    e.fproj[f] = pr;
+    e.fbary[f][0] = c0, e.fbary[f][1] = c1;
+    W2 nrm;
+    if (unit(w2(ab.y, -ab.x), NCB_EPS, nrm)) {
+        e.fn[f] = nrm, e.dead[f] = 0;
+    } else {
+        e.fn[f] = w2(0.f, 0.f), e.dead[f] = 1;
+    }
+    return inside;
+}
+__device__ void face_points(const Poly2& e, int f, W2& p1, W2& p2) {
+    const MinkowskiPt &a = e.v[e.fa[f]], &b = e.v[e.fb[f]];
+    p1 = a.o1 * e.fbary[f][0] + b.o1 * e.fbary[f][1];
+    p2 = a.o2 * e.fbary[f][0] + b.o2 * e.fbary[f][1];
+}
+// returns 1 found, 0 None, -1 the reference would panic (peek on an empty heap), -2 capacity exceeded
+__device__ int epa2(const Operand2& g1, const Operand2& g2, const Tri2& s, Poly2& e, W2& p1, W2& p2, W2& n_out) {
+    e.nv = e.nf = e.nh = 0;
+    e.overflow = false;
+    for (int i = 0; i <= s.dim; ++i) e.v[e.nv++] = s.v[i];
+    if (s.dim == 0) {
+        // vertex-vertex: a normal inside both vertices' normal cones, by rotating towards the tangents (at most 100 turns each)
+        W2 n = w2(0.f, 1.f), tg;
+        for (int it = 0; it < 100; ++it) {
+            if (!unit(support(g1, n) - e.v[0].o1, TOL100, tg) || dot(n, tg) < TOL100) break;
+            n = w2(-tg.y, tg.x);
+        }
+        for (int it = 0; it < 100; ++it) {
+            if (!unit(support(g2, -n) - e.v[0].o2, TOL100, tg) || dot(-n, tg) < TOL100) break;
+            n = w2(-tg.y, tg.x);
+        }
+        p1 = p2 = w2(0.f, 0.f), n_out = n;
+        return 1;
+    }
+    if (s.dim == 2) {
+        if (perp(e.v[1].p - e.v[0].p, e.v[2].p - e.v[0].p) < 0.f) {
+            MinkowskiPt t = e.v[1];
+            e.v[1] = e.v[2];
+            e.v[2] = t;
+        }
+        bool in0 = face_make(e, 0, 0, 1, true), in1 = face_make(e, 1, 1, 2, true), in2 = face_make(e, 2, 2, 0, true);
+        e.nf = 3;
+        const bool ins[3] = {in0, in1, in2};
+        for (int f = 0; f < 3; ++f)
+            if (ins[f]) {
+                float nd = -dot(e.fn[f], e.v[f].p);
+                if (nd > TOL10) return 0;  // FaceId::new -> None -> `?`
+                heap_push(e, f, nd);
+            }
+    } else {
+        face_make(e, 0, 0, 1, false);
+        face_make(e, 1, 1, 0, false);
+        e.nf = 2;
+        float d0 = dot(e.fn[0], e.v[0].p), d1 = dot(e.fn[1], e.v[1].p);
+        if (d0 > TOL10) return 0;
+        heap_push(e, 0, d0);
+        if (d1 > TOL10) return 0;
+        heap_push(e, 1, d1);
+    }
+    if (e.nh == 0) return -1;
+    int best = e.hid[0];
+    float upper = NCB_FMAX;
+    int fid;
+    float key;
+    for (int it = 0; heap_pop(e, fid, key);) {
+        if (e.dead[fid]) continue;
+        W2 fnorm = e.fn[fid];
+        int fa = e.fa[fid], fb = e.fb[fid];
+        if (e.nv >= E2_VERTS || e.nf + 2 > E2_FACES) return -2;
+        MinkowskiPt c = minkowski(g1, g2, fnorm);
+        int nid = e.nv;
+        e.v[e.nv++] = c;
+        float cand = dot(c.p, fnorm);
+        if (cand < upper) best = fid, upper = cand;
+        float cur = -key;
+        if (upper - cur < TOL100) {
+            face_points(e, best, p1, p2);
+            n_out = e.fn[best];
+            return 1;
+        }
+        const int ea[2] = {fa, nid}, eb[2] = {nid, fb};
+        // both new faces are built before either is examined (the reference fills `new_faces` first)
+        bool inside[2];
+        inside[0] = face_make(e, e.nf, ea[0], eb[0], true);
+        inside[1] = face_make(e, e.nf + 1, ea[1], eb[1], true);
+        for (int k = 0; k < 2; ++k) {
+            int f = e.nf;
+            if (inside[k]) {
+                float d = dot(e.fn[f], e.fproj[f]);
+                if (d < cur) {  // numerical trouble: take this face
+                    face_points(e, f, p1, p2);
+                    n_out = e.fn[f];
+                    return 1;
+                }
+                if (!e.dead[f]) {
+                    if (-d > TOL10) return 0;
+                    heap_push(e, f, -d);
+                    if (e.overflow) return -2;
+                }
+            }
+            e.nf++;
+        }
+        if (++it > 10000) return 0;
+    }
+    face_points(e, best, p1, p2);
+    n_out = e.fn[best];
+    return 1;
+}
+
+struct Hit2 {
+    W2 w1, w2, n;
+    float depth;
+};
+
+__device__ bool ball_ball(W2 c1, float r1, W2 c2, float r2, float prediction, Hit2& h) {
+    W2 d = c2 - c1;
+    float d2 = nsq(d), sum = r1 + r2, lim = sum + prediction;
+    if (!(d2 < lim * lim)) return false;
+    W2 n = d2 != 0.f ? normalized(d) : w2(1.f, 0.f);
+    h.w1 = c1 + n * r1, h.w2 = c2 + n * (-r2), h.n = n, h.depth = sum - sqrtf(d2);
+    return true;
+}
+
+// AABB::project_point_with_feature for the cuboid's box, then contact_ball_convex_polyhedron
+__device__ bool ball_cuboid(W2 center, float radius, const Operand2& box, float prediction, Hit2& h) {
+    float he[2] = {box.a, box.b};
+    W2 l = to_local(box.m, center);
+    float lp[2] = {l.x, l.y}, below[2], above[2], shift[2];
+    for (int i = 0; i < 2; ++i) {
+        below[i] = -he[i] - lp[i], above[i] = lp[i] - he[i];
+        shift[i] = fmaxf(below[i], 0.f) - fmaxf(above[i], 0.f);
+    }
+    bool inside = shift[0] == 0.f && shift[1] == 0.f;
+    if (inside) {  // solid = false: move to the nearest side
+        float best = -NCB_FMAX;
+        bool low = false;
+        int axis = 0;
+        for (int i = 0; i < 2; ++i) {
+            if (below[i] < above[i]) {
+                if (above[i] > best) axis = i, low = false, best = above[i];
+            } else if (below[i] > best) {
+                axis = i, low = true, best = below[i];
+            }
+        }
+        shift[0] = shift[1] = 0.f;
+        shift[axis] = low ? best : -best;
+    }
+    lp[0] += shift[0], lp[1] += shift[1];
+    W2 world2 = to_world(box.m, w2(lp[0], lp[1]));
+    W2 dpt = world2 - center, dir, normal;
+    float dist, depth;
+    if (unit_get(dpt, NCB_EPS, dir, dist)) {
+        depth = inside ? dist + radius : -dist + radius;
+        normal = inside ? -dir : dir;
+    } else {
+        // the centre lies on the boundary: the feature's own normal, in the cuboid's LOCAL frame like the reference (:50)
+        int zeros = (shift[0] == 0.f) + (shift[1] == 0.f);
+        int moved_axis = shift[0] != 0.f ? 0 : 1;
+        W2 fnrm;
+        if (zeros == 2) {
+            int face = -1;
+            for (int i = 0; i < 2 && face < 0; ++i) {
+                if (lp[i] > he[i] - NCB_EPS)
+                    face = i;
+                else if (lp[i] <= -he[i] + NCB_EPS)
+                    face = i + 2;
+            }
+            if (face < 0) return false;  // FeatureId::Unknown
+            fnrm = w2(face == 0 ? 1.f : face == 2 ? -1.f : 0.f, face == 1 ? 1.f : face == 3 ? -1.f : 0.f);
+        } else if (zeros == 1) {
+            bool neg = lp[moved_axis] < (-he[moved_axis] + he[moved_axis]) * 0.5f;
+            fnrm = moved_axis == 0 ? w2(neg ? -1.f : 1.f, 0.f) : w2(0.f, neg ? -1.f : 1.f);
+        } else {
+            fnrm = normalized(w2(lp[0] < 0.f ? -1.f : 1.f, lp[1] < 0.f ? -1.f : 1.f));
+        }
+        depth = radius;
+        normal = -fnrm;
+    }
+    if (!(depth >= -prediction)) return false;
+    h.w1 = center + normal * radius, h.w2 = world2, h.n = normal, h.depth = depth;
+    return true;
+}
+
+struct Args2 {
+    uint32_t n;
+    const uint32_t *type1, *type2;
+    const float4 *param1, *param2, *pose1, *pose2;
+    const float* poly;
+    float prediction;
+    uint8_t* found;
+    float* out;
+    uint32_t* counters;  // [0] reference panics, [1] EPA capacity overflows
+};
+__device__ __forceinline__ Operand2 load_operand(uint32_t t, float4 p, float4 m, const float* poly) {
+    Operand2 g;
+    g.kind = t, g.a = p.x, g.b = p.y, g.pts = nullptr, g.npts = 0;
+    if (t == D2_POLYGON) g.pts = poly + 2 * (size_t)p.x, g.npts = (uint32_t)p.y;
+    g.m.t = w2(m.x, m.y), g.m.re = m.z, g.m.im = m.w;
+    return g;
+}
+__global__ void __launch_bounds__(64) k_contact2d(Args2 A) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.n) return;
+    Operand2 g1 = load_operand(__ldg(&A.type1[k]), __ldg(&A.param1[k]), __ldg(&A.pose1[k]), A.poly);
+    Operand2 g2 = load_operand(__ldg(&A.type2[k]), __ldg(&A.param2[k]), __ldg(&A.pose2[k]), A.poly);
+    Hit2 h;
+    h.w1 = h.w2 = h.n = w2(0.f, 0.f), h.depth = 0.f;
+    bool ok = false;
+    if (g1.kind == D2_BALL && g2.kind == D2_BALL) {
+        ok = ball_ball(g1.m.t, g1.a, g2.m.t, g2.a, A.prediction, h);
+    } else if (g1.kind == D2_BALL) {
+        ok = ball_cuboid(g1.m.t, g1.a, g2, A.prediction, h);
+    } else if (g2.kind == D2_BALL) {  // contact_convex_polyhedron_ball: the ball query, flipped
+        ok = ball_cuboid(g2.m.t, g2.a, g1, A.prediction, h);
+        if (ok) {
+            W2 t = h.w1;
+            h.w1 = h.w2, h.w2 = t, h.n = -h.n;
+        }
+    } else {
+        W2 d0;
+        if (!unit(g2.m.t - g1.m.t, NCB_EPS, d0)) d0 = w2(1.f, 0.f);
+        Tri2 s;
+        for (int i = 0; i < 3; ++i) s.v[i].p = s.v[i].o1 = s.v[i].o2 = w2(0.f, 0.f), s.old_idx[i] = i;
+        s.bary[0] = s.bary[1] = s.old_bary[0] = s.old_bary[1] = 0.f;
+        s.dim = s.old_dim = 0;
+        s.v[0] = minkowski(g1, g2, d0);
+        W2 p1, p2, n;
+        int r = gjk2(g1, g2, A.prediction, s, p1, p2, n);
+        ok = r == G_POINTS;
+        if (r == G_INSIDE) {
+            Poly2 e;
+            int q = epa2(g1, g2, s, e, p1, p2, n);
+            ok = q == 1;
+            if (q == -1) atomicAdd(&A.counters[0], 1u);
+            if (q == -2) atomicAdd(&A.counters[1], 1u);
+        }
+        if (ok) h.w1 = p1, h.w2 = p2, h.n = n, h.depth = -dot(n, p2 - p1);
+    }
+    A.found[k] = ok ? 1 : 0;
+    float* o = A.out + 7 * (size_t)k;
+    o[0] = h.w1.x, o[1] = h.w1.y, o[2] = h.w2.x, o[3] = h.w2.y, o[4] = h.n.x, o[5] = h.n.y, o[6] = h.depth;
+}
+
+}  // namespace d2
+}  // namespace ncb
+
+using namespace ncb;
+
+#define CK2(call)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            char b__[512];                                                                                \
+            snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            ctx->err = b__;                                                                               \
+            return NCB_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+extern "C" {
+
+int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const float* param1, const float* pose1, const uint32_t* type2,
+                  const float* param2, const float* pose2, const float* poly_points, uint32_t n_poly_points, float prediction, uint8_t* found,
+                  float* out, uint32_t* ref_panics, uint32_t* epa_overflow) {
+    if (!ctx || (n_pairs && (!type1 || !param1 || !pose1 || !type2 || !param2 || !pose2 || !found || !out))) return NCB_ERR_ARG;
+    if (ref_panics) *ref_panics = 0;
+    if (epa_overflow) *epa_overflow = 0;
+    if (n_pairs == 0) return NCB_OK;
+    // input validation before device state is touched
+    for (uint32_t k = 0; k < n_pairs; ++k) {
+        for (int side = 0; side < 2; ++side) {
+            uint32_t t = side ? type2[k] : type1[k];
+            const float* p = (side ? param2 : param1) + 4 * (size_t)k;
+            if (t > 2) {
+                ctx->err = "ncb2d_contact: unknown 2-D shape type";
+                return NCB_ERR_UNSUPPORTED;
+            }
+            if (t == 2) {
+                if (!poly_points || p[1] < 1.f || p[0] < 0.f || (uint64_t)p[0] + (uint64_t)p[1] > n_poly_points) {
+                    ctx->err = "ncb2d_contact: polygon point range outside poly_points";
+                    return NCB_ERR_ARG;
+                }
+            }
+        }
+        bool b1 = type1[k] == 0, b2 = type2[k] == 0;
+        if ((b1 && type2[k] == 2) || (b2 && type1[k] == 2)) {
+            ctx->err = "ncb2d_contact: ball x convex polygon is not built (ConvexPolygon::project_point_with_feature)";
+            return NCB_ERR_UNSUPPORTED;
+        }
+    }
+    CK2(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    size_t n = n_pairs;
+    DevBuf<uint32_t> d_t;   // type1 | type2 | counters
+    DevBuf<float4> d_f4;    // param1 | param2 | pose1 | pose2
+    DevBuf<float> d_poly, d_out;
+    DevBuf<uint8_t> d_found;
+    CK2(d_t.reserve(2 * n + 2));
+    CK2(d_f4.reserve(4 * n));
+    CK2(d_poly.reserve(2 * (size_t)(n_poly_points ? n_poly_points : 1)));
+    CK2(d_out.reserve(7 * n));
+    CK2(d_found.reserve(n));
+    CK2(cudaMemcpyAsync(d_t.p, type1, 4 * n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_t.p + n, type2, 4 * n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemsetAsync(d_t.p + 2 * n, 0, 8, s));
+    CK2(cudaMemcpyAsync(d_f4.p, param1, 16 * n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_f4.p + n, param2, 16 * n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_f4.p + 2 * n, pose1, 16 * n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_f4.p + 3 * n, pose2, 16 * n, cudaMemcpyHostToDevice, s));
+    if (n_poly_points) CK2(cudaMemcpyAsync(d_poly.p, poly_points, 8 * (size_t)n_poly_points, cudaMemcpyHostToDevice, s));
+    d2::Args2 A;
+    A.n = n_pairs;
+    A.type1 = d_t.p, A.type2 = d_t.p + n;
+    A.param1 = d_f4.p, A.param2 = d_f4.p + n, A.pose1 = d_f4.p + 2 * n, A.pose2 = d_f4.p + 3 * n;
+    A.poly = d_poly.p;
+    A.prediction = prediction;
+    A.found = d_found.p, A.out = d_out.p;
+    A.counters = d_t.p + 2 * n;
+    d2::k_contact2d<<<(n_pairs + 63) / 64, 64, 0, s>>>(A);
+    CK2(cudaGetLastError());
+    uint32_t cnt[2] = {0, 0};
+    CK2(cudaMemcpyAsync(found, d_found.p, n, cudaMemcpyDeviceToHost, s));
+    CK2(cudaMemcpyAsync(out, d_out.p, 28 * n, cudaMemcpyDeviceToHost, s));
+    CK2(cudaMemcpyAsync(cnt, d_t.p + 2 * n, 8, cudaMemcpyDeviceToHost, s));
+    CK2(cudaStreamSynchronize(s));
+    if (ref_panics) *ref_panics = cnt[0];
+    if (epa_overflow) *epa_overflow = cnt[1];
+    return NCB_OK;
+}
+
+}  // extern "C"

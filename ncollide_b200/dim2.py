@@ -1,0 +1,64 @@
+"""Host mirror of the first ncollide2d slice on the device (``ncb2d_contact``, csrc/dim2.cu): ``ncollide2d::query::contact`` for
+batches of 2-D shape pairs.  Shapes mirror ``Ball::new(radius)``, ``Cuboid::new(half_extents)`` and ``ConvexPolygon::try_new(points)``
+of the 2-D crate; a pose is ``Isometry2::new(translation, angle)``: (x, y, cos(angle), sin(angle)) with cos / sin from the host libm,
+like the reference's ``UnitComplex::new``."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._ffi import as_f32, as_u32, ptr
+
+BALL, CUBOID, POLYGON = 0, 1, 2
+
+
+def isometry2(translation, angle):
+    """``Isometry2::new(translation, angle)`` rows (x, y, re, im); angle in radians (scalar or array)."""
+    t = as_f32(translation).reshape(-1, 2)
+    a = np.broadcast_to(np.asarray(angle, dtype=np.float32).reshape(-1), (len(t),))
+    return np.ascontiguousarray(np.stack([t[:, 0], t[:, 1], np.cos(a, dtype=np.float32), np.sin(a, dtype=np.float32)], axis=1), dtype=np.float32)
+
+
+class Shapes2D:
+    """A batch of 2-D shapes: ``type`` [n] and ``param`` [n, 4]; polygons index into a shared point array."""
+
+    def __init__(self):
+        self.type, self.param, self.points = [], [], []
+
+    def ball(self, radius):
+        self.type.append(BALL), self.param.append((radius, 0, 0, 0))
+        return self
+
+    def cuboid(self, hx, hy):
+        self.type.append(CUBOID), self.param.append((hx, hy, 0, 0))
+        return self
+
+    def polygon(self, points):
+        """Convex polygon given by its vertices in counter-clockwise order (``ConvexPolygon::try_new``)."""
+        pts = as_f32(points).reshape(-1, 2)
+        self.type.append(POLYGON), self.param.append((len(self.points), len(pts), 0, 0))
+        self.points.extend(pts.tolist())
+        return self
+
+    def arrays(self):
+        return as_u32(self.type), as_f32(self.param).reshape(-1, 4), as_f32(self.points if self.points else [[0, 0]]).reshape(-1, 2)
+
+
+def contact(ctx, type1, param1, pose1, type2, param2, pose2, poly_points=None, prediction=0.0):
+    """``query::contact`` for every pair k: (type1[k], param1[k]) at pose1[k] against (type2[k], param2[k]) at pose2[k].
+    Returns (found [n] bool, contacts [n, 7] = world1, world2, normal, depth, info dict)."""
+    t1, t2 = as_u32(type1).reshape(-1), as_u32(type2).reshape(-1)
+    p1, p2 = as_f32(param1).reshape(-1, 4), as_f32(param2).reshape(-1, 4)
+    m1, m2 = as_f32(pose1).reshape(-1, 4), as_f32(pose2).reshape(-1, 4)
+    n = len(t1)
+    if not (len(t2) == len(p1) == len(p2) == len(m1) == len(m2) == n):
+        raise ValueError("one type / param / pose row per pair and side")
+    pts = as_f32(poly_points).reshape(-1, 2) if poly_points is not None else None
+    found = np.zeros(n, dtype=np.uint8)
+    out = np.zeros((n, 7), dtype=np.float32)
+    panics, over = C.c_uint32(0), C.c_uint32(0)
+    ctx.check(ctx.lib.ncb2d_contact(ctx.h, C.c_uint32(n), ptr(t1), ptr(p1), ptr(m1), ptr(t2), ptr(p2), ptr(m2), ptr(pts),
+                                    C.c_uint32(0 if pts is None else len(pts)), C.c_float(prediction), ptr(found), ptr(out), C.byref(panics),
+                                    C.byref(over)), "ncb2d_contact")
+    return found.astype(bool), out, {"ref_panics": panics.value, "epa_overflow": over.value}

@@ -1,0 +1,657 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see na.hpp header).
+// ncollide2d: `query::contact` between 2-D balls, cuboids and convex polygons, restated from the reference
+// (the crate is the same source tree built with feature "dim2", build/ncollide2d/Cargo.toml):
+//   query/contact/contact_shape_shape.rs:15-60 (dispatch), contact_ball_ball.rs:8-38, contact_ball_convex_polyhedron.rs:12-75,
+//   contact_support_map_support_map.rs:9-79, query/algorithms/gjk.rs:76-177,367-388 (DIM = 2), voronoi_simplex2.rs:20-168,
+//   epa2.rs:15-378, cso_point.rs:70-85, query/point/point_segment.rs:52-91, point_triangle.rs:60-305 (dim2 branches),
+//   point_aabb.rs:14-135 + point_cuboid.rs:17-26, shape/cuboid.rs:137-145,469-503 (support point, 2-D feature normals),
+//   shape/ball.rs:29-48, shape/convex_polygon.rs (support point = utils/point_cloud_support_point.rs:6-24), utils/ccw_face_normal.rs:8-14.
+// nalgebra's Isometry2 = Translation2 * UnitComplex: rotation * v = (re x - im y, im x + re y) (unit_complex_ops.rs); not vendored, restated.
+// PINNED on the reference's own 2-D known-answer tests: build/ncollide2d/tests/geometry/epa2.rs (cuboid / cuboid: depth == 0.5 / 1.8 and
+// normal == -x / -y exactly; issue #181 does not panic) and ball_cuboid_contact.rs (f32 and f64) — tests/test_dim2.py.
+#include <algorithm>
+#include <vector>
+#include "na.hpp"
+#include "oracle.h"
+
+namespace orc {
+namespace d2 {
+
+struct P2 {
+    real x, y;
+};
+static inline P2 p2(real x, real y) { return P2{x, y}; }
+static inline P2 operator+(P2 a, P2 b) { return {a.x + b.x, a.y + b.y}; }
+static inline P2 operator-(P2 a, P2 b) { return {a.x - b.x, a.y - b.y}; }
+static inline P2 operator-(P2 a) { return {-a.x, -a.y}; }
+static inline P2 operator*(P2 a, real s) { return {a.x * s, a.y * s}; }
+static inline P2 operator/(P2 a, real s) { return {a.x / s, a.y / s}; }
+static inline real dot(P2 a, P2 b) { return a.x * b.x + a.y * b.y; }
+static inline real perp(P2 a, P2 b) { return a.x * b.y - a.y * b.x; }
+static inline real nsq(P2 a) { return dot(a, a); }
+static inline bool unit_try_new_and_get(P2 a, real min_norm, P2* out, real* n_out) {
+    real sq = nsq(a);
+    if (sq > min_norm * min_norm) {
+        real n = std::sqrt(sq);
+        *out = a / n;
+        *n_out = n;
+        return true;
+    }
+    return false;
+}
+static inline bool unit_try_new(P2 a, real min_norm, P2* out) {
+    real n;
+    return unit_try_new_and_get(a, min_norm, out, &n);
+}
+static inline P2 normalize(P2 a) { return a / std::sqrt(nsq(a)); }
+
+struct Iso2 {
+    P2 t;
+    real re, im;
+};
+static inline P2 rot(const Iso2& m, P2 v) { return {m.re * v.x - m.im * v.y, m.im * v.x + m.re * v.y}; }
+static inline P2 inv_rot(const Iso2& m, P2 v) { return {m.re * v.x + m.im * v.y, -m.im * v.x + m.re * v.y}; }  // conjugate: im -> -im
+static inline P2 mul_point(const Iso2& m, P2 p) { return rot(m, p) + m.t; }
+static inline P2 inv_point(const Iso2& m, P2 p) { return inv_rot(m, p - m.t); }
+
+enum { BALL2 = 0, CUBOID2 = 1, POLYGON2 = 2 };
+struct Shape2 {
+    uint32_t type;
+    real radius;
+    P2 he;
+    const real* pts;
+    uint32_t npts;
+};
+
+// SupportMap::support_point
+static P2 support_point(const Shape2& g, const Iso2& m, P2 dir) {
+    if (g.type == BALL2) {  // ball.rs:29-48: support_point_toward(m, Unit::new_normalize(dir)) = translation + dir * radius
+        P2 d = normalize(dir);
+        return m.t + d * g.radius;
+    }
+    P2 ld = inv_rot(m, dir);
+    P2 lp;
+    if (g.type == CUBOID2) {
+        lp = p2(std::copysign(g.he.x, ld.x), std::copysign(g.he.y, ld.y));
+    } else {  // point_cloud_support_point: first maximum
+        uint32_t best = 0;
+        real best_dot = g.pts[0] * ld.x + g.pts[1] * ld.y;
+        for (uint32_t i = 1; i < g.npts; ++i) {
+            real d = g.pts[2 * i] * ld.x + g.pts[2 * i + 1] * ld.y;
+            if (d > best_dot) best_dot = d, best = i;
+        }
+        lp = p2(g.pts[2 * best], g.pts[2 * best + 1]);
+    }
+    return mul_point(m, lp);
+}
+
+struct CSO {
+    P2 point, orig1, orig2;
+};
+static CSO cso_from_shapes(const Iso2& m1, const Shape2& g1, const Iso2& m2, const Shape2& g2, P2 dir) {
+    CSO c;
+    c.orig1 = support_point(g1, m1, dir);
+    c.orig2 = support_point(g2, m2, -dir);
+    c.point = c.orig1 - c.orig2;
+    return c;
+}
+
+static const real EPS_TOL = EPS * real(10);  // gjk::eps_tol()
+
+// ---- VoronoiSimplex (voronoi_simplex2.rs) -----------------------------------------------------------------------------------
+struct Simplex2 {
+    int prev_vertices[3] = {0, 1, 2};
+    int prev_dim = 0;
+    real prev_proj[2] = {0, 0};
+    CSO vertices[3];
+    real proj[2] = {0, 0};
+    int dim = 0;
+    Simplex2() {
+        for (auto& v : vertices) v.point = v.orig1 = v.orig2 = p2(0, 0);
+    }
+    void swap(int a, int b) {
+        std::swap(vertices[a], vertices[b]);
+        std::swap(prev_vertices[a], prev_vertices[b]);
+    }
+    void reset(const CSO& pt) {
+        prev_dim = 0, dim = 0;
+        vertices[0] = pt;
+    }
+    bool add_point(const CSO& pt) {
+        prev_dim = dim;
+        prev_proj[0] = proj[0], prev_proj[1] = proj[1];
+        prev_vertices[0] = 0, prev_vertices[1] = 1, prev_vertices[2] = 2;
+        for (int i = 0; i < dim + 1; ++i)
+            if (nsq(vertices[i].point - pt.point) < EPS_TOL) return false;
+        dim += 1;
+        vertices[dim] = pt;
+        return true;
+    }
+    P2 project_origin_and_reduce() {
+        const P2 O = p2(0, 0);
+        if (dim == 0) {
+            proj[0] = 1;
+            return vertices[0].point;
+        }
+        if (dim == 1) {  // Segment::project_point_with_location (point_segment.rs:52-91), identity isometry
+            P2 a = vertices[0].point, b = vertices[1].point;
+            P2 ab = b - a, ap = O - a;
+            real ab_ap = dot(ab, ap), sqnab = nsq(ab);
+            if (ab_ap <= 0) {
+                proj[0] = 1, dim = 0;
+                return a;
+            }
+            if (ab_ap >= sqnab) {
+                proj[0] = 1;
+                swap(0, 1);
+                dim = 0;
+                return b;
+            }
+            real u = ab_ap / sqnab;
+            proj[0] = real(1) - u, proj[1] = u;
+            return a + ab * u;
+        }
+        // Triangle::project_point_with_location, dim2 (point_triangle.rs:60-250), solid = true
+        P2 a = vertices[0].point, b = vertices[1].point, c = vertices[2].point;
+        P2 ab = b - a, ac = c - a, ap = O - a;
+        real ab_ap = dot(ab, ap), ac_ap = dot(ac, ap);
+        if (ab_ap <= 0 && ac_ap <= 0) {
+            swap(0, 0), proj[0] = 1, dim = 0;
+            return a;
+        }
+        P2 bp = O - b;
+        real ab_bp = dot(ab, bp), ac_bp = dot(ac, bp);
+        if (ab_bp >= 0 && ac_bp <= ab_bp) {
+            swap(0, 1), proj[0] = 1, dim = 0;
+            return b;
+        }
+        P2 cp = O - c;
+        real ab_cp = dot(ab, cp), ac_cp = dot(ac, cp);
+        if (ac_cp >= 0 && ab_cp <= ac_cp) {
+            swap(0, 2), proj[0] = 1, dim = 0;
+            return c;
+        }
+        P2 bc = c - b;
+        real n = perp(ab, ac);
+        real vc = n * perp(ab, ap);
+        if (vc < 0 && ab_ap >= 0 && ab_bp <= 0) {  // OnEdge(0)
+            real v = ab_ap / nsq(ab);
+            proj[0] = real(1) - v, proj[1] = v;
+            dim = 1;
+            return a + ab * v;
+        }
+        real vb = -n * perp(ac, cp);
+        if (vb < 0 && ac_ap >= 0 && ac_cp <= 0) {  // OnEdge(2): swap(1, 2), proj = coords
+            real w = ac_ap / nsq(ac);
+            swap(1, 2);
+            proj[0] = real(1) - w, proj[1] = w;
+            dim = 1;
+            return a + ac * w;
+        }
+        real va = n * perp(bc, bp);
+        if (va < 0 && ac_bp - ab_bp >= 0 && ab_cp - ac_cp >= 0) {  // OnEdge(1): swap(0, 2), proj = [coords[1], coords[0]]
+            real w = dot(bc, bp) / nsq(bc);
+            swap(0, 2);
+            proj[0] = w, proj[1] = real(1) - w;
+            dim = 1;
+            return b + bc * w;
+        }
+        return O;  // OnFace in 2-D + solid: the point itself (OnSolid); the simplex keeps dimension 2
+    }
+};
+
+// gjk.rs:367-388
+static void gjk_result(const Simplex2& s, bool prev, P2* p1, P2* p2_) {
+    P2 r0 = p2(0, 0), r1 = p2(0, 0);
+    if (prev) {
+        for (int i = 0; i < s.prev_dim + 1; ++i) {
+            real coord = s.prev_proj[i];
+            const CSO& pt = s.vertices[s.prev_vertices[i]];
+            r0 = r0 + pt.orig1 * coord;
+            r1 = r1 + pt.orig2 * coord;
+        }
+    } else {
+        for (int i = 0; i < s.dim + 1; ++i) {
+            real coord = s.proj[i];
+            r0 = r0 + s.vertices[i].orig1 * coord;
+            r1 = r1 + s.vertices[i].orig2 * coord;
+        }
+    }
+    *p1 = r0, *p2_ = r1;
+}
+
+enum { R_INTERSECTION = 0, R_CLOSEST = 1, R_NONE = 3 };
+// gjk::closest_points, exact_dist = true (gjk.rs:76-177), DIM = 2
+static int gjk_closest_points(const Iso2& m1, const Shape2& g1, const Iso2& m2, const Shape2& g2, real max_dist, Simplex2& s, P2* p1, P2* p2_,
+                              P2* out_dir) {
+    const real eps_rel = std::sqrt(EPS_TOL);
+    P2 proj = s.project_origin_and_reduce();
+    P2 old_dir, pd;
+    if (!unit_try_new(proj, 0, &pd)) return R_INTERSECTION;
+    old_dir = -pd;
+    real max_bound = FMAX;
+    P2 dir;
+    int niter = 0;
+    for (;;) {
+        real old_max_bound = max_bound, dist;
+        if (!unit_try_new_and_get(-proj, EPS_TOL, &dir, &dist)) return R_INTERSECTION;
+        max_bound = dist;
+        if (max_bound >= old_max_bound) {
+            gjk_result(s, true, p1, p2_);
+            *out_dir = old_dir;
+            return R_CLOSEST;
+        }
+        CSO cso = cso_from_shapes(m1, g1, m2, g2, dir);
+        real min_bound = -dot(dir, cso.point);
+        if (min_bound > max_dist) {
+            *out_dir = dir;
+            return R_NONE;
+        } else if (max_bound - min_bound <= eps_rel * max_bound) {
+            gjk_result(s, false, p1, p2_);
+            *out_dir = dir;
+            return R_CLOSEST;
+        }
+        if (!s.add_point(cso)) {
+            gjk_result(s, false, p1, p2_);
+            *out_dir = dir;
+            return R_CLOSEST;
+        }
+        old_dir = dir;
+        proj = s.project_origin_and_reduce();
+        if (s.dim == 2) {
+            if (min_bound >= EPS_TOL) {
+                gjk_result(s, true, p1, p2_);
+                *out_dir = old_dir;
+                return R_CLOSEST;
+            }
+            return R_INTERSECTION;
+        }
+        if (++niter == 10000) {
+            *out_dir = p2(1, 0);
+            return R_NONE;
+        }
+    }
+}
+
+// ---- EPA (epa2.rs) ----------------------------------------------------------------------------------------------------------
+struct FaceId2 {
+    size_t id;
+    real neg_dist;
+};
+struct Heap2 {  // Rust std BinaryHeap<FaceId> (max-heap on neg_dist; Ord::cmp via <, >)
+    std::vector<FaceId2> data;
+    static bool le(const FaceId2& a, const FaceId2& b) { return a.neg_dist <= b.neg_dist; }  // PartialOrd `<=` (sift_up / sift_down_to_bottom)
+    void sift_up(size_t start, size_t pos) {
+        FaceId2 elt = data[pos];
+        while (pos > start) {
+            size_t parent = (pos - 1) / 2;
+            if (le(elt, data[parent])) break;
+            data[pos] = data[parent];
+            pos = parent;
+        }
+        data[pos] = elt;
+    }
+    void push(FaceId2 f) {
+        data.push_back(f);
+        sift_up(0, data.size() - 1);
+    }
+    bool pop(FaceId2* out) {
+        if (data.empty()) return false;
+        FaceId2 item = data.back();
+        data.pop_back();
+        if (!data.empty()) {
+            std::swap(item, data[0]);
+            size_t end = data.size(), pos = 0, child = 1;
+            FaceId2 elt = data[0];
+            while (end >= 2 && child <= end - 2) {
+                if (le(data[child], data[child + 1])) child += 1;
+                data[pos] = data[child];
+                pos = child;
+                child = 2 * pos + 1;
+            }
+            if (child == end - 1) {
+                data[pos] = data[child];
+                pos = child;
+            }
+            data[pos] = elt;
+            sift_up(0, pos);
+        }
+        *out = item;
+        return true;
+    }
+};
+struct Face2 {
+    size_t pts[2];
+    P2 normal, proj;
+    real bcoords[2];
+    bool deleted;
+};
+// epa2.rs:352-378
+static bool project_origin_seg(P2 a, P2 b, P2* res, real bc[2]) {
+    P2 ab = b - a, ap = -a;
+    real ab_ap = dot(ab, ap), sqnab = nsq(ab);
+    if (sqnab == 0) return false;
+    if (ab_ap < -EPS_TOL || ab_ap > sqnab + EPS_TOL) return false;
+    real pos = ab_ap / sqnab;
+    *res = a + ab * pos;
+    bc[0] = real(1) - pos, bc[1] = pos;
+    return true;
+}
+static Face2 face_new_with_proj(const std::vector<CSO>& v, P2 proj, const real bc[2], size_t p0, size_t p1) {
+    Face2 f;
+    f.pts[0] = p0, f.pts[1] = p1, f.proj = proj, f.bcoords[0] = bc[0], f.bcoords[1] = bc[1];
+    P2 ab = v[p1].point - v[p0].point;  // ccw_face_normal (dim2): (ab.y, -ab.x) normalised
+    if (unit_try_new(p2(ab.y, -ab.x), EPS, &f.normal)) {
+        f.deleted = false;
+    } else {
+        f.normal = p2(0, 0);
+        f.deleted = true;
+    }
+    return f;
+}
+static Face2 face_new(const std::vector<CSO>& v, size_t p0, size_t p1, bool* inside) {
+    P2 proj;
+    real bc[2];
+    if (project_origin_seg(v[p0].point, v[p1].point, &proj, bc)) {
+        *inside = true;
+        return face_new_with_proj(v, proj, bc, p0, p1);
+    }
+    real z[2] = {0, 0};
+    *inside = false;
+    return face_new_with_proj(v, p2(0, 0), z, p0, p1);
+}
+static void face_closest_points(const Face2& f, const std::vector<CSO>& v, P2* a, P2* b) {
+    *a = v[f.pts[0]].orig1 * f.bcoords[0] + v[f.pts[1]].orig1 * f.bcoords[1];
+    *b = v[f.pts[0]].orig2 * f.bcoords[0] + v[f.pts[1]].orig2 * f.bcoords[1];
+}
+// FaceId::new: None when neg_dist > eps_tol (the `?` in the callers returns None from closest_points)
+#define PUSH_OR_FAIL(ID, ND)              \
+    do {                                  \
+        if ((ND) > EPS_TOL) return false; \
+        heap.push(FaceId2{(ID), (ND)});   \
+    } while (0)
+
+static bool epa_closest_points(const Iso2& m1, const Shape2& g1, const Iso2& m2, const Shape2& g2, const Simplex2& simplex, P2* o1, P2* o2,
+                               P2* on, int* panicked) {
+    const real eps_tol = EPS * real(100);
+    std::vector<CSO> vertices;
+    std::vector<Face2> faces;
+    Heap2 heap;
+    for (int i = 0; i < simplex.dim + 1; ++i) vertices.push_back(simplex.vertices[i]);
+    if (simplex.dim == 0) {
+        P2 n = p2(0, 1);
+        P2 orig1 = vertices[0].orig1;
+        for (int it = 0; it < 100; ++it) {
+            P2 supp1 = support_point(g1, m1, n), tangent;
+            if (unit_try_new(supp1 - orig1, eps_tol, &tangent)) {
+                if (dot(n, tangent) < eps_tol) break;
+                n = p2(-tangent.y, tangent.x);
+            } else
+                break;
+        }
+        P2 orig2 = vertices[0].orig2;
+        for (int it = 0; it < 100; ++it) {
+            P2 supp2 = support_point(g2, m2, -n), tangent;
+            if (unit_try_new(supp2 - orig2, eps_tol, &tangent)) {
+                if (dot(-n, tangent) < eps_tol) break;
+                n = p2(-tangent.y, tangent.x);
+            } else
+                break;
+        }
+        *o1 = p2(0, 0), *o2 = p2(0, 0), *on = n;
+        return true;
+    } else if (simplex.dim == 2) {
+        P2 dp1 = vertices[1].point - vertices[0].point, dp2 = vertices[2].point - vertices[0].point;
+        if (perp(dp1, dp2) < 0) std::swap(vertices[1], vertices[2]);
+        bool in1, in2, in3;
+        Face2 f1 = face_new(vertices, 0, 1, &in1), f2 = face_new(vertices, 1, 2, &in2), f3 = face_new(vertices, 2, 0, &in3);
+        faces.push_back(f1), faces.push_back(f2), faces.push_back(f3);
+        if (in1) PUSH_OR_FAIL(0, -dot(faces[0].normal, vertices[0].point));
+        if (in2) PUSH_OR_FAIL(1, -dot(faces[1].normal, vertices[1].point));
+        if (in3) PUSH_OR_FAIL(2, -dot(faces[2].normal, vertices[2].point));
+    } else {
+        real one_zero[2] = {1, 0};
+        faces.push_back(face_new_with_proj(vertices, p2(0, 0), one_zero, 0, 1));
+        faces.push_back(face_new_with_proj(vertices, p2(0, 0), one_zero, 1, 0));
+        real dist1 = dot(faces[0].normal, vertices[0].point), dist2 = dot(faces[1].normal, vertices[1].point);
+        PUSH_OR_FAIL(0, dist1);
+        PUSH_OR_FAIL(1, dist2);
+    }
+    int niter = 0;
+    real max_dist = FMAX;
+    if (heap.data.empty()) {  // heap.peek().unwrap() on an empty heap: the reference panics here
+        *panicked = 1;
+        return false;
+    }
+    FaceId2 best_face_id = heap.data[0];
+    FaceId2 face_id;
+    while (heap.pop(&face_id)) {
+        Face2 face = faces[face_id.id];
+        if (face.deleted) continue;
+        CSO cso = cso_from_shapes(m1, g1, m2, g2, face.normal);
+        size_t support_point_id = vertices.size();
+        vertices.push_back(cso);
+        real candidate_max_dist = dot(cso.point, face.normal);
+        if (candidate_max_dist < max_dist) best_face_id = face_id, max_dist = candidate_max_dist;
+        real curr_dist = -face_id.neg_dist;
+        if (max_dist - curr_dist < eps_tol) {
+            const Face2& bf = faces[best_face_id.id];
+            face_closest_points(bf, vertices, o1, o2);
+            *on = bf.normal;
+            return true;
+        }
+        bool in[2];
+        Face2 nf[2] = {face_new(vertices, face.pts[0], support_point_id, &in[0]), face_new(vertices, support_point_id, face.pts[1], &in[1])};
+        for (int k = 0; k < 2; ++k) {
+            if (in[k]) {
+                real dist = dot(nf[k].normal, nf[k].proj);
+                if (dist < curr_dist) {
+                    face_closest_points(nf[k], vertices, o1, o2);
+                    *on = nf[k].normal;
+                    return true;
+                }
+                if (!nf[k].deleted) PUSH_OR_FAIL(faces.size(), -dist);
+            }
+            faces.push_back(nf[k]);
+        }
+        if (++niter > 10000) return false;
+    }
+    const Face2& bf = faces[best_face_id.id];
+    face_closest_points(bf, vertices, o1, o2);
+    *on = bf.normal;
+    return true;
+}
+
+struct Contact2 {
+    P2 w1, w2, n;
+    real depth;
+};
+
+// contact_support_map_support_map (contact_support_map_support_map.rs:9-79)
+static bool contact_sm_sm(const Iso2& m1, const Shape2& g1, const Iso2& m2, const Shape2& g2, real prediction, Contact2* c, int* panicked) {
+    P2 dir;
+    if (!unit_try_new(m2.t - m1.t, EPS, &dir)) dir = p2(1, 0);
+    Simplex2 s;
+    s.reset(cso_from_shapes(m1, g1, m2, g2, dir));
+    P2 p1, p2_, n;
+    int r = gjk_closest_points(m1, g1, m2, g2, prediction, s, &p1, &p2_, &n);
+    if (r == R_NONE) return false;
+    if (r == R_INTERSECTION) {
+        if (!epa_closest_points(m1, g1, m2, g2, s, &p1, &p2_, &n, panicked)) return false;  // NoIntersection(x axis)
+    }
+    c->w1 = p1, c->w2 = p2_, c->n = n;
+    c->depth = -dot(n, p2_ - p1);  // Contact::new_wo_depth
+    return true;
+}
+
+// contact_ball_ball.rs:8-38
+static bool contact_ball_ball(P2 c1, real r1, P2 c2, real r2, real prediction, Contact2* c) {
+    P2 delta = c2 - c1;
+    real dsq = nsq(delta), sum = r1 + r2, sum_err = sum + prediction;
+    if (dsq < sum_err * sum_err) {
+        P2 n = dsq != 0 ? normalize(delta) : p2(1, 0);
+        c->w1 = c1 + n * r1, c->w2 = c2 + n * (-r2), c->n = n, c->depth = sum - std::sqrt(dsq);
+        return true;
+    }
+    return false;
+}
+
+enum { F_UNKNOWN = 0xffffffffu, F_FACE = 0x40000000u, F_VERTEX = 0x80000000u };
+// Cuboid::project_point_with_feature -> AABB (point_aabb.rs:14-135), dim2
+static P2 cuboid_project(const Shape2& g, const Iso2& m, P2 pt, bool* inside_out, uint32_t* feature) {
+    P2 mins = -g.he, maxs = g.he;
+    P2 ls = inv_point(m, pt);
+    real mp[2] = {mins.x - ls.x, mins.y - ls.y}, pm[2] = {ls.x - maxs.x, ls.y - maxs.y};
+    real shift[2];
+    for (int i = 0; i < 2; ++i) shift[i] = std::fmax(mp[i], real(0)) - std::fmax(pm[i], real(0));
+    bool inside = shift[0] == 0 && shift[1] == 0;
+    real lp[2] = {ls.x, ls.y};
+    if (!inside) {
+        lp[0] += shift[0], lp[1] += shift[1];
+    } else {  // solid = false
+        real best = -FMAX;
+        bool is_mins = false;
+        int best_id = 0;
+        for (int i = 0; i < 2; ++i) {
+            if (mp[i] < pm[i]) {
+                if (pm[i] > best) best_id = i, is_mins = false, best = pm[i];
+            } else if (mp[i] > best) {
+                best_id = i, is_mins = true, best = mp[i];
+            }
+        }
+        shift[0] = shift[1] = 0;
+        shift[best_id] = is_mins ? best : -best;
+        lp[0] += shift[0], lp[1] += shift[1];
+    }
+    *inside_out = inside;
+    P2 proj = mul_point(m, p2(lp[0], lp[1]));
+    int nzero = 0, last_not_zero = 0;
+    for (int i = 0; i < 2; ++i) {
+        if (shift[i] == 0)
+            nzero++;
+        else
+            last_not_zero = i;
+    }
+    real mn[2] = {mins.x, mins.y}, mx[2] = {maxs.x, maxs.y};
+    if (nzero == 2) {
+        *feature = F_UNKNOWN;
+        for (int i = 0; i < 2; ++i) {
+            if (lp[i] > mx[i] - EPS) {
+                *feature = F_FACE | (uint32_t)i;
+                break;
+            }
+            if (lp[i] <= mn[i] + EPS) {
+                *feature = F_FACE | (uint32_t)(i + 2);
+                break;
+            }
+        }
+    } else if (nzero == 1) {
+        real center = (mn[last_not_zero] + mx[last_not_zero]) * real(0.5);  // na::center(mins, maxs)
+        *feature = F_FACE | (uint32_t)(lp[last_not_zero] < center ? last_not_zero + 2 : last_not_zero);
+    } else {
+        uint32_t id = 0;
+        for (int i = 0; i < 2; ++i) {
+            real center = (mn[i] + mx[i]) * real(0.5);
+            if (lp[i] < center) id |= 1u << i;
+        }
+        *feature = F_VERTEX | id;
+    }
+    return proj;
+}
+// cuboid.rs:469-503 (dim2)
+static P2 cuboid_feature_normal(uint32_t f) {
+    uint32_t id = f & 0xffffu;
+    if (f & F_FACE) {
+        real d[2] = {0, 0};
+        if (id < 2)
+            d[id] = 1;
+        else
+            d[id - 2] = -1;
+        return p2(d[0], d[1]);
+    }
+    P2 d = p2(0, 0);
+    switch (id) {
+        case 0: d = p2(1, 1); break;
+        case 1: d = p2(-1, 1); break;
+        case 3: d = p2(-1, -1); break;
+        default: d = p2(1, -1); break;
+    }
+    return normalize(d);
+}
+// contact_ball_convex_polyhedron.rs:12-62 with a cuboid
+static bool contact_ball_cuboid(P2 center, real radius, const Iso2& m2, const Shape2& g2, real prediction, Contact2* c) {
+    bool inside;
+    uint32_t f2;
+    P2 world2 = cuboid_project(g2, m2, center, &inside, &f2);
+    P2 dpt = world2 - center, dir, normal;
+    real dist, depth;
+    if (unit_try_new_and_get(dpt, EPS, &dir, &dist)) {
+        if (inside)
+            depth = dist + radius, normal = -dir;
+        else
+            depth = -dist + radius, normal = dir;
+    } else {
+        if (f2 == F_UNKNOWN) return false;
+        depth = radius;
+        normal = -cuboid_feature_normal(f2);  // as in the reference: the LOCAL feature normal is used as is (:50), not rotated by m2
+    }
+    if (depth >= -prediction) {
+        c->w1 = center + normal * radius, c->w2 = world2, c->n = normal, c->depth = depth;
+        return true;
+    }
+    return false;
+}
+
+}  // namespace d2
+}  // namespace orc
+
+using namespace orc;
+using namespace orc::d2;
+
+extern "C" {
+
+// query::contact for n pairs.  type: 0 ball, 1 cuboid, 2 convex polygon; param (4 reals per shape): ball (radius), cuboid (hx, hy),
+// polygon (first point, point count) into poly_points (x, y); pose (4 reals): translation x, y, rotation re, im (UnitComplex).
+// found[p]: 1 Some, 0 None, 2 = pair kind not restated (ball x polygon).  out (7 reals): world1, world2, normal, depth.
+// panics (optional): number of pairs on which the reference would panic (heap.peek().unwrap() on an empty heap, epa2.rs:279).
+void orc2_contact(uint64_t n, const uint32_t* type1, const real* param1, const real* pose1, const uint32_t* type2, const real* param2,
+                  const real* pose2, const real* poly_points, real prediction, uint8_t* found, real* out, uint32_t* panics) {
+    auto shape = [&](uint32_t t, const real* p) {
+        Shape2 g;
+        g.type = t, g.radius = p[0], g.he = p2(p[0], p[1]), g.pts = nullptr, g.npts = 0;
+        if (t == POLYGON2) g.pts = poly_points + 2 * (size_t)p[0], g.npts = (uint32_t)p[1];
+        return g;
+    };
+    uint32_t np = 0;
+    for (uint64_t k = 0; k < n; ++k) {
+        Shape2 g1 = shape(type1[k], param1 + 4 * k), g2 = shape(type2[k], param2 + 4 * k);
+        Iso2 m1 = {p2(pose1[4 * k], pose1[4 * k + 1]), pose1[4 * k + 2], pose1[4 * k + 3]};
+        Iso2 m2 = {p2(pose2[4 * k], pose2[4 * k + 1]), pose2[4 * k + 2], pose2[4 * k + 3]};
+        Contact2 c = {p2(0, 0), p2(0, 0), p2(0, 0), 0};
+        bool ok = false;
+        int panicked = 0;
+        uint8_t code = 0;
+        if (g1.type == BALL2 && g2.type == BALL2) {
+            ok = contact_ball_ball(m1.t, g1.radius, m2.t, g2.radius, prediction, &c);
+        } else if (g1.type == BALL2 && g2.type == CUBOID2) {
+            ok = contact_ball_cuboid(m1.t, g1.radius, m2, g2, prediction, &c);
+        } else if (g1.type == CUBOID2 && g2.type == BALL2) {  // contact_convex_polyhedron_ball: flip
+            ok = contact_ball_cuboid(m2.t, g2.radius, m1, g1, prediction, &c);
+            if (ok) {
+                std::swap(c.w1, c.w2);
+                c.n = -c.n;
+            }
+        } else if (g1.type == BALL2 || g2.type == BALL2) {
+            code = 2;  // ball x polygon: ConvexPolygon::project_point_with_feature is not restated
+        } else {
+            ok = contact_sm_sm(m1, g1, m2, g2, prediction, &c, &panicked);
+        }
+        np += panicked;
+        found[k] = code ? code : (ok ? 1 : 0);
+        real* o = out + 7 * k;
+        o[0] = c.w1.x, o[1] = c.w1.y, o[2] = c.w2.x, o[3] = c.w2.y, o[4] = c.n.x, o[5] = c.n.y, o[6] = c.depth;
+    }
+    if (panics) *panics = np;
+}
+
+}  // extern "C"

@@ -168,6 +168,12 @@ void orc_trimesh_ray_cast(const orc_trimesh*, const real* pose, uint64_t n_rays,
                           real max_toi, int mode, real* toi, uint32_t* face, real* normal);
 void orc_aabb_toi_with_ray(const real* minmax, const real* origin, const real* dir, real max_toi, int solid, real* toi);
 
+/* ncollide2d query::contact for n pairs of 2-D shapes (oracle/dim2.cpp).  type: 0 ball, 1 cuboid, 2 convex polygon; param: 4 reals per
+ * shape (radius | hx, hy | first point, count); pose: 4 reals (translation x y, UnitComplex re im); found: 1 Some, 0 None, 2 not restated;
+ * out: 7 reals per pair (world1, world2, normal, depth). */
+void orc2_contact(uint64_t n, const uint32_t* type1, const real* param1, const real* pose1, const uint32_t* type2, const real* param2,
+                  const real* pose2, const real* poly_points, real prediction, uint8_t* found, real* out, uint32_t* panics);
+
 #ifdef __cplusplus
 }
 #endif

@@ -252,6 +252,23 @@ class Oracle:
     def trimesh(self, verts, tris):
         return OracleTriMesh(self, verts, tris)
 
+    def contact2d(self, type1, param1, pose1, type2, param2, pose2, poly_points=None, prediction=0.0):
+        """ncollide2d ``query::contact`` for n pairs (oracle/dim2.cpp).  Returns (found u8 [1 Some, 0 None, 2 not restated],
+        out[n,7] = world1, world2, normal, depth, panics)."""
+        dt = self.dtype
+        t1, t2 = np.ascontiguousarray(type1, dtype=np.uint32), np.ascontiguousarray(type2, dtype=np.uint32)
+        p1, p2 = np.ascontiguousarray(param1, dtype=dt).reshape(-1, 4), np.ascontiguousarray(param2, dtype=dt).reshape(-1, 4)
+        m1, m2 = np.ascontiguousarray(pose1, dtype=dt).reshape(-1, 4), np.ascontiguousarray(pose2, dtype=dt).reshape(-1, 4)
+        pts = np.ascontiguousarray(poly_points if poly_points is not None else np.zeros((1, 2)), dtype=dt).reshape(-1, 2)
+        n = len(t1)
+        found = np.zeros(n, dtype=np.uint8)
+        out = np.zeros((n, 7), dtype=dt)
+        panics = C.c_uint32(0)
+        vp = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+        self.lib.orc2_contact(C.c_uint64(n), vp(t1), vp(p1), vp(m1), vp(t2), vp(p2), vp(m2), vp(pts), self.creal(prediction), vp(found), vp(out),
+                              C.byref(panics))
+        return found, out, panics.value
+
     def broad_phase_persistent(self, margin):
         return OracleBroadPhase(self, margin)
 

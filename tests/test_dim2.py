@@ -1,0 +1,183 @@
+"""ncollide2d, first slice: batched ``query::contact`` between 2-D balls, cuboids and convex polygons.
+
+CPU: the oracle (oracle/dim2.cpp) on the reference's own 2-D known-answer tests — build/ncollide2d/tests/geometry/epa2.rs (cuboid /
+cuboid EPA: depth == 0.5 / 1.8 and normal == -x / -y EXACTLY; the issue-#181 walk never panics) and ball_cuboid_contact.rs (f32 and
+f64, both operand orders) — and against an independent separating-axis / closest-feature computation in numpy f64.
+GPU: the device (csrc/dim2.cu, ``ncb2d_contact``) against the oracle in f32 on seeded random pairs, and on the same KATs."""
+import numpy as np
+import pytest
+
+from ncollide_b200 import dim2
+
+F = np.float32
+
+
+def random_pairs(n, seed, kinds=(0, 1, 2), spread=1.2):
+    """n random pairs; returns (t1, p1, m1, t2, p2, m2, points).  Ball x polygon is avoided (not built)."""
+    rng = np.random.default_rng(seed)
+    sh = dim2.Shapes2D()
+    t1 = rng.choice(kinds, size=n)
+    t2 = rng.choice(kinds, size=n)
+    clash = ((t1 == 0) & (t2 == 2)) | ((t1 == 2) & (t2 == 0))
+    t2[clash] = 1
+    for t in np.concatenate([t1, t2]):
+        if t == 0:
+            sh.ball(rng.uniform(0.2, 0.6))
+        elif t == 1:
+            sh.cuboid(rng.uniform(0.2, 0.6), rng.uniform(0.2, 0.6))
+        else:
+            k = int(rng.integers(3, 13))
+            ang = np.sort(rng.uniform(0, 2 * np.pi, size=k))
+            ang += np.arange(k) * 1e-3  # no coincident vertices
+            a, b = rng.uniform(0.25, 0.6, size=2)
+            sh.polygon(np.stack([a * np.cos(ang), b * np.sin(ang)], axis=1))
+    typ, par, pts = sh.arrays()
+    c1 = rng.uniform(-5, 5, size=(n, 2))
+    c2 = c1 + rng.uniform(-spread, spread, size=(n, 2))
+    degenerate = rng.random(n) < 0.03
+    c2[degenerate] = c1[degenerate]  # coincident centres: the x-axis start direction
+    a1, a2 = rng.uniform(-np.pi, np.pi, size=n), rng.uniform(-np.pi, np.pi, size=n)
+    axis_aligned = rng.random(n) < 0.2
+    a1[axis_aligned] = 0.0
+    a2[axis_aligned] = rng.choice([0.0, np.pi / 2], size=int(axis_aligned.sum()))
+    return typ[:n], par[:n], dim2.isometry2(c1, a1), typ[n:], par[n:], dim2.isometry2(c2, a2), pts
+
+
+# ---- CPU: the oracle on the reference's known-answer tests ---------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["oracle64", "oracle"])
+def test_oracle_epa2_cuboid_cuboid_kat(which, request):
+    """build/ncollide2d/tests/geometry/epa2.rs::cuboid_cuboid_EPA (exact equalities, f64 in the reference; f32 too here)."""
+    orc = request.getfixturevalue(which)
+    t, p = [1, 1], [[2, 1, 0, 0]] * 2
+    found, out, panics = orc.contact2d(t, p, [[3.5, 0, 1, 0], [0, 0.2, 1, 0]], t, p, [[0, 0, 1, 0]] * 2, prediction=10.0)
+    assert found.tolist() == [1, 1] and panics == 0
+    assert out[0, 6] == 0.5 and out[0, 4] == -1.0 and out[0, 5] == 0.0
+    assert out[1, 6] == 1.8 and out[1, 4] == 0.0 and out[1, 5] == -1.0
+
+
+@pytest.mark.parametrize("which", ["oracle64", "oracle"])
+def test_oracle_ball_cuboid_contact_kat(which, request):
+    """build/ncollide2d/tests/geometry/ball_cuboid_contact.rs: Some(contact) in both operand orders, f64 and f32."""
+    orc = request.getfixturevalue(which)
+    cub, ball = [0.5, 0.5, 0, 0], [0.5, 0, 0, 0]
+    mc, mb = [0, 4, 1, 0], [0.0517938, 3.05178815, 1, 0]
+    found, out, _ = orc.contact2d([1, 0], [cub, ball], [mc, mb], [0, 1], [ball, cub], [mb, mc], prediction=0.0)
+    assert found.tolist() == [1, 1]
+    assert np.allclose(out[0, 4:6], -out[1, 4:6]) and np.isclose(out[0, 6], out[1, 6]) and out[0, 6] > 0
+
+
+def test_oracle_issue_181_walk_never_panics(oracle64):
+    """epa2.rs::cuboids_large_size_ratio_issue_181: a (10, 10) cuboid walks and spins against a (300, 1.5) cuboid at angle 1.5,
+    pushed out along the deepest contact after every query ("used to panic").  20 000 of the reference's 200 000 steps here."""
+    a, b = [10, 10, 0, 0], [300, 1.5, 0, 0]
+    mb = [5.0, 0.0, np.cos(1.5), np.sin(1.5)]
+    px, py, angle, hits = 0.0, 0.0, 0.0, 0
+    for _ in range(20000):
+        px += 0.0001
+        angle += 0.005
+        found, out, panics = oracle64.contact2d([1], [a], [[px, py, np.cos(angle), np.sin(angle)]], [1], [b], [mb], prediction=0.0)
+        assert panics == 0 and np.isfinite(out).all()
+        if found[0]:
+            hits += 1
+            px -= out[0, 4] * out[0, 6]
+            py -= out[0, 5] * out[0, 6]
+    assert hits > 1000
+
+
+def _world_polygon(t, p, m, pts):
+    if t == 1:
+        loc = np.array([[p[0], p[1]], [-p[0], p[1]], [-p[0], -p[1]], [p[0], -p[1]]], dtype=np.float64)
+    else:
+        loc = pts[int(p[0]) : int(p[0]) + int(p[1])].astype(np.float64)
+    re, im = float(m[2]), float(m[3])
+    return np.stack([re * loc[:, 0] - im * loc[:, 1] + m[0], im * loc[:, 0] + re * loc[:, 1] + m[1]], axis=1)
+
+
+def _sat_signed_distance(A, B):
+    """Independent check: signed distance between two convex polygons (> 0 separated, < 0 penetration depth) — the largest
+    separation over the edge normals of both, refined by vertex-to-edge / vertex-to-vertex distances when separated."""
+    best = -np.inf
+    for P, Q in ((A, B), (B, A)):
+        e = np.roll(P, -1, axis=0) - P
+        nrm = np.stack([e[:, 1], -e[:, 0]], axis=1)
+        nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+        sep = ((Q[None, :, :] - P[:, None, :]) * nrm[:, None, :]).sum(axis=2).min(axis=1)
+        best = max(best, sep.max())
+    if best <= 0:
+        return best
+    d = np.inf
+    for P, Q in ((A, B), (B, A)):  # separated: exact distance = min over vertex / edge pairs
+        a, b2 = P, np.roll(P, -1, axis=0)
+        ab = b2 - a
+        for q in Q:
+            t = np.clip(((q - a) * ab).sum(axis=1) / (ab * ab).sum(axis=1), 0, 1)
+            d = min(d, np.linalg.norm(a + ab * t[:, None] - q, axis=1).min())
+    return d
+
+
+def test_oracle_against_separating_axes(oracle64):
+    """ORACLE check (f64): depth of contact_support_map_support_map == the separating-axis answer for convex polygons / cuboids."""
+    t1, p1, m1, t2, p2, m2, pts = random_pairs(1500, 5, kinds=(1, 2))
+    found, out, panics = oracle64.contact2d(t1, p1, m1, t2, p2, m2, pts, prediction=0.3)
+    assert panics == 0 and found.max() <= 1
+    checked = 0
+    for k in range(len(t1)):
+        sd = _sat_signed_distance(_world_polygon(t1[k], p1[k], m1[k], pts), _world_polygon(t2[k], p2[k], m2[k], pts))
+        if sd > 0.3 + 1e-6:
+            assert not found[k], (k, sd)
+        elif sd < 0.3 - 1e-6:
+            assert found[k], (k, sd)
+            assert abs(out[k, 6] - (-sd)) < 2e-5 * max(1.0, abs(sd)), (k, out[k, 6], -sd)
+            assert abs(np.hypot(out[k, 4], out[k, 5]) - 1) < 1e-6
+            checked += 1
+    assert checked > 500
+
+
+# ---- GPU: device vs oracle -----------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ctx():
+    from ncollide_b200.world import Context
+
+    c = Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.gpu
+def test_device_kats(ctx):
+    t, p = [1, 1], [[2, 1, 0, 0]] * 2
+    found, out, info = dim2.contact(ctx, t, p, [[3.5, 0, 1, 0], [0, 0.2, 1, 0]], t, p, [[0, 0, 1, 0]] * 2, prediction=10.0)
+    assert found.all() and info == {"ref_panics": 0, "epa_overflow": 0}
+    assert out[0, 6] == F(0.5) and tuple(out[0, 4:6]) == (-1.0, 0.0)
+    assert out[1, 6] == F(1.8) and tuple(out[1, 4:6]) == (0.0, -1.0)
+    cub, ball = [0.5, 0.5, 0, 0], [0.5, 0, 0, 0]
+    mc, mb = [0, 4, 1, 0], [0.0517938, 3.05178815, 1, 0]
+    found, out, _ = dim2.contact(ctx, [1, 0], [cub, ball], [mc, mb], [0, 1], [ball, cub], [mb, mc])
+    assert found.all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,kinds,prediction", [(1, (0, 1, 2), 0.0), (2, (1, 2), 0.02), (3, (0, 1), 0.3), (4, (2,), 0.05), (6, (1,), 0.0)])
+def test_device_contact_matches_oracle(ctx, oracle, seed, kinds, prediction):
+    t1, p1, m1, t2, p2, m2, pts = random_pairs(60000, seed, kinds)
+    found, out, info = dim2.contact(ctx, t1, p1, m1, t2, p2, m2, pts, prediction)
+    ofound, oout, opanics = oracle.contact2d(t1, p1, m1, t2, p2, m2, pts, prediction)
+    assert info["epa_overflow"] == 0 and info["ref_panics"] == opanics
+    assert np.array_equal(found, ofound.astype(bool)), f"{(found != ofound.astype(bool)).sum()} Some / None answers differ"
+    hit = found
+    assert hit.sum() > 10000 and (~hit).sum() > 1000
+    assert np.allclose(out[hit], oout[hit], rtol=1e-4, atol=1e-5)
+    same = (out[hit].view(np.uint32) == np.ascontiguousarray(oout[hit], dtype=np.float32).view(np.uint32)).mean()
+    assert same > 0.999, f"only {same:.5f} of the contact words are bit-identical"
+
+
+@pytest.mark.gpu
+def test_device_refuses_what_is_not_built(ctx):
+    from ncollide_b200._ffi import NcbError
+
+    sh = dim2.Shapes2D().ball(0.5).polygon([[0, 0], [1, 0], [0, 1]])
+    typ, par, pts = sh.arrays()
+    with pytest.raises(NcbError):
+        dim2.contact(ctx, typ[:1], par[:1], [[0, 0, 1, 0]], typ[1:], par[1:], [[0.2, 0, 1, 0]], pts)
+    with pytest.raises(NcbError):
+        dim2.contact(ctx, [7], [[1, 0, 0, 0]], [[0, 0, 1, 0]], [1], [[1, 1, 0, 0]], [[0.2, 0, 1, 0]])
