@@ -572,6 +572,10 @@ def run_native(args):
             widened["proximity_sensors"] = bench_proximity(ctx, scene)
         except Exception as ex:  # noqa: BLE001
             widened["proximity_sensors"] = {"error": repr(ex)[:200]}
+        try:
+            widened["dim2_contact"] = bench_dim2(ctx)
+        except Exception as ex:  # noqa: BLE001
+            widened["dim2_contact"] = {"error": repr(ex)[:200]}
 
     # ---- secondary worlds (after everything else: they replace the world on the device) -----------------------------------
     #   strong scaling: ONE fixed 8 M-object cfg3 world at every N (the driver's N = 1, 2, 4, 8 runs give the curve);
@@ -767,6 +771,54 @@ def bench_widened(ctx, scene):
         "world_ray_queries": {"workload": f"{n_rays} rays, first_interference_with_ray within 20 units, {n}-object world (ncb_sim_ray_cast)",
                               "ms": min(rt[1:]), "Mrays_per_s": n_rays / (min(rt[1:]) / 1e3) / 1e6, "hits": rows},
     }
+
+
+def bench_dim2(ctx, n_pairs=1_000_000, cpu_sample=100_000):
+    """Widened row N4 (2-D build, first slice): ncollide2d query::contact for a batch of random 2-D cuboid / polygon / ball pairs
+    through ncb2d_contact (host buffers: shapes + poses in, contacts out; wall clock), next to the oracle on one host core."""
+    from ncollide_b200 import dim2
+
+    rng = np.random.default_rng(21)
+    sh = dim2.Shapes2D()
+    t1 = rng.choice([0, 1, 2], size=n_pairs)
+    t2 = rng.choice([0, 1, 2], size=n_pairs)
+    # a small library of shapes, indexed at random (building a million Python shape objects would dominate)
+    lib_t, lib_p = [], []
+    for t in (0, 1, 2):
+        for _ in range(64):
+            if t == 0:
+                sh.ball(rng.uniform(0.2, 0.6))
+            elif t == 1:
+                sh.cuboid(rng.uniform(0.2, 0.6), rng.uniform(0.2, 0.6))
+            else:
+                k = int(rng.integers(3, 13))
+                ang = np.sort(rng.uniform(0, 2 * np.pi, size=k)) + np.arange(k) * 1e-3
+                sh.polygon(np.stack([0.5 * np.cos(ang), 0.35 * np.sin(ang)], axis=1))
+    typ, par, pts, nrm = sh.arrays()
+    pick1, pick2 = t1 * 64 + rng.integers(0, 64, size=n_pairs), t2 * 64 + rng.integers(0, 64, size=n_pairs)
+    c1 = rng.uniform(-50, 50, size=(n_pairs, 2))
+    m1 = dim2.isometry2(c1, rng.uniform(-np.pi, np.pi, size=n_pairs))
+    m2 = dim2.isometry2(c1 + rng.uniform(-1.2, 1.2, size=(n_pairs, 2)), rng.uniform(-np.pi, np.pi, size=n_pairs))
+    args = (typ[pick1], par[pick1], m1, typ[pick2], par[pick2], m2, pts)
+    dim2.contact(ctx, *args, prediction=0.02, poly_normals=nrm)
+    t0 = time.perf_counter()
+    found, out, info = dim2.contact(ctx, *args, prediction=0.02, poly_normals=nrm)
+    ms = (time.perf_counter() - t0) * 1e3
+    res = {"workload": f"{n_pairs} random 2-D pairs (balls, cuboids, convex polygons of 3-12 vertices), query::contact with prediction 0.02",
+           "ms": ms, "Mpairs_per_s": n_pairs / ms / 1e3, "contacts_found": int(found.sum()), **info}
+    try:
+        from oracle.pyoracle import Oracle
+
+        orc = Oracle()
+        sl = slice(0, cpu_sample)
+        t0 = time.perf_counter()
+        of, oo, _ = orc.contact2d(args[0][sl], args[1][sl], args[2][sl], args[3][sl], args[4][sl], args[5][sl], pts, prediction=0.02, poly_normals=nrm)
+        cms = (time.perf_counter() - t0) * 1e3
+        res["cpu_baseline"] = {"Mpairs_per_s": cpu_sample / cms / 1e3, "cores": 1, "kind": "port", "sample": f"the first {cpu_sample} pairs",
+                               "answers_equal": bool(np.array_equal(of.astype(bool), found[sl]))}
+    except Exception as ex:  # noqa: BLE001
+        res["cpu_baseline"] = {"error": repr(ex)[:120]}
+    return res
 
 
 def bench_proximity(ctx, scene, fraction=0.2, reps=6):

@@ -410,19 +410,21 @@ const char* ncb_version(void);
 
 /* ---- ncollide2d, first slice: batched query::contact between 2-D shapes ----------------------------------- */
 /* ncollide2d::query::contact(m1, g1, m2, g2, prediction) (query/contact/contact_shape_shape.rs:15-60) for n_pairs pairs of 2-D balls,
- * cuboids and convex polygons: contact_ball_ball, contact_ball_convex_polyhedron (ball x cuboid, either order) and
- * contact_support_map_support_map = 2-D GJK (gjk.rs:76-177 over voronoi_simplex2.rs) + 2-D EPA (epa2.rs).
+ * cuboids and convex polygons: contact_ball_ball, contact_ball_convex_polyhedron (ball x cuboid / polygon, either order; the polygon
+ * case projects the ball centre with GJK / EPA, point_support_map.rs:14-55) and contact_support_map_support_map = 2-D GJK
+ * (gjk.rs:76-177 over voronoi_simplex2.rs) + 2-D EPA (epa2.rs).
  * Host buffers.  type: NCB2D_BALL / _CUBOID / _POLYGON; param: 4 floats per shape (radius | hx, hy | first point, point count into
- * poly_points); pose: 4 floats per shape = Isometry2 (translation x, y; UnitComplex re, im = cos, sin of the angle, evaluated by the
+ * poly_points; poly_normals = ConvexPolygon::normals aligned with poly_points, convex_polygon.rs:34-66, needed when a ball meets a
+ * polygon); pose: 4 floats per shape = Isometry2 (translation x, y; UnitComplex re, im = cos, sin of the angle, evaluated by the
  * caller like Isometry2::new does).  found[p] = 1 for Some(contact), 0 for None; out: 7 floats per pair (world1 xy, world2 xy, normal
  * xy, depth).  ref_panics counts pairs on which the reference itself would panic (epa2.rs:279, peek on an empty heap), epa_overflow
- * pairs whose polytope outgrew the device capacity (72 vertices; they answer None).  NCB_ERR_UNSUPPORTED: ball x polygon (not built). */
+ * pairs whose polytope outgrew the device capacity (72 vertices; they answer None). */
 #define NCB2D_BALL 0u
 #define NCB2D_CUBOID 1u
 #define NCB2D_POLYGON 2u
 int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const float* param1, const float* pose1, const uint32_t* type2,
-                  const float* param2, const float* pose2, const float* poly_points, uint32_t n_poly_points, float prediction,
-                  uint8_t* found, float* out, uint32_t* ref_panics, uint32_t* epa_overflow);
+                  const float* param2, const float* pose2, const float* poly_points, const float* poly_normals, uint32_t n_poly_points,
+                  float prediction, uint8_t* found, float* out, uint32_t* ref_panics, uint32_t* epa_overflow);
 
 #ifdef __cplusplus
 }

@@ -14,8 +14,9 @@
 //   support maps                          shape/ball.rs:29-48, shape/cuboid.rs:137-145, shape/convex_polygon.rs + utils/point_cloud_support_point.rs:6-24
 // Same arithmetic contract as the 3-D path: --fmad=false, IEEE division / sqrt, nalgebra's evaluation order
 // (UnitComplex * v = (re x - im y, im x + re y); Isometry2 * p = rotation * p + translation).
-// Not in this slice: ball x polygon (ConvexPolygon::project_point_with_feature), the manifold generators / ConvexPolygonalFeature2,
-// the 2-D broad phase and world.  ncb2d_contact answers NCB_ERR_UNSUPPORTED for a ball x polygon pair.
+//   ball x convex polygon                 query/point/point_support_map.rs:14-55,120-146 (GJK / EPA projection of the ball centre),
+//                                         shape/convex_polygon.rs:139-152,186-203 (feature normal, support feature)
+// Not in this slice: the manifold generators / ConvexPolygonalFeature2, the 2-D broad phase and world.
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -63,15 +64,18 @@ __device__ __forceinline__ W2 to_local(const Pose2& m, W2 p) { return unrotate(m
 #define D2_BALL 0u
 #define D2_CUBOID 1u
 #define D2_POLYGON 2u
+#define D2_ORIGIN 3u  // special_support_maps::ConstantOrigin
 struct Operand2 {
     uint32_t kind;
     float a, b;          // radius | half extents
     const float* pts;    // polygon vertices (x, y)
+    const float* nrm;    // polygon edge normals (ConvexPolygon::normals), may be null when no ball meets a polygon
     uint32_t npts;
     Pose2 m;
 };
 
 __device__ W2 support(const Operand2& g, W2 dir) {
+    if (g.kind == D2_ORIGIN) return g.m.t;
     if (g.kind == D2_BALL) return g.m.t + normalized(dir) * g.a;  // support_point_toward(m, Unit::new_normalize(dir)): the rotation plays no part
     W2 ld = unrotate(g.m, dir), lp;
     if (g.kind == D2_CUBOID) {
@@ -515,38 +519,109 @@ __device__ bool ball_cuboid(W2 center, float radius, const Operand2& box, float 
     return true;
 }
 
+// ConvexPolygon::project_point_with_feature + contact_ball_convex_polyhedron: the ball centre is projected on the polygon with
+// GJK against the constant origin (EPA when it lies inside), in the frame translated by -centre
+__device__ bool ball_polygon(W2 center, float radius, const Operand2& poly, float prediction, float cos_one_degree, Hit2& h, int& epa_status) {
+    Operand2 g = poly, origin;
+    g.m.t = (-center) + poly.m.t;
+    origin.kind = D2_ORIGIN, origin.a = origin.b = 0.f, origin.pts = origin.nrm = nullptr, origin.npts = 0;
+    origin.m.t = w2(0.f, 0.f), origin.m.re = 1.f, origin.m.im = 0.f;
+    W2 d0;
+    if (!unit(-g.m.t, NCB_EPS, d0)) d0 = w2(1.f, 0.f);
+    Tri2 s;
+    for (int i = 0; i < 3; ++i) s.v[i].p = s.v[i].o1 = s.v[i].o2 = w2(0.f, 0.f), s.old_idx[i] = i;
+    s.bary[0] = s.bary[1] = s.old_bary[0] = s.old_bary[1] = 0.f;
+    s.dim = s.old_dim = 0;
+    s.v[0] = minkowski(g, origin, d0);
+    W2 p1, p2, n;
+    bool inside = gjk2(g, origin, NCB_FMAX, s, p1, p2, n) != G_POINTS;
+    W2 world2;
+    if (!inside) {
+        world2 = p1 + center;
+    } else {
+        Poly2 e;
+        epa_status = epa2(g, origin, s, e, p1, p2, n);
+        world2 = epa_status == 1 ? p1 + center : center;
+    }
+    W2 back = center - world2;
+    W2 ldir = unrotate(poly.m, inside ? -back : back), lu;
+    int face = -1, vert = -1;
+    if (unit(ldir, NCB_EPS, lu)) {  // support_feature_id_toward
+        for (uint32_t i = 0; i < poly.npts && face < 0; ++i)
+            if (__ldg(poly.nrm + 2 * i) * lu.x + __ldg(poly.nrm + 2 * i + 1) * lu.y >= cos_one_degree) face = (int)i;
+        if (face < 0) {
+            vert = 0;
+            float best = __ldg(poly.pts) * lu.x + __ldg(poly.pts + 1) * lu.y;
+            for (uint32_t i = 1; i < poly.npts; ++i) {
+                float d = __ldg(poly.pts + 2 * i) * lu.x + __ldg(poly.pts + 2 * i + 1) * lu.y;
+                if (d > best) best = d, vert = (int)i;
+            }
+        }
+    }
+    W2 dpt = world2 - center, dir, normal;
+    float dist, depth;
+    if (unit_get(dpt, NCB_EPS, dir, dist)) {
+        depth = inside ? dist + radius : -dist + radius;
+        normal = inside ? -dir : dir;
+    } else {
+        if (face < 0 && vert < 0) return false;  // FeatureId::Unknown
+        W2 fnrm;
+        if (face >= 0) {
+            fnrm = w2(__ldg(poly.nrm + 2 * face), __ldg(poly.nrm + 2 * face + 1));
+        } else {
+            int prev = vert == 0 ? (int)poly.npts - 1 : vert - 1;
+            fnrm = normalized(w2(__ldg(poly.nrm + 2 * prev), __ldg(poly.nrm + 2 * prev + 1)) + w2(__ldg(poly.nrm + 2 * vert), __ldg(poly.nrm + 2 * vert + 1)));
+        }
+        depth = radius;
+        normal = -fnrm;
+    }
+    if (!(depth >= -prediction)) return false;
+    h.w1 = center + normal * radius, h.w2 = world2, h.n = normal, h.depth = depth;
+    return true;
+}
+
 struct Args2 {
     uint32_t n;
     const uint32_t *type1, *type2;
     const float4 *param1, *param2, *pose1, *pose2;
     const float* poly;
+    const float* poly_nrm;
     float prediction;
+    float cos_one_degree;  // cos(pi / 180) in f32 from the host libm (convex_polygon.rs:187-188)
     uint8_t* found;
     float* out;
     uint32_t* counters;  // [0] reference panics, [1] EPA capacity overflows
 };
-__device__ __forceinline__ Operand2 load_operand(uint32_t t, float4 p, float4 m, const float* poly) {
+__device__ __forceinline__ Operand2 load_operand(uint32_t t, float4 p, float4 m, const float* poly, const float* poly_nrm) {
     Operand2 g;
-    g.kind = t, g.a = p.x, g.b = p.y, g.pts = nullptr, g.npts = 0;
-    if (t == D2_POLYGON) g.pts = poly + 2 * (size_t)p.x, g.npts = (uint32_t)p.y;
+    g.kind = t, g.a = p.x, g.b = p.y, g.pts = g.nrm = nullptr, g.npts = 0;
+    if (t == D2_POLYGON) {
+        g.pts = poly + 2 * (size_t)p.x, g.npts = (uint32_t)p.y;
+        g.nrm = poly_nrm ? poly_nrm + 2 * (size_t)p.x : nullptr;
+    }
     g.m.t = w2(m.x, m.y), g.m.re = m.z, g.m.im = m.w;
     return g;
 }
 __global__ void __launch_bounds__(64) k_contact2d(Args2 A) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= A.n) return;
-    Operand2 g1 = load_operand(__ldg(&A.type1[k]), __ldg(&A.param1[k]), __ldg(&A.pose1[k]), A.poly);
-    Operand2 g2 = load_operand(__ldg(&A.type2[k]), __ldg(&A.param2[k]), __ldg(&A.pose2[k]), A.poly);
+    Operand2 g1 = load_operand(__ldg(&A.type1[k]), __ldg(&A.param1[k]), __ldg(&A.pose1[k]), A.poly, A.poly_nrm);
+    Operand2 g2 = load_operand(__ldg(&A.type2[k]), __ldg(&A.param2[k]), __ldg(&A.pose2[k]), A.poly, A.poly_nrm);
     Hit2 h;
     h.w1 = h.w2 = h.n = w2(0.f, 0.f), h.depth = 0.f;
     bool ok = false;
     if (g1.kind == D2_BALL && g2.kind == D2_BALL) {
         ok = ball_ball(g1.m.t, g1.a, g2.m.t, g2.a, A.prediction, h);
-    } else if (g1.kind == D2_BALL) {
-        ok = ball_cuboid(g1.m.t, g1.a, g2, A.prediction, h);
-    } else if (g2.kind == D2_BALL) {  // contact_convex_polyhedron_ball: the ball query, flipped
-        ok = ball_cuboid(g2.m.t, g2.a, g1, A.prediction, h);
-        if (ok) {
+    } else if (g1.kind == D2_BALL || g2.kind == D2_BALL) {  // contact_ball_convex_polyhedron; with the ball second: the same query, flipped
+        const bool flip = g1.kind != D2_BALL;
+        const Operand2& ball = flip ? g2 : g1;
+        const Operand2& other = flip ? g1 : g2;
+        int q = 1;
+        ok = other.kind == D2_CUBOID ? ball_cuboid(ball.m.t, ball.a, other, A.prediction, h)
+                                     : ball_polygon(ball.m.t, ball.a, other, A.prediction, A.cos_one_degree, h, q);
+        if (q == -1) atomicAdd(&A.counters[0], 1u);
+        if (q == -2) atomicAdd(&A.counters[1], 1u);
+        if (ok && flip) {
             W2 t = h.w1;
             h.w1 = h.w2, h.w2 = t, h.n = -h.n;
         }
@@ -594,8 +669,8 @@ using namespace ncb;
 extern "C" {
 
 int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const float* param1, const float* pose1, const uint32_t* type2,
-                  const float* param2, const float* pose2, const float* poly_points, uint32_t n_poly_points, float prediction, uint8_t* found,
-                  float* out, uint32_t* ref_panics, uint32_t* epa_overflow) {
+                  const float* param2, const float* pose2, const float* poly_points, const float* poly_normals, uint32_t n_poly_points,
+                  float prediction, uint8_t* found, float* out, uint32_t* ref_panics, uint32_t* epa_overflow) {
     if (!ctx || (n_pairs && (!type1 || !param1 || !pose1 || !type2 || !param2 || !pose2 || !found || !out))) return NCB_ERR_ARG;
     if (ref_panics) *ref_panics = 0;
     if (epa_overflow) *epa_overflow = 0;
@@ -617,9 +692,9 @@ int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const f
             }
         }
         bool b1 = type1[k] == 0, b2 = type2[k] == 0;
-        if ((b1 && type2[k] == 2) || (b2 && type1[k] == 2)) {
-            ctx->err = "ncb2d_contact: ball x convex polygon is not built (ConvexPolygon::project_point_with_feature)";
-            return NCB_ERR_UNSUPPORTED;
+        if (((b1 && type2[k] == 2) || (b2 && type1[k] == 2)) && !poly_normals) {
+            ctx->err = "ncb2d_contact: a ball x convex polygon pair needs poly_normals (ConvexPolygon::normals)";
+            return NCB_ERR_ARG;
         }
     }
     CK2(cudaSetDevice(ctx->device));
@@ -627,7 +702,7 @@ int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const f
     size_t n = n_pairs;
     DevBuf<uint32_t> d_t;   // type1 | type2 | counters
     DevBuf<float4> d_f4;    // param1 | param2 | pose1 | pose2
-    DevBuf<float> d_poly, d_out;
+    DevBuf<float> d_poly, d_nrm, d_out;
     DevBuf<uint8_t> d_found;
     CK2(d_t.reserve(2 * n + 2));
     CK2(d_f4.reserve(4 * n));
@@ -642,12 +717,18 @@ int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const f
     CK2(cudaMemcpyAsync(d_f4.p + 2 * n, pose1, 16 * n, cudaMemcpyHostToDevice, s));
     CK2(cudaMemcpyAsync(d_f4.p + 3 * n, pose2, 16 * n, cudaMemcpyHostToDevice, s));
     if (n_poly_points) CK2(cudaMemcpyAsync(d_poly.p, poly_points, 8 * (size_t)n_poly_points, cudaMemcpyHostToDevice, s));
+    if (n_poly_points && poly_normals) {
+        CK2(d_nrm.reserve(2 * (size_t)n_poly_points));
+        CK2(cudaMemcpyAsync(d_nrm.p, poly_normals, 8 * (size_t)n_poly_points, cudaMemcpyHostToDevice, s));
+    }
     d2::Args2 A;
     A.n = n_pairs;
     A.type1 = d_t.p, A.type2 = d_t.p + n;
     A.param1 = d_f4.p, A.param2 = d_f4.p + n, A.pose1 = d_f4.p + 2 * n, A.pose2 = d_f4.p + 3 * n;
     A.poly = d_poly.p;
+    A.poly_nrm = (n_poly_points && poly_normals) ? d_nrm.p : nullptr;
     A.prediction = prediction;
+    A.cos_one_degree = cosf((float)(3.14159265358979323846 / 180.0));
     A.found = d_found.p, A.out = d_out.p;
     A.counters = d_t.p + 2 * n;
     d2::k_contact2d<<<(n_pairs + 63) / 64, 64, 0, s>>>(A);

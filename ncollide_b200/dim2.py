@@ -11,6 +11,8 @@ import numpy as np
 from ._ffi import as_f32, as_u32, ptr
 
 BALL, CUBOID, POLYGON = 0, 1, 2
+F32 = np.float32
+EPS = np.finfo(np.float32).eps
 
 
 def isometry2(translation, angle):
@@ -24,7 +26,7 @@ class Shapes2D:
     """A batch of 2-D shapes: ``type`` [n] and ``param`` [n, 4]; polygons index into a shared point array."""
 
     def __init__(self):
-        self.type, self.param, self.points = [], [], []
+        self.type, self.param, self.points, self.normals = [], [], [], []
 
     def ball(self, radius):
         self.type.append(BALL), self.param.append((radius, 0, 0, 0))
@@ -35,17 +37,46 @@ class Shapes2D:
         return self
 
     def polygon(self, points):
-        """Convex polygon given by its vertices in counter-clockwise order (``ConvexPolygon::try_new``)."""
-        pts = as_f32(points).reshape(-1, 2)
-        self.type.append(POLYGON), self.param.append((len(self.points), len(pts), 0, 0))
-        self.points.extend(pts.tolist())
+        """``ConvexPolygon::try_new(points)`` (shape/convex_polygon.rs:29-71): vertices of a counter-clockwise convex polyline;
+        edge normals are computed and vertices between (nearly) collinear edges are removed, in f32 like the reference.
+        Raises ValueError where the reference returns None."""
+        pts = [np.asarray(p, dtype=F32) for p in as_f32(points).reshape(-1, 2)]
+        n = len(pts)
+        eps = F32(np.sqrt(EPS))
+        normals = []
+        for i1 in range(n):
+            ab = pts[(i1 + 1) % n] - pts[i1]
+            res = np.array([ab[1], -ab[0]], dtype=F32)  # ccw_face_normal (dim2)
+            sq = F32(F32(res[0] * res[0]) + F32(res[1] * res[1]))
+            if not sq > F32(EPS * EPS):
+                raise ValueError("ConvexPolygon::try_new: consecutive points are identical")
+            normals.append((res / np.sqrt(sq, dtype=F32)).astype(F32))
+
+        def dot(a, b):
+            return F32(F32(a[0] * b[0]) + F32(a[1] * b[1]))
+
+        removed = 1 if dot(normals[0], normals[-1]) > F32(1) - eps else 0
+        for i2 in range(1, n):
+            if dot(normals[i2 - 1], normals[i2]) > F32(1) - eps:
+                removed += 1
+            else:
+                pts[i2 - removed] = pts[i2]
+                normals[i2 - removed] = normals[i2]
+        keep = n - removed
+        if keep == 0:
+            raise ValueError("ConvexPolygon::try_new: no vertex left")
+        self.type.append(POLYGON), self.param.append((len(self.points), keep, 0, 0))
+        self.points.extend(p.tolist() for p in pts[:keep])
+        self.normals.extend(q.tolist() for q in normals[:keep])
         return self
 
     def arrays(self):
-        return as_u32(self.type), as_f32(self.param).reshape(-1, 4), as_f32(self.points if self.points else [[0, 0]]).reshape(-1, 2)
+        """(type [n], param [n, 4], points [m, 2], normals [m, 2])"""
+        return (as_u32(self.type), as_f32(self.param).reshape(-1, 4), as_f32(self.points if self.points else [[0, 0]]).reshape(-1, 2),
+                as_f32(self.normals if self.normals else [[0, 0]]).reshape(-1, 2))
 
 
-def contact(ctx, type1, param1, pose1, type2, param2, pose2, poly_points=None, prediction=0.0):
+def contact(ctx, type1, param1, pose1, type2, param2, pose2, poly_points=None, prediction=0.0, poly_normals=None):
     """``query::contact`` for every pair k: (type1[k], param1[k]) at pose1[k] against (type2[k], param2[k]) at pose2[k].
     Returns (found [n] bool, contacts [n, 7] = world1, world2, normal, depth, info dict)."""
     t1, t2 = as_u32(type1).reshape(-1), as_u32(type2).reshape(-1)
@@ -55,10 +86,13 @@ def contact(ctx, type1, param1, pose1, type2, param2, pose2, poly_points=None, p
     if not (len(t2) == len(p1) == len(p2) == len(m1) == len(m2) == n):
         raise ValueError("one type / param / pose row per pair and side")
     pts = as_f32(poly_points).reshape(-1, 2) if poly_points is not None else None
+    nrm = as_f32(poly_normals).reshape(-1, 2) if poly_normals is not None else None
+    if nrm is not None and (pts is None or len(nrm) != len(pts)):
+        raise ValueError("one normal per polygon point")
     found = np.zeros(n, dtype=np.uint8)
     out = np.zeros((n, 7), dtype=np.float32)
     panics, over = C.c_uint32(0), C.c_uint32(0)
-    ctx.check(ctx.lib.ncb2d_contact(ctx.h, C.c_uint32(n), ptr(t1), ptr(p1), ptr(m1), ptr(t2), ptr(p2), ptr(m2), ptr(pts),
+    ctx.check(ctx.lib.ncb2d_contact(ctx.h, C.c_uint32(n), ptr(t1), ptr(p1), ptr(m1), ptr(t2), ptr(p2), ptr(m2), ptr(pts), ptr(nrm),
                                     C.c_uint32(0 if pts is None else len(pts)), C.c_float(prediction), ptr(found), ptr(out), C.byref(panics),
                                     C.byref(over)), "ncb2d_contact")
     return found.astype(bool), out, {"ref_panics": panics.value, "epa_overflow": over.value}

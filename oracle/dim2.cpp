@@ -54,17 +54,19 @@ static inline P2 inv_rot(const Iso2& m, P2 v) { return {m.re * v.x + m.im * v.y,
 static inline P2 mul_point(const Iso2& m, P2 p) { return rot(m, p) + m.t; }
 static inline P2 inv_point(const Iso2& m, P2 p) { return inv_rot(m, p - m.t); }
 
-enum { BALL2 = 0, CUBOID2 = 1, POLYGON2 = 2 };
+enum { BALL2 = 0, CUBOID2 = 1, POLYGON2 = 2, ORIGIN2 = 3 };  // ORIGIN2: special_support_maps::ConstantOrigin
 struct Shape2 {
     uint32_t type;
     real radius;
     P2 he;
     const real* pts;
+    const real* normals;  // ConvexPolygon::normals (one per edge i -> i + 1), from try_new
     uint32_t npts;
 };
 
 // SupportMap::support_point
 static P2 support_point(const Shape2& g, const Iso2& m, P2 dir) {
+    if (g.type == ORIGIN2) return m.t;  // ConstantOrigin: m * Point::origin()
     if (g.type == BALL2) {  // ball.rs:29-48: support_point_toward(m, Unit::new_normalize(dir)) = translation + dir * radius
         P2 d = normalize(dir);
         return m.t + d * g.radius;
@@ -602,6 +604,73 @@ static bool contact_ball_cuboid(P2 center, real radius, const Iso2& m2, const Sh
     return false;
 }
 
+// point_projection_on_support_map (point_support_map.rs:14-55) with solid = false, for a convex polygon
+static P2 polygon_project(const Shape2& g, const Iso2& m_in, P2 point, bool* inside, int* panicked) {
+    Iso2 m = m_in;
+    m.t = (-point) + m_in.t;  // Translation::from(-point.coords) * m
+    Iso2 id = {p2(0, 0), 1, 0};
+    Shape2 origin;
+    origin.type = ORIGIN2, origin.radius = 0, origin.he = p2(0, 0), origin.pts = origin.normals = nullptr, origin.npts = 0;
+    P2 dir;
+    if (!unit_try_new(-m.t, EPS, &dir)) dir = p2(1, 0);
+    Simplex2 s;
+    s.reset(cso_from_shapes(m, g, id, origin, dir));
+    P2 p1, p2_, n;
+    int r = gjk_closest_points(m, g, id, origin, FMAX, s, &p1, &p2_, &n);  // gjk::project_origin
+    if (r == R_CLOSEST) {
+        *inside = false;
+        return p1 + point;
+    }
+    *inside = true;
+    if (epa_closest_points(m, g, id, origin, s, &p1, &p2_, &n, panicked)) return p1 + point;  // EPA::project_origin
+    return point;
+}
+// ConvexPolygon::support_feature_id_toward (convex_polygon.rs:186-203) / feature_normal (:139-152)
+static uint32_t polygon_feature_toward(const Shape2& g, P2 local_dir) {
+    const real ceps = std::cos(real(3.14159265358979323846 / 180.0));
+    for (uint32_t i = 0; i < g.npts; ++i)
+        if (g.normals[2 * i] * local_dir.x + g.normals[2 * i + 1] * local_dir.y >= ceps) return F_FACE | i;
+    uint32_t best = 0;
+    real best_dot = g.pts[0] * local_dir.x + g.pts[1] * local_dir.y;
+    for (uint32_t i = 1; i < g.npts; ++i) {
+        real d = g.pts[2 * i] * local_dir.x + g.pts[2 * i + 1] * local_dir.y;
+        if (d > best_dot) best_dot = d, best = i;
+    }
+    return F_VERTEX | best;
+}
+static P2 polygon_feature_normal(const Shape2& g, uint32_t f) {
+    uint32_t id = f & 0xffffu;
+    if (f & F_FACE) return p2(g.normals[2 * id], g.normals[2 * id + 1]);
+    uint32_t id1 = id == 0 ? g.npts - 1 : id - 1;
+    return normalize(p2(g.normals[2 * id1], g.normals[2 * id1 + 1]) + p2(g.normals[2 * id], g.normals[2 * id + 1]));
+}
+// contact_ball_convex_polyhedron.rs:12-62 with a convex polygon (ConvexPolygon::project_point_with_feature, point_support_map.rs:120-146)
+static bool contact_ball_polygon(P2 center, real radius, const Iso2& m2, const Shape2& g2, real prediction, Contact2* c, int* panicked) {
+    bool inside;
+    P2 world2 = polygon_project(g2, m2, center, &inside, panicked);
+    P2 dpt_f = center - world2;
+    P2 local_dir = inv_rot(m2, inside ? -dpt_f : dpt_f), ld;
+    uint32_t f2 = F_UNKNOWN;
+    if (unit_try_new(local_dir, EPS, &ld)) f2 = polygon_feature_toward(g2, ld);
+    P2 dpt = world2 - center, dir, normal;
+    real dist, depth;
+    if (unit_try_new_and_get(dpt, EPS, &dir, &dist)) {
+        if (inside)
+            depth = dist + radius, normal = -dir;
+        else
+            depth = -dist + radius, normal = dir;
+    } else {
+        if (f2 == F_UNKNOWN) return false;
+        depth = radius;
+        normal = -polygon_feature_normal(g2, f2);
+    }
+    if (depth >= -prediction) {
+        c->w1 = center + normal * radius, c->w2 = world2, c->n = normal, c->depth = depth;
+        return true;
+    }
+    return false;
+}
+
 }  // namespace d2
 }  // namespace orc
 
@@ -612,14 +681,18 @@ extern "C" {
 
 // query::contact for n pairs.  type: 0 ball, 1 cuboid, 2 convex polygon; param (4 reals per shape): ball (radius), cuboid (hx, hy),
 // polygon (first point, point count) into poly_points (x, y); pose (4 reals): translation x, y, rotation re, im (UnitComplex).
-// found[p]: 1 Some, 0 None, 2 = pair kind not restated (ball x polygon).  out (7 reals): world1, world2, normal, depth.
+// poly_normals: ConvexPolygon::normals aligned with poly_points (needed for ball x polygon).  found[p]: 1 Some, 0 None, 2 = ball x polygon without normals.  out (7 reals): world1, world2, normal, depth.
 // panics (optional): number of pairs on which the reference would panic (heap.peek().unwrap() on an empty heap, epa2.rs:279).
 void orc2_contact(uint64_t n, const uint32_t* type1, const real* param1, const real* pose1, const uint32_t* type2, const real* param2,
-                  const real* pose2, const real* poly_points, real prediction, uint8_t* found, real* out, uint32_t* panics) {
+                  const real* pose2, const real* poly_points, const real* poly_normals, real prediction, uint8_t* found, real* out,
+                  uint32_t* panics) {
     auto shape = [&](uint32_t t, const real* p) {
         Shape2 g;
-        g.type = t, g.radius = p[0], g.he = p2(p[0], p[1]), g.pts = nullptr, g.npts = 0;
-        if (t == POLYGON2) g.pts = poly_points + 2 * (size_t)p[0], g.npts = (uint32_t)p[1];
+        g.type = t, g.radius = p[0], g.he = p2(p[0], p[1]), g.pts = g.normals = nullptr, g.npts = 0;
+        if (t == POLYGON2) {
+            g.pts = poly_points + 2 * (size_t)p[0], g.npts = (uint32_t)p[1];
+            g.normals = poly_normals ? poly_normals + 2 * (size_t)p[0] : nullptr;
+        }
         return g;
     };
     uint32_t np = 0;
@@ -641,8 +714,16 @@ void orc2_contact(uint64_t n, const uint32_t* type1, const real* param1, const r
                 std::swap(c.w1, c.w2);
                 c.n = -c.n;
             }
+        } else if (g1.type == BALL2 && g2.type == POLYGON2 && g2.normals) {
+            ok = contact_ball_polygon(m1.t, g1.radius, m2, g2, prediction, &c, &panicked);
+        } else if (g1.type == POLYGON2 && g2.type == BALL2 && g1.normals) {
+            ok = contact_ball_polygon(m2.t, g2.radius, m1, g1, prediction, &c, &panicked);
+            if (ok) {
+                std::swap(c.w1, c.w2);
+                c.n = -c.n;
+            }
         } else if (g1.type == BALL2 || g2.type == BALL2) {
-            code = 2;  // ball x polygon: ConvexPolygon::project_point_with_feature is not restated
+            code = 2;  // ball x polygon without the polygon's normals
         } else {
             ok = contact_sm_sm(m1, g1, m2, g2, prediction, &c, &panicked);
         }

@@ -172,7 +172,8 @@ void orc_aabb_toi_with_ray(const real* minmax, const real* origin, const real* d
  * shape (radius | hx, hy | first point, count); pose: 4 reals (translation x y, UnitComplex re im); found: 1 Some, 0 None, 2 not restated;
  * out: 7 reals per pair (world1, world2, normal, depth). */
 void orc2_contact(uint64_t n, const uint32_t* type1, const real* param1, const real* pose1, const uint32_t* type2, const real* param2,
-                  const real* pose2, const real* poly_points, real prediction, uint8_t* found, real* out, uint32_t* panics);
+                  const real* pose2, const real* poly_points, const real* poly_normals, real prediction, uint8_t* found, real* out,
+                  uint32_t* panics);
 
 #ifdef __cplusplus
 }

@@ -252,7 +252,7 @@ class Oracle:
     def trimesh(self, verts, tris):
         return OracleTriMesh(self, verts, tris)
 
-    def contact2d(self, type1, param1, pose1, type2, param2, pose2, poly_points=None, prediction=0.0):
+    def contact2d(self, type1, param1, pose1, type2, param2, pose2, poly_points=None, prediction=0.0, poly_normals=None):
         """ncollide2d ``query::contact`` for n pairs (oracle/dim2.cpp).  Returns (found u8 [1 Some, 0 None, 2 not restated],
         out[n,7] = world1, world2, normal, depth, panics)."""
         dt = self.dtype
@@ -265,8 +265,9 @@ class Oracle:
         out = np.zeros((n, 7), dtype=dt)
         panics = C.c_uint32(0)
         vp = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
-        self.lib.orc2_contact(C.c_uint64(n), vp(t1), vp(p1), vp(m1), vp(t2), vp(p2), vp(m2), vp(pts), self.creal(prediction), vp(found), vp(out),
-                              C.byref(panics))
+        nrm = np.ascontiguousarray(poly_normals, dtype=dt).reshape(-1, 2) if poly_normals is not None else None
+        self.lib.orc2_contact(C.c_uint64(n), vp(t1), vp(p1), vp(m1), vp(t2), vp(p2), vp(m2), vp(pts), vp(nrm) if nrm is not None else None,
+                              self.creal(prediction), vp(found), vp(out), C.byref(panics))
         return found, out, panics.value
 
     def broad_phase_persistent(self, margin):

@@ -13,13 +13,11 @@ F = np.float32
 
 
 def random_pairs(n, seed, kinds=(0, 1, 2), spread=1.2):
-    """n random pairs; returns (t1, p1, m1, t2, p2, m2, points).  Ball x polygon is avoided (not built)."""
+    """n random pairs; returns (t1, p1, m1, t2, p2, m2, points, normals)."""
     rng = np.random.default_rng(seed)
     sh = dim2.Shapes2D()
     t1 = rng.choice(kinds, size=n)
     t2 = rng.choice(kinds, size=n)
-    clash = ((t1 == 0) & (t2 == 2)) | ((t1 == 2) & (t2 == 0))
-    t2[clash] = 1
     for t in np.concatenate([t1, t2]):
         if t == 0:
             sh.ball(rng.uniform(0.2, 0.6))
@@ -31,7 +29,7 @@ def random_pairs(n, seed, kinds=(0, 1, 2), spread=1.2):
             ang += np.arange(k) * 1e-3  # no coincident vertices
             a, b = rng.uniform(0.25, 0.6, size=2)
             sh.polygon(np.stack([a * np.cos(ang), b * np.sin(ang)], axis=1))
-    typ, par, pts = sh.arrays()
+    typ, par, pts, nrm = sh.arrays()
     c1 = rng.uniform(-5, 5, size=(n, 2))
     c2 = c1 + rng.uniform(-spread, spread, size=(n, 2))
     degenerate = rng.random(n) < 0.03
@@ -40,7 +38,7 @@ def random_pairs(n, seed, kinds=(0, 1, 2), spread=1.2):
     axis_aligned = rng.random(n) < 0.2
     a1[axis_aligned] = 0.0
     a2[axis_aligned] = rng.choice([0.0, np.pi / 2], size=int(axis_aligned.sum()))
-    return typ[:n], par[:n], dim2.isometry2(c1, a1), typ[n:], par[n:], dim2.isometry2(c2, a2), pts
+    return typ[:n], par[:n], dim2.isometry2(c1, a1), typ[n:], par[n:], dim2.isometry2(c2, a2), pts, nrm
 
 
 # ---- CPU: the oracle on the reference's known-answer tests ---------------------------------------------------------------------
@@ -117,8 +115,8 @@ def _sat_signed_distance(A, B):
 
 def test_oracle_against_separating_axes(oracle64):
     """ORACLE check (f64): depth of contact_support_map_support_map == the separating-axis answer for convex polygons / cuboids."""
-    t1, p1, m1, t2, p2, m2, pts = random_pairs(1500, 5, kinds=(1, 2))
-    found, out, panics = oracle64.contact2d(t1, p1, m1, t2, p2, m2, pts, prediction=0.3)
+    t1, p1, m1, t2, p2, m2, pts, nrm = random_pairs(1500, 5, kinds=(1, 2))
+    found, out, panics = oracle64.contact2d(t1, p1, m1, t2, p2, m2, pts, prediction=0.3, poly_normals=nrm)
     assert panics == 0 and found.max() <= 1
     checked = 0
     for k in range(len(t1)):
@@ -131,6 +129,44 @@ def test_oracle_against_separating_axes(oracle64):
             assert abs(np.hypot(out[k, 4], out[k, 5]) - 1) < 1e-6
             checked += 1
     assert checked > 500
+
+
+def test_oracle_ball_polygon_against_point_distance(oracle64):
+    """ORACLE check (f64): contact_ball_convex_polyhedron with a ConvexPolygon (GJK / EPA projection of the centre) against the
+    distance from the centre to the polygon computed edge by edge in numpy."""
+    t1, p1, m1, t2, p2, m2, pts, nrm = random_pairs(1200, 8, kinds=(0, 2), spread=0.9)
+    keep = (t1 == 0) & (t2 == 2)
+    t1, p1, m1, t2, p2, m2 = t1[keep], p1[keep], m1[keep], t2[keep], p2[keep], m2[keep]
+    found, out, panics = oracle64.contact2d(t1, p1, m1, t2, p2, m2, pts, prediction=0.1, poly_normals=nrm)
+    assert panics == 0
+    checked = inside_seen = 0
+    for k in range(len(t1)):
+        P = _world_polygon(2, p2[k], m2[k], pts)
+        c, r = m1[k, :2].astype(np.float64), float(p1[k, 0])
+        a, b = P, np.roll(P, -1, axis=0)
+        ab = b - a
+        t = np.clip(((c - a) * ab).sum(axis=1) / (ab * ab).sum(axis=1), 0, 1)
+        dist = np.linalg.norm(a + ab * t[:, None] - c, axis=1).min()
+        inside = bool(np.all(ab[:, 0] * (c - a)[:, 1] - ab[:, 1] * (c - a)[:, 0] >= 0))
+        depth = r + dist if inside else r - dist
+        if depth < -0.1 - 1e-6:
+            assert not found[k]
+        elif depth > -0.1 + 1e-6 and dist > 1e-6:
+            assert found[k], (k, depth)
+            assert abs(out[k, 6] - depth) < 1e-5, (k, out[k, 6], depth)
+            checked += 1
+            inside_seen += inside
+    assert checked > 200 and inside_seen > 20
+
+
+def test_polygon_try_new_mirror():
+    """Shapes2D.polygon mirrors ConvexPolygon::try_new: unit normals per edge, vertices between collinear edges removed."""
+    sh = dim2.Shapes2D().polygon([[0, 0], [1, 0], [2, 0], [2, 2], [0, 2]])  # (1, 0) lies on the edge (0,0)-(2,0)
+    typ, par, pts, nrm = sh.arrays()
+    assert par[0, 1] == 4 and pts[:4].tolist() == [[0, 0], [2, 0], [2, 2], [0, 2]]
+    assert np.allclose(nrm[:4], [[0, -1], [1, 0], [0, 1], [-1, 0]])
+    with pytest.raises(ValueError):
+        dim2.Shapes2D().polygon([[0, 0], [0, 0], [1, 1]])
 
 
 # ---- GPU: device vs oracle -----------------------------------------------------------------------------------------------------
@@ -157,11 +193,12 @@ def test_device_kats(ctx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed,kinds,prediction", [(1, (0, 1, 2), 0.0), (2, (1, 2), 0.02), (3, (0, 1), 0.3), (4, (2,), 0.05), (6, (1,), 0.0)])
+@pytest.mark.parametrize("seed,kinds,prediction", [(1, (0, 1, 2), 0.0), (2, (1, 2), 0.02), (3, (0, 1), 0.3), (4, (2,), 0.05), (6, (1,), 0.0),
+                                                   (7, (0, 2), 0.05)])
 def test_device_contact_matches_oracle(ctx, oracle, seed, kinds, prediction):
-    t1, p1, m1, t2, p2, m2, pts = random_pairs(60000, seed, kinds)
-    found, out, info = dim2.contact(ctx, t1, p1, m1, t2, p2, m2, pts, prediction)
-    ofound, oout, opanics = oracle.contact2d(t1, p1, m1, t2, p2, m2, pts, prediction)
+    t1, p1, m1, t2, p2, m2, pts, nrm = random_pairs(60000, seed, kinds)
+    found, out, info = dim2.contact(ctx, t1, p1, m1, t2, p2, m2, pts, prediction, poly_normals=nrm)
+    ofound, oout, opanics = oracle.contact2d(t1, p1, m1, t2, p2, m2, pts, prediction, poly_normals=nrm)
     assert info["epa_overflow"] == 0 and info["ref_panics"] == opanics
     assert np.array_equal(found, ofound.astype(bool)), f"{(found != ofound.astype(bool)).sum()} Some / None answers differ"
     hit = found
@@ -172,12 +209,14 @@ def test_device_contact_matches_oracle(ctx, oracle, seed, kinds, prediction):
 
 
 @pytest.mark.gpu
-def test_device_refuses_what_is_not_built(ctx):
+def test_device_refuses_bad_input(ctx):
     from ncollide_b200._ffi import NcbError
 
     sh = dim2.Shapes2D().ball(0.5).polygon([[0, 0], [1, 0], [0, 1]])
-    typ, par, pts = sh.arrays()
-    with pytest.raises(NcbError):
+    typ, par, pts, nrm = sh.arrays()
+    with pytest.raises(NcbError):  # a ball meets a polygon, but the polygon's normals were not given
         dim2.contact(ctx, typ[:1], par[:1], [[0, 0, 1, 0]], typ[1:], par[1:], [[0.2, 0, 1, 0]], pts)
+    found, out, _ = dim2.contact(ctx, typ[:1], par[:1], [[0.3, 0.3, 1, 0]], typ[1:], par[1:], [[0.0, 0, 1, 0]], pts, poly_normals=nrm)
+    assert found[0] and out[0, 6] > 0.5  # the centre is inside the triangle
     with pytest.raises(NcbError):
         dim2.contact(ctx, [7], [[1, 0, 0, 0]], [[0, 0, 1, 0]], [1], [[1, 1, 0, 0]], [[0.2, 0, 1, 0]])
