@@ -426,6 +426,32 @@ int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const f
                   const float* param2, const float* pose2, const float* poly_points, const float* poly_normals, uint32_t n_poly_points,
                   float prediction, uint8_t* found, float* out, uint32_t* ref_panics, uint32_t* epa_overflow);
 
+/* A fresh ncollide2d CollisionWorld of balls, cuboids and convex polygons (host SoA): pos = translation x y, rot = UnitComplex re im,
+ * shape_param as in ncb2d_contact, groups = 3 words per object or NULL, query_limit / ang_pred = GeometricQueryType::Contacts(linear,
+ * angular); poly_normals is required when the world holds polygons. */
+typedef struct ncb2d_objects {
+    uint32_t n;
+    const float* pos;
+    const float* rot;
+    const uint32_t* shape_type;
+    const float* shape_param;
+    const uint32_t* groups;
+    const float* query_limit;
+    const float* ang_pred;
+    const float* poly_points;
+    const float* poly_normals;
+    uint32_t n_poly_points;
+} ncb2d_objects;
+/* ncollide2d CollisionWorld::update for such a world (pipeline/world.rs:104-119): fat AABBs -> broad-phase pairs (object1 = larger handle,
+ * like the 3-D path) -> contact manifolds from BallBall / BallConvexPolyhedron / ConvexPolyhedronConvexPolyhedron generators with 2-D
+ * features and clipping (shape/convex_polygonal_feature2.rs).  Output: pairs (2 words each, emission order), manifold_start / _count per
+ * pair, contacts (7 floats: world1, world2, normal, depth) and features (2 words per contact: kind << 30 | id, kind 1 = face, 2 = vertex;
+ * a ball's feature is face 0).  diag (optional, 4 words): reference panics, EPA capacity overflows, manifolds beyond 4 contacts,
+ * traversal-stack overflows — all expected 0.  Returns 1 when an output was truncated (the needed counts are in n_pairs / n_contacts). */
+int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* objs, float margin, uint32_t* pairs, uint32_t cap_pairs, uint32_t* manifold_start,
+                       uint8_t* manifold_count, float* contacts, uint32_t* features, uint32_t cap_contacts, uint32_t* n_pairs,
+                       uint32_t* n_contacts, uint32_t* diag);
+
 #ifdef __cplusplus
 }
 #endif

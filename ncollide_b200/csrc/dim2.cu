@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 #include "ncb_internal.h"
 #include "vec.cuh"  // NCB_EPS / NCB_FMAX only: the 2-D types are this file's own
 
@@ -460,7 +461,10 @@ __device__ bool ball_ball(W2 c1, float r1, W2 c2, float r2, float prediction, Hi
 }
 
 // AABB::project_point_with_feature for the cuboid's box, then contact_ball_convex_polyhedron
-__device__ bool ball_cuboid(W2 center, float radius, const Operand2& box, float prediction, Hit2& h) {
+#define FEAT2_UNKNOWN 0xffffffffu
+#define FEAT2_FACE 0x40000000u    // | face index
+#define FEAT2_VERTEX 0x80000000u  // | vertex index
+__device__ bool ball_cuboid(W2 center, float radius, const Operand2& box, float prediction, Hit2& h, uint32_t* feature = nullptr) {
     float he[2] = {box.a, box.b};
     W2 l = to_local(box.m, center);
     float lp[2] = {l.x, l.y}, below[2], above[2], shift[2];
@@ -485,6 +489,23 @@ __device__ bool ball_cuboid(W2 center, float radius, const Operand2& box, float 
     }
     lp[0] += shift[0], lp[1] += shift[1];
     W2 world2 = to_world(box.m, w2(lp[0], lp[1]));
+    if (feature) {  // AABB::project_point_with_feature (point_aabb.rs:83-134, dim2): the manifold generator reports it with the contact
+        int z = (shift[0] == 0.f) + (shift[1] == 0.f), moved = shift[0] != 0.f ? 0 : 1;
+        uint32_t f = FEAT2_UNKNOWN;
+        if (z == 2) {
+            for (int i = 0; i < 2 && f == FEAT2_UNKNOWN; ++i) {
+                if (lp[i] > he[i] - NCB_EPS)
+                    f = FEAT2_FACE | (uint32_t)i;
+                else if (lp[i] <= -he[i] + NCB_EPS)
+                    f = FEAT2_FACE | (uint32_t)(i + 2);
+            }
+        } else if (z == 1) {
+            f = FEAT2_FACE | (uint32_t)(lp[moved] < (-he[moved] + he[moved]) * 0.5f ? moved + 2 : moved);
+        } else {
+            f = FEAT2_VERTEX | (lp[0] < 0.f ? 1u : 0u) | (lp[1] < 0.f ? 2u : 0u);
+        }
+        *feature = f;
+    }
     W2 dpt = world2 - center, dir, normal;
     float dist, depth;
     if (unit_get(dpt, NCB_EPS, dir, dist)) {
@@ -521,7 +542,8 @@ __device__ bool ball_cuboid(W2 center, float radius, const Operand2& box, float 
 
 // ConvexPolygon::project_point_with_feature + contact_ball_convex_polyhedron: the ball centre is projected on the polygon with
 // GJK against the constant origin (EPA when it lies inside), in the frame translated by -centre
-__device__ bool ball_polygon(W2 center, float radius, const Operand2& poly, float prediction, float cos_one_degree, Hit2& h, int& epa_status) {
+__device__ bool ball_polygon(W2 center, float radius, const Operand2& poly, float prediction, float cos_one_degree, Hit2& h, int& epa_status,
+                             uint32_t* feature = nullptr) {
     Operand2 g = poly, origin;
     g.m.t = (-center) + poly.m.t;
     origin.kind = D2_ORIGIN, origin.a = origin.b = 0.f, origin.pts = origin.nrm = nullptr, origin.npts = 0;
@@ -558,6 +580,7 @@ __device__ bool ball_polygon(W2 center, float radius, const Operand2& poly, floa
             }
         }
     }
+    if (feature) *feature = face >= 0 ? (FEAT2_FACE | (uint32_t)face) : vert >= 0 ? (FEAT2_VERTEX | (uint32_t)vert) : FEAT2_UNKNOWN;
     W2 dpt = world2 - center, dir, normal;
     float dist, depth;
     if (unit_get(dpt, NCB_EPS, dir, dist)) {
@@ -578,6 +601,303 @@ __device__ bool ball_polygon(W2 center, float radius, const Operand2& poly, floa
     if (!(depth >= -prediction)) return false;
     h.w1 = center + normal * radius, h.w2 = world2, h.n = normal, h.depth = depth;
     return true;
+}
+
+// =============================================================================================================================
+// 2-D world update: fat AABBs, the broad phase of the 3-D path on boxes with z = 0 (the pair set is the set of intersecting fat
+// boxes whatever the tree), and the contact-manifold generators of the 2-D crate:
+//   AABBs        bounding_volume/aabb_ball.rs:8-13, aabb_cuboid.rs:9-14, aabb_convex_polygon.rs + aabb_utils.rs:59-79,
+//                pipeline/object/collision_object.rs:89-93 (query limit), dbvt_broad_phase.rs:341 (margin)
+//   generators   ball_ball_manifold_generator.rs:29-66, ball_convex_polyhedron_manifold_generator.rs:29-116,
+//                convex_polyhedron_convex_polyhedron_manifold_generator.rs:81-165 with shape/convex_polygonal_feature2.rs:95-236,
+//                shape/cuboid.rs:186-226,279-350 (dim2), shape/convex_polygon.rs:123-184
+//   manifold     query/contact/contact_manifold.rs:165-236 (fresh manifold, DistanceBased(0.02))
+// =============================================================================================================================
+__device__ __forceinline__ Operand2 load_operand(uint32_t t, float4 p, float4 m, const float* poly, const float* poly_nrm);
+struct Edge2 {  // ConvexPolygonalFeature in 2-D: at most two vertices
+    W2 v[2];
+    uint32_t vid[2], fid;
+    W2 normal;
+    int nv;
+    bool has_normal;
+};
+__device__ __forceinline__ void edge_clear(Edge2& e) { e.nv = 0, e.has_normal = false, e.fid = FEAT2_UNKNOWN; }
+__device__ __forceinline__ void edge_to_world(Edge2& e, const Pose2& m) {
+    e.v[0] = to_world(m, e.v[0]), e.v[1] = to_world(m, e.v[1]);
+    if (e.has_normal) e.normal = rotate(m, e.normal);
+}
+__device__ void box_face(const Operand2& g, int i, Edge2& e) {
+    edge_clear(e);
+    int i1 = i < 2 ? i : i - 2, i2 = (i1 + 1) % 2;
+    float sign = i < 2 ? 1.f : -1.f;
+    float c[2] = {g.a, g.b};
+    c[i1] *= sign;
+    c[i2] *= (i1 == 0) ? -sign : sign;
+    W2 p1 = w2(c[0], c[1]);
+    c[i2] = -c[i2];
+    W2 p2 = w2(c[0], c[1]);
+    uint32_t id1 = sign < 0.f ? (1u << i1) : 0u, id2 = id1;
+    if ((i2 == 0 ? p1.x : p1.y) < 0.f)
+        id1 |= 1u << i2;
+    else
+        id2 |= 1u << i2;
+    e.v[0] = p1, e.vid[0] = FEAT2_VERTEX | id1;
+    e.v[1] = p2, e.vid[1] = FEAT2_VERTEX | id2;
+    e.nv = 2;
+    e.normal = i1 == 0 ? w2(sign, 0.f) : w2(0.f, sign), e.has_normal = true;
+    e.fid = FEAT2_FACE | (uint32_t)i;
+}
+__device__ void ngon_face(const Operand2& g, uint32_t ia, Edge2& e) {
+    edge_clear(e);
+    uint32_t ib = (ia + 1) % g.npts;
+    e.v[0] = w2(__ldg(g.pts + 2 * ia), __ldg(g.pts + 2 * ia + 1)), e.vid[0] = FEAT2_VERTEX | ia;
+    e.v[1] = w2(__ldg(g.pts + 2 * ib), __ldg(g.pts + 2 * ib + 1)), e.vid[1] = FEAT2_VERTEX | ib;
+    e.nv = 2;
+    e.normal = w2(__ldg(g.nrm + 2 * ia), __ldg(g.nrm + 2 * ia + 1)), e.has_normal = true;
+    e.fid = FEAT2_FACE | ia;
+}
+__device__ void face_toward(const Operand2& g, W2 dir, Edge2& e) {
+    W2 ld = unrotate(g.m, dir);
+    if (g.kind == D2_CUBOID) {
+        int iamax = fabsf(ld.y) > fabsf(ld.x) ? 1 : 0;
+        box_face(g, (iamax == 0 ? ld.x : ld.y) > 0.f ? iamax : iamax + 2, e);
+    } else {
+        uint32_t arg = 0;
+        float best = __ldg(g.nrm) * ld.x + __ldg(g.nrm + 1) * ld.y;
+        for (uint32_t i = 1; i < g.npts; ++i) {
+            float d = __ldg(g.nrm + 2 * i) * ld.x + __ldg(g.nrm + 2 * i + 1) * ld.y;
+            if (d > best) best = d, arg = i;
+        }
+        ngon_face(g, arg, e);
+    }
+    edge_to_world(e, g.m);
+}
+__device__ void feature_toward(const Operand2& g, W2 dir, float cang, Edge2& e) {
+    if (g.kind != D2_CUBOID) {  // ConvexPolygon::support_feature_toward is its support face
+        face_toward(g, dir, e);
+        return;
+    }
+    W2 ld = unrotate(g.m, dir);
+    float l[2] = {ld.x, ld.y}, sp[2] = {g.a, g.b};
+    edge_clear(e);
+    uint32_t id = 0;
+    for (int i = 0; i < 2; ++i) {
+        float sign = signbit(l[i]) ? -1.f : 1.f;  // f32::signum (-0.0 -> -1.0); NaN directions do not reach this point
+        if (sign * l[i] >= cang) {
+            box_face(g, sign > 0.f ? i : i + 2, e);
+            edge_to_world(e, g.m);
+            return;
+        }
+        if (sign < 0.f) id |= 1u << i;
+        sp[i] *= sign;
+    }
+    e.v[0] = to_world(g.m, w2(sp[0], sp[1])), e.vid[0] = FEAT2_VERTEX | id, e.nv = 1;
+    e.fid = FEAT2_VERTEX | id;
+}
+
+#define MAN2_MAX 4
+struct Manifold2d {
+    Hit2 c[MAN2_MAX];
+    uint32_t f1[MAN2_MAX], f2[MAN2_MAX];
+    W2 track[MAN2_MAX];
+    int n;
+    bool overflow;
+};
+__device__ void man_push(Manifold2d& mf, const Hit2& h, uint32_t f1, uint32_t f2, W2 tracking) {
+    int hit = mf.n;
+    float lim = 0.02f * 0.02f;
+    for (int i = 0; i < mf.n; ++i) {
+        float d = nsq(tracking - mf.track[i]);
+        if (d < lim) lim = d, hit = i;
+    }
+    if (hit == mf.n) {
+        if (mf.n == MAN2_MAX) {
+            mf.overflow = true;
+            return;
+        }
+        mf.n++;
+    } else if (!(h.depth > mf.c[hit].depth)) {
+        return;  // the contact already there is deeper
+    }
+    mf.c[hit] = h, mf.f1[hit] = f1, mf.f2[hit] = f2, mf.track[hit] = tracking;
+}
+// ConvexPolygonalFeature::clip in 2-D: the overlap of the two segments along the direction orthogonal to the normal
+__device__ void clip_edges(const Edge2& a, const Edge2& b, W2 normal, float prediction, const Pose2& m1, Manifold2d& mf, int& n_new) {
+    if (a.nv <= 1 || b.nv <= 1) return;
+    W2 ortho = w2(-normal.y, normal.x);
+    W2 a0 = a.v[0], a1 = a.v[1], b0 = b.v[0], b1 = b.v[1];
+    float ra0 = dot(a0 - a0, ortho), ra1 = dot(a1 - a0, ortho), rb0 = dot(b0 - a0, ortho), rb1 = dot(b1 - a0, ortho);
+    uint32_t fa0 = a.vid[0], fa1 = a.vid[1], fb0 = b.vid[0], fb1 = b.vid[1];
+    if (ra1 < ra0) {
+        float t = ra0;
+        ra0 = ra1, ra1 = t;
+        uint32_t u = fa0;
+        fa0 = fa1, fa1 = u;
+        W2 p = a0;
+        a0 = a1, a1 = p;
+    }
+    if (rb1 < rb0) {
+        float t = rb0;
+        rb0 = rb1, rb1 = t;
+        uint32_t u = fb0;
+        fb0 = fb1, fb1 = u;
+        W2 p = b0;
+        b0 = b1, b1 = p;
+    }
+    if (rb0 > ra1 || ra0 > rb1) return;
+    float la = ra1 - ra0, lb = rb1 - rb0;
+    // both candidates are found first and pushed afterwards, in the reference's order
+    Hit2 cand[2];
+    uint32_t cf1[2], cf2[2];
+    for (int side = 0; side < 2; ++side) {
+        W2 w1, w2_;
+        bool on_a = side == 0 ? rb0 > ra0 : rb1 < ra1;  // the end point of b's range falls inside a's range: project it on a
+        if (on_a) {
+            float k = ((side == 0 ? rb0 : rb1) - ra0) / la;
+            w1 = w2(a0.x * (1.f - k) + a1.x * k, a0.y * (1.f - k) + a1.y * k);
+            w2_ = side == 0 ? b0 : b1;
+            cf1[side] = a.fid, cf2[side] = side == 0 ? fb0 : fb1;
+        } else {
+            float k = ((side == 0 ? ra0 : ra1) - rb0) / lb;
+            w1 = side == 0 ? a0 : a1;
+            w2_ = w2(b0.x * (1.f - k) + b1.x * k, b0.y * (1.f - k) + b1.y * k);
+            cf1[side] = side == 0 ? fa0 : fa1, cf2[side] = b.fid;
+        }
+        cand[side].w1 = w1, cand[side].w2 = w2_, cand[side].n = normal, cand[side].depth = -dot(normal, w2_ - w1);
+    }
+    for (int side = 0; side < 2; ++side)
+        if (-cand[side].depth <= prediction) {
+            n_new++;
+            if (cf1[side] != FEAT2_UNKNOWN && cf2[side] != FEAT2_UNKNOWN) man_push(mf, cand[side], cf1[side], cf2[side], to_local(m1, cand[side].w1));
+        }
+}
+
+struct World2Args {
+    uint32_t n;
+    const float2 *pos, *rot;
+    const uint32_t* type;
+    const float4* param;
+    const float *qlimit, *cos_ang;
+    const float *poly, *poly_nrm;
+    float margin, cos_one_degree;
+    float4 *aabb_lo, *aabb_hi;
+    // narrow phase
+    const uint2* pairs;
+    const uint32_t* n_pairs_dev;
+    uint32_t cap_pairs, cap_contacts;
+    uint32_t* manifold_start;
+    uint8_t* manifold_count;
+    float* contacts;     // 7 floats per contact
+    uint32_t* features;  // 2 words per contact
+    uint32_t* counters;  // [0] contacts allocated, [1] reference panics, [2] EPA overflows, [3] manifold overflows
+};
+__device__ __forceinline__ Operand2 world_operand(const World2Args& A, uint32_t i) {
+    float2 t = __ldg(&A.pos[i]), r = __ldg(&A.rot[i]);
+    return load_operand(__ldg(&A.type[i]), __ldg(&A.param[i]), make_float4(t.x, t.y, r.x, r.y), A.poly, A.poly_nrm);
+}
+__global__ void __launch_bounds__(256) k_aabb2d(World2Args A) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    Operand2 g = world_operand(A, i);
+    W2 lo, hi;
+    if (g.kind == D2_BALL) {
+        lo = w2(g.m.t.x + (-g.a), g.m.t.y + (-g.a)), hi = w2(g.m.t.x + g.a, g.m.t.y + g.a);
+    } else if (g.kind == D2_CUBOID) {
+        float are = fabsf(g.m.re), aim = fabsf(g.m.im);
+        W2 w = w2(are * g.a + aim * g.b, aim * g.a + are * g.b);
+        lo = g.m.t - w, hi = g.m.t + w;
+    } else {
+        W2 p = to_world(g.m, w2(__ldg(g.pts), __ldg(g.pts + 1)));
+        lo = hi = p;
+        for (uint32_t k = 1; k < g.npts; ++k) {
+            p = to_world(g.m, w2(__ldg(g.pts + 2 * k), __ldg(g.pts + 2 * k + 1)));
+            lo = w2(fminf(lo.x, p.x), fminf(lo.y, p.y)), hi = w2(fmaxf(hi.x, p.x), fmaxf(hi.y, p.y));
+        }
+    }
+    float ql = __ldg(&A.qlimit[i]), mg = A.margin;
+    // the 3-D broad phase reads float4 boxes; the w of the upper corner carries the shape type (ball 0, cuboid 1, polygon = the hull code 2)
+    A.aabb_lo[i] = make_float4((lo.x + (-ql)) + (-mg), (lo.y + (-ql)) + (-mg), 0.f, 0.f);
+    A.aabb_hi[i] = make_float4((hi.x + ql) + mg, (hi.y + ql) + mg, 0.f, __uint_as_float(g.kind));
+}
+__global__ void __launch_bounds__(64) k_narrow2d(World2Args A) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t np = min(*A.n_pairs_dev, A.cap_pairs);
+    if (p >= np) return;
+    uint2 pr = __ldg(&A.pairs[p]);
+    Operand2 g1 = world_operand(A, pr.x), g2 = world_operand(A, pr.y);
+    float linear = __ldg(&A.qlimit[pr.x]) + __ldg(&A.qlimit[pr.y]);
+    Manifold2d mf;
+    mf.n = 0, mf.overflow = false;
+    const uint32_t FACE0 = FEAT2_FACE | 0u;
+    Hit2 h;
+    if (g1.kind == D2_BALL && g2.kind == D2_BALL) {
+        if (ball_ball(g1.m.t, g1.a, g2.m.t, g2.a, linear, h)) man_push(mf, h, FACE0, FACE0, w2(0.f, 0.f));
+    } else if (g1.kind == D2_BALL || g2.kind == D2_BALL) {
+        const bool flip = g1.kind != D2_BALL;
+        const Operand2& ball = flip ? g2 : g1;
+        const Operand2& other = flip ? g1 : g2;
+        uint32_t f2 = FEAT2_UNKNOWN;
+        int q = 1;
+        bool ok = other.kind == D2_CUBOID ? ball_cuboid(ball.m.t, ball.a, other, linear, h, &f2)
+                                          : ball_polygon(ball.m.t, ball.a, other, linear, A.cos_one_degree, h, q, &f2);
+        if (q == -1) atomicAdd(&A.counters[1], 1u);
+        if (q == -2) atomicAdd(&A.counters[2], 1u);
+        if (ok) {
+            if (f2 == FEAT2_UNKNOWN) {
+                atomicAdd(&A.counters[1], 1u);  // "Feature id cannot be unknown."
+            } else if (!flip) {
+                man_push(mf, h, FACE0, f2, w2(0.f, 0.f));
+            } else {
+                W2 t = h.w1;
+                h.w1 = h.w2, h.w2 = t, h.n = -h.n;
+                man_push(mf, h, f2, FACE0, w2(0.f, 0.f));
+            }
+        }
+    } else {
+        W2 d0;
+        if (!unit(g2.m.t - g1.m.t, NCB_EPS, d0)) d0 = w2(1.f, 0.f);
+        Tri2 s;
+        for (int i = 0; i < 3; ++i) s.v[i].p = s.v[i].o1 = s.v[i].o2 = w2(0.f, 0.f), s.old_idx[i] = i;
+        s.bary[0] = s.bary[1] = s.old_bary[0] = s.old_bary[1] = 0.f;
+        s.dim = s.old_dim = 0;
+        s.v[0] = minkowski(g1, g2, d0);
+        W2 p1, p2, n;
+        int r = gjk2(g1, g2, linear, s, p1, p2, n);
+        bool ok = r == G_POINTS;
+        if (r == G_INSIDE) {
+            Poly2 e;
+            int q = epa2(g1, g2, s, e, p1, p2, n);
+            ok = q == 1;
+            if (q == -1) atomicAdd(&A.counters[1], 1u);
+            if (q == -2) atomicAdd(&A.counters[2], 1u);
+        }
+        if (ok) {
+            h.w1 = p1, h.w2 = p2, h.n = n, h.depth = -dot(n, p2 - p1);
+            Edge2 fa, fb;
+            if (h.depth > 0.f) {
+                face_toward(g1, n, fa);
+                face_toward(g2, -n, fb);
+            } else {
+                feature_toward(g1, n, __ldg(&A.cos_ang[pr.x]), fa);
+                feature_toward(g2, -n, __ldg(&A.cos_ang[pr.y]), fb);
+            }
+            int n_new = 0;
+            clip_edges(fa, fb, n, linear, g1.m, mf, n_new);
+            if (n_new == 0 && fa.fid != FEAT2_UNKNOWN && fb.fid != FEAT2_UNKNOWN) man_push(mf, h, fa.fid, fb.fid, to_local(g1.m, h.w1));
+        }
+    }
+    if (mf.overflow) atomicAdd(&A.counters[3], 1u);
+    uint32_t start = mf.n ? atomicAdd(&A.counters[0], (uint32_t)mf.n) : 0u;
+    A.manifold_start[p] = start;
+    A.manifold_count[p] = (uint8_t)mf.n;
+    for (int k = 0; k < mf.n; ++k) {
+        uint32_t dst = start + k;
+        if (dst >= A.cap_contacts) break;
+        float* o = A.contacts + 7 * (size_t)dst;
+        const Hit2& c = mf.c[k];
+        o[0] = c.w1.x, o[1] = c.w1.y, o[2] = c.w2.x, o[3] = c.w2.y, o[4] = c.n.x, o[5] = c.n.y, o[6] = c.depth;
+        A.features[2 * (size_t)dst] = mf.f1[k], A.features[2 * (size_t)dst + 1] = mf.f2[k];
+    }
 }
 
 struct Args2 {
@@ -741,6 +1061,117 @@ int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const f
     if (ref_panics) *ref_panics = cnt[0];
     if (epa_overflow) *epa_overflow = cnt[1];
     return NCB_OK;
+}
+
+// CollisionWorld::update of ncollide2d for a fresh world of balls, cuboids and convex polygons (pipeline/world.rs:104-119 with the 2-D
+// generators above).  Host buffers in and out.  The broad phase is the 3-D path's LBVH on boxes with z = 0: it uses the context's
+// broad-phase scratch, so do not interleave it with a stepping world (ncb_sim_*) of the same context.
+int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint32_t* pairs, uint32_t cap_pairs, uint32_t* manifold_start,
+                       uint8_t* manifold_count, float* contacts, uint32_t* features, uint32_t cap_contacts, uint32_t* n_pairs,
+                       uint32_t* n_contacts, uint32_t* diag) {
+    if (!ctx || !o || !n_pairs || !n_contacts) return NCB_ERR_ARG;
+    *n_pairs = *n_contacts = 0;
+    if (diag) diag[0] = diag[1] = diag[2] = diag[3] = 0;
+    uint32_t n = o->n;
+    if (n == 0) return NCB_OK;
+    if (!o->pos || !o->rot || !o->shape_type || !o->shape_param || !o->query_limit || !o->ang_pred) return NCB_ERR_ARG;
+    bool any_poly = false;
+    for (uint32_t i = 0; i < n; ++i) {  // validation before device state is touched
+        uint32_t t = o->shape_type[i];
+        if (t > 2) {
+            ctx->err = "ncb2d_world_update: unknown 2-D shape type";
+            return NCB_ERR_UNSUPPORTED;
+        }
+        if (t == 2) {
+            const float* p = o->shape_param + 4 * (size_t)i;
+            any_poly = true;
+            if (!o->poly_points || !o->poly_normals || p[1] < 1.f || p[0] < 0.f || (uint64_t)p[0] + (uint64_t)p[1] > o->n_poly_points) {
+                ctx->err = "ncb2d_world_update: polygon point range outside poly_points / normals missing";
+                return NCB_ERR_ARG;
+            }
+        }
+    }
+    CK2(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    DevBuf<float2> d_pos, d_rot;
+    DevBuf<uint32_t> d_type, d_groups, d_start, d_feat, d_cnt;
+    DevBuf<float4> d_param;
+    DevBuf<float> d_ql, d_cang, d_poly, d_nrm, d_contacts;
+    DevBuf<uint8_t> d_count;
+    CK2(d_pos.reserve(n));
+    CK2(d_rot.reserve(n));
+    CK2(d_type.reserve(n));
+    CK2(d_param.reserve(n));
+    CK2(d_ql.reserve(n));
+    CK2(d_cang.reserve(n));
+    CK2(d_cnt.reserve(4));
+    std::vector<float> cang(n);
+    for (uint32_t i = 0; i < n; ++i) cang[i] = cosf(o->ang_pred[i]);  // ContactPrediction / support_feature_toward: angle.cos() with the host libm
+    CK2(cudaMemcpyAsync(d_pos.p, o->pos, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_rot.p, o->rot, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_type.p, o->shape_type, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_param.p, o->shape_param, 16 * (size_t)n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_ql.p, o->query_limit, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_cang.p, cang.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+    if (o->groups) {
+        CK2(d_groups.reserve(3 * (size_t)n));
+        CK2(cudaMemcpyAsync(d_groups.p, o->groups, 12 * (size_t)n, cudaMemcpyHostToDevice, s));
+    }
+    if (any_poly) {
+        CK2(d_poly.reserve(2 * (size_t)o->n_poly_points));
+        CK2(d_nrm.reserve(2 * (size_t)o->n_poly_points));
+        CK2(cudaMemcpyAsync(d_poly.p, o->poly_points, 8 * (size_t)o->n_poly_points, cudaMemcpyHostToDevice, s));
+        CK2(cudaMemcpyAsync(d_nrm.p, o->poly_normals, 8 * (size_t)o->n_poly_points, cudaMemcpyHostToDevice, s));
+    }
+    int r = reserve_broad(ctx, n);
+    if (r) return r;
+    d2::World2Args A;
+    memset(&A, 0, sizeof A);
+    A.n = n;
+    A.pos = d_pos.p, A.rot = d_rot.p, A.type = d_type.p, A.param = d_param.p, A.qlimit = d_ql.p, A.cos_ang = d_cang.p;
+    A.poly = d_poly.p, A.poly_nrm = d_nrm.p;
+    A.margin = margin;
+    A.cos_one_degree = cosf((float)(3.14159265358979323846 / 180.0));
+    A.aabb_lo = ctx->aabb_lo.p, A.aabb_hi = ctx->aabb_hi.p;
+    size_t capp = cap_pairs ? cap_pairs : 1;
+    r = reserve_pairs(ctx, capp);
+    if (r) return r;
+    r = reset_counters(ctx);
+    if (r) return r;
+    d2::k_aabb2d<<<(n + 255) / 256, 256, 0, s>>>(A);
+    CK2(cudaGetLastError());
+    CK2(launch_lbvh_build(ctx, n, nullptr));
+    CK2(launch_pair_search(ctx, n, o->groups ? d_groups.p : nullptr, 0, 0xffffffffu, (uint32_t)capp, -1));
+    // narrow phase over the emitted pairs (count read on the device)
+    size_t capc = cap_contacts ? cap_contacts : 1;
+    CK2(d_start.reserve(capp));
+    CK2(d_count.reserve(capp));
+    CK2(d_contacts.reserve(7 * capc));
+    CK2(d_feat.reserve(2 * capc));
+    CK2(cudaMemsetAsync(d_cnt.p, 0, 16, s));
+    A.pairs = ctx->pairs_raw.p;
+    A.n_pairs_dev = &ctx->counters.p->n_pairs;
+    A.cap_pairs = (uint32_t)capp, A.cap_contacts = (uint32_t)capc;
+    A.manifold_start = d_start.p, A.manifold_count = d_count.p, A.contacts = d_contacts.p, A.features = d_feat.p;
+    A.counters = d_cnt.p;
+    d2::k_narrow2d<<<(uint32_t)((capp + 63) / 64), 64, 0, s>>>(A);
+    CK2(cudaGetLastError());
+    r = read_counters(ctx);
+    if (r) return r;
+    uint32_t cnt[4];
+    CK2(cudaMemcpyAsync(cnt, d_cnt.p, 16, cudaMemcpyDeviceToHost, s));
+    CK2(cudaStreamSynchronize(s));
+    uint32_t np = ctx->last_counters.n_pairs, nc = cnt[0];
+    *n_pairs = np, *n_contacts = nc;
+    if (diag) diag[0] = cnt[1], diag[1] = cnt[2], diag[2] = cnt[3], diag[3] = ctx->last_counters.stack_overflow;
+    uint32_t wp = np < cap_pairs ? np : cap_pairs, wc = nc < cap_contacts ? nc : cap_contacts;
+    if (pairs && wp) CK2(cudaMemcpyAsync(pairs, ctx->pairs_raw.p, 8 * (size_t)wp, cudaMemcpyDeviceToHost, s));
+    if (manifold_start && wp) CK2(cudaMemcpyAsync(manifold_start, d_start.p, 4 * (size_t)wp, cudaMemcpyDeviceToHost, s));
+    if (manifold_count && wp) CK2(cudaMemcpyAsync(manifold_count, d_count.p, wp, cudaMemcpyDeviceToHost, s));
+    if (contacts && wc) CK2(cudaMemcpyAsync(contacts, d_contacts.p, 28 * (size_t)wc, cudaMemcpyDeviceToHost, s));
+    if (features && wc) CK2(cudaMemcpyAsync(features, d_feat.p, 8 * (size_t)wc, cudaMemcpyDeviceToHost, s));
+    CK2(cudaStreamSynchronize(s));
+    return (np > cap_pairs || nc > cap_contacts) ? 1 : NCB_OK;
 }
 
 }  // extern "C"

@@ -96,3 +96,53 @@ def contact(ctx, type1, param1, pose1, type2, param2, pose2, poly_points=None, p
                                     C.c_uint32(0 if pts is None else len(pts)), C.c_float(prediction), ptr(found), ptr(out), C.byref(panics),
                                     C.byref(over)), "ncb2d_contact")
     return found.astype(bool), out, {"ref_panics": panics.value, "epa_overflow": over.value}
+
+
+class World2D:
+    """A fresh ``ncollide2d::CollisionWorld``: objects = (shape, Isometry2, CollisionGroups, GeometricQueryType::Contacts(linear, angular)).
+    ``shapes`` is a Shapes2D batch (one entry per object); ``pos`` [n, 2], ``angle`` [n]."""
+
+    def __init__(self, shapes: Shapes2D, pos, angle, margin=0.02, linear=0.02, angular=0.0, groups=None):
+        self.type, self.param, self.points, self.normals = shapes.arrays()
+        self.n = len(self.type)
+        self.pos = as_f32(pos).reshape(-1, 2)
+        a = np.broadcast_to(np.asarray(angle, dtype=np.float32).reshape(-1), (self.n,))
+        self.rot = np.ascontiguousarray(np.stack([np.cos(a, dtype=np.float32), np.sin(a, dtype=np.float32)], axis=1), dtype=np.float32)
+        self.margin = float(margin)
+        self.query_limit = np.ascontiguousarray(np.broadcast_to(np.asarray(linear, dtype=np.float32).reshape(-1), (self.n,)), dtype=np.float32)
+        self.ang_pred = np.ascontiguousarray(np.broadcast_to(np.asarray(angular, dtype=np.float32).reshape(-1), (self.n,)), dtype=np.float32)
+        self.groups = None if groups is None else as_u32(groups).reshape(-1, 3)
+        if len(self.pos) != self.n:
+            raise ValueError("one position per shape")
+
+
+class _Objects2DC(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("pos", C.c_void_p), ("rot", C.c_void_p), ("shape_type", C.c_void_p), ("shape_param", C.c_void_p),
+                ("groups", C.c_void_p), ("query_limit", C.c_void_p), ("ang_pred", C.c_void_p), ("poly_points", C.c_void_p),
+                ("poly_normals", C.c_void_p), ("n_poly_points", C.c_uint32)]
+
+
+def world_update(ctx, w: World2D):
+    """``CollisionWorld::update`` of a fresh 2-D world (``ncb2d_world_update``).  Returns a dict: pairs [P, 2] (object1 = larger handle),
+    manifold_start / manifold_count [P], contacts [C, 7] (world1, world2, normal, depth), features [C, 2], diag."""
+    o = _Objects2DC()
+    o.n = w.n
+    o.pos, o.rot, o.shape_type, o.shape_param = (a.ctypes.data for a in (w.pos, w.rot, w.type, w.param))
+    o.groups = w.groups.ctypes.data if w.groups is not None else None
+    o.query_limit, o.ang_pred = w.query_limit.ctypes.data, w.ang_pred.ctypes.data
+    o.poly_points, o.poly_normals, o.n_poly_points = w.points.ctypes.data, w.normals.ctypes.data, len(w.points)
+    cap_p, cap_c = max(8 * w.n, 1024), max(8 * w.n, 1024)
+    while True:
+        pairs = np.zeros((cap_p, 2), dtype=np.uint32)
+        start, count = np.zeros(cap_p, dtype=np.uint32), np.zeros(cap_p, dtype=np.uint8)
+        contacts, feats = np.zeros((cap_c, 7), dtype=np.float32), np.zeros((cap_c, 2), dtype=np.uint32)
+        npairs, ncont = C.c_uint32(0), C.c_uint32(0)
+        diag = np.zeros(4, dtype=np.uint32)
+        r = ctx.check(ctx.lib.ncb2d_world_update(ctx.h, C.byref(o), C.c_float(w.margin), ptr(pairs), C.c_uint32(cap_p), ptr(start), ptr(count),
+                                                 ptr(contacts), ptr(feats), C.c_uint32(cap_c), C.byref(npairs), C.byref(ncont), ptr(diag)),
+                      "ncb2d_world_update")
+        if r == 0:
+            P, Cn = npairs.value, ncont.value
+            return {"pairs": pairs[:P], "manifold_start": start[:P], "manifold_count": count[:P], "contacts": contacts[:Cn], "features": feats[:Cn],
+                    "diag": dict(zip(("ref_panics", "epa_overflow", "manifold_overflow", "stack_overflow"), diag.tolist()))}
+        cap_p, cap_c = max(cap_p, npairs.value + 1024), max(cap_c, ncont.value + 1024)

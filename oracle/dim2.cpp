@@ -671,6 +671,257 @@ static bool contact_ball_polygon(P2 center, real radius, const Iso2& m2, const S
     return false;
 }
 
+// =============================================================================================================================
+// World update in 2-D: AABBs (bounding_volume/aabb_ball.rs:8-13, aabb_cuboid.rs:9-14, aabb_convex_polygon.rs + aabb_utils.rs:59-79,
+// loosened like pipeline/object/collision_object.rs:89-93 + dbvt_broad_phase.rs:341) and the contact-manifold generators
+// (ball_ball_manifold_generator.rs, ball_convex_polyhedron_manifold_generator.rs, convex_polyhedron_convex_polyhedron_manifold_generator.rs
+// with shape/convex_polygonal_feature2.rs and the dim2 branches of shape/cuboid.rs / shape/convex_polygon.rs), pushed into a fresh
+// ContactManifold with DistanceBased(0.02) tracking (query/contact/contact_manifold.rs:165-236).
+// =============================================================================================================================
+struct Feature2 {  // ConvexPolygonalFeature (2-D)
+    P2 v[2];
+    int nv = 0;
+    bool has_normal = false;
+    P2 normal = {0, 0};
+    uint32_t fid = F_UNKNOWN, vid[2] = {F_UNKNOWN, F_UNKNOWN};
+    void clear() { nv = 0, has_normal = false, fid = F_UNKNOWN; }
+    void push(P2 p, uint32_t id) { v[nv] = p, vid[nv] = id, nv++; }
+    void transform_by(const Iso2& m) {
+        for (auto& p : v) p = mul_point(m, p);  // both slots, like the reference's loop over the array
+        if (has_normal) normal = rot(m, normal);
+    }
+};
+// Cuboid::face (cuboid.rs:186-226, dim2)
+static void cuboid_face(const Shape2& g, uint32_t i, Feature2& out) {
+    out.clear();
+    uint32_t i1 = i < 2 ? i : i - 2;
+    real sign = i < 2 ? real(1) : real(-1);
+    uint32_t i2 = (i1 + 1) % 2;
+    real vertex[2] = {g.he.x, g.he.y};
+    vertex[i1] *= sign;
+    vertex[i2] *= (i1 == 0) ? -sign : sign;
+    P2 p1 = p2(vertex[0], vertex[1]);
+    vertex[i2] = -vertex[i2];
+    P2 p2_ = p2(vertex[0], vertex[1]);
+    uint32_t vid1 = sign < 0 ? (1u << i1) : 0u, vid2 = vid1;
+    real p1_i2 = i2 == 0 ? p1.x : p1.y;
+    if (p1_i2 < 0)
+        vid1 |= 1u << i2;
+    else
+        vid2 |= 1u << i2;
+    out.push(p1, F_VERTEX | vid1);
+    out.push(p2_, F_VERTEX | vid2);
+    real nrm[2] = {0, 0};
+    nrm[i1] = sign;
+    out.normal = p2(nrm[0], nrm[1]), out.has_normal = true;
+    out.fid = F_FACE | i;
+}
+static void polygon_face(const Shape2& g, uint32_t ia, Feature2& out) {  // convex_polygon.rs:123-135
+    out.clear();
+    uint32_t ib = (ia + 1) % g.npts;
+    out.push(p2(g.pts[2 * ia], g.pts[2 * ia + 1]), F_VERTEX | ia);
+    out.push(p2(g.pts[2 * ib], g.pts[2 * ib + 1]), F_VERTEX | ib);
+    out.normal = p2(g.normals[2 * ia], g.normals[2 * ia + 1]), out.has_normal = true;
+    out.fid = F_FACE | ia;
+}
+static void support_face_toward(const Shape2& g, const Iso2& m, P2 dir, Feature2& out) {
+    P2 ld = inv_rot(m, dir);
+    if (g.type == CUBOID2) {  // cuboid.rs:279-308
+        real l[2] = {ld.x, ld.y};
+        int iamax = 0;
+        real amax = std::fabs(l[0]);
+        if (std::fabs(l[1]) > amax) iamax = 1;
+        cuboid_face(g, l[iamax] > 0 ? iamax : iamax + 2, out);
+    } else {  // convex_polygon.rs:154-172
+        uint32_t best = 0;
+        real max_dot = g.normals[0] * ld.x + g.normals[1] * ld.y;
+        for (uint32_t i = 1; i < g.npts; ++i) {
+            real d = g.normals[2 * i] * ld.x + g.normals[2 * i + 1] * ld.y;
+            if (d > max_dot) max_dot = d, best = i;
+        }
+        polygon_face(g, best, out);
+    }
+    out.transform_by(m);
+}
+static real signum(real x) { return std::isnan(x) ? x : (std::signbit(x) ? real(-1) : real(1)); }  // f32::signum: -0.0 -> -1.0
+static void support_feature_toward(const Shape2& g, const Iso2& m, P2 dir, real cang, Feature2& out) {
+    if (g.type != CUBOID2) {  // convex_polygon.rs:174-184: the support face
+        support_face_toward(g, m, dir, out);
+        return;
+    }
+    P2 ld = inv_rot(m, dir);  // cuboid.rs:310-350 (dim2)
+    real l[2] = {ld.x, ld.y}, sp[2] = {g.he.x, g.he.y};
+    out.clear();
+    uint32_t spid = 0;
+    for (int i1 = 0; i1 < 2; ++i1) {
+        real sign = signum(l[i1]);
+        if (sign * l[i1] >= cang) {
+            cuboid_face(g, sign > 0 ? i1 : i1 + 2, out);
+            out.transform_by(m);
+            return;
+        }
+        if (sign < 0) spid |= 1u << i1;
+        sp[i1] *= sign;
+    }
+    out.push(mul_point(m, p2(sp[0], sp[1])), F_VERTEX | spid);
+    out.fid = F_VERTEX | spid;
+}
+
+struct Cand2 {
+    Contact2 c;
+    uint32_t f1, f2;
+};
+// ConvexPolygonalFeature::clip (convex_polygonal_feature2.rs:95-180)
+static void clip2(const Feature2& self, const Feature2& other, P2 normal, real prediction, std::vector<Cand2>& out) {
+    if (self.nv <= 1 || other.nv <= 1) return;
+    P2 ortho = p2(-normal.y, normal.x);
+    P2 s1a = self.v[0], s1b = self.v[1], s2a = other.v[0], s2b = other.v[1];
+    P2 ref = s1a;
+    real r1[2] = {dot(s1a - ref, ortho), dot(s1b - ref, ortho)}, r2[2] = {dot(s2a - ref, ortho), dot(s2b - ref, ortho)};
+    uint32_t f1[2] = {self.vid[0], self.vid[1]}, f2[2] = {other.vid[0], other.vid[1]};
+    if (r1[1] < r1[0]) std::swap(r1[0], r1[1]), std::swap(f1[0], f1[1]), std::swap(s1a, s1b);
+    if (r2[1] < r2[0]) std::swap(r2[0], r2[1]), std::swap(f2[0], f2[1]), std::swap(s2a, s2b);
+    if (r2[0] > r1[1] || r1[0] > r2[1]) return;
+    real len1 = r1[1] - r1[0], len2 = r2[1] - r2[0];
+    auto point_at = [](P2 a, P2 b, real bc) { return p2(a.x * (real(1) - bc) + b.x * bc, a.y * (real(1) - bc) + b.y * bc); };  // a * c0 + b.coords * c1
+    auto emit = [&](P2 w1, P2 w2, uint32_t fa, uint32_t fb) {
+        Contact2 c;
+        c.w1 = w1, c.w2 = w2, c.n = normal, c.depth = -dot(normal, w2 - w1);
+        if (-c.depth <= prediction) out.push_back({c, fa, fb});
+    };
+    if (r2[0] > r1[0])
+        emit(point_at(s1a, s1b, (r2[0] - r1[0]) / len1), s2a, self.fid, f2[0]);
+    else
+        emit(s1a, point_at(s2a, s2b, (r1[0] - r2[0]) / len2), f1[0], other.fid);
+    if (r2[1] < r1[1])
+        emit(point_at(s1a, s1b, (r2[1] - r1[0]) / len1), s2b, self.fid, f2[1]);
+    else
+        emit(s1b, point_at(s2a, s2b, (r1[1] - r2[0]) / len2), f1[1], other.fid);
+}
+
+struct Manifold2 {  // a fresh ContactManifold, DistanceBased(0.02)
+    std::vector<Cand2> c;
+    std::vector<P2> track;
+    void push(const Contact2& ct, uint32_t f1, uint32_t f2, P2 tracking_pt) {
+        const real threshold = real(0.02);
+        size_t closest = c.size();
+        real closest_dist = threshold * threshold;
+        for (size_t i = 0; i < c.size(); ++i) {
+            real d = nsq(tracking_pt - track[i]);
+            if (d < closest_dist) closest_dist = d, closest = i;
+        }
+        if (closest == c.size()) {
+            c.push_back({ct, f1, f2});
+            track.push_back(tracking_pt);
+        } else if (ct.depth > c[closest].c.depth) {  // a contact of this update is matched: the deeper one stays (:203-216)
+            c[closest] = {ct, f1, f2};
+            track[closest] = tracking_pt;
+        }
+    }
+};
+
+struct Box2 {
+    P2 lo, hi;
+};
+static Box2 shape_aabb2(const Shape2& g, const Iso2& m) {
+    P2 lo, hi;
+    if (g.type == BALL2) {
+        lo = p2(m.t.x + (-g.radius), m.t.y + (-g.radius)), hi = p2(m.t.x + g.radius, m.t.y + g.radius);
+    } else if (g.type == CUBOID2) {
+        real are = std::fabs(m.re), aim = std::fabs(m.im);
+        P2 w = p2(are * g.he.x + aim * g.he.y, aim * g.he.x + are * g.he.y);
+        lo = m.t - w, hi = m.t + w;
+    } else {
+        P2 wp = mul_point(m, p2(g.pts[0], g.pts[1]));
+        lo = hi = wp;
+        for (uint32_t i = 1; i < g.npts; ++i) {
+            wp = mul_point(m, p2(g.pts[2 * i], g.pts[2 * i + 1]));
+            lo = p2(std::fmin(lo.x, wp.x), std::fmin(lo.y, wp.y)), hi = p2(std::fmax(hi.x, wp.x), std::fmax(hi.y, wp.y));
+        }
+    }
+    return Box2{lo, hi};
+}
+
+// one pair through its generator; returns the manifold in push order
+static void generate_contacts2(const Shape2& g1, const Iso2& m1, const Shape2& g2, const Iso2& m2, real linear, real cang1, real cang2, Manifold2& mf,
+                               int* panicked) {
+    const uint32_t FACE0 = F_FACE | 0u;
+    if (g1.type == BALL2 && g2.type == BALL2) {
+        Contact2 c;
+        if (contact_ball_ball(m1.t, g1.radius, m2.t, g2.radius, linear, &c)) mf.push(c, FACE0, FACE0, p2(0, 0));
+        return;
+    }
+    if (g1.type == BALL2 || g2.type == BALL2) {  // BallConvexPolyhedronManifoldGenerator::new(flip = ball is second)
+        bool flip = g1.type != BALL2;
+        const Shape2& ball = flip ? g2 : g1;
+        const Shape2& cp = flip ? g1 : g2;
+        const Iso2& mb = flip ? m2 : m1;
+        const Iso2& mc = flip ? m1 : m2;
+        bool inside;
+        uint32_t f2 = F_UNKNOWN;
+        P2 world2;
+        if (cp.type == CUBOID2) {
+            world2 = cuboid_project(cp, mc, mb.t, &inside, &f2);
+        } else {
+            world2 = polygon_project(cp, mc, mb.t, &inside, panicked);
+            P2 back = mb.t - world2, ld;
+            if (unit_try_new(inv_rot(mc, inside ? -back : back), EPS, &ld)) f2 = polygon_feature_toward(cp, ld);
+        }
+        P2 dpt = world2 - mb.t, dir, normal;
+        real dist, depth;
+        if (unit_try_new_and_get(dpt, EPS, &dir, &dist)) {
+            depth = inside ? dist + ball.radius : -dist + ball.radius;
+            normal = inside ? -dir : dir;
+        } else {
+            if (f2 == F_UNKNOWN) return;
+            depth = ball.radius;
+            normal = -(cp.type == CUBOID2 ? cuboid_feature_normal(f2) : polygon_feature_normal(cp, f2));
+        }
+        if (depth >= -linear) {
+            if (f2 == F_UNKNOWN) {  // "Feature id cannot be unknown."
+                *panicked += 1;
+                return;
+            }
+            P2 world1 = mb.t + normal * ball.radius;
+            Contact2 c;
+            if (!flip) {
+                c.w1 = world1, c.w2 = world2, c.n = normal, c.depth = depth;
+                mf.push(c, FACE0, f2, p2(0, 0));
+            } else {
+                c.w1 = world2, c.w2 = world1, c.n = -normal, c.depth = depth;
+                mf.push(c, f2, FACE0, p2(0, 0));
+            }
+        }
+        return;
+    }
+    // ConvexPolyhedronConvexPolyhedronManifoldGenerator (fresh: last_gjk_dir = None)
+    P2 dir0;
+    if (!unit_try_new(m2.t - m1.t, EPS, &dir0)) dir0 = p2(1, 0);
+    Simplex2 s;
+    s.reset(cso_from_shapes(m1, g1, m2, g2, dir0));
+    P2 w1, w2, n;
+    int r = gjk_closest_points(m1, g1, m2, g2, linear, s, &w1, &w2, &n);
+    if (r == R_NONE) return;
+    if (r == R_INTERSECTION && !epa_closest_points(m1, g1, m2, g2, s, &w1, &w2, &n, panicked)) return;
+    Contact2 ct;
+    ct.w1 = w1, ct.w2 = w2, ct.n = n, ct.depth = -dot(n, w2 - w1);
+    Feature2 fa, fb;
+    if (ct.depth > 0) {
+        support_face_toward(g1, m1, n, fa);
+        support_face_toward(g2, m2, -n, fb);
+    } else {
+        support_feature_toward(g1, m1, n, cang1, fa);
+        support_feature_toward(g2, m2, -n, cang2, fb);
+    }
+    std::vector<Cand2> fresh;
+    clip2(fa, fb, n, linear, fresh);
+    if (fresh.empty()) fresh.push_back({ct, fa.fid, fb.fid});
+    for (auto& k : fresh) {  // add_contact_to_manifold (:182-236): Unknown features are dropped; tracking point = local1
+        if (k.f1 == F_UNKNOWN || k.f2 == F_UNKNOWN) continue;
+        mf.push(k.c, k.f1, k.f2, inv_point(m1, k.c.w1));
+    }
+}
+
 }  // namespace d2
 }  // namespace orc
 
@@ -733,6 +984,64 @@ void orc2_contact(uint64_t n, const uint32_t* type1, const real* param1, const r
         o[0] = c.w1.x, o[1] = c.w1.y, o[2] = c.w2.x, o[3] = c.w2.y, o[4] = c.n.x, o[5] = c.n.y, o[6] = c.depth;
     }
     if (panics) *panics = np;
+}
+
+// ---- 2-D world -------------------------------------------------------------------------------------------------------------
+struct orc2_objects {
+    uint32_t n;
+    const real* pos;          // 2 per object
+    const real* rot;          // re, im per object
+    const uint32_t* type;
+    const real* param;        // 4 per object
+    const real* query_limit;
+    const real* ang_pred;
+    const real* poly_points;
+    const real* poly_normals;
+};
+static Shape2 obj_shape(const orc2_objects* o, uint32_t i) {
+    Shape2 g;
+    const real* p = o->param + 4 * (size_t)i;
+    g.type = o->type[i], g.radius = p[0], g.he = p2(p[0], p[1]), g.pts = g.normals = nullptr, g.npts = 0;
+    if (g.type == POLYGON2) g.pts = o->poly_points + 2 * (size_t)p[0], g.normals = o->poly_normals + 2 * (size_t)p[0], g.npts = (uint32_t)p[1];
+    return g;
+}
+static Iso2 obj_iso(const orc2_objects* o, uint32_t i) { return Iso2{p2(o->pos[2 * i], o->pos[2 * i + 1]), o->rot[2 * i], o->rot[2 * i + 1]}; }
+
+// fat AABBs as 6 reals (mins xyz, maxs xyz, z = 0): ((shape AABB -/+ query_limit) -/+ margin), usable with orc_broad_phase
+void orc2_compute_aabbs(const orc2_objects* o, real margin, real* out) {
+    for (uint32_t i = 0; i < o->n; ++i) {
+        Box2 a = shape_aabb2(obj_shape(o, i), obj_iso(o, i));
+        real ql = o->query_limit[i];
+        real mm[4] = {a.lo.x + (-ql), a.lo.y + (-ql), a.hi.x + ql, a.hi.y + ql};
+        out[6 * i] = mm[0] + (-margin), out[6 * i + 1] = mm[1] + (-margin), out[6 * i + 2] = 0;
+        out[6 * i + 3] = mm[2] + margin, out[6 * i + 4] = mm[3] + margin, out[6 * i + 5] = 0;
+    }
+}
+// Contact manifolds of the given pairs (object1, object2): manifold_off[P + 1], contacts = 9 reals (world1, world2, normal, depth, f1, f2
+// as reals holding the 32-bit feature codes: kind << 30 | id with kind 1 = face, 2 = vertex).  Returns the number of contacts.
+uint64_t orc2_narrow_phase(const orc2_objects* o, uint64_t n_pairs, const uint32_t* pairs, uint32_t* manifold_off, real* contacts, uint32_t* feats,
+                           uint64_t cap, uint32_t* panics) {
+    uint64_t nc = 0;
+    int panicked = 0;
+    for (uint64_t k = 0; k < n_pairs; ++k) {
+        uint32_t i1 = pairs[2 * k], i2 = pairs[2 * k + 1];
+        Manifold2 mf;
+        real linear = o->query_limit[i1] + o->query_limit[i2];
+        generate_contacts2(obj_shape(o, i1), obj_iso(o, i1), obj_shape(o, i2), obj_iso(o, i2), linear, std::cos(o->ang_pred[i1]),
+                           std::cos(o->ang_pred[i2]), mf, &panicked);
+        manifold_off[k] = (uint32_t)nc;
+        for (auto& c : mf.c) {
+            if (nc < cap) {
+                real* q = contacts + 7 * nc;
+                q[0] = c.c.w1.x, q[1] = c.c.w1.y, q[2] = c.c.w2.x, q[3] = c.c.w2.y, q[4] = c.c.n.x, q[5] = c.c.n.y, q[6] = c.c.depth;
+                feats[2 * nc] = c.f1, feats[2 * nc + 1] = c.f2;
+            }
+            nc++;
+        }
+    }
+    manifold_off[n_pairs] = (uint32_t)nc;
+    if (panics) *panics = (uint32_t)panicked;
+    return nc;
 }
 
 }  // extern "C"

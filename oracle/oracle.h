@@ -175,6 +175,12 @@ void orc2_contact(uint64_t n, const uint32_t* type1, const real* param1, const r
                   const real* pose2, const real* poly_points, const real* poly_normals, real prediction, uint8_t* found, real* out,
                   uint32_t* panics);
 
+/* 2-D world (oracle/dim2.cpp): fat AABBs as 6 reals with z = 0 (usable with orc_broad_phase), and the contact manifolds of given pairs. */
+struct orc2_objects;
+void orc2_compute_aabbs(const struct orc2_objects* o, real margin, real* out);
+uint64_t orc2_narrow_phase(const struct orc2_objects* o, uint64_t n_pairs, const uint32_t* pairs, uint32_t* manifold_off, real* contacts,
+                           uint32_t* feats, uint64_t cap, uint32_t* panics);
+
 #ifdef __cplusplus
 }
 #endif

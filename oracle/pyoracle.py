@@ -270,6 +270,35 @@ class Oracle:
                               self.creal(prediction), vp(found), vp(out), C.byref(panics))
         return found, out, panics.value
 
+    def world_update2d(self, w):
+        """ncollide2d fresh-world update for a ncollide_b200.dim2.World2D: (pairs [P,2] canonical, offsets [P+1], contacts [C,7], features [C,2],
+        panics).  Fat AABBs (oracle/dim2.cpp) -> the 3-D oracle's broad phase on boxes with z = 0 -> the 2-D generators."""
+        dt = self.dtype
+
+        class O2(C.Structure):
+            _fields_ = [("n", C.c_uint32), ("pos", C.c_void_p), ("rot", C.c_void_p), ("type", C.c_void_p), ("param", C.c_void_p),
+                        ("query_limit", C.c_void_p), ("ang_pred", C.c_void_p), ("poly_points", C.c_void_p), ("poly_normals", C.c_void_p)]
+
+        keep = [np.ascontiguousarray(a, dtype=dt) for a in (w.pos, w.rot, w.param, w.query_limit, w.ang_pred, w.points, w.normals)]
+        typ = np.ascontiguousarray(w.type, dtype=np.uint32)
+        o = O2(w.n, keep[0].ctypes.data, keep[1].ctypes.data, typ.ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data, keep[4].ctypes.data,
+               keep[5].ctypes.data, keep[6].ctypes.data)
+        fat = np.zeros((w.n, 6), dtype=dt)
+        self.lib.orc2_compute_aabbs(C.byref(o), self.creal(w.margin), C.c_void_p(fat.ctypes.data))
+        pairs = self.broad_phase(fat, w.groups, mode=1)
+        P = len(pairs)
+        cap = max(4 * P, 64)
+        off = np.zeros(P + 1, dtype=np.uint32)
+        contacts = np.zeros((cap, 7), dtype=dt)
+        feats = np.zeros((cap, 2), dtype=np.uint32)
+        panics = C.c_uint32(0)
+        self.lib.orc2_narrow_phase.restype = C.c_uint64
+        pr = np.ascontiguousarray(pairs, dtype=np.uint32)
+        nc = self.lib.orc2_narrow_phase(C.byref(o), C.c_uint64(P), C.c_void_p(pr.ctypes.data), C.c_void_p(off.ctypes.data),
+                                        C.c_void_p(contacts.ctypes.data), C.c_void_p(feats.ctypes.data), C.c_uint64(cap), C.byref(panics))
+        assert nc <= cap
+        return pairs, off, contacts[:nc], feats[:nc], panics.value, fat
+
     def broad_phase_persistent(self, margin):
         return OracleBroadPhase(self, margin)
 

@@ -220,3 +220,80 @@ def test_device_refuses_bad_input(ctx):
     assert found[0] and out[0, 6] > 0.5  # the centre is inside the triangle
     with pytest.raises(NcbError):
         dim2.contact(ctx, [7], [[1, 0, 0, 0]], [[0, 0, 1, 0]], [1], [[1, 1, 0, 0]], [[0.2, 0, 1, 0]])
+
+
+# ---- 2-D world update ----------------------------------------------------------------------------------------------------------
+def random_world(n, seed, kinds=(0, 1, 2), density=2.5, angular=0.0, linear=0.02, with_groups=False):
+    rng = np.random.default_rng(seed)
+    sh = dim2.Shapes2D()
+    for t in rng.choice(kinds, size=n):
+        if t == 0:
+            sh.ball(rng.uniform(0.25, 0.5))
+        elif t == 1:
+            sh.cuboid(rng.uniform(0.25, 0.5), rng.uniform(0.25, 0.5))
+        else:
+            k = int(rng.integers(3, 11))
+            ang = np.sort(rng.uniform(0, 2 * np.pi, size=k)) + np.arange(k) * 1e-2
+            sh.polygon(np.stack([rng.uniform(0.3, 0.5) * np.cos(ang), rng.uniform(0.3, 0.5) * np.sin(ang)], axis=1))
+    side = np.sqrt(n * 0.8 / density) * 1.0
+    pos = rng.uniform(0, side, size=(n, 2))
+    angle = rng.uniform(-np.pi, np.pi, size=n)
+    angle[rng.random(n) < 0.25] = 0.0  # axis-aligned boxes: face-face contacts with two clipped points
+    groups = None
+    if with_groups:
+        groups = np.tile(np.array([0x3FFFFFFF, 0x3FFFFFFF, 0], dtype=np.uint32), (n, 1))
+        groups[rng.random(n) < 0.3] = (2, 0x3FFFFFFF & ~2, 0)  # members of group 1 that do not talk to each other
+    return dim2.World2D(sh, pos, angle, margin=0.02, linear=linear, angular=angular, groups=groups)
+
+
+def _canon(p):
+    p = np.sort(np.asarray(p, dtype=np.int64).reshape(-1, 2), axis=1)
+    return p[np.lexsort((p[:, 1], p[:, 0]))]
+
+
+def test_oracle_world2d_properties(oracle64):
+    """ORACLE check (f64, CPU): pairs == brute force over the fat boxes; every contact's depth / normal is consistent; a face-face
+    contact of two axis-aligned boxes has two points; resting cuboids on a big cuboid touch with depth == overlap exactly."""
+    w = random_world(400, 31)
+    pairs, off, contacts, feats, panics, fat = oracle64.world_update2d(w)
+    assert panics == 0
+    lo, hi = fat[:, :2], fat[:, 3:5]
+    brute = [(i, j) for i in range(w.n) for j in range(i) if np.all(lo[i] <= hi[j]) and np.all(lo[j] <= hi[i])]
+    assert np.array_equal(_canon(pairs), _canon(brute))
+    assert np.all(pairs[:, 0] > pairs[:, 1])
+    n = contacts[:, 4:6]
+    assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-9)
+    assert np.allclose(contacts[:, 6], -np.einsum("ij,ij->i", n, contacts[:, 2:4] - contacts[:, 0:2]), atol=1e-9)
+    assert (np.diff(off.astype(np.int64)) == 2).sum() > 5  # clipped face-face manifolds exist
+    # known answer: a unit box resting 0.1 deep in a wide box: two contacts, depth 0.1, normal -y for (upper, lower) order
+    sh = dim2.Shapes2D().cuboid(5, 0.5).cuboid(0.5, 0.5)
+    kw = dim2.World2D(sh, [[0, 0], [0.3, 0.9]], [0, 0], margin=0.02, linear=0.02)
+    pairs, off, contacts, feats, panics, _ = oracle64.world_update2d(kw)
+    assert pairs.tolist() == [[1, 0]] and off.tolist() == [0, 2]
+    assert np.allclose(contacts[:, 6], 0.1) and np.allclose(contacts[:, 4:6], [[0, -1], [0, -1]])
+    assert sorted(np.round(contacts[:, 0], 6).tolist()) == [-0.2, 0.8]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,seed,kinds,angular,groups", [(3000, 41, (0, 1, 2), 0.0, False), (2500, 42, (1, 2), 0.05, True), (2000, 43, (0, 1), 0.0, False),
+                                                         (4000, 44, (2,), 0.2, False), (50000, 45, (0, 1, 2), 0.0, False)])
+def test_device_world2d_matches_oracle(ctx, oracle, n, seed, kinds, angular, groups):
+    """ncb2d_world_update against the oracle: pair set and orientation exact, manifold sizes and feature ids exact, contacts within
+    1e-4 / 1e-5 (and almost all words bit-identical)."""
+    w = random_world(n, seed, kinds, angular=angular, with_groups=groups)
+    r = dim2.world_update(ctx, w)
+    pairs, off, ocontacts, ofeats, panics, _ = oracle.world_update2d(w)
+    assert r["diag"] == {"ref_panics": panics, "epa_overflow": 0, "manifold_overflow": 0, "stack_overflow": 0}
+    assert np.array_equal(_canon(r["pairs"]), _canon(pairs)) and np.all(r["pairs"][:, 0] > r["pairs"][:, 1])
+    want = {tuple(p): (ocontacts[a:b], ofeats[a:b]) for p, a, b in zip(pairs.tolist(), off[:-1].tolist(), off[1:].tolist())}
+    words = same = 0
+    for p, st, k in zip(r["pairs"].tolist(), r["manifold_start"].tolist(), r["manifold_count"].tolist()):
+        oc, of = want[tuple(p)]
+        assert k == len(oc), (p, k, len(oc))
+        dc, df = r["contacts"][st : st + k], r["features"][st : st + k]
+        assert np.array_equal(df, of), (p, df, of)
+        assert np.allclose(dc, oc, rtol=1e-4, atol=1e-5), (p, dc, oc)
+        words += dc.size
+        same += int((dc.view(np.uint32) == np.ascontiguousarray(oc, dtype=np.float32).view(np.uint32)).sum())
+    assert len(r["contacts"]) == len(ocontacts) > n // 4
+    assert same / words > 0.999
