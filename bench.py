@@ -806,10 +806,27 @@ def bench_dim2(ctx, n_pairs=1_000_000, cpu_sample=100_000):
     ms = (time.perf_counter() - t0) * 1e3
     res = {"workload": f"{n_pairs} random 2-D pairs (balls, cuboids, convex polygons of 3-12 vertices), query::contact with prediction 0.02",
            "ms": ms, "Mpairs_per_s": n_pairs / ms / 1e3, "contacts_found": int(found.sum()), **info}
+    # the 2-D world update: 1 M objects (balls, cuboids, polygons), about 3 fat-box neighbours each
+    n_w = n_pairs
+    side = float(np.sqrt(n_w * 0.8 / 2.5))
+    w = dim2.World2D.from_library(sh, rng.integers(0, 192, size=n_w), rng.uniform(0, side, size=(n_w, 2)), rng.uniform(-np.pi, np.pi, size=n_w))
+    dim2.world_update(ctx, w)
+    t0 = time.perf_counter()
+    wr = dim2.world_update(ctx, w)
+    wms = (time.perf_counter() - t0) * 1e3
+    res["world_update"] = {"workload": f"{n_w} 2-D objects, fresh-world update through ncb2d_world_update (host buffers in and out)", "ms": wms,
+                           "pairs": int(len(wr["pairs"])), "contacts": int(len(wr["contacts"])), **wr["diag"]}
     try:
         from oracle.pyoracle import Oracle
 
         orc = Oracle()
+        n_cw = 100_000
+        cw = dim2.World2D.from_library(sh, rng.integers(0, 192, size=n_cw), rng.uniform(0, side * np.sqrt(n_cw / n_w), size=(n_cw, 2)),
+                                       rng.uniform(-np.pi, np.pi, size=n_cw))
+        t0 = time.perf_counter()
+        op = orc.world_update2d(cw)
+        res["world_update"]["cpu_baseline"] = {"ms": (time.perf_counter() - t0) * 1e3, "objects": n_cw, "pairs": int(len(op[0])), "cores": 1,
+                                               "kind": "port", "note": "sweep broad phase of the oracle, not the DBVT"}
         sl = slice(0, cpu_sample)
         t0 = time.perf_counter()
         of, oo, _ = orc.contact2d(args[0][sl], args[1][sl], args[2][sl], args[3][sl], args[4][sl], args[5][sl], pts, prediction=0.02, poly_normals=nrm)

@@ -116,6 +116,24 @@ class World2D:
             raise ValueError("one position per shape")
 
 
+    @classmethod
+    def from_library(cls, shapes: Shapes2D, pick, pos, angle, **kw):
+        """A world whose object k is a copy of library shape ``pick[k]`` (large synthetic worlds without a Python loop per object)."""
+        w = cls.__new__(cls)
+        typ, par, w.points, w.normals = shapes.arrays()
+        pick = np.asarray(pick, dtype=np.int64)
+        w.type, w.param = np.ascontiguousarray(typ[pick]), np.ascontiguousarray(par[pick])
+        w.n = len(pick)
+        w.pos = as_f32(pos).reshape(-1, 2)
+        a = np.broadcast_to(np.asarray(angle, dtype=np.float32).reshape(-1), (w.n,))
+        w.rot = np.ascontiguousarray(np.stack([np.cos(a, dtype=np.float32), np.sin(a, dtype=np.float32)], axis=1), dtype=np.float32)
+        w.margin = float(kw.get("margin", 0.02))
+        w.query_limit = np.full(w.n, kw.get("linear", 0.02), dtype=np.float32)
+        w.ang_pred = np.full(w.n, kw.get("angular", 0.0), dtype=np.float32)
+        w.groups = None
+        return w
+
+
 class _Objects2DC(C.Structure):
     _fields_ = [("n", C.c_uint32), ("pos", C.c_void_p), ("rot", C.c_void_p), ("shape_type", C.c_void_p), ("shape_param", C.c_void_p),
                 ("groups", C.c_void_p), ("query_limit", C.c_void_p), ("ang_pred", C.c_void_p), ("poly_points", C.c_void_p),
