@@ -261,7 +261,7 @@ int ncb_world_update_sharded(ncb_ctx* ctx, float margin, int rank, int world, nc
 int ncb_world_update_routed(ncb_ctx* ctx, int stage, float margin, int rank, int world, uint32_t begin, uint32_t end, int with_poses,
                             ncb_update_counts* counts);
 /* Device buffers of the routed update, for the caller's collectives.  which: 0 bounds (6 f32), 1 histogram (1024 i32), 2 / 3 owner
- * buckets send / recv, 4 regions (6 * world f32), 5 / 6 ghost buckets send / recv; *bytes = the extent the collective covers. */
+ * buckets send / recv, 4 regions (8 sub-boxes x 6 f32 per rank), 5 / 6 ghost buckets send / recv; *bytes = the extent the collective covers. */
 void* ncb_route_buffer(ncb_ctx* ctx, int which, int world, uint64_t* bytes);
 /* Peer-memory exchange for the routed update (NVLink P2P instead of NCCL inside the step).  ncb_route_p2p_alloc allocates this rank's
  * receive buffers (buckets of largest-block + 1 records: they cannot overflow) and exports them: `handles` receives 3 cudaIpcMemHandle_t

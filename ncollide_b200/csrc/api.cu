@@ -783,7 +783,7 @@ int ncb_world_update_sharded(ncb_ctx* ctx, float margin, int rank, int world, nc
 // its box meets.  The caller performs one collective on the buffers of ncb_route_buffer between the stages:
 //   stage 0 (AABBs + centre bounds of the own block)   -> all-reduce MAX  of buffer 0 (6 floats)
 //   stage 1 (bins + histogram)                          -> all-reduce SUM  of buffer 1 (SHARD_BINS ints)
-//   stage 2 (owner buckets + regions)                   -> all-to-all      buffer 2 -> 3, all-reduce MAX of buffer 4 (6 * world floats)
+//   stage 2 (owner buckets + regions)                   -> all-to-all      buffer 2 -> 3, all-reduce MAX of buffer 4 (8 sub-boxes x 6 floats per rank)
 //   stage 3 (ghost buckets)                             -> all-to-all      buffer 5 -> 6
 //   stage 4 (unpack, local LBVH, pair search, narrow phase; fills counts).  Returns NCB_ROUTE_REPEAT when a bucket was too
 //            small somewhere: the capacities have been raised (identically on every rank), repeat from stage 2.
@@ -805,8 +805,8 @@ static int routed_stage(ncb_ctx* ctx, int stage, float margin, int rank, int wor
         CK(R.hist.reserve(SHARD_BINS));
         CK(R.split.reserve(SHARD_MAX_RANKS + 1));
         CK(R.bins.reserve(n_own ? n_own : 1));
-        CK(R.region_i.reserve(SHARD_MAX_RANKS * 6));
-        CK(R.region_f.reserve(SHARD_MAX_RANKS * 6));
+        CK(R.region_i.reserve(SHARD_MAX_RANKS * SHARD_SUBS * 6));
+        CK(R.region_f.reserve(SHARD_MAX_RANKS * SHARD_SUBS * 6));
         CK(R.counts.reserve(2 * SHARD_MAX_RANKS));
         CK(ctx->shard.reserve(1));
         CK(ctx->counters.reserve(1));
@@ -849,11 +849,11 @@ static int routed_stage(ncb_ctx* ctx, int stage, float margin, int rank, int wor
             CK(R.recv_g.reserve((size_t)world * R.cap_g * w));
         }
         CK(launch_route_stage(ctx, 2, rank, world, begin, end, R));
-        if (p2p) CK(launch_p2p_push(ctx, R, R.region_f.p, 6 * (uint32_t)world, 2, 3));
+        if (p2p) CK(launch_p2p_push(ctx, R, R.region_f.p, SHARD_SUBS * 6 * (uint32_t)world, 2, 3));
         return NCB_OK;
     }
     if (stage == 3) {
-        if (p2p) CK(launch_p2p_wait_reduce(ctx, R, 3, 2, 6 * (uint32_t)world, 0, R.region_f.p));
+        if (p2p) CK(launch_p2p_wait_reduce(ctx, R, 3, 2, SHARD_SUBS * 6 * (uint32_t)world, 0, R.region_f.p));
         CK(launch_route_stage(ctx, 3, rank, world, begin, end, R));
         if (p2p) CK(launch_p2p_push(ctx, R, nullptr, 0, 2, 4));
         timer_mark(ctx, "route", 5);
@@ -1004,7 +1004,7 @@ int ncb_route_p2p_close(ncb_ctx* ctx) {
 }
 
 // Buffers of the routed update for the caller's collectives: which = 0 bounds (6 f32), 1 histogram (SHARD_BINS i32), 2 / 3 owner
-// buckets send / recv, 4 regions (6 * SHARD_MAX_RANKS f32; the first 6 * world are used), 5 / 6 ghost buckets send / recv.
+// buckets send / recv, 4 regions (8 sub-boxes x 6 f32 per rank), 5 / 6 ghost buckets send / recv.
 // *bytes = the extent a collective covers (for 2 / 3 / 5 / 6: world equal parts).  Valid after the stage that precedes the collective.
 void* ncb_route_buffer(ncb_ctx* ctx, int which, int world, uint64_t* bytes) {
     if (!ctx) return nullptr;
@@ -1016,7 +1016,7 @@ void* ncb_route_buffer(ncb_ctx* ctx, int which, int world, uint64_t* bytes) {
         case 1: p = R.hist.p, b = SHARD_BINS * sizeof(int); break;
         case 2: p = R.send_o.p, b = (uint64_t)world * R.cap_o * R.recw * sizeof(float4); break;
         case 3: p = R.recv_o.p, b = (uint64_t)world * R.cap_o * R.recw * sizeof(float4); break;
-        case 4: p = R.region_f.p, b = (uint64_t)world * 6 * sizeof(float); break;
+        case 4: p = R.region_f.p, b = (uint64_t)world * SHARD_SUBS * 6 * sizeof(float); break;
         case 5: p = R.send_g.p, b = (uint64_t)world * R.cap_g * R.recw * sizeof(float4); break;
         case 6: p = R.recv_g.p, b = (uint64_t)world * R.cap_g * R.recw * sizeof(float4); break;
         default: break;

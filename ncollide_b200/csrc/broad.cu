@@ -516,8 +516,11 @@ __global__ void __launch_bounds__(256) k_route_owned(const float4* __restrict__ 
                                                      const float4* __restrict__ rot, uint32_t begin, uint32_t end, const uint32_t* __restrict__ bins,
                                                      const uint32_t* __restrict__ split, int world, uint32_t cap, int recw, RouteDst dst,
                                                      uint32_t* __restrict__ counts, int* __restrict__ region) {
-    __shared__ int s_reg[SHARD_MAX_RANKS][6];
-    for (int k = threadIdx.x; k < SHARD_MAX_RANKS * 6; k += blockDim.x) (&s_reg[0][0])[k] = (k % 6) < 3 ? 0x7f7fffff : (int)0x80800000;
+    // A rank's region is kept as SHARD_SUBS boxes, one per top-level Morton octant of its bin range, not as one union box: an
+    // equal-count boundary that falls one bin short of an octant boundary would otherwise stretch the union box across the
+    // scene and double that rank's ghosts (measured at 4 ranks: one rank's broad phase took 2x, profiles/r2_multi_gpu.txt).
+    __shared__ int s_reg[SHARD_MAX_RANKS * SHARD_SUBS][6];
+    for (int k = threadIdx.x; k < SHARD_MAX_RANKS * SHARD_SUBS * 6; k += blockDim.x) (&s_reg[0][0])[k] = (k % 6) < 3 ? 0x7f7fffff : (int)0x80800000;
     __syncthreads();
     uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (i < end) {
@@ -542,12 +545,13 @@ __global__ void __launch_bounds__(256) k_route_owned(const float4* __restrict__ 
             }
         }
         if (bin < SHARD_BINS) {  // infinite boxes do not shape a region
-            atomicMin(&s_reg[owner][0], f2o(a.x)), atomicMin(&s_reg[owner][1], f2o(a.y)), atomicMin(&s_reg[owner][2], f2o(a.z));
-            atomicMax(&s_reg[owner][3], f2o(b.x)), atomicMax(&s_reg[owner][4], f2o(b.y)), atomicMax(&s_reg[owner][5], f2o(b.z));
+            int* r6 = s_reg[owner * SHARD_SUBS + (int)(bin / (SHARD_BINS / SHARD_SUBS))];
+            atomicMin(&r6[0], f2o(a.x)), atomicMin(&r6[1], f2o(a.y)), atomicMin(&r6[2], f2o(a.z));
+            atomicMax(&r6[3], f2o(b.x)), atomicMax(&r6[4], f2o(b.y)), atomicMax(&r6[5], f2o(b.z));
         }
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < world * 6; k += blockDim.x) {
+    for (int k = threadIdx.x; k < world * SHARD_SUBS * 6; k += blockDim.x) {
         int v = (&s_reg[0][0])[k];
         if ((k % 6) < 3) {
             if (v != 0x7f7fffff) atomicMin(&region[k], v);
@@ -565,15 +569,16 @@ __global__ void k_route_finish(const uint32_t* __restrict__ counts, int world, R
     uint32_t mx = 0;
     for (int q = 0; q < world; ++q) mx = max(mx, counts[q]);
     if (t < world) dst.p[t][0] = make_float4(__uint_as_float(counts[t]), __uint_as_float(mx), 0.f, 0.f);
-    if (region_f && t < world * 6) region_f[t] = (t % 6) < 3 ? -o2f(region[t]) : o2f(region[t]);
+    if (region_f)
+        for (int k = t; k < world * SHARD_SUBS * 6; k += blockDim.x) region_f[k] = (k % 6) < 3 ? -o2f(region[k]) : o2f(region[k]);
 }
 // stage 3: ghosts = own objects whose box meets the region of a rank that does not own them (inclusive test, like AABB::intersects)
 __global__ void __launch_bounds__(256) k_route_ghosts(const float4* __restrict__ lo, const float4* __restrict__ hi, const float* __restrict__ pos,
                                                       const float4* __restrict__ rot, uint32_t begin, uint32_t end, const uint32_t* __restrict__ bins,
                                                       const uint32_t* __restrict__ split, const float* __restrict__ region_f, int world, uint32_t cap,
                                                       int recw, RouteDst dst, uint32_t* __restrict__ counts) {
-    __shared__ float s_r[SHARD_MAX_RANKS][6];
-    for (int k = threadIdx.x; k < world * 6; k += blockDim.x) (&s_r[0][0])[k] = (k % 6) < 3 ? -region_f[k] : region_f[k];
+    __shared__ float s_r[SHARD_MAX_RANKS * SHARD_SUBS][6];
+    for (int k = threadIdx.x; k < world * SHARD_SUBS * 6; k += blockDim.x) (&s_r[0][0])[k] = (k % 6) < 3 ? -region_f[k] : region_f[k];
     __syncthreads();
     uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= end) return;
@@ -581,7 +586,11 @@ __global__ void __launch_bounds__(256) k_route_ghosts(const float4* __restrict__
     int owner = route_owner(split, world, __ldg(&bins[i - begin]));
     for (int q = 0; q < world; ++q) {
         if (q == owner) continue;
-        bool take = a.x <= s_r[q][3] && a.y <= s_r[q][4] && a.z <= s_r[q][5] && b.x >= s_r[q][0] && b.y >= s_r[q][1] && b.z >= s_r[q][2];
+        bool take = false;
+        for (int sub = 0; sub < SHARD_SUBS && !take; ++sub) {  // an empty sub-box has min = +MAX, max = -MAX: never met
+            const float* r6 = s_r[q * SHARD_SUBS + sub];
+            take = a.x <= r6[3] && a.y <= r6[4] && a.z <= r6[5] && b.x >= r6[0] && b.y >= r6[1] && b.z >= r6[2];
+        }
         if (!take) continue;
         uint32_t k = atomicAdd(&counts[q], 1u);
         if (k + 1 < cap) {
@@ -676,8 +685,8 @@ cudaError_t launch_route_stage(ncb_ctx* c, int stage, int rank, int world, uint3
             break;
         }
         case 2: {
-            int z[SHARD_MAX_RANKS * 6];
-            for (int k = 0; k < SHARD_MAX_RANKS * 6; ++k) z[k] = (k % 6) < 3 ? 0x7f7fffff : (int)0x80800000;
+            int z[SHARD_MAX_RANKS * SHARD_SUBS * 6];
+            for (int k = 0; k < SHARD_MAX_RANKS * SHARD_SUBS * 6; ++k) z[k] = (k % 6) < 3 ? 0x7f7fffff : (int)0x80800000;
             cudaMemcpyAsync(R.region_i.p, z, sizeof z, cudaMemcpyHostToDevice, s);
             cudaMemsetAsync(R.counts.p, 0, 2 * SHARD_MAX_RANKS * sizeof(uint32_t), s);
             k_route_split<<<1, 32, 0, s>>>(R.hist.p, world, R.split.p);

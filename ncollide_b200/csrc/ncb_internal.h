@@ -149,6 +149,7 @@ struct PersistArgs {
 
 #define SHARD_BINS 1024
 #define SHARD_MAX_RANKS 16
+#define SHARD_SUBS 8  // sub-boxes of a rank's region in the routed sharding: one per top-level octant of the Morton bins
 struct ShardScratch {
     uint32_t hist[SHARD_BINS];
     uint32_t split[SHARD_MAX_RANKS + 1];
@@ -222,6 +223,7 @@ struct RouteBufs {
 #define P2P_FLAGS_OFF (3 * SHARD_MAX_RANKS * P2P_SLOT_WORDS)
 #define P2P_ERR_OFF (P2P_FLAGS_OFF + 32)
 #define P2P_META_WORDS (P2P_ERR_OFF + 32)
+static_assert(SHARD_MAX_RANKS * SHARD_SUBS * 6 <= P2P_SLOT_WORDS, "a rank's region boxes must fit one meta slot");
 struct RouteDst {
     float4* p[SHARD_MAX_RANKS];  // where the bucket for destination q starts (local send buffer, or the peer's recv buffer)
 };
