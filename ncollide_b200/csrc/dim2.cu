@@ -772,6 +772,165 @@ __device__ void clip_edges(const Edge2& a, const Edge2& b, W2 normal, float pred
         }
 }
 
+// bounding_volume::aabb(shape, m) in 2-D
+__device__ void aabb_of_shape(const Operand2& g, W2& lo, W2& hi) {
+    if (g.kind == D2_BALL) {
+        lo = w2(g.m.t.x + (-g.a), g.m.t.y + (-g.a)), hi = w2(g.m.t.x + g.a, g.m.t.y + g.a);
+    } else if (g.kind == D2_CUBOID) {
+        float are = fabsf(g.m.re), aim = fabsf(g.m.im);
+        W2 w = w2(are * g.a + aim * g.b, aim * g.a + are * g.b);
+        lo = g.m.t - w, hi = g.m.t + w;
+    } else {
+        W2 p = to_world(g.m, w2(__ldg(g.pts), __ldg(g.pts + 1)));
+        lo = hi = p;
+        for (uint32_t k = 1; k < g.npts; ++k) {
+            p = to_world(g.m, w2(__ldg(g.pts + 2 * k), __ldg(g.pts + 2 * k + 1)));
+            lo = w2(fminf(lo.x, p.x), fminf(lo.y, p.y)), hi = w2(fmaxf(hi.x, p.x), fmaxf(hi.y, p.y));
+        }
+    }
+}
+// One pair through its ContactManifoldGenerator into a fresh manifold.  flags: bit 0 = the reference would panic, bit 1 = EPA capacity.
+__device__ void manifold_of_pair(const Operand2& g1, const Operand2& g2, float linear, float cang1, float cang2, float cos_one_degree,
+                                 Manifold2d& mf, int& flags) {
+    mf.n = 0, mf.overflow = false;
+    const uint32_t FACE0 = FEAT2_FACE | 0u;
+    Hit2 h;
+    if (g1.kind == D2_BALL && g2.kind == D2_BALL) {
+        if (ball_ball(g1.m.t, g1.a, g2.m.t, g2.a, linear, h)) man_push(mf, h, FACE0, FACE0, w2(0.f, 0.f));
+    } else if (g1.kind == D2_BALL || g2.kind == D2_BALL) {
+        const bool flip = g1.kind != D2_BALL;
+        const Operand2& ball = flip ? g2 : g1;
+        const Operand2& other = flip ? g1 : g2;
+        uint32_t f2 = FEAT2_UNKNOWN;
+        int q = 1;
+        bool ok = other.kind == D2_CUBOID ? ball_cuboid(ball.m.t, ball.a, other, linear, h, &f2)
+                                          : ball_polygon(ball.m.t, ball.a, other, linear, cos_one_degree, h, q, &f2);
+        if (q == -1) flags |= 1;
+        if (q == -2) flags |= 2;
+        if (ok) {
+            if (f2 == FEAT2_UNKNOWN) {
+                flags |= 1;  // "Feature id cannot be unknown."
+            } else if (!flip) {
+                man_push(mf, h, FACE0, f2, w2(0.f, 0.f));
+            } else {
+                W2 t = h.w1;
+                h.w1 = h.w2, h.w2 = t, h.n = -h.n;
+                man_push(mf, h, f2, FACE0, w2(0.f, 0.f));
+            }
+        }
+    } else {
+        W2 d0;
+        if (!unit(g2.m.t - g1.m.t, NCB_EPS, d0)) d0 = w2(1.f, 0.f);
+        Tri2 s;
+        for (int i = 0; i < 3; ++i) s.v[i].p = s.v[i].o1 = s.v[i].o2 = w2(0.f, 0.f), s.old_idx[i] = i;
+        s.bary[0] = s.bary[1] = s.old_bary[0] = s.old_bary[1] = 0.f;
+        s.dim = s.old_dim = 0;
+        s.v[0] = minkowski(g1, g2, d0);
+        W2 p1, p2, n;
+        int r = gjk2(g1, g2, linear, s, p1, p2, n);
+        bool ok = r == G_POINTS;
+        if (r == G_INSIDE) {
+            Poly2 e;
+            int q = epa2(g1, g2, s, e, p1, p2, n);
+            ok = q == 1;
+            if (q == -1) flags |= 1;
+            if (q == -2) flags |= 2;
+        }
+        if (ok) {
+            h.w1 = p1, h.w2 = p2, h.n = n, h.depth = -dot(n, p2 - p1);
+            Edge2 fa, fb;
+            if (h.depth > 0.f) {
+                face_toward(g1, n, fa);
+                face_toward(g2, -n, fb);
+            } else {
+                feature_toward(g1, n, cang1, fa);
+                feature_toward(g2, -n, cang2, fb);
+            }
+            int n_new = 0;
+            clip_edges(fa, fb, n, linear, g1.m, mf, n_new);
+            if (n_new == 0 && fa.fid != FEAT2_UNKNOWN && fb.fid != FEAT2_UNKNOWN) man_push(mf, h, fa.fid, fb.fid, to_local(g1.m, h.w1));
+        }
+    }
+}
+struct Args2 {
+    uint32_t n;
+    const uint32_t *type1, *type2;
+    const float4 *param1, *param2, *pose1, *pose2;
+    const float* poly;
+    const float* poly_nrm;
+    float prediction;
+    float cos_one_degree;  // cos(pi / 180) in f32 from the host libm (convex_polygon.rs:187-188)
+    uint8_t* found;
+    float* out;
+    uint32_t* counters;  // [0] reference panics, [1] EPA capacity overflows
+};
+__device__ __forceinline__ Operand2 load_operand(uint32_t t, float4 p, float4 m, const float* poly, const float* poly_nrm) {
+    Operand2 g;
+    g.kind = t, g.a = p.x, g.b = p.y, g.pts = g.nrm = nullptr, g.npts = 0;
+    if (t == D2_POLYGON) {
+        g.pts = poly + 2 * (size_t)p.x, g.npts = (uint32_t)p.y;
+        g.nrm = poly_nrm ? poly_nrm + 2 * (size_t)p.x : nullptr;
+    }
+    g.m.t = w2(m.x, m.y), g.m.re = m.z, g.m.im = m.w;
+    return g;
+}
+// query::contact for one pair.  flags: bit 0 = the reference would panic, bit 1 = EPA capacity exceeded.
+__device__ bool contact_of_pair(const Operand2& g1, const Operand2& g2, float prediction, float cos_one_degree, Hit2& h, int& flags) {
+    h.w1 = h.w2 = h.n = w2(0.f, 0.f), h.depth = 0.f;
+    bool ok = false;
+    if (g1.kind == D2_BALL && g2.kind == D2_BALL) {
+        ok = ball_ball(g1.m.t, g1.a, g2.m.t, g2.a, prediction, h);
+    } else if (g1.kind == D2_BALL || g2.kind == D2_BALL) {  // contact_ball_convex_polyhedron; with the ball second: the same query, flipped
+        const bool flip = g1.kind != D2_BALL;
+        const Operand2& ball = flip ? g2 : g1;
+        const Operand2& other = flip ? g1 : g2;
+        int q = 1;
+        ok = other.kind == D2_CUBOID ? ball_cuboid(ball.m.t, ball.a, other, prediction, h)
+                                     : ball_polygon(ball.m.t, ball.a, other, prediction, cos_one_degree, h, q);
+        if (q == -1) flags |= 1;
+        if (q == -2) flags |= 2;
+        if (ok && flip) {
+            W2 t = h.w1;
+            h.w1 = h.w2, h.w2 = t, h.n = -h.n;
+        }
+    } else {
+        W2 d0;
+        if (!unit(g2.m.t - g1.m.t, NCB_EPS, d0)) d0 = w2(1.f, 0.f);
+        Tri2 s;
+        for (int i = 0; i < 3; ++i) s.v[i].p = s.v[i].o1 = s.v[i].o2 = w2(0.f, 0.f), s.old_idx[i] = i;
+        s.bary[0] = s.bary[1] = s.old_bary[0] = s.old_bary[1] = 0.f;
+        s.dim = s.old_dim = 0;
+        s.v[0] = minkowski(g1, g2, d0);
+        W2 p1, p2, n;
+        int r = gjk2(g1, g2, prediction, s, p1, p2, n);
+        ok = r == G_POINTS;
+        if (r == G_INSIDE) {
+            Poly2 e;
+            int q = epa2(g1, g2, s, e, p1, p2, n);
+            ok = q == 1;
+            if (q == -1) flags |= 1;
+            if (q == -2) flags |= 2;
+        }
+        if (ok) h.w1 = p1, h.w2 = p2, h.n = n, h.depth = -dot(n, p2 - p1);
+    }
+    return ok;
+}
+
+#ifndef NCB_HOST_SHIM  // kernels and the host entry points: CUDA only (tests/host_shim compiles the per-pair functions above for the host)
+__global__ void __launch_bounds__(64) k_contact2d(Args2 A) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.n) return;
+    Operand2 g1 = load_operand(__ldg(&A.type1[k]), __ldg(&A.param1[k]), __ldg(&A.pose1[k]), A.poly, A.poly_nrm);
+    Operand2 g2 = load_operand(__ldg(&A.type2[k]), __ldg(&A.param2[k]), __ldg(&A.pose2[k]), A.poly, A.poly_nrm);
+    Hit2 h;
+    int flags = 0;
+    bool ok = contact_of_pair(g1, g2, A.prediction, A.cos_one_degree, h, flags);
+    if (flags & 1) atomicAdd(&A.counters[0], 1u);
+    if (flags & 2) atomicAdd(&A.counters[1], 1u);
+    A.found[k] = ok ? 1 : 0;
+    float* o = A.out + 7 * (size_t)k;
+    o[0] = h.w1.x, o[1] = h.w1.y, o[2] = h.w2.x, o[3] = h.w2.y, o[4] = h.n.x, o[5] = h.n.y, o[6] = h.depth;
+}
 struct World2Args {
     uint32_t n;
     const float2 *pos, *rot;
@@ -800,20 +959,7 @@ __global__ void __launch_bounds__(256) k_aabb2d(World2Args A) {
     if (i >= A.n) return;
     Operand2 g = world_operand(A, i);
     W2 lo, hi;
-    if (g.kind == D2_BALL) {
-        lo = w2(g.m.t.x + (-g.a), g.m.t.y + (-g.a)), hi = w2(g.m.t.x + g.a, g.m.t.y + g.a);
-    } else if (g.kind == D2_CUBOID) {
-        float are = fabsf(g.m.re), aim = fabsf(g.m.im);
-        W2 w = w2(are * g.a + aim * g.b, aim * g.a + are * g.b);
-        lo = g.m.t - w, hi = g.m.t + w;
-    } else {
-        W2 p = to_world(g.m, w2(__ldg(g.pts), __ldg(g.pts + 1)));
-        lo = hi = p;
-        for (uint32_t k = 1; k < g.npts; ++k) {
-            p = to_world(g.m, w2(__ldg(g.pts + 2 * k), __ldg(g.pts + 2 * k + 1)));
-            lo = w2(fminf(lo.x, p.x), fminf(lo.y, p.y)), hi = w2(fmaxf(hi.x, p.x), fmaxf(hi.y, p.y));
-        }
-    }
+    aabb_of_shape(g, lo, hi);
     float ql = __ldg(&A.qlimit[i]), mg = A.margin;
     // the 3-D broad phase reads float4 boxes; the w of the upper corner carries the shape type (ball 0, cuboid 1, polygon = the hull code 2)
     A.aabb_lo[i] = make_float4((lo.x + (-ql)) + (-mg), (lo.y + (-ql)) + (-mg), 0.f, 0.f);
@@ -827,65 +973,10 @@ __global__ void __launch_bounds__(64) k_narrow2d(World2Args A) {
     Operand2 g1 = world_operand(A, pr.x), g2 = world_operand(A, pr.y);
     float linear = __ldg(&A.qlimit[pr.x]) + __ldg(&A.qlimit[pr.y]);
     Manifold2d mf;
-    mf.n = 0, mf.overflow = false;
-    const uint32_t FACE0 = FEAT2_FACE | 0u;
-    Hit2 h;
-    if (g1.kind == D2_BALL && g2.kind == D2_BALL) {
-        if (ball_ball(g1.m.t, g1.a, g2.m.t, g2.a, linear, h)) man_push(mf, h, FACE0, FACE0, w2(0.f, 0.f));
-    } else if (g1.kind == D2_BALL || g2.kind == D2_BALL) {
-        const bool flip = g1.kind != D2_BALL;
-        const Operand2& ball = flip ? g2 : g1;
-        const Operand2& other = flip ? g1 : g2;
-        uint32_t f2 = FEAT2_UNKNOWN;
-        int q = 1;
-        bool ok = other.kind == D2_CUBOID ? ball_cuboid(ball.m.t, ball.a, other, linear, h, &f2)
-                                          : ball_polygon(ball.m.t, ball.a, other, linear, A.cos_one_degree, h, q, &f2);
-        if (q == -1) atomicAdd(&A.counters[1], 1u);
-        if (q == -2) atomicAdd(&A.counters[2], 1u);
-        if (ok) {
-            if (f2 == FEAT2_UNKNOWN) {
-                atomicAdd(&A.counters[1], 1u);  // "Feature id cannot be unknown."
-            } else if (!flip) {
-                man_push(mf, h, FACE0, f2, w2(0.f, 0.f));
-            } else {
-                W2 t = h.w1;
-                h.w1 = h.w2, h.w2 = t, h.n = -h.n;
-                man_push(mf, h, f2, FACE0, w2(0.f, 0.f));
-            }
-        }
-    } else {
-        W2 d0;
-        if (!unit(g2.m.t - g1.m.t, NCB_EPS, d0)) d0 = w2(1.f, 0.f);
-        Tri2 s;
-        for (int i = 0; i < 3; ++i) s.v[i].p = s.v[i].o1 = s.v[i].o2 = w2(0.f, 0.f), s.old_idx[i] = i;
-        s.bary[0] = s.bary[1] = s.old_bary[0] = s.old_bary[1] = 0.f;
-        s.dim = s.old_dim = 0;
-        s.v[0] = minkowski(g1, g2, d0);
-        W2 p1, p2, n;
-        int r = gjk2(g1, g2, linear, s, p1, p2, n);
-        bool ok = r == G_POINTS;
-        if (r == G_INSIDE) {
-            Poly2 e;
-            int q = epa2(g1, g2, s, e, p1, p2, n);
-            ok = q == 1;
-            if (q == -1) atomicAdd(&A.counters[1], 1u);
-            if (q == -2) atomicAdd(&A.counters[2], 1u);
-        }
-        if (ok) {
-            h.w1 = p1, h.w2 = p2, h.n = n, h.depth = -dot(n, p2 - p1);
-            Edge2 fa, fb;
-            if (h.depth > 0.f) {
-                face_toward(g1, n, fa);
-                face_toward(g2, -n, fb);
-            } else {
-                feature_toward(g1, n, __ldg(&A.cos_ang[pr.x]), fa);
-                feature_toward(g2, -n, __ldg(&A.cos_ang[pr.y]), fb);
-            }
-            int n_new = 0;
-            clip_edges(fa, fb, n, linear, g1.m, mf, n_new);
-            if (n_new == 0 && fa.fid != FEAT2_UNKNOWN && fb.fid != FEAT2_UNKNOWN) man_push(mf, h, fa.fid, fb.fid, to_local(g1.m, h.w1));
-        }
-    }
+    int flags = 0;
+    manifold_of_pair(g1, g2, linear, __ldg(&A.cos_ang[pr.x]), __ldg(&A.cos_ang[pr.y]), A.cos_one_degree, mf, flags);
+    if (flags & 1) atomicAdd(&A.counters[1], 1u);
+    if (flags & 2) atomicAdd(&A.counters[2], 1u);
     if (mf.overflow) atomicAdd(&A.counters[3], 1u);
     uint32_t start = mf.n ? atomicAdd(&A.counters[0], (uint32_t)mf.n) : 0u;
     A.manifold_start[p] = start;
@@ -900,81 +991,14 @@ __global__ void __launch_bounds__(64) k_narrow2d(World2Args A) {
     }
 }
 
-struct Args2 {
-    uint32_t n;
-    const uint32_t *type1, *type2;
-    const float4 *param1, *param2, *pose1, *pose2;
-    const float* poly;
-    const float* poly_nrm;
-    float prediction;
-    float cos_one_degree;  // cos(pi / 180) in f32 from the host libm (convex_polygon.rs:187-188)
-    uint8_t* found;
-    float* out;
-    uint32_t* counters;  // [0] reference panics, [1] EPA capacity overflows
-};
-__device__ __forceinline__ Operand2 load_operand(uint32_t t, float4 p, float4 m, const float* poly, const float* poly_nrm) {
-    Operand2 g;
-    g.kind = t, g.a = p.x, g.b = p.y, g.pts = g.nrm = nullptr, g.npts = 0;
-    if (t == D2_POLYGON) {
-        g.pts = poly + 2 * (size_t)p.x, g.npts = (uint32_t)p.y;
-        g.nrm = poly_nrm ? poly_nrm + 2 * (size_t)p.x : nullptr;
-    }
-    g.m.t = w2(m.x, m.y), g.m.re = m.z, g.m.im = m.w;
-    return g;
-}
-__global__ void __launch_bounds__(64) k_contact2d(Args2 A) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= A.n) return;
-    Operand2 g1 = load_operand(__ldg(&A.type1[k]), __ldg(&A.param1[k]), __ldg(&A.pose1[k]), A.poly, A.poly_nrm);
-    Operand2 g2 = load_operand(__ldg(&A.type2[k]), __ldg(&A.param2[k]), __ldg(&A.pose2[k]), A.poly, A.poly_nrm);
-    Hit2 h;
-    h.w1 = h.w2 = h.n = w2(0.f, 0.f), h.depth = 0.f;
-    bool ok = false;
-    if (g1.kind == D2_BALL && g2.kind == D2_BALL) {
-        ok = ball_ball(g1.m.t, g1.a, g2.m.t, g2.a, A.prediction, h);
-    } else if (g1.kind == D2_BALL || g2.kind == D2_BALL) {  // contact_ball_convex_polyhedron; with the ball second: the same query, flipped
-        const bool flip = g1.kind != D2_BALL;
-        const Operand2& ball = flip ? g2 : g1;
-        const Operand2& other = flip ? g1 : g2;
-        int q = 1;
-        ok = other.kind == D2_CUBOID ? ball_cuboid(ball.m.t, ball.a, other, A.prediction, h)
-                                     : ball_polygon(ball.m.t, ball.a, other, A.prediction, A.cos_one_degree, h, q);
-        if (q == -1) atomicAdd(&A.counters[0], 1u);
-        if (q == -2) atomicAdd(&A.counters[1], 1u);
-        if (ok && flip) {
-            W2 t = h.w1;
-            h.w1 = h.w2, h.w2 = t, h.n = -h.n;
-        }
-    } else {
-        W2 d0;
-        if (!unit(g2.m.t - g1.m.t, NCB_EPS, d0)) d0 = w2(1.f, 0.f);
-        Tri2 s;
-        for (int i = 0; i < 3; ++i) s.v[i].p = s.v[i].o1 = s.v[i].o2 = w2(0.f, 0.f), s.old_idx[i] = i;
-        s.bary[0] = s.bary[1] = s.old_bary[0] = s.old_bary[1] = 0.f;
-        s.dim = s.old_dim = 0;
-        s.v[0] = minkowski(g1, g2, d0);
-        W2 p1, p2, n;
-        int r = gjk2(g1, g2, A.prediction, s, p1, p2, n);
-        ok = r == G_POINTS;
-        if (r == G_INSIDE) {
-            Poly2 e;
-            int q = epa2(g1, g2, s, e, p1, p2, n);
-            ok = q == 1;
-            if (q == -1) atomicAdd(&A.counters[0], 1u);
-            if (q == -2) atomicAdd(&A.counters[1], 1u);
-        }
-        if (ok) h.w1 = p1, h.w2 = p2, h.n = n, h.depth = -dot(n, p2 - p1);
-    }
-    A.found[k] = ok ? 1 : 0;
-    float* o = A.out + 7 * (size_t)k;
-    o[0] = h.w1.x, o[1] = h.w1.y, o[2] = h.w2.x, o[3] = h.w2.y, o[4] = h.n.x, o[5] = h.n.y, o[6] = h.depth;
-}
+#endif  // NCB_HOST_SHIM (kernels)
 
 }  // namespace d2
 }  // namespace ncb
 
 using namespace ncb;
 
+#ifndef NCB_HOST_SHIM
 #define CK2(call)                                                                                         \
     do {                                                                                                  \
         cudaError_t e__ = (call);                                                                         \
@@ -1175,3 +1199,5 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
 }
 
 }  // extern "C"
+#endif  // NCB_HOST_SHIM (host entry points)
+

@@ -297,3 +297,65 @@ def test_device_world2d_matches_oracle(ctx, oracle, n, seed, kinds, angular, gro
         same += int((dc.view(np.uint32) == np.ascontiguousarray(oc, dtype=np.float32).view(np.uint32)).sum())
     assert len(r["contacts"]) == len(ocontacts) > n // 4
     assert same / words > 0.999
+
+
+# ---- CPU: the DEVICE source compiled for the host (tests/host_shim/dim2_host.cpp) against the oracle, bit for bit ------------------
+@pytest.fixture(scope="module")
+def dim2_shim():
+    from test_device_source_on_host import _build_shim
+
+    return _build_shim("libdim2_host.so", "dim2_host.cpp")
+
+
+def _vp(a):
+    import ctypes as C
+
+    return C.c_void_p(a.ctypes.data)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("seed,kinds,prediction", [(11, (0, 1, 2), 0.0), (12, (1, 2), 0.02), (13, (0, 1), 0.3), (14, (2,), 0.05), (15, (0, 2), 0.1)])
+def test_device_source_contact_equals_oracle_bit_for_bit(dim2_shim, oracle, seed, kinds, prediction):
+    """query::contact: the functions k_contact2d runs per pair, compiled for the host with -ffp-contract=off (= --fmad=false), give
+    the oracle's answer in every bit — 2-D GJK, EPA2, the ball / cuboid / polygon projections."""
+    import ctypes as C
+
+    t1, p1, m1, t2, p2, m2, pts, nrm = random_pairs(40000, seed, kinds)
+    n = len(t1)
+    found, out, flags = np.zeros(n, dtype=np.uint8), np.zeros((n, 7), dtype=np.float32), np.zeros(2, dtype=np.uint32)
+    dim2_shim.shim2_contact(C.c_uint64(n), _vp(t1), _vp(p1), _vp(m1), _vp(t2), _vp(p2), _vp(m2), _vp(pts), _vp(nrm), C.c_float(prediction),
+                            _vp(found), _vp(out), _vp(flags))
+    ofound, oout, opanics = oracle.contact2d(t1, p1, m1, t2, p2, m2, pts, prediction, poly_normals=nrm)
+    assert flags.tolist() == [opanics, 0]
+    assert np.array_equal(found, ofound)
+    hit = found.astype(bool)
+    assert hit.sum() > 5000
+    assert np.array_equal(_bits(out[hit]), _bits(oout[hit])), f"{(_bits(out[hit]) != _bits(oout[hit])).sum()} words differ"
+
+
+@pytest.mark.parametrize("n,seed,kinds,angular", [(2500, 51, (0, 1, 2), 0.0), (2000, 52, (1, 2), 0.1), (1500, 53, (2,), 0.3)])
+def test_device_source_world2d_equals_oracle_bit_for_bit(dim2_shim, oracle, n, seed, kinds, angular):
+    """The 2-D world's AABBs and manifolds from the device source on the host: boxes, manifold sizes, feature ids and every contact
+    word equal the oracle's."""
+    import ctypes as C
+
+    w = random_world(n, seed, kinds, angular=angular)
+    pairs, off, ocontacts, ofeats, panics, fat = oracle.world_update2d(w)
+    boxes = np.zeros((w.n, 6), dtype=np.float32)
+    dim2_shim.shim2_aabbs(C.c_uint32(w.n), _vp(w.pos), _vp(w.rot), _vp(w.type), _vp(w.param), _vp(w.query_limit), _vp(w.points), _vp(w.normals),
+                          C.c_float(w.margin), _vp(boxes))
+    assert np.array_equal(_bits(boxes), _bits(fat))
+    P = len(pairs)
+    pr = np.ascontiguousarray(pairs, dtype=np.uint32)
+    doff, dc, df = np.zeros(P + 1, dtype=np.uint32), np.zeros((4 * P + 16, 7), dtype=np.float32), np.zeros((4 * P + 16, 2), dtype=np.uint32)
+    flags = np.zeros(3, dtype=np.uint32)
+    dim2_shim.shim2_narrow.restype = C.c_uint64
+    nc = dim2_shim.shim2_narrow(C.c_uint32(w.n), _vp(w.pos), _vp(w.rot), _vp(w.type), _vp(w.param), _vp(w.query_limit), _vp(w.ang_pred),
+                                _vp(w.points), _vp(w.normals), C.c_uint64(P), _vp(pr), _vp(doff), _vp(dc), _vp(df), C.c_uint64(len(dc)), _vp(flags))
+    assert flags.tolist() == [panics, 0, 0]
+    assert np.array_equal(doff, off) and nc == len(ocontacts) > n // 4
+    assert np.array_equal(df[:nc], ofeats)
+    assert np.array_equal(_bits(dc[:nc]), _bits(ocontacts))
