@@ -65,7 +65,8 @@ __device__ __forceinline__ W2 to_local(const Pose2& m, W2 p) { return unrotate(m
 #define D2_BALL 0u
 #define D2_CUBOID 1u
 #define D2_POLYGON 2u
-#define D2_ORIGIN 3u  // special_support_maps::ConstantOrigin
+#define D2_PLANE 3u   // shape/plane.rs: (a, b) = the unit normal; the code of the 3-D path's plane, so the broad phase treats its box as an outlier
+#define D2_ORIGIN 7u  // special_support_maps::ConstantOrigin
 struct Operand2 {
     uint32_t kind;
     float a, b;          // radius | half extents
@@ -774,7 +775,9 @@ __device__ void clip_edges(const Edge2& a, const Edge2& b, W2 normal, float pred
 
 // bounding_volume::aabb(shape, m) in 2-D
 __device__ void aabb_of_shape(const Operand2& g, W2& lo, W2& hi) {
-    if (g.kind == D2_BALL) {
+    if (g.kind == D2_PLANE) {  // aabb_plane.rs:13-21: half of f32::MAX either way; the 3-D broad phase keeps such boxes out of the tree
+        lo = w2(-NCB_FMAX * 0.5f, -NCB_FMAX * 0.5f), hi = w2(NCB_FMAX * 0.5f, NCB_FMAX * 0.5f);
+    } else if (g.kind == D2_BALL) {
         lo = w2(g.m.t.x + (-g.a), g.m.t.y + (-g.a)), hi = w2(g.m.t.x + g.a, g.m.t.y + g.a);
     } else if (g.kind == D2_CUBOID) {
         float are = fabsf(g.m.re), aim = fabsf(g.m.im);
@@ -795,8 +798,48 @@ __device__ void manifold_of_pair(const Operand2& g1, const Operand2& g2, float l
     mf.n = 0, mf.overflow = false;
     const uint32_t FACE0 = FEAT2_FACE | 0u;
     Hit2 h;
-    if (g1.kind == D2_BALL && g2.kind == D2_BALL) {
+    if (g1.kind == D2_PLANE && g2.kind == D2_PLANE) {
+        // no contact algorithm for two planes: the pair has no interaction edge
+    } else if (g1.kind == D2_BALL && g2.kind == D2_BALL) {
         if (ball_ball(g1.m.t, g1.a, g2.m.t, g2.a, linear, h)) man_push(mf, h, FACE0, FACE0, w2(0.f, 0.f));
+    } else if (g1.kind == D2_PLANE || g2.kind == D2_PLANE) {
+        // PlaneBallManifoldGenerator / PlaneConvexPolyhedronManifoldGenerator (plane_ball_manifold_generator.rs:40-77,
+        // plane_convex_polyhedron_manifold_generator.rs:40-85), flip = the plane is the second object
+        const bool flip = g1.kind != D2_PLANE;
+        const Operand2& pl = flip ? g2 : g1;
+        const Operand2& ot = flip ? g1 : g2;
+        W2 n = rotate(pl.m, w2(pl.a, pl.b)), center = pl.m.t;
+        if (ot.kind == D2_BALL) {
+            float dist = dot(ot.m.t - center, n), depth = -dist + ot.a;
+            if (depth > -linear) {
+                W2 on_plane = ot.m.t + n * (-dist), on_ball = ot.m.t + n * (-ot.a);
+                if (!flip)
+                    h.w1 = on_plane, h.w2 = on_ball, h.n = n;
+                else
+                    h.w1 = on_ball, h.w2 = on_plane, h.n = -n;
+                h.depth = depth;
+                man_push(mf, h, FACE0, FACE0, w2(0.f, 0.f));
+            }
+        } else {
+            Edge2 f;
+            face_toward(ot, -n, f);
+            for (int i = 0; i < 2; ++i) {  // both slots of the feature's vertex array, like the reference's iteration
+                W2 on_shape = f.v[i];
+                float dist = dot(on_shape - center, n);
+                if (dist <= linear) {
+                    W2 on_plane = on_shape + (-n) * dist;
+                    W2 track = to_local(ot.m, on_shape);
+                    h.depth = -dist;
+                    if (!flip) {
+                        h.w1 = on_plane, h.w2 = on_shape, h.n = n;
+                        man_push(mf, h, FACE0, f.vid[i], track);
+                    } else {
+                        h.w1 = on_shape, h.w2 = on_plane, h.n = -n;
+                        man_push(mf, h, f.vid[i], FACE0, track);
+                    }
+                }
+            }
+        }
     } else if (g1.kind == D2_BALL || g2.kind == D2_BALL) {
         const bool flip = g1.kind != D2_BALL;
         const Operand2& ball = flip ? g2 : g1;
@@ -874,12 +917,29 @@ __device__ __forceinline__ Operand2 load_operand(uint32_t t, float4 p, float4 m,
     g.m.t = w2(m.x, m.y), g.m.re = m.z, g.m.im = m.w;
     return g;
 }
+// contact_plane_support_map (query/contact/contact_plane_support_map.rs:8-28)
+__device__ bool plane_support(const Operand2& plane, const Operand2& other, float prediction, Hit2& h) {
+    W2 n = rotate(plane.m, w2(plane.a, plane.b));
+    W2 deepest = other.kind == D2_BALL ? other.m.t + (-n) * other.a : support(other, -n);  // support_point_toward: a ball takes the unit direction as is
+    float distance = dot(n, plane.m.t - deepest);
+    if (!(distance > -prediction)) return false;
+    h.w1 = deepest + n * distance, h.w2 = deepest, h.n = n, h.depth = distance;
+    return true;
+}
+
 // query::contact for one pair.  flags: bit 0 = the reference would panic, bit 1 = EPA capacity exceeded.
 __device__ bool contact_of_pair(const Operand2& g1, const Operand2& g2, float prediction, float cos_one_degree, Hit2& h, int& flags) {
     h.w1 = h.w2 = h.n = w2(0.f, 0.f), h.depth = 0.f;
     bool ok = false;
     if (g1.kind == D2_BALL && g2.kind == D2_BALL) {
         ok = ball_ball(g1.m.t, g1.a, g2.m.t, g2.a, prediction, h);
+    } else if (g1.kind == D2_PLANE || g2.kind == D2_PLANE) {  // contact_plane_support_map / contact_support_map_plane (plane x plane is refused on the host)
+        const bool flip = g1.kind != D2_PLANE;
+        ok = plane_support(flip ? g2 : g1, flip ? g1 : g2, prediction, h);
+        if (ok && flip) {
+            W2 t = h.w1;
+            h.w1 = h.w2, h.w2 = t, h.n = -h.n;
+        }
     } else if (g1.kind == D2_BALL || g2.kind == D2_BALL) {  // contact_ball_convex_polyhedron; with the ball second: the same query, flipped
         const bool flip = g1.kind != D2_BALL;
         const Operand2& ball = flip ? g2 : g1;
@@ -1024,7 +1084,7 @@ int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const f
         for (int side = 0; side < 2; ++side) {
             uint32_t t = side ? type2[k] : type1[k];
             const float* p = (side ? param2 : param1) + 4 * (size_t)k;
-            if (t > 2) {
+            if (t > 3) {
                 ctx->err = "ncb2d_contact: unknown 2-D shape type";
                 return NCB_ERR_UNSUPPORTED;
             }
@@ -1034,6 +1094,10 @@ int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const f
                     return NCB_ERR_ARG;
                 }
             }
+        }
+        if (type1[k] == 3 && type2[k] == 3) {
+            ctx->err = "ncb2d_contact: no algorithm for plane x plane (the reference panics)";
+            return NCB_ERR_UNSUPPORTED;
         }
         bool b1 = type1[k] == 0, b2 = type2[k] == 0;
         if (((b1 && type2[k] == 2) || (b2 && type1[k] == 2)) && !poly_normals) {
@@ -1102,7 +1166,7 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     bool any_poly = false;
     for (uint32_t i = 0; i < n; ++i) {  // validation before device state is touched
         uint32_t t = o->shape_type[i];
-        if (t > 2) {
+        if (t > 3) {
             ctx->err = "ncb2d_world_update: unknown 2-D shape type";
             return NCB_ERR_UNSUPPORTED;
         }

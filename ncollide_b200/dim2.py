@@ -10,7 +10,7 @@ import numpy as np
 
 from ._ffi import as_f32, as_u32, ptr
 
-BALL, CUBOID, POLYGON = 0, 1, 2
+BALL, CUBOID, POLYGON, PLANE = 0, 1, 2, 3
 F32 = np.float32
 EPS = np.finfo(np.float32).eps
 
@@ -34,6 +34,13 @@ class Shapes2D:
 
     def cuboid(self, hx, hy):
         self.type.append(CUBOID), self.param.append((hx, hy, 0, 0))
+        return self
+
+    def plane(self, normal):
+        """``Plane::new(Unit::new_normalize(normal))`` (a half-space in 2-D); the normal is normalised in f32."""
+        v = as_f32(normal).reshape(2)
+        nrm = np.sqrt(F32(F32(v[0] * v[0]) + F32(v[1] * v[1])), dtype=F32)
+        self.type.append(PLANE), self.param.append((F32(v[0] / nrm), F32(v[1] / nrm), 0, 0))
         return self
 
     def polygon(self, points):

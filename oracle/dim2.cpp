@@ -54,7 +54,7 @@ static inline P2 inv_rot(const Iso2& m, P2 v) { return {m.re * v.x + m.im * v.y,
 static inline P2 mul_point(const Iso2& m, P2 p) { return rot(m, p) + m.t; }
 static inline P2 inv_point(const Iso2& m, P2 p) { return inv_rot(m, p - m.t); }
 
-enum { BALL2 = 0, CUBOID2 = 1, POLYGON2 = 2, ORIGIN2 = 3 };  // ORIGIN2: special_support_maps::ConstantOrigin
+enum { BALL2 = 0, CUBOID2 = 1, POLYGON2 = 2, PLANE2 = 3, ORIGIN2 = 7 };  // PLANE2: param = unit normal; ORIGIN2: special_support_maps::ConstantOrigin
 struct Shape2 {
     uint32_t type;
     real radius;
@@ -498,6 +498,19 @@ static bool contact_ball_ball(P2 c1, real r1, P2 c2, real r2, real prediction, C
     return false;
 }
 
+// contact_plane_support_map (contact_plane_support_map.rs:8-28): `other.support_point_toward(mother, -plane_normal)`
+static bool contact_plane_sm(const Iso2& mp, P2 plane_n_local, const Iso2& mo, const Shape2& other, real prediction, Contact2* c) {
+    P2 n = rot(mp, plane_n_local);
+    P2 deepest = other.type == BALL2 ? mo.t + (-n) * other.radius  // Ball::support_point_toward: the unit direction is used as is
+                                     : support_point(other, mo, -n);
+    real distance = dot(n, mp.t - deepest);
+    if (distance > -prediction) {
+        c->w1 = deepest + n * distance, c->w2 = deepest, c->n = n, c->depth = distance;
+        return true;
+    }
+    return false;
+}
+
 enum { F_UNKNOWN = 0xffffffffu, F_FACE = 0x40000000u, F_VERTEX = 0x80000000u };
 // Cuboid::project_point_with_feature -> AABB (point_aabb.rs:14-135), dim2
 static P2 cuboid_project(const Shape2& g, const Iso2& m, P2 pt, bool* inside_out, uint32_t* feature) {
@@ -825,7 +838,10 @@ struct Box2 {
 };
 static Box2 shape_aabb2(const Shape2& g, const Iso2& m) {
     P2 lo, hi;
-    if (g.type == BALL2) {
+    if (g.type == PLANE2) {  // aabb_plane.rs:13-21
+        real mx = FMAX * real(0.5);
+        lo = p2(-mx, -mx), hi = p2(mx, mx);
+    } else if (g.type == BALL2) {
         lo = p2(m.t.x + (-g.radius), m.t.y + (-g.radius)), hi = p2(m.t.x + g.radius, m.t.y + g.radius);
     } else if (g.type == CUBOID2) {
         real are = std::fabs(m.re), aim = std::fabs(m.im);
@@ -846,9 +862,52 @@ static Box2 shape_aabb2(const Shape2& g, const Iso2& m) {
 static void generate_contacts2(const Shape2& g1, const Iso2& m1, const Shape2& g2, const Iso2& m2, real linear, real cang1, real cang2, Manifold2& mf,
                                int* panicked) {
     const uint32_t FACE0 = F_FACE | 0u;
+    if (g1.type == PLANE2 && g2.type == PLANE2) return;  // no contact algorithm: no interaction edge
     if (g1.type == BALL2 && g2.type == BALL2) {
         Contact2 c;
         if (contact_ball_ball(m1.t, g1.radius, m2.t, g2.radius, linear, &c)) mf.push(c, FACE0, FACE0, p2(0, 0));
+        return;
+    }
+    if (g1.type == PLANE2 || g2.type == PLANE2) {
+        bool flip = g1.type != PLANE2;
+        const Shape2& pl = flip ? g2 : g1;
+        const Shape2& ot = flip ? g1 : g2;
+        const Iso2& mp = flip ? m2 : m1;
+        const Iso2& mo = flip ? m1 : m2;
+        P2 n = rot(mp, pl.he), center = mp.t;
+        if (ot.type == BALL2) {  // PlaneBallManifoldGenerator (plane_ball_manifold_generator.rs:40-77)
+            real dist = dot(mo.t - center, n), depth = -dist + ot.radius;
+            if (depth > -linear) {
+                P2 world1 = mo.t + n * (-dist), world2 = mo.t + n * (-ot.radius);
+                Contact2 c;
+                if (!flip) {
+                    c.w1 = world1, c.w2 = world2, c.n = n, c.depth = depth;
+                    mf.push(c, FACE0, FACE0, p2(0, 0));
+                } else {
+                    c.w1 = world2, c.w2 = world1, c.n = -n, c.depth = depth;
+                    mf.push(c, FACE0, FACE0, p2(0, 0));
+                }
+            }
+            return;
+        }
+        Feature2 f;  // PlaneConvexPolyhedronManifoldGenerator (plane_convex_polyhedron_manifold_generator.rs:40-85): both array slots
+        support_face_toward(ot, mo, -n, f);
+        for (int i = 0; i < 2; ++i) {
+            P2 world2 = f.v[i];
+            real dist = dot(world2 - center, n);
+            if (dist <= linear) {
+                P2 world1 = world2 + (-n) * dist;
+                P2 local2 = inv_point(mo, world2);
+                Contact2 c;
+                if (!flip) {
+                    c.w1 = world1, c.w2 = world2, c.n = n, c.depth = -dist;
+                    mf.push(c, FACE0, f.vid[i], local2);
+                } else {
+                    c.w1 = world2, c.w2 = world1, c.n = -n, c.depth = -dist;
+                    mf.push(c, f.vid[i], FACE0, local2);
+                }
+            }
+        }
         return;
     }
     if (g1.type == BALL2 || g2.type == BALL2) {  // BallConvexPolyhedronManifoldGenerator::new(flip = ball is second)
@@ -955,8 +1014,18 @@ void orc2_contact(uint64_t n, const uint32_t* type1, const real* param1, const r
         bool ok = false;
         int panicked = 0;
         uint8_t code = 0;
-        if (g1.type == BALL2 && g2.type == BALL2) {
+        if (g1.type == PLANE2 && g2.type == PLANE2) {
+            code = 2;  // the reference panics: "No algorithm known to compute a contact point between the given pair of shapes."
+        } else if (g1.type == BALL2 && g2.type == BALL2) {
             ok = contact_ball_ball(m1.t, g1.radius, m2.t, g2.radius, prediction, &c);
+        } else if (g1.type == PLANE2) {
+            ok = contact_plane_sm(m1, g1.he, m2, g2, prediction, &c);
+        } else if (g2.type == PLANE2) {  // contact_support_map_plane: flipped
+            ok = contact_plane_sm(m2, g2.he, m1, g1, prediction, &c);
+            if (ok) {
+                std::swap(c.w1, c.w2);
+                c.n = -c.n;
+            }
         } else if (g1.type == BALL2 && g2.type == CUBOID2) {
             ok = contact_ball_cuboid(m1.t, g1.radius, m2, g2, prediction, &c);
         } else if (g1.type == CUBOID2 && g2.type == BALL2) {  // contact_convex_polyhedron_ball: flip

@@ -18,11 +18,14 @@ def random_pairs(n, seed, kinds=(0, 1, 2), spread=1.2):
     sh = dim2.Shapes2D()
     t1 = rng.choice(kinds, size=n)
     t2 = rng.choice(kinds, size=n)
+    t2[(t1 == 3) & (t2 == 3)] = 1  # plane x plane has no algorithm (the reference panics)
     for t in np.concatenate([t1, t2]):
         if t == 0:
             sh.ball(rng.uniform(0.2, 0.6))
         elif t == 1:
             sh.cuboid(rng.uniform(0.2, 0.6), rng.uniform(0.2, 0.6))
+        elif t == 3:
+            sh.plane(rng.normal(size=2))
         else:
             k = int(rng.integers(3, 13))
             ang = np.sort(rng.uniform(0, 2 * np.pi, size=k))
@@ -194,7 +197,7 @@ def test_device_kats(ctx):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed,kinds,prediction", [(1, (0, 1, 2), 0.0), (2, (1, 2), 0.02), (3, (0, 1), 0.3), (4, (2,), 0.05), (6, (1,), 0.0),
-                                                   (7, (0, 2), 0.05)])
+                                                   (7, (0, 2), 0.05), (8, (0, 1, 2, 3), 0.05)])
 def test_device_contact_matches_oracle(ctx, oracle, seed, kinds, prediction):
     t1, p1, m1, t2, p2, m2, pts, nrm = random_pairs(60000, seed, kinds)
     found, out, info = dim2.contact(ctx, t1, p1, m1, t2, p2, m2, pts, prediction, poly_normals=nrm)
@@ -223,10 +226,10 @@ def test_device_refuses_bad_input(ctx):
 
 
 # ---- 2-D world update ----------------------------------------------------------------------------------------------------------
-def random_world(n, seed, kinds=(0, 1, 2), density=2.5, angular=0.0, linear=0.02, with_groups=False):
+def random_world(n, seed, kinds=(0, 1, 2), density=2.5, angular=0.0, linear=0.02, with_groups=False, planes=0):
     rng = np.random.default_rng(seed)
     sh = dim2.Shapes2D()
-    for t in rng.choice(kinds, size=n):
+    for t in rng.choice(kinds, size=n - planes):
         if t == 0:
             sh.ball(rng.uniform(0.25, 0.5))
         elif t == 1:
@@ -239,6 +242,10 @@ def random_world(n, seed, kinds=(0, 1, 2), density=2.5, angular=0.0, linear=0.02
     pos = rng.uniform(0, side, size=(n, 2))
     angle = rng.uniform(-np.pi, np.pi, size=n)
     angle[rng.random(n) < 0.25] = 0.0  # axis-aligned boxes: face-face contacts with two clipped points
+    for k in range(planes):  # half-spaces through the scene: a floor, then tilted walls (the last handles: object 1 of their pairs)
+        sh.plane((0.0, 1.0) if k == 0 else rng.normal(size=2))
+        pos[n - planes + k] = (side / 2, 0.4) if k == 0 else rng.uniform(0.3 * side, 0.7 * side, size=2)
+        angle[n - planes + k] = 0.0 if k == 0 else rng.uniform(-np.pi, np.pi)
     groups = None
     if with_groups:
         groups = np.tile(np.array([0x3FFFFFFF, 0x3FFFFFFF, 0], dtype=np.uint32), (n, 1))
@@ -272,15 +279,26 @@ def test_oracle_world2d_properties(oracle64):
     assert pairs.tolist() == [[1, 0]] and off.tolist() == [0, 2]
     assert np.allclose(contacts[:, 6], 0.1) and np.allclose(contacts[:, 4:6], [[0, -1], [0, -1]])
     assert sorted(np.round(contacts[:, 0], 6).tolist()) == [-0.2, 0.8]
+    # known answers with a floor (half-space y <= 0, normal +y): a ball 0.3 above it (radius 0.5) and a unit box sunk 0.1 into it
+    sh = dim2.Shapes2D().plane((0, 2)).ball(0.5).cuboid(0.5, 0.5)
+    kw = dim2.World2D(sh, [[0, 0], [3, 0.3], [-3, 0.4]], [0, 0, 0], margin=0.02, linear=0.02)
+    pairs, off, contacts, feats, panics, _ = oracle64.world_update2d(kw)
+    got = {tuple(p): contacts[a:b] for p, a, b in zip(pairs.tolist(), off[:-1].tolist(), off[1:].tolist())}
+    ball = got[(1, 0)]  # object 1 = the ball (larger handle): the generator is flipped, the normal points from the ball to the plane
+    assert len(ball) == 1 and np.allclose(ball[0], [3, -0.2, 3, 0.0, 0, -1, 0.2])
+    box = got[(2, 0)]
+    assert len(box) == 2 and np.allclose(box[:, 6], 0.1) and np.allclose(box[:, 4:6], [[0, -1], [0, -1]])
+    assert sorted(np.round(box[:, 0], 6).tolist()) == [-3.5, -2.5] and np.allclose(box[:, 1], -0.1) and np.allclose(box[:, 3], 0.0)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,seed,kinds,angular,groups", [(3000, 41, (0, 1, 2), 0.0, False), (2500, 42, (1, 2), 0.05, True), (2000, 43, (0, 1), 0.0, False),
-                                                         (4000, 44, (2,), 0.2, False), (50000, 45, (0, 1, 2), 0.0, False)])
-def test_device_world2d_matches_oracle(ctx, oracle, n, seed, kinds, angular, groups):
+@pytest.mark.parametrize("n,seed,kinds,angular,groups,planes", [(3000, 41, (0, 1, 2), 0.0, False, 0), (2500, 42, (1, 2), 0.05, True, 0),
+                                                                (2000, 43, (0, 1), 0.0, False, 0), (4000, 44, (2,), 0.2, False, 0),
+                                                                (50000, 45, (0, 1, 2), 0.0, False, 0), (3000, 46, (0, 1, 2), 0.0, False, 4)])
+def test_device_world2d_matches_oracle(ctx, oracle, n, seed, kinds, angular, groups, planes):
     """ncb2d_world_update against the oracle: pair set and orientation exact, manifold sizes and feature ids exact, contacts within
     1e-4 / 1e-5 (and almost all words bit-identical)."""
-    w = random_world(n, seed, kinds, angular=angular, with_groups=groups)
+    w = random_world(n, seed, kinds, angular=angular, with_groups=groups, planes=planes)
     r = dim2.world_update(ctx, w)
     pairs, off, ocontacts, ofeats, panics, _ = oracle.world_update2d(w)
     assert r["diag"] == {"ref_panics": panics, "epa_overflow": 0, "manifold_overflow": 0, "stack_overflow": 0}
@@ -317,7 +335,8 @@ def _bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
 
-@pytest.mark.parametrize("seed,kinds,prediction", [(11, (0, 1, 2), 0.0), (12, (1, 2), 0.02), (13, (0, 1), 0.3), (14, (2,), 0.05), (15, (0, 2), 0.1)])
+@pytest.mark.parametrize("seed,kinds,prediction", [(11, (0, 1, 2), 0.0), (12, (1, 2), 0.02), (13, (0, 1), 0.3), (14, (2,), 0.05), (15, (0, 2), 0.1),
+                                                   (16, (0, 1, 2, 3), 0.05)])
 def test_device_source_contact_equals_oracle_bit_for_bit(dim2_shim, oracle, seed, kinds, prediction):
     """query::contact: the functions k_contact2d runs per pair, compiled for the host with -ffp-contract=off (= --fmad=false), give
     the oracle's answer in every bit — 2-D GJK, EPA2, the ball / cuboid / polygon projections."""
@@ -336,13 +355,14 @@ def test_device_source_contact_equals_oracle_bit_for_bit(dim2_shim, oracle, seed
     assert np.array_equal(_bits(out[hit]), _bits(oout[hit])), f"{(_bits(out[hit]) != _bits(oout[hit])).sum()} words differ"
 
 
-@pytest.mark.parametrize("n,seed,kinds,angular", [(2500, 51, (0, 1, 2), 0.0), (2000, 52, (1, 2), 0.1), (1500, 53, (2,), 0.3)])
-def test_device_source_world2d_equals_oracle_bit_for_bit(dim2_shim, oracle, n, seed, kinds, angular):
+@pytest.mark.parametrize("n,seed,kinds,angular,planes", [(2500, 51, (0, 1, 2), 0.0, 0), (2000, 52, (1, 2), 0.1, 0), (1500, 53, (2,), 0.3, 0),
+                                                         (1800, 54, (0, 1, 2), 0.0, 3)])
+def test_device_source_world2d_equals_oracle_bit_for_bit(dim2_shim, oracle, n, seed, kinds, angular, planes):
     """The 2-D world's AABBs and manifolds from the device source on the host: boxes, manifold sizes, feature ids and every contact
     word equal the oracle's."""
     import ctypes as C
 
-    w = random_world(n, seed, kinds, angular=angular)
+    w = random_world(n, seed, kinds, angular=angular, planes=planes)
     pairs, off, ocontacts, ofeats, panics, fat = oracle.world_update2d(w)
     boxes = np.zeros((w.n, 6), dtype=np.float32)
     dim2_shim.shim2_aabbs(C.c_uint32(w.n), _vp(w.pos), _vp(w.rot), _vp(w.type), _vp(w.param), _vp(w.query_limit), _vp(w.points), _vp(w.normals),
