@@ -810,11 +810,31 @@ def bench_dim2(ctx, n_pairs=1_000_000, cpu_sample=100_000):
     n_w = n_pairs
     side = float(np.sqrt(n_w * 0.8 / 2.5))
     w = dim2.World2D.from_library(sh, rng.integers(0, 192, size=n_w), rng.uniform(0, side, size=(n_w, 2)), rng.uniform(-np.pi, np.pi, size=n_w))
-    dim2.world_update(ctx, w)
+    import torch
+
+    def pin(shape, dtype):
+        t = torch.empty(int(np.prod(shape)) * np.dtype(dtype).itemsize, dtype=torch.uint8).pin_memory()
+        return t, t.numpy().view(dtype).reshape(shape)
+
+    keep2 = []
+    for f in ("pos", "rot", "type", "param", "query_limit", "ang_pred"):  # page-locked inputs, like the 3-D end-to-end arm
+        t, a = pin(getattr(w, f).shape, getattr(w, f).dtype)
+        a[...] = getattr(w, f)
+        keep2.append(t)
+        setattr(w, f, a)
+    first = dim2.world_update(ctx, w)
+    cap_p, cap_c = len(first["pairs"]) + 4096, len(first["contacts"]) + 4096
+    pb = {}
+    for k, shp, dt in (("pairs", (cap_p, 2), np.uint32), ("start", (cap_p,), np.uint32), ("count", (cap_p,), np.uint8),
+                       ("contacts", (cap_c, 7), np.float32), ("features", (cap_c, 2), np.uint32)):
+        t, pb[k] = pin(shp, dt)
+        keep2.append(t)
+    dim2.world_update(ctx, w, bufs=pb)
     t0 = time.perf_counter()
-    wr = dim2.world_update(ctx, w)
-    wms = (time.perf_counter() - t0) * 1e3
-    res["world_update"] = {"workload": f"{n_w} 2-D objects, fresh-world update through ncb2d_world_update (host buffers in and out)", "ms": wms,
+    for _ in range(3):
+        wr = dim2.world_update(ctx, w, bufs=pb)
+    wms = (time.perf_counter() - t0) * 1e3 / 3
+    res["world_update"] = {"workload": f"{n_w} 2-D objects, fresh-world update through ncb2d_world_update (page-locked host buffers in and out)", "ms": wms,
                            "pairs": int(len(wr["pairs"])), "contacts": int(len(wr["contacts"])), **wr["diag"]}
     try:
         from oracle.pyoracle import Oracle

@@ -445,7 +445,7 @@ typedef struct ncb2d_objects {
 } ncb2d_objects;
 /* ncollide2d CollisionWorld::update for such a world (pipeline/world.rs:104-119): fat AABBs -> broad-phase pairs (object1 = larger handle,
  * like the 3-D path) -> contact manifolds from BallBall / BallConvexPolyhedron / ConvexPolyhedronConvexPolyhedron generators with 2-D
- * features and clipping (shape/convex_polygonal_feature2.rs).  Output: pairs (2 words each, emission order), manifold_start / _count per
+ * features and clipping (shape/convex_polygonal_feature2.rs).  Output: pairs (2 words each, grouped by generator), manifold_start / _count per
  * pair, contacts (7 floats: world1, world2, normal, depth) and features (2 words per contact: kind << 30 | id, kind 1 = face, 2 = vertex;
  * a ball's feature is face 0).  diag (optional, 4 words): reference panics, EPA capacity overflows, manifolds beyond 4 contacts,
  * traversal-stack overflows — all expected 0.  Returns 1 when an output was truncated (the needed counts are in n_pairs / n_contacts). */

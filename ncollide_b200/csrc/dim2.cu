@@ -17,7 +17,9 @@
 //   ball x convex polygon                 query/point/point_support_map.rs:14-55,120-146 (GJK / EPA projection of the ball centre),
 //                                         shape/convex_polygon.rs:139-152,186-203 (feature normal, support feature)
 // Not in this slice: the manifold generators / ConvexPolygonalFeature2, the 2-D broad phase and world.
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -1181,11 +1183,22 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     }
     CK2(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    DevBuf<float2> d_pos, d_rot;
-    DevBuf<uint32_t> d_type, d_groups, d_start, d_feat, d_cnt;
-    DevBuf<float4> d_param;
-    DevBuf<float> d_ql, d_cang, d_poly, d_nrm, d_contacts;
-    DevBuf<uint8_t> d_count;
+    // NCB2D_PROFILE=1: wall time per phase (with a stream synchronisation at every boundary) on stderr
+    static const bool prof = getenv("NCB2D_PROFILE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!prof) return;
+        cudaStreamSynchronize(s);
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[2d] %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
+    // the device buffers live in the context (no cudaMalloc / cudaFree per update once they have grown to the world's size)
+    DevBuf<float2>&d_pos = ctx->d2.pos, &d_rot = ctx->d2.rot;
+    DevBuf<uint32_t>&d_type = ctx->d2.type, &d_groups = ctx->d2.groups, &d_start = ctx->d2.start, &d_feat = ctx->d2.feat, &d_cnt = ctx->d2.cnt;
+    DevBuf<float4>& d_param = ctx->d2.param;
+    DevBuf<float>&d_ql = ctx->d2.ql, &d_cang = ctx->d2.cang, &d_poly = ctx->d2.poly, &d_nrm = ctx->d2.nrm, &d_contacts = ctx->d2.contacts;
+    DevBuf<uint8_t>& d_count = ctx->d2.count;
     CK2(d_pos.reserve(n));
     CK2(d_rot.reserve(n));
     CK2(d_type.reserve(n));
@@ -1213,6 +1226,7 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     }
     int r = reserve_broad(ctx, n);
     if (r) return r;
+    mark("alloc+h2d");
     d2::World2Args A;
     memset(&A, 0, sizeof A);
     A.n = n;
@@ -1230,20 +1244,24 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     CK2(cudaGetLastError());
     CK2(launch_lbvh_build(ctx, n, nullptr));
     CK2(launch_pair_search(ctx, n, o->groups ? d_groups.p : nullptr, 0, 0xffffffffu, (uint32_t)capp, -1));
-    // narrow phase over the emitted pairs (count read on the device)
+    // the 3-D path's counting sort by pair kind (the 2-D type codes are the 3-D ones): warps of the narrow kernel then hold one generator
+    CK2(launch_pair_sort(ctx, (uint32_t)capp, nullptr));
+    mark("broad");
+    // narrow phase over the sorted pairs (count read on the device)
     size_t capc = cap_contacts ? cap_contacts : 1;
     CK2(d_start.reserve(capp));
     CK2(d_count.reserve(capp));
     CK2(d_contacts.reserve(7 * capc));
     CK2(d_feat.reserve(2 * capc));
     CK2(cudaMemsetAsync(d_cnt.p, 0, 16, s));
-    A.pairs = ctx->pairs_raw.p;
+    A.pairs = ctx->pairs.p;
     A.n_pairs_dev = &ctx->counters.p->n_pairs;
     A.cap_pairs = (uint32_t)capp, A.cap_contacts = (uint32_t)capc;
     A.manifold_start = d_start.p, A.manifold_count = d_count.p, A.contacts = d_contacts.p, A.features = d_feat.p;
     A.counters = d_cnt.p;
     d2::k_narrow2d<<<(uint32_t)((capp + 63) / 64), 64, 0, s>>>(A);
     CK2(cudaGetLastError());
+    mark("narrow");
     r = read_counters(ctx);
     if (r) return r;
     uint32_t cnt[4];
@@ -1253,12 +1271,13 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     *n_pairs = np, *n_contacts = nc;
     if (diag) diag[0] = cnt[1], diag[1] = cnt[2], diag[2] = cnt[3], diag[3] = ctx->last_counters.stack_overflow;
     uint32_t wp = np < cap_pairs ? np : cap_pairs, wc = nc < cap_contacts ? nc : cap_contacts;
-    if (pairs && wp) CK2(cudaMemcpyAsync(pairs, ctx->pairs_raw.p, 8 * (size_t)wp, cudaMemcpyDeviceToHost, s));
+    if (pairs && wp) CK2(cudaMemcpyAsync(pairs, ctx->pairs.p, 8 * (size_t)wp, cudaMemcpyDeviceToHost, s));
     if (manifold_start && wp) CK2(cudaMemcpyAsync(manifold_start, d_start.p, 4 * (size_t)wp, cudaMemcpyDeviceToHost, s));
     if (manifold_count && wp) CK2(cudaMemcpyAsync(manifold_count, d_count.p, wp, cudaMemcpyDeviceToHost, s));
     if (contacts && wc) CK2(cudaMemcpyAsync(contacts, d_contacts.p, 28 * (size_t)wc, cudaMemcpyDeviceToHost, s));
     if (features && wc) CK2(cudaMemcpyAsync(features, d_feat.p, 8 * (size_t)wc, cudaMemcpyDeviceToHost, s));
     CK2(cudaStreamSynchronize(s));
+    mark("d2h");
     return (np > cap_pairs || nc > cap_contacts) ? 1 : NCB_OK;
 }
 

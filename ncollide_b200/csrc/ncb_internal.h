@@ -331,6 +331,14 @@ struct ncb_ctx {
     ncb::DevBuf<uint32_t> loc_type, local_of;
     ncb::DevBuf<float2> loc_ang_cs;
     ncb::DevBuf<uint2> pairs_local;
+    // ncollide2d slice (dim2.cu): device copies of the last 2-D world / pair batch and its results, kept between calls
+    struct Dim2Bufs {
+        ncb::DevBuf<float2> pos, rot;
+        ncb::DevBuf<uint32_t> type, groups, start, feat, cnt;
+        ncb::DevBuf<float4> param;
+        ncb::DevBuf<float> ql, cang, poly, nrm, contacts;
+        ncb::DevBuf<uint8_t> count;
+    } d2;
 };
 
 // api.cu helpers shared with sim.cu

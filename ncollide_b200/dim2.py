@@ -147,9 +147,11 @@ class _Objects2DC(C.Structure):
                 ("poly_normals", C.c_void_p), ("n_poly_points", C.c_uint32)]
 
 
-def world_update(ctx, w: World2D):
+def world_update(ctx, w: World2D, bufs=None):
     """``CollisionWorld::update`` of a fresh 2-D world (``ncb2d_world_update``).  Returns a dict: pairs [P, 2] (object1 = larger handle),
-    manifold_start / manifold_count [P], contacts [C, 7] (world1, world2, normal, depth), features [C, 2], diag."""
+    manifold_start / manifold_count [P], contacts [C, 7] (world1, world2, normal, depth), features [C, 2], diag.
+    bufs: optional dict of preallocated (e.g. page-locked) result arrays "pairs" [cap, 2] u32, "start" [cap] u32, "count" [cap] u8,
+    "contacts" [cap_c, 7] f32, "features" [cap_c, 2] u32 — used as they are when large enough."""
     o = _Objects2DC()
     o.n = w.n
     o.pos, o.rot, o.shape_type, o.shape_param = (a.ctypes.data for a in (w.pos, w.rot, w.type, w.param))
@@ -158,9 +160,14 @@ def world_update(ctx, w: World2D):
     o.poly_points, o.poly_normals, o.n_poly_points = w.points.ctypes.data, w.normals.ctypes.data, len(w.points)
     cap_p, cap_c = max(8 * w.n, 1024), max(8 * w.n, 1024)
     while True:
-        pairs = np.zeros((cap_p, 2), dtype=np.uint32)
-        start, count = np.zeros(cap_p, dtype=np.uint32), np.zeros(cap_p, dtype=np.uint8)
-        contacts, feats = np.zeros((cap_c, 7), dtype=np.float32), np.zeros((cap_c, 2), dtype=np.uint32)
+        if bufs is not None:
+            pairs, start, count, contacts, feats = (bufs[k] for k in ("pairs", "start", "count", "contacts", "features"))
+            cap_p, cap_c = min(len(pairs), len(start), len(count)), min(len(contacts), len(feats))
+            bufs = None  # a retry (too small) falls back to fresh arrays
+        else:
+            pairs = np.zeros((cap_p, 2), dtype=np.uint32)
+            start, count = np.zeros(cap_p, dtype=np.uint32), np.zeros(cap_p, dtype=np.uint8)
+            contacts, feats = np.zeros((cap_c, 7), dtype=np.float32), np.zeros((cap_c, 2), dtype=np.uint32)
         npairs, ncont = C.c_uint32(0), C.c_uint32(0)
         diag = np.zeros(4, dtype=np.uint32)
         r = ctx.check(ctx.lib.ncb2d_world_update(ctx.h, C.byref(o), C.c_float(w.margin), ptr(pairs), C.c_uint32(cap_p), ptr(start), ptr(count),
