@@ -427,6 +427,12 @@ int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const f
                   const float* param2, const float* pose2, const float* poly_points, const float* poly_normals, uint32_t n_poly_points,
                   float prediction, uint8_t* found, float* out, uint32_t* ref_panics, uint32_t* epa_overflow);
 
+/* ncollide2d::query::proximity(m1, g1, m2, g2, margin) (query/proximity/proximity_shape_shape.rs:8-33) for a batch, one margin per
+ * pair: proximity_ball_ball, proximity_plane_support_map (either order), proximity_support_map_support_map (2-D GJK with
+ * exact_dist = false; balls are support maps here).  out: NCB_PROXIMITY_INTERSECTING / _WITHIN_MARGIN / _DISJOINT per pair. */
+int ncb2d_proximity(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const float* param1, const float* pose1, const uint32_t* type2,
+                    const float* param2, const float* pose2, const float* poly_points, uint32_t n_poly_points, const float* margins,
+                    uint8_t* out);
 /* A fresh ncollide2d CollisionWorld of balls, cuboids and convex polygons (host SoA): pos = translation x y, rot = UnitComplex re im,
  * shape_param as in ncb2d_contact, groups = 3 words per object or NULL, query_limit / ang_pred = GeometricQueryType::Contacts(linear,
  * angular); poly_normals is required when the world holds polygons. */

@@ -929,6 +929,50 @@ __device__ bool plane_support(const Operand2& plane, const Operand2& other, floa
     return true;
 }
 
+// query::proximity for one pair (query/proximity/proximity_shape_shape.rs:8-33): proximity_ball_ball.rs:8-36,
+// proximity_plane_support_map.rs:9-47 (either order), proximity_support_map_support_map.rs:12-75 = the GJK above with exact_dist = false
+// (gjk.rs:76-177: its Proximity exits).  Returns NCB_PROXIMITY_INTERSECTING / _WITHIN_MARGIN / _DISJOINT.
+__device__ uint8_t proximity_of_pair(const Operand2& g1, const Operand2& g2, float margin) {
+    if (g1.kind == D2_BALL && g2.kind == D2_BALL) {
+        float d2 = nsq(g2.m.t - g1.m.t), sum = g1.a + g2.a, lim = sum + margin;
+        if (d2 <= lim * lim) return d2 <= sum * sum ? NCB_PROXIMITY_INTERSECTING : NCB_PROXIMITY_WITHIN_MARGIN;
+        return NCB_PROXIMITY_DISJOINT;
+    }
+    if (g1.kind == D2_PLANE || g2.kind == D2_PLANE) {
+        const Operand2& pl = g1.kind == D2_PLANE ? g1 : g2;
+        const Operand2& ot = g1.kind == D2_PLANE ? g2 : g1;
+        W2 n = rotate(pl.m, w2(pl.a, pl.b));
+        W2 deepest = ot.kind == D2_BALL ? ot.m.t + (-n) * ot.a : support(ot, -n);
+        float distance = dot(n, pl.m.t - deepest);
+        if (distance >= -margin) return distance >= 0.f ? NCB_PROXIMITY_INTERSECTING : NCB_PROXIMITY_WITHIN_MARGIN;
+        return NCB_PROXIMITY_DISJOINT;
+    }
+    const float rel = sqrtf(TOL10);
+    W2 dir, u;
+    if (!unit(g2.m.t - g1.m.t, NCB_EPS, dir)) dir = w2(1.f, 0.f);
+    Tri2 s;
+    for (int i = 0; i < 3; ++i) s.v[i].p = s.v[i].o1 = s.v[i].o2 = w2(0.f, 0.f), s.old_idx[i] = i;
+    s.bary[0] = s.bary[1] = s.old_bary[0] = s.old_bary[1] = 0.f;
+    s.dim = s.old_dim = 0;
+    s.v[0] = minkowski(g1, g2, dir);
+    W2 proj = tri_project(s);
+    if (!unit(proj, 0.f, u)) return NCB_PROXIMITY_INTERSECTING;
+    float upper = NCB_FMAX;
+    for (int it = 0;; ++it) {
+        float prev_upper = upper, len;
+        if (!unit_get(-proj, TOL10, dir, len)) return NCB_PROXIMITY_INTERSECTING;
+        upper = len;
+        if (upper >= prev_upper) return NCB_PROXIMITY_WITHIN_MARGIN;
+        MinkowskiPt c = minkowski(g1, g2, dir);
+        float lower = -dot(dir, c.p);
+        if (lower > margin) return NCB_PROXIMITY_DISJOINT;
+        if ((lower > 0.f && upper <= margin) || upper - lower <= rel * upper || !tri_add(s, c)) return NCB_PROXIMITY_WITHIN_MARGIN;
+        proj = tri_project(s);
+        if (s.dim == 2) return lower >= TOL10 ? NCB_PROXIMITY_WITHIN_MARGIN : NCB_PROXIMITY_INTERSECTING;
+        if (it + 1 == 10000) return NCB_PROXIMITY_DISJOINT;
+    }
+}
+
 // query::contact for one pair.  flags: bit 0 = the reference would panic, bit 1 = EPA capacity exceeded.
 __device__ bool contact_of_pair(const Operand2& g1, const Operand2& g2, float prediction, float cos_one_degree, Hit2& h, int& flags) {
     h.w1 = h.w2 = h.n = w2(0.f, 0.f), h.depth = 0.f;
@@ -993,6 +1037,14 @@ __global__ void __launch_bounds__(64) k_contact2d(Args2 A) {
     float* o = A.out + 7 * (size_t)k;
     o[0] = h.w1.x, o[1] = h.w1.y, o[2] = h.w2.x, o[3] = h.w2.y, o[4] = h.n.x, o[5] = h.n.y, o[6] = h.depth;
 }
+__global__ void __launch_bounds__(128) k_proximity2d(Args2 A, const float* __restrict__ margins, uint8_t* __restrict__ status) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.n) return;
+    Operand2 g1 = load_operand(__ldg(&A.type1[k]), __ldg(&A.param1[k]), __ldg(&A.pose1[k]), A.poly, A.poly_nrm);
+    Operand2 g2 = load_operand(__ldg(&A.type2[k]), __ldg(&A.param2[k]), __ldg(&A.pose2[k]), A.poly, A.poly_nrm);
+    status[k] = proximity_of_pair(g1, g2, __ldg(&margins[k]));
+}
+
 struct World2Args {
     uint32_t n;
     const float2 *pos, *rot;
@@ -1150,6 +1202,67 @@ int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const f
     CK2(cudaStreamSynchronize(s));
     if (ref_panics) *ref_panics = cnt[0];
     if (epa_overflow) *epa_overflow = cnt[1];
+    return NCB_OK;
+}
+
+// ncollide2d::query::proximity(m1, g1, m2, g2, margin) for a batch (one margin per pair); out: NCB_PROXIMITY_* per pair.
+int ncb2d_proximity(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const float* param1, const float* pose1, const uint32_t* type2,
+                    const float* param2, const float* pose2, const float* poly_points, uint32_t n_poly_points, const float* margins,
+                    uint8_t* out) {
+    if (!ctx || (n_pairs && (!type1 || !param1 || !pose1 || !type2 || !param2 || !pose2 || !margins || !out))) return NCB_ERR_ARG;
+    if (n_pairs == 0) return NCB_OK;
+    for (uint32_t k = 0; k < n_pairs; ++k) {
+        for (int side = 0; side < 2; ++side) {
+            uint32_t t = side ? type2[k] : type1[k];
+            const float* p = (side ? param2 : param1) + 4 * (size_t)k;
+            if (t > 3) {
+                ctx->err = "ncb2d_proximity: unknown 2-D shape type";
+                return NCB_ERR_UNSUPPORTED;
+            }
+            if (t == 2 && (!poly_points || p[1] < 1.f || p[0] < 0.f || (uint64_t)p[0] + (uint64_t)p[1] > n_poly_points)) {
+                ctx->err = "ncb2d_proximity: polygon point range outside poly_points";
+                return NCB_ERR_ARG;
+            }
+        }
+        if (type1[k] == 3 && type2[k] == 3) {
+            ctx->err = "ncb2d_proximity: no algorithm for plane x plane (the reference panics)";
+            return NCB_ERR_UNSUPPORTED;
+        }
+        if (!(margins[k] >= 0.f)) {
+            ctx->err = "ncb2d_proximity: the proximity margin must be positive or zero";
+            return NCB_ERR_ARG;
+        }
+    }
+    CK2(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    size_t n = n_pairs;
+    DevBuf<uint32_t> d_t;
+    DevBuf<float4> d_f4;
+    DevBuf<float> d_poly, d_mg;
+    DevBuf<uint8_t> d_out;
+    CK2(d_t.reserve(2 * n));
+    CK2(d_f4.reserve(4 * n));
+    CK2(d_poly.reserve(2 * (size_t)(n_poly_points ? n_poly_points : 1)));
+    CK2(d_mg.reserve(n));
+    CK2(d_out.reserve(n));
+    CK2(cudaMemcpyAsync(d_t.p, type1, 4 * n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_t.p + n, type2, 4 * n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_f4.p, param1, 16 * n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_f4.p + n, param2, 16 * n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_f4.p + 2 * n, pose1, 16 * n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_f4.p + 3 * n, pose2, 16 * n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_mg.p, margins, 4 * n, cudaMemcpyHostToDevice, s));
+    if (n_poly_points) CK2(cudaMemcpyAsync(d_poly.p, poly_points, 8 * (size_t)n_poly_points, cudaMemcpyHostToDevice, s));
+    d2::Args2 A;
+    memset(&A, 0, sizeof A);
+    A.n = n_pairs;
+    A.type1 = d_t.p, A.type2 = d_t.p + n;
+    A.param1 = d_f4.p, A.param2 = d_f4.p + n, A.pose1 = d_f4.p + 2 * n, A.pose2 = d_f4.p + 3 * n;
+    A.poly = d_poly.p;
+    d2::k_proximity2d<<<(n_pairs + 127) / 128, 128, 0, s>>>(A, d_mg.p, d_out.p);
+    CK2(cudaGetLastError());
+    CK2(cudaMemcpyAsync(out, d_out.p, n, cudaMemcpyDeviceToHost, s));
+    CK2(cudaStreamSynchronize(s));
     return NCB_OK;
 }
 

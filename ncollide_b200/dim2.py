@@ -105,6 +105,20 @@ def contact(ctx, type1, param1, pose1, type2, param2, pose2, poly_points=None, p
     return found.astype(bool), out, {"ref_panics": panics.value, "epa_overflow": over.value}
 
 
+def proximity(ctx, type1, param1, pose1, type2, param2, pose2, poly_points=None, margins=0.0):
+    """``ncollide2d::query::proximity`` per pair (``ncb2d_proximity``): 0 Intersecting, 1 WithinMargin, 2 Disjoint."""
+    t1, t2 = as_u32(type1).reshape(-1), as_u32(type2).reshape(-1)
+    p1, p2 = as_f32(param1).reshape(-1, 4), as_f32(param2).reshape(-1, 4)
+    m1, m2 = as_f32(pose1).reshape(-1, 4), as_f32(pose2).reshape(-1, 4)
+    n = len(t1)
+    pts = as_f32(poly_points).reshape(-1, 2) if poly_points is not None else None
+    mg = np.ascontiguousarray(np.broadcast_to(np.asarray(margins, dtype=np.float32).reshape(-1), (n,)), dtype=np.float32)
+    out = np.zeros(n, dtype=np.uint8)
+    ctx.check(ctx.lib.ncb2d_proximity(ctx.h, C.c_uint32(n), ptr(t1), ptr(p1), ptr(m1), ptr(t2), ptr(p2), ptr(m2), ptr(pts),
+                                      C.c_uint32(0 if pts is None else len(pts)), ptr(mg), ptr(out)), "ncb2d_proximity")
+    return out
+
+
 class World2D:
     """A fresh ``ncollide2d::CollisionWorld``: objects = (shape, Isometry2, CollisionGroups, GeometricQueryType::Contacts(linear, angular)).
     ``shapes`` is a Shapes2D batch (one entry per object); ``pos`` [n, 2], ``angle`` [n]."""

@@ -684,6 +684,50 @@ static bool contact_ball_polygon(P2 center, real radius, const Iso2& m2, const S
     return false;
 }
 
+// ---- query::proximity in 2-D (query/proximity/proximity_shape_shape.rs:8-33) -----------------------------------------------------
+enum { PX_INTERSECTING = 0, PX_WITHIN_MARGIN = 1, PX_DISJOINT = 2 };
+// proximity_ball_ball.rs:8-36
+static int proximity_ball_ball(P2 c1, real r1, P2 c2, real r2, real margin) {
+    real dsq = nsq(c2 - c1), sum = r1 + r2, sum_err = sum + margin;
+    if (dsq <= sum_err * sum_err) return dsq <= sum * sum ? PX_INTERSECTING : PX_WITHIN_MARGIN;
+    return PX_DISJOINT;
+}
+// proximity_plane_support_map.rs:9-47
+static int proximity_plane_sm(const Iso2& mp, P2 plane_n_local, const Iso2& mo, const Shape2& other, real margin) {
+    P2 n = rot(mp, plane_n_local);
+    P2 deepest = other.type == BALL2 ? mo.t + (-n) * other.radius : support_point(other, mo, -n);
+    real distance = dot(n, mp.t - deepest);
+    if (distance >= -margin) return distance >= 0 ? PX_INTERSECTING : PX_WITHIN_MARGIN;
+    return PX_DISJOINT;
+}
+// proximity_support_map_support_map (proximity_support_map_support_map.rs:12-75) = gjk::closest_points with exact_dist = false
+static int proximity_sm_sm(const Iso2& m1, const Shape2& g1, const Iso2& m2, const Shape2& g2, real max_dist) {
+    const real eps_rel = std::sqrt(EPS_TOL);
+    P2 dir;
+    if (!unit_try_new(m2.t - m1.t, EPS, &dir)) dir = p2(1, 0);
+    Simplex2 s;
+    s.reset(cso_from_shapes(m1, g1, m2, g2, dir));
+    P2 proj = s.project_origin_and_reduce(), pd;
+    if (!unit_try_new(proj, 0, &pd)) return PX_INTERSECTING;
+    real max_bound = FMAX;
+    int niter = 0;
+    for (;;) {
+        real old_max_bound = max_bound, dist;
+        if (!unit_try_new_and_get(-proj, EPS_TOL, &dir, &dist)) return PX_INTERSECTING;
+        max_bound = dist;
+        if (max_bound >= old_max_bound) return PX_WITHIN_MARGIN;
+        CSO cso = cso_from_shapes(m1, g1, m2, g2, dir);
+        real min_bound = -dot(dir, cso.point);
+        if (min_bound > max_dist) return PX_DISJOINT;
+        if (min_bound > 0 && max_bound <= max_dist) return PX_WITHIN_MARGIN;
+        if (max_bound - min_bound <= eps_rel * max_bound) return PX_WITHIN_MARGIN;
+        if (!s.add_point(cso)) return PX_WITHIN_MARGIN;
+        proj = s.project_origin_and_reduce();
+        if (s.dim == 2) return min_bound >= EPS_TOL ? PX_WITHIN_MARGIN : PX_INTERSECTING;
+        if (++niter == 10000) return PX_DISJOINT;
+    }
+}
+
 // =============================================================================================================================
 // World update in 2-D: AABBs (bounding_volume/aabb_ball.rs:8-13, aabb_cuboid.rs:9-14, aabb_convex_polygon.rs + aabb_utils.rs:59-79,
 // loosened like pipeline/object/collision_object.rs:89-93 + dbvt_broad_phase.rs:341) and the contact-manifold generators
@@ -1053,6 +1097,35 @@ void orc2_contact(uint64_t n, const uint32_t* type1, const real* param1, const r
         o[0] = c.w1.x, o[1] = c.w1.y, o[2] = c.w2.x, o[3] = c.w2.y, o[4] = c.n.x, o[5] = c.n.y, o[6] = c.depth;
     }
     if (panics) *panics = np;
+}
+
+// query::proximity for n pairs (margin per pair); out: 0 Intersecting, 1 WithinMargin, 2 Disjoint, 255 = plane x plane (the reference panics)
+void orc2_proximity(uint64_t n, const uint32_t* type1, const real* param1, const real* pose1, const uint32_t* type2, const real* param2,
+                    const real* pose2, const real* poly_points, const real* margins, uint8_t* out) {
+    for (uint64_t k = 0; k < n; ++k) {
+        auto shape = [&](uint32_t t, const real* p) {
+            Shape2 g;
+            g.type = t, g.radius = p[0], g.he = p2(p[0], p[1]), g.pts = g.normals = nullptr, g.npts = 0;
+            if (t == POLYGON2) g.pts = poly_points + 2 * (size_t)p[0], g.npts = (uint32_t)p[1];
+            return g;
+        };
+        Shape2 g1 = shape(type1[k], param1 + 4 * k), g2 = shape(type2[k], param2 + 4 * k);
+        Iso2 m1 = {p2(pose1[4 * k], pose1[4 * k + 1]), pose1[4 * k + 2], pose1[4 * k + 3]};
+        Iso2 m2 = {p2(pose2[4 * k], pose2[4 * k + 1]), pose2[4 * k + 2], pose2[4 * k + 3]};
+        real margin = margins[k];
+        int r;
+        if (g1.type == PLANE2 && g2.type == PLANE2)
+            r = 255;
+        else if (g1.type == BALL2 && g2.type == BALL2)
+            r = proximity_ball_ball(m1.t, g1.radius, m2.t, g2.radius, margin);
+        else if (g1.type == PLANE2)
+            r = proximity_plane_sm(m1, g1.he, m2, g2, margin);
+        else if (g2.type == PLANE2)
+            r = proximity_plane_sm(m2, g2.he, m1, g1, margin);
+        else
+            r = proximity_sm_sm(m1, g1, m2, g2, margin);
+        out[k] = (uint8_t)r;
+    }
 }
 
 // ---- 2-D world -------------------------------------------------------------------------------------------------------------

@@ -270,6 +270,18 @@ class Oracle:
                               self.creal(prediction), vp(found), vp(out), C.byref(panics))
         return found, out, panics.value
 
+    def proximity2d(self, type1, param1, pose1, type2, param2, pose2, poly_points, margins):
+        """ncollide2d ``query::proximity`` per pair: 0 Intersecting, 1 WithinMargin, 2 Disjoint."""
+        dt = self.dtype
+        t1, t2 = np.ascontiguousarray(type1, dtype=np.uint32), np.ascontiguousarray(type2, dtype=np.uint32)
+        arrs = [np.ascontiguousarray(a, dtype=dt) for a in (param1, pose1, param2, pose2, poly_points if poly_points is not None else np.zeros((1, 2)))]
+        n = len(t1)
+        mg = np.ascontiguousarray(np.broadcast_to(np.asarray(margins, dtype=dt).reshape(-1), (n,)), dtype=dt)
+        out = np.zeros(n, dtype=np.uint8)
+        vp = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+        self.lib.orc2_proximity(C.c_uint64(n), vp(t1), vp(arrs[0]), vp(arrs[1]), vp(t2), vp(arrs[2]), vp(arrs[3]), vp(arrs[4]), vp(mg), vp(out))
+        return out
+
     def world_update2d(self, w):
         """ncollide2d fresh-world update for a ncollide_b200.dim2.World2D: (pairs [P,2] canonical, offsets [P+1], contacts [C,7], features [C,2],
         panics).  Fat AABBs (oracle/dim2.cpp) -> the 3-D oracle's broad phase on boxes with z = 0 -> the 2-D generators."""

@@ -29,6 +29,17 @@ void shim2_contact(uint64_t n, const uint32_t* type1, const float* param1, const
     }
 }
 
+void shim2_proximity(uint64_t n, const uint32_t* type1, const float* param1, const float* pose1, const uint32_t* type2, const float* param2,
+                     const float* pose2, const float* poly, const float* margins, uint8_t* out) {
+    for (uint64_t k = 0; k < n; ++k) {
+        const float4* p1 = reinterpret_cast<const float4*>(param1) + k;
+        const float4* p2 = reinterpret_cast<const float4*>(param2) + k;
+        const float4* m1 = reinterpret_cast<const float4*>(pose1) + k;
+        const float4* m2 = reinterpret_cast<const float4*>(pose2) + k;
+        out[k] = proximity_of_pair(load_operand(type1[k], *p1, *m1, poly, nullptr), load_operand(type2[k], *p2, *m2, poly, nullptr), margins[k]);
+    }
+}
+
 static Operand2 obj(uint32_t i, const float* pos, const float* rot, const uint32_t* type, const float* param, const float* poly, const float* nrm) {
     float4 p = reinterpret_cast<const float4*>(param)[i];
     return load_operand(type[i], p, make_float4(pos[2 * i], pos[2 * i + 1], rot[2 * i], rot[2 * i + 1]), poly, nrm);

@@ -172,6 +172,50 @@ def test_polygon_try_new_mirror():
         dim2.Shapes2D().polygon([[0, 0], [0, 0], [1, 1]])
 
 
+# ---- query::proximity ----------------------------------------------------------------------------------------------------------
+def _proximity_kat_args():
+    """examples2d/proximity_query2d.rs: ball(1) at (1,1) / (2,2) / (3,3) against the unit-half-extent cuboid at the origin, margin 1."""
+    ball, cub, one = [1, 0, 0, 0], [1, 1, 0, 0], [0, 0, 1, 0]
+    return [0] * 3, [ball] * 3, [[1, 1, 1, 0], [2, 2, 1, 0], [3, 3, 1, 0]], [1] * 3, [cub] * 3, [one] * 3
+
+
+@pytest.mark.parametrize("which", ["oracle64", "oracle"])
+def test_oracle_proximity_kat(which, request):
+    """The reference's example asserts Intersecting, WithinMargin, Disjoint."""
+    orc = request.getfixturevalue(which)
+    t1, p1, m1, t2, p2, m2 = _proximity_kat_args()
+    assert orc.proximity2d(t1, p1, m1, t2, p2, m2, None, 1.0).tolist() == [0, 1, 2]
+    assert orc.proximity2d(t2, p2, m2, t1, p1, m1, None, 1.0).tolist() == [0, 1, 2]
+
+
+def test_oracle_proximity_against_separating_axes(oracle64):
+    """ORACLE check (f64): the status is the separating-axis signed distance sorted into (-inf, 0], (0, margin], (margin, inf)."""
+    t1, p1, m1, t2, p2, m2, pts, nrm = random_pairs(1500, 21, kinds=(1, 2))
+    margins = np.random.default_rng(3).uniform(0.0, 0.4, size=len(t1))
+    got = oracle64.proximity2d(t1, p1, m1, t2, p2, m2, pts, margins)
+    seen = [0, 0, 0]
+    for k in range(len(t1)):
+        sd = _sat_signed_distance(_world_polygon(t1[k], p1[k], m1[k], pts), _world_polygon(t2[k], p2[k], m2[k], pts))
+        if min(abs(sd), abs(sd - margins[k])) < 1e-6:
+            continue
+        want = 0 if sd < 0 else (1 if sd < margins[k] else 2)
+        assert got[k] == want, (k, sd, margins[k], got[k])
+        seen[want] += 1
+    assert min(seen) > 100
+
+
+def test_oracle_proximity_agrees_with_contact(oracle64):
+    """Balls, planes and support maps: Intersecting <=> contact depth >= 0 at prediction 0; Disjoint <=> no contact at prediction = margin."""
+    t1, p1, m1, t2, p2, m2, pts, nrm = random_pairs(3000, 22, kinds=(0, 1, 2, 3))
+    margin = 0.15
+    got = oracle64.proximity2d(t1, p1, m1, t2, p2, m2, pts, margin)
+    found, out, _ = oracle64.contact2d(t1, p1, m1, t2, p2, m2, pts, margin, poly_normals=nrm)
+    clear = ~found.astype(bool) | (np.abs(out[:, 6]) > 1e-9) & (np.abs(out[:, 6] + margin) > 1e-9)
+    want = np.where(~found.astype(bool), 2, np.where(out[:, 6] > 0, 0, 1))
+    assert np.array_equal(got[clear], want[clear]), np.flatnonzero(got[clear] != want[clear])[:10]
+    assert min(np.bincount(got, minlength=3)) > 200
+
+
 # ---- GPU: device vs oracle -----------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def ctx():
@@ -223,6 +267,23 @@ def test_device_refuses_bad_input(ctx):
     assert found[0] and out[0, 6] > 0.5  # the centre is inside the triangle
     with pytest.raises(NcbError):
         dim2.contact(ctx, [7], [[1, 0, 0, 0]], [[0, 0, 1, 0]], [1], [[1, 1, 0, 0]], [[0.2, 0, 1, 0]])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,kinds", [(31, (0, 1, 2)), (32, (1, 2)), (33, (0, 1, 2, 3))])
+def test_device_proximity_matches_oracle(ctx, oracle, seed, kinds):
+    from ncollide_b200._ffi import NcbError
+
+    t1, p1, m1, t2, p2, m2 = _proximity_kat_args()
+    assert dim2.proximity(ctx, t1, p1, m1, t2, p2, m2, None, 1.0).tolist() == [0, 1, 2]
+    t1, p1, m1, t2, p2, m2, pts, nrm = random_pairs(60000, seed, kinds)
+    margins = np.random.default_rng(seed).uniform(0.0, 0.4, size=len(t1)).astype(np.float32)
+    got = dim2.proximity(ctx, t1, p1, m1, t2, p2, m2, pts, margins)
+    want = oracle.proximity2d(t1, p1, m1, t2, p2, m2, pts, margins)
+    assert min(np.bincount(want, minlength=3)) > 3000
+    assert (got != want).sum() <= 2, f"{(got != want).sum()} statuses differ"  # libm sqrt / fma-free arithmetic: identical in practice
+    with pytest.raises(NcbError):  # plane x plane: the reference has no algorithm for it
+        dim2.proximity(ctx, [3], [[0, 1, 0, 0]], [[0, 0, 1, 0]], [3], [[0, 1, 0, 0]], [[0, 1, 1, 0]], None, 0.1)
 
 
 # ---- 2-D world update ----------------------------------------------------------------------------------------------------------
@@ -379,3 +440,18 @@ def test_device_source_world2d_equals_oracle_bit_for_bit(dim2_shim, oracle, n, s
     assert np.array_equal(doff, off) and nc == len(ocontacts) > n // 4
     assert np.array_equal(df[:nc], ofeats)
     assert np.array_equal(_bits(dc[:nc]), _bits(ocontacts))
+
+
+@pytest.mark.parametrize("seed,kinds", [(61, (0, 1, 2)), (62, (1, 2)), (63, (0, 1, 2, 3)), (64, (2,))])
+def test_device_source_proximity_equals_oracle(dim2_shim, oracle, seed, kinds):
+    """query::proximity from the device source on the host: every status equals the oracle's (GJK's proximity exits included)."""
+    import ctypes as C
+
+    t1, p1, m1, t2, p2, m2, pts, nrm = random_pairs(40000, seed, kinds)
+    margins = np.random.default_rng(seed).uniform(0.0, 0.4, size=len(t1)).astype(np.float32)
+    margins[::7] = 0.0
+    out = np.full(len(t1), 9, dtype=np.uint8)
+    dim2_shim.shim2_proximity(C.c_uint64(len(t1)), _vp(t1), _vp(p1), _vp(m1), _vp(t2), _vp(p2), _vp(m2), _vp(pts), _vp(margins), _vp(out))
+    want = oracle.proximity2d(t1, p1, m1, t2, p2, m2, pts, margins)
+    assert np.array_equal(out, want), np.flatnonzero(out != want)[:10]
+    assert min(np.bincount(want, minlength=3)) > 2000
