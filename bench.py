@@ -531,6 +531,10 @@ def run_native(args):
             rays["cpu_baseline"] = rays_cpu_baseline(n_tris, min(RAY_CPU_SAMPLE, n_rays))
         if args.rays_only:
             if rank == 0:
+                try:
+                    rays["dim2_polyline_rays"] = bench_polyline_rays(ctx)
+                except Exception as ex:  # noqa: BLE001
+                    rays["dim2_polyline_rays"] = {"error": repr(ex)[:200]}
                 print(json.dumps(rays))
             ctx.close()
             return 0
@@ -576,6 +580,10 @@ def run_native(args):
             widened["dim2_contact"] = bench_dim2(ctx)
         except Exception as ex:  # noqa: BLE001
             widened["dim2_contact"] = {"error": repr(ex)[:200]}
+        try:
+            widened["dim2_polyline_rays"] = bench_polyline_rays(ctx)
+        except Exception as ex:  # noqa: BLE001
+            widened["dim2_polyline_rays"] = {"error": repr(ex)[:200]}
 
     # ---- secondary worlds (after everything else: they replace the world on the device) -----------------------------------
     #   strong scaling: ONE fixed 8 M-object cfg3 world at every N (the driver's N = 1, 2, 4, 8 runs give the curve);
@@ -855,6 +863,76 @@ def bench_dim2(ctx, n_pairs=1_000_000, cpu_sample=100_000):
                                "answers_equal": bool(np.array_equal(of.astype(bool), found[sl]))}
     except Exception as ex:  # noqa: BLE001
         res["cpu_baseline"] = {"error": repr(ex)[:120]}
+    return res
+
+
+def bench_polyline_rays(ctx, n_edges=1_000_000, n_rays=1_000_000, cpu_sample=100_000):
+    """Widened row N4 (2-D build): RayCast for Polyline, 1 M rays against a 1 M-edge height profile.  Device-resident rays timed with CUDA
+    events on the context's stream (it is torch's current stream here), and the host-buffer call (page-locked buffers, wall clock)."""
+    import ctypes as C
+
+    import torch
+
+    from ncollide_b200 import dim2
+    from ncollide_b200.scenes import make_polyline_scene
+
+    pts, edges, o, d = make_polyline_scene("terrain", n_edges, n_rays, 31)
+    pl = dim2.Polyline(ctx, pts, edges)
+
+    def pin(a):
+        t = torch.from_numpy(a.copy()).pin_memory()
+        return t, t.numpy()
+
+    keep = []
+    to, po = pin(o)
+    td, pd = pin(d)
+    out = {}
+    for k, shp, dt in (("toi", (n_rays,), np.float32), ("feature", (n_rays,), np.uint32), ("normal", (n_rays, 2), np.float32)):
+        t, out[k] = pin(np.zeros(shp, dtype=dt))
+        keep.append(t)
+    pl.toi_and_normal_with_ray(None, po, pd, out=out)
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        toi, feat, nrm = pl.toi_and_normal_with_ray(None, po, pd, out=out)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    e2e_ms = float(np.median(ts))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_o, d_d = to.to(dev), td.to(dev)
+    d_toi, d_feat = torch.empty(n_rays, dtype=torch.float32, device=dev), torch.empty(n_rays, dtype=torch.int32, device=dev)
+    d_n = torch.empty((n_rays, 2), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream()  # main() made it the context's stream
+
+    def cast():
+        ctx.check(ctx.lib.ncb2d_polyline_ray_cast_device(pl.h, None, C.c_uint32(n_rays), C.c_void_p(d_o.data_ptr()), C.c_void_p(d_d.data_ptr()),
+                                                         C.c_float(np.finfo(np.float32).max), None, C.c_void_p(d_toi.data_ptr()),
+                                                         C.c_void_p(d_feat.data_ptr()), C.c_void_p(d_n.data_ptr())), "ncb2d_polyline_ray_cast_device")
+
+    cast()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(10):
+        cast()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / 10
+    same = bool(np.array_equal(d_toi.cpu().numpy().view(np.uint32), toi.view(np.uint32)))
+    res = {"workload": f"{n_rays} rays against a {n_edges}-edge Polyline (noisy height profile), toi_and_normal_with_ray",
+           "device_ms": dev_ms, "device_Mrays_per_s": n_rays / dev_ms / 1e3, "e2e_ms": e2e_ms, "e2e_Mrays_per_s": n_rays / e2e_ms / 1e3,
+           "hits": int((toi >= 0).sum()), "device_equals_host_call": same, "traversal_overflows": int(ctx.traversal_overflows())}
+    try:
+        from oracle.pyoracle import Oracle
+
+        op = Oracle().polyline(pts, edges)
+        t0 = time.perf_counter()
+        ot, of, on = op.ray_cast(o[:cpu_sample], d[:cpu_sample], mode=0)
+        cms = (time.perf_counter() - t0) * 1e3
+        res["cpu_baseline"] = {"Mrays_per_s": cpu_sample / cms / 1e3, "cores": 1, "kind": "port", "sample": f"the first {cpu_sample} rays",
+                               "toi_equal": bool(np.array_equal(ot.view(np.uint32), toi[:cpu_sample].view(np.uint32)))}
+    except Exception as ex:  # noqa: BLE001
+        res["cpu_baseline"] = {"error": repr(ex)[:120]}
+    pl.close()
     return res
 
 

@@ -459,6 +459,23 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* objs, float margin, ui
                        uint8_t* manifold_count, float* contacts, uint32_t* features, uint32_t cap_contacts, uint32_t* n_pairs,
                        uint32_t* n_contacts, uint32_t* diag);
 
+/* ---- ncollide2d: RayCast for Polyline (the 2-D counterpart of the TriMesh ray path) -------------------------------------------------- */
+/* Polyline::new(points, indices) (shape/polyline.rs:57-120): 2 floats per point, 2 point indices per edge; edges == NULL builds the
+ * line strip 0-1, 1-2, ... like `indices = None`.  One leaf per edge (Segment::local_aabb), device BVH.  The handle is a ncb_mesh. */
+int ncb2d_polyline_create(ncb_ctx* ctx, uint32_t n_points, const float* xy, uint32_t n_edges, const uint32_t* edges, ncb_mesh** out);
+void ncb2d_polyline_destroy(ncb_mesh* polyline);
+/* RayCast::toi_and_normal_with_ray for a batch (query/ray/ray_polyline.rs:22-50,113-146; the segment test is RayCast for Segment, dim2,
+ * query/ray/ray_support_map.rs:219-293).  pose = Isometry2 (x, y, re, im) or NULL; origins / dirs 2 floats per ray; max_tois optional (one
+ * limit per ray).  toi < 0 = None; feature = edge, or edge + n_edges when the segment answered FeatureId::Face(1) (ray_polyline.rs:41-45);
+ * normal (optional, 2 floats) = pose * the segment's scaled normal, NOT normalised, as the reference returns it.  As in the reference,
+ * max_toi limits the AABB tests only: a segment hit beyond it is reported when its AABB was entered before it.  Host buffers, chunked
+ * upload | cast | download like ncb_trimesh_ray_cast_uv. */
+int ncb2d_polyline_ray_cast(ncb_mesh* polyline, const float* pose, uint32_t n_rays, const float* origins, const float* dirs, float max_toi,
+                            const float* max_tois, float* toi, uint32_t* feature, float* normal);
+/* Same with device-resident rays / results (8-byte aligned device pointers; pose on the host); asynchronous on the context's stream. */
+int ncb2d_polyline_ray_cast_device(ncb_mesh* polyline, const float* pose, uint32_t n_rays, const float* d_origins, const float* d_dirs,
+                                   float max_toi, const float* d_max_tois, float* d_toi, uint32_t* d_feature, float* d_normal);
+
 #ifdef __cplusplus
 }
 #endif

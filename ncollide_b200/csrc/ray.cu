@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 #ifndef NCB_HOST_SHIM  // tests/host_shim compiles slab_toi / ray_triangle for the host (test infrastructure)
 #include <cub/cub.cuh>
 #endif
@@ -38,6 +39,8 @@ struct ncb_mesh {
     ncb::DevBuf<float4> nodes4;  // 4-wide BVH: 8 float4 per binary node id (children of its two children), see k_build_bvh4
     ncb::DevBuf<float> uvs;      // per-vertex texture coordinates (TriMesh::uvs), optional
     int use_wide = 1;
+    int dim2 = 0;                    // 1: a ncollide2d Polyline (n_verts points, n_tris edges; verts / tris hold 2 words per entry)
+    ncb::DevBuf<float4> seg_packed;  // Polyline: a.x a.y b.x b.y per leaf, Morton order
     // host-buffer entry: the batch is cut into chunks that run [upload, cast, download] on a small pool of streams, so the copy
     // engines and the SMs work on different chunks at the same time and the casts of neighbouring chunks overlap
     static const int N_STREAMS = 4;
@@ -166,6 +169,26 @@ __global__ void __launch_bounds__(256) k_pack_tris(const float* __restrict__ ver
     out[3 * (size_t)pos + 2] = make_float4(verts[3 * ic], verts[3 * ic + 1], verts[3 * ic + 2], 0.f);
 }
 
+// Polyline::new (shape/polyline.rs:78-90): Segment::local_aabb = local_support_map_aabb (aabb_utils.rs:34-56) over
+// Segment::local_support_point (segment.rs:182-191: a if a . dir > b . dir, else b); boxes get z = 0 for the 3-D LBVH build.
+__global__ void __launch_bounds__(256) k_seg_aabb(const float* __restrict__ pts, const uint32_t* __restrict__ edges, uint32_t ne,
+                                                  float4* __restrict__ lo, float4* __restrict__ hi) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    uint32_t ia = __ldg(edges + 2 * e), ib = __ldg(edges + 2 * e + 1);
+    float ax = __ldg(pts + 2 * ia), ay = __ldg(pts + 2 * ia + 1), bx = __ldg(pts + 2 * ib), by = __ldg(pts + 2 * ib + 1);
+    lo[e] = make_float4(-ax > -bx ? ax : bx, -ay > -by ? ay : by, 0.f, 0.f);
+    hi[e] = make_float4(ax > bx ? ax : bx, ay > by ? ay : by, 0.f, 0.f);
+}
+__global__ void __launch_bounds__(256) k_pack_segs(const float* __restrict__ pts, const uint32_t* __restrict__ edges,
+                                                   const float4* __restrict__ leaf_lo, uint32_t ne, float4* __restrict__ out) {
+    uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= ne) return;
+    uint32_t e = __float_as_uint(__ldg(&leaf_lo[pos].w));
+    uint32_t ia = __ldg(edges + 2 * e), ib = __ldg(edges + 2 * e + 1);
+    out[pos] = make_float4(pts[2 * ia], pts[2 * ia + 1], pts[2 * ib], pts[2 * ib + 1]);
+}
+
 #endif  // NCB_HOST_SHIM
 
 // AABB::toi_with_ray(identity, ray, max_toi, solid = true) (ray_aabb.rs:13-50): returns tmin or -1 (miss).
@@ -247,6 +270,92 @@ NCB_HD bool ray_triangle(V3 a, V3 b, V3 c, V3 o, V3 dir, float& toi, V3& n_out, 
         if (vw) vw[0] = v * invd, vw[1] = w * invd;
     }
     return true;
+}
+
+// ---- ncollide2d: Polyline ray casting (query/ray/ray_polyline.rs) ------------------------------------------------------------------
+// AABB::toi_with_ray with DIM = 2 (ray_aabb.rs:13-50)
+NCB_HD float slab_toi2(float lox, float loy, float hix, float hiy, float ox, float oy, float dx, float dy, float ivx, float ivy, float max_toi) {
+    float tmin = 0.f, tmax = max_toi;
+    if (dx == 0.f) {
+        if (ox < lox || ox > hix) return -1.f;
+    } else {
+        float n = (lox - ox) * ivx, f = (hix - ox) * ivx;
+        if (n > f) {
+            float t = n;
+            n = f;
+            f = t;
+        }
+        tmin = fmaxf(tmin, n);
+        tmax = fminf(tmax, f);
+        if (tmin > tmax) return -1.f;
+    }
+    if (dy == 0.f) {
+        if (oy < loy || oy > hiy) return -1.f;
+    } else {
+        float n = (loy - oy) * ivy, f = (hiy - oy) * ivy;
+        if (n > f) {
+            float t = n;
+            n = f;
+            f = t;
+        }
+        tmin = fmaxf(tmin, n);
+        tmax = fminf(tmax, f);
+        if (tmin > tmax) return -1.f;
+    }
+    return tmin;
+}
+
+// RayCast for Segment::toi_and_normal_with_ray, dim2 (query/ray/ray_support_map.rs:219-293) with the segment in the ray's frame:
+// closest_points_line_line_parameters_eps (closest_points_line_line.rs:27-70), then the collinear / crossing cases.  The normal is
+// the segment's SCALED normal and max_toi is not applied, as in the reference.  feature: 0 Face(0) or a Vertex, 1 Face(1).
+NCB_HD bool segment_ray2(float ax, float ay, float bx, float by, float ox, float oy, float dx, float dy, float& toi, float& nx, float& ny,
+                         int& face1) {
+    const float eps = NCB_EPS;
+    float sdx = bx - ax, sdy = by - ay;
+    float rx = ox - ax, ry = oy - ay;
+    float a = dx * dx + dy * dy, e = sdx * sdx + sdy * sdy, f = sdx * rx + sdy * ry;
+    float s, t;
+    bool parallel = false;
+    if (a <= eps && e <= eps) {
+        s = 0.f, t = 0.f;
+    } else if (a <= eps) {
+        s = 0.f, t = f / e;
+    } else {
+        float c = dx * rx + dy * ry;
+        if (e <= eps) {
+            s = -c / a, t = 0.f;
+        } else {
+            float b = dx * sdx + dy * sdy;
+            float ae = a * e, bb = b * b, denom = ae - bb;
+            parallel = denom <= eps || ulps_eq(ae, bb);
+            s = !parallel ? (b * f - c * e) / denom : 0.f;
+            t = (b * s + f) / e;
+        }
+    }
+    nx = sdy, ny = -sdx;
+    face1 = 0;
+    if (parallel) {
+        float px = ax - ox, py = ay - oy;
+        if (!(fabsf(px * nx + py * ny) < eps)) return false;
+        float dist1 = px * dx + py * dy;
+        float dist2 = dist1 + (sdx * dx + sdy * dy);
+        bool p1 = dist1 >= 0.f, p2 = dist2 >= 0.f;
+        if (p1 && p2) {
+            toi = (dist1 <= dist2 ? dist1 : dist2) / (dx * dx + dy * dy);
+            return true;
+        }
+        if (p1 || p2) {
+            toi = 0.f;
+            return true;
+        }
+        return false;
+    }
+    if (s >= 0.f && t >= 0.f && t <= 1.f) {
+        toi = s;
+        if (nx * dx + ny * dy > 0.f) nx = -nx, ny = -ny, face1 = 1;
+        return true;
+    }
+    return false;
 }
 
 #ifndef NCB_HOST_SHIM  // the traversal kernel and the host entry points: CUDA only
@@ -374,6 +483,79 @@ __global__ void __launch_bounds__(256) k_build_bvh4(const float4* __restrict__ n
     out[7] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// The walk over the 4-wide tree, shared by the TriMesh (DIM 3) and the Polyline (DIM 2: the z planes are never read) kernels.
+// B carries the best hit so far (B.have, B.toi); leaf(position) tests one primitive and may lower it.
+template <int DIM, class BT, class LeafFn>
+__device__ __forceinline__ void traverse_bvh4(const float4* __restrict__ nodes4, V3 o, V3 d, V3 inv, float max_toi, uint32_t* trav_overflow, BT& B,
+                                              LeafFn leaf) {
+    uint32_t stack[64];
+    float stack_t[64];
+    int sp = 0;
+    uint32_t node = 0;
+    for (;;) {
+        const float4* rec = nodes4 + 8 * (size_t)node;
+        float4 lx = __ldg(rec), ly = __ldg(rec + 1), hx = __ldg(rec + 3), hy = __ldg(rec + 4);
+        float4 idw = __ldg(rec + 6);
+        uint32_t id[4] = {__float_as_uint(idw.x), __float_as_uint(idw.y), __float_as_uint(idw.z), __float_as_uint(idw.w)};
+        float t[4];
+        if (DIM == 3) {
+            float4 lz = __ldg(rec + 2), hz = __ldg(rec + 5);
+            t[0] = slab_toi(make_float4(lx.x, ly.x, lz.x, 0.f), make_float4(hx.x, hy.x, hz.x, 0.f), o, d, inv, max_toi);
+            t[1] = slab_toi(make_float4(lx.y, ly.y, lz.y, 0.f), make_float4(hx.y, hy.y, hz.y, 0.f), o, d, inv, max_toi);
+            t[2] = id[2] == EMPTY_CHILD ? -1.f : slab_toi(make_float4(lx.z, ly.z, lz.z, 0.f), make_float4(hx.z, hy.z, hz.z, 0.f), o, d, inv, max_toi);
+            t[3] = id[3] == EMPTY_CHILD ? -1.f : slab_toi(make_float4(lx.w, ly.w, lz.w, 0.f), make_float4(hx.w, hy.w, hz.w, 0.f), o, d, inv, max_toi);
+        } else {
+            t[0] = slab_toi2(lx.x, ly.x, hx.x, hy.x, o.x, o.y, d.x, d.y, inv.x, inv.y, max_toi);
+            t[1] = slab_toi2(lx.y, ly.y, hx.y, hy.y, o.x, o.y, d.x, d.y, inv.x, inv.y, max_toi);
+            t[2] = id[2] == EMPTY_CHILD ? -1.f : slab_toi2(lx.z, ly.z, hx.z, hy.z, o.x, o.y, d.x, d.y, inv.x, inv.y, max_toi);
+            t[3] = id[3] == EMPTY_CHILD ? -1.f : slab_toi2(lx.w, ly.w, hx.w, hy.w, o.x, o.y, d.x, d.y, inv.x, inv.y, max_toi);
+        }
+        // leaves at once (their primitives may lower the bound for the internal children)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (t[k] >= 0.f && (id[k] & LEAF_BIT)) {
+                if (!(B.have && t[k] > B.toi)) leaf(id[k] & ~LEAF_BIT);
+                t[k] = -1.f;
+            }
+        // internal children still worth a visit, nearest first
+        uint32_t cn[4];
+        float ct[4];
+        int nc = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (t[k] >= 0.f && !(B.have && t[k] > B.toi)) {
+                int j = nc++;
+                while (j > 0 && ct[j - 1] > t[k]) {
+                    ct[j] = ct[j - 1], cn[j] = cn[j - 1];
+                    --j;
+                }
+                ct[j] = t[k], cn[j] = id[k];
+            }
+        if (nc > 0) {
+            for (int j = nc - 1; j >= 1; --j) {  // farthest first, so that the nearest of them is popped first
+                if (sp < 64) {
+                    stack[sp] = cn[j], stack_t[sp] = ct[j];
+                    sp++;
+                } else {
+                    atomicAdd(trav_overflow, 1u);
+                }
+            }
+            node = cn[0];
+        } else {
+            bool found = false;
+            while (sp > 0) {
+                sp--;
+                if (!(B.have && stack_t[sp] > B.toi)) {
+                    node = stack[sp];
+                    found = true;
+                    break;
+                }
+            }
+            if (!found) break;
+        }
+    }
+}
+
 template <bool UV>
 __global__ void __launch_bounds__(128) k_ray_cast4(RayArgs A) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,66 +574,85 @@ __global__ void __launch_bounds__(128) k_ray_cast4(RayArgs A) {
         float4 lo = __ldg(&A.leaf_lo[0]), hi = __ldg(&A.leaf_hi[0]);
         if (slab_toi(lo, hi, o, d, inv, max_toi) >= 0.f) ray_test_leaf<UV>(A.tri_packed, 0, o, d, max_toi, B);
     } else if (A.n_tris >= 2) {
-        uint32_t stack[64];
-        float stack_t[64];
-        int sp = 0;
-        uint32_t node = 0;
-        for (;;) {
-            const float4* rec = A.nodes4 + 8 * (size_t)node;
-            float4 lx = __ldg(rec), ly = __ldg(rec + 1), lz = __ldg(rec + 2), hx = __ldg(rec + 3), hy = __ldg(rec + 4), hz = __ldg(rec + 5);
-            float4 idw = __ldg(rec + 6);
-            uint32_t id[4] = {__float_as_uint(idw.x), __float_as_uint(idw.y), __float_as_uint(idw.z), __float_as_uint(idw.w)};
-            float t[4];
-            t[0] = slab_toi(make_float4(lx.x, ly.x, lz.x, 0.f), make_float4(hx.x, hy.x, hz.x, 0.f), o, d, inv, max_toi);
-            t[1] = slab_toi(make_float4(lx.y, ly.y, lz.y, 0.f), make_float4(hx.y, hy.y, hz.y, 0.f), o, d, inv, max_toi);
-            t[2] = id[2] == EMPTY_CHILD ? -1.f : slab_toi(make_float4(lx.z, ly.z, lz.z, 0.f), make_float4(hx.z, hy.z, hz.z, 0.f), o, d, inv, max_toi);
-            t[3] = id[3] == EMPTY_CHILD ? -1.f : slab_toi(make_float4(lx.w, ly.w, lz.w, 0.f), make_float4(hx.w, hy.w, hz.w, 0.f), o, d, inv, max_toi);
-            // leaves at once (their triangles may lower the bound for the internal children)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (t[k] >= 0.f && (id[k] & LEAF_BIT)) {
-                    if (!(B.have && t[k] > B.toi)) ray_test_leaf<UV>(A.tri_packed, id[k] & ~LEAF_BIT, o, d, max_toi, B);
-                    t[k] = -1.f;
-                }
-            // internal children still worth a visit, nearest first
-            uint32_t cn[4];
-            float ct[4];
-            int nc = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (t[k] >= 0.f && !(B.have && t[k] > B.toi)) {
-                    int j = nc++;
-                    while (j > 0 && ct[j - 1] > t[k]) {
-                        ct[j] = ct[j - 1], cn[j] = cn[j - 1];
-                        --j;
-                    }
-                    ct[j] = t[k], cn[j] = id[k];
-                }
-            if (nc > 0) {
-                for (int j = nc - 1; j >= 1; --j) {  // farthest first, so that the nearest of them is popped first
-                    if (sp < 64) {
-                        stack[sp] = cn[j], stack_t[sp] = ct[j];
-                        sp++;
-                    } else {
-                        atomicAdd(A.trav_overflow, 1u);
-                    }
-                }
-                node = cn[0];
-            } else {
-                bool found = false;
-                while (sp > 0) {
-                    sp--;
-                    if (!(B.have && stack_t[sp] > B.toi)) {
-                        node = stack[sp];
-                        found = true;
-                        break;
-                    }
-                }
-                if (!found) break;
-            }
-        }
+        traverse_bvh4<3>(A.nodes4, o, d, inv, max_toi, A.trav_overflow, B,
+                         [&](uint32_t leaf_pos) { ray_test_leaf<UV>(A.tri_packed, leaf_pos, o, d, max_toi, B); });
     }
     ray_write_hit(A, r, B);
+}
+
+// RayCast for Polyline::toi_and_normal_with_ray (ray_polyline.rs:22-50,113-146): one thread per ray over the 4-wide tree of the
+// edges' AABBs.  Accepted hits = edges whose AABB passes the slab test (with max_toi) and whose segment is hit (max_toi NOT applied,
+// like RayCast for Segment in 2-D); the minimum toi wins, ties -> smallest edge.
+struct Ray2Args {
+    const float4* nodes4;
+    const float4* leaf_lo;   // .w = edge id of the leaf
+    const float4* leaf_hi;
+    const float4* seg_packed;  // a.x a.y b.x b.y per leaf, leaf order
+    uint32_t n_edges;
+    float pose[4];           // x y re im
+    int has_pose;
+    const float* origins;    // 2 floats per ray
+    const float* dirs;
+    uint32_t n_rays;
+    float max_toi;
+    const float* max_tois;
+    float* toi;
+    uint32_t* feature;
+    float* normal;           // 2 floats per ray (nullable)
+    uint32_t* trav_overflow;
+};
+struct Ray2Best {
+    float toi, nx, ny;
+    uint32_t edge;
+    int face1;
+    bool have;
+};
+__device__ __forceinline__ void ray2_test_leaf(const Ray2Args& A, uint32_t leaf_pos, float ox, float oy, float dx, float dy, Ray2Best& B) {
+    float4 sg = __ldg(A.seg_packed + leaf_pos);
+    float toi, nx, ny;
+    int face1;
+    if (segment_ray2(sg.x, sg.y, sg.z, sg.w, ox, oy, dx, dy, toi, nx, ny, face1)) {
+        uint32_t e = __float_as_uint(__ldg(&A.leaf_lo[leaf_pos].w));
+        if (!B.have || toi < B.toi || (toi == B.toi && e < B.edge)) B.have = true, B.toi = toi, B.edge = e, B.nx = nx, B.ny = ny, B.face1 = face1;
+    }
+}
+__global__ void __launch_bounds__(128) k_ray_cast4_polyline(Ray2Args A) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= A.n_rays) return;
+    float2 o2 = __ldg(reinterpret_cast<const float2*>(A.origins) + r), d2 = __ldg(reinterpret_cast<const float2*>(A.dirs) + r);
+    float ox = o2.x, oy = o2.y, dx = d2.x, dy = d2.y;
+    if (A.has_pose) {  // ray.inverse_transform_by(m): the conjugate rotation of (origin - translation) and of dir
+        float px = ox - A.pose[0], py = oy - A.pose[1], re = A.pose[2], im = A.pose[3];
+        ox = re * px + im * py, oy = -im * px + re * py;
+        float qx = dx, qy = dy;
+        dx = re * qx + im * qy, dy = -im * qx + re * qy;
+    }
+    const float max_toi = A.max_tois ? __ldg(A.max_tois + r) : A.max_toi;
+    Ray2Best B;
+    B.toi = NCB_FMAX, B.nx = B.ny = 0.f, B.edge = 0xffffffffu, B.face1 = 0, B.have = false;
+    const V3 o = v3(ox, oy, 0.f), d = v3(dx, dy, 0.f), inv = v3(1.f / dx, 1.f / dy, 0.f);
+    if (A.n_edges == 1) {
+        float4 lo = __ldg(&A.leaf_lo[0]), hi = __ldg(&A.leaf_hi[0]);
+        if (slab_toi2(lo.x, lo.y, hi.x, hi.y, ox, oy, dx, dy, inv.x, inv.y, max_toi) >= 0.f) ray2_test_leaf(A, 0, ox, oy, dx, dy, B);
+    } else if (A.n_edges >= 2) {
+        traverse_bvh4<2>(A.nodes4, o, d, inv, max_toi, A.trav_overflow, B, [&](uint32_t leaf_pos) { ray2_test_leaf(A, leaf_pos, ox, oy, dx, dy, B); });
+    }
+    if (B.have) {
+        A.toi[r] = B.toi;
+        A.feature[r] = B.face1 ? B.edge + A.n_edges : B.edge;  // ray_polyline.rs:41-45
+        if (A.normal) {  // m * res.normal
+            float nx = B.nx, ny = B.ny;
+            if (A.has_pose) {
+                float re = A.pose[2], im = A.pose[3];
+                nx = re * B.nx - im * B.ny, ny = im * B.nx + re * B.ny;
+            }
+            reinterpret_cast<float2*>(A.normal)[r] = make_float2(nx, ny);
+        }
+    } else {
+        A.toi[r] = -1.f;
+        A.feature[r] = 0xffffffffu;
+        if (A.normal) reinterpret_cast<float2*>(A.normal)[r] = make_float2(0.f, 0.f);
+    }
 }
 
 template <bool TILE>
@@ -565,19 +766,23 @@ using namespace ncb;
 
 extern "C" {
 
-int ncb_trimesh_create(ncb_ctx* ctx, uint32_t n_verts, const float* xyz, uint32_t n_tris, const uint32_t* idx, ncb_mesh** out) {
+// TriMesh::new (dim2 == 0: 3 floats per vertex, 3 indices per triangle) and Polyline::new (dim2 == 1: 2 floats per point, 2 indices per edge)
+static int mesh_create(ncb_ctx* ctx, int dim2, uint32_t n_verts, const float* xyz, uint32_t n_tris, const uint32_t* idx, ncb_mesh** out) {
+    const size_t W = dim2 ? 2 : 3;  // words per vertex and per primitive
+    const char* who = dim2 ? "ncb2d_polyline_create: " : "ncb_trimesh_create: ";
     if (!ctx || !out || (n_verts && !xyz) || (n_tris && !idx)) return NCB_ERR_ARG;
     *out = nullptr;
     CKM(cudaSetDevice(ctx->device));
-    for (size_t k = 0; k < 3 * (size_t)n_tris; ++k)
+    for (size_t k = 0; k < W * (size_t)n_tris; ++k)
         if (idx[k] >= n_verts) {
-            ctx->err = "ncb_trimesh_create: vertex index out of range";
+            ctx->err = std::string(who) + "vertex index out of range";
             return NCB_ERR_ARG;
         }
     ncb_mesh* m = new ncb_mesh;
     m->owner = ctx;
     m->n_verts = n_verts;
     m->n_tris = n_tris;
+    m->dim2 = dim2;
     ncb_ctx* b = new ncb_ctx;
     b->device = ctx->device;
     b->stream = ctx->stream;
@@ -586,14 +791,14 @@ int ncb_trimesh_create(ncb_ctx* ctx, uint32_t n_verts, const float* xyz, uint32_
     cudaStream_t s = ctx->stream;
     cudaError_t e = cudaSuccess;
     auto fail = [&](const char* what) {
-        ctx->err = std::string("ncb_trimesh_create: ") + what + ": " + cudaGetErrorString(e);
+        ctx->err = std::string(who) + what + ": " + cudaGetErrorString(e);
         ncb_trimesh_destroy(m);
         return NCB_ERR_CUDA;
     };
-    if ((e = m->verts.reserve(3 * (size_t)n_verts + 3)) != cudaSuccess) return fail("alloc verts");
-    if ((e = m->tris.reserve(3 * (size_t)n_tris + 3)) != cudaSuccess) return fail("alloc tris");
-    if (n_verts && (e = cudaMemcpyAsync(m->verts.p, xyz, 12 * (size_t)n_verts, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail("copy");
-    if (n_tris && (e = cudaMemcpyAsync(m->tris.p, idx, 12 * (size_t)n_tris, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail("copy");
+    if ((e = m->verts.reserve(W * (size_t)n_verts + 3)) != cudaSuccess) return fail("alloc verts");
+    if ((e = m->tris.reserve(W * (size_t)n_tris + 3)) != cudaSuccess) return fail("alloc tris");
+    if (n_verts && (e = cudaMemcpyAsync(m->verts.p, xyz, 4 * W * (size_t)n_verts, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail("copy");
+    if (n_tris && (e = cudaMemcpyAsync(m->tris.p, idx, 4 * W * (size_t)n_tris, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail("copy");
     if (n_tris) {
         uint32_t n = n_tris;
         if ((e = b->aabb_lo.reserve(n)) != cudaSuccess || (e = b->aabb_hi.reserve(n)) != cudaSuccess || (e = b->keys_a.reserve(n)) != cudaSuccess ||
@@ -610,19 +815,27 @@ int ncb_trimesh_create(ncb_ctx* ctx, uint32_t n_verts, const float* xyz, uint32_
             z.bounds[3 + k] = (int)0x80800000;
         }
         if ((e = cudaMemcpyAsync(b->counters.p, &z, sizeof z, cudaMemcpyHostToDevice, s)) != cudaSuccess) return fail("counters");
-        k_tri_aabb<<<(n + 255) / 256, 256, 0, s>>>(m->verts.p, m->tris.p, n, b->aabb_lo.p, b->aabb_hi.p);
-        if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_tri_aabb");
+        if (dim2)
+            k_seg_aabb<<<(n + 255) / 256, 256, 0, s>>>(m->verts.p, m->tris.p, n, b->aabb_lo.p, b->aabb_hi.p);
+        else
+            k_tri_aabb<<<(n + 255) / 256, 256, 0, s>>>(m->verts.p, m->tris.p, n, b->aabb_lo.p, b->aabb_hi.p);
+        if ((e = cudaGetLastError()) != cudaSuccess) return fail("primitive AABBs");
         if ((e = launch_lbvh_build(b, n, nullptr)) != cudaSuccess) return fail("lbvh build");
-        if ((e = m->tri_packed.reserve(3 * (size_t)n)) != cudaSuccess) return fail("alloc packed triangles");
-        k_pack_tris<<<(n + 255) / 256, 256, 0, s>>>(m->verts.p, m->tris.p, b->leaf_lo.p, n, m->tri_packed.p);
-        if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_pack_tris");
+        if (dim2) {
+            if ((e = m->seg_packed.reserve(n)) != cudaSuccess) return fail("alloc packed segments");
+            k_pack_segs<<<(n + 255) / 256, 256, 0, s>>>(m->verts.p, m->tris.p, b->leaf_lo.p, n, m->seg_packed.p);
+        } else {
+            if ((e = m->tri_packed.reserve(3 * (size_t)n)) != cudaSuccess) return fail("alloc packed triangles");
+            k_pack_tris<<<(n + 255) / 256, 256, 0, s>>>(m->verts.p, m->tris.p, b->leaf_lo.p, n, m->tri_packed.p);
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) return fail("pack primitives");
         if (n >= 2) {
             if ((e = m->nodes4.reserve(8 * (size_t)(n - 1))) != cudaSuccess) return fail("alloc 4-wide nodes");
             k_build_bvh4<<<(n + 255) / 256, 256, 0, s>>>(b->nodes.p, n, m->nodes4.p);
             if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_build_bvh4");
         }
         if ((e = m->top_tile.reserve(TOP_SLOTS * 4)) != cudaSuccess) return fail("alloc top tile");
-        if (n >= 2) k_build_top_tile<<<1, 256, 0, s>>>(b->nodes.p, n, m->top_tile.p);
+        if (n >= 2 && !dim2) k_build_top_tile<<<1, 256, 0, s>>>(b->nodes.p, n, m->top_tile.p);
         if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_build_top_tile");
         // mesh bounds = union of the root's two child boxes (or the single leaf box)
         float4 rec[4];
@@ -650,6 +863,20 @@ int ncb_trimesh_create(ncb_ctx* ctx, uint32_t n_verts, const float* xyz, uint32_
     return NCB_OK;
 }
 
+int ncb_trimesh_create(ncb_ctx* ctx, uint32_t n_verts, const float* xyz, uint32_t n_tris, const uint32_t* idx, ncb_mesh** out) {
+    return mesh_create(ctx, 0, n_verts, xyz, n_tris, idx, out);
+}
+
+// Polyline::new(points, Some(indices)) (shape/polyline.rs:57-120); edges == NULL: the line strip 0-1, 1-2, ... (n_edges is ignored)
+int ncb2d_polyline_create(ncb_ctx* ctx, uint32_t n_points, const float* xy, uint32_t n_edges, const uint32_t* edges, ncb_mesh** out) {
+    if (edges || !ctx || !out) return mesh_create(ctx, 1, n_points, xy, n_edges, edges, out);
+    uint32_t ne = n_points ? n_points - 1 : 0;
+    std::vector<uint32_t> strip(2 * (size_t)ne);
+    for (uint32_t i = 0; i < ne; ++i) strip[2 * i] = i, strip[2 * i + 1] = i + 1;
+    return mesh_create(ctx, 1, n_points, xy, ne, strip.data(), out);
+}
+void ncb2d_polyline_destroy(ncb_mesh* m) { ncb_trimesh_destroy(m); }
+
 void ncb_trimesh_destroy(ncb_mesh* m) {
     if (!m) return;
     if (m->owner) {
@@ -664,7 +891,7 @@ void ncb_trimesh_destroy(ncb_mesh* m) {
         delete b;
     }
     m->verts.release(), m->tris.release(), m->d_in.release(), m->d_out.release(), m->tri_packed.release(), m->top_tile.release();
-    m->nodes4.release(), m->uvs.release();
+    m->nodes4.release(), m->uvs.release(), m->seg_packed.release();
     for (int k = 0; k < ncb_mesh::N_STREAMS; ++k) {
         if (m->chunk_stream[k]) cudaStreamDestroy(m->chunk_stream[k]);
         if (m->ev_end[k]) cudaEventDestroy(m->ev_end[k]);
@@ -676,7 +903,7 @@ void ncb_trimesh_destroy(ncb_mesh* m) {
 
 // TriMesh::uvs (shape/trimesh.rs: `uvs: Option<Vec<Point2<N>>>`): per-vertex texture coordinates, or NULL to clear them.
 int ncb_trimesh_set_uvs(ncb_mesh* m, const float* uvs) {
-    if (!m) return NCB_ERR_ARG;
+    if (!m || m->dim2) return NCB_ERR_ARG;
     ncb_ctx* ctx = m->owner;
     CKM(cudaSetDevice(ctx->device));
     if (!uvs) {
@@ -686,6 +913,18 @@ int ncb_trimesh_set_uvs(ncb_mesh* m, const float* uvs) {
     CKM(m->uvs.reserve(2 * (size_t)m->n_verts + 2));
     CKM(cudaMemcpyAsync(m->uvs.p, uvs, 8 * (size_t)m->n_verts, cudaMemcpyHostToDevice, ctx->stream));
     CKM(cudaStreamSynchronize(ctx->stream));
+    return NCB_OK;
+}
+
+static int ensure_chunk_streams(ncb_mesh* m) {
+    ncb_ctx* ctx = m->owner;
+    if (m->pipeline_ready) return NCB_OK;
+    for (int k = 0; k < ncb_mesh::N_STREAMS; ++k) {
+        CKM(cudaStreamCreateWithFlags(&m->chunk_stream[k], cudaStreamNonBlocking));
+        CKM(cudaEventCreateWithFlags(&m->ev_end[k], cudaEventDisableTiming));
+    }
+    CKM(cudaEventCreateWithFlags(&m->ev_begin, cudaEventDisableTiming));
+    m->pipeline_ready = true;
     return NCB_OK;
 }
 
@@ -768,7 +1007,7 @@ static int launch_ray_cast(ncb_mesh* m, const float* pose, uint32_t n_rays, cons
 
 int ncb_trimesh_ray_cast_device(ncb_mesh* m, const float* pose, uint32_t n_rays, const float* d_origins, const float* d_dirs, float max_toi,
                                 float* d_toi, uint32_t* d_face, float* d_normal) {
-    if (!m || (n_rays && (!d_origins || !d_dirs || !d_toi || !d_face))) return NCB_ERR_ARG;
+    if (!m || m->dim2 || (n_rays && (!d_origins || !d_dirs || !d_toi || !d_face))) return NCB_ERR_ARG;
     ncb_ctx* ctx = m->owner;
     CKM(cudaSetDevice(ctx->device));
     if (n_rays == 0) return NCB_OK;
@@ -781,7 +1020,7 @@ int ncb_trimesh_ray_cast_device(ncb_mesh* m, const float* pose, uint32_t n_rays,
 // their sum.  max_tois: per-ray limits (NULL: max_toi for every ray).
 int ncb_trimesh_ray_cast_uv(ncb_mesh* m, const float* pose, uint32_t n_rays, const float* origins, const float* dirs, float max_toi,
                             const float* max_tois, float* toi, uint32_t* face, float* normal, float* uv) {
-    if (!m || (n_rays && (!origins || !dirs || !toi || !face))) return NCB_ERR_ARG;
+    if (!m || m->dim2 || (n_rays && (!origins || !dirs || !toi || !face))) return NCB_ERR_ARG;
     ncb_ctx* ctx = m->owner;
     CKM(cudaSetDevice(ctx->device));
     if (n_rays == 0) return NCB_OK;
@@ -789,14 +1028,7 @@ int ncb_trimesh_ray_cast_uv(ncb_mesh* m, const float* pose, uint32_t n_rays, con
     size_t n = n_rays;
     CKM(m->d_in.reserve(7 * n));
     CKM(m->d_out.reserve(7 * n));
-    if (!m->pipeline_ready) {
-        for (int k = 0; k < ncb_mesh::N_STREAMS; ++k) {
-            CKM(cudaStreamCreateWithFlags(&m->chunk_stream[k], cudaStreamNonBlocking));
-            CKM(cudaEventCreateWithFlags(&m->ev_end[k], cudaEventDisableTiming));
-        }
-        CKM(cudaEventCreateWithFlags(&m->ev_begin, cudaEventDisableTiming));
-        m->pipeline_ready = true;
-    }
+    if (int rc = ensure_chunk_streams(m)) return rc;
     float* d_o = m->d_in.p;
     float* d_d = m->d_in.p + 3 * n;
     float* d_mt = m->d_in.p + 6 * n;
@@ -844,6 +1076,90 @@ int ncb_trimesh_ray_cast_uv(ncb_mesh* m, const float* pose, uint32_t n_rays, con
 int ncb_trimesh_ray_cast(ncb_mesh* m, const float* pose, uint32_t n_rays, const float* origins, const float* dirs, float max_toi, float* toi,
                          uint32_t* face, float* normal) {
     return ncb_trimesh_ray_cast_uv(m, pose, n_rays, origins, dirs, max_toi, nullptr, toi, face, normal, nullptr);
+}
+
+// ---- ncollide2d Polyline -----------------------------------------------------------------------------------------------------------
+static int launch_ray_cast2(ncb_mesh* m, const float* pose, uint32_t n_rays, const float* d_origins, const float* d_dirs, float max_toi,
+                            const float* d_max_tois, float* d_toi, uint32_t* d_feature, float* d_normal, cudaStream_t stream) {
+    ncb_ctx* ctx = m->owner;
+    Ray2Args A;
+    A.nodes4 = m->nodes4.p;
+    A.leaf_lo = m->bvh->leaf_lo.p;
+    A.leaf_hi = m->bvh->leaf_hi.p;
+    A.seg_packed = m->seg_packed.p;
+    A.n_edges = m->n_tris;
+    A.has_pose = pose != nullptr;
+    A.pose[0] = pose ? pose[0] : 0.f, A.pose[1] = pose ? pose[1] : 0.f, A.pose[2] = pose ? pose[2] : 1.f, A.pose[3] = pose ? pose[3] : 0.f;
+    A.origins = d_origins;
+    A.dirs = d_dirs;
+    A.n_rays = n_rays;
+    A.max_toi = max_toi;
+    A.max_tois = d_max_tois;
+    A.toi = d_toi;
+    A.feature = d_feature;
+    A.normal = d_normal;
+    A.trav_overflow = trav_overflow_counter(ctx);
+    k_ray_cast4_polyline<<<(n_rays + 127) / 128, 128, 0, stream>>>(A);
+    CKM(cudaGetLastError());
+    return NCB_OK;
+}
+
+int ncb2d_polyline_ray_cast_device(ncb_mesh* m, const float* pose, uint32_t n_rays, const float* d_origins, const float* d_dirs, float max_toi,
+                                   const float* d_max_tois, float* d_toi, uint32_t* d_feature, float* d_normal) {
+    if (!m || !m->dim2 || (n_rays && (!d_origins || !d_dirs || !d_toi || !d_feature))) return NCB_ERR_ARG;
+    ncb_ctx* ctx = m->owner;
+    CKM(cudaSetDevice(ctx->device));
+    if (n_rays == 0) return NCB_OK;
+    return launch_ray_cast2(m, pose, n_rays, d_origins, d_dirs, max_toi, d_max_tois, d_toi, d_feature, d_normal, ctx->stream);
+}
+
+// Host buffers in, host buffers out: the chunk pipeline of ncb_trimesh_ray_cast_uv (16-20 B per ray in, 8-16 B out).
+int ncb2d_polyline_ray_cast(ncb_mesh* m, const float* pose, uint32_t n_rays, const float* origins, const float* dirs, float max_toi,
+                            const float* max_tois, float* toi, uint32_t* feature, float* normal) {
+    if (!m || !m->dim2 || (n_rays && (!origins || !dirs || !toi || !feature))) return NCB_ERR_ARG;
+    ncb_ctx* ctx = m->owner;
+    CKM(cudaSetDevice(ctx->device));
+    if (n_rays == 0) return NCB_OK;
+    cudaStream_t s = ctx->stream;
+    size_t n = n_rays;
+    CKM(m->d_in.reserve(5 * n + 8));
+    CKM(m->d_out.reserve(4 * n + 8));
+    if (int rc = ensure_chunk_streams(m)) return rc;
+    float* d_o = m->d_in.p;
+    float* d_d = m->d_in.p + 2 * n;
+    float* d_mt = m->d_in.p + 4 * n;
+    float* d_n = m->d_out.p;  // float2 per ray first: 8-byte aligned
+    float* d_toi = m->d_out.p + 2 * n;
+    uint32_t* d_feat = reinterpret_cast<uint32_t*>(m->d_out.p + 3 * n);
+    static int chunk_rays = getenv("NCB_RAY_CHUNK") ? atoi(getenv("NCB_RAY_CHUNK")) : 262144;
+    uint32_t per = (uint32_t)(chunk_rays > 0 ? chunk_rays : 262144);
+    per = (per + 127) & ~127u;
+    uint32_t n_chunks = (n_rays + per - 1) / per;
+    if (n_chunks > 32) {
+        per = ((n_rays + 31) / 32 + 127) & ~127u;
+        n_chunks = (n_rays + per - 1) / per;
+    }
+    CKM(cudaEventRecord(m->ev_begin, s));
+    int used = (int)std::min<uint32_t>(n_chunks, ncb_mesh::N_STREAMS);
+    for (int j = 0; j < used; ++j) CKM(cudaStreamWaitEvent(m->chunk_stream[j], m->ev_begin, 0));
+    int rc = NCB_OK;
+    for (uint32_t k = 0; k < n_chunks && rc == NCB_OK; ++k) {
+        cudaStream_t cs = m->chunk_stream[k % ncb_mesh::N_STREAMS];
+        size_t off = (size_t)k * per, cnt = std::min<size_t>(per, n - off);
+        CKM(cudaMemcpyAsync(d_o + 2 * off, origins + 2 * off, 8 * cnt, cudaMemcpyHostToDevice, cs));
+        CKM(cudaMemcpyAsync(d_d + 2 * off, dirs + 2 * off, 8 * cnt, cudaMemcpyHostToDevice, cs));
+        if (max_tois) CKM(cudaMemcpyAsync(d_mt + off, max_tois + off, 4 * cnt, cudaMemcpyHostToDevice, cs));
+        rc = launch_ray_cast2(m, pose, (uint32_t)cnt, d_o + 2 * off, d_d + 2 * off, max_toi, max_tois ? d_mt + off : nullptr, d_toi + off,
+                              d_feat + off, normal ? d_n + 2 * off : nullptr, cs);
+        if (rc) break;
+        CKM(cudaMemcpyAsync(toi + off, d_toi + off, 4 * cnt, cudaMemcpyDeviceToHost, cs));
+        CKM(cudaMemcpyAsync(feature + off, d_feat + off, 4 * cnt, cudaMemcpyDeviceToHost, cs));
+        if (normal) CKM(cudaMemcpyAsync(normal + 2 * off, d_n + 2 * off, 8 * cnt, cudaMemcpyDeviceToHost, cs));
+    }
+    for (int j = 0; j < used; ++j) cudaStreamSynchronize(m->chunk_stream[j]);
+    if (rc) return rc;
+    CKM(cudaGetLastError());
+    return NCB_OK;
 }
 
 }  // extern "C"

@@ -119,6 +119,54 @@ def proximity(ctx, type1, param1, pose1, type2, param2, pose2, poly_points=None,
     return out
 
 
+class Polyline:
+    """``ncollide2d::shape::Polyline::new(points, indices)`` with ``RayCast::toi_and_normal_with_ray`` for a batch of rays
+    (``ncb2d_polyline_create`` / ``ncb2d_polyline_ray_cast``).  ``edges`` None = the line strip."""
+
+    def __init__(self, ctx, points, edges=None):
+        self.ctx = ctx
+        self.points = as_f32(points).reshape(-1, 2)
+        self.edges = as_u32(edges).reshape(-1, 2) if edges is not None else None
+        self.n_edges = len(self.edges) if self.edges is not None else max(len(self.points) - 1, 0)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.ncb2d_polyline_create(ctx.h, C.c_uint32(len(self.points)), ptr(self.points), C.c_uint32(self.n_edges), ptr(self.edges),
+                                                C.byref(h)), "ncb2d_polyline_create")
+        self.h = h
+
+    def toi_and_normal_with_ray(self, pose, origins, dirs, max_toi=None, want_normals=True, out=None):
+        """pose: None or (x, y, re, im).  max_toi: None, one value, or one per ray.  Returns (toi [-1 = None], feature [edge, or
+        edge + n_edges for the segment's Face(1)], normals [the scaled segment normal, as in the reference])."""
+        o, d = as_f32(origins).reshape(-1, 2), as_f32(dirs).reshape(-1, 2)
+        n = len(o)
+        out = out or {}
+        toi = out.get("toi") if out.get("toi") is not None else np.zeros(n, dtype=np.float32)
+        feat = out.get("feature") if out.get("feature") is not None else np.zeros(n, dtype=np.uint32)
+        normal = (out.get("normal") if out.get("normal") is not None else np.zeros((n, 2), dtype=np.float32)) if want_normals else None
+        p = as_f32(pose) if pose is not None else None
+        per_ray = None
+        if max_toi is None:
+            max_toi = np.finfo(np.float32).max
+        elif np.ndim(max_toi) > 0:
+            per_ray = as_f32(max_toi).reshape(-1)
+            if len(per_ray) != n:
+                raise ValueError("one max_toi per ray")
+            max_toi = 0.0
+        self.ctx.check(self.ctx.lib.ncb2d_polyline_ray_cast(self.h, ptr(p), C.c_uint32(n), ptr(o), ptr(d), C.c_float(max_toi), ptr(per_ray),
+                                                            ptr(toi), ptr(feat), ptr(normal)), "ncb2d_polyline_ray_cast")
+        return toi, feat, normal
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.ncb2d_polyline_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class World2D:
     """A fresh ``ncollide2d::CollisionWorld``: objects = (shape, Isometry2, CollisionGroups, GeometricQueryType::Contacts(linear, angular)).
     ``shapes`` is a Shapes2D batch (one entry per object); ``pos`` [n, 2], ``angle`` [n]."""

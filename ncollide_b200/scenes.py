@@ -248,3 +248,31 @@ def make_ray_scene(kind, n_tris, n_rays, seed=1004, random_pose=False):
         pose=pose,
         name=f"cfg4_{kind}_{len(tris)}tris_{n_rays}rays",
     )
+
+
+def make_polyline_scene(kind, n_edges, n_rays, seed=2004):
+    """ncollide2d Polyline ray scenes: (points [p, 2], edges [m, 2] or None for the line strip, origins [r, 2], dirs [r, 2]).
+    "terrain": one noisy height profile as a line strip, rays from above pointing down; "soup": short random segments scattered over a
+    square (explicit edge list), rays in every direction; a share of the rays is axis-aligned (the slab test's dir == 0 branch)."""
+    rng = np.random.default_rng(seed)
+    if kind == "terrain":
+        x = np.arange(n_edges + 1, dtype=np.float64) * 0.25
+        y = 2.0 * np.sin(x * 0.05) + 0.7 * np.sin(x * 0.31 + 1.0) + 0.15 * rng.standard_normal(n_edges + 1)
+        pts, edges = np.stack([x, y], axis=1), None
+        o = np.stack([rng.uniform(x[0], x[-1], n_rays), rng.uniform(4.0, 9.0, n_rays)], axis=1)
+        d = rng.standard_normal((n_rays, 2))
+        d[:, 1] = -np.abs(d[:, 1])
+    else:
+        side = 40.0 * (n_edges / 10_000.0) ** 0.5
+        a = rng.uniform(0, side, size=(n_edges, 2))
+        b = a + rng.uniform(-0.6, 0.6, size=(n_edges, 2))
+        flat = rng.random(n_edges) < 0.1  # axis-aligned segments: degenerate boxes, rays parallel to them
+        b[flat, 1] = a[flat, 1]
+        pts = np.concatenate([a, b])
+        edges = np.stack([np.arange(n_edges), np.arange(n_edges) + n_edges], axis=1).astype(np.uint32)
+        o = rng.uniform(0, side, size=(n_rays, 2))
+        d = rng.standard_normal((n_rays, 2))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    axis = rng.random(n_rays) < 0.05
+    d[axis] = np.where(rng.random((int(axis.sum()), 1)) < 0.5, [[0.0, -1.0]], [[1.0, 0.0]])
+    return (np.ascontiguousarray(pts, dtype=F32), edges, np.ascontiguousarray(o, dtype=F32), np.ascontiguousarray(d, dtype=F32))

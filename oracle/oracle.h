@@ -168,6 +168,16 @@ void orc_trimesh_ray_cast(const orc_trimesh*, const real* pose, uint64_t n_rays,
                           real max_toi, int mode, real* toi, uint32_t* face, real* normal);
 void orc_aabb_toi_with_ray(const real* minmax, const real* origin, const real* dir, real max_toi, int solid, real* toi);
 
+/* ncollide2d Polyline ray casting (oracle/ray.cpp).  idx: 2 point indices per edge (NULL: the line strip 0-1, 1-2, ...).  pose = x y re im
+ * or NULL.  mode as above.  feature = edge, or edge + n_edges for FeatureId::Face(1) of the segment; normal = the segment's scaled normal. */
+typedef struct orc2_polyline orc2_polyline;
+orc2_polyline* orc2_polyline_create(uint32_t n_points, const real* xy, uint32_t n_edges, const uint32_t* idx);
+void orc2_polyline_destroy(orc2_polyline*);
+void orc2_polyline_ray_cast(const orc2_polyline*, const real* pose, uint64_t n_rays, const real* origins, const real* dirs, real max_toi,
+                            const real* max_tois, int mode, real* toi, uint32_t* feature, real* normal);
+/* Segment::toi_and_normal_with_ray (dim2); ab = a.x a.y b.x b.y; returns 1 for Some; feature = kind << 30 | id (1 Face, 2 Vertex). */
+int orc2_segment_ray_cast(const real* ab, const real* pose, const real* origin, const real* dir, real* toi, real* normal, uint32_t* feature);
+
 /* ncollide2d query::contact for n pairs of 2-D shapes (oracle/dim2.cpp).  type: 0 ball, 1 cuboid, 2 convex polygon; param: 4 reals per
  * shape (radius | hx, hy | first point, count); pose: 4 reals (translation x y, UnitComplex re im); found: 1 Some, 0 None, 2 not restated;
  * out: 7 reals per pair (world1, world2, normal, depth). */

@@ -252,6 +252,21 @@ class Oracle:
     def trimesh(self, verts, tris):
         return OracleTriMesh(self, verts, tris)
 
+    def polyline(self, points, edges=None):
+        return OraclePolyline(self, points, edges)
+
+    def segment_ray_cast(self, a, b, origin, direction, pose=None):
+        """ncollide2d ``Segment::toi_and_normal_with_ray``: None or (toi, normal, (feature kind [1 Face, 2 Vertex], id))."""
+        dt = self.dtype
+        ab = np.ascontiguousarray(list(a) + list(b), dtype=dt)
+        o, d = np.ascontiguousarray(origin, dtype=dt), np.ascontiguousarray(direction, dtype=dt)
+        p = np.ascontiguousarray(pose, dtype=dt) if pose is not None else None
+        toi, normal, feat = np.zeros(1, dtype=dt), np.zeros(2, dtype=dt), C.c_uint32(0)
+        vp = lambda x: C.c_void_p(x.ctypes.data) if x is not None else None  # noqa: E731
+        if not self.lib.orc2_segment_ray_cast(vp(ab), vp(p), vp(o), vp(d), vp(toi), vp(normal), C.byref(feat)):
+            return None
+        return toi[0], normal, (feat.value >> 30, feat.value & 0x3FFFFFFF)
+
     def contact2d(self, type1, param1, pose1, type2, param2, pose2, poly_points=None, prediction=0.0, poly_normals=None):
         """ncollide2d ``query::contact`` for n pairs (oracle/dim2.cpp).  Returns (found u8 [1 Some, 0 None, 2 not restated],
         out[n,7] = world1, world2, normal, depth, panics)."""
@@ -502,6 +517,44 @@ class OracleSim:
     def __del__(self):
         try:
             self.o.lib.orc_sim_destroy(self.h)
+        except Exception:
+            pass
+
+
+class OraclePolyline:
+    """ncollide2d ``Polyline`` (points [n, 2], edges [m, 2] or None for the line strip) with ``toi_and_normal_with_ray`` for a batch."""
+
+    def __init__(self, oracle, points, edges=None):
+        self.o = oracle
+        p = np.ascontiguousarray(points, dtype=oracle.dtype).reshape(-1, 2)
+        e = np.ascontiguousarray(edges, dtype=np.uint32).reshape(-1, 2) if edges is not None else None
+        self.nedges = len(e) if e is not None else max(len(p) - 1, 0)
+        oracle.lib.orc2_polyline_create.restype = C.c_void_p
+        self.h = C.c_void_p(oracle.lib.orc2_polyline_create(C.c_uint32(len(p)), C.c_void_p(p.ctypes.data), C.c_uint32(self.nedges),
+                                                            C.c_void_p(e.ctypes.data) if e is not None else None))
+
+    def ray_cast(self, origins, dirs, max_toi=None, pose=None, mode=0):
+        """(toi, feature, normal): toi < 0 = None; feature = edge or edge + n_edges (the segment's Face(1)); max_toi scalar or per ray."""
+        dt = self.o.dtype
+        o = np.ascontiguousarray(origins, dtype=dt).reshape(-1, 2)
+        d = np.ascontiguousarray(dirs, dtype=dt).reshape(-1, 2)
+        n = len(o)
+        toi, feat, normal = np.zeros(n, dtype=dt), np.zeros(n, dtype=np.uint32), np.zeros((n, 2), dtype=dt)
+        per = None
+        if max_toi is None:
+            max_toi = np.finfo(dt).max
+        elif np.ndim(max_toi) > 0:
+            per = np.ascontiguousarray(max_toi, dtype=dt)
+            max_toi = 0.0
+        p = np.ascontiguousarray(pose, dtype=dt) if pose is not None else None
+        vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None  # noqa: E731
+        self.o.lib.orc2_polyline_ray_cast(self.h, vp(p), C.c_uint64(n), vp(o), vp(d), self.o.creal(max_toi), vp(per), C.c_int(mode), vp(toi),
+                                          vp(feat), vp(normal))
+        return toi, feat, normal
+
+    def __del__(self):
+        try:
+            self.o.lib.orc2_polyline_destroy(self.h)
         except Exception:
             pass
 

@@ -55,4 +55,47 @@ void shim_trimesh_ray_cast(uint32_t n_tris, const float* verts, const uint32_t* 
         }
     }
 }
+
+// ncollide2d Polyline: the device semantics by brute force (k_seg_aabb's leaf box, slab_toi2, segment_ray2, k_ray_cast4_polyline's
+// epilogue): minimum toi over the edges whose box is entered and whose segment is hit, ties -> smallest edge.
+void shim2_polyline_ray_cast(uint32_t n_edges, const float* pts, const uint32_t* edges, const float* pose, uint64_t n_rays, const float* origins,
+                             const float* dirs, float max_toi_all, const float* max_tois, float* toi_out, uint32_t* feature_out, float* normal_out) {
+    for (uint64_t r = 0; r < n_rays; ++r) {
+        float ox = origins[2 * r], oy = origins[2 * r + 1], dx = dirs[2 * r], dy = dirs[2 * r + 1];
+        if (pose) {
+            float px = ox - pose[0], py = oy - pose[1], re = pose[2], im = pose[3];
+            ox = re * px + im * py, oy = -im * px + re * py;
+            float qx = dx, qy = dy;
+            dx = re * qx + im * qy, dy = -im * qx + re * qy;
+        }
+        const float max_toi = max_tois ? max_tois[r] : max_toi_all;
+        const float ivx = 1.f / dx, ivy = 1.f / dy;
+        bool have = false;
+        float best = NCB_FMAX, bnx = 0.f, bny = 0.f;
+        uint32_t best_edge = 0xffffffffu;
+        int best_face1 = 0;
+        for (uint32_t e = 0; e < n_edges; ++e) {
+            const float* a = pts + 2 * (size_t)edges[2 * e];
+            const float* b = pts + 2 * (size_t)edges[2 * e + 1];
+            float lox = -a[0] > -b[0] ? a[0] : b[0], loy = -a[1] > -b[1] ? a[1] : b[1];
+            float hix = a[0] > b[0] ? a[0] : b[0], hiy = a[1] > b[1] ? a[1] : b[1];
+            if (!(slab_toi2(lox, loy, hix, hiy, ox, oy, dx, dy, ivx, ivy, max_toi) >= 0.f)) continue;
+            float toi, nx, ny;
+            int face1;
+            if (segment_ray2(a[0], a[1], b[0], b[1], ox, oy, dx, dy, toi, nx, ny, face1))
+                if (!have || toi < best || (toi == best && e < best_edge)) have = true, best = toi, best_edge = e, bnx = nx, bny = ny, best_face1 = face1;
+        }
+        if (have) {
+            toi_out[r] = best;
+            feature_out[r] = best_face1 ? best_edge + n_edges : best_edge;
+            float nx = bnx, ny = bny;
+            if (pose) nx = pose[2] * bnx - pose[3] * bny, ny = pose[3] * bnx + pose[2] * bny;
+            normal_out[2 * r] = nx, normal_out[2 * r + 1] = ny;
+        } else {
+            toi_out[r] = -1.f;
+            feature_out[r] = 0xffffffffu;
+            normal_out[2 * r] = normal_out[2 * r + 1] = 0.f;
+        }
+    }
+}
 }

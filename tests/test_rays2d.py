@@ -1,0 +1,201 @@
+"""ncollide2d ``RayCast for Polyline`` (the 2-D counterpart of the TriMesh ray path).
+
+CPU: the oracle (oracle/ray.cpp, 2-D part) on the reference's own known-answer tests — build/ncollide2d/tests/geometry/ray_cast.rs, the
+ten ``Segment`` cases (exact ``Some(0.0)`` / ``Some(1.0)`` / ``None``) and the geometry of ``convexpoly_raycast_fuzz`` against the same
+square as a closed polyline; the reference-faithful best-first search against the brute-force definition the device follows; an
+independent f64 intersection in numpy; the device source compiled for the host against the oracle, bit for bit.
+GPU: ``ncb2d_polyline_ray_cast`` against the oracle, bit for bit."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from ncollide_b200 import dim2
+from ncollide_b200.scenes import make_polyline_scene
+
+F = np.float32
+FMAX = np.finfo(np.float32).max
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+# ---- CPU: known-answer tests -----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["oracle", "oracle64"])
+def test_oracle_segment_ray_kats(which, request):
+    """build/ncollide2d/tests/geometry/ray_cast.rs, in file order."""
+    R = request.getfixturevalue(which).segment_ray_cast
+    assert R((2, 1), (2, 0), (0, 0), (0, 1)) is None  # issue_178_parallel_raycast
+    assert R((2, 1), (2, -1), (0, 0), (0, 1)) is None  # parallel_raycast
+    assert R((0, 1), (0, -1), (0, 0), (0, 1))[0] == 0.0  # collinear_raycast_starting_on_segment
+    assert R((0, 1), (0, -1), (0, -2), (0, 1))[0] == 1.0  # collinear_raycast_starting_bellow_segment
+    assert R((0, 1), (0, -1), (0, 2), (0, 1)) is None  # collinear_raycast_starting_above_segment
+    assert R((0, -10), (0, 10), (-1, 0), (1, 0)) is not None  # perpendicular_raycast_starting_behind_sement
+    assert R((0, -10), (0, 10), (1, 0), (1, 0)) is None  # perpendicular_raycast_starting_in_front_of_sement
+    assert R((0, -10), (0, 10), (0, 3), (1, 0))[0] == 0.0  # perpendicular_raycast_starting_on_segment
+    assert R((0, -10), (0, 10), (0, 11), (1, 0)) is None  # perpendicular_raycast_starting_above_segment
+    assert R((0, -10), (0, 10), (0, -11), (1, 0)) is None  # perpendicular_raycast_starting_bellow_segment
+    # the features and the scaled normal of the two collinear hits (ray_support_map.rs:251-270)
+    toi, n, feat = R((0, 1), (0, -1), (0, -2), (0, 1))
+    assert feat == (2, 1) and tuple(n) == (-2.0, 0.0)
+    assert R((0, 1), (0, -1), (0, 0), (0, 1))[2] == (1, 0)
+
+
+def test_oracle_square_polyline_fuzz(oracle64):
+    """The rays of ray_cast.rs::convexpoly_raycast_fuzz against the same square as a closed Polyline: every ray hits the front face
+    at a distance in [1, sqrt(2))."""
+    sq = oracle64.polyline([[2, 1], [2, 2], [1, 2], [1, 1]], [[0, 1], [1, 2], [2, 3], [3, 0]])
+    i = np.arange(10_000)
+    o = np.stack([np.full(len(i), 3.0), 1.0 + i * 1e-4], axis=1)
+    d = np.array([0.0, 2.0]) - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    toi, feat, n = sq.ray_cast(o, d)
+    assert (toi >= 1.0).all() and (toi < np.sqrt(2.0)).all()
+    assert set(np.unique(feat % 4).tolist()) <= {0, 1}  # the right edge, and the top edge for the last rays
+
+
+def _scene(kind, n_edges, n_rays, seed, pose=None):
+    """A polyline scene; with a pose, the rays are moved along with the polyline (rounded to f32 in the world frame)."""
+    pts, edges, o, d = make_polyline_scene(kind, n_edges, n_rays, seed)
+    if pose is not None:
+        rot = np.array([[pose[2], -pose[3]], [pose[3], pose[2]]], dtype=np.float64)
+        o = np.ascontiguousarray(o.astype(np.float64) @ rot.T + np.asarray(pose[:2], dtype=np.float64), dtype=F)
+        d = np.ascontiguousarray(d.astype(np.float64) @ rot.T, dtype=F)
+    return pts, edges, o, d
+
+
+@pytest.mark.parametrize("kind", ["terrain", "soup"])
+def test_oracle_best_first_equals_definition(oracle, kind):
+    """ray_polyline.rs's best-first search (mode 0) returns the minimum toi over the accepted hits (mode 1), the same edge and normal
+    outside exact ties."""
+    pose = np.array([1.5, -2.0, np.cos(0.4), np.sin(0.4)], dtype=F) if kind == "soup" else None
+    pts, edges, o, d = _scene(kind, 3000, 4000, 5, pose)
+    pl = oracle.polyline(pts, edges)
+    t0, f0, n0 = pl.ray_cast(o, d, pose=pose, mode=0)
+    t1, f1, n1 = pl.ray_cast(o, d, pose=pose, mode=1)
+    assert np.array_equal(bits(t0), bits(t1))
+    same = f0 == f1
+    assert (~same).sum() <= 5 and np.array_equal(bits(n0[same]), bits(n1[same]))
+    assert (t1 >= 0).sum() > 1000 and (t1 < 0).sum() > (0 if kind == "terrain" else 100)
+
+
+def test_oracle_against_numpy_intersections(oracle64):
+    """ORACLE check (f64): toi == the smallest ray parameter over all segments, computed independently with a 2 x 2 solve."""
+    pts, edges, o, d = _scene("soup", 600, 800, 6)
+    pl = oracle64.polyline(pts, edges)
+    toi, feat, n = pl.ray_cast(o, d)
+    a, b = pts[edges[:, 0]].astype(np.float64), pts[edges[:, 1]].astype(np.float64)
+    e = b - a
+    checked = 0
+    for r in range(len(o)):
+        oo, dd = o[r].astype(np.float64), d[r].astype(np.float64)
+        den = dd[0] * e[:, 1] - dd[1] * e[:, 0]
+        ok = np.abs(den) > 1e-9
+        w = a - oo
+        s = np.where(ok, (w[:, 0] * e[:, 1] - w[:, 1] * e[:, 0]) / np.where(ok, den, 1), np.inf)
+        t = np.where(ok, (w[:, 0] * dd[1] - w[:, 1] * dd[0]) / np.where(ok, den, 1), np.inf)
+        hit = ok & (s >= 0) & (t >= 0) & (t <= 1)
+        margin = ok & (np.minimum(np.abs(t), np.abs(t - 1)) < 1e-7)
+        if margin.any() or (~ok).any() and np.abs(den[~ok]).max() > 0:
+            continue
+        if hit.any():
+            k = int(np.argmin(np.where(hit, s, np.inf)))
+            assert abs(toi[r] - s[k]) < 1e-9 * max(1.0, s[k]), (r, toi[r], s[k])
+            assert feat[r] % len(edges) == k
+            nn = n[r] / np.linalg.norm(n[r])
+            assert nn @ dd <= 1e-12 and abs(nn @ e[k]) < 1e-9 * np.linalg.norm(e[k])  # faces the ray, perpendicular to the edge
+        else:
+            assert toi[r] < 0
+        checked += 1
+    assert checked > 500
+
+
+def test_oracle_max_toi_limits_the_boxes_only(oracle):
+    """RayCast for Segment (dim2) never compares its hit with max_toi: a polyline hit is cut off only when the edge's AABB is not
+    entered within max_toi (ray_support_map.rs:219-293, ray_polyline.rs:113-146)."""
+    pl = oracle.polyline([[0, 0], [10, 10]])  # one diagonal edge: its AABB is the square [0, 10]^2
+    o, d = [[5.0, -1.0]], [[0.0, 1.0]]  # enters the box at toi 1, meets the segment at toi 6
+    assert pl.ray_cast(o, d, max_toi=0.5)[0][0] < 0
+    assert pl.ray_cast(o, d, max_toi=2.0)[0][0] == 6.0
+    assert pl.ray_cast(o, d)[0][0] == 6.0
+
+
+# ---- CPU: the DEVICE source compiled for the host against the oracle, bit for bit ------------------------------------------------
+@pytest.fixture(scope="module")
+def ray_shim():
+    from test_device_source_on_host import _build_shim
+
+    return _build_shim("libray_host.so", "ray_host.cpp")
+
+
+def _vp(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+@pytest.mark.parametrize("kind,posed,limited", [("terrain", False, False), ("soup", True, False), ("soup", False, True), ("terrain", True, True)])
+def test_device_source_equals_oracle_bit_for_bit(ray_shim, oracle, kind, posed, limited):
+    pose = np.array([0.5, 2.0, np.cos(-0.7), np.sin(-0.7)], dtype=F) if posed else None
+    pts, edges, o, d = _scene(kind, 2500, 3000, 9, pose)
+    if edges is None:
+        edges = np.stack([np.arange(len(pts) - 1), np.arange(1, len(pts))], axis=1).astype(np.uint32)
+    limits = np.random.default_rng(3).uniform(2.0, 14.0, size=len(o)).astype(F) if limited else None
+    n = len(o)
+    toi, feat, nrm = np.zeros(n, dtype=F), np.zeros(n, dtype=np.uint32), np.zeros((n, 2), dtype=F)
+    ray_shim.shim2_polyline_ray_cast(C.c_uint32(len(edges)), _vp(pts), _vp(edges), _vp(pose), C.c_uint64(n), _vp(o), _vp(d), C.c_float(FMAX),
+                                     _vp(limits), _vp(toi), _vp(feat), _vp(nrm))
+    ot, of, on = oracle.polyline(pts, edges).ray_cast(o, d, max_toi=limits, pose=pose, mode=1)
+    assert np.array_equal(bits(toi), bits(ot)) and np.array_equal(feat, of) and np.array_equal(bits(nrm), bits(on))
+    assert (ot >= 0).sum() > 500 and (ot < 0).sum() > (100 if limited else 0)
+
+
+# ---- GPU ---------------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ctx():
+    from ncollide_b200.world import Context
+
+    c = Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n_edges,posed,limited", [("terrain", 200_000, False, False), ("soup", 150_000, True, False),
+                                                       ("soup", 50_000, False, True), ("terrain", 3, True, True), ("soup", 1, False, False)])
+def test_device_polyline_rays_match_oracle(ctx, oracle, kind, n_edges, posed, limited):
+    pose = np.array([0.5, 2.0, np.cos(1.1), np.sin(1.1)], dtype=F) if posed else None
+    pts, edges, o, d = _scene(kind, n_edges, 30_000, 12, pose)
+    limits = np.random.default_rng(4).uniform(2.0, 14.0, size=len(o)).astype(F) if limited else None
+    pl = dim2.Polyline(ctx, pts, edges)
+    toi, feat, nrm = pl.toi_and_normal_with_ray(pose, o, d, max_toi=limits)
+    op = oracle.polyline(pts, edges)
+    ot, of, on = op.ray_cast(o[:6000], d[:6000], max_toi=None if limits is None else limits[:6000], pose=pose, mode=1)  # the definition
+    assert np.array_equal(bits(toi[:6000]), bits(ot)) and np.array_equal(feat[:6000], of) and np.array_equal(bits(nrm[:6000]), bits(on))
+    rt, rf, rn = op.ray_cast(o, d, max_toi=limits, pose=pose, mode=0)  # the reference's best-first search
+    assert np.array_equal(bits(toi), bits(rt))
+    same = feat == rf
+    assert (~same).sum() <= 5 and np.array_equal(bits(nrm[same]), bits(rn[same]))
+    if n_edges > 1000:
+        assert (toi >= 0).sum() > 5000
+    assert ctx.traversal_overflows() == 0
+    toi2, feat2, none = pl.toi_and_normal_with_ray(pose, o, d, max_toi=limits, want_normals=False)
+    assert none is None and np.array_equal(bits(toi2), bits(toi)) and np.array_equal(feat2, feat)
+    pl.close()
+
+
+@pytest.mark.gpu
+def test_device_polyline_edge_cases(ctx):
+    from ncollide_b200._ffi import NcbError
+
+    empty = dim2.Polyline(ctx, np.zeros((1, 2), dtype=F))  # one point: no edge
+    toi, feat, nrm = empty.toi_and_normal_with_ray(None, [[0, 0]], [[1, 0]])
+    assert toi[0] == -1 and feat[0] == 0xFFFFFFFF and not nrm.any()
+    pl = dim2.Polyline(ctx, [[0, 1], [0, -1]])
+    toi, feat, nrm = pl.toi_and_normal_with_ray(None, [[0, 0], [0, -2], [0, 2]], [[0, 1]] * 3)  # the collinear known-answer tests
+    assert toi.tolist() == [0.0, 1.0, -1.0]
+    assert len(pl.toi_and_normal_with_ray(None, np.zeros((0, 2)), np.zeros((0, 2)))[0]) == 0
+    with pytest.raises(NcbError):
+        dim2.Polyline(ctx, [[0, 0], [1, 1]], [[0, 2]])  # index out of range
+    with pytest.raises(NcbError):  # a Polyline is not a TriMesh
+        ctx.check(ctx.lib.ncb_trimesh_set_uvs(pl.h, None), "ncb_trimesh_set_uvs")
+    pl.close(), empty.close()
