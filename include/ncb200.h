@@ -433,6 +433,13 @@ int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const f
 int ncb2d_proximity(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const float* param1, const float* pose1, const uint32_t* type2,
                     const float* param2, const float* pose2, const float* poly_points, uint32_t n_poly_points, const float* margins,
                     uint8_t* out);
+/* ncollide2d RayCast::toi_and_normal_with_ray(m, ray, max_toi, solid = true) of shape k for ray k, for a batch (query/ray/ray_ball.rs,
+ * ray_cuboid.rs + ray_aabb.rs, ray_plane.rs, ray_support_map.rs:165-189 = ConvexPolygon through gjk::cast_ray, query/algorithms/gjk.rs:
+ * 180-365).  type / param / pose as in ncb2d_contact; rays: 5 floats (origin x y, dir x y, max_toi).  found: 1 Some / 0 None; out: 3
+ * floats (toi, normal x y); feature: 1 << 30 | face id (cuboid: ray_aabb.rs:62-66, far side + 3 as in the reference), 0xffffffff for
+ * FeatureId::Unknown (polygons). */
+int ncb2d_ray_cast(ncb_ctx* ctx, uint32_t n, const uint32_t* type, const float* param, const float* pose, const float* poly_points,
+                   uint32_t n_poly_points, const float* rays, uint8_t* found, float* out, uint32_t* feature);
 /* A fresh ncollide2d CollisionWorld of balls, cuboids and convex polygons (host SoA): pos = translation x y, rot = UnitComplex re im,
  * shape_param as in ncb2d_contact, groups = 3 words per object or NULL, query_limit / ang_pred = GeometricQueryType::Contacts(linear,
  * angular); poly_normals is required when the world holds polygons. */

@@ -973,6 +973,185 @@ __device__ uint8_t proximity_of_pair(const Operand2& g1, const Operand2& g2, flo
     }
 }
 
+// ---- RayCast for the 2-D shapes, solid = true ------------------------------------------------------------------------------------------
+//   query/ray/ray_ball.rs:15-142, ray_cuboid.rs + ray_aabb.rs:52-75,183-300 (the far-side face id carries the reference's `+ 3`),
+//   ray_plane.rs:9-79, ray_support_map.rs:15-60,165-189 (ConvexPolygon) -> gjk::cast_ray (gjk.rs:180-365) on the simplex above.
+struct RayHit2 {
+    bool hit;
+    float toi;
+    W2 n;
+    uint32_t feature;
+};
+__device__ __forceinline__ RayHit2 ray2_miss() { return RayHit2{false, 0.f, W2{0.f, 0.f}, FEAT2_UNKNOWN}; }
+
+__device__ RayHit2 ray2_ball(W2 center, float radius, W2 o, W2 d, float max_toi) {
+    RayHit2 h = ray2_miss();
+    W2 dc = o - center;
+    float a = nsq(d), b = dot(dc, d), c = nsq(dc) - radius * radius;
+    bool inside = false;
+    float t = 0.f;
+    if (a == 0.f) {
+        if (c > 0.f) return h;
+        inside = true;
+    } else if (c > 0.f && b > 0.f) {
+        return h;
+    } else {
+        float delta = b * b - a * c;
+        if (delta < 0.f) return h;
+        t = (-b - sqrtf(delta)) / a;
+        if (t <= 0.f) inside = true, t = 0.f;
+    }
+    if (!(t <= max_toi)) return h;
+    W2 normal = normalized((o + d * t) - center);
+    h.hit = true, h.toi = t, h.n = inside ? -normal : normal, h.feature = FEAT2_FACE;
+    return h;
+}
+
+__device__ RayHit2 ray2_cuboid(const Operand2& g, W2 o_w, W2 d_w, float max_toi) {
+    RayHit2 h = ray2_miss();
+    W2 o = to_local(g.m, o_w), d = unrotate(g.m, d_w);
+    const float oo[2] = {o.x, o.y}, dd[2] = {d.x, d.y}, he[2] = {g.a, g.b};
+    float tmax = NCB_FMAX, tmin = -NCB_FMAX;
+    int near_side = 0, far_side = 0;
+    bool near_diag = false;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        if (dd[i] == 0.f) {
+            if (oo[i] < -he[i] || oo[i] > he[i]) return h;
+        } else {
+            float denom = 1.f / dd[i];
+            float nr = (-he[i] - oo[i]) * denom, fr = (he[i] - oo[i]) * denom;
+            bool flip = false;
+            if (nr > fr) {
+                float t = nr;
+                nr = fr, fr = t, flip = true;
+            }
+            if (nr > tmin)
+                tmin = nr, near_side = flip ? -(i + 1) : (i + 1), near_diag = false;
+            else if (nr == tmin)
+                near_diag = true;
+            if (fr < tmax) tmax = fr, far_side = !flip ? -(i + 1) : (i + 1);
+            if (tmax < 0.f || tmin > tmax) return h;
+        }
+    }
+    W2 near_n = w2(0.f, 0.f);
+    if (near_diag)
+        near_n = -normalized(d);
+    else if (near_side == 1 || near_side == -1)
+        near_n.x = near_side < 0 ? 1.f : -1.f;
+    else if (near_side == 2 || near_side == -2)
+        near_n.y = near_side < 0 ? 1.f : -1.f;
+    float t;
+    W2 n;
+    int side;
+    if (tmin < 0.f)
+        t = 0.f, n = w2(0.f, 0.f), side = far_side;
+    else if (tmin <= max_toi)
+        t = tmin, n = near_n, side = near_side;
+    else
+        return h;
+    h.hit = true, h.toi = t, h.n = rotate(g.m, n);
+    h.feature = FEAT2_FACE | ((uint32_t)(side < 0 ? (-side - 1 + 3) : (side - 1)) & 0x3fffffffu);
+    return h;
+}
+
+__device__ RayHit2 ray2_plane(const Operand2& g, W2 o_w, W2 d_w, float max_toi) {
+    RayHit2 h = ray2_miss();
+    W2 o = to_local(g.m, o_w), d = unrotate(g.m, d_w), pn = w2(g.a, g.b);
+    float dot_normal_dpos = dot(pn, -o);
+    if (dot_normal_dpos > 0.f) {
+        h.hit = true, h.toi = 0.f, h.feature = FEAT2_FACE;
+        return h;
+    }
+    float t = dot_normal_dpos / dot(pn, d);
+    if (t >= 0.f && t <= max_toi) h.hit = true, h.toi = t, h.n = rotate(g.m, pn), h.feature = FEAT2_FACE;
+    return h;
+}
+
+__device__ __forceinline__ bool ray2_plane_toi(W2 center, W2 normal, W2 origin, W2 dir, float& t_out) {  // ray_plane.rs:9-42
+    float denom = dot(normal, dir);
+    if (relative_eq(denom, 0.f)) return false;
+    float t = dot(normal, center - origin) / denom;
+    if (t >= 0.f) {
+        t_out = t;
+        return true;
+    }
+    return false;
+}
+
+// RayCast for ConvexPolygon: gjk::cast_ray on the Minkowski difference polygon - ConstantOrigin, in the polygon's frame
+__device__ RayHit2 ray2_polygon(const Operand2& g, W2 o_w, W2 d_w, float max_toi) {
+    RayHit2 h = ray2_miss();
+    W2 ray_origin = to_local(g.m, o_w), ray_dir = unrotate(g.m, d_w);
+    Operand2 loc = g, org;  // the polygon at the identity, and special_support_maps::ConstantOrigin
+    loc.m.t = w2(0.f, 0.f), loc.m.re = 1.f, loc.m.im = 0.f;
+    org = loc, org.kind = D2_ORIGIN;
+    const float rel = sqrtf(TOL10);
+    float ray_length = sqrtf(nsq(ray_dir));
+    if (relative_eq(ray_length, 0.f)) return h;
+    float ltoi = 0.f;
+    W2 cur_o = ray_origin, cur_d = ray_dir / ray_length;
+    W2 ldir = -cur_d, dir;
+    Tri2 s;
+    for (int i = 0; i < 3; ++i) s.v[i].p = s.v[i].o1 = s.v[i].o2 = w2(0.f, 0.f), s.old_idx[i] = i;
+    s.bary[0] = s.bary[1] = s.old_bary[0] = s.old_bary[1] = 0.f;
+    s.dim = s.old_dim = 0;
+    s.v[0] = minkowski(loc, org, -cur_d);
+    s.v[0].p = s.v[0].p + (-cur_o);
+    W2 proj = tri_project(s);
+    float upper = NCB_FMAX;
+    bool last_chance = false;
+    for (int it = 0;; ++it) {
+        float prev_upper = upper, len;
+        if (!unit_get(-proj, TOL10, dir, len)) break;  // Some((ltoi / ray_length, ldir))
+        upper = len;
+        MinkowskiPt sp;
+        if (upper >= prev_upper) {
+            last_chance = true;
+            sp.p = sp.o1 = proj + cur_o, sp.o2 = w2(0.f, 0.f);
+        } else {
+            sp = minkowski(loc, org, dir);
+        }
+        if (last_chance && ltoi > 0.f) break;
+        float t;
+        if (ray2_plane_toi(sp.p, dir, cur_o, cur_d, t)) {
+            if (dot(dir, cur_d) < 0.f && t > 0.f) {
+                ldir = dir;
+                ltoi += t;
+                if (ltoi / ray_length > max_toi) return h;
+                W2 shift = cur_d * t;
+                cur_o = cur_o + shift;
+                upper = NCB_FMAX;
+                for (int i = 0; i <= s.dim; ++i) s.v[i].p = s.v[i].p + (-shift);
+                last_chance = false;
+            }
+        } else if (dot(dir, cur_d) > TOL10) {
+            return h;
+        }
+        if (last_chance) return h;
+        float lower = -dot(dir, sp.p - cur_o);
+        if (upper - lower <= rel * upper) return h;
+        sp.p = sp.p + (-cur_o);
+        (void)tri_add(s, sp);
+        proj = tri_project(s);
+        if (s.dim == 2) {
+            if (lower >= TOL10) return h;
+            break;
+        }
+        if (it + 1 == 10000) return h;
+    }
+    h.hit = true, h.toi = ltoi / ray_length, h.n = rotate(g.m, ldir), h.feature = FEAT2_UNKNOWN;
+    return h;
+}
+
+// RayCast::toi_and_normal_with_ray(m, ray, max_toi, true) of one shape
+__device__ RayHit2 shape_ray_cast2(const Operand2& g, W2 o, W2 d, float max_toi) {
+    if (g.kind == D2_BALL) return ray2_ball(g.m.t, g.a, o, d, max_toi);
+    if (g.kind == D2_CUBOID) return ray2_cuboid(g, o, d, max_toi);
+    if (g.kind == D2_POLYGON) return ray2_polygon(g, o, d, max_toi);
+    return ray2_plane(g, o, d, max_toi);
+}
+
 // query::contact for one pair.  flags: bit 0 = the reference would panic, bit 1 = EPA capacity exceeded.
 __device__ bool contact_of_pair(const Operand2& g1, const Operand2& g2, float prediction, float cos_one_degree, Hit2& h, int& flags) {
     h.w1 = h.w2 = h.n = w2(0.f, 0.f), h.depth = 0.f;
@@ -1043,6 +1222,18 @@ __global__ void __launch_bounds__(128) k_proximity2d(Args2 A, const float* __res
     Operand2 g1 = load_operand(__ldg(&A.type1[k]), __ldg(&A.param1[k]), __ldg(&A.pose1[k]), A.poly, A.poly_nrm);
     Operand2 g2 = load_operand(__ldg(&A.type2[k]), __ldg(&A.param2[k]), __ldg(&A.pose2[k]), A.poly, A.poly_nrm);
     status[k] = proximity_of_pair(g1, g2, __ldg(&margins[k]));
+}
+
+// one thread per (shape, ray): rays = origin x y, dir x y, max_toi
+__global__ void __launch_bounds__(128) k_ray2d(Args2 A, const float* __restrict__ rays, float* __restrict__ out, uint32_t* __restrict__ feature) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.n) return;
+    Operand2 g = load_operand(__ldg(&A.type1[k]), __ldg(&A.param1[k]), __ldg(&A.pose1[k]), A.poly, nullptr);
+    const float* q = rays + 5 * (size_t)k;
+    RayHit2 h = shape_ray_cast2(g, w2(__ldg(q), __ldg(q + 1)), w2(__ldg(q + 2), __ldg(q + 3)), __ldg(q + 4));
+    A.found[k] = h.hit ? 1 : 0;
+    out[3 * (size_t)k] = h.toi, out[3 * (size_t)k + 1] = h.n.x, out[3 * (size_t)k + 2] = h.n.y;
+    feature[k] = h.hit ? h.feature : FEAT2_UNKNOWN;
 }
 
 struct World2Args {
@@ -1262,6 +1453,55 @@ int ncb2d_proximity(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const
     d2::k_proximity2d<<<(n_pairs + 127) / 128, 128, 0, s>>>(A, d_mg.p, d_out.p);
     CK2(cudaGetLastError());
     CK2(cudaMemcpyAsync(out, d_out.p, n, cudaMemcpyDeviceToHost, s));
+    CK2(cudaStreamSynchronize(s));
+    return NCB_OK;
+}
+
+// RayCast::toi_and_normal_with_ray(m, ray, max_toi, solid = true) of shape k for ray k, for a batch.
+int ncb2d_ray_cast(ncb_ctx* ctx, uint32_t n, const uint32_t* type, const float* param, const float* pose, const float* poly_points,
+                   uint32_t n_poly_points, const float* rays, uint8_t* found, float* out, uint32_t* feature) {
+    if (!ctx || (n && (!type || !param || !pose || !rays || !found || !out || !feature))) return NCB_ERR_ARG;
+    if (n == 0) return NCB_OK;
+    for (uint32_t k = 0; k < n; ++k) {
+        const float* p = param + 4 * (size_t)k;
+        if (type[k] > 3) {
+            ctx->err = "ncb2d_ray_cast: unknown 2-D shape type";
+            return NCB_ERR_UNSUPPORTED;
+        }
+        if (type[k] == 2 && (!poly_points || p[1] < 1.f || p[0] < 0.f || (uint64_t)p[0] + (uint64_t)p[1] > n_poly_points)) {
+            ctx->err = "ncb2d_ray_cast: polygon point range outside poly_points";
+            return NCB_ERR_ARG;
+        }
+    }
+    CK2(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    size_t m = n;
+    DevBuf<uint32_t> d_t;
+    DevBuf<float4> d_f4;
+    DevBuf<float> d_poly, d_rays, d_out;
+    DevBuf<uint8_t> d_found;
+    CK2(d_t.reserve(2 * m));
+    CK2(d_f4.reserve(2 * m));
+    CK2(d_poly.reserve(2 * (size_t)(n_poly_points ? n_poly_points : 1)));
+    CK2(d_rays.reserve(5 * m));
+    CK2(d_out.reserve(3 * m));
+    CK2(d_found.reserve(m));
+    CK2(cudaMemcpyAsync(d_t.p, type, 4 * m, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_f4.p, param, 16 * m, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_f4.p + m, pose, 16 * m, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(d_rays.p, rays, 20 * m, cudaMemcpyHostToDevice, s));
+    if (n_poly_points) CK2(cudaMemcpyAsync(d_poly.p, poly_points, 8 * (size_t)n_poly_points, cudaMemcpyHostToDevice, s));
+    d2::Args2 A;
+    memset(&A, 0, sizeof A);
+    A.n = n;
+    A.type1 = d_t.p, A.param1 = d_f4.p, A.pose1 = d_f4.p + m;
+    A.poly = d_poly.p;
+    A.found = d_found.p;
+    d2::k_ray2d<<<(n + 127) / 128, 128, 0, s>>>(A, d_rays.p, d_out.p, d_t.p + m);
+    CK2(cudaGetLastError());
+    CK2(cudaMemcpyAsync(found, d_found.p, m, cudaMemcpyDeviceToHost, s));
+    CK2(cudaMemcpyAsync(out, d_out.p, 12 * m, cudaMemcpyDeviceToHost, s));
+    CK2(cudaMemcpyAsync(feature, d_t.p + m, 4 * m, cudaMemcpyDeviceToHost, s));
     CK2(cudaStreamSynchronize(s));
     return NCB_OK;
 }

@@ -119,6 +119,19 @@ def proximity(ctx, type1, param1, pose1, type2, param2, pose2, poly_points=None,
     return out
 
 
+def ray_cast(ctx, types, params, poses, rays, poly_points=None):
+    """``RayCast::toi_and_normal_with_ray(m, ray, max_toi, solid = true)`` of shape k for ray k (``ncb2d_ray_cast``).
+    rays [n, 5] = origin, dir, max_toi.  Returns (found, out [n, 3] = toi, normal, feature)."""
+    t = as_u32(types).reshape(-1)
+    n = len(t)
+    p, m, q = as_f32(params).reshape(-1, 4), as_f32(poses).reshape(-1, 4), as_f32(rays).reshape(-1, 5)
+    pts = as_f32(poly_points).reshape(-1, 2) if poly_points is not None else None
+    found, out, feat = np.zeros(n, dtype=np.uint8), np.zeros((n, 3), dtype=np.float32), np.zeros(n, dtype=np.uint32)
+    ctx.check(ctx.lib.ncb2d_ray_cast(ctx.h, C.c_uint32(n), ptr(t), ptr(p), ptr(m), ptr(pts), C.c_uint32(0 if pts is None else len(pts)), ptr(q),
+                                     ptr(found), ptr(out), ptr(feat)), "ncb2d_ray_cast")
+    return found.astype(bool), out, feat
+
+
 class Polyline:
     """``ncollide2d::shape::Polyline::new(points, indices)`` with ``RayCast::toi_and_normal_with_ray`` for a batch of rays
     (``ncb2d_polyline_create`` / ``ncb2d_polyline_ray_cast``).  ``edges`` None = the line strip."""

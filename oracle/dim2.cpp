@@ -1025,6 +1025,210 @@ static void generate_contacts2(const Shape2& g1, const Iso2& m1, const Shape2& g
     }
 }
 
+// ---- RayCast for the 2-D shapes (solid = true, what the world queries and the reference's tests use) ----------------------------------
+//   query/ray/ray_ball.rs:15-142 (Ball), ray_cuboid.rs + ray_aabb.rs:52-75,183-300 (Cuboid = its local AABB; note the `+ 3` of the
+//   far-side face id, hard-coded for both dimensions), ray_plane.rs:9-79, ray_support_map.rs:15-60,165-189 (ConvexPolygon through
+//   gjk::cast_ray), query/algorithms/gjk.rs:180-365 (minkowski_ray_cast, DIM = 2), query/ray/ray.rs:36-41.
+struct RayHit2 {
+    bool hit = false;
+    real toi = 0;
+    P2 n = {0, 0};
+    uint32_t feature = 0xffffffffu;  // kind << 30 | id (1 Face), 0xffffffff Unknown
+};
+static const uint32_t FACE2 = 0x40000000u;
+
+static RayHit2 ray2_ball(P2 center, real radius, P2 o, P2 d, real max_toi) {
+    RayHit2 h;
+    P2 dcenter = o - center;
+    real a = nsq(d), b = dot(dcenter, d), c = nsq(dcenter) - radius * radius;
+    bool inside = false;
+    real t = 0;
+    if (a == real(0)) {
+        if (c > real(0)) return h;
+        inside = true;
+    } else if (c > real(0) && b > real(0)) {
+        return h;
+    } else {
+        real delta = b * b - a * c;
+        if (delta < real(0)) return h;
+        t = (-b - std::sqrt(delta)) / a;
+        if (t <= real(0)) inside = true, t = 0;  // solid
+    }
+    if (!(t <= max_toi)) return h;
+    P2 pos = (o + d * t) - center;
+    P2 normal = normalize(pos);
+    h.hit = true, h.toi = t, h.n = inside ? -normal : normal, h.feature = FACE2;
+    return h;
+}
+
+static RayHit2 ray2_cuboid(P2 he, const Iso2& m, P2 o_w, P2 d_w, real max_toi) {
+    RayHit2 h;
+    P2 o = inv_point(m, o_w), d = inv_rot(m, d_w);
+    const real oo[2] = {o.x, o.y}, dd[2] = {d.x, d.y}, mn[2] = {-he.x, -he.y}, mx[2] = {he.x, he.y};
+    real tmax = FMAX, tmin = -FMAX;  // clip_line (ray_aabb.rs:183-279)
+    int near_side = 0, far_side = 0;
+    bool near_diag = false;
+    for (int i = 0; i < 2; ++i) {
+        if (dd[i] == real(0)) {
+            if (oo[i] < mn[i] || oo[i] > mx[i]) return h;
+        } else {
+            real denom = real(1) / dd[i];
+            real near = (mn[i] - oo[i]) * denom, far = (mx[i] - oo[i]) * denom;
+            bool flip = false;
+            if (near > far) flip = true, std::swap(near, far);
+            if (near > tmin)
+                tmin = near, near_side = flip ? -(i + 1) : (i + 1), near_diag = false;
+            else if (near == tmin)
+                near_diag = true;
+            if (far < tmax) tmax = far, far_side = !flip ? -(i + 1) : (i + 1);
+            if (tmax < real(0) || tmin > tmax) return h;
+        }
+    }
+    P2 near_n = p2(0, 0);
+    if (near_diag)
+        near_n = -normalize(d);
+    else if (near_side != 0) {
+        real* c = &near_n.x;
+        if (near_side < 0)
+            c[-near_side - 1] = real(1);
+        else
+            c[near_side - 1] = -real(1);
+    }
+    real t;
+    P2 n;
+    int side;
+    if (tmin < real(0))
+        t = 0, n = p2(0, 0), side = far_side;  // ray_aabb (:282-300), solid
+    else if (tmin <= max_toi)
+        t = tmin, n = near_n, side = near_side;
+    else
+        return h;
+    h.hit = true, h.toi = t, h.n = rot(m, n);
+    h.feature = FACE2 | ((uint32_t)(side < 0 ? (-side - 1 + 3) : (side - 1)) & 0x3fffffffu);
+    return h;
+}
+
+static RayHit2 ray2_plane(P2 pn, const Iso2& m, P2 o_w, P2 d_w, real max_toi) {
+    RayHit2 h;
+    P2 o = inv_point(m, o_w), d = inv_rot(m, d_w);
+    P2 dpos = -o;
+    real dot_normal_dpos = dot(pn, dpos);
+    if (dot_normal_dpos > real(0)) {  // solid: the origin is inside the half-space
+        h.hit = true, h.toi = 0, h.n = p2(0, 0), h.feature = FACE2;
+        return h;
+    }
+    real t = dot_normal_dpos / dot(pn, d);
+    if (t >= real(0) && t <= max_toi) h.hit = true, h.toi = t, h.n = rot(m, pn), h.feature = FACE2;
+    return h;
+}
+
+static bool ray2_toi_with_plane(P2 center, P2 normal, P2 origin, P2 dir, real* t_out) {  // ray_plane.rs:9-42
+    P2 dpos = center - origin;
+    real denom = dot(normal, dir);
+    if (relative_eq(denom, real(0))) return false;
+    real t = dot(normal, dpos) / denom;
+    if (t >= real(0)) {
+        *t_out = t;
+        return true;
+    }
+    return false;
+}
+
+// gjk::cast_ray = minkowski_ray_cast(m1, g1, identity, ConstantOrigin, ...) (gjk.rs:180-365), DIM = 2
+static bool minkowski_ray_cast2(const Iso2& m1, const Shape2& g1, const Iso2& m2, const Shape2& g2, P2 ray_origin, P2 ray_dir, real max_toi,
+                                Simplex2& simplex, real* toi_out, P2* normal_out) {
+    const real eps_rel = std::sqrt(EPS_TOL);
+    real ray_length = std::sqrt(nsq(ray_dir));
+    if (relative_eq(ray_length, real(0))) return false;
+    real ltoi = 0;
+    P2 curr_origin = ray_origin, curr_dir = ray_dir / ray_length;
+    P2 dir0 = -curr_dir, ldir = dir0;
+    CSO sp0 = cso_from_shapes(m1, g1, m2, g2, dir0);
+    sp0.point = sp0.point + (-curr_origin);  // translate(&-origin.coords): only `point` moves
+    simplex.reset(sp0);
+    P2 proj = simplex.project_origin_and_reduce();
+    real max_bound = FMAX;
+    P2 dir;
+    int niter = 0;
+    bool last_chance = false;
+    for (;;) {
+        real old_max_bound = max_bound, dist;
+        if (unit_try_new_and_get(-proj, EPS_TOL, &dir, &dist))
+            max_bound = dist;
+        else {
+            *toi_out = ltoi / ray_length, *normal_out = ldir;
+            return true;
+        }
+        CSO support_point;
+        if (max_bound >= old_max_bound) {
+            last_chance = true;
+            P2 p = proj + curr_origin;
+            support_point = CSO{p, p, p2(0, 0)};  // CSOPoint::single_point
+        } else {
+            support_point = cso_from_shapes(m1, g1, m2, g2, dir);
+        }
+        if (last_chance && ltoi > real(0)) {
+            *toi_out = ltoi / ray_length, *normal_out = ldir;
+            return true;
+        }
+        real t;
+        if (ray2_toi_with_plane(support_point.point, dir, curr_origin, curr_dir, &t)) {
+            if (dot(dir, curr_dir) < real(0) && t > real(0)) {
+                ldir = dir;
+                ltoi += t;
+                if (ltoi / ray_length > max_toi) return false;
+                P2 shift = curr_dir * t;
+                curr_origin = curr_origin + shift;
+                max_bound = FMAX;
+                for (int i = 0; i < simplex.dim + 1; ++i) simplex.vertices[i].point = simplex.vertices[i].point + (-shift);
+                last_chance = false;
+            }
+        } else if (dot(dir, curr_dir) > EPS_TOL) {
+            return false;
+        }
+        if (last_chance) return false;
+        real min_bound = -dot(dir, support_point.point - curr_origin);
+        if (max_bound - min_bound <= eps_rel * max_bound) return false;  // improved_fixed_point_support is off
+        CSO tp = support_point;
+        tp.point = tp.point + (-curr_origin);
+        (void)simplex.add_point(tp);
+        proj = simplex.project_origin_and_reduce();
+        if (simplex.dim == 2) {
+            if (min_bound >= EPS_TOL) return false;
+            *toi_out = ltoi / ray_length, *normal_out = ldir;
+            return true;
+        }
+        if (++niter == 10000) return false;
+    }
+}
+
+// RayCast for ConvexPolygon (ray_support_map.rs:165-189 -> :15-60), solid = true
+static RayHit2 ray2_polygon(const Shape2& g, const Iso2& m, P2 o_w, P2 d_w, real max_toi) {
+    RayHit2 h;
+    P2 o = inv_point(m, o_w), d = inv_rot(m, d_w);
+    Shape2 origin;
+    origin.type = ORIGIN2, origin.radius = 0, origin.he = p2(0, 0), origin.pts = origin.normals = nullptr, origin.npts = 0;
+    Iso2 id = {p2(0, 0), real(1), real(0)};
+    Simplex2 simplex;
+    P2 supp = support_point(g, id, -d);
+    P2 p = supp - o;
+    simplex.reset(CSO{p, p, p2(0, 0)});  // replaced by minkowski_ray_cast's own reset, like in the reference
+    real toi;
+    P2 normal;
+    if (!minkowski_ray_cast2(id, g, id, origin, o, d, max_toi, simplex, &toi, &normal)) return h;
+    h.hit = true, h.toi = toi, h.n = rot(m, normal), h.feature = 0xffffffffu;
+    return h;
+}
+
+static RayHit2 shape_ray_cast2(const Shape2& g, const Iso2& m, P2 o, P2 d, real max_toi) {
+    switch (g.type) {
+        case BALL2: return ray2_ball(m.t, g.radius, o, d, max_toi);
+        case CUBOID2: return ray2_cuboid(g.he, m, o, d, max_toi);
+        case POLYGON2: return ray2_polygon(g, m, o, d, max_toi);
+        default: return ray2_plane(g.he, m, o, d, max_toi);
+    }
+}
+
 }  // namespace d2
 }  // namespace orc
 
@@ -1125,6 +1329,24 @@ void orc2_proximity(uint64_t n, const uint32_t* type1, const real* param1, const
         else
             r = proximity_sm_sm(m1, g1, m2, g2, margin);
         out[k] = (uint8_t)r;
+    }
+}
+
+// RayCast::toi_and_normal_with_ray(m, ray, max_toi, solid = true) of shape k for ray k; rays: origin x y, dir x y, max_toi;
+// found 1 Some / 0 None; out: toi, normal x y; feature: kind << 30 | id (1 Face) or 0xffffffff (Unknown).
+void orc2_ray_cast(uint64_t n, const uint32_t* type, const real* param, const real* pose, const real* poly_points, const real* rays,
+                   uint8_t* found, real* out, uint32_t* feature) {
+    for (uint64_t k = 0; k < n; ++k) {
+        const real* p = param + 4 * k;
+        Shape2 g;
+        g.type = type[k], g.radius = p[0], g.he = p2(p[0], p[1]), g.pts = g.normals = nullptr, g.npts = 0;
+        if (g.type == POLYGON2) g.pts = poly_points + 2 * (size_t)p[0], g.npts = (uint32_t)p[1];
+        Iso2 m = {p2(pose[4 * k], pose[4 * k + 1]), pose[4 * k + 2], pose[4 * k + 3]};
+        const real* q = rays + 5 * k;
+        RayHit2 h = shape_ray_cast2(g, m, p2(q[0], q[1]), p2(q[2], q[3]), q[4]);
+        found[k] = h.hit ? 1 : 0;
+        out[3 * k] = h.toi, out[3 * k + 1] = h.n.x, out[3 * k + 2] = h.n.y;
+        feature[k] = h.hit ? h.feature : 0xffffffffu;
     }
 }
 

@@ -168,6 +168,10 @@ void orc_trimesh_ray_cast(const orc_trimesh*, const real* pose, uint64_t n_rays,
                           real max_toi, int mode, real* toi, uint32_t* face, real* normal);
 void orc_aabb_toi_with_ray(const real* minmax, const real* origin, const real* dir, real max_toi, int solid, real* toi);
 
+/* ncollide2d RayCast::toi_and_normal_with_ray(m, ray, max_toi, solid = true) of shape k for ray k (oracle/dim2.cpp).  rays: 5 reals
+ * (origin, dir, max_toi); out: 3 reals (toi, normal); feature: kind << 30 | id or 0xffffffff. */
+void orc2_ray_cast(uint64_t n, const uint32_t* type, const real* param, const real* pose, const real* poly_points, const real* rays,
+                   uint8_t* found, real* out, uint32_t* feature);
 /* ncollide2d Polyline ray casting (oracle/ray.cpp).  idx: 2 point indices per edge (NULL: the line strip 0-1, 1-2, ...).  pose = x y re im
  * or NULL.  mode as above.  feature = edge, or edge + n_edges for FeatureId::Face(1) of the segment; normal = the segment's scaled normal. */
 typedef struct orc2_polyline orc2_polyline;

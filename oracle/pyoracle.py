@@ -252,6 +252,19 @@ class Oracle:
     def trimesh(self, verts, tris):
         return OracleTriMesh(self, verts, tris)
 
+    def ray_cast2d(self, types, params, poses, rays, poly_points=None):
+        """ncollide2d ``RayCast::toi_and_normal_with_ray`` (solid) of shape k for ray k [origin, dir, max_toi]:
+        (found u8, out [toi, normal], feature)."""
+        dt = self.dtype
+        t = np.ascontiguousarray(types, dtype=np.uint32)
+        n = len(t)
+        p, m, q = (np.ascontiguousarray(a, dtype=dt) for a in (params, poses, rays))
+        pts = np.ascontiguousarray(poly_points if poly_points is not None else np.zeros((1, 2)), dtype=dt)
+        found, out, feat = np.zeros(n, dtype=np.uint8), np.zeros((n, 3), dtype=dt), np.zeros(n, dtype=np.uint32)
+        vp = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+        self.lib.orc2_ray_cast(C.c_uint64(n), vp(t), vp(p), vp(m), vp(pts), vp(q), vp(found), vp(out), vp(feat))
+        return found, out, feat
+
     def polyline(self, points, edges=None):
         return OraclePolyline(self, points, edges)
 

@@ -40,6 +40,19 @@ void shim2_proximity(uint64_t n, const uint32_t* type1, const float* param1, con
     }
 }
 
+void shim2_ray_cast(uint64_t n, const uint32_t* type, const float* param, const float* pose, const float* poly, const float* rays, uint8_t* found,
+                    float* out, uint32_t* feature) {
+    for (uint64_t k = 0; k < n; ++k) {
+        const float4* p = reinterpret_cast<const float4*>(param) + k;
+        const float4* m = reinterpret_cast<const float4*>(pose) + k;
+        const float* q = rays + 5 * k;
+        RayHit2 h = shape_ray_cast2(load_operand(type[k], *p, *m, poly, nullptr), w2(q[0], q[1]), w2(q[2], q[3]), q[4]);
+        found[k] = h.hit ? 1 : 0;
+        out[3 * k] = h.toi, out[3 * k + 1] = h.n.x, out[3 * k + 2] = h.n.y;
+        feature[k] = h.hit ? h.feature : 0xffffffffu;
+    }
+}
+
 static Operand2 obj(uint32_t i, const float* pos, const float* rot, const uint32_t* type, const float* param, const float* poly, const float* nrm) {
     float4 p = reinterpret_cast<const float4*>(param)[i];
     return load_operand(type[i], p, make_float4(pos[2 * i], pos[2 * i + 1], rot[2 * i], rot[2 * i + 1]), poly, nrm);

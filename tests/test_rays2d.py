@@ -199,3 +199,161 @@ def test_device_polyline_edge_cases(ctx):
     with pytest.raises(NcbError):  # a Polyline is not a TriMesh
         ctx.check(ctx.lib.ncb_trimesh_set_uvs(pl.h, None), "ncb_trimesh_set_uvs")
     pl.close(), empty.close()
+
+
+# ---- RayCast for the 2-D shapes (ball, cuboid, convex polygon, plane) ---------------------------------------------------------------
+def random_shape_rays(n, seed, kinds=(0, 1, 2, 3)):
+    """n (shape, pose, ray) triples: rays aimed near the shape from 1-4 units away, a share starting inside, some axis-aligned."""
+    rng = np.random.default_rng(seed)
+    sh = dim2.Shapes2D()
+    t = rng.choice(kinds, size=n)
+    for k in t:
+        if k == 0:
+            sh.ball(rng.uniform(0.2, 0.7))
+        elif k == 1:
+            sh.cuboid(rng.uniform(0.2, 0.7), rng.uniform(0.2, 0.7))
+        elif k == 3:
+            sh.plane(rng.normal(size=2))
+        else:
+            m = int(rng.integers(3, 11))
+            ang = np.sort(rng.uniform(0, 2 * np.pi, size=m)) + np.arange(m) * 1e-3
+            a, b = rng.uniform(0.25, 0.7, size=2)
+            sh.polygon(np.stack([a * np.cos(ang), b * np.sin(ang)], axis=1))
+    typ, par, pts, nrm = sh.arrays()
+    c = rng.uniform(-5, 5, size=(n, 2))
+    angle = rng.uniform(-np.pi, np.pi, size=n)
+    angle[rng.random(n) < 0.2] = 0.0
+    pose = dim2.isometry2(c, angle)
+    o = c + rng.normal(size=(n, 2)) * rng.uniform(0.0, 3.0, size=(n, 1))
+    target = c + rng.uniform(-0.8, 0.8, size=(n, 2))
+    d = target - o
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-9)
+    d *= rng.uniform(0.3, 3.0, size=(n, 1))  # ray.dir need not be a unit vector
+    axis = rng.random(n) < 0.1
+    d[axis] = np.where(rng.random((int(axis.sum()), 1)) < 0.5, [[0.0, -1.0]], [[1.0, 0.0]])
+    d[rng.random(n) < 0.005] = 0.0  # the zero direction: None, or Some(0) from inside
+    max_toi = np.where(rng.random(n) < 0.3, rng.uniform(0.2, 3.0, size=n), FMAX)
+    rays = np.concatenate([o, d, max_toi[:, None]], axis=1).astype(F)
+    return typ, par, pose, rays, pts
+
+
+@pytest.mark.parametrize("which", ["oracle64", "oracle"])
+def test_oracle_convexpoly_raycast_fuzz(which, request):
+    """build/ncollide2d/tests/geometry/ray_cast.rs::convexpoly_raycast_fuzz, as written (f64 in the reference; f32 too here): every
+    ray hits the front face of the square, at a distance in [1, sqrt(2))."""
+    orc = request.getfixturevalue(which)
+    pts = np.array([[2, 1], [2, 2], [1, 2], [1, 1]], dtype=np.float64)
+    i = np.arange(10_000)
+    o = np.stack([np.full(len(i), 3.0), 1.0 + i * 1e-4], axis=1)
+    d = np.array([0.0, 2.0]) - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d, np.full((len(i), 1), np.finfo(orc.dtype).max)], axis=1)
+    n = len(i)
+    found, out, feat = orc.ray_cast2d([2] * n, [[0, 4, 0, 0]] * n, [[0, 0, 1, 0]] * n, rays, pts)
+    assert found.all(), "Failed to collide with any face"
+    slack = 0.0 if orc.dtype == np.float64 else 2e-6
+    assert (out[:, 0] >= 1.0 - slack).all() and (out[:, 0] < np.sqrt(2.0)).all()
+
+
+def test_oracle_shape_rays_against_numpy(oracle64):
+    """ORACLE check (f64): toi against closed forms — circle / half-plane equations, and for cuboids and polygons the nearest
+    crossing of the boundary edges (0 from inside)."""
+    typ, par, pose, rays, pts = random_shape_rays(4000, 41)
+    found, out, feat = oracle64.ray_cast2d(typ, par, pose, rays, pts)
+    checked = {0: 0, 1: 0, 2: 0, 3: 0}
+    for k in range(len(typ)):
+        o, d, lim = rays[k, :2].astype(np.float64), rays[k, 2:4].astype(np.float64), float(rays[k, 4])
+        m = pose[k].astype(np.float64)
+        if not d.any():
+            continue
+        want = None  # None = miss
+        if typ[k] == 0:
+            dc, r = o - m[:2], float(par[k, 0])
+            a, b, c = d @ d, dc @ d, dc @ dc - r * r
+            if c <= 0:
+                want = 0.0
+            elif b <= 0 and b * b - a * c >= 0:
+                want = (-b - np.sqrt(b * b - a * c)) / a
+        elif typ[k] == 3:
+            nw = np.array([m[2] * par[k, 0] - m[3] * par[k, 1], m[3] * par[k, 0] + m[2] * par[k, 1]], dtype=np.float64)
+            dist = nw @ (o - m[:2])
+            if dist < 0:
+                want = 0.0
+            elif nw @ d < 0:
+                want = -dist / (nw @ d)
+        else:
+            if typ[k] == 1:
+                hx, hy = float(par[k, 0]), float(par[k, 1])
+                loc = np.array([[hx, hy], [-hx, hy], [-hx, -hy], [hx, -hy]])
+            else:
+                loc = pts[int(par[k, 0]) : int(par[k, 0]) + int(par[k, 1])].astype(np.float64)
+            P = np.stack([m[2] * loc[:, 0] - m[3] * loc[:, 1] + m[0], m[3] * loc[:, 0] + m[2] * loc[:, 1] + m[1]], axis=1)
+            a, e = P, np.roll(P, -1, axis=0) - P
+            inside = bool(np.all(e[:, 0] * (o - a)[:, 1] - e[:, 1] * (o - a)[:, 0] >= 0))
+            den = d[0] * e[:, 1] - d[1] * e[:, 0]
+            ok = np.abs(den) > 1e-12
+            w = a - o
+            s = np.where(ok, (w[:, 0] * e[:, 1] - w[:, 1] * e[:, 0]) / np.where(ok, den, 1), np.inf)
+            t = np.where(ok, (w[:, 0] * d[1] - w[:, 1] * d[0]) / np.where(ok, den, 1), np.inf)
+            hit = ok & (s >= 0) & (t >= 0) & (t <= 1)
+            if np.any(ok & (np.minimum(np.abs(t), np.abs(t - 1)) < 1e-6) & (s >= 0)):
+                continue  # through a vertex: either answer
+            if inside:
+                want = 0.0
+            elif hit.any():
+                want = float(s[hit].min())
+        if want is not None and abs(want - lim) < 1e-6 * max(1.0, lim):
+            continue
+        if want is None or want > lim:
+            assert not found[k], (k, typ[k], want, out[k])
+        else:
+            assert found[k], (k, typ[k], want)
+            assert abs(out[k, 0] - want) < 1e-6 * max(1.0, want), (k, typ[k], out[k, 0], want)
+            if want > 0:
+                assert abs(np.hypot(out[k, 1], out[k, 2]) - 1) < 1e-6 and out[k, 1:] @ d <= 1e-9
+            checked[int(typ[k])] += 1
+    assert min(checked.values()) > 200, checked
+
+
+@pytest.fixture(scope="module")
+def dim2_shim():
+    from test_device_source_on_host import _build_shim
+
+    return _build_shim("libdim2_host.so", "dim2_host.cpp")
+
+
+@pytest.mark.parametrize("seed,kinds", [(51, (0, 1, 2, 3)), (52, (2,)), (53, (0, 1))])
+def test_device_source_shape_rays_equal_oracle_bit_for_bit(dim2_shim, oracle, seed, kinds):
+    typ, par, pose, rays, pts = random_shape_rays(30_000, seed, kinds)
+    n = len(typ)
+    found, out, feat = np.zeros(n, dtype=np.uint8), np.zeros((n, 3), dtype=F), np.zeros(n, dtype=np.uint32)
+    dim2_shim.shim2_ray_cast(C.c_uint64(n), _vp(typ), _vp(par), _vp(pose), _vp(pts), _vp(rays), _vp(found), _vp(out), _vp(feat))
+    ofound, oout, ofeat = oracle.ray_cast2d(typ, par, pose, rays, pts)
+    assert np.array_equal(found, ofound) and np.array_equal(feat, ofeat)
+    hit = found.astype(bool)
+    assert np.array_equal(bits(out[hit]), bits(oout[hit]))
+    assert hit.sum() > n // 4 and (~hit).sum() > n // 10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,kinds", [(61, (0, 1, 2, 3)), (62, (2,)), (63, (0, 1, 3))])
+def test_device_shape_rays_match_oracle(ctx, oracle, seed, kinds):
+    typ, par, pose, rays, pts = random_shape_rays(120_000, seed, kinds)
+    found, out, feat = dim2.ray_cast(ctx, typ, par, pose, rays, pts)
+    ofound, oout, ofeat = oracle.ray_cast2d(typ, par, pose, rays, pts)
+    assert np.array_equal(found, ofound.astype(bool)) and np.array_equal(feat, ofeat)
+    assert np.array_equal(bits(out[found]), bits(oout[found])), f"{(bits(out[found]) != bits(oout[found])).sum()} words differ"
+    assert found.sum() > 30_000 and (~found).sum() > 10_000
+
+
+@pytest.mark.gpu
+def test_device_convexpoly_raycast_fuzz(ctx):
+    pts = np.array([[2, 1], [2, 2], [1, 2], [1, 1]], dtype=F)
+    i = np.arange(10_000)
+    o = np.stack([np.full(len(i), 3.0), 1.0 + i * 1e-4], axis=1)
+    d = np.array([0.0, 2.0]) - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d, np.full((len(i), 1), FMAX)], axis=1).astype(F)
+    n = len(i)
+    found, out, feat = dim2.ray_cast(ctx, [2] * n, [[0, 4, 0, 0]] * n, [[0, 0, 1, 0]] * n, rays, pts)
+    assert found.all() and (out[:, 0] >= 1.0 - 2e-6).all() and (out[:, 0] < np.sqrt(2.0)).all()
