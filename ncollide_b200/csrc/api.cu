@@ -259,6 +259,12 @@ int ncb_set_hulls(ncb_ctx* ctx, const ncb_hull_library* L) {
     CK(upload(ctx, L->fadj_off, nh + 1, &H.fadj_off));
     CK(upload(ctx, L->vadj_off, nh + 1, &H.vadj_off));
     CK(upload(ctx, L->points, 3 * (size_t)nv, &H.points));
+    {
+        std::vector<float4> padded(nv);
+        for (uint32_t v = 0; v < nv; ++v) padded[v] = make_float4(L->points[3 * (size_t)v], L->points[3 * (size_t)v + 1], L->points[3 * (size_t)v + 2], 0.f);
+        CK(upload(ctx, padded.data(), nv, &H.points4));
+        CK(cudaStreamSynchronize(ctx->stream));  // `padded` goes away
+    }
     CK(upload(ctx, L->vert_first_adj, nv, &H.vert_first_adj));
     CK(upload(ctx, L->vert_num_adj, nv, &H.vert_num_adj));
     CK(upload(ctx, L->face_first, nf, &H.face_first));

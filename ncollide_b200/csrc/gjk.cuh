@@ -64,15 +64,25 @@ struct SupportS {
     int kind;
     V3 he;
     uint32_t nverts;
+#ifndef NCB_HOST_SHIM
+    const float4* pts4;  // vertices padded to 16 B (DevHulls::points4): one load per vertex
+    NCB_HD V3 pt(uint32_t i) const {
+        float4 q = __ldg(pts4 + i);
+        return v3(q.x, q.y, q.z);
+    }
+#else  // the host shim reads the packed array of the hull view
     const float* pts;
+    NCB_HD V3 pt(uint32_t i) const { return v3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]); }
+#endif
     NCB_HD uint32_t nv() const { return nverts; }
-    NCB_HD V3 pt(uint32_t i) const { return v3(__ldg(pts + 3 * i), __ldg(pts + 3 * i + 1), __ldg(pts + 3 * i + 2)); }
 };
+#ifdef NCB_HOST_SHIM
 NCB_HD SupportS slim_support(const Support& g) {
     SupportS r;
     r.kind = g.kind, r.he = g.he, r.nverts = g.hull.nv, r.pts = g.hull.pts;
     return r;
 }
+#endif
 
 template <class G>
 NCB_HD V3 local_support_point(const G& g, V3 dir) {
@@ -145,6 +155,10 @@ NCB_HD V3 proj_segment(V3 a, V3 b, V3 p, Loc& loc) {
 
 // solid = true variant only (the one the simplex and EPA use).  POINT = false: only the location (region + barycentric
 // coordinates) is wanted; the decisions and the coordinates come from the same expressions either way.
+// Code shape: the three edge regions share ONE tail (the quotient, the location record, the point) — a region test only selects its
+// operands.  The kernels that run this are instruction-fetch bound (profiles/r2_ncu_gjk_fetch_bound.txt): one copy of each tail keeps
+// the code short, and lanes of a warp that land in different edge regions run the tail together.  Values are those of the
+// straight-line version, expression for expression.
 template <bool POINT>
 NCB_HD V3 proj_triangle_core(V3 a, V3 b, V3 c, V3 p, Loc& loc) {
     V3 ab = b - a, ac = c - a, ap = p - a;
@@ -168,22 +182,25 @@ NCB_HD V3 proj_triangle_core(V3 a, V3 b, V3 c, V3 p, Loc& loc) {
     V3 bc = c - b;
     V3 n = cross(ab, ac);
     float vc = dot(n, cross(ab, ap));
+    int edge = -1;  // the edge region found, with the operands of its tail: coordinate = num / norm_squared(dir), point = from + dir * coordinate
+    float num = 0.f;
+    V3 from = a, dir = ab;
+    float vb = 0.f, va = 0.f;
     if (vc < 0.f && ab_ap >= 0.f && ab_bp <= 0.f) {
-        float v = ab_ap / norm_squared(ab);
-        loc = mkloc(LOC_EDGE, 0, 1.f - v, v);
-        return POINT ? a + ab * v : a;
+        edge = 0, num = ab_ap;
+    } else {
+        vb = -dot(n, cross(ac, cp));
+        if (vb < 0.f && ac_ap >= 0.f && ac_cp <= 0.f) {
+            edge = 2, num = ac_ap, dir = ac;
+        } else {
+            va = dot(n, cross(bc, bp));
+            if (va < 0.f && ac_bp - ab_bp >= 0.f && ab_cp - ac_cp >= 0.f) edge = 1, num = dot(bc, bp), from = b, dir = bc;
+        }
     }
-    float vb = -dot(n, cross(ac, cp));
-    if (vb < 0.f && ac_ap >= 0.f && ac_cp <= 0.f) {
-        float w = ac_ap / norm_squared(ac);
-        loc = mkloc(LOC_EDGE, 2, 1.f - w, w);
-        return POINT ? a + ac * w : a;
-    }
-    float va = dot(n, cross(bc, bp));
-    if (va < 0.f && ac_bp - ab_bp >= 0.f && ab_cp - ac_cp >= 0.f) {
-        float w = dot(bc, bp) / norm_squared(bc);
-        loc = mkloc(LOC_EDGE, 1, 1.f - w, w);
-        return POINT ? b + bc * w : a;
+    if (edge >= 0) {
+        float w = num / norm_squared(dir);
+        loc = mkloc(LOC_EDGE, edge, 1.f - w, w);
+        return POINT ? from + dir * w : a;
     }
     int clockwise = dot(n, ap) >= 0.f ? 0 : 1;
     if (va + vb + vc != 0.f) {
@@ -197,37 +214,19 @@ NCB_HD V3 proj_triangle_core(V3 a, V3 b, V3 c, V3 p, Loc& loc) {
 }
 static __device__ __noinline__ V3 proj_triangle(V3 a, V3 b, V3 c, V3 p, Loc& loc) { return proj_triangle_core<true>(a, b, c, p, loc); }
 
-NCB_HD bool tetra_edge(int i, V3 a, V3 nabc, V3 nabd, V3 ap, V3 ab, float ap_ab, float bp_ab, float& dabc, float& dabd, V3& proj,
-                       Loc& loc) {
+// Tetrahedron::project_point_with_location's edge and face tests (point_tetrahedron.rs): the test of a region; its tail (quotients,
+// location, point) exists once in proj_tetrahedron.
+NCB_HD bool tetra_edge_test(V3 nabc, V3 nabd, V3 ap, V3 ab, float ap_ab, float bp_ab, float& dabc, float& dabd) {
     float ab_ab = ap_ab - bp_ab;
     V3 ap_x_ab = cross(ap, ab);
     dabc = dot(ap_x_ab, nabc);
     dabd = dot(ap_x_ab, nabd);
-    if (ab_ab != 0.f && dabc >= 0.f && dabd >= 0.f && ap_ab >= 0.f && ap_ab <= ab_ab) {
-        float u = ap_ab / ab_ab;
-        loc = mkloc(LOC_EDGE, i, 1.f - u, u);
-        proj = a + ab * u;
-        return true;
-    }
-    return false;
+    return ab_ab != 0.f && dabc >= 0.f && dabd >= 0.f && ap_ab >= 0.f && ap_ab <= ab_ab;
 }
-NCB_HD bool tetra_face(int i, V3 a, V3 b, V3 c, V3 ap, V3 bp, V3 cp, V3 ab, V3 ac, V3 ad, float dabc, float dbca, float dacb, V3& proj,
-                       Loc& loc) {
+NCB_HD bool tetra_face_test(V3 ap, V3 ab, V3 ac, V3 ad, float dabc, float dbca, float dacb, V3& n) {
     if (dabc < 0.f && dbca < 0.f && dacb < 0.f) {
-        V3 n = cross(ab, ac);
-        if (dot(n, ad) * dot(n, ap) < 0.f) {
-            V3 normal;
-            if (!try_normalize(n, NCB_EPS, normal)) return false;
-            float vc = dot(normal, cross(ap, bp));
-            float va = dot(normal, cross(bp, cp));
-            float vb = dot(normal, cross(cp, ap));
-            float denom = va + vb + vc;
-            float inv_denom = 1.f / denom;
-            float b0 = va * inv_denom, b1 = vb * inv_denom, b2 = vc * inv_denom;
-            loc = mkloc(LOC_FACE, i, b0, b1, b2);
-            proj = a * b0 + b * b1 + c * b2;
-            return true;
-        }
+        n = cross(ab, ac);
+        return dot(n, ad) * dot(n, ap) < 0.f;
     }
     return false;
 }
@@ -256,26 +255,62 @@ static __device__ __noinline__ V3 proj_tetrahedron(V3 a, V3 b, V3 c, V3 d, V3 p,
         loc = mkloc(LOC_VERTEX, 3);
         return d;
     }
-    V3 proj;
-    V3 nabc = cross(ab, ac), nabd = cross(ab, ad);
-    float dabc, dabd;
-    if (tetra_edge(0, a, nabc, nabd, ap, ab, ap_ab, bp_ab, dabc, dabd, proj, loc)) return proj;
-    V3 nacd = cross(ac, ad);
-    float dacd, dacb;
-    if (tetra_edge(1, a, nacd, -nabc, ap, ac, ap_ac, cp_ac, dacd, dacb, proj, loc)) return proj;
-    float dadb, dadc;
-    if (tetra_edge(2, a, -nabd, -nacd, ap, ad, ap_ad, dp_ad, dadb, dadc, proj, loc)) return proj;
-    V3 nbcd = cross(bc, bd);
-    float dbca, dbcd;
-    if (tetra_edge(3, b, nabc, nbcd, bp, bc, bp_bc, cp_bc, dbca, dbcd, proj, loc)) return proj;
-    float dbdc, dbda;
-    if (tetra_edge(4, b, -nbcd, nabd, bp, bd, bp_bd, dp_bd, dbdc, dbda, proj, loc)) return proj;
-    float dcda, dcdb;
-    if (tetra_edge(5, c, nacd, nbcd, cp, cd, cp_cd, dp_cd, dcda, dcdb, proj, loc)) return proj;
-    if (tetra_face(0, a, b, c, ap, bp, cp, ab, ac, ad, dabc, dbca, dacb, proj, loc)) return proj;
-    if (tetra_face(1, a, b, d, ap, bp, dp, ab, ad, ac, dadb, dabd, dbda, proj, loc)) return proj;
-    if (tetra_face(2, a, c, d, ap, cp, dp, ac, ad, ab, dacd, dcda, dadc, proj, loc)) return proj;
-    if (tetra_face(3, b, c, d, bp, cp, dp, bc, bd, -ab, dbcd, dcdb, dbdc, proj, loc)) return proj;
+    // the six edge regions, in the reference's order; the first that holds gives the operands of the shared tail
+    V3 nabc = cross(ab, ac), nabd = cross(ab, ad), nacd, nbcd;
+    float dabc, dabd, dacd, dacb, dadb, dadc, dbca, dbcd, dbdc, dbda, dcda, dcdb;
+    int edge = -1;
+    V3 from = a, dir = ab;
+    float num = ap_ab, den = ap_ab - bp_ab;
+    if (tetra_edge_test(nabc, nabd, ap, ab, ap_ab, bp_ab, dabc, dabd)) {
+        edge = 0;
+    } else {
+        nacd = cross(ac, ad);
+        if (tetra_edge_test(nacd, -nabc, ap, ac, ap_ac, cp_ac, dacd, dacb)) {
+            edge = 1, dir = ac, num = ap_ac, den = ap_ac - cp_ac;
+        } else if (tetra_edge_test(-nabd, -nacd, ap, ad, ap_ad, dp_ad, dadb, dadc)) {
+            edge = 2, dir = ad, num = ap_ad, den = ap_ad - dp_ad;
+        } else {
+            nbcd = cross(bc, bd);
+            if (tetra_edge_test(nabc, nbcd, bp, bc, bp_bc, cp_bc, dbca, dbcd))
+                edge = 3, from = b, dir = bc, num = bp_bc, den = bp_bc - cp_bc;
+            else if (tetra_edge_test(-nbcd, nabd, bp, bd, bp_bd, dp_bd, dbdc, dbda))
+                edge = 4, from = b, dir = bd, num = bp_bd, den = bp_bd - dp_bd;
+            else if (tetra_edge_test(nacd, nbcd, cp, cd, cp_cd, dp_cd, dcda, dcdb))
+                edge = 5, from = c, dir = cd, num = cp_cd, den = cp_cd - dp_cd;
+        }
+    }
+    if (edge >= 0) {
+        float u = num / den;
+        loc = mkloc(LOC_EDGE, edge, 1.f - u, u);
+        return from + dir * u;
+    }
+    // the four face regions: a face whose normal is too short to normalise is skipped, like the reference's `return false`
+    for (int first = 0; first < 4;) {
+        int face = -1;
+        V3 n, fa = a, fb = b, fc = c, fap = ap, fbp = bp, fcp = cp;
+        if (first <= 0 && tetra_face_test(ap, ab, ac, ad, dabc, dbca, dacb, n)) {
+            face = 0;
+        } else if (first <= 1 && tetra_face_test(ap, ab, ad, ac, dadb, dabd, dbda, n)) {
+            face = 1, fc = d, fcp = dp;
+        } else if (first <= 2 && tetra_face_test(ap, ac, ad, ab, dacd, dcda, dadc, n)) {
+            face = 2, fb = c, fc = d, fbp = cp, fcp = dp;
+        } else if (first <= 3 && tetra_face_test(bp, bc, bd, -ab, dbcd, dcdb, dbdc, n)) {
+            face = 3, fa = b, fb = c, fc = d, fap = bp, fbp = cp, fcp = dp;
+        }
+        if (face < 0) break;
+        V3 normal;
+        if (try_normalize(n, NCB_EPS, normal)) {
+            float vc = dot(normal, cross(fap, fbp));
+            float va = dot(normal, cross(fbp, fcp));
+            float vb = dot(normal, cross(fcp, fap));
+            float denom = va + vb + vc;
+            float inv_denom = 1.f / denom;
+            float b0 = va * inv_denom, b1 = vb * inv_denom, b2 = vc * inv_denom;
+            loc = mkloc(LOC_FACE, face, b0, b1, b2);
+            return fa * b0 + fb * b1 + fc * b2;
+        }
+        first = face + 1;
+    }
     loc = mkloc(LOC_SOLID, 0);
     return p;
 }

@@ -80,6 +80,7 @@ struct DevHulls {
     uint32_t n_hulls;
     const uint32_t *vert_off, *face_off, *edge_off, *fadj_off, *vadj_off;
     const float* points;
+    const float4* points4;  // the same vertices padded to 16 B: one load per vertex in the support scans of GJK / EPA
     const uint32_t *vert_first_adj, *vert_num_adj;
     const uint32_t *face_first, *face_num;
     const float* face_normal;

@@ -50,12 +50,20 @@ NCB_HD SupportS load_slim_support(const DevObjects& o, const DevHulls& H, uint32
     g.kind = type == NCB_SHAPE_CUBOID ? 0 : 1;
     g.he = v3(p.x, p.y, p.z);
     g.nverts = 0;
+#ifndef NCB_HOST_SHIM
+    g.pts4 = nullptr;
+#else
     g.pts = nullptr;
+#endif
     if (type == NCB_SHAPE_CONVEX_HULL) {
         uint32_t h = (uint32_t)p.x;
         uint32_t v0 = __ldg(H.vert_off + h);
         g.nverts = __ldg(H.vert_off + h + 1) - v0;
+#ifndef NCB_HOST_SHIM
+        g.pts4 = H.points4 + v0;
+#else
         g.pts = H.points + 3 * (size_t)v0;
+#endif
     }
     return g;
 }
