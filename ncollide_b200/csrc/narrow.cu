@@ -595,7 +595,7 @@ NCB_HD bool point_in_poly2d(V2 pt, const V2* poly, int n) {
     if (n == 0) return false;
     float sign = 0.f;
     for (int i1 = 0; i1 < n; ++i1) {
-        int i2 = (i1 + 1) % n;
+        int i2 = i1 + 1 == n ? 0 : i1 + 1;  // (i1 + 1) % n without the integer division
         V2 seg_dir = V2{poly[i2].x - poly[i1].x, poly[i2].y - poly[i1].y};
         V2 dpt = V2{pt.x - poly[i1].x, pt.y - poly[i1].y};
         float perp = dpt.x * seg_dir.y - dpt.y * seg_dir.x;
@@ -656,14 +656,15 @@ NCB_HD bool feature_ok_for_manifold(const Feature& ft, uint32_t f) {
     uint32_t kind = FID_KIND(f);
     if (kind == NCB_FEATURE_FACE || kind == NCB_FEATURE_VERTEX) return true;
     if (kind == NCB_FEATURE_EDGE) {
-        for (int i1 = 0; i1 < ft.nv; ++i1) {
-            if (i1 < ft.ne && ft.eid[i1] == f) {
-                int i2 = (i1 + 1) % ft.nv;
-                V3 d;
-                return unit_try_new(ft.v[i2] - ft.v[i1], NCB_EPS, d);
-            }
-        }
-        return false;
+        // the first i1 < min(nv, ne) with eid[i1] == f; scanned from the back without a data-dependent exit, so the loads of the
+        // (local-memory) id array do not wait for one another
+        int lim = ft.nv < ft.ne ? ft.nv : ft.ne, i1 = -1;
+#pragma unroll 4
+        for (int i = lim - 1; i >= 0; --i) i1 = ft.eid[i] == f ? i : i1;
+        if (i1 < 0) return false;
+        int i2 = i1 + 1 == ft.nv ? 0 : i1 + 1;
+        V3 d;
+        return unit_try_new(ft.v[i2] - ft.v[i1], NCB_EPS, d);
     }
     return false;
 }
@@ -678,7 +679,7 @@ NCB_HD void feature_geometry(const Feature& ft, uint32_t f, const Iso& m, uint32
     } else if (kind == NCB_FEATURE_EDGE) {
         for (int i1 = 0; i1 < ft.nv; ++i1) {
             if (i1 < ft.ne && ft.eid[i1] == f) {
-                int i2 = (i1 + 1) % ft.nv;
+                int i2 = i1 + 1 == ft.nv ? 0 : i1 + 1;
                 V3 d = v3(0.f, 0.f, 0.f);
                 unit_try_new(ft.v[i2] - ft.v[i1], NCB_EPS, d);
                 g = G_LINE, dir = iso_inv_vec(m, d);
@@ -784,9 +785,9 @@ __device__ __noinline__ void clip(const Feature& self, const Feature& other, V3 
     }
     int nedges1 = feat_nedges(self), nedges2 = feat_nedges(other);
     for (int i1 = 0; i1 < nedges1; ++i1) {
-        int j1 = (i1 + 1) % self.nv;
+        int j1 = i1 + 1 == self.nv ? 0 : i1 + 1;
         for (int i2 = 0; i2 < nedges2; ++i2) {
-            int j2 = (i2 + 1) % other.nv;
+            int j2 = i2 + 1 == other.nv ? 0 : i2 + 1;
             float s, t;
             if (seg_seg_2d(poly1[i1], poly1[j1], poly2[i2], poly2[j2], s, t)) {
                 V3 world1 = self.v[i1] * (1.f - s) + self.v[j1] * s;
