@@ -455,6 +455,8 @@ typedef struct ncb2d_objects {
     const float* poly_points;
     const float* poly_normals;
     uint32_t n_poly_points;
+    const uint8_t* query_kind; /* NULL: every object is GeometricQueryType::Contacts(query_limit, ang_pred); else per object 0 Contacts,
+                                  1 Proximity(query_limit): a sensor */
 } ncb2d_objects;
 /* ncollide2d CollisionWorld::update for such a world (pipeline/world.rs:104-119): fat AABBs -> broad-phase pairs (object1 = larger handle,
  * like the 3-D path) -> contact manifolds from BallBall / BallConvexPolyhedron / ConvexPolyhedronConvexPolyhedron generators with 2-D
@@ -465,6 +467,10 @@ typedef struct ncb2d_objects {
 int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* objs, float margin, uint32_t* pairs, uint32_t cap_pairs, uint32_t* manifold_start,
                        uint8_t* manifold_count, float* contacts, uint32_t* features, uint32_t cap_contacts, uint32_t* n_pairs,
                        uint32_t* n_contacts, uint32_t* diag);
+/* Proximity status of every pair of the last ncb2d_world_update, in the order of its pairs: NCB_PROXIMITY_* for pairs with a sensor (the
+ * narrow phase runs the proximity detector instead of a contact generator on them, narrow_phase.rs:138-167: BallBall / PlaneSupportMap /
+ * SupportMapSupportMap detectors with margin = the two query limits added; their manifolds are empty), NCB_PROXIMITY_NONE for the others. */
+int ncb2d_world_fetch_proximity(ncb_ctx* ctx, uint8_t* prox, uint32_t cap_pairs);
 
 /* ---- ncollide2d: RayCast for Polyline (the 2-D counterpart of the TriMesh ray path) -------------------------------------------------- */
 /* Polyline::new(points, indices) (shape/polyline.rs:57-120): 2 floats per point, 2 point indices per edge; edges == NULL builds the

@@ -1254,6 +1254,8 @@ struct World2Args {
     float* contacts;     // 7 floats per contact
     uint32_t* features;  // 2 words per contact
     uint32_t* counters;  // [0] contacts allocated, [1] reference panics, [2] EPA overflows, [3] manifold overflows
+    const uint8_t* qkind;  // nullptr, or per object 1 = GeometricQueryType::Proximity (a sensor)
+    uint8_t* prox;         // per pair: NCB_PROXIMITY_* for sensor pairs, NCB_PROXIMITY_NONE otherwise
 };
 __device__ __forceinline__ Operand2 world_operand(const World2Args& A, uint32_t i) {
     float2 t = __ldg(&A.pos[i]), r = __ldg(&A.rot[i]);
@@ -1279,7 +1281,14 @@ __global__ void __launch_bounds__(64) k_narrow2d(World2Args A) {
     float linear = __ldg(&A.qlimit[pr.x]) + __ldg(&A.qlimit[pr.y]);
     Manifold2d mf;
     int flags = 0;
-    manifold_of_pair(g1, g2, linear, __ldg(&A.cos_ang[pr.x]), __ldg(&A.cos_ang[pr.y]), A.cos_one_degree, mf, flags);
+    const bool sensor = A.qkind && (__ldg(&A.qkind[pr.x]) | __ldg(&A.qkind[pr.y]));
+    if (sensor) {  // Interaction::Proximity (narrow_phase.rs:138-167): the proximity dispatcher's detector, margin = the two limits added
+        mf.n = 0, mf.overflow = false;
+        A.prox[p] = (g1.kind == D2_PLANE && g2.kind == D2_PLANE) ? (uint8_t)NCB_PROXIMITY_NONE : proximity_of_pair(g1, g2, linear);
+    } else {
+        if (A.prox) A.prox[p] = (uint8_t)NCB_PROXIMITY_NONE;
+        manifold_of_pair(g1, g2, linear, __ldg(&A.cos_ang[pr.x]), __ldg(&A.cos_ang[pr.y]), A.cos_one_degree, mf, flags);
+    }
     if (flags & 1) atomicAdd(&A.counters[1], 1u);
     if (flags & 2) atomicAdd(&A.counters[2], 1u);
     if (mf.overflow) atomicAdd(&A.counters[3], 1u);
@@ -1525,6 +1534,10 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
             ctx->err = "ncb2d_world_update: unknown 2-D shape type";
             return NCB_ERR_UNSUPPORTED;
         }
+        if (o->query_kind && o->query_kind[i] > 1) {
+            ctx->err = "ncb2d_world_update: query_kind must be 0 (Contacts) or 1 (Proximity)";
+            return NCB_ERR_ARG;
+        }
         if (t == 2) {
             const float* p = o->shape_param + 4 * (size_t)i;
             any_poly = true;
@@ -1577,6 +1590,10 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
         CK2(cudaMemcpyAsync(d_poly.p, o->poly_points, 8 * (size_t)o->n_poly_points, cudaMemcpyHostToDevice, s));
         CK2(cudaMemcpyAsync(d_nrm.p, o->poly_normals, 8 * (size_t)o->n_poly_points, cudaMemcpyHostToDevice, s));
     }
+    if (o->query_kind) {
+        CK2(ctx->d2.qkind.reserve(n));
+        CK2(cudaMemcpyAsync(ctx->d2.qkind.p, o->query_kind, n, cudaMemcpyHostToDevice, s));
+    }
     int r = reserve_broad(ctx, n);
     if (r) return r;
     mark("alloc+h2d");
@@ -1612,6 +1629,8 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     A.cap_pairs = (uint32_t)capp, A.cap_contacts = (uint32_t)capc;
     A.manifold_start = d_start.p, A.manifold_count = d_count.p, A.contacts = d_contacts.p, A.features = d_feat.p;
     A.counters = d_cnt.p;
+    CK2(ctx->d2.prox.reserve(capp));
+    A.qkind = o->query_kind ? ctx->d2.qkind.p : nullptr, A.prox = ctx->d2.prox.p;
     d2::k_narrow2d<<<(uint32_t)((capp + 63) / 64), 64, 0, s>>>(A);
     CK2(cudaGetLastError());
     mark("narrow");
@@ -1622,6 +1641,7 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     CK2(cudaStreamSynchronize(s));
     uint32_t np = ctx->last_counters.n_pairs, nc = cnt[0];
     *n_pairs = np, *n_contacts = nc;
+    ctx->d2.last_pairs = np < capp ? np : (uint32_t)capp;
     if (diag) diag[0] = cnt[1], diag[1] = cnt[2], diag[2] = cnt[3], diag[3] = ctx->last_counters.stack_overflow;
     uint32_t wp = np < cap_pairs ? np : cap_pairs, wc = nc < cap_contacts ? nc : cap_contacts;
     if (pairs && wp) CK2(cudaMemcpyAsync(pairs, ctx->pairs.p, 8 * (size_t)wp, cudaMemcpyDeviceToHost, s));
@@ -1632,6 +1652,17 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     CK2(cudaStreamSynchronize(s));
     mark("d2h");
     return (np > cap_pairs || nc > cap_contacts) ? 1 : NCB_OK;
+}
+
+int ncb2d_world_fetch_proximity(ncb_ctx* ctx, uint8_t* prox, uint32_t cap_pairs) {
+    if (!ctx || (cap_pairs && !prox)) return NCB_ERR_ARG;
+    CK2(cudaSetDevice(ctx->device));
+    uint32_t np = ctx->d2.last_pairs, w = np < cap_pairs ? np : cap_pairs;
+    if (w) {
+        CK2(cudaMemcpyAsync(prox, ctx->d2.prox.p, w, cudaMemcpyDeviceToHost, ctx->stream));
+        CK2(cudaStreamSynchronize(ctx->stream));
+    }
+    return np > cap_pairs ? 1 : NCB_OK;
 }
 
 }  // extern "C"

@@ -338,7 +338,8 @@ struct ncb_ctx {
         ncb::DevBuf<uint32_t> type, groups, start, feat, cnt;
         ncb::DevBuf<float4> param;
         ncb::DevBuf<float> ql, cang, poly, nrm, contacts;
-        ncb::DevBuf<uint8_t> count;
+        ncb::DevBuf<uint8_t> count, qkind, prox;
+        uint32_t last_pairs = 0;  // pairs of the last update (ncb2d_world_fetch_proximity)
     } d2;
 };
 

@@ -194,8 +194,16 @@ class World2D:
         self.query_limit = np.ascontiguousarray(np.broadcast_to(np.asarray(linear, dtype=np.float32).reshape(-1), (self.n,)), dtype=np.float32)
         self.ang_pred = np.ascontiguousarray(np.broadcast_to(np.asarray(angular, dtype=np.float32).reshape(-1), (self.n,)), dtype=np.float32)
         self.groups = None if groups is None else as_u32(groups).reshape(-1, 3)
+        self.query_kind = None  # or uint8 [n]: 1 = GeometricQueryType::Proximity(query_limit), a sensor (set_sensors)
         if len(self.pos) != self.n:
             raise ValueError("one position per shape")
+
+    def set_sensors(self, mask):
+        """Objects with mask != 0 become ``GeometricQueryType::Proximity(query_limit)``: pairs with one get a proximity status instead of a manifold."""
+        self.query_kind = np.ascontiguousarray(np.asarray(mask) != 0, dtype=np.uint8)
+        if len(self.query_kind) != self.n:
+            raise ValueError("one flag per object")
+        return self
 
 
     @classmethod
@@ -213,13 +221,14 @@ class World2D:
         w.query_limit = np.full(w.n, kw.get("linear", 0.02), dtype=np.float32)
         w.ang_pred = np.full(w.n, kw.get("angular", 0.0), dtype=np.float32)
         w.groups = None
+        w.query_kind = None
         return w
 
 
 class _Objects2DC(C.Structure):
     _fields_ = [("n", C.c_uint32), ("pos", C.c_void_p), ("rot", C.c_void_p), ("shape_type", C.c_void_p), ("shape_param", C.c_void_p),
                 ("groups", C.c_void_p), ("query_limit", C.c_void_p), ("ang_pred", C.c_void_p), ("poly_points", C.c_void_p),
-                ("poly_normals", C.c_void_p), ("n_poly_points", C.c_uint32)]
+                ("poly_normals", C.c_void_p), ("n_poly_points", C.c_uint32), ("query_kind", C.c_void_p)]
 
 
 def world_update(ctx, w: World2D, bufs=None):
@@ -233,6 +242,7 @@ def world_update(ctx, w: World2D, bufs=None):
     o.groups = w.groups.ctypes.data if w.groups is not None else None
     o.query_limit, o.ang_pred = w.query_limit.ctypes.data, w.ang_pred.ctypes.data
     o.poly_points, o.poly_normals, o.n_poly_points = w.points.ctypes.data, w.normals.ctypes.data, len(w.points)
+    o.query_kind = w.query_kind.ctypes.data if getattr(w, "query_kind", None) is not None else None
     cap_p, cap_c = max(8 * w.n, 1024), max(8 * w.n, 1024)
     while True:
         if bufs is not None:
@@ -250,6 +260,10 @@ def world_update(ctx, w: World2D, bufs=None):
                       "ncb2d_world_update")
         if r == 0:
             P, Cn = npairs.value, ncont.value
-            return {"pairs": pairs[:P], "manifold_start": start[:P], "manifold_count": count[:P], "contacts": contacts[:Cn], "features": feats[:Cn],
+            prox = None
+            if o.query_kind:
+                prox = np.zeros(P, dtype=np.uint8)
+                ctx.check(ctx.lib.ncb2d_world_fetch_proximity(ctx.h, ptr(prox), C.c_uint32(P)), "ncb2d_world_fetch_proximity")
+            return {"proximity": prox, "pairs": pairs[:P], "manifold_start": start[:P], "manifold_count": count[:P], "contacts": contacts[:Cn], "features": feats[:Cn],
                     "diag": dict(zip(("ref_panics", "epa_overflow", "manifold_overflow", "stack_overflow"), diag.tolist()))}
         cap_p, cap_c = max(cap_p, npairs.value + 1024), max(cap_c, ncont.value + 1024)

@@ -1361,6 +1361,7 @@ struct orc2_objects {
     const real* ang_pred;
     const real* poly_points;
     const real* poly_normals;
+    const uint8_t* query_kind;  // NULL, or per object 1 = GeometricQueryType::Proximity
 };
 static Shape2 obj_shape(const orc2_objects* o, uint32_t i) {
     Shape2 g;
@@ -1383,14 +1384,34 @@ void orc2_compute_aabbs(const orc2_objects* o, real margin, real* out) {
 }
 // Contact manifolds of the given pairs (object1, object2): manifold_off[P + 1], contacts = 9 reals (world1, world2, normal, depth, f1, f2
 // as reals holding the 32-bit feature codes: kind << 30 | id with kind 1 = face, 2 = vertex).  Returns the number of contacts.
+// prox (optional): per pair the status of the proximity detector for pairs with a sensor (narrow_phase.rs:138-167; a fresh detector:
+// BallBall / PlaneSupportMap / SupportMapSupportMap with sep_axis = None), 255 for contact pairs and for plane x plane (no detector).
 uint64_t orc2_narrow_phase(const orc2_objects* o, uint64_t n_pairs, const uint32_t* pairs, uint32_t* manifold_off, real* contacts, uint32_t* feats,
-                           uint64_t cap, uint32_t* panics) {
+                           uint64_t cap, uint32_t* panics, uint8_t* prox) {
     uint64_t nc = 0;
     int panicked = 0;
     for (uint64_t k = 0; k < n_pairs; ++k) {
         uint32_t i1 = pairs[2 * k], i2 = pairs[2 * k + 1];
         Manifold2 mf;
         real linear = o->query_limit[i1] + o->query_limit[i2];
+        bool sensor = o->query_kind && (o->query_kind[i1] || o->query_kind[i2]);
+        if (prox) prox[k] = 255;
+        if (sensor) {
+            Shape2 g1 = obj_shape(o, i1), g2 = obj_shape(o, i2);
+            Iso2 m1 = obj_iso(o, i1), m2 = obj_iso(o, i2);
+            int r = 255;
+            if (g1.type == PLANE2 && g2.type == PLANE2)
+                r = 255;
+            else if (g1.type == BALL2 && g2.type == BALL2)
+                r = proximity_ball_ball(m1.t, g1.radius, m2.t, g2.radius, linear);
+            else if (g1.type == PLANE2)
+                r = proximity_plane_sm(m1, g1.he, m2, g2, linear);
+            else if (g2.type == PLANE2)
+                r = proximity_plane_sm(m2, g2.he, m1, g1, linear);
+            else
+                r = proximity_sm_sm(m1, g1, m2, g2, linear);
+            if (prox) prox[k] = (uint8_t)r;
+        } else
         generate_contacts2(obj_shape(o, i1), obj_iso(o, i1), obj_shape(o, i2), obj_iso(o, i2), linear, std::cos(o->ang_pred[i1]),
                            std::cos(o->ang_pred[i2]), mf, &panicked);
         manifold_off[k] = (uint32_t)nc;

@@ -193,7 +193,7 @@ void orc2_contact(uint64_t n, const uint32_t* type1, const real* param1, const r
 struct orc2_objects;
 void orc2_compute_aabbs(const struct orc2_objects* o, real margin, real* out);
 uint64_t orc2_narrow_phase(const struct orc2_objects* o, uint64_t n_pairs, const uint32_t* pairs, uint32_t* manifold_off, real* contacts,
-                           uint32_t* feats, uint64_t cap, uint32_t* panics);
+                           uint32_t* feats, uint64_t cap, uint32_t* panics, uint8_t* prox);
 
 /* ncollide2d query::proximity for n pairs, one margin per pair; out: 0 Intersecting, 1 WithinMargin, 2 Disjoint, 255 plane x plane. */
 void orc2_proximity(uint64_t n, const uint32_t* type1, const real* param1, const real* pose1, const uint32_t* type2, const real* param2,

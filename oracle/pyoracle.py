@@ -317,12 +317,14 @@ class Oracle:
 
         class O2(C.Structure):
             _fields_ = [("n", C.c_uint32), ("pos", C.c_void_p), ("rot", C.c_void_p), ("type", C.c_void_p), ("param", C.c_void_p),
-                        ("query_limit", C.c_void_p), ("ang_pred", C.c_void_p), ("poly_points", C.c_void_p), ("poly_normals", C.c_void_p)]
+                        ("query_limit", C.c_void_p), ("ang_pred", C.c_void_p), ("poly_points", C.c_void_p), ("poly_normals", C.c_void_p),
+                        ("query_kind", C.c_void_p)]
 
         keep = [np.ascontiguousarray(a, dtype=dt) for a in (w.pos, w.rot, w.param, w.query_limit, w.ang_pred, w.points, w.normals)]
         typ = np.ascontiguousarray(w.type, dtype=np.uint32)
+        qk = np.ascontiguousarray(w.query_kind, dtype=np.uint8) if getattr(w, "query_kind", None) is not None else None
         o = O2(w.n, keep[0].ctypes.data, keep[1].ctypes.data, typ.ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data, keep[4].ctypes.data,
-               keep[5].ctypes.data, keep[6].ctypes.data)
+               keep[5].ctypes.data, keep[6].ctypes.data, qk.ctypes.data if qk is not None else None)
         fat = np.zeros((w.n, 6), dtype=dt)
         self.lib.orc2_compute_aabbs(C.byref(o), self.creal(w.margin), C.c_void_p(fat.ctypes.data))
         pairs = self.broad_phase(fat, w.groups, mode=1)
@@ -334,9 +336,12 @@ class Oracle:
         panics = C.c_uint32(0)
         self.lib.orc2_narrow_phase.restype = C.c_uint64
         pr = np.ascontiguousarray(pairs, dtype=np.uint32)
+        prox = np.full(P, 255, dtype=np.uint8)
         nc = self.lib.orc2_narrow_phase(C.byref(o), C.c_uint64(P), C.c_void_p(pr.ctypes.data), C.c_void_p(off.ctypes.data),
-                                        C.c_void_p(contacts.ctypes.data), C.c_void_p(feats.ctypes.data), C.c_uint64(cap), C.byref(panics))
+                                        C.c_void_p(contacts.ctypes.data), C.c_void_p(feats.ctypes.data), C.c_uint64(cap), C.byref(panics),
+                                        C.c_void_p(prox.ctypes.data))
         assert nc <= cap
+        self.last_proximity2d = prox  # per pair: 0 / 1 / 2 for pairs with a sensor, 255 otherwise
         return pairs, off, contacts[:nc], feats[:nc], panics.value, fat
 
     def broad_phase_persistent(self, margin):

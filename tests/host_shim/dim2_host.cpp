@@ -71,9 +71,21 @@ void shim2_aabbs(uint32_t n, const float* pos, const float* rot, const uint32_t*
 }
 
 // k_narrow2d over given pairs: manifold_off[P + 1], contacts (7 floats), features (2 words); returns the number of contacts
+// qkind / prox may be NULL (no sensors): k_narrow2d's body per pair
+uint64_t shim2_narrow_sensors(uint32_t n, const float* pos, const float* rot, const uint32_t* type, const float* param, const float* qlimit,
+                              const float* ang_pred, const float* poly, const float* nrm, uint64_t n_pairs, const uint32_t* pairs,
+                              uint32_t* manifold_off, float* contacts, uint32_t* feats, uint64_t cap, uint32_t* flag_counts, const uint8_t* qkind,
+                              uint8_t* prox);
 uint64_t shim2_narrow(uint32_t n, const float* pos, const float* rot, const uint32_t* type, const float* param, const float* qlimit,
                       const float* ang_pred, const float* poly, const float* nrm, uint64_t n_pairs, const uint32_t* pairs, uint32_t* manifold_off,
                       float* contacts, uint32_t* feats, uint64_t cap, uint32_t* flag_counts) {
+    return shim2_narrow_sensors(n, pos, rot, type, param, qlimit, ang_pred, poly, nrm, n_pairs, pairs, manifold_off, contacts, feats, cap, flag_counts,
+                                nullptr, nullptr);
+}
+uint64_t shim2_narrow_sensors(uint32_t n, const float* pos, const float* rot, const uint32_t* type, const float* param, const float* qlimit,
+                              const float* ang_pred, const float* poly, const float* nrm, uint64_t n_pairs, const uint32_t* pairs,
+                              uint32_t* manifold_off, float* contacts, uint32_t* feats, uint64_t cap, uint32_t* flag_counts, const uint8_t* qkind,
+                              uint8_t* prox) {
     (void)n;
     const float c1 = cosf((float)(3.14159265358979323846 / 180.0));
     uint64_t nc = 0;
@@ -82,8 +94,14 @@ uint64_t shim2_narrow(uint32_t n, const float* pos, const float* rot, const uint
         uint32_t i1 = pairs[2 * p], i2 = pairs[2 * p + 1];
         Manifold2d mf;
         int flags = 0;
-        manifold_of_pair(obj(i1, pos, rot, type, param, poly, nrm), obj(i2, pos, rot, type, param, poly, nrm), qlimit[i1] + qlimit[i2],
-                         cosf(ang_pred[i1]), cosf(ang_pred[i2]), c1, mf, flags);
+        Operand2 g1 = obj(i1, pos, rot, type, param, poly, nrm), g2 = obj(i2, pos, rot, type, param, poly, nrm);
+        if (qkind && (qkind[i1] | qkind[i2])) {
+            mf.n = 0, mf.overflow = false;
+            prox[p] = (g1.kind == D2_PLANE && g2.kind == D2_PLANE) ? (uint8_t)NCB_PROXIMITY_NONE : proximity_of_pair(g1, g2, qlimit[i1] + qlimit[i2]);
+        } else {
+            if (prox) prox[p] = (uint8_t)NCB_PROXIMITY_NONE;
+            manifold_of_pair(g1, g2, qlimit[i1] + qlimit[i2], cosf(ang_pred[i1]), cosf(ang_pred[i2]), c1, mf, flags);
+        }
         flag_counts[0] += flags & 1, flag_counts[1] += (flags >> 1) & 1, flag_counts[2] += mf.overflow ? 1 : 0;
         manifold_off[p] = (uint32_t)nc;
         for (int k = 0; k < mf.n; ++k, ++nc) {

@@ -455,3 +455,71 @@ def test_device_source_proximity_equals_oracle(dim2_shim, oracle, seed, kinds):
     want = oracle.proximity2d(t1, p1, m1, t2, p2, m2, pts, margins)
     assert np.array_equal(out, want), np.flatnonzero(out != want)[:10]
     assert min(np.bincount(want, minlength=3)) > 2000
+
+
+# ---- sensors in the 2-D world (GeometricQueryType::Proximity) -------------------------------------------------------------------
+def _sensor_world(n, seed, planes=0):
+    w = random_world(n, seed, (0, 1, 2), planes=planes)
+    w.set_sensors(np.random.default_rng(seed).random(w.n) < 0.25)
+    return w
+
+
+def test_oracle_world2d_sensors(oracle64):
+    """ORACLE properties: a pair with a sensor carries no manifold and the status query::proximity gives for the two shapes with
+    margin = the two query limits added; the other pairs' manifolds are those of the same world without sensors."""
+    w = _sensor_world(2500, 71, planes=2)
+    pairs, off, contacts, feats, panics, fat = oracle64.world_update2d(w)
+    prox = oracle64.last_proximity2d
+    sensor = (w.query_kind[pairs[:, 0]] | w.query_kind[pairs[:, 1]]).astype(bool)
+    both_planes = (w.type[pairs[:, 0]] == 3) & (w.type[pairs[:, 1]] == 3)
+    assert sensor.sum() > 500 and (~sensor).sum() > 500
+    assert (prox[~sensor] == 255).all() and (prox[sensor & ~both_planes] <= 2).all()
+    assert (np.diff(off)[sensor] == 0).all()
+    i1, i2 = pairs[sensor & ~both_planes, 0], pairs[sensor & ~both_planes, 1]
+    pose = lambda i: np.concatenate([w.pos[i], w.rot[i]], axis=1)  # noqa: E731
+    want = oracle64.proximity2d(w.type[i1], w.param[i1], pose(i1), w.type[i2], w.param[i2], pose(i2), w.points, w.query_limit[i1] + w.query_limit[i2])
+    assert np.array_equal(prox[sensor & ~both_planes], want)
+    assert min(np.bincount(want, minlength=3)[:2]) > 50
+    plain = random_world(2500, 71, (0, 1, 2), planes=2)
+    p2, off2, c2, f2, _, _ = oracle64.world_update2d(plain)
+    assert np.array_equal(p2, pairs)
+    for k in np.flatnonzero(~sensor)[:400]:
+        assert np.array_equal(contacts[off[k] : off[k + 1]], c2[off2[k] : off2[k + 1]])
+
+
+def test_device_source_world2d_sensors_equal_oracle(dim2_shim, oracle):
+    import ctypes as C
+
+    w = _sensor_world(2500, 72, planes=2)
+    pairs, off, ocontacts, ofeats, panics, fat = oracle.world_update2d(w)
+    oprox = oracle.last_proximity2d
+    P = len(pairs)
+    pr = np.ascontiguousarray(pairs, dtype=np.uint32)
+    doff, dc, df = np.zeros(P + 1, dtype=np.uint32), np.zeros((4 * P + 16, 7), dtype=np.float32), np.zeros((4 * P + 16, 2), dtype=np.uint32)
+    flags, prox = np.zeros(3, dtype=np.uint32), np.zeros(P, dtype=np.uint8)
+    dim2_shim.shim2_narrow_sensors.restype = C.c_uint64
+    nc = dim2_shim.shim2_narrow_sensors(C.c_uint32(w.n), _vp(w.pos), _vp(w.rot), _vp(w.type), _vp(w.param), _vp(w.query_limit), _vp(w.ang_pred),
+                                        _vp(w.points), _vp(w.normals), C.c_uint64(P), _vp(pr), _vp(doff), _vp(dc), _vp(df), C.c_uint64(len(dc)),
+                                        _vp(flags), _vp(w.query_kind), _vp(prox))
+    assert np.array_equal(prox, oprox) and (prox != 255).sum() > 500
+    assert np.array_equal(doff, off) and nc == len(ocontacts)
+    assert np.array_equal(_bits(dc[:nc]), _bits(ocontacts)) and np.array_equal(df[:nc], ofeats)
+
+
+@pytest.mark.gpu
+def test_device_world2d_sensors_match_oracle(ctx, oracle):
+    from ncollide_b200._ffi import NcbError
+
+    w = _sensor_world(6000, 73, planes=2)
+    res = dim2.world_update(ctx, w)
+    pairs, off, ocontacts, ofeats, panics, fat = oracle.world_update2d(w)
+    oprox = oracle.last_proximity2d
+    got = {tuple(p): k for k, p in enumerate(res["pairs"].tolist())}
+    assert len(got) == len(pairs) and set(got) == set(map(tuple, pairs.tolist()))
+    order = np.array([got[tuple(p)] for p in pairs.tolist()])
+    assert np.array_equal(res["proximity"][order], oprox)
+    assert (oprox != 255).sum() > 1000 and min(np.bincount(oprox[oprox != 255], minlength=3)[:2]) > 50
+    assert np.array_equal(res["manifold_count"][order], np.diff(off))
+    w.query_kind[0] = 7
+    with pytest.raises(NcbError):
+        dim2.world_update(ctx, w)
