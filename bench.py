@@ -809,11 +809,14 @@ def bench_dim2(ctx, n_pairs=1_000_000, cpu_sample=100_000):
     m2 = dim2.isometry2(c1 + rng.uniform(-1.2, 1.2, size=(n_pairs, 2)), rng.uniform(-np.pi, np.pi, size=n_pairs))
     args = (typ[pick1], par[pick1], m1, typ[pick2], par[pick2], m2, pts)
     dim2.contact(ctx, *args, prediction=0.02, poly_normals=nrm)
-    t0 = time.perf_counter()
-    found, out, info = dim2.contact(ctx, *args, prediction=0.02, poly_normals=nrm)
-    ms = (time.perf_counter() - t0) * 1e3
+    tms = []
+    for _ in range(3):  # pageable host buffers: the median of three calls (a single call has been seen at 8x under host memory pressure)
+        t0 = time.perf_counter()
+        found, out, info = dim2.contact(ctx, *args, prediction=0.02, poly_normals=nrm)
+        tms.append((time.perf_counter() - t0) * 1e3)
+    ms = float(np.median(tms))
     res = {"workload": f"{n_pairs} random 2-D pairs (balls, cuboids, convex polygons of 3-12 vertices), query::contact with prediction 0.02",
-           "ms": ms, "Mpairs_per_s": n_pairs / ms / 1e3, "contacts_found": int(found.sum()), **info}
+           "ms": ms, "ms_calls": [round(t, 2) for t in tms], "Mpairs_per_s": n_pairs / ms / 1e3, "contacts_found": int(found.sum()), **info}
     # the 2-D world update: 1 M objects (balls, cuboids, polygons), about 3 fat-box neighbours each
     n_w = n_pairs
     side = float(np.sqrt(n_w * 0.8 / 2.5))
