@@ -471,6 +471,15 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* objs, float margin, ui
  * narrow phase runs the proximity detector instead of a contact generator on them, narrow_phase.rs:138-167: BallBall / PlaneSupportMap /
  * SupportMapSupportMap detectors with margin = the two query limits added; their manifolds are empty), NCB_PROXIMITY_NONE for the others. */
 int ncb2d_world_fetch_proximity(ncb_ctx* ctx, uint8_t* prox, uint32_t cap_pairs);
+/* World ray queries of ncollide2d: glue::interferences_with_ray (first_only = 0) / first_interference_with_ray (first_only = 1)
+ * (pipeline/glue/query.rs:13-77,183-224) against the world of the last ncb2d_world_update (its objects and broad-phase boxes stay on the
+ * device).  rays[5 n] = origin x y, dir x y, max_toi; groups = the query's CollisionGroups (membership, whitelist, blacklist) or NULL.
+ * A candidate is an object whose stored (fat) box the ray enters within max_toi; it is kept when the groups allow it and its shape's
+ * RayCast::toi_and_normal_with_ray(position, ray, max_toi, solid = true) answers Some.  Rows sorted by (ray, handle): idx[2 k] = (ray,
+ * handle), val[3 k] = (toi, normal), feat[k] as in ncb2d_ray_cast; first_only keeps the smallest toi per ray (ties: smallest handle).
+ * cap in rows; *n_out = rows found; returns 1 when truncated. */
+int ncb2d_world_ray_cast(ncb_ctx* ctx, uint32_t n_rays, const float* rays, const uint32_t* groups, int first_only, uint32_t* idx, float* val,
+                         uint32_t* feat, uint32_t cap, uint32_t* n_out);
 
 /* ---- ncollide2d: RayCast for Polyline (the 2-D counterpart of the TriMesh ray path) -------------------------------------------------- */
 /* Polyline::new(points, indices) (shape/polyline.rs:57-120): 2 floats per point, 2 point indices per edge; edges == NULL builds the

@@ -17,6 +17,9 @@
 //   ball x convex polygon                 query/point/point_support_map.rs:14-55,120-146 (GJK / EPA projection of the ball centre),
 //                                         shape/convex_polygon.rs:139-152,186-203 (feature normal, support feature)
 // Not in this slice: the manifold generators / ConvexPolygonalFeature2, the 2-D broad phase and world.
+#ifndef NCB_HOST_SHIM
+#include <cub/cub.cuh>
+#endif
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -1305,6 +1308,133 @@ __global__ void __launch_bounds__(64) k_narrow2d(World2Args A) {
     }
 }
 
+// ---- world ray queries: glue::interferences_with_ray / first_interference_with_ray (pipeline/glue/query.rs:13-77,183-224) -------------
+// against the world of the last ncb2d_world_update: candidates = objects whose stored (fat) box the ray enters within max_toi
+// (AABB::toi_with_ray, DIM = 2), the query's collision groups, then the shape's RayCast.  One thread per ray over the update's LBVH.
+struct WorldRay2Args {
+    World2Args W;
+    const float4 *leaf_lo, *leaf_hi, *nodes;
+    uint32_t n_tree;         // leaves in the tree; [n_tree, W.n) are the outliers (planes), tested one by one
+    const uint32_t* groups;  // 3 words per object, or nullptr (default groups)
+    uint32_t qg[3];
+    int use_groups;
+    const float* rays;       // origin x y, dir x y, max_toi
+    uint32_t n_rays;
+    unsigned long long* keys;  // ray << 32 | handle
+    float4* vals;              // toi, normal x y, -
+    uint32_t* feats;
+    uint32_t cap;
+    uint32_t* counter;
+    uint32_t* trav_overflow;
+};
+template <bool FIRST>
+__device__ __forceinline__ void world_ray_leaf(const WorldRay2Args& A, uint32_t ri, W2 o, W2 d, float max_toi, uint32_t handle, RayHit2& best,
+                                               uint32_t& best_h) {
+    if (A.use_groups) {  // CollisionGroups::can_interact_with_groups (collision_groups.rs:353-359); objects without groups have the defaults
+        uint32_t m1 = 0x3fffffffu, w1 = 0x3fffffffu, b1 = 0u;
+        if (A.groups) m1 = __ldg(&A.groups[3 * handle]), w1 = __ldg(&A.groups[3 * handle + 1]), b1 = __ldg(&A.groups[3 * handle + 2]);
+        if (!((m1 & A.qg[2]) == 0 && (A.qg[0] & b1) == 0 && (m1 & A.qg[1]) != 0 && (A.qg[0] & w1) != 0)) return;
+    }
+    RayHit2 h = shape_ray_cast2(world_operand(A.W, handle), o, d, max_toi);
+    if (!h.hit) return;
+    if (FIRST) {
+        if (!best.hit || h.toi < best.toi || (h.toi == best.toi && handle < best_h)) best = h, best_h = handle;
+    } else {
+        uint32_t k = atomicAdd(A.counter, 1u);
+        if (k < A.cap) {
+            A.keys[k] = ((unsigned long long)ri << 32) | handle;
+            A.vals[k] = make_float4(h.toi, h.n.x, h.n.y, 0.f);
+            A.feats[k] = h.feature;
+        }
+    }
+}
+__device__ __forceinline__ bool slab2(float4 lo, float4 hi, W2 o, W2 d, W2 inv, float max_toi) {  // ray_aabb.rs:13-50, DIM = 2
+    float tmin = 0.f, tmax = max_toi;
+    if (d.x == 0.f) {
+        if (o.x < lo.x || o.x > hi.x) return false;
+    } else {
+        float a = (lo.x - o.x) * inv.x, b = (hi.x - o.x) * inv.x;
+        tmin = fmaxf(tmin, fminf(a, b)), tmax = fminf(tmax, fmaxf(a, b));
+        if (tmin > tmax) return false;
+    }
+    if (d.y == 0.f) {
+        if (o.y < lo.y || o.y > hi.y) return false;
+    } else {
+        float a = (lo.y - o.y) * inv.y, b = (hi.y - o.y) * inv.y;
+        tmin = fmaxf(tmin, fminf(a, b)), tmax = fminf(tmax, fmaxf(a, b));
+        if (tmin > tmax) return false;
+    }
+    return true;
+}
+template <bool FIRST>
+__global__ void __launch_bounds__(128) k_world_ray2d(WorldRay2Args A) {
+    uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ri >= A.n_rays) return;
+    const float* q = A.rays + 5 * (size_t)ri;
+    const W2 o = w2(__ldg(q), __ldg(q + 1)), d = w2(__ldg(q + 2), __ldg(q + 3)), inv = w2(1.f / d.x, 1.f / d.y);
+    const float max_toi = __ldg(q + 4);
+    RayHit2 best = ray2_miss();
+    uint32_t best_h = 0;
+    const uint32_t m = A.n_tree;
+    if (m >= 2) {
+        uint32_t stack[64];
+        int sp = 0;
+        uint32_t node = 0;
+        for (;;) {
+            const float4* rec = A.nodes + 4 * (size_t)node;
+            float4 Llo = __ldg(rec + 0), Lhi = __ldg(rec + 1), Rlo = __ldg(rec + 2), Rhi = __ldg(rec + 3);
+            uint32_t left = __float_as_uint(Llo.w), right = __float_as_uint(Lhi.w);
+            bool goL = slab2(Llo, Lhi, o, d, inv, max_toi), goR = slab2(Rlo, Rhi, o, d, inv, max_toi);
+            if (goL && (left & 0x80000000u)) {
+                world_ray_leaf<FIRST>(A, ri, o, d, max_toi, __float_as_uint(__ldg(&A.leaf_lo[left & 0x7fffffffu].w)), best, best_h);
+                goL = false;
+            }
+            if (goR && (right & 0x80000000u)) {
+                world_ray_leaf<FIRST>(A, ri, o, d, max_toi, __float_as_uint(__ldg(&A.leaf_lo[right & 0x7fffffffu].w)), best, best_h);
+                goR = false;
+            }
+            if (goL && goR) {
+                if (sp < 64)
+                    stack[sp++] = right;
+                else
+                    atomicAdd(A.trav_overflow, 1u);
+                node = left;
+            } else if (goL) {
+                node = left;
+            } else if (goR) {
+                node = right;
+            } else {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+        }
+    } else if (m == 1) {
+        float4 lo = __ldg(&A.leaf_lo[0]), hi = __ldg(&A.leaf_hi[0]);
+        if (slab2(lo, hi, o, d, inv, max_toi)) world_ray_leaf<FIRST>(A, ri, o, d, max_toi, __float_as_uint(lo.w), best, best_h);
+    }
+    for (uint32_t k = m; k < A.W.n; ++k) {
+        float4 lo = __ldg(&A.leaf_lo[k]), hi = __ldg(&A.leaf_hi[k]);
+        if (slab2(lo, hi, o, d, inv, max_toi)) world_ray_leaf<FIRST>(A, ri, o, d, max_toi, __float_as_uint(lo.w), best, best_h);
+    }
+    if (FIRST && best.hit) {
+        uint32_t k = atomicAdd(A.counter, 1u);
+        if (k < A.cap) {
+            A.keys[k] = ((unsigned long long)ri << 32) | best_h;
+            A.vals[k] = make_float4(best.toi, best.n.x, best.n.y, 0.f);
+            A.feats[k] = best.feature;
+        }
+    }
+}
+__global__ void k_iota2d(uint32_t* p, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+__global__ void k_gather_rows2d(const uint32_t* __restrict__ order, const float4* __restrict__ vals, const uint32_t* __restrict__ feats, uint32_t n,
+                                float4* __restrict__ vals_out, uint32_t* __restrict__ feats_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vals_out[i] = vals[order[i]], feats_out[i] = feats[order[i]];
+}
+
 #endif  // NCB_HOST_SHIM (kernels)
 
 }  // namespace d2
@@ -1549,6 +1679,7 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     }
     CK2(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
+    ctx->d2.last_n = 0, ctx->d2.last_pairs = 0;  // set again when this update has succeeded
     // NCB2D_PROFILE=1: wall time per phase (with a stream synchronisation at every boundary) on stderr
     static const bool prof = getenv("NCB2D_PROFILE") != nullptr;
     auto t_last = std::chrono::steady_clock::now();
@@ -1642,6 +1773,7 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     uint32_t np = ctx->last_counters.n_pairs, nc = cnt[0];
     *n_pairs = np, *n_contacts = nc;
     ctx->d2.last_pairs = np < capp ? np : (uint32_t)capp;
+    ctx->d2.last_n = n, ctx->d2.last_groups = o->groups != nullptr;
     if (diag) diag[0] = cnt[1], diag[1] = cnt[2], diag[2] = cnt[3], diag[3] = ctx->last_counters.stack_overflow;
     uint32_t wp = np < cap_pairs ? np : cap_pairs, wc = nc < cap_contacts ? nc : cap_contacts;
     if (pairs && wp) CK2(cudaMemcpyAsync(pairs, ctx->pairs.p, 8 * (size_t)wp, cudaMemcpyDeviceToHost, s));
@@ -1652,6 +1784,80 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     CK2(cudaStreamSynchronize(s));
     mark("d2h");
     return (np > cap_pairs || nc > cap_contacts) ? 1 : NCB_OK;
+}
+
+// glue::interferences_with_ray (first_only = 0) / first_interference_with_ray (first_only = 1) against the world of the last
+// ncb2d_world_update.  Rows sorted by (ray, handle); returns 1 when they were truncated at cap.
+int ncb2d_world_ray_cast(ncb_ctx* ctx, uint32_t n_rays, const float* rays, const uint32_t* groups, int first_only, uint32_t* idx, float* val,
+                         uint32_t* feat, uint32_t cap, uint32_t* n_out) {
+    if (!ctx || !n_out || (n_rays && !rays) || (cap && (!idx || !val || !feat))) return NCB_ERR_ARG;
+    *n_out = 0;
+    uint32_t n = ctx->d2.last_n;
+    if (n == 0) {
+        ctx->err = "ncb2d_world_ray_cast: no 2-D world on the device (call ncb2d_world_update first)";
+        return NCB_ERR_ARG;
+    }
+    if (n_rays == 0) return NCB_OK;
+    CK2(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    auto& D = ctx->d2;
+    size_t capd = cap ? cap : 1;
+    CK2(D.q_rays.reserve(5 * (size_t)n_rays));
+    CK2(D.q_keys.reserve(capd));
+    CK2(D.q_keys2.reserve(capd));
+    CK2(D.q_vals.reserve(capd));
+    CK2(D.q_vals2.reserve(capd));
+    CK2(D.q_feat.reserve(capd));
+    CK2(D.q_feat2.reserve(capd));
+    CK2(D.q_order.reserve(capd));
+    CK2(D.q_order2.reserve(capd));
+    CK2(D.q_cnt.reserve(1));
+    CK2(cudaMemcpyAsync(D.q_rays.p, rays, 20 * (size_t)n_rays, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemsetAsync(D.q_cnt.p, 0, 4, s));
+    d2::WorldRay2Args A;
+    memset(&A, 0, sizeof A);
+    A.W.n = n;
+    A.W.pos = D.pos.p, A.W.rot = D.rot.p, A.W.type = D.type.p, A.W.param = D.param.p, A.W.poly = D.poly.p;
+    A.leaf_lo = ctx->leaf_lo.p, A.leaf_hi = ctx->leaf_hi.p, A.nodes = ctx->nodes.p;
+    A.n_tree = n - ctx->last_counters.n_outliers;
+    A.groups = D.last_groups ? D.groups.p : nullptr;
+    A.use_groups = groups != nullptr;
+    if (groups) A.qg[0] = groups[0], A.qg[1] = groups[1], A.qg[2] = groups[2];
+    A.rays = D.q_rays.p, A.n_rays = n_rays;
+    A.keys = D.q_keys.p, A.vals = D.q_vals.p, A.feats = D.q_feat.p, A.cap = cap, A.counter = D.q_cnt.p;
+    A.trav_overflow = trav_overflow_counter(ctx);
+    if (first_only)
+        d2::k_world_ray2d<true><<<(n_rays + 127) / 128, 128, 0, s>>>(A);
+    else
+        d2::k_world_ray2d<false><<<(n_rays + 127) / 128, 128, 0, s>>>(A);
+    CK2(cudaGetLastError());
+    uint32_t found = 0;
+    CK2(cudaMemcpyAsync(&found, D.q_cnt.p, 4, cudaMemcpyDeviceToHost, s));
+    CK2(cudaStreamSynchronize(s));
+    *n_out = found;
+    uint32_t w = found < cap ? found : cap;
+    if (w == 0) return found > cap ? 1 : NCB_OK;
+    // rows in (ray, handle) order: 64-bit radix sort of the keys with their positions, then one gather
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)w, 0, 64);
+    CK2(D.q_tmp.reserve(tmp + 256));
+    d2::k_iota2d<<<(w + 255) / 256, 256, 0, s>>>(D.q_order.p, w);
+    tmp = D.q_tmp.cap;
+    CK2(cub::DeviceRadixSort::SortPairs(D.q_tmp.p, tmp, D.q_keys.p, D.q_keys2.p, D.q_order.p, D.q_order2.p, (int)w, 0, 64, s));
+    d2::k_gather_rows2d<<<(w + 255) / 256, 256, 0, s>>>(D.q_order2.p, D.q_vals.p, D.q_feat.p, w, D.q_vals2.p, D.q_feat2.p);
+    CK2(cudaGetLastError());
+    std::vector<unsigned long long> hk(w);
+    std::vector<float4> hv(w);
+    CK2(cudaMemcpyAsync(hk.data(), D.q_keys2.p, 8 * (size_t)w, cudaMemcpyDeviceToHost, s));
+    CK2(cudaMemcpyAsync(hv.data(), D.q_vals2.p, 16 * (size_t)w, cudaMemcpyDeviceToHost, s));
+    CK2(cudaMemcpyAsync(feat, D.q_feat2.p, 4 * (size_t)w, cudaMemcpyDeviceToHost, s));
+    CK2(cudaStreamSynchronize(s));
+    for (uint32_t k = 0; k < w; ++k) {
+        idx[2 * (size_t)k] = (uint32_t)(hk[k] >> 32), idx[2 * (size_t)k + 1] = (uint32_t)hk[k];
+        val[3 * (size_t)k] = hv[k].x, val[3 * (size_t)k + 1] = hv[k].y, val[3 * (size_t)k + 2] = hv[k].z;
+    }
+    return found > cap ? 1 : NCB_OK;
 }
 
 int ncb2d_world_fetch_proximity(ncb_ctx* ctx, uint8_t* prox, uint32_t cap_pairs) {

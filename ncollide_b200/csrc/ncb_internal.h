@@ -340,6 +340,13 @@ struct ncb_ctx {
         ncb::DevBuf<float> ql, cang, poly, nrm, contacts;
         ncb::DevBuf<uint8_t> count, qkind, prox;
         uint32_t last_pairs = 0;  // pairs of the last update (ncb2d_world_fetch_proximity)
+        uint32_t last_n = 0;      // objects of the last update, whose boxes / tree are still in the context (ncb2d_world_ray_cast)
+        bool last_groups = false;
+        ncb::DevBuf<float> q_rays;
+        ncb::DevBuf<unsigned long long> q_keys, q_keys2;
+        ncb::DevBuf<float4> q_vals, q_vals2;
+        ncb::DevBuf<uint32_t> q_feat, q_feat2, q_order, q_order2, q_cnt;
+        ncb::DevBuf<uint8_t> q_tmp;
     } d2;
 };
 

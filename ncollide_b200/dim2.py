@@ -132,6 +132,24 @@ def ray_cast(ctx, types, params, poses, rays, poly_points=None):
     return found.astype(bool), out, feat
 
 
+def world_ray_cast(ctx, rays, groups=None, first_only=False):
+    """``CollisionWorld::interferences_with_ray`` / ``first_interference_with_ray`` of the 2-D world of the last ``world_update``
+    (``ncb2d_world_ray_cast``).  rays [n, 5] = origin, dir, max_toi; groups = (membership, whitelist, blacklist) or None.
+    Returns (idx [k, 2] = (ray, handle), val [k, 3] = (toi, normal), feature [k]), sorted by (ray, handle)."""
+    q = as_f32(rays).reshape(-1, 5)
+    g = as_u32(groups).reshape(3) if groups is not None else None
+    cap = max(4 * len(q), 1024)
+    while True:
+        idx, val, feat = np.zeros((cap, 2), dtype=np.uint32), np.zeros((cap, 3), dtype=np.float32), np.zeros(cap, dtype=np.uint32)
+        n_out = C.c_uint32(0)
+        r = ctx.check(ctx.lib.ncb2d_world_ray_cast(ctx.h, C.c_uint32(len(q)), ptr(q), ptr(g), C.c_int(1 if first_only else 0), ptr(idx), ptr(val),
+                                                   ptr(feat), C.c_uint32(cap), C.byref(n_out)), "ncb2d_world_ray_cast")
+        if r == 0:
+            k = n_out.value
+            return idx[:k], val[:k], feat[:k]
+        cap = n_out.value + 1024
+
+
 class Polyline:
     """``ncollide2d::shape::Polyline::new(points, indices)`` with ``RayCast::toi_and_normal_with_ray`` for a batch of rays
     (``ncb2d_polyline_create`` / ``ncb2d_polyline_ray_cast``).  ``edges`` None = the line strip."""

@@ -1350,6 +1350,24 @@ void orc2_ray_cast(uint64_t n, const uint32_t* type, const real* param, const re
     }
 }
 
+// AABB::toi_with_ray's hit test, DIM = 2 (ray_aabb.rs:13-50)
+static bool box_hit_by_ray2(const real* mm, P2 o, P2 d, real max_toi) {
+    real tmin = 0, tmax = max_toi;
+    const real oo[2] = {o.x, o.y}, dd[2] = {d.x, d.y};
+    for (int i = 0; i < 2; ++i) {
+        if (dd[i] == real(0)) {
+            if (oo[i] < mm[i] || oo[i] > mm[3 + i]) return false;
+        } else {
+            real denom = real(1) / dd[i];
+            real near = (mm[i] - oo[i]) * denom, far = (mm[3 + i] - oo[i]) * denom;
+            if (near > far) std::swap(near, far);
+            tmin = std::fmax(tmin, near), tmax = std::fmin(tmax, far);
+            if (tmin > tmax) return false;
+        }
+    }
+    return true;
+}
+
 // ---- 2-D world -------------------------------------------------------------------------------------------------------------
 struct orc2_objects {
     uint32_t n;
@@ -1427,6 +1445,42 @@ uint64_t orc2_narrow_phase(const orc2_objects* o, uint64_t n_pairs, const uint32
     manifold_off[n_pairs] = (uint32_t)nc;
     if (panics) *panics = (uint32_t)panicked;
     return nc;
+}
+
+
+// glue::interferences_with_ray / first_interference_with_ray (pipeline/glue/query.rs:13-77,183-224) over a 2-D world by brute force:
+// boxes = the broad phase's stored boxes (6 reals per object: mins xyz, maxs xyz, z unused), obj_groups = 3 words per object or NULL
+// (defaults), groups = the query's or NULL.  Rows in (ray, handle) order; first_only: the smallest toi per ray, ties -> smallest handle.
+uint64_t orc2_world_ray_cast(const orc2_objects* o, const real* boxes, const uint32_t* obj_groups, uint64_t n_rays, const real* rays,
+                             const uint32_t* groups, int first_only, uint32_t* idx, real* val, uint32_t* feat, uint64_t cap) {
+    uint64_t k = 0;
+    for (uint64_t r = 0; r < n_rays; ++r) {
+        const real* q = rays + 5 * r;
+        P2 ro = p2(q[0], q[1]), rd = p2(q[2], q[3]);
+        RayHit2 best;
+        uint32_t best_h = 0;
+        for (uint32_t h = 0; h < o->n; ++h) {
+            if (!box_hit_by_ray2(boxes + 6 * (size_t)h, ro, rd, q[4])) continue;
+            if (groups) {
+                uint32_t m1 = 0x3fffffffu, w1 = 0x3fffffffu, b1 = 0;
+                if (obj_groups) m1 = obj_groups[3 * h], w1 = obj_groups[3 * h + 1], b1 = obj_groups[3 * h + 2];
+                if (!((m1 & groups[2]) == 0 && (groups[0] & b1) == 0 && (m1 & groups[1]) != 0 && (groups[0] & w1) != 0)) continue;
+            }
+            RayHit2 hit = shape_ray_cast2(obj_shape(o, h), obj_iso(o, h), ro, rd, q[4]);
+            if (!hit.hit) continue;
+            if (first_only) {
+                if (!best.hit || hit.toi < best.toi) best = hit, best_h = h;
+            } else {
+                if (k < cap) idx[2 * k] = (uint32_t)r, idx[2 * k + 1] = h, val[3 * k] = hit.toi, val[3 * k + 1] = hit.n.x, val[3 * k + 2] = hit.n.y, feat[k] = hit.feature;
+                k++;
+            }
+        }
+        if (first_only && best.hit) {
+            if (k < cap) idx[2 * k] = (uint32_t)r, idx[2 * k + 1] = best_h, val[3 * k] = best.toi, val[3 * k + 1] = best.n.x, val[3 * k + 2] = best.n.y, feat[k] = best.feature;
+            k++;
+        }
+    }
+    return k;
 }
 
 }  // extern "C"

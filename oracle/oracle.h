@@ -195,6 +195,11 @@ void orc2_compute_aabbs(const struct orc2_objects* o, real margin, real* out);
 uint64_t orc2_narrow_phase(const struct orc2_objects* o, uint64_t n_pairs, const uint32_t* pairs, uint32_t* manifold_off, real* contacts,
                            uint32_t* feats, uint64_t cap, uint32_t* panics, uint8_t* prox);
 
+/* glue::interferences_with_ray / first_interference_with_ray over a 2-D world by brute force (boxes: 6 reals per object as written by
+ * orc2_compute_aabbs); rows (ray, handle) sorted; returns the number of rows (may exceed cap). */
+uint64_t orc2_world_ray_cast(const struct orc2_objects* o, const real* boxes, const uint32_t* obj_groups, uint64_t n_rays, const real* rays,
+                             const uint32_t* groups, int first_only, uint32_t* idx, real* val, uint32_t* feat, uint64_t cap);
+
 /* ncollide2d query::proximity for n pairs, one margin per pair; out: 0 Intersecting, 1 WithinMargin, 2 Disjoint, 255 plane x plane. */
 void orc2_proximity(uint64_t n, const uint32_t* type1, const real* param1, const real* pose1, const uint32_t* type2, const real* param2,
                     const real* pose2, const real* poly_points, const real* margins, uint8_t* out);

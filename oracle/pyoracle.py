@@ -344,6 +344,34 @@ class Oracle:
         self.last_proximity2d = prox  # per pair: 0 / 1 / 2 for pairs with a sensor, 255 otherwise
         return pairs, off, contacts[:nc], feats[:nc], panics.value, fat
 
+    def world_ray_cast2d(self, w, rays, groups=None, first_only=False):
+        """ncollide2d ``interferences_with_ray`` / ``first_interference_with_ray`` over a dim2.World2D (after a fresh update): rows
+        (idx [k, 2] = (ray, handle), val [k, 3] = (toi, normal), feature [k]) in (ray, handle) order."""
+        dt = self.dtype
+
+        class O2(C.Structure):
+            _fields_ = [("n", C.c_uint32), ("pos", C.c_void_p), ("rot", C.c_void_p), ("type", C.c_void_p), ("param", C.c_void_p),
+                        ("query_limit", C.c_void_p), ("ang_pred", C.c_void_p), ("poly_points", C.c_void_p), ("poly_normals", C.c_void_p),
+                        ("query_kind", C.c_void_p)]
+
+        keep = [np.ascontiguousarray(a, dtype=dt) for a in (w.pos, w.rot, w.param, w.query_limit, w.ang_pred, w.points, w.normals)]
+        typ = np.ascontiguousarray(w.type, dtype=np.uint32)
+        o = O2(w.n, keep[0].ctypes.data, keep[1].ctypes.data, typ.ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data, keep[4].ctypes.data,
+               keep[5].ctypes.data, keep[6].ctypes.data, None)
+        fat = np.zeros((w.n, 6), dtype=dt)
+        self.lib.orc2_compute_aabbs(C.byref(o), self.creal(w.margin), C.c_void_p(fat.ctypes.data))
+        q = np.ascontiguousarray(rays, dtype=dt).reshape(-1, 5)
+        og = np.ascontiguousarray(w.groups, dtype=np.uint32) if w.groups is not None else None
+        g = np.ascontiguousarray(groups, dtype=np.uint32) if groups is not None else None
+        vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None  # noqa: E731
+        cap = max(64 * len(q), 1024)
+        idx, val, feat = np.zeros((cap, 2), dtype=np.uint32), np.zeros((cap, 3), dtype=dt), np.zeros(cap, dtype=np.uint32)
+        self.lib.orc2_world_ray_cast.restype = C.c_uint64
+        k = self.lib.orc2_world_ray_cast(C.byref(o), vp(fat), vp(og), C.c_uint64(len(q)), vp(q), vp(g), C.c_int(1 if first_only else 0), vp(idx),
+                                         vp(val), vp(feat), C.c_uint64(cap))
+        assert k <= cap
+        return idx[:k], val[:k], feat[:k]
+
     def broad_phase_persistent(self, margin):
         return OracleBroadPhase(self, margin)
 

@@ -357,3 +357,58 @@ def test_device_convexpoly_raycast_fuzz(ctx):
     n = len(i)
     found, out, feat = dim2.ray_cast(ctx, [2] * n, [[0, 4, 0, 0]] * n, [[0, 0, 1, 0]] * n, rays, pts)
     assert found.all() and (out[:, 0] >= 1.0 - 2e-6).all() and (out[:, 0] < np.sqrt(2.0)).all()
+
+
+# ---- world ray queries of the 2-D world (interferences_with_ray / first_interference_with_ray) -------------------------------------
+def _ray_world(n, seed, planes=2, with_groups=True):
+    from test_dim2 import random_world
+
+    w = random_world(n, seed, (0, 1, 2), planes=planes, with_groups=with_groups)
+    rng = np.random.default_rng(seed + 1)
+    lo, hi = w.pos.min(axis=0), w.pos.max(axis=0)
+    m = 4000
+    o = rng.uniform(lo - 1.0, hi + 1.0, size=(m, 2))
+    d = rng.normal(size=(m, 2))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[rng.random(m) < 0.05] = [1.0, 0.0]
+    max_toi = np.where(rng.random(m) < 0.5, rng.uniform(0.5, 6.0, size=m), FMAX)
+    return w, np.concatenate([o, d, max_toi[:, None]], axis=1).astype(F)
+
+
+def test_oracle_world_ray_queries_2d(oracle):
+    """ORACLE properties: the first interference of a ray is the row with the smallest toi among all its interferences (ties: smallest
+    handle); a query whose blacklist names every group sees nothing; every toi respects max_toi."""
+    w, rays = _ray_world(1500, 81)
+    idx, val, feat = oracle.world_ray_cast2d(w, rays)
+    fidx, fval, ffeat = oracle.world_ray_cast2d(w, rays, first_only=True)
+    assert len(idx) > 3000 and (val[:, 0] <= rays[idx[:, 0], 4]).all() and (val[:, 0] >= 0).all()
+    assert np.array_equal(np.unique(idx[:, 0]), fidx[:, 0])
+    order = np.lexsort((idx[:, 1], val[:, 0], idx[:, 0]))
+    first = order[np.unique(idx[order, 0], return_index=True)[1]]
+    assert np.array_equal(idx[first], fidx) and np.array_equal(bits(val[first]), bits(fval)) and np.array_equal(feat[first], ffeat)
+    none, _, _ = oracle.world_ray_cast2d(w, rays, groups=(0x3FFFFFFF, 0x3FFFFFFF, 0x3FFFFFFF))
+    assert len(none) == 0
+    some, _, _ = oracle.world_ray_cast2d(w, rays, groups=(1 << 3, 0x3FFFFFFF, 1 << 5))
+    assert 0 < len(some) < len(idx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("groups", [None, (1 << 3, 0x3FFFFFFF, 1 << 5)])
+def test_device_world_ray_queries_2d(ctx, oracle, groups):
+    from ncollide_b200._ffi import NcbError
+
+    w, rays = _ray_world(5000, 82)
+    dim2.world_update(ctx, w)
+    for first_only in (False, True):
+        idx, val, feat = dim2.world_ray_cast(ctx, rays, groups=groups, first_only=first_only)
+        oidx, oval, ofeat = oracle.world_ray_cast2d(w, rays, groups=groups, first_only=first_only)
+        assert len(oidx) > 1000
+        assert np.array_equal(idx, oidx) and np.array_equal(feat, ofeat)
+        assert np.array_equal(bits(val), bits(oval)), f"{(bits(val) != bits(oval)).sum()} words differ"
+    assert ctx.traversal_overflows() == 0
+    from ncollide_b200.world import Context
+
+    fresh = Context(0)
+    with pytest.raises(NcbError):
+        dim2.world_ray_cast(fresh, rays)  # no 2-D world on that context
+    fresh.close()
