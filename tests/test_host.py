@@ -182,6 +182,70 @@ def test_oracle_ray_bvt_matches_brute_force(oracle):
         assert np.abs(np.einsum("ij,ij->i", p - tri[:, 0], nn)).max() < 1e-3
 
 
+def test_oracle_trimesh_rays_against_moller_trumbore(oracle64):
+    """ORACLE check (f64) for the part of the path the reference has no test for: TriMesh first hits against an independent
+    Moller-Trumbore intersection over ALL triangles in numpy — toi, the triangle, front / back face (face + T) and the unit normal
+    facing the ray; per-ray max_toi cuts hits beyond it."""
+    from ncollide_b200.scenes import make_ray_scene
+
+    checked = back = cut = 0
+    for kind in ("terrain", "soup"):
+        rs = make_ray_scene(kind, 900 if kind == "terrain" else 4000, 700 if kind == "terrain" else 1500, seed=11, random_pose=(kind == "soup"))
+        om = oracle64.trimesh(rs.verts, rs.tris)
+        pose = rs.pose.astype(np.float64) if kind == "soup" else None
+        if pose is not None:  # the rays were drawn in the mesh's frame: move them along with the mesh
+            pose[3:] /= np.linalg.norm(pose[3:])  # a unit quaternion in f64 (the f32 one is unit only to 1e-7)
+            from ncollide_b200.scenes import transform_rays
+
+            rs.origins, rs.dirs = transform_rays(pose, rs.origins, rs.dirs)
+        rng = np.random.default_rng(3)
+        limits = np.where(rng.random(len(rs.origins)) < 0.4, rng.uniform(1.0, 8.0, len(rs.origins)), 1e30)
+        toi, face, normal, _ = om.ray_cast_uv(rs.origins, rs.dirs, max_toi=limits, pose=pose, mode=0)
+        V = rs.verts.astype(np.float64)
+        if pose is not None:  # world-space triangles; q * v evaluated like nalgebra does (the f32 quaternion is a unit one only to 1e-7)
+            t, qv, qw = pose[:3].astype(np.float64), pose[3:6].astype(np.float64), float(pose[6])
+            tt2 = 2 * np.cross(qv, V)
+            V = V + qw * tt2 + np.cross(qv, tt2) + t
+        A, B, Cc = V[rs.tris[:, 0]], V[rs.tris[:, 1]], V[rs.tris[:, 2]]
+        e1, e2 = B - A, Cc - A
+        nrm = np.cross(e1, e2)
+        T = len(rs.tris)
+        for r in range(len(rs.origins)):
+            o, d = rs.origins[r].astype(np.float64), rs.dirs[r].astype(np.float64)
+            pv = np.cross(d, e2)
+            det = np.einsum("ij,ij->i", e1, pv)
+            ok = np.abs(det) > 1e-12
+            inv = 1.0 / np.where(ok, det, 1.0)
+            tv = o - A
+            u = np.einsum("ij,ij->i", tv, pv) * inv
+            qv = np.cross(tv, e1)
+            v = (qv @ d) * inv
+            tt = np.einsum("ij,ij->i", e2, qv) * inv
+            inside = ok & (u >= 0) & (v >= 0) & (u + v <= 1) & (tt >= 0)
+            near_edge = ok & (tt >= 0) & (np.minimum(np.minimum(np.abs(u), np.abs(v)), np.abs(1 - u - v)) < 1e-7) & (u > -1e-6) & (v > -1e-6) & (u + v < 1 + 1e-6)
+            if near_edge.any():
+                continue
+            if not inside.any():
+                assert toi[r] < 0, (kind, r)
+                continue
+            k = int(np.argmin(np.where(inside, tt, np.inf)))
+            if abs(tt[k] - limits[r]) < 1e-6 * max(1.0, limits[r]):
+                continue
+            if tt[k] > limits[r]:
+                assert toi[r] < 0, (kind, r, tt[k], limits[r])
+                cut += 1
+                continue
+            tol = 1e-9 if pose is None else 1e-7  # posed: the oracle works in the mesh's frame, numpy in the world's
+            assert abs(toi[r] - tt[k]) < tol * max(1.0, tt[k]), (kind, r, toi[r], tt[k])
+            is_back = nrm[k] @ d > 0
+            assert face[r] == k + (T if is_back else 0), (kind, r, face[r], k, is_back)
+            want_n = nrm[k] / np.linalg.norm(nrm[k]) * (-1.0 if is_back else 1.0)
+            assert np.allclose(normal[r], want_n, atol=tol * 10), (kind, r)
+            checked += 1
+            back += bool(is_back)
+    assert checked > 500 and back > 50 and cut > 20, (checked, back, cut)
+
+
 def test_golden_fixtures_match_the_oracle(oracle):
     """tests/golden/*.npz were produced by tests/golden/make_golden.py from the oracle at commit time; they pin the
     oracle (and, under -m gpu, the device) against silent drift."""
