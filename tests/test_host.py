@@ -157,6 +157,77 @@ def test_oracle_contact_invariants(oracle):
     assert np.allclose(c2["normal"], -c1["normal"], atol=1e-6) and np.allclose(c2["world1"], c1["world2"], atol=1e-6)
 
 
+def _rotation_matrices(q):
+    """nalgebra's UnitQuaternion::to_rotation_matrix for rows of (i, j, k, w)."""
+    i, j, k, w = (q[:, c].astype(np.float64) for c in range(4))
+    R = np.empty((len(q), 3, 3))
+    R[:, 0, 0], R[:, 0, 1], R[:, 0, 2] = w * w + i * i - j * j - k * k, 2 * (i * j - w * k), 2 * (w * j + i * k)
+    R[:, 1, 0], R[:, 1, 1], R[:, 1, 2] = 2 * (w * k + i * j), w * w - i * i + j * j - k * k, 2 * (j * k - w * i)
+    R[:, 2, 0], R[:, 2, 1], R[:, 2, 2] = 2 * (i * k - w * j), 2 * (w * i + j * k), w * w - i * i - j * j + k * k
+    return R
+
+
+def test_oracle_aabbs_at_arbitrary_rotations_against_numpy(oracle64):
+    """ORACLE check (f64) for an unpinned item (no reference test holds AABB values of rotated shapes): the tight AABB of every ball,
+    cuboid and convex hull of a randomly rotated world against numpy — centre -+ r, centre -+ |R| half_extents, min / max of the
+    rotated hull vertices."""
+    from ncollide_b200.scenes import make_world_scene
+
+    s = make_world_scene(3000, 31, (1, 1, 1), side=20.0, n_hulls=32)
+    s.rot = (s.rot.astype(np.float64) / np.linalg.norm(s.rot.astype(np.float64), axis=1, keepdims=True)).astype(np.float64)
+    tight = oracle64.compute_aabbs(s, mode=0)
+    R, t = _rotation_matrices(s.rot), s.pos.astype(np.float64)
+    seen = [0, 0, 0]
+    for k in range(s.n):
+        typ, par = int(s.shape_type[k]), s.shape_param[k].astype(np.float64)
+        if typ == 0:
+            lo, hi = t[k] - par[0], t[k] + par[0]
+        elif typ == 1:
+            he = np.abs(R[k]) @ par[:3]
+            lo, hi = t[k] - he, t[k] + he
+        else:
+            h = int(par[0])
+            P = s.hulls.points[s.hulls.vert_off[h] : s.hulls.vert_off[h + 1]].astype(np.float64) @ R[k].T + t[k]
+            lo, hi = P.min(axis=0), P.max(axis=0)
+        assert np.allclose(tight[k, :3], lo, atol=1e-9) and np.allclose(tight[k, 3:], hi, atol=1e-9), (k, typ)
+        seen[typ] += 1
+    assert min(seen) > 500
+
+
+def test_oracle_cuboid_penetration_against_separating_axes(oracle64):
+    """ORACLE check (f64) for an unpinned item (manifold contents): for interpenetrating cuboids the deepest contact of the manifold is
+    the EPA penetration depth, which for boxes is the smallest overlap over the 15 separating-axis candidates; and pairs the axes
+    separate by more than the prediction have no contact."""
+    from ncollide_b200.scenes import make_world_scene
+
+    s = make_world_scene(1800, 33, (0, 1, 0), side=9.0, n_hulls=1)
+    s.rot = s.rot.astype(np.float64) / np.linalg.norm(s.rot.astype(np.float64), axis=1, keepdims=True)
+    fat = oracle64.compute_aabbs(s)
+    pairs = oracle64.broad_phase(fat, s.groups, 1)
+    c, off, algo, stats = oracle64.narrow_phase(s, pairs)
+    R, t = _rotation_matrices(s.rot), s.pos.astype(np.float64)
+    deep = apart = 0
+    for p, (i1, i2) in enumerate(pairs):
+        A, B, ha, hb = R[i1], R[i2], s.shape_param[i1, :3].astype(np.float64), s.shape_param[i2, :3].astype(np.float64)
+        d = t[i2] - t[i1]
+        axes = [A[:, k] for k in range(3)] + [B[:, k] for k in range(3)]
+        for a in range(3):
+            for b in range(3):
+                x = np.cross(A[:, a], B[:, b])
+                if np.linalg.norm(x) > 1e-6:
+                    axes.append(x / np.linalg.norm(x))
+        overlap = min((np.abs(A.T @ ax) @ ha) + (np.abs(B.T @ ax) @ hb) - abs(d @ ax) for ax in axes)
+        depths = c["depth"][off[p] : off[p + 1]]
+        if overlap > 1e-3:  # interpenetrating: min overlap == penetration depth
+            assert len(depths) > 0, (p, overlap)
+            assert abs(depths.max() - overlap) < 1e-6 * max(1.0, overlap), (p, depths.max(), overlap)
+            deep += 1
+        elif overlap < -0.04 - 1e-6:  # a separating axis with a gap beyond linear1 + linear2: nothing to report
+            assert len(depths) == 0, (p, overlap)
+            apart += 1
+    assert deep > 150 and apart > 20, (deep, apart)
+
+
 def test_oracle_ray_bvt_matches_brute_force(oracle):
     from ncollide_b200.scenes import make_ray_scene
 
