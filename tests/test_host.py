@@ -228,6 +228,65 @@ def test_oracle_cuboid_penetration_against_separating_axes(oracle64):
     assert deep > 150 and apart > 20, (deep, apart)
 
 
+def test_oracle_hull_penetration_against_separating_axes(oracle64):
+    """The same check for convex hulls (and hull x cuboid): candidate axes = the face normals of both polytopes and the cross products
+    of their edge directions; the smallest overlap of the projected vertex sets == the depth query::contact (EPA) reports."""
+    from ncollide_b200.scenes import WorldScene, make_world_scene
+
+    s = make_world_scene(700, 35, (0, 1, 2), side=5.5, n_hulls=24)
+    s.rot = s.rot.astype(np.float64) / np.linalg.norm(s.rot.astype(np.float64), axis=1, keepdims=True)
+    fat = oracle64.compute_aabbs(s)
+    pairs = oracle64.broad_phase(fat, s.groups, 1)
+    c, off, algo, stats = oracle64.narrow_phase(s, pairs)
+    R, t, H = _rotation_matrices(s.rot), s.pos.astype(np.float64), s.hulls
+    local = {}
+
+    def polytope(i):
+        """world vertices, world face normals, world edge directions of object i"""
+        if s.shape_type[i] == 1:
+            he = s.shape_param[i, :3].astype(np.float64)
+            V = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=np.float64) * he
+            return V @ R[i].T + t[i], R[i].T.copy(), R[i].T.copy()
+        h = int(s.shape_param[i, 0])
+        if h not in local:  # faces and edges recomputed from the vertices by qhull in f64 (the library's own tables merge nearly
+            from scipy.spatial import ConvexHull  # coplanar triangles, which moves a face normal by ~1e-4)
+
+            V = H.points[H.vert_off[h] : H.vert_off[h + 1]].astype(np.float64)
+            ch = ConvexHull(V)
+            tri = ch.simplices
+            E = np.concatenate([V[tri[:, 1]] - V[tri[:, 0]], V[tri[:, 2]] - V[tri[:, 1]], V[tri[:, 0]] - V[tri[:, 2]]])
+            local[h] = (V, ch.equations[:, :3].copy(), E / np.linalg.norm(E, axis=1, keepdims=True))
+        V, N, E = local[h]
+        return V @ R[i].T + t[i], N @ R[i].T, E @ R[i].T
+
+    deep = 0
+    for p, (i1, i2) in enumerate(pairs):
+        if s.shape_type[i1] == 1 and s.shape_type[i2] == 1:
+            continue
+        Va, Na, Ea = polytope(i1)
+        Vb, Nb, Eb = polytope(i2)
+        X = np.cross(Ea[:, None, :], Eb[None, :, :]).reshape(-1, 3)
+        ln = np.linalg.norm(X, axis=1)
+        axes = np.concatenate([Na, Nb, X[ln > 1e-6] / ln[ln > 1e-6, None]])
+        pa, pb = Va @ axes.T, Vb @ axes.T
+        overlap = np.minimum(pa.max(axis=0) - pb.min(axis=0), pb.max(axis=0) - pa.min(axis=0)).min()
+        depths = c["depth"][off[p] : off[p + 1]]
+        if overlap > 1e-3:
+            # (the manifold itself holds clipped feature points measured along the EPA normal against the other shape's face plane:
+            # its deepest contact equals the penetration depth for boxes, above, and only approximates it for general hulls)
+            assert len(depths) > 0
+            # query::contact of the same two shapes reports the EPA depth itself
+            two = WorldScene(pos=s.pos[[i1, i2]], rot=s.rot[[i1, i2]], shape_type=s.shape_type[[i1, i2]], shape_param=s.shape_param[[i1, i2]],
+                             groups=s.groups[[i1, i2]], query_limit=s.query_limit[[i1, i2]], ang_pred=s.ang_pred[[i1, i2]], hulls=s.hulls,
+                             margin=s.margin)
+            q = oracle64.query_contact(two, 0.04)
+            assert q is not None and abs(q["depth"] - overlap) < 1e-7 * max(1.0, overlap), (p, q["depth"], overlap)
+            deep += 1
+        elif overlap < -0.04 - 1e-6:
+            assert len(depths) == 0, (p, overlap)
+    assert deep > 100, deep
+
+
 def test_oracle_ray_bvt_matches_brute_force(oracle):
     from ncollide_b200.scenes import make_ray_scene
 
