@@ -480,6 +480,12 @@ int ncb2d_world_fetch_proximity(ncb_ctx* ctx, uint8_t* prox, uint32_t cap_pairs)
  * cap in rows; *n_out = rows found; returns 1 when truncated. */
 int ncb2d_world_ray_cast(ncb_ctx* ctx, uint32_t n_rays, const float* rays, const uint32_t* groups, int first_only, uint32_t* idx, float* val,
                          uint32_t* feat, uint32_t cap, uint32_t* n_out);
+/* glue::interferences_with_aabb (kind 0; 4 floats per query: mins x y, maxs x y) / interferences_with_point (kind 2; 2 floats)
+ * (pipeline/glue/query.rs:79-181) against the world of the last ncb2d_world_update: candidates from the stored boxes, the query's collision
+ * groups, and for points the shape's PointQuery::contains_point (ball, cuboid, plane; convex polygon through gjk::project_origin).
+ * idx[2 k] = (query, handle), sorted; cap in rows; returns 1 when truncated. */
+int ncb2d_world_query(ncb_ctx* ctx, int kind, uint32_t n_queries, const float* queries, const uint32_t* groups, uint32_t* idx, uint32_t cap,
+                      uint32_t* n_out);
 
 /* ---- ncollide2d: RayCast for Polyline (the 2-D counterpart of the TriMesh ray path) -------------------------------------------------- */
 /* Polyline::new(points, indices) (shape/polyline.rs:57-120): 2 floats per point, 2 point indices per edge; edges == NULL builds the

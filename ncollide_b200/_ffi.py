@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = [
     "ncb_world_update_device", "ncb_world_fetch", "ncb_world_update", "ncb_world_update_poses", "ncb_device_ptr", "ncb_world_update_stage", "ncb_world_update_sharded", "ncb_world_update_routed", "ncb_route_buffer", "ncb_route_p2p_alloc", "ncb_route_p2p_connect", "ncb_route_p2p_close", "ncb_world_fetch_early",
     "ncb_profile_enable", "ncb_profile_get", "ncb_trimesh_create", "ncb_trimesh_destroy", "ncb_trimesh_ray_cast",
     "ncb_trimesh_ray_cast_device", "ncb_trimesh_ray_cast_uv", "ncb_trimesh_set_uvs", "ncb2d_contact", "ncb2d_world_update", "ncb2d_proximity", "ncb2d_polyline_create", "ncb2d_polyline_destroy", "ncb2d_polyline_ray_cast",
-    "ncb2d_polyline_ray_cast_device", "ncb2d_ray_cast", "ncb2d_world_fetch_proximity", "ncb2d_world_ray_cast",
+    "ncb2d_polyline_ray_cast_device", "ncb2d_ray_cast", "ncb2d_world_fetch_proximity", "ncb2d_world_ray_cast", "ncb2d_world_query",
     "ncb_bp_create", "ncb_bp_destroy", "ncb_bp_create_proxies", "ncb_bp_set_bounding_volumes", "ncb_bp_remove", "ncb_bp_update",
     "ncb_sim_create", "ncb_sim_destroy", "ncb_sim_set_positions", "ncb_sim_set_collision_groups", "ncb_sim_step", "ncb_sim_sizes", "ncb_sim_fetch", "ncb_sim_remove", "ncb_sim_add", "ncb_sim_ray_cast", "ncb_sim_query",
     "ncb_set_query_types", "ncb_proximity", "ncb_world_fetch_proximity", "ncb_sim_fetch_proximity", "ncb_sim_add_with_query_types",

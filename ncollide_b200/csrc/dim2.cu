@@ -1155,6 +1155,30 @@ __device__ RayHit2 shape_ray_cast2(const Operand2& g, W2 o, W2 d, float max_toi)
     return ray2_plane(g, o, d, max_toi);
 }
 
+// PointQuery::contains_point of one shape (point_ball.rs:45-47, point_cuboid.rs:34-38 -> point_aabb.rs:153-156, point_plane.rs:44-48;
+// ConvexPolygon: the default, project_point(..).is_inside = gjk::project_origin finds the point inside, point_support_map.rs:14-55)
+__device__ bool shape_contains_point2(const Operand2& g, W2 pt) {
+    if (g.kind == D2_BALL) return nsq(to_local(g.m, pt)) <= g.a * g.a;
+    if (g.kind == D2_CUBOID) {
+        W2 l = to_local(g.m, pt);
+        return !(l.x < -g.a || l.x > g.a || l.y < -g.b || l.y > g.b);
+    }
+    if (g.kind == D2_PLANE) return dot(w2(g.a, g.b), to_local(g.m, pt)) <= 0.f;
+    Operand2 s = g, origin;
+    s.m.t = (-pt) + g.m.t;  // Translation::from(-point) * m
+    origin.kind = D2_ORIGIN, origin.a = origin.b = 0.f, origin.pts = origin.nrm = nullptr, origin.npts = 0;
+    origin.m.t = w2(0.f, 0.f), origin.m.re = 1.f, origin.m.im = 0.f;
+    W2 d0;
+    if (!unit(-s.m.t, NCB_EPS, d0)) d0 = w2(1.f, 0.f);
+    Tri2 sx;
+    for (int i = 0; i < 3; ++i) sx.v[i].p = sx.v[i].o1 = sx.v[i].o2 = w2(0.f, 0.f), sx.old_idx[i] = i;
+    sx.bary[0] = sx.bary[1] = sx.old_bary[0] = sx.old_bary[1] = 0.f;
+    sx.dim = sx.old_dim = 0;
+    sx.v[0] = minkowski(s, origin, d0);
+    W2 p1, p2, n;
+    return gjk2(s, origin, NCB_FMAX, sx, p1, p2, n) != G_POINTS;
+}
+
 // query::contact for one pair.  flags: bit 0 = the reference would panic, bit 1 = EPA capacity exceeded.
 __device__ bool contact_of_pair(const Operand2& g1, const Operand2& g2, float prediction, float cos_one_degree, Hit2& h, int& flags) {
     h.w1 = h.w2 = h.n = w2(0.f, 0.f), h.depth = 0.f;
@@ -1423,6 +1447,72 @@ __global__ void __launch_bounds__(128) k_world_ray2d(WorldRay2Args A) {
             A.vals[k] = make_float4(best.toi, best.n.x, best.n.y, 0.f);
             A.feats[k] = best.feature;
         }
+    }
+}
+// glue::interferences_with_aabb (KIND 0: mins x y, maxs x y) / interferences_with_point (KIND 2: x y) (pipeline/glue/query.rs:79-181)
+template <int KIND>
+__device__ __forceinline__ bool box_test2(const float* q, float4 lo, float4 hi) {
+    if (KIND == 0) return lo.x <= q[2] && lo.y <= q[3] && hi.x >= q[0] && hi.y >= q[1];  // AABB::intersects
+    return !(q[0] < lo.x || q[0] > hi.x || q[1] < lo.y || q[1] > hi.y);                   // AABB::contains_local_point
+}
+template <int KIND>
+__device__ __forceinline__ void world_query_leaf(const WorldRay2Args& A, uint32_t qi, const float* q, uint32_t handle) {
+    if (A.use_groups) {
+        uint32_t m1 = 0x3fffffffu, w1 = 0x3fffffffu, b1 = 0u;
+        if (A.groups) m1 = __ldg(&A.groups[3 * handle]), w1 = __ldg(&A.groups[3 * handle + 1]), b1 = __ldg(&A.groups[3 * handle + 2]);
+        if (!((m1 & A.qg[2]) == 0 && (A.qg[0] & b1) == 0 && (m1 & A.qg[1]) != 0 && (A.qg[0] & w1) != 0)) return;
+    }
+    if (KIND == 2 && !shape_contains_point2(world_operand(A.W, handle), w2(q[0], q[1]))) return;
+    uint32_t k = atomicAdd(A.counter, 1u);
+    if (k < A.cap) A.keys[k] = ((unsigned long long)qi << 32) | handle;
+}
+template <int KIND>
+__global__ void __launch_bounds__(128) k_world_query2d(WorldRay2Args A) {
+    const int W = KIND == 0 ? 4 : 2;
+    uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= A.n_rays) return;
+    float q[4];
+    for (int k = 0; k < W; ++k) q[k] = __ldg(A.rays + (size_t)W * qi + k);
+    const uint32_t m = A.n_tree;
+    if (m >= 2) {
+        uint32_t stack[64];
+        int sp = 0;
+        uint32_t node = 0;
+        for (;;) {
+            const float4* rec = A.nodes + 4 * (size_t)node;
+            float4 Llo = __ldg(rec + 0), Lhi = __ldg(rec + 1), Rlo = __ldg(rec + 2), Rhi = __ldg(rec + 3);
+            uint32_t left = __float_as_uint(Llo.w), right = __float_as_uint(Lhi.w);
+            bool goL = box_test2<KIND>(q, Llo, Lhi), goR = box_test2<KIND>(q, Rlo, Rhi);
+            if (goL && (left & 0x80000000u)) {
+                world_query_leaf<KIND>(A, qi, q, __float_as_uint(__ldg(&A.leaf_lo[left & 0x7fffffffu].w)));
+                goL = false;
+            }
+            if (goR && (right & 0x80000000u)) {
+                world_query_leaf<KIND>(A, qi, q, __float_as_uint(__ldg(&A.leaf_lo[right & 0x7fffffffu].w)));
+                goR = false;
+            }
+            if (goL && goR) {
+                if (sp < 64)
+                    stack[sp++] = right;
+                else
+                    atomicAdd(A.trav_overflow, 1u);
+                node = left;
+            } else if (goL) {
+                node = left;
+            } else if (goR) {
+                node = right;
+            } else {
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+        }
+    } else if (m == 1) {
+        float4 lo = __ldg(&A.leaf_lo[0]), hi = __ldg(&A.leaf_hi[0]);
+        if (box_test2<KIND>(q, lo, hi)) world_query_leaf<KIND>(A, qi, q, __float_as_uint(lo.w));
+    }
+    for (uint32_t k = m; k < A.W.n; ++k) {
+        float4 lo = __ldg(&A.leaf_lo[k]), hi = __ldg(&A.leaf_hi[k]);
+        if (box_test2<KIND>(q, lo, hi)) world_query_leaf<KIND>(A, qi, q, __float_as_uint(lo.w));
     }
 }
 __global__ void k_iota2d(uint32_t* p, uint32_t n) {
@@ -1857,6 +1947,62 @@ int ncb2d_world_ray_cast(ncb_ctx* ctx, uint32_t n_rays, const float* rays, const
         idx[2 * (size_t)k] = (uint32_t)(hk[k] >> 32), idx[2 * (size_t)k + 1] = (uint32_t)hk[k];
         val[3 * (size_t)k] = hv[k].x, val[3 * (size_t)k + 1] = hv[k].y, val[3 * (size_t)k + 2] = hv[k].z;
     }
+    return found > cap ? 1 : NCB_OK;
+}
+
+// glue::interferences_with_aabb (kind 0) / interferences_with_point (kind 2) against the world of the last ncb2d_world_update.
+int ncb2d_world_query(ncb_ctx* ctx, int kind, uint32_t n_queries, const float* queries, const uint32_t* groups, uint32_t* idx, uint32_t cap,
+                      uint32_t* n_out) {
+    if (!ctx || !n_out || (kind != 0 && kind != 2) || (n_queries && !queries) || (cap && !idx)) return NCB_ERR_ARG;
+    *n_out = 0;
+    uint32_t n = ctx->d2.last_n;
+    if (n == 0) {
+        ctx->err = "ncb2d_world_query: no 2-D world on the device (call ncb2d_world_update first)";
+        return NCB_ERR_ARG;
+    }
+    if (n_queries == 0) return NCB_OK;
+    CK2(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    auto& D = ctx->d2;
+    const size_t W = kind == 0 ? 4 : 2, capd = cap ? cap : 1;
+    CK2(D.q_rays.reserve(W * (size_t)n_queries));
+    CK2(D.q_keys.reserve(capd));
+    CK2(D.q_keys2.reserve(capd));
+    CK2(D.q_cnt.reserve(1));
+    CK2(cudaMemcpyAsync(D.q_rays.p, queries, 4 * W * (size_t)n_queries, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemsetAsync(D.q_cnt.p, 0, 4, s));
+    d2::WorldRay2Args A;
+    memset(&A, 0, sizeof A);
+    A.W.n = n;
+    A.W.pos = D.pos.p, A.W.rot = D.rot.p, A.W.type = D.type.p, A.W.param = D.param.p, A.W.poly = D.poly.p;
+    A.leaf_lo = ctx->leaf_lo.p, A.leaf_hi = ctx->leaf_hi.p, A.nodes = ctx->nodes.p;
+    A.n_tree = n - ctx->last_counters.n_outliers;
+    A.groups = D.last_groups ? D.groups.p : nullptr;
+    A.use_groups = groups != nullptr;
+    if (groups) A.qg[0] = groups[0], A.qg[1] = groups[1], A.qg[2] = groups[2];
+    A.rays = D.q_rays.p, A.n_rays = n_queries;
+    A.keys = D.q_keys.p, A.cap = cap, A.counter = D.q_cnt.p;
+    A.trav_overflow = trav_overflow_counter(ctx);
+    if (kind == 0)
+        d2::k_world_query2d<0><<<(n_queries + 127) / 128, 128, 0, s>>>(A);
+    else
+        d2::k_world_query2d<2><<<(n_queries + 127) / 128, 128, 0, s>>>(A);
+    CK2(cudaGetLastError());
+    uint32_t found = 0;
+    CK2(cudaMemcpyAsync(&found, D.q_cnt.p, 4, cudaMemcpyDeviceToHost, s));
+    CK2(cudaStreamSynchronize(s));
+    *n_out = found;
+    uint32_t w = found < cap ? found : cap;
+    if (w == 0) return found > cap ? 1 : NCB_OK;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)w, 0, 64);
+    CK2(D.q_tmp.reserve(tmp + 256));
+    tmp = D.q_tmp.cap;
+    CK2(cub::DeviceRadixSort::SortKeys(D.q_tmp.p, tmp, D.q_keys.p, D.q_keys2.p, (int)w, 0, 64, s));
+    std::vector<unsigned long long> hk(w);
+    CK2(cudaMemcpyAsync(hk.data(), D.q_keys2.p, 8 * (size_t)w, cudaMemcpyDeviceToHost, s));
+    CK2(cudaStreamSynchronize(s));
+    for (uint32_t k = 0; k < w; ++k) idx[2 * (size_t)k] = (uint32_t)(hk[k] >> 32), idx[2 * (size_t)k + 1] = (uint32_t)hk[k];
     return found > cap ? 1 : NCB_OK;
 }
 

@@ -150,6 +150,23 @@ def world_ray_cast(ctx, rays, groups=None, first_only=False):
         cap = n_out.value + 1024
 
 
+def world_query(ctx, kind, queries, groups=None):
+    """``interferences_with_aabb`` (kind "aabb": rows of mins x y, maxs x y) / ``interferences_with_point`` (kind "point": x y) of the
+    2-D world of the last ``world_update`` (``ncb2d_world_query``).  Returns idx [k, 2] = (query, handle), sorted."""
+    k = {"aabb": 0, "point": 2}[kind]
+    q = as_f32(queries).reshape(-1, 4 if k == 0 else 2)
+    g = as_u32(groups).reshape(3) if groups is not None else None
+    cap = max(8 * len(q), 1024)
+    while True:
+        idx = np.zeros((cap, 2), dtype=np.uint32)
+        n_out = C.c_uint32(0)
+        r = ctx.check(ctx.lib.ncb2d_world_query(ctx.h, C.c_int(k), C.c_uint32(len(q)), ptr(q), ptr(g), ptr(idx), C.c_uint32(cap), C.byref(n_out)),
+                      "ncb2d_world_query")
+        if r == 0:
+            return idx[: n_out.value]
+        cap = n_out.value + 1024
+
+
 class Polyline:
     """``ncollide2d::shape::Polyline::new(points, indices)`` with ``RayCast::toi_and_normal_with_ray`` for a batch of rays
     (``ncb2d_polyline_create`` / ``ncb2d_polyline_ray_cast``).  ``edges`` None = the line strip."""

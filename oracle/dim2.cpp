@@ -1350,6 +1350,28 @@ void orc2_ray_cast(uint64_t n, const uint32_t* type, const real* param, const re
     }
 }
 
+// PointQuery::contains_point (point_ball.rs:45-47, point_cuboid.rs:34-38, point_plane.rs:44-48; ConvexPolygon: the trait's default,
+// project_point(m, pt, false).is_inside, point_query.rs:50-52 + point_support_map.rs:14-55)
+static bool contains_point2(const Shape2& g, const Iso2& m, P2 pt) {
+    if (g.type == BALL2) return nsq(inv_point(m, pt)) <= g.radius * g.radius;
+    if (g.type == CUBOID2) {
+        P2 l = inv_point(m, pt);
+        return !(l.x < -g.he.x || l.x > g.he.x || l.y < -g.he.y || l.y > g.he.y);
+    }
+    if (g.type == PLANE2) return dot(g.he, inv_point(m, pt)) <= real(0);
+    Iso2 ms = m;
+    ms.t = (-pt) + m.t;
+    Iso2 id = {p2(0, 0), 1, 0};
+    Shape2 origin;
+    origin.type = ORIGIN2, origin.radius = 0, origin.he = p2(0, 0), origin.pts = origin.normals = nullptr, origin.npts = 0;
+    P2 dir;
+    if (!unit_try_new(-ms.t, EPS, &dir)) dir = p2(1, 0);
+    Simplex2 s;
+    s.reset(cso_from_shapes(ms, g, id, origin, dir));
+    P2 p1, p2_, n;
+    return gjk_closest_points(ms, g, id, origin, FMAX, s, &p1, &p2_, &n) != R_CLOSEST;
+}
+
 // AABB::toi_with_ray's hit test, DIM = 2 (ray_aabb.rs:13-50)
 static bool box_hit_by_ray2(const real* mm, P2 o, P2 d, real max_toi) {
     real tmin = 0, tmax = max_toi;
@@ -1477,6 +1499,45 @@ uint64_t orc2_world_ray_cast(const orc2_objects* o, const real* boxes, const uin
         }
         if (first_only && best.hit) {
             if (k < cap) idx[2 * k] = (uint32_t)r, idx[2 * k + 1] = best_h, val[3 * k] = best.toi, val[3 * k + 1] = best.n.x, val[3 * k + 2] = best.n.y, feat[k] = best.feature;
+            k++;
+        }
+    }
+    return k;
+}
+
+void orc2_contains_point(uint64_t n, const uint32_t* type, const real* param, const real* pose, const real* poly_points, const real* pts,
+                         uint8_t* out) {
+    for (uint64_t k = 0; k < n; ++k) {
+        const real* p = param + 4 * k;
+        Shape2 g;
+        g.type = type[k], g.radius = p[0], g.he = p2(p[0], p[1]), g.pts = g.normals = nullptr, g.npts = 0;
+        if (g.type == POLYGON2) g.pts = poly_points + 2 * (size_t)p[0], g.npts = (uint32_t)p[1];
+        Iso2 m = {p2(pose[4 * k], pose[4 * k + 1]), pose[4 * k + 2], pose[4 * k + 3]};
+        out[k] = contains_point2(g, m, p2(pts[2 * k], pts[2 * k + 1])) ? 1 : 0;
+    }
+}
+
+// glue::interferences_with_aabb (kind 0: 4 reals) / interferences_with_point (kind 2: 2 reals) by brute force; rows (query, handle) sorted
+uint64_t orc2_world_query(const orc2_objects* o, const real* boxes, const uint32_t* obj_groups, int kind, uint64_t n_queries, const real* queries,
+                          const uint32_t* groups, uint32_t* idx, uint64_t cap) {
+    uint64_t k = 0;
+    const int W = kind == 0 ? 4 : 2;
+    for (uint64_t qi = 0; qi < n_queries; ++qi) {
+        const real* q = queries + W * qi;
+        for (uint32_t h = 0; h < o->n; ++h) {
+            const real* b = boxes + 6 * (size_t)h;
+            if (kind == 0) {
+                if (!(b[0] <= q[2] && b[1] <= q[3] && b[3] >= q[0] && b[4] >= q[1])) continue;
+            } else {
+                if (q[0] < b[0] || q[0] > b[3] || q[1] < b[1] || q[1] > b[4]) continue;
+            }
+            if (groups) {
+                uint32_t m1 = 0x3fffffffu, w1 = 0x3fffffffu, b1 = 0;
+                if (obj_groups) m1 = obj_groups[3 * h], w1 = obj_groups[3 * h + 1], b1 = obj_groups[3 * h + 2];
+                if (!((m1 & groups[2]) == 0 && (groups[0] & b1) == 0 && (m1 & groups[1]) != 0 && (groups[0] & w1) != 0)) continue;
+            }
+            if (kind == 2 && !contains_point2(obj_shape(o, h), obj_iso(o, h), p2(q[0], q[1]))) continue;
+            if (k < cap) idx[2 * k] = (uint32_t)qi, idx[2 * k + 1] = h;
             k++;
         }
     }

@@ -200,6 +200,12 @@ uint64_t orc2_narrow_phase(const struct orc2_objects* o, uint64_t n_pairs, const
 uint64_t orc2_world_ray_cast(const struct orc2_objects* o, const real* boxes, const uint32_t* obj_groups, uint64_t n_rays, const real* rays,
                              const uint32_t* groups, int first_only, uint32_t* idx, real* val, uint32_t* feat, uint64_t cap);
 
+/* PointQuery::contains_point of shape k for point k; interferences_with_aabb (kind 0) / interferences_with_point (kind 2) by brute force. */
+void orc2_contains_point(uint64_t n, const uint32_t* type, const real* param, const real* pose, const real* poly_points, const real* pts,
+                         uint8_t* out);
+uint64_t orc2_world_query(const struct orc2_objects* o, const real* boxes, const uint32_t* obj_groups, int kind, uint64_t n_queries,
+                          const real* queries, const uint32_t* groups, uint32_t* idx, uint64_t cap);
+
 /* ncollide2d query::proximity for n pairs, one margin per pair; out: 0 Intersecting, 1 WithinMargin, 2 Disjoint, 255 plane x plane. */
 void orc2_proximity(uint64_t n, const uint32_t* type1, const real* param1, const real* pose1, const uint32_t* type2, const real* param2,
                     const real* pose2, const real* poly_points, const real* margins, uint8_t* out);

@@ -372,6 +372,44 @@ class Oracle:
         assert k <= cap
         return idx[:k], val[:k], feat[:k]
 
+    def contains_point2d(self, types, params, poses, pts, poly_points=None):
+        """ncollide2d ``PointQuery::contains_point`` of shape k for point k -> bool [n]."""
+        dt = self.dtype
+        t = np.ascontiguousarray(types, dtype=np.uint32)
+        p, m, q = (np.ascontiguousarray(a, dtype=dt) for a in (params, poses, pts))
+        pp = np.ascontiguousarray(poly_points if poly_points is not None else np.zeros((1, 2)), dtype=dt)
+        out = np.zeros(len(t), dtype=np.uint8)
+        vp = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+        self.lib.orc2_contains_point(C.c_uint64(len(t)), vp(t), vp(p), vp(m), vp(pp), vp(q), vp(out))
+        return out.astype(bool)
+
+    def world_query2d(self, w, kind, queries, groups=None):
+        """ncollide2d ``interferences_with_aabb`` ("aabb") / ``interferences_with_point`` ("point") over a dim2.World2D: idx [k, 2]."""
+        dt = self.dtype
+
+        class O2(C.Structure):
+            _fields_ = [("n", C.c_uint32), ("pos", C.c_void_p), ("rot", C.c_void_p), ("type", C.c_void_p), ("param", C.c_void_p),
+                        ("query_limit", C.c_void_p), ("ang_pred", C.c_void_p), ("poly_points", C.c_void_p), ("poly_normals", C.c_void_p),
+                        ("query_kind", C.c_void_p)]
+
+        keep = [np.ascontiguousarray(a, dtype=dt) for a in (w.pos, w.rot, w.param, w.query_limit, w.ang_pred, w.points, w.normals)]
+        typ = np.ascontiguousarray(w.type, dtype=np.uint32)
+        o = O2(w.n, keep[0].ctypes.data, keep[1].ctypes.data, typ.ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data, keep[4].ctypes.data,
+               keep[5].ctypes.data, keep[6].ctypes.data, None)
+        fat = np.zeros((w.n, 6), dtype=dt)
+        self.lib.orc2_compute_aabbs(C.byref(o), self.creal(w.margin), C.c_void_p(fat.ctypes.data))
+        k = {"aabb": 0, "point": 2}[kind]
+        q = np.ascontiguousarray(queries, dtype=dt).reshape(-1, 4 if k == 0 else 2)
+        og = np.ascontiguousarray(w.groups, dtype=np.uint32) if w.groups is not None else None
+        g = np.ascontiguousarray(groups, dtype=np.uint32) if groups is not None else None
+        vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None  # noqa: E731
+        cap = max(64 * len(q), 1024)
+        idx = np.zeros((cap, 2), dtype=np.uint32)
+        self.lib.orc2_world_query.restype = C.c_uint64
+        n = self.lib.orc2_world_query(C.byref(o), vp(fat), vp(og), C.c_int(k), C.c_uint64(len(q)), vp(q), vp(g), vp(idx), C.c_uint64(cap))
+        assert n <= cap
+        return idx[:n]
+
     def broad_phase_persistent(self, margin):
         return OracleBroadPhase(self, margin)
 

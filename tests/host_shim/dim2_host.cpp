@@ -53,6 +53,15 @@ void shim2_ray_cast(uint64_t n, const uint32_t* type, const float* param, const 
     }
 }
 
+void shim2_contains_point(uint64_t n, const uint32_t* type, const float* param, const float* pose, const float* poly, const float* pts,
+                          uint8_t* out) {
+    for (uint64_t k = 0; k < n; ++k) {
+        const float4* p = reinterpret_cast<const float4*>(param) + k;
+        const float4* m = reinterpret_cast<const float4*>(pose) + k;
+        out[k] = shape_contains_point2(load_operand(type[k], *p, *m, poly, nullptr), w2(pts[2 * k], pts[2 * k + 1])) ? 1 : 0;
+    }
+}
+
 static Operand2 obj(uint32_t i, const float* pos, const float* rot, const uint32_t* type, const float* param, const float* poly, const float* nrm) {
     float4 p = reinterpret_cast<const float4*>(param)[i];
     return load_operand(type[i], p, make_float4(pos[2 * i], pos[2 * i + 1], rot[2 * i], rot[2 * i + 1]), poly, nrm);

@@ -412,3 +412,85 @@ def test_device_world_ray_queries_2d(ctx, oracle, groups):
     with pytest.raises(NcbError):
         dim2.world_ray_cast(fresh, rays)  # no 2-D world on that context
     fresh.close()
+
+
+# ---- point / AABB queries of the 2-D world ---------------------------------------------------------------------------------------
+def _shape_points(n, seed):
+    typ, par, pose, rays, pts = random_shape_rays(n, seed)
+    rng = np.random.default_rng(seed + 5)
+    q = pose[:, :2] + rng.normal(size=(n, 2)) * rng.uniform(0.0, 0.9, size=(n, 1))
+    return typ, par, pose, np.ascontiguousarray(q, dtype=F), pts
+
+
+def test_oracle_contains_point_against_numpy(oracle64):
+    """ORACLE check (f64): contains_point against closed forms (disc, box, half-plane) and, for polygons, the sign of the cross products
+    along the boundary."""
+    typ, par, pose, q, pts = _shape_points(6000, 91)
+    got = oracle64.contains_point2d(typ, par, pose, q, pts)
+    seen = {0: [0, 0], 1: [0, 0], 2: [0, 0], 3: [0, 0]}
+    for k in range(len(typ)):
+        m = pose[k].astype(np.float64)
+        d = q[k].astype(np.float64) - m[:2]
+        loc = np.array([m[2] * d[0] + m[3] * d[1], -m[3] * d[0] + m[2] * d[1]])
+        if typ[k] == 0:
+            val = float(par[k, 0]) - np.hypot(*loc)
+        elif typ[k] == 1:
+            val = float(min(par[k, 0] - abs(loc[0]), par[k, 1] - abs(loc[1])))
+        elif typ[k] == 3:
+            val = -float(par[k, 0] * loc[0] + par[k, 1] * loc[1])
+        else:
+            P = pts[int(par[k, 0]) : int(par[k, 0]) + int(par[k, 1])].astype(np.float64)
+            e = np.roll(P, -1, axis=0) - P
+            cr = (e[:, 0] * (loc - P)[:, 1] - e[:, 1] * (loc - P)[:, 0]) / np.linalg.norm(e, axis=1)
+            val = float(cr.min())
+        if abs(val) < 1e-6:
+            continue
+        assert got[k] == (val > 0), (k, typ[k], val)
+        seen[int(typ[k])][int(val > 0)] += 1
+    assert min(min(v) for v in seen.values()) > 100, seen
+
+
+def test_device_source_contains_point_equals_oracle(dim2_shim, oracle):
+    typ, par, pose, q, pts = _shape_points(40_000, 92)
+    out = np.zeros(len(typ), dtype=np.uint8)
+    dim2_shim.shim2_contains_point(C.c_uint64(len(typ)), _vp(typ), _vp(par), _vp(pose), _vp(pts), _vp(q), _vp(out))
+    want = oracle.contains_point2d(typ, par, pose, q, pts)
+    assert np.array_equal(out.astype(bool), want) and 5000 < want.sum() < 35_000
+
+
+def _world_queries(w, seed, m=3000):
+    rng = np.random.default_rng(seed)
+    lo, hi = w.pos.min(axis=0), w.pos.max(axis=0)
+    pts = rng.uniform(lo, hi, size=(m, 2)).astype(F)
+    c = rng.uniform(lo, hi, size=(m, 2))
+    he = rng.uniform(0.05, 1.5, size=(m, 2))
+    return pts, np.concatenate([c - he, c + he], axis=1).astype(F)
+
+
+def test_oracle_world_point_and_aabb_queries_2d(oracle):
+    w, _ = _ray_world(1500, 83)
+    pts, boxes = _world_queries(w, 84)
+    ip = oracle.world_query2d(w, "point", pts)
+    ib = oracle.world_query2d(w, "aabb", boxes)
+    assert len(ip) > 300 and len(ib) > 3000
+    pose = np.concatenate([w.pos, w.rot], axis=1)
+    inside = oracle.contains_point2d(w.type[ip[:, 1]], w.param[ip[:, 1]], pose[ip[:, 1]], pts[ip[:, 0]], w.points)
+    assert inside.all()
+    assert len(oracle.world_query2d(w, "point", pts, groups=(0x3FFFFFFF, 0x3FFFFFFF, 0x3FFFFFFF))) == 0
+    # a box query sees at least what a point query at its centre sees
+    centres = ((boxes[:, :2] + boxes[:, 2:]) * 0.5).astype(F)
+    ic = oracle.world_query2d(w, "point", centres)
+    assert set(map(tuple, ic.tolist())) <= set(map(tuple, ib.tolist()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("groups", [None, (1 << 3, 0x3FFFFFFF, 1 << 5)])
+def test_device_world_point_and_aabb_queries_2d(ctx, oracle, groups):
+    w, _ = _ray_world(5000, 85)
+    pts, boxes = _world_queries(w, 86, m=6000)
+    dim2.world_update(ctx, w)
+    for kind, q in (("point", pts), ("aabb", boxes)):
+        got = dim2.world_query(ctx, kind, q, groups=groups)
+        want = oracle.world_query2d(w, kind, q, groups=groups)
+        assert len(want) > 200 and np.array_equal(got, want), (kind, len(got), len(want))
+    assert ctx.traversal_overflows() == 0
