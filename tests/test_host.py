@@ -287,6 +287,58 @@ def test_oracle_hull_penetration_against_separating_axes(oracle64):
     assert deep > 100, deep
 
 
+def test_oracle_gjk_distance_against_quadratic_program(oracle64):
+    """ORACLE check (f64): for separated hull / cuboid pairs query::contact(prediction = 1) reports depth = -distance (GJK); the distance
+    is recomputed as the quadratic program min |A^T l - B^T m|^2 over convex weights (SLSQP), and the witness points must realise it."""
+    from scipy.optimize import minimize
+
+    from ncollide_b200.scenes import WorldScene, make_world_scene
+
+    s = make_world_scene(500, 37, (0, 1, 2), side=7.0, n_hulls=24)
+    s.rot = s.rot.astype(np.float64) / np.linalg.norm(s.rot.astype(np.float64), axis=1, keepdims=True)
+    s.query_limit[:] = 0.5
+    fat = oracle64.compute_aabbs(s)
+    pairs = oracle64.broad_phase(fat, s.groups, 1)
+    R, t, H = _rotation_matrices(s.rot), s.pos.astype(np.float64), s.hulls
+
+    def vertices(i):
+        if s.shape_type[i] == 1:
+            he = s.shape_param[i, :3].astype(np.float64)
+            V = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=np.float64) * he
+        else:
+            h = int(s.shape_param[i, 0])
+            V = H.points[H.vert_off[h] : H.vert_off[h + 1]].astype(np.float64)
+        return V @ R[i].T + t[i]
+
+    checked = 0
+    for i1, i2 in pairs[:600]:
+        two = WorldScene(pos=s.pos[[i1, i2]], rot=s.rot[[i1, i2]], shape_type=s.shape_type[[i1, i2]], shape_param=s.shape_param[[i1, i2]],
+                         groups=s.groups[[i1, i2]], query_limit=s.query_limit[[i1, i2]], ang_pred=s.ang_pred[[i1, i2]], hulls=s.hulls, margin=s.margin)
+        q = oracle64.query_contact(two, 1.0)
+        if q is None or q["depth"] > -1e-3:
+            continue
+        A, B = vertices(i1), vertices(i2)
+        na, nb = len(A), len(B)
+
+        def f(x):
+            d = x[:na] @ A - x[na:] @ B
+            return d @ d
+
+        def g(x):
+            d = x[:na] @ A - x[na:] @ B
+            return np.concatenate([2 * A @ d, -2 * B @ d])
+
+        cons = [{"type": "eq", "fun": lambda x: x[:na].sum() - 1, "jac": lambda x: np.concatenate([np.ones(na), np.zeros(nb)])},
+                {"type": "eq", "fun": lambda x: x[na:].sum() - 1, "jac": lambda x: np.concatenate([np.zeros(na), np.ones(nb)])}]
+        x0 = np.concatenate([np.full(na, 1 / na), np.full(nb, 1 / nb)])
+        r = minimize(f, x0, jac=g, bounds=[(0, 1)] * (na + nb), constraints=cons, method="SLSQP", options={"ftol": 1e-15, "maxiter": 500})
+        dist = np.sqrt(r.fun)
+        assert abs(-q["depth"] - dist) < 2e-6 * max(1.0, dist), (i1, i2, q["depth"], dist)
+        assert abs(np.linalg.norm(q["world2"] - q["world1"]) - dist) < 2e-6  # the witness points are that far apart
+        checked += 1
+    assert checked > 100, checked
+
+
 def test_oracle_ray_bvt_matches_brute_force(oracle):
     from ncollide_b200.scenes import make_ray_scene
 
