@@ -339,6 +339,53 @@ def test_oracle_gjk_distance_against_quadratic_program(oracle64):
     assert checked > 100, checked
 
 
+def test_oracle_ball_hull_contact_against_point_to_polytope_distance(oracle64):
+    """ORACLE check (f64): the BallConvexPolyhedron generator's depth for ball x hull pairs == radius - distance(centre, hull) with the
+    distance from a quadratic program when the centre is outside, and radius + the distance to the nearest face plane (qhull) when it is
+    inside (the EPA projection)."""
+    from scipy.optimize import minimize
+    from scipy.spatial import ConvexHull
+
+    from ncollide_b200.scenes import make_world_scene
+
+    s = make_world_scene(900, 39, (1, 0, 1), side=5.0, n_hulls=24)
+    s.rot = s.rot.astype(np.float64) / np.linalg.norm(s.rot.astype(np.float64), axis=1, keepdims=True)
+    ball = s.shape_type == 0
+    s.shape_param[ball, 0] = np.random.default_rng(1).uniform(0.05, 0.5, size=int(ball.sum()))  # small balls: some end up inside a hull
+    fat = oracle64.compute_aabbs(s)
+    pairs = oracle64.broad_phase(fat, s.groups, 1)
+    c, off, algo, stats = oracle64.narrow_phase(s, pairs)
+    R, t, H = _rotation_matrices(s.rot), s.pos.astype(np.float64), s.hulls
+    planes = {}
+    outside = inside = 0
+    for p, (i1, i2) in enumerate(pairs):
+        if s.shape_type[i1] == s.shape_type[i2]:
+            continue
+        ib, ih = (i1, i2) if s.shape_type[i1] == 0 else (i2, i1)
+        h = int(s.shape_param[ih, 0])
+        V = H.points[H.vert_off[h] : H.vert_off[h + 1]].astype(np.float64)
+        if h not in planes:
+            planes[h] = ConvexHull(V).equations.copy()
+        centre = (t[ib] - t[ih]) @ R[ih]  # the ball's centre in the hull's frame
+        r = float(s.shape_param[ib, 0])
+        signed = (planes[h][:, :3] @ centre + planes[h][:, 3]).max()  # < 0: inside, the distance to the nearest face plane is -signed
+        if signed < -1e-6:
+            want = r - signed
+            inside += 1
+        else:
+            res = minimize(lambda x: (x @ V - centre) @ (x @ V - centre), np.full(len(V), 1 / len(V)), jac=lambda x: 2 * V @ (x @ V - centre),
+                           bounds=[(0, 1)] * len(V), constraints=[{"type": "eq", "fun": lambda x: x.sum() - 1, "jac": lambda x: np.ones(len(V))}],
+                           method="SLSQP", options={"ftol": 1e-15, "maxiter": 500})
+            want = r - np.sqrt(res.fun)
+            outside += 1
+        depths = c["depth"][off[p] : off[p + 1]]
+        if want < -0.04 - 1e-5:
+            assert len(depths) == 0, (p, want)
+        elif want > -0.04 + 1e-5:
+            assert len(depths) == 1 and abs(depths[0] - want) < 3e-6, (p, depths, want)
+    assert outside > 100 and inside > 10, (outside, inside)
+
+
 def test_oracle_ray_bvt_matches_brute_force(oracle):
     from ncollide_b200.scenes import make_ray_scene
 
