@@ -386,6 +386,46 @@ def test_oracle_ball_hull_contact_against_point_to_polytope_distance(oracle64):
     assert outside > 100 and inside > 10, (outside, inside)
 
 
+def test_oracle_contact_points_lie_on_their_shapes(oracle64):
+    """ORACLE check (f64) of the manifold contents: world1 lies on the boundary of shape 1 and world2 on the boundary of shape 2 — a
+    sphere, a box surface, or the surface of the qhull polytope of the hull's vertices — for every contact of a mixed world."""
+    from scipy.spatial import ConvexHull
+
+    from ncollide_b200.scenes import make_world_scene
+
+    s = make_world_scene(1500, 41, (1, 1, 1), side=7.0, n_hulls=24, angular=0.03)
+    s.rot = s.rot.astype(np.float64) / np.linalg.norm(s.rot.astype(np.float64), axis=1, keepdims=True)
+    fat = oracle64.compute_aabbs(s)
+    pairs = oracle64.broad_phase(fat, s.groups, 1)
+    c, off, algo, stats = oracle64.narrow_phase(s, pairs)
+    R, t, H = _rotation_matrices(s.rot), s.pos.astype(np.float64), s.hulls
+    planes = {}
+
+    def surface_distance(i, p):
+        loc = (p - t[i]) @ R[i]
+        typ = int(s.shape_type[i])
+        if typ == 0:
+            return np.linalg.norm(loc) - float(s.shape_param[i, 0])
+        if typ == 1:
+            return float((np.abs(loc) - s.shape_param[i, :3].astype(np.float64)).max())
+        h = int(s.shape_param[i, 0])
+        if h not in planes:
+            planes[h] = ConvexHull(H.points[H.vert_off[h] : H.vert_off[h + 1]].astype(np.float64)).equations.copy()
+        return float((planes[h][:, :3] @ loc + planes[h][:, 3]).max())
+
+    dist = {0: [], 1: [], 2: []}
+    for p, (i1, i2) in enumerate(pairs):
+        for k in range(off[p], off[p + 1]):
+            dist[int(s.shape_type[i1])].append(abs(surface_distance(i1, c["world1"][k])))
+            dist[int(s.shape_type[i2])].append(abs(surface_distance(i2, c["world2"][k])))
+    assert min(len(v) for v in dist.values()) > 800
+    assert max(dist[0]) < 1e-12 and max(dist[1]) < 1e-12
+    # hulls: a face of the ConvexHull tables may merge nearly coplanar triangles (try_new's tolerance); a contact projected onto such a
+    # face's plane then sits up to a few mm off the exact polytope — the reference's own behaviour, seen on < 1 % of the contacts
+    hull = np.array(dist[2])
+    assert np.percentile(hull, 99) < 1e-6 and hull.max() < 5e-3, (np.percentile(hull, 99), hull.max())
+
+
 def test_oracle_ray_bvt_matches_brute_force(oracle):
     from ncollide_b200.scenes import make_ray_scene
 
