@@ -423,6 +423,7 @@ const char* ncb_version(void);
 #define NCB2D_CUBOID 1u
 #define NCB2D_POLYGON 2u
 #define NCB2D_PLANE 3u /* shape/plane.rs in 2-D (a half-space): shape_param = the unit normal (nx, ny) */
+#define NCB2D_SEGMENT 4u /* shape/segment.rs: shape_param = (a.x, a.y, b.x, b.y), a != b; a ConvexPolyhedron with two vertices and two faces */
 int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const float* param1, const float* pose1, const uint32_t* type2,
                   const float* param2, const float* pose2, const float* poly_points, const float* poly_normals, uint32_t n_poly_points,
                   float prediction, uint8_t* found, float* out, uint32_t* ref_panics, uint32_t* epa_overflow);

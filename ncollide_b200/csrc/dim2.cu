@@ -71,10 +71,12 @@ __device__ __forceinline__ W2 to_local(const Pose2& m, W2 p) { return unrotate(m
 #define D2_CUBOID 1u
 #define D2_POLYGON 2u
 #define D2_PLANE 3u   // shape/plane.rs: (a, b) = the unit normal; the code of the 3-D path's plane, so the broad phase treats its box as an outlier
+#define D2_SEGMENT 4u  // shape/segment.rs: (a, b) = point a, (c, d) = point b
 #define D2_ORIGIN 7u  // special_support_maps::ConstantOrigin
 struct Operand2 {
     uint32_t kind;
-    float a, b;          // radius | half extents
+    float a, b;          // radius | half extents | segment point a
+    float c, d;          // segment point b
     const float* pts;    // polygon vertices (x, y)
     const float* nrm;    // polygon edge normals (ConvexPolygon::normals), may be null when no ball meets a polygon
     uint32_t npts;
@@ -87,6 +89,8 @@ __device__ W2 support(const Operand2& g, W2 dir) {
     W2 ld = unrotate(g.m, dir), lp;
     if (g.kind == D2_CUBOID) {
         lp = w2(copysignf(g.a, ld.x), copysignf(g.b, ld.y));
+    } else if (g.kind == D2_SEGMENT) {  // segment.rs:182-191
+        lp = dot(w2(g.a, g.b), ld) > dot(w2(g.c, g.d), ld) ? w2(g.a, g.b) : w2(g.c, g.d);
     } else {
         uint32_t arg = 0;
         float best = __ldg(g.pts) * ld.x + __ldg(g.pts + 1) * ld.y;
@@ -548,6 +552,46 @@ __device__ bool ball_cuboid(W2 center, float radius, const Operand2& box, float 
 
 // ConvexPolygon::project_point_with_feature + contact_ball_convex_polyhedron: the ball centre is projected on the polygon with
 // GJK against the constant origin (EPA when it lies inside), in the frame translated by -centre
+// Segment::project_point_with_feature (query/point/point_segment.rs:14-91, dim2) + Segment::feature_normal (segment.rs:237-284), then
+// contact_ball_convex_polyhedron (contact_ball_convex_polyhedron.rs:12-62)
+__device__ bool ball_segment(W2 center, float radius, const Operand2& seg, float prediction, Hit2& h, uint32_t* feature = nullptr) {
+    W2 a = w2(seg.a, seg.b), b = w2(seg.c, seg.d), ls = to_local(seg.m, center);
+    W2 ab = b - a, ap = ls - a;
+    float ab_ap = dot(ab, ap), sqnab = nsq(ab);
+    W2 world2;
+    uint32_t f;
+    bool on_edge = false;
+    if (ab_ap <= 0.f) {
+        f = FEAT2_VERTEX | 0u, world2 = to_world(seg.m, a);
+    } else if (ab_ap >= sqnab) {
+        f = FEAT2_VERTEX | 1u, world2 = to_world(seg.m, b);
+    } else {
+        float u = ab_ap / sqnab;
+        world2 = to_world(seg.m, a + ab * u);
+        on_edge = true;
+    }
+    const bool inside = relative_eq(world2.x, center.x) && relative_eq(world2.y, center.y);
+    if (on_edge) f = perp(center - world2, ab) >= 0.f ? (FEAT2_FACE | 0u) : (FEAT2_FACE | 1u);
+    if (feature) *feature = f;
+    W2 dpt = world2 - center, dir, normal;
+    float dist, depth;
+    if (unit_get(dpt, NCB_EPS, dir, dist)) {
+        depth = inside ? dist + radius : -dist + radius;
+        normal = inside ? -dir : dir;
+    } else {
+        W2 sd, fn = w2(0.f, 1.f);  // feature_normal: no direction -> the y axis
+        if (unit(ab, NCB_EPS, sd)) {
+            uint32_t id = f & 0xffffu;
+            fn = (f & FEAT2_VERTEX) ? (id == 0 ? sd : -sd) : (id == 0 ? w2(sd.y, -sd.x) : w2(-sd.y, sd.x));
+        }
+        depth = radius;
+        normal = -fn;
+    }
+    if (!(depth >= -prediction)) return false;
+    h.w1 = center + normal * radius, h.w2 = world2, h.n = normal, h.depth = depth;
+    return true;
+}
+
 __device__ bool ball_polygon(W2 center, float radius, const Operand2& poly, float prediction, float cos_one_degree, Hit2& h, int& epa_status,
                              uint32_t* feature = nullptr) {
     Operand2 g = poly, origin;
@@ -662,7 +706,27 @@ __device__ void ngon_face(const Operand2& g, uint32_t ia, Edge2& e) {
     e.normal = w2(__ldg(g.nrm + 2 * ia), __ldg(g.nrm + 2 * ia + 1)), e.has_normal = true;
     e.fid = FEAT2_FACE | ia;
 }
+// Segment::face (segment.rs:212-235, dim2) for the segment (a, b); a degenerate one is the vertex a
+__device__ void segment_face(W2 a, W2 b, uint32_t id, Edge2& e) {
+    edge_clear(e);
+    W2 ab = b - a, nrm;
+    if (unit(w2(ab.y, -ab.x), NCB_EPS, nrm)) {
+        e.fid = FEAT2_FACE | id, e.nv = 2, e.has_normal = true;
+        if (id == 0)
+            e.v[0] = a, e.vid[0] = FEAT2_VERTEX | 0u, e.v[1] = b, e.vid[1] = FEAT2_VERTEX | 1u, e.normal = nrm;
+        else
+            e.v[0] = b, e.vid[0] = FEAT2_VERTEX | 1u, e.v[1] = a, e.vid[1] = FEAT2_VERTEX | 0u, e.normal = -nrm;
+    } else {
+        e.v[0] = a, e.vid[0] = FEAT2_VERTEX | 0u, e.nv = 1, e.fid = FEAT2_VERTEX | 0u;
+    }
+}
 __device__ void face_toward(const Operand2& g, W2 dir, Edge2& e) {
+    if (g.kind == D2_SEGMENT) {  // segment.rs:286-299 (dim2): the world `dir` against the LOCAL segment direction, as in the reference
+        W2 a = w2(g.a, g.b), b = w2(g.c, g.d);
+        segment_face(a, b, perp(dir, b - a) >= 0.f ? 0u : 1u, e);
+        edge_to_world(e, g.m);
+        return;
+    }
     W2 ld = unrotate(g.m, dir);
     if (g.kind == D2_CUBOID) {
         int iamax = fabsf(ld.y) > fabsf(ld.x) ? 1 : 0;
@@ -678,7 +742,21 @@ __device__ void face_toward(const Operand2& g, W2 dir, Edge2& e) {
     }
     edge_to_world(e, g.m);
 }
-__device__ void feature_toward(const Operand2& g, W2 dir, float cang, Edge2& e) {
+__device__ void feature_toward(const Operand2& g, W2 dir, float cang, float sang, Edge2& e) {
+    if (g.kind == D2_SEGMENT) {  // segment.rs:315-345 (dim2), sang = sin(angular prediction)
+        edge_clear(e);
+        W2 a = to_world(g.m, w2(g.a, g.b)), b = to_world(g.m, w2(g.c, g.d)), sd;
+        if (unit(b - a, NCB_EPS, sd)) {
+            float c = dot(dir, sd);
+            if (c > sang)
+                e.fid = FEAT2_VERTEX | 1u, e.v[0] = b, e.vid[0] = FEAT2_VERTEX | 1u, e.nv = 1;
+            else if (c < -sang)
+                e.fid = FEAT2_VERTEX | 0u, e.v[0] = a, e.vid[0] = FEAT2_VERTEX | 0u, e.nv = 1;
+            else
+                segment_face(a, b, perp(dir, sd) >= 0.f ? 0u : 1u, e);
+        }
+        return;
+    }
     if (g.kind != D2_CUBOID) {  // ConvexPolygon::support_feature_toward is its support face
         face_toward(g, dir, e);
         return;
@@ -788,6 +866,9 @@ __device__ void aabb_of_shape(const Operand2& g, W2& lo, W2& hi) {
         float are = fabsf(g.m.re), aim = fabsf(g.m.im);
         W2 w = w2(are * g.a + aim * g.b, aim * g.a + are * g.b);
         lo = g.m.t - w, hi = g.m.t + w;
+    } else if (g.kind == D2_SEGMENT) {  // support_map_aabb (aabb_utils.rs:9-31): one support point per axis direction
+        hi = w2(support(g, w2(1.f, 0.f)).x, support(g, w2(0.f, 1.f)).y);
+        lo = w2(support(g, w2(-1.f, 0.f)).x, support(g, w2(0.f, -1.f)).y);
     } else {
         W2 p = to_world(g.m, w2(__ldg(g.pts), __ldg(g.pts + 1)));
         lo = hi = p;
@@ -798,7 +879,7 @@ __device__ void aabb_of_shape(const Operand2& g, W2& lo, W2& hi) {
     }
 }
 // One pair through its ContactManifoldGenerator into a fresh manifold.  flags: bit 0 = the reference would panic, bit 1 = EPA capacity.
-__device__ void manifold_of_pair(const Operand2& g1, const Operand2& g2, float linear, float cang1, float cang2, float cos_one_degree,
+__device__ void manifold_of_pair(const Operand2& g1, const Operand2& g2, float linear, float cang1, float cang2, float sang1, float sang2, float cos_one_degree,
                                  Manifold2d& mf, int& flags) {
     mf.n = 0, mf.overflow = false;
     const uint32_t FACE0 = FEAT2_FACE | 0u;
@@ -851,8 +932,9 @@ __device__ void manifold_of_pair(const Operand2& g1, const Operand2& g2, float l
         const Operand2& other = flip ? g1 : g2;
         uint32_t f2 = FEAT2_UNKNOWN;
         int q = 1;
-        bool ok = other.kind == D2_CUBOID ? ball_cuboid(ball.m.t, ball.a, other, linear, h, &f2)
-                                          : ball_polygon(ball.m.t, ball.a, other, linear, cos_one_degree, h, q, &f2);
+        bool ok = other.kind == D2_CUBOID    ? ball_cuboid(ball.m.t, ball.a, other, linear, h, &f2)
+                  : other.kind == D2_SEGMENT ? ball_segment(ball.m.t, ball.a, other, linear, h, &f2)
+                                             : ball_polygon(ball.m.t, ball.a, other, linear, cos_one_degree, h, q, &f2);
         if (q == -1) flags |= 1;
         if (q == -2) flags |= 2;
         if (ok) {
@@ -891,8 +973,8 @@ __device__ void manifold_of_pair(const Operand2& g1, const Operand2& g2, float l
                 face_toward(g1, n, fa);
                 face_toward(g2, -n, fb);
             } else {
-                feature_toward(g1, n, cang1, fa);
-                feature_toward(g2, -n, cang2, fb);
+                feature_toward(g1, n, cang1, sang1, fa);
+                feature_toward(g2, -n, cang2, sang2, fb);
             }
             int n_new = 0;
             clip_edges(fa, fb, n, linear, g1.m, mf, n_new);
@@ -914,7 +996,7 @@ struct Args2 {
 };
 __device__ __forceinline__ Operand2 load_operand(uint32_t t, float4 p, float4 m, const float* poly, const float* poly_nrm) {
     Operand2 g;
-    g.kind = t, g.a = p.x, g.b = p.y, g.pts = g.nrm = nullptr, g.npts = 0;
+    g.kind = t, g.a = p.x, g.b = p.y, g.c = p.z, g.d = p.w, g.pts = g.nrm = nullptr, g.npts = 0;
     if (t == D2_POLYGON) {
         g.pts = poly + 2 * (size_t)p.x, g.npts = (uint32_t)p.y;
         g.nrm = poly_nrm ? poly_nrm + 2 * (size_t)p.x : nullptr;
@@ -1147,8 +1229,57 @@ __device__ RayHit2 ray2_polygon(const Operand2& g, W2 o_w, W2 d_w, float max_toi
     return h;
 }
 
+// RayCast for Segment, dim2 (query/ray/ray_support_map.rs:219-293): line / line parameters (closest_points_line_line.rs:27-70) on the
+// segment moved by its pose, the collinear cases; the SCALED normal; max_toi is not applied, as in the reference
+__device__ RayHit2 ray2_segment(const Operand2& g, W2 o, W2 d) {
+    RayHit2 h = ray2_miss();
+    W2 a = to_world(g.m, w2(g.a, g.b)), b = to_world(g.m, w2(g.c, g.d));
+    W2 sd = b - a, r = o - a;
+    float aa = nsq(d), e = nsq(sd), f = dot(sd, r), s, t;
+    bool parallel = false;
+    if (aa <= NCB_EPS && e <= NCB_EPS) {
+        s = 0.f, t = 0.f;
+    } else if (aa <= NCB_EPS) {
+        s = 0.f, t = f / e;
+    } else {
+        float c = dot(d, r);
+        if (e <= NCB_EPS) {
+            s = -c / aa, t = 0.f;
+        } else {
+            float bq = dot(d, sd), ae = aa * e, bb = bq * bq, denom = ae - bb;
+            parallel = denom <= NCB_EPS || ulps_eq(ae, bb);
+            s = !parallel ? (bq * f - c * e) / denom : 0.f;
+            t = (bq * s + f) / e;
+        }
+    }
+    W2 nrm = w2(sd.y, -sd.x);
+    if (parallel) {
+        W2 dpos = a - o;
+        if (fabsf(dot(dpos, nrm)) < NCB_EPS) {
+            float dist1 = dot(dpos, d), dist2 = dist1 + dot(sd, d);
+            if (dist1 >= 0.f && dist2 >= 0.f) {
+                h.hit = true, h.n = nrm;
+                if (dist1 <= dist2)
+                    h.toi = dist1 / nsq(d), h.feature = FEAT2_VERTEX | 0u;
+                else
+                    h.toi = dist2 / nsq(d), h.feature = FEAT2_VERTEX | 1u;
+            } else if (dist1 >= 0.f || dist2 >= 0.f) {
+                h.hit = true, h.toi = 0.f, h.n = nrm, h.feature = FEAT2_FACE | 0u;
+            }
+        }
+    } else if (s >= 0.f && t >= 0.f && t <= 1.f) {
+        h.hit = true, h.toi = s;
+        if (dot(nrm, d) > 0.f)
+            h.n = -nrm, h.feature = FEAT2_FACE | 1u;
+        else
+            h.n = nrm, h.feature = FEAT2_FACE | 0u;
+    }
+    return h;
+}
+
 // RayCast::toi_and_normal_with_ray(m, ray, max_toi, true) of one shape
 __device__ RayHit2 shape_ray_cast2(const Operand2& g, W2 o, W2 d, float max_toi) {
+    if (g.kind == D2_SEGMENT) return ray2_segment(g, o, d);
     if (g.kind == D2_BALL) return ray2_ball(g.m.t, g.a, o, d, max_toi);
     if (g.kind == D2_CUBOID) return ray2_cuboid(g, o, d, max_toi);
     if (g.kind == D2_POLYGON) return ray2_polygon(g, o, d, max_toi);
@@ -1164,6 +1295,12 @@ __device__ bool shape_contains_point2(const Operand2& g, W2 pt) {
         return !(l.x < -g.a || l.x > g.a || l.y < -g.b || l.y > g.b);
     }
     if (g.kind == D2_PLANE) return dot(w2(g.a, g.b), to_local(g.m, pt)) <= 0.f;
+    if (g.kind == D2_SEGMENT) {  // the trait's default on Segment::project_point: relative_eq!(proj, pt) (point_segment.rs:52-91)
+        W2 a = w2(g.a, g.b), ab = w2(g.c, g.d) - a, ap = to_local(g.m, pt) - a;
+        float ab_ap = dot(ab, ap), sq = nsq(ab);
+        W2 proj = ab_ap <= 0.f ? to_world(g.m, a) : ab_ap >= sq ? to_world(g.m, w2(g.c, g.d)) : to_world(g.m, a + ab * (ab_ap / sq));
+        return relative_eq(proj.x, pt.x) && relative_eq(proj.y, pt.y);
+    }
     Operand2 s = g, origin;
     s.m.t = (-pt) + g.m.t;  // Translation::from(-point) * m
     origin.kind = D2_ORIGIN, origin.a = origin.b = 0.f, origin.pts = origin.nrm = nullptr, origin.npts = 0;
@@ -1197,8 +1334,9 @@ __device__ bool contact_of_pair(const Operand2& g1, const Operand2& g2, float pr
         const Operand2& ball = flip ? g2 : g1;
         const Operand2& other = flip ? g1 : g2;
         int q = 1;
-        ok = other.kind == D2_CUBOID ? ball_cuboid(ball.m.t, ball.a, other, prediction, h)
-                                     : ball_polygon(ball.m.t, ball.a, other, prediction, cos_one_degree, h, q);
+        ok = other.kind == D2_CUBOID    ? ball_cuboid(ball.m.t, ball.a, other, prediction, h)
+             : other.kind == D2_SEGMENT ? ball_segment(ball.m.t, ball.a, other, prediction, h)
+                                        : ball_polygon(ball.m.t, ball.a, other, prediction, cos_one_degree, h, q);
         if (q == -1) flags |= 1;
         if (q == -2) flags |= 2;
         if (ok && flip) {
@@ -1268,7 +1406,7 @@ struct World2Args {
     const float2 *pos, *rot;
     const uint32_t* type;
     const float4* param;
-    const float *qlimit, *cos_ang;
+    const float *qlimit, *cos_ang, *sin_ang;  // cos / sin of the angular prediction, from the host libm like the reference's
     const float *poly, *poly_nrm;
     float margin, cos_one_degree;
     float4 *aabb_lo, *aabb_hi;
@@ -1314,7 +1452,8 @@ __global__ void __launch_bounds__(64) k_narrow2d(World2Args A) {
         A.prox[p] = (g1.kind == D2_PLANE && g2.kind == D2_PLANE) ? (uint8_t)NCB_PROXIMITY_NONE : proximity_of_pair(g1, g2, linear);
     } else {
         if (A.prox) A.prox[p] = (uint8_t)NCB_PROXIMITY_NONE;
-        manifold_of_pair(g1, g2, linear, __ldg(&A.cos_ang[pr.x]), __ldg(&A.cos_ang[pr.y]), A.cos_one_degree, mf, flags);
+        manifold_of_pair(g1, g2, linear, __ldg(&A.cos_ang[pr.x]), __ldg(&A.cos_ang[pr.y]), __ldg(&A.sin_ang[pr.x]), __ldg(&A.sin_ang[pr.y]),
+                         A.cos_one_degree, mf, flags);
     }
     if (flags & 1) atomicAdd(&A.counters[1], 1u);
     if (flags & 2) atomicAdd(&A.counters[2], 1u);
@@ -1558,9 +1697,13 @@ int ncb2d_contact(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const f
         for (int side = 0; side < 2; ++side) {
             uint32_t t = side ? type2[k] : type1[k];
             const float* p = (side ? param2 : param1) + 4 * (size_t)k;
-            if (t > 3) {
+            if (t > 4) {
                 ctx->err = "ncb2d_contact: unknown 2-D shape type";
                 return NCB_ERR_UNSUPPORTED;
+            }
+            if (t == 4 && p[0] == p[2] && p[1] == p[3]) {
+                ctx->err = "ncb2d_contact: a segment needs two different end points";
+                return NCB_ERR_ARG;
             }
             if (t == 2) {
                 if (!poly_points || p[1] < 1.f || p[0] < 0.f || (uint64_t)p[0] + (uint64_t)p[1] > n_poly_points) {
@@ -1635,9 +1778,13 @@ int ncb2d_proximity(ncb_ctx* ctx, uint32_t n_pairs, const uint32_t* type1, const
         for (int side = 0; side < 2; ++side) {
             uint32_t t = side ? type2[k] : type1[k];
             const float* p = (side ? param2 : param1) + 4 * (size_t)k;
-            if (t > 3) {
+            if (t > 4) {
                 ctx->err = "ncb2d_proximity: unknown 2-D shape type";
                 return NCB_ERR_UNSUPPORTED;
+            }
+            if (t == 4 && p[0] == p[2] && p[1] == p[3]) {
+                ctx->err = "ncb2d_proximity: a segment needs two different end points";
+                return NCB_ERR_ARG;
             }
             if (t == 2 && (!poly_points || p[1] < 1.f || p[0] < 0.f || (uint64_t)p[0] + (uint64_t)p[1] > n_poly_points)) {
                 ctx->err = "ncb2d_proximity: polygon point range outside poly_points";
@@ -1693,9 +1840,13 @@ int ncb2d_ray_cast(ncb_ctx* ctx, uint32_t n, const uint32_t* type, const float* 
     if (n == 0) return NCB_OK;
     for (uint32_t k = 0; k < n; ++k) {
         const float* p = param + 4 * (size_t)k;
-        if (type[k] > 3) {
+        if (type[k] > 4) {
             ctx->err = "ncb2d_ray_cast: unknown 2-D shape type";
             return NCB_ERR_UNSUPPORTED;
+        }
+        if (type[k] == 4 && p[0] == p[2] && p[1] == p[3]) {
+            ctx->err = "ncb2d_ray_cast: a segment needs two different end points";
+            return NCB_ERR_ARG;
         }
         if (type[k] == 2 && (!poly_points || p[1] < 1.f || p[0] < 0.f || (uint64_t)p[0] + (uint64_t)p[1] > n_poly_points)) {
             ctx->err = "ncb2d_ray_cast: polygon point range outside poly_points";
@@ -1750,9 +1901,13 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     bool any_poly = false;
     for (uint32_t i = 0; i < n; ++i) {  // validation before device state is touched
         uint32_t t = o->shape_type[i];
-        if (t > 3) {
+        if (t > 4) {
             ctx->err = "ncb2d_world_update: unknown 2-D shape type";
             return NCB_ERR_UNSUPPORTED;
+        }
+        if (t == 4 && o->shape_param[4 * (size_t)i] == o->shape_param[4 * (size_t)i + 2] && o->shape_param[4 * (size_t)i + 1] == o->shape_param[4 * (size_t)i + 3]) {
+            ctx->err = "ncb2d_world_update: a segment needs two different end points";
+            return NCB_ERR_ARG;
         }
         if (o->query_kind && o->query_kind[i] > 1) {
             ctx->err = "ncb2d_world_update: query_kind must be 0 (Contacts) or 1 (Proximity)";
@@ -1792,15 +1947,18 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     CK2(d_param.reserve(n));
     CK2(d_ql.reserve(n));
     CK2(d_cang.reserve(n));
+    CK2(ctx->d2.sang.reserve(n));
     CK2(d_cnt.reserve(4));
     std::vector<float> cang(n);
-    for (uint32_t i = 0; i < n; ++i) cang[i] = cosf(o->ang_pred[i]);  // ContactPrediction / support_feature_toward: angle.cos() with the host libm
+    std::vector<float> sang(n);
+    for (uint32_t i = 0; i < n; ++i) cang[i] = cosf(o->ang_pred[i]), sang[i] = sinf(o->ang_pred[i]);  // ContactPrediction: angle.cos() / .sin() with the host libm
     CK2(cudaMemcpyAsync(d_pos.p, o->pos, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
     CK2(cudaMemcpyAsync(d_rot.p, o->rot, 8 * (size_t)n, cudaMemcpyHostToDevice, s));
     CK2(cudaMemcpyAsync(d_type.p, o->shape_type, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
     CK2(cudaMemcpyAsync(d_param.p, o->shape_param, 16 * (size_t)n, cudaMemcpyHostToDevice, s));
     CK2(cudaMemcpyAsync(d_ql.p, o->query_limit, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
     CK2(cudaMemcpyAsync(d_cang.p, cang.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+    CK2(cudaMemcpyAsync(ctx->d2.sang.p, sang.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, s));
     if (o->groups) {
         CK2(d_groups.reserve(3 * (size_t)n));
         CK2(cudaMemcpyAsync(d_groups.p, o->groups, 12 * (size_t)n, cudaMemcpyHostToDevice, s));
@@ -1821,7 +1979,7 @@ int ncb2d_world_update(ncb_ctx* ctx, const ncb2d_objects* o, float margin, uint3
     d2::World2Args A;
     memset(&A, 0, sizeof A);
     A.n = n;
-    A.pos = d_pos.p, A.rot = d_rot.p, A.type = d_type.p, A.param = d_param.p, A.qlimit = d_ql.p, A.cos_ang = d_cang.p;
+    A.pos = d_pos.p, A.rot = d_rot.p, A.type = d_type.p, A.param = d_param.p, A.qlimit = d_ql.p, A.cos_ang = d_cang.p, A.sin_ang = ctx->d2.sang.p;
     A.poly = d_poly.p, A.poly_nrm = d_nrm.p;
     A.margin = margin;
     A.cos_one_degree = cosf((float)(3.14159265358979323846 / 180.0));

@@ -337,7 +337,7 @@ struct ncb_ctx {
         ncb::DevBuf<float2> pos, rot;
         ncb::DevBuf<uint32_t> type, groups, start, feat, cnt;
         ncb::DevBuf<float4> param;
-        ncb::DevBuf<float> ql, cang, poly, nrm, contacts;
+        ncb::DevBuf<float> ql, cang, sang, poly, nrm, contacts;
         ncb::DevBuf<uint8_t> count, qkind, prox;
         uint32_t last_pairs = 0;  // pairs of the last update (ncb2d_world_fetch_proximity)
         uint32_t last_n = 0;      // objects of the last update, whose boxes / tree are still in the context (ncb2d_world_ray_cast)

@@ -10,7 +10,7 @@ import numpy as np
 
 from ._ffi import as_f32, as_u32, ptr
 
-BALL, CUBOID, POLYGON, PLANE = 0, 1, 2, 3
+BALL, CUBOID, POLYGON, PLANE, SEGMENT = 0, 1, 2, 3, 4
 F32 = np.float32
 EPS = np.finfo(np.float32).eps
 
@@ -41,6 +41,14 @@ class Shapes2D:
         v = as_f32(normal).reshape(2)
         nrm = np.sqrt(F32(F32(v[0] * v[0]) + F32(v[1] * v[1])), dtype=F32)
         self.type.append(PLANE), self.param.append((F32(v[0] / nrm), F32(v[1] / nrm), 0, 0))
+        return self
+
+    def segment(self, a, b):
+        """``Segment::new(a, b)`` (shape/segment.rs): the two end points in the shape's frame, a != b."""
+        a, b = as_f32(a).reshape(2), as_f32(b).reshape(2)
+        if a[0] == b[0] and a[1] == b[1]:
+            raise ValueError("a segment needs two different end points")
+        self.type.append(SEGMENT), self.param.append((a[0], a[1], b[0], b[1]))
         return self
 
     def polygon(self, points):

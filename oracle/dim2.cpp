@@ -54,11 +54,12 @@ static inline P2 inv_rot(const Iso2& m, P2 v) { return {m.re * v.x + m.im * v.y,
 static inline P2 mul_point(const Iso2& m, P2 p) { return rot(m, p) + m.t; }
 static inline P2 inv_point(const Iso2& m, P2 p) { return inv_rot(m, p - m.t); }
 
-enum { BALL2 = 0, CUBOID2 = 1, POLYGON2 = 2, PLANE2 = 3, ORIGIN2 = 7 };  // PLANE2: param = unit normal; ORIGIN2: special_support_maps::ConstantOrigin
+enum { BALL2 = 0, CUBOID2 = 1, POLYGON2 = 2, PLANE2 = 3, SEGMENT2 = 4, ORIGIN2 = 7 };  // SEGMENT2: param = a.x a.y b.x b.y (shape/segment.rs)  // PLANE2: param = unit normal; ORIGIN2: special_support_maps::ConstantOrigin
 struct Shape2 {
     uint32_t type;
     real radius;
     P2 he;
+    P2 sb = {0, 0};  // SEGMENT2: a = he, b = sb
     const real* pts;
     const real* normals;  // ConvexPolygon::normals (one per edge i -> i + 1), from try_new
     uint32_t npts;
@@ -75,6 +76,8 @@ static P2 support_point(const Shape2& g, const Iso2& m, P2 dir) {
     P2 lp;
     if (g.type == CUBOID2) {
         lp = p2(std::copysign(g.he.x, ld.x), std::copysign(g.he.y, ld.y));
+    } else if (g.type == SEGMENT2) {  // segment.rs:182-191: a if a . dir > b . dir, else b
+        lp = dot(g.he, ld) > dot(g.sb, ld) ? g.he : g.sb;
     } else {  // point_cloud_support_point: first maximum
         uint32_t best = 0;
         real best_dot = g.pts[0] * ld.x + g.pts[1] * ld.y;
@@ -593,6 +596,60 @@ static P2 cuboid_feature_normal(uint32_t f) {
     }
     return normalize(d);
 }
+// Segment::project_point_with_feature (query/point/point_segment.rs:14-91, dim2): is_inside = relative_eq!(proj, pt)
+static P2 segment_project(const Shape2& g, const Iso2& m, P2 pt, bool* inside, uint32_t* feature) {
+    P2 ls = inv_point(m, pt), a = g.he, b = g.sb;
+    P2 ab = b - a, ap = ls - a;
+    real ab_ap = dot(ab, ap), sqnab = nsq(ab);
+    P2 proj;
+    bool on_edge = false;
+    if (ab_ap <= 0) {
+        *feature = F_VERTEX | 0u, proj = mul_point(m, a);
+    } else if (ab_ap >= sqnab) {
+        *feature = F_VERTEX | 1u, proj = mul_point(m, b);
+    } else {
+        real u = ab_ap / sqnab;
+        proj = mul_point(m, a + ab * u);
+        on_edge = true;
+    }
+    *inside = relative_eq(proj.x, pt.x) && relative_eq(proj.y, pt.y);
+    if (on_edge) {  // dim2: the side of the segment the point is on
+        P2 dpt = pt - proj;
+        *feature = perp(dpt, ab) >= 0 ? (F_FACE | 0u) : (F_FACE | 1u);
+    }
+    return proj;
+}
+// Segment::feature_normal (segment.rs:237-284, dim2); no direction (a == b): the y axis
+static P2 segment_feature_normal(const Shape2& g, uint32_t f) {
+    P2 dir;
+    if (!unit_try_new(g.sb - g.he, EPS, &dir)) return p2(0, 1);
+    uint32_t id = f & 0xffffu;
+    if (f & F_VERTEX) return id == 0 ? dir : -dir;
+    return id == 0 ? p2(dir.y, -dir.x) : p2(-dir.y, dir.x);
+}
+// contact_ball_convex_polyhedron.rs:12-62 with a segment
+static bool contact_ball_segment(P2 center, real radius, const Iso2& m2, const Shape2& g2, real prediction, Contact2* c) {
+    bool inside;
+    uint32_t f2;
+    P2 world2 = segment_project(g2, m2, center, &inside, &f2);
+    P2 dpt = world2 - center, dir, normal;
+    real dist, depth;
+    if (unit_try_new_and_get(dpt, EPS, &dir, &dist)) {
+        if (inside)
+            depth = dist + radius, normal = -dir;
+        else
+            depth = -dist + radius, normal = dir;
+    } else {
+        depth = radius;
+        normal = -segment_feature_normal(g2, f2);
+    }
+    if (depth >= -prediction) {
+        c->w1 = center + normal * radius, c->w2 = world2, c->n = normal, c->depth = depth;
+        return true;
+    }
+    return false;
+}
+
 // contact_ball_convex_polyhedron.rs:12-62 with a cuboid
 static bool contact_ball_cuboid(P2 center, real radius, const Iso2& m2, const Shape2& g2, real prediction, Contact2* c) {
     bool inside;
@@ -781,7 +838,30 @@ static void polygon_face(const Shape2& g, uint32_t ia, Feature2& out) {  // conv
     out.normal = p2(g.normals[2 * ia], g.normals[2 * ia + 1]), out.has_normal = true;
     out.fid = F_FACE | ia;
 }
+// Segment::face (segment.rs:212-235, dim2); a degenerate segment is the single vertex a
+static void segment_face(P2 a, P2 b, uint32_t id, Feature2& out) {
+    out.clear();
+    P2 ab = b - a, nrm;
+    if (unit_try_new(p2(ab.y, -ab.x), EPS, &nrm)) {  // utils::ccw_face_normal
+        out.fid = F_FACE | id;
+        if (id == 0) {
+            out.push(a, F_VERTEX | 0u), out.push(b, F_VERTEX | 1u);
+            out.normal = nrm, out.has_normal = true;
+        } else {
+            out.push(b, F_VERTEX | 1u), out.push(a, F_VERTEX | 0u);
+            out.normal = -nrm, out.has_normal = true;
+        }
+    } else {
+        out.push(a, F_VERTEX | 0u);
+        out.fid = F_VERTEX | 0u;
+    }
+}
 static void support_face_toward(const Shape2& g, const Iso2& m, P2 dir, Feature2& out) {
+    if (g.type == SEGMENT2) {  // segment.rs:286-299 (dim2): `dir` is NOT brought into the segment's frame (as in the reference)
+        segment_face(g.he, g.sb, perp(dir, g.sb - g.he) >= 0 ? 0u : 1u, out);
+        out.transform_by(m);
+        return;
+    }
     P2 ld = inv_rot(m, dir);
     if (g.type == CUBOID2) {  // cuboid.rs:279-308
         real l[2] = {ld.x, ld.y};
@@ -801,7 +881,21 @@ static void support_face_toward(const Shape2& g, const Iso2& m, P2 dir, Feature2
     out.transform_by(m);
 }
 static real signum(real x) { return std::isnan(x) ? x : (std::signbit(x) ? real(-1) : real(1)); }  // f32::signum: -0.0 -> -1.0
-static void support_feature_toward(const Shape2& g, const Iso2& m, P2 dir, real cang, Feature2& out) {
+static void support_feature_toward(const Shape2& g, const Iso2& m, P2 dir, real cang, real sang, Feature2& out) {
+    if (g.type == SEGMENT2) {  // segment.rs:315-345 (dim2): eps.sin() is the angular prediction's sine
+        out.clear();
+        P2 a = mul_point(m, g.he), b = mul_point(m, g.sb), sd;  // self.transformed(transform)
+        if (unit_try_new(b - a, EPS, &sd)) {
+            real c = dot(dir, sd);
+            if (c > sang)
+                out.fid = F_VERTEX | 1u, out.push(b, F_VERTEX | 1u);
+            else if (c < -sang)
+                out.fid = F_VERTEX | 0u, out.push(a, F_VERTEX | 0u);
+            else
+                segment_face(a, b, perp(dir, sd) >= 0 ? 0u : 1u, out);
+        }
+        return;
+    }
     if (g.type != CUBOID2) {  // convex_polygon.rs:174-184: the support face
         support_face_toward(g, m, dir, out);
         return;
@@ -891,6 +985,9 @@ static Box2 shape_aabb2(const Shape2& g, const Iso2& m) {
         real are = std::fabs(m.re), aim = std::fabs(m.im);
         P2 w = p2(are * g.he.x + aim * g.he.y, aim * g.he.x + are * g.he.y);
         lo = m.t - w, hi = m.t + w;
+    } else if (g.type == SEGMENT2) {  // aabb_segment.rs -> support_map_aabb (aabb_utils.rs:9-31): one support point per axis direction
+        hi = p2(support_point(g, m, p2(1, 0)).x, support_point(g, m, p2(0, 1)).y);
+        lo = p2(support_point(g, m, p2(-1, 0)).x, support_point(g, m, p2(0, -1)).y);
     } else {
         P2 wp = mul_point(m, p2(g.pts[0], g.pts[1]));
         lo = hi = wp;
@@ -903,8 +1000,8 @@ static Box2 shape_aabb2(const Shape2& g, const Iso2& m) {
 }
 
 // one pair through its generator; returns the manifold in push order
-static void generate_contacts2(const Shape2& g1, const Iso2& m1, const Shape2& g2, const Iso2& m2, real linear, real cang1, real cang2, Manifold2& mf,
-                               int* panicked) {
+static void generate_contacts2(const Shape2& g1, const Iso2& m1, const Shape2& g2, const Iso2& m2, real linear, real cang1, real cang2, real sang1,
+                               real sang2, Manifold2& mf, int* panicked) {
     const uint32_t FACE0 = F_FACE | 0u;
     if (g1.type == PLANE2 && g2.type == PLANE2) return;  // no contact algorithm: no interaction edge
     if (g1.type == BALL2 && g2.type == BALL2) {
@@ -965,6 +1062,8 @@ static void generate_contacts2(const Shape2& g1, const Iso2& m1, const Shape2& g
         P2 world2;
         if (cp.type == CUBOID2) {
             world2 = cuboid_project(cp, mc, mb.t, &inside, &f2);
+        } else if (cp.type == SEGMENT2) {
+            world2 = segment_project(cp, mc, mb.t, &inside, &f2);
         } else {
             world2 = polygon_project(cp, mc, mb.t, &inside, panicked);
             P2 back = mb.t - world2, ld;
@@ -978,7 +1077,7 @@ static void generate_contacts2(const Shape2& g1, const Iso2& m1, const Shape2& g
         } else {
             if (f2 == F_UNKNOWN) return;
             depth = ball.radius;
-            normal = -(cp.type == CUBOID2 ? cuboid_feature_normal(f2) : polygon_feature_normal(cp, f2));
+            normal = -(cp.type == CUBOID2 ? cuboid_feature_normal(f2) : cp.type == SEGMENT2 ? segment_feature_normal(cp, f2) : polygon_feature_normal(cp, f2));
         }
         if (depth >= -linear) {
             if (f2 == F_UNKNOWN) {  // "Feature id cannot be unknown."
@@ -1013,8 +1112,8 @@ static void generate_contacts2(const Shape2& g1, const Iso2& m1, const Shape2& g
         support_face_toward(g1, m1, n, fa);
         support_face_toward(g2, m2, -n, fb);
     } else {
-        support_feature_toward(g1, m1, n, cang1, fa);
-        support_feature_toward(g2, m2, -n, cang2, fb);
+        support_feature_toward(g1, m1, n, cang1, sang1, fa);
+        support_feature_toward(g2, m2, -n, cang2, sang2, fb);
     }
     std::vector<Cand2> fresh;
     clip2(fa, fb, n, linear, fresh);
@@ -1220,7 +1319,56 @@ static RayHit2 ray2_polygon(const Shape2& g, const Iso2& m, P2 o_w, P2 d_w, real
     return h;
 }
 
+// RayCast for Segment, dim2 (query/ray/ray_support_map.rs:219-293): the segment moved by m, line / line parameters
+// (closest_points_line_line.rs:27-70), the collinear cases; the normal is the SCALED normal and max_toi is never applied
+static RayHit2 ray2_segment(const Shape2& g, const Iso2& m, P2 o, P2 d) {
+    RayHit2 h;
+    P2 a = mul_point(m, g.he), b = mul_point(m, g.sb);
+    P2 sd = b - a, r = o - a;
+    real aa = nsq(d), e = nsq(sd), f = dot(sd, r), s, t;
+    bool parallel = false;
+    if (aa <= EPS && e <= EPS) {
+        s = 0, t = 0;
+    } else if (aa <= EPS) {
+        s = 0, t = f / e;
+    } else {
+        real c = dot(d, r);
+        if (e <= EPS) {
+            s = -c / aa, t = 0;
+        } else {
+            real bq = dot(d, sd), ae = aa * e, bb = bq * bq, denom = ae - bb;
+            parallel = denom <= EPS || ulps_eq(ae, bb);
+            s = !parallel ? (bq * f - c * e) / denom : real(0);
+            t = (bq * s + f) / e;
+        }
+    }
+    P2 nrm = p2(sd.y, -sd.x);
+    if (parallel) {
+        P2 dpos = a - o;
+        if (std::fabs(dot(dpos, nrm)) < EPS) {
+            real dist1 = dot(dpos, d), dist2 = dist1 + dot(sd, d);
+            if (dist1 >= 0 && dist2 >= 0) {
+                h.hit = true, h.n = nrm;
+                if (dist1 <= dist2)
+                    h.toi = dist1 / nsq(d), h.feature = 0x80000000u | 0u;
+                else
+                    h.toi = dist2 / nsq(d), h.feature = 0x80000000u | 1u;
+            } else if (dist1 >= 0 || dist2 >= 0) {
+                h.hit = true, h.toi = 0, h.n = nrm, h.feature = FACE2 | 0u;
+            }
+        }
+    } else if (s >= 0 && t >= 0 && t <= 1) {
+        h.hit = true, h.toi = s;
+        if (dot(nrm, d) > 0)
+            h.n = -nrm, h.feature = FACE2 | 1u;
+        else
+            h.n = nrm, h.feature = FACE2 | 0u;
+    }
+    return h;
+}
+
 static RayHit2 shape_ray_cast2(const Shape2& g, const Iso2& m, P2 o, P2 d, real max_toi) {
+    if (g.type == SEGMENT2) return ray2_segment(g, m, o, d);
     switch (g.type) {
         case BALL2: return ray2_ball(m.t, g.radius, o, d, max_toi);
         case CUBOID2: return ray2_cuboid(g.he, m, o, d, max_toi);
@@ -1246,7 +1394,7 @@ void orc2_contact(uint64_t n, const uint32_t* type1, const real* param1, const r
                   uint32_t* panics) {
     auto shape = [&](uint32_t t, const real* p) {
         Shape2 g;
-        g.type = t, g.radius = p[0], g.he = p2(p[0], p[1]), g.pts = g.normals = nullptr, g.npts = 0;
+        g.type = t, g.radius = p[0], g.he = p2(p[0], p[1]), g.sb = p2(p[2], p[3]), g.pts = g.normals = nullptr, g.npts = 0;
         if (t == POLYGON2) {
             g.pts = poly_points + 2 * (size_t)p[0], g.npts = (uint32_t)p[1];
             g.normals = poly_normals ? poly_normals + 2 * (size_t)p[0] : nullptr;
@@ -1282,6 +1430,14 @@ void orc2_contact(uint64_t n, const uint32_t* type1, const real* param1, const r
                 std::swap(c.w1, c.w2);
                 c.n = -c.n;
             }
+        } else if (g1.type == BALL2 && g2.type == SEGMENT2) {
+            ok = contact_ball_segment(m1.t, g1.radius, m2, g2, prediction, &c);
+        } else if (g1.type == SEGMENT2 && g2.type == BALL2) {
+            ok = contact_ball_segment(m2.t, g2.radius, m1, g1, prediction, &c);
+            if (ok) {
+                std::swap(c.w1, c.w2);
+                c.n = -c.n;
+            }
         } else if (g1.type == BALL2 && g2.type == POLYGON2 && g2.normals) {
             ok = contact_ball_polygon(m1.t, g1.radius, m2, g2, prediction, &c, &panicked);
         } else if (g1.type == POLYGON2 && g2.type == BALL2 && g1.normals) {
@@ -1309,7 +1465,7 @@ void orc2_proximity(uint64_t n, const uint32_t* type1, const real* param1, const
     for (uint64_t k = 0; k < n; ++k) {
         auto shape = [&](uint32_t t, const real* p) {
             Shape2 g;
-            g.type = t, g.radius = p[0], g.he = p2(p[0], p[1]), g.pts = g.normals = nullptr, g.npts = 0;
+            g.type = t, g.radius = p[0], g.he = p2(p[0], p[1]), g.sb = p2(p[2], p[3]), g.pts = g.normals = nullptr, g.npts = 0;
             if (t == POLYGON2) g.pts = poly_points + 2 * (size_t)p[0], g.npts = (uint32_t)p[1];
             return g;
         };
@@ -1339,7 +1495,7 @@ void orc2_ray_cast(uint64_t n, const uint32_t* type, const real* param, const re
     for (uint64_t k = 0; k < n; ++k) {
         const real* p = param + 4 * k;
         Shape2 g;
-        g.type = type[k], g.radius = p[0], g.he = p2(p[0], p[1]), g.pts = g.normals = nullptr, g.npts = 0;
+        g.type = type[k], g.radius = p[0], g.he = p2(p[0], p[1]), g.sb = p2(p[2], p[3]), g.pts = g.normals = nullptr, g.npts = 0;
         if (g.type == POLYGON2) g.pts = poly_points + 2 * (size_t)p[0], g.npts = (uint32_t)p[1];
         Iso2 m = {p2(pose[4 * k], pose[4 * k + 1]), pose[4 * k + 2], pose[4 * k + 3]};
         const real* q = rays + 5 * k;
@@ -1359,6 +1515,12 @@ static bool contains_point2(const Shape2& g, const Iso2& m, P2 pt) {
         return !(l.x < -g.he.x || l.x > g.he.x || l.y < -g.he.y || l.y > g.he.y);
     }
     if (g.type == PLANE2) return dot(g.he, inv_point(m, pt)) <= real(0);
+    if (g.type == SEGMENT2) {  // the trait's default: project_point(m, pt, false).is_inside, i.e. relative_eq!(proj, pt) (point_segment.rs:88)
+        bool inside;
+        uint32_t f;
+        (void)segment_project(g, m, pt, &inside, &f);
+        return inside;
+    }
     Iso2 ms = m;
     ms.t = (-pt) + m.t;
     Iso2 id = {p2(0, 0), 1, 0};
@@ -1406,7 +1568,7 @@ struct orc2_objects {
 static Shape2 obj_shape(const orc2_objects* o, uint32_t i) {
     Shape2 g;
     const real* p = o->param + 4 * (size_t)i;
-    g.type = o->type[i], g.radius = p[0], g.he = p2(p[0], p[1]), g.pts = g.normals = nullptr, g.npts = 0;
+    g.type = o->type[i], g.radius = p[0], g.he = p2(p[0], p[1]), g.sb = p2(p[2], p[3]), g.pts = g.normals = nullptr, g.npts = 0;
     if (g.type == POLYGON2) g.pts = o->poly_points + 2 * (size_t)p[0], g.normals = o->poly_normals + 2 * (size_t)p[0], g.npts = (uint32_t)p[1];
     return g;
 }
@@ -1453,7 +1615,7 @@ uint64_t orc2_narrow_phase(const orc2_objects* o, uint64_t n_pairs, const uint32
             if (prox) prox[k] = (uint8_t)r;
         } else
         generate_contacts2(obj_shape(o, i1), obj_iso(o, i1), obj_shape(o, i2), obj_iso(o, i2), linear, std::cos(o->ang_pred[i1]),
-                           std::cos(o->ang_pred[i2]), mf, &panicked);
+                           std::cos(o->ang_pred[i2]), std::sin(o->ang_pred[i1]), std::sin(o->ang_pred[i2]), mf, &panicked);
         manifold_off[k] = (uint32_t)nc;
         for (auto& c : mf.c) {
             if (nc < cap) {
@@ -1510,7 +1672,7 @@ void orc2_contains_point(uint64_t n, const uint32_t* type, const real* param, co
     for (uint64_t k = 0; k < n; ++k) {
         const real* p = param + 4 * k;
         Shape2 g;
-        g.type = type[k], g.radius = p[0], g.he = p2(p[0], p[1]), g.pts = g.normals = nullptr, g.npts = 0;
+        g.type = type[k], g.radius = p[0], g.he = p2(p[0], p[1]), g.sb = p2(p[2], p[3]), g.pts = g.normals = nullptr, g.npts = 0;
         if (g.type == POLYGON2) g.pts = poly_points + 2 * (size_t)p[0], g.npts = (uint32_t)p[1];
         Iso2 m = {p2(pose[4 * k], pose[4 * k + 1]), pose[4 * k + 2], pose[4 * k + 3]};
         out[k] = contains_point2(g, m, p2(pts[2 * k], pts[2 * k + 1])) ? 1 : 0;

@@ -109,7 +109,7 @@ uint64_t shim2_narrow_sensors(uint32_t n, const float* pos, const float* rot, co
             prox[p] = (g1.kind == D2_PLANE && g2.kind == D2_PLANE) ? (uint8_t)NCB_PROXIMITY_NONE : proximity_of_pair(g1, g2, qlimit[i1] + qlimit[i2]);
         } else {
             if (prox) prox[p] = (uint8_t)NCB_PROXIMITY_NONE;
-            manifold_of_pair(g1, g2, qlimit[i1] + qlimit[i2], cosf(ang_pred[i1]), cosf(ang_pred[i2]), c1, mf, flags);
+            manifold_of_pair(g1, g2, qlimit[i1] + qlimit[i2], cosf(ang_pred[i1]), cosf(ang_pred[i2]), sinf(ang_pred[i1]), sinf(ang_pred[i2]), c1, mf, flags);
         }
         flag_counts[0] += flags & 1, flag_counts[1] += (flags >> 1) & 1, flag_counts[2] += mf.overflow ? 1 : 0;
         manifold_off[p] = (uint32_t)nc;

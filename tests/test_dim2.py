@@ -26,6 +26,9 @@ def random_pairs(n, seed, kinds=(0, 1, 2), spread=1.2):
             sh.cuboid(rng.uniform(0.2, 0.6), rng.uniform(0.2, 0.6))
         elif t == 3:
             sh.plane(rng.normal(size=2))
+        elif t == 4:
+            a = rng.uniform(-0.6, 0.6, size=2)
+            sh.segment(a, a + rng.uniform(0.2, 0.9) * np.array([np.cos(th := rng.uniform(0, 2 * np.pi)), np.sin(th)]))
         else:
             k = int(rng.integers(3, 13))
             ang = np.sort(rng.uniform(0, 2 * np.pi, size=k))
@@ -88,6 +91,8 @@ def test_oracle_issue_181_walk_never_panics(oracle64):
 def _world_polygon(t, p, m, pts):
     if t == 1:
         loc = np.array([[p[0], p[1]], [-p[0], p[1]], [-p[0], -p[1]], [p[0], -p[1]]], dtype=np.float64)
+    elif t == 4:
+        loc = np.array([[p[0], p[1]], [p[2], p[3]]], dtype=np.float64)
     else:
         loc = pts[int(p[0]) : int(p[0]) + int(p[1])].astype(np.float64)
     re, im = float(m[2]), float(m[3])
@@ -295,6 +300,9 @@ def random_world(n, seed, kinds=(0, 1, 2), density=2.5, angular=0.0, linear=0.02
             sh.ball(rng.uniform(0.25, 0.5))
         elif t == 1:
             sh.cuboid(rng.uniform(0.25, 0.5), rng.uniform(0.25, 0.5))
+        elif t == 4:
+            a = rng.uniform(-0.4, 0.4, size=2)
+            sh.segment(a, a + rng.uniform(0.3, 0.8) * np.array([np.cos(th := rng.uniform(0, 2 * np.pi)), np.sin(th)]))
         else:
             k = int(rng.integers(3, 11))
             ang = np.sort(rng.uniform(0, 2 * np.pi, size=k)) + np.arange(k) * 1e-2
@@ -523,3 +531,129 @@ def test_device_world2d_sensors_match_oracle(ctx, oracle):
     w.query_kind[0] = 7
     with pytest.raises(NcbError):
         dim2.world_update(ctx, w)
+
+
+# ---- Segment as a shape (shape/segment.rs, dim2) --------------------------------------------------------------------------------
+def test_oracle_segments_against_separating_axes(oracle64):
+    """ORACLE check (f64): segment x cuboid / polygon / segment through contact_support_map_support_map against the separating-axis
+    answer (the Minkowski difference's faces come from the polygon's edges and the segment's two sides)."""
+    t1, p1, m1, t2, p2, m2, pts, nrm = random_pairs(2500, 101, kinds=(1, 2, 4), spread=0.9)
+    keep = (t1 == 4) | (t2 == 4)
+    t1, p1, m1, t2, p2, m2 = t1[keep], p1[keep], m1[keep], t2[keep], p2[keep], m2[keep]
+    found, out, panics = oracle64.contact2d(t1, p1, m1, t2, p2, m2, pts, prediction=0.3, poly_normals=nrm)
+    assert panics == 0
+    checked = deep = 0
+    for k in range(len(t1)):
+        A, B = _world_polygon(t1[k], p1[k], m1[k], pts), _world_polygon(t2[k], p2[k], m2[k], pts)
+        if t1[k] == 4 and t2[k] == 4:
+            da, db = A[1] - A[0], B[1] - B[0]
+            if abs(da[0] * db[1] - da[1] * db[0]) < 1e-3 * np.linalg.norm(da) * np.linalg.norm(db):
+                continue  # (nearly) parallel segments: a degenerate Minkowski difference
+        sd = _sat_signed_distance(A, B)
+        if sd > 0.3 + 1e-6:
+            assert not found[k], (k, sd)
+        elif sd < 0.3 - 1e-6:
+            assert found[k], (k, sd)
+            assert abs(out[k, 6] - (-sd)) < 2e-5 * max(1.0, abs(sd)), (k, t1[k], t2[k], out[k, 6], -sd)
+            checked += 1
+            deep += sd < -1e-3
+    assert checked > 500 and deep > 100, (checked, deep)
+
+
+def test_oracle_ball_segment_against_point_segment_distance(oracle64):
+    """ORACLE check (f64): contact_ball_convex_polyhedron with a Segment: depth = radius - distance(centre, segment), both orders."""
+    t1, p1, m1, t2, p2, m2, pts, nrm = random_pairs(3000, 102, kinds=(0, 4), spread=0.9)
+    keep = t1 != t2
+    t1, p1, m1, t2, p2, m2 = t1[keep], p1[keep], m1[keep], t2[keep], p2[keep], m2[keep]
+    found, out, panics = oracle64.contact2d(t1, p1, m1, t2, p2, m2, pts, prediction=0.1)
+    checked = 0
+    for k in range(len(t1)):
+        ball_first = t1[k] == 0
+        c = (m1 if ball_first else m2)[k, :2].astype(np.float64)
+        r = float((p1 if ball_first else p2)[k, 0])
+        S = _world_polygon(4, (p2 if ball_first else p1)[k], (m2 if ball_first else m1)[k], pts)
+        ab = S[1] - S[0]
+        u = np.clip(((c - S[0]) @ ab) / (ab @ ab), 0, 1)
+        depth = r - np.linalg.norm(S[0] + ab * u - c)
+        if abs(depth + 0.1) < 1e-6:
+            continue
+        assert bool(found[k]) == (depth > -0.1), (k, depth)
+        if found[k]:
+            assert abs(out[k, 6] - depth) < 1e-9, (k, out[k, 6], depth)
+            n = out[k, 4:6] if ball_first else -out[k, 4:6]
+            assert n @ (S[0] + ab * u - c) >= -1e-12  # the normal points from the ball towards the segment
+            checked += 1
+    assert checked > 500
+
+
+def test_shapes2d_segment():
+    sh = dim2.Shapes2D().segment((0, 1), (2, 3))
+    typ, par, pts, nrm = sh.arrays()
+    assert typ.tolist() == [4] and par[0].tolist() == [0, 1, 2, 3]
+    with pytest.raises(ValueError):
+        dim2.Shapes2D().segment((1, 1), (1, 1))
+
+
+@pytest.mark.parametrize("seed,kinds,prediction", [(111, (0, 1, 2, 4), 0.05), (112, (4,), 0.1), (113, (3, 4), 0.05), (114, (2, 4), 0.0)])
+def test_device_source_segment_contacts_equal_oracle_bit_for_bit(dim2_shim, oracle, seed, kinds, prediction):
+    import ctypes as C
+
+    t1, p1, m1, t2, p2, m2, pts, nrm = random_pairs(40000, seed, kinds)
+    n = len(t1)
+    found, out, flags = np.zeros(n, dtype=np.uint8), np.zeros((n, 7), dtype=np.float32), np.zeros(2, dtype=np.uint32)
+    dim2_shim.shim2_contact(C.c_uint64(n), _vp(t1), _vp(p1), _vp(m1), _vp(t2), _vp(p2), _vp(m2), _vp(pts), _vp(nrm), C.c_float(prediction),
+                            _vp(found), _vp(out), _vp(flags))
+    ofound, oout, opanics = oracle.contact2d(t1, p1, m1, t2, p2, m2, pts, prediction, poly_normals=nrm)
+    assert flags.tolist() == [opanics, 0] and np.array_equal(found, ofound)
+    hit = found.astype(bool)
+    assert hit.sum() > 2000 and np.array_equal(_bits(out[hit]), _bits(oout[hit]))
+    margins = np.random.default_rng(seed).uniform(0.0, 0.4, size=n).astype(np.float32)
+    st = np.full(n, 9, dtype=np.uint8)
+    dim2_shim.shim2_proximity(C.c_uint64(n), _vp(t1), _vp(p1), _vp(m1), _vp(t2), _vp(p2), _vp(m2), _vp(pts), _vp(margins), _vp(st))
+    assert np.array_equal(st, oracle.proximity2d(t1, p1, m1, t2, p2, m2, pts, margins))
+
+
+@pytest.mark.parametrize("n,seed,kinds,angular,planes", [(2500, 121, (0, 1, 2, 4), 0.0, 0), (2000, 122, (1, 4), 0.1, 2), (1500, 123, (4,), 0.3, 0)])
+def test_device_source_world2d_with_segments_equals_oracle(dim2_shim, oracle, n, seed, kinds, angular, planes):
+    import ctypes as C
+
+    w = random_world(n, seed, kinds, angular=angular, planes=planes)
+    pairs, off, ocontacts, ofeats, panics, fat = oracle.world_update2d(w)
+    boxes = np.zeros((w.n, 6), dtype=np.float32)
+    dim2_shim.shim2_aabbs(C.c_uint32(w.n), _vp(w.pos), _vp(w.rot), _vp(w.type), _vp(w.param), _vp(w.query_limit), _vp(w.points), _vp(w.normals),
+                          C.c_float(w.margin), _vp(boxes))
+    assert np.array_equal(_bits(boxes), _bits(fat))
+    P = len(pairs)
+    pr = np.ascontiguousarray(pairs, dtype=np.uint32)
+    doff, dc, df = np.zeros(P + 1, dtype=np.uint32), np.zeros((4 * P + 16, 7), dtype=np.float32), np.zeros((4 * P + 16, 2), dtype=np.uint32)
+    flags = np.zeros(3, dtype=np.uint32)
+    dim2_shim.shim2_narrow.restype = C.c_uint64
+    nc = dim2_shim.shim2_narrow(C.c_uint32(w.n), _vp(w.pos), _vp(w.rot), _vp(w.type), _vp(w.param), _vp(w.query_limit), _vp(w.ang_pred),
+                                _vp(w.points), _vp(w.normals), C.c_uint64(P), _vp(pr), _vp(doff), _vp(dc), _vp(df), C.c_uint64(len(dc)), _vp(flags))
+    assert flags.tolist() == [panics, 0, 0]
+    assert np.array_equal(doff, off) and nc == len(ocontacts) > n // 5
+    assert np.array_equal(df[:nc], ofeats) and np.array_equal(_bits(dc[:nc]), _bits(ocontacts))
+
+
+@pytest.mark.gpu
+def test_device_segments_match_oracle(ctx, oracle):
+    t1, p1, m1, t2, p2, m2, pts, nrm = random_pairs(60000, 131, (0, 1, 2, 3, 4))
+    found, out, info = dim2.contact(ctx, t1, p1, m1, t2, p2, m2, pts, 0.05, poly_normals=nrm)
+    ofound, oout, opanics = oracle.contact2d(t1, p1, m1, t2, p2, m2, pts, 0.05, poly_normals=nrm)
+    assert info["epa_overflow"] == 0 and info["ref_panics"] == opanics and np.array_equal(found, ofound.astype(bool))
+    assert np.allclose(out[found], oout[found], rtol=1e-4, atol=1e-5)
+    assert (out[found].view(np.uint32) == np.ascontiguousarray(oout[found], dtype=np.float32).view(np.uint32)).mean() > 0.999
+    w = random_world(6000, 132, (0, 1, 2, 4), angular=0.1, planes=2)
+    res = dim2.world_update(ctx, w)
+    pairs, off, ocontacts, ofeats, panics, fat = oracle.world_update2d(w)
+    got = {tuple(p): k for k, p in enumerate(res["pairs"].tolist())}
+    assert len(got) == len(pairs) and set(got) == set(map(tuple, pairs.tolist()))
+    order = np.array([got[tuple(p)] for p in pairs.tolist()])
+    assert np.array_equal(res["manifold_count"][order], np.diff(off)) and res["diag"]["ref_panics"] == panics
+    for k in np.flatnonzero(np.diff(off))[:3000]:
+        a = res["contacts"][res["manifold_start"][order[k]] : res["manifold_start"][order[k]] + res["manifold_count"][order[k]]]
+        assert np.allclose(a, ocontacts[off[k] : off[k + 1]], rtol=1e-4, atol=1e-5), k
+    from ncollide_b200._ffi import NcbError
+
+    with pytest.raises(NcbError):  # a segment with identical end points
+        dim2.contact(ctx, [4], [[1, 1, 1, 1]], [[0, 0, 1, 0]], [0], [[0.5, 0, 0, 0]], [[0.2, 0, 1, 0]])

@@ -214,6 +214,9 @@ def random_shape_rays(n, seed, kinds=(0, 1, 2, 3)):
             sh.cuboid(rng.uniform(0.2, 0.7), rng.uniform(0.2, 0.7))
         elif k == 3:
             sh.plane(rng.normal(size=2))
+        elif k == 4:
+            a = rng.uniform(-0.6, 0.6, size=2)
+            sh.segment(a, a + rng.uniform(0.2, 0.9) * np.array([np.cos(th := rng.uniform(0, 2 * np.pi)), np.sin(th)]))
         else:
             m = int(rng.integers(3, 11))
             ang = np.sort(rng.uniform(0, 2 * np.pi, size=m)) + np.arange(m) * 1e-3
@@ -494,3 +497,54 @@ def test_device_world_point_and_aabb_queries_2d(ctx, oracle, groups):
         want = oracle.world_query2d(w, kind, q, groups=groups)
         assert len(want) > 200 and np.array_equal(got, want), (kind, len(got), len(want))
     assert ctx.traversal_overflows() == 0
+
+
+# ---- Segment as a shape: rays and points -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["oracle", "oracle64"])
+def test_oracle_segment_shape_ray_kats(which, request):
+    """The ten Segment tests of ray_cast.rs once more, through the shape entry (type 4, identity pose) instead of the polyline's."""
+    orc = request.getfixturevalue(which)
+    big = np.finfo(orc.dtype).max
+    cases = [((2, 1, 2, 0), (0, 0, 0, 1), None), ((2, 1, 2, -1), (0, 0, 0, 1), None), ((0, 1, 0, -1), (0, 0, 0, 1), 0.0),
+             ((0, 1, 0, -1), (0, -2, 0, 1), 1.0), ((0, 1, 0, -1), (0, 2, 0, 1), None), ((0, -10, 0, 10), (-1, 0, 1, 0), 1.0),
+             ((0, -10, 0, 10), (1, 0, 1, 0), None), ((0, -10, 0, 10), (0, 3, 1, 0), 0.0), ((0, -10, 0, 10), (0, 11, 1, 0), None),
+             ((0, -10, 0, 10), (0, -11, 1, 0), None)]
+    n = len(cases)
+    found, out, feat = orc.ray_cast2d([4] * n, [c[0] for c in cases], [[0, 0, 1, 0]] * n, [list(c[1]) + [big] for c in cases])
+    for k, (_, _, want) in enumerate(cases):
+        assert bool(found[k]) == (want is not None), k
+        if want is not None:
+            assert out[k, 0] == want, (k, out[k])
+
+
+@pytest.mark.parametrize("seed", [141, 142])
+def test_device_source_segment_rays_and_points_equal_oracle(dim2_shim, oracle, seed):
+    typ, par, pose, rays, pts = random_shape_rays(30_000, seed, kinds=(1, 4))
+    n = len(typ)
+    found, out, feat = np.zeros(n, dtype=np.uint8), np.zeros((n, 3), dtype=F), np.zeros(n, dtype=np.uint32)
+    dim2_shim.shim2_ray_cast(C.c_uint64(n), _vp(typ), _vp(par), _vp(pose), _vp(pts), _vp(rays), _vp(found), _vp(out), _vp(feat))
+    ofound, oout, ofeat = oracle.ray_cast2d(typ, par, pose, rays, pts)
+    assert np.array_equal(found, ofound) and np.array_equal(feat, ofeat)
+    hit = found.astype(bool)
+    assert np.array_equal(bits(out[hit]), bits(oout[hit])) and (hit & (typ == 4)).sum() > 2000
+    rng = np.random.default_rng(seed)
+    q = (pose[:, :2] + rng.normal(size=(n, 2)) * 0.4).astype(F)
+    on = rng.random(n) < 0.3  # points ON the segment (a point of it, rounded to f32): the only ones a segment can contain
+    seg = typ == 4
+    u = rng.random(n)[:, None]
+    loc = par[:, :2] * (1 - u) + par[:, 2:] * u
+    world = np.stack([pose[:, 2] * loc[:, 0] - pose[:, 3] * loc[:, 1] + pose[:, 0], pose[:, 3] * loc[:, 0] + pose[:, 2] * loc[:, 1] + pose[:, 1]], axis=1)
+    q[on & seg] = world[on & seg].astype(F)
+    inside = np.zeros(n, dtype=np.uint8)
+    dim2_shim.shim2_contains_point(C.c_uint64(n), _vp(typ), _vp(par), _vp(pose), _vp(pts), _vp(q), _vp(inside))
+    want = oracle.contains_point2d(typ, par, pose, q, pts)
+    assert np.array_equal(inside.astype(bool), want) and want[seg].sum() > 200
+
+
+@pytest.mark.gpu
+def test_device_segment_rays_match_oracle(ctx, oracle):
+    typ, par, pose, rays, pts = random_shape_rays(80_000, 143, kinds=(0, 1, 2, 3, 4))
+    found, out, feat = dim2.ray_cast(ctx, typ, par, pose, rays, pts)
+    ofound, oout, ofeat = oracle.ray_cast2d(typ, par, pose, rays, pts)
+    assert np.array_equal(found, ofound.astype(bool)) and np.array_equal(feat, ofeat)
+    assert np.array_equal(bits(out[found]), bits(oout[found])) and (found & (typ == 4)).sum() > 3000
