@@ -547,4 +547,5 @@ def test_device_segment_rays_match_oracle(ctx, oracle):
     found, out, feat = dim2.ray_cast(ctx, typ, par, pose, rays, pts)
     ofound, oout, ofeat = oracle.ray_cast2d(typ, par, pose, rays, pts)
     assert np.array_equal(found, ofound.astype(bool)) and np.array_equal(feat, ofeat)
-    assert np.array_equal(bits(out[found]), bits(oout[found])) and (found & (typ == 4)).sum() > 3000
+    assert np.array_equal(bits(out[found]), bits(oout[found])), f"{(bits(out[found]) != bits(oout[found])).sum()} words differ"
+    assert (found & (typ == 4)).sum() > 1000
