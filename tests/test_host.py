@@ -134,6 +134,32 @@ def test_oracle_broad_phase_variants_agree(oracle, cfg, n):
     assert np.array_equal(fat[finite, :3], ((tight[finite, :3] + -ql) + -m))
 
 
+def test_oracle_pair_set_against_numpy_brute_force(oracle):
+    """ORACLE check for an unpinned item (pair identities): the broad phase's pair set == every pair of fat boxes that intersect
+    (closed intervals, AABB::intersects) and whose collision groups allow the interaction, enumerated by numpy over all N^2 / 2 pairs."""
+    from ncollide_b200.scenes import config_scene
+
+    s = config_scene(3, 4000)
+    rng = np.random.default_rng(3)
+    s.groups = s.groups.copy()
+    pick = rng.random(s.n) < 0.3
+    s.groups[pick] = (1 << 2, 0x3FFFFFFF & ~(1 << 2), 0)       # members of group 2 that do not whitelist their own group
+    s.groups[rng.random(s.n) < 0.05] = (1 << 4, 0x3FFFFFFF, 1 << 2)  # group 4 blacklists group 2
+    fat = oracle.compute_aabbs(s)
+    got = canon(oracle.broad_phase(fat, s.groups, 0))
+    lo, hi = fat[:, :3], fat[:, 3:]
+    want = []
+    m, w, b = (s.groups[:, k].astype(np.uint64) for k in range(3))
+    for i in range(s.n):
+        hit = np.all(lo[i] <= hi[i + 1 :], axis=1) & np.all(lo[i + 1 :] <= hi[i], axis=1)
+        j = np.flatnonzero(hit) + i + 1
+        # CollisionGroups::can_interact_with_groups (collision_groups.rs:353-359), both ways
+        ok = ((m[i] & b[j]) == 0) & ((m[j] & b[i]) == 0) & ((m[i] & w[j]) != 0) & ((m[j] & w[i]) != 0)
+        want += [(i, int(k)) for k in j[ok]]
+    want = canon(np.array(want, dtype=np.uint32))
+    assert len(want) > 3000 and np.array_equal(got, want)
+
+
 def test_oracle_contact_invariants(oracle):
     from ncollide_b200.scenes import make_world_scene
 
