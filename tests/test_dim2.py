@@ -657,3 +657,30 @@ def test_device_segments_match_oracle(ctx, oracle):
 
     with pytest.raises(NcbError):  # a segment with identical end points
         dim2.contact(ctx, [4], [[1, 1, 1, 1]], [[0, 0, 1, 0]], [0], [[0.5, 0, 0, 0]], [[0.2, 0, 1, 0]])
+
+
+# ---- more of the reference's own 2-D examples, pinned on the oracle and on the device source (host shim) ---------------------------
+def test_reference_examples_contact_point_and_ray_queries_2d(oracle, oracle64, dim2_shim):
+    """examples2d/contact_query2d.rs (depth > 0 / depth < 0 / None for the ball at (1,1), (2,2), (3,3), prediction 1),
+    examples2d/solid_point_query2d.rs (cuboid (1, 2): the origin is 1 inside, (2, 2) is 1 outside — read off the ball x cuboid contact
+    depth, radius 0.25) and examples2d/solid_ray_cast2d.rs (the solid cast from inside answers 0.0, the ray from (2, 2) misses)."""
+    import ctypes as C
+
+    ball, cub, one = [1, 0, 0, 0], [1, 1, 0, 0], [0, 0, 1, 0]
+    args = ([0] * 3, [ball] * 3, [[1, 1, 1, 0], [2, 2, 1, 0], [3, 3, 1, 0]], [1] * 3, [cub] * 3, [one] * 3)
+    for orc in (oracle, oracle64):
+        found, out, _ = orc.contact2d(*args, prediction=1.0)
+        assert found.tolist() == [1, 1, 0] and out[0, 6] > 0 and out[1, 6] < 0
+        small, box = [0.25, 0, 0, 0], [1, 2, 0, 0]
+        found, out, _ = orc.contact2d([0, 0], [small] * 2, [[0, 0, 1, 0], [2, 2, 1, 0]], [1, 1], [box] * 2, [one] * 2, prediction=2.0)
+        assert found.all() and out[0, 6] == 1.25 and out[1, 6] == -0.75  # distance_to_point(.., false) == -1.0 / 1.0
+        assert orc.contains_point2d([1, 1], [box] * 2, [one] * 2, [[0, 0], [2, 2]]).tolist() == [True, False]
+        big = np.finfo(orc.dtype).max
+        f, o, _ = orc.ray_cast2d([1, 1], [box] * 2, [one] * 2, [[0, 0, 0, 1, big], [2, 2, 1, 1, big]])
+        assert f.tolist() == [1, 0] and o[0, 0] == 0.0
+    # the device source on the host gives the same answers
+    t1, p1, m1, t2, p2, m2 = (np.ascontiguousarray(a, dtype=dt) for a, dt in zip(args, (np.uint32, F, F, np.uint32, F, F)))
+    found, out, flags = np.zeros(3, dtype=np.uint8), np.zeros((3, 7), dtype=F), np.zeros(2, dtype=np.uint32)
+    dim2_shim.shim2_contact(C.c_uint64(3), _vp(t1), _vp(p1), _vp(m1), _vp(t2), _vp(p2), _vp(m2), None, None, C.c_float(1.0), _vp(found), _vp(out),
+                            _vp(flags))
+    assert found.tolist() == [1, 1, 0] and out[0, 6] > 0 and out[1, 6] < 0
