@@ -68,6 +68,22 @@ def test_contact_query3d_signs(oracle64):
     assert q((3, 3, 3)) is None
 
 
+@pytest.mark.parametrize("which", ["oracle", "oracle64"])
+def test_solid_point_query3d(which, request):
+    # build/ncollide3d/examples/solid_point_query3d.rs:8-33: cuboid (1, 2, 2); the origin is inside, 1 from the boundary
+    # (distance_to_point(.., false) == -1.0); (2, 2, 2) is 1 outside.  Read off contains_point and the ball x cuboid contact depth.
+    orc = request.getfixturevalue(which)
+    dt = orc.dtype
+
+    def q(p):
+        s = scene_of([(BALL, [0.25], p), (CUBOID, [1, 2, 2], (0, 0, 0))], dtype=dt)
+        return orc.query_contact(s, 2.0)
+
+    assert q((0, 0, 0))["depth"] == 1.25 and q((2, 2, 2))["depth"] == -0.75
+    s = scene_of([(CUBOID, [1, 2, 2], (0, 0, 0))], dtype=dt)
+    assert orc.shape_contains_point_batch(s, [0, 0], [(0, 0, 0), (2, 2, 2)]).tolist() == [1, 0]
+
+
 def test_just_touching_cuboids_no_nan(oracle):
     # build/ncollide3d/tests/geometry/contact.rs:8-26 (issue #182): must not panic / NaN
     s = scene_of([(CUBOID, [0.5, 0.5, 0.1], (0, 0, 0)), (CUBOID, [0.5, 0.5, 0.1], (0, 1, 0))], linear=0.0, margin=0.02)
