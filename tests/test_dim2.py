@@ -678,6 +678,9 @@ def test_reference_examples_contact_point_and_ray_queries_2d(oracle, oracle64, d
         big = np.finfo(orc.dtype).max
         f, o, _ = orc.ray_cast2d([1, 1], [box] * 2, [one] * 2, [[0, 0, 0, 1, big], [2, 2, 1, 1, big]])
         assert f.tolist() == [1, 0] and o[0, 0] == 0.0
+        # examples2d/distance_query2d.rs: the ball at (0, 1) intersects the cuboid (distance 0), at (0, 3) it is 1.0 away (epsilon 1e-7)
+        found, out, _ = orc.contact2d([0, 0], [ball] * 2, [[0, 1, 1, 0], [0, 3, 1, 0]], [1, 1], [cub] * 2, [one] * 2, prediction=2.0)
+        assert found.all() and out[0, 6] >= 0 and abs(-out[1, 6] - 1.0) <= 1e-7
     # the device source on the host gives the same answers
     t1, p1, m1, t2, p2, m2 = (np.ascontiguousarray(a, dtype=dt) for a, dt in zip(args, (np.uint32, F, F, np.uint32, F, F)))
     found, out, flags = np.zeros(3, dtype=np.uint8), np.zeros((3, 7), dtype=F), np.zeros(2, dtype=np.uint32)

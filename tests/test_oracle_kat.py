@@ -84,6 +84,18 @@ def test_solid_point_query3d(which, request):
     assert orc.shape_contains_point_batch(s, [0, 0], [(0, 0, 0), (2, 2, 2)]).tolist() == [1, 0]
 
 
+@pytest.mark.parametrize("which", ["oracle", "oracle64"])
+def test_distance_query3d(which, request):
+    # build/ncollide3d/examples/distance_query3d.rs:8-21: the ball (1) at (0, 1, 0) intersects the cuboid (1, 1, 1): distance 0; at
+    # (0, 3, 0) the distance is 1.0 (epsilon 1e-7).  query::distance is the GJK distance query::contact reports as -depth.
+    orc = request.getfixturevalue(which)
+
+    def depth(p):
+        return orc.query_contact(scene_of([(BALL, [1.0], p), (CUBOID, [1, 1, 1], (0, 0, 0))], dtype=orc.dtype), 2.0)["depth"]
+
+    assert depth((0, 1, 0)) >= 0 and abs(-depth((0, 3, 0)) - 1.0) <= 1e-7
+
+
 def test_just_touching_cuboids_no_nan(oracle):
     # build/ncollide3d/tests/geometry/contact.rs:8-26 (issue #182): must not panic / NaN
     s = scene_of([(CUBOID, [0.5, 0.5, 0.1], (0, 0, 0)), (CUBOID, [0.5, 0.5, 0.1], (0, 1, 0))], linear=0.0, margin=0.02)

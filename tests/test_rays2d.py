@@ -549,3 +549,15 @@ def test_device_segment_rays_match_oracle(ctx, oracle):
     assert np.array_equal(found, ofound.astype(bool)) and np.array_equal(feat, ofeat)
     assert np.array_equal(bits(out[found]), bits(oout[found])), f"{(bits(out[found]) != bits(oout[found])).sum()} words differ"
     assert (found & (typ == 4)).sum() > 1000
+
+
+def test_reference_example_first_ray_intersect_2d(oracle):
+    """examples2d/first_ray_intersect.rs: a world of two balls and two cuboids along the x axis (margin 0.02, Contacts(0, 0), default
+    groups); the ray from the origin towards +x first meets the ball of radius 0.5 centred at (1, 0): toi == 0.5; towards -x: None."""
+    sh = dim2.Shapes2D().ball(0.5).ball(0.75).cuboid(0.5, 0.75).cuboid(1.0, 0.5)
+    w = dim2.World2D(sh, [[1, 0], [2, 0], [3, 0], [4, 2]], 0.0, margin=0.02, linear=0.0, angular=0.0)
+    groups = (0x3FFFFFFF, 0x3FFFFFFF, 0)  # CollisionGroups::new()
+    idx, val, feat = oracle.world_ray_cast2d(w, [[0, 0, 1, 0, FMAX], [0, 0, -1, 0, FMAX]], groups=groups, first_only=True)
+    assert idx.tolist() == [[0, 0]] and val[0, 0] == 0.5
+    every, vals, _ = oracle.world_ray_cast2d(w, [[0, 0, 1, 0, FMAX]], groups=groups)
+    assert every[:, 1].tolist() == [0, 1, 2] and vals[:, 0].tolist() == [0.5, 1.25, 2.5]  # the three shapes on the axis, not the box at y = 2
