@@ -687,3 +687,13 @@ def test_reference_examples_contact_point_and_ray_queries_2d(oracle, oracle64, d
     dim2_shim.shim2_contact(C.c_uint64(3), _vp(t1), _vp(p1), _vp(m1), _vp(t2), _vp(p2), _vp(m2), None, None, C.c_float(1.0), _vp(found), _vp(out),
                             _vp(flags))
     assert found.tolist() == [1, 1, 0] and out[0, 6] > 0 and out[1, 6] < 0
+
+
+def test_reference_example_dbvt_broad_phase2d(oracle):
+    """examples2d/dbvt_broad_phase2d.rs: four balls of radius 0.5 on the corners of a square of side 0.5, broad-phase margin 0.2:
+    6 interferences; without the first two proxies: 1."""
+    pos = np.array([[0, 0], [0, 0.5], [0.5, 0], [0.5, 0.5]], dtype=F)
+    four = dim2.World2D(dim2.Shapes2D().ball(0.5).ball(0.5).ball(0.5).ball(0.5), pos, 0.0, margin=0.2, linear=0.0)
+    assert len(oracle.world_update2d(four)[0]) == 6
+    two = dim2.World2D(dim2.Shapes2D().ball(0.5).ball(0.5), pos[2:], 0.0, margin=0.2, linear=0.0)
+    assert len(oracle.world_update2d(two)[0]) == 1
