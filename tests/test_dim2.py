@@ -697,3 +697,50 @@ def test_reference_example_dbvt_broad_phase2d(oracle):
     assert len(oracle.world_update2d(four)[0]) == 6
     two = dim2.World2D(dim2.Shapes2D().ball(0.5).ball(0.5), pos[2:], 0.0, margin=0.2, linear=0.0)
     assert len(oracle.world_update2d(two)[0]) == 1
+
+
+def test_oracle_world2d_contact_points_lie_on_their_shapes(oracle64):
+    """ORACLE check (f64) of the 2-D manifolds: world1 lies on the boundary of object 1 and world2 on the boundary of object 2 (circle,
+    box outline, polygon outline, segment, half-plane line); depth == -n . (w2 - w1); normals are unit vectors."""
+    w = random_world(2500, 151, (0, 1, 2, 4), angular=0.05, planes=2)
+    pairs, off, c, feats, panics, fat = oracle64.world_update2d(w)
+    assert panics == 0 and len(c) > 1500
+
+    def boundary_distance(i, p):
+        m = np.array([w.pos[i, 0], w.pos[i, 1], w.rot[i, 0], w.rot[i, 1]], dtype=np.float64)
+        d = p - m[:2]
+        loc = np.array([m[2] * d[0] + m[3] * d[1], -m[3] * d[0] + m[2] * d[1]])
+        t, par = int(w.type[i]), w.param[i].astype(np.float64)
+        if t == 0:
+            return abs(np.hypot(*loc) - par[0])
+        if t == 3:
+            return abs(par[0] * loc[0] + par[1] * loc[1])
+        if t == 1:
+            P = np.array([[par[0], par[1]], [-par[0], par[1]], [-par[0], -par[1]], [par[0], -par[1]]])
+        elif t == 4:
+            P = np.array([[par[0], par[1]], [par[2], par[3]]])
+        else:
+            P = w.points[int(par[0]) : int(par[0]) + int(par[1])].astype(np.float64)
+        a, b = P, np.roll(P, -1, axis=0)
+        ab = b - a
+        u = np.clip(((loc - a) * ab).sum(axis=1) / (ab * ab).sum(axis=1), 0, 1)
+        return np.linalg.norm(a + ab * u[:, None] - loc, axis=1).min()
+
+    def convex(i):  # random_world's angular offsets can wrap the last vertex past the first one: such a polygon is not convex
+        if w.type[i] != 2:  # (ConvexPolygon::try_new does not check either) and the projection of an inner point is not defined
+            return True
+        P = w.points[int(w.param[i, 0]) : int(w.param[i, 0]) + int(w.param[i, 1])].astype(np.float64)
+        e = np.roll(P, -1, axis=0) - P
+        f = np.roll(e, -1, axis=0)
+        return bool(np.all(e[:, 0] * f[:, 1] - e[:, 1] * f[:, 0] > 0))
+
+    worst, skipped = 0.0, 0
+    for p, (i1, i2) in enumerate(pairs):
+        if not (convex(i1) and convex(i2)):
+            skipped += off[p + 1] - off[p]
+            continue
+        for k in range(off[p], off[p + 1]):
+            w1, w2, n, depth = c[k, 0:2], c[k, 2:4], c[k, 4:6], c[k, 6]
+            worst = max(worst, boundary_distance(i1, w1), boundary_distance(i2, w2))
+            assert abs(np.hypot(*n) - 1) < 5e-7 and abs(depth + n @ (w2 - w1)) < 1e-6 * max(1.0, abs(depth))  # the f32 rotations / normals are unit to 1e-7
+    assert worst < 1e-6 and skipped < len(c) // 4, (worst, skipped)
