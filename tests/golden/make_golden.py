@@ -103,10 +103,46 @@ def make_capsules(o):
     print("capsules", s.n, "objects", len(pairs), "pairs", int((algo >= 7).sum()), "capsule pairs", len(c), "contacts")
 
 
+def make_dim2(o):
+    """ncollide2d: a 600-object world of all five shape kinds with two planes and sensors (pairs, manifolds, features, proximity
+    statuses), 400 world rays (all / first), 400 shape ray casts and a 300-edge polyline with 400 rays."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_dim2 import random_world
+    from test_rays2d import random_shape_rays
+
+    from ncollide_b200.scenes import make_polyline_scene
+
+    w = random_world(600, 2201, (0, 1, 2, 4), angular=0.05, planes=2, with_groups=True)
+    w.set_sensors(np.random.default_rng(2202).random(w.n) < 0.2)
+    pairs, off, c, feats, panics, fat = o.world_update2d(w)
+    d = dict(pos=w.pos, rot=w.rot, type=w.type, param=w.param, points=w.points, normals=w.normals, query_limit=w.query_limit, ang_pred=w.ang_pred,
+             groups=w.groups, query_kind=w.query_kind, margin=np.float32(w.margin), fat=fat, pairs=pairs, off=off, contacts=c, feats=feats,
+             prox=o.last_proximity2d, panics=np.uint32(panics))
+    rng = np.random.default_rng(2203)
+    lo, hi = w.pos.min(axis=0), w.pos.max(axis=0)
+    dirs = rng.normal(size=(400, 2))
+    rays = np.concatenate([rng.uniform(lo, hi, size=(400, 2)), dirs / np.linalg.norm(dirs, axis=1, keepdims=True), rng.uniform(1.0, 8.0, size=(400, 1))],
+                          axis=1).astype(np.float32)
+    idx, val, ft = o.world_ray_cast2d(w, rays)
+    idx1, val1, ft1 = o.world_ray_cast2d(w, rays, first_only=True)
+    d.update(q_rays=rays, q_idx=idx, q_val=val, q_feat=ft, q_first_idx=idx1, q_first_val=val1, q_first_feat=ft1)
+    typ, par, pose, srays, spts = random_shape_rays(400, 2204, kinds=(0, 1, 2, 3, 4))
+    f, out, sf = o.ray_cast2d(typ, par, pose, srays, spts)
+    d.update(s_type=typ, s_param=par, s_pose=pose, s_rays=srays, s_points=spts, s_found=f, s_out=out, s_feat=sf)
+    pts, edges, po, pd = make_polyline_scene("terrain", 300, 400, 2205)
+    toi, pf, pn = o.polyline(pts, edges).ray_cast(po, pd, mode=0)
+    d.update(p_points=pts, p_origins=po, p_dirs=pd, p_toi=toi, p_feat=pf, p_normal=pn)
+    np.savez_compressed(os.path.join(HERE, "dim2_world_600.npz"), **d)
+    print("dim2", w.n, "objects", len(pairs), "pairs", len(c), "contacts", int((o.last_proximity2d != 255).sum()), "sensor pairs", len(idx), "ray rows")
+
+
 def main():
     from oracle.pyoracle import Oracle
 
     o = Oracle()
+    if len(sys.argv) > 1 and sys.argv[1] == "dim2":  # only the 2-D fixture (the others stay as they are)
+        make_dim2(o)
+        return
     scenes = {
         "world_cfg1_balls_300": config_scene(1, 300),
         "world_cfg2_mixed_plane_400": config_scene(2, 400),
@@ -147,6 +183,7 @@ def main():
     print("sim", [len(r["pairs"]) for r in log], "pairs per step,", len(idx), "ray hits")
     make_proximity(o)
     make_capsules(o)
+    make_dim2(o)
     for kind in ("terrain", "soup"):
         rs = make_ray_scene(kind, 2000, 600, seed=1004)
         om = o.trimesh(rs.verts, rs.tris)

@@ -744,3 +744,59 @@ def test_oracle_world2d_contact_points_lie_on_their_shapes(oracle64):
             worst = max(worst, boundary_distance(i1, w1), boundary_distance(i2, w2))
             assert abs(np.hypot(*n) - 1) < 5e-7 and abs(depth + n @ (w2 - w1)) < 1e-6 * max(1.0, abs(depth))  # the f32 rotations / normals are unit to 1e-7
     assert worst < 1e-6 and skipped < len(c) // 4, (worst, skipped)
+
+
+# ---- the committed 2-D fixture (tests/golden/dim2_world_600.npz, made by tests/golden/make_golden.py dim2) ---------------------------
+def _dim2_fixture():
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dim2_world_600.npz"))
+    w = dim2.World2D.__new__(dim2.World2D)
+    for k in ("pos", "rot", "type", "param", "points", "normals", "query_limit", "ang_pred", "groups", "query_kind"):
+        setattr(w, k, np.ascontiguousarray(z[k]))
+    w.n, w.margin = len(w.type), float(z["margin"])
+    return z, w
+
+
+def test_dim2_golden_fixture_oracle(oracle):
+    """Guards the 2-D restatement against drift: the oracle reproduces the committed world (boxes, pairs, manifolds, features, sensor
+    statuses), its ray queries, the shape ray casts and the polyline casts, bit for bit."""
+    z, w = _dim2_fixture()
+    pairs, off, c, feats, panics, fat = oracle.world_update2d(w)
+    assert np.array_equal(_bits(fat), _bits(z["fat"])) and np.array_equal(pairs, z["pairs"]) and np.array_equal(off, z["off"])
+    assert np.array_equal(_bits(c), _bits(z["contacts"])) and np.array_equal(feats, z["feats"]) and panics == int(z["panics"])
+    assert np.array_equal(oracle.last_proximity2d, z["prox"])
+    for first, tag in ((False, "q_"), (True, "q_first_")):
+        idx, val, ft = oracle.world_ray_cast2d(w, z["q_rays"], first_only=first)
+        assert np.array_equal(idx, z[tag + "idx"]) and np.array_equal(_bits(val), _bits(z[tag + "val"])) and np.array_equal(ft, z[tag + "feat"])
+    f, out, sf = oracle.ray_cast2d(z["s_type"], z["s_param"], z["s_pose"], z["s_rays"], z["s_points"])
+    assert np.array_equal(f, z["s_found"]) and np.array_equal(_bits(out), _bits(z["s_out"])) and np.array_equal(sf, z["s_feat"])
+    toi, pf, pn = oracle.polyline(z["p_points"], None).ray_cast(z["p_origins"], z["p_dirs"], mode=0)
+    assert np.array_equal(_bits(toi), _bits(z["p_toi"])) and np.array_equal(pf, z["p_feat"]) and np.array_equal(_bits(pn), _bits(z["p_normal"]))
+
+
+def test_dim2_golden_fixture_device_source(dim2_shim):
+    """The device source on the host replays the fixture WITHOUT the oracle: boxes, manifolds, features, sensor statuses, shape rays."""
+    import ctypes as C
+
+    z, w = _dim2_fixture()
+    boxes = np.zeros((w.n, 6), dtype=np.float32)
+    dim2_shim.shim2_aabbs(C.c_uint32(w.n), _vp(w.pos), _vp(w.rot), _vp(w.type), _vp(w.param), _vp(w.query_limit), _vp(w.points), _vp(w.normals),
+                          C.c_float(w.margin), _vp(boxes))
+    assert np.array_equal(_bits(boxes), _bits(z["fat"]))
+    pr = np.ascontiguousarray(z["pairs"], dtype=np.uint32)
+    P = len(pr)
+    doff, dc, df = np.zeros(P + 1, dtype=np.uint32), np.zeros((4 * P + 16, 7), dtype=np.float32), np.zeros((4 * P + 16, 2), dtype=np.uint32)
+    flags, prox = np.zeros(3, dtype=np.uint32), np.full(P, 255, dtype=np.uint8)
+    dim2_shim.shim2_narrow_sensors.restype = C.c_uint64
+    nc = dim2_shim.shim2_narrow_sensors(C.c_uint32(w.n), _vp(w.pos), _vp(w.rot), _vp(w.type), _vp(w.param), _vp(w.query_limit), _vp(w.ang_pred),
+                                        _vp(w.points), _vp(w.normals), C.c_uint64(P), _vp(pr), _vp(doff), _vp(dc), _vp(df), C.c_uint64(len(dc)),
+                                        _vp(flags), _vp(w.query_kind), _vp(prox))
+    assert np.array_equal(doff, z["off"]) and nc == len(z["contacts"]) and np.array_equal(prox, z["prox"])
+    assert np.array_equal(_bits(dc[:nc]), _bits(z["contacts"])) and np.array_equal(df[:nc], z["feats"])
+    n = len(z["s_type"])
+    f, out, sf = np.zeros(n, dtype=np.uint8), np.zeros((n, 3), dtype=np.float32), np.zeros(n, dtype=np.uint32)
+    st, sp, sm, sr, spts = (np.ascontiguousarray(z[k]) for k in ("s_type", "s_param", "s_pose", "s_rays", "s_points"))
+    dim2_shim.shim2_ray_cast(C.c_uint64(n), _vp(st), _vp(sp), _vp(sm), _vp(spts), _vp(sr), _vp(f), _vp(out), _vp(sf))
+    hit = f.astype(bool)
+    assert np.array_equal(f, z["s_found"]) and np.array_equal(sf, z["s_feat"]) and np.array_equal(_bits(out[hit]), _bits(z["s_out"][hit]))
