@@ -478,7 +478,9 @@ int ncb2d_world_fetch_proximity(ncb_ctx* ctx, uint8_t* prox, uint32_t cap_pairs)
  * A candidate is an object whose stored (fat) box the ray enters within max_toi; it is kept when the groups allow it and its shape's
  * RayCast::toi_and_normal_with_ray(position, ray, max_toi, solid = true) answers Some.  Rows sorted by (ray, handle): idx[2 k] = (ray,
  * handle), val[3 k] = (toi, normal), feat[k] as in ncb2d_ray_cast; first_only keeps the smallest toi per ray (ties: smallest handle).
- * cap in rows; *n_out = rows found; returns 1 when truncated. */
+ * cap in rows; *n_out = rows found; returns 1 when truncated.  The queries read the context's broad-phase buffers as the last
+ * ncb2d_world_update left them: any other update on the same context (3-D world, stepping world) invalidates them — query before it,
+ * or keep a context per world. */
 int ncb2d_world_ray_cast(ncb_ctx* ctx, uint32_t n_rays, const float* rays, const uint32_t* groups, int first_only, uint32_t* idx, float* val,
                          uint32_t* feat, uint32_t cap, uint32_t* n_out);
 /* glue::interferences_with_aabb (kind 0; 4 floats per query: mins x y, maxs x y) / interferences_with_point (kind 2; 2 floats)
